@@ -1,0 +1,194 @@
+/*
+ * lstur_b200.h — C ABI of the B200-native LSTUR training/scoring hot path.
+ *
+ * Drop-in boundary for the path named in BASELINE.json.  The
+ * reference (nvagus/mnexp) is pure Python on Keras/TensorFlow: it has no FFI
+ * of its own; its "operator API" for this path is the set of Keras layer call
+ * sites in task/paper.py / task/cook.py / models.py.  Each entry point below
+ * names the reference call site(s) it replaces.  The Python shim
+ * (mnexp_b200/task/paper.py) implements the reference's model-builder surface
+ * on top of these calls via ctypes; INTEGRATION.md shows the binding.
+ *
+ * Conventions: every pointer is a DEVICE pointer owned by the caller (any
+ * allocator), row-major, fp32 / int32 unless stated; `ld*` are leading
+ * dimensions in elements; all work is enqueued on `stream`; return value is
+ * LSTUR_OK or a negative LSTUR_ERR_* with text in lstur_last_error().  No
+ * global state besides the thread-local error string; one plan per
+ * stream/rank.  There is no CPU fallback.
+ */
+#ifndef LSTUR_B200_H_
+#define LSTUR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define LSTUR_OK 0
+#define LSTUR_ERR_ARG (-1)
+#define LSTUR_ERR_CUDA (-2)
+#define LSTUR_ERR_UNSUPPORTED (-3)
+#define LSTUR_ERR_WORKSPACE (-4)
+
+#define LSTUR_GEMM_RELU 1
+#define LSTUR_GEMM_ACCUM 2
+
+/* user-encoder architectures (task/paper.py:596-626, task/cook.py:146-168) */
+#define LSTUR_ARCH_INI 0       /* paper 'igru' / cook 'ingru': GRU(initial_state=user_emb) — LSTUR-ini  */
+#define LSTUR_ARCH_CON_DENSE 1 /* paper 'gru': Dense([GRU ‖ user_emb])                    — LSTUR-con  */
+#define LSTUR_ARCH_CON_CAT 2   /* paper 'ngru','hgru','dgru' / cook 'igru': [GRU ‖ user_emb]           */
+#define LSTUR_ARCH_NOID 3      /* paper 'nigru' / cook 'gru': GRU only                                 */
+#define LSTUR_ARCH_ADD 4       /* paper 'pgru' / cook 'agru': GRU + user_emb                           */
+#define LSTUR_ARCH_VO 5        /* 'vo': user_emb only                                                  */
+
+#define LSTUR_SCORE_DOT 0      /* task/paper.py:446-447 */
+
+#define LSTUR_ACT_HARD_SIGMOID 0 /* Keras <= 2.2.x GRU recurrent_activation default */
+#define LSTUR_ACT_SIGMOID 1      /* Keras >= 2.3 */
+
+#define LSTUR_PREC_FP32 0    /* FFMA everywhere: verification mode, ~1e-6 of the oracle */
+#define LSTUR_PREC_BF16_TC 1 /* title Conv1D on tcgen05 (bf16 in, fp32 accumulate in TMEM) */
+
+const char* lstur_last_error(void);
+const char* lstur_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Fine-grained operators (each validated against oracle/ in tests/)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Window.get_title(): np.stack([docs[i].title ...]) task/seq2vec.py:25-30; candidates
+ * task/paper.py:538-541.  tokens[n,:] = doc_tokens[doc_ids[n],:]; ids outside [0,n_docs) read doc 0. */
+int lstur_token_gather(int N, int L, int n_docs, const int* doc_tokens, const int* doc_ids, int* tokens,
+                       cudaStream_t stream);
+
+/* keras Embedding(mask_zero=False) + Dropout, task/paper.py:132-138,142,147, into the zero-haloed
+ * title buffer Xp (N, L+KS-1, E) consumed by the fp32 conv GEMM. */
+int lstur_embed_gather_pad(int N, int L, int E, int V, int KS, const float* word_emb, const int* tokens, float* Xp,
+                           float dropout, unsigned seed, cudaStream_t stream);
+
+/* C[M,N] (+)= op(A).op(B) + bias, optional ReLU: keras Dense / Conv1D-as-GEMM / all weight gradients. */
+size_t lstur_gemm_f32_workspace_bytes(int M, int N, int K, int* splits_out);
+int lstur_gemm_f32(int transA, int transB, int M, int N, int K, const float* A, long long lda, const float* B,
+                   long long ldb, float* C, long long ldc, const float* bias, int flags, void* workspace,
+                   size_t workspace_bytes, cudaStream_t stream);
+
+/* pad mask + Masking + Dropout + models.SimpleAttentionMaskSupport (task/paper.py:150-158, models.py:474-489). */
+int lstur_attn_pool_fwd(int N, int L, int F, float* C, long long title_stride, const int* tokens, const float* att_w,
+                        const float* att_b, float* pooled, long long ldp, float* a_out, float* w_out, float dropout,
+                        unsigned seed, cudaStream_t stream);
+int lstur_attn_bwd_grid(int N);
+int lstur_attn_pool_bwd(int N, int L, int Lrows, int F, const float* Cd, long long title_stride, const float* a_in,
+                        const float* w_in, const float* d_pooled, long long lddp, const float* att_w, float* dPre,
+                        long long dpre_title_stride, float dropout, float* d_att_w, float* d_conv_b, float* d_att_b,
+                        int accumulate, float* partials, size_t partial_bytes, cudaStream_t stream);
+int lstur_colsum(long long rows, int cols, const float* in, long long ld, float* out, int accumulate,
+                 float* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* models.ComputeMasking(0) + multiply Lambda + Masking() (models.py:25-27, task/paper.py:644-645, 592). */
+int lstur_hist_mask_apply(int rows, int L, int D, const int* tokens, float* H, long long ldh, float* hm, float* gm,
+                          cudaStream_t stream);
+
+/* user-ID Embedding lookup (task/paper.py:589-591), optional per-row scale (cook id_keep, task/cook.py:141-142). */
+int lstur_row_gather(int B, int D, int n_rows, const float* table, const int* ids, const float* scale, float* out,
+                     long long ldo, cudaStream_t stream);
+
+/* keras GRU recurrence (task/paper.py:596-613); XW = H.Wx + b is a GEMM done by the caller. */
+int lstur_transpose(int rows, int cols, const float* in, float* out, cudaStream_t stream);
+int lstur_gru_fwd(int B, int W, int G, const float* XW, const float* gm, const float* h0, long long ldh0,
+                  const float* Wh, int rec_act, float* hT, long long ldo, float* Z, float* R, float* HH, float* HP,
+                  float* RH, cudaStream_t stream);
+int lstur_gru_bwd(int B, int W, int G, const float* gm, const float* Z, const float* R, const float* HH,
+                  const float* HP, const float* WhT, int rec_act, const float* dhT, long long lddh, float* dA,
+                  float* dh0, long long lddh0, cudaStream_t stream);
+
+/* dot scorer + softmax + categorical_crossentropy fwd(+bwd) (task/paper.py:446-447, 460-464, 657);
+ * sigmoid test head (task/paper.py:661-665). */
+int lstur_score_softmax_ce(int B, int C, int D, const float* u, long long ldu, const float* d, long long ldd,
+                           const float* label, float* logits, float* probs, float* loss_rows, float* loss_mean,
+                           float* du, long long lddu, float* dd, long long lddd, float grad_scale,
+                           cudaStream_t stream);
+int lstur_score_sigmoid(long long n_pairs, int C, int D, const float* u, long long ldu, const float* d, long long ldd,
+                        float* out, int apply_sigmoid, cudaStream_t stream);
+
+/* keras.optimizers.Adam (task/paper.py:656): dense, and row-sparse for embedding tables. */
+int lstur_adam_dense(long long n, float* p, const float* g, float* m, float* v, float lr, int t, float beta1,
+                     float beta2, float eps, float grad_scale, cudaStream_t stream);
+int lstur_adam_rows(int max_rows, const int* n_rows_dev, int D, const int* rows, const float* g_rows, float* p,
+                    float* m, float* v, float lr, int t, float beta1, float beta2, float eps, float grad_scale,
+                    cudaStream_t stream);
+
+/* Embedding backward = index dedup + segment-sorted scatter-add (deterministic). */
+int lstur_sort_unique_i32(int n, const int* keys, int* sorted_pos, int* uniq, int* seg_start, int* inverse,
+                          int* n_uniq, cudaStream_t stream);
+int lstur_segment_sum_rows(int n, int D, const int* n_uniq, const int* seg_start, const int* sorted_pos,
+                           const float* src, long long lds, float* out, cudaStream_t stream);
+int lstur_rows_add(int max_rows, const int* n_rows_dev, int D, const int* rows, const float* g_rows, float* table,
+                   cudaStream_t stream);
+int lstur_axpby(long long n, float a, const float* x, float b, float* y, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole-path plan: Seq2VecPaperSoftmaxId._build_model (task/paper.py:635-665) /
+ * Cook._build_model (task/cook.py:214-277) as one forward / backward / update sequence.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct lstur_config {
+  int B, W, C, L;      /* rows per rank, window_size, 1+negative_samples, title_shape        */
+  int E, F, KS;        /* textual_embedding_dim, title_filter_shape = (F, KS)                 */
+  int use_dense;       /* 1: Dense(F->Dd) after pooling (paper.py:159); 0: cook.py            */
+  int Dd;              /* title-vector dim: user_embedding_dim if use_dense else F            */
+  int dv, ds;          /* vertical / subvertical embedding dims, 0 = off (cook.py:99-113)     */
+  int G, Ue, U;        /* GRU units, user-embedding dim, user-vector dim                      */
+  int arch, score_model, rec_act, precision;
+  int V, n_users, n_docs;
+  float dropout;
+  int save_for_backward; /* 0: inference plan (smaller workspace)                            */
+} lstur_config;
+
+typedef struct lstur_weights {
+  const float* dense;      /* flat dense parameters, layout from lstur_plan_dense_offset()    */
+  const float* word_emb;   /* (V,E)                                                            */
+  const float* user_emb;   /* (n_users,Ue) or NULL                                             */
+  const int* doc_tokens;   /* (n_docs,L) or NULL when batches carry tokens                     */
+  const int* doc_vert;     /* (n_docs) or NULL                                                 */
+  const int* doc_subvert;  /* (n_docs) or NULL                                                 */
+} lstur_weights;
+
+typedef struct lstur_batch {
+  const int* user;       /* (B)                                                                */
+  const int* hist_doc;   /* (B,W) doc ids, left-padded with 0 — or NULL if hist_tok given      */
+  const int* cand_doc;   /* (B,C) doc ids, positive first                                      */
+  const int* hist_tok;   /* (B,W,L) tokens (reference data protocol, task/paper.py:538-541)    */
+  const int* cand_tok;   /* (B,C,L)                                                            */
+  const float* label;    /* (B,C) one-hot or NULL (= positive at column 0, task/paper.py:529)  */
+  const float* user_scale; /* (B) multiplier on the user embedding or NULL (dgru / id_keep)    */
+} lstur_batch;
+
+typedef struct lstur_plan lstur_plan;
+
+int lstur_plan_create(const lstur_config* cfg, lstur_plan** out);
+void lstur_plan_destroy(lstur_plan* plan);
+size_t lstur_plan_workspace_bytes(const lstur_plan* plan);
+long long lstur_plan_dense_count(const lstur_plan* plan);
+/* name in {conv_w, conv_b, att_w, att_b, dense_w, dense_b, vert_emb, subvert_emb, gru_wx, gru_wh, gru_b,
+ * con_w, con_b}; returns LSTUR_ERR_ARG if the tensor does not exist in this configuration. */
+int lstur_plan_dense_offset(const lstur_plan* plan, const char* name, long long* offset, long long* count);
+/* named views into the workspace after forward/backward (for tests and the Python shim):
+ * tokens, pooled, doc_vec, hist_mask, user_vec, logits, probs, loss, d_user_rows, user_rows, n_user_rows */
+int lstur_plan_view(const lstur_plan* plan, void* workspace, const char* name, void** ptr, long long* count);
+
+int lstur_forward(const lstur_plan* plan, const lstur_weights* w, const lstur_batch* b, void* workspace,
+                  int training, unsigned seed, cudaStream_t stream);
+/* dense_grad (dense_count floats) is overwritten.  User-embedding gradient is left as unique rows in the
+ * workspace (views user_rows / d_user_rows / n_user_rows).  grad_scale multiplies d(loss): 1/global_batch. */
+int lstur_backward(const lstur_plan* plan, const lstur_weights* w, const lstur_batch* b, void* workspace,
+                   float* dense_grad, float grad_scale, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSTUR_B200_H_ */

@@ -1,0 +1,228 @@
+// Pad-token mask + Masking + Dropout + additive-attention pooling, forward and backward.
+//
+// Reference: task/paper.py:150-158 (Lambda pad mask, Masking, Dropout) and
+// models.SimpleAttentionMaskSupport.call models.py:474-489:
+//   C <- C*[tok!=0];  m = any_f(C != 0);  C <- dropout(C*m)
+//   a = tanh(C.ka + ba);  e = exp(a)*m;  w = e/(sum_t e + 1e-7);  p = sum_t w_t C_t
+// These are the un-fused (verification) kernels; the tensor-core conv kernel
+// carries the same arithmetic in its epilogue.
+#include "common.cuh"
+
+namespace lstur {
+
+constexpr int ATT_THREADS = 128;
+constexpr int ATT_MAX_L = 256;
+
+// One CTA per title.  C (in/out): conv+bias+relu on entry, attention input on exit.
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_pool_fwd_kernel(int N, int L, int F, float* __restrict__ C, long long title_stride,
+                     const int* __restrict__ tok, const float* __restrict__ ka, const float* __restrict__ ba,
+                     float* __restrict__ p, long long ldp, float* __restrict__ a_out, float* __restrict__ w_out,
+                     uint32_t drop_thr, float inv_keep, uint32_t seed) {
+  __shared__ float sa[ATT_MAX_L], se[ATT_MAX_L];
+  const int n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* Cn = C + (long long)n * title_stride;
+  const float bias = ba[0];
+  for (int t = warp; t < L; t += ATT_THREADS / 32) {
+    const int tk = tok[(long long)n * L + t];
+    float dot = 0.f;
+    int any = 0;
+    const uint64_t base = ((uint64_t)n * L + t) * (uint64_t)F;
+    for (int f = lane; f < F; f += 32) {
+      float v = tk != 0 ? Cn[(long long)t * F + f] : 0.f;
+      any |= (v != 0.f);
+      if (drop_thr) v = (rng_u32(seed, base + f) >> 8) >= drop_thr ? v * inv_keep : 0.f;
+      Cn[(long long)t * F + f] = v;
+      dot = fmaf(v, ka[f], dot);
+    }
+    any = warp_or(any);
+    dot = warp_sum(dot);
+    if (lane == 0) {
+      float a = tanhf(dot + bias);
+      sa[t] = a;
+      se[t] = any ? expf(a) : 0.f;
+    }
+  }
+  __syncthreads();
+  float S = 0.f;
+  for (int t = 0; t < L; ++t) S += se[t];
+  const float invS = 1.f / (S + 1e-7f);
+  for (int t = tid; t < L; t += ATT_THREADS) {
+    if (a_out) a_out[(long long)n * L + t] = sa[t];
+    if (w_out) w_out[(long long)n * L + t] = se[t] * invS;
+  }
+  for (int f = tid; f < F; f += ATT_THREADS) {
+    float acc = 0.f;
+    for (int t = 0; t < L; ++t) acc = fmaf(se[t] * invS, Cn[(long long)t * F + f], acc);
+    p[(long long)n * ldp + f] = acc;
+  }
+}
+
+// Backward of the block above.  Grid-strided over titles; each CTA keeps
+// per-thread partial sums of d(ka), d(conv bias) and d(ba) and writes them to
+// partials[cta][2F+1] (reduced afterwards in a fixed order -> deterministic).
+//   dPre = d(loss)/d(conv pre-activation) incl. ReLU/pad/Masking/Dropout gates.
+template <int FPT>
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_pool_bwd_kernel(int N, int L, int Lrows, int F, const float* __restrict__ Cd, long long title_stride,
+                     const float* __restrict__ a_in, const float* __restrict__ w_in, const float* __restrict__ dp,
+                     long long lddp, const float* __restrict__ ka, float* __restrict__ dPre,
+                     long long dpre_title_stride, float inv_keep, float* __restrict__ partials) {
+  __shared__ float sdw[ATT_MAX_L], sdz[ATT_MAX_L], sw[ATT_MAX_L];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float dka[FPT], dbc[FPT], dba = 0.f;
+#pragma unroll
+  for (int i = 0; i < FPT; ++i) dka[i] = dbc[i] = 0.f;
+  for (int n = blockIdx.x; n < N; n += gridDim.x) {
+    const float* Cn = Cd + (long long)n * title_stride;
+    const float* dpn = dp + (long long)n * lddp;
+    float* dPn = dPre + (long long)n * dpre_title_stride;
+    for (int t = warp; t < L; t += ATT_THREADS / 32) {
+      float dot = 0.f;
+      for (int f = lane; f < F; f += 32) dot = fmaf(Cn[(long long)t * F + f], dpn[f], dot);
+      dot = warp_sum(dot);
+      if (lane == 0) {
+        sdw[t] = dot;
+        sw[t] = w_in[(long long)n * L + t];
+      }
+    }
+    __syncthreads();
+    float q = 0.f;
+    for (int t = 0; t < L; ++t) q = fmaf(sdw[t], sw[t], q);
+    for (int t = tid; t < L; t += ATT_THREADS) {
+      float a = a_in[(long long)n * L + t];
+      sdz[t] = (sdw[t] - q) * sw[t] * (1.f - a * a);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < FPT; ++i) {
+      int f = tid + i * ATT_THREADS;
+      if (f < F) {
+        const float dpf = dpn[f], kaf = ka[f];
+        for (int t = 0; t < L; ++t) {
+          float c = Cn[(long long)t * F + f];
+          float g = fmaf(sw[t], dpf, sdz[t] * kaf);
+          float dpre = c > 0.f ? g * inv_keep : 0.f;
+          dPn[(long long)t * F + f] = dpre;
+          dka[i] = fmaf(sdz[t], c, dka[i]);
+          dbc[i] += dpre;
+        }
+        for (int t = L; t < Lrows; ++t) dPn[(long long)t * F + f] = 0.f;
+      }
+    }
+    if (tid == 0)
+      for (int t = 0; t < L; ++t) dba += sdz[t];
+    __syncthreads();
+  }
+  float* out = partials + (long long)blockIdx.x * (2 * F + 1);
+#pragma unroll
+  for (int i = 0; i < FPT; ++i) {
+    int f = tid + i * ATT_THREADS;
+    if (f < F) {
+      out[f] = dka[i];
+      out[F + f] = dbc[i];
+    }
+  }
+  if (tid == 0) out[2 * F] = dba;
+}
+
+// out[c] (+)= sum_r in[r*ld + c], two fixed-order stages (deterministic).
+__global__ void colsum_stage1_kernel(long long rows, int cols, const float* __restrict__ in, long long ld,
+                                     int rows_per_chunk, float* __restrict__ partial) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  long long r0 = (long long)blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
+  float s = 0.f;
+  for (long long r = r0; r < r1; ++r) s += in[r * ld + c];
+  partial[(long long)blockIdx.y * cols + c] = s;
+}
+__global__ void colsum_stage2_kernel(int chunks, int cols, const float* __restrict__ partial, float* __restrict__ out,
+                                     int accumulate) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int k = 0; k < chunks; ++k) s += partial[(long long)k * cols + c];
+  out[c] = accumulate ? out[c] + s : s;
+}
+
+// partials[grid][2F+1] -> d_att_w[F], d_conv_b[F], d_att_b[1] in a fixed order.
+__global__ void attn_bwd_reduce_kernel(int grid, int F, const float* __restrict__ partials, float* __restrict__ d_att_w,
+                                       float* __restrict__ d_conv_b, float* __restrict__ d_att_b, int accumulate) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > 2 * F) return;
+  float s = 0.f;
+  for (int g = 0; g < grid; ++g) s += partials[(long long)g * (2 * F + 1) + c];
+  float* dst = c < F ? d_att_w + c : (c < 2 * F ? d_conv_b + (c - F) : d_att_b);
+  *dst = accumulate ? *dst + s : s;
+}
+
+}  // namespace lstur
+
+using namespace lstur;
+
+extern "C" int lstur_attn_pool_fwd(int N, int L, int F, float* C, long long title_stride, const int* tokens,
+                                   const float* att_w, const float* att_b, float* pooled, long long ldp, float* a_out,
+                                   float* w_out, float dropout, unsigned seed, cudaStream_t stream) {
+  LSTUR_REQUIRE(N >= 0 && L > 0 && L <= ATT_MAX_L && F > 0 && dropout >= 0.f && dropout < 1.f, "lstur_attn_pool_fwd");
+  if (N == 0) return LSTUR_OK;
+  attn_pool_fwd_kernel<<<N, ATT_THREADS, 0, stream>>>(N, L, F, C, title_stride, tokens, att_w, att_b, pooled, ldp, a_out,
+                                                      w_out, dropout > 0.f ? dropout_threshold(dropout) : 0u,
+                                                      1.f / (1.f - dropout), seed);
+  LSTUR_CHECK_LAUNCH("lstur_attn_pool_fwd");
+  return LSTUR_OK;
+}
+
+extern "C" int lstur_attn_bwd_grid(int N) { return N < 148 * 4 ? (N > 0 ? N : 1) : 148 * 4; }
+
+extern "C" int lstur_colsum(long long rows, int cols, const float* in, long long ld, float* out, int accumulate,
+                            float* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  LSTUR_REQUIRE(rows >= 0 && cols > 0, "lstur_colsum");
+  int chunks = (int)((rows + 255) / 256);
+  if (chunks > 1024) chunks = 1024;
+  if (chunks < 1) chunks = 1;
+  LSTUR_REQUIRE(workspace != nullptr && workspace_bytes >= (size_t)chunks * cols * sizeof(float), "lstur_colsum");
+  int rpc = (int)((rows + chunks - 1) / chunks);
+  if (rpc < 1) rpc = 1;
+  dim3 g1(cdiv(cols, 128), chunks);
+  colsum_stage1_kernel<<<g1, 128, 0, stream>>>(rows, cols, in, ld, rpc, workspace);
+  LSTUR_CHECK_LAUNCH("lstur_colsum(stage1)");
+  colsum_stage2_kernel<<<cdiv(cols, 128), 128, 0, stream>>>(chunks, cols, workspace, out, accumulate);
+  LSTUR_CHECK_LAUNCH("lstur_colsum(stage2)");
+  return LSTUR_OK;
+}
+
+// partials must hold lstur_attn_bwd_grid(N) * (2F+1) floats; after the call
+// d_att_w[F], d_conv_b[F], d_att_b[1] are written (or accumulated).
+extern "C" int lstur_attn_pool_bwd(int N, int L, int Lrows, int F, const float* Cd, long long title_stride,
+                                   const float* a_in, const float* w_in, const float* d_pooled, long long lddp,
+                                   const float* att_w, float* dPre, long long dpre_title_stride, float dropout,
+                                   float* d_att_w, float* d_conv_b, float* d_att_b, int accumulate, float* partials,
+                                   size_t partial_bytes, cudaStream_t stream) {
+  LSTUR_REQUIRE(N >= 0 && L > 0 && L <= ATT_MAX_L && Lrows >= L && F > 0 && F <= 8 * ATT_THREADS, "lstur_attn_pool_bwd");
+  int grid = lstur_attn_bwd_grid(N);
+  size_t need = (size_t)grid * (2 * F + 1) * sizeof(float);
+  LSTUR_REQUIRE(partials != nullptr && partial_bytes >= need, "lstur_attn_pool_bwd");
+  if (N == 0) {
+    if (!accumulate) {
+      cudaMemsetAsync(d_att_w, 0, F * sizeof(float), stream);
+      cudaMemsetAsync(d_conv_b, 0, F * sizeof(float), stream);
+      cudaMemsetAsync(d_att_b, 0, sizeof(float), stream);
+    }
+    return LSTUR_OK;
+  }
+  float inv_keep = 1.f / (1.f - dropout);
+  int fpt = cdiv(F, ATT_THREADS);
+#define LAUNCH(FPT_)                                                                                                  \
+  attn_pool_bwd_kernel<FPT_><<<grid, ATT_THREADS, 0, stream>>>(N, L, Lrows, F, Cd, title_stride, a_in, w_in, d_pooled, \
+                                                               lddp, att_w, dPre, dpre_title_stride, inv_keep, partials)
+  if (fpt <= 1) LAUNCH(1);
+  else if (fpt <= 2) LAUNCH(2);
+  else if (fpt <= 4) LAUNCH(4);
+  else LAUNCH(8);
+#undef LAUNCH
+  LSTUR_CHECK_LAUNCH("lstur_attn_pool_bwd");
+  attn_bwd_reduce_kernel<<<cdiv(2 * F + 1, 128), 128, 0, stream>>>(grid, F, partials, d_att_w, d_conv_b, d_att_b,
+                                                                     accumulate);
+  LSTUR_CHECK_LAUNCH("lstur_attn_pool_bwd(reduce)");
+  return LSTUR_OK;
+}

@@ -1,0 +1,455 @@
+// Whole-path plan: forward / backward of the LSTUR training graph on one stream.
+//
+// Mirrors Seq2VecPaperSoftmaxId._build_model (task/paper.py:635-665): TimeDistributed news
+// encoder over the B*W clicked titles and the B*C candidates, ComputeMasking multiply, user
+// encoder (user-ID embedding + masked GRU), dot scorer, softmax + categorical cross-entropy.
+// Host-side code only sequences kernels and carves the caller-provided workspace; all arithmetic
+// is in the kernels of this directory.
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace lstur {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+struct Region {
+  size_t off;       // bytes into workspace
+  long long count;  // elements (4-byte)
+};
+
+}  // namespace lstur
+
+struct lstur_plan {
+  lstur_config c;
+  int N, Nh, Nc, Lp, D;
+  std::map<std::string, lstur::Region> ws;     // workspace regions
+  std::map<std::string, lstur::Region> dense;  // dense-parameter layout (off in floats)
+  size_t ws_bytes = 0;
+  long long dense_count = 0;
+  size_t gemm_ws_bytes = 0;
+};
+
+using namespace lstur;
+
+extern "C" const char* lstur_last_error(void) { return g_err; }
+extern "C" const char* lstur_version(void) { return "lstur_b200 0.1 (sm_100a)"; }
+
+// conv tensor-core path (conv_tc.cu)
+extern "C" int lstur_conv_tc_available(void);
+
+namespace {
+
+void add_ws(lstur_plan* p, const char* name, long long count) {
+  size_t off = (p->ws_bytes + 255) & ~(size_t)255;
+  p->ws[name] = Region{off, count};
+  p->ws_bytes = off + (size_t)count * 4;
+}
+void add_dense(lstur_plan* p, const char* name, long long count) {
+  long long off = (p->dense_count + 3) & ~3LL;
+  p->dense[name] = Region{(size_t)off, count};
+  p->dense_count = off + count;
+}
+template <typename T>
+T* W(const lstur_plan* p, void* ws, const char* name) {
+  auto it = p->ws.find(name);
+  return it == p->ws.end() ? nullptr : (T*)((char*)ws + it->second.off);
+}
+const float* DP(const lstur_plan* p, const float* dense, const char* name) {
+  auto it = p->dense.find(name);
+  return it == p->dense.end() ? nullptr : dense + it->second.off;
+}
+float* DG(const lstur_plan* p, float* dense, const char* name) {
+  auto it = p->dense.find(name);
+  return it == p->dense.end() ? nullptr : dense + it->second.off;
+}
+void track_gemm(lstur_plan* p, int M, int N, int K) {
+  size_t b = lstur_gemm_f32_workspace_bytes(M, N, K, nullptr);
+  if (b > p->gemm_ws_bytes) p->gemm_ws_bytes = b;
+}
+
+#define RC(x)              \
+  do {                     \
+    int rc__ = (x);        \
+    if (rc__) return rc__; \
+  } while (0)
+
+}  // namespace
+
+extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
+  LSTUR_REQUIRE(cfg && out, "lstur_plan_create");
+  const lstur_config& c = *cfg;
+  LSTUR_REQUIRE(c.B > 0 && c.W > 0 && c.C >= 1 && c.C <= 32 && c.L > 0 && c.L <= 256, "lstur_plan_create");
+  LSTUR_REQUIRE(c.E > 0 && c.F > 0 && c.KS >= 1 && c.KS <= c.L, "lstur_plan_create");
+  LSTUR_REQUIRE(c.dropout >= 0.f && c.dropout < 1.f, "lstur_plan_create");
+  if (c.score_model != LSTUR_SCORE_DOT) {
+    set_error("lstur_plan_create: score_model %d not implemented (NotImplementedError, task/paper.py:457)", c.score_model);
+    return LSTUR_ERR_UNSUPPORTED;
+  }
+  if (c.arch < LSTUR_ARCH_INI || c.arch > LSTUR_ARCH_VO) {
+    set_error("lstur_plan_create: Unsupport user model (task/paper.py:630)");
+    return LSTUR_ERR_UNSUPPORTED;
+  }
+  if (c.dv != 0 || c.ds != 0) {
+    set_error("lstur_plan_create: vertical/subvertical concat not implemented yet");
+    return LSTUR_ERR_UNSUPPORTED;
+  }
+  const int Dd = c.use_dense ? c.Dd : c.F;
+  const int D = Dd + c.dv + c.ds;
+  const bool has_gru = c.arch != LSTUR_ARCH_VO;
+  const bool has_user = c.arch != LSTUR_ARCH_NOID;
+  LSTUR_REQUIRE(!has_gru || (c.G > 0 && c.G % 4 == 0 && c.G <= 1024), "lstur_plan_create");
+  LSTUR_REQUIRE(!has_user || (c.Ue > 0 && c.n_users > 0), "lstur_plan_create");
+  // user-vector dim implied by the architecture
+  int U = c.arch == LSTUR_ARCH_INI ? c.G : c.arch == LSTUR_ARCH_CON_DENSE ? c.U : c.arch == LSTUR_ARCH_CON_CAT ? c.G + c.Ue
+          : c.arch == LSTUR_ARCH_NOID ? c.G : c.arch == LSTUR_ARCH_ADD ? c.G : c.Ue;
+  LSTUR_REQUIRE(U == c.U, "lstur_plan_create(U inconsistent with arch)");
+  LSTUR_REQUIRE(c.arch != LSTUR_ARCH_INI || c.Ue == c.G, "lstur_plan_create(ini needs Ue == G)");
+  LSTUR_REQUIRE(c.arch != LSTUR_ARCH_ADD || c.Ue == c.G, "lstur_plan_create(add needs Ue == G)");
+  LSTUR_REQUIRE(U == D, "lstur_plan_create('dot' scorer needs user dim == doc dim)");
+  if (c.precision == LSTUR_PREC_BF16_TC && !lstur_conv_tc_available()) {
+    set_error("lstur_plan_create: tensor-core conv path not built");
+    return LSTUR_ERR_UNSUPPORTED;
+  }
+
+  lstur_plan* p = new lstur_plan();
+  p->c = c;
+  p->c.Dd = Dd;
+  p->Nh = c.B * c.W;
+  p->Nc = c.B * c.C;
+  p->N = p->Nh + p->Nc;
+  p->Lp = c.L + c.KS - 1;
+  p->D = D;
+  const long long N = p->N, Nh = p->Nh, B = c.B, Lp = p->Lp;
+  const int G = c.G, F = c.F, E = c.E;
+  const bool bw = c.save_for_backward != 0;
+
+  // ---- dense parameter layout
+  add_dense(p, "conv_w", (long long)c.KS * E * F);
+  add_dense(p, "conv_b", F);
+  add_dense(p, "att_w", F);
+  add_dense(p, "att_b", 1);
+  if (c.use_dense) {
+    add_dense(p, "dense_w", (long long)F * Dd);
+    add_dense(p, "dense_b", Dd);
+  }
+  if (has_gru) {
+    add_dense(p, "gru_wx", (long long)D * 3 * G);
+    add_dense(p, "gru_wh", (long long)G * 3 * G);
+    add_dense(p, "gru_b", 3 * G);
+  }
+  if (c.arch == LSTUR_ARCH_CON_DENSE) {
+    add_dense(p, "con_w", (long long)(G + c.Ue) * c.U);
+    add_dense(p, "con_b", c.U);
+  }
+  p->dense_count = (p->dense_count + 3) & ~3LL;
+
+  // ---- workspace
+  add_ws(p, "tokens", N * c.L);
+  add_ws(p, "Xp", N * Lp * E);
+  add_ws(p, "Cp", N * Lp * F);
+  add_ws(p, "att_a", N * c.L);
+  add_ws(p, "att_w", N * c.L);
+  add_ws(p, "pooled", N * F);
+  add_ws(p, "doc_vec", N * D);
+  add_ws(p, "hist_mask", Nh);
+  add_ws(p, "gru_mask", Nh);
+  if (has_user) add_ws(p, "u0", B * c.Ue);
+  if (has_gru) {
+    add_ws(p, "XW", Nh * 3 * G);
+    add_ws(p, "hT", B * G);
+    if (bw) {
+      for (const char* n : {"Z", "R", "HH", "HP", "RH"}) add_ws(p, n, Nh * G);
+    }
+  }
+  if (c.arch == LSTUR_ARCH_CON_DENSE || c.arch == LSTUR_ARCH_CON_CAT) add_ws(p, "cat", B * (G + c.Ue));
+  add_ws(p, "user_vec", B * c.U);
+  add_ws(p, "logits", B * c.C);
+  add_ws(p, "probs", B * c.C);
+  add_ws(p, "loss_rows", B);
+  add_ws(p, "loss", 1);
+  track_gemm(p, (int)(N * Lp), F, c.KS * E);
+  track_gemm(p, (int)N, Dd, F);
+  if (bw) {
+    add_ws(p, "d_user_vec", B * c.U);
+    add_ws(p, "d_doc_vec", N * D);
+    add_ws(p, "d_pooled", N * F);
+    add_ws(p, "dPre", N * Lp * F);
+    add_ws(p, "attn_partials", (long long)lstur_attn_bwd_grid((int)N) * (2 * F + 1));
+    if (has_gru) {
+      add_ws(p, "WhT", (long long)3 * G * G);
+      add_ws(p, "dA", Nh * 3 * G);
+      add_ws(p, "dh0", B * G);
+    }
+    if (c.arch == LSTUR_ARCH_CON_DENSE) add_ws(p, "d_cat", B * (G + c.Ue));
+    if (has_user) {
+      add_ws(p, "sorted_pos", B);
+      add_ws(p, "user_rows", B);
+      add_ws(p, "seg_start", B + 1);
+      add_ws(p, "inverse", B);
+      add_ws(p, "n_user_rows", 1);
+      add_ws(p, "d_user_rows", B * c.Ue);
+    }
+    track_gemm(p, c.KS * E, F, (int)(N * Lp));
+    track_gemm(p, F, Dd, (int)N);
+    track_gemm(p, (int)N, F, Dd);
+    if (has_gru) {
+      track_gemm(p, D, 3 * G, (int)Nh);
+      track_gemm(p, G, 2 * G, (int)Nh);
+      track_gemm(p, (int)Nh, D, 3 * G);
+    }
+    if (c.arch == LSTUR_ARCH_CON_DENSE) track_gemm(p, G + c.Ue, c.U, (int)B);
+  }
+  if (has_gru) track_gemm(p, (int)Nh, 3 * G, D);
+  add_ws(p, "gemm_ws", (long long)(p->gemm_ws_bytes / 4) + 4);
+  {
+    int cols = 3 * G > D ? 3 * G : D;
+    if (c.U > cols) cols = c.U;
+    add_ws(p, "colsum_ws", (long long)1024 * cols);
+  }
+  p->ws_bytes = (p->ws_bytes + 255) & ~(size_t)255;
+  *out = p;
+  return LSTUR_OK;
+}
+
+extern "C" void lstur_plan_destroy(lstur_plan* plan) { delete plan; }
+extern "C" size_t lstur_plan_workspace_bytes(const lstur_plan* plan) { return plan ? plan->ws_bytes : 0; }
+extern "C" long long lstur_plan_dense_count(const lstur_plan* plan) { return plan ? plan->dense_count : 0; }
+
+extern "C" int lstur_plan_dense_offset(const lstur_plan* plan, const char* name, long long* offset, long long* count) {
+  LSTUR_REQUIRE(plan && name, "lstur_plan_dense_offset");
+  auto it = plan->dense.find(name);
+  if (it == plan->dense.end()) {
+    set_error("lstur_plan_dense_offset: no tensor '%s' in this configuration", name);
+    return LSTUR_ERR_ARG;
+  }
+  if (offset) *offset = (long long)it->second.off;
+  if (count) *count = it->second.count;
+  return LSTUR_OK;
+}
+
+extern "C" int lstur_plan_view(const lstur_plan* plan, void* workspace, const char* name, void** ptr, long long* count) {
+  LSTUR_REQUIRE(plan && name && ptr, "lstur_plan_view");
+  auto it = plan->ws.find(name);
+  if (it == plan->ws.end()) {
+    set_error("lstur_plan_view: no workspace region '%s'", name);
+    return LSTUR_ERR_ARG;
+  }
+  *ptr = (char*)workspace + it->second.off;
+  if (count) *count = it->second.count;
+  return LSTUR_OK;
+}
+
+// tensor-core news encoder (conv_tc.cu); declared here, defined there.
+extern "C" int lstur_news_encoder_tc_fwd_internal(const lstur_plan* plan, const lstur_weights* w, void* workspace,
+                                                  int training, unsigned seed, cudaStream_t stream);
+
+extern "C" int lstur_forward(const lstur_plan* p, const lstur_weights* w, const lstur_batch* b, void* ws, int training,
+                             unsigned seed, cudaStream_t st) {
+  LSTUR_REQUIRE(p && w && b && ws, "lstur_forward");
+  LSTUR_REQUIRE(w->dense && w->word_emb && b->user, "lstur_forward");
+  const lstur_config& c = p->c;
+  const int N = p->N, Nh = p->Nh, Nc = p->Nc, Lp = p->Lp, D = p->D, L = c.L, E = c.E, F = c.F, G = c.G, B = c.B;
+  const bool bw = c.save_for_backward != 0;
+  LSTUR_REQUIRE(!training || bw, "lstur_forward(training needs a save_for_backward plan)");
+  const float drop = training ? c.dropout : 0.f;
+  int* tok = W<int>(p, ws, "tokens");
+  // 1. title tokens (k0)
+  if (b->hist_tok) {
+    LSTUR_REQUIRE(b->cand_tok != nullptr, "lstur_forward");
+    cudaMemcpyAsync(tok, b->hist_tok, (size_t)Nh * L * 4, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(tok + (size_t)Nh * L, b->cand_tok, (size_t)Nc * L * 4, cudaMemcpyDeviceToDevice, st);
+  } else {
+    LSTUR_REQUIRE(b->hist_doc && b->cand_doc && w->doc_tokens, "lstur_forward");
+    RC(lstur_token_gather(Nh, L, c.n_docs, w->doc_tokens, b->hist_doc, tok, st));
+    RC(lstur_token_gather(Nc, L, c.n_docs, w->doc_tokens, b->cand_doc, tok + (size_t)Nh * L, st));
+  }
+  float* pooled = W<float>(p, ws, "pooled");
+  float* docv = W<float>(p, ws, "doc_vec");
+  void* gws = W<void>(p, ws, "gemm_ws");
+  const size_t gwsb = p->gemm_ws_bytes;
+  // 2. news encoder (k1-k7)
+  if (c.precision == LSTUR_PREC_BF16_TC) {
+    RC(lstur_news_encoder_tc_fwd_internal(p, w, ws, training, seed, st));
+  } else {
+    float* Xp = W<float>(p, ws, "Xp");
+    float* Cp = W<float>(p, ws, "Cp");
+    RC(lstur_embed_gather_pad(N, L, E, c.V, c.KS, w->word_emb, tok, Xp, drop, seed * 2u + 0u, st));
+    RC(lstur_gemm_f32(0, 0, N * Lp - (c.KS - 1), F, c.KS * E, Xp, E, DP(p, w->dense, "conv_w"), F, Cp, F,
+                      DP(p, w->dense, "conv_b"), LSTUR_GEMM_RELU, gws, gwsb, st));
+    RC(lstur_attn_pool_fwd(N, L, F, Cp, (long long)Lp * F, tok, DP(p, w->dense, "att_w"), DP(p, w->dense, "att_b"),
+                           pooled, F, W<float>(p, ws, "att_a"), W<float>(p, ws, "att_w"), drop, seed * 2u + 1u, st));
+  }
+  if (c.use_dense) {
+    RC(lstur_gemm_f32(0, 0, N, c.Dd, F, pooled, F, DP(p, w->dense, "dense_w"), c.Dd, docv, D,
+                      DP(p, w->dense, "dense_b"), 0, gws, gwsb, st));
+  } else {
+    cudaMemcpy2DAsync(docv, (size_t)D * 4, pooled, (size_t)F * 4, (size_t)F * 4, N, cudaMemcpyDeviceToDevice, st);
+  }
+  // 3. history mask (k9)
+  RC(lstur_hist_mask_apply(Nh, L, D, tok, docv, D, W<float>(p, ws, "hist_mask"), W<float>(p, ws, "gru_mask"), st));
+  // 4. user embedding (k10)
+  float* uvec = W<float>(p, ws, "user_vec");
+  float* u0 = W<float>(p, ws, "u0");
+  float* cat = W<float>(p, ws, "cat");
+  const bool has_gru = c.arch != LSTUR_ARCH_VO, has_user = c.arch != LSTUR_ARCH_NOID;
+  if (has_user) {
+    LSTUR_REQUIRE(w->user_emb != nullptr, "lstur_forward");
+    RC(lstur_row_gather(B, c.Ue, c.n_users, w->user_emb, b->user, b->user_scale, u0, c.Ue, st));
+  }
+  // 5. GRU (k11-k12)
+  if (has_gru) {
+    float* XW = W<float>(p, ws, "XW");
+    RC(lstur_gemm_f32(0, 0, Nh, 3 * G, D, docv, D, DP(p, w->dense, "gru_wx"), 3 * G, XW, 3 * G,
+                      DP(p, w->dense, "gru_b"), 0, gws, gwsb, st));
+    float* hT = W<float>(p, ws, "hT");
+    float* hdst = hT;
+    long long ldo = G;
+    if (c.arch == LSTUR_ARCH_INI || c.arch == LSTUR_ARCH_NOID) hdst = uvec;
+    if (cat) { hdst = cat; ldo = G + c.Ue; }
+    RC(lstur_gru_fwd(B, c.W, G, XW, W<float>(p, ws, "gru_mask"), c.arch == LSTUR_ARCH_INI ? u0 : nullptr, c.Ue,
+                     DP(p, w->dense, "gru_wh"), c.rec_act, hdst, ldo, bw ? W<float>(p, ws, "Z") : nullptr,
+                     bw ? W<float>(p, ws, "R") : nullptr, bw ? W<float>(p, ws, "HH") : nullptr,
+                     bw ? W<float>(p, ws, "HP") : nullptr, bw ? W<float>(p, ws, "RH") : nullptr, st));
+    if (cat) {
+      cudaMemcpy2DAsync(cat + G, (size_t)(G + c.Ue) * 4, u0, (size_t)c.Ue * 4, (size_t)c.Ue * 4, B,
+                        cudaMemcpyDeviceToDevice, st);
+      if (c.arch == LSTUR_ARCH_CON_DENSE) {
+        RC(lstur_gemm_f32(0, 0, B, c.U, G + c.Ue, cat, G + c.Ue, DP(p, w->dense, "con_w"), c.U, uvec, c.U,
+                          DP(p, w->dense, "con_b"), 0, gws, gwsb, st));
+      } else {
+        cudaMemcpyAsync(uvec, cat, (size_t)B * c.U * 4, cudaMemcpyDeviceToDevice, st);
+      }
+    } else if (c.arch == LSTUR_ARCH_ADD) {
+      cudaMemcpyAsync(uvec, hT, (size_t)B * G * 4, cudaMemcpyDeviceToDevice, st);
+      RC(lstur_axpby((long long)B * G, 1.f, u0, 1.f, uvec, st));
+    }
+  } else {
+    cudaMemcpyAsync(uvec, u0, (size_t)B * c.Ue * 4, cudaMemcpyDeviceToDevice, st);
+  }
+  // 6. score + softmax + loss (k13-k14)
+  RC(lstur_score_softmax_ce(B, c.C, D, uvec, c.U, docv + (size_t)Nh * D, D, b->label, W<float>(p, ws, "logits"),
+                            W<float>(p, ws, "probs"), W<float>(p, ws, "loss_rows"), W<float>(p, ws, "loss"), nullptr, 0,
+                            nullptr, 0, 0.f, st));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("lstur_forward: %s", cudaGetErrorString(e));
+    return LSTUR_ERR_CUDA;
+  }
+  return LSTUR_OK;
+}
+
+extern "C" int lstur_news_encoder_tc_bwd_internal(const lstur_plan* plan, const lstur_weights* w, void* workspace,
+                                                  float* dense_grad, cudaStream_t stream);
+
+extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const lstur_batch* b, void* ws,
+                              float* dgrad, float grad_scale, cudaStream_t st) {
+  LSTUR_REQUIRE(p && w && b && ws && dgrad, "lstur_backward");
+  const lstur_config& c = p->c;
+  LSTUR_REQUIRE(c.save_for_backward != 0, "lstur_backward");
+  const int N = p->N, Nh = p->Nh, Lp = p->Lp, D = p->D, L = c.L, E = c.E, F = c.F, G = c.G, B = c.B;
+  void* gws = W<void>(p, ws, "gemm_ws");
+  const size_t gwsb = p->gemm_ws_bytes;
+  float* cws = W<float>(p, ws, "colsum_ws");
+  const size_t cwsb = p->ws.at("colsum_ws").count * 4;
+  float* docv = W<float>(p, ws, "doc_vec");
+  float* uvec = W<float>(p, ws, "user_vec");
+  float* d_uvec = W<float>(p, ws, "d_user_vec");
+  float* d_docv = W<float>(p, ws, "d_doc_vec");
+  const bool has_gru = c.arch != LSTUR_ARCH_VO, has_user = c.arch != LSTUR_ARCH_NOID;
+  cudaMemsetAsync(dgrad, 0, (size_t)p->dense_count * 4, st);
+  // 1. loss / score backward
+  RC(lstur_score_softmax_ce(B, c.C, D, uvec, c.U, docv + (size_t)Nh * D, D, b->label, nullptr, nullptr, nullptr, nullptr,
+                            d_uvec, c.U, d_docv + (size_t)Nh * D, D, grad_scale, st));
+  // 2. user-encoder head backward
+  const float* dhT = d_uvec;
+  long long lddh = c.U;
+  const float* du0 = nullptr;
+  long long lddu0 = 0;
+  if (c.arch == LSTUR_ARCH_CON_DENSE) {
+    float* cat = W<float>(p, ws, "cat");
+    float* d_cat = W<float>(p, ws, "d_cat");
+    const int K2 = G + c.Ue;
+    RC(lstur_gemm_f32(0, 1, B, K2, c.U, d_uvec, c.U, DP(p, w->dense, "con_w"), c.U, d_cat, K2, nullptr, 0, gws, gwsb, st));
+    RC(lstur_gemm_f32(1, 0, K2, c.U, B, cat, K2, d_uvec, c.U, DG(p, dgrad, "con_w"), c.U, nullptr, 0, gws, gwsb, st));
+    RC(lstur_colsum(B, c.U, d_uvec, c.U, DG(p, dgrad, "con_b"), 0, cws, cwsb, st));
+    dhT = d_cat; lddh = K2; du0 = d_cat + G; lddu0 = K2;
+  } else if (c.arch == LSTUR_ARCH_CON_CAT) {
+    du0 = d_uvec + G; lddu0 = c.U;
+  } else if (c.arch == LSTUR_ARCH_ADD || c.arch == LSTUR_ARCH_VO) {
+    du0 = d_uvec; lddu0 = c.U;
+  }
+  // 3. GRU backward
+  if (has_gru) {
+    float* WhT = W<float>(p, ws, "WhT");
+    float* dA = W<float>(p, ws, "dA");
+    float* dh0 = W<float>(p, ws, "dh0");
+    RC(lstur_transpose(G, 3 * G, DP(p, w->dense, "gru_wh"), WhT, st));
+    RC(lstur_gru_bwd(B, c.W, G, W<float>(p, ws, "gru_mask"), W<float>(p, ws, "Z"), W<float>(p, ws, "R"),
+                     W<float>(p, ws, "HH"), W<float>(p, ws, "HP"), WhT, c.rec_act, dhT, lddh, dA, dh0, G, st));
+    RC(lstur_colsum(Nh, 3 * G, dA, 3 * G, DG(p, dgrad, "gru_b"), 0, cws, cwsb, st));
+    RC(lstur_gemm_f32(1, 0, D, 3 * G, Nh, docv, D, dA, 3 * G, DG(p, dgrad, "gru_wx"), 3 * G, nullptr, 0, gws, gwsb, st));
+    RC(lstur_gemm_f32(1, 0, G, 2 * G, Nh, W<float>(p, ws, "HP"), G, dA, 3 * G, DG(p, dgrad, "gru_wh"), 3 * G, nullptr, 0,
+                      gws, gwsb, st));
+    RC(lstur_gemm_f32(1, 0, G, G, Nh, W<float>(p, ws, "RH"), G, dA + 2 * G, 3 * G, DG(p, dgrad, "gru_wh") + 2 * G, 3 * G,
+                      nullptr, 0, gws, gwsb, st));
+    // dH = dA . Wx^T  (rows of masked steps are zero because dA is zero there)
+    RC(lstur_gemm_f32(0, 1, Nh, D, 3 * G, dA, 3 * G, DP(p, w->dense, "gru_wx"), 3 * G, d_docv, D, nullptr, 0, gws, gwsb, st));
+    if (c.arch == LSTUR_ARCH_INI) { du0 = dh0; lddu0 = G; }
+  } else {
+    cudaMemsetAsync(d_docv, 0, (size_t)Nh * D * 4, st);
+  }
+  // 4. user-embedding gradient: dedup + segment-sorted sum (k10 backward)
+  if (has_user) {
+    RC(lstur_sort_unique_i32(B, b->user, W<int>(p, ws, "sorted_pos"), W<int>(p, ws, "user_rows"),
+                             W<int>(p, ws, "seg_start"), W<int>(p, ws, "inverse"), W<int>(p, ws, "n_user_rows"), st));
+    if (b->user_scale) {
+      set_error("lstur_backward: user_scale backward not implemented");
+      return LSTUR_ERR_UNSUPPORTED;
+    }
+    RC(lstur_segment_sum_rows(B, c.Ue, W<int>(p, ws, "n_user_rows"), W<int>(p, ws, "seg_start"),
+                              W<int>(p, ws, "sorted_pos"), du0, lddu0, W<float>(p, ws, "d_user_rows"), st));
+  }
+  // 5. news-encoder backward over all N titles
+  float* d_pooled = W<float>(p, ws, "d_pooled");
+  float* pooled = W<float>(p, ws, "pooled");
+  const float* dpool = d_pooled;
+  long long lddp = F;
+  if (c.use_dense) {
+    RC(lstur_gemm_f32(0, 1, N, F, c.Dd, d_docv, D, DP(p, w->dense, "dense_w"), c.Dd, d_pooled, F, nullptr, 0, gws, gwsb, st));
+    RC(lstur_gemm_f32(1, 0, F, c.Dd, N, pooled, F, d_docv, D, DG(p, dgrad, "dense_w"), c.Dd, nullptr, 0, gws, gwsb, st));
+    RC(lstur_colsum(N, c.Dd, d_docv, D, DG(p, dgrad, "dense_b"), 0, cws, cwsb, st));
+  } else {
+    dpool = d_docv; lddp = D;
+  }
+  if (c.precision == LSTUR_PREC_BF16_TC) {
+    RC(lstur_news_encoder_tc_bwd_internal(p, w, ws, dgrad, st));
+  } else {
+    float* dPre = W<float>(p, ws, "dPre");
+    const float drop = c.dropout;  // backward always follows a training forward
+    RC(lstur_attn_pool_bwd(N, L, Lp, F, W<float>(p, ws, "Cp"), (long long)Lp * F, W<float>(p, ws, "att_a"),
+                           W<float>(p, ws, "att_w"), dpool, lddp, DP(p, w->dense, "att_w"), dPre, (long long)Lp * F,
+                           drop, DG(p, dgrad, "att_w"), DG(p, dgrad, "conv_b"), DG(p, dgrad, "att_b"), 0,
+                           W<float>(p, ws, "attn_partials"), (size_t)p->ws.at("attn_partials").count * 4, st));
+    // d_conv_w[(j,e),f] = sum_m Xp[m+j, e] * dPre[m, f]
+    RC(lstur_gemm_f32(1, 0, c.KS * E, F, N * Lp - (c.KS - 1), W<float>(p, ws, "Xp"), E, dPre, F, DG(p, dgrad, "conv_w"), F,
+                      nullptr, 0, gws, gwsb, st));
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("lstur_backward: %s", cudaGetErrorString(e));
+    return LSTUR_ERR_CUDA;
+  }
+  return LSTUR_OK;
+}

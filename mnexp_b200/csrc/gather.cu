@@ -1,0 +1,138 @@
+// Integer / gather kernels of the LSTUR path (HBM-bound byte movers).
+//
+//  token_gather      Window.get_title / np.stack([docs[i].title …])       task/seq2vec.py:25-30, task/paper.py:538-541
+//  embed_gather      keras Embedding(mask_zero=False) + Dropout            task/paper.py:132-138,142,147
+//  hist_mask_apply   models.ComputeMasking(0) + multiply + Masking()       models.py:25-27, task/paper.py:644-645,592
+//  row_gather        user-ID Embedding lookup                              task/paper.py:589-591
+//  vert_concat       [title ‖ Vemb[vert] ‖ Semb[subvert]]                  task/cook.py:99-113
+#include "common.cuh"
+
+namespace lstur {
+
+// tokens[n, :] = doc_tokens[doc_ids[n], :]   — int32, bit-exact. One warp per title row.
+__global__ void token_gather_kernel(int N, int L, int n_docs, const int* __restrict__ doc_tokens,
+                                    const int* __restrict__ doc_ids, int* __restrict__ tokens) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  int d = doc_ids[warp];
+  d = (d < 0 || d >= n_docs) ? 0 : d;  // out-of-range ids read the pad doc
+  const int* src = doc_tokens + (long long)d * L;
+  int* dst = tokens + (long long)warp * L;
+  for (int l = lane; l < L; l += 32) dst[l] = __ldg(src + l);
+}
+
+// Xp[n, pl+t, :] = word_emb[tok[n,t], :] * dropout with pl=(KS-1)/2 zero rows before and KS-1-pl after
+// (TF 'SAME' padding); title stride Lp = L+KS-1 rows.
+// One warp per padded row; float4 vectorised when E % 4 == 0.
+__global__ void embed_gather_pad_kernel(int N, int L, int E, int V, int KS, const float* __restrict__ word_emb,
+                                        const int* __restrict__ tok, float* __restrict__ Xp, uint32_t drop_thr,
+                                        float inv_keep, uint32_t seed) {
+  long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  const int Lp = L + KS - 1;
+  if (row >= (long long)N * Lp) return;
+  int n = (int)(row / Lp), t = (int)(row % Lp) - (KS - 1) / 2;
+  float* dst = Xp + row * E;
+  if (t < 0 || t >= L) {
+    for (int e = lane; e < E; e += 32) dst[e] = 0.f;
+    return;
+  }
+  int id = tok[(long long)n * L + t];
+  id = (id < 0 || id >= V) ? 0 : id;
+  const float* src = word_emb + (long long)id * E;
+  const uint64_t base = ((uint64_t)n * L + t) * (uint64_t)E;
+  if ((E & 3) == 0) {
+    for (int e = lane * 4; e < E; e += 128) {
+      float4 v = __ldg((const float4*)(src + e));
+      if (drop_thr) {
+        v.x = (rng_u32(seed, base + e + 0) >> 8) >= drop_thr ? v.x * inv_keep : 0.f;
+        v.y = (rng_u32(seed, base + e + 1) >> 8) >= drop_thr ? v.y * inv_keep : 0.f;
+        v.z = (rng_u32(seed, base + e + 2) >> 8) >= drop_thr ? v.z * inv_keep : 0.f;
+        v.w = (rng_u32(seed, base + e + 3) >> 8) >= drop_thr ? v.w * inv_keep : 0.f;
+      }
+      *(float4*)(dst + e) = v;
+    }
+  } else {
+    for (int e = lane; e < E; e += 32) {
+      float v = __ldg(src + e);
+      if (drop_thr) v = (rng_u32(seed, base + e) >> 8) >= drop_thr ? v * inv_keep : 0.f;
+      dst[e] = v;
+    }
+  }
+}
+
+// For the B*W history titles: hm = any(tok != 0); H[row,:] *= hm; gm = any(H != 0).
+__global__ void hist_mask_apply_kernel(int rows, int L, int D, const int* __restrict__ tok, float* __restrict__ H,
+                                       long long ldh, float* __restrict__ hm_out, float* __restrict__ gm_out) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  int nz = 0;
+  for (int l = lane; l < L; l += 32) nz |= (tok[(long long)warp * L + l] != 0);
+  nz = warp_or(nz);
+  float* h = H + (long long)warp * ldh;
+  int any = 0;
+  for (int d = lane; d < D; d += 32) {
+    float v = nz ? h[d] : 0.f;
+    h[d] = v;
+    any |= (v != 0.f);
+  }
+  any = warp_or(any);
+  if (lane == 0) {
+    if (hm_out) hm_out[warp] = nz ? 1.f : 0.f;
+    gm_out[warp] = any ? 1.f : 0.f;
+  }
+}
+
+// out[b, :] = table[ids[b], :] * (scale ? scale[b] : 1)
+__global__ void row_gather_kernel(int B, int D, int n_rows, const float* __restrict__ table,
+                                  const int* __restrict__ ids, const float* __restrict__ scale,
+                                  float* __restrict__ out, long long ldo) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  int id = ids[warp];
+  id = (id < 0 || id >= n_rows) ? 0 : id;
+  float s = scale ? scale[warp] : 1.f;
+  for (int d = lane; d < D; d += 32) out[(long long)warp * ldo + d] = __ldg(table + (long long)id * D + d) * s;
+}
+
+}  // namespace lstur
+
+using namespace lstur;
+
+extern "C" int lstur_token_gather(int N, int L, int n_docs, const int* doc_tokens, const int* doc_ids, int* tokens,
+                                  cudaStream_t stream) {
+  LSTUR_REQUIRE(N >= 0 && L > 0 && n_docs > 0, "lstur_token_gather");
+  if (N == 0) return LSTUR_OK;
+  token_gather_kernel<<<cdiv((long long)N * 32, 256), 256, 0, stream>>>(N, L, n_docs, doc_tokens, doc_ids, tokens);
+  LSTUR_CHECK_LAUNCH("lstur_token_gather");
+  return LSTUR_OK;
+}
+
+extern "C" int lstur_embed_gather_pad(int N, int L, int E, int V, int KS, const float* word_emb, const int* tokens,
+                                      float* Xp, float dropout, unsigned seed, cudaStream_t stream) {
+  LSTUR_REQUIRE(N >= 0 && L > 0 && E > 0 && KS >= 1 && dropout >= 0.f && dropout < 1.f, "lstur_embed_gather_pad");
+  if (N == 0) return LSTUR_OK;
+  long long rows = (long long)N * (L + KS - 1);
+  embed_gather_pad_kernel<<<cdiv(rows * 32, 256), 256, 0, stream>>>(
+      N, L, E, V, KS, word_emb, tokens, Xp, dropout > 0.f ? dropout_threshold(dropout) : 0u, 1.f / (1.f - dropout), seed);
+  LSTUR_CHECK_LAUNCH("lstur_embed_gather_pad");
+  return LSTUR_OK;
+}
+
+extern "C" int lstur_hist_mask_apply(int rows, int L, int D, const int* tokens, float* H, long long ldh, float* hm,
+                                     float* gm, cudaStream_t stream) {
+  LSTUR_REQUIRE(rows >= 0 && L > 0 && D > 0 && gm != nullptr, "lstur_hist_mask_apply");
+  if (rows == 0) return LSTUR_OK;
+  hist_mask_apply_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, stream>>>(rows, L, D, tokens, H, ldh, hm, gm);
+  LSTUR_CHECK_LAUNCH("lstur_hist_mask_apply");
+  return LSTUR_OK;
+}
+
+extern "C" int lstur_row_gather(int B, int D, int n_rows, const float* table, const int* ids, const float* scale,
+                                float* out, long long ldo, cudaStream_t stream) {
+  LSTUR_REQUIRE(B >= 0 && D > 0 && n_rows > 0, "lstur_row_gather");
+  if (B == 0) return LSTUR_OK;
+  row_gather_kernel<<<cdiv((long long)B * 32, 256), 256, 0, stream>>>(B, D, n_rows, table, ids, scale, out, ldo);
+  LSTUR_CHECK_LAUNCH("lstur_row_gather");
+  return LSTUR_OK;
+}

@@ -1,0 +1,125 @@
+// Dot-product click scorer + (1+K)-way softmax + Keras categorical cross-entropy, fused fwd+bwd;
+// and the sigmoid scoring head of the test model.
+//
+// Reference: _score_model 'dot' task/paper.py:446-447; softmax over the concatenated
+// logits :460-464; loss=keras.losses.categorical_crossentropy :657 — on probabilities:
+// p <- p/sum(p); p <- clip(p,1e-7,1-1e-7); l = -sum_j y_j log p_j; mean over batch [K]
+// (SURVEY.md §9.5-9.6).  Test head: sigmoid(score) task/paper.py:661-665.
+#include "common.cuh"
+
+namespace lstur {
+
+// One warp per batch row; lane c owns candidate c (C <= 32).
+__global__ void score_softmax_ce_kernel(int B, int C, int D, const float* __restrict__ u, long long ldu,
+                                        const float* __restrict__ d, long long ldd, const float* __restrict__ label,
+                                        float* __restrict__ logits, float* __restrict__ probs,
+                                        float* __restrict__ loss_rows, float* __restrict__ du, long long lddu,
+                                        float* __restrict__ dd, long long lddd, float grad_scale) {
+  int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const float* ub = u + (long long)b * ldu;
+  float s_mine = -INFINITY;
+  for (int c = 0; c < C; ++c) {
+    const float* dc = d + ((long long)b * C + c) * ldd;
+    float acc = 0.f;
+    for (int k = lane; k < D; k += 32) acc = fmaf(ub[k], dc[k], acc);
+    acc = warp_sum(acc);
+    if (lane == c) s_mine = acc;
+  }
+  float mx = s_mine;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float e = lane < C ? expf(s_mine - mx) : 0.f;
+  float p = e / warp_sum(e);
+  float y = lane < C ? (label ? label[(long long)b * C + lane] : (lane == 0 ? 1.f : 0.f)) : 0.f;
+  float q = p / warp_sum(p);  // keras renormalises before the clip
+  bool inrange = (q >= 1e-7f) && (q <= 1.f - 1e-7f);
+  float qc = fminf(fmaxf(q, 1e-7f), 1.f - 1e-7f);
+  float l = lane < C ? -y * logf(qc) : 0.f;
+  l = warp_sum(l);
+  if (lane < C) {
+    if (logits) logits[(long long)b * C + lane] = s_mine;
+    if (probs) probs[(long long)b * C + lane] = p;
+  }
+  if (lane == 0 && loss_rows) loss_rows[b] = l;
+  if (!du) return;
+  // g_j = dL/dp_j = -y_j/p_j inside the clip range, else 0;  ds_k = p_k (g_k - sum_j g_j p_j)
+  float g = (lane < C && inrange && y != 0.f) ? -y / q : 0.f;
+  float gp = warp_sum(g * p);
+  float ds = lane < C ? p * (g - gp) * grad_scale : 0.f;
+  float* dub = du + (long long)b * lddu;
+  for (int k0 = 0; k0 < D; k0 += 32) {
+    int k = k0 + lane;
+    float uk = k < D ? ub[k] : 0.f, acc = 0.f;
+    for (int c = 0; c < C; ++c) {
+      float dsc = __shfl_sync(0xffffffffu, ds, c);
+      if (k < D) {
+        acc = fmaf(dsc, d[((long long)b * C + c) * ldd + k], acc);
+        dd[((long long)b * C + c) * lddd + k] = dsc * uk;
+      }
+    }
+    if (k < D) dub[k] = acc;
+  }
+}
+
+// out[i] = sigmoid(u[row(i)] . d[i]),  row(i) = i / C.  One warp per pair.
+__global__ void score_sigmoid_kernel(long long n, int C, int D, const float* __restrict__ u, long long ldu,
+                                     const float* __restrict__ d, long long ldd, float* __restrict__ out,
+                                     int apply_sigmoid) {
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const float* ub = u + (i / C) * ldu;
+  const float* di = d + i * ldd;
+  float acc = 0.f;
+  for (int k = lane; k < D; k += 32) acc = fmaf(ub[k], di[k], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) out[i] = apply_sigmoid ? 1.f / (1.f + expf(-acc)) : acc;
+}
+
+__global__ void mean_kernel(int n, const float* __restrict__ x, float* __restrict__ out) {
+  __shared__ float s[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += x[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) out[0] = v / (float)n;
+  }
+}
+
+}  // namespace lstur
+
+using namespace lstur;
+
+// u (B,D) ld=ldu; d (B*C, D) ld=ldd; label (B,C) or NULL (positive = column 0).
+// du/dd may be NULL for forward only.  grad_scale = 1/global_batch.
+extern "C" int lstur_score_softmax_ce(int B, int C, int D, const float* u, long long ldu, const float* d, long long ldd,
+                                      const float* label, float* logits, float* probs, float* loss_rows,
+                                      float* loss_mean, float* du, long long lddu, float* dd, long long lddd,
+                                      float grad_scale, cudaStream_t stream) {
+  LSTUR_REQUIRE(B >= 0 && C >= 1 && C <= 32 && D > 0, "lstur_score_softmax_ce");
+  LSTUR_REQUIRE((du == nullptr) == (dd == nullptr), "lstur_score_softmax_ce");
+  LSTUR_REQUIRE(loss_mean == nullptr || loss_rows != nullptr, "lstur_score_softmax_ce");
+  if (B == 0) return LSTUR_OK;
+  score_softmax_ce_kernel<<<cdiv((long long)B * 32, 128), 128, 0, stream>>>(B, C, D, u, ldu, d, ldd, label, logits, probs,
+                                                                          loss_rows, du, lddu, dd, lddd, grad_scale);
+  LSTUR_CHECK_LAUNCH("lstur_score_softmax_ce");
+  if (loss_mean) {
+    mean_kernel<<<1, 256, 0, stream>>>(B, loss_rows, loss_mean);
+    LSTUR_CHECK_LAUNCH("lstur_score_softmax_ce(mean)");
+  }
+  return LSTUR_OK;
+}
+
+extern "C" int lstur_score_sigmoid(long long n_pairs, int C, int D, const float* u, long long ldu, const float* d,
+                                   long long ldd, float* out, int apply_sigmoid, cudaStream_t stream) {
+  LSTUR_REQUIRE(n_pairs >= 0 && C >= 1 && D > 0, "lstur_score_sigmoid");
+  if (n_pairs == 0) return LSTUR_OK;
+  score_sigmoid_kernel<<<cdiv(n_pairs * 32, 256), 256, 0, stream>>>(n_pairs, C, D, u, ldu, d, ldd, out, apply_sigmoid);
+  LSTUR_CHECK_LAUNCH("lstur_score_sigmoid");
+  return LSTUR_OK;
+}

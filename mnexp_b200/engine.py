@@ -1,0 +1,212 @@
+"""Host-side engine: owns device buffers (via torch) and drives the C-ABI plan.
+
+torch is plumbing only — allocation, streams, torch.distributed.  Every FLOP of
+the LSTUR path runs in liblstur_b200.so (mnexp_b200/csrc).  Construction raises
+if CUDA or the shared library is unavailable: there is no CPU fallback.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lstur_batch, lstur_config, lstur_weights
+
+ARCH = {  # reference arch names -> engine arch; paper.py names
+    'igru': 0, 'gru': 1, 'ngru': 2, 'hgru': 2, 'dgru': 2, 'nigru': 3, 'pgru': 4, 'vo': 5,
+}
+COOK_ARCH = {'ingru': 0, 'igru': 2, 'gru': 3, 'agru': 4, 'vo': 5}   # task/cook.py:146-168
+DENSE_NAMES = ('conv_w', 'conv_b', 'att_w', 'att_b', 'dense_w', 'dense_b', 'vert_emb', 'subvert_emb',
+               'gru_wx', 'gru_wh', 'gru_b', 'con_w', 'con_b')
+PREC = {'fp32': 0, 'bf16_tc': 1}
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+class LsturEngine:
+    """One replica of the LSTUR model on one GPU.
+
+    params: dict of numpy arrays (names: oracle/lstur_numpy.py docstring).
+    """
+
+    def __init__(self, params, B, W, C, L, arch='igru', flavour='paper', dropout=0.0, lr=1e-3,
+                 recurrent_activation='hard_sigmoid', precision='fp32', doc_tokens=None, device=None,
+                 training=True, sparse_user_adam=True, trainable_word_emb=False):
+        if not torch.cuda.is_available():
+            raise _lib.LsturError('LsturEngine needs a CUDA device (no CPU fallback)')
+        self.lib = _lib.load()
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        if trainable_word_emb:
+            raise NotImplementedError('textual_embedding_trainable=True is not implemented yet')
+        amap = ARCH if flavour == 'paper' else COOK_ARCH
+        if arch not in amap:
+            raise Exception('Unsupport user model')                      # task/paper.py:630
+        self.arch_name, self.arch = arch, amap[arch]
+        ks, E, F = params['conv_w'].shape
+        use_dense = 'dense_w' in params
+        Dd = params['dense_w'].shape[1] if use_dense else F
+        G = params['gru_wh'].shape[0] if 'gru_wh' in params else 0
+        Ue = params['user_emb'].shape[1] if 'user_emb' in params and self.arch != 3 else 0
+        U = {0: G, 1: params['con_w'].shape[1] if 'con_w' in params else 0, 2: G + Ue, 3: G, 4: G, 5: Ue}[self.arch]
+        self.cfg = lstur_config(
+            B=B, W=W, C=C, L=L, E=E, F=F, KS=ks, use_dense=int(use_dense), Dd=Dd, dv=0, ds=0, G=G, Ue=Ue, U=U,
+            arch=self.arch, score_model=0, rec_act=0 if recurrent_activation == 'hard_sigmoid' else 1,
+            precision=PREC[precision], V=params['word_emb'].shape[0],
+            n_users=params['user_emb'].shape[0] if Ue else 0,
+            n_docs=0 if doc_tokens is None else doc_tokens.shape[0], dropout=float(dropout),
+            save_for_backward=int(training))
+        self.B, self.W, self.C, self.L, self.D, self.U, self.Ue, self.G = B, W, C, L, Dd, U, Ue, G
+        plan = ctypes.c_void_p()
+        _lib.check(self.lib.lstur_plan_create(ctypes.byref(self.cfg), ctypes.byref(plan)))
+        self.plan = plan
+        dev = self.device
+        self.n_dense = int(self.lib.lstur_plan_dense_count(plan))
+        self.dense = torch.zeros(self.n_dense, dtype=torch.float32, device=dev)
+        self.layout = {}
+        for name in DENSE_NAMES:
+            off, cnt = ctypes.c_longlong(), ctypes.c_longlong()
+            if self.lib.lstur_plan_dense_offset(plan, name.encode(), ctypes.byref(off), ctypes.byref(cnt)) == 0:
+                self.layout[name] = (off.value, cnt.value, tuple(np.asarray(params[name]).shape))
+        self.word_emb = torch.as_tensor(np.ascontiguousarray(params['word_emb'], dtype=np.float32)).to(dev)
+        self.user_emb = torch.as_tensor(np.ascontiguousarray(params['user_emb'], dtype=np.float32)).to(dev) if Ue else None
+        self.doc_tokens = None if doc_tokens is None else torch.as_tensor(np.ascontiguousarray(doc_tokens, dtype=np.int32)).to(dev)
+        self.set_weights_dict(params)
+        ws_bytes = int(self.lib.lstur_plan_workspace_bytes(plan))
+        self.ws_bytes = ws_bytes
+        self.ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        self.training_plan = bool(training)
+        if training:
+            self.dense_grad = torch.zeros_like(self.dense)
+            self.adam_m = torch.zeros_like(self.dense)
+            self.adam_v = torch.zeros_like(self.dense)
+            if Ue:
+                self.user_m = torch.zeros_like(self.user_emb)
+                self.user_v = torch.zeros_like(self.user_emb)
+                self.user_grad_dense = None if sparse_user_adam else torch.zeros_like(self.user_emb)
+        self.sparse_user_adam = sparse_user_adam
+        self.lr = float(lr)
+        self.t = 0
+        self.step_seed = 0
+        self.gpu_launches = 0
+        self._w = lstur_weights(dense=self.dense.data_ptr(), word_emb=self.word_emb.data_ptr(),
+                                user_emb=self.user_emb.data_ptr() if Ue else None,
+                                doc_tokens=self.doc_tokens.data_ptr() if self.doc_tokens is not None else None,
+                                doc_vert=None, doc_subvert=None)
+
+    def __del__(self):
+        try:
+            if getattr(self, 'plan', None):
+                self.lib.lstur_plan_destroy(self.plan)
+                self.plan = None
+        except Exception:
+            pass
+
+    # ---- weights ------------------------------------------------------------------------
+    def set_weights_dict(self, params):
+        host = np.zeros(self.n_dense, dtype=np.float32)
+        for name, (off, cnt, shape) in self.layout.items():
+            host[off:off + cnt] = np.asarray(params[name], dtype=np.float32).reshape(-1)
+        self.dense.copy_(torch.from_numpy(host))
+        if 'word_emb' in params:
+            self.word_emb.copy_(torch.as_tensor(np.ascontiguousarray(params['word_emb'], dtype=np.float32)))
+        if self.user_emb is not None and 'user_emb' in params:
+            self.user_emb.copy_(torch.as_tensor(np.ascontiguousarray(params['user_emb'], dtype=np.float32)))
+
+    def _unflatten(self, flat):
+        host = flat.detach().cpu().numpy()
+        return {name: host[off:off + cnt].reshape(shape).copy() for name, (off, cnt, shape) in self.layout.items()}
+
+    def get_weights_dict(self):
+        out = self._unflatten(self.dense)
+        out['word_emb'] = self.word_emb.cpu().numpy()
+        if self.user_emb is not None:
+            out['user_emb'] = self.user_emb.cpu().numpy()
+        return out
+
+    def get_grads_dict(self):
+        """Dense gradients plus the (densified) user-embedding gradient of the last backward."""
+        out = self._unflatten(self.dense_grad)
+        if self.user_emb is not None:
+            g = np.zeros(tuple(self.user_emb.shape), dtype=np.float32)
+            n = int(self.view('n_user_rows', torch.int32)[0])
+            rows = self.view('user_rows', torch.int32)[:n].cpu().numpy()
+            g[rows] = self.view('d_user_rows').reshape(-1, self.Ue)[:n].cpu().numpy()
+            out['user_emb'] = g
+        return out
+
+    # ---- workspace views ------------------------------------------------------------------
+    def view(self, name, dtype=torch.float32):
+        ptr, cnt = ctypes.c_void_p(), ctypes.c_longlong()
+        _lib.check(self.lib.lstur_plan_view(self.plan, _ptr(self.ws), name.encode(), ctypes.byref(ptr), ctypes.byref(cnt)))
+        off = ptr.value - self.ws.data_ptr()
+        return self.ws[off:off + 4 * cnt.value].view(dtype)
+
+    # ---- batches --------------------------------------------------------------------------
+    def to_device_batch(self, batch, non_blocking=False):
+        """dict of host arrays/tensors -> dict of int32/float32 device tensors."""
+        out = {}
+        for k, v in batch.items():
+            if v is None:
+                continue
+            t = v if torch.is_tensor(v) else torch.from_numpy(np.ascontiguousarray(v))
+            if k == 'label' or k == 'user_scale':
+                t = t.to(self.device, dtype=torch.float32, non_blocking=non_blocking)
+            else:
+                t = t.to(self.device, non_blocking=non_blocking)
+                if t.dtype != torch.int32:
+                    t = t.to(torch.int32)          # reference feeds float64 token ids (document.py:39); ids < 2^24
+            out[k] = t.contiguous()
+        return out
+
+    def _cbatch(self, db):
+        g = lambda k: db[k].data_ptr() if k in db else None
+        return lstur_batch(user=g('user'), hist_doc=g('hist_doc'), cand_doc=g('cand_doc'), hist_tok=g('hist_tok'),
+                           cand_tok=g('cand_tok'), label=g('label'), user_scale=g('user_scale'))
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- the hot path ---------------------------------------------------------------------
+    def forward(self, db, training=False, seed=0):
+        cb = self._cbatch(db)
+        _lib.check(self.lib.lstur_forward(self.plan, ctypes.byref(self._w), ctypes.byref(cb), _ptr(self.ws),
+                                          int(training), ctypes.c_uint(seed), self._stream()))
+        return self.view('probs').reshape(self.B, self.C)
+
+    def backward(self, db, grad_scale=None):
+        cb = self._cbatch(db)
+        gs = 1.0 / self.B if grad_scale is None else grad_scale
+        _lib.check(self.lib.lstur_backward(self.plan, ctypes.byref(self._w), ctypes.byref(cb), _ptr(self.ws),
+                                           _ptr(self.dense_grad), ctypes.c_float(gs), self._stream()))
+
+    def apply_adam(self, b1=0.9, b2=0.999, eps=1e-7):
+        self.t += 1
+        st = self._stream()
+        _lib.check(self.lib.lstur_adam_dense(self.n_dense, _ptr(self.dense), _ptr(self.dense_grad), _ptr(self.adam_m),
+                                             _ptr(self.adam_v), self.lr, self.t, b1, b2, eps, 1.0, st))
+        if self.user_emb is not None:
+            rows, nrows, grows = self.view('user_rows', torch.int32), self.view('n_user_rows', torch.int32), self.view('d_user_rows')
+            if self.sparse_user_adam:
+                _lib.check(self.lib.lstur_adam_rows(self.B, _ptr(nrows), self.Ue, _ptr(rows), _ptr(grows),
+                                                    _ptr(self.user_emb), _ptr(self.user_m), _ptr(self.user_v),
+                                                    self.lr, self.t, b1, b2, eps, 1.0, st))
+            else:   # reference semantics: dense Adam over the whole table
+                self.user_grad_dense.zero_()
+                _lib.check(self.lib.lstur_rows_add(self.B, _ptr(nrows), self.Ue, _ptr(rows), _ptr(grows),
+                                                   _ptr(self.user_grad_dense), st))
+                _lib.check(self.lib.lstur_adam_dense(self.user_emb.numel(), _ptr(self.user_emb), _ptr(self.user_grad_dense),
+                                                     _ptr(self.user_m), _ptr(self.user_v), self.lr, self.t, b1, b2, eps, 1.0, st))
+
+    def train_step(self, db, seed=None):
+        """forward + backward + Adam on a device batch; returns the loss as a 1-element device tensor."""
+        self.step_seed += 1
+        self.forward(db, training=True, seed=self.step_seed if seed is None else seed)
+        self.backward(db)
+        self.apply_adam()
+        return self.view('loss')
+
+    def loss(self):
+        return float(self.view('loss')[0])

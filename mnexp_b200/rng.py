@@ -1,0 +1,37 @@
+"""numpy replica of the device dropout RNG (csrc/common.cuh: lowbias32 / rng_u32).
+
+Lets tests replay the exact GPU dropout masks into the oracle (the reference's
+TF RNG cannot be matched — SURVEY.md §7 — so dropout parity is defined on our
+own counter-based stream)."""
+import numpy as np
+
+
+def lowbias32(x):
+    x = x.astype(np.uint32)
+    x ^= x >> np.uint32(16)
+    x = (x * np.uint32(0x7feb352d)).astype(np.uint32)
+    x ^= x >> np.uint32(15)
+    x = (x * np.uint32(0x846ca68b)).astype(np.uint32)
+    x ^= x >> np.uint32(16)
+    return x
+
+
+def rng_u32(seed, idx):
+    idx = np.asarray(idx, dtype=np.uint64)
+    lo = (idx & np.uint64(0xffffffff)).astype(np.uint32)
+    hi = (idx >> np.uint64(32)).astype(np.uint32)
+    k = (np.uint64(0x9e3779b9) * np.uint64((int(seed) + 1) & 0xffffffff)) & np.uint64(0xffffffff)
+    with np.errstate(over='ignore'):
+        inner = lowbias32((hi + np.uint32(k)).astype(np.uint32))
+    return lowbias32(lo ^ inner)
+
+
+def dropout_multiplier(seed, n, p, dtype=np.float64):
+    """Inverted-dropout multipliers for flat element indices 0..n-1."""
+    if p <= 0:
+        return np.ones(n, dtype=dtype)
+    thr = np.uint32(int(np.float32(p) * np.float32(16777216.0)))
+    u = rng_u32(seed, np.arange(n, dtype=np.uint64))
+    keep = (u >> np.uint32(8)) >= thr
+    inv = np.float32(1.0) / (np.float32(1.0) - np.float32(p))
+    return np.where(keep, dtype(inv), dtype(0))

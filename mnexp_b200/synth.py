@@ -1,0 +1,179 @@
+"""Seeded synthetic Vocab / DocMeta / ClickData / weights / batches.
+
+The reference's datasets are private (README.md:8), so every measurement and
+parity run uses data of the reference's shapes generated here:
+
+* Vocab     : (V,E) fp32 N(0,0.1²), row 0 = zeros — what
+              ``utils.load_textual_embedding`` yields for a missing index
+              (utils.py:43-49).
+* DocMeta   : doc ids 1..n_news (+ pad doc 0 = all-zero title,
+              task/seq2vec.py:104-108); title tokens Zipf(1.1) over 1..V-1,
+              right-zero-padded to L (document.py:37-54); vertical in 1..15,
+              subvertical in 1..306 (utils.py:153-228).
+* ClickData : per-sample history of h clicks, left-padded with doc 0 to W
+              (task/seq2vec.py:17-49); 1 positive + K negatives sampled with
+              replacement (task/paper.py:17-18), positive first (:529).
+* weights   : Keras initialisers.
+"""
+from dataclasses import dataclass, asdict
+
+import numpy as np
+
+
+@dataclass
+class Shape:
+    name: str
+    n_users: int
+    n_news: int
+    vocab: int
+    L: int = 30           # title_shape
+    W: int = 50           # window_size
+    K: int = 4            # negative_samples
+    B: int = 64           # batch_size
+    E: int = 300          # textual_embedding_dim
+    F: int = 400          # title_filter_shape[0]
+    k: int = 3            # title_filter_shape[1]
+    U: int = 200          # user_embedding_dim
+    arch: str = 'igru'
+
+    def dict(self):
+        return asdict(self)
+
+
+# BASELINE.json configs[0..4]
+SHAPES = {
+    'C1': Shape('C1', 1_000, 5_000, 30_000, B=64, arch='igru'),
+    'C2': Shape('C2', 50_000, 50_000, 30_000, B=1024, arch='gru'),
+    'C3': Shape('C3', 1_000_000, 130_000, 100_000, B=1024, arch='igru'),
+    'C4': Shape('C4', 1_000_000, 130_000, 100_000, B=1024, arch='igru'),
+    'C5': Shape('C5', 1_000_000, 130_000, 100_000, L=50, W=200, B=2048, arch='igru'),
+    'tiny': Shape('tiny', 50, 80, 120, L=7, W=5, K=2, B=6, E=12, F=16, U=8),
+}
+
+
+def _zipf_cdf(n, s):
+    p = 1.0 / np.arange(1, n + 1, dtype=np.float64) ** s
+    c = np.cumsum(p)
+    return c / c[-1]
+
+
+def _zipf_sample(rng, cdf, size):
+    return np.searchsorted(cdf, rng.random(size), side='left').astype(np.int64)
+
+
+def make_vocab(V, E, seed=1234):
+    rng = np.random.default_rng(seed)
+    emb = (rng.standard_normal((V, E)) * 0.1).astype(np.float32)
+    emb[0] = 0.0
+    return emb
+
+
+def make_docs(n_news, L, V, seed=1235):
+    """-> tokens (n_news+1, L) int32 (row 0 = pad doc), vert (n_news+1,), subvert (n_news+1,)."""
+    rng = np.random.default_rng(seed)
+    n = n_news + 1
+    length = np.clip(np.rint(rng.normal(0.6 * L, 0.2 * L, n)), min(3, L), L).astype(np.int64)
+    cdf = _zipf_cdf(V - 1, 1.1)
+    tok = (_zipf_sample(rng, cdf, (n, L)) + 1).astype(np.int32)
+    tok[np.arange(L)[None, :] >= length[:, None]] = 0
+    tok[0] = 0
+    vert = rng.integers(1, 16, n).astype(np.int32)
+    subvert = rng.integers(1, 307, n).astype(np.int32)
+    vert[0] = 0
+    subvert[0] = 0
+    return tok, vert, subvert
+
+
+def make_batches(shape, n_batches, seed=1236, B=None):
+    """Pre-tensorised int32 batches: user (B,), hist_doc (B,W) left-padded with 0,
+    cand_doc (B,1+K) positive first.  Returns a list of dicts plus the realised
+    fraction of left-padded history slots."""
+    rng = np.random.default_rng(seed)
+    B = B or shape.B
+    W, K = shape.W, shape.K
+    cdf = _zipf_cdf(shape.n_news, 1.05)
+    out, pad = [], 0
+    for _ in range(n_batches):
+        user = rng.integers(0, shape.n_users, B).astype(np.int32)
+        h = np.clip(rng.geometric(1.0 / (0.6 * W), B), 1, 3 * W)
+        h = np.minimum(h, W)
+        hist = (_zipf_sample(rng, cdf, (B, W)) + 1).astype(np.int32)
+        hist[np.arange(W)[None, :] < (W - h)[:, None]] = 0          # left padding
+        cand = (_zipf_sample(rng, cdf, (B, 1 + K)) + 1).astype(np.int32)
+        pad += int((hist == 0).sum())
+        out.append(dict(user=user, hist_doc=hist, cand_doc=cand))
+    return out, pad / float(n_batches * B * W)
+
+
+def _glorot(rng, shape, fan_in, fan_out):
+    lim = np.sqrt(6.0 / (fan_in + fan_out))
+    return rng.uniform(-lim, lim, shape).astype(np.float32)
+
+
+def _orthogonal(rng, rows, cols):
+    a = rng.standard_normal((rows, cols))
+    u, _, vt = np.linalg.svd(a, full_matrices=False)
+    q = u if u.shape == (rows, cols) else vt
+    return q.astype(np.float32)
+
+
+def make_weights(shape, arch=None, seed=1237, word_emb=None, score_model='dot', cook=False,
+                 dv=15, ds=35, bias_noise=0.0):
+    """Keras-initialised parameter dict (names: oracle/lstur_numpy.py docstring).
+
+    bias_noise > 0 replaces the all-zero bias initialisers by small normals so
+    parity tests exercise the bias paths."""
+    arch = arch or shape.arch
+    rng = np.random.default_rng(seed)
+    E, F, k, U = shape.E, shape.F, shape.k, shape.U
+    bz = lambda n: (rng.standard_normal(n) * bias_noise).astype(np.float32)
+    P = {}
+    P['word_emb'] = make_vocab(shape.vocab, E) if word_emb is None else word_emb
+    P['conv_w'] = _glorot(rng, (k, E, F), k * E, k * F)
+    P['conv_b'] = bz(F)
+    P['att_w'] = _glorot(rng, (F,), F, 1)
+    P['att_b'] = bz(1)
+    if cook:
+        D = F + dv + ds
+        P['vert_emb'] = rng.uniform(-0.05, 0.05, (16, dv)).astype(np.float32)
+        P['subvert_emb'] = rng.uniform(-0.05, 0.05, (307, ds)).astype(np.float32)
+    else:
+        D = U
+        P['dense_w'] = _glorot(rng, (F, U), F, U)
+        P['dense_b'] = bz(U)
+    G = U // 2 if arch == 'hgru' else U
+    Ue = U // 2 if arch == 'hgru' else U
+    if arch != 'nigru':
+        P['user_emb'] = rng.uniform(-0.05, 0.05, (shape.n_users, Ue)).astype(np.float32)
+    if arch != 'vo':
+        P['gru_wx'] = _glorot(rng, (D, 3 * G), D, 3 * G)
+        P['gru_wh'] = np.concatenate([_orthogonal(rng, G, G) for _ in range(3)], 1)
+        P['gru_b'] = bz(3 * G)
+    if arch == 'gru':
+        P['con_w'] = _glorot(rng, (G + Ue, U), G + Ue, U)
+        P['con_b'] = bz(U)
+    if score_model == 'ddot':
+        Du = 2 * U if arch in ('ngru', 'dgru') else U
+        P['su_w'] = _glorot(rng, (Du, U), Du, U)
+        P['su_b'] = bz(U)
+        P['sd_w'] = _glorot(rng, (D, U), D, U)
+        P['sd_b'] = bz(U)
+    return P
+
+
+# ---- TSV writers in the reference's on-disk formats (README.md:7-23) -------------------------
+def write_vocab_tsv(path, emb):
+    """Vocab.tsv rows ``…\\t<index>\\t<space-separated floats>`` (utils.py:37-41); index 0 omitted."""
+    with open(path, 'w') as f:
+        for i in range(1, emb.shape[0]):
+            f.write('w%d\t%d\t%s\n' % (i, i, ' '.join(repr(float(x)) for x in emb[i])))
+
+
+def write_docmeta_tsv(path, tok, vert=None, subvert=None):
+    """DocMeta.tsv: col1 = doc id, col4 = title tokens, col5 = body tokens (task/seq2vec.py:96-101);
+    cols 2,3 carry vertical / subvertical names in the DaysId variants (task/paper.py:803-820)."""
+    with open(path, 'w') as f:
+        for i in range(1, tok.shape[0]):
+            t = ' '.join(str(int(x)) for x in tok[i] if x != 0)
+            f.write('d%d\t%d\tv%d\ts%d\t%s\t%s\n' % (i, i, 0 if vert is None else vert[i],
+                                                      0 if subvert is None else subvert[i], t, t))

@@ -1,0 +1,191 @@
+"""torch-CPU restatement of the reference LSTUR graph with autograd + Keras Adam.
+
+TEST INFRASTRUCTURE — see ``oracle/__init__.py`` ("parity unpinned").  Second,
+independent implementation of the semantics in ``lstur_numpy``;
+used (a) in float64 for gradient ground truth, (b) in float32 with all host
+threads as the timed "reference-equivalent CPU restatement" baseline
+ — the literal Keras/TF-1.x path cannot be imported here.
+
+Reference sites: news encoder task/paper.py:132-160; user encoder :584-633;
+scorer :443-464; assembly/loss/optimizer :635-665; custom layers
+models.py:20-30, 444-492.
+"""
+import math
+
+import torch
+
+EPS = 1e-7
+
+
+def hard_sigmoid(x):
+    return torch.clamp(0.2 * x + 0.5, 0.0, 1.0)
+
+
+def news_encoder(tok, P, use_dense=True, dropout=0.0, training=False, drop_x=None, drop_c=None):
+    """task/paper.py:141-160.  tok (N,L) long."""
+    X = P['word_emb'][tok]
+    if drop_x is not None:
+        X = X * drop_x
+    elif training and dropout > 0:
+        X = torch.nn.functional.dropout(X, dropout, True)
+    Wc = P['conv_w']
+    k = Wc.shape[0]
+    N, L, E = X.shape
+    pl = (k - 1) // 2
+    Xp = torch.nn.functional.pad(X, (0, 0, pl, k - 1 - pl))
+    C = P['conv_b'] + sum(Xp[:, j:j + L] @ Wc[j] for j in range(k))
+    C = torch.relu(C)
+    C = C * (tok != 0).to(C.dtype).unsqueeze(-1)
+    m = (C.detach() != 0).any(-1).to(C.dtype)
+    C = C * m.unsqueeze(-1)
+    if drop_c is not None:
+        C = C * drop_c
+    elif training and dropout > 0:
+        C = torch.nn.functional.dropout(C, dropout, True)
+    a = torch.tanh(C @ P['att_w'].reshape(-1) + P['att_b'].reshape(-1)[0])
+    e = torch.exp(a) * m
+    w = e / (e.sum(-1, keepdim=True) + EPS)
+    p = (C * w.unsqueeze(-1)).sum(1)
+    return p @ P['dense_w'] + P['dense_b'] if use_dense else p
+
+
+def gru_last_state(H, h0, Wx, Wh, b, recurrent_activation='hard_sigmoid'):
+    """Keras-2.2 GRU, reset_after=False, masked steps carry state."""
+    ra = hard_sigmoid if recurrent_activation == 'hard_sigmoid' else torch.sigmoid
+    B, W, D = H.shape
+    G = Wh.shape[0]
+    gm = (H.detach() != 0).any(-1)
+    h = H.new_zeros((B, G)) if h0 is None else h0
+    XW = H @ Wx + b
+    for t in range(W):
+        x = XW[:, t]
+        z = ra(x[:, :G] + h @ Wh[:, :G])
+        r = ra(x[:, G:2 * G] + h @ Wh[:, G:2 * G])
+        hh = torch.tanh(x[:, 2 * G:] + (r * h) @ Wh[:, 2 * G:])
+        hn = z * h + (1.0 - z) * hh
+        h = torch.where(gm[:, t:t + 1], hn, h)
+    return h
+
+
+def user_encoder(arch, user, H, P, recurrent_activation='hard_sigmoid', u0_scale=None):
+    """task/paper.py:584-633."""
+    u0 = P['user_emb'][user.reshape(-1)] if 'user_emb' in P and arch != 'nigru' else None
+    if u0 is not None and u0_scale is not None:
+        u0 = u0 * u0_scale
+    gru = lambda h0: gru_last_state(H, h0, P['gru_wx'], P['gru_wh'], P['gru_b'], recurrent_activation)
+    if arch == 'igru':
+        return gru(u0)
+    if arch == 'gru':
+        return torch.cat([gru(None), u0], -1) @ P['con_w'] + P['con_b']
+    if arch in ('ngru', 'hgru', 'dgru'):
+        return torch.cat([gru(None), u0], -1)
+    if arch == 'pgru':
+        return gru(None) + u0
+    if arch == 'nigru':
+        return gru(None)
+    if arch == 'vo':
+        return u0
+    raise Exception('Unsupport user model')
+
+
+def score(u, d, P=None, score_model='dot', flavour='paper'):
+    if score_model == 'dot':
+        return torch.einsum('bu,bcu->bc', u, d)
+    if score_model == 'ddot':
+        uh = u @ P['su_w'] + P['su_b']
+        dh = d @ P['sd_w'] + P['sd_b']
+        if flavour == 'paper':
+            uh, dh = torch.tanh(uh), torch.tanh(dh)
+        return torch.einsum('bu,bcu->bc', uh, dh)
+    if score_model == 'dnn':
+        j = torch.cat([u[:, None].expand(-1, d.shape[1], -1), d], -1)
+        hid = torch.relu(j @ P['sh_w'] + P['sh_b'])
+        return (hid @ P['so_w'] + P['so_b'])[..., 0]
+    raise NotImplementedError
+
+
+def categorical_crossentropy(y, p):
+    p = p / p.sum(-1, keepdim=True)
+    p = torch.clamp(p, EPS, 1.0 - EPS)
+    return (-(y * torch.log(p)).sum(-1)).mean()
+
+
+def forward(P, user, clicked_tok, cand_tok, arch='igru', score_model='dot',
+            recurrent_activation='hard_sigmoid', dropout=0.0, training=False, aux=False):
+    """Seq2VecPaperSoftmaxId._build_model — task/paper.py:635-665."""
+    B, W, L = clicked_tok.shape
+    C = cand_tok.shape[1]
+    dh = news_encoder(clicked_tok.reshape(B * W, L), P, dropout=dropout, training=training).reshape(B, W, -1)
+    hm = (clicked_tok != 0).any(-1).to(dh.dtype)
+    H = dh * hm.unsqueeze(-1)
+    u = user_encoder(arch, user, H, P, recurrent_activation)
+    dc = news_encoder(cand_tok.reshape(B * C, L), P, dropout=dropout, training=training).reshape(B, C, -1)
+    s = score(u, dc, P, score_model)
+    probs = torch.softmax(s, -1)
+    if aux:
+        return dict(probs=probs, logits=s, user_vec=u, cand_vec=dc, hist_vec=H)
+    return probs
+
+
+def loss_fn(P, user, clicked_tok, cand_tok, label=None, **kw):
+    probs = forward(P, user, clicked_tok, cand_tok, **kw)
+    if label is None:
+        label = torch.zeros_like(probs)
+        label[:, 0] = 1.0
+    return categorical_crossentropy(label, probs)
+
+
+class KerasAdam:
+    """keras.optimizers.Adam 2.2.x, dense for every tensor incl. embedding tables."""
+
+    def __init__(self, params, lr=1e-3, b1=0.9, b2=0.999, eps=1e-7):
+        self.params, self.lr, self.b1, self.b2, self.eps = params, lr, b1, b2, eps
+        self.t = 0
+        self.m = {k: torch.zeros_like(v) for k, v in params.items()}
+        self.v = {k: torch.zeros_like(v) for k, v in params.items()}
+
+    @torch.no_grad()
+    def step(self, grads):
+        self.t += 1
+        lr_t = self.lr * math.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t)
+        for k, g in grads.items():
+            if g is None:
+                continue
+            self.m[k].mul_(self.b1).add_(g, alpha=1.0 - self.b1)
+            self.v[k].mul_(self.b2).addcmul_(g, g, value=1.0 - self.b2)
+            self.params[k].sub_(lr_t * self.m[k] / (self.v[k].sqrt() + self.eps))
+
+
+class LsturOracle:
+    """Trainable oracle model: params dict of leaf tensors + KerasAdam."""
+
+    def __init__(self, params_np, arch='igru', score_model='dot', dtype=torch.float64, lr=1e-3,
+                 trainable_word_emb=False, dropout=0.0, recurrent_activation='hard_sigmoid'):
+        self.arch, self.score_model, self.dropout = arch, score_model, dropout
+        self.ra = recurrent_activation
+        self.P = {k: torch.tensor(v, dtype=dtype) for k, v in params_np.items()}
+        self.trainable = [k for k in self.P if k != 'word_emb' or trainable_word_emb]
+        for k in self.trainable:
+            self.P[k].requires_grad_(True)
+        self.opt = KerasAdam({k: self.P[k] for k in self.trainable}, lr=lr)
+
+    def _ints(self, user, clicked_tok, cand_tok):
+        t = lambda x: torch.as_tensor(x).long()
+        return t(user), t(clicked_tok), t(cand_tok)
+
+    def forward(self, user, clicked_tok, cand_tok, training=False, aux=False):
+        u, c, d = self._ints(user, clicked_tok, cand_tok)
+        return forward(self.P, u, c, d, arch=self.arch, score_model=self.score_model, recurrent_activation=self.ra,
+                       dropout=self.dropout, training=training, aux=aux)
+
+    def loss_and_grads(self, user, clicked_tok, cand_tok, training=False):
+        u, c, d = self._ints(user, clicked_tok, cand_tok)
+        loss = loss_fn(self.P, u, c, d, arch=self.arch, score_model=self.score_model, recurrent_activation=self.ra,
+                       dropout=self.dropout, training=training)
+        gs = torch.autograd.grad(loss, [self.P[k] for k in self.trainable], allow_unused=True)
+        return loss.detach(), dict(zip(self.trainable, gs))
+
+    def train_step(self, user, clicked_tok, cand_tok, training=True):
+        loss, grads = self.loss_and_grads(user, clicked_tok, cand_tok, training=training)
+        self.opt.step(grads)
+        return float(loss)
