@@ -57,6 +57,8 @@ typedef struct CUstream_st* cudaStream_t;
 
 const char* lstur_last_error(void);
 const char* lstur_version(void);
+/* number of kernels this library has launched so far in this process (bench.py "gpu_launches") */
+unsigned long long lstur_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Fine-grained operators (each validated against oracle/ in tests/)
@@ -180,6 +182,14 @@ int lstur_plan_dense_offset(const lstur_plan* plan, const char* name, long long*
 /* named views into the workspace after forward/backward (for tests and the Python shim):
  * tokens, pooled, doc_vec, hist_mask, user_vec, logits, probs, loss, d_user_rows, user_rows, n_user_rows */
 int lstur_plan_view(const lstur_plan* plan, void* workspace, const char* name, void** ptr, long long* count);
+
+/* Measurement hook: record the two CUDA events (cudaEvent_t) around one kernel of the step. */
+#define LSTUR_PROBE_NONE 0
+#define LSTUR_PROBE_CONV_FWD 1
+#define LSTUR_PROBE_CONV_WGRAD 2
+#define LSTUR_PROBE_GATHER 3
+#define LSTUR_PROBE_GRU_FWD 4
+int lstur_plan_set_probe(lstur_plan* plan, int probe_id, void* start_event, void* stop_event);
 
 int lstur_forward(const lstur_plan* plan, const lstur_weights* w, const lstur_batch* b, void* workspace,
                   int training, unsigned seed, cudaStream_t stream);

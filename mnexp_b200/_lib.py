@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, 'lib', 'liblstur_b200.so')
 _SCALARS = {
     'int': ctypes.c_int, 'unsigned': ctypes.c_uint, 'float': ctypes.c_float, 'long long': ctypes.c_longlong,
     'size_t': ctypes.c_size_t, 'cudaStream_t': ctypes.c_void_p, 'void': None,
+    'unsigned long long': ctypes.c_ulonglong,
 }
 
 
@@ -41,7 +42,7 @@ def parse_header(path=HEADER):
     src = re.sub(r'//[^\n]*', '', src)
     src = re.sub(r'typedef struct \w+ \{.*?\} \w+;', '', src, flags=re.S)
     protos = {}
-    for m in re.finditer(r'\b(const char\*|int|void|size_t|long long)\s+(lstur_\w+)\s*\(([^)]*)\)\s*;', src):
+    for m in re.finditer(r'\b(const char\*|unsigned long long|int|void|size_t|long long)\s+(lstur_\w+)\s*\(([^)]*)\)\s*;', src):
         ret, name, args = m.group(1), m.group(2), m.group(3).strip()
         argtypes = []
         if args and args != 'void':

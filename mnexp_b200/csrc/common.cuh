@@ -10,9 +10,11 @@
 namespace lstur {
 
 void set_error(const char* fmt, ...);
+extern unsigned long long g_launch_count;   // kernels launched through this library (bench.py: gpu_launches)
 
 #define LSTUR_CHECK_LAUNCH(name)                                              \
   do {                                                                        \
+    ++lstur::g_launch_count;                                                  \
     cudaError_t e__ = cudaGetLastError();                                     \
     if (e__ != cudaSuccess) {                                                 \
       lstur::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \

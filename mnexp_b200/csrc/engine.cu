@@ -17,6 +17,7 @@
 namespace lstur {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launch_count = 0;
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -39,12 +40,25 @@ struct lstur_plan {
   size_t ws_bytes = 0;
   long long dense_count = 0;
   size_t gemm_ws_bytes = 0;
+  // optional CUDA events recorded around one kernel of the step (bench.py roofline probe)
+  int probe_id = 0;
+  cudaEvent_t probe_start = nullptr, probe_stop = nullptr;
 };
 
 using namespace lstur;
 
 extern "C" const char* lstur_last_error(void) { return g_err; }
 extern "C" const char* lstur_version(void) { return "lstur_b200 0.1 (sm_100a)"; }
+extern "C" unsigned long long lstur_launch_count(void) { return g_launch_count; }
+extern "C" int lstur_plan_set_probe(lstur_plan* plan, int probe_id, void* start_event, void* stop_event) {
+  LSTUR_REQUIRE(plan != nullptr, "lstur_plan_set_probe");
+  plan->probe_id = probe_id;
+  plan->probe_start = (cudaEvent_t)start_event;
+  plan->probe_stop = (cudaEvent_t)stop_event;
+  return LSTUR_OK;
+}
+#define PROBE_BEGIN(p, id, st) do { if ((p)->probe_id == (id) && (p)->probe_start) cudaEventRecord((p)->probe_start, st); } while (0)
+#define PROBE_END(p, id, st) do { if ((p)->probe_id == (id) && (p)->probe_stop) cudaEventRecord((p)->probe_stop, st); } while (0)
 
 // conv tensor-core path (conv_tc.cu)
 extern "C" int lstur_conv_tc_available(void);
@@ -200,6 +214,7 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
       add_ws(p, "inverse", B);
       add_ws(p, "n_user_rows", 1);
       add_ws(p, "d_user_rows", B * c.Ue);
+      add_ws(p, "d_u0", B * c.Ue);
     }
     track_gemm(p, c.KS * E, F, (int)(N * Lp));
     track_gemm(p, F, Dd, (int)N);
@@ -285,9 +300,13 @@ extern "C" int lstur_forward(const lstur_plan* p, const lstur_weights* w, const 
   } else {
     float* Xp = W<float>(p, ws, "Xp");
     float* Cp = W<float>(p, ws, "Cp");
+    PROBE_BEGIN(p, LSTUR_PROBE_GATHER, st);
     RC(lstur_embed_gather_pad(N, L, E, c.V, c.KS, w->word_emb, tok, Xp, drop, seed * 2u + 0u, st));
+    PROBE_END(p, LSTUR_PROBE_GATHER, st);
+    PROBE_BEGIN(p, LSTUR_PROBE_CONV_FWD, st);
     RC(lstur_gemm_f32(0, 0, N * Lp - (c.KS - 1), F, c.KS * E, Xp, E, DP(p, w->dense, "conv_w"), F, Cp, F,
                       DP(p, w->dense, "conv_b"), LSTUR_GEMM_RELU, gws, gwsb, st));
+    PROBE_END(p, LSTUR_PROBE_CONV_FWD, st);
     RC(lstur_attn_pool_fwd(N, L, F, Cp, (long long)Lp * F, tok, DP(p, w->dense, "att_w"), DP(p, w->dense, "att_b"),
                            pooled, F, W<float>(p, ws, "att_a"), W<float>(p, ws, "att_w"), drop, seed * 2u + 1u, st));
   }
@@ -420,6 +439,9 @@ extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const
     }
     RC(lstur_segment_sum_rows(B, c.Ue, W<int>(p, ws, "n_user_rows"), W<int>(p, ws, "seg_start"),
                               W<int>(p, ws, "sorted_pos"), du0, lddu0, W<float>(p, ws, "d_user_rows"), st));
+    // contiguous per-sample copy for the data-parallel sparse exchange
+    cudaMemcpy2DAsync(W<float>(p, ws, "d_u0"), (size_t)c.Ue * 4, du0, (size_t)lddu0 * 4, (size_t)c.Ue * 4, B,
+                      cudaMemcpyDeviceToDevice, st);
   }
   // 5. news-encoder backward over all N titles
   float* d_pooled = W<float>(p, ws, "d_pooled");
@@ -443,8 +465,10 @@ extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const
                            drop, DG(p, dgrad, "att_w"), DG(p, dgrad, "conv_b"), DG(p, dgrad, "att_b"), 0,
                            W<float>(p, ws, "attn_partials"), (size_t)p->ws.at("attn_partials").count * 4, st));
     // d_conv_w[(j,e),f] = sum_m Xp[m+j, e] * dPre[m, f]
+    PROBE_BEGIN(p, LSTUR_PROBE_CONV_WGRAD, st);
     RC(lstur_gemm_f32(1, 0, c.KS * E, F, N * Lp - (c.KS - 1), W<float>(p, ws, "Xp"), E, dPre, F, DG(p, dgrad, "conv_w"), F,
                       nullptr, 0, gws, gwsb, st));
+    PROBE_END(p, LSTUR_PROBE_CONV_WGRAD, st);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

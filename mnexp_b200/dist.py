@@ -1,0 +1,77 @@
+"""Data-parallel LSTUR training: one process per GPU, batch sharded per rank.
+
+The reference has no distribution at all (settings.py:97-99 drops the node-* options); this is the
+exchange step a DP replica set needs: (1) one flat all-reduce of the dense-gradient arena,
+(2) an all-gather of the per-sample user ids and user-embedding gradient rows, after which every
+rank runs the same deterministic dedup + segment-sorted sum + row-sparse Adam, so replicas stay
+bit-identical without broadcasting weights.
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .engine import _ptr
+
+
+def exchange(dense_grad, user_ids, d_u0, group=None):
+    """Collective part only (works on gloo/CPU tensors too — exercised by tests/test_dist_cpu.py).
+
+    dense_grad is summed in place across ranks; returns (all_ids (world*B,), all_rows (world*B, Ue))
+    in rank-major order, or (None, None) when the model has no user embedding."""
+    dist.all_reduce(dense_grad, op=dist.ReduceOp.SUM, group=group)
+    if user_ids is None:
+        return None, None
+    world = dist.get_world_size(group)
+    all_ids = torch.empty(world * user_ids.numel(), dtype=user_ids.dtype, device=user_ids.device)
+    all_rows = torch.empty((world * d_u0.shape[0], d_u0.shape[1]), dtype=d_u0.dtype, device=d_u0.device)
+    dist.all_gather_into_tensor(all_ids, user_ids.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_rows, d_u0.contiguous(), group=group)
+    return all_ids, all_rows
+
+
+def shard_batch(batch, rank, world):
+    """Contiguous split of a global batch (dict of arrays with leading dim B_global) across ranks."""
+    out = {}
+    for k, v in batch.items():
+        n = v.shape[0]
+        assert n % world == 0, 'global batch must divide by world size'
+        per = n // world
+        out[k] = v[rank * per:(rank + 1) * per]
+    return out
+
+
+class DataParallel:
+    def __init__(self, engine, group=None):
+        self.eng, self.group = engine, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        e = engine
+        if e.user_emb is not None and self.world > 1:
+            n = self.world * e.B
+            dev = e.device
+            i32 = lambda k: torch.empty(k, dtype=torch.int32, device=dev)
+            self.sorted_pos, self.rows, self.seg, self.inv, self.nrows = i32(n), i32(n), i32(n + 1), i32(n), i32(1)
+            self.grows = torch.empty((n, e.Ue), dtype=torch.float32, device=dev)
+
+    def train_step(self, db):
+        e = self.eng
+        if self.world == 1:
+            return e.train_step(db)
+        e.step_seed += 1
+        e.forward(db, training=True, seed=e.step_seed * self.world + self.rank)
+        e.backward(db, grad_scale=1.0 / (e.B * self.world))          # mean over the GLOBAL batch
+        has_user = e.user_emb is not None
+        ids, rows = exchange(e.dense_grad, db['user'] if has_user else None,
+                             e.view('d_u0').reshape(e.B, e.Ue) if has_user else None, self.group)
+        ur = None
+        if has_user:
+            n, st, L = ids.numel(), e._stream(), e.lib
+            _lib.check(L.lstur_sort_unique_i32(n, _ptr(ids), _ptr(self.sorted_pos), _ptr(self.rows), _ptr(self.seg),
+                                               _ptr(self.inv), _ptr(self.nrows), st))
+            _lib.check(L.lstur_segment_sum_rows(n, e.Ue, _ptr(self.nrows), _ptr(self.seg), _ptr(self.sorted_pos),
+                                                _ptr(rows), e.Ue, _ptr(self.grows), st))
+            ur = (n, self.rows, self.nrows, self.grows)
+        e.apply_adam(user_rows=ur)
+        return e.view('loss')

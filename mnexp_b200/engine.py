@@ -139,10 +139,15 @@ class LsturEngine:
 
     # ---- workspace views ------------------------------------------------------------------
     def view(self, name, dtype=torch.float32):
+        key = (name, dtype)
+        cache = self.__dict__.setdefault('_views', {})
+        if key in cache:
+            return cache[key]
         ptr, cnt = ctypes.c_void_p(), ctypes.c_longlong()
         _lib.check(self.lib.lstur_plan_view(self.plan, _ptr(self.ws), name.encode(), ctypes.byref(ptr), ctypes.byref(cnt)))
         off = ptr.value - self.ws.data_ptr()
-        return self.ws[off:off + 4 * cnt.value].view(dtype)
+        cache[key] = self.ws[off:off + 4 * cnt.value].view(dtype)
+        return cache[key]
 
     # ---- batches --------------------------------------------------------------------------
     def to_device_batch(self, batch, non_blocking=False):
@@ -182,23 +187,34 @@ class LsturEngine:
         _lib.check(self.lib.lstur_backward(self.plan, ctypes.byref(self._w), ctypes.byref(cb), _ptr(self.ws),
                                            _ptr(self.dense_grad), ctypes.c_float(gs), self._stream()))
 
-    def apply_adam(self, b1=0.9, b2=0.999, eps=1e-7):
+    def apply_adam(self, b1=0.9, b2=0.999, eps=1e-7, user_rows=None):
+        """Keras Adam on the dense arena and the user table.  user_rows = (max_rows, rows, n_rows, g_rows)
+        device tensors overrides the local unique rows (data-parallel: globally exchanged rows)."""
         self.t += 1
         st = self._stream()
         _lib.check(self.lib.lstur_adam_dense(self.n_dense, _ptr(self.dense), _ptr(self.dense_grad), _ptr(self.adam_m),
                                              _ptr(self.adam_v), self.lr, self.t, b1, b2, eps, 1.0, st))
         if self.user_emb is not None:
-            rows, nrows, grows = self.view('user_rows', torch.int32), self.view('n_user_rows', torch.int32), self.view('d_user_rows')
+            if user_rows is None:
+                user_rows = (self.B, self.view('user_rows', torch.int32), self.view('n_user_rows', torch.int32),
+                             self.view('d_user_rows'))
+            mx, rows, nrows, grows = user_rows
             if self.sparse_user_adam:
-                _lib.check(self.lib.lstur_adam_rows(self.B, _ptr(nrows), self.Ue, _ptr(rows), _ptr(grows),
+                _lib.check(self.lib.lstur_adam_rows(mx, _ptr(nrows), self.Ue, _ptr(rows), _ptr(grows),
                                                     _ptr(self.user_emb), _ptr(self.user_m), _ptr(self.user_v),
                                                     self.lr, self.t, b1, b2, eps, 1.0, st))
             else:   # reference semantics: dense Adam over the whole table (SURVEY §9.7)
                 self.user_grad_dense.zero_()
-                _lib.check(self.lib.lstur_rows_add(self.B, _ptr(nrows), self.Ue, _ptr(rows), _ptr(grows),
+                _lib.check(self.lib.lstur_rows_add(mx, _ptr(nrows), self.Ue, _ptr(rows), _ptr(grows),
                                                    _ptr(self.user_grad_dense), st))
                 _lib.check(self.lib.lstur_adam_dense(self.user_emb.numel(), _ptr(self.user_emb), _ptr(self.user_grad_dense),
                                                      _ptr(self.user_m), _ptr(self.user_v), self.lr, self.t, b1, b2, eps, 1.0, st))
+
+    def set_probe(self, probe_id, ev_start=None, ev_stop=None):
+        """Record two torch.cuda.Event around one kernel of the step (bench.py roofline)."""
+        a = ctypes.c_void_p(ev_start.cuda_event) if ev_start is not None else None
+        b = ctypes.c_void_p(ev_stop.cuda_event) if ev_stop is not None else None
+        _lib.check(self.lib.lstur_plan_set_probe(self.plan, probe_id, a, b))
 
     def train_step(self, db, seed=None):
         """forward + backward + Adam on a device batch; returns the loss as a 1-element device tensor."""
