@@ -166,7 +166,7 @@ def main():
     lib = _lib.load()
     precision = args.precision
     if precision == 'auto':
-        precision = 'bf16_tc' if lib.lstur_conv_tc_available() else 'fp32'
+        precision = 'fp16_tc' if lib.lstur_conv_tc_available() else 'fp32'
     n_batches = 6
     tok, P, batches, pad_frac = build_workload(sh, n_batches, rank, B)
     eng = LsturEngine(P, B, sh.W, 1 + sh.K, sh.L, arch=sh.arch, doc_tokens=tok, dropout=0.2, lr=1e-3,
@@ -185,7 +185,7 @@ def main():
     barrier()
     # ---- timed region: device-resident inputs, CUDA events, probe events around the dominant kernel
     probe_id = 1
-    probes = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    probes = [(eng.new_event(), eng.new_event()) for _ in range(args.steps)]
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -207,7 +207,7 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms[0])
     value = B * world * args.steps / (ms_total / 1e3)
-    probe_ms = float(np.mean([a.elapsed_time(b) for a, b in probes]))
+    probe_ms = float(np.mean([eng.elapsed_ms(a, b) for a, b in probes]))
     loss_last = eng.loss()
 
     # ---- e2e: host (pinned) batches in, loss out, every step
@@ -249,7 +249,7 @@ def main():
         cpu.pop('ms_per_step', None)
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
-                dtype='bf16' if precision == 'bf16_tc' else 'f32', data='synthetic',
+                dtype={'bf16_tc': 'bf16', 'fp16_tc': 'f16'}.get(precision, 'f32'), data='synthetic',
                 config=dict(config, precision=precision, l2='inputs larger than L2: %d distinct batches, >%d MB activations per step'
                                                           % (n_batches, eng.ws_bytes >> 20),
                             user_adam='row-sparse (documented deviation from dense Keras-Adam)', hist_pad_frac=round(pad_frac, 3)),

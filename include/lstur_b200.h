@@ -54,6 +54,7 @@ typedef struct CUstream_st* cudaStream_t;
 
 #define LSTUR_PREC_FP32 0    /* FFMA everywhere: verification mode, ~1e-6 of the oracle */
 #define LSTUR_PREC_BF16_TC 1 /* title Conv1D on tcgen05 (bf16 in, fp32 accumulate in TMEM) */
+#define LSTUR_PREC_FP16_TC 2 /* same instruction and rate with fp16 operands: 8x smaller rounding error */
 
 const char* lstur_last_error(void);
 const char* lstur_version(void);
@@ -74,6 +75,25 @@ int lstur_token_gather(int N, int L, int n_docs, const int* doc_tokens, const in
 int lstur_embed_gather_pad(int N, int L, int E, int V, int KS, const float* word_emb, const int* tokens, float* Xp,
                            float dropout, unsigned seed, cudaStream_t stream);
 
+int lstur_embed_gather_pad_tcrng(int N, int L, int E, int V, int KS, int Ep, const float* word_emb, const int* tokens,
+                                 float* Xp, float dropout, unsigned seed, cudaStream_t stream);
+
+/* Tensor-core news encoder (tcgen05/TMEM): Embedding + Dropout + Conv1D(F,3,'same',relu) + pad mask + Masking +
+ * Dropout + SimpleAttentionMaskSupport in ONE kernel (task/paper.py:141-158, models.py:474-489).
+ * emb_16: (V, lstur_tc_padded_e(E)) 16-bit table from lstur_pack_word_emb_16; wimg: lstur_tc_wimg_elems(E,F)
+ * 16-bit elements from lstur_pack_conv_w_tc.  c_out_16 (n_titles,L,F) receives the attention input (saved for
+ * backward).  fp16 != 0: IEEE half operands (10-bit mantissa, meets the 1e-3 parity bound); 0: bfloat16. */
+int lstur_conv_tc_available(void);
+int lstur_tc_supported(int L, int E, int F, int KS);
+int lstur_tc_padded_e(int E);
+long long lstur_tc_wimg_elems(int E, int F);
+int lstur_pack_word_emb_16(long long V, int E, const float* word_emb, void* emb_16, int fp16, cudaStream_t stream);
+int lstur_pack_conv_w_tc(int E, int F, const float* conv_w, void* wimg, int fp16, cudaStream_t stream);
+int lstur_news_conv_tc_fwd(int n_titles, int L, int E, int F, int V, const int* tokens, const void* emb_16,
+                           const void* wimg, const float* conv_b, const float* att_w, const float* att_b,
+                           void* c_out_16, float* pooled, float* att_a, float* att_wt, float dropout, unsigned seed,
+                           int fp16, int max_ctas, cudaStream_t stream);
+
 /* C[M,N] (+)= op(A).op(B) + bias, optional ReLU: keras Dense / Conv1D-as-GEMM / all weight gradients. */
 size_t lstur_gemm_f32_workspace_bytes(int M, int N, int K, int* splits_out);
 int lstur_gemm_f32(int transA, int transB, int M, int N, int K, const float* A, long long lda, const float* B,
@@ -89,6 +109,11 @@ int lstur_attn_pool_bwd(int N, int L, int Lrows, int F, const float* Cd, long lo
                         const float* w_in, const float* d_pooled, long long lddp, const float* att_w, float* dPre,
                         long long dpre_title_stride, float dropout, float* d_att_w, float* d_conv_b, float* d_att_b,
                         int accumulate, float* partials, size_t partial_bytes, cudaStream_t stream);
+int lstur_attn_pool_bwd_16(int fp16, int N, int L, int Lrows, int F, const void* Cd_16, long long title_stride,
+                             const float* a_in, const float* w_in, const float* d_pooled, long long lddp,
+                             const float* att_w, float* dPre, long long dpre_title_stride, float dropout,
+                             float* d_att_w, float* d_conv_b, float* d_att_b, int accumulate, float* partials,
+                             size_t partial_bytes, cudaStream_t stream);
 int lstur_colsum(long long rows, int cols, const float* in, long long ld, float* out, int accumulate,
                  float* workspace, size_t workspace_bytes, cudaStream_t stream);
 
@@ -190,6 +215,9 @@ int lstur_plan_view(const lstur_plan* plan, void* workspace, const char* name, v
 #define LSTUR_PROBE_GATHER 3
 #define LSTUR_PROBE_GRU_FWD 4
 int lstur_plan_set_probe(lstur_plan* plan, int probe_id, void* start_event, void* stop_event);
+int lstur_event_create(void** ev);
+int lstur_event_destroy(void* ev);
+int lstur_event_elapsed_ms(void* start_event, void* stop_event, float* ms);
 
 int lstur_forward(const lstur_plan* plan, const lstur_weights* w, const lstur_batch* b, void* workspace,
                   int training, unsigned seed, cudaStream_t stream);

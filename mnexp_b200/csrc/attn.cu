@@ -6,6 +6,8 @@
 //   a = tanh(C.ka + ba);  e = exp(a)*m;  w = e/(sum_t e + 1e-7);  p = sum_t w_t C_t
 // These are the un-fused (verification) kernels; the tensor-core conv kernel
 // carries the same arithmetic in its epilogue.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace lstur {
@@ -62,9 +64,13 @@ attn_pool_fwd_kernel(int N, int L, int F, float* __restrict__ C, long long title
 // per-thread partial sums of d(ka), d(conv bias) and d(ba) and writes them to
 // partials[cta][2F+1] (reduced afterwards in a fixed order -> deterministic).
 //   dPre = d(loss)/d(conv pre-activation) incl. ReLU/pad/Masking/Dropout gates.
-template <int FPT>
+__device__ __forceinline__ float ldc(const float* p, long long i) { return p[i]; }
+__device__ __forceinline__ float ldc(const __nv_bfloat16* p, long long i) { return __bfloat162float(p[i]); }
+__device__ __forceinline__ float ldc(const __half* p, long long i) { return __half2float(p[i]); }
+
+template <int FPT, typename CT>
 __global__ void __launch_bounds__(ATT_THREADS)
-attn_pool_bwd_kernel(int N, int L, int Lrows, int F, const float* __restrict__ Cd, long long title_stride,
+attn_pool_bwd_kernel(int N, int L, int Lrows, int F, const CT* __restrict__ Cd, long long title_stride,
                      const float* __restrict__ a_in, const float* __restrict__ w_in, const float* __restrict__ dp,
                      long long lddp, const float* __restrict__ ka, float* __restrict__ dPre,
                      long long dpre_title_stride, float inv_keep, float* __restrict__ partials) {
@@ -74,12 +80,12 @@ attn_pool_bwd_kernel(int N, int L, int Lrows, int F, const float* __restrict__ C
 #pragma unroll
   for (int i = 0; i < FPT; ++i) dka[i] = dbc[i] = 0.f;
   for (int n = blockIdx.x; n < N; n += gridDim.x) {
-    const float* Cn = Cd + (long long)n * title_stride;
+    const CT* Cn = Cd + (long long)n * title_stride;
     const float* dpn = dp + (long long)n * lddp;
     float* dPn = dPre + (long long)n * dpre_title_stride;
     for (int t = warp; t < L; t += ATT_THREADS / 32) {
       float dot = 0.f;
-      for (int f = lane; f < F; f += 32) dot = fmaf(Cn[(long long)t * F + f], dpn[f], dot);
+      for (int f = lane; f < F; f += 32) dot = fmaf(ldc(Cn, (long long)t * F + f), dpn[f], dot);
       dot = warp_sum(dot);
       if (lane == 0) {
         sdw[t] = dot;
@@ -100,7 +106,7 @@ attn_pool_bwd_kernel(int N, int L, int Lrows, int F, const float* __restrict__ C
       if (f < F) {
         const float dpf = dpn[f], kaf = ka[f];
         for (int t = 0; t < L; ++t) {
-          float c = Cn[(long long)t * F + f];
+          float c = ldc(Cn, (long long)t * F + f);
           float g = fmaf(sw[t], dpf, sdz[t] * kaf);
           float dpre = c > 0.f ? g * inv_keep : 0.f;
           dPn[(long long)t * F + f] = dpre;
@@ -193,11 +199,11 @@ extern "C" int lstur_colsum(long long rows, int cols, const float* in, long long
 
 // partials must hold lstur_attn_bwd_grid(N) * (2F+1) floats; after the call
 // d_att_w[F], d_conv_b[F], d_att_b[1] are written (or accumulated).
-extern "C" int lstur_attn_pool_bwd(int N, int L, int Lrows, int F, const float* Cd, long long title_stride,
-                                   const float* a_in, const float* w_in, const float* d_pooled, long long lddp,
-                                   const float* att_w, float* dPre, long long dpre_title_stride, float dropout,
-                                   float* d_att_w, float* d_conv_b, float* d_att_b, int accumulate, float* partials,
-                                   size_t partial_bytes, cudaStream_t stream) {
+static int attn_pool_bwd_impl(int c_is_bf16, int N, int L, int Lrows, int F, const void* Cd_, long long title_stride,
+                              const float* a_in, const float* w_in, const float* d_pooled, long long lddp,
+                              const float* att_w, float* dPre, long long dpre_title_stride, float dropout,
+                              float* d_att_w, float* d_conv_b, float* d_att_b, int accumulate, float* partials,
+                              size_t partial_bytes, cudaStream_t stream) {
   LSTUR_REQUIRE(N >= 0 && L > 0 && L <= ATT_MAX_L && Lrows >= L && F > 0 && F <= 8 * ATT_THREADS, "lstur_attn_pool_bwd");
   int grid = lstur_attn_bwd_grid(N);
   size_t need = (size_t)grid * (2 * F + 1) * sizeof(float);
@@ -212,9 +218,22 @@ extern "C" int lstur_attn_pool_bwd(int N, int L, int Lrows, int F, const float* 
   }
   float inv_keep = 1.f / (1.f - dropout);
   int fpt = cdiv(F, ATT_THREADS);
-#define LAUNCH(FPT_)                                                                                                  \
-  attn_pool_bwd_kernel<FPT_><<<grid, ATT_THREADS, 0, stream>>>(N, L, Lrows, F, Cd, title_stride, a_in, w_in, d_pooled, \
-                                                               lddp, att_w, dPre, dpre_title_stride, inv_keep, partials)
+#define LAUNCH(FPT_)                                                                                                \
+  do {                                                                                                              \
+    if (c_is_bf16 == 1)                                                                                             \
+      attn_pool_bwd_kernel<FPT_, __nv_bfloat16><<<grid, ATT_THREADS, 0, stream>>>(                                  \
+          N, L, Lrows, F, (const __nv_bfloat16*)Cd_, title_stride, a_in, w_in, d_pooled, lddp, att_w, dPre,         \
+          dpre_title_stride, inv_keep, partials);                                                                   \
+    else if (c_is_bf16 == 2)                                                                                        \
+      attn_pool_bwd_kernel<FPT_, __half><<<grid, ATT_THREADS, 0, stream>>>(                                         \
+          N, L, Lrows, F, (const __half*)Cd_, title_stride, a_in, w_in, d_pooled, lddp, att_w, dPre,                \
+          dpre_title_stride, inv_keep, partials);                                                                   \
+    else                                                                                                            \
+      attn_pool_bwd_kernel<FPT_, float><<<grid, ATT_THREADS, 0, stream>>>(N, L, Lrows, F, (const float*)Cd_,         \
+                                                                          title_stride, a_in, w_in, d_pooled, lddp, \
+                                                                          att_w, dPre, dpre_title_stride, inv_keep, \
+                                                                          partials);                                \
+  } while (0)
   if (fpt <= 1) LAUNCH(1);
   else if (fpt <= 2) LAUNCH(2);
   else if (fpt <= 4) LAUNCH(4);
@@ -225,4 +244,25 @@ extern "C" int lstur_attn_pool_bwd(int N, int L, int Lrows, int F, const float* 
                                                                      accumulate);
   LSTUR_CHECK_LAUNCH("lstur_attn_pool_bwd(reduce)");
   return LSTUR_OK;
+}
+
+extern "C" int lstur_attn_pool_bwd(int N, int L, int Lrows, int F, const float* Cd, long long title_stride,
+                                   const float* a_in, const float* w_in, const float* d_pooled, long long lddp,
+                                   const float* att_w, float* dPre, long long dpre_title_stride, float dropout,
+                                   float* d_att_w, float* d_conv_b, float* d_att_b, int accumulate, float* partials,
+                                   size_t partial_bytes, cudaStream_t stream) {
+  return attn_pool_bwd_impl(0, N, L, Lrows, F, Cd, title_stride, a_in, w_in, d_pooled, lddp, att_w, dPre,
+                            dpre_title_stride, dropout, d_att_w, d_conv_b, d_att_b, accumulate, partials, partial_bytes,
+                            stream);
+}
+
+// Same, with the attention input saved as 16-bit floats by the tensor-core forward (fp16 != 0: half, else bf16).
+extern "C" int lstur_attn_pool_bwd_16(int fp16, int N, int L, int Lrows, int F, const void* Cd_bf16, long long title_stride,
+                                        const float* a_in, const float* w_in, const float* d_pooled, long long lddp,
+                                        const float* att_w, float* dPre, long long dpre_title_stride, float dropout,
+                                        float* d_att_w, float* d_conv_b, float* d_att_b, int accumulate,
+                                        float* partials, size_t partial_bytes, cudaStream_t stream) {
+  return attn_pool_bwd_impl(fp16 ? 2 : 1, N, L, Lrows, F, Cd_bf16, title_stride, a_in, w_in, d_pooled, lddp, att_w, dPre,
+                            dpre_title_stride, dropout, d_att_w, d_conv_b, d_att_b, accumulate, partials, partial_bytes,
+                            stream);
 }

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "plan.h"
 
 namespace lstur {
 
@@ -25,25 +26,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-struct Region {
-  size_t off;       // bytes into workspace
-  long long count;  // elements (4-byte)
-};
-
 }  // namespace lstur
-
-struct lstur_plan {
-  lstur_config c;
-  int N, Nh, Nc, Lp, D;
-  std::map<std::string, lstur::Region> ws;     // workspace regions
-  std::map<std::string, lstur::Region> dense;  // dense-parameter layout (off in floats)
-  size_t ws_bytes = 0;
-  long long dense_count = 0;
-  size_t gemm_ws_bytes = 0;
-  // optional CUDA events recorded around one kernel of the step (bench.py roofline probe)
-  int probe_id = 0;
-  cudaEvent_t probe_start = nullptr, probe_stop = nullptr;
-};
 
 using namespace lstur;
 
@@ -57,8 +40,19 @@ extern "C" int lstur_plan_set_probe(lstur_plan* plan, int probe_id, void* start_
   plan->probe_stop = (cudaEvent_t)stop_event;
   return LSTUR_OK;
 }
-#define PROBE_BEGIN(p, id, st) do { if ((p)->probe_id == (id) && (p)->probe_start) cudaEventRecord((p)->probe_start, st); } while (0)
-#define PROBE_END(p, id, st) do { if ((p)->probe_id == (id) && (p)->probe_stop) cudaEventRecord((p)->probe_stop, st); } while (0)
+extern "C" int lstur_event_create(void** ev) {
+  LSTUR_REQUIRE(ev != nullptr, "lstur_event_create");
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) { set_error("cudaEventCreate failed"); return LSTUR_ERR_CUDA; }
+  *ev = (void*)e;
+  return LSTUR_OK;
+}
+extern "C" int lstur_event_destroy(void* ev) { return cudaEventDestroy((cudaEvent_t)ev) == cudaSuccess ? LSTUR_OK : LSTUR_ERR_CUDA; }
+extern "C" int lstur_event_elapsed_ms(void* a, void* b, float* ms) {
+  cudaError_t e = cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b);
+  if (e != cudaSuccess) { set_error("cudaEventElapsedTime: %s", cudaGetErrorString(e)); return LSTUR_ERR_CUDA; }
+  return LSTUR_OK;
+}
 
 // conv tensor-core path (conv_tc.cu)
 extern "C" int lstur_conv_tc_available(void);
@@ -75,29 +69,10 @@ void add_dense(lstur_plan* p, const char* name, long long count) {
   p->dense[name] = Region{(size_t)off, count};
   p->dense_count = off + count;
 }
-template <typename T>
-T* W(const lstur_plan* p, void* ws, const char* name) {
-  auto it = p->ws.find(name);
-  return it == p->ws.end() ? nullptr : (T*)((char*)ws + it->second.off);
-}
-const float* DP(const lstur_plan* p, const float* dense, const char* name) {
-  auto it = p->dense.find(name);
-  return it == p->dense.end() ? nullptr : dense + it->second.off;
-}
-float* DG(const lstur_plan* p, float* dense, const char* name) {
-  auto it = p->dense.find(name);
-  return it == p->dense.end() ? nullptr : dense + it->second.off;
-}
 void track_gemm(lstur_plan* p, int M, int N, int K) {
   size_t b = lstur_gemm_f32_workspace_bytes(M, N, K, nullptr);
   if (b > p->gemm_ws_bytes) p->gemm_ws_bytes = b;
 }
-
-#define RC(x)              \
-  do {                     \
-    int rc__ = (x);        \
-    if (rc__) return rc__; \
-  } while (0)
 
 }  // namespace
 
@@ -132,8 +107,8 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
   LSTUR_REQUIRE(c.arch != LSTUR_ARCH_INI || c.Ue == c.G, "lstur_plan_create(ini needs Ue == G)");
   LSTUR_REQUIRE(c.arch != LSTUR_ARCH_ADD || c.Ue == c.G, "lstur_plan_create(add needs Ue == G)");
   LSTUR_REQUIRE(U == D, "lstur_plan_create('dot' scorer needs user dim == doc dim)");
-  if (c.precision == LSTUR_PREC_BF16_TC && !lstur_conv_tc_available()) {
-    set_error("lstur_plan_create: tensor-core conv path not built");
+  if ((c.precision == LSTUR_PREC_BF16_TC || c.precision == LSTUR_PREC_FP16_TC) && !lstur_tc_supported(c.L, c.E, c.F, c.KS)) {
+    set_error("lstur_plan_create: shape (L=%d,E=%d,F=%d,KS=%d) not supported by the tensor-core conv kernel", c.L, c.E, c.F, c.KS);
     return LSTUR_ERR_UNSUPPORTED;
   }
 
@@ -170,9 +145,15 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
   p->dense_count = (p->dense_count + 3) & ~3LL;
 
   // ---- workspace
+  const bool tcp = (c.precision == LSTUR_PREC_BF16_TC || c.precision == LSTUR_PREC_FP16_TC);
   add_ws(p, "tokens", N * c.L);
-  add_ws(p, "Xp", N * Lp * E);
-  add_ws(p, "Cp", N * Lp * F);
+  if (!tcp || bw) add_ws(p, "Xp", N * Lp * E);
+  if (!tcp) add_ws(p, "Cp", N * Lp * F);
+  if (tcp) {
+    add_ws(p, "emb_bf16", ((long long)c.V * lstur_tc_padded_e(E) + 1) / 2);
+    add_ws(p, "wimg", (lstur_tc_wimg_elems(E, F) + 1) / 2);
+    add_ws(p, "C16", (N * c.L * F + 1) / 2);
+  }
   add_ws(p, "att_a", N * c.L);
   add_ws(p, "att_w", N * c.L);
   add_ws(p, "pooled", N * F);
@@ -279,6 +260,8 @@ extern "C" int lstur_forward(const lstur_plan* p, const lstur_weights* w, const 
   const bool bw = c.save_for_backward != 0;
   LSTUR_REQUIRE(!training || bw, "lstur_forward(training needs a save_for_backward plan)");
   const float drop = training ? c.dropout : 0.f;
+  const_cast<lstur_plan*>(p)->last_seed = seed;
+  const_cast<lstur_plan*>(p)->last_training = training;
   int* tok = W<int>(p, ws, "tokens");
   // 1. title tokens (k0)
   if (b->hist_tok) {
@@ -295,7 +278,7 @@ extern "C" int lstur_forward(const lstur_plan* p, const lstur_weights* w, const 
   void* gws = W<void>(p, ws, "gemm_ws");
   const size_t gwsb = p->gemm_ws_bytes;
   // 2. news encoder (k1-k7)
-  if (c.precision == LSTUR_PREC_BF16_TC) {
+  if ((c.precision == LSTUR_PREC_BF16_TC || c.precision == LSTUR_PREC_FP16_TC)) {
     RC(lstur_news_encoder_tc_fwd_internal(p, w, ws, training, seed, st));
   } else {
     float* Xp = W<float>(p, ws, "Xp");
@@ -369,8 +352,6 @@ extern "C" int lstur_forward(const lstur_plan* p, const lstur_weights* w, const 
   return LSTUR_OK;
 }
 
-extern "C" int lstur_news_encoder_tc_bwd_internal(const lstur_plan* plan, const lstur_weights* w, void* workspace,
-                                                  float* dense_grad, cudaStream_t stream);
 
 extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const lstur_batch* b, void* ws,
                               float* dgrad, float grad_scale, cudaStream_t st) {
@@ -455,8 +436,20 @@ extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const
   } else {
     dpool = d_docv; lddp = D;
   }
-  if (c.precision == LSTUR_PREC_BF16_TC) {
-    RC(lstur_news_encoder_tc_bwd_internal(p, w, ws, dgrad, st));
+  if ((c.precision == LSTUR_PREC_BF16_TC || c.precision == LSTUR_PREC_FP16_TC)) {
+    // interim: attention backward from the saved bf16 C, then the fp32 wgrad GEMM on a re-gathered X
+    float* dPre = W<float>(p, ws, "dPre");
+    float* Xp = W<float>(p, ws, "Xp");
+    RC(lstur_attn_pool_bwd_16(c.precision == LSTUR_PREC_FP16_TC, N, L, Lp, F, W<void>(p, ws, "C16"), (long long)L * F, W<float>(p, ws, "att_a"),
+                                W<float>(p, ws, "att_w"), dpool, lddp, DP(p, w->dense, "att_w"), dPre, (long long)Lp * F,
+                                c.dropout, DG(p, dgrad, "att_w"), DG(p, dgrad, "conv_b"), DG(p, dgrad, "att_b"), 0,
+                                W<float>(p, ws, "attn_partials"), (size_t)p->ws.at("attn_partials").count * 4, st));
+    RC(lstur_embed_gather_pad_tcrng(N, L, E, c.V, c.KS, lstur_tc_padded_e(E), w->word_emb, W<int>(p, ws, "tokens"), Xp,
+                                    c.dropout, p->last_seed * 2u, st));
+    PROBE_BEGIN(p, LSTUR_PROBE_CONV_WGRAD, st);
+    RC(lstur_gemm_f32(1, 0, c.KS * E, F, N * Lp - (c.KS - 1), Xp, E, dPre, F, DG(p, dgrad, "conv_w"), F, nullptr, 0, gws,
+                      gwsb, st));
+    PROBE_END(p, LSTUR_PROBE_CONV_WGRAD, st);
   } else {
     float* dPre = W<float>(p, ws, "dPre");
     const float drop = c.dropout;  // backward always follows a training forward

@@ -19,7 +19,7 @@ ARCH = {  # reference arch names -> engine arch; paper.py name
 COOK_ARCH = {'ingru': 0, 'igru': 2, 'gru': 3, 'agru': 4, 'vo': 5}   # task/cook.py:146-168
 DENSE_NAMES = ('conv_w', 'conv_b', 'att_w', 'att_b', 'dense_w', 'dense_b', 'vert_emb', 'subvert_emb',
                'gru_wx', 'gru_wh', 'gru_b', 'con_w', 'con_b')
-PREC = {'fp32': 0, 'bf16_tc': 1}
+PREC = {'fp32': 0, 'bf16_tc': 1, 'fp16_tc': 2}
 
 
 def _ptr(t):
@@ -210,11 +210,19 @@ class LsturEngine:
                 _lib.check(self.lib.lstur_adam_dense(self.user_emb.numel(), _ptr(self.user_emb), _ptr(self.user_grad_dense),
                                                      _ptr(self.user_m), _ptr(self.user_v), self.lr, self.t, b1, b2, eps, 1.0, st))
 
+    def new_event(self):
+        ev = ctypes.c_void_p()
+        _lib.check(self.lib.lstur_event_create(ctypes.byref(ev)))
+        return ev
+
+    def elapsed_ms(self, a, b):
+        ms = ctypes.c_float()
+        _lib.check(self.lib.lstur_event_elapsed_ms(a, b, ctypes.byref(ms)))
+        return ms.value
+
     def set_probe(self, probe_id, ev_start=None, ev_stop=None):
-        """Record two torch.cuda.Event around one kernel of the step (bench.py roofline)."""
-        a = ctypes.c_void_p(ev_start.cuda_event) if ev_start is not None else None
-        b = ctypes.c_void_p(ev_stop.cuda_event) if ev_stop is not None else None
-        _lib.check(self.lib.lstur_plan_set_probe(self.plan, probe_id, a, b))
+        """Record two CUDA events (new_event()) around one kernel of the step (bench.py roofline)."""
+        _lib.check(self.lib.lstur_plan_set_probe(self.plan, probe_id, ev_start, ev_stop))
 
     def train_step(self, db, seed=None):
         """forward + backward + Adam on a device batch; returns the loss as a 1-element device tensor."""

@@ -1,0 +1,183 @@
+"""GPU parity tests for the tensor-core (tcgen05/TMEM, bf16) news encoder and the bf16_tc engine mode.
+
+Tolerance: north_star's 1e-3 relative (max|a-b| / max|b|) on encoder outputs, scores and loss against the
+float64 oracle; a tighter check against the oracle fed with bf16-rounded operands isolates kernel bugs from
+the (expected) bf16 input rounding.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from mnexp_b200 import rng, synth
+from oracle import lstur_numpy as on
+from oracle import lstur_torch as ot
+
+pytestmark = pytest.mark.gpu
+TOL_SPEC = 1e-3
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def P_(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def round16(x, fp16):
+    return torch.as_tensor(np.asarray(x, dtype=np.float32)).to(torch.float16 if fp16 else torch.bfloat16).to(torch.float32).numpy()
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def run_tc_encoder(lib, tok, P, dropout=0.0, seed=0, max_ctas=0, fp16=1):
+    N, L = tok.shape
+    ks, E, F = P['conv_w'].shape
+    V = P['word_emb'].shape[0]
+    Ep = lib.lstur_tc_padded_e(E)
+    dev = lambda x, dt: torch.as_tensor(np.ascontiguousarray(x)).to(dt).cuda()
+    dt16 = torch.float16 if fp16 else torch.bfloat16
+    emb = torch.zeros((V, Ep), dtype=dt16, device='cuda')
+    wimg = torch.zeros(lib.lstur_tc_wimg_elems(E, F), dtype=dt16, device='cuda')
+    we, cw = dev(P['word_emb'], torch.float32), dev(P['conv_w'], torch.float32)
+    assert lib.lstur_pack_word_emb_16(V, E, P_(we), P_(emb), fp16, stream()) == 0
+    assert lib.lstur_pack_conv_w_tc(E, F, P_(cw), P_(wimg), fp16, stream()) == 0
+    t = dev(tok, torch.int32)
+    cb, aw, ab = dev(P['conv_b'], torch.float32), dev(P['att_w'].reshape(-1), torch.float32), dev(np.asarray(P['att_b']).reshape(1), torch.float32)
+    c_out = torch.full((N, L, F), float('nan'), dtype=dt16, device='cuda')
+    pooled = torch.full((N, F), float('nan'), device='cuda')
+    a = torch.full((N, L), float('nan'), device='cuda')
+    w = torch.full((N, L), float('nan'), device='cuda')
+    rc = lib.lstur_news_conv_tc_fwd(N, L, E, F, V, P_(t), P_(emb), P_(wimg), P_(cb), P_(aw), P_(ab), P_(c_out), P_(pooled),
+                                    P_(a), P_(w), ctypes.c_float(dropout), seed, fp16, max_ctas, stream())
+    assert rc == 0, lib.lstur_last_error()
+    torch.cuda.synchronize()
+    return c_out.float().cpu().numpy(), pooled.cpu().numpy(), a.cpu().numpy(), w.cpu().numpy()
+
+
+def check_attention_given_c(tok, P, c, pooled, a, w):
+    """Attention pooling must be exact (fp32 rounding only) given the kernel's own saved bf16 C."""
+    m = (c != 0).any(-1).astype(np.float64)
+    p_ref, att = on.attention_pool(c.astype(np.float64), m, P['att_w'].astype(np.float64).reshape(-1),
+                                   float(np.asarray(P['att_b']).reshape(-1)[0]))
+    assert rel(a, att['a']) < 1e-5
+    assert rel(w, att['w']) < 1e-5
+    assert rel(pooled, p_ref) < 1e-5
+
+
+def make_enc_case(N, L, E, F, V=500, seed=0, bias=0.05):
+    g = np.random.default_rng(seed)
+    sh = synth.Shape('t', 10, 10, V, L=L, E=E, F=F, U=8)
+    P = synth.make_weights(sh, arch='nigru', seed=seed, bias_noise=bias)
+    P['word_emb'] = (g.standard_normal((V, E)) * 0.1).astype(np.float32)   # row 0 is a normal row (mask_zero=False)
+    length = g.integers(1, L + 1, N)
+    tok = g.integers(1, V, (N, L)).astype(np.int32)
+    tok[np.arange(L)[None] >= length[:, None]] = 0
+    if N > 2:
+        tok[1] = 0                     # an all-pad title
+    return tok, P
+
+
+@pytest.mark.parametrize('N,L,E,F', [(4, 30, 64, 16), (1, 30, 64, 64), (5, 7, 12, 32), (9, 31, 128, 256),
+                                     (130, 30, 300, 400), (7, 30, 300, 272), (1500, 30, 300, 400)])
+@pytest.mark.parametrize('fp16', [1, 0])
+def test_tc_news_encoder_forward(lib, N, L, E, F, fp16):
+    tok, P = make_enc_case(N, L, E, F, seed=N + L + E + F)
+    c, pooled, a, w = run_tc_encoder(lib, tok, P, fp16=fp16)
+    # (1) kernel exactness: oracle fed the same 16-bit-rounded operands; C itself is stored in 16 bits
+    Pq = dict(P, word_emb=round16(P['word_emb'], fp16), conv_w=round16(P['conv_w'], fp16))
+    _, aux = on.news_encoder(tok, Pq, use_dense=False, aux=True)
+    assert rel(c, aux['C']) < (8e-4 if fp16 else 6e-3)
+    check_attention_given_c(tok, P, c, pooled, a, w)
+    # (2) spec tolerance vs the true fp32-weights oracle (fp16 operands meet 1e-3; bf16 does not)
+    _, aux32 = on.news_encoder(tok, P, use_dense=False, aux=True)
+    assert rel(pooled, aux32['p']) < (1e-3 if fp16 else 6e-3)
+    # all-pad title pools to exactly 0
+    if N > 2:
+        assert np.all(pooled[1] == 0)
+
+
+def test_tc_matches_across_grid_sizes(lib):
+    """Persistent-CTA tile scheduling: 1 CTA looping over all tiles == one tile per CTA (bitwise)."""
+    tok, P = make_enc_case(300, 30, 300, 400, seed=3)
+    r1 = run_tc_encoder(lib, tok, P, max_ctas=1)
+    r2 = run_tc_encoder(lib, tok, P, max_ctas=0)
+    for x, y in zip(r1, r2):
+        assert np.array_equal(x, y)
+
+
+def tc_dropout_masks(seed, N, L, E, Ep, F, p):
+    thr = int(np.float32(p) * np.float32(65536.0))
+    inv = np.float32(1) / (np.float32(1) - np.float32(p))
+    def mask(sd, rows, width, used):
+        n_pairs = rows * width // 2
+        h = rng.rng_u32(sd, np.arange(n_pairs, dtype=np.uint64))
+        lo, hi = (h & np.uint32(0xffff)) >= thr, (h >> np.uint32(16)) >= thr
+        m = np.stack([lo, hi], -1).reshape(rows, width)[:, :used]
+        return np.where(m, np.float64(inv), 0.0)
+    return mask(seed * 2, N * L, Ep, E).reshape(N, L, E), mask(seed * 2 + 1, N * L, F, F).reshape(N, L, F)
+
+
+def test_tc_dropout_replay(lib):
+    N, L, E, F = 37, 30, 300, 400
+    tok, P = make_enc_case(N, L, E, F, seed=11)
+    p, seed = 0.2, 5
+    c, pooled, a, w = run_tc_encoder(lib, tok, P, dropout=p, seed=seed)
+    dx, dc = tc_dropout_masks(seed, N, L, E, lib.lstur_tc_padded_e(E), F, p)
+    Pq = dict(P, word_emb=round16(P['word_emb'], 1), conv_w=round16(P['conv_w'], 1))
+    _, aux = on.news_encoder(tok, Pq, use_dense=False, aux=True, drop_x=dx, drop_c=dc)
+    assert rel(c, aux['C']) < 8e-4
+    check_attention_given_c(tok, P, c, pooled, a, w)
+    assert abs(float((dx == 0).mean()) - p) < 0.01 and abs(float((dc == 0).mean()) - p) < 0.01
+
+
+def make_case(shape_name='tiny', arch='igru', seed=0):
+    sh = synth.SHAPES[shape_name]
+    tok, _, _ = synth.make_docs(sh.n_news, sh.L, sh.vocab)
+    P = synth.make_weights(sh, arch=arch, bias_noise=0.05, seed=1237 + seed)
+    (b,), _ = synth.make_batches(sh, 1, seed=1236 + seed)
+    return sh, tok, P, b
+
+
+@pytest.mark.parametrize('shape,arch', [('tiny', 'igru'), ('C1', 'igru'), ('C1', 'gru')])
+@pytest.mark.parametrize('relu_open', [False, True])
+def test_engine_fp16_tc_forward_and_grads(lib, shape, arch, relu_open):
+    """relu_open=True shifts the conv bias by +1 so every pre-activation is positive: then no ReLU gate can flip
+    between the fp16 forward and the float64 oracle and gradients must agree to rounding (2e-2 incl. cancellation-heavy sums).  With live gates a
+    ~1e-3 fraction of near-zero pre-activations flips, which perturbs d(conv_w) by a few % in max-norm — the usual
+    ReLU discontinuity, bounded here by cosine > 0.995."""
+    from mnexp_b200.engine import LsturEngine
+    sh, tok, P, b = make_case(shape, arch)
+    if relu_open:
+        P = dict(P, conv_b=P['conv_b'] + np.float32(1.0))
+    eng = LsturEngine(P, sh.B, sh.W, 1 + sh.K, sh.L, arch=arch, doc_tokens=tok, precision='fp16_tc')
+    db = eng.to_device_batch(b)
+    eng.forward(db, training=True, seed=1)
+    eng.backward(db)
+    torch.cuda.synchronize()
+    ora = ot.LsturOracle(P, arch=arch)
+    out = ora.forward(b['user'], tok[b['hist_doc']], tok[b['cand_doc']], aux=True)
+    nh = sh.B * sh.W
+    dv = eng.view('doc_vec').reshape(-1, eng.D).cpu().numpy()
+    assert rel(dv[:nh], out['hist_vec'].detach().numpy().reshape(nh, -1)) < TOL_SPEC
+    assert rel(dv[nh:], out['cand_vec'].detach().numpy().reshape(-1, eng.D)) < TOL_SPEC
+    assert rel(eng.view('user_vec').reshape(sh.B, -1).cpu().numpy(), out['user_vec'].detach().numpy()) < TOL_SPEC
+    assert rel(eng.view('logits').reshape(sh.B, -1).cpu().numpy(), out['logits'].detach().numpy()) < TOL_SPEC
+    assert rel(eng.view('probs').reshape(sh.B, -1).cpu().numpy(), out['probs'].detach().numpy()) < TOL_SPEC
+    loss, ref = ora.loss_and_grads(b['user'], tok[b['hist_doc']], tok[b['cand_doc']])
+    assert abs(eng.loss() - float(loss)) < TOL_SPEC * max(1.0, abs(float(loss)))
+    got = eng.get_grads_dict()
+    for k, g in ref.items():
+        g = g.numpy().astype(np.float64).ravel()
+        h = got[k].astype(np.float64).ravel()
+        if relu_open:
+            assert rel(h, g) < 2e-2, k      # att_w / att_b grads are cancellation-heavy sums (sum_t dz_t ~ 0)
+        else:
+            cos = float(h @ g / max(np.linalg.norm(h) * np.linalg.norm(g), 1e-300))
+            assert cos > 0.995, (k, cos)
+            assert abs(np.linalg.norm(h) / np.linalg.norm(g) - 1.0) < 0.02, k
