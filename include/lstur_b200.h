@@ -94,6 +94,18 @@ int lstur_news_conv_tc_fwd(int n_titles, int L, int E, int F, int V, const int* 
                            void* c_out_16, float* pooled, float* att_a, float* att_wt, float dropout, unsigned seed,
                            int fp16, int max_ctas, cudaStream_t stream);
 
+/* Backward of the tensor-core news encoder: attention/ReLU/mask backward emitting dPre as 16-bit K-block images
+ * (lstur_attn_pool_bwd_img), then the Conv1D weight gradient on tcgen05 (lstur_conv_wgrad_tc). */
+int lstur_attn_pool_bwd_img(int fp16, int N, int L, int F, const void* Cd_16, const float* a_in, const float* w_in,
+                            const float* d_pooled, long long lddp, const float* att_w, void* dpre_img, float dropout,
+                            float* d_att_w, float* d_conv_b, float* d_att_b, int accumulate, float* partials,
+                            size_t partial_bytes, cudaStream_t stream);
+size_t lstur_tc_dpre_img_bytes(int n_titles, int F);
+size_t lstur_tc_wgrad_partial_bytes(int n_titles, int E, int F);
+int lstur_conv_wgrad_tc(int n_titles, int L, int E, int F, int V, const int* tokens, const void* emb_16,
+                        const void* dpre_img, float* d_conv_w, float dropout, unsigned seed, int fp16,
+                        void* partial_ws, size_t partial_bytes, cudaStream_t stream);
+
 /* C[M,N] (+)= op(A).op(B) + bias, optional ReLU: keras Dense / Conv1D-as-GEMM / all weight gradients. */
 size_t lstur_gemm_f32_workspace_bytes(int M, int N, int K, int* splits_out);
 int lstur_gemm_f32(int transA, int transB, int M, int N, int K, const float* A, long long lda, const float* B,

@@ -68,7 +68,20 @@ __device__ __forceinline__ float ldc(const float* p, long long i) { return p[i];
 __device__ __forceinline__ float ldc(const __nv_bfloat16* p, long long i) { return __bfloat162float(p[i]); }
 __device__ __forceinline__ float ldc(const __half* p, long long i) { return __half2float(p[i]); }
 
-template <int FPT, typename CT>
+// OUT = 0: dPre as fp32 rows (title stride dpre_title_stride, rows L..Lrows-1 zeroed).
+// OUT = 1/2: dPre as bf16/fp16 K-block images for the tensor-core wgrad (conv_tc.cu): slot row R = n*32+t lives in
+//   block R/64 at  (f/64)*8192 + (R%64)*128 + ((((f%64)/8) ^ (R%8)) << 4) + (f%8)*2  — MN-major SWIZZLE_128B.
+__device__ __forceinline__ void store_dpre_img(void* img, int out_mode, int ngroups, int n, int t, int f, float v) {
+  const long long R = (long long)n * 32 + t;
+  const long long kb = R >> 6;
+  const int k = (int)(R & 63);
+  const long long byte = kb * ((long long)ngroups * 8192) + (long long)(f >> 6) * 8192 + k * 128 +
+                         ((((f & 63) >> 3) ^ (k & 7)) << 4) + (f & 7) * 2;
+  if (out_mode == 2) *reinterpret_cast<__half*>((char*)img + byte) = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+  else *reinterpret_cast<__nv_bfloat16*>((char*)img + byte) = __float2bfloat16_rn(v);
+}
+
+template <int FPT, typename CT, int OUT>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_pool_bwd_kernel(int N, int L, int Lrows, int F, const CT* __restrict__ Cd, long long title_stride,
                      const float* __restrict__ a_in, const float* __restrict__ w_in, const float* __restrict__ dp,
@@ -109,11 +122,15 @@ attn_pool_bwd_kernel(int N, int L, int Lrows, int F, const CT* __restrict__ Cd, 
           float c = ldc(Cn, (long long)t * F + f);
           float g = fmaf(sw[t], dpf, sdz[t] * kaf);
           float dpre = c > 0.f ? g * inv_keep : 0.f;
-          dPn[(long long)t * F + f] = dpre;
+          if (OUT == 0) dPn[(long long)t * F + f] = dpre;
+          else store_dpre_img(dPre, OUT, (F + 63) >> 6, n, t, f, dpre);
           dka[i] = fmaf(sdz[t], c, dka[i]);
           dbc[i] += dpre;
         }
-        for (int t = L; t < Lrows; ++t) dPn[(long long)t * F + f] = 0.f;
+        for (int t = L; t < Lrows; ++t) {
+          if (OUT == 0) dPn[(long long)t * F + f] = 0.f;
+          else store_dpre_img(dPre, OUT, (F + 63) >> 6, n, t, f, 0.f);
+        }
       }
     }
     if (tid == 0)
@@ -199,7 +216,7 @@ extern "C" int lstur_colsum(long long rows, int cols, const float* in, long long
 
 // partials must hold lstur_attn_bwd_grid(N) * (2F+1) floats; after the call
 // d_att_w[F], d_conv_b[F], d_att_b[1] are written (or accumulated).
-static int attn_pool_bwd_impl(int c_is_bf16, int N, int L, int Lrows, int F, const void* Cd_, long long title_stride,
+static int attn_pool_bwd_impl(int c_is_bf16, int out_mode, int N, int L, int Lrows, int F, const void* Cd_, long long title_stride,
                               const float* a_in, const float* w_in, const float* d_pooled, long long lddp,
                               const float* att_w, float* dPre, long long dpre_title_stride, float dropout,
                               float* d_att_w, float* d_conv_b, float* d_att_b, int accumulate, float* partials,
@@ -218,27 +235,24 @@ static int attn_pool_bwd_impl(int c_is_bf16, int N, int L, int Lrows, int F, con
   }
   float inv_keep = 1.f / (1.f - dropout);
   int fpt = cdiv(F, ATT_THREADS);
-#define LAUNCH(FPT_)                                                                                                \
-  do {                                                                                                              \
-    if (c_is_bf16 == 1)                                                                                             \
-      attn_pool_bwd_kernel<FPT_, __nv_bfloat16><<<grid, ATT_THREADS, 0, stream>>>(                                  \
-          N, L, Lrows, F, (const __nv_bfloat16*)Cd_, title_stride, a_in, w_in, d_pooled, lddp, att_w, dPre,         \
-          dpre_title_stride, inv_keep, partials);                                                                   \
-    else if (c_is_bf16 == 2)                                                                                        \
-      attn_pool_bwd_kernel<FPT_, __half><<<grid, ATT_THREADS, 0, stream>>>(                                         \
-          N, L, Lrows, F, (const __half*)Cd_, title_stride, a_in, w_in, d_pooled, lddp, att_w, dPre,                \
-          dpre_title_stride, inv_keep, partials);                                                                   \
-    else                                                                                                            \
-      attn_pool_bwd_kernel<FPT_, float><<<grid, ATT_THREADS, 0, stream>>>(N, L, Lrows, F, (const float*)Cd_,         \
-                                                                          title_stride, a_in, w_in, d_pooled, lddp, \
-                                                                          att_w, dPre, dpre_title_stride, inv_keep, \
-                                                                          partials);                                \
+#define LAUNCH_T(FPT_, CT_, OUT_)                                                                                  \
+  attn_pool_bwd_kernel<FPT_, CT_, OUT_><<<grid, ATT_THREADS, 0, stream>>>(N, L, Lrows, F, (const CT_*)Cd_, title_stride, \
+                                                                          a_in, w_in, d_pooled, lddp, att_w, dPre,  \
+                                                                          dpre_title_stride, inv_keep, partials)
+#define LAUNCH(FPT_)                                              \
+  do {                                                            \
+    if (c_is_bf16 == 1 && out_mode == 0) LAUNCH_T(FPT_, __nv_bfloat16, 0); \
+    else if (c_is_bf16 == 2 && out_mode == 0) LAUNCH_T(FPT_, __half, 0);   \
+    else if (c_is_bf16 == 1) LAUNCH_T(FPT_, __nv_bfloat16, 1);    \
+    else if (c_is_bf16 == 2) LAUNCH_T(FPT_, __half, 2);           \
+    else LAUNCH_T(FPT_, float, 0);                                \
   } while (0)
   if (fpt <= 1) LAUNCH(1);
   else if (fpt <= 2) LAUNCH(2);
   else if (fpt <= 4) LAUNCH(4);
   else LAUNCH(8);
 #undef LAUNCH
+#undef LAUNCH_T
   LSTUR_CHECK_LAUNCH("lstur_attn_pool_bwd");
   attn_bwd_reduce_kernel<<<cdiv(2 * F + 1, 128), 128, 0, stream>>>(grid, F, partials, d_att_w, d_conv_b, d_att_b,
                                                                      accumulate);
@@ -251,7 +265,7 @@ extern "C" int lstur_attn_pool_bwd(int N, int L, int Lrows, int F, const float* 
                                    const float* att_w, float* dPre, long long dpre_title_stride, float dropout,
                                    float* d_att_w, float* d_conv_b, float* d_att_b, int accumulate, float* partials,
                                    size_t partial_bytes, cudaStream_t stream) {
-  return attn_pool_bwd_impl(0, N, L, Lrows, F, Cd, title_stride, a_in, w_in, d_pooled, lddp, att_w, dPre,
+  return attn_pool_bwd_impl(0, 0, N, L, Lrows, F, Cd, title_stride, a_in, w_in, d_pooled, lddp, att_w, dPre,
                             dpre_title_stride, dropout, d_att_w, d_conv_b, d_att_b, accumulate, partials, partial_bytes,
                             stream);
 }
@@ -262,7 +276,23 @@ extern "C" int lstur_attn_pool_bwd_16(int fp16, int N, int L, int Lrows, int F, 
                                         const float* att_w, float* dPre, long long dpre_title_stride, float dropout,
                                         float* d_att_w, float* d_conv_b, float* d_att_b, int accumulate,
                                         float* partials, size_t partial_bytes, cudaStream_t stream) {
-  return attn_pool_bwd_impl(fp16 ? 2 : 1, N, L, Lrows, F, Cd_bf16, title_stride, a_in, w_in, d_pooled, lddp, att_w, dPre,
+  return attn_pool_bwd_impl(fp16 ? 2 : 1, 0, N, L, Lrows, F, Cd_bf16, title_stride, a_in, w_in, d_pooled, lddp, att_w, dPre,
                             dpre_title_stride, dropout, d_att_w, d_conv_b, d_att_b, accumulate, partials, partial_bytes,
                             stream);
+}
+
+// Tensor-core backward: same arithmetic, dPre emitted as 16-bit K-block images for lstur_conv_wgrad_tc
+// (lstur_tc_dpre_img_bytes(N,F) bytes; 32-row title slots, pad rows zero).
+extern "C" int lstur_attn_pool_bwd_img(int fp16, int N, int L, int F, const void* Cd_16, const float* a_in,
+                                       const float* w_in, const float* d_pooled, long long lddp, const float* att_w,
+                                       void* dpre_img, float dropout, float* d_att_w, float* d_conv_b, float* d_att_b,
+                                       int accumulate, float* partials, size_t partial_bytes, cudaStream_t stream) {
+  LSTUR_REQUIRE(L <= 31 && dpre_img != nullptr, "lstur_attn_pool_bwd_img");
+  if (N & 1) {  // the last 64-row K block is only half covered by titles: clear it first
+    size_t blk = (size_t)((F + 63) / 64) * 8192;
+    cudaMemsetAsync((char*)dpre_img + (size_t)(N / 2) * blk, 0, blk, stream);
+  }
+  return attn_pool_bwd_impl(fp16 ? 2 : 1, 1, N, L, 32, F, Cd_16, (long long)L * F, a_in, w_in, d_pooled, lddp, att_w,
+                            (float*)dpre_img, 0, dropout, d_att_w, d_conv_b, d_att_b, accumulate, partials,
+                            partial_bytes, stream);
 }

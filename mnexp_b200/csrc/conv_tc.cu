@@ -493,6 +493,239 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
   }
 }
 
+
+// =====================================================================================================
+// Conv1D weight gradient on tcgen05:  dW[(j,e), f] = sum_m X[m+j-1, e] * dPre[m, f]
+//   (backward of keras Conv1D, task/paper.py:146; X = dropout(Embedding(tok)), dPre from attn bwd)
+// GEMM view: M = 3*Ep rows (j,e) split in 128-row slices (one per CTA.x), N = F, K = token slot rows.
+// Both operands are "MN-major" (the reduction index = token is the slow index of the row-major data):
+//   A[K=token][M=e] : gathered embedding rows — the same 128B-swizzled row image as in the forward, but
+//                     described to the tensor core as MN-major (64-element groups, LBO between groups).
+//   B[K=token][N=f] : dPre, written by the attention-backward kernel directly as pre-swizzled K-block
+//                     images (64 tokens x ceil(F/64) groups x 128 B), fetched with one bulk copy each.
+// The token range is split over CTA.y; partial sums go to global and are reduced in a fixed order.
+constexpr int WG_KTOK = 64;                         // tokens (K rows) per pipeline stage = 2 title slots
+constexpr int WG_GROUP_BYTES = WG_KTOK * 128;       // one 64-element group of one stage: 8 KB
+constexpr int WG_A_STAGE_BYTES = 2 * WG_GROUP_BYTES;
+constexpr int WG_STAGES = 3;
+
+// MN-major SWIZZLE_128B descriptor: LBO = byte stride between 64-element MN groups, SBO = byte stride between
+// 8-row K groups (1024).
+__device__ __forceinline__ uint64_t make_desc_mn128(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N, bool fp16) {
+  return make_idesc(M, N, fp16) | (1u << 15) | (1u << 16);   // a_major = b_major = MN
+}
+
+struct WgradParams {
+  int n_titles, L, F, EC, Ep, V;
+  int n_kblocks, kb_per_split, n_slices, ngroups;
+  const int* tok;
+  const uint16_t* emb;        // (V, Ep)
+  const uint16_t* dpre_img;   // n_kblocks * ngroups * 8 KB
+  float* partial;             // [splits][n_slices*128][F]
+  uint32_t drop_thr16, seed_x;
+  float scale;
+};
+
+template <bool FP16>
+__global__ void __launch_bounds__(384, 1) conv_wgrad_tc_kernel(const WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int F = p.F;
+  const uint32_t b_stage_bytes = (uint32_t)p.ngroups * WG_GROUP_BYTES;
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = a_base + WG_STAGES * WG_A_STAGE_BYTES;
+  const uint32_t misc_base = b_base + WG_STAGES * b_stage_bytes;
+  uint8_t* misc_gen = smem_gen + (misc_base - smem_base);
+  const uint32_t bar_full = misc_base, bar_empty = misc_base + 32, bar_t_full = misc_base + 64;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(misc_gen + 80);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = blockIdx.x, split = blockIdx.y;
+  const int kb_beg = split * p.kb_per_split;
+  const int kb_end = min(p.n_kblocks, kb_beg + p.kb_per_split);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 5);    // 4 producer warps + the B loader's expect_tx arrival
+      mbar_init(bar_empty + 8 * s, 1);   // tcgen05.commit
+    }
+    mbar_init(bar_t_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int n0 = F > 256 ? 256 : F, n1 = F - n0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb_beg; kb < kb_end; ++kb) {
+        mbar_wait(bar_empty + 8 * s, ph ^ 1, 11);
+        mbar_expect_tx(bar_full + 8 * s, b_stage_bytes);
+        bulk_g2s(b_base + s * b_stage_bytes, (const uint8_t*)p.dpre_img + (size_t)kb * b_stage_bytes, b_stage_bytes,
+                 bar_full + 8 * s);
+        if (++s == WG_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc0 = make_idesc_mn(TILE_M, n0, FP16), idesc1 = make_idesc_mn(TILE_M, n1 > 0 ? n1 : 16, FP16);
+      int s = 0;
+      uint32_t ph = 0, accum = 0;
+      for (int kb = kb_beg; kb < kb_end; ++kb) {
+        mbar_wait(bar_full + 8 * s, ph, 12);
+        tc_fence_after();
+        const uint32_t a_addr = a_base + s * WG_A_STAGE_BYTES, b_addr = b_base + s * b_stage_bytes;
+#pragma unroll
+        for (int kk = 0; kk < WG_KTOK / 16; ++kk) {
+          const uint64_t ad = make_desc_mn128(a_addr + kk * 2048, WG_GROUP_BYTES);
+          umma_bf16(tmem_base, ad, make_desc_mn128(b_addr + kk * 2048, WG_GROUP_BYTES), idesc0, accum);
+          if (n1 > 0)
+            umma_bf16(tmem_base + n0, ad, make_desc_mn128(b_addr + 4 * WG_GROUP_BYTES + kk * 2048, WG_GROUP_BYTES), idesc1,
+                      accum);
+          accum = 1;
+        }
+        umma_commit(bar_empty + 8 * s);
+        if (++s == WG_STAGES) { s = 0; ph ^= 1; }
+      }
+      umma_commit(bar_t_full);
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // A producers: rows = tokens of the K block, two 64-column chunks (u0,u1) of this CTA's (tap, e) slice
+    const int pw = warp - 4, rsub = lane >> 3, piece = lane & 7;
+    int uj[2], uc[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      int u = 2 * slice + i;
+      uj[i] = u < TAPS * p.EC ? u / p.EC : -1;
+      uc[i] = u < TAPS * p.EC ? u % p.EC : 0;
+    }
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = kb_beg; kb < kb_end; ++kb) {
+      int ids[4];
+      long long mrow[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = pw * 16 + 4 * i + rsub;
+        const long long R = (long long)kb * WG_KTOK + r;
+        const int n = (int)(R / SLOT), t = (int)(R % SLOT);
+        int id = -1;
+        if (n < p.n_titles && t < p.L) {
+          id = p.tok[(long long)n * p.L + t];
+          id = (id < 0 || id >= p.V) ? 0 : id;
+        }
+        ids[i] = id;
+        mrow[i] = (long long)n * p.L + t;
+      }
+      mbar_wait(bar_empty + 8 * s, ph ^ 1, 13);
+      const uint32_t stage = a_base + s * WG_A_STAGE_BYTES;
+#pragma unroll
+      for (int ui = 0; ui < 2; ++ui) {
+        uint4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v[i] = make_uint4(0, 0, 0, 0);
+          if (ids[i] >= 0 && uj[ui] >= 0)
+            v[i] = __ldg((const uint4*)(p.emb + (long long)ids[i] * p.Ep + uc[ui] * KBLK + piece * 8));
+        }
+        if (p.drop_thr16 && uj[ui] >= 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (ids[i] < 0) continue;
+            const uint64_t pair0 = ((uint64_t)mrow[i] * (uint64_t)p.Ep + (uint64_t)(uc[ui] * KBLK + piece * 8)) >> 1;
+            uint32_t* w = reinterpret_cast<uint32_t*>(&v[i]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint32_t h = rng_u32(p.seed_x, pair0 + q);
+              uint32_t m = ((h & 0xffffu) >= p.drop_thr16 ? 0x0000ffffu : 0u) | ((h >> 16) >= p.drop_thr16 ? 0xffff0000u : 0u);
+              w[q] &= m;
+            }
+          }
+        }
+        const int j = uj[ui] < 0 ? 1 : uj[ui];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = pw * 16 + 4 * i + rsub;
+          const int rr = (r + 1 - j) & (WG_KTOK - 1);
+          const uint32_t addr = stage + ui * WG_GROUP_BYTES + rr * 128 + ((piece ^ (rr & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v[i].x), "r"(v[i].y), "r"(v[i].z),
+                       "r"(v[i].w)
+                       : "memory");
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * s);
+      if (++s == WG_STAGES) { s = 0; ph ^= 1; }
+    }
+  } else if (warp >= 8) {
+    // epilogue (once): TMEM -> scaled fp32 partial sums in global memory
+    const int q = warp & 3;
+    mbar_wait(bar_t_full, 0, 14);
+    tc_fence_after();
+    const int row = q * 32 + lane;
+    float* dst = p.partial + ((size_t)split * p.n_slices * TILE_M + (size_t)slice * TILE_M + row) * F;
+    const int nch = (F + 31) / 32;
+    for (int ch = 0; ch < nch; ++ch) {
+      const int c0 = ch * 32, ncols = min(32, F - c0);
+      uint32_t r[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      if (ncols == 32) { TMEM_LD_32(taddr, r); } else { TMEM_LD_16(taddr, r); }
+      tmem_ld_wait();
+      if (kb_end > kb_beg) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          if (i < ncols)
+            *reinterpret_cast<float4*>(dst + c0 + i) =
+                make_float4(__uint_as_float(r[i]) * p.scale, __uint_as_float(r[i + 1]) * p.scale,
+                            __uint_as_float(r[i + 2]) * p.scale, __uint_as_float(r[i + 3]) * p.scale);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          if (i < ncols) *reinterpret_cast<float4*>(dst + c0 + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// d_conv_w[j][e][f] = sum_split partial[split][j*Ep + e][f]   (fixed order, deterministic)
+__global__ void wgrad_reduce_kernel(int E, int Ep, int F, int splits, int rows_total, const float* __restrict__ partial,
+                                    float* __restrict__ dW) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)TAPS * E * F) return;
+  int f = (int)(i % F);
+  int je = (int)(i / F);
+  int j = je / E, e = je % E;
+  long long row = (long long)j * Ep + e;
+  float acc = 0.f;
+  for (int s = 0; s < splits; ++s) acc += partial[((long long)s * rows_total + row) * F + f];
+  dW[i] = acc;
+}
+
 }  // namespace tc
 }  // namespace lstur
 
@@ -596,3 +829,69 @@ extern "C" int lstur_news_encoder_tc_fwd_internal(const lstur_plan* p, const lst
   return LSTUR_OK;
 }
 
+
+// ---- wgrad host side ------------------------------------------------------------------------------
+extern "C" int lstur_tc_wgrad_kblocks(int n_titles) { return (n_titles * tc::SLOT + tc::WG_KTOK - 1) / tc::WG_KTOK; }
+extern "C" int lstur_tc_wgrad_groups(int F) { return (F + 63) / 64; }
+// bytes of the dPre image consumed by lstur_conv_wgrad_tc
+extern "C" size_t lstur_tc_dpre_img_bytes(int n_titles, int F) {
+  return (size_t)lstur_tc_wgrad_kblocks(n_titles) * lstur_tc_wgrad_groups(F) * tc::WG_GROUP_BYTES;
+}
+extern "C" int lstur_tc_wgrad_splits(int n_titles, int E) {
+  int n_slices = (tc::TAPS * lstur_tc_padded_e(E) + tc::TILE_M - 1) / tc::TILE_M;
+  int kb = lstur_tc_wgrad_kblocks(n_titles);
+  int sms = 148;
+  int splits = sms / n_slices;
+  if (splits < 1) splits = 1;
+  if (splits > kb) splits = kb;
+  return splits;
+}
+extern "C" size_t lstur_tc_wgrad_partial_bytes(int n_titles, int E, int F) {
+  int n_slices = (tc::TAPS * lstur_tc_padded_e(E) + tc::TILE_M - 1) / tc::TILE_M;
+  return (size_t)lstur_tc_wgrad_splits(n_titles, E) * n_slices * tc::TILE_M * F * sizeof(float);
+}
+
+// d_conv_w (3,E,F) = sum over tokens of X[m+j-1,e] * dPre[m,f]; X re-gathered from emb_16 with the forward's dropout
+// stream (seed), dPre given as the K-block image written by lstur_attn_pool_bwd_img.
+extern "C" int lstur_conv_wgrad_tc(int n_titles, int L, int E, int F, int V, const int* tokens, const void* emb_16,
+                                   const void* dpre_img, float* d_conv_w, float dropout, unsigned seed, int fp16,
+                                   void* partial_ws, size_t partial_bytes, cudaStream_t stream) {
+  LSTUR_REQUIRE(n_titles >= 0 && lstur_tc_supported(L, E, F, 3), "lstur_conv_wgrad_tc");
+  if (n_titles == 0) {
+    cudaMemsetAsync(d_conv_w, 0, (size_t)3 * E * F * sizeof(float), stream);
+    return LSTUR_OK;
+  }
+  tc::WgradParams p;
+  p.n_titles = n_titles; p.L = L; p.F = F; p.Ep = lstur_tc_padded_e(E); p.EC = p.Ep / tc::KBLK; p.V = V;
+  p.n_kblocks = lstur_tc_wgrad_kblocks(n_titles);
+  p.n_slices = (tc::TAPS * p.Ep + tc::TILE_M - 1) / tc::TILE_M;
+  int splits = lstur_tc_wgrad_splits(n_titles, E);
+  p.kb_per_split = (p.n_kblocks + splits - 1) / splits;
+  p.ngroups = lstur_tc_wgrad_groups(F);
+  p.tok = tokens; p.emb = (const uint16_t*)emb_16; p.dpre_img = (const uint16_t*)dpre_img;
+  p.partial = (float*)partial_ws;
+  LSTUR_REQUIRE(partial_ws != nullptr && partial_bytes >= lstur_tc_wgrad_partial_bytes(n_titles, E, F), "lstur_conv_wgrad_tc");
+  p.drop_thr16 = dropout > 0.f ? (uint32_t)(dropout * 65536.0f) : 0u;
+  p.seed_x = seed * 2u;
+  p.scale = 1.f / (1.f - dropout);
+  size_t smem = 1024 + (size_t)tc::WG_STAGES * (tc::WG_A_STAGE_BYTES + (size_t)p.ngroups * tc::WG_GROUP_BYTES) + 256;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(tc::conv_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tc::conv_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("lstur_conv_wgrad_tc: cannot opt in to %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+      return LSTUR_ERR_CUDA;
+    }
+    attr_smem = smem;
+  }
+  dim3 grid(p.n_slices, splits);
+  if (fp16) tc::conv_wgrad_tc_kernel<true><<<grid, 384, smem, stream>>>(p);
+  else tc::conv_wgrad_tc_kernel<false><<<grid, 384, smem, stream>>>(p);
+  LSTUR_CHECK_LAUNCH("lstur_conv_wgrad_tc");
+  long long n = (long long)3 * E * F;
+  tc::wgrad_reduce_kernel<<<cdiv(n, 256), 256, 0, stream>>>(E, p.Ep, F, splits, p.n_slices * tc::TILE_M, p.partial, d_conv_w);
+  LSTUR_CHECK_LAUNCH("lstur_conv_wgrad_tc(reduce)");
+  return LSTUR_OK;
+}

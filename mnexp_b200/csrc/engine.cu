@@ -147,7 +147,7 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
   // ---- workspace
   const bool tcp = (c.precision == LSTUR_PREC_BF16_TC || c.precision == LSTUR_PREC_FP16_TC);
   add_ws(p, "tokens", N * c.L);
-  if (!tcp || bw) add_ws(p, "Xp", N * Lp * E);
+  if (!tcp) add_ws(p, "Xp", N * Lp * E);
   if (!tcp) add_ws(p, "Cp", N * Lp * F);
   if (tcp) {
     add_ws(p, "emb_bf16", ((long long)c.V * lstur_tc_padded_e(E) + 1) / 2);
@@ -174,13 +174,18 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
   add_ws(p, "probs", B * c.C);
   add_ws(p, "loss_rows", B);
   add_ws(p, "loss", 1);
-  track_gemm(p, (int)(N * Lp), F, c.KS * E);
+  const bool tcp0 = c.precision == LSTUR_PREC_BF16_TC || c.precision == LSTUR_PREC_FP16_TC;
+  if (!tcp0) track_gemm(p, (int)(N * Lp), F, c.KS * E);
   track_gemm(p, (int)N, Dd, F);
   if (bw) {
     add_ws(p, "d_user_vec", B * c.U);
     add_ws(p, "d_doc_vec", N * D);
     add_ws(p, "d_pooled", N * F);
-    add_ws(p, "dPre", N * Lp * F);
+    if (!tcp) add_ws(p, "dPre", N * Lp * F);
+    if (tcp) {
+      add_ws(p, "dpre_img", (long long)(lstur_tc_dpre_img_bytes((int)N, F) / 4));
+      add_ws(p, "wgrad_partial", (long long)(lstur_tc_wgrad_partial_bytes((int)N, E, F) / 4));
+    }
     add_ws(p, "attn_partials", (long long)lstur_attn_bwd_grid((int)N) * (2 * F + 1));
     if (has_gru) {
       add_ws(p, "WhT", (long long)3 * G * G);
@@ -197,7 +202,7 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
       add_ws(p, "d_user_rows", B * c.Ue);
       add_ws(p, "d_u0", B * c.Ue);
     }
-    track_gemm(p, c.KS * E, F, (int)(N * Lp));
+    if (!tcp) track_gemm(p, c.KS * E, F, (int)(N * Lp));
     track_gemm(p, F, Dd, (int)N);
     track_gemm(p, (int)N, F, Dd);
     if (has_gru) {
@@ -437,18 +442,16 @@ extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const
     dpool = d_docv; lddp = D;
   }
   if ((c.precision == LSTUR_PREC_BF16_TC || c.precision == LSTUR_PREC_FP16_TC)) {
-    // interim: attention backward from the saved bf16 C, then the fp32 wgrad GEMM on a re-gathered X
-    float* dPre = W<float>(p, ws, "dPre");
-    float* Xp = W<float>(p, ws, "Xp");
-    RC(lstur_attn_pool_bwd_16(c.precision == LSTUR_PREC_FP16_TC, N, L, Lp, F, W<void>(p, ws, "C16"), (long long)L * F, W<float>(p, ws, "att_a"),
-                                W<float>(p, ws, "att_w"), dpool, lddp, DP(p, w->dense, "att_w"), dPre, (long long)Lp * F,
-                                c.dropout, DG(p, dgrad, "att_w"), DG(p, dgrad, "conv_b"), DG(p, dgrad, "att_b"), 0,
-                                W<float>(p, ws, "attn_partials"), (size_t)p->ws.at("attn_partials").count * 4, st));
-    RC(lstur_embed_gather_pad_tcrng(N, L, E, c.V, c.KS, lstur_tc_padded_e(E), w->word_emb, W<int>(p, ws, "tokens"), Xp,
-                                    c.dropout, p->last_seed * 2u, st));
+    const int fp16 = c.precision == LSTUR_PREC_FP16_TC;
+    void* img = W<void>(p, ws, "dpre_img");
+    RC(lstur_attn_pool_bwd_img(fp16, N, L, F, W<void>(p, ws, "C16"), W<float>(p, ws, "att_a"), W<float>(p, ws, "att_w"),
+                               dpool, lddp, DP(p, w->dense, "att_w"), img, c.dropout, DG(p, dgrad, "att_w"),
+                               DG(p, dgrad, "conv_b"), DG(p, dgrad, "att_b"), 0, W<float>(p, ws, "attn_partials"),
+                               (size_t)p->ws.at("attn_partials").count * 4, st));
     PROBE_BEGIN(p, LSTUR_PROBE_CONV_WGRAD, st);
-    RC(lstur_gemm_f32(1, 0, c.KS * E, F, N * Lp - (c.KS - 1), Xp, E, dPre, F, DG(p, dgrad, "conv_w"), F, nullptr, 0, gws,
-                      gwsb, st));
+    RC(lstur_conv_wgrad_tc(N, L, E, F, c.V, W<int>(p, ws, "tokens"), W<void>(p, ws, "emb_bf16"), img,
+                           DG(p, dgrad, "conv_w"), c.dropout, p->last_seed, fp16, W<void>(p, ws, "wgrad_partial"),
+                           (size_t)p->ws.at("wgrad_partial").count * 4, st));
     PROBE_END(p, LSTUR_PROBE_CONV_WGRAD, st);
   } else {
     float* dPre = W<float>(p, ws, "dPre");

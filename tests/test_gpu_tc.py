@@ -181,3 +181,49 @@ def test_engine_fp16_tc_forward_and_grads(lib, shape, arch, relu_open):
             cos = float(h @ g / max(np.linalg.norm(h) * np.linalg.norm(g), 1e-300))
             assert cos > 0.995, (k, cos)
             assert abs(np.linalg.norm(h) / np.linalg.norm(g) - 1.0) < 0.02, k
+
+
+def dpre_image(dpre, fp16=1):
+    """numpy restatement of the K-block image layout documented in csrc/attn.cu (store_dpre_img)."""
+    N, L, F = dpre.shape
+    ng = (F + 63) // 64
+    nkb = (N * 32 + 63) // 64
+    img = np.zeros(nkb * ng * 8192 // 2, dtype=np.float16 if fp16 else np.uint16)
+    n, t, f = np.meshgrid(np.arange(N), np.arange(L), np.arange(F), indexing='ij')
+    R = n * 32 + t
+    kb, k = R >> 6, R & 63
+    byte = kb * (ng * 8192) + (f >> 6) * 8192 + k * 128 + ((((f & 63) >> 3) ^ (k & 7)) << 4) + (f & 7) * 2
+    if fp16:
+        img[byte.ravel() // 2] = dpre.astype(np.float16).ravel()
+    else:
+        img[byte.ravel() // 2] = torch.as_tensor(dpre.ravel()).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    return img
+
+
+@pytest.mark.parametrize('N,L,E,F', [(2, 30, 64, 64), (5, 7, 12, 32), (3, 31, 128, 256), (64, 30, 300, 400),
+                                     (1001, 30, 300, 400)])
+@pytest.mark.parametrize('fp16', [1, 0])
+def test_tc_conv_wgrad(lib, N, L, E, F, fp16):
+    tok, P = make_enc_case(N, L, E, F, seed=N + E)
+    g = np.random.default_rng(N)
+    dpre = (g.standard_normal((N, L, F)) * (g.random((N, L, F)) < 0.5)).astype(np.float32)
+    V = P['word_emb'].shape[0]
+    Ep = lib.lstur_tc_padded_e(E)
+    dt16 = torch.float16 if fp16 else torch.bfloat16
+    emb = torch.zeros((V, Ep), dtype=dt16, device='cuda')
+    we = torch.as_tensor(P['word_emb']).cuda()
+    assert lib.lstur_pack_word_emb_16(V, E, P_(we), P_(emb), fp16, stream()) == 0
+    img = torch.as_tensor(dpre_image(dpre, fp16).view(np.int16)).cuda()
+    assert img.numel() * 2 == lib.lstur_tc_dpre_img_bytes(N, F)
+    nb = lib.lstur_tc_wgrad_partial_bytes(N, E, F)
+    ws = torch.empty(nb, dtype=torch.uint8, device='cuda')
+    dW = torch.full((3, E, F), float('nan'), device='cuda')
+    t = torch.as_tensor(tok).cuda()
+    rc = lib.lstur_conv_wgrad_tc(N, L, E, F, V, P_(t), P_(emb), P_(img), P_(dW), ctypes.c_float(0.0), 0, fp16, P_(ws), nb, stream())
+    assert rc == 0, lib.lstur_last_error()
+    torch.cuda.synchronize()
+    X = round16(P['word_emb'], fp16).astype(np.float64)[tok]                 # (N,L,E)
+    Xp = np.zeros((N, L + 2, E)); Xp[:, 1:L + 1] = X
+    d16 = round16(dpre, fp16).astype(np.float64)
+    ref = np.stack([np.einsum('nte,ntf->ef', Xp[:, j:j + L], d16) for j in range(3)])
+    assert rel(dW.cpu().numpy(), ref) < 2e-5
