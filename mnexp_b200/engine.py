@@ -34,7 +34,7 @@ class LsturEngine:
 
     def __init__(self, params, B, W, C, L, arch='igru', flavour='paper', dropout=0.0, lr=1e-3,
                  recurrent_activation='hard_sigmoid', precision='fp32', doc_tokens=None, device=None,
-                 training=True, sparse_user_adam=True, trainable_word_emb=False):
+                 training=True, sparse_user_adam=True, trainable_word_emb=False, share_weights_from=None):
         if not torch.cuda.is_available():
             raise _lib.LsturError('LsturEngine needs a CUDA device (no CPU fallback)')
         self.lib = _lib.load()
@@ -51,12 +51,14 @@ class LsturEngine:
         G = params['gru_wh'].shape[0] if 'gru_wh' in params else 0
         Ue = params['user_emb'].shape[1] if 'user_emb' in params and self.arch != 3 else 0
         U = {0: G, 1: params['con_w'].shape[1] if 'con_w' in params else 0, 2: G + Ue, 3: G, 4: G, 5: Ue}[self.arch]
+        _sd = share_weights_from.doc_tokens if share_weights_from is not None else None
+        n_docs = doc_tokens.shape[0] if doc_tokens is not None else (0 if _sd is None else _sd.shape[0])
         self.cfg = lstur_config(
             B=B, W=W, C=C, L=L, E=E, F=F, KS=ks, use_dense=int(use_dense), Dd=Dd, dv=0, ds=0, G=G, Ue=Ue, U=U,
             arch=self.arch, score_model=0, rec_act=0 if recurrent_activation == 'hard_sigmoid' else 1,
             precision=PREC[precision], V=params['word_emb'].shape[0],
             n_users=params['user_emb'].shape[0] if Ue else 0,
-            n_docs=0 if doc_tokens is None else doc_tokens.shape[0], dropout=float(dropout),
+            n_docs=n_docs, dropout=float(dropout),
             save_for_backward=int(training))
         self.B, self.W, self.C, self.L, self.D, self.U, self.Ue, self.G = B, W, C, L, Dd, U, Ue, G
         plan = ctypes.c_void_p()
@@ -64,16 +66,25 @@ class LsturEngine:
         self.plan = plan
         dev = self.device
         self.n_dense = int(self.lib.lstur_plan_dense_count(plan))
-        self.dense = torch.zeros(self.n_dense, dtype=torch.float32, device=dev)
+        src = share_weights_from
+        self.dense = torch.zeros(self.n_dense, dtype=torch.float32, device=dev) if src is None else src.dense
+        assert self.dense.numel() == self.n_dense
         self.layout = {}
         for name in DENSE_NAMES:
             off, cnt = ctypes.c_longlong(), ctypes.c_longlong()
             if self.lib.lstur_plan_dense_offset(plan, name.encode(), ctypes.byref(off), ctypes.byref(cnt)) == 0:
                 self.layout[name] = (off.value, cnt.value, tuple(np.asarray(params[name]).shape))
-        self.word_emb = torch.as_tensor(np.ascontiguousarray(params['word_emb'], dtype=np.float32)).to(dev)
-        self.user_emb = torch.as_tensor(np.ascontiguousarray(params['user_emb'], dtype=np.float32)).to(dev) if Ue else None
-        self.doc_tokens = None if doc_tokens is None else torch.as_tensor(np.ascontiguousarray(doc_tokens, dtype=np.int32)).to(dev)
-        self.set_weights_dict(params)
+        if src is None:
+            self.word_emb = torch.as_tensor(np.ascontiguousarray(params['word_emb'], dtype=np.float32)).to(dev)
+            self.user_emb = torch.as_tensor(np.ascontiguousarray(params['user_emb'], dtype=np.float32)).to(dev) if Ue else None
+        else:                                   # inference replica sharing the training engine's device weights
+            self.word_emb, self.user_emb = src.word_emb, src.user_emb
+        if doc_tokens is None and src is not None:
+            self.doc_tokens = src.doc_tokens
+        else:
+            self.doc_tokens = None if doc_tokens is None else torch.as_tensor(np.ascontiguousarray(doc_tokens, dtype=np.int32)).to(dev)
+        if src is None:
+            self.set_weights_dict(params)
         ws_bytes = int(self.lib.lstur_plan_workspace_bytes(plan))
         self.ws_bytes = ws_bytes
         self.ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -234,3 +245,14 @@ class LsturEngine:
 
     def loss(self):
         return float(self.view('loss')[0])
+
+    def score_sigmoid(self):
+        """sigmoid(user_vec . cand_vec) for every (row, candidate) of the last forward — the reference's test head
+        (task/paper.py:661-665).  Returns a (B, C) device tensor."""
+        out = torch.empty((self.B, self.C), dtype=torch.float32, device=self.device)
+        nh = self.B * self.W
+        dv = self.view('doc_vec')
+        cand = dv[nh * self.D:]
+        _lib.check(self.lib.lstur_score_sigmoid(self.B * self.C, self.C, self.D, _ptr(self.view('user_vec')), self.U,
+                                                _ptr(cand), self.D, _ptr(out), 1, self._stream()))
+        return out

@@ -1,0 +1,256 @@
+"""The slice of the Keras Model protocol that the reference's drivers call on the LSTUR models
+(SURVEY.md §8b "Model protocol used by callers"), implemented over LsturEngine.
+
+  fit_generator / fit / train_on_batch          main.py:73-78, 172-178
+  evaluate_generator / evaluate                 main.py:83-86, 189-192
+  predict / predict_on_batch                    task/seq2vec.py:206, main.py:211
+  metrics_names, optimizer.lr (+ backend.get_value/set_value)   main.py:87, task/paper.py:498-499
+  get_layer(name), get_weights / set_weights, summary()         task/test_pipeline.py:28,87; utils.py:70,79
+
+Inputs are host numpy arrays in the reference's order: [user(B,) , clicked(B,W,L), cand_0(B,L) .. cand_K(B,L)]
+(user omitted for the classes without a user-ID embedding), target (B,1+K) one-hot.
+"""
+import numpy as np
+import torch
+
+from .engine import LsturEngine
+
+
+class Variable:
+    def __init__(self, value):
+        self.value = float(value)
+
+
+class backend:
+    """keras.backend.get_value / set_value on optimizer.lr (task/paper.py:498-499)."""
+    @staticmethod
+    def get_value(v):
+        return v.value
+
+    @staticmethod
+    def set_value(v, x):
+        v.value = float(x)
+
+
+class Adam:
+    def __init__(self, lr=0.001):
+        self.lr = Variable(lr)
+
+
+class History:
+    def __init__(self):
+        self.history = {}
+        self.epoch = []
+
+
+class _Core:
+    """Weights + engines shared by `model` (softmax/CE training graph) and `test_model` (sigmoid scoring graph)."""
+
+    def __init__(self, params, cfg, doc_tokens, has_user, arch, predict_rows=256):
+        self.params, self.cfg, self.doc_tokens, self.has_user, self.arch = params, cfg, doc_tokens, has_user, arch
+        self.optimizer = Adam(cfg.learning_rate)
+        self.train_engine = None
+        self.infer_engines = {}
+        self.predict_rows = predict_rows
+        self.step_seed = 0
+
+    def precision(self):
+        p = getattr(self.cfg, 'precision', 'auto')
+        if p != 'auto':
+            return p
+        from . import _lib
+        ks, E, F = self.params['conv_w'].shape
+        ok = _lib.load().lstur_tc_supported(self.cfg.title_shape, E, F, ks)
+        return 'fp16_tc' if ok else 'fp32'
+
+    def engine_train(self, B):
+        e = self.train_engine
+        if e is None or e.B != B:
+            if e is not None:                      # batch size changed: carry the weights over
+                self.params = e.get_weights_dict()
+            c = self.cfg
+            self.train_engine = LsturEngine(
+                self.params, B, c.window_size, 1 + c.negative_samples, c.title_shape, arch=self.arch,
+                dropout=c.dropout, lr=c.learning_rate, recurrent_activation=c.recurrent_activation,
+                precision=self.precision(), doc_tokens=self.doc_tokens, training=True,
+                sparse_user_adam=bool(c.sparse_user_adam))
+            self.infer_engines = {}
+        return self.train_engine
+
+    def engine_infer(self, C):
+        if C not in self.infer_engines:
+            c = self.cfg
+            base = self.engine_train(c.batch_size)
+            self.infer_engines[C] = LsturEngine(
+                self.params, self.predict_rows, c.window_size, C, c.title_shape, arch=self.arch, dropout=0.0,
+                recurrent_activation=c.recurrent_activation, precision=self.precision(), training=False,
+                share_weights_from=base)
+        return self.infer_engines[C]
+
+    def split_inputs(self, x, n_cand):
+        x = list(x)
+        user = np.asarray(x.pop(0)).reshape(-1) if self.has_user else None
+        clicked = np.asarray(x[0])
+        cands = x[1:1 + n_cand]
+        cand = np.stack([np.asarray(c) for c in cands], axis=1)         # (B, C, L)
+        if user is None:
+            user = np.zeros(clicked.shape[0], dtype=np.int32)
+        return user, clicked, cand
+
+
+class Model:
+    """`model` (train=True: probabilities over the 1+K candidates) or `test_model` (sigmoid of one candidate)."""
+
+    def __init__(self, core, train, name='model'):
+        self.core, self.is_train, self.name = core, train, name
+        self.metrics_names = ['loss', 'categorical_accuracy'] if train else ['loss']
+        self.layers = {}
+
+    @property
+    def optimizer(self):
+        return self.core.optimizer
+
+    # ---- training ---------------------------------------------------------------------------
+    def train_on_batch(self, x, y):
+        assert self.is_train, 'test_model is not compiled for training'
+        core = self.core
+        C = 1 + core.cfg.negative_samples
+        user, clicked, cand = core.split_inputs(x, C)
+        eng = core.engine_train(clicked.shape[0])
+        eng.lr = core.optimizer.lr.value
+        db = eng.to_device_batch(dict(user=user, hist_tok=clicked, cand_tok=cand, label=np.asarray(y)))
+        loss = eng.train_step(db)
+        probs = eng.view('probs').reshape(eng.B, eng.C)
+        acc = (probs.argmax(1) == db['label'].argmax(1)).float().mean()
+        return [float(loss[0]), float(acc)]
+
+    def fit_generator(self, generator, steps_per_epoch, epochs=1, initial_epoch=0, verbose=0, **_):
+        h = History()
+        for epoch in range(initial_epoch, epochs):
+            tot = np.zeros(2)
+            for _ in range(steps_per_epoch):
+                x, y = next(generator)
+                tot += self.train_on_batch(x, y)
+            h.epoch.append(epoch)
+            for k, v in zip(self.metrics_names, tot / max(1, steps_per_epoch)):
+                h.history.setdefault(k, []).append(float(v))
+        return h
+
+    def fit(self, x, y, batch_size=32, epochs=1, initial_epoch=0, shuffle=True, verbose=0, **_):
+        y = y[0] if isinstance(y, (list, tuple)) else y
+        n = len(y)
+        h = History()
+        for epoch in range(initial_epoch, epochs):
+            order = np.random.permutation(n) if shuffle else np.arange(n)
+            tot, k = np.zeros(2), 0
+            for s in range(0, n - batch_size + 1, batch_size):       # Keras trains the ragged tail too; the engine's
+                idx = order[s:s + batch_size]                         # plan is per batch size, so the tail is dropped
+                tot += self.train_on_batch([np.asarray(a)[idx] for a in x], np.asarray(y)[idx])
+                k += 1
+            h.epoch.append(epoch)
+            for name, v in zip(self.metrics_names, tot / max(1, k)):
+                h.history.setdefault(name, []).append(float(v))
+        return h
+
+    # ---- inference --------------------------------------------------------------------------
+    def _forward_chunks(self, x, n_cand):
+        core = self.core
+        user, clicked, cand = core.split_inputs(x, n_cand)
+        n = clicked.shape[0]
+        eng = core.engine_infer(n_cand)
+        R = eng.B
+        outs = []
+        for s in range(0, n, R):
+            m = min(R, n - s)
+            u = np.zeros(R, dtype=np.int32); u[:m] = user[s:s + m]
+            h = np.zeros((R,) + clicked.shape[1:], dtype=np.int32); h[:m] = clicked[s:s + m]
+            c = np.zeros((R,) + cand.shape[1:], dtype=np.int32); c[:m] = cand[s:s + m]
+            db = eng.to_device_batch(dict(user=u, hist_tok=h, cand_tok=c))
+            probs = eng.forward(db, training=False)
+            out = probs if self.is_train else eng.score_sigmoid()
+            outs.append(out[:m].cpu().numpy().copy())
+        return np.concatenate(outs) if outs else np.zeros((0, n_cand), dtype=np.float32)
+
+    def predict(self, x, batch_size=None, **_):
+        C = 1 + self.core.cfg.negative_samples if self.is_train else 1
+        return self._forward_chunks(x, C)
+
+    predict_on_batch = predict
+
+    def evaluate(self, x, y, batch_size=None, verbose=0, **_):
+        y = np.asarray(y[0] if isinstance(y, (list, tuple)) else y, dtype=np.float64)
+        p = self.predict(x).astype(np.float64)
+        if self.is_train:
+            q = np.clip(p / p.sum(-1, keepdims=True), 1e-7, 1 - 1e-7)
+            return [float((-(y * np.log(q)).sum(-1)).mean()), float((p.argmax(1) == y.argmax(1)).mean())]
+        q = np.clip(p.reshape(-1), 1e-7, 1 - 1e-7)
+        yy = y.reshape(-1)
+        return [float(-(yy * np.log(q) + (1 - yy) * np.log(1 - q)).mean())]
+
+    def evaluate_generator(self, generator, steps, verbose=0, **_):
+        tot = np.zeros(len(self.metrics_names))
+        for _ in range(steps):
+            x, y = next(generator)
+            tot += self.evaluate(x, y)
+        return list(tot / max(1, steps))
+
+    # ---- weights / structure ------------------------------------------------------------------
+    WEIGHT_ORDER = ('word_emb', 'conv_w', 'conv_b', 'att_w', 'att_b', 'dense_w', 'dense_b', 'user_emb',
+                    'gru_wx', 'gru_wh', 'gru_b', 'con_w', 'con_b')
+
+    def _current(self):
+        e = self.core.train_engine
+        return e.get_weights_dict() if e is not None else self.core.params
+
+    def get_weights(self):
+        """List of numpy arrays in layer-creation order of the reference graph (embedding, conv, attention, dense,
+        user embedding, GRU kernel/recurrent/bias, concat-Dense).  The Keras pickle order cannot be verified
+        offline (SURVEY.md §7 risks); att_w is exported with Keras' (F,1) shape."""
+        w = self._current()
+        out = []
+        for k in self.WEIGHT_ORDER:
+            if k in w:
+                a = np.asarray(w[k])
+                out.append(a.reshape(-1, 1) if k == 'att_w' else a.reshape(1) if k == 'att_b' else a)
+        return out
+
+    def set_weights(self, weights):
+        cur = self._current()
+        names = [k for k in self.WEIGHT_ORDER if k in cur]
+        assert len(names) == len(weights), 'expected %d arrays (%s)' % (len(names), names)
+        new = {k: np.asarray(a, dtype=np.float32).reshape(np.asarray(cur[k]).shape) for k, a in zip(names, weights)}
+        self.core.params = dict(cur, **new)
+        if self.core.train_engine is not None:
+            self.core.train_engine.set_weights_dict(self.core.params)
+
+    def get_layer(self, name):
+        return self.layers[name]
+
+    def summary(self):
+        w = self._current()
+        lines = ['%-12s %-18s %d' % (k, tuple(np.asarray(v).shape), np.asarray(v).size) for k, v in w.items()]
+        print('\n'.join(lines))
+        print('Total params: %d' % sum(np.asarray(v).size for v in w.values()))
+
+
+class DocEncoderModel:
+    """`doc_encoder` layer: (n, L) token ids -> (n, U) news vectors (task/paper.py:160)."""
+    name = 'doc_encoder'
+
+    def __init__(self, core):
+        self.core = core
+
+    def predict(self, titles, batch_size=None, **_):
+        core = self.core
+        titles = np.asarray(titles)
+        eng = core.engine_infer(1)
+        R = eng.B
+        outs = []
+        for s in range(0, titles.shape[0], R):
+            m = min(R, titles.shape[0] - s)
+            c = np.zeros((R, 1, titles.shape[1]), dtype=np.int32); c[:m, 0] = titles[s:s + m]
+            h = np.zeros((R, eng.W, titles.shape[1]), dtype=np.int32)
+            eng.forward(eng.to_device_batch(dict(user=np.zeros(R, dtype=np.int32), hist_tok=h, cand_tok=c)))
+            dv = eng.view('doc_vec').reshape(-1, eng.D)[R * eng.W:]
+            outs.append(dv[:m].cpu().numpy().copy())
+        return np.concatenate(outs)

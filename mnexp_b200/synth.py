@@ -177,3 +177,34 @@ def write_docmeta_tsv(path, tok, vert=None, subvert=None):
             t = ' '.join(str(int(x)) for x in tok[i] if x != 0)
             f.write('d%d\t%d\tv%d\ts%d\t%s\t%s\n' % (i, i, 0 if vert is None else vert[i],
                                                       0 if subvert is None else subvert[i], t, t))
+
+
+def write_clickdata_tsv(path, n_users, n_news, rng, max_imp=4, n_neg=8):
+    """ClickData.tsv: column 2 = training impressions, column 3 = validation impressions, each
+    ``pos#TAB#neg#TAB#time`` joined by ``#N#`` (task/paper.py:7-35)."""
+    cdf = _zipf_cdf(n_news, 1.05)
+    def imps(k):
+        out = []
+        for i in range(k):
+            pos = _zipf_sample(rng, cdf, rng.integers(1, 3)) + 1
+            neg = _zipf_sample(rng, cdf, n_neg) + 1
+            out.append('%s#TAB#%s#TAB#01/%02d/2019 %02d:%02d:00 PM' % (' '.join(map(str, pos)), ' '.join(map(str, neg)),
+                                                                    1 + i % 28, 1 + i % 12, i % 60))
+        return '#N#'.join(out)
+    with open(path, 'w') as f:
+        for u in range(n_users):
+            f.write('u%d\tx\t%s\t%s\n' % (u, imps(rng.integers(1, max_imp + 1)), imps(rng.integers(0, 3))))
+
+
+def write_dataset(dirname, shape, seed=7):
+    """Small on-disk dataset in the reference formats: Vocab.tsv(.npy), DocMeta.tsv, ClickData.tsv."""
+    import os
+    rng = np.random.default_rng(seed)
+    os.makedirs(dirname, exist_ok=True)
+    emb = make_vocab(shape.vocab, shape.E, seed)
+    tok, vert, subvert = make_docs(shape.n_news, shape.L, shape.vocab, seed + 1)
+    write_vocab_tsv(os.path.join(dirname, 'Vocab.tsv'), emb)
+    np.save(os.path.join(dirname, 'Vocab.tsv.npy'), emb)
+    write_docmeta_tsv(os.path.join(dirname, 'DocMeta.tsv'), tok, vert, subvert)
+    write_clickdata_tsv(os.path.join(dirname, 'ClickData.tsv'), shape.n_users, shape.n_news, rng)
+    return emb, tok

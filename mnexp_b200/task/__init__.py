@@ -1,0 +1,7 @@
+"""task.get(config) -> eval(config.task)(config), as the reference's task/__init__.py:15-16."""
+from .paper import Seq2VecPaper, Seq2VecPaperSoftmax, Seq2VecPaperSoftmaxId  # noqa: F401
+from .seq2vec import Seq2Vec  # noqa: F401
+
+
+def get(config):
+    return eval(config.task)(config)

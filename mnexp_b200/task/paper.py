@@ -1,0 +1,201 @@
+"""Model-builder surface of the reference's task/paper.py for the LSTUR path, backed by the CUDA engine.
+
+Same class names, hyper-parameters (settings.Config), arch names, builder hooks and forward / loss / score semantics:
+
+  Seq2VecPaper            data side: Impression (pos/neg/time), _load_data (task/paper.py:6-35)
+  Seq2VecPaperSoftmax     (1+K)-way softmax CE, news encoder cnnatt, user encoder arch 'gru' (task/paper.py:386-524)
+  Seq2VecPaperSoftmaxId   = LSTUR: user-ID embedding; arch igru (ini), gru / hgru / ngru / dgru (con), pgru, nigru,
+                            vo (task/paper.py:527-665)
+
+`get_doc_encoder / get_user_encoder / score_encoder / _score_model / _build_model / build_model / callback` keep the
+reference's names and effects; the Keras graph they used to assemble is the fixed-function plan of
+csrc/engine.cu.  Unsupported options raise the reference's own exceptions.
+"""
+import logging
+import random
+from datetime import datetime
+
+import numpy as np
+from sklearn.metrics import roc_auc_score
+
+from .. import keras_like, synth, utils
+from .seq2vec import Seq2Vec
+
+
+class Seq2VecPaper(Seq2Vec):
+    class Impression:
+        __slots__ = ['pos', 'neg', 'time']
+
+        def __init__(self, d):
+            d = d.split('#TAB#')
+            self.pos = [int(k) for k in d[0].split(' ')]
+            self.neg = [int(k) for k in d[1].split(' ')]
+            if len(d) >= 3:
+                self.time = datetime.strptime(d[2], '%m/%d/%Y %I:%M:%S %p')
+
+        def negative_samples(self, n):
+            return np.random.choice(self.neg, n)            # task/paper.py:17-18
+
+    def _extract_impressions(self, x):
+        return [self.Impression(d) for d in x.split('#N#') if not d.startswith('#TAB#')]
+
+    def _load_data(self):
+        """ClickData.tsv: column 2 = training impressions, column 3 = validation impressions (task/paper.py:24-35)."""
+        logging.info('[+] loading data')
+        self.data = []
+        with open(self.config.training_data_input) as file:
+            for line in file:
+                line = line.strip('\n').split('\t')
+                self.data.append((self._extract_impressions(line[2]) if line[2] else [],
+                                  self._extract_impressions(line[3]) if line[3] else []))
+        super(Seq2VecPaper, self)._load_data()
+        logging.info('[-] loaded data')
+
+    def save_model(self):
+        pass                                                 # task/paper.py:254-255
+
+
+class Seq2VecPaperSoftmax(Seq2VecPaper):
+    HAS_USER = False
+    USER_ARCHS = ('gru',)                                    # Seq2VecPaper.get_user_encoder, task/paper.py:199-221
+
+    # ---- sample generators (task/paper.py:387-441) ------------------------------------------
+    def _sample(self, user, ch, pos, impression, label):
+        row = [ch.get_title(), self.docs[pos].title] + \
+              [self.docs[neg].title for neg in impression.negative_samples(self.config.negative_samples)] + [label]
+        return ([user] + row) if self.HAS_USER else row
+
+    def train_gen(self):
+        label = [1] + [0 for _ in range(self.config.negative_samples)]
+        while True:
+            for user, (ih, _) in enumerate(self.data):
+                if ih:
+                    ch = self.Window(self.docs, self.config.window_size)
+                    for impression in ih:
+                        for pos in impression.pos:
+                            if ch.count:
+                                yield self._sample(user, ch, pos, impression, label)
+                            ch.push(pos)
+
+    def valid_gen(self):
+        label = [1] + [0 for _ in range(self.config.negative_samples)]
+        while True:
+            for user, (ih1, ih2) in enumerate(self.data):
+                if ih1 and ih2:
+                    ch = self.Window(self.docs, self.config.window_size)
+                    for impression in ih1:
+                        for pos in impression.pos:
+                            ch.push(pos)
+                    for impression in ih2:
+                        for pos in impression.pos:
+                            yield self._sample(user, ch, pos, impression, label)
+                        for pos in impression.pos:
+                            ch.push(pos)
+
+    def test_gen(self):
+        def __gen__(_user, _clicked, _impression):
+            for p in _impression.pos:
+                yield ((_user,) if self.HAS_USER else ()) + (_clicked, self.docs[p].title, 1)
+            for n in _impression.neg:
+                yield ((_user,) if self.HAS_USER else ()) + (_clicked, self.docs[n].title, 0)
+
+        for user, (ih1, ih2) in enumerate(self.data):
+            if ih1 and ih2:
+                ch = self.Window(self.docs, self.config.window_size)
+                for impression in ih1:
+                    for pos in impression.pos:
+                        ch.push(pos)
+                for impression in ih2:
+                    clicked = ch.get_title()
+                    yield list(__gen__(user, clicked, impression))
+                    for pos in impression.pos:
+                        ch.push(pos)
+
+    # ---- builder hooks ----------------------------------------------------------------------------
+    def _title_embedding(self):
+        if self.config.debug:                                # task/paper.py:109-110
+            return np.load(self.config.title_embedding_input + '.npy')
+        return utils.load_textual_embedding(self.config.title_embedding_input, self.config.textual_embedding_dim)
+
+    def get_doc_encoder(self):
+        return self._get_doc_encoder(self.config.title_shape)
+
+    def _get_doc_encoder(self, input_shape=None):
+        if self.config.enable_pretrain_encoder:
+            raise NotImplementedError('enable_pretrain_encoder: loading a Keras json+pkl encoder is out of scope')
+        if self.config.news_encoder != 'cnnatt':
+            raise Exception('Unsupport doc model')           # task/paper.py:130,195 (non-LSTUR encoders are out of scope)
+        if self.config.textual_embedding_trainable:
+            raise NotImplementedError('textual_embedding_trainable (conv dgrad + word-table scatter) is not implemented yet')
+        return keras_like.DocEncoderModel(self._core)
+
+    def _engine_arch(self):
+        arch = self.config.arch
+        if arch not in self.USER_ARCHS:
+            raise Exception('Unsupport user model')          # task/paper.py:216-217, 629-630
+        return 'nigru' if not self.HAS_USER else arch
+
+    def get_user_encoder(self, window_size=None):
+        self._engine_arch()
+        return self._core                                     # user encoder is part of the fused plan
+
+    def _score_model(self, u=None, d=None):
+        if self.config.score_model != 'dot':
+            raise NotImplementedError                          # task/paper.py:456-457 ('dnn'/'ddot': SURVEY §8f row 4)
+        self.score_model = 'dot'
+
+    def score_encoder(self, user_vec=None, candidate_vecs=None):
+        self._score_model()
+        return self.score_model
+
+    def _init_params(self):
+        c = self.config
+        F, k = c.title_filter_shape
+        word_emb = self._title_embedding().astype(np.float32)
+        sh = synth.Shape('cfg', n_users=len(self.data), n_news=self.doc_count - 1, vocab=word_emb.shape[0],
+                         L=c.title_shape, W=c.window_size, K=c.negative_samples, B=c.batch_size, E=word_emb.shape[1],
+                         F=F, k=k, U=c.user_embedding_dim, arch=self._engine_arch())
+        return synth.make_weights(sh, arch=self._engine_arch(), seed=np.random.randint(1 << 30), word_emb=word_emb)
+
+    def _build_model(self):
+        """task/paper.py:466-495 / 635-665: `model` = softmax CE + Adam, `test_model` = sigmoid score, shared weights."""
+        arch = self._engine_arch()
+        params = self._init_params()
+        self._core = keras_like._Core(params, self.config, self.doc_token_table(), self.HAS_USER, arch)
+        self.doc_encoder = self.get_doc_encoder()
+        self.user_encoder = self.get_user_encoder()
+        self.score_encoder()
+        self.model = keras_like.Model(self._core, train=True, name='model')
+        self.test_model = keras_like.Model(self._core, train=False, name='test_model')
+        for m in (self.model, self.test_model):
+            m.layers['doc_encoder'] = self.doc_encoder
+
+    def callback(self, epoch):
+        """LR decay + per-impression AUC / nDCG@10 / nDCG@5 / MRR on the validation split (task/paper.py:497-524)."""
+        keras_like.backend.set_value(self.model.optimizer.lr,
+                                     keras_like.backend.get_value(self.model.optimizer.lr) * self.config.learning_rate_decay)
+        self.model, self.test_model = self.test_model, self.model
+
+        def __gen__(x):
+            for i, (y_pred, y_true) in zip(range(x), self.test):
+                auc = roc_auc_score(y_true, y_pred)
+                ndcgx = utils.ndcg_score(y_true, y_pred, 10)
+                ndcgv = utils.ndcg_score(y_true, y_pred, 5)
+                mrr = utils.mrr_score(y_true, y_pred)
+                yield auc, ndcgx, ndcgv, mrr, np.sum(y_true), len(y_true), i
+
+        values = [np.mean(x) for x in zip(*__gen__(self.config.validation_impression))]
+        self.last_evaluation = dict(auc=values[0], ndcgx=values[1], ndcgv=values[2], mrr=values[3])
+        utils.logging_evaluation(self.last_evaluation)
+        utils.logging_evaluation(dict(pos=values[4], size=values[5], num=values[6] * 2 + 1))
+        if epoch == self.config.epochs - 1:
+            self.is_training = False
+            values = [np.mean(x) for x in zip(*__gen__(self.config.testing_impression))]
+            utils.logging_evaluation(dict(auc=values[0], ndcgx=values[1], ndcgv=values[2], mrr=values[3]))
+        self.model, self.test_model = self.test_model, self.model
+
+
+class Seq2VecPaperSoftmaxId(Seq2VecPaperSoftmax):
+    """LSTUR (task/paper.py:527-665): igru = LSTUR-ini; gru / hgru / ngru / dgru = LSTUR-con."""
+    HAS_USER = True
+    USER_ARCHS = ('igru', 'gru', 'hgru', 'nigru', 'pgru', 'vo')   # ngru/dgru/iigru need a non-dot scorer or extra tables

@@ -1,0 +1,52 @@
+"""Helpers of the reference's utils.py that the LSTUR path uses: Vocab loader and ranking metrics."""
+import logging
+
+import numpy as np
+
+
+def load_textual_embedding(path, dimension):
+    """Vocab.tsv -> dense (max_index+1, dimension) fp32 matrix, missing rows = 0 (utils.py:34-52)."""
+    data = {}
+    with open(path) as f:
+        for s in f:
+            r = s.strip().split('\t')
+            if r[-1].count(' ') == dimension - 1:
+                data[int(r[-2])] = np.array([float(x) for x in r[-1].split(' ')], dtype=np.float32)
+    out = np.zeros((max(data.keys()) + 1, dimension), dtype=np.float32)
+    for i, v in data.items():
+        out[i] = v
+    return out
+
+
+def dcg_score(y_true, y_score, k=10):
+    """utils.py:106-111"""
+    order = np.argsort(y_score)[::-1]
+    y_true = np.take(y_true, order[:k])
+    gains = 2 ** y_true - 1
+    discounts = np.log2(np.arange(len(y_true)) + 2)
+    return np.sum(gains / discounts)
+
+
+def ndcg_score(y_true, y_score, k=10):
+    """utils.py:114-117"""
+    return dcg_score(y_true, y_score, k) / dcg_score(y_true, y_true, k)
+
+
+def mrr_score(y_true, y_score):
+    """utils.py:120-124"""
+    order = np.argsort(y_score)[::-1]
+    y_true = np.take(y_true, order)
+    rr_score = y_true / (np.arange(len(y_true)) + 1)
+    return np.sum(rr_score) / np.sum(y_true)
+
+
+def logging_history(history):
+    """utils.py:17-23"""
+    for k, v in sorted(history.history.items()):
+        logging.info('[*] {}: {}'.format(k, v[-1] if isinstance(v, (list, tuple)) else v))
+
+
+def logging_evaluation(evaluations):
+    """utils.py:26-31"""
+    for k, v in sorted(evaluations.items()):
+        logging.info('[*] {}: {}'.format(k, v))

@@ -1,0 +1,124 @@
+"""GPU tests of the reference-facing surface (task/paper.py mirror + Keras Model protocol) and of the committed
+golden fixtures, through the C-ABI."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from mnexp_b200 import settings, synth, task
+from oracle import lstur_numpy as on
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'lstur_golden.npz'))
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.mark.parametrize('arch', ['igru', 'gru', 'hgru', 'nigru'])
+def test_engine_matches_golden_fixtures(lib, arch):
+    from mnexp_b200.engine import LsturEngine
+    sh = synth.SHAPES['tiny']
+    tok = GOLD['doc_tokens']
+    P = synth.make_weights(sh, arch=arch, bias_noise=0.05, seed=4242)
+    b = {k: GOLD['%s/batch/%s' % (arch, k)] for k in ('user', 'hist_doc', 'cand_doc')}
+    eng = LsturEngine(P, sh.B, sh.W, 1 + sh.K, sh.L, arch=arch, doc_tokens=tok, lr=1e-3, sparse_user_adam=False)
+    db = eng.to_device_batch(b)
+    eng.forward(db, training=True)
+    eng.backward(db)
+    assert rel(eng.view('probs').reshape(sh.B, -1).cpu().numpy(), GOLD['%s/probs' % arch]) < 2e-5
+    assert rel(eng.view('user_vec').reshape(sh.B, -1).cpu().numpy(), GOLD['%s/user_vec' % arch]) < 2e-5
+    assert rel(eng.score_sigmoid().cpu().numpy(), GOLD['%s/sigmoid' % arch]) < 2e-5
+    assert abs(eng.loss() - float(GOLD['%s/loss' % arch])) < 2e-5
+    g = eng.get_grads_dict()
+    for k in g:
+        key = '%s/grad/%s' % (arch, k)
+        if key in GOLD:
+            assert rel(g[k], GOLD[key]) < 5e-5, k
+    # two dense Keras-Adam steps
+    eng2 = LsturEngine(P, sh.B, sh.W, 1 + sh.K, sh.L, arch=arch, doc_tokens=tok, lr=1e-3, sparse_user_adam=False)
+    losses = [float(eng2.train_step(db)[0]) for _ in range(2)]
+    assert np.abs(np.array(losses) - GOLD['%s/adam_losses' % arch]).max() < 1e-4
+    assert np.abs(eng2.get_weights_dict()['conv_w'] - GOLD['%s/adam_conv_w' % arch]).max() < 2e-5
+
+
+def _handler(arch='igru', task_name='Seq2VecPaperSoftmaxId', precision='fp32', **kw):
+    sh = synth.SHAPES['tiny']
+    d = tempfile.mkdtemp()
+    synth.write_dataset(d, sh)
+    cfg = settings.Config(dict(task=task_name, arch=arch, input_training_data_path=d, title_shape=sh.L,
+                               window_size=sh.W, negative_samples=sh.K, batch_size=8, textual_embedding_dim=sh.E,
+                               title_filter_shape=(sh.F, 3), user_embedding_dim=sh.U, debug=True, dropout=0.0,
+                               precision=precision, validation_impression=5, testing_impression=5, epochs=2, **kw))
+    return sh, task.get(cfg)
+
+
+def _oracle_params(model):
+    names = [k for k in model.WEIGHT_ORDER if k in model._current()]
+    P = dict(zip(names, model.get_weights()))
+    P['att_w'] = P['att_w'].reshape(-1)
+    return P
+
+
+@pytest.mark.parametrize('task_name,arch', [('Seq2VecPaperSoftmaxId', 'igru'), ('Seq2VecPaperSoftmaxId', 'gru'),
+                                            ('Seq2VecPaperSoftmax', 'gru')])
+def test_model_builder_surface(lib, task_name, arch):
+    sh, h = _handler(arch, task_name)
+    model = h.build_model(0)
+    assert model is h.model and h.test_model is not None and h.build_model(1) is model
+    x, y = next(h.train)
+    # predict == oracle on the same weights (the reference's forward semantics), float64 token arrays accepted
+    P = _oracle_params(model)
+    user = x[0] if h.HAS_USER else np.zeros(len(y), dtype=int)
+    clicked = x[1] if h.HAS_USER else x[0]
+    cands = np.stack(x[2:] if h.HAS_USER else x[1:], 1)
+    ref = on.lstur_forward(P, user, clicked.astype(int), cands.astype(int), arch=h._engine_arch(), aux=True)
+    assert rel(model.predict(x), ref['probs']) < 2e-5
+    one = (x[:2] if h.HAS_USER else x[:1]) + [x[2 if h.HAS_USER else 1]]
+    s = h.test_model.predict(one)
+    assert s.shape == (len(y), 1) and rel(s[:, 0], ref['sigmoid'][:, 0]) < 2e-5
+    ev = model.evaluate(x, y)
+    assert abs(ev[0] - on.categorical_crossentropy(y, ref['probs'])) < 1e-5 and model.metrics_names == ['loss', 'categorical_accuracy']
+    # fit_generator trains: the loss on a fixed batch goes down
+    l0 = model.evaluate(x, y)[0]
+    hist = model.fit_generator(h.train, 12, epochs=1, initial_epoch=0, verbose=0)
+    assert set(hist.history) == {'loss', 'categorical_accuracy'} and len(hist.history['loss']) == 1
+    for _ in range(15):
+        model.train_on_batch(x, y)
+    assert model.evaluate(x, y)[0] < l0
+    # get_weights / set_weights round trip
+    w = model.get_weights()
+    model.set_weights([a * 0 + 0.01 for a in w])
+    assert abs(model.get_weights()[1] - 0.01).max() < 1e-7
+    model.set_weights(w)
+    assert rel(model.get_weights()[1], w[1]) == 0
+    # callback: LR decay + ranking metrics over validation impressions (task/paper.py:497-524)
+    lr0 = model.optimizer.lr.value
+    h.callback(0)
+    assert abs(h.model.optimizer.lr.value - lr0 * h.config.learning_rate_decay) < 1e-12
+    assert 0.0 <= h.last_evaluation['auc'] <= 1.0 and h.model is model
+    # doc_encoder layer by name (task/test_pipeline.py:28)
+    dv = model.get_layer('doc_encoder').predict(clicked[0])
+    assert rel(dv, on.news_encoder(clicked[0].astype(int), _oracle_params(model))) < 5e-5
+
+
+def test_surface_tensor_core_precision(lib):
+    sh = synth.Shape('t16', 50, 80, 120, L=7, W=5, K=2, B=6, E=12, F=16, U=8)
+    d = tempfile.mkdtemp()
+    synth.write_dataset(d, sh)
+    cfg = settings.Config(dict(task='Seq2VecPaperSoftmaxId', arch='igru', input_training_data_path=d, title_shape=sh.L,
+                               window_size=sh.W, negative_samples=sh.K, batch_size=8, textual_embedding_dim=sh.E,
+                               title_filter_shape=(sh.F, 3), user_embedding_dim=sh.U, debug=True, dropout=0.2))
+    h = task.get(cfg)
+    model = h.build_model(0)
+    assert h._core.precision() == 'fp16_tc'
+    x, y = next(h.train)
+    P = _oracle_params(model)
+    ref = on.lstur_forward(P, x[0], x[1].astype(int), np.stack(x[2:], 1).astype(int), arch='igru')
+    assert rel(model.predict(x), ref) < 1e-3
+    hist = model.fit_generator(h.train, 5, epochs=1)
+    assert np.isfinite(hist.history['loss'][0])

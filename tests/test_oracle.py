@@ -1,0 +1,158 @@
+"""CPU tests that pin the oracle (oracle/) — the reference has no tests or golden vectors for this path
+(SURVEY.md §4, §8c), so the oracle is validated by: two independent implementations, hand-computable micro
+cases, finite differences, structural invariants and committed golden fixtures."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from mnexp_b200 import synth
+from oracle import lstur_numpy as on
+from oracle import lstur_torch as ot
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'lstur_golden.npz'))
+SH = synth.SHAPES['tiny']
+TOK = GOLD['doc_tokens']
+
+
+def case(arch, seed=4242, bseed=99):
+    P = synth.make_weights(SH, arch=arch, bias_noise=0.05, seed=seed)
+    (b,), _ = synth.make_batches(SH, 1, seed=bseed)
+    return P, b, TOK[b['hist_doc']], TOK[b['cand_doc']]
+
+
+@pytest.mark.parametrize('arch', ['igru', 'gru', 'hgru', 'nigru'])
+def test_oracle_reproduces_golden(arch):
+    assert np.array_equal(synth.make_docs(SH.n_news, SH.L, SH.vocab)[0], TOK)
+    P, b, ct, cd = case(arch)
+    for k in ('user', 'hist_doc', 'cand_doc'):
+        assert np.array_equal(b[k], GOLD['%s/batch/%s' % (arch, k)])
+    r = on.lstur_forward(P, b['user'], ct, cd, arch=arch, aux=True)
+    for k in ('probs', 'logits', 'sigmoid', 'user_vec', 'cand_vec', 'hist_vec'):
+        np.testing.assert_allclose(r[k], GOLD['%s/%s' % (arch, k)], rtol=1e-12, atol=1e-14)
+    ora = ot.LsturOracle(P, arch=arch)
+    loss, grads = ora.loss_and_grads(b['user'], ct, cd)
+    assert abs(float(loss) - float(GOLD['%s/loss' % arch])) < 1e-12
+    for k, g in grads.items():
+        np.testing.assert_allclose(g.numpy(), GOLD['%s/grad/%s' % (arch, k)], rtol=1e-9, atol=1e-13)
+
+
+@pytest.mark.parametrize('arch', ['igru', 'gru', 'hgru', 'nigru', 'pgru', 'vo'])
+def test_numpy_and_torch_implementations_agree(arch):
+    P, b, ct, cd = case(arch, seed=7)
+    pn = on.lstur_forward(P, b['user'], ct, cd, arch=arch)
+    pt = ot.LsturOracle(P, arch=arch).forward(b['user'], ct, cd).detach().numpy()
+    assert np.abs(pn - pt).max() < 1e-12
+    p32 = ot.LsturOracle(P, arch=arch, dtype=torch.float32).forward(b['user'], ct, cd).detach().numpy()
+    assert np.abs(pn - p32).max() < 1e-4 * np.abs(pn).max() + 1e-6
+
+
+def test_scalar_loop_restatements():
+    P, b, ct, cd = case('igru')
+    P64 = {k: v.astype(np.float64) for k, v in P.items()}
+    assert np.abs(on.news_encoder(TOK[:6], P) - on.news_encoder_loops(TOK[:6], P64)).max() < 1e-12
+    g = np.random.default_rng(0)
+    H = g.standard_normal((3, 4, SH.U))
+    H[0, :2] = 0
+    h0 = g.standard_normal((3, SH.U))
+    a = on.gru_last_state(H, h0, P64['gru_wx'], P64['gru_wh'], P64['gru_b'])
+    assert np.abs(a - on.gru_loops(H, h0, P64['gru_wx'], P64['gru_wh'], P64['gru_b'])).max() < 1e-12
+
+
+def test_hand_computed_news_encoder():
+    """L=3, E=1, F=1, k=3, all weights 1: C_t = x_{t-1}+x_t+x_{t+1} (zero outside), a=tanh(C), softmax-like pooling."""
+    P = dict(word_emb=np.array([[0.], [1.], [2.]]), conv_w=np.ones((3, 1, 1)), conv_b=np.zeros(1), att_w=np.ones(1),
+             att_b=np.zeros(1), dense_w=np.ones((1, 1)), dense_b=np.zeros(1))
+    tok = np.array([[1, 2, 0]])                  # x = 1, 2, (pad row 0 = 0)
+    C = np.array([1 + 2, 1 + 2 + 0, 0.0])        # position 2 is a pad token -> masked
+    e = np.exp(np.tanh(C)) * np.array([1, 1, 0])
+    want = (e / (e.sum() + 1e-7) * C).sum()
+    assert abs(on.news_encoder(tok, P)[0, 0] - want) < 1e-12
+    # mask_zero=False: a real token next to a pad convolves with row 0 of the table, whatever it holds
+    P2 = dict(P, word_emb=np.array([[5.], [1.], [2.]]))
+    C2 = np.array([1 + 2, 1 + 2 + 5, 0.0])
+    e2 = np.exp(np.tanh(C2)) * np.array([1, 1, 0])
+    assert abs(on.news_encoder(tok, P2)[0, 0] - (e2 / (e2.sum() + 1e-7) * C2).sum()) < 1e-12
+    # all-pad title: pooled = 0, doc vector = dense bias
+    assert on.news_encoder(np.zeros((1, 3), int), dict(P, dense_b=np.array([0.25])))[0, 0] == 0.25
+
+
+def test_hand_computed_gru_step():
+    """U=1, one step, all weights 1, h0=0.5: z=r=hs(x+h), hh=tanh(x+r*h), h'=z*h+(1-z)*hh."""
+    hs = lambda v: min(1.0, max(0.0, 0.2 * v + 0.5))
+    x, h = 2.0, 0.5
+    z = r = hs(x + h)
+    want = z * h + (1 - z) * math.tanh(x + r * h)
+    got = on.gru_last_state(np.array([[[x]]]), np.array([[h]]), np.ones((1, 3)), np.ones((1, 3)), np.zeros(3))
+    assert abs(got[0, 0] - want) < 1e-15
+    # sigmoid recurrent activation (Keras >= 2.3) is a parameter
+    sg = lambda v: 1 / (1 + math.exp(-v))
+    z = r = sg(x + h)
+    got = on.gru_last_state(np.array([[[x]]]), np.array([[h]]), np.ones((1, 3)), np.ones((1, 3)), np.zeros(3), 'sigmoid')
+    assert abs(got[0, 0] - (z * h + (1 - z) * math.tanh(x + r * h))) < 1e-15
+
+
+@pytest.mark.parametrize('arch', ['igru', 'gru'])
+def test_autograd_matches_finite_differences(arch):
+    P, b, ct, cd = case(arch, seed=11)
+    ora = ot.LsturOracle(P, arch=arch)
+    _, grads = ora.loss_and_grads(b['user'], ct, cd)
+    g = np.random.default_rng(3)
+    P64 = {k: v.astype(np.float64) for k, v in P.items()}
+    for name in ('conv_w', 'att_w', 'dense_w', 'gru_wx', 'gru_wh', 'gru_b', 'user_emb'):
+        d = g.standard_normal(P64[name].shape)
+        if name == 'user_emb':
+            d[np.setdiff1d(np.arange(d.shape[0]), b['user'])] = 0
+        eps = 1e-6
+        lp = on.lstur_loss(dict(P64, **{name: P64[name] + eps * d}), b['user'], ct, cd, arch=arch)
+        lm = on.lstur_loss(dict(P64, **{name: P64[name] - eps * d}), b['user'], ct, cd, arch=arch)
+        fd = (lp - lm) / (2 * eps)
+        an = float((grads[name].numpy() * d).sum())
+        assert abs(fd - an) < 1e-6 * max(1.0, abs(an)), name
+
+
+def test_invariants():
+    P, b, ct, cd = case('igru', seed=13)
+    base = on.lstur_forward(P, b['user'], ct, cd, aux=True)
+    # extra left padding of the history changes nothing (masked steps carry the state)
+    ct2 = np.concatenate([np.zeros_like(ct[:, :3]), ct], 1)
+    assert np.abs(on.lstur_forward(P, b['user'], ct2, cd) - base['probs']).max() < 1e-13
+    # permuting the candidates permutes the probabilities
+    perm = np.array([2, 0, 1])
+    assert np.abs(on.lstur_forward(P, b['user'], ct, cd[:, perm]) - base['probs'][:, perm]).max() < 1e-13
+    # all-masked history: ini -> h_T = h0 ; con (nigru) -> 0
+    z = np.zeros_like(ct)
+    assert np.array_equal(on.lstur_forward(P, b['user'], z, cd, aux=True)['user_vec'], P['user_emb'][b['user']].astype(np.float64))
+    Pn = synth.make_weights(SH, arch='nigru', seed=13)
+    assert np.all(on.lstur_forward(Pn, b['user'], z, cd, arch='nigru', aux=True)['user_vec'] == 0)
+    # decomposed pipeline == full model (task/test_pipeline.py:214-265 `test_correct`)
+    dv = on.news_encoder(ct.reshape(-1, SH.L), P).reshape(ct.shape[0], SH.W, -1) * on.history_mask(ct)[..., None]
+    u = on.user_encoder('igru', b['user'], dv, P)
+    s = on.score(u, on.news_encoder(cd.reshape(-1, SH.L), P).reshape(cd.shape[0], cd.shape[1], -1))
+    assert np.abs(on.sigmoid(s) - base['sigmoid']).max() < 1e-13
+
+
+def test_keras_adam_semantics():
+    # first step: dp = -lr * g * sqrt(1-b2) / (sqrt(1-b2)|g| + eps)  ~ -lr*sign(g)
+    g = np.array([0.3, -2.0, 1e-3])
+    p, m, v = on.adam_step(np.zeros(3), g, np.zeros(3), np.zeros(3), 1, 1e-3)
+    want = -1e-3 * math.sqrt(1 - 0.999) / (1 - 0.9) * (0.1 * g) / (np.sqrt(0.001 * g * g) + 1e-7)
+    np.testing.assert_allclose(p, want, rtol=1e-12)
+    assert np.abs(p + 1e-3 * np.sign(g)).max() < 5e-6          # |g| >> eps/sqrt(1-b2) = 3.2e-6
+    # dense semantics: a row whose gradient is zero after one non-zero step keeps moving on its momentum
+    p2, m2, v2 = on.adam_step(p, np.zeros(3), m, v, 2, 1e-3)
+    assert np.all(np.abs(p2 - p) > 1e-5)
+    # torch KerasAdam == numpy adam_step
+    P = {'w': torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64)}
+    opt = ot.KerasAdam(P, lr=1e-3)
+    opt.step({'w': torch.tensor(g)})
+    np.testing.assert_allclose(P['w'].numpy(), np.array([1.0, 2.0, 3.0]) + p, rtol=1e-12)
+
+
+def test_categorical_crossentropy_clip():
+    y = np.array([[1.0, 0, 0]])
+    assert abs(on.categorical_crossentropy(y, np.array([[0.5, 0.25, 0.25]])) - math.log(2)) < 1e-12
+    assert abs(on.categorical_crossentropy(y, np.array([[0.0, 0.5, 0.5]])) + math.log(1e-7)) < 1e-9      # clipped
+    assert abs(on.categorical_crossentropy(y, np.array([[2.0, 1.0, 1.0]])) - math.log(2)) < 1e-12       # renormalised
