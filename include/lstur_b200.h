@@ -112,6 +112,12 @@ int lstur_gemm_f32(int transA, int transB, int M, int N, int K, const float* A, 
                    long long ldb, float* C, long long ldc, const float* bias, int flags, void* workspace,
                    size_t workspace_bytes, cudaStream_t stream);
 
+/* Same contract on the tensor cores (tcgen05, operands rounded to fp16 while staged, fp32 accumulate). */
+size_t lstur_gemm_tc_workspace_bytes(int M, int N, int K);
+int lstur_gemm_tc(int transA, int transB, int M, int N, int K, const float* A, long long lda, const float* B,
+                  long long ldb, float* C, long long ldc, const float* bias, int flags, void* workspace,
+                  size_t workspace_bytes, cudaStream_t stream);
+
 /* pad mask + Masking + Dropout + models.SimpleAttentionMaskSupport (task/paper.py:150-158, models.py:474-489). */
 int lstur_attn_pool_fwd(int N, int L, int F, float* C, long long title_stride, const int* tokens, const float* att_w,
                         const float* att_b, float* pooled, long long ldp, float* a_out, float* w_out, float dropout,

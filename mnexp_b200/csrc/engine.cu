@@ -71,7 +71,14 @@ void add_dense(lstur_plan* p, const char* name, long long count) {
 }
 void track_gemm(lstur_plan* p, int M, int N, int K) {
   size_t b = lstur_gemm_f32_workspace_bytes(M, N, K, nullptr);
+  size_t b2 = lstur_gemm_tc_workspace_bytes(M, N, K);
+  if (b2 > b) b = b2;
   if (b > p->gemm_ws_bytes) p->gemm_ws_bytes = b;
+}
+typedef int (*gemm_fn)(int, int, int, int, int, const float*, long long, const float*, long long, float*, long long,
+                       const float*, int, void*, size_t, cudaStream_t);
+inline gemm_fn pick_gemm(const lstur_plan* p) {
+  return (p->c.precision == LSTUR_PREC_BF16_TC || p->c.precision == LSTUR_PREC_FP16_TC) ? lstur_gemm_tc : lstur_gemm_f32;
 }
 
 }  // namespace
@@ -263,6 +270,7 @@ extern "C" int lstur_forward(const lstur_plan* p, const lstur_weights* w, const 
   const lstur_config& c = p->c;
   const int N = p->N, Nh = p->Nh, Nc = p->Nc, Lp = p->Lp, D = p->D, L = c.L, E = c.E, F = c.F, G = c.G, B = c.B;
   const bool bw = c.save_for_backward != 0;
+  const gemm_fn GEMM = pick_gemm(p);
   LSTUR_REQUIRE(!training || bw, "lstur_forward(training needs a save_for_backward plan)");
   const float drop = training ? c.dropout : 0.f;
   const_cast<lstur_plan*>(p)->last_seed = seed;
@@ -299,7 +307,7 @@ extern "C" int lstur_forward(const lstur_plan* p, const lstur_weights* w, const 
                            pooled, F, W<float>(p, ws, "att_a"), W<float>(p, ws, "att_w"), drop, seed * 2u + 1u, st));
   }
   if (c.use_dense) {
-    RC(lstur_gemm_f32(0, 0, N, c.Dd, F, pooled, F, DP(p, w->dense, "dense_w"), c.Dd, docv, D,
+    RC(GEMM(0, 0, N, c.Dd, F, pooled, F, DP(p, w->dense, "dense_w"), c.Dd, docv, D,
                       DP(p, w->dense, "dense_b"), 0, gws, gwsb, st));
   } else {
     cudaMemcpy2DAsync(docv, (size_t)D * 4, pooled, (size_t)F * 4, (size_t)F * 4, N, cudaMemcpyDeviceToDevice, st);
@@ -318,7 +326,7 @@ extern "C" int lstur_forward(const lstur_plan* p, const lstur_weights* w, const 
   // 5. GRU (k11-k12)
   if (has_gru) {
     float* XW = W<float>(p, ws, "XW");
-    RC(lstur_gemm_f32(0, 0, Nh, 3 * G, D, docv, D, DP(p, w->dense, "gru_wx"), 3 * G, XW, 3 * G,
+    RC(GEMM(0, 0, Nh, 3 * G, D, docv, D, DP(p, w->dense, "gru_wx"), 3 * G, XW, 3 * G,
                       DP(p, w->dense, "gru_b"), 0, gws, gwsb, st));
     float* hT = W<float>(p, ws, "hT");
     float* hdst = hT;
@@ -333,7 +341,7 @@ extern "C" int lstur_forward(const lstur_plan* p, const lstur_weights* w, const 
       cudaMemcpy2DAsync(cat + G, (size_t)(G + c.Ue) * 4, u0, (size_t)c.Ue * 4, (size_t)c.Ue * 4, B,
                         cudaMemcpyDeviceToDevice, st);
       if (c.arch == LSTUR_ARCH_CON_DENSE) {
-        RC(lstur_gemm_f32(0, 0, B, c.U, G + c.Ue, cat, G + c.Ue, DP(p, w->dense, "con_w"), c.U, uvec, c.U,
+        RC(GEMM(0, 0, B, c.U, G + c.Ue, cat, G + c.Ue, DP(p, w->dense, "con_w"), c.U, uvec, c.U,
                           DP(p, w->dense, "con_b"), 0, gws, gwsb, st));
       } else {
         cudaMemcpyAsync(uvec, cat, (size_t)B * c.U * 4, cudaMemcpyDeviceToDevice, st);
@@ -366,6 +374,7 @@ extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const
   const int N = p->N, Nh = p->Nh, Lp = p->Lp, D = p->D, L = c.L, E = c.E, F = c.F, G = c.G, B = c.B;
   void* gws = W<void>(p, ws, "gemm_ws");
   const size_t gwsb = p->gemm_ws_bytes;
+  const gemm_fn GEMM = pick_gemm(p);
   float* cws = W<float>(p, ws, "colsum_ws");
   const size_t cwsb = p->ws.at("colsum_ws").count * 4;
   float* docv = W<float>(p, ws, "doc_vec");
@@ -386,8 +395,8 @@ extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const
     float* cat = W<float>(p, ws, "cat");
     float* d_cat = W<float>(p, ws, "d_cat");
     const int K2 = G + c.Ue;
-    RC(lstur_gemm_f32(0, 1, B, K2, c.U, d_uvec, c.U, DP(p, w->dense, "con_w"), c.U, d_cat, K2, nullptr, 0, gws, gwsb, st));
-    RC(lstur_gemm_f32(1, 0, K2, c.U, B, cat, K2, d_uvec, c.U, DG(p, dgrad, "con_w"), c.U, nullptr, 0, gws, gwsb, st));
+    RC(GEMM(0, 1, B, K2, c.U, d_uvec, c.U, DP(p, w->dense, "con_w"), c.U, d_cat, K2, nullptr, 0, gws, gwsb, st));
+    RC(GEMM(1, 0, K2, c.U, B, cat, K2, d_uvec, c.U, DG(p, dgrad, "con_w"), c.U, nullptr, 0, gws, gwsb, st));
     RC(lstur_colsum(B, c.U, d_uvec, c.U, DG(p, dgrad, "con_b"), 0, cws, cwsb, st));
     dhT = d_cat; lddh = K2; du0 = d_cat + G; lddu0 = K2;
   } else if (c.arch == LSTUR_ARCH_CON_CAT) {
@@ -404,13 +413,13 @@ extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const
     RC(lstur_gru_bwd(B, c.W, G, W<float>(p, ws, "gru_mask"), W<float>(p, ws, "Z"), W<float>(p, ws, "R"),
                      W<float>(p, ws, "HH"), W<float>(p, ws, "HP"), WhT, c.rec_act, dhT, lddh, dA, dh0, G, st));
     RC(lstur_colsum(Nh, 3 * G, dA, 3 * G, DG(p, dgrad, "gru_b"), 0, cws, cwsb, st));
-    RC(lstur_gemm_f32(1, 0, D, 3 * G, Nh, docv, D, dA, 3 * G, DG(p, dgrad, "gru_wx"), 3 * G, nullptr, 0, gws, gwsb, st));
-    RC(lstur_gemm_f32(1, 0, G, 2 * G, Nh, W<float>(p, ws, "HP"), G, dA, 3 * G, DG(p, dgrad, "gru_wh"), 3 * G, nullptr, 0,
+    RC(GEMM(1, 0, D, 3 * G, Nh, docv, D, dA, 3 * G, DG(p, dgrad, "gru_wx"), 3 * G, nullptr, 0, gws, gwsb, st));
+    RC(GEMM(1, 0, G, 2 * G, Nh, W<float>(p, ws, "HP"), G, dA, 3 * G, DG(p, dgrad, "gru_wh"), 3 * G, nullptr, 0,
                       gws, gwsb, st));
-    RC(lstur_gemm_f32(1, 0, G, G, Nh, W<float>(p, ws, "RH"), G, dA + 2 * G, 3 * G, DG(p, dgrad, "gru_wh") + 2 * G, 3 * G,
+    RC(GEMM(1, 0, G, G, Nh, W<float>(p, ws, "RH"), G, dA + 2 * G, 3 * G, DG(p, dgrad, "gru_wh") + 2 * G, 3 * G,
                       nullptr, 0, gws, gwsb, st));
     // dH = dA . Wx^T  (rows of masked steps are zero because dA is zero there)
-    RC(lstur_gemm_f32(0, 1, Nh, D, 3 * G, dA, 3 * G, DP(p, w->dense, "gru_wx"), 3 * G, d_docv, D, nullptr, 0, gws, gwsb, st));
+    RC(GEMM(0, 1, Nh, D, 3 * G, dA, 3 * G, DP(p, w->dense, "gru_wx"), 3 * G, d_docv, D, nullptr, 0, gws, gwsb, st));
     if (c.arch == LSTUR_ARCH_INI) { du0 = dh0; lddu0 = G; }
   } else {
     cudaMemsetAsync(d_docv, 0, (size_t)Nh * D * 4, st);
@@ -435,8 +444,8 @@ extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const
   const float* dpool = d_pooled;
   long long lddp = F;
   if (c.use_dense) {
-    RC(lstur_gemm_f32(0, 1, N, F, c.Dd, d_docv, D, DP(p, w->dense, "dense_w"), c.Dd, d_pooled, F, nullptr, 0, gws, gwsb, st));
-    RC(lstur_gemm_f32(1, 0, F, c.Dd, N, pooled, F, d_docv, D, DG(p, dgrad, "dense_w"), c.Dd, nullptr, 0, gws, gwsb, st));
+    RC(GEMM(0, 1, N, F, c.Dd, d_docv, D, DP(p, w->dense, "dense_w"), c.Dd, d_pooled, F, nullptr, 0, gws, gwsb, st));
+    RC(GEMM(1, 0, F, c.Dd, N, pooled, F, d_docv, D, DG(p, dgrad, "dense_w"), c.Dd, nullptr, 0, gws, gwsb, st));
     RC(lstur_colsum(N, c.Dd, d_docv, D, DG(p, dgrad, "dense_b"), 0, cws, cwsb, st));
   } else {
     dpool = d_docv; lddp = D;

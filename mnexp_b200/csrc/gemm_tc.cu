@@ -1,0 +1,293 @@
+// Generic tensor-core GEMM (tcgen05.mma, fp16 operands, fp32 accumulate in TMEM) on fp32 global operands.
+//
+//   C[M,N] (+)= op(A)[M,K] . op(B)[K,N] (+ bias[N]) (relu)
+//
+// Replaces gemm_f32 in tensor-core precision for the plain dense contractions of the LSTUR path:
+// Dense(F->U) (task/paper.py:159), the GRU input projection (keras GRU, task/paper.py:612) and all of their
+// input / weight gradients.  Operands stay fp32 in HBM; producer warps convert to fp16 while staging 16-byte
+// pieces into 128B-swizzled shared-memory tiles.  An operand whose K index is contiguous in memory (A
+// non-transposed, B transposed) is staged K-major; one whose M/N index is contiguous (A transposed — the
+// weight-gradient case — or B non-transposed) is staged MN-major, so no transposition ever happens in memory:
+// only the UMMA descriptor's major-ness bits differ.  Split-K over CTA.z with a fixed-order reduction.
+// Warp roles (512 threads): w1 MMA issuer + TMEM alloc, w4-11 producers, w12-15 epilogue.
+#include "tc_common.cuh"
+
+namespace lstur {
+namespace tc {
+
+constexpr int G_KBLK = 64;
+constexpr int G_STAGES = 4;
+constexpr int G_A_BYTES = TILE_M * 128;    // 16 KB (either major-ness)
+constexpr int G_B_BYTES = 256 * 128;       // up to N tile 256
+constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
+constexpr int G_THREADS = 512;
+constexpr int G_PRODUCERS = 256;
+
+struct GemmParams {
+  int M, N, K;
+  const float* A; long long lda;
+  const float* B; long long ldb;
+  float* C; long long ldc;
+  const float* bias;
+  int flags, ntile, k_per_split, vec_ok;
+  float* partial;
+};
+
+// 8 consecutive floats -> 8 fp16 (16 bytes), zero-filled outside [0, s_lim) x [0, c_lim)
+__device__ __forceinline__ uint4 load_piece(const float* __restrict__ base, long long ld, int s_idx, int s_lim, int c0,
+                                            int c_lim, bool vec_ok) {
+  float v[8];
+  if (s_idx < s_lim && c0 + 8 <= c_lim && vec_ok) {
+    const float4* p = reinterpret_cast<const float4*>(base + (long long)s_idx * ld + c0);
+    float4 a = __ldg(p), b = __ldg(p + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      v[i] = (s_idx < s_lim && c0 + i < c_lim) ? __ldg(base + (long long)s_idx * ld + c0 + i) : 0.f;
+  }
+  uint4 o;
+  __half2 h;
+  h = __floats2half2_rn(v[0], v[1]); o.x = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2half2_rn(v[2], v[3]); o.y = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2half2_rn(v[4], v[5]); o.z = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2half2_rn(v[6], v[7]); o.w = *reinterpret_cast<uint32_t*>(&h);
+  return o;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// TA: A is stored [K,M] (M contiguous) -> MN-major.  TB: B is stored [N,K] (K contiguous) -> K-major.
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t misc_base = smem_base + G_STAGES * G_STAGE_BYTES;
+  uint8_t* misc_gen = smem_gen + (misc_base - smem_base);
+  const uint32_t bar_full = misc_base, bar_empty = misc_base + 64, bar_t_full = misc_base + 128;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(misc_gen + 144);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TILE_M, n0 = blockIdx.x * p.ntile;
+  const int nt = min(p.ntile, p.N - n0);                     // valid columns of this tile
+  const int nmma = (nt + 15) & ~15;                          // UMMA N (multiple of 16)
+  const int kbeg = blockIdx.z * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
+  const int nkb = kend > kbeg ? (kend - kbeg + G_KBLK - 1) / G_KBLK : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < G_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, G_PRODUCERS / 32);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_t_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(256)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(TILE_M, nmma, true) | (TA ? (1u << 15) : 0u) | (!TB ? (1u << 16) : 0u);
+      int s = 0;
+      uint32_t ph = 0, accum = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(bar_full + 8 * s, ph, 21);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + s * G_STAGE_BYTES, b_addr = a_addr + G_A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < G_KBLK / 16; ++kk) {
+          const uint64_t ad = TA ? make_desc_mn128(a_addr + kk * 2048, 8192) : make_desc_k128(a_addr + kk * 32);
+          const uint64_t bd = TB ? make_desc_k128(b_addr + kk * 32) : make_desc_mn128(b_addr + kk * 2048, 8192);
+          umma_bf16(tmem_base, ad, bd, idesc, accum);
+          accum = 1;
+        }
+        umma_commit(bar_empty + 8 * s);
+        if (++s == G_STAGES) { s = 0; ph ^= 1; }
+      }
+      umma_commit(bar_t_full);
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // ---- producers: fp32 global -> fp16 swizzled tiles
+    const int pt = threadIdx.x - 128;        // 0..255
+    const int bgroups = (nmma + 63) >> 6;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int k0 = kbeg + kb * G_KBLK;
+      mbar_wait(bar_empty + 8 * s, ph ^ 1, 22);
+      const uint32_t a_addr = smem_base + s * G_STAGE_BYTES, b_addr = a_addr + G_A_BYTES;
+      // A: 1024 pieces
+#pragma unroll 4
+      for (int i = pt; i < 1024; i += G_PRODUCERS) {
+        const int c = i & 7, r = i >> 3;   // K-major: r = tile row (0..127); MN-major: r = (group, k row)
+        if (!TA) {
+          uint4 v = load_piece(p.A, p.lda, m0 + r, p.M, k0 + 8 * c, kend, p.vec_ok);
+          sts128(a_addr + r * 128 + ((c ^ (r & 7)) << 4), v);
+        } else {
+          const int g = r >> 6, kr = r & 63;
+          uint4 v = load_piece(p.A, p.lda, k0 + kr, kend, m0 + g * 64 + 8 * c, p.M, p.vec_ok);
+          sts128(a_addr + g * 8192 + kr * 128 + ((c ^ (kr & 7)) << 4), v);
+        }
+      }
+      if (TB) {
+        for (int i = pt; i < nmma * 8; i += G_PRODUCERS) {
+          const int c = i & 7, r = i >> 3;
+          uint4 v = load_piece(p.B, p.ldb, n0 + r, n0 + nt, k0 + 8 * c, kend, p.vec_ok);
+          sts128(b_addr + r * 128 + ((c ^ (r & 7)) << 4), v);
+        }
+      } else {
+        for (int i = pt; i < bgroups * 512; i += G_PRODUCERS) {
+          const int c = i & 7, r = i >> 3;
+          const int g = r >> 6, kr = r & 63;
+          uint4 v = load_piece(p.B, p.ldb, k0 + kr, kend, n0 + g * 64 + 8 * c, n0 + nt, p.vec_ok);
+          sts128(b_addr + g * 8192 + kr * 128 + ((c ^ (kr & 7)) << 4), v);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * s);
+      if (++s == G_STAGES) { s = 0; ph ^= 1; }
+    }
+  } else if (warp >= 12) {
+    // ---- epilogue
+    const int q = warp & 3;
+    mbar_wait(bar_t_full, 0, 23);
+    tc_fence_after();
+    const int gm = m0 + q * 32 + lane;
+    const bool split = gridDim.z > 1;
+    float* crow = split ? p.partial + ((long long)blockIdx.z * p.M + gm) * p.N : p.C + (long long)gm * p.ldc;
+    const bool vec_st = split ? (p.N % 4 == 0) : (p.ldc % 4 == 0 && (((uintptr_t)p.C) & 15) == 0);
+    for (int c0 = 0; c0 < nmma; c0 += 32) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      if (nmma - c0 >= 32) { TMEM_LD_32(taddr, r); } else { TMEM_LD_16(taddr, r); }
+      tmem_ld_wait();
+      if (gm >= p.M) continue;
+      const int ncols = min(32, nt - c0);
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        if (i >= ncols) break;
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float x = nkb > 0 ? __uint_as_float(r[i + u]) : 0.f;
+          const int gn = n0 + c0 + i + u;
+          if (!split && i + u < ncols) {
+            if (p.bias) x += p.bias[gn];
+            if (p.flags & LSTUR_GEMM_ACCUM) x += crow[gn];
+            if (p.flags & LSTUR_GEMM_RELU) x = fmaxf(x, 0.f);
+          }
+          v[u] = x;
+        }
+        if (i + 4 <= ncols && vec_st && ((n0 + c0 + i) & 3) == 0) {
+          *reinterpret_cast<float4*>(crow + n0 + c0 + i) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (i + u < ncols) crow[n0 + c0 + i + u] = v[u];
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+  }
+}
+
+__global__ void gemm_tc_splitk_reduce_kernel(int M, int N, int splits, const float* __restrict__ partial,
+                                             float* __restrict__ C, long long ldc, const float* __restrict__ bias,
+                                             int flags) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)M * N) return;
+  int gm = (int)(i / N), gn = (int)(i % N);
+  float v = 0.f;
+  for (int s = 0; s < splits; ++s) v += partial[(long long)s * M * N + i];
+  if (bias) v += bias[gn];
+  if (flags & LSTUR_GEMM_ACCUM) v += C[(long long)gm * ldc + gn];
+  if (flags & LSTUR_GEMM_RELU) v = fmaxf(v, 0.f);
+  C[(long long)gm * ldc + gn] = v;
+}
+
+}  // namespace tc
+}  // namespace lstur
+
+using namespace lstur;
+
+static void gemm_tc_tiling(int M, int N, int K, int* ntile, int* splits) {
+  int nparts = (N + 255) / 256;
+  int nt = ((N + nparts - 1) / nparts + 15) & ~15;
+  if (nt > 256) nt = 256;
+  long long tiles = (long long)((M + tc::TILE_M - 1) / tc::TILE_M) * ((N + nt - 1) / nt);
+  int sp = 1;
+  if (tiles < 148 && K >= 2048) {
+    sp = (int)(148 / tiles);
+    int maxs = K / 512;
+    if (sp > maxs) sp = maxs;
+    if (sp < 1) sp = 1;
+  }
+  *ntile = nt;
+  *splits = sp;
+}
+
+extern "C" size_t lstur_gemm_tc_workspace_bytes(int M, int N, int K) {
+  int nt, sp;
+  gemm_tc_tiling(M, N, K, &nt, &sp);
+  return sp > 1 ? (size_t)sp * M * N * sizeof(float) : 0;
+}
+
+// Same contract as lstur_gemm_f32 (fp32 in / fp32 out); operands are rounded to fp16 inside the kernel.
+extern "C" int lstur_gemm_tc(int transA, int transB, int M, int N, int K, const float* A, long long lda, const float* B,
+                             long long ldb, float* C, long long ldc, const float* bias, int flags, void* workspace,
+                             size_t workspace_bytes, cudaStream_t stream) {
+  LSTUR_REQUIRE(M >= 0 && N >= 0 && K >= 0, "lstur_gemm_tc");
+  if (M == 0 || N == 0) return LSTUR_OK;
+  tc::GemmParams p;
+  int splits;
+  gemm_tc_tiling(M, N, K, &p.ntile, &splits);
+  size_t need = splits > 1 ? (size_t)splits * M * N * sizeof(float) : 0;
+  if (need > workspace_bytes || (need && !workspace)) splits = 1;
+  int kps = ((K + splits - 1) / splits + tc::G_KBLK - 1) / tc::G_KBLK * tc::G_KBLK;
+  if (kps == 0) kps = tc::G_KBLK;
+  splits = K > 0 ? (K + kps - 1) / kps : 1;
+  p.M = M; p.N = N; p.K = K; p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.bias = bias;
+  p.flags = flags; p.k_per_split = kps; p.partial = (float*)workspace;
+  p.vec_ok = (lda % 4 == 0) && (ldb % 4 == 0) && ((((uintptr_t)A) & 15) == 0) && ((((uintptr_t)B) & 15) == 0);
+  size_t smem = 1024 + (size_t)tc::G_STAGES * tc::G_STAGE_BYTES + 256;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaSuccess;
+    e = cudaFuncSetAttribute(tc::gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("lstur_gemm_tc: cannot opt in to %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+      return LSTUR_ERR_CUDA;
+    }
+    attr = true;
+  }
+  dim3 grid((N + p.ntile - 1) / p.ntile, (M + tc::TILE_M - 1) / tc::TILE_M, splits);
+#define LAUNCH(TA_, TB_) tc::gemm_tc_kernel<TA_, TB_><<<grid, tc::G_THREADS, smem, stream>>>(p)
+  if (!transA && !transB) LAUNCH(false, false);
+  else if (transA && !transB) LAUNCH(true, false);
+  else if (!transA && transB) LAUNCH(false, true);
+  else LAUNCH(true, true);
+#undef LAUNCH
+  LSTUR_CHECK_LAUNCH("lstur_gemm_tc");
+  if (splits > 1) {
+    long long n = (long long)M * N;
+    tc::gemm_tc_splitk_reduce_kernel<<<cdiv(n, 256), 256, 0, stream>>>(M, N, splits, p.partial, C, ldc, bias, flags);
+    LSTUR_CHECK_LAUNCH("lstur_gemm_tc(splitk_reduce)");
+  }
+  return LSTUR_OK;
+}

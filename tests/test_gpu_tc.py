@@ -227,3 +227,25 @@ def test_tc_conv_wgrad(lib, N, L, E, F, fp16):
     d16 = round16(dpre, fp16).astype(np.float64)
     ref = np.stack([np.einsum('nte,ntf->ef', Xp[:, j:j + L], d16) for j in range(3)])
     assert rel(dW.cpu().numpy(), ref) < 2e-5
+
+
+@pytest.mark.parametrize('ta,tb', [(0, 0), (1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize('M,N,K', [(1, 1, 1), (130, 72, 33), (400, 200, 56320), (200, 600, 5000), (51200, 600, 200),
+                                   (257, 304, 200), (128, 256, 64), (1000, 400, 200)])
+def test_gemm_tc(lib, ta, tb, M, N, K):
+    if M * K > 3e7 and ta:
+        pytest.skip('covered by the non-transposed case')
+    g = np.random.default_rng(M * 7 + N * 3 + K + ta * 2 + tb)
+    A = g.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
+    Bm = g.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+    bias = g.standard_normal(N).astype(np.float32)
+    C = torch.full((M, N), float('nan'), device='cuda')
+    nb = lib.lstur_gemm_tc_workspace_bytes(M, N, K)
+    ws = torch.empty(max(nb, 4), dtype=torch.uint8, device='cuda')
+    a_d, b_d, bias_d = torch.as_tensor(A).cuda(), torch.as_tensor(Bm).cuda(), torch.as_tensor(bias).cuda()
+    rc = lib.lstur_gemm_tc(ta, tb, M, N, K, P_(a_d), A.shape[1], P_(b_d), Bm.shape[1], P_(C), N, P_(bias_d), 1, P_(ws), nb, stream())
+    assert rc == 0, lib.lstur_last_error()
+    torch.cuda.synchronize()
+    A16, B16 = round16(A, 1).astype(np.float64), round16(Bm, 1).astype(np.float64)
+    ref = np.maximum((A16.T if ta else A16) @ (B16.T if tb else B16) + bias, 0)
+    assert rel(C.cpu().numpy(), ref) < 2e-5
