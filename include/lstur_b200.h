@@ -38,6 +38,7 @@ typedef struct CUstream_st* cudaStream_t;
 
 #define LSTUR_GEMM_RELU 1
 #define LSTUR_GEMM_ACCUM 2
+#define LSTUR_GEMM_PRECISE 4 /* lstur_gemm_tc only: 3-term fp16 split (~fp32 accuracy) */
 
 /* user-encoder architectures (task/paper.py:596-626, task/cook.py:146-168) */
 #define LSTUR_ARCH_INI 0       /* paper 'igru' / cook 'ingru': GRU(initial_state=user_emb) — LSTUR-ini  */

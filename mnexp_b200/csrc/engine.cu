@@ -308,7 +308,7 @@ extern "C" int lstur_forward(const lstur_plan* p, const lstur_weights* w, const 
   }
   if (c.use_dense) {
     RC(GEMM(0, 0, N, c.Dd, F, pooled, F, DP(p, w->dense, "dense_w"), c.Dd, docv, D,
-                      DP(p, w->dense, "dense_b"), 0, gws, gwsb, st));
+                      DP(p, w->dense, "dense_b"), LSTUR_GEMM_PRECISE, gws, gwsb, st));
   } else {
     cudaMemcpy2DAsync(docv, (size_t)D * 4, pooled, (size_t)F * 4, (size_t)F * 4, N, cudaMemcpyDeviceToDevice, st);
   }
@@ -327,7 +327,7 @@ extern "C" int lstur_forward(const lstur_plan* p, const lstur_weights* w, const 
   if (has_gru) {
     float* XW = W<float>(p, ws, "XW");
     RC(GEMM(0, 0, Nh, 3 * G, D, docv, D, DP(p, w->dense, "gru_wx"), 3 * G, XW, 3 * G,
-                      DP(p, w->dense, "gru_b"), 0, gws, gwsb, st));
+                      DP(p, w->dense, "gru_b"), LSTUR_GEMM_PRECISE, gws, gwsb, st));
     float* hT = W<float>(p, ws, "hT");
     float* hdst = hT;
     long long ldo = G;
@@ -342,7 +342,7 @@ extern "C" int lstur_forward(const lstur_plan* p, const lstur_weights* w, const 
                         cudaMemcpyDeviceToDevice, st);
       if (c.arch == LSTUR_ARCH_CON_DENSE) {
         RC(GEMM(0, 0, B, c.U, G + c.Ue, cat, G + c.Ue, DP(p, w->dense, "con_w"), c.U, uvec, c.U,
-                          DP(p, w->dense, "con_b"), 0, gws, gwsb, st));
+                          DP(p, w->dense, "con_b"), LSTUR_GEMM_PRECISE, gws, gwsb, st));
       } else {
         cudaMemcpyAsync(uvec, cat, (size_t)B * c.U * 4, cudaMemcpyDeviceToDevice, st);
       }

@@ -19,7 +19,8 @@ constexpr int G_KBLK = 64;
 constexpr int G_STAGES = 4;
 constexpr int G_A_BYTES = TILE_M * 128;    // 16 KB (either major-ness)
 constexpr int G_B_BYTES = 256 * 128;       // up to N tile 256
-constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
+constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;          // single-term fp16
+constexpr int G_STAGE_BYTES_S3 = 2 * (G_A_BYTES + G_B_BYTES);  // hi + lo tiles for the 3-term split
 constexpr int G_THREADS = 512;
 constexpr int G_PRODUCERS = 256;
 
@@ -34,8 +35,9 @@ struct GemmParams {
 };
 
 // 8 consecutive floats -> 8 fp16 (16 bytes), zero-filled outside [0, s_lim) x [0, c_lim)
+template <bool SPLIT>
 __device__ __forceinline__ uint4 load_piece(const float* __restrict__ base, long long ld, int s_idx, int s_lim, int c0,
-                                            int c_lim, bool vec_ok) {
+                                            int c_lim, bool vec_ok, uint4& lo) {
   float v[8];
   if (s_idx < s_lim && c0 + 8 <= c_lim && vec_ok) {
     const float4* p = reinterpret_cast<const float4*>(base + (long long)s_idx * ld + c0);
@@ -46,25 +48,35 @@ __device__ __forceinline__ uint4 load_piece(const float* __restrict__ base, long
     for (int i = 0; i < 8; ++i)
       v[i] = (s_idx < s_lim && c0 + i < c_lim) ? __ldg(base + (long long)s_idx * ld + c0 + i) : 0.f;
   }
-  uint4 o;
-  __half2 h;
-  h = __floats2half2_rn(v[0], v[1]); o.x = *reinterpret_cast<uint32_t*>(&h);
-  h = __floats2half2_rn(v[2], v[3]); o.y = *reinterpret_cast<uint32_t*>(&h);
-  h = __floats2half2_rn(v[4], v[5]); o.z = *reinterpret_cast<uint32_t*>(&h);
-  h = __floats2half2_rn(v[6], v[7]); o.w = *reinterpret_cast<uint32_t*>(&h);
-  return o;
+  uint32_t o[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    o[i] = *reinterpret_cast<uint32_t*>(&h);
+    if (SPLIT) {   // x = hi + lo with hi = fp16(x), lo = fp16(x - hi): ~22 mantissa bits across the pair
+      float2 hf = __half22float2(h);
+      __half2 r = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+      l[i] = *reinterpret_cast<uint32_t*>(&r);
+    }
+  }
+  if (SPLIT) lo = make_uint4(l[0], l[1], l[2], l[3]);
+  return make_uint4(o[0], o[1], o[2], o[3]);
 }
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 // TA: A is stored [K,M] (M contiguous) -> MN-major.  TB: B is stored [N,K] (K contiguous) -> K-major.
-template <bool TA, bool TB>
+// SPLIT: 3-term fp16 split (Ahi.Bhi + Alo.Bhi + Ahi.Blo) for ~fp32 accuracy on the forward-path GEMMs.
+template <bool TA, bool TB, bool SPLIT>
 __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const GemmParams p) {
+  constexpr int STAGES = SPLIT ? 2 : G_STAGES;
+  constexpr int STAGE_BYTES = SPLIT ? G_STAGE_BYTES_S3 : G_STAGE_BYTES;
+  constexpr int LO_OFF = G_A_BYTES + G_B_BYTES;     // lo tiles follow the hi tiles inside a stage
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t misc_base = smem_base + G_STAGES * G_STAGE_BYTES;
+  const uint32_t misc_base = smem_base + STAGES * STAGE_BYTES;
   uint8_t* misc_gen = smem_gen + (misc_base - smem_base);
   const uint32_t bar_full = misc_base, bar_empty = misc_base + 64, bar_t_full = misc_base + 128;
   uint32_t* tmem_ptr_smem = (uint32_t*)(misc_gen + 144);
@@ -76,7 +88,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const GemmParams 
   const int nkb = kend > kbeg ? (kend - kbeg + G_KBLK - 1) / G_KBLK : 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < G_STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, G_PRODUCERS / 32);
       mbar_init(bar_empty + 8 * s, 1);
     }
@@ -101,16 +113,22 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const GemmParams 
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(bar_full + 8 * s, ph, 21);
         tc_fence_after();
-        const uint32_t a_addr = smem_base + s * G_STAGE_BYTES, b_addr = a_addr + G_A_BYTES;
+        const uint32_t a_addr = smem_base + s * STAGE_BYTES, b_addr = a_addr + G_A_BYTES;
 #pragma unroll
         for (int kk = 0; kk < G_KBLK / 16; ++kk) {
           const uint64_t ad = TA ? make_desc_mn128(a_addr + kk * 2048, 8192) : make_desc_k128(a_addr + kk * 32);
           const uint64_t bd = TB ? make_desc_k128(b_addr + kk * 32) : make_desc_mn128(b_addr + kk * 2048, 8192);
           umma_bf16(tmem_base, ad, bd, idesc, accum);
           accum = 1;
+          if (SPLIT) {
+            const uint64_t al = TA ? make_desc_mn128(a_addr + LO_OFF + kk * 2048, 8192) : make_desc_k128(a_addr + LO_OFF + kk * 32);
+            const uint64_t bl = TB ? make_desc_k128(b_addr + LO_OFF + kk * 32) : make_desc_mn128(b_addr + LO_OFF + kk * 2048, 8192);
+            umma_bf16(tmem_base, al, bd, idesc, 1);
+            umma_bf16(tmem_base, ad, bl, idesc, 1);
+          }
         }
         umma_commit(bar_empty + 8 * s);
-        if (++s == G_STAGES) { s = 0; ph ^= 1; }
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
       umma_commit(bar_t_full);
     }
@@ -123,38 +141,43 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const GemmParams 
     for (int kb = 0; kb < nkb; ++kb) {
       const int k0 = kbeg + kb * G_KBLK;
       mbar_wait(bar_empty + 8 * s, ph ^ 1, 22);
-      const uint32_t a_addr = smem_base + s * G_STAGE_BYTES, b_addr = a_addr + G_A_BYTES;
+      const uint32_t a_addr = smem_base + s * STAGE_BYTES, b_addr = a_addr + G_A_BYTES;
+      uint4 lo;
       // A: 1024 pieces
 #pragma unroll 4
       for (int i = pt; i < 1024; i += G_PRODUCERS) {
         const int c = i & 7, r = i >> 3;   // K-major: r = tile row (0..127); MN-major: r = (group, k row)
         if (!TA) {
-          uint4 v = load_piece(p.A, p.lda, m0 + r, p.M, k0 + 8 * c, kend, p.vec_ok);
+          uint4 v = load_piece<SPLIT>(p.A, p.lda, m0 + r, p.M, k0 + 8 * c, kend, p.vec_ok, lo);
           sts128(a_addr + r * 128 + ((c ^ (r & 7)) << 4), v);
+          if (SPLIT) sts128(a_addr + LO_OFF + r * 128 + ((c ^ (r & 7)) << 4), lo);
         } else {
           const int g = r >> 6, kr = r & 63;
-          uint4 v = load_piece(p.A, p.lda, k0 + kr, kend, m0 + g * 64 + 8 * c, p.M, p.vec_ok);
+          uint4 v = load_piece<SPLIT>(p.A, p.lda, k0 + kr, kend, m0 + g * 64 + 8 * c, p.M, p.vec_ok, lo);
           sts128(a_addr + g * 8192 + kr * 128 + ((c ^ (kr & 7)) << 4), v);
+          if (SPLIT) sts128(a_addr + LO_OFF + g * 8192 + kr * 128 + ((c ^ (kr & 7)) << 4), lo);
         }
       }
       if (TB) {
         for (int i = pt; i < nmma * 8; i += G_PRODUCERS) {
           const int c = i & 7, r = i >> 3;
-          uint4 v = load_piece(p.B, p.ldb, n0 + r, n0 + nt, k0 + 8 * c, kend, p.vec_ok);
+          uint4 v = load_piece<SPLIT>(p.B, p.ldb, n0 + r, n0 + nt, k0 + 8 * c, kend, p.vec_ok, lo);
           sts128(b_addr + r * 128 + ((c ^ (r & 7)) << 4), v);
+          if (SPLIT) sts128(b_addr + LO_OFF + r * 128 + ((c ^ (r & 7)) << 4), lo);
         }
       } else {
         for (int i = pt; i < bgroups * 512; i += G_PRODUCERS) {
           const int c = i & 7, r = i >> 3;
           const int g = r >> 6, kr = r & 63;
-          uint4 v = load_piece(p.B, p.ldb, k0 + kr, kend, n0 + g * 64 + 8 * c, n0 + nt, p.vec_ok);
+          uint4 v = load_piece<SPLIT>(p.B, p.ldb, k0 + kr, kend, n0 + g * 64 + 8 * c, n0 + nt, p.vec_ok, lo);
           sts128(b_addr + g * 8192 + kr * 128 + ((c ^ (kr & 7)) << 4), v);
+          if (SPLIT) sts128(b_addr + LO_OFF + g * 8192 + kr * 128 + ((c ^ (kr & 7)) << 4), lo);
         }
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_full + 8 * s);
-      if (++s == G_STAGES) { s = 0; ph ^= 1; }
+      if (++s == STAGES) { s = 0; ph ^= 1; }
     }
   } else if (warp >= 12) {
     // ---- epilogue
@@ -262,22 +285,29 @@ extern "C" int lstur_gemm_tc(int transA, int transB, int M, int N, int K, const 
   p.M = M; p.N = N; p.K = K; p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.bias = bias;
   p.flags = flags; p.k_per_split = kps; p.partial = (float*)workspace;
   p.vec_ok = (lda % 4 == 0) && (ldb % 4 == 0) && ((((uintptr_t)A) & 15) == 0) && ((((uintptr_t)B) & 15) == 0);
-  size_t smem = 1024 + (size_t)tc::G_STAGES * tc::G_STAGE_BYTES + 256;
+  const bool split3 = (flags & LSTUR_GEMM_PRECISE) != 0;
+  size_t smem = 1024 + (split3 ? (size_t)2 * tc::G_STAGE_BYTES_S3 : (size_t)tc::G_STAGES * tc::G_STAGE_BYTES) + 256;
   static bool attr = false;
   if (!attr) {
+    const int big = 1024 + 2 * tc::G_STAGE_BYTES_S3 + 256;
     cudaError_t e = cudaSuccess;
-    e = cudaFuncSetAttribute(tc::gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#define SETATTR(TA_, TB_, S_) \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<TA_, TB_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)
+    SETATTR(false, false, false); SETATTR(true, false, false); SETATTR(false, true, false); SETATTR(true, true, false);
+    SETATTR(false, false, true); SETATTR(true, false, true); SETATTR(false, true, true); SETATTR(true, true, true);
+#undef SETATTR
     if (e != cudaSuccess) {
-      set_error("lstur_gemm_tc: cannot opt in to %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+      set_error("lstur_gemm_tc: cannot opt in to %d B of shared memory: %s", big, cudaGetErrorString(e));
       return LSTUR_ERR_CUDA;
     }
     attr = true;
   }
   dim3 grid((N + p.ntile - 1) / p.ntile, (M + tc::TILE_M - 1) / tc::TILE_M, splits);
-#define LAUNCH(TA_, TB_) tc::gemm_tc_kernel<TA_, TB_><<<grid, tc::G_THREADS, smem, stream>>>(p)
+#define LAUNCH(TA_, TB_)                                                                    \
+  do {                                                                                      \
+    if (split3) tc::gemm_tc_kernel<TA_, TB_, true><<<grid, tc::G_THREADS, smem, stream>>>(p); \
+    else tc::gemm_tc_kernel<TA_, TB_, false><<<grid, tc::G_THREADS, smem, stream>>>(p);       \
+  } while (0)
   if (!transA && !transB) LAUNCH(false, false);
   else if (transA && !transB) LAUNCH(true, false);
   else if (!transA && transB) LAUNCH(false, true);

@@ -249,3 +249,11 @@ def test_gemm_tc(lib, ta, tb, M, N, K):
     A16, B16 = round16(A, 1).astype(np.float64), round16(Bm, 1).astype(np.float64)
     ref = np.maximum((A16.T if ta else A16) @ (B16.T if tb else B16) + bias, 0)
     assert rel(C.cpu().numpy(), ref) < 2e-5
+    # 3-term split mode (LSTUR_GEMM_PRECISE): close to the un-rounded fp32 operands
+    C.fill_(float('nan'))
+    rc = lib.lstur_gemm_tc(ta, tb, M, N, K, P_(a_d), A.shape[1], P_(b_d), Bm.shape[1], P_(C), N, P_(bias_d), 1 | 4, P_(ws), nb, stream())
+    assert rc == 0, lib.lstur_last_error()
+    torch.cuda.synchronize()
+    A64, B64 = A.astype(np.float64), Bm.astype(np.float64)
+    ref = np.maximum((A64.T if ta else A64) @ (B64.T if tb else B64) + bias, 0)
+    assert rel(C.cpu().numpy(), ref) < (5e-6 if K < 10000 else 3e-5)      # fp32 accumulation over K terms
