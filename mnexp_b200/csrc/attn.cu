@@ -168,6 +168,143 @@ __global__ void colsum_stage2_kernel(int chunks, int cols, const float* __restri
   out[c] = accumulate ? out[c] + s : s;
 }
 
+// Tensor-core-mode backward (v2): the title's 16-bit C tile is staged once in shared memory with 16-byte loads,
+// every thread owns one 8-column chunk (fixed columns -> private d att_w / d conv_b accumulators) and writes dPre
+// as 16-byte pieces straight into the MN-major swizzled K-block image consumed by conv_wgrad_tc_kernel.
+// HBM traffic = read C once + write dPre once.
+template <typename CT>
+__device__ __forceinline__ void unpack8(const uint4& u, float* v);
+template <>
+__device__ __forceinline__ void unpack8<__half>(const uint4& u, float* v) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <>
+__device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& u, float* v) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <typename CT>
+__device__ __forceinline__ uint4 pack8(const float* v);
+template <>
+__device__ __forceinline__ uint4 pack8<__half>(const float* v) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    h[i] = __floats2half2_rn(fminf(fmaxf(v[2 * i], -65504.f), 65504.f), fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f));
+  return u;
+}
+template <>
+__device__ __forceinline__ uint4 pack8<__nv_bfloat16>(const float* v) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  return u;
+}
+
+template <typename CT>
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_bwd_img_kernel(int N, int L, int F, const CT* __restrict__ Cd, const float* __restrict__ a_in,
+                    const float* __restrict__ w_in, const float* __restrict__ dp, long long lddp,
+                    const float* __restrict__ ka, uint8_t* __restrict__ img, float inv_keep,
+                    float* __restrict__ partials) {
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  const int nchunk = F >> 3;                       // 16-byte chunks per row
+  uint4* sC = reinterpret_cast<uint4*>(att_smem);  // [L][nchunk]
+  float* sdp = reinterpret_cast<float*>(att_smem + (size_t)32 * nchunk * 16);   // [F]
+  float* ska = sdp + F;                                                           // [F]
+  float* sred = ska + F;                                                          // [2][64][16] reduction scratch
+  __shared__ float sdw[32], sdz[32], sw[32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c = tid & 63, tg = tid >> 6;           // chunk owned by this thread, row group (0/1)
+  const bool c_ok = c < nchunk;
+  const int ngroups = (F + 63) >> 6;
+  const long long blk_bytes = (long long)ngroups * 8192;
+  for (int f = tid; f < F; f += ATT_THREADS) ska[f] = ka[f];
+  float dka[8], dbc[8], dba = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dka[i] = dbc[i] = 0.f;
+  for (int n = blockIdx.x; n < N; n += gridDim.x) {
+    __syncthreads();   // previous title fully consumed (also orders the ska fill on the first trip)
+    const uint4* src = reinterpret_cast<const uint4*>(Cd + (long long)n * L * F);
+    for (int i = tid; i < L * nchunk; i += ATT_THREADS) sC[i] = __ldg(src + i);
+    for (int f = tid; f < F; f += ATT_THREADS) sdp[f] = dp[(long long)n * lddp + f];
+    if (tid < L) sw[tid] = w_in[(long long)n * L + tid];
+    __syncthreads();
+    for (int t = warp; t < L; t += ATT_THREADS / 32) {
+      float dot = 0.f;
+      for (int cc = lane; cc < nchunk; cc += 32) {
+        float v[8];
+        unpack8<CT>(sC[t * nchunk + cc], v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dot = fmaf(v[i], sdp[cc * 8 + i], dot);
+      }
+      dot = warp_sum(dot);
+      if (lane == 0) sdw[t] = dot;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      float q = 0.f;
+      for (int t = 0; t < L; ++t) q = fmaf(sdw[t], sw[t], q);
+      if (tid < L) {
+        const float a = a_in[(long long)n * L + tid];
+        sdz[tid] = (sdw[tid] - q) * sw[tid] * (1.f - a * a);
+      }
+    }
+    __syncthreads();
+    if (c_ok) {
+      float dpf[8], kaf[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { dpf[i] = sdp[c * 8 + i]; kaf[i] = ska[c * 8 + i]; }
+      const int g = c >> 3, piece = c & 7;
+      for (int t = tg; t < 32; t += 2) {
+        float o[8];
+        if (t < L) {
+          float v[8];
+          unpack8<CT>(sC[t * nchunk + c], v);
+          const float wt = sw[t], dzt = sdz[t];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float gi = fmaf(wt, dpf[i], dzt * kaf[i]);
+            o[i] = v[i] > 0.f ? gi * inv_keep : 0.f;
+            dka[i] = fmaf(dzt, v[i], dka[i]);
+            dbc[i] += o[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = 0.f;
+        }
+        const long long R = (long long)n * 32 + t;
+        const int k = (int)(R & 63);
+        uint8_t* dst = img + (R >> 6) * blk_bytes + (long long)g * 8192 + k * 128 + ((piece ^ (k & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst) = pack8<CT>(o);
+      }
+    }
+    if (tid == 0)
+      for (int t = 0; t < L; ++t) dba += sdz[t];
+  }
+  // combine the two row groups, then one partial row per CTA
+  __syncthreads();
+  if (tg == 1 && c_ok) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sred[c * 16 + i] = dka[i]; sred[c * 16 + 8 + i] = dbc[i]; }
+  }
+  __syncthreads();
+  float* out = partials + (long long)blockIdx.x * (2 * F + 1);
+  if (tg == 0 && c_ok) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      out[c * 8 + i] = dka[i] + sred[c * 16 + i];
+      out[F + c * 8 + i] = dbc[i] + sred[c * 16 + 8 + i];
+    }
+  }
+  if (tid == 0) out[2 * F] = dba;
+}
+
 // partials[grid][2F+1] -> d_att_w[F], d_conv_b[F], d_att_b[1] in a fixed order.
 __global__ void attn_bwd_reduce_kernel(int grid, int F, const float* __restrict__ partials, float* __restrict__ d_att_w,
                                        float* __restrict__ d_conv_b, float* __restrict__ d_att_b, int accumulate) {
@@ -287,12 +424,36 @@ extern "C" int lstur_attn_pool_bwd_img(int fp16, int N, int L, int F, const void
                                        const float* w_in, const float* d_pooled, long long lddp, const float* att_w,
                                        void* dpre_img, float dropout, float* d_att_w, float* d_conv_b, float* d_att_b,
                                        int accumulate, float* partials, size_t partial_bytes, cudaStream_t stream) {
-  LSTUR_REQUIRE(L <= 31 && dpre_img != nullptr, "lstur_attn_pool_bwd_img");
+  LSTUR_REQUIRE(N >= 0 && L >= 1 && L <= 31 && F % 8 == 0 && F <= 512 && dpre_img != nullptr, "lstur_attn_pool_bwd_img");
+  int grid = lstur_attn_bwd_grid(N);
+  LSTUR_REQUIRE(partials != nullptr && partial_bytes >= (size_t)grid * (2 * F + 1) * sizeof(float), "lstur_attn_pool_bwd_img");
+  if (N == 0) {
+    if (!accumulate) {
+      cudaMemsetAsync(d_att_w, 0, F * sizeof(float), stream);
+      cudaMemsetAsync(d_conv_b, 0, F * sizeof(float), stream);
+      cudaMemsetAsync(d_att_b, 0, sizeof(float), stream);
+    }
+    return LSTUR_OK;
+  }
   if (N & 1) {  // the last 64-row K block is only half covered by titles: clear it first
     size_t blk = (size_t)((F + 63) / 64) * 8192;
     cudaMemsetAsync((char*)dpre_img + (size_t)(N / 2) * blk, 0, blk, stream);
   }
-  return attn_pool_bwd_impl(fp16 ? 2 : 1, 1, N, L, 32, F, Cd_16, (long long)L * F, a_in, w_in, d_pooled, lddp, att_w,
-                            (float*)dpre_img, 0, dropout, d_att_w, d_conv_b, d_att_b, accumulate, partials,
-                            partial_bytes, stream);
+  const float inv_keep = 1.f / (1.f - dropout);
+  size_t smem = (size_t)32 * (F / 8) * 16 + (size_t)2 * F * sizeof(float) + (size_t)64 * 16 * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaFuncSetAttribute(attn_bwd_img_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(attn_bwd_img_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
+  if (fp16)
+    attn_bwd_img_kernel<__half><<<grid, ATT_THREADS, smem, stream>>>(N, L, F, (const __half*)Cd_16, a_in, w_in, d_pooled, lddp,
+                                                                     att_w, (uint8_t*)dpre_img, inv_keep, partials);
+  else
+    attn_bwd_img_kernel<__nv_bfloat16><<<grid, ATT_THREADS, smem, stream>>>(N, L, F, (const __nv_bfloat16*)Cd_16, a_in, w_in,
+                                                                            d_pooled, lddp, att_w, (uint8_t*)dpre_img,
+                                                                            inv_keep, partials);
+  LSTUR_CHECK_LAUNCH("lstur_attn_pool_bwd_img");
+  attn_bwd_reduce_kernel<<<cdiv(2 * F + 1, 128), 128, 0, stream>>>(grid, F, partials, d_att_w, d_conv_b, d_att_b, accumulate);
+  LSTUR_CHECK_LAUNCH("lstur_attn_pool_bwd_img(reduce)");
+  return LSTUR_OK;
 }
