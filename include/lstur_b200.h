@@ -85,6 +85,7 @@ int lstur_embed_gather_pad_tcrng(int N, int L, int E, int V, int KS, int Ep, con
  * 16-bit elements from lstur_pack_conv_w_tc.  c_out_16 (n_titles,L,F) receives the attention input (saved for
  * backward).  fp16 != 0: IEEE half operands (10-bit mantissa, meets the 1e-3 parity bound); 0: bfloat16. */
 int lstur_conv_tc_available(void);
+int lstur_tc_set_trace(void* dev_buf);   /* profiling hook: clock64 stamps of CTA 0's warp roles; NULL disables */
 int lstur_tc_supported(int L, int E, int F, int KS);
 int lstur_tc_padded_e(int E);
 long long lstur_tc_wimg_elems(int E, int F);

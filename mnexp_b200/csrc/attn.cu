@@ -70,13 +70,11 @@ __device__ __forceinline__ float ldc(const __half* p, long long i) { return __ha
 
 // OUT = 0: dPre as fp32 rows (title stride dpre_title_stride, rows L..Lrows-1 zeroed).
 // OUT = 1/2: dPre as bf16/fp16 K-block images for the tensor-core wgrad (conv_tc.cu): slot row R = n*32+t lives in
-//   block R/64 at  (f/64)*8192 + (R%64)*128 + ((((f%64)/8) ^ (R%8)) << 4) + (f%8)*2  — MN-major SWIZZLE_128B.
+//   block n (one 32-row title slot) at  (f/64)*4096 + t*128 + ((((f%64)/8) ^ (t%8)) << 4) + (f%8)*2  — MN-major
+//   SWIZZLE_128B.
 __device__ __forceinline__ void store_dpre_img(void* img, int out_mode, int ngroups, int n, int t, int f, float v) {
-  const long long R = (long long)n * 32 + t;
-  const long long kb = R >> 6;
-  const int k = (int)(R & 63);
-  const long long byte = kb * ((long long)ngroups * 8192) + (long long)(f >> 6) * 8192 + k * 128 +
-                         ((((f & 63) >> 3) ^ (k & 7)) << 4) + (f & 7) * 2;
+  const long long byte = (long long)n * ((long long)ngroups * 4096) + (long long)(f >> 6) * 4096 + t * 128 +
+                         ((((f & 63) >> 3) ^ (t & 7)) << 4) + (f & 7) * 2;
   if (out_mode == 2) *reinterpret_cast<__half*>((char*)img + byte) = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
   else *reinterpret_cast<__nv_bfloat16*>((char*)img + byte) = __float2bfloat16_rn(v);
 }
@@ -223,7 +221,7 @@ attn_bwd_img_kernel(int N, int L, int F, const CT* __restrict__ Cd, const float*
   const int c = tid & 63, tg = tid >> 6;           // chunk owned by this thread, row group (0/1)
   const bool c_ok = c < nchunk;
   const int ngroups = (F + 63) >> 6;
-  const long long blk_bytes = (long long)ngroups * 8192;
+  const long long blk_bytes = (long long)ngroups * 4096;
   for (int f = tid; f < F; f += ATT_THREADS) ska[f] = ka[f];
   float dka[8], dbc[8], dba = 0.f;
 #pragma unroll
@@ -278,9 +276,7 @@ attn_bwd_img_kernel(int N, int L, int F, const CT* __restrict__ Cd, const float*
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] = 0.f;
         }
-        const long long R = (long long)n * 32 + t;
-        const int k = (int)(R & 63);
-        uint8_t* dst = img + (R >> 6) * blk_bytes + (long long)g * 8192 + k * 128 + ((piece ^ (k & 7)) << 4);
+        uint8_t* dst = img + (long long)n * blk_bytes + (long long)g * 4096 + t * 128 + ((piece ^ (t & 7)) << 4);
         *reinterpret_cast<uint4*>(dst) = pack8<CT>(o);
       }
     }
@@ -434,10 +430,6 @@ extern "C" int lstur_attn_pool_bwd_img(int fp16, int N, int L, int F, const void
       cudaMemsetAsync(d_att_b, 0, sizeof(float), stream);
     }
     return LSTUR_OK;
-  }
-  if (N & 1) {  // the last 64-row K block is only half covered by titles: clear it first
-    size_t blk = (size_t)((F + 63) / 64) * 8192;
-    cudaMemsetAsync((char*)dpre_img + (size_t)(N / 2) * blk, 0, blk, stream);
   }
   const float inv_keep = 1.f / (1.f - dropout);
   size_t smem = (size_t)32 * (F / 8) * 16 + (size_t)2 * F * sizeof(float) + (size_t)64 * 16 * sizeof(float);

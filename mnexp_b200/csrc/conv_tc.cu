@@ -18,6 +18,8 @@
 //   consumption order, so one cp.async.bulk (TMA, UBLKCP) per K block lands an MMA-ready tile.
 // Warp roles (512 threads): w0 B loader, w1 TMEM alloc + MMA issuer, w4-7 A producers,
 //   w8-15 epilogue (TMEM lane quarter = warp%4, column half = (warp-8)/4).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace lstur {
@@ -25,12 +27,25 @@ namespace tc {
 
 constexpr int SLOT = 32;                      // rows per title slot
 constexpr int TPT = TILE_M / SLOT;            // titles per tile
-constexpr int KBLK = 64;                      // K elements per block (128 B of bf16)
-constexpr int A_TAP_BYTES = TILE_M * 128;     // 16 KB
+constexpr int EPAD = 64;                      // embedding rows are padded to a multiple of 64 columns
+constexpr int KBLK = 32;                      // K elements per pipeline block: 64-byte rows, SWIZZLE_64B
+constexpr int ROWB = KBLK * 2;                // bytes per shared-memory row
+constexpr int A_TAP_BYTES = TILE_M * ROWB;    // 8 KB
 constexpr int TAPS = 3;
-constexpr int A_STAGE_BYTES = TAPS * A_TAP_BYTES;
-constexpr int NUM_A_STAGES = 2;
-constexpr int NUM_B_STAGES = 2;
+constexpr int A_STAGE_BYTES = TAPS * A_TAP_BYTES;   // 24 KB: the three shifted tap tiles of one 32-column chunk
+constexpr int NUM_A_STAGES = 3;
+constexpr int NUM_B_STAGES = 5;               // deep ring: covers TMA + barrier round-trip latency
+
+// K-major SWIZZLE_64B descriptor: rows of 64 B, 8-row atoms of 512 B (16B chunk index XOR (row>>1)&3)
+__device__ __forceinline__ uint64_t make_desc_k64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
 constexpr int THREADS = 512;
 
 // ------------------------------------------------------------------ operand packing kernels
@@ -44,7 +59,7 @@ __global__ void pack_emb_bf16_kernel(long long V, int E, int Ep, const float* __
   dst[i] = to16(e < E ? src[v * E + e] : 0.f, fp16);
 }
 
-// conv_w fp32 (3,E,F) -> per K block i = c*3 + j an [F rows][64 k] bf16 image, K-major, 128B-swizzled.
+// conv_w fp32 (3,E,F) -> per K block i = c*3 + j an [F rows][32 k] 16-bit image, K-major, 64B-swizzled.
 __global__ void pack_conv_w_kernel(int E, int F, int EC, const float* __restrict__ Wc, uint16_t* __restrict__ img,
                                    bool fp16) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -56,7 +71,7 @@ __global__ void pack_conv_w_kernel(int E, int F, int EC, const float* __restrict
   int c = blk / TAPS, j = blk % TAPS;
   int e = c * KBLK + kk;
   float v = e < E ? Wc[((long long)j * E + e) * F + f] : 0.f;
-  long long byte = (long long)f * 128 + ((((kk >> 3) ^ (f & 7)) << 4) | ((kk & 7) << 1));
+  long long byte = (long long)f * ROWB + ((((kk >> 3) ^ ((f >> 1) & 3)) << 4) | ((kk & 7) << 1));
   img[blk * per_blk + byte / 2] = to16(v, fp16);
 }
 
@@ -64,7 +79,7 @@ struct FwdParams {
   int n_titles, L, F, EC, Ep, V;
   const int* tok;                 // (n_titles, L)
   const uint16_t* emb;            // (V, Ep) fp16 or bf16
-  const uint16_t* wimg;           // EC*3 blocks of F*64
+  const uint16_t* wimg;           // EC*3 blocks of F*32 (EC = Ep/32)
   const float* conv_b;            // (F)
   const float* att_w;             // (F)
   const float* att_b;             // (1)
@@ -75,26 +90,93 @@ struct FwdParams {
   uint32_t drop_thr16;            // 0 = no dropout; keep iff h16 >= thr
   float inv_keep;
   uint32_t seed_x, seed_c;
+  long long* trace;               // optional clock64 trace of CTA 0 (tools/perf_conv.py); null in production
+};
+#define TRACE(it, slot)                                                                    \
+  do {                                                                                     \
+    if (p.trace && blockIdx.x == 0 && (it) < 8) p.trace[(it) * 16 + (slot)] = clock64();   \
+  } while (0)
+
+struct EpiCtx {
+  float xs, inv_keep;
+  uint32_t thr, base_lo, inner0, inner1;
+  const float* s_bias;
+  const float* s_ka;
 };
 
-template <bool FP16>
+// Epilogue pass 1 for NCOLS accumulator columns of one token row: bias + ReLU (+ dropout) -> 16-bit C (stored),
+// attention-logit partial sum z (from the ROUNDED values, so forward and backward see the same C) and the row max.
+template <bool FP16, bool DROP, int NCOLS>
+__device__ __forceinline__ void epi_pass1_chunk(const EpiCtx& ec, uint32_t taddr, int c0, bool live, bool valid,
+                                                uint16_t* crow, float& z, float& vmax) {
+  uint32_t r[32];
+  if (NCOLS == 32) { TMEM_LD_32(taddr, r); } else { TMEM_LD_16(taddr, r); }
+  tmem_ld_wait();
+  uint32_t packed[NCOLS / 2];
+  if (live) {
+#pragma unroll
+    for (int g = 0; g < NCOLS / 4; ++g) {
+      const float4 b4 = *reinterpret_cast<const float4*>(ec.s_bias + c0 + 4 * g);
+      const float4 k4 = *reinterpret_cast<const float4*>(ec.s_ka + c0 + 4 * g);
+      float v0 = fmaxf(fmaf(__uint_as_float(r[4 * g + 0]), ec.xs, b4.x), 0.f);
+      float v1 = fmaxf(fmaf(__uint_as_float(r[4 * g + 1]), ec.xs, b4.y), 0.f);
+      float v2 = fmaxf(fmaf(__uint_as_float(r[4 * g + 2]), ec.xs, b4.z), 0.f);
+      float v3 = fmaxf(fmaf(__uint_as_float(r[4 * g + 3]), ec.xs, b4.w), 0.f);
+      vmax = fmaxf(vmax, fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)));      // Masking(): any(C != 0) before the dropout
+      if (DROP) {
+        const uint32_t lo0 = ec.base_lo + (uint32_t)((c0 >> 1) + 2 * g), lo1 = lo0 + 1u;
+        const uint32_t h0 = lowbias32(lo0 ^ (lo0 < ec.base_lo ? ec.inner1 : ec.inner0));
+        const uint32_t h1 = lowbias32(lo1 ^ (lo1 < ec.base_lo ? ec.inner1 : ec.inner0));
+        v0 = (h0 & 0xffffu) >= ec.thr ? v0 * ec.inv_keep : 0.f;
+        v1 = (h0 >> 16) >= ec.thr ? v1 * ec.inv_keep : 0.f;
+        v2 = (h1 & 0xffffu) >= ec.thr ? v2 * ec.inv_keep : 0.f;
+        v3 = (h1 >> 16) >= ec.thr ? v3 * ec.inv_keep : 0.f;
+      }
+      const uint32_t p0 = pack16x2<FP16>(v0, v1), p1 = pack16x2<FP16>(v2, v3);
+      packed[2 * g] = p0;
+      packed[2 * g + 1] = p1;
+      z = fmaf(lo16<FP16>(p0), k4.x, z);
+      z = fmaf(hi16<FP16>(p0), k4.y, z);
+      z = fmaf(lo16<FP16>(p1), k4.z, z);
+      z = fmaf(hi16<FP16>(p1), k4.w, z);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NCOLS / 2; ++i) packed[i] = 0u;
+  }
+  if (valid) {
+    uint4* dst = reinterpret_cast<uint4*>(crow + c0);
+#pragma unroll
+    for (int g = 0; g < NCOLS / 8; ++g) dst[g] = make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+  }
+}
+
+__device__ __forceinline__ void epi_load_chunk(const uint16_t* crow, int c0, int F, bool live, uint4* v) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    v[g] = make_uint4(0, 0, 0, 0);
+    if (live && c0 + 8 * g < F) v[g] = *reinterpret_cast<const uint4*>(crow + c0 + 8 * g);
+  }
+}
+
+template <bool FP16, bool DROP>
 __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int F = p.F, EC = p.EC;
-  const uint32_t b_stage_bytes = (uint32_t)F * 128u;
+  const uint32_t b_stage_bytes = (uint32_t)F * ROWB;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = a_base + NUM_A_STAGES * A_STAGE_BYTES;
   const uint32_t misc_base = b_base + NUM_B_STAGES * b_stage_bytes;
   uint8_t* misc_gen = smem_gen + (misc_base - smem_base);
-  // barriers: a_full[2], a_empty[2], b_full[2], b_empty[2], tmem_full, tmem_empty  (8 B each)
-  const uint32_t bar_a_full = misc_base, bar_a_empty = misc_base + 16, bar_b_full = misc_base + 32,
-                 bar_b_empty = misc_base + 48, bar_t_full = misc_base + 64, bar_t_empty = misc_base + 72;
-  uint32_t* tmem_ptr_smem = (uint32_t*)(misc_gen + 80);
-  float* s_z = (float*)(misc_gen + 128);          // [2 parity][2 halves][128 rows]
-  int* s_any = (int*)(misc_gen + 128 + 2048);     // [2][2][128]
-  float* s_bias = (float*)(misc_gen + 128 + 4096);  // [F]
+  // barriers (8 B each): a_full[<=4] a_empty[<=4] b_full[<=6] b_empty[<=6] tmem_full tmem_empty
+  const uint32_t bar_a_full = misc_base, bar_a_empty = misc_base + 32, bar_b_full = misc_base + 64,
+                 bar_b_empty = misc_base + 112, bar_t_full = misc_base + 160, bar_t_empty = misc_base + 168;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(misc_gen + 176);
+  float* s_z = (float*)(misc_gen + 256);          // [2 parity][2 halves][128 rows]
+  int* s_any = (int*)(misc_gen + 256 + 2048);     // [2][2][128]
+  float* s_bias = (float*)(misc_gen + 256 + 4096);  // [F]
   float* s_ka = s_bias + F;                          // [F]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -134,9 +216,12 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
     if (lane == 0) {
       int sb = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         for (int i = 0; i < EC * TAPS; ++i) {
           mbar_wait(bar_b_empty + 8 * sb, ph ^ 1, 1);
+          if (i == 0) TRACE(it, 9);
+          if (i == EC * TAPS - 1) TRACE(it, 10);
           mbar_expect_tx(bar_b_full + 8 * sb, b_stage_bytes);
           bulk_g2s(b_base + sb * b_stage_bytes, (const uint8_t*)p.wimg + (size_t)i * b_stage_bytes, b_stage_bytes,
                    bar_b_full + 8 * sb);
@@ -150,13 +235,16 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
       const uint32_t idesc0 = make_idesc(TILE_M, n0, FP16), idesc1 = make_idesc(TILE_M, n1 > 0 ? n1 : 16, FP16);
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0, pht = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         mbar_wait(bar_t_empty, pht ^ 1, 2);
         tc_fence_after();
+        TRACE(it, 0);
         uint32_t accum = 0;
         for (int c = 0; c < EC; ++c) {
           mbar_wait(bar_a_full + 8 * sa, pha, 3);
           tc_fence_after();
+          if (c == 0) TRACE(it, 1);
           for (int j = 0; j < TAPS; ++j) {
             mbar_wait(bar_b_full + 8 * sb, phb, 4);
             tc_fence_after();
@@ -164,9 +252,9 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
             const uint32_t b_addr = b_base + sb * b_stage_bytes;
 #pragma unroll
             for (int kk = 0; kk < KBLK / 16; ++kk) {
-              const uint64_t ad = make_desc_k128(a_addr + kk * 32);
-              umma_bf16(tmem_base, ad, make_desc_k128(b_addr + kk * 32), idesc0, accum);
-              if (n1 > 0) umma_bf16(tmem_base + n0, ad, make_desc_k128(b_addr + 256 * 128 + kk * 32), idesc1, accum);
+              const uint64_t ad = make_desc_k64(a_addr + kk * 32);
+              umma_bf16(tmem_base, ad, make_desc_k64(b_addr + kk * 32), idesc0, accum);
+              if (n1 > 0) umma_bf16(tmem_base + n0, ad, make_desc_k64(b_addr + 256 * ROWB + kk * 32), idesc1, accum);
               accum = 1;
             }
             umma_commit(bar_b_empty + 8 * sb);
@@ -175,42 +263,62 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
           umma_commit(bar_a_empty + 8 * sa);
           if (++sa == NUM_A_STAGES) { sa = 0; pha ^= 1; }
         }
+        TRACE(it, 2);
         umma_commit(bar_t_full);
         pht ^= 1;
       }
     }
   } else if (warp >= 4 && warp < 8) {
     // ===================== A producers: embedding gather -> three shifted swizzled tap tiles =====================
+    // lane -> (row within a group of 8, 16-byte piece of the 64-byte row); loads for chunk c+1 (and the token ids of
+    // the next tile) are issued before chunk c is hashed and stored, so L2 latency is off the critical path.
     const int pw = warp - 4;                 // title slot of the tile
-    const int rsub = lane >> 3, piece = lane & 7;
+    const int rsub = lane >> 2, piece = lane & 3;
     int sa = 0;
     uint32_t pha = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    auto load_ids = [&](int tile, int* ids) {
       const int n = tile * TPT + pw;
-      int ids[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        int t = 4 * i + rsub;
+      for (int i = 0; i < 4; ++i) {
+        const int t = 8 * i + rsub;
         int id = -1;
-        if (n < p.n_titles && t < p.L) {
+        if (tile < n_tiles && n < p.n_titles && t < p.L) {
           id = p.tok[(long long)n * p.L + t];
           id = (id < 0 || id >= p.V) ? 0 : id;
         }
         ids[i] = id;
       }
+    };
+    auto load_rows = [&](const int* ids, int c, uint4* v) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[i] = make_uint4(0, 0, 0, 0);
+        if (ids[i] >= 0) v[i] = __ldg((const uint4*)(p.emb + (long long)ids[i] * p.Ep + c * KBLK + piece * 8));
+      }
+    };
+    int ids[4], ids_next[4];
+    uint4 v[4], v_next[4];
+    load_ids(blockIdx.x, ids);
+    load_rows(ids, 0, v_next);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int n = tile * TPT + pw;
+      if (warp == 4 && lane == 0) TRACE(it, 7);
       for (int c = 0; c < EC; ++c) {
-        mbar_wait(bar_a_empty + 8 * sa, pha ^ 1, 5);
-        uint4 v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          v[i] = make_uint4(0, 0, 0, 0);
-          if (ids[i] >= 0) v[i] = __ldg((const uint4*)(p.emb + (long long)ids[i] * p.Ep + c * KBLK + piece * 8));
+        for (int i = 0; i < 4; ++i) v[i] = v_next[i];
+        if (c + 1 < EC) {
+          load_rows(ids, c + 1, v_next);
+          if (c + 2 == EC) load_ids(tile + gridDim.x, ids_next);
+        } else {
+          if (EC == 1) load_ids(tile + gridDim.x, ids_next);
+          load_rows(ids_next, 0, v_next);
         }
-        if (p.drop_thr16) {
+        if (DROP) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 4; ++i) {
             if (ids[i] < 0) continue;
-            const int t = 4 * i + rsub;
+            const int t = 8 * i + rsub;
             const uint64_t pair0 = (((uint64_t)n * p.L + t) * (uint64_t)p.Ep + (uint64_t)(c * KBLK + piece * 8)) >> 1;
             uint32_t* w = reinterpret_cast<uint32_t*>(&v[i]);
 #pragma unroll
@@ -221,14 +329,15 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
             }
           }
         }
+        mbar_wait(bar_a_empty + 8 * sa, pha ^ 1, 5);
         const uint32_t stage = a_base + sa * A_STAGE_BYTES;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = pw * SLOT + 4 * i + rsub;
+        for (int i = 0; i < 4; ++i) {
+          const int r = pw * SLOT + 8 * i + rsub;
 #pragma unroll
           for (int j = 0; j < TAPS; ++j) {
             const int rr = (r + 1 - j) & (TILE_M - 1);
-            const uint32_t addr = stage + j * A_TAP_BYTES + rr * 128 + ((piece ^ (rr & 7)) << 4);
+            const uint32_t addr = stage + j * A_TAP_BYTES + rr * ROWB + ((piece ^ ((rr >> 1) & 3)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v[i].x), "r"(v[i].y), "r"(v[i].z),
                          "r"(v[i].w)
                          : "memory");
@@ -238,6 +347,11 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_a_full + 8 * sa);
         if (++sa == NUM_A_STAGES) { sa = 0; pha ^= 1; }
+        if (c + 1 == EC) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ids[i] = ids_next[i];
+          if (warp == 4 && lane == 0) TRACE(it, 8);
+        }
       }
     }
   } else if (warp >= 8) {
@@ -249,73 +363,49 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
     const int ch_split = (nch + 1) / 2;
     const int ch_beg = half == 0 ? 0 : ch_split, ch_end = half == 0 ? ch_split : nch;
     const float att_bias = p.att_b[0];
-    const float xs = p.drop_thr16 ? p.inv_keep : 1.f;   // input-dropout scale folded into the epilogue
+    EpiCtx ec;
+    ec.xs = DROP ? p.inv_keep : 1.f;   // input-dropout scale folded into the epilogue
+    ec.inv_keep = p.inv_keep;
+    ec.thr = p.drop_thr16;
+    ec.s_bias = s_bias;
+    ec.s_ka = s_ka;
     uint32_t pht = 0;
     int par = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int n = tile * TPT + q, t = lane;
       const bool valid = n < p.n_titles && t < p.L;
       const long long m = (long long)n * p.L + t;
       const int tk = valid ? p.tok[m] : 0;
       uint16_t* crow = p.c_out + m * F;
+      if (DROP) {
+        const uint64_t base = ((uint64_t)m * (uint64_t)F) >> 1;     // F is even: pair index of (m, f) = base + f/2
+        ec.base_lo = (uint32_t)base;
+        const uint32_t hi = (uint32_t)(base >> 32), k = 0x9e3779b9u * (p.seed_c + 1u);
+        ec.inner0 = lowbias32(hi + k);
+        ec.inner1 = lowbias32(hi + 1u + k);
+      }
       mbar_wait(bar_t_full, pht, 6);
       pht ^= 1;
       tc_fence_after();
-      float z = 0.f;
-      int any = 0;
+      if (warp == 8 && lane == 0) TRACE(it, 3);
+      float z = 0.f, vmax = 0.f;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
       for (int ch = ch_beg; ch < ch_end; ++ch) {
         const int c0 = ch * 32;
-        const int ncols = min(32, F - c0);
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-        if (ncols == 32) {
-          TMEM_LD_32(taddr, r);
-        } else {
-          TMEM_LD_16(taddr, r);
-#pragma unroll
-          for (int i = 16; i < 32; ++i) r[i] = 0;
-        }
-        tmem_ld_wait();
-        uint32_t packed[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const int f = c0 + i;
-          float v0 = 0.f, v1 = 0.f;
-          if (i < ncols && tk != 0) {
-            v0 = fmaxf(fmaf(__uint_as_float(r[i]), xs, s_bias[f]), 0.f);
-            v1 = fmaxf(fmaf(__uint_as_float(r[i + 1]), xs, s_bias[f + 1]), 0.f);
-            any |= (v0 > 0.f) | (v1 > 0.f);
-            if (p.drop_thr16) {
-              const uint32_t h = rng_u32(p.seed_c, (uint64_t)(m * F + f) >> 1);
-              v0 = (h & 0xffffu) >= p.drop_thr16 ? v0 * p.inv_keep : 0.f;
-              v1 = (h >> 16) >= p.drop_thr16 ? v1 * p.inv_keep : 0.f;
-            }
-          }
-          const uint32_t pk = pack16x2<FP16>(v0, v1);
-          packed[i >> 1] = pk;
-          if (i < ncols) {
-            z = fmaf(lo16<FP16>(pk), s_ka[f], z);
-            z = fmaf(hi16<FP16>(pk), s_ka[f + 1], z);
-          }
-        }
-        if (valid) {
-          uint4* dst = reinterpret_cast<uint4*>(crow + c0);
-          dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-          dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-          if (ncols == 32) {
-            dst[2] = make_uint4(packed[8], packed[9], packed[10], packed[11]);
-            dst[3] = make_uint4(packed[12], packed[13], packed[14], packed[15]);
-          }
-        }
+        if (F - c0 >= 32) epi_pass1_chunk<FP16, DROP, 32>(ec, trow + c0, c0, tk != 0, valid, crow, z, vmax);
+        else epi_pass1_chunk<FP16, DROP, 16>(ec, trow + c0, c0, tk != 0, valid, crow, z, vmax);
       }
       // TMEM drained: let the MMA warp start the next tile while we pool
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_t_empty);
+      if (warp == 8 && lane == 0) TRACE(it, 4);
       const int row = q * 32 + lane;
       s_z[(par * 2 + half) * 128 + row] = z;
-      s_any[(par * 2 + half) * 128 + row] = any;
+      s_any[(par * 2 + half) * 128 + row] = vmax > 0.f ? 1 : 0;
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (warp == 8 && lane == 0) TRACE(it, 5);
       const float zt = s_z[(par * 2) * 128 + row] + s_z[(par * 2 + 1) * 128 + row];
       const int anyt = s_any[(par * 2) * 128 + row] | s_any[(par * 2 + 1) * 128 + row];
       par ^= 1;
@@ -327,26 +417,25 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
         if (p.att_a) p.att_a[m] = a;
         if (p.att_wt) p.att_wt[m] = w;
       }
-      // pass 2: pooled[n, f] = sum_t w_t * C[t, f]; butterfly reduce-scatter over the 32 lanes (rows)
+      // pass 2: pooled[n, f] = sum_t w_t * C[t, f]; butterfly reduce-scatter over the 32 lanes (rows).  The row is
+      // re-read from global (own writes, L2) one chunk ahead of the reduction.
+      const bool live = valid && w != 0.f;
+      uint4 nxt[4];
+      epi_load_chunk(crow, ch_beg * 32, F, live, nxt);
       for (int ch = ch_beg; ch < ch_end; ++ch) {
         const int c0 = ch * 32;
         const int ncols = min(32, F - c0);
+        uint4 cur[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) cur[g] = nxt[g];
+        if (ch + 1 < ch_end) epi_load_chunk(crow, c0 + 32, F, live, nxt);
         float x[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) x[i] = 0.f;
-        if (valid && w != 0.f) {
-          const uint4* src = reinterpret_cast<const uint4*>(crow + c0);
-          const int nv = ncols == 32 ? 4 : 2;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (g < nv) {
-              const uint4 u = src[g];
-              x[g * 8 + 0] = w * lo16<FP16>(u.x); x[g * 8 + 1] = w * hi16<FP16>(u.x);
-              x[g * 8 + 2] = w * lo16<FP16>(u.y); x[g * 8 + 3] = w * hi16<FP16>(u.y);
-              x[g * 8 + 4] = w * lo16<FP16>(u.z); x[g * 8 + 5] = w * hi16<FP16>(u.z);
-              x[g * 8 + 6] = w * lo16<FP16>(u.w); x[g * 8 + 7] = w * hi16<FP16>(u.w);
-            }
-          }
+        for (int g = 0; g < 4; ++g) {
+          x[g * 8 + 0] = w * lo16<FP16>(cur[g].x); x[g * 8 + 1] = w * hi16<FP16>(cur[g].x);
+          x[g * 8 + 2] = w * lo16<FP16>(cur[g].y); x[g * 8 + 3] = w * hi16<FP16>(cur[g].y);
+          x[g * 8 + 4] = w * lo16<FP16>(cur[g].z); x[g * 8 + 5] = w * hi16<FP16>(cur[g].z);
+          x[g * 8 + 6] = w * lo16<FP16>(cur[g].w); x[g * 8 + 7] = w * hi16<FP16>(cur[g].w);
         }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
@@ -360,6 +449,7 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
         }
         if (n < p.n_titles && lane < ncols) p.pooled[(long long)n * F + c0 + lane] = x[0];
       }
+      if (warp == 8 && lane == 0) TRACE(it, 6);
     }
   }
   __syncthreads();
@@ -379,20 +469,22 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
 //   B[K=token][N=f] : dPre, written by the attention-backward kernel directly as pre-swizzled K-block
 //                     images (64 tokens x ceil(F/64) groups x 128 B), fetched with one bulk copy each.
 // The token range is split over CTA.y; partial sums go to global and are reduced in a fixed order.
-constexpr int WG_KTOK = 64;                         // tokens (K rows) per pipeline stage = 2 title slots
-constexpr int WG_GROUP_BYTES = WG_KTOK * 128;       // one 64-element group of one stage: 8 KB
+constexpr int WG_KTOK = 32;                         // tokens (K rows) per pipeline stage = one title slot
+constexpr int WG_GROUP_BYTES = WG_KTOK * 128;       // one 64-element group of one stage: 4 KB
 constexpr int WG_A_STAGE_BYTES = 2 * WG_GROUP_BYTES;
-constexpr int WG_STAGES = 3;
+constexpr int WG_STAGES = 6;
 
 struct WgradParams {
   int n_titles, L, F, EC, Ep, V;
   int n_kblocks, kb_per_split, n_slices, ngroups;
+  int cluster;                // CTAs per cluster along x (= slices sharing one dPre stream), 1 = no multicast
   const int* tok;
   const uint16_t* emb;        // (V, Ep)
   const uint16_t* dpre_img;   // n_kblocks * ngroups * 8 KB
   float* partial;             // [splits][n_slices*128][F]
   uint32_t drop_thr16, seed_x;
   float scale;
+  long long* trace;           // optional: accumulated wait cycles of CTA (0,0)'s roles (tools/perf_conv.py)
 };
 
 template <bool FP16>
@@ -406,17 +498,20 @@ __global__ void __launch_bounds__(384, 1) conv_wgrad_tc_kernel(const WgradParams
   const uint32_t b_base = a_base + WG_STAGES * WG_A_STAGE_BYTES;
   const uint32_t misc_base = b_base + WG_STAGES * b_stage_bytes;
   uint8_t* misc_gen = smem_gen + (misc_base - smem_base);
-  const uint32_t bar_full = misc_base, bar_empty = misc_base + 32, bar_t_full = misc_base + 64;
-  uint32_t* tmem_ptr_smem = (uint32_t*)(misc_gen + 80);
+  const uint32_t bar_full = misc_base, bar_empty = misc_base + 64, bar_t_full = misc_base + 128;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(misc_gen + 144);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slice = blockIdx.x, split = blockIdx.y;
+  const int CS = p.cluster;
+  const uint32_t crank = CS > 1 ? cluster_ctarank() : 0;
+  const uint16_t cmask = (uint16_t)((1u << CS) - 1u);
   const int kb_beg = split * p.kb_per_split;
   const int kb_end = min(p.n_kblocks, kb_beg + p.kb_per_split);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < WG_STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 5);    // 4 producer warps + the B loader's expect_tx arrival
-      mbar_init(bar_empty + 8 * s, 1);   // tcgen05.commit
+      mbar_init(bar_empty + 8 * s, CS);  // tcgen05.commit from every CTA of the cluster (stage reused cluster-wide)
     }
     mbar_init(bar_t_full, 1);
     fence_barrier_init();
@@ -429,19 +524,32 @@ __global__ void __launch_bounds__(384, 1) conv_wgrad_tc_kernel(const WgradParams
   }
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();     // peers' barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int n0 = F > 256 ? 256 : F, n1 = F - n0;
 
   if (warp == 0) {
     if (lane == 0) {
+      // each CTA fetches 1/CS of the dPre block and multicasts it to every CTA of the cluster
+      const uint32_t chunk = ((b_stage_bytes / CS) + 15u) & ~15u;
+      const uint32_t my_off = crank * chunk;
+      const uint32_t my_len = my_off < b_stage_bytes ? min(chunk, b_stage_bytes - my_off) : 0u;
       int s = 0;
       uint32_t ph = 0;
+      long long twl = 0;
       for (int kb = kb_beg; kb < kb_end; ++kb) {
+        long long t0 = clock64();
         mbar_wait(bar_empty + 8 * s, ph ^ 1, 11);
+        twl += clock64() - t0;
+        if (kb + 1 == kb_end && p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[5] = twl;
         mbar_expect_tx(bar_full + 8 * s, b_stage_bytes);
-        bulk_g2s(b_base + s * b_stage_bytes, (const uint8_t*)p.dpre_img + (size_t)kb * b_stage_bytes, b_stage_bytes,
-                 bar_full + 8 * s);
+        const uint8_t* src = (const uint8_t*)p.dpre_img + (size_t)kb * b_stage_bytes + my_off;
+        if (CS > 1) {
+          if (my_len) bulk_g2s_mc(b_base + s * b_stage_bytes + my_off, src, my_len, bar_full + 8 * s, cmask);
+        } else {
+          bulk_g2s(b_base + s * b_stage_bytes, src, b_stage_bytes, bar_full + 8 * s);
+        }
         if (++s == WG_STAGES) { s = 0; ph ^= 1; }
       }
     }
@@ -450,8 +558,11 @@ __global__ void __launch_bounds__(384, 1) conv_wgrad_tc_kernel(const WgradParams
       const uint32_t idesc0 = make_idesc_mn(TILE_M, n0, FP16), idesc1 = make_idesc_mn(TILE_M, n1 > 0 ? n1 : 16, FP16);
       int s = 0;
       uint32_t ph = 0, accum = 0;
+      long long tw = 0, t_start = clock64();
       for (int kb = kb_beg; kb < kb_end; ++kb) {
+        long long t0 = clock64();
         mbar_wait(bar_full + 8 * s, ph, 12);
+        tw += clock64() - t0;
         tc_fence_after();
         const uint32_t a_addr = a_base + s * WG_A_STAGE_BYTES, b_addr = b_base + s * b_stage_bytes;
 #pragma unroll
@@ -463,14 +574,18 @@ __global__ void __launch_bounds__(384, 1) conv_wgrad_tc_kernel(const WgradParams
                       accum);
           accum = 1;
         }
-        umma_commit(bar_empty + 8 * s);
+        if (CS > 1) umma_commit_mc(bar_empty + 8 * s, cmask);
+        else umma_commit(bar_empty + 8 * s);
         if (++s == WG_STAGES) { s = 0; ph ^= 1; }
       }
       umma_commit(bar_t_full);
+      if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) { p.trace[0] = tw; p.trace[1] = clock64() - t_start; p.trace[2] = kb_end - kb_beg; }
     }
   } else if (warp >= 4 && warp < 8) {
-    // A producers: rows = tokens of the K block, two 64-column chunks (u0,u1) of this CTA's (tap, e) slice
-    const int pw = warp - 4, rsub = lane >> 3, piece = lane & 7;
+    // A producers: one K block = the 32 token rows of title n = kb; thread -> (row r, piece pair q): 16-byte pieces
+    // 2q, 2q+1 of both 64-column chunks (u0,u1) of this CTA's (tap, e) slice.  Next block's ids / rows are prefetched.
+    const int pt = threadIdx.x - 128;          // 0..127
+    const int r = pt >> 2, q = pt & 3;
     int uj[2], uc[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -478,58 +593,68 @@ __global__ void __launch_bounds__(384, 1) conv_wgrad_tc_kernel(const WgradParams
       uj[i] = u < TAPS * p.EC ? u / p.EC : -1;
       uc[i] = u < TAPS * p.EC ? u % p.EC : 0;
     }
+    auto load_id = [&](int kb) {
+      int id = -1;
+      if (kb < kb_end && kb < p.n_titles && r < p.L) {
+        id = p.tok[(long long)kb * p.L + r];
+        id = (id < 0 || id >= p.V) ? 0 : id;
+      }
+      return id;
+    };
+    auto load_rows = [&](int id, uint4* v) {
+#pragma unroll
+      for (int ui = 0; ui < 2; ++ui)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          v[ui * 2 + h] = make_uint4(0, 0, 0, 0);
+          if (id >= 0 && uj[ui] >= 0)
+            v[ui * 2 + h] = __ldg((const uint4*)(p.emb + (long long)id * p.Ep + uc[ui] * EPAD + (2 * q + h) * 8));
+        }
+    };
     int s = 0;
     uint32_t ph = 0;
+    long long twait = 0, t_start = clock64();
+    int id = load_id(kb_beg), id_next = load_id(kb_beg + 1);
+    uint4 v[4], v_next[4];
+    load_rows(id, v_next);
     for (int kb = kb_beg; kb < kb_end; ++kb) {
-      int ids[4];
-      long long mrow[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = pw * 16 + 4 * i + rsub;
-        const long long R = (long long)kb * WG_KTOK + r;
-        const int n = (int)(R / SLOT), t = (int)(R % SLOT);
-        int id = -1;
-        if (n < p.n_titles && t < p.L) {
-          id = p.tok[(long long)n * p.L + t];
-          id = (id < 0 || id >= p.V) ? 0 : id;
-        }
-        ids[i] = id;
-        mrow[i] = (long long)n * p.L + t;
-      }
-      mbar_wait(bar_empty + 8 * s, ph ^ 1, 13);
-      const uint32_t stage = a_base + s * WG_A_STAGE_BYTES;
+      for (int i = 0; i < 4; ++i) v[i] = v_next[i];
+      const int id_cur = id;
+      id = id_next;
+      load_rows(id, v_next);
+      id_next = load_id(kb + 2);
+      if (p.drop_thr16 && id_cur >= 0) {
+        const uint64_t mrow = (uint64_t)kb * p.L + r;
 #pragma unroll
-      for (int ui = 0; ui < 2; ++ui) {
-        uint4 v[4];
+        for (int ui = 0; ui < 2; ++ui) {
+          if (uj[ui] < 0) continue;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          v[i] = make_uint4(0, 0, 0, 0);
-          if (ids[i] >= 0 && uj[ui] >= 0)
-            v[i] = __ldg((const uint4*)(p.emb + (long long)ids[i] * p.Ep + uc[ui] * KBLK + piece * 8));
-        }
-        if (p.drop_thr16 && uj[ui] >= 0) {
+          for (int h = 0; h < 2; ++h) {
+            const uint64_t pair0 = (mrow * (uint64_t)p.Ep + (uint64_t)(uc[ui] * EPAD + (2 * q + h) * 8)) >> 1;
+            uint32_t* w = reinterpret_cast<uint32_t*>(&v[ui * 2 + h]);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (ids[i] < 0) continue;
-            const uint64_t pair0 = ((uint64_t)mrow[i] * (uint64_t)p.Ep + (uint64_t)(uc[ui] * KBLK + piece * 8)) >> 1;
-            uint32_t* w = reinterpret_cast<uint32_t*>(&v[i]);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint32_t h = rng_u32(p.seed_x, pair0 + q);
-              uint32_t m = ((h & 0xffffu) >= p.drop_thr16 ? 0x0000ffffu : 0u) | ((h >> 16) >= p.drop_thr16 ? 0xffff0000u : 0u);
-              w[q] &= m;
+            for (int x = 0; x < 4; ++x) {
+              uint32_t hsh = rng_u32(p.seed_x, pair0 + x);
+              uint32_t m = ((hsh & 0xffffu) >= p.drop_thr16 ? 0x0000ffffu : 0u) | ((hsh >> 16) >= p.drop_thr16 ? 0xffff0000u : 0u);
+              w[x] &= m;
             }
           }
         }
-        const int j = uj[ui] < 0 ? 1 : uj[ui];
+      }
+      long long t0 = clock64();
+      mbar_wait(bar_empty + 8 * s, ph ^ 1, 13);
+      twait += clock64() - t0;
+      const uint32_t stage = a_base + s * WG_A_STAGE_BYTES;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = pw * 16 + 4 * i + rsub;
-          const int rr = (r + 1 - j) & (WG_KTOK - 1);
-          const uint32_t addr = stage + ui * WG_GROUP_BYTES + rr * 128 + ((piece ^ (rr & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v[i].x), "r"(v[i].y), "r"(v[i].z),
-                       "r"(v[i].w)
-                       : "memory");
+      for (int ui = 0; ui < 2; ++ui) {
+        const int j = uj[ui] < 0 ? 1 : uj[ui];
+        const int rr = (r + 1 - j) & (WG_KTOK - 1);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t addr = stage + ui * WG_GROUP_BYTES + rr * 128 + (((2 * q + h) ^ (rr & 7)) << 4);
+          const uint4 x = v[ui * 2 + h];
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w) : "memory");
         }
       }
       fence_proxy_async();
@@ -537,6 +662,7 @@ __global__ void __launch_bounds__(384, 1) conv_wgrad_tc_kernel(const WgradParams
       if (lane == 0) mbar_arrive(bar_full + 8 * s);
       if (++s == WG_STAGES) { s = 0; ph ^= 1; }
     }
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && pt == 0) { p.trace[3] = twait; p.trace[4] = clock64() - t_start; }
   } else if (warp >= 8) {
     // epilogue (once): TMEM -> scaled fp32 partial sums in global memory
     const int q = warp & 3;
@@ -567,6 +693,7 @@ __global__ void __launch_bounds__(384, 1) conv_wgrad_tc_kernel(const WgradParams
     tc_fence_before();
   }
   __syncthreads();
+  if (CS > 1) cluster_sync_all();     // no CTA leaves while peers may still multicast into it / arrive on its barriers
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
@@ -597,7 +724,7 @@ using namespace lstur;
 extern "C" int lstur_conv_tc_available(void) { return 1; }
 
 // Padded embedding width (multiple of the 64-element K block).
-extern "C" int lstur_tc_padded_e(int E) { return (E + tc::KBLK - 1) / tc::KBLK * tc::KBLK; }
+extern "C" int lstur_tc_padded_e(int E) { return (E + tc::EPAD - 1) / tc::EPAD * tc::EPAD; }
 // Elements (bf16) of the packed conv-weight image.
 extern "C" long long lstur_tc_wimg_elems(int E, int F) {
   return (long long)(lstur_tc_padded_e(E) / tc::KBLK) * tc::TAPS * F * tc::KBLK;
@@ -629,6 +756,10 @@ extern "C" int lstur_tc_supported(int L, int E, int F, int KS) {
          (F <= 256 || F - 256 >= 16);
 }
 
+static void* g_tc_trace_ptr = nullptr;
+// Debug/profiling hook: device buffer of 8*16 int64 receiving clock64() stamps of CTA 0's warp roles (NULL = off).
+extern "C" int lstur_tc_set_trace(void* dev_buf) { g_tc_trace_ptr = dev_buf; return LSTUR_OK; }
+
 // Fused news-encoder forward (k1-k6): tokens (n_titles,L) -> C (bf16, saved), pooled (n_titles,F), att a / w.
 extern "C" int lstur_news_conv_tc_fwd(int n_titles, int L, int E, int F, int V, const int* tokens, const void* emb_bf16,
                                       const void* wimg, const float* conv_b, const float* att_w, const float* att_b,
@@ -645,14 +776,16 @@ extern "C" int lstur_news_conv_tc_fwd(int n_titles, int L, int E, int F, int V, 
   p.drop_thr16 = dropout > 0.f ? (uint32_t)(dropout * 65536.0f) : 0u;
   p.inv_keep = 1.f / (1.f - dropout);
   p.seed_x = seed * 2u; p.seed_c = seed * 2u + 1u;
-  size_t smem = 1024 + (size_t)tc::NUM_A_STAGES * tc::A_STAGE_BYTES + (size_t)tc::NUM_B_STAGES * F * 128 + 128 + 4096 +
+  p.trace = (long long*)g_tc_trace_ptr;
+  size_t smem = 1024 + (size_t)tc::NUM_A_STAGES * tc::A_STAGE_BYTES + (size_t)tc::NUM_B_STAGES * F * tc::ROWB + 256 + 4096 +
                 (size_t)2 * F * sizeof(float);
   static bool attr_set = false;
   static size_t attr_smem = 0;
   if (!attr_set || smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(tc::news_conv_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tc::news_conv_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tc::news_conv_tc_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::news_conv_tc_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::news_conv_tc_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::news_conv_tc_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("lstur_news_conv_tc_fwd: cannot opt in to %zu B of shared memory: %s", smem, cudaGetErrorString(e));
       return LSTUR_ERR_CUDA;
@@ -665,8 +798,11 @@ extern "C" int lstur_news_conv_tc_fwd(int n_titles, int L, int E, int F, int V, 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   int grid = n_tiles < sms ? n_tiles : sms;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  if (fp16) tc::news_conv_tc_fwd_kernel<true><<<grid, tc::THREADS, smem, stream>>>(p);
-  else tc::news_conv_tc_fwd_kernel<false><<<grid, tc::THREADS, smem, stream>>>(p);
+  const bool drop = p.drop_thr16 != 0;
+  if (fp16 && drop) tc::news_conv_tc_fwd_kernel<true, true><<<grid, tc::THREADS, smem, stream>>>(p);
+  else if (fp16) tc::news_conv_tc_fwd_kernel<true, false><<<grid, tc::THREADS, smem, stream>>>(p);
+  else if (drop) tc::news_conv_tc_fwd_kernel<false, true><<<grid, tc::THREADS, smem, stream>>>(p);
+  else tc::news_conv_tc_fwd_kernel<false, false><<<grid, tc::THREADS, smem, stream>>>(p);
   LSTUR_CHECK_LAUNCH("lstur_news_conv_tc_fwd");
   return LSTUR_OK;
 }
@@ -691,7 +827,7 @@ extern "C" int lstur_news_encoder_tc_fwd_internal(const lstur_plan* p, const lst
 
 
 // ---- wgrad host side ------------------------------------------------------------------------------
-extern "C" int lstur_tc_wgrad_kblocks(int n_titles) { return (n_titles * tc::SLOT + tc::WG_KTOK - 1) / tc::WG_KTOK; }
+extern "C" int lstur_tc_wgrad_kblocks(int n_titles) { return n_titles; }   // one 32-row slot = one K block
 extern "C" int lstur_tc_wgrad_groups(int F) { return (F + 63) / 64; }
 // bytes of the dPre image consumed by lstur_conv_wgrad_tc
 extern "C" size_t lstur_tc_dpre_img_bytes(int n_titles, int F) {
@@ -722,7 +858,7 @@ extern "C" int lstur_conv_wgrad_tc(int n_titles, int L, int E, int F, int V, con
     return LSTUR_OK;
   }
   tc::WgradParams p;
-  p.n_titles = n_titles; p.L = L; p.F = F; p.Ep = lstur_tc_padded_e(E); p.EC = p.Ep / tc::KBLK; p.V = V;
+  p.n_titles = n_titles; p.L = L; p.F = F; p.Ep = lstur_tc_padded_e(E); p.EC = p.Ep / tc::EPAD; p.V = V;
   p.n_kblocks = lstur_tc_wgrad_kblocks(n_titles);
   p.n_slices = (tc::TAPS * p.Ep + tc::TILE_M - 1) / tc::TILE_M;
   int splits = lstur_tc_wgrad_splits(n_titles, E);
@@ -734,6 +870,7 @@ extern "C" int lstur_conv_wgrad_tc(int n_titles, int L, int E, int F, int V, con
   p.drop_thr16 = dropout > 0.f ? (uint32_t)(dropout * 65536.0f) : 0u;
   p.seed_x = seed * 2u;
   p.scale = 1.f / (1.f - dropout);
+  p.trace = (long long*)g_tc_trace_ptr;
   size_t smem = 1024 + (size_t)tc::WG_STAGES * (tc::WG_A_STAGE_BYTES + (size_t)p.ngroups * tc::WG_GROUP_BYTES) + 256;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
@@ -746,9 +883,50 @@ extern "C" int lstur_conv_wgrad_tc(int n_titles, int L, int E, int F, int V, con
     }
     attr_smem = smem;
   }
-  dim3 grid(p.n_slices, splits);
-  if (fp16) tc::conv_wgrad_tc_kernel<true><<<grid, 384, smem, stream>>>(p);
-  else tc::conv_wgrad_tc_kernel<false><<<grid, 384, smem, stream>>>(p);
+  // Cluster multicast of the dPre stream (one L2 read for all slices) is correct but measured SLOWER on B200
+  // (only 15 clusters of 8 fit in one wave and the slices run in lockstep): off unless LSTUR_MULTICAST=1.
+  p.cluster = (p.n_slices >= 2 && p.n_slices <= 8 && getenv("LSTUR_MULTICAST")) ? p.n_slices : 1;
+  if (p.cluster > 1) {
+    // all clusters must be co-resident in ONE wave (a cluster needs `cluster` SMs of the same GPC): ask the runtime
+    static int max_clusters[9] = {0};
+    if (!max_clusters[p.cluster]) {
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(p.cluster, 1);
+      q.blockDim = dim3(384);
+      q.dynamicSmemBytes = smem;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = p.cluster; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa; q.numAttrs = 1;
+      int nc = 0;
+      cudaError_t e = fp16 ? cudaOccupancyMaxActiveClusters(&nc, tc::conv_wgrad_tc_kernel<true>, &q)
+                           : cudaOccupancyMaxActiveClusters(&nc, tc::conv_wgrad_tc_kernel<false>, &q);
+      if (e != cudaSuccess || nc < 1) { cudaGetLastError(); nc = 1; p.cluster = 1; }
+      max_clusters[p.cluster] = nc;
+    }
+    if (p.cluster > 1 && splits > max_clusters[p.cluster]) splits = max_clusters[p.cluster];
+    p.kb_per_split = (p.n_kblocks + splits - 1) / splits;
+  }
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.n_slices, splits);
+    cfg.blockDim = dim3(384);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = p.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = fp16 ? cudaLaunchKernelEx(&cfg, tc::conv_wgrad_tc_kernel<true>, p)
+                         : cudaLaunchKernelEx(&cfg, tc::conv_wgrad_tc_kernel<false>, p);
+    if (e != cudaSuccess) {
+      set_error("lstur_conv_wgrad_tc: launch failed: %s", cudaGetErrorString(e));
+      return LSTUR_ERR_CUDA;
+    }
+  }
   LSTUR_CHECK_LAUNCH("lstur_conv_wgrad_tc");
   long long n = (long long)3 * E * F;
   tc::wgrad_reduce_kernel<<<cdiv(n, 256), 256, 0, stream>>>(E, p.Ep, F, splits, p.n_slices * tc::TILE_M, p.partial, d_conv_w);

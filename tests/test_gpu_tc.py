@@ -187,12 +187,9 @@ def dpre_image(dpre, fp16=1):
     """numpy restatement of the K-block image layout documented in csrc/attn.cu (store_dpre_img)."""
     N, L, F = dpre.shape
     ng = (F + 63) // 64
-    nkb = (N * 32 + 63) // 64
-    img = np.zeros(nkb * ng * 8192 // 2, dtype=np.float16 if fp16 else np.uint16)
+    img = np.zeros(N * ng * 4096 // 2, dtype=np.float16 if fp16 else np.uint16)
     n, t, f = np.meshgrid(np.arange(N), np.arange(L), np.arange(F), indexing='ij')
-    R = n * 32 + t
-    kb, k = R >> 6, R & 63
-    byte = kb * (ng * 8192) + (f >> 6) * 8192 + k * 128 + ((((f & 63) >> 3) ^ (k & 7)) << 4) + (f & 7) * 2
+    byte = n * (ng * 4096) + (f >> 6) * 4096 + t * 128 + ((((f & 63) >> 3) ^ (t & 7)) << 4) + (f & 7) * 2
     if fp16:
         img[byte.ravel() // 2] = dpre.astype(np.float16).ravel()
     else:
