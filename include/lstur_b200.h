@@ -153,6 +153,23 @@ int lstur_gru_fwd(int B, int W, int G, const float* XW, const float* gm, const f
 int lstur_gru_bwd(int B, int W, int G, const float* gm, const float* Z, const float* R, const float* HH,
                   const float* HP, const float* WhT, int rec_act, const float* dhT, long long lddh, float* dA,
                   float* dh0, long long lddh0, cudaStream_t stream);
+/* The two implementations behind lstur_gru_fwd/bwd.  _cluster: recurrent weights resident in the shared memory of a
+ * thread-block cluster for the whole launch, state exchanged through distributed shared memory (gru_cl.cu);
+ * row_order (B) optionally permutes the batch rows inside the kernel (length-sorted tiles skip padded steps) or NULL.
+ * _streaming: weights streamed from L2 every step (any G <= 1024). */
+int lstur_gru_cluster_supported(int B, int W, int G);
+int lstur_gru_fwd_cluster(int B, int W, int G, const float* XW, const float* gm, const float* h0, long long ldh0,
+                          const float* Wh, int rec_act, float* hT, long long ldo, float* Z, float* R, float* HH,
+                          float* HP, float* RH, const int* row_order, cudaStream_t stream);
+int lstur_gru_bwd_cluster(int B, int W, int G, const float* gm, const float* Z, const float* R, const float* HH,
+                          const float* HP, const float* WhT, int rec_act, const float* dhT, long long lddh, float* dA,
+                          float* dh0, long long lddh0, const int* row_order, cudaStream_t stream);
+int lstur_gru_fwd_streaming(int B, int W, int G, const float* XW, const float* gm, const float* h0, long long ldh0,
+                            const float* Wh, int rec_act, float* hT, long long ldo, float* Z, float* R, float* HH,
+                            float* HP, float* RH, cudaStream_t stream);
+int lstur_gru_bwd_streaming(int B, int W, int G, const float* gm, const float* Z, const float* R, const float* HH,
+                            const float* HP, const float* WhT, int rec_act, const float* dhT, long long lddh,
+                            float* dA, float* dh0, long long lddh0, cudaStream_t stream);
 
 /* dot scorer + softmax + categorical_crossentropy fwd(+bwd) (task/paper.py:446-447, 460-464, 657);
  * sigmoid test head (task/paper.py:661-665). */

@@ -304,11 +304,11 @@ extern "C" int lstur_transpose(int rows, int cols, const float* in, float* out, 
 
 // XW (B,W,3G) = H.Wx + b precomputed; h0 may be NULL (zeros).  Z,R,HH,HP,RH are
 // (B,W,G) saved tensors for the backward pass, all NULL for inference.
-extern "C" int lstur_gru_fwd(int B, int W, int G, const float* XW, const float* gm, const float* h0, long long ldh0,
+extern "C" int lstur_gru_fwd_streaming(int B, int W, int G, const float* XW, const float* gm, const float* h0, long long ldh0,
                              const float* Wh, int rec_act, float* hT, long long ldo, float* Z, float* R, float* HH,
                              float* HP, float* RH, cudaStream_t stream) {
-  LSTUR_REQUIRE(B >= 0 && W > 0 && G > 0 && G % 4 == 0 && G <= 1024, "lstur_gru_fwd");
-  LSTUR_REQUIRE((Z && R && HH && HP && RH) || (!Z && !R && !HH && !HP && !RH), "lstur_gru_fwd");
+  LSTUR_REQUIRE(B >= 0 && W > 0 && G > 0 && G % 4 == 0 && G <= 1024, "lstur_gru_fwd_streaming");
+  LSTUR_REQUIRE((Z && R && HH && HP && RH) || (!Z && !R && !HH && !HP && !RH), "lstur_gru_fwd_streaming");
   if (B == 0) return LSTUR_OK;
   int threads = cdiv(G, 32) * 32;
   size_t smem = (size_t)2 * GRU_BT * G * sizeof(float);
@@ -316,14 +316,14 @@ extern "C" int lstur_gru_fwd(int B, int W, int G, const float* XW, const float* 
     cudaFuncSetAttribute(gru_fwd_kernel<GRU_BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   gru_fwd_kernel<GRU_BT><<<cdiv(B, GRU_BT), threads, smem, stream>>>(B, W, G, XW, gm, h0, ldh0, Wh, rec_act, hT, ldo, Z,
                                                                       R, HH, HP, RH);
-  LSTUR_CHECK_LAUNCH("lstur_gru_fwd");
+  LSTUR_CHECK_LAUNCH("lstur_gru_fwd_streaming");
   return LSTUR_OK;
 }
 
-extern "C" int lstur_gru_bwd(int B, int W, int G, const float* gm, const float* Z, const float* R, const float* HH,
+extern "C" int lstur_gru_bwd_streaming(int B, int W, int G, const float* gm, const float* Z, const float* R, const float* HH,
                              const float* HP, const float* WhT, int rec_act, const float* dhT, long long lddh,
                              float* dA, float* dh0, long long lddh0, cudaStream_t stream) {
-  LSTUR_REQUIRE(B >= 0 && W > 0 && G > 0 && G % 4 == 0 && G <= 1024, "lstur_gru_bwd");
+  LSTUR_REQUIRE(B >= 0 && W > 0 && G > 0 && G % 4 == 0 && G <= 1024, "lstur_gru_bwd_streaming");
   if (B == 0) return LSTUR_OK;
   int threads = cdiv(G, 32) * 32;
   size_t smem = (size_t)3 * GRU_BT * G * sizeof(float);
@@ -331,6 +331,23 @@ extern "C" int lstur_gru_bwd(int B, int W, int G, const float* gm, const float* 
     cudaFuncSetAttribute(gru_bwd_kernel<GRU_BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   gru_bwd_kernel<GRU_BT><<<cdiv(B, GRU_BT), threads, smem, stream>>>(B, W, G, gm, Z, R, HH, HP, WhT, rec_act, dhT, lddh,
                                                                       dA, dh0, lddh0);
-  LSTUR_CHECK_LAUNCH("lstur_gru_bwd");
+  LSTUR_CHECK_LAUNCH("lstur_gru_bwd_streaming");
   return LSTUR_OK;
+}
+
+// Dispatchers: shared-memory-resident cluster kernels (gru_cl.cu) when the shape fits, else the streaming kernels.
+extern "C" int lstur_gru_fwd(int B, int W, int G, const float* XW, const float* gm, const float* h0, long long ldh0,
+                             const float* Wh, int rec_act, float* hT, long long ldo, float* Z, float* R, float* HH,
+                             float* HP, float* RH, cudaStream_t stream) {
+  if (lstur_gru_cluster_supported(B, W, G))
+    return lstur_gru_fwd_cluster(B, W, G, XW, gm, h0, ldh0, Wh, rec_act, hT, ldo, Z, R, HH, HP, RH, nullptr, stream);
+  return lstur_gru_fwd_streaming(B, W, G, XW, gm, h0, ldh0, Wh, rec_act, hT, ldo, Z, R, HH, HP, RH, stream);
+}
+
+extern "C" int lstur_gru_bwd(int B, int W, int G, const float* gm, const float* Z, const float* R, const float* HH,
+                             const float* HP, const float* WhT, int rec_act, const float* dhT, long long lddh,
+                             float* dA, float* dh0, long long lddh0, cudaStream_t stream) {
+  if (lstur_gru_cluster_supported(B, W, G))
+    return lstur_gru_bwd_cluster(B, W, G, gm, Z, R, HH, HP, WhT, rec_act, dhT, lddh, dA, dh0, lddh0, nullptr, stream);
+  return lstur_gru_bwd_streaming(B, W, G, gm, Z, R, HH, HP, WhT, rec_act, dhT, lddh, dA, dh0, lddh0, stream);
 }

@@ -181,6 +181,12 @@ def test_gradients_match_autograd(L, arch):
         if g is None:
             continue
         assert k in got, k
+        if k == 'att_b':
+            # scalar sum of d a over every token: the softmax constraint makes its terms cancel almost exactly, so the
+            # error is bounded against the scale of the un-cancelled sibling d att_w (same terms weighted by C)
+            scale = max(abs(float(g)), float(np.abs(ref['att_w'].numpy()).max()))
+            assert abs(float(np.asarray(got[k]).reshape(-1)[0]) - float(g)) < 5e-5 * scale, k
+            continue
         assert rel(got[k], g.numpy()) < 5e-5, k
 
 
