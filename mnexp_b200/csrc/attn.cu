@@ -69,12 +69,14 @@ __device__ __forceinline__ float ldc(const __nv_bfloat16* p, long long i) { retu
 __device__ __forceinline__ float ldc(const __half* p, long long i) { return __half2float(p[i]); }
 
 // OUT = 0: dPre as fp32 rows (title stride dpre_title_stride, rows L..Lrows-1 zeroed).
-// OUT = 1/2: dPre as bf16/fp16 K-block images for the tensor-core wgrad (conv_tc.cu): slot row R = n*32+t lives in
-//   block n (one 32-row title slot) at  (f/64)*4096 + t*128 + ((((f%64)/8) ^ (t%8)) << 4) + (f%8)*2  — MN-major
-//   SWIZZLE_128B.
-__device__ __forceinline__ void store_dpre_img(void* img, int out_mode, int ngroups, int n, int t, int f, float v) {
-  const long long byte = (long long)n * ((long long)ngroups * 4096) + (long long)(f >> 6) * 4096 + t * 128 +
-                         ((((f & 63) >> 3) ^ (t & 7)) << 4) + (f & 7) * 2;
+// OUT = 1/2: dPre as bf16/fp16 K-block images for the tensor-core wgrad (conv_tc.cu): one block per 32-row title
+//   slot n, [half h = f / (F/2)][64-column group g][32 rows][128 B]; with fl = f - h*F/2 the element lives at
+//   ((h*ngh + fl/64)*4096 + t*128 + ((((fl%64)/8) ^ (t%8)) << 4) + (fl%8)*2  — MN-major SWIZZLE_128B, one half per CTA of
+//   the wgrad's CTA pair.  ngh = ceil(F/2/64).
+__device__ __forceinline__ void store_dpre_img(void* img, int out_mode, int ngh, int Fh, int n, int t, int f, float v) {
+  const int h = f >= Fh ? 1 : 0, fl = f - h * Fh;
+  const long long byte = (long long)n * ((long long)2 * ngh * 4096) + (long long)(h * ngh + (fl >> 6)) * 4096 + t * 128 +
+                         ((((fl & 63) >> 3) ^ (t & 7)) << 4) + (fl & 7) * 2;
   if (out_mode == 2) *reinterpret_cast<__half*>((char*)img + byte) = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
   else *reinterpret_cast<__nv_bfloat16*>((char*)img + byte) = __float2bfloat16_rn(v);
 }
@@ -121,13 +123,13 @@ attn_pool_bwd_kernel(int N, int L, int Lrows, int F, const CT* __restrict__ Cd, 
           float g = fmaf(sw[t], dpf, sdz[t] * kaf);
           float dpre = c > 0.f ? g * inv_keep : 0.f;
           if (OUT == 0) dPn[(long long)t * F + f] = dpre;
-          else store_dpre_img(dPre, OUT, (F + 63) >> 6, n, t, f, dpre);
+          else store_dpre_img(dPre, OUT, ((F >> 1) + 63) >> 6, F >> 1, n, t, f, dpre);
           dka[i] = fmaf(sdz[t], c, dka[i]);
           dbc[i] += dpre;
         }
         for (int t = L; t < Lrows; ++t) {
           if (OUT == 0) dPn[(long long)t * F + f] = 0.f;
-          else store_dpre_img(dPre, OUT, (F + 63) >> 6, n, t, f, 0.f);
+          else store_dpre_img(dPre, OUT, ((F >> 1) + 63) >> 6, F >> 1, n, t, f, 0.f);
         }
       }
     }
@@ -220,8 +222,8 @@ attn_bwd_img_kernel(int N, int L, int F, const CT* __restrict__ Cd, const float*
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c = tid & 63, tg = tid >> 6;           // chunk owned by this thread, row group (0/1)
   const bool c_ok = c < nchunk;
-  const int ngroups = (F + 63) >> 6;
-  const long long blk_bytes = (long long)ngroups * 4096;
+  const int Fh = F >> 1, ngh = (Fh + 63) >> 6;     // image: [half][group][32 rows][128 B] per title (see store_dpre_img)
+  const long long blk_bytes = (long long)2 * ngh * 4096;
   for (int f = tid; f < F; f += ATT_THREADS) ska[f] = ka[f];
   float dka[8], dbc[8], dba = 0.f;
 #pragma unroll
@@ -258,7 +260,8 @@ attn_bwd_img_kernel(int N, int L, int F, const CT* __restrict__ Cd, const float*
       float dpf[8], kaf[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) { dpf[i] = sdp[c * 8 + i]; kaf[i] = ska[c * 8 + i]; }
-      const int g = c >> 3, piece = c & 7;
+      const int hf = (c * 8 >= Fh) ? 1 : 0, fl = c * 8 - hf * Fh;
+      const int g = hf * ngh + (fl >> 6), piece = (fl & 63) >> 3;
       for (int t = tg; t < 32; t += 2) {
         float o[8];
         if (t < L) {
@@ -420,7 +423,7 @@ extern "C" int lstur_attn_pool_bwd_img(int fp16, int N, int L, int F, const void
                                        const float* w_in, const float* d_pooled, long long lddp, const float* att_w,
                                        void* dpre_img, float dropout, float* d_att_w, float* d_conv_b, float* d_att_b,
                                        int accumulate, float* partials, size_t partial_bytes, cudaStream_t stream) {
-  LSTUR_REQUIRE(N >= 0 && L >= 1 && L <= 31 && F % 8 == 0 && F <= 512 && dpre_img != nullptr, "lstur_attn_pool_bwd_img");
+  LSTUR_REQUIRE(N >= 0 && L >= 1 && L <= 31 && F % 16 == 0 && F <= 512 && dpre_img != nullptr, "lstur_attn_pool_bwd_img");
   int grid = lstur_attn_bwd_grid(N);
   LSTUR_REQUIRE(partials != nullptr && partial_bytes >= (size_t)grid * (2 * F + 1) * sizeof(float), "lstur_attn_pool_bwd_img");
   if (N == 0) {

@@ -18,6 +18,7 @@
 //   consumption order, so one cp.async.bulk (TMA, UBLKCP) per K block lands an MMA-ready tile.
 // Warp roles (512 threads): w0 B loader, w1 TMEM alloc + MMA issuer, w4-7 A producers,
 //   w8-15 epilogue (TMEM lane quarter = warp%4, column half = (warp-8)/4).
+#include <limits.h>
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -276,28 +277,30 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
     const int rsub = lane >> 2, piece = lane & 3;
     int sa = 0;
     uint32_t pha = 0;
+    constexpr int kNoToken = INT_MIN;
     auto load_ids = [&](int tile, int* ids) {
       const int n = tile * TPT + pw;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int t = 8 * i + rsub;
-        int id = -1;
-        if (tile < n_tiles && n < p.n_titles && t < p.L) {
-          id = p.tok[(long long)n * p.L + t];
-          id = (id < 0 || id >= p.V) ? 0 : id;
-        }
-        ids[i] = id;
+        // raw id: not inspected here (no stall on the load); clamped when the rows are requested
+        ids[i] = (tile < n_tiles && n < p.n_titles && t < p.L) ? __ldg(p.tok + (long long)n * p.L + t) : kNoToken;
       }
     };
     auto load_rows = [&](const int* ids, int c, uint4* v) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         v[i] = make_uint4(0, 0, 0, 0);
-        if (ids[i] >= 0) v[i] = __ldg((const uint4*)(p.emb + (long long)ids[i] * p.Ep + c * KBLK + piece * 8));
+        if (ids[i] != kNoToken) {
+          const int id = (ids[i] < 0 || ids[i] >= p.V) ? 0 : ids[i];
+          v[i] = __ldg((const uint4*)(p.emb + (long long)id * p.Ep + c * KBLK + piece * 8));
+        }
       }
     };
     int ids[4], ids_next[4];
     uint4 v[4], v_next[4];
+    uint32_t row_lo[4], row_in0[4], row_in1[4];
+    const uint32_t kseed = 0x9e3779b9u * (p.seed_x + 1u);
     load_ids(blockIdx.x, ids);
     load_rows(ids, 0, v_next);
     int it = 0;
@@ -315,15 +318,25 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
           load_rows(ids_next, 0, v_next);
         }
         if (DROP) {
+          if (c == 0) {   // per tile: pair index of column 0 of each of this thread's rows, inner hash of its high word
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint64_t rowpair = (((uint64_t)n * p.L + (8 * i + rsub)) * (uint64_t)p.Ep) >> 1;
+              const uint32_t hi = (uint32_t)(rowpair >> 32);
+              row_lo[i] = (uint32_t)rowpair;
+              row_in0[i] = lowbias32(hi + kseed);
+              row_in1[i] = row_lo[i] > 0xfffff000u ? lowbias32(hi + 1u + kseed) : row_in0[i];
+            }
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            if (ids[i] < 0) continue;
-            const int t = 8 * i + rsub;
-            const uint64_t pair0 = (((uint64_t)n * p.L + t) * (uint64_t)p.Ep + (uint64_t)(c * KBLK + piece * 8)) >> 1;
+            if (ids[i] == kNoToken) continue;
+            const uint32_t lo0 = row_lo[i] + (uint32_t)((c * KBLK + piece * 8) >> 1);
             uint32_t* w = reinterpret_cast<uint32_t*>(&v[i]);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              uint32_t h = rng_u32(p.seed_x, pair0 + q);
+              const uint32_t lo = lo0 + q;
+              const uint32_t h = lowbias32(lo ^ (lo < row_lo[i] ? row_in1[i] : row_in0[i]));
               uint32_t m = ((h & 0xffffu) >= p.drop_thr16 ? 0x0000ffffu : 0u) | ((h >> 16) >= p.drop_thr16 ? 0xffff0000u : 0u);
               w[q] &= m;
             }
@@ -462,130 +475,152 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
 // =====================================================================================================
 // Conv1D weight gradient on tcgen05:  dW[(j,e), f] = sum_m X[m+j-1, e] * dPre[m, f]
 //   (backward of keras Conv1D, task/paper.py:146; X = dropout(Embedding(tok)), dPre from attn bwd)
-// GEMM view: M = 3*Ep rows (j,e) split in 128-row slices (one per CTA.x), N = F, K = token slot rows.
+// GEMM view: M = 3*Ep rows (j,e) in 128-row slices, N = F, K = token slot rows.
 // Both operands are "MN-major" (the reduction index = token is the slow index of the row-major data):
 //   A[K=token][M=e] : gathered embedding rows — the same 128B-swizzled row image as in the forward, but
 //                     described to the tensor core as MN-major (64-element groups, LBO between groups).
 //   B[K=token][N=f] : dPre, written by the attention-backward kernel directly as pre-swizzled K-block
-//                     images (64 tokens x ceil(F/64) groups x 128 B), fetched with one bulk copy each.
+//                     images, fetched with one bulk copy each.
+// CTA pairs (cta_group::2, M = 256): two adjacent slices share one dPre stream.  Each CTA stages its own A
+// slice and only ITS HALF of dPre's columns (f in [rank*F/2, (rank+1)*F/2)), so the shared-memory traffic per
+// SM (TMA writes + tensor-core operand reads, the limiter of the single-CTA version: 36 KB written + 34 KB read per
+// 400-cycle K block) halves for B; the pair's MMA reads both halves.  Accumulator column c maps to
+//   f = half*Fh + (c % n0h)            for c <  2*n0h   (half = c / n0h,  first MMA,  n0h = min(Fh,128))
+//   f = half*Fh + n0h + (c' % n1h)     for c' = c-2*n0h (half = c'/ n1h,  second MMA, n1h = Fh - n0h).
+// The peer CTA's producer warps arrive directly on the leader's stage-full barrier (remote mbarrier arrive; one of them
+// first waits for the peer's own bulk copy); stage-empty and accumulator-full events come back to both CTAs through
+// the multicast commit.
 // The token range is split over CTA.y; partial sums go to global and are reduced in a fixed order.
-constexpr int WG_KTOK = 32;                         // tokens (K rows) per pipeline stage = one title slot
-constexpr int WG_GROUP_BYTES = WG_KTOK * 128;       // one 64-element group of one stage: 4 KB
-constexpr int WG_A_STAGE_BYTES = 2 * WG_GROUP_BYTES;
-constexpr int WG_STAGES = 6;
+constexpr int WG_KTOK = 32;                         // tokens (K rows) per title slot
+constexpr int WG_GROUP_BYTES = WG_KTOK * 128;       // one 64-element group of one title: 4 KB
+constexpr int WG_A_TILE_BYTES = 2 * WG_GROUP_BYTES; // A of one title: two 64-column chunks
+constexpr int WG_TPS = 2;                           // titles per pipeline stage (amortises the per-stage handshake,
+                                                    // ~500 cycles of issue-thread + commit latency, over 800 MMA cycles)
+constexpr int WG_STAGES = 4;
+constexpr int WG_THREADS = 384;
 
 struct WgradParams {
   int n_titles, L, F, EC, Ep, V;
-  int n_kblocks, kb_per_split, n_slices, ngroups;
-  int cluster;                // CTAs per cluster along x (= slices sharing one dPre stream), 1 = no multicast
+  int n_kblocks, kb_per_split, n_slices, ngh;    // ngh = 64-column groups per F half; kb_per_split % WG_TPS == 0
   const int* tok;
   const uint16_t* emb;        // (V, Ep)
-  const uint16_t* dpre_img;   // n_kblocks * ngroups * 8 KB
+  const uint16_t* dpre_img;   // n_kblocks * 2 * ngh * 4 KB
   float* partial;             // [splits][n_slices*128][F]
   uint32_t drop_thr16, seed_x;
   float scale;
   long long* trace;           // optional: accumulated wait cycles of CTA (0,0)'s roles (tools/perf_conv.py)
+  int dbg;                    // experiments (LSTUR_WGRAD_DBG): 2 = skip all MMAs, 4 = skip bulk copies, 8 = producers only signal
 };
 
 template <bool FP16>
-__global__ void __launch_bounds__(384, 1) conv_wgrad_tc_kernel(const WgradParams p) {
+__global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const int F = p.F;
-  const uint32_t b_stage_bytes = (uint32_t)p.ngroups * WG_GROUP_BYTES;
+  const int F = p.F, Fh = F >> 1;
+  const int n0h = Fh > 128 ? 128 : Fh, n1h = Fh - n0h;
+  const uint32_t b_tile_bytes = (uint32_t)p.ngh * WG_GROUP_BYTES;          // this CTA's half of one title's dPre
+  const uint32_t a_stage_bytes = WG_TPS * WG_A_TILE_BYTES, b_stage_bytes = WG_TPS * b_tile_bytes;
   const uint32_t a_base = smem_base;
-  const uint32_t b_base = a_base + WG_STAGES * WG_A_STAGE_BYTES;
+  const uint32_t b_base = a_base + WG_STAGES * a_stage_bytes;
   const uint32_t misc_base = b_base + WG_STAGES * b_stage_bytes;
   uint8_t* misc_gen = smem_gen + (misc_base - smem_base);
   const uint32_t bar_full = misc_base, bar_empty = misc_base + 64, bar_t_full = misc_base + 128;
   uint32_t* tmem_ptr_smem = (uint32_t*)(misc_gen + 144);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slice = blockIdx.x, split = blockIdx.y;
-  const int CS = p.cluster;
-  const uint32_t crank = CS > 1 ? cluster_ctarank() : 0;
-  const uint16_t cmask = (uint16_t)((1u << CS) - 1u);
+  const uint32_t crank = cluster_ctarank();     // 0 = leader (issues the pair's MMAs)
   const int kb_beg = split * p.kb_per_split;
   const int kb_end = min(p.n_kblocks, kb_beg + p.kb_per_split);
+  const int n_stage_blocks = kb_end > kb_beg ? (kb_end - kb_beg + WG_TPS - 1) / WG_TPS : 0;
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < WG_STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 5);    // 4 producer warps + the B loader's expect_tx arrival
-      mbar_init(bar_empty + 8 * s, CS);  // tcgen05.commit from every CTA of the cluster (stage reused cluster-wide)
+      // leader: its 8 producer warps + its B loader's expect_tx arrival + the 8 producer warps of the peer (remote
+      // arrives; the peer's warp 4 first waits for the peer's own bulk copies).  peer: only its B loader's expect_tx.
+      mbar_init(bar_full + 8 * s, crank == 0 ? 17 : 1);
+      mbar_init(bar_empty + 8 * s, 1);   // multicast tcgen05.commit of the leader
     }
     mbar_init(bar_t_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
                  "r"(TMEM_COLS)
                  : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
-  if (CS > 1) cluster_sync_all();     // peers' barriers are initialised before any multicast / remote arrive
+  cluster_sync_all();     // both CTAs' barriers and tensor memory exist before any remote arrive / pair MMA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const int n0 = F > 256 ? 256 : F, n1 = F - n0;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // each CTA fetches 1/CS of the dPre block and multicasts it to every CTA of the cluster
-      const uint32_t chunk = ((b_stage_bytes / CS) + 15u) & ~15u;
-      const uint32_t my_off = crank * chunk;
-      const uint32_t my_len = my_off < b_stage_bytes ? min(chunk, b_stage_bytes - my_off) : 0u;
+    if (lane == 0) {   // B loader: this CTA's half of the dPre columns of the WG_TPS titles of every stage
       int s = 0;
       uint32_t ph = 0;
       long long twl = 0;
-      for (int kb = kb_beg; kb < kb_end; ++kb) {
-        long long t0 = clock64();
+      for (int sb = 0; sb < n_stage_blocks; ++sb) {
+        long long t0 = tracing ? clock64() : 0;
         mbar_wait(bar_empty + 8 * s, ph ^ 1, 11);
-        twl += clock64() - t0;
-        if (kb + 1 == kb_end && p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[5] = twl;
-        mbar_expect_tx(bar_full + 8 * s, b_stage_bytes);
-        const uint8_t* src = (const uint8_t*)p.dpre_img + (size_t)kb * b_stage_bytes + my_off;
-        if (CS > 1) {
-          if (my_len) bulk_g2s_mc(b_base + s * b_stage_bytes + my_off, src, my_len, bar_full + 8 * s, cmask);
+        if (tracing) { twl += clock64() - t0; p.trace[5] = twl; }
+        if (p.dbg & 4) {
+          mbar_arrive(bar_full + 8 * s);
         } else {
-          bulk_g2s(b_base + s * b_stage_bytes, src, b_stage_bytes, bar_full + 8 * s);
+          mbar_expect_tx(bar_full + 8 * s, b_stage_bytes);
+#pragma unroll
+          for (int t = 0; t < WG_TPS; ++t) {
+            // a title past the end re-reads the last valid block: finite values, multiplied by the zero A rows
+            const int kb = min(kb_beg + sb * WG_TPS + t, p.n_kblocks - 1);
+            const uint8_t* src = (const uint8_t*)p.dpre_img + ((size_t)kb * 2 + crank) * b_tile_bytes;
+            bulk_g2s(b_base + s * b_stage_bytes + t * b_tile_bytes, src, b_tile_bytes, bar_full + 8 * s);
+          }
         }
         if (++s == WG_STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc0 = make_idesc_mn(TILE_M, n0, FP16), idesc1 = make_idesc_mn(TILE_M, n1 > 0 ? n1 : 16, FP16);
+    if (lane == 0 && crank == 0) {   // MMA issuer of the pair
+      const uint32_t idesc0 = make_idesc_mn(2 * TILE_M, 2 * n0h, FP16), idesc1 = make_idesc_mn(2 * TILE_M, n1h > 0 ? 2 * n1h : 16, FP16);
+      const uint32_t b1_off = (uint32_t)(n0h / 64) * WG_GROUP_BYTES;
       int s = 0;
       uint32_t ph = 0, accum = 0;
-      long long tw = 0, t_start = clock64();
-      for (int kb = kb_beg; kb < kb_end; ++kb) {
-        long long t0 = clock64();
+      long long tw = 0, t_start = tracing ? clock64() : 0;
+      for (int sb = 0; sb < n_stage_blocks; ++sb) {
+        long long t0 = tracing ? clock64() : 0;
         mbar_wait(bar_full + 8 * s, ph, 12);
-        tw += clock64() - t0;
+        if (tracing) tw += clock64() - t0;
         tc_fence_after();
-        const uint32_t a_addr = a_base + s * WG_A_STAGE_BYTES, b_addr = b_base + s * b_stage_bytes;
+        if (!(p.dbg & 2)) {
 #pragma unroll
-        for (int kk = 0; kk < WG_KTOK / 16; ++kk) {
-          const uint64_t ad = make_desc_mn128(a_addr + kk * 2048, WG_GROUP_BYTES);
-          umma_bf16(tmem_base, ad, make_desc_mn128(b_addr + kk * 2048, WG_GROUP_BYTES), idesc0, accum);
-          if (n1 > 0)
-            umma_bf16(tmem_base + n0, ad, make_desc_mn128(b_addr + 4 * WG_GROUP_BYTES + kk * 2048, WG_GROUP_BYTES), idesc1,
-                      accum);
-          accum = 1;
+          for (int t = 0; t < WG_TPS; ++t) {
+            const uint32_t a_addr = a_base + s * a_stage_bytes + t * WG_A_TILE_BYTES;
+            const uint32_t b_addr = b_base + s * b_stage_bytes + t * b_tile_bytes;
+#pragma unroll
+            for (int kk = 0; kk < WG_KTOK / 16; ++kk) {
+              const uint64_t ad = make_desc_mn128(a_addr + kk * 2048, WG_GROUP_BYTES);
+              umma_f16_2cta(tmem_base, ad, make_desc_mn128(b_addr + kk * 2048, WG_GROUP_BYTES), idesc0, accum);
+              if (n1h > 0)
+                umma_f16_2cta(tmem_base + 2 * n0h, ad, make_desc_mn128(b_addr + b1_off + kk * 2048, WG_GROUP_BYTES), idesc1, accum);
+              accum = 1;
+            }
+          }
         }
-        if (CS > 1) umma_commit_mc(bar_empty + 8 * s, cmask);
-        else umma_commit(bar_empty + 8 * s);
+        umma_commit_2cta(bar_empty + 8 * s, 3);
         if (++s == WG_STAGES) { s = 0; ph ^= 1; }
       }
-      umma_commit(bar_t_full);
-      if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) { p.trace[0] = tw; p.trace[1] = clock64() - t_start; p.trace[2] = kb_end - kb_beg; }
+      umma_commit_2cta(bar_t_full, 3);
+      if (tracing) { p.trace[0] = tw; p.trace[1] = clock64() - t_start; p.trace[2] = n_stage_blocks; }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // A producers: one K block = the 32 token rows of title n = kb; thread -> (row r, piece pair q): 16-byte pieces
-    // 2q, 2q+1 of both 64-column chunks (u0,u1) of this CTA's (tap, e) slice.  Next block's ids / rows are prefetched.
-    const int pt = threadIdx.x - 128;          // 0..127
-    const int r = pt >> 2, q = pt & 3;
+  }
+  if (warp >= 4) {
+    // A producers (8 warps; warps 8-11 run the epilogue afterwards).  Per stage a thread handles (row r, 16-byte piece
+    // q) of both 64-column chunks (u0,u1) of this CTA's (tap, e) slice for each of the stage's titles.  Dropout
+    // replays the forward's stream: hash(pair index), the inner hash of the high word hoisted out of the per-pair work.
+    const int pt = threadIdx.x - 128;          // 0..255
+    const int r = pt >> 3, q = pt & 7;
     int uj[2], uc[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -593,109 +628,135 @@ __global__ void __launch_bounds__(384, 1) conv_wgrad_tc_kernel(const WgradParams
       uj[i] = u < TAPS * p.EC ? u / p.EC : -1;
       uc[i] = u < TAPS * p.EC ? u % p.EC : 0;
     }
-    auto load_id = [&](int kb) {
-      int id = -1;
-      if (kb < kb_end && kb < p.n_titles && r < p.L) {
-        id = p.tok[(long long)kb * p.L + r];
-        id = (id < 0 || id >= p.V) ? 0 : id;
-      }
-      return id;
-    };
+    // The token id is NOT inspected when it is loaded (that would stall the warp for the load's full latency every
+    // stage); validity is kept in the row index and the id is clamped when its embedding rows are requested.
+    constexpr int kNoTitle = INT_MIN;
+    auto load_id = [&](int kb) { return (kb < kb_end && r < p.L) ? __ldg(p.tok + (long long)kb * p.L + r) : kNoTitle; };
     auto load_rows = [&](int id, uint4* v) {
-#pragma unroll
-      for (int ui = 0; ui < 2; ++ui)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          v[ui * 2 + h] = make_uint4(0, 0, 0, 0);
-          if (id >= 0 && uj[ui] >= 0)
-            v[ui * 2 + h] = __ldg((const uint4*)(p.emb + (long long)id * p.Ep + uc[ui] * EPAD + (2 * q + h) * 8));
-        }
-    };
-    int s = 0;
-    uint32_t ph = 0;
-    long long twait = 0, t_start = clock64();
-    int id = load_id(kb_beg), id_next = load_id(kb_beg + 1);
-    uint4 v[4], v_next[4];
-    load_rows(id, v_next);
-    for (int kb = kb_beg; kb < kb_end; ++kb) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = v_next[i];
-      const int id_cur = id;
-      id = id_next;
-      load_rows(id, v_next);
-      id_next = load_id(kb + 2);
-      if (p.drop_thr16 && id_cur >= 0) {
-        const uint64_t mrow = (uint64_t)kb * p.L + r;
-#pragma unroll
-        for (int ui = 0; ui < 2; ++ui) {
-          if (uj[ui] < 0) continue;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint64_t pair0 = (mrow * (uint64_t)p.Ep + (uint64_t)(uc[ui] * EPAD + (2 * q + h) * 8)) >> 1;
-            uint32_t* w = reinterpret_cast<uint32_t*>(&v[ui * 2 + h]);
-#pragma unroll
-            for (int x = 0; x < 4; ++x) {
-              uint32_t hsh = rng_u32(p.seed_x, pair0 + x);
-              uint32_t m = ((hsh & 0xffffu) >= p.drop_thr16 ? 0x0000ffffu : 0u) | ((hsh >> 16) >= p.drop_thr16 ? 0xffff0000u : 0u);
-              w[x] &= m;
-            }
-          }
-        }
-      }
-      long long t0 = clock64();
-      mbar_wait(bar_empty + 8 * s, ph ^ 1, 13);
-      twait += clock64() - t0;
-      const uint32_t stage = a_base + s * WG_A_STAGE_BYTES;
+      const bool ok = id != kNoTitle;
+      id = (id < 0 || id >= p.V) ? 0 : id;
 #pragma unroll
       for (int ui = 0; ui < 2; ++ui) {
-        const int j = uj[ui] < 0 ? 1 : uj[ui];
-        const int rr = (r + 1 - j) & (WG_KTOK - 1);
+        v[ui] = make_uint4(0, 0, 0, 0);
+        if (ok && uj[ui] >= 0) v[ui] = __ldg((const uint4*)(p.emb + (long long)id * p.Ep + uc[ui] * EPAD + q * 8));
+      }
+    };
+    const uint32_t kseed = 0x9e3779b9u * (p.seed_x + 1u);
+    int s = 0;
+    uint32_t ph = 0;
+    long long twait = 0, t_start = tracing ? clock64() : 0;
+    // Gather pipeline: the rows of stage sb+1 and the token ids of stage sb+2 are requested while stage sb is hashed
+    // and stored.
+    uint4 vq[3][WG_TPS][2];   // vq[sb % 3]: rows of the titles of stage sb (requested two stages earlier: the gather's
+                              // L2/HBM latency under load is about one stage period)
+    int idn[WG_TPS];          // token ids of the titles of stage sb+2 while stage sb is stored
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const uint32_t addr = stage + ui * WG_GROUP_BYTES + rr * 128 + (((2 * q + h) ^ (rr & 7)) << 4);
-          const uint4 x = v[ui * 2 + h];
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w) : "memory");
+    for (int t = 0; t < WG_TPS; ++t) load_rows(load_id(kb_beg + t), vq[0][t]);
+#pragma unroll
+    for (int t = 0; t < WG_TPS; ++t) load_rows(load_id(kb_beg + WG_TPS + t), vq[1][t]);
+#pragma unroll
+    for (int t = 0; t < WG_TPS; ++t) idn[t] = load_id(kb_beg + 2 * WG_TPS + t);
+    auto drop_rows = [&](int kb, uint4* v) {
+      const uint64_t rowpair = (((uint64_t)kb * p.L + r) * (uint64_t)p.Ep) >> 1;   // Ep is even
+      const uint32_t base_lo = (uint32_t)rowpair, hi = (uint32_t)(rowpair >> 32);
+      const uint32_t inner0 = lowbias32(hi + kseed);
+      const uint32_t inner1 = base_lo > 0xfffff000u ? lowbias32(hi + 1u + kseed) : inner0;   // carry into the high word
+#pragma unroll
+      for (int ui = 0; ui < 2; ++ui) {
+        if (uj[ui] < 0) continue;
+        const uint32_t lo0 = base_lo + (uint32_t)((uc[ui] * EPAD + q * 8) >> 1);
+        uint32_t* w = reinterpret_cast<uint32_t*>(&v[ui]);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          const uint32_t lo = lo0 + x;
+          const uint32_t hsh = lowbias32(lo ^ (lo < base_lo ? inner1 : inner0));
+          const uint32_t m = ((hsh & 0xffffu) >= p.drop_thr16 ? 0x0000ffffu : 0u) | ((hsh >> 16) >= p.drop_thr16 ? 0xffff0000u : 0u);
+          w[x] &= m;
         }
       }
-      fence_proxy_async();
+    };
+    auto stage_step = [&](int sb, uint4 (*cur)[2], uint4 (*nxt)[2]) {
+      const int kb0 = kb_beg + sb * WG_TPS;
+      if (!(p.dbg & 8)) {
+#pragma unroll
+        for (int t = 0; t < WG_TPS; ++t) {
+          load_rows(idn[t], nxt[t]);                       // stage sb+2
+          idn[t] = load_id(kb0 + 3 * WG_TPS + t);          // stage sb+3
+        }
+        if (p.drop_thr16) {
+#pragma unroll
+          for (int t = 0; t < WG_TPS; ++t) drop_rows(kb0 + t, cur[t]);
+        }
+      }
+      long long t0 = tracing ? clock64() : 0;
+      if (lane == 0) mbar_wait(bar_empty + 8 * s, ph ^ 1, 13);   // one poller per warp
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_full + 8 * s);
+      if (tracing) twait += clock64() - t0;
+      if (!(p.dbg & 8)) {
+        const uint32_t stage = a_base + s * a_stage_bytes;
+#pragma unroll
+        for (int t = 0; t < WG_TPS; ++t)
+#pragma unroll
+          for (int ui = 0; ui < 2; ++ui) {
+            const int j = uj[ui] < 0 ? 1 : uj[ui];
+            const int rr = (r + 1 - j) & (WG_KTOK - 1);
+            const uint32_t addr = stage + t * WG_A_TILE_BYTES + ui * WG_GROUP_BYTES + rr * 128 + ((q ^ (rr & 7)) << 4);
+            const uint4 x = cur[t][ui];
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w) : "memory");
+          }
+        fence_proxy_async();
+      }
+      __syncwarp();
+      if (lane == 0) {
+        if (crank == 0) {
+          mbar_arrive(bar_full + 8 * s);
+        } else {
+          if (warp == 4) mbar_wait(bar_full + 8 * s, ph, 16);   // this CTA's halves of dPre have landed
+          mbar_arrive_remote(map_to_cta(bar_full + 8 * s, 0));
+        }
+      }
       if (++s == WG_STAGES) { s = 0; ph ^= 1; }
+    };
+    for (int sb = 0; sb < n_stage_blocks; sb += 3) {
+      stage_step(sb, vq[0], vq[2]);
+      if (sb + 1 < n_stage_blocks) stage_step(sb + 1, vq[1], vq[0]);
+      if (sb + 2 < n_stage_blocks) stage_step(sb + 2, vq[2], vq[1]);
     }
-    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && pt == 0) { p.trace[3] = twait; p.trace[4] = clock64() - t_start; }
-  } else if (warp >= 8) {
-    // epilogue (once): TMEM -> scaled fp32 partial sums in global memory
+    if (tracing && pt == 0) { p.trace[3] = twait; p.trace[4] = clock64() - t_start; }
+  }
+  if (warp >= 8) {
+    // epilogue (once): TMEM -> scaled fp32 partial sums in global memory; accumulator columns are mapped back to f
     const int q = warp & 3;
     mbar_wait(bar_t_full, 0, 14);
     tc_fence_after();
     const int row = q * 32 + lane;
     float* dst = p.partial + ((size_t)split * p.n_slices * TILE_M + (size_t)slice * TILE_M + row) * F;
-    const int nch = (F + 31) / 32;
-    for (int ch = 0; ch < nch; ++ch) {
-      const int c0 = ch * 32, ncols = min(32, F - c0);
-      uint32_t r[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      if (ncols == 32) { TMEM_LD_32(taddr, r); } else { TMEM_LD_16(taddr, r); }
-      tmem_ld_wait();
-      if (kb_end > kb_beg) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          if (i < ncols)
-            *reinterpret_cast<float4*>(dst + c0 + i) =
-                make_float4(__uint_as_float(r[i]) * p.scale, __uint_as_float(r[i + 1]) * p.scale,
-                            __uint_as_float(r[i + 2]) * p.scale, __uint_as_float(r[i + 3]) * p.scale);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          if (i < ncols) *reinterpret_cast<float4*>(dst + c0 + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool any = n_stage_blocks > 0 && !(p.dbg & 2);
+    for (int seg = 0; seg < 4; ++seg) {
+      const int nseg = seg < 2 ? n0h : n1h;
+      const int c_beg = seg < 2 ? seg * n0h : 2 * n0h + (seg - 2) * n1h;
+      const int f_beg = (seg & 1) * Fh + (seg < 2 ? 0 : n0h);
+      for (int c = 0; c < nseg; c += 8) {
+        uint32_t rv[8];
+        TMEM_LD_8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c_beg + c), rv);
+        tmem_ld_wait();
+        float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi4 = lo;
+        if (any) {
+          lo = make_float4(__uint_as_float(rv[0]) * p.scale, __uint_as_float(rv[1]) * p.scale, __uint_as_float(rv[2]) * p.scale,
+                           __uint_as_float(rv[3]) * p.scale);
+          hi4 = make_float4(__uint_as_float(rv[4]) * p.scale, __uint_as_float(rv[5]) * p.scale, __uint_as_float(rv[6]) * p.scale,
+                            __uint_as_float(rv[7]) * p.scale);
+        }
+        *reinterpret_cast<float4*>(dst + f_beg + c) = lo;
+        *reinterpret_cast<float4*>(dst + f_beg + c + 4) = hi4;
       }
     }
     tc_fence_before();
   }
   __syncthreads();
-  if (CS > 1) cluster_sync_all();     // no CTA leaves while peers may still multicast into it / arrive on its barriers
+  cluster_sync_all();     // no CTA leaves while the pair's MMAs / remote arrives may still target it
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -828,13 +889,18 @@ extern "C" int lstur_news_encoder_tc_fwd_internal(const lstur_plan* p, const lst
 
 // ---- wgrad host side ------------------------------------------------------------------------------
 extern "C" int lstur_tc_wgrad_kblocks(int n_titles) { return n_titles; }   // one 32-row slot = one K block
-extern "C" int lstur_tc_wgrad_groups(int F) { return (F + 63) / 64; }
-// bytes of the dPre image consumed by lstur_conv_wgrad_tc
+// 64-column groups per half of the F columns (each CTA of a pair stages one half)
+extern "C" int lstur_tc_wgrad_groups(int F) { return (F / 2 + 63) / 64; }
+// bytes of the dPre image consumed by lstur_conv_wgrad_tc: per title [half][group][32 rows][128 B]
 extern "C" size_t lstur_tc_dpre_img_bytes(int n_titles, int F) {
-  return (size_t)lstur_tc_wgrad_kblocks(n_titles) * lstur_tc_wgrad_groups(F) * tc::WG_GROUP_BYTES;
+  return (size_t)lstur_tc_wgrad_kblocks(n_titles) * 2 * lstur_tc_wgrad_groups(F) * tc::WG_GROUP_BYTES;
+}
+static int wgrad_slices(int E) {
+  int n = (tc::TAPS * lstur_tc_padded_e(E) + tc::TILE_M - 1) / tc::TILE_M;
+  return (n + 1) & ~1;   // CTA pairs
 }
 extern "C" int lstur_tc_wgrad_splits(int n_titles, int E) {
-  int n_slices = (tc::TAPS * lstur_tc_padded_e(E) + tc::TILE_M - 1) / tc::TILE_M;
+  int n_slices = wgrad_slices(E);
   int kb = lstur_tc_wgrad_kblocks(n_titles);
   int sms = 148;
   int splits = sms / n_slices;
@@ -843,8 +909,7 @@ extern "C" int lstur_tc_wgrad_splits(int n_titles, int E) {
   return splits;
 }
 extern "C" size_t lstur_tc_wgrad_partial_bytes(int n_titles, int E, int F) {
-  int n_slices = (tc::TAPS * lstur_tc_padded_e(E) + tc::TILE_M - 1) / tc::TILE_M;
-  return (size_t)lstur_tc_wgrad_splits(n_titles, E) * n_slices * tc::TILE_M * F * sizeof(float);
+  return (size_t)lstur_tc_wgrad_splits(n_titles, E) * wgrad_slices(E) * tc::TILE_M * F * sizeof(float);
 }
 
 // d_conv_w (3,E,F) = sum over tokens of X[m+j-1,e] * dPre[m,f]; X re-gathered from emb_16 with the forward's dropout
@@ -860,10 +925,11 @@ extern "C" int lstur_conv_wgrad_tc(int n_titles, int L, int E, int F, int V, con
   tc::WgradParams p;
   p.n_titles = n_titles; p.L = L; p.F = F; p.Ep = lstur_tc_padded_e(E); p.EC = p.Ep / tc::EPAD; p.V = V;
   p.n_kblocks = lstur_tc_wgrad_kblocks(n_titles);
-  p.n_slices = (tc::TAPS * p.Ep + tc::TILE_M - 1) / tc::TILE_M;
+  p.n_slices = wgrad_slices(E);
   int splits = lstur_tc_wgrad_splits(n_titles, E);
   p.kb_per_split = (p.n_kblocks + splits - 1) / splits;
-  p.ngroups = lstur_tc_wgrad_groups(F);
+  p.kb_per_split = (p.kb_per_split + tc::WG_TPS - 1) / tc::WG_TPS * tc::WG_TPS;   // whole pipeline stages per split
+  p.ngh = lstur_tc_wgrad_groups(F);
   p.tok = tokens; p.emb = (const uint16_t*)emb_16; p.dpre_img = (const uint16_t*)dpre_img;
   p.partial = (float*)partial_ws;
   LSTUR_REQUIRE(partial_ws != nullptr && partial_bytes >= lstur_tc_wgrad_partial_bytes(n_titles, E, F), "lstur_conv_wgrad_tc");
@@ -871,7 +937,8 @@ extern "C" int lstur_conv_wgrad_tc(int n_titles, int L, int E, int F, int V, con
   p.seed_x = seed * 2u;
   p.scale = 1.f / (1.f - dropout);
   p.trace = (long long*)g_tc_trace_ptr;
-  size_t smem = 1024 + (size_t)tc::WG_STAGES * (tc::WG_A_STAGE_BYTES + (size_t)p.ngroups * tc::WG_GROUP_BYTES) + 256;
+  p.dbg = getenv("LSTUR_WGRAD_DBG") ? atoi(getenv("LSTUR_WGRAD_DBG")) : 0;
+  size_t smem = 1024 + (size_t)tc::WG_STAGES * tc::WG_TPS * (tc::WG_A_TILE_BYTES + (size_t)p.ngh * tc::WG_GROUP_BYTES) + 256;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(tc::conv_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -883,39 +950,15 @@ extern "C" int lstur_conv_wgrad_tc(int n_titles, int L, int E, int F, int V, con
     }
     attr_smem = smem;
   }
-  // Cluster multicast of the dPre stream (one L2 read for all slices) is correct but measured SLOWER on B200
-  // (only 15 clusters of 8 fit in one wave and the slices run in lockstep): off unless LSTUR_MULTICAST=1.
-  p.cluster = (p.n_slices >= 2 && p.n_slices <= 8 && getenv("LSTUR_MULTICAST")) ? p.n_slices : 1;
-  if (p.cluster > 1) {
-    // all clusters must be co-resident in ONE wave (a cluster needs `cluster` SMs of the same GPC): ask the runtime
-    static int max_clusters[9] = {0};
-    if (!max_clusters[p.cluster]) {
-      cudaLaunchConfig_t q = {};
-      q.gridDim = dim3(p.cluster, 1);
-      q.blockDim = dim3(384);
-      q.dynamicSmemBytes = smem;
-      cudaLaunchAttribute qa[1];
-      qa[0].id = cudaLaunchAttributeClusterDimension;
-      qa[0].val.clusterDim.x = p.cluster; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
-      q.attrs = qa; q.numAttrs = 1;
-      int nc = 0;
-      cudaError_t e = fp16 ? cudaOccupancyMaxActiveClusters(&nc, tc::conv_wgrad_tc_kernel<true>, &q)
-                           : cudaOccupancyMaxActiveClusters(&nc, tc::conv_wgrad_tc_kernel<false>, &q);
-      if (e != cudaSuccess || nc < 1) { cudaGetLastError(); nc = 1; p.cluster = 1; }
-      max_clusters[p.cluster] = nc;
-    }
-    if (p.cluster > 1 && splits > max_clusters[p.cluster]) splits = max_clusters[p.cluster];
-    p.kb_per_split = (p.n_kblocks + splits - 1) / splits;
-  }
   {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(p.n_slices, splits);
-    cfg.blockDim = dim3(384);
+    cfg.blockDim = dim3(tc::WG_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = p.cluster;
+    attr[0].id = cudaLaunchAttributeClusterDimension;   // CTA pair = two adjacent slices of the same token split
+    attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;

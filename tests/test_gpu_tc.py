@@ -186,10 +186,13 @@ def test_engine_fp16_tc_forward_and_grads(lib, shape, arch, relu_open):
 def dpre_image(dpre, fp16=1):
     """numpy restatement of the K-block image layout documented in csrc/attn.cu (store_dpre_img)."""
     N, L, F = dpre.shape
-    ng = (F + 63) // 64
-    img = np.zeros(N * ng * 4096 // 2, dtype=np.float16 if fp16 else np.uint16)
+    Fh = F // 2
+    ngh = (Fh + 63) // 64
+    img = np.zeros(N * 2 * ngh * 4096 // 2, dtype=np.float16 if fp16 else np.uint16)
     n, t, f = np.meshgrid(np.arange(N), np.arange(L), np.arange(F), indexing='ij')
-    byte = n * (ng * 4096) + (f >> 6) * 4096 + t * 128 + ((((f & 63) >> 3) ^ (t & 7)) << 4) + (f & 7) * 2
+    h = (f >= Fh).astype(np.int64)
+    fl = f - h * Fh
+    byte = n * (2 * ngh * 4096) + (h * ngh + (fl >> 6)) * 4096 + t * 128 + ((((fl & 63) >> 3) ^ (t & 7)) << 4) + (fl & 7) * 2
     if fp16:
         img[byte.ravel() // 2] = dpre.astype(np.float16).ravel()
     else:
