@@ -236,6 +236,9 @@ typedef struct lstur_plan lstur_plan;
 
 int lstur_plan_create(const lstur_config* cfg, lstur_plan** out);
 void lstur_plan_destroy(lstur_plan* plan);
+/* The 16-bit operand copy of the word table is packed once and reused while the table is frozen (reference default,
+ * main.py:36); call this after writing word_emb so the next lstur_forward re-packs it. */
+int lstur_plan_invalidate_tables(lstur_plan* plan);
 size_t lstur_plan_workspace_bytes(const lstur_plan* plan);
 long long lstur_plan_dense_count(const lstur_plan* plan);
 /* name in {conv_w, conv_b, att_w, att_b, dense_w, dense_b, vert_emb, subvert_emb, gru_wx, gru_wh, gru_b,

@@ -8,6 +8,8 @@
 // carries the same arithmetic in its epilogue.
 #include <cuda_fp16.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace lstur {
@@ -331,7 +333,16 @@ extern "C" int lstur_attn_pool_fwd(int N, int L, int F, float* C, long long titl
   return LSTUR_OK;
 }
 
-extern "C" int lstur_attn_bwd_grid(int N) { return N < 148 * 4 ? (N > 0 ? N : 1) : 148 * 4; }
+// CTAs of the attention-backward kernels: 6 per SM (shared memory: ~33 KB per CTA at F=400), one title per CTA trip
+extern "C" int lstur_attn_bwd_grid(int N) {
+  static int per_sm = 0;
+  if (!per_sm) {
+    const char* e = getenv("LSTUR_ATTN_CTAS_PER_SM");
+    per_sm = e ? atoi(e) : 6;
+    if (per_sm < 1 || per_sm > 16) per_sm = 6;
+  }
+  return N < 148 * per_sm ? (N > 0 ? N : 1) : 148 * per_sm;
+}
 
 extern "C" int lstur_colsum(long long rows, int cols, const float* in, long long ld, float* out, int accumulate,
                             float* workspace, size_t workspace_bytes, cudaStream_t stream) {

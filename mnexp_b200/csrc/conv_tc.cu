@@ -34,8 +34,6 @@ constexpr int ROWB = KBLK * 2;                // bytes per shared-memory row
 constexpr int A_TAP_BYTES = TILE_M * ROWB;    // 8 KB
 constexpr int TAPS = 3;
 constexpr int A_STAGE_BYTES = TAPS * A_TAP_BYTES;   // 24 KB: the three shifted tap tiles of one 32-column chunk
-constexpr int NUM_A_STAGES = 3;
-constexpr int NUM_B_STAGES = 5;               // deep ring: covers TMA + barrier round-trip latency
 
 // K-major SWIZZLE_64B descriptor: rows of 64 B, 8-row atoms of 512 B (16B chunk index XOR (row>>1)&3)
 __device__ __forceinline__ uint64_t make_desc_k64(uint32_t saddr) {
@@ -88,184 +86,237 @@ struct FwdParams {
   float* pooled;                  // (n_titles, F)
   float* att_a;                   // (n_titles, L) or null
   float* att_wt;                  // (n_titles, L) or null
-  uint32_t drop_thr16;            // 0 = no dropout; keep iff h16 >= thr
+  uint32_t drop_thr16;            // 0 = no dropout (quad stream threshold, 15 bits)
+  uint32_t drop_addend;           // quad_addend(threshold)
   float inv_keep;
   uint32_t seed_x, seed_c;
-  long long* trace;               // optional clock64 trace of CTA 0 (tools/perf_conv.py); null in production
+  int dbg;                        // experiments (LSTUR_FWD_DBG): 1 = epilogue only hands the accumulator back, 2 = producers only signal
 };
-#define TRACE(it, slot)                                                                    \
-  do {                                                                                     \
-    if (p.trace && blockIdx.x == 0 && (it) < 8) p.trace[(it) * 16 + (slot)] = clock64();   \
-  } while (0)
+
+// Stage = one 32-column chunk of the embedding: the three shifted tap tiles of this CTA's 128 token rows (A, 24 KB)
+// and this CTA's half of the weight rows of the three taps (B, 3 x F/2 x 64 B).
+constexpr int NUM_STAGES = 3;
 
 struct EpiCtx {
-  float xs, inv_keep;
-  uint32_t thr, base_lo, inner0, inner1;
-  const float* s_bias;
+  float sx;                       // scale applied to the accumulator (input-dropout and conv-dropout keep scales)
+  const float* s_bias;            // conv bias x conv-dropout keep scale (ReLU is positively homogeneous)
   const float* s_ka;
+  uint32_t thr, base_lo, inner0, inner1;   // conv-dropout stream of this thread's token row (thr = quad_addend)
 };
 
-// Epilogue pass 1 for NCOLS accumulator columns of one token row: bias + ReLU (+ dropout) -> 16-bit C (stored),
-// attention-logit partial sum z (from the ROUNDED values, so forward and backward see the same C) and the row max.
-template <bool FP16, bool DROP, int NCOLS>
-__device__ __forceinline__ void epi_pass1_chunk(const EpiCtx& ec, uint32_t taddr, int c0, bool live, bool valid,
-                                                uint16_t* crow, float& z, float& vmax) {
-  uint32_t r[32];
-  if (NCOLS == 32) { TMEM_LD_32(taddr, r); } else { TMEM_LD_16(taddr, r); }
+// Epilogue pass 1 for NC accumulator columns of one token row -> features [f0, f0+NC): scale + bias + ReLU (+ pad-token
+// mask) -> conv dropout -> 16-bit C stored to global, attention-logit partial sum z (from the ROUNDED values, so forward
+// and backward see the same C).  The conv-dropout keep SCALE is folded into the accumulator scale and the bias (ReLU is
+// positively homogeneous), so dropping is a bitwise AND on the packed pair.
+// Per-warp staging buffer that turns row-per-lane register tiles into coalesced global accesses: a lane holds 64 B of
+// ITS token row, but a warp-wide 16-byte access with one row per lane touches 32 different 128-byte lines (and half of
+// every 32-byte sector).  Through the buffer, 4 lanes cover the 64 B of one row, so an instruction touches 8 lines and
+// only full sectors — the epilogue of the previous version was bound by exactly these L1 line transactions.
+constexpr int STG_ROW_U4 = 5;                       // 4 pieces + 1 pad (80-byte rows: conflict-free 16-byte accesses)
+constexpr int STG_WARP_BYTES = 32 * STG_ROW_U4 * 16;
+
+struct RowIO {
+  uint4* stg;            // this warp's staging buffer
+  uint16_t* title;       // c_out of token 0 of this warp's title (rows are F apart), or null if the title is invalid
+  int F, L, lane;
+  // write `npieces` 16-byte pieces of every lane's row (features [f0, f0 + 8*npieces)) to global
+  __device__ __forceinline__ void store(const uint32_t* packed, int f0, int npieces) const {
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g < npieces) stg[lane * STG_ROW_U4 + g] = make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+    __syncwarp();
+    if (title) {
+      const int piece = lane & 3;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = (lane >> 2) + 8 * i;
+        if (row < L && piece < npieces)
+          *reinterpret_cast<uint4*>(title + (long long)row * F + f0 + piece * 8) = stg[row * STG_ROW_U4 + piece];
+      }
+    }
+    __syncwarp();
+  }
+  // issue the coalesced global loads of features [f0, f0 + 8*npieces) of the warp's rows
+  __device__ __forceinline__ void load_issue(int f0, int npieces, uint4* v) const {
+    const int piece = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = (lane >> 2) + 8 * i;
+      v[i] = make_uint4(0, 0, 0, 0);
+      if (title && row < L && piece < npieces) v[i] = *reinterpret_cast<const uint4*>(title + (long long)row * F + f0 + piece * 8);
+    }
+  }
+  // hand every lane the 4 pieces of ITS row
+  __device__ __forceinline__ void load_finish(const uint4* v, uint4* mine) const {
+    const int piece = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) stg[((lane >> 2) + 8 * i) * STG_ROW_U4 + piece] = v[i];
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) mine[g] = stg[lane * STG_ROW_U4 + g];
+    __syncwarp();
+  }
+};
+
+// Epilogue pass 1 for NC accumulator columns of one token row -> features [f0, f0+NC): scale + bias + ReLU (+ pad-token
+// mask) -> conv dropout -> 16-bit C stored to global, attention-logit partial sum z (from the ROUNDED values, so forward
+// and backward see the same C).  The conv-dropout keep SCALE is folded into the accumulator scale and the bias (ReLU is
+// positively homogeneous), so dropping is a bitwise AND on the packed pair.
+template <bool FP16, bool DROP, int NC>
+__device__ __forceinline__ void epi_pass1_chunk(const EpiCtx& ec, const RowIO& io, uint32_t taddr, int f0, bool live, float& z,
+                                                float& vmax) {
+  uint32_t r[NC];
+  if (NC == 32) { TMEM_LD_32(taddr, r); } else if (NC == 16) { TMEM_LD_16(taddr, r); } else { TMEM_LD_8(taddr, r); }
   tmem_ld_wait();
-  uint32_t packed[NCOLS / 2];
+  uint32_t packed[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) packed[i] = 0u;
   if (live) {
 #pragma unroll
-    for (int g = 0; g < NCOLS / 4; ++g) {
-      const float4 b4 = *reinterpret_cast<const float4*>(ec.s_bias + c0 + 4 * g);
-      const float4 k4 = *reinterpret_cast<const float4*>(ec.s_ka + c0 + 4 * g);
-      float v0 = fmaxf(fmaf(__uint_as_float(r[4 * g + 0]), ec.xs, b4.x), 0.f);
-      float v1 = fmaxf(fmaf(__uint_as_float(r[4 * g + 1]), ec.xs, b4.y), 0.f);
-      float v2 = fmaxf(fmaf(__uint_as_float(r[4 * g + 2]), ec.xs, b4.z), 0.f);
-      float v3 = fmaxf(fmaf(__uint_as_float(r[4 * g + 3]), ec.xs, b4.w), 0.f);
+    for (int g = 0; g < NC / 4; ++g) {
+      const float4 b4 = *reinterpret_cast<const float4*>(ec.s_bias + f0 + 4 * g);
+      const float v0 = fmaxf(fmaf(__uint_as_float(r[4 * g + 0]), ec.sx, b4.x), 0.f);
+      const float v1 = fmaxf(fmaf(__uint_as_float(r[4 * g + 1]), ec.sx, b4.y), 0.f);
+      const float v2 = fmaxf(fmaf(__uint_as_float(r[4 * g + 2]), ec.sx, b4.z), 0.f);
+      const float v3 = fmaxf(fmaf(__uint_as_float(r[4 * g + 3]), ec.sx, b4.w), 0.f);
       vmax = fmaxf(vmax, fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)));      // Masking(): any(C != 0) before the dropout
-      if (DROP) {
-        const uint32_t lo0 = ec.base_lo + (uint32_t)((c0 >> 1) + 2 * g), lo1 = lo0 + 1u;
-        const uint32_t h0 = lowbias32(lo0 ^ (lo0 < ec.base_lo ? ec.inner1 : ec.inner0));
-        const uint32_t h1 = lowbias32(lo1 ^ (lo1 < ec.base_lo ? ec.inner1 : ec.inner0));
-        v0 = (h0 & 0xffffu) >= ec.thr ? v0 * ec.inv_keep : 0.f;
-        v1 = (h0 >> 16) >= ec.thr ? v1 * ec.inv_keep : 0.f;
-        v2 = (h1 & 0xffffu) >= ec.thr ? v2 * ec.inv_keep : 0.f;
-        v3 = (h1 >> 16) >= ec.thr ? v3 * ec.inv_keep : 0.f;
+      uint32_t p0 = pack16x2<FP16>(v0, v1), p1 = pack16x2<FP16>(v2, v3);
+      if (DROP) {   // the keep scale is already folded into sx / s_bias: dropping is a pure zeroing of the packed halves
+        const uint32_t lo = ec.base_lo + (uint32_t)((f0 >> 2) + g);          // quad index of features f0+4g .. +3
+        uint32_t u0, u1;
+        quad_hash(lo ^ (lo < ec.base_lo ? ec.inner1 : ec.inner0), u0, u1);
+        p0 &= quad_mask(u0, ec.thr);
+        p1 &= quad_mask(u1, ec.thr);
       }
-      const uint32_t p0 = pack16x2<FP16>(v0, v1), p1 = pack16x2<FP16>(v2, v3);
       packed[2 * g] = p0;
       packed[2 * g + 1] = p1;
+      const float4 k4 = *reinterpret_cast<const float4*>(ec.s_ka + f0 + 4 * g);
       z = fmaf(lo16<FP16>(p0), k4.x, z);
       z = fmaf(hi16<FP16>(p0), k4.y, z);
       z = fmaf(lo16<FP16>(p1), k4.z, z);
       z = fmaf(hi16<FP16>(p1), k4.w, z);
     }
-  } else {
-#pragma unroll
-    for (int i = 0; i < NCOLS / 2; ++i) packed[i] = 0u;
   }
-  if (valid) {
-    uint4* dst = reinterpret_cast<uint4*>(crow + c0);
-#pragma unroll
-    for (int g = 0; g < NCOLS / 8; ++g) dst[g] = make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
-  }
+  io.store(packed, f0, NC / 8);
+}
+// one accumulator segment [ca, ca+n) -> features [f0, f0+n), n a multiple of 8
+template <bool FP16, bool DROP>
+__device__ __forceinline__ void epi_pass1_segment(const EpiCtx& ec, const RowIO& io, uint32_t trow, int ca, int f0, int n,
+                                                  bool live, float& z, float& vmax) {
+  int c = 0;
+  for (; c + 32 <= n; c += 32) epi_pass1_chunk<FP16, DROP, 32>(ec, io, trow + ca + c, f0 + c, live, z, vmax);
+  if (c + 16 <= n) { epi_pass1_chunk<FP16, DROP, 16>(ec, io, trow + ca + c, f0 + c, live, z, vmax); c += 16; }
+  if (c + 8 <= n) epi_pass1_chunk<FP16, DROP, 8>(ec, io, trow + ca + c, f0 + c, live, z, vmax);
 }
 
-__device__ __forceinline__ void epi_load_chunk(const uint16_t* crow, int c0, int F, bool live, uint4* v) {
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    v[g] = make_uint4(0, 0, 0, 0);
-    if (live && c0 + 8 * g < F) v[g] = *reinterpret_cast<const uint4*>(crow + c0 + 8 * g);
-  }
-}
-
+// CTA pairs (cta_group::2): CTA `rank` of a pair owns the token tile 2*tp + rank (its own A rows, its own 128 x F
+// accumulator in tensor memory) and stages only the weight rows f in [rank*F/2, (rank+1)*F/2); the pair's MMAs
+// (M = 256, issued by rank 0) read both halves, which halves the weight bytes every SM has to pull through its shared
+// memory — the limiter of the single-CTA version.  Accumulator column c holds feature
+//   f = half*Fh + (c % n0h)         for c <  2*n0h    (half = c / n0h,  first MMA,  n0h = min(Fh,128))
+//   f = half*Fh + n0h + (c' % n1h)  for c' = c-2*n0h  (half = c'/ n1h,  second MMA, n1h = Fh - n0h)
+// so an epilogue thread of column half `half` sees one contiguous feature range [half*Fh, (half+1)*Fh).
 template <bool FP16, bool DROP>
 __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const int F = p.F, EC = p.EC;
-  const uint32_t b_stage_bytes = (uint32_t)F * ROWB;
-  const uint32_t a_base = smem_base;
-  const uint32_t b_base = a_base + NUM_A_STAGES * A_STAGE_BYTES;
-  const uint32_t misc_base = b_base + NUM_B_STAGES * b_stage_bytes;
+  const int F = p.F, EC = p.EC, Fh = F >> 1;
+  const int n0h = Fh > 128 ? 128 : Fh, n1h = Fh - n0h;
+  const uint32_t b_tap_bytes = (uint32_t)Fh * ROWB;                 // this CTA's weight rows of one tap
+  const uint32_t stage_bytes = A_STAGE_BYTES + TAPS * b_tap_bytes;  // multiple of 512 (Fh % 8 == 0)
+  const uint32_t misc_base = smem_base + NUM_STAGES * stage_bytes;
   uint8_t* misc_gen = smem_gen + (misc_base - smem_base);
-  // barriers (8 B each): a_full[<=4] a_empty[<=4] b_full[<=6] b_empty[<=6] tmem_full tmem_empty
-  const uint32_t bar_a_full = misc_base, bar_a_empty = misc_base + 32, bar_b_full = misc_base + 64,
-                 bar_b_empty = misc_base + 112, bar_t_full = misc_base + 160, bar_t_empty = misc_base + 168;
-  uint32_t* tmem_ptr_smem = (uint32_t*)(misc_gen + 176);
+  // barriers (8 B each): full[4] empty[4] tmem_full tmem_empty
+  const uint32_t bar_full = misc_base, bar_empty = misc_base + 32, bar_t_full = misc_base + 64, bar_t_empty = misc_base + 72;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(misc_gen + 80);
   float* s_z = (float*)(misc_gen + 256);          // [2 parity][2 halves][128 rows]
   int* s_any = (int*)(misc_gen + 256 + 2048);     // [2][2][128]
-  float* s_bias = (float*)(misc_gen + 256 + 4096);  // [F]
+  float* s_bias = (float*)(misc_gen + 256 + 4096);  // [F]  (x conv-dropout keep scale)
   float* s_ka = s_bias + F;                          // [F]
+  uint4* s_stg = (uint4*)(misc_gen + 256 + 4096 + (((size_t)2 * F * sizeof(float) + 15) & ~(size_t)15));   // [8 warps] staging
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
   const int n_tiles = (p.n_titles + TPT - 1) / TPT;
+  const int n_tp = (n_tiles + 1) / 2;                  // tile pairs
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const float ik = DROP ? p.inv_keep : 1.f;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NUM_A_STAGES; ++s) {
-      mbar_init(bar_a_full + 8 * s, 4);   // one arrival per producer warp
-      mbar_init(bar_a_empty + 8 * s, 1);  // tcgen05.commit
+    for (int s = 0; s < NUM_STAGES; ++s) {
+      // leader: its 4 producer warps + its weight loader's expect_tx arrival + the peer's 4 producer warps (remote
+      // arrives; the peer's warp 4 first waits for the peer's own bulk copies).  peer: only its loader's expect_tx.
+      mbar_init(bar_full + 8 * s, crank == 0 ? 9 : 1);
+      mbar_init(bar_empty + 8 * s, 1);    // multicast tcgen05.commit of the leader
     }
-    for (int s = 0; s < NUM_B_STAGES; ++s) {
-      mbar_init(bar_b_full + 8 * s, 1);   // expect_tx arrival + bytes
-      mbar_init(bar_b_empty + 8 * s, 1);
-    }
-    mbar_init(bar_t_full, 1);
-    mbar_init(bar_t_empty, 8);            // one arrival per epilogue warp
+    mbar_init(bar_t_full, 1);              // multicast tcgen05.commit of the leader
+    mbar_init(bar_t_empty, 16);            // (leader) one arrival per epilogue warp of BOTH CTAs
     fence_barrier_init();
   }
   for (int f = threadIdx.x; f < F; f += THREADS) {
-    s_bias[f] = p.conv_b[f];
+    s_bias[f] = p.conv_b[f] * ik;
     s_ka[f] = p.att_w[f];
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
                  "r"(TMEM_COLS)
                  : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const int n0 = F > 256 ? 256 : F, n1 = F - n0;
 
   if (warp == 0) {
-    // ===================== B loader (TMA bulk copies of pre-swizzled weight blocks) =====================
+    // ===================== weight loader (TMA bulk copies of this CTA's rows of the pre-swizzled K blocks) ===========
     if (lane == 0) {
-      int sb = 0;
+      int s = 0;
       uint32_t ph = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        for (int i = 0; i < EC * TAPS; ++i) {
-          mbar_wait(bar_b_empty + 8 * sb, ph ^ 1, 1);
-          if (i == 0) TRACE(it, 9);
-          if (i == EC * TAPS - 1) TRACE(it, 10);
-          mbar_expect_tx(bar_b_full + 8 * sb, b_stage_bytes);
-          bulk_g2s(b_base + sb * b_stage_bytes, (const uint8_t*)p.wimg + (size_t)i * b_stage_bytes, b_stage_bytes,
-                   bar_b_full + 8 * sb);
-          if (++sb == NUM_B_STAGES) { sb = 0; ph ^= 1; }
+      for (int tp = pair; tp < n_tp; tp += n_pairs) {
+        for (int c = 0; c < EC; ++c) {
+          mbar_wait(bar_empty + 8 * s, ph ^ 1, 1);
+          mbar_expect_tx(bar_full + 8 * s, TAPS * b_tap_bytes);
+#pragma unroll
+          for (int j = 0; j < TAPS; ++j)
+            bulk_g2s(smem_base + s * stage_bytes + A_STAGE_BYTES + j * b_tap_bytes,
+                     (const uint8_t*)p.wimg + ((size_t)(c * TAPS + j) * F + (size_t)crank * Fh) * ROWB, b_tap_bytes,
+                     bar_full + 8 * s);
+          if (++s == NUM_STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc0 = make_idesc(TILE_M, n0, FP16), idesc1 = make_idesc(TILE_M, n1 > 0 ? n1 : 16, FP16);
-      int sa = 0, sb = 0;
-      uint32_t pha = 0, phb = 0, pht = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    // ===================== MMA issuer of the pair =====================
+    if (lane == 0 && crank == 0) {
+      const uint32_t idesc0 = make_idesc(2 * TILE_M, 2 * n0h, FP16), idesc1 = make_idesc(2 * TILE_M, n1h > 0 ? 2 * n1h : 16, FP16);
+      int s = 0;
+      uint32_t ph = 0, pht = 0;
+      for (int tp = pair; tp < n_tp; tp += n_pairs) {
         mbar_wait(bar_t_empty, pht ^ 1, 2);
         tc_fence_after();
-        TRACE(it, 0);
         uint32_t accum = 0;
         for (int c = 0; c < EC; ++c) {
-          mbar_wait(bar_a_full + 8 * sa, pha, 3);
+          mbar_wait(bar_full + 8 * s, ph, 3);
           tc_fence_after();
-          if (c == 0) TRACE(it, 1);
+          const uint32_t a_stage = smem_base + s * stage_bytes, b_stage = a_stage + A_STAGE_BYTES;
+#pragma unroll
           for (int j = 0; j < TAPS; ++j) {
-            mbar_wait(bar_b_full + 8 * sb, phb, 4);
-            tc_fence_after();
-            const uint32_t a_addr = a_base + sa * A_STAGE_BYTES + j * A_TAP_BYTES;
-            const uint32_t b_addr = b_base + sb * b_stage_bytes;
+            const uint32_t a_addr = a_stage + j * A_TAP_BYTES, b_addr = b_stage + j * b_tap_bytes;
 #pragma unroll
             for (int kk = 0; kk < KBLK / 16; ++kk) {
               const uint64_t ad = make_desc_k64(a_addr + kk * 32);
-              umma_bf16(tmem_base, ad, make_desc_k64(b_addr + kk * 32), idesc0, accum);
-              if (n1 > 0) umma_bf16(tmem_base + n0, ad, make_desc_k64(b_addr + 256 * ROWB + kk * 32), idesc1, accum);
+              umma_f16_2cta(tmem_base, ad, make_desc_k64(b_addr + kk * 32), idesc0, accum);
+              if (n1h > 0) umma_f16_2cta(tmem_base + 2 * n0h, ad, make_desc_k64(b_addr + n0h * ROWB + kk * 32), idesc1, accum);
               accum = 1;
             }
-            umma_commit(bar_b_empty + 8 * sb);
-            if (++sb == NUM_B_STAGES) { sb = 0; phb ^= 1; }
           }
-          umma_commit(bar_a_empty + 8 * sa);
-          if (++sa == NUM_A_STAGES) { sa = 0; pha ^= 1; }
+          umma_commit_2cta(bar_empty + 8 * s, 3);
+          if (++s == NUM_STAGES) { s = 0; ph ^= 1; }
         }
-        TRACE(it, 2);
-        umma_commit(bar_t_full);
+        umma_commit_2cta(bar_t_full, 3);
         pht ^= 1;
       }
     }
@@ -275,16 +326,16 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
     // the next tile) are issued before chunk c is hashed and stored, so L2 latency is off the critical path.
     const int pw = warp - 4;                 // title slot of the tile
     const int rsub = lane >> 2, piece = lane & 3;
-    int sa = 0;
-    uint32_t pha = 0;
+    int s = 0;
+    uint32_t ph = 0;
     constexpr int kNoToken = INT_MIN;
-    auto load_ids = [&](int tile, int* ids) {
-      const int n = tile * TPT + pw;
+    auto load_ids = [&](int tp, int* ids) {
+      const int n = (2 * tp + (int)crank) * TPT + pw;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int t = 8 * i + rsub;
         // raw id: not inspected here (no stall on the load); clamped when the rows are requested
-        ids[i] = (tile < n_tiles && n < p.n_titles && t < p.L) ? __ldg(p.tok + (long long)n * p.L + t) : kNoToken;
+        ids[i] = (tp < n_tp && n < p.n_titles && t < p.L) ? __ldg(p.tok + (long long)n * p.L + t) : kNoToken;
       }
     };
     auto load_rows = [&](const int* ids, int c, uint4* v) {
@@ -300,50 +351,50 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
     int ids[4], ids_next[4];
     uint4 v[4], v_next[4];
     uint32_t row_lo[4], row_in0[4], row_in1[4];
-    const uint32_t kseed = 0x9e3779b9u * (p.seed_x + 1u);
-    load_ids(blockIdx.x, ids);
+    load_ids(pair, ids);
     load_rows(ids, 0, v_next);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const int n = tile * TPT + pw;
-      if (warp == 4 && lane == 0) TRACE(it, 7);
+    for (int tp = pair; tp < n_tp; tp += n_pairs) {
+      const int n = (2 * tp + (int)crank) * TPT + pw;
       for (int c = 0; c < EC; ++c) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) v[i] = v_next[i];
         if (c + 1 < EC) {
           load_rows(ids, c + 1, v_next);
-          if (c + 2 == EC) load_ids(tile + gridDim.x, ids_next);
+          if (c + 2 == EC) load_ids(tp + n_pairs, ids_next);
         } else {
-          if (EC == 1) load_ids(tile + gridDim.x, ids_next);
+          if (EC == 1) load_ids(tp + n_pairs, ids_next);
           load_rows(ids_next, 0, v_next);
         }
         if (DROP) {
           if (c == 0) {   // per tile: pair index of column 0 of each of this thread's rows, inner hash of its high word
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const uint64_t rowpair = (((uint64_t)n * p.L + (8 * i + rsub)) * (uint64_t)p.Ep) >> 1;
-              const uint32_t hi = (uint32_t)(rowpair >> 32);
-              row_lo[i] = (uint32_t)rowpair;
-              row_in0[i] = lowbias32(hi + kseed);
-              row_in1[i] = row_lo[i] > 0xfffff000u ? lowbias32(hi + 1u + kseed) : row_in0[i];
+              const uint64_t rowquad = (((uint64_t)n * p.L + (8 * i + rsub)) * (uint64_t)p.Ep) >> 2;
+              const uint32_t hi = (uint32_t)(rowquad >> 32);
+              row_lo[i] = (uint32_t)rowquad;
+              row_in0[i] = quad_key(hi, p.seed_x);
+              row_in1[i] = row_lo[i] > 0xfffff000u ? quad_key(hi + 1u, p.seed_x) : row_in0[i];
             }
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             if (ids[i] == kNoToken) continue;
-            const uint32_t lo0 = row_lo[i] + (uint32_t)((c * KBLK + piece * 8) >> 1);
+            const uint32_t lo0 = row_lo[i] + (uint32_t)((c * KBLK + piece * 8) >> 2);
             uint32_t* w = reinterpret_cast<uint32_t*>(&v[i]);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 2; ++q) {     // two quads per 16-byte piece
               const uint32_t lo = lo0 + q;
-              const uint32_t h = lowbias32(lo ^ (lo < row_lo[i] ? row_in1[i] : row_in0[i]));
-              uint32_t m = ((h & 0xffffu) >= p.drop_thr16 ? 0x0000ffffu : 0u) | ((h >> 16) >= p.drop_thr16 ? 0xffff0000u : 0u);
-              w[q] &= m;
+              uint32_t u0, u1;
+              quad_hash(lo ^ (lo < row_lo[i] ? row_in1[i] : row_in0[i]), u0, u1);
+              w[2 * q] &= quad_mask(u0, p.drop_addend);
+              w[2 * q + 1] &= quad_mask(u1, p.drop_addend);
             }
           }
         }
-        mbar_wait(bar_a_empty + 8 * sa, pha ^ 1, 5);
-        const uint32_t stage = a_base + sa * A_STAGE_BYTES;
+        if (lane == 0) mbar_wait(bar_empty + 8 * s, ph ^ 1, 5);   // one poller per warp
+        __syncwarp();
+        const uint32_t stage = smem_base + s * stage_bytes;
+        if (!(p.dbg & 2))
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int r = pw * SLOT + 8 * i + rsub;
@@ -358,67 +409,78 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_a_full + 8 * sa);
-        if (++sa == NUM_A_STAGES) { sa = 0; pha ^= 1; }
+        if (lane == 0) {
+          if (crank == 0) {
+            mbar_arrive(bar_full + 8 * s);
+          } else {
+            if (warp == 4) mbar_wait(bar_full + 8 * s, ph, 7);   // this CTA's weight rows have landed
+            mbar_arrive_remote(map_to_cta(bar_full + 8 * s, 0));
+          }
+        }
+        if (++s == NUM_STAGES) { s = 0; ph ^= 1; }
         if (c + 1 == EC) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) ids[i] = ids_next[i];
-          if (warp == 4 && lane == 0) TRACE(it, 8);
         }
       }
     }
   } else if (warp >= 8) {
     // ===================== epilogue: bias/ReLU/masks/dropout/attention pooling =====================
-    // Thread (q, lane) owns token row 32q+lane of the tile = token `lane` of title tile*4+q; the two
-    // column halves of a row are handled by warps ew and ew+4 and combined through shared memory.
+    // Thread (q, lane) owns token row 32q+lane of this CTA's tile = token `lane` of title tile*4+q; the two feature
+    // halves of a row are handled by warps ew and ew+4 and combined through shared memory.
     const int ew = warp - 8, q = ew & 3, half = ew >> 2;
-    const int nch = (F + 31) / 32;
-    const int ch_split = (nch + 1) / 2;
-    const int ch_beg = half == 0 ? 0 : ch_split, ch_end = half == 0 ? ch_split : nch;
+    const int f_beg = half * Fh, f_end = f_beg + Fh;
     const float att_bias = p.att_b[0];
     EpiCtx ec;
-    ec.xs = DROP ? p.inv_keep : 1.f;   // input-dropout scale folded into the epilogue
-    ec.inv_keep = p.inv_keep;
-    ec.thr = p.drop_thr16;
+    ec.sx = DROP ? p.inv_keep * p.inv_keep : 1.f;   // input-dropout and conv-dropout keep scales
     ec.s_bias = s_bias;
     ec.s_ka = s_ka;
+    ec.thr = p.drop_addend;
     uint32_t pht = 0;
     int par = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const int n = tile * TPT + q, t = lane;
+    RowIO io;
+    io.stg = s_stg + (size_t)ew * (STG_WARP_BYTES / 16);
+    io.F = F; io.L = p.L; io.lane = lane;
+    for (int tp = pair; tp < n_tp; tp += n_pairs) {
+      const int n = (2 * tp + (int)crank) * TPT + q, t = lane;
       const bool valid = n < p.n_titles && t < p.L;
       const long long m = (long long)n * p.L + t;
       const int tk = valid ? p.tok[m] : 0;
-      uint16_t* crow = p.c_out + m * F;
+      io.title = n < p.n_titles ? p.c_out + (long long)n * p.L * F : nullptr;
       if (DROP) {
-        const uint64_t base = ((uint64_t)m * (uint64_t)F) >> 1;     // F is even: pair index of (m, f) = base + f/2
+        const uint64_t base = ((uint64_t)(valid ? m : 0) * (uint64_t)F) >> 2;     // F % 4 == 0: quad index of (m, f) = base + f/4
         ec.base_lo = (uint32_t)base;
-        const uint32_t hi = (uint32_t)(base >> 32), k = 0x9e3779b9u * (p.seed_c + 1u);
-        ec.inner0 = lowbias32(hi + k);
-        ec.inner1 = lowbias32(hi + 1u + k);
+        const uint32_t hi = (uint32_t)(base >> 32);
+        ec.inner0 = quad_key(hi, p.seed_c);
+        ec.inner1 = quad_key(hi + 1u, p.seed_c);
       }
       mbar_wait(bar_t_full, pht, 6);
       pht ^= 1;
       tc_fence_after();
-      if (warp == 8 && lane == 0) TRACE(it, 3);
       float z = 0.f, vmax = 0.f;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-      for (int ch = ch_beg; ch < ch_end; ++ch) {
-        const int c0 = ch * 32;
-        if (F - c0 >= 32) epi_pass1_chunk<FP16, DROP, 32>(ec, trow + c0, c0, tk != 0, valid, crow, z, vmax);
-        else epi_pass1_chunk<FP16, DROP, 16>(ec, trow + c0, c0, tk != 0, valid, crow, z, vmax);
+      if (p.dbg & 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (crank == 0) mbar_arrive(bar_t_empty);
+          else mbar_arrive_remote(map_to_cta(bar_t_empty, 0));
+        }
+        continue;
       }
-      // TMEM drained: let the MMA warp start the next tile while we pool
+      // ---- pass 1: drain this row's accumulator columns (kept short: the next tile's MMAs wait for it)
+      epi_pass1_segment<FP16, DROP>(ec, io, trow, half * n0h, f_beg, n0h, tk != 0, z, vmax);
+      if (n1h > 0) epi_pass1_segment<FP16, DROP>(ec, io, trow, 2 * n0h + half * n1h, f_beg + n0h, n1h, tk != 0, z, vmax);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_t_empty);
-      if (warp == 8 && lane == 0) TRACE(it, 4);
+      if (lane == 0) {
+        if (crank == 0) mbar_arrive(bar_t_empty);
+        else mbar_arrive_remote(map_to_cta(bar_t_empty, 0));
+      }
       const int row = q * 32 + lane;
       s_z[(par * 2 + half) * 128 + row] = z;
       s_any[(par * 2 + half) * 128 + row] = vmax > 0.f ? 1 : 0;
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (warp == 8 && lane == 0) TRACE(it, 5);
       const float zt = s_z[(par * 2) * 128 + row] + s_z[(par * 2 + 1) * 128 + row];
       const int anyt = s_any[(par * 2) * 128 + row] | s_any[(par * 2 + 1) * 128 + row];
       par ^= 1;
@@ -430,18 +492,15 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
         if (p.att_a) p.att_a[m] = a;
         if (p.att_wt) p.att_wt[m] = w;
       }
-      // pass 2: pooled[n, f] = sum_t w_t * C[t, f]; butterfly reduce-scatter over the 32 lanes (rows).  The row is
-      // re-read from global (own writes, L2) one chunk ahead of the reduction.
-      const bool live = valid && w != 0.f;
+      // ---- pass 2: pooled[n, f] = sum_t w_t * C[t, f]; butterfly reduce-scatter over the 32 lanes (rows).  The rows
+      // are re-read from global (own warp's writes, L2) one chunk ahead of the reduction.
       uint4 nxt[4];
-      epi_load_chunk(crow, ch_beg * 32, F, live, nxt);
-      for (int ch = ch_beg; ch < ch_end; ++ch) {
-        const int c0 = ch * 32;
-        const int ncols = min(32, F - c0);
+      io.load_issue(f_beg, min(4, (f_end - f_beg) >> 3), nxt);
+      for (int c0 = f_beg; c0 < f_end; c0 += 32) {
+        const int ncols = min(32, f_end - c0);
         uint4 cur[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) cur[g] = nxt[g];
-        if (ch + 1 < ch_end) epi_load_chunk(crow, c0 + 32, F, live, nxt);
+        io.load_finish(nxt, cur);
+        if (c0 + 32 < f_end) io.load_issue(c0 + 32, min(4, (f_end - c0 - 32) >> 3), nxt);
         float x[32];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -462,12 +521,12 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
         }
         if (n < p.n_titles && lane < ncols) p.pooled[(long long)n * F + c0 + lane] = x[0];
       }
-      if (warp == 8 && lane == 0) TRACE(it, 6);
     }
   }
   __syncthreads();
+  cluster_sync_all();     // no CTA leaves while the pair's MMAs / remote arrives may still target it
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -506,7 +565,7 @@ struct WgradParams {
   const uint16_t* emb;        // (V, Ep)
   const uint16_t* dpre_img;   // n_kblocks * 2 * ngh * 4 KB
   float* partial;             // [splits][n_slices*128][F]
-  uint32_t drop_thr16, seed_x;
+  uint32_t drop_thr16, drop_addend, seed_x;   // quad-stream threshold (0 = no dropout) and its mask addend
   float scale;
   long long* trace;           // optional: accumulated wait cycles of CTA (0,0)'s roles (tools/perf_conv.py)
   int dbg;                    // experiments (LSTUR_WGRAD_DBG): 2 = skip all MMAs, 4 = skip bulk copies, 8 = producers only signal
@@ -641,7 +700,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const Wgra
         if (ok && uj[ui] >= 0) v[ui] = __ldg((const uint4*)(p.emb + (long long)id * p.Ep + uc[ui] * EPAD + q * 8));
       }
     };
-    const uint32_t kseed = 0x9e3779b9u * (p.seed_x + 1u);
     int s = 0;
     uint32_t ph = 0;
     long long twait = 0, t_start = tracing ? clock64() : 0;
@@ -657,21 +715,22 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const Wgra
 #pragma unroll
     for (int t = 0; t < WG_TPS; ++t) idn[t] = load_id(kb_beg + 2 * WG_TPS + t);
     auto drop_rows = [&](int kb, uint4* v) {
-      const uint64_t rowpair = (((uint64_t)kb * p.L + r) * (uint64_t)p.Ep) >> 1;   // Ep is even
-      const uint32_t base_lo = (uint32_t)rowpair, hi = (uint32_t)(rowpair >> 32);
-      const uint32_t inner0 = lowbias32(hi + kseed);
-      const uint32_t inner1 = base_lo > 0xfffff000u ? lowbias32(hi + 1u + kseed) : inner0;   // carry into the high word
+      const uint64_t rowquad = (((uint64_t)kb * p.L + r) * (uint64_t)p.Ep) >> 2;   // Ep % 4 == 0
+      const uint32_t base_lo = (uint32_t)rowquad, hi = (uint32_t)(rowquad >> 32);
+      const uint32_t inner0 = quad_key(hi, p.seed_x);
+      const uint32_t inner1 = base_lo > 0xfffff000u ? quad_key(hi + 1u, p.seed_x) : inner0;   // carry into the high word
 #pragma unroll
       for (int ui = 0; ui < 2; ++ui) {
         if (uj[ui] < 0) continue;
-        const uint32_t lo0 = base_lo + (uint32_t)((uc[ui] * EPAD + q * 8) >> 1);
+        const uint32_t lo0 = base_lo + (uint32_t)((uc[ui] * EPAD + q * 8) >> 2);
         uint32_t* w = reinterpret_cast<uint32_t*>(&v[ui]);
 #pragma unroll
-        for (int x = 0; x < 4; ++x) {
+        for (int x = 0; x < 2; ++x) {     // two quads per 16-byte piece
           const uint32_t lo = lo0 + x;
-          const uint32_t hsh = lowbias32(lo ^ (lo < base_lo ? inner1 : inner0));
-          const uint32_t m = ((hsh & 0xffffu) >= p.drop_thr16 ? 0x0000ffffu : 0u) | ((hsh >> 16) >= p.drop_thr16 ? 0xffff0000u : 0u);
-          w[x] &= m;
+          uint32_t u0, u1;
+          quad_hash(lo ^ (lo < base_lo ? inner1 : inner0), u0, u1);
+          w[2 * x] &= quad_mask(u0, p.drop_addend);
+          w[2 * x + 1] &= quad_mask(u1, p.drop_addend);
         }
       }
     };
@@ -834,12 +893,13 @@ extern "C" int lstur_news_conv_tc_fwd(int n_titles, int L, int E, int F, int V, 
   p.tok = tokens; p.emb = (const uint16_t*)emb_bf16; p.wimg = (const uint16_t*)wimg;
   p.conv_b = conv_b; p.att_w = att_w; p.att_b = att_b;
   p.c_out = (uint16_t*)c_out_bf16; p.pooled = pooled; p.att_a = att_a; p.att_wt = att_wt;
-  p.drop_thr16 = dropout > 0.f ? (uint32_t)(dropout * 65536.0f) : 0u;
+  p.drop_thr16 = dropout > 0.f ? quad_thr15(dropout) : 0u;
+  p.drop_addend = quad_addend(p.drop_thr16);
   p.inv_keep = 1.f / (1.f - dropout);
   p.seed_x = seed * 2u; p.seed_c = seed * 2u + 1u;
-  p.trace = (long long*)g_tc_trace_ptr;
-  size_t smem = 1024 + (size_t)tc::NUM_A_STAGES * tc::A_STAGE_BYTES + (size_t)tc::NUM_B_STAGES * F * tc::ROWB + 256 + 4096 +
-                (size_t)2 * F * sizeof(float);
+  p.dbg = getenv("LSTUR_FWD_DBG") ? atoi(getenv("LSTUR_FWD_DBG")) : 0;
+  size_t smem = 1024 + (size_t)tc::NUM_STAGES * (tc::A_STAGE_BYTES + (size_t)tc::TAPS * (F / 2) * tc::ROWB) + 256 + 4096 +
+                (((size_t)2 * F * sizeof(float) + 15) & ~(size_t)15) + (size_t)8 * tc::STG_WARP_BYTES;
   static bool attr_set = false;
   static size_t attr_smem = 0;
   if (!attr_set || smem > attr_smem) {
@@ -855,15 +915,35 @@ extern "C" int lstur_news_conv_tc_fwd(int n_titles, int L, int E, int F, int V, 
     attr_smem = smem;
   }
   int n_tiles = (n_titles + tc::TPT - 1) / tc::TPT;
+  int n_tp = (n_tiles + 1) / 2;             // CTA pairs take two token tiles at a time
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-  int grid = n_tiles < sms ? n_tiles : sms;
-  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  int pairs = n_tp < sms / 2 ? n_tp : sms / 2;
+  if (max_ctas > 0 && pairs > max_ctas / 2) pairs = max_ctas / 2 > 0 ? max_ctas / 2 : 1;
   const bool drop = p.drop_thr16 != 0;
-  if (fp16 && drop) tc::news_conv_tc_fwd_kernel<true, true><<<grid, tc::THREADS, smem, stream>>>(p);
-  else if (fp16) tc::news_conv_tc_fwd_kernel<true, false><<<grid, tc::THREADS, smem, stream>>>(p);
-  else if (drop) tc::news_conv_tc_fwd_kernel<false, true><<<grid, tc::THREADS, smem, stream>>>(p);
-  else tc::news_conv_tc_fwd_kernel<false, false><<<grid, tc::THREADS, smem, stream>>>(p);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(tc::THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e;
+    if (fp16 && drop) e = cudaLaunchKernelEx(&cfg, tc::news_conv_tc_fwd_kernel<true, true>, p);
+    else if (fp16) e = cudaLaunchKernelEx(&cfg, tc::news_conv_tc_fwd_kernel<true, false>, p);
+    else if (drop) e = cudaLaunchKernelEx(&cfg, tc::news_conv_tc_fwd_kernel<false, true>, p);
+    else e = cudaLaunchKernelEx(&cfg, tc::news_conv_tc_fwd_kernel<false, false>, p);
+    if (e != cudaSuccess) {
+      set_error("lstur_news_conv_tc_fwd: launch failed: %s", cudaGetErrorString(e));
+      return LSTUR_ERR_CUDA;
+    }
+  }
   LSTUR_CHECK_LAUNCH("lstur_news_conv_tc_fwd");
   return LSTUR_OK;
 }
@@ -875,7 +955,11 @@ extern "C" int lstur_news_encoder_tc_fwd_internal(const lstur_plan* p, const lst
   void* wimg = W<void>(p, ws, "wimg");
   LSTUR_REQUIRE(emb && wimg, "lstur_news_encoder_tc_fwd_internal");
   const int fp16 = c.precision == LSTUR_PREC_FP16_TC;
-  RC(lstur_pack_word_emb_16(c.V, c.E, w->word_emb, emb, fp16, st));
+  if (p->emb16_src != (const void*)w->word_emb || p->emb16_dst != emb) {
+    RC(lstur_pack_word_emb_16(c.V, c.E, w->word_emb, emb, fp16, st));
+    const_cast<lstur_plan*>(p)->emb16_src = w->word_emb;
+    const_cast<lstur_plan*>(p)->emb16_dst = emb;
+  }
   RC(lstur_pack_conv_w_tc(c.E, c.F, DP(p, w->dense, "conv_w"), wimg, fp16, st));
   PROBE_BEGIN(p, LSTUR_PROBE_CONV_FWD, st);
   RC(lstur_news_conv_tc_fwd(p->N, c.L, c.E, c.F, c.V, W<int>(p, ws, "tokens"), emb, wimg, DP(p, w->dense, "conv_b"),
@@ -933,7 +1017,8 @@ extern "C" int lstur_conv_wgrad_tc(int n_titles, int L, int E, int F, int V, con
   p.tok = tokens; p.emb = (const uint16_t*)emb_16; p.dpre_img = (const uint16_t*)dpre_img;
   p.partial = (float*)partial_ws;
   LSTUR_REQUIRE(partial_ws != nullptr && partial_bytes >= lstur_tc_wgrad_partial_bytes(n_titles, E, F), "lstur_conv_wgrad_tc");
-  p.drop_thr16 = dropout > 0.f ? (uint32_t)(dropout * 65536.0f) : 0u;
+  p.drop_thr16 = dropout > 0.f ? quad_thr15(dropout) : 0u;
+  p.drop_addend = quad_addend(p.drop_thr16);
   p.seed_x = seed * 2u;
   p.scale = 1.f / (1.f - dropout);
   p.trace = (long long*)g_tc_trace_ptr;

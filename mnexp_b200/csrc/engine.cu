@@ -232,6 +232,13 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
 }
 
 extern "C" void lstur_plan_destroy(lstur_plan* plan) { delete plan; }
+// The caller wrote the word-embedding table (or moved the workspace): derived copies must be rebuilt on the next forward.
+extern "C" int lstur_plan_invalidate_tables(lstur_plan* plan) {
+  LSTUR_REQUIRE(plan != nullptr, "lstur_plan_invalidate_tables");
+  plan->emb16_src = nullptr;
+  plan->emb16_dst = nullptr;
+  return LSTUR_OK;
+}
 extern "C" size_t lstur_plan_workspace_bytes(const lstur_plan* plan) { return plan ? plan->ws_bytes : 0; }
 extern "C" long long lstur_plan_dense_count(const lstur_plan* plan) { return plan ? plan->dense_count : 0; }
 

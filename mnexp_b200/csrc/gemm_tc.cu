@@ -34,11 +34,9 @@ struct GemmParams {
   float* partial;
 };
 
-// 8 consecutive floats -> 8 fp16 (16 bytes), zero-filled outside [0, s_lim) x [0, c_lim)
-template <bool SPLIT>
-__device__ __forceinline__ uint4 load_piece(const float* __restrict__ base, long long ld, int s_idx, int s_lim, int c0,
-                                            int c_lim, bool vec_ok, uint4& lo) {
-  float v[8];
+// 8 consecutive floats of row s_idx starting at column c0, zero-filled outside [0, s_lim) x [0, c_lim)
+__device__ __forceinline__ void load_raw(const float* __restrict__ base, long long ld, int s_idx, int s_lim, int c0, int c_lim,
+                                         bool vec_ok, float* v) {
   if (s_idx < s_lim && c0 + 8 <= c_lim && vec_ok) {
     const float4* p = reinterpret_cast<const float4*>(base + (long long)s_idx * ld + c0);
     float4 a = __ldg(p), b = __ldg(p + 1);
@@ -48,6 +46,10 @@ __device__ __forceinline__ uint4 load_piece(const float* __restrict__ base, long
     for (int i = 0; i < 8; ++i)
       v[i] = (s_idx < s_lim && c0 + i < c_lim) ? __ldg(base + (long long)s_idx * ld + c0 + i) : 0.f;
   }
+}
+// 8 floats -> 8 fp16 (16 bytes) [+ the 8 fp16 residuals]
+template <bool SPLIT>
+__device__ __forceinline__ uint4 cvt_piece(const float* v, uint4& lo) {
   uint32_t o[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -138,41 +140,59 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const GemmParams 
     const int bgroups = (nmma + 63) >> 6;
     int s = 0;
     uint32_t ph = 0;
+    // A thread stages pieces i = pt + it*256: 4 of A (it < 4) and up to 8 of B.  The global loads of a whole batch of
+    // pieces are issued before any of them is converted and stored (one memory round trip per batch instead of one per
+    // piece), and the first batch of a K block is requested before waiting for its stage to drain.
+    const int nb_pieces = TB ? nmma * 8 : bgroups * 512;      // B pieces of this tile per K block
+    constexpr int BATCH = 6;
     for (int kb = 0; kb < nkb; ++kb) {
       const int k0 = kbeg + kb * G_KBLK;
-      mbar_wait(bar_empty + 8 * s, ph ^ 1, 22);
       const uint32_t a_addr = smem_base + s * STAGE_BYTES, b_addr = a_addr + G_A_BYTES;
-      uint4 lo;
-      // A: 1024 pieces
-#pragma unroll 4
-      for (int i = pt; i < 1024; i += G_PRODUCERS) {
-        const int c = i & 7, r = i >> 3;   // K-major: r = tile row (0..127); MN-major: r = (group, k row)
-        if (!TA) {
-          uint4 v = load_piece<SPLIT>(p.A, p.lda, m0 + r, p.M, k0 + 8 * c, kend, p.vec_ok, lo);
-          sts128(a_addr + r * 128 + ((c ^ (r & 7)) << 4), v);
-          if (SPLIT) sts128(a_addr + LO_OFF + r * 128 + ((c ^ (r & 7)) << 4), lo);
+      auto piece_load = [&](int idx, float* v) {
+        if (idx < 4) {
+          const int i = pt + idx * G_PRODUCERS, c = i & 7, r = i >> 3;
+          if (!TA) load_raw(p.A, p.lda, m0 + r, p.M, k0 + 8 * c, kend, p.vec_ok, v);
+          else load_raw(p.A, p.lda, k0 + (r & 63), kend, m0 + (r >> 6) * 64 + 8 * c, p.M, p.vec_ok, v);
         } else {
-          const int g = r >> 6, kr = r & 63;
-          uint4 v = load_piece<SPLIT>(p.A, p.lda, k0 + kr, kend, m0 + g * 64 + 8 * c, p.M, p.vec_ok, lo);
-          sts128(a_addr + g * 8192 + kr * 128 + ((c ^ (kr & 7)) << 4), v);
-          if (SPLIT) sts128(a_addr + LO_OFF + g * 8192 + kr * 128 + ((c ^ (kr & 7)) << 4), lo);
+          const int i = pt + (idx - 4) * G_PRODUCERS, c = i & 7, r = i >> 3;
+          if (i < nb_pieces) {
+            if (TB) load_raw(p.B, p.ldb, n0 + r, n0 + nt, k0 + 8 * c, kend, p.vec_ok, v);
+            else load_raw(p.B, p.ldb, k0 + (r & 63), kend, n0 + (r >> 6) * 64 + 8 * c, n0 + nt, p.vec_ok, v);
+          }
         }
-      }
-      if (TB) {
-        for (int i = pt; i < nmma * 8; i += G_PRODUCERS) {
-          const int c = i & 7, r = i >> 3;
-          uint4 v = load_piece<SPLIT>(p.B, p.ldb, n0 + r, n0 + nt, k0 + 8 * c, kend, p.vec_ok, lo);
-          sts128(b_addr + r * 128 + ((c ^ (r & 7)) << 4), v);
-          if (SPLIT) sts128(b_addr + LO_OFF + r * 128 + ((c ^ (r & 7)) << 4), lo);
+      };
+      auto piece_store = [&](int idx, const float* v) {
+        uint4 lo;
+        if (idx < 4) {
+          const int i = pt + idx * G_PRODUCERS, c = i & 7, r = i >> 3;
+          const uint4 hi = cvt_piece<SPLIT>(v, lo);
+          const uint32_t off = !TA ? (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4))
+                                   : (uint32_t)((r >> 6) * 8192 + (r & 63) * 128 + ((c ^ (r & 7)) << 4));
+          sts128(a_addr + off, hi);
+          if (SPLIT) sts128(a_addr + LO_OFF + off, lo);
+        } else {
+          const int i = pt + (idx - 4) * G_PRODUCERS, c = i & 7, r = i >> 3;
+          if (i < nb_pieces) {
+            const uint4 hi = cvt_piece<SPLIT>(v, lo);
+            const uint32_t off = TB ? (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4))
+                                    : (uint32_t)((r >> 6) * 8192 + (r & 63) * 128 + ((c ^ (r & 7)) << 4));
+            sts128(b_addr + off, hi);
+            if (SPLIT) sts128(b_addr + LO_OFF + off, lo);
+          }
         }
-      } else {
-        for (int i = pt; i < bgroups * 512; i += G_PRODUCERS) {
-          const int c = i & 7, r = i >> 3;
-          const int g = r >> 6, kr = r & 63;
-          uint4 v = load_piece<SPLIT>(p.B, p.ldb, k0 + kr, kend, n0 + g * 64 + 8 * c, n0 + nt, p.vec_ok, lo);
-          sts128(b_addr + g * 8192 + kr * 128 + ((c ^ (kr & 7)) << 4), v);
-          if (SPLIT) sts128(b_addr + LO_OFF + g * 8192 + kr * 128 + ((c ^ (kr & 7)) << 4), lo);
-        }
+      };
+      float v[BATCH][8];
+#pragma unroll
+      for (int j = 0; j < BATCH; ++j) piece_load(j, v[j]);
+      if (lane == 0) mbar_wait(bar_empty + 8 * s, ph ^ 1, 22);
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < BATCH; ++j) piece_store(j, v[j]);
+      if (nb_pieces > (BATCH - 4) * G_PRODUCERS) {
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) piece_load(BATCH + j, v[j]);
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) piece_store(BATCH + j, v[j]);
       }
       fence_proxy_async();
       __syncwarp();

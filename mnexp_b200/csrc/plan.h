@@ -23,6 +23,10 @@ struct lstur_plan {
   // optional CUDA events recorded around one kernel of the step (bench.py roofline probe)
   int probe_id = 0;
   cudaEvent_t probe_start = nullptr, probe_stop = nullptr;
+  // the 16-bit copy of the (frozen) word table in the workspace is re-packed only when its source / destination
+  // changes or lstur_plan_invalidate_tables() was called (the table was written)
+  const void* emb16_src = nullptr;
+  void* emb16_dst = nullptr;
   unsigned last_seed = 0;   // seed / mode of the last forward (backward replays its dropout streams)
   int last_training = 0;
 };

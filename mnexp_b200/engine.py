@@ -79,6 +79,10 @@ class LsturEngine:
             self.user_emb = torch.as_tensor(np.ascontiguousarray(params['user_emb'], dtype=np.float32)).to(dev) if Ue else None
         else:                                   # inference replica sharing the training engine's device weights
             self.word_emb, self.user_emb = src.word_emb, src.user_emb
+        # version of the word table shared by every engine that aliases it: the plan keeps a 16-bit operand copy that
+        # is re-packed only when the table was written (lstur_plan_invalidate_tables)
+        self._emb_version = [0] if src is None else src._emb_version
+        self._emb_seen = -1
         if doc_tokens is None and src is not None:
             self.doc_tokens = src.doc_tokens
         else:
@@ -123,6 +127,7 @@ class LsturEngine:
         self.dense.copy_(torch.from_numpy(host))
         if 'word_emb' in params:
             self.word_emb.copy_(torch.as_tensor(np.ascontiguousarray(params['word_emb'], dtype=np.float32)))
+            self._emb_version[0] += 1
         if self.user_emb is not None and 'user_emb' in params:
             self.user_emb.copy_(torch.as_tensor(np.ascontiguousarray(params['user_emb'], dtype=np.float32)))
 
@@ -188,6 +193,9 @@ class LsturEngine:
     # ---- the hot path ---------------------------------------------------------------------
     def forward(self, db, training=False, seed=0):
         cb = self._cbatch(db)
+        if self._emb_seen != self._emb_version[0]:
+            _lib.check(self.lib.lstur_plan_invalidate_tables(self.plan))
+            self._emb_seen = self._emb_version[0]
         _lib.check(self.lib.lstur_forward(self.plan, ctypes.byref(self._w), ctypes.byref(cb), _ptr(self.ws),
                                           int(training), ctypes.c_uint(seed), self._stream()))
         return self.view('probs').reshape(self.B, self.C)

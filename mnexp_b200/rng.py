@@ -35,3 +35,27 @@ def dropout_multiplier(seed, n, p, dtype=np.float64):
     keep = (u >> np.uint32(8)) >= thr
     inv = np.float32(1.0) / (np.float32(1.0) - np.float32(p))
     return np.where(keep, dtype(inv), dtype(0))
+
+
+def _mulfold(a, m):
+    p = a.astype(np.uint64) * np.uint64(m)
+    return ((p & np.uint64(0xffffffff)) ^ (p >> np.uint64(32))).astype(np.uint32)
+
+
+def quad_keep(seed, n, p):
+    """Keep flags (bool, n) of the tensor-core path's dropout stream (csrc/common.cuh: quad_hash): one hash per four
+    consecutive elements, 15-bit fields compared with floor(p * 32768).  n must be a multiple of 4."""
+    assert n % 4 == 0
+    q = np.arange(n // 4, dtype=np.uint64)
+    lo = (q & np.uint64(0xffffffff)).astype(np.uint32)
+    hi = (q >> np.uint64(32)).astype(np.uint32)
+    k = (np.uint64(0x9e3779b9) * np.uint64((int(seed) + 1) & 0xffffffff)) & np.uint64(0xffffffff)
+    with np.errstate(over='ignore'):
+        key = lowbias32((hi + np.uint32(k)).astype(np.uint32))
+    b = _mulfold(lo ^ key, 0x9E3779B1)
+    u0 = _mulfold(b ^ np.uint32(0x85EBCA6B), 0xC2B2AE35)
+    u1 = _mulfold(b ^ np.uint32(0x27D4EB2F), 0x165667B1)
+    thr = np.uint32(int(np.float32(p) * np.float32(32768.0)))
+    f = np.stack([u0 & np.uint32(0x7fff), (u0 >> np.uint32(16)) & np.uint32(0x7fff),
+                  u1 & np.uint32(0x7fff), (u1 >> np.uint32(16)) & np.uint32(0x7fff)], -1)
+    return (f >= thr).reshape(-1)

@@ -29,7 +29,7 @@ def test_host_only_entry_points(lib):
     assert lib.lstur_tc_supported(50, 300, 400, 3) == 0          # L > 31 needs the 64-row slot variant
     assert lib.lstur_tc_supported(30, 300, 400, 5) == 0
     assert lib.lstur_tc_wimg_elems(300, 400) == 3 * 320 * 400
-    assert lib.lstur_attn_bwd_grid(10) == 10 and lib.lstur_attn_bwd_grid(10 ** 6) == 148 * 4
+    assert lib.lstur_attn_bwd_grid(10) == 10 and lib.lstur_attn_bwd_grid(10 ** 6) % 148 == 0
 
 
 def _plan(lib, **kw):

@@ -112,13 +112,9 @@ def test_tc_matches_across_grid_sizes(lib):
 
 
 def tc_dropout_masks(seed, N, L, E, Ep, F, p):
-    thr = int(np.float32(p) * np.float32(65536.0))
     inv = np.float32(1) / (np.float32(1) - np.float32(p))
     def mask(sd, rows, width, used):
-        n_pairs = rows * width // 2
-        h = rng.rng_u32(sd, np.arange(n_pairs, dtype=np.uint64))
-        lo, hi = (h & np.uint32(0xffff)) >= thr, (h >> np.uint32(16)) >= thr
-        m = np.stack([lo, hi], -1).reshape(rows, width)[:, :used]
+        m = rng.quad_keep(sd, rows * width, p).reshape(rows, width)[:, :used]
         return np.where(m, np.float64(inv), 0.0)
     return mask(seed * 2, N * L, Ep, E).reshape(N, L, E), mask(seed * 2 + 1, N * L, F, F).reshape(N, L, F)
 

@@ -31,16 +31,6 @@ for drop in (0.0, 0.2):
         print('fwd dropout=%.1f ctas=%3d  %.3f ms  %.0f TFLOP/s' % (drop, ctas or 148, ms, flop / ms / 1e9))
 
 trace = torch.zeros(8 * 16, dtype=torch.int64, device='cuda')
-names = ['mma:tmem_empty', 'mma:a_full0', 'mma:issued', 'epi:t_full', 'epi:pass1_end', 'epi:barsync', 'epi:pass2_end', 'prod:start', 'prod:end', 'bld:first', 'bld:last']
-for drop in (0.0, 0.2):
-    lib.lstur_tc_set_trace(P_(trace))
-    run(drop, 0, reps=1)
-    lib.lstur_tc_set_trace(None)
-    tr = trace.cpu().numpy().reshape(8, 16)
-    t0 = tr[2, 0]
-    print('--- trace dropout=%.1f (cycles relative to MMA start of tile iter 2)' % drop)
-    for it in (2, 3, 4):
-        print('iter', it, ' '.join('%s=%d' % (n, tr[it, i] - t0) for i, n in enumerate(names)))
 
 # ---- wgrad
 nb = lib.lstur_tc_dpre_img_bytes(N, F)
