@@ -9,7 +9,7 @@
 // non-transposed, B transposed) is staged K-major; one whose M/N index is contiguous (A transposed — the
 // weight-gradient case — or B non-transposed) is staged MN-major, so no transposition ever happens in memory:
 // only the UMMA descriptor's major-ness bits differ.  Split-K over CTA.z with a fixed-order reduction.
-// Warp roles (512 threads): w1 MMA issuer + TMEM alloc, w4-11 producers, w12-15 epilogue.
+// Warp roles (416 threads): w0 MMA issuer + TMEM alloc, w1-8 producers, w9-12 epilogue.
 #include "tc_common.cuh"
 
 namespace lstur {
@@ -21,7 +21,7 @@ constexpr int G_A_BYTES = TILE_M * 128;    // 16 KB (either major-ness)
 constexpr int G_B_BYTES = 256 * 128;       // up to N tile 256
 constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;          // single-term fp16
 constexpr int G_STAGE_BYTES_S3 = 2 * (G_A_BYTES + G_B_BYTES);  // hi + lo tiles for the 3-term split
-constexpr int G_THREADS = 512;
+constexpr int G_THREADS = 416;   // w0 MMA issuer + TMEM alloc, w1-8 producers, w9-12 epilogue (152 registers per thread)
 constexpr int G_PRODUCERS = 256;
 
 struct GemmParams {
@@ -31,6 +31,7 @@ struct GemmParams {
   float* C; long long ldc;
   const float* bias;
   int flags, ntile, k_per_split, vec_ok;
+  int tiles_m, tiles_n, splits;
   float* partial;
 };
 
@@ -70,6 +71,9 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
 
 // TA: A is stored [K,M] (M contiguous) -> MN-major.  TB: B is stored [N,K] (K contiguous) -> K-major.
 // SPLIT: 3-term fp16 split (Ahi.Bhi + Alo.Bhi + Ahi.Blo) for ~fp32 accuracy on the forward-path GEMMs.
+// Persistent: a CTA walks the (m, n, k-split) tiles t = blockIdx.x, +gridDim.x, ... (n fastest, so CTAs that run
+// together share an A tile in L2); the shared-memory stage ring runs across tile boundaries and two 256-column
+// accumulators in tensor memory let the epilogue of one tile overlap the loads and MMAs of the next.
 template <bool TA, bool TB, bool SPLIT>
 __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const GemmParams p) {
   constexpr int STAGES = SPLIT ? 2 : G_STAGES;
@@ -80,25 +84,40 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const GemmParams 
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t misc_base = smem_base + STAGES * STAGE_BYTES;
   uint8_t* misc_gen = smem_gen + (misc_base - smem_base);
-  const uint32_t bar_full = misc_base, bar_empty = misc_base + 64, bar_t_full = misc_base + 128;
-  uint32_t* tmem_ptr_smem = (uint32_t*)(misc_gen + 144);
+  const uint32_t bar_full = misc_base, bar_empty = misc_base + 64, bar_t_full = misc_base + 128, bar_t_empty = misc_base + 144;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(misc_gen + 160);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TILE_M, n0 = blockIdx.x * p.ntile;
-  const int nt = min(p.ntile, p.N - n0);                     // valid columns of this tile
-  const int nmma = (nt + 15) & ~15;                          // UMMA N (multiple of 16)
-  const int kbeg = blockIdx.z * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
-  const int nkb = kend > kbeg ? (kend - kbeg + G_KBLK - 1) / G_KBLK : 0;
+  const int n_tiles = p.tiles_m * p.tiles_n * p.splits;
+
+  // tile index -> (m0, n0, split) and derived extents
+  struct Tile { int m0, n0, nt, nmma, z, kbeg, kend, nkb; };
+  auto tile_of = [&](int t) {
+    Tile x;
+    const int tn = t % p.tiles_n, tm = (t / p.tiles_n) % p.tiles_m;
+    x.z = t / (p.tiles_n * p.tiles_m);
+    x.m0 = tm * TILE_M;
+    x.n0 = tn * p.ntile;
+    x.nt = min(p.ntile, p.N - x.n0);                       // valid columns of this tile
+    x.nmma = (x.nt + 15) & ~15;                            // UMMA N (multiple of 16)
+    x.kbeg = x.z * p.k_per_split;
+    x.kend = min(p.K, x.kbeg + p.k_per_split);
+    x.nkb = x.kend > x.kbeg ? (x.kend - x.kbeg + G_KBLK - 1) / G_KBLK : 0;
+    return x;
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, G_PRODUCERS / 32);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    mbar_init(bar_t_full, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_t_full + 8 * a, 1);
+      mbar_init(bar_t_empty + 8 * a, 4);     // the four epilogue warps
+    }
     fence_barrier_init();
   }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(256)
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -107,143 +126,165 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const GemmParams 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp == 1) {
+  if (warp == 0) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(TILE_M, nmma, true) | (TA ? (1u << 15) : 0u) | (!TB ? (1u << 16) : 0u);
-      int s = 0;
-      uint32_t ph = 0, accum = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(bar_full + 8 * s, ph, 21);
+      int s = 0, acc = 0;
+      uint32_t ph = 0, pht[2] = {0, 0};
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const Tile x = tile_of(t);
+        const uint32_t idesc = make_idesc(TILE_M, x.nmma, true) | (TA ? (1u << 15) : 0u) | (!TB ? (1u << 16) : 0u);
+        mbar_wait(bar_t_empty + 8 * acc, pht[acc] ^ 1, 24);      // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = smem_base + s * STAGE_BYTES, b_addr = a_addr + G_A_BYTES;
+        const uint32_t tacc = tmem_base + acc * 256;
+        uint32_t accum = 0;
+        for (int kb = 0; kb < x.nkb; ++kb) {
+          mbar_wait(bar_full + 8 * s, ph, 21);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + s * STAGE_BYTES, b_addr = a_addr + G_A_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < G_KBLK / 16; ++kk) {
-          const uint64_t ad = TA ? make_desc_mn128(a_addr + kk * 2048, 8192) : make_desc_k128(a_addr + kk * 32);
-          const uint64_t bd = TB ? make_desc_k128(b_addr + kk * 32) : make_desc_mn128(b_addr + kk * 2048, 8192);
-          umma_bf16(tmem_base, ad, bd, idesc, accum);
-          accum = 1;
-          if (SPLIT) {
-            const uint64_t al = TA ? make_desc_mn128(a_addr + LO_OFF + kk * 2048, 8192) : make_desc_k128(a_addr + LO_OFF + kk * 32);
-            const uint64_t bl = TB ? make_desc_k128(b_addr + LO_OFF + kk * 32) : make_desc_mn128(b_addr + LO_OFF + kk * 2048, 8192);
-            umma_bf16(tmem_base, al, bd, idesc, 1);
-            umma_bf16(tmem_base, ad, bl, idesc, 1);
+          for (int kk = 0; kk < G_KBLK / 16; ++kk) {
+            const uint64_t ad = TA ? make_desc_mn128(a_addr + kk * 2048, 8192) : make_desc_k128(a_addr + kk * 32);
+            const uint64_t bd = TB ? make_desc_k128(b_addr + kk * 32) : make_desc_mn128(b_addr + kk * 2048, 8192);
+            umma_bf16(tacc, ad, bd, idesc, accum);
+            accum = 1;
+            if (SPLIT) {
+              const uint64_t al = TA ? make_desc_mn128(a_addr + LO_OFF + kk * 2048, 8192) : make_desc_k128(a_addr + LO_OFF + kk * 32);
+              const uint64_t bl = TB ? make_desc_k128(b_addr + LO_OFF + kk * 32) : make_desc_mn128(b_addr + LO_OFF + kk * 2048, 8192);
+              umma_bf16(tacc, al, bd, idesc, 1);
+              umma_bf16(tacc, ad, bl, idesc, 1);
+            }
           }
+          umma_commit(bar_empty + 8 * s);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(bar_empty + 8 * s);
-        if (++s == STAGES) { s = 0; ph ^= 1; }
+        umma_commit(bar_t_full + 8 * acc);
+        pht[acc] ^= 1;
+        acc ^= 1;
       }
-      umma_commit(bar_t_full);
     }
-  } else if (warp >= 4 && warp < 12) {
+  } else if (warp >= 1 && warp < 9) {
     // ---- producers: fp32 global -> fp16 swizzled tiles
-    const int pt = threadIdx.x - 128;        // 0..255
-    const int bgroups = (nmma + 63) >> 6;
+    const int pt = threadIdx.x - 32;         // 0..255
     int s = 0;
     uint32_t ph = 0;
     // A thread stages pieces i = pt + it*256: 4 of A (it < 4) and up to 8 of B.  The global loads of a whole batch of
     // pieces are issued before any of them is converted and stored (one memory round trip per batch instead of one per
     // piece), and the first batch of a K block is requested before waiting for its stage to drain.
-    const int nb_pieces = TB ? nmma * 8 : bgroups * 512;      // B pieces of this tile per K block
     constexpr int BATCH = 6;
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int k0 = kbeg + kb * G_KBLK;
-      const uint32_t a_addr = smem_base + s * STAGE_BYTES, b_addr = a_addr + G_A_BYTES;
-      auto piece_load = [&](int idx, float* v) {
-        if (idx < 4) {
-          const int i = pt + idx * G_PRODUCERS, c = i & 7, r = i >> 3;
-          if (!TA) load_raw(p.A, p.lda, m0 + r, p.M, k0 + 8 * c, kend, p.vec_ok, v);
-          else load_raw(p.A, p.lda, k0 + (r & 63), kend, m0 + (r >> 6) * 64 + 8 * c, p.M, p.vec_ok, v);
-        } else {
-          const int i = pt + (idx - 4) * G_PRODUCERS, c = i & 7, r = i >> 3;
-          if (i < nb_pieces) {
-            if (TB) load_raw(p.B, p.ldb, n0 + r, n0 + nt, k0 + 8 * c, kend, p.vec_ok, v);
-            else load_raw(p.B, p.ldb, k0 + (r & 63), kend, n0 + (r >> 6) * 64 + 8 * c, n0 + nt, p.vec_ok, v);
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const Tile x = tile_of(t);
+      const int m0 = x.m0, n0 = x.n0, nt = x.nt, kend = x.kend;
+      const int bgroups = (x.nmma + 63) >> 6;
+      const int nb_pieces = TB ? x.nmma * 8 : bgroups * 512;      // B pieces of this tile per K block
+      for (int kb = 0; kb < x.nkb; ++kb) {
+        const int k0 = x.kbeg + kb * G_KBLK;
+        const uint32_t a_addr = smem_base + s * STAGE_BYTES, b_addr = a_addr + G_A_BYTES;
+        auto piece_load = [&](int idx, float* v) {
+          if (idx < 4) {
+            const int i = pt + idx * G_PRODUCERS, c = i & 7, r = i >> 3;
+            if (!TA) load_raw(p.A, p.lda, m0 + r, p.M, k0 + 8 * c, kend, p.vec_ok, v);
+            else load_raw(p.A, p.lda, k0 + (r & 63), kend, m0 + (r >> 6) * 64 + 8 * c, p.M, p.vec_ok, v);
+          } else {
+            const int i = pt + (idx - 4) * G_PRODUCERS, c = i & 7, r = i >> 3;
+            if (i < nb_pieces) {
+              if (TB) load_raw(p.B, p.ldb, n0 + r, n0 + nt, k0 + 8 * c, kend, p.vec_ok, v);
+              else load_raw(p.B, p.ldb, k0 + (r & 63), kend, n0 + (r >> 6) * 64 + 8 * c, n0 + nt, p.vec_ok, v);
+            }
           }
-        }
-      };
-      auto piece_store = [&](int idx, const float* v) {
-        uint4 lo;
-        if (idx < 4) {
-          const int i = pt + idx * G_PRODUCERS, c = i & 7, r = i >> 3;
-          const uint4 hi = cvt_piece<SPLIT>(v, lo);
-          const uint32_t off = !TA ? (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4))
-                                   : (uint32_t)((r >> 6) * 8192 + (r & 63) * 128 + ((c ^ (r & 7)) << 4));
-          sts128(a_addr + off, hi);
-          if (SPLIT) sts128(a_addr + LO_OFF + off, lo);
-        } else {
-          const int i = pt + (idx - 4) * G_PRODUCERS, c = i & 7, r = i >> 3;
-          if (i < nb_pieces) {
+        };
+        auto piece_store = [&](int idx, const float* v) {
+          uint4 lo;
+          if (idx < 4) {
+            const int i = pt + idx * G_PRODUCERS, c = i & 7, r = i >> 3;
             const uint4 hi = cvt_piece<SPLIT>(v, lo);
-            const uint32_t off = TB ? (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4))
-                                    : (uint32_t)((r >> 6) * 8192 + (r & 63) * 128 + ((c ^ (r & 7)) << 4));
-            sts128(b_addr + off, hi);
-            if (SPLIT) sts128(b_addr + LO_OFF + off, lo);
+            const uint32_t off = !TA ? (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4))
+                                     : (uint32_t)((r >> 6) * 8192 + (r & 63) * 128 + ((c ^ (r & 7)) << 4));
+            sts128(a_addr + off, hi);
+            if (SPLIT) sts128(a_addr + LO_OFF + off, lo);
+          } else {
+            const int i = pt + (idx - 4) * G_PRODUCERS, c = i & 7, r = i >> 3;
+            if (i < nb_pieces) {
+              const uint4 hi = cvt_piece<SPLIT>(v, lo);
+              const uint32_t off = TB ? (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4))
+                                      : (uint32_t)((r >> 6) * 8192 + (r & 63) * 128 + ((c ^ (r & 7)) << 4));
+              sts128(b_addr + off, hi);
+              if (SPLIT) sts128(b_addr + LO_OFF + off, lo);
+            }
           }
+        };
+        float v[BATCH][8];
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) piece_load(j, v[j]);
+        if (lane == 0) mbar_wait(bar_empty + 8 * s, ph ^ 1, 22);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) piece_store(j, v[j]);
+        if (nb_pieces > (BATCH - 4) * G_PRODUCERS) {
+#pragma unroll
+          for (int j = 0; j < BATCH; ++j) piece_load(BATCH + j, v[j]);
+#pragma unroll
+          for (int j = 0; j < BATCH; ++j) piece_store(BATCH + j, v[j]);
         }
-      };
-      float v[BATCH][8];
-#pragma unroll
-      for (int j = 0; j < BATCH; ++j) piece_load(j, v[j]);
-      if (lane == 0) mbar_wait(bar_empty + 8 * s, ph ^ 1, 22);
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < BATCH; ++j) piece_store(j, v[j]);
-      if (nb_pieces > (BATCH - 4) * G_PRODUCERS) {
-#pragma unroll
-        for (int j = 0; j < BATCH; ++j) piece_load(BATCH + j, v[j]);
-#pragma unroll
-        for (int j = 0; j < BATCH; ++j) piece_store(BATCH + j, v[j]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * s);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_full + 8 * s);
-      if (++s == STAGES) { s = 0; ph ^= 1; }
     }
-  } else if (warp >= 12) {
-    // ---- epilogue
+  } else if (warp >= 9) {
+    // ---- epilogue (TMEM lane quarter = warp % 4)
     const int q = warp & 3;
-    mbar_wait(bar_t_full, 0, 23);
-    tc_fence_after();
-    const int gm = m0 + q * 32 + lane;
-    const bool split = gridDim.z > 1;
-    float* crow = split ? p.partial + ((long long)blockIdx.z * p.M + gm) * p.N : p.C + (long long)gm * p.ldc;
-    const bool vec_st = split ? (p.N % 4 == 0) : (p.ldc % 4 == 0 && (((uintptr_t)p.C) & 15) == 0);
-    for (int c0 = 0; c0 < nmma; c0 += 32) {
-      uint32_t r[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      if (nmma - c0 >= 32) { TMEM_LD_32(taddr, r); } else { TMEM_LD_16(taddr, r); }
-      tmem_ld_wait();
-      if (gm >= p.M) continue;
-      const int ncols = min(32, nt - c0);
+    int acc = 0;
+    uint32_t pht[2] = {0, 0};
+    const bool split = p.splits > 1;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const Tile x = tile_of(t);
+      mbar_wait(bar_t_full + 8 * acc, pht[acc], 23);
+      pht[acc] ^= 1;
+      tc_fence_after();
+      const int gm = x.m0 + q * 32 + lane;
+      float* crow = split ? p.partial + ((long long)x.z * p.M + gm) * p.N : p.C + (long long)gm * p.ldc;
+      const bool vec_st = split ? (p.N % 4 == 0) : (p.ldc % 4 == 0 && (((uintptr_t)p.C) & 15) == 0);
+      for (int c0 = 0; c0 < x.nmma; c0 += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        if (x.nmma - c0 >= 32) { TMEM_LD_32(taddr, r); } else { TMEM_LD_16(taddr, r); }
+        tmem_ld_wait();
+        if (gm >= p.M) continue;
+        const int ncols = min(32, x.nt - c0);
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        if (i >= ncols) break;
-        float v[4];
+        for (int i = 0; i < 32; i += 4) {
+          if (i >= ncols) break;
+          float v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          float x = nkb > 0 ? __uint_as_float(r[i + u]) : 0.f;
-          const int gn = n0 + c0 + i + u;
-          if (!split && i + u < ncols) {
-            if (p.bias) x += p.bias[gn];
-            if (p.flags & LSTUR_GEMM_ACCUM) x += crow[gn];
-            if (p.flags & LSTUR_GEMM_RELU) x = fmaxf(x, 0.f);
+          for (int u = 0; u < 4; ++u) {
+            float xv = x.nkb > 0 ? __uint_as_float(r[i + u]) : 0.f;
+            const int gn = x.n0 + c0 + i + u;
+            if (!split && i + u < ncols) {
+              if (p.bias) xv += p.bias[gn];
+              if (p.flags & LSTUR_GEMM_ACCUM) xv += crow[gn];
+              if (p.flags & LSTUR_GEMM_RELU) xv = fmaxf(xv, 0.f);
+            }
+            v[u] = xv;
           }
-          v[u] = x;
-        }
-        if (i + 4 <= ncols && vec_st && ((n0 + c0 + i) & 3) == 0) {
-          *reinterpret_cast<float4*>(crow + n0 + c0 + i) = make_float4(v[0], v[1], v[2], v[3]);
-        } else {
+          if (i + 4 <= ncols && vec_st && ((x.n0 + c0 + i) & 3) == 0) {
+            *reinterpret_cast<float4*>(crow + x.n0 + c0 + i) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (i + u < ncols) crow[n0 + c0 + i + u] = v[u];
+            for (int u = 0; u < 4; ++u)
+              if (i + u < ncols) crow[x.n0 + c0 + i + u] = v[u];
+          }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_t_empty + 8 * acc);     // accumulator free for the tile after next
+      acc ^= 1;
     }
-    tc_fence_before();
   }
   __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -322,7 +363,13 @@ extern "C" int lstur_gemm_tc(int transA, int transB, int M, int N, int K, const 
     }
     attr = true;
   }
-  dim3 grid((N + p.ntile - 1) / p.ntile, (M + tc::TILE_M - 1) / tc::TILE_M, splits);
+  p.tiles_n = (N + p.ntile - 1) / p.ntile;
+  p.tiles_m = (M + tc::TILE_M - 1) / tc::TILE_M;
+  p.splits = splits;
+  const long long n_tiles = (long long)p.tiles_m * p.tiles_n * splits;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  dim3 grid((unsigned)(n_tiles < sms ? n_tiles : sms));
 #define LAUNCH(TA_, TB_)                                                                    \
   do {                                                                                      \
     if (split3) tc::gemm_tc_kernel<TA_, TB_, true><<<grid, tc::G_THREADS, smem, stream>>>(p); \
