@@ -208,36 +208,94 @@ __device__ __forceinline__ uint4 pack8<__nv_bfloat16>(const float* v) {
   return u;
 }
 
+constexpr int IMG_THREADS = 256;     // 64 chunk columns x 4 row groups
 template <typename CT>
-__global__ void __launch_bounds__(ATT_THREADS)
+__global__ void __launch_bounds__(IMG_THREADS)
 attn_bwd_img_kernel(int N, int L, int F, const CT* __restrict__ Cd, const float* __restrict__ a_in,
                     const float* __restrict__ w_in, const float* __restrict__ dp, long long lddp,
                     const float* __restrict__ ka, uint8_t* __restrict__ img, float inv_keep,
                     float* __restrict__ partials) {
   extern __shared__ __align__(16) uint8_t att_smem[];
   const int nchunk = F >> 3;                       // 16-byte chunks per row
-  uint4* sC = reinterpret_cast<uint4*>(att_smem);  // [L][nchunk]
-  float* sdp = reinterpret_cast<float*>(att_smem + (size_t)32 * nchunk * 16);   // [F]
-  float* ska = sdp + F;                                                           // [F]
-  float* sred = ska + F;                                                          // [2][64][16] reduction scratch
+  // Two title buffers: the (contiguous, L*F*2-byte) saved C of the NEXT title is fetched with one bulk copy while the
+  // current one is processed; its d_pooled row and attention weights are prefetched into registers.
+  const size_t buf_bytes = (size_t)32 * nchunk * 16;
+  float* sdp = reinterpret_cast<float*>(att_smem + 2 * buf_bytes);   // [F]
+  float* ska = sdp + F;                                              // [F]
+  float* sred = ska + F;                                             // [3][64][16] reduction scratch
   __shared__ float sdw[32], sdz[32], sw[32];
+  __shared__ __align__(8) unsigned long long s_bar[2];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int c = tid & 63, tg = tid >> 6;           // chunk owned by this thread, row group (0/1)
+  const int c = tid & 63, tg = tid >> 6;           // chunk owned by this thread, row group (0..3)
   const bool c_ok = c < nchunk;
   const int Fh = F >> 1, ngh = (Fh + 63) >> 6;     // image: [half][group][32 rows][128 B] per title (see store_dpre_img)
   const long long blk_bytes = (long long)2 * ngh * 4096;
-  for (int f = tid; f < F; f += ATT_THREADS) ska[f] = ka[f];
+  const uint32_t title_bytes = (uint32_t)L * F * sizeof(CT);
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
+  const uint32_t buf0 = (uint32_t)__cvta_generic_to_shared(att_smem);
+  auto fetch_title = [&](int n, int b) {   // one thread
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * b), "r"(title_bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     buf0 + (uint32_t)(b * buf_bytes)),
+                 "l"(Cd + (long long)n * L * F), "r"(title_bytes), "r"(bar0 + 8 * b)
+                 : "memory");
+  };
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int f = tid; f < F; f += IMG_THREADS) ska[f] = ka[f];
+  __syncthreads();
   float dka[8], dbc[8], dba = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) dka[i] = dbc[i] = 0.f;
-  for (int n = blockIdx.x; n < N; n += gridDim.x) {
-    __syncthreads();   // previous title fully consumed (also orders the ska fill on the first trip)
-    const uint4* src = reinterpret_cast<const uint4*>(Cd + (long long)n * L * F);
-    for (int i = tid; i < L * nchunk; i += ATT_THREADS) sC[i] = __ldg(src + i);
-    for (int f = tid; f < F; f += ATT_THREADS) sdp[f] = dp[(long long)n * lddp + f];
-    if (tid < L) sw[tid] = w_in[(long long)n * L + tid];
+  constexpr int DPR = 2;                            // d_pooled values per thread (F <= DPR * IMG_THREADS)
+  float ndp[DPR], nw = 0.f, na = 0.f;
+  auto prefetch_small = [&](int n) {
+#pragma unroll
+    for (int i = 0; i < DPR; ++i) {
+      const int f = tid + i * IMG_THREADS;
+      ndp[i] = (n < N && f < F) ? dp[(long long)n * lddp + f] : 0.f;
+    }
+    nw = (n < N && tid < L) ? w_in[(long long)n * L + tid] : 0.f;
+    na = (n < N && tid < L) ? a_in[(long long)n * L + tid] : 0.f;
+  };
+  if (blockIdx.x < N) {
+    if (tid == 0) fetch_title(blockIdx.x, 0);
+    prefetch_small(blockIdx.x);
+  }
+  uint32_t phase[2] = {0, 0};
+  int it = 0;
+  for (int n = blockIdx.x; n < N; n += gridDim.x, ++it) {
+    const int b = it & 1;
+    const uint4* sC = reinterpret_cast<const uint4*>(att_smem + b * buf_bytes);  // [L][nchunk]
+    __syncthreads();   // previous title fully consumed: its buffer, sdp and sw may be overwritten
+    const int n_next = n + gridDim.x;
+    if (tid == 0 && n_next < N) fetch_title(n_next, b ^ 1);
+#pragma unroll
+    for (int i = 0; i < DPR; ++i) {
+      const int f = tid + i * IMG_THREADS;
+      if (f < F) sdp[f] = ndp[i];
+    }
+    if (tid < L) sw[tid] = nw;
+    const float a_cur = na;
+    prefetch_small(n_next);
+    {   // wait for this title's bulk copy
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar0 + 8 * b), "r"(phase[b])
+            : "memory");
+      }
+      phase[b] ^= 1;
+    }
     __syncthreads();
-    for (int t = warp; t < L; t += ATT_THREADS / 32) {
+    for (int t = warp; t < L; t += IMG_THREADS / 32) {
       float dot = 0.f;
       for (int cc = lane; cc < nchunk; cc += 32) {
         float v[8];
@@ -252,10 +310,7 @@ attn_bwd_img_kernel(int N, int L, int F, const CT* __restrict__ Cd, const float*
     if (tid < 32) {
       float q = 0.f;
       for (int t = 0; t < L; ++t) q = fmaf(sdw[t], sw[t], q);
-      if (tid < L) {
-        const float a = a_in[(long long)n * L + tid];
-        sdz[tid] = (sdw[tid] - q) * sw[tid] * (1.f - a * a);
-      }
+      if (tid < L) sdz[tid] = (sdw[tid] - q) * sw[tid] * (1.f - a_cur * a_cur);
     }
     __syncthreads();
     if (c_ok) {
@@ -264,7 +319,7 @@ attn_bwd_img_kernel(int N, int L, int F, const CT* __restrict__ Cd, const float*
       for (int i = 0; i < 8; ++i) { dpf[i] = sdp[c * 8 + i]; kaf[i] = ska[c * 8 + i]; }
       const int hf = (c * 8 >= Fh) ? 1 : 0, fl = c * 8 - hf * Fh;
       const int g = hf * ngh + (fl >> 6), piece = (fl & 63) >> 3;
-      for (int t = tg; t < 32; t += 2) {
+      for (int t = tg; t < 32; t += 4) {
         float o[8];
         if (t < L) {
           float v[8];
@@ -288,19 +343,22 @@ attn_bwd_img_kernel(int N, int L, int F, const CT* __restrict__ Cd, const float*
     if (tid == 0)
       for (int t = 0; t < L; ++t) dba += sdz[t];
   }
-  // combine the two row groups, then one partial row per CTA
+  // combine the four row groups in a fixed order, then one partial row per CTA
   __syncthreads();
-  if (tg == 1 && c_ok) {
+  if (tg > 0 && c_ok) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { sred[c * 16 + i] = dka[i]; sred[c * 16 + 8 + i] = dbc[i]; }
+    for (int i = 0; i < 8; ++i) { sred[((tg - 1) * 64 + c) * 16 + i] = dka[i]; sred[((tg - 1) * 64 + c) * 16 + 8 + i] = dbc[i]; }
   }
   __syncthreads();
   float* out = partials + (long long)blockIdx.x * (2 * F + 1);
   if (tg == 0 && c_ok) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      out[c * 8 + i] = dka[i] + sred[c * 16 + i];
-      out[F + c * 8 + i] = dbc[i] + sred[c * 16 + 8 + i];
+      float a = dka[i], bsum = dbc[i];
+#pragma unroll
+      for (int g = 0; g < 3; ++g) { a += sred[(g * 64 + c) * 16 + i]; bsum += sred[(g * 64 + c) * 16 + 8 + i]; }
+      out[c * 8 + i] = a;
+      out[F + c * 8 + i] = bsum;
     }
   }
   if (tid == 0) out[2 * F] = dba;
@@ -333,13 +391,13 @@ extern "C" int lstur_attn_pool_fwd(int N, int L, int F, float* C, long long titl
   return LSTUR_OK;
 }
 
-// CTAs of the attention-backward kernels: 6 per SM (shared memory: ~33 KB per CTA at F=400), one title per CTA trip
+// CTAs of the attention-backward kernels: 3 per SM (shared memory: two 25.6 KB title buffers + 7 KB per CTA at F=400)
 extern "C" int lstur_attn_bwd_grid(int N) {
   static int per_sm = 0;
   if (!per_sm) {
     const char* e = getenv("LSTUR_ATTN_CTAS_PER_SM");
-    per_sm = e ? atoi(e) : 6;
-    if (per_sm < 1 || per_sm > 16) per_sm = 6;
+    per_sm = e ? atoi(e) : 3;
+    if (per_sm < 1 || per_sm > 16) per_sm = 3;
   }
   return N < 148 * per_sm ? (N > 0 ? N : 1) : 148 * per_sm;
 }
@@ -446,16 +504,16 @@ extern "C" int lstur_attn_pool_bwd_img(int fp16, int N, int L, int F, const void
     return LSTUR_OK;
   }
   const float inv_keep = 1.f / (1.f - dropout);
-  size_t smem = (size_t)32 * (F / 8) * 16 + (size_t)2 * F * sizeof(float) + (size_t)64 * 16 * sizeof(float);
+  size_t smem = (size_t)2 * 32 * (F / 8) * 16 + (size_t)2 * F * sizeof(float) + (size_t)3 * 64 * 16 * sizeof(float);
   if (smem > 48 * 1024) {
     cudaFuncSetAttribute(attn_bwd_img_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(attn_bwd_img_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
   if (fp16)
-    attn_bwd_img_kernel<__half><<<grid, ATT_THREADS, smem, stream>>>(N, L, F, (const __half*)Cd_16, a_in, w_in, d_pooled, lddp,
+    attn_bwd_img_kernel<__half><<<grid, IMG_THREADS, smem, stream>>>(N, L, F, (const __half*)Cd_16, a_in, w_in, d_pooled, lddp,
                                                                      att_w, (uint8_t*)dpre_img, inv_keep, partials);
   else
-    attn_bwd_img_kernel<__nv_bfloat16><<<grid, ATT_THREADS, smem, stream>>>(N, L, F, (const __nv_bfloat16*)Cd_16, a_in, w_in,
+    attn_bwd_img_kernel<__nv_bfloat16><<<grid, IMG_THREADS, smem, stream>>>(N, L, F, (const __nv_bfloat16*)Cd_16, a_in, w_in,
                                                                             d_pooled, lddp, att_w, (uint8_t*)dpre_img,
                                                                             inv_keep, partials);
   LSTUR_CHECK_LAUNCH("lstur_attn_pool_bwd_img");
