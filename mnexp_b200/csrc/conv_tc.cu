@@ -102,6 +102,7 @@ struct EpiCtx {
   const float* s_bias;            // conv bias x conv-dropout keep scale (ReLU is positively homogeneous)
   const float* s_ka;
   uint32_t thr, base_lo, inner0, inner1;   // conv-dropout stream of this thread's token row (thr = quad_addend)
+  int dbg;
 };
 
 // Epilogue pass 1 for NC accumulator columns of one token row -> features [f0, f0+NC): scale + bias + ReLU (+ pad-token
@@ -164,7 +165,7 @@ struct RowIO {
 // positively homogeneous), so dropping is a bitwise AND on the packed pair.
 template <bool FP16, bool DROP, int NC>
 __device__ __forceinline__ void epi_pass1_chunk(const EpiCtx& ec, const RowIO& io, uint32_t taddr, int f0, bool live, float& z,
-                                                float& vmax) {
+                                                uint32_t& anybits) {
   uint32_t r[NC];
   if (NC == 32) { TMEM_LD_32(taddr, r); } else if (NC == 16) { TMEM_LD_16(taddr, r); } else { TMEM_LD_8(taddr, r); }
   tmem_ld_wait();
@@ -175,12 +176,12 @@ __device__ __forceinline__ void epi_pass1_chunk(const EpiCtx& ec, const RowIO& i
 #pragma unroll
     for (int g = 0; g < NC / 4; ++g) {
       const float4 b4 = *reinterpret_cast<const float4*>(ec.s_bias + f0 + 4 * g);
-      const float v0 = fmaxf(fmaf(__uint_as_float(r[4 * g + 0]), ec.sx, b4.x), 0.f);
-      const float v1 = fmaxf(fmaf(__uint_as_float(r[4 * g + 1]), ec.sx, b4.y), 0.f);
-      const float v2 = fmaxf(fmaf(__uint_as_float(r[4 * g + 2]), ec.sx, b4.z), 0.f);
-      const float v3 = fmaxf(fmaf(__uint_as_float(r[4 * g + 3]), ec.sx, b4.w), 0.f);
-      vmax = fmaxf(vmax, fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)));      // Masking(): any(C != 0) before the dropout
-      uint32_t p0 = pack16x2<FP16>(v0, v1), p1 = pack16x2<FP16>(v2, v3);
+      const float v0 = fmaf(__uint_as_float(r[4 * g + 0]), ec.sx, b4.x);
+      const float v1 = fmaf(__uint_as_float(r[4 * g + 1]), ec.sx, b4.y);
+      const float v2 = fmaf(__uint_as_float(r[4 * g + 2]), ec.sx, b4.z);
+      const float v3 = fmaf(__uint_as_float(r[4 * g + 3]), ec.sx, b4.w);
+      uint32_t p0 = pack16x2_relu<FP16>(v0, v1), p1 = pack16x2_relu<FP16>(v2, v3);   // ReLU fused into the conversion
+      anybits |= p0 | p1;      // Masking(): any(C != 0) before the dropout, on the values the model actually stores
       if (DROP) {   // the keep scale is already folded into sx / s_bias: dropping is a pure zeroing of the packed halves
         const uint32_t lo = ec.base_lo + (uint32_t)((f0 >> 2) + g);          // quad index of features f0+4g .. +3
         uint32_t u0, u1;
@@ -197,16 +198,16 @@ __device__ __forceinline__ void epi_pass1_chunk(const EpiCtx& ec, const RowIO& i
       z = fmaf(hi16<FP16>(p1), k4.w, z);
     }
   }
-  io.store(packed, f0, NC / 8);
+  if (!(ec.dbg & 8)) io.store(packed, f0, NC / 8);
 }
 // one accumulator segment [ca, ca+n) -> features [f0, f0+n), n a multiple of 8
 template <bool FP16, bool DROP>
 __device__ __forceinline__ void epi_pass1_segment(const EpiCtx& ec, const RowIO& io, uint32_t trow, int ca, int f0, int n,
-                                                  bool live, float& z, float& vmax) {
+                                                  bool live, float& z, uint32_t& anybits) {
   int c = 0;
-  for (; c + 32 <= n; c += 32) epi_pass1_chunk<FP16, DROP, 32>(ec, io, trow + ca + c, f0 + c, live, z, vmax);
-  if (c + 16 <= n) { epi_pass1_chunk<FP16, DROP, 16>(ec, io, trow + ca + c, f0 + c, live, z, vmax); c += 16; }
-  if (c + 8 <= n) epi_pass1_chunk<FP16, DROP, 8>(ec, io, trow + ca + c, f0 + c, live, z, vmax);
+  for (; c + 32 <= n; c += 32) epi_pass1_chunk<FP16, DROP, 32>(ec, io, trow + ca + c, f0 + c, live, z, anybits);
+  if (c + 16 <= n) { epi_pass1_chunk<FP16, DROP, 16>(ec, io, trow + ca + c, f0 + c, live, z, anybits); c += 16; }
+  if (c + 8 <= n) epi_pass1_chunk<FP16, DROP, 8>(ec, io, trow + ca + c, f0 + c, live, z, anybits);
 }
 
 // CTA pairs (cta_group::2): CTA `rank` of a pair owns the token tile 2*tp + rank (its own A rows, its own 128 x F
@@ -436,6 +437,7 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
     ec.s_bias = s_bias;
     ec.s_ka = s_ka;
     ec.thr = p.drop_addend;
+    ec.dbg = p.dbg;
     uint32_t pht = 0;
     int par = 0;
     RowIO io;
@@ -457,7 +459,8 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
       mbar_wait(bar_t_full, pht, 6);
       pht ^= 1;
       tc_fence_after();
-      float z = 0.f, vmax = 0.f;
+      float z = 0.f;
+      uint32_t vmax = 0u;      // OR of the packed pre-dropout values of this row half
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
       if (p.dbg & 1) {
         tc_fence_before();
@@ -479,7 +482,7 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
       }
       const int row = q * 32 + lane;
       s_z[(par * 2 + half) * 128 + row] = z;
-      s_any[(par * 2 + half) * 128 + row] = vmax > 0.f ? 1 : 0;
+      s_any[(par * 2 + half) * 128 + row] = vmax != 0u ? 1 : 0;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const float zt = s_z[(par * 2) * 128 + row] + s_z[(par * 2 + 1) * 128 + row];
       const int anyt = s_any[(par * 2) * 128 + row] | s_any[(par * 2 + 1) * 128 + row];
@@ -492,34 +495,45 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
         if (p.att_a) p.att_a[m] = a;
         if (p.att_wt) p.att_wt[m] = w;
       }
-      // ---- pass 2: pooled[n, f] = sum_t w_t * C[t, f]; butterfly reduce-scatter over the 32 lanes (rows).  The rows
-      // are re-read from global (own warp's writes, L2) one chunk ahead of the reduction.
+      // ---- pass 2: pooled[n, f] = sum_t w_t * C[t, f].  The stored rows are re-read (own warp's writes, L2) in the
+      // coalesced mapping — lane (r8 = lane/4, piece = lane%4) holds piece `piece` of rows r8, r8+8, r8+16, r8+24 —
+      // weighted with those rows' attention weights, and the 8 lanes that share a piece finish with a 3-stage
+      // reduce-scatter (7 shuffles per 32 features): no shared-memory staging on this pass.
+      if (p.dbg & 4) continue;
+      float wr[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) wr[i] = __shfl_sync(0xffffffffu, w, (lane >> 2) + 8 * i);
       uint4 nxt[4];
       io.load_issue(f_beg, min(4, (f_end - f_beg) >> 3), nxt);
+      const int jfeat = ((lane >> 2) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 4) & 1);   // feature of the piece this lane ends with
       for (int c0 = f_beg; c0 < f_end; c0 += 32) {
-        const int ncols = min(32, f_end - c0);
+        const int np = min(4, (f_end - c0) >> 3);
         uint4 cur[4];
-        io.load_finish(nxt, cur);
-        if (c0 + 32 < f_end) io.load_issue(c0 + 32, min(4, (f_end - c0 - 32) >> 3), nxt);
-        float x[32];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          x[g * 8 + 0] = w * lo16<FP16>(cur[g].x); x[g * 8 + 1] = w * hi16<FP16>(cur[g].x);
-          x[g * 8 + 2] = w * lo16<FP16>(cur[g].y); x[g * 8 + 3] = w * hi16<FP16>(cur[g].y);
-          x[g * 8 + 4] = w * lo16<FP16>(cur[g].z); x[g * 8 + 5] = w * hi16<FP16>(cur[g].z);
-          x[g * 8 + 6] = w * lo16<FP16>(cur[g].w); x[g * 8 + 7] = w * hi16<FP16>(cur[g].w);
+        for (int g = 0; g < 4; ++g) cur[g] = nxt[g];
+        if (c0 + 32 < f_end) io.load_issue(c0 + 32, min(4, (f_end - c0 - 32) >> 3), nxt);
+        float x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          x[0] = fmaf(wr[i], lo16<FP16>(cur[i].x), x[0]); x[1] = fmaf(wr[i], hi16<FP16>(cur[i].x), x[1]);
+          x[2] = fmaf(wr[i], lo16<FP16>(cur[i].y), x[2]); x[3] = fmaf(wr[i], hi16<FP16>(cur[i].y), x[3]);
+          x[4] = fmaf(wr[i], lo16<FP16>(cur[i].z), x[4]); x[5] = fmaf(wr[i], hi16<FP16>(cur[i].z), x[5]);
+          x[6] = fmaf(wr[i], lo16<FP16>(cur[i].w), x[6]); x[7] = fmaf(wr[i], hi16<FP16>(cur[i].w), x[7]);
         }
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
+        for (int st = 0; st < 3; ++st) {
+          const int off = 4 << st, half_n = 4 >> st;
           const bool up = (lane & off) != 0;
 #pragma unroll
-          for (int k = 0; k < off; ++k) {
-            const float send = up ? x[k] : x[k + off];
-            const float keep = up ? x[k + off] : x[k];
+          for (int k = 0; k < half_n; ++k) {
+            const float send = up ? x[k] : x[k + half_n];
+            const float keep = up ? x[k + half_n] : x[k];
             x[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
           }
         }
-        if (n < p.n_titles && lane < ncols) p.pooled[(long long)n * F + c0 + lane] = x[0];
+        if (n < p.n_titles && (lane & 3) < np) p.pooled[(long long)n * F + c0 + (lane & 3) * 8 + jfeat] = x[0];
       }
     }
   }

@@ -169,6 +169,14 @@ __device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
   }
 }
+// max(x, 0) + round to 16 bits (saturating) + pack, one F2FP instruction
+template <bool FP16>
+__device__ __forceinline__ uint32_t pack16x2_relu(float lo, float hi) {
+  uint32_t r;
+  if (FP16) asm("cvt.rn.satfinite.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.satfinite.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 template <bool FP16>
 __device__ __forceinline__ float lo16(uint32_t w) {
   if (FP16) return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu)));
