@@ -266,6 +266,16 @@ int lstur_forward(const lstur_plan* plan, const lstur_weights* w, const lstur_ba
 int lstur_backward(const lstur_plan* plan, const lstur_weights* w, const lstur_batch* b, void* workspace,
                    float* dense_grad, float grad_scale, cudaStream_t stream);
 
+/* Decomposed inference (task/test_pipeline.py:37-211; BASELINE config 4): encode documents once, then run the user
+ * encoder and scorer against the cached vectors.  lstur_encode_docs handles n <= B*(W+C) documents per call
+ * (doc_ids on the device, weights->doc_tokens required); lstur_forward_docvecs gathers history / candidate vectors from
+ * doc_vec_table (n_rows, ld == document-vector width) — an all-zero row (unknown / pad document) is a masked history
+ * slot — and leaves probs / logits / user_vec in the workspace like lstur_forward. */
+int lstur_encode_docs(const lstur_plan* plan, const lstur_weights* weights, void* workspace, int n, const int* doc_ids,
+                      float* doc_vec_out, long long ldo, cudaStream_t stream);
+int lstur_forward_docvecs(const lstur_plan* plan, const lstur_weights* weights, const lstur_batch* batch, void* workspace,
+                          const float* doc_vec_table, long long ld, int n_rows, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

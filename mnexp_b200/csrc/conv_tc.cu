@@ -962,8 +962,8 @@ extern "C" int lstur_news_conv_tc_fwd(int n_titles, int L, int E, int F, int V, 
   return LSTUR_OK;
 }
 
-extern "C" int lstur_news_encoder_tc_fwd_internal(const lstur_plan* p, const lstur_weights* w, void* ws, int training,
-                                                  unsigned seed, cudaStream_t st) {
+extern "C" int lstur_news_encoder_tc_fwd_internal(const lstur_plan* p, const lstur_weights* w, void* ws, int n_titles,
+                                                  int training, unsigned seed, cudaStream_t st) {
   const lstur_config& c = p->c;
   void* emb = W<void>(p, ws, "emb_bf16");
   void* wimg = W<void>(p, ws, "wimg");
@@ -976,7 +976,7 @@ extern "C" int lstur_news_encoder_tc_fwd_internal(const lstur_plan* p, const lst
   }
   RC(lstur_pack_conv_w_tc(c.E, c.F, DP(p, w->dense, "conv_w"), wimg, fp16, st));
   PROBE_BEGIN(p, LSTUR_PROBE_CONV_FWD, st);
-  RC(lstur_news_conv_tc_fwd(p->N, c.L, c.E, c.F, c.V, W<int>(p, ws, "tokens"), emb, wimg, DP(p, w->dense, "conv_b"),
+  RC(lstur_news_conv_tc_fwd(n_titles, c.L, c.E, c.F, c.V, W<int>(p, ws, "tokens"), emb, wimg, DP(p, w->dense, "conv_b"),
                             DP(p, w->dense, "att_w"), DP(p, w->dense, "att_b"), W<void>(p, ws, "C16"),
                             W<float>(p, ws, "pooled"), W<float>(p, ws, "att_a"), W<float>(p, ws, "att_w"),
                             training ? c.dropout : 0.f, seed, fp16, 0, st));

@@ -268,59 +268,54 @@ extern "C" int lstur_plan_view(const lstur_plan* plan, void* workspace, const ch
 
 // tensor-core news encoder (conv_tc.cu); declared here, defined there.
 extern "C" int lstur_news_encoder_tc_fwd_internal(const lstur_plan* plan, const lstur_weights* w, void* workspace,
-                                                  int training, unsigned seed, cudaStream_t stream);
+                                                  int n_titles, int training, unsigned seed, cudaStream_t stream);
 
-extern "C" int lstur_forward(const lstur_plan* p, const lstur_weights* w, const lstur_batch* b, void* ws, int training,
-                             unsigned seed, cudaStream_t st) {
-  LSTUR_REQUIRE(p && w && b && ws, "lstur_forward");
-  LSTUR_REQUIRE(w->dense && w->word_emb && b->user, "lstur_forward");
+namespace {
+
+// News encoder (k1-k7) over the first n title slots of the workspace: tokens[0..n) -> doc_vec[0..n).
+int encode_titles(const lstur_plan* p, const lstur_weights* w, void* ws, int n, int training, unsigned seed, cudaStream_t st) {
   const lstur_config& c = p->c;
-  const int N = p->N, Nh = p->Nh, Nc = p->Nc, Lp = p->Lp, D = p->D, L = c.L, E = c.E, F = c.F, G = c.G, B = c.B;
-  const bool bw = c.save_for_backward != 0;
+  const int Lp = p->Lp, D = p->D, L = c.L, E = c.E, F = c.F;
   const gemm_fn GEMM = pick_gemm(p);
-  LSTUR_REQUIRE(!training || bw, "lstur_forward(training needs a save_for_backward plan)");
   const float drop = training ? c.dropout : 0.f;
-  const_cast<lstur_plan*>(p)->last_seed = seed;
-  const_cast<lstur_plan*>(p)->last_training = training;
   int* tok = W<int>(p, ws, "tokens");
-  // 1. title tokens (k0)
-  if (b->hist_tok) {
-    LSTUR_REQUIRE(b->cand_tok != nullptr, "lstur_forward");
-    cudaMemcpyAsync(tok, b->hist_tok, (size_t)Nh * L * 4, cudaMemcpyDeviceToDevice, st);
-    cudaMemcpyAsync(tok + (size_t)Nh * L, b->cand_tok, (size_t)Nc * L * 4, cudaMemcpyDeviceToDevice, st);
-  } else {
-    LSTUR_REQUIRE(b->hist_doc && b->cand_doc && w->doc_tokens, "lstur_forward");
-    RC(lstur_token_gather(Nh, L, c.n_docs, w->doc_tokens, b->hist_doc, tok, st));
-    RC(lstur_token_gather(Nc, L, c.n_docs, w->doc_tokens, b->cand_doc, tok + (size_t)Nh * L, st));
-  }
   float* pooled = W<float>(p, ws, "pooled");
   float* docv = W<float>(p, ws, "doc_vec");
   void* gws = W<void>(p, ws, "gemm_ws");
   const size_t gwsb = p->gemm_ws_bytes;
-  // 2. news encoder (k1-k7)
   if ((c.precision == LSTUR_PREC_BF16_TC || c.precision == LSTUR_PREC_FP16_TC)) {
-    RC(lstur_news_encoder_tc_fwd_internal(p, w, ws, training, seed, st));
+    RC(lstur_news_encoder_tc_fwd_internal(p, w, ws, n, training, seed, st));
   } else {
     float* Xp = W<float>(p, ws, "Xp");
     float* Cp = W<float>(p, ws, "Cp");
     PROBE_BEGIN(p, LSTUR_PROBE_GATHER, st);
-    RC(lstur_embed_gather_pad(N, L, E, c.V, c.KS, w->word_emb, tok, Xp, drop, seed * 2u + 0u, st));
+    RC(lstur_embed_gather_pad(n, L, E, c.V, c.KS, w->word_emb, tok, Xp, drop, seed * 2u + 0u, st));
     PROBE_END(p, LSTUR_PROBE_GATHER, st);
     PROBE_BEGIN(p, LSTUR_PROBE_CONV_FWD, st);
-    RC(lstur_gemm_f32(0, 0, N * Lp - (c.KS - 1), F, c.KS * E, Xp, E, DP(p, w->dense, "conv_w"), F, Cp, F,
+    RC(lstur_gemm_f32(0, 0, n * Lp - (c.KS - 1), F, c.KS * E, Xp, E, DP(p, w->dense, "conv_w"), F, Cp, F,
                       DP(p, w->dense, "conv_b"), LSTUR_GEMM_RELU, gws, gwsb, st));
     PROBE_END(p, LSTUR_PROBE_CONV_FWD, st);
-    RC(lstur_attn_pool_fwd(N, L, F, Cp, (long long)Lp * F, tok, DP(p, w->dense, "att_w"), DP(p, w->dense, "att_b"),
+    RC(lstur_attn_pool_fwd(n, L, F, Cp, (long long)Lp * F, tok, DP(p, w->dense, "att_w"), DP(p, w->dense, "att_b"),
                            pooled, F, W<float>(p, ws, "att_a"), W<float>(p, ws, "att_w"), drop, seed * 2u + 1u, st));
   }
   if (c.use_dense) {
-    RC(GEMM(0, 0, N, c.Dd, F, pooled, F, DP(p, w->dense, "dense_w"), c.Dd, docv, D,
+    RC(GEMM(0, 0, n, c.Dd, F, pooled, F, DP(p, w->dense, "dense_w"), c.Dd, docv, D,
                       DP(p, w->dense, "dense_b"), LSTUR_GEMM_PRECISE, gws, gwsb, st));
   } else {
-    cudaMemcpy2DAsync(docv, (size_t)D * 4, pooled, (size_t)F * 4, (size_t)F * 4, N, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpy2DAsync(docv, (size_t)D * 4, pooled, (size_t)F * 4, (size_t)F * 4, n, cudaMemcpyDeviceToDevice, st);
   }
-  // 3. history mask (k9)
-  RC(lstur_hist_mask_apply(Nh, L, D, tok, docv, D, W<float>(p, ws, "hist_mask"), W<float>(p, ws, "gru_mask"), st));
+  return LSTUR_OK;
+}
+
+// User encoder + scorer + loss (k10-k14) on doc_vec / gru_mask already in the workspace.
+int user_and_score(const lstur_plan* p, const lstur_weights* w, const lstur_batch* b, void* ws, cudaStream_t st) {
+  const lstur_config& c = p->c;
+  const int Nh = p->Nh, D = p->D, G = c.G, B = c.B;
+  const bool bw = c.save_for_backward != 0;
+  const gemm_fn GEMM = pick_gemm(p);
+  float* docv = W<float>(p, ws, "doc_vec");
+  void* gws = W<void>(p, ws, "gemm_ws");
+  const size_t gwsb = p->gemm_ws_bytes;
   // 4. user embedding (k10)
   float* uvec = W<float>(p, ws, "user_vec");
   float* u0 = W<float>(p, ws, "u0");
@@ -370,6 +365,76 @@ extern "C" int lstur_forward(const lstur_plan* p, const lstur_weights* w, const 
     return LSTUR_ERR_CUDA;
   }
   return LSTUR_OK;
+}
+
+}  // namespace
+
+extern "C" int lstur_forward(const lstur_plan* p, const lstur_weights* w, const lstur_batch* b, void* ws, int training,
+                             unsigned seed, cudaStream_t st) {
+  LSTUR_REQUIRE(p && w && b && ws, "lstur_forward");
+  LSTUR_REQUIRE(w->dense && w->word_emb && b->user, "lstur_forward");
+  const lstur_config& c = p->c;
+  const int N = p->N, Nh = p->Nh, Nc = p->Nc, D = p->D, L = c.L;
+  const bool bw = c.save_for_backward != 0;
+  LSTUR_REQUIRE(!training || bw, "lstur_forward(training needs a save_for_backward plan)");
+  const_cast<lstur_plan*>(p)->last_seed = seed;
+  const_cast<lstur_plan*>(p)->last_training = training;
+  int* tok = W<int>(p, ws, "tokens");
+  // 1. title tokens (k0)
+  if (b->hist_tok) {
+    LSTUR_REQUIRE(b->cand_tok != nullptr, "lstur_forward");
+    cudaMemcpyAsync(tok, b->hist_tok, (size_t)Nh * L * 4, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(tok + (size_t)Nh * L, b->cand_tok, (size_t)Nc * L * 4, cudaMemcpyDeviceToDevice, st);
+  } else {
+    LSTUR_REQUIRE(b->hist_doc && b->cand_doc && w->doc_tokens, "lstur_forward");
+    RC(lstur_token_gather(Nh, L, c.n_docs, w->doc_tokens, b->hist_doc, tok, st));
+    RC(lstur_token_gather(Nc, L, c.n_docs, w->doc_tokens, b->cand_doc, tok + (size_t)Nh * L, st));
+  }
+  // 2. news encoder (k1-k7)
+  RC(encode_titles(p, w, ws, N, training, seed, st));
+  // 3. history mask (k9)
+  RC(lstur_hist_mask_apply(Nh, L, D, tok, W<float>(p, ws, "doc_vec"), D, W<float>(p, ws, "hist_mask"),
+                           W<float>(p, ws, "gru_mask"), st));
+  return user_and_score(p, w, b, ws, st);
+}
+
+// ---- decomposed inference (task/test_pipeline.py:37-211): doc vectors once, then users against the cached vectors
+// doc_vec_out[i, :] = doc_encoder(title of doc_ids[i]) for n <= B*(W+C) documents (test_doc_vec, :37-75).
+extern "C" int lstur_encode_docs(const lstur_plan* p, const lstur_weights* w, void* ws, int n, const int* doc_ids,
+                                 float* doc_vec_out, long long ldo, cudaStream_t st) {
+  LSTUR_REQUIRE(p && w && ws && w->dense && w->word_emb && w->doc_tokens, "lstur_encode_docs");
+  LSTUR_REQUIRE(n >= 0 && n <= p->N && doc_ids && doc_vec_out && ldo >= p->D, "lstur_encode_docs");
+  if (n == 0) return LSTUR_OK;
+  const lstur_config& c = p->c;
+  RC(lstur_token_gather(n, c.L, c.n_docs, w->doc_tokens, doc_ids, W<int>(p, ws, "tokens"), st));
+  RC(encode_titles(p, w, ws, n, 0, 0u, st));
+  cudaMemcpy2DAsync(doc_vec_out, (size_t)ldo * 4, W<float>(p, ws, "doc_vec"), (size_t)p->D * 4, (size_t)p->D * 4, n,
+                    cudaMemcpyDeviceToDevice, st);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("lstur_encode_docs: %s", cudaGetErrorString(e));
+    return LSTUR_ERR_CUDA;
+  }
+  return LSTUR_OK;
+}
+
+// User encoder + scorer over cached document vectors (test_user_vec / test_user_doc_score, :77-211): history and
+// candidate vectors are rows of doc_vec_table (n_rows, ld); a history slot whose vector is all zero (unknown / pad
+// document, :104-108) is masked, exactly as keras Masking() does inside the user encoder.
+extern "C" int lstur_forward_docvecs(const lstur_plan* p, const lstur_weights* w, const lstur_batch* b, void* ws,
+                                     const float* doc_vec_table, long long ld, int n_rows, cudaStream_t st) {
+  LSTUR_REQUIRE(p && w && b && ws && w->dense && b->user && b->hist_doc && b->cand_doc, "lstur_forward_docvecs");
+  LSTUR_REQUIRE(doc_vec_table && ld >= p->D && n_rows > 0, "lstur_forward_docvecs");
+  const lstur_config& c = p->c;
+  const int Nh = p->Nh, Nc = p->Nc, D = p->D;
+  const_cast<lstur_plan*>(p)->last_training = 0;
+  float* docv = W<float>(p, ws, "doc_vec");
+  // lstur_row_gather reads `ld`-strided rows when table rows are wider than D: gather D columns per row
+  LSTUR_REQUIRE(ld == D, "lstur_forward_docvecs(ld must equal the document-vector width)");
+  RC(lstur_row_gather(Nh, D, n_rows, doc_vec_table, b->hist_doc, nullptr, docv, D, st));
+  RC(lstur_row_gather(Nc, D, n_rows, doc_vec_table, b->cand_doc, nullptr, docv + (size_t)Nh * D, D, st));
+  RC(lstur_hist_mask_apply(Nh, c.L, D, nullptr, docv, D, W<float>(p, ws, "hist_mask"), W<float>(p, ws, "gru_mask"), st));
+  return user_and_score(p, w, b, ws, st);
 }
 
 

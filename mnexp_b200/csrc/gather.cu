@@ -77,9 +77,12 @@ __global__ void hist_mask_apply_kernel(int rows, int L, int D, const int* __rest
                                        long long ldh, float* __restrict__ hm_out, float* __restrict__ gm_out) {
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
-  int nz = 0;
-  for (int l = lane; l < L; l += 32) nz |= (tok[(long long)warp * L + l] != 0);
-  nz = warp_or(nz);
+  int nz = 1;       // tok == null (cached document vectors): only the Masking() part, gm = any(H != 0)
+  if (tok) {
+    nz = 0;
+    for (int l = lane; l < L; l += 32) nz |= (tok[(long long)warp * L + l] != 0);
+    nz = warp_or(nz);
+  }
   float* h = H + (long long)warp * ldh;
   int any = 0;
   for (int d = lane; d < D; d += 32) {
@@ -89,7 +92,7 @@ __global__ void hist_mask_apply_kernel(int rows, int L, int D, const int* __rest
   }
   any = warp_or(any);
   if (lane == 0) {
-    if (hm_out) hm_out[warp] = nz ? 1.f : 0.f;
+    if (hm_out) hm_out[warp] = (tok ? nz : any) ? 1.f : 0.f;
     gm_out[warp] = any ? 1.f : 0.f;
   }
 }

@@ -200,6 +200,43 @@ class LsturEngine:
                                           int(training), ctypes.c_uint(seed), self._stream()))
         return self.view('probs').reshape(self.B, self.C)
 
+    # ---- decomposed inference (task/test_pipeline.py:37-211; BASELINE config 4) ---------------------------------
+    def encode_docs(self, doc_ids):
+        """doc_encoder.predict over documents given by id (TestPipeline.test_doc_vec): -> (n, D) device tensor.
+        Processed in chunks of B*(W+C) titles, the title capacity of this engine's plan."""
+        ids = doc_ids if torch.is_tensor(doc_ids) else torch.as_tensor(np.ascontiguousarray(doc_ids))
+        ids = ids.to(self.device, dtype=torch.int32).contiguous()
+        n = int(ids.numel())
+        out = torch.empty((n, self.D), dtype=torch.float32, device=self.device)
+        if self._emb_seen != self._emb_version[0]:
+            _lib.check(self.lib.lstur_plan_invalidate_tables(self.plan))
+            self._emb_seen = self._emb_version[0]
+        cap = self.B * (self.W + self.C)
+        for i in range(0, n, cap):
+            m = min(cap, n - i)
+            _lib.check(self.lib.lstur_encode_docs(self.plan, ctypes.byref(self._w), _ptr(self.ws), m,
+                                                  ctypes.c_void_p(ids.data_ptr() + 4 * i),
+                                                  ctypes.c_void_p(out.data_ptr() + 4 * i * self.D), self.D, self._stream()))
+        return out
+
+    def build_doc_table(self):
+        """Vectors of every document of the token table, row 0 (the pad / unknown document) zeroed: the reference's
+        pipeline leaves history slots without a known document at zero (task/test_pipeline.py:100-108)."""
+        n_docs = int(self.doc_tokens.shape[0])
+        table = self.encode_docs(torch.arange(n_docs, dtype=torch.int32, device=self.device))
+        table[0].zero_()
+        return table
+
+    def forward_docvecs(self, db, table):
+        """User encoder + scorer over cached document vectors (TestPipeline.test_user_vec / test_user_doc_score);
+        db carries user, hist_doc (B,W), cand_doc (B,C).  Returns the (B, C) softmax probabilities; score_sigmoid()
+        gives the test head as after forward()."""
+        cb = self._cbatch(db)
+        assert table.dtype == torch.float32 and table.is_contiguous() and table.shape[1] == self.D
+        _lib.check(self.lib.lstur_forward_docvecs(self.plan, ctypes.byref(self._w), ctypes.byref(cb), _ptr(self.ws),
+                                                  _ptr(table), self.D, int(table.shape[0]), self._stream()))
+        return self.view('probs').reshape(self.B, self.C)
+
     def backward(self, db, grad_scale=None):
         cb = self._cbatch(db)
         gs = 1.0 / self.B if grad_scale is None else grad_scale

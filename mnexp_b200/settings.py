@@ -72,6 +72,17 @@ class Config:
         return os.path.join(self.log_dir, 'log{}.txt'.format(self.name))
 
     @property
+    def pipeline_inputs(self):
+        """settings.py:169-174"""
+        return (os.path.join(self.pipeline_input, 'docs.tsv'), os.path.join(self.pipeline_input, 'UserClick.tsv'),
+                os.path.join(self.pipeline_input, 'userDocPair.tsv'))
+
+    @property
+    def pipeline_output(self):
+        """settings.py:176-178"""
+        return os.path.join(self.pipeline_input, 'score_' + self.name + '.tsv')
+
+    @property
     def train_npz_input(self):
         return os.path.join(self.input_training_data_path, 'train_{}days_{}window.npz').format(self.days, self.window_size)
 

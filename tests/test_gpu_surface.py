@@ -122,3 +122,70 @@ def test_surface_tensor_core_precision(lib):
     assert rel(model.predict(x), ref) < 1e-3
     hist = model.fit_generator(h.train, 5, epochs=1)
     assert np.isfinite(hist.history['loss'][0])
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'fp16_tc'])
+@pytest.mark.parametrize('arch', ['igru', 'gru'])
+def test_decomposed_pipeline_matches_full_model(lib, arch, precision):
+    from mnexp_b200.engine import LsturEngine
+    """The reference's own self-check (task/test_pipeline.py:257-265): scoring through cached document vectors
+    (doc_encoder once per document, then user_encoder + dot) equals the full model on the same impressions."""
+    sh = synth.SHAPES['C1']
+    tok, _, _ = synth.make_docs(sh.n_news, sh.L, sh.vocab)
+    P = synth.make_weights(sh, arch=arch, bias_noise=0.05)
+    (b,), _ = synth.make_batches(sh, 1)
+    eng = LsturEngine(P, sh.B, sh.W, 1 + sh.K, sh.L, arch=arch, doc_tokens=tok, precision=precision, training=False)
+    db = eng.to_device_batch(b)
+    full = eng.forward(db).cpu().numpy().copy()
+    full_sig = eng.score_sigmoid().cpu().numpy().copy()
+    table = eng.build_doc_table()
+    assert table.shape == (tok.shape[0], eng.D) and float(table[0].abs().max()) == 0.0
+    dec = eng.forward_docvecs(db, table).cpu().numpy().copy()
+    dec_sig = eng.score_sigmoid().cpu().numpy()
+    # the same kernels encode a document wherever its title sits in a batch: fp32 results agree to rounding of the
+    # differently-tiled GEMMs, the tensor-core path bit for bit in the encoder
+    tol = 1e-5
+    assert np.abs(dec - full).max() < tol and np.abs(dec_sig - full_sig).max() < tol
+    # and against the float64 oracle through cached vectors
+    ref = on.lstur_forward(P, b['user'], tok[b['hist_doc']], tok[b['cand_doc']], arch=arch)
+    assert np.abs(dec - ref).max() / np.abs(ref).max() < (2e-5 if precision == 'fp32' else 1e-3)
+
+
+def test_pipeline_files_mirror(lib):
+    """TestPipeline over the reference's three pipeline files (docs.tsv / UserClick.tsv / userDocPair.tsv):
+    test_correct's two printed numbers agree, and every written score is the dot product of the cached vectors."""
+    from mnexp_b200.task.test_pipeline import TestPipeline
+    sh, h = _handler('igru', pipeline_input=tempfile.mkdtemp(), name='t')
+    h.build_model(0)
+    cfg = h.config
+    g = np.random.default_rng(3)
+    docs = sorted(k for k in h.docs if k != 0)[:40]
+    with open(cfg.pipeline_inputs[0], 'w') as f:
+        for d in docs:
+            toks = [int(x) for x in h.docs[d].title if x != 0] or [1]
+            f.write('d%d\t%s\n' % (d, ' '.join(map(str, toks))))
+    users = []
+    with open(cfg.pipeline_inputs[1], 'w') as f:
+        for u in range(11):
+            clicks = ['d%d' % docs[i] for i in g.integers(0, len(docs), g.integers(1, sh.W + 3))]
+            if u == 3:
+                clicks.append('d_unknown')                  # not in docs.tsv: stays a zero vector
+            users.append((str(u), 'x', clicks))
+            f.write('%d\tx\t%s\n' % (u, '#N#'.join(clicks)))
+    with open(cfg.pipeline_inputs[2], 'w') as f:
+        for u in range(11):
+            for d in g.integers(0, len(docs), 3):
+                f.write('%d\tx\td%d\n' % (u, docs[d]))
+        f.write('999\tx\td%d\n' % docs[0])                   # unknown user: skipped like the reference does
+    tp = TestPipeline(cfg)
+    tp.load_model(h)
+    tp.test_doc_vec()
+    tp.test_user_vec()
+    tp.test_user_doc_score()
+    assert len(tp.doc_vec) == len(docs) and len(tp.user_vec) == 11
+    lines = [l.rstrip('\n').split('\t') for l in open(cfg.pipeline_output)]
+    assert len(lines) == 33
+    for uid, ut, d, sc in lines:
+        assert abs(float(sc) - float(np.dot(tp.user_vec[uid + ut].astype(np.float64), tp.doc_vec[d].astype(np.float64)))) < 1e-6
+    pred, sigm = tp.test_correct()
+    assert abs(float(np.asarray(pred).reshape(-1)[0]) - float(np.asarray(sigm).reshape(-1)[0])) < 1e-5
