@@ -196,6 +196,19 @@ int lstur_rows_add(int max_rows, const int* n_rows_dev, int D, const int* rows, 
                    cudaStream_t stream);
 int lstur_axpby(long long n, float a, const float* x, float b, float* y, cudaStream_t stream);
 
+/* Cook.get_doc_encoder concat (task/cook.py:99-113): doc_vec[n, col0 .. col0+dv) = vert_emb[doc_vert[doc_ids[n]]],
+ * doc_vec[n, col0+dv .. +ds) = subvert_emb[doc_subvert[doc_ids[n]]]; the looked-up ids are kept in title_vert /
+ * title_subvert (n) for the backward.  lstur_small_table_grad is the Embedding backward of such a small table:
+ * d_table[r, :] = sum over titles n with ids[n] == r of d_doc_vec[n, col0 .. col0+dim), two-stage, fixed order. */
+int lstur_vert_concat(int n, int D, int col0, int dv, int ds, int n_docs, int n_vert, int n_subvert, const int* doc_ids,
+                      const int* doc_vert, const int* doc_subvert, const float* vert_emb, const float* subvert_emb,
+                      float* doc_vec, int* title_vert, int* title_subvert, cudaStream_t stream);
+size_t lstur_small_table_grad_workspace_bytes(int n_rows, int dim);
+int lstur_small_table_grad(int n, int D, int col0, int dim, int n_rows, const int* ids, const float* d_doc_vec,
+                           float* d_table, float* workspace, size_t workspace_bytes, cudaStream_t stream);
+/* x[b, 0..D) *= scale[b]  (backward of the user-vector multiplier: dgru whole-vector dropout, cook id_keep) */
+int lstur_scale_rows(int B, int D, const float* scale, float* x, long long ld, cudaStream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Whole-path plan: Seq2VecPaperSoftmaxId._build_model (task/paper.py:635-665) /
  * Cook._build_model (task/cook.py:214-277) as one forward / backward / update sequence.
@@ -211,6 +224,7 @@ typedef struct lstur_config {
   int V, n_users, n_docs;
   float dropout;
   int save_for_backward; /* 0: inference plan (smaller workspace)                            */
+  int n_vert, n_subvert; /* rows of the vertical / subvertical tables (16 / 307, utils.py:153-228) */
 } lstur_config;
 
 typedef struct lstur_weights {

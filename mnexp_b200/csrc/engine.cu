@@ -97,10 +97,7 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
     set_error("lstur_plan_create: Unsupport user model (task/paper.py:630)");
     return LSTUR_ERR_UNSUPPORTED;
   }
-  if (c.dv != 0 || c.ds != 0) {
-    set_error("lstur_plan_create: vertical/subvertical concat not implemented yet");
-    return LSTUR_ERR_UNSUPPORTED;
-  }
+  LSTUR_REQUIRE(c.dv >= 0 && c.ds >= 0 && (c.dv == 0 || c.n_vert > 0) && (c.ds == 0 || c.n_subvert > 0), "lstur_plan_create");
   const int Dd = c.use_dense ? c.Dd : c.F;
   const int D = Dd + c.dv + c.ds;
   const bool has_gru = c.arch != LSTUR_ARCH_VO;
@@ -140,6 +137,8 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
     add_dense(p, "dense_w", (long long)F * Dd);
     add_dense(p, "dense_b", Dd);
   }
+  if (c.dv) add_dense(p, "vert_emb", (long long)c.n_vert * c.dv);
+  if (c.ds) add_dense(p, "subvert_emb", (long long)c.n_subvert * c.ds);
   if (has_gru) {
     add_dense(p, "gru_wx", (long long)D * 3 * G);
     add_dense(p, "gru_wh", (long long)G * 3 * G);
@@ -165,6 +164,15 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
   add_ws(p, "att_w", N * c.L);
   add_ws(p, "pooled", N * F);
   add_ws(p, "doc_vec", N * D);
+  if (c.dv + c.ds) {
+    add_ws(p, "title_vert", N);
+    add_ws(p, "title_subvert", N);
+    if (bw) {
+      size_t a = c.dv ? lstur_small_table_grad_workspace_bytes(c.n_vert, c.dv) : 0;
+      size_t b2 = c.ds ? lstur_small_table_grad_workspace_bytes(c.n_subvert, c.ds) : 0;
+      add_ws(p, "vert_grad_ws", (long long)((a > b2 ? a : b2) / 4) + 4);
+    }
+  }
   add_ws(p, "hist_mask", Nh);
   add_ws(p, "gru_mask", Nh);
   if (has_user) add_ws(p, "u0", B * c.Ue);
@@ -392,6 +400,18 @@ extern "C" int lstur_forward(const lstur_plan* p, const lstur_weights* w, const 
   }
   // 2. news encoder (k1-k7)
   RC(encode_titles(p, w, ws, N, training, seed, st));
+  if (c.dv + c.ds) {   // [title ‖ Vemb[vert] ‖ Semb[subvert]] (task/cook.py:99-113), doc-id protocol only
+    LSTUR_REQUIRE(b->hist_doc && b->cand_doc && (c.dv == 0 || w->doc_vert) && (c.ds == 0 || w->doc_subvert),
+                  "lstur_forward(vertical concat needs doc ids and the doc_vert / doc_subvert tables)");
+    float* docv = W<float>(p, ws, "doc_vec");
+    int* tv = W<int>(p, ws, "title_vert");
+    int* ts = W<int>(p, ws, "title_subvert");
+    RC(lstur_vert_concat(Nh, D, c.Dd, c.dv, c.ds, c.n_docs, c.n_vert, c.n_subvert, b->hist_doc, w->doc_vert, w->doc_subvert,
+                         DP(p, w->dense, "vert_emb"), DP(p, w->dense, "subvert_emb"), docv, tv, ts, st));
+    RC(lstur_vert_concat(Nc, D, c.Dd, c.dv, c.ds, c.n_docs, c.n_vert, c.n_subvert, b->cand_doc, w->doc_vert, w->doc_subvert,
+                         DP(p, w->dense, "vert_emb"), DP(p, w->dense, "subvert_emb"), docv + (size_t)Nh * D, tv + Nh, ts + Nh,
+                         st));
+  }
   // 3. history mask (k9)
   RC(lstur_hist_mask_apply(Nh, L, D, tok, W<float>(p, ws, "doc_vec"), D, W<float>(p, ws, "hist_mask"),
                            W<float>(p, ws, "gru_mask"), st));
@@ -500,15 +520,22 @@ extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const
   if (has_user) {
     RC(lstur_sort_unique_i32(B, b->user, W<int>(p, ws, "sorted_pos"), W<int>(p, ws, "user_rows"),
                              W<int>(p, ws, "seg_start"), W<int>(p, ws, "inverse"), W<int>(p, ws, "n_user_rows"), st));
-    if (b->user_scale) {
-      set_error("lstur_backward: user_scale backward not implemented");
-      return LSTUR_ERR_UNSUPPORTED;
-    }
+    // contiguous per-sample copy (also what the data-parallel sparse exchange sends); the user-vector multiplier
+    // (dgru / id_keep) scales the gradient of its embedding row
+    float* d_u0 = W<float>(p, ws, "d_u0");
+    cudaMemcpy2DAsync(d_u0, (size_t)c.Ue * 4, du0, (size_t)lddu0 * 4, (size_t)c.Ue * 4, B, cudaMemcpyDeviceToDevice, st);
+    if (b->user_scale) RC(lstur_scale_rows(B, c.Ue, b->user_scale, d_u0, c.Ue, st));
     RC(lstur_segment_sum_rows(B, c.Ue, W<int>(p, ws, "n_user_rows"), W<int>(p, ws, "seg_start"),
-                              W<int>(p, ws, "sorted_pos"), du0, lddu0, W<float>(p, ws, "d_user_rows"), st));
-    // contiguous per-sample copy for the data-parallel sparse exchange
-    cudaMemcpy2DAsync(W<float>(p, ws, "d_u0"), (size_t)c.Ue * 4, du0, (size_t)lddu0 * 4, (size_t)c.Ue * 4, B,
-                      cudaMemcpyDeviceToDevice, st);
+                              W<int>(p, ws, "sorted_pos"), d_u0, c.Ue, W<float>(p, ws, "d_user_rows"), st));
+  }
+  // 5a. vertical / subvertical Embedding backward (task/cook.py:99-103): the extra columns of d doc_vec
+  if (c.dv + c.ds) {
+    float* vws = W<float>(p, ws, "vert_grad_ws");
+    const size_t vwsb = p->ws.at("vert_grad_ws").count * 4;
+    if (c.dv) RC(lstur_small_table_grad(N, D, c.Dd, c.dv, c.n_vert, W<int>(p, ws, "title_vert"), d_docv,
+                                        DG(p, dgrad, "vert_emb"), vws, vwsb, st));
+    if (c.ds) RC(lstur_small_table_grad(N, D, c.Dd + c.dv, c.ds, c.n_subvert, W<int>(p, ws, "title_subvert"), d_docv,
+                                        DG(p, dgrad, "subvert_emb"), vws, vwsb, st));
   }
   // 5. news-encoder backward over all N titles
   float* d_pooled = W<float>(p, ws, "d_pooled");

@@ -109,6 +109,57 @@ __global__ void row_gather_kernel(int B, int D, int n_rows, const float* __restr
   for (int d = lane; d < D; d += 32) out[(long long)warp * ldo + d] = __ldg(table + (long long)id * D + d) * s;
 }
 
+
+// One warp per title: ids -> vertical / subvertical rows -> the extra columns of the document vector.
+__global__ void vert_concat_kernel(int n, int D, int col0, int dv, int ds, int n_docs, int n_vert, int n_sub,
+                                   const int* __restrict__ doc_ids, const int* __restrict__ doc_vert,
+                                   const int* __restrict__ doc_subvert, const float* __restrict__ vert_emb,
+                                   const float* __restrict__ subvert_emb, float* __restrict__ docv,
+                                   int* __restrict__ tv, int* __restrict__ ts) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  int d = doc_ids[warp];
+  d = (d < 0 || d >= n_docs) ? 0 : d;
+  int v = dv ? doc_vert[d] : 0, sv = ds ? doc_subvert[d] : 0;
+  v = (v < 0 || v >= n_vert) ? 0 : v;
+  sv = (sv < 0 || sv >= n_sub) ? 0 : sv;
+  float* row = docv + (long long)warp * D + col0;
+  for (int j = lane; j < dv; j += 32) row[j] = vert_emb[(long long)v * dv + j];
+  for (int j = lane; j < ds; j += 32) row[dv + j] = subvert_emb[(long long)sv * ds + j];
+  if (lane == 0) {
+    if (tv) tv[warp] = v;
+    if (ts) ts[warp] = sv;
+  }
+}
+
+// Stage 1 of the small-table Embedding backward: CTA (r, k) adds, in ascending title order, the gradient columns of
+// the titles of chunk k whose id is r.  Stage 2 adds the chunk partials in ascending chunk order.
+constexpr int STG_CHUNKS = 64;
+__global__ void small_table_grad1_kernel(int n, int D, int col0, int dim, const int* __restrict__ ids,
+                                         const float* __restrict__ dd, float* __restrict__ partial) {
+  const int r = blockIdx.x, k = blockIdx.y, n_rows = gridDim.x;
+  const int per = (n + STG_CHUNKS - 1) / STG_CHUNKS;
+  const int beg = k * per, end = min(n, beg + per);
+  float acc = 0.f;
+  const int j = threadIdx.x;
+  for (int i = beg; i < end; ++i)
+    if (ids[i] == r && j < dim) acc += dd[(long long)i * D + col0 + j];
+  if (j < dim) partial[((long long)k * n_rows + r) * dim + j] = acc;
+}
+__global__ void small_table_grad2_kernel(int n_rows, int dim, const float* __restrict__ partial, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * dim) return;
+  float acc = 0.f;
+  for (int k = 0; k < STG_CHUNKS; ++k) acc += partial[(long long)k * n_rows * dim + i];
+  out[i] = acc;
+}
+__global__ void scale_rows_kernel(int B, int D, const float* __restrict__ scale, float* __restrict__ x, long long ld) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * D) return;
+  const int b = (int)(i / D), d = (int)(i % D);
+  x[(long long)b * ld + d] *= scale[b];
+}
+
 }  // namespace lstur
 
 using namespace lstur;
@@ -163,5 +214,44 @@ extern "C" int lstur_row_gather(int B, int D, int n_rows, const float* table, co
   if (B == 0) return LSTUR_OK;
   row_gather_kernel<<<cdiv((long long)B * 32, 256), 256, 0, stream>>>(B, D, n_rows, table, ids, scale, out, ldo);
   LSTUR_CHECK_LAUNCH("lstur_row_gather");
+  return LSTUR_OK;
+}
+
+extern "C" int lstur_vert_concat(int n, int D, int col0, int dv, int ds, int n_docs, int n_vert, int n_subvert, const int* doc_ids,
+                                 const int* doc_vert, const int* doc_subvert, const float* vert_emb, const float* subvert_emb,
+                                 float* doc_vec, int* title_vert, int* title_subvert, cudaStream_t stream) {
+  LSTUR_REQUIRE(n >= 0 && dv >= 0 && ds >= 0 && col0 >= 0 && col0 + dv + ds <= D && doc_ids && doc_vec, "lstur_vert_concat");
+  LSTUR_REQUIRE((dv == 0 || (doc_vert && vert_emb && n_vert > 0)) && (ds == 0 || (doc_subvert && subvert_emb && n_subvert > 0)),
+                "lstur_vert_concat");
+  if (n == 0 || dv + ds == 0) return LSTUR_OK;
+  vert_concat_kernel<<<cdiv((long long)n * 32, 256), 256, 0, stream>>>(n, D, col0, dv, ds, n_docs, n_vert, n_subvert, doc_ids,
+                                                                       doc_vert, doc_subvert, vert_emb, subvert_emb, doc_vec,
+                                                                       title_vert, title_subvert);
+  LSTUR_CHECK_LAUNCH("lstur_vert_concat");
+  return LSTUR_OK;
+}
+
+extern "C" size_t lstur_small_table_grad_workspace_bytes(int n_rows, int dim) {
+  return (size_t)STG_CHUNKS * n_rows * dim * sizeof(float);
+}
+
+extern "C" int lstur_small_table_grad(int n, int D, int col0, int dim, int n_rows, const int* ids, const float* d_doc_vec,
+                                      float* d_table, float* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  LSTUR_REQUIRE(n >= 0 && dim > 0 && dim <= 1024 && n_rows > 0 && col0 >= 0 && col0 + dim <= D && d_table, "lstur_small_table_grad");
+  LSTUR_REQUIRE(workspace && workspace_bytes >= lstur_small_table_grad_workspace_bytes(n_rows, dim), "lstur_small_table_grad");
+  LSTUR_REQUIRE(n == 0 || (ids && d_doc_vec), "lstur_small_table_grad");
+  const int threads = (dim + 31) / 32 * 32;
+  small_table_grad1_kernel<<<dim3(n_rows, STG_CHUNKS), threads, 0, stream>>>(n, D, col0, dim, ids, d_doc_vec, workspace);
+  LSTUR_CHECK_LAUNCH("lstur_small_table_grad(stage 1)");
+  small_table_grad2_kernel<<<cdiv((long long)n_rows * dim, 256), 256, 0, stream>>>(n_rows, dim, workspace, d_table);
+  LSTUR_CHECK_LAUNCH("lstur_small_table_grad(stage 2)");
+  return LSTUR_OK;
+}
+
+extern "C" int lstur_scale_rows(int B, int D, const float* scale, float* x, long long ld, cudaStream_t stream) {
+  LSTUR_REQUIRE(B >= 0 && D > 0 && scale && x && ld >= D, "lstur_scale_rows");
+  if (B == 0) return LSTUR_OK;
+  scale_rows_kernel<<<cdiv((long long)B * D, 256), 256, 0, stream>>>(B, D, scale, x, ld);
+  LSTUR_CHECK_LAUNCH("lstur_scale_rows");
   return LSTUR_OK;
 }

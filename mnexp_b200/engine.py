@@ -34,7 +34,8 @@ class LsturEngine:
 
     def __init__(self, params, B, W, C, L, arch='igru', flavour='paper', dropout=0.0, lr=1e-3,
                  recurrent_activation='hard_sigmoid', precision='fp32', doc_tokens=None, device=None,
-                 training=True, sparse_user_adam=True, trainable_word_emb=False, share_weights_from=None):
+                 training=True, sparse_user_adam=True, trainable_word_emb=False, share_weights_from=None,
+                 doc_vert=None, doc_subvert=None):
         if not torch.cuda.is_available():
             raise _lib.LsturError('LsturEngine needs a CUDA device (no CPU fallback)')
         self.lib = _lib.load()
@@ -51,16 +52,20 @@ class LsturEngine:
         G = params['gru_wh'].shape[0] if 'gru_wh' in params else 0
         Ue = params['user_emb'].shape[1] if 'user_emb' in params and self.arch != 3 else 0
         U = {0: G, 1: params['con_w'].shape[1] if 'con_w' in params else 0, 2: G + Ue, 3: G, 4: G, 5: Ue}[self.arch]
+        # Cook.get_doc_encoder concat (task/cook.py:99-113): [title | Vemb[vert] | Semb[subvert]]
+        dv = params['vert_emb'].shape[1] if 'vert_emb' in params else 0
+        ds = params['subvert_emb'].shape[1] if 'subvert_emb' in params else 0
         _sd = share_weights_from.doc_tokens if share_weights_from is not None else None
         n_docs = doc_tokens.shape[0] if doc_tokens is not None else (0 if _sd is None else _sd.shape[0])
         self.cfg = lstur_config(
-            B=B, W=W, C=C, L=L, E=E, F=F, KS=ks, use_dense=int(use_dense), Dd=Dd, dv=0, ds=0, G=G, Ue=Ue, U=U,
+            B=B, W=W, C=C, L=L, E=E, F=F, KS=ks, use_dense=int(use_dense), Dd=Dd, dv=dv, ds=ds, G=G, Ue=Ue, U=U,
             arch=self.arch, score_model=0, rec_act=0 if recurrent_activation == 'hard_sigmoid' else 1,
             precision=PREC[precision], V=params['word_emb'].shape[0],
             n_users=params['user_emb'].shape[0] if Ue else 0,
             n_docs=n_docs, dropout=float(dropout),
-            save_for_backward=int(training))
-        self.B, self.W, self.C, self.L, self.D, self.U, self.Ue, self.G = B, W, C, L, Dd, U, Ue, G
+            save_for_backward=int(training),
+            n_vert=params['vert_emb'].shape[0] if dv else 0, n_subvert=params['subvert_emb'].shape[0] if ds else 0)
+        self.B, self.W, self.C, self.L, self.D, self.U, self.Ue, self.G = B, W, C, L, Dd + dv + ds, U, Ue, G
         plan = ctypes.c_void_p()
         _lib.check(self.lib.lstur_plan_create(ctypes.byref(self.cfg), ctypes.byref(plan)))
         self.plan = plan
@@ -87,6 +92,9 @@ class LsturEngine:
             self.doc_tokens = src.doc_tokens
         else:
             self.doc_tokens = None if doc_tokens is None else torch.as_tensor(np.ascontiguousarray(doc_tokens, dtype=np.int32)).to(dev)
+        i32dev = lambda a: None if a is None else torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+        self.doc_vert = i32dev(doc_vert) if src is None or doc_vert is not None else src.doc_vert
+        self.doc_subvert = i32dev(doc_subvert) if src is None or doc_subvert is not None else src.doc_subvert
         if src is None:
             self.set_weights_dict(params)
         ws_bytes = int(self.lib.lstur_plan_workspace_bytes(plan))
@@ -109,7 +117,8 @@ class LsturEngine:
         self._w = lstur_weights(dense=self.dense.data_ptr(), word_emb=self.word_emb.data_ptr(),
                                 user_emb=self.user_emb.data_ptr() if Ue else None,
                                 doc_tokens=self.doc_tokens.data_ptr() if self.doc_tokens is not None else None,
-                                doc_vert=None, doc_subvert=None)
+                                doc_vert=self.doc_vert.data_ptr() if self.doc_vert is not None else None,
+                                doc_subvert=self.doc_subvert.data_ptr() if self.doc_subvert is not None else None)
 
     def __del__(self):
         try:

@@ -197,19 +197,31 @@ def weighted_bce(y, p, gain, K):
     return float(-0.5 * (1 + K) * np.mean(y * np.log(p + 1e-8) * gain + (1 - y) * np.log(1 - p + 1e-8) / K))
 
 
+def _doc_vectors(tok, P, vert=None, subvert=None):
+    """paper.py doc encoder, or cook.py's [title ‖ Vemb[vert] ‖ Semb[subvert]] when vertical ids are given."""
+    d = news_encoder(tok, P, use_dense='dense_w' in P)
+    parts = [d]
+    if vert is not None and 'vert_emb' in P:
+        parts.append(P['vert_emb'].astype(np.float64)[np.asarray(vert).astype(np.int64).reshape(-1)])
+    if subvert is not None and 'subvert_emb' in P:
+        parts.append(P['subvert_emb'].astype(np.float64)[np.asarray(subvert).astype(np.int64).reshape(-1)])
+    return np.concatenate(parts, -1) if len(parts) > 1 else d
+
+
 def lstur_forward(P, user, clicked_tok, cand_tok, arch='igru', score_model='dot',
-                  recurrent_activation='hard_sigmoid', aux=False):
+                  recurrent_activation='hard_sigmoid', aux=False, hist_vert=None, hist_subvert=None, cand_vert=None,
+                  cand_subvert=None, u0_scale=None):
     """Seq2VecPaperSoftmaxId._build_model forward — task/paper.py:635-665.
 
     clicked_tok (B,W,L), cand_tok (B,C,L) -> softmax probs (B,C) and the
     test-model sigmoid scores."""
     B, W, L = clicked_tok.shape
     C = cand_tok.shape[1]
-    dh = news_encoder(clicked_tok.reshape(B * W, L), P).reshape(B, W, -1)
+    dh = _doc_vectors(clicked_tok.reshape(B * W, L), P, hist_vert, hist_subvert).reshape(B, W, -1)
     hm = history_mask(clicked_tok)
-    H = dh * hm[..., None]                                    # task/paper.py:644-645
-    u = user_encoder(arch, user, H, P, recurrent_activation)
-    dc = news_encoder(cand_tok.reshape(B * C, L), P).reshape(B, C, -1)
+    H = dh * hm[..., None]                                    # task/paper.py:644-645, task/cook.py:250
+    u = user_encoder(arch, user, H, P, recurrent_activation, u0_scale=u0_scale)
+    dc = _doc_vectors(cand_tok.reshape(B * C, L), P, cand_vert, cand_subvert).reshape(B, C, -1)
     s = score(u, dc, P, score_model)
     out = dict(probs=softmax(s), logits=s, sigmoid=sigmoid(s), user_vec=u, cand_vec=dc, hist_vec=H, hist_mask=hm)
     return out if aux else out['probs']

@@ -110,16 +110,30 @@ def categorical_crossentropy(y, p):
     return (-(y * torch.log(p)).sum(-1)).mean()
 
 
+def _doc_vectors(tok, P, vert=None, subvert=None, **kw):
+    """paper.py doc encoder, or cook.py's [title ‖ Vemb[vert] ‖ Semb[subvert]] (task/cook.py:99-113)."""
+    d = news_encoder(tok, P, use_dense='dense_w' in P, **kw)
+    parts = [d]
+    if vert is not None and 'vert_emb' in P:
+        parts.append(P['vert_emb'][torch.as_tensor(vert).long().reshape(-1)])
+    if subvert is not None and 'subvert_emb' in P:
+        parts.append(P['subvert_emb'][torch.as_tensor(subvert).long().reshape(-1)])
+    return torch.cat(parts, -1) if len(parts) > 1 else d
+
+
 def forward(P, user, clicked_tok, cand_tok, arch='igru', score_model='dot',
-            recurrent_activation='hard_sigmoid', dropout=0.0, training=False, aux=False):
+            recurrent_activation='hard_sigmoid', dropout=0.0, training=False, aux=False, hist_vert=None,
+            hist_subvert=None, cand_vert=None, cand_subvert=None, u0_scale=None):
     """Seq2VecPaperSoftmaxId._build_model — task/paper.py:635-665."""
     B, W, L = clicked_tok.shape
     C = cand_tok.shape[1]
-    dh = news_encoder(clicked_tok.reshape(B * W, L), P, dropout=dropout, training=training).reshape(B, W, -1)
+    dh = _doc_vectors(clicked_tok.reshape(B * W, L), P, hist_vert, hist_subvert, dropout=dropout,
+                      training=training).reshape(B, W, -1)
     hm = (clicked_tok != 0).any(-1).to(dh.dtype)
     H = dh * hm.unsqueeze(-1)
-    u = user_encoder(arch, user, H, P, recurrent_activation)
-    dc = news_encoder(cand_tok.reshape(B * C, L), P, dropout=dropout, training=training).reshape(B, C, -1)
+    u = user_encoder(arch, user, H, P, recurrent_activation, u0_scale=u0_scale)
+    dc = _doc_vectors(cand_tok.reshape(B * C, L), P, cand_vert, cand_subvert, dropout=dropout,
+                      training=training).reshape(B, C, -1)
     s = score(u, dc, P, score_model)
     probs = torch.softmax(s, -1)
     if aux:

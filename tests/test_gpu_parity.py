@@ -261,3 +261,52 @@ def test_c1_shape_forward_and_grads(L):
     got = eng.get_grads_dict()
     for k, g in ref.items():
         assert rel(got[k], g.numpy()) < 1e-4, k
+
+
+# ---------------------------------------------------------------- cook.py variant: vertical concat + id_keep
+@pytest.mark.parametrize('precision', ['fp32', 'fp16_tc'])
+def test_cook_vertical_concat_and_id_keep(L, precision):
+    """Cook.get_doc_encoder (task/cook.py:99-113): d' = [title_vec(F) | Vemb[vert] | Semb[subvert]], no Dense;
+    history concat masked by the title tokens (:236-250); user vector scaled by Dropout(1-id_keep)(idx_mask)
+    (:141-142, here an explicit per-row multiplier).  Forward vs the float64 oracle, gradients vs autograd."""
+    import dataclasses
+    from mnexp_b200.engine import LsturEngine
+    dv, ds = 3, 5
+    base = synth.SHAPES['tiny']
+    sh = dataclasses.replace(base, name='cook', U=base.F + dv + ds)
+    tok, vert, subvert = synth.make_docs(sh.n_news, sh.L, sh.vocab)
+    P = synth.make_weights(sh, arch='igru', bias_noise=0.05, cook=True, dv=dv, ds=ds)
+    (b,), _ = synth.make_batches(sh, 1, seed=77)
+    g = np.random.default_rng(5)
+    scale = (g.random(sh.B) < 0.7).astype(np.float32) / np.float32(0.7)          # idx_mask * dropout / id_keep
+    b = dict(b, user_scale=scale)
+    eng = LsturEngine(P, sh.B, sh.W, 1 + sh.K, sh.L, arch='ingru', flavour='cook', doc_tokens=tok, doc_vert=vert,
+                      doc_subvert=subvert, precision=precision)
+    assert eng.D == sh.F + dv + ds
+    db = eng.to_device_batch(b)
+    probs = eng.forward(db, training=True, seed=1).cpu().numpy().copy()          # dropout 0: training only saves state
+    kw = dict(hist_vert=vert[b['hist_doc']], hist_subvert=subvert[b['hist_doc']], cand_vert=vert[b['cand_doc']],
+              cand_subvert=subvert[b['cand_doc']])
+    ref = on.lstur_forward(P, b['user'], tok[b['hist_doc']], tok[b['cand_doc']], arch='igru', aux=True,
+                           u0_scale=scale[:, None].astype(np.float64), **kw)
+    tol = TOL_FP32 if precision == 'fp32' else TOL_SPEC
+    docv = eng.view('doc_vec').reshape(-1, eng.D).cpu().numpy()
+    nh = sh.B * sh.W
+    assert rel(docv[nh:], ref['cand_vec'].reshape(-1, eng.D)) < tol
+    assert np.array_equal(docv[nh:, sh.F:sh.F + dv], P['vert_emb'][vert[b['cand_doc']].reshape(-1)])      # gathers are exact
+    assert np.array_equal(docv[nh:, sh.F + dv:], P['subvert_emb'][subvert[b['cand_doc']].reshape(-1)])
+    assert rel(docv[:nh], ref['hist_vec'].reshape(nh, -1)) < tol
+    assert rel(probs, ref['probs']) < tol
+    if precision != 'fp32':
+        return
+    eng.backward(db)
+    torch.cuda.synchronize()
+    got = eng.get_grads_dict()
+    Pt = {k: torch.tensor(v, dtype=torch.float64, requires_grad=(k != 'word_emb')) for k, v in P.items()}
+    t = lambda x: torch.as_tensor(np.asarray(x)).long()
+    loss = ot.loss_fn(Pt, t(b['user']), t(tok[b['hist_doc']]), t(tok[b['cand_doc']]), arch='igru',
+                      u0_scale=torch.tensor(scale[:, None], dtype=torch.float64), **kw)
+    names = [k for k in Pt if k != 'word_emb']
+    grads = dict(zip(names, torch.autograd.grad(loss, [Pt[k] for k in names], allow_unused=True)))
+    for k in ('vert_emb', 'subvert_emb', 'conv_w', 'gru_wx', 'gru_wh', 'user_emb', 'att_w'):
+        assert rel(got[k], grads[k].numpy()) < 5e-5, k
