@@ -43,6 +43,19 @@ def peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0), 'fallback'
 
 
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this same command (profiles/r01_ncu_full_summary.json); None if absent."""
+    p = os.path.join(ROOT, 'profiles', 'r01_ncu_full_summary.json')
+    try:
+        for row in json.load(open(p)):
+            if kernel_substr in row['kernel']:
+                return (row['dram_read_GB'] + row['dram_write_GB']) * 1e9
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md)."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
@@ -240,12 +253,14 @@ def main():
     conv_tflops = fl['conv_fwd'] * B / (probe_ms / 1e3) / 1e12
     roofline = dict(bound='tensor', kernel='title Conv1D forward (implicit GEMM), precision=%s' % precision,
                     achieved=conv_tflops, peak=tensor_peak, unit='TFLOP/s', frac=conv_tflops / tensor_peak,
-                    traffic=None, peak_kind='%s bf16_tflops_sustained' % pk_kind, kernel_ms=probe_ms,
+                    traffic=ncu_traffic('news_conv_tc_fwd') if (B == sh.B and sh.name == 'C3') else None,
+                    traffic_unit='bytes of DRAM traffic per launch (ncu --set full, profiles/r01_ncu_full_summary.json)',
+                    peak_kind='%s bf16_tflops_sustained' % pk_kind, kernel_ms=probe_ms,
                     step_frac_of_train_roofline=(value / world) * fl['train'] / (tensor_peak * 1e12),
                     flops_per_impression_train=fl['train'])
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference_run(sh, 2, 1, args.cpu_sample)
+        cpu = cpu_reference_run(sh, 6, 1, args.cpu_sample)
         cpu.pop('ms_per_step', None)
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
