@@ -10,6 +10,8 @@
 // weight-gradient case — or B non-transposed) is staged MN-major, so no transposition ever happens in memory:
 // only the UMMA descriptor's major-ness bits differ.  Split-K over CTA.z with a fixed-order reduction.
 // Warp roles (416 threads): w0 MMA issuer + TMEM alloc, w1-8 producers, w9-12 epilogue.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace lstur {
@@ -288,6 +290,277 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const GemmParams 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Asynchronously staged variant (used when every operand row is 16-byte addressable): the fp32 operand tiles of the
+// next TWO K blocks are always in flight as cp.async copies into a raw shared-memory ring (2 x 64 KB), so the memory
+// system sees a deep request queue instead of one register round trip per batch of pieces; the producer warps only
+// convert raw fp32 -> swizzled fp16 tiles (shared to shared).  N tile <= 128, two 128-column accumulators.
+constexpr int GA_NT = 128;                       // max N tile
+constexpr int GA_RAW_A = TILE_M * G_KBLK * 4;    // 32 KB
+constexpr int GA_RAW_B = GA_NT * G_KBLK * 4;     // 32 KB
+constexpr int GA_RAW_STAGE = GA_RAW_A + GA_RAW_B;
+constexpr int GA_F16_A = TILE_M * 128;           // 16 KB
+constexpr int GA_F16_B = GA_NT * 128;            // 16 KB
+constexpr int GA_F16_STAGE = GA_F16_A + GA_F16_B;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;     // src-size 0: the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void lds8(uint32_t addr, float* v) {
+  float4 a, b;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(addr));
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(addr + 16));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+template <bool TA, bool TB, bool SPLIT>
+__global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_async_kernel(const GemmParams p) {
+  constexpr int FST = SPLIT ? 1 : 2;                                   // fp16 stages
+  constexpr int F16_STAGE = SPLIT ? 2 * GA_F16_STAGE : GA_F16_STAGE;   // hi (+ lo) tiles
+  constexpr int LO_OFF = GA_F16_STAGE;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t f16_base = smem_base, raw_base = smem_base + FST * F16_STAGE;
+  const uint32_t misc_base = raw_base + 2 * GA_RAW_STAGE;
+  uint8_t* misc_gen = smem_gen + (misc_base - smem_base);
+  const uint32_t bar_full = misc_base, bar_empty = misc_base + 64, bar_t_full = misc_base + 128, bar_t_empty = misc_base + 144;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(misc_gen + 160);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = p.tiles_m * p.tiles_n * p.splits;
+
+  struct Tile { int m0, n0, nt, nmma, z, kbeg, kend, nkb; };
+  auto tile_of = [&](int t) {
+    Tile x;
+    const int tn = t % p.tiles_n, tm = (t / p.tiles_n) % p.tiles_m;
+    x.z = t / (p.tiles_n * p.tiles_m);
+    x.m0 = tm * TILE_M;
+    x.n0 = tn * p.ntile;
+    x.nt = min(p.ntile, p.N - x.n0);
+    x.nmma = (x.nt + 15) & ~15;
+    x.kbeg = x.z * p.k_per_split;
+    x.kend = min(p.K, x.kbeg + p.k_per_split);
+    x.nkb = x.kend > x.kbeg ? (x.kend - x.kbeg + G_KBLK - 1) / G_KBLK : 0;
+    return x;
+  };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < FST; ++s) {
+      mbar_init(bar_full + 8 * s, G_PRODUCERS / 32);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_t_full + 8 * a, 1);
+      mbar_init(bar_t_empty + 8 * a, 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(256)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0, acc = 0;
+      uint32_t ph = 0, pht[2] = {0, 0};
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const Tile x = tile_of(t);
+        const uint32_t idesc = make_idesc(TILE_M, x.nmma, true) | (TA ? (1u << 15) : 0u) | (!TB ? (1u << 16) : 0u);
+        mbar_wait(bar_t_empty + 8 * acc, pht[acc] ^ 1, 24);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + acc * 128;
+        uint32_t accum = 0;
+        for (int kb = 0; kb < x.nkb; ++kb) {
+          mbar_wait(bar_full + 8 * s, ph, 21);
+          tc_fence_after();
+          const uint32_t a_addr = f16_base + s * F16_STAGE, b_addr = a_addr + GA_F16_A;
+#pragma unroll
+          for (int kk = 0; kk < G_KBLK / 16; ++kk) {
+            const uint64_t ad = TA ? make_desc_mn128(a_addr + kk * 2048, 8192) : make_desc_k128(a_addr + kk * 32);
+            const uint64_t bd = TB ? make_desc_k128(b_addr + kk * 32) : make_desc_mn128(b_addr + kk * 2048, 8192);
+            umma_bf16(tacc, ad, bd, idesc, accum);
+            accum = 1;
+            if (SPLIT) {
+              const uint64_t al = TA ? make_desc_mn128(a_addr + LO_OFF + kk * 2048, 8192) : make_desc_k128(a_addr + LO_OFF + kk * 32);
+              const uint64_t bl = TB ? make_desc_k128(b_addr + LO_OFF + kk * 32) : make_desc_mn128(b_addr + LO_OFF + kk * 2048, 8192);
+              umma_bf16(tacc, al, bd, idesc, 1);
+              umma_bf16(tacc, ad, bl, idesc, 1);
+            }
+          }
+          umma_commit(bar_empty + 8 * s);
+          if (++s == FST) { s = 0; ph ^= 1; }
+        }
+        umma_commit(bar_t_full + 8 * acc);
+        pht[acc] ^= 1;
+        acc ^= 1;
+      }
+    }
+  } else if (warp >= 1 && warp < 9) {
+    // ---- producers
+    const int pt = threadIdx.x - 32;         // 0..255
+    struct Iter { int t, kb; Tile x; };
+    auto first = [&]() {
+      Iter it;
+      it.t = blockIdx.x; it.kb = 0;
+      while (it.t < n_tiles && (it.x = tile_of(it.t)).nkb == 0) it.t += gridDim.x;
+      return it;
+    };
+    auto advance = [&](Iter& it) {
+      if (it.t >= n_tiles) return;
+      if (++it.kb < it.x.nkb) return;
+      it.kb = 0;
+      it.t += gridDim.x;
+      while (it.t < n_tiles && (it.x = tile_of(it.t)).nkb == 0) it.t += gridDim.x;
+    };
+    // request the raw fp32 tiles of K block `it` into raw stage rs (a group is committed even when nothing is left)
+    auto issue = [&](const Iter& it, int rs) {
+      if (it.t < n_tiles) {
+        const Tile& x = it.x;
+        const int k0 = x.kbeg + it.kb * G_KBLK;
+        const uint32_t ra = raw_base + rs * GA_RAW_STAGE, rb = ra + GA_RAW_A;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {            // A: 2048 16-byte chunks
+          const int ch = pt + i * G_PRODUCERS;
+          if (!TA) {
+            const int r = ch >> 4, c = ch & 15;
+            const bool ok = (x.m0 + r < p.M) && (k0 + 4 * c < x.kend);
+            cp_async16(ra + r * 256 + c * 16, p.A + (long long)(ok ? x.m0 + r : 0) * p.lda + (ok ? k0 + 4 * c : 0), ok);
+          } else {
+            const int kr = ch >> 5, c = ch & 31;
+            const bool ok = (k0 + kr < x.kend) && (x.m0 + 4 * c < p.M);
+            cp_async16(ra + kr * 512 + c * 16, p.A + (long long)(ok ? k0 + kr : 0) * p.lda + (ok ? x.m0 + 4 * c : 0), ok);
+          }
+        }
+        if (TB) {
+          for (int ch = pt; ch < x.nmma * 16; ch += G_PRODUCERS) {
+            const int r = ch >> 4, c = ch & 15;
+            const bool ok = (r < x.nt) && (k0 + 4 * c < x.kend);
+            cp_async16(rb + r * 256 + c * 16, p.B + (long long)(ok ? x.n0 + r : 0) * p.ldb + (ok ? k0 + 4 * c : 0), ok);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int ch = pt + i * G_PRODUCERS, kr = ch >> 5, c = ch & 31;
+            const bool ok = (k0 + kr < x.kend) && (4 * c < x.nt);
+            cp_async16(rb + kr * 512 + c * 16, p.B + (long long)(ok ? k0 + kr : 0) * p.ldb + (ok ? x.n0 + 4 * c : 0), ok);
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    Iter cur = first(), pre = cur;
+    issue(pre, 0); advance(pre);
+    issue(pre, 1); advance(pre);
+    int s = 0, rs = 0;
+    uint32_t ph = 0;
+    while (cur.t < n_tiles) {
+      const Tile& x = cur.x;
+      asm volatile("cp.async.wait_group 1;" ::: "memory");      // this thread's copies of the current K block have landed
+      asm volatile("bar.sync 1, 256;" ::: "memory");            // ... and everyone else's
+      if (lane == 0) mbar_wait(bar_empty + 8 * s, ph ^ 1, 22);
+      __syncwarp();
+      const uint32_t ra = raw_base + rs * GA_RAW_STAGE, rb = ra + GA_RAW_A;
+      const uint32_t a_addr = f16_base + s * F16_STAGE, b_addr = a_addr + GA_F16_A;
+      const int bgroups = (x.nmma + 63) >> 6;
+      const int nb_pieces = TB ? x.nmma * 8 : bgroups * 512;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {            // A: 1024 pieces of 8 elements
+        const int pi = pt + i * G_PRODUCERS, c = pi & 7, r = pi >> 3;
+        float v[8];
+        uint4 lo;
+        uint32_t src, off;
+        if (!TA) { src = ra + r * 256 + c * 32; off = (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+        else { const int g = r >> 6, kr = r & 63; src = ra + kr * 512 + (g * 64 + 8 * c) * 4; off = (uint32_t)(g * 8192 + kr * 128 + ((c ^ (kr & 7)) << 4)); }
+        lds8(src, v);
+        const uint4 hi = cvt_piece<SPLIT>(v, lo);
+        sts128(a_addr + off, hi);
+        if (SPLIT) sts128(a_addr + LO_OFF + off, lo);
+      }
+      for (int pi = pt; pi < nb_pieces; pi += G_PRODUCERS) {
+        const int c = pi & 7, r = pi >> 3;
+        float v[8];
+        uint4 lo;
+        uint32_t src, off;
+        if (TB) { src = rb + r * 256 + c * 32; off = (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+        else { const int g = r >> 6, kr = r & 63; src = rb + kr * 512 + (g * 64 + 8 * c) * 4; off = (uint32_t)(g * 8192 + kr * 128 + ((c ^ (kr & 7)) << 4)); }
+        lds8(src, v);
+        const uint4 hi = cvt_piece<SPLIT>(v, lo);
+        sts128(b_addr + off, hi);
+        if (SPLIT) sts128(b_addr + LO_OFF + off, lo);
+      }
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 256;" ::: "memory");            // the raw stage is fully consumed: refill it
+      issue(pre, rs); advance(pre);
+      if (lane == 0) mbar_arrive(bar_full + 8 * s);
+      if (++s == FST) { s = 0; ph ^= 1; }
+      rs ^= 1;
+      advance(cur);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else if (warp >= 9) {
+    // ---- epilogue (TMEM lane quarter = warp % 4)
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t pht[2] = {0, 0};
+    const bool split = p.splits > 1;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const Tile x = tile_of(t);
+      mbar_wait(bar_t_full + 8 * acc, pht[acc], 23);
+      pht[acc] ^= 1;
+      tc_fence_after();
+      const int gm = x.m0 + q * 32 + lane;
+      float* crow = split ? p.partial + ((long long)x.z * p.M + gm) * p.N : p.C + (long long)gm * p.ldc;
+      const bool vec_st = split ? (p.N % 4 == 0) : (p.ldc % 4 == 0 && (((uintptr_t)p.C) & 15) == 0);
+      for (int c0 = 0; c0 < x.nmma; c0 += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + acc * 128 + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        if (x.nmma - c0 >= 32) { TMEM_LD_32(taddr, r); } else { TMEM_LD_16(taddr, r); }
+        tmem_ld_wait();
+        if (gm >= p.M) continue;
+        const int ncols = min(32, x.nt - c0);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          if (i >= ncols) break;
+          float v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float xv = x.nkb > 0 ? __uint_as_float(r[i + u]) : 0.f;
+            const int gn = x.n0 + c0 + i + u;
+            if (!split && i + u < ncols) {
+              if (p.bias) xv += p.bias[gn];
+              if (p.flags & LSTUR_GEMM_ACCUM) xv += crow[gn];
+              if (p.flags & LSTUR_GEMM_RELU) xv = fmaxf(xv, 0.f);
+            }
+            v[u] = xv;
+          }
+          if (i + 4 <= ncols && vec_st && ((x.n0 + c0 + i) & 3) == 0) {
+            *reinterpret_cast<float4*>(crow + x.n0 + c0 + i) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (i + u < ncols) crow[x.n0 + c0 + i + u] = v[u];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_t_empty + 8 * acc);
+      acc ^= 1;
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+  }
+}
+
 __global__ void gemm_tc_splitk_reduce_kernel(int M, int N, int splits, const float* __restrict__ partial,
                                              float* __restrict__ C, long long ldc, const float* __restrict__ bias,
                                              int flags) {
@@ -307,10 +580,11 @@ __global__ void gemm_tc_splitk_reduce_kernel(int M, int N, int splits, const flo
 
 using namespace lstur;
 
-static void gemm_tc_tiling(int M, int N, int K, int* ntile, int* splits) {
-  int nparts = (N + 255) / 256;
+static bool g_gemm_async = true;     // LSTUR_GEMM_ASYNC=0 selects the register-staged kernel everywhere (A/B testing)
+static void gemm_tc_tiling(int M, int N, int K, int* ntile, int* splits, int max_nt = 256) {
+  int nparts = (N + max_nt - 1) / max_nt;
   int nt = ((N + nparts - 1) / nparts + 15) & ~15;
-  if (nt > 256) nt = 256;
+  if (nt > max_nt) nt = max_nt;
   long long tiles = (long long)((M + tc::TILE_M - 1) / tc::TILE_M) * ((N + nt - 1) / nt);
   int sp = 1;
   if (tiles < 148 && K >= 2048) {
@@ -324,8 +598,10 @@ static void gemm_tc_tiling(int M, int N, int K, int* ntile, int* splits) {
 }
 
 extern "C" size_t lstur_gemm_tc_workspace_bytes(int M, int N, int K) {
-  int nt, sp;
+  int nt, sp, sp2;
   gemm_tc_tiling(M, N, K, &nt, &sp);
+  gemm_tc_tiling(M, N, K, &nt, &sp2, tc::GA_NT);
+  if (sp2 > sp) sp = sp2;
   return sp > 1 ? (size_t)sp * M * N * sizeof(float) : 0;
 }
 
@@ -337,7 +613,19 @@ extern "C" int lstur_gemm_tc(int transA, int transB, int M, int N, int K, const 
   if (M == 0 || N == 0) return LSTUR_OK;
   tc::GemmParams p;
   int splits;
-  gemm_tc_tiling(M, N, K, &p.ntile, &splits);
+  static bool env_read = false;
+  if (!env_read) {
+    const char* e = getenv("LSTUR_GEMM_ASYNC");
+    if (e && atoi(e) == 0) g_gemm_async = false;
+    env_read = true;
+  }
+  // cp.async staging needs every 16-byte chunk of an operand row to be aligned and entirely inside or outside the matrix
+  const bool rows16 = (lda % 4 == 0) && (ldb % 4 == 0) && ((((uintptr_t)A) & 15) == 0) && ((((uintptr_t)B) & 15) == 0) &&
+                      ((transA ? M : K) % 4 == 0) && ((transB ? K : N) % 4 == 0);
+  // Measured at the LSTUR shapes (tools/perf_gemm.py): the cp.async ring wins for the long-K weight-gradient GEMMs
+  // (A transposed, split-K: 192 -> 106 us), the register-staged kernel with its wider N tile for the short-K ones.
+  const bool use_async = g_gemm_async && rows16 && K > 0 && transA;
+  gemm_tc_tiling(M, N, K, &p.ntile, &splits, use_async ? tc::GA_NT : 256);
   size_t need = splits > 1 ? (size_t)splits * M * N * sizeof(float) : 0;
   if (need > workspace_bytes || (need && !workspace)) splits = 1;
   int kps = ((K + splits - 1) / splits + tc::G_KBLK - 1) / tc::G_KBLK * tc::G_KBLK;
@@ -370,10 +658,30 @@ extern "C" int lstur_gemm_tc(int transA, int transB, int M, int N, int K, const 
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   dim3 grid((unsigned)(n_tiles < sms ? n_tiles : sms));
-#define LAUNCH(TA_, TB_)                                                                    \
-  do {                                                                                      \
-    if (split3) tc::gemm_tc_kernel<TA_, TB_, true><<<grid, tc::G_THREADS, smem, stream>>>(p); \
-    else tc::gemm_tc_kernel<TA_, TB_, false><<<grid, tc::G_THREADS, smem, stream>>>(p);       \
+  const size_t smem_async = 1024 + (size_t)2 * tc::GA_F16_STAGE + (size_t)2 * tc::GA_RAW_STAGE + 256;
+  static bool attr_async = false;
+  if (use_async && !attr_async) {
+    cudaError_t e = cudaSuccess;
+#define SETATTR(TA_, TB_, S_) \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_async_kernel<TA_, TB_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_async)
+    SETATTR(false, false, false); SETATTR(true, false, false); SETATTR(false, true, false); SETATTR(true, true, false);
+    SETATTR(false, false, true); SETATTR(true, false, true); SETATTR(false, true, true); SETATTR(true, true, true);
+#undef SETATTR
+    if (e != cudaSuccess) {
+      set_error("lstur_gemm_tc: cannot opt in to %zu B of shared memory: %s", smem_async, cudaGetErrorString(e));
+      return LSTUR_ERR_CUDA;
+    }
+    attr_async = true;
+  }
+#define LAUNCH(TA_, TB_)                                                                                \
+  do {                                                                                                  \
+    if (use_async) {                                                                                    \
+      if (split3) tc::gemm_tc_async_kernel<TA_, TB_, true><<<grid, tc::G_THREADS, smem_async, stream>>>(p);  \
+      else tc::gemm_tc_async_kernel<TA_, TB_, false><<<grid, tc::G_THREADS, smem_async, stream>>>(p);        \
+    } else {                                                                                            \
+      if (split3) tc::gemm_tc_kernel<TA_, TB_, true><<<grid, tc::G_THREADS, smem, stream>>>(p);         \
+      else tc::gemm_tc_kernel<TA_, TB_, false><<<grid, tc::G_THREADS, smem, stream>>>(p);               \
+    }                                                                                                   \
   } while (0)
   if (!transA && !transB) LAUNCH(false, false);
   else if (transA && !transB) LAUNCH(true, false);
