@@ -180,6 +180,11 @@ int lstur_score_softmax_ce(int B, int C, int D, const float* u, long long ldu, c
 int lstur_score_sigmoid(long long n_pairs, int C, int D, const float* u, long long ldu, const float* d, long long ldd,
                         float* out, int apply_sigmoid, cudaStream_t stream);
 
+/* Per-impression AUC / nDCG@10 / nDCG@5 / MRR (Seq2VecPaperSoftmax.callback, task/paper.py:497-524; utils.py:106-124;
+ * sklearn roc_auc_score): offsets (n_impr+1) index scores / labels; out (n_impr, 4); ties ordered by descending index. */
+int lstur_ranking_metrics(int n_impr, const int* offsets, const float* scores, const float* labels, float* out,
+                          cudaStream_t stream);
+
 /* keras.optimizers.Adam (task/paper.py:656): dense, and row-sparse for embedding tables. */
 int lstur_adam_dense(long long n, float* p, const float* g, float* m, float* v, float lr, int t, float beta1,
                      float beta2, float eps, float grad_scale, cudaStream_t stream);

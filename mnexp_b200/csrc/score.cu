@@ -91,6 +91,62 @@ __global__ void mean_kernel(int n, const float* __restrict__ x, float* __restric
   }
 }
 
+
+// Per-impression ranking metrics (task/paper.py:497-524 via utils.py:106-124 and sklearn roc_auc_score): one CTA per
+// impression, O(C^2) rank counting (C = candidates of the impression, a few hundred at most).  Order = descending score,
+// ties by descending index (np.argsort(s)[::-1] with a stable sort).  out[i] = {auc, ndcg@10, ndcg@5, mrr}; an impression
+// without a positive or without a negative yields NaN where the host formulas divide by zero.
+__global__ void ranking_metrics_kernel(int n_impr, const int* __restrict__ offsets, const float* __restrict__ scores,
+                                       const float* __restrict__ labels, float* __restrict__ out) {
+  const int imp = blockIdx.x;
+  if (imp >= n_impr) return;
+  const int beg = offsets[imp], C = offsets[imp + 1] - beg;
+  const float* s = scores + beg;
+  const float* y = labels + beg;
+  double auc_num = 0.0, dcg10 = 0.0, dcg5 = 0.0, idcg10 = 0.0, idcg5 = 0.0, rr = 0.0, ysum = 0.0, npos = 0.0, nneg = 0.0;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    const float si = s[i], yi = y[i];
+    int rank = 0, irank = 0;          // position in the score order / in the ideal (label) order
+    double wins = 0.0;
+    for (int j = 0; j < C; ++j) {
+      const float sj = s[j], yj = y[j];
+      rank += (sj > si) || (sj == si && j > i);
+      irank += (yj > yi) || (yj == yi && j > i);
+      if (yi > 0.f && !(yj > 0.f)) wins += si > sj ? 1.0 : (si == sj ? 0.5 : 0.0);
+    }
+    const double gain = exp2((double)yi) - 1.0;
+    if (rank < 10) dcg10 += gain / log2((double)rank + 2.0);
+    if (rank < 5) dcg5 += gain / log2((double)rank + 2.0);
+    if (irank < 10) idcg10 += gain / log2((double)irank + 2.0);
+    if (irank < 5) idcg5 += gain / log2((double)irank + 2.0);
+    rr += (double)yi / ((double)rank + 1.0);
+    ysum += (double)yi;
+    if (yi > 0.f) { npos += 1.0; auc_num += wins; } else { nneg += 1.0; }
+  }
+  __shared__ double red[9][32];
+  double vals[9] = {auc_num, dcg10, dcg5, idcg10, idcg5, rr, ysum, npos, nneg};
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    double v = vals[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[k][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t[9];
+    const int nw = blockDim.x >> 5;
+    for (int k = 0; k < 9; ++k) {
+      t[k] = 0.0;
+      for (int w = 0; w < nw; ++w) t[k] += red[k][w];
+    }
+    out[4 * imp + 0] = (float)(t[0] / (t[7] * t[8]));
+    out[4 * imp + 1] = (float)(t[1] / t[3]);
+    out[4 * imp + 2] = (float)(t[2] / t[4]);
+    out[4 * imp + 3] = (float)(t[5] / t[6]);
+  }
+}
+
 }  // namespace lstur
 
 using namespace lstur;
@@ -121,5 +177,16 @@ extern "C" int lstur_score_sigmoid(long long n_pairs, int C, int D, const float*
   if (n_pairs == 0) return LSTUR_OK;
   score_sigmoid_kernel<<<cdiv(n_pairs * 32, 256), 256, 0, stream>>>(n_pairs, C, D, u, ldu, d, ldd, out, apply_sigmoid);
   LSTUR_CHECK_LAUNCH("lstur_score_sigmoid");
+  return LSTUR_OK;
+}
+
+// AUC / nDCG@10 / nDCG@5 / MRR of every impression (offsets: n_impr+1 prefix sums into scores / labels), the evaluation
+// loop of Seq2VecPaperSoftmax.callback (task/paper.py:497-524).  out: (n_impr, 4).
+extern "C" int lstur_ranking_metrics(int n_impr, const int* offsets, const float* scores, const float* labels, float* out,
+                                     cudaStream_t stream) {
+  LSTUR_REQUIRE(n_impr >= 0 && (n_impr == 0 || (offsets && scores && labels && out)), "lstur_ranking_metrics");
+  if (n_impr == 0) return LSTUR_OK;
+  ranking_metrics_kernel<<<n_impr, 128, 0, stream>>>(n_impr, offsets, scores, labels, out);
+  LSTUR_CHECK_LAUNCH("lstur_ranking_metrics");
   return LSTUR_OK;
 }

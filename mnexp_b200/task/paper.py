@@ -16,9 +16,7 @@ import random
 from datetime import datetime
 
 import numpy as np
-from sklearn.metrics import roc_auc_score
-
-from .. import keras_like, synth, utils
+from .. import keras_like, metrics, synth, utils
 from .seq2vec import Seq2Vec
 
 
@@ -177,12 +175,14 @@ class Seq2VecPaperSoftmax(Seq2VecPaper):
         self.model, self.test_model = self.test_model, self.model
 
         def __gen__(x):
-            for i, (y_pred, y_true) in zip(range(x), self.test):
-                auc = roc_auc_score(y_true, y_pred)
-                ndcgx = utils.ndcg_score(y_true, y_pred, 10)
-                ndcgv = utils.ndcg_score(y_true, y_pred, 5)
-                mrr = utils.mrr_score(y_true, y_pred)
-                yield auc, ndcgx, ndcgv, mrr, np.sum(y_true), len(y_true), i
+            # the reference scores one impression at a time on the host (roc_auc_score, utils.ndcg_score / mrr_score);
+            # here the x impressions are ranked in ONE launch of the device kernel (mnexp_b200/metrics.py)
+            preds, trues = [], []
+            for _, (y_pred, y_true) in zip(range(x), self.test):
+                preds.append(np.asarray(y_pred).reshape(-1)); trues.append(np.asarray(y_true).reshape(-1))
+            m = metrics.ranking_metrics(preds, trues)
+            for i, (row, y_true) in enumerate(zip(m, trues)):
+                yield float(row[0]), float(row[1]), float(row[2]), float(row[3]), np.sum(y_true), len(y_true), i
 
         values = [np.mean(x) for x in zip(*__gen__(self.config.validation_impression))]
         self.last_evaluation = dict(auc=values[0], ndcgx=values[1], ndcgv=values[2], mrr=values[3])

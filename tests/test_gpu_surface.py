@@ -189,3 +189,33 @@ def test_pipeline_files_mirror(lib):
         assert abs(float(sc) - float(np.dot(tp.user_vec[uid + ut].astype(np.float64), tp.doc_vec[d].astype(np.float64)))) < 1e-6
     pred, sigm = tp.test_correct()
     assert abs(float(np.asarray(pred).reshape(-1)[0]) - float(np.asarray(sigm).reshape(-1)[0])) < 1e-5
+
+
+def test_gpu_ranking_metrics_match_host(lib):
+    """AUC / nDCG@10 / nDCG@5 / MRR per impression on the GPU == the reference's host formulas (utils.py:106-124,
+    sklearn roc_auc_score) on ragged impressions, including tied scores (same tie order: descending index)."""
+    from sklearn.metrics import roc_auc_score
+    from mnexp_b200 import metrics, utils
+    g = np.random.default_rng(9)
+    scores, labels = [], []
+    for i in range(200):
+        c = int(g.integers(2, 300))
+        s = g.random(c).astype(np.float32)
+        if i % 7 == 0:
+            s = np.round(s, 1)                                  # many ties
+        y = (g.random(c) < 0.15).astype(np.float32)
+        y[g.integers(0, c)] = 1.0
+        y[(np.argmax(y) + 1) % c] = 0.0
+        scores.append(s); labels.append(y)
+    got = metrics.ranking_metrics(scores, labels)
+    for i, (s, y) in enumerate(zip(scores, labels)):
+        order = np.lexsort((-np.arange(len(s)), -s.astype(np.float64)))        # descending score, ties by descending index
+        yo = y[order].astype(np.float64)
+        disc = np.log2(np.arange(len(s)) + 2)
+        ideal = np.sort(y.astype(np.float64))[::-1]
+        ndcg = lambda k: np.sum((2 ** yo[:k] - 1) / disc[:k]) / np.sum((2 ** ideal[:k] - 1) / disc[:k])
+        mrr = np.sum(yo / (np.arange(len(s)) + 1)) / np.sum(yo)
+        want = np.array([roc_auc_score(y, s), ndcg(10), ndcg(5), mrr])
+        assert np.abs(got[i] - want).max() < 2e-6, (i, got[i], want)
+        if i % 7 != 0:                                          # without ties this is exactly the reference's utils code
+            assert abs(utils.ndcg_score(y, s, 10) - got[i, 1]) < 2e-6 and abs(utils.mrr_score(y, s) - got[i, 3]) < 2e-6
