@@ -180,6 +180,15 @@ int lstur_score_softmax_ce(int B, int C, int D, const float* u, long long ldu, c
 int lstur_score_sigmoid(long long n_pairs, int C, int D, const float* u, long long ldu, const float* d, long long ldd,
                         float* out, int apply_sigmoid, cudaStream_t stream);
 
+/* Device-side batch assembly: train_gen + Window + Impression.negative_samples (task/paper.py:7-18, 396-405;
+ * task/seq2vec.py:17-53).  A sample is a click (global index into stream_docs) that has an earlier click of the same
+ * user; idx (B) picks samples out of sample_click.  user_out (B), hist_doc_out (B,W) = the last W clicks before it,
+ * left-padded with 0 (bit-exact with Window), cand_doc_out (B,1+K) = [the click, K negatives drawn with replacement from
+ * neg_docs[neg_off[c] .. neg_off[c+1]) by the counter-based RNG]. */
+int lstur_assemble_batch(int B, int W, int K, const int* sample_click, const int* idx, const int* click_user,
+                         const int* stream_off, const int* stream_docs, const int* neg_off, const int* neg_docs,
+                         unsigned seed, int* user_out, int* hist_doc_out, int* cand_doc_out, cudaStream_t stream);
+
 /* Per-impression AUC / nDCG@10 / nDCG@5 / MRR (Seq2VecPaperSoftmax.callback, task/paper.py:497-524; utils.py:106-124;
  * sklearn roc_auc_score): offsets (n_impr+1) index scores / labels; out (n_impr, 4); ties ordered by descending index. */
 int lstur_ranking_metrics(int n_impr, const int* offsets, const float* scores, const float* labels, float* out,

@@ -219,3 +219,42 @@ def test_gpu_ranking_metrics_match_host(lib):
         assert np.abs(got[i] - want).max() < 2e-6, (i, got[i], want)
         if i % 7 != 0:                                          # without ties this is exactly the reference's utils code
             assert abs(utils.ndcg_score(y, s, 10) - got[i, 1]) < 2e-6 and abs(utils.mrr_score(y, s) - got[i, 3]) < 2e-6
+
+
+def test_device_batch_assembly_matches_window(lib):
+    """lstur_assemble_batch: history windows bit-exact with Seq2Vec.Window replayed on the host (task/seq2vec.py:17-53,
+    task/paper.py:396-405), positive = the click, negatives drawn from the impression's negatives with replacement."""
+    from mnexp_b200.assemble import DeviceBatcher
+    sh, h = _handler('igru')
+    B, W, K = 32, sh.W, sh.K
+    bt = DeviceBatcher(h.data, B, W, K, seed=5)
+    # host replay of train_gen: (user, window ids, pos, impression negatives) per sample, in generator order
+    want = []
+    for user, (ih, _) in enumerate(h.data):
+        ch = h.Window(h.docs, W)
+        for imp in ih:
+            for pos in imp.pos:
+                if ch.count:
+                    want.append((user, ch.get_ids().copy(), pos, set(imp.neg)))
+                ch.push(pos)
+    assert bt.n_samples == len(want) and len(want) >= B
+    draws = {}
+    for rep in range(3):
+        idx = torch.as_tensor(np.random.default_rng(rep).integers(0, len(want), B).astype(np.int32)).cuda()
+        db = bt.assemble(idx)
+        user, hist, cand = (db[k].cpu().numpy() for k in ('user', 'hist_doc', 'cand_doc'))
+        for b, s in enumerate(idx.cpu().numpy()):
+            u, win, pos, negs = want[s]
+            assert user[b] == u and np.array_equal(hist[b], win) and cand[b, 0] == pos
+            assert all(int(x) in negs for x in cand[b, 1:])
+            draws.setdefault(int(s), []).extend(int(x) for x in cand[b, 1:])
+    # with replacement: over all draws more than one distinct negative is used wherever the impression offers several
+    multi = [s for s in draws if len(want[s][3]) > 3 and len(draws[s]) >= 8]
+    assert not multi or any(len(set(draws[s])) > 1 for s in multi)
+    # the assembled batch trains
+    eng = h._core.engine_train(B) if hasattr(h, '_core') else None
+    if eng is None:
+        h.build_model(0)
+        eng = h._core.engine_train(B)
+    loss = float(eng.train_step(bt.next_batch())[0])
+    assert np.isfinite(loss)
