@@ -164,6 +164,12 @@ int lstur_gru_fwd_cluster(int B, int W, int G, const float* XW, const float* gm,
 int lstur_gru_bwd_cluster(int B, int W, int G, const float* gm, const float* Z, const float* R, const float* HH,
                           const float* HP, const float* WhT, int rec_act, const float* dhT, long long lddh, float* dA,
                           float* dh0, long long lddh0, const int* row_order, cudaStream_t stream);
+/* Tensor-core recurrence (tcgen05, fp16 hi/lo 3-term split, fp32 accumulate): same arguments and saved tensors as
+ * lstur_gru_fwd_cluster.  Used by the plan in the tensor-core precision modes when lstur_gru_tc_supported(). */
+int lstur_gru_tc_supported(int B, int W, int G);
+int lstur_gru_fwd_tc(int B, int W, int G, const float* XW, const float* gm, const float* h0, long long ldh0,
+                     const float* Wh, int rec_act, float* hT, long long ldo, float* Z, float* R, float* HH,
+                     float* HP, float* RH, const int* row_order, cudaStream_t stream);
 int lstur_gru_fwd_streaming(int B, int W, int G, const float* XW, const float* gm, const float* h0, long long ldh0,
                             const float* Wh, int rec_act, float* hT, long long ldo, float* Z, float* R, float* HH,
                             float* HP, float* RH, cudaStream_t stream);

@@ -6,6 +6,7 @@
 // Host-side code only sequences kernels and carves the caller-provided workspace; all arithmetic
 // is in the kernels of this directory.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -343,10 +344,20 @@ int user_and_score(const lstur_plan* p, const lstur_weights* w, const lstur_batc
     long long ldo = G;
     if (c.arch == LSTUR_ARCH_INI || c.arch == LSTUR_ARCH_NOID) hdst = uvec;
     if (cat) { hdst = cat; ldo = G + c.Ue; }
-    RC(lstur_gru_fwd(B, c.W, G, XW, W<float>(p, ws, "gru_mask"), c.arch == LSTUR_ARCH_INI ? u0 : nullptr, c.Ue,
-                     DP(p, w->dense, "gru_wh"), c.rec_act, hdst, ldo, bw ? W<float>(p, ws, "Z") : nullptr,
-                     bw ? W<float>(p, ws, "R") : nullptr, bw ? W<float>(p, ws, "HH") : nullptr,
-                     bw ? W<float>(p, ws, "HP") : nullptr, bw ? W<float>(p, ws, "RH") : nullptr, st));
+    // tensor-core precision modes run the recurrence on tcgen05 (gru_tc.cu) when its weights fit tensor memory
+    const bool tc_gru = (c.precision == LSTUR_PREC_BF16_TC || c.precision == LSTUR_PREC_FP16_TC) &&
+                        lstur_gru_tc_supported(B, c.W, G) && !getenv("LSTUR_GRU_TC_OFF");
+    if (tc_gru) {
+      RC(lstur_gru_fwd_tc(B, c.W, G, XW, W<float>(p, ws, "gru_mask"), c.arch == LSTUR_ARCH_INI ? u0 : nullptr, c.Ue,
+                          DP(p, w->dense, "gru_wh"), c.rec_act, hdst, ldo, bw ? W<float>(p, ws, "Z") : nullptr,
+                          bw ? W<float>(p, ws, "R") : nullptr, bw ? W<float>(p, ws, "HH") : nullptr,
+                          bw ? W<float>(p, ws, "HP") : nullptr, bw ? W<float>(p, ws, "RH") : nullptr, nullptr, st));
+    } else {
+      RC(lstur_gru_fwd(B, c.W, G, XW, W<float>(p, ws, "gru_mask"), c.arch == LSTUR_ARCH_INI ? u0 : nullptr, c.Ue,
+                       DP(p, w->dense, "gru_wh"), c.rec_act, hdst, ldo, bw ? W<float>(p, ws, "Z") : nullptr,
+                       bw ? W<float>(p, ws, "R") : nullptr, bw ? W<float>(p, ws, "HH") : nullptr,
+                       bw ? W<float>(p, ws, "HP") : nullptr, bw ? W<float>(p, ws, "RH") : nullptr, st));
+    }
     if (cat) {
       cudaMemcpy2DAsync(cat + G, (size_t)(G + c.Ue) * 4, u0, (size_t)c.Ue * 4, (size_t)c.Ue * 4, B,
                         cudaMemcpyDeviceToDevice, st);

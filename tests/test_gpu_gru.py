@@ -71,7 +71,13 @@ def run(lib, impl, XW, gm, Wh, h0, dhT, act, order=None):
     dh0 = torch.full((B, G), float('nan'), device='cuda')
     a = 0 if act == 'hard_sigmoid' else 1
     od = torch.tensor(order, dtype=torch.int32).cuda() if order is not None else None
-    if impl == 'cluster':
+    if impl == 'tc':        # tensor-core forward; its saved tensors feed the cluster backward
+        assert lib.lstur_gru_tc_supported(B, W, G) == 1
+        rc = lib.lstur_gru_fwd_tc(B, W, G, P_(XWd), P_(gmd), P_(h0d), G, P_(Whd), a, P_(hT), G, *[P_(s) for s in sv], P_(od), stream())
+        assert rc == 0, lib.lstur_last_error()
+        rc = lib.lstur_gru_bwd_cluster(B, W, G, P_(gmd), *[P_(s) for s in sv[:4]], P_(WhT), a, P_(dhTd), G, P_(dA), P_(dh0), G, P_(od), stream())
+        assert rc == 0, lib.lstur_last_error()
+    elif impl == 'cluster':
         assert lib.lstur_gru_cluster_supported(B, W, G) == 1
         rc = lib.lstur_gru_fwd_cluster(B, W, G, P_(XWd), P_(gmd), P_(h0d), G, P_(Whd), a, P_(hT), G, *[P_(s) for s in sv], P_(od), stream())
         assert rc == 0, lib.lstur_last_error()
@@ -117,3 +123,36 @@ def test_gru_row_order_is_a_pure_permutation(lib):
     b = run(lib, 'cluster', XW, gm, Wh, h0, dhT, 'hard_sigmoid', order=order)
     for x, y in zip(a[:3], b[:3]):
         assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize('B,W,G,ini,act,pad', [
+    (1, 3, 8, True, 'hard_sigmoid', 'left'),
+    (7, 5, 8, False, 'hard_sigmoid', 'holes'),
+    (64, 50, 200, True, 'hard_sigmoid', 'left'),
+    (50, 12, 104, False, 'sigmoid', 'holes'),
+    (300, 20, 64, True, 'hard_sigmoid', 'left'),
+    (1024, 50, 200, True, 'hard_sigmoid', 'left'),
+    (130, 9, 224, True, 'sigmoid', 'left'),               # largest width whose weights fit tensor memory
+])
+def test_gru_tensor_core_recurrence_vs_oracle(lib, B, W, G, ini, act, pad):
+    """tcgen05 recurrence (3-term fp16 split of Wh and of the state, fp32 accumulate): fp32-like accuracy."""
+    XW, gm, Wh, h0, dhT = make(B, W, G, seed=B + W + G, ini=ini, pad=pad)
+    hT_ref, dA_ref, dh0_ref = oracle(XW, Wh, h0, dhT, act)
+    hT, dA, dh0, sv = run(lib, 'tc', XW, gm, Wh, h0, dhT, act)
+    assert rel(hT, hT_ref) < TOL
+    assert rel(dA, dA_ref) < 5 * TOL
+    if ini:
+        assert rel(dh0, dh0_ref) < 5 * TOL
+    assert all(np.isfinite(s).all() for s in sv)
+    ref = run(lib, 'cluster', XW, gm, Wh, h0, dhT, act)
+    for x, y in zip(sv, ref[3]):
+        assert rel(x, y) < TOL
+
+
+def test_gru_tensor_core_row_order(lib):
+    B, W, G = 200, 30, 200
+    XW, gm, Wh, h0, dhT = make(B, W, G, seed=3)
+    order = np.argsort(-gm.sum(1), kind='stable').astype(np.int32)
+    a = run(lib, 'tc', XW, gm, Wh, h0, dhT, 'hard_sigmoid')
+    b = run(lib, 'tc', XW, gm, Wh, h0, dhT, 'hard_sigmoid', order=order)
+    assert rel(b[0], a[0]) < TOL
