@@ -36,6 +36,9 @@ constexpr int TMEM_COLS = 512;
 __device__ __forceinline__ float rec_act(float x, int act) {
   return act == LSTUR_ACT_HARD_SIGMOID ? hard_sigmoid_f(x) : __fdividef(1.f, 1.f + __expf(-x));
 }
+__device__ __forceinline__ float rec_act_grad(float y, int act) {
+  return act == LSTUR_ACT_HARD_SIGMOID ? ((y > 0.f && y < 1.f) ? 0.2f : 0.f) : y * (1.f - y);
+}
 __device__ __forceinline__ float tanh_fast(float x) {
   const float e = __expf(-2.f * fabsf(x));                // in (0, 1]: no overflow
   return copysignf(__fdividef(1.f - e, 1.f + e), x);
@@ -445,6 +448,355 @@ __global__ void __launch_bounds__(THREADS, 1) gru_fwd_tc_kernel(const Params p) 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// BPTT on the tensor cores.  Thread (unit k, 8 batch rows) keeps d h[:, k] in registers.  Per step:
+//   dah, daz (elementwise) -> own slice of S_dah / S_daz -> peers;   phase A:  drh_k = sum_j dah_j Wh[k][2G+j]  (critical)
+//   and, behind it on the tensor core, dhp_k = sum_j daz_j Wh[k][j];  dar = drh * hp * act'(r) -> S_dar -> peers;
+//   phase B: dhp_k += sum_j dar_j Wh[k][G+j].   The three weight slices (rows k of Wh, fp16) stay in tensor memory; the
+// exchanged operands are fp16 hi + lo of the value times a per-tile power of two (set from max|dhT| of the tile's rows,
+// so the fp16 range is centred on the tile's gradients; conversions saturate), i.e. 2 MMAs per k step:
+// W_hi.S_hi + W_hi.S_lo.  The weight rounding (2^-12 relative) is that of every other backward GEMM of the tensor-core
+// modes.  Matrix rows 64..127 repeat rows 0..63, so all eight epilogue warps read accumulators (8 batch rows each).
+// S_daz is double-buffered by step parity: its MMAs run off the critical path and may still be in flight when the
+// peers' next slices arrive.
+struct BwdParams {
+  int B, W, G, UC, act;
+  const float* gm;
+  const int* row_order;
+  const float *Z, *R, *HH, *HP;   // (B, W, G)
+  const float* Wh;                // (G, 3G)
+  const float* dhT; long long lddh;
+  float* dA;                      // (B, W, 3G)
+  float* dh0; long long lddh0;
+};
+constexpr int BROWS = 8;            // batch rows per epilogue thread in the backward kernel
+
+__host__ __device__ inline size_t bwd_smem_bytes(int G, int W) {
+  const int KS16 = (G + 15) / 16;
+  return (size_t)10 * KS16 * 1024 + (size_t)W * NROWS + (size_t)((W + 15) / 16) * 16 + 256 + 1024;
+}
+
+__global__ void __launch_bounds__(THREADS, 1) gru_bwd_tc_kernel(const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int G = p.G, UC = p.UC, W = p.W, G3 = 3 * G;
+  const int ksteps = (G + 15) / 16, KC = ksteps * 8;
+  const uint32_t s_bytes = (uint32_t)ksteps * 1024;
+  // S buffers (hi, lo each): dah | daz[0] | daz[1] | dar
+  const uint32_t S_dah = smem_base, S_daz = S_dah + 2 * s_bytes, S_dar = S_dah + 8 * s_bytes;
+  const uint32_t oGM = 10 * s_bytes;
+  const uint32_t oAny = oGM + (uint32_t)W * NROWS;
+  const uint32_t oBar = (oAny + (uint32_t)((W + 15) / 16) * 16 + 15u) & ~15u;
+  uint8_t* sGM = sm + oGM;
+  uint8_t* sAny = sm + oAny;
+  const uint32_t bar_a = smem_base + oBar, bar_r = bar_a + 8, bar_dA = bar_a + 16, bar_dB = bar_a + 24;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + oBar + 32);
+  float* sMax = reinterpret_cast<float*>(sm + oBar + 40);
+  int* sRow = reinterpret_cast<int*>(sm + oBar + 64);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rank = (int)cluster_ctarank();
+  constexpr int CS = 4;
+  const int tile = blockIdx.x / CS, b0 = tile * NROWS;
+  const int own_units = max(0, min(UC, G - rank * UC));
+  const uint32_t own_off = (uint32_t)(rank * UC) * 64u, own_bytes = (uint32_t)own_units * 64u;
+  const uint32_t xbytes = (uint32_t)(G - own_units) * 64u * 2u;      // one operand (hi + lo) from the three peers
+
+  if (tid == 0) {
+    mbar_init(bar_a, 1);
+    mbar_init(bar_r, 1);
+    mbar_init(bar_dA, 1);
+    mbar_init(bar_dB, 1);
+    *sMax = 0.f;
+    fence_barrier_init();
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (uint32_t i = tid; i < oGM / 16; i += THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < W * NROWS; i += THREADS) {
+    const int t = i / NROWS, n = i % NROWS;
+    int b = -1;
+    if (b0 + n < p.B) b = p.row_order ? p.row_order[b0 + n] : b0 + n;
+    sGM[i] = (b >= 0 && p.gm[(long long)b * W + t] != 0.f) ? 1 : 0;
+    if (t == 0) sRow[n] = b;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tDrh = tmem_base, tDhp = tmem_base + 32, tAh = tmem_base + 64, tAz = tAh + KC, tAr = tAz + KC;
+  for (int t = tid; t < W; t += THREADS) {
+    int any = 0;
+    for (int n = 0; n < NROWS; ++n) any |= sGM[t * NROWS + n];
+    sAny[t] = (uint8_t)any;
+  }
+  {   // per-tile scale: max |dhT| over the tile's rows (every CTA of the cluster computes the same value)
+    float mx = 0.f;
+    for (int i = tid; i < NROWS * G; i += THREADS) {
+      const int b = sRow[i / G];
+      if (b >= 0) mx = fmaxf(mx, fabsf(p.dhT[(long long)b * p.lddh + i % G]));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0 && mx > 0.f) atomicMax(reinterpret_cast<int*>(sMax), __float_as_int(mx));
+  }
+  if (warp < 8) {
+    // weight rows -> tensor memory (fp16): lane m holds Wh[rank*UC + (m & 63)][gate*G + j], j = column*2 (+1)
+    const int m = (warp & 3) * 32 + lane, u = m & 63, k = rank * UC + u;
+    const bool rowact = u < UC && k < G;
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    for (int ks = warp >> 2; ks < ksteps; ks += 2) {
+      uint32_t wh[8], wz[8], wr[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float a[2] = {0.f, 0.f}, b[2] = {0.f, 0.f}, c[2] = {0.f, 0.f};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = ks * 16 + 2 * q + e;
+          if (rowact && j < G) {
+            const float* row = p.Wh + (long long)k * G3;
+            b[e] = __ldg(row + j); c[e] = __ldg(row + G + j); a[e] = __ldg(row + 2 * G + j);
+          }
+        }
+        const __half2 ha = __floats2half2_rn(a[0], a[1]), hb = __floats2half2_rn(b[0], b[1]), hc = __floats2half2_rn(c[0], c[1]);
+        wh[q] = *reinterpret_cast<const uint32_t*>(&ha);
+        wz[q] = *reinterpret_cast<const uint32_t*>(&hb);
+        wr[q] = *reinterpret_cast<const uint32_t*>(&hc);
+      }
+      tmem_st8(tAh + lane_addr + 8 * ks, wh);
+      tmem_st8(tAz + lane_addr + 8 * ks, wz);
+      tmem_st8(tAr + lane_addr + 8 * ks, wr);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  fence_proxy_async();
+  cluster_sync_all();
+  // scale = 2^e with max * scale in [2^3, 2^4)
+  float scale = 1.f, inv_scale = 1.f;
+  {
+    const float mx = *sMax;
+    if (mx > 0.f && mx < 3.0e38f) {
+      int e;
+      frexpf(mx, &e);                       // mx = f * 2^e, f in [0.5, 1)
+      e = max(-100, min(100, 4 - e));
+      scale = ldexpf(1.f, e);
+      inv_scale = ldexpf(1.f, -e);
+    }
+  }
+  auto send_op = [&](uint32_t S, uint32_t bar) {      // hi and lo slices of one operand to every peer
+    if (own_bytes) {
+#pragma unroll
+      for (int c = 1; c < CS; ++c) {
+        const uint32_t peer = (uint32_t)((rank + c) % CS);
+        const uint32_t rbar = map_to_cta(bar, peer);
+        bulk_s2peer(map_to_cta(S + own_off, peer), S + own_off, own_bytes, rbar);
+        bulk_s2peer(map_to_cta(S + s_bytes + own_off, peer), S + s_bytes + own_off, own_bytes, rbar);
+      }
+    }
+  };
+
+  if (warp == 8) {
+    // ===================== MMA issuer =====================
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc(128, NROWS, true) | (1u << 16);
+    uint32_t ph_a = 0, ph_r = 0, par = 0;
+    for (int t = W - 1; t >= 0; --t) {
+      if (!sAny[t]) continue;
+      const uint32_t Sz = S_daz + par * 2 * s_bytes;
+      mbar_wait(bar_a, ph_a, 41);
+      ph_a ^= 1;
+      tc_fence_after();
+      if (leader) {
+        for (int ks = 0; ks < ksteps; ++ks) {
+          umma_ts(tDrh, tAh + 8 * ks, desc_mn64(S_dah + (uint32_t)ks * 1024), idesc, ks > 0);
+          umma_ts(tDrh, tAh + 8 * ks, desc_mn64(S_dah + s_bytes + (uint32_t)ks * 1024), idesc, 1);
+        }
+        umma_commit(bar_dA);
+        for (int ks = 0; ks < ksteps; ++ks) {     // off the critical path: overlaps the dar epilogue and exchange
+          umma_ts(tDhp, tAz + 8 * ks, desc_mn64(Sz + (uint32_t)ks * 1024), idesc, ks > 0);
+          umma_ts(tDhp, tAz + 8 * ks, desc_mn64(Sz + s_bytes + (uint32_t)ks * 1024), idesc, 1);
+        }
+      }
+      __syncwarp();
+      mbar_wait(bar_r, ph_r, 42);
+      ph_r ^= 1;
+      tc_fence_after();
+      if (leader) {
+        for (int ks = 0; ks < ksteps; ++ks) {
+          umma_ts(tDhp, tAr + 8 * ks, desc_mn64(S_dar + (uint32_t)ks * 1024), idesc, 1);
+          umma_ts(tDhp, tAr + 8 * ks, desc_mn64(S_dar + s_bytes + (uint32_t)ks * 1024), idesc, 1);
+        }
+        umma_commit(bar_dB);
+      }
+      __syncwarp();
+      par ^= 1;
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int quarter = warp & 3, half = warp >> 2;
+    const int m = quarter * 32 + lane;
+    const int u = m & 63, k = rank * UC + u;
+    const bool act = u < UC && k < G;
+    const int n0 = ((quarter >> 1) * 2 + half) * BROWS;      // this thread's 8 batch rows
+    const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
+    const int chunk_pos = ((n0 >> 3) ^ ((k >> 1) & 3)) << 4;  // 16-byte chunk of the unit's 64-byte row
+    // scaled fp16 hi/lo of 8 values -> own row of the local S buffer
+    auto put8 = [&](uint32_t S, const float* v) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float a = v[2 * q] * scale, b = v[2 * q + 1] * scale;
+        uint32_t h;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h));
+        uint32_t l;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(b - hf.y), "f"(a - hf.x));
+        hi[q] = h; lo[q] = l;
+      }
+      uint8_t* row = sm + (S - smem_base) + (size_t)k * 64 + chunk_pos;
+      *reinterpret_cast<uint4*>(row) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(row + s_bytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      fence_proxy_async();
+    };
+    long long rowoff[BROWS];      // element offset of (row, step 0, unit k) in the (B, W, G) tensors, or -1
+    float dh[BROWS];
+#pragma unroll
+    for (int i = 0; i < BROWS; ++i) {
+      const int b = sRow[n0 + i];
+      rowoff[i] = (b >= 0 && act) ? (long long)b * W * G + k : -1;
+      dh[i] = rowoff[i] >= 0 ? p.dhT[(long long)b * p.lddh + k] : 0.f;
+    }
+    auto load_saved = [&](int t, float* z, float* r, float* hh, float* hp) {
+#pragma unroll
+      for (int i = 0; i < BROWS; ++i) {
+        const long long o = rowoff[i] + (long long)t * G;
+        const bool ok = rowoff[i] >= 0 && t >= 0;
+        z[i] = ok ? __ldg(p.Z + o) : 0.f;
+        r[i] = ok ? __ldg(p.R + o) : 0.f;
+        hh[i] = ok ? __ldg(p.HH + o) : 0.f;
+        hp[i] = ok ? __ldg(p.HP + o) : 0.f;
+      }
+    };
+    auto next_active = [&](int t) {
+      --t;
+      while (t >= 0 && !sAny[t]) --t;
+      return t;
+    };
+    float nz[BROWS], nr[BROWS], nhh[BROWS], nhp[BROWS];
+    int t = next_active(W);
+    load_saved(t, nz, nr, nhh, nhp);
+    // steps after the last active one (none of the tile's rows is on): dA = 0
+    auto zero_steps = [&](int t_hi, int t_lo) {      // steps t_lo < s < t_hi
+      for (int s = t_hi - 1; s > t_lo; --s)
+#pragma unroll
+        for (int i = 0; i < BROWS; ++i)
+          if (rowoff[i] >= 0) {
+            float* d = p.dA + (rowoff[i] - k + (long long)s * G) * 3 + k;
+            d[0] = 0.f; d[G] = 0.f; d[2 * G] = 0.f;
+          }
+    };
+    zero_steps(W, t);
+    uint32_t ph_dA = 0, ph_dB = 0, par = 0;
+    while (t >= 0) {
+      float z[BROWS], r[BROWS], hh[BROWS], hp[BROWS], dah[BROWS], daz[BROWS];
+      uint32_t onmask = 0;
+#pragma unroll
+      for (int i = 0; i < BROWS; ++i) {
+        z[i] = nz[i]; r[i] = nr[i]; hh[i] = nhh[i]; hp[i] = nhp[i];
+        const bool on = rowoff[i] >= 0 && sGM[t * NROWS + n0 + i] != 0;
+        if (on) onmask |= 1u << i;
+        dah[i] = on ? dh[i] * (1.f - z[i]) * (1.f - hh[i] * hh[i]) : 0.f;
+        daz[i] = on ? dh[i] * (hp[i] - hh[i]) * rec_act_grad(z[i], p.act) : 0.f;
+      }
+      if (act) {
+        put8(S_dah, dah);
+        put8(S_daz + par * 2 * s_bytes, daz);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tid == 0) {
+        mbar_arrive_expect(bar_a, 2 * xbytes);
+        send_op(S_dah, bar_a);
+        send_op(S_daz + par * 2 * s_bytes, bar_a);
+      }
+      // off the critical path: this step's dA (z and candidate parts), the next active step's saved activations
+      const int tn = next_active(t);
+#pragma unroll
+      for (int i = 0; i < BROWS; ++i)
+        if (rowoff[i] >= 0) {
+          float* d = p.dA + (rowoff[i] - k + (long long)t * G) * 3 + k;
+          d[0] = daz[i];
+          d[2 * G] = dah[i];
+        }
+      load_saved(tn, nz, nr, nhh, nhp);
+      // ---- phase A result: drh
+      mbar_wait(bar_dA, ph_dA, 43);
+      ph_dA ^= 1;
+      tc_fence_after();
+      float dar[BROWS], dhn[BROWS];
+      {
+        uint32_t d[BROWS];
+        TMEM_LD_8(tDrh + tlane + n0, d);
+        tmem_ld_wait();
+        tc_fence_before();
+#pragma unroll
+        for (int i = 0; i < BROWS; ++i) {
+          const float drh = __uint_as_float(d[i]) * inv_scale;
+          const bool on = (onmask >> i) & 1;
+          dar[i] = on ? drh * hp[i] * rec_act_grad(r[i], p.act) : 0.f;
+          dhn[i] = fmaf(drh, r[i], dh[i] * z[i]);
+        }
+      }
+      if (act) put8(S_dar, dar);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tid == 0) {
+        mbar_arrive_expect(bar_r, xbytes);
+        send_op(S_dar, bar_r);
+      }
+#pragma unroll
+      for (int i = 0; i < BROWS; ++i)
+        if (rowoff[i] >= 0) p.dA[(rowoff[i] - k + (long long)t * G) * 3 + G + k] = dar[i];
+      zero_steps(t, tn);
+      // ---- phase B result: dhp
+      mbar_wait(bar_dB, ph_dB, 44);
+      ph_dB ^= 1;
+      tc_fence_after();
+      {
+        uint32_t d[BROWS];
+        TMEM_LD_8(tDhp + tlane + n0, d);
+        tmem_ld_wait();
+        tc_fence_before();
+#pragma unroll
+        for (int i = 0; i < BROWS; ++i)
+          if ((onmask >> i) & 1) dh[i] = fmaf(__uint_as_float(d[i]), inv_scale, dhn[i]);
+      }
+      par ^= 1;
+      t = tn;
+    }
+    if (p.dh0) {
+#pragma unroll
+      for (int i = 0; i < BROWS; ++i)
+        if (rowoff[i] >= 0) {
+          const int b = sRow[n0 + i];
+          p.dh0[(long long)b * p.lddh0 + k] = dh[i];
+        }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 }  // namespace grutc
 }  // namespace lstur
 
@@ -456,7 +808,7 @@ extern "C" int lstur_gru_tc_supported(int B, int W, int G) {
   const int UC = (G + 3) / 4;
   if (UC > 64) return 0;
   if (64 + 4 * ((G + 15) / 16) * 8 > grutc::TMEM_COLS) return 0;      // 2 accumulators + four weight parts in tensor memory
-  return grutc::smem_bytes(G, W) <= 227 * 1024 ? 1 : 0;
+  return (grutc::smem_bytes(G, W) <= 227 * 1024 && grutc::bwd_smem_bytes(G, W) <= 227 * 1024) ? 1 : 0;
 }
 
 extern "C" int lstur_gru_fwd_tc(int B, int W, int G, const float* XW, const float* gm, const float* h0, long long ldh0,
@@ -495,5 +847,43 @@ extern "C" int lstur_gru_fwd_tc(int B, int W, int G, const float* XW, const floa
     return LSTUR_ERR_CUDA;
   }
   LSTUR_CHECK_LAUNCH("lstur_gru_fwd_tc");
+  return LSTUR_OK;
+}
+
+extern "C" int lstur_gru_bwd_tc(int B, int W, int G, const float* gm, const float* Z, const float* R, const float* HH,
+                                const float* HP, const float* Wh, int rec_act, const float* dhT, long long lddh, float* dA,
+                                float* dh0, long long lddh0, const int* row_order, cudaStream_t stream) {
+  LSTUR_REQUIRE(B >= 0 && W > 0 && G > 0 && gm && Z && R && HH && HP && Wh && dhT && dA, "lstur_gru_bwd_tc");
+  LSTUR_REQUIRE(lstur_gru_tc_supported(B > 0 ? B : 1, W, G), "lstur_gru_bwd_tc(shape)");
+  if (B == 0) return LSTUR_OK;
+  grutc::BwdParams p = {};
+  p.B = B; p.W = W; p.G = G; p.UC = (G + 3) / 4; p.act = rec_act;
+  p.gm = gm; p.row_order = row_order; p.Z = Z; p.R = R; p.HH = HH; p.HP = HP; p.Wh = Wh;
+  p.dhT = dhT; p.lddh = lddh; p.dA = dA; p.dh0 = dh0; p.lddh0 = lddh0;
+  const size_t smem = grutc::bwd_smem_bytes(G, W);
+  cudaError_t e = cudaFuncSetAttribute(grutc::gru_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("lstur_gru_bwd_tc: cannot opt in to %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+    return LSTUR_ERR_CUDA;
+  }
+  const int tiles = (B + grutc::NROWS - 1) / grutc::NROWS;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(tiles * 4);
+  cfg.blockDim = dim3(grutc::THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 4;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, grutc::gru_bwd_tc_kernel, p);
+  if (e != cudaSuccess) {
+    set_error("lstur_gru_bwd_tc: launch failed: %s", cudaGetErrorString(e));
+    return LSTUR_ERR_CUDA;
+  }
+  LSTUR_CHECK_LAUNCH("lstur_gru_bwd_tc");
   return LSTUR_OK;
 }

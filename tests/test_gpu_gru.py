@@ -71,7 +71,14 @@ def run(lib, impl, XW, gm, Wh, h0, dhT, act, order=None):
     dh0 = torch.full((B, G), float('nan'), device='cuda')
     a = 0 if act == 'hard_sigmoid' else 1
     od = torch.tensor(order, dtype=torch.int32).cuda() if order is not None else None
-    if impl == 'tc':        # tensor-core forward; its saved tensors feed the cluster backward
+    if impl in ('tcb', 'tctc'):        # tensor-core backward after the fp32 cluster forward ('tcb') or the tensor-core one
+        assert lib.lstur_gru_tc_supported(B, W, G) == 1
+        fwd = lib.lstur_gru_fwd_cluster if impl == 'tcb' else lib.lstur_gru_fwd_tc
+        rc = fwd(B, W, G, P_(XWd), P_(gmd), P_(h0d), G, P_(Whd), a, P_(hT), G, *[P_(s) for s in sv], P_(od), stream())
+        assert rc == 0, lib.lstur_last_error()
+        rc = lib.lstur_gru_bwd_tc(B, W, G, P_(gmd), *[P_(s) for s in sv[:4]], P_(Whd), a, P_(dhTd), G, P_(dA), P_(dh0), G, P_(od), stream())
+        assert rc == 0, lib.lstur_last_error()
+    elif impl == 'tc':        # tensor-core forward; its saved tensors feed the cluster backward
         assert lib.lstur_gru_tc_supported(B, W, G) == 1
         rc = lib.lstur_gru_fwd_tc(B, W, G, P_(XWd), P_(gmd), P_(h0d), G, P_(Whd), a, P_(hT), G, *[P_(s) for s in sv], P_(od), stream())
         assert rc == 0, lib.lstur_last_error()
@@ -156,3 +163,27 @@ def test_gru_tensor_core_row_order(lib):
     a = run(lib, 'tc', XW, gm, Wh, h0, dhT, 'hard_sigmoid')
     b = run(lib, 'tc', XW, gm, Wh, h0, dhT, 'hard_sigmoid', order=order)
     assert rel(b[0], a[0]) < TOL
+
+
+@pytest.mark.parametrize('impl', ['tcb', 'tctc'])
+@pytest.mark.parametrize('B,W,G,ini,act,pad,gscale', [
+    (1, 3, 8, True, 'hard_sigmoid', 'left', 1.0),
+    (7, 5, 8, False, 'hard_sigmoid', 'holes', 1e-6),       # tiny gradients: the per-tile scale keeps them in fp16 range
+    (64, 50, 200, True, 'hard_sigmoid', 'left', 1.0 / 1024),
+    (50, 12, 104, False, 'sigmoid', 'holes', 1e4),
+    (300, 20, 64, True, 'hard_sigmoid', 'left', 1.0),
+    (1024, 50, 200, True, 'hard_sigmoid', 'left', 1.0 / 1024),
+    (130, 9, 224, True, 'sigmoid', 'left', 1.0),
+])
+def test_gru_tensor_core_bptt_vs_oracle(lib, impl, B, W, G, ini, act, pad, gscale):
+    """tcgen05 BPTT: weights enter as fp16 (2^-12 relative rounding, like the other tensor-core-mode backward GEMMs), the
+    exchanged gradients as fp16 hi+lo under a per-tile power-of-two scale.  Tolerance 2e-3 of the largest gradient."""
+    XW, gm, Wh, h0, dhT = make(B, W, G, seed=B + W + G, ini=ini, pad=pad)
+    dhT = dhT * gscale
+    hT_ref, dA_ref, dh0_ref = oracle(XW, Wh, h0, dhT, act)
+    hT, dA, dh0, sv = run(lib, impl, XW, gm, Wh, h0, dhT, act)
+    assert np.isfinite(dA).all()
+    assert rel(dA, dA_ref) < 2e-3
+    if ini:
+        assert rel(dh0, dh0_ref) < 2e-3
+    assert np.all(dA[gm == 0] == 0)
