@@ -295,22 +295,40 @@ attn_bwd_img_kernel(int N, int L, int F, const CT* __restrict__ Cd, const float*
       phase[b] ^= 1;
     }
     __syncthreads();
-    for (int t = warp; t < L; t += IMG_THREADS / 32) {
-      float dot = 0.f;
-      for (int cc = lane; cc < nchunk; cc += 32) {
-        float v[8];
-        unpack8<CT>(sC[t * nchunk + cc], v);
+    {   // d w_t = c_t . d_pooled: a lane keeps its (at most two) chunks of d_pooled in registers for all rows
+      float dpa[2][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dot = fmaf(v[i], sdp[cc * 8 + i], dot);
+      for (int k = 0; k < 2; ++k) {
+        const int cc = lane + 32 * k;
+        const float4 lo = cc < nchunk ? *reinterpret_cast<const float4*>(sdp + cc * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 hi = cc < nchunk ? *reinterpret_cast<const float4*>(sdp + cc * 8 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        dpa[k][0] = lo.x; dpa[k][1] = lo.y; dpa[k][2] = lo.z; dpa[k][3] = lo.w;
+        dpa[k][4] = hi.x; dpa[k][5] = hi.y; dpa[k][6] = hi.z; dpa[k][7] = hi.w;
       }
-      dot = warp_sum(dot);
-      if (lane == 0) sdw[t] = dot;
+      for (int t = warp; t < L; t += IMG_THREADS / 32) {
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int cc = lane + 32 * k;
+          if (cc < nchunk) {
+            float v[8];
+            unpack8<CT>(sC[t * nchunk + cc], v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dot = fmaf(v[i], dpa[k][i], dot);
+          }
+        }
+        dot = warp_sum(dot);
+        if (lane == 0) sdw[t] = dot;
+      }
     }
     __syncthreads();
     if (tid < 32) {
-      float q = 0.f;
-      for (int t = 0; t < L; ++t) q = fmaf(sdw[t], sw[t], q);
-      if (tid < L) sdz[tid] = (sdw[tid] - q) * sw[tid] * (1.f - a_cur * a_cur);
+      const float dwt = tid < L ? sdw[tid] : 0.f, wt = tid < L ? sw[tid] : 0.f;
+      const float q = warp_sum(dwt * wt);
+      const float dz = tid < L ? (dwt - q) * wt * (1.f - a_cur * a_cur) : 0.f;
+      if (tid < L) sdz[tid] = dz;
+      const float dzs = warp_sum(dz);
+      if (tid == 0) dba += dzs;
     }
     __syncthreads();
     if (c_ok) {
@@ -340,8 +358,6 @@ attn_bwd_img_kernel(int N, int L, int F, const CT* __restrict__ Cd, const float*
         *reinterpret_cast<uint4*>(dst) = pack8<CT>(o);
       }
     }
-    if (tid == 0)
-      for (int t = 0; t < L; ++t) dba += sdz[t];
   }
   // combine the four row groups in a fixed order, then one partial row per CTA
   __syncthreads();
