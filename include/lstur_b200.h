@@ -47,8 +47,12 @@ typedef struct CUstream_st* cudaStream_t;
 #define LSTUR_ARCH_NOID 3      /* paper 'nigru' / cook 'gru': GRU only                                 */
 #define LSTUR_ARCH_ADD 4       /* paper 'pgru' / cook 'agru': GRU + user_emb                           */
 #define LSTUR_ARCH_VO 5        /* 'vo': user_emb only                                                  */
+#define LSTUR_ARCH_AVG 6       /* paper 'niavg': GlobalAveragePoolingMaskSupport of the history (models.py:422-441) */
 
 #define LSTUR_SCORE_DOT 0      /* task/paper.py:446-447 */
+#define LSTUR_SCORE_DNN 1      /* Dense(Hs, relu)([u ‖ d]) -> Dense(1), task/paper.py:448-451 */
+#define LSTUR_SCORE_DDOT 2     /* tanh Dense(Hs) on both sides, then dot, task/paper.py:452-455 */
+#define LSTUR_SCORE_DDOT_LINEAR 3 /* cook flavour: linear Dense(Hs) on both sides, task/cook.py:206-209 */
 
 #define LSTUR_ACT_HARD_SIGMOID 0 /* Keras <= 2.2.x GRU recurrent_activation default */
 #define LSTUR_ACT_SIGMOID 1      /* Keras >= 2.3 */
@@ -200,6 +204,25 @@ int lstur_assemble_batch(int B, int W, int K, const int* sample_click, const int
                          const int* stream_off, const int* stream_docs, const int* neg_off, const int* neg_docs,
                          unsigned seed, int* user_out, int* hist_doc_out, int* cand_doc_out, cudaStream_t stream);
 
+/* Pieces of the 'dnn' / 'ddot' scorers (task/paper.py:448-455) and of 'niavg' (models.py:422-441) around the GEMMs:
+ * pair rows [u[b] ‖ d[(b,c)]] and their gradient split (du summed over the C candidates in a fixed order), the output
+ * Dense(1), its backward (dhid, and dl*hid whose column sums are d w2), tanh and its backward, the masked mean. */
+int lstur_pair_concat(long long n_pairs, int C, int U, int D, const float* u, long long ldu, const float* d,
+                      long long ldd, float* out, cudaStream_t stream);
+int lstur_pair_split(int B, int C, int U, int D, const float* dcat, float* du, long long lddu, float* dd, long long lddd,
+                     cudaStream_t stream);
+int lstur_rowdot_bias(long long n, int H, const float* h, const float* w, const float* bias, float* out,
+                      cudaStream_t stream);
+int lstur_dnn_out_bwd(long long n, int H, const float* hid, const float* w2, const float* dlogit, float* dhid,
+                      float* whid, cudaStream_t stream);
+int lstur_fill(long long n, float v, float* x, cudaStream_t stream);
+int lstur_tanh_fwd(long long n, float* x, cudaStream_t stream);
+int lstur_tanh_bwd(long long n, const float* y, float* g, cudaStream_t stream);
+int lstur_masked_mean_fwd(int B, int W, int D, const float* H, const float* mask, float* out, long long ldo,
+                          cudaStream_t stream);
+int lstur_masked_mean_bwd(int B, int W, int D, const float* dout, long long ldd, const float* mask, const float* keep,
+                          float* dH, cudaStream_t stream);
+
 /* Per-impression AUC / nDCG@10 / nDCG@5 / MRR (Seq2VecPaperSoftmax.callback, task/paper.py:497-524; utils.py:106-124;
  * sklearn roc_auc_score): offsets (n_impr+1) index scores / labels; out (n_impr, 4); ties ordered by descending index. */
 int lstur_ranking_metrics(int n_impr, const int* offsets, const float* scores, const float* labels, float* out,
@@ -250,6 +273,7 @@ typedef struct lstur_config {
   float dropout;
   int save_for_backward; /* 0: inference plan (smaller workspace)                            */
   int n_vert, n_subvert; /* rows of the vertical / subvertical tables (16 / 307, utils.py:153-228) */
+  int Hs;                /* hidden width of the 'dnn' / 'ddot' scorers (= user_embedding_dim), 0 for 'dot'   */
 } lstur_config;
 
 typedef struct lstur_weights {

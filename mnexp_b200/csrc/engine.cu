@@ -90,28 +90,30 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
   LSTUR_REQUIRE(c.B > 0 && c.W > 0 && c.C >= 1 && c.C <= 32 && c.L > 0 && c.L <= 256, "lstur_plan_create");
   LSTUR_REQUIRE(c.E > 0 && c.F > 0 && c.KS >= 1 && c.KS <= c.L, "lstur_plan_create");
   LSTUR_REQUIRE(c.dropout >= 0.f && c.dropout < 1.f, "lstur_plan_create");
-  if (c.score_model != LSTUR_SCORE_DOT) {
+  if (c.score_model < LSTUR_SCORE_DOT || c.score_model > LSTUR_SCORE_DDOT_LINEAR) {
     set_error("lstur_plan_create: score_model %d not implemented (NotImplementedError, task/paper.py:457)", c.score_model);
     return LSTUR_ERR_UNSUPPORTED;
   }
-  if (c.arch < LSTUR_ARCH_INI || c.arch > LSTUR_ARCH_VO) {
+  if (c.arch < LSTUR_ARCH_INI || c.arch > LSTUR_ARCH_AVG) {
     set_error("lstur_plan_create: Unsupport user model (task/paper.py:630)");
     return LSTUR_ERR_UNSUPPORTED;
   }
   LSTUR_REQUIRE(c.dv >= 0 && c.ds >= 0 && (c.dv == 0 || c.n_vert > 0) && (c.ds == 0 || c.n_subvert > 0), "lstur_plan_create");
   const int Dd = c.use_dense ? c.Dd : c.F;
   const int D = Dd + c.dv + c.ds;
-  const bool has_gru = c.arch != LSTUR_ARCH_VO;
-  const bool has_user = c.arch != LSTUR_ARCH_NOID;
+  const bool has_gru = c.arch != LSTUR_ARCH_VO && c.arch != LSTUR_ARCH_AVG;
+  const bool has_user = c.arch != LSTUR_ARCH_NOID && c.arch != LSTUR_ARCH_AVG;
+  const bool dot = c.score_model == LSTUR_SCORE_DOT, dnn = c.score_model == LSTUR_SCORE_DNN, ddot = !dot && !dnn;
+  LSTUR_REQUIRE(dot || c.Hs > 0, "lstur_plan_create('dnn' / 'ddot' scorers need Hs)");
   LSTUR_REQUIRE(!has_gru || (c.G > 0 && c.G % 4 == 0 && c.G <= 1024), "lstur_plan_create");
   LSTUR_REQUIRE(!has_user || (c.Ue > 0 && c.n_users > 0), "lstur_plan_create");
   // user-vector dim implied by the architecture
   int U = c.arch == LSTUR_ARCH_INI ? c.G : c.arch == LSTUR_ARCH_CON_DENSE ? c.U : c.arch == LSTUR_ARCH_CON_CAT ? c.G + c.Ue
-          : c.arch == LSTUR_ARCH_NOID ? c.G : c.arch == LSTUR_ARCH_ADD ? c.G : c.Ue;
+          : c.arch == LSTUR_ARCH_NOID ? c.G : c.arch == LSTUR_ARCH_ADD ? c.G : c.arch == LSTUR_ARCH_AVG ? D : c.Ue;
   LSTUR_REQUIRE(U == c.U, "lstur_plan_create(U inconsistent with arch)");
   LSTUR_REQUIRE(c.arch != LSTUR_ARCH_INI || c.Ue == c.G, "lstur_plan_create(ini needs Ue == G)");
   LSTUR_REQUIRE(c.arch != LSTUR_ARCH_ADD || c.Ue == c.G, "lstur_plan_create(add needs Ue == G)");
-  LSTUR_REQUIRE(U == D, "lstur_plan_create('dot' scorer needs user dim == doc dim)");
+  LSTUR_REQUIRE(!dot || U == D, "lstur_plan_create('dot' scorer needs user dim == doc dim)");
   if ((c.precision == LSTUR_PREC_BF16_TC || c.precision == LSTUR_PREC_FP16_TC) && !lstur_tc_supported(c.L, c.E, c.F, c.KS)) {
     set_error("lstur_plan_create: shape (L=%d,E=%d,F=%d,KS=%d) not supported by the tensor-core conv kernel", c.L, c.E, c.F, c.KS);
     return LSTUR_ERR_UNSUPPORTED;
@@ -148,6 +150,17 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
   if (c.arch == LSTUR_ARCH_CON_DENSE) {
     add_dense(p, "con_w", (long long)(G + c.Ue) * c.U);
     add_dense(p, "con_b", c.U);
+  }
+  if (dnn) {
+    add_dense(p, "sh_w", (long long)(c.U + D) * c.Hs);
+    add_dense(p, "sh_b", c.Hs);
+    add_dense(p, "so_w", c.Hs);
+    add_dense(p, "so_b", 1);
+  } else if (ddot) {
+    add_dense(p, "su_w", (long long)c.U * c.Hs);
+    add_dense(p, "su_b", c.Hs);
+    add_dense(p, "sd_w", (long long)D * c.Hs);
+    add_dense(p, "sd_b", c.Hs);
   }
   p->dense_count = (p->dense_count + 3) & ~3LL;
 
@@ -186,6 +199,18 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
   }
   if (c.arch == LSTUR_ARCH_CON_DENSE || c.arch == LSTUR_ARCH_CON_CAT) add_ws(p, "cat", B * (G + c.Ue));
   add_ws(p, "user_vec", B * c.U);
+  if (dnn) {
+    add_ws(p, "sc_cat", (long long)p->Nc * (c.U + D));
+    add_ws(p, "sc_hid", (long long)p->Nc * c.Hs);
+    add_ws(p, "sc_raw", p->Nc);
+    add_ws(p, "sc_ones", B);
+    track_gemm(p, (int)p->Nc, c.Hs, c.U + D);
+  } else if (ddot) {
+    add_ws(p, "sc_uh", B * c.Hs);
+    add_ws(p, "sc_dh", (long long)p->Nc * c.Hs);
+    track_gemm(p, (int)B, c.Hs, c.U);
+    track_gemm(p, (int)p->Nc, c.Hs, D);
+  }
   add_ws(p, "logits", B * c.C);
   add_ws(p, "probs", B * c.C);
   add_ws(p, "loss_rows", B);
@@ -209,6 +234,22 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
       add_ws(p, "dh0", B * G);
     }
     if (c.arch == LSTUR_ARCH_CON_DENSE) add_ws(p, "d_cat", B * (G + c.Ue));
+    if (dnn) {
+      add_ws(p, "sc_dhid", (long long)p->Nc * c.Hs);
+      add_ws(p, "sc_whid", (long long)p->Nc * c.Hs);
+      add_ws(p, "sc_dcat", (long long)p->Nc * (c.U + D));
+      add_ws(p, "sc_dlogit", p->Nc);
+      add_ws(p, "sc_scratch", B);
+      track_gemm(p, c.U + D, c.Hs, (int)p->Nc);
+      track_gemm(p, (int)p->Nc, c.U + D, c.Hs);
+    } else if (ddot) {
+      add_ws(p, "sc_duh", B * c.Hs);
+      add_ws(p, "sc_ddh", (long long)p->Nc * c.Hs);
+      track_gemm(p, c.U, c.Hs, (int)B);
+      track_gemm(p, D, c.Hs, (int)p->Nc);
+      track_gemm(p, (int)B, c.U, c.Hs);
+      track_gemm(p, (int)p->Nc, D, c.Hs);
+    }
     if (has_user) {
       add_ws(p, "sorted_pos", B);
       add_ws(p, "user_rows", B);
@@ -233,6 +274,7 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
   {
     int cols = 3 * G > D ? 3 * G : D;
     if (c.U > cols) cols = c.U;
+    if (c.Hs > cols) cols = c.Hs;
     add_ws(p, "colsum_ws", (long long)1024 * cols);
   }
   p->ws_bytes = (p->ws_bytes + 255) & ~(size_t)255;
@@ -329,7 +371,8 @@ int user_and_score(const lstur_plan* p, const lstur_weights* w, const lstur_batc
   float* uvec = W<float>(p, ws, "user_vec");
   float* u0 = W<float>(p, ws, "u0");
   float* cat = W<float>(p, ws, "cat");
-  const bool has_gru = c.arch != LSTUR_ARCH_VO, has_user = c.arch != LSTUR_ARCH_NOID;
+  const bool has_gru = c.arch != LSTUR_ARCH_VO && c.arch != LSTUR_ARCH_AVG;
+  const bool has_user = c.arch != LSTUR_ARCH_NOID && c.arch != LSTUR_ARCH_AVG;
   if (has_user) {
     LSTUR_REQUIRE(w->user_emb != nullptr, "lstur_forward");
     RC(lstur_row_gather(B, c.Ue, c.n_users, w->user_emb, b->user, b->user_scale, u0, c.Ue, st));
@@ -371,13 +414,48 @@ int user_and_score(const lstur_plan* p, const lstur_weights* w, const lstur_batc
       cudaMemcpyAsync(uvec, hT, (size_t)B * G * 4, cudaMemcpyDeviceToDevice, st);
       RC(lstur_axpby((long long)B * G, 1.f, u0, 1.f, uvec, st));
     }
+  } else if (c.arch == LSTUR_ARCH_AVG) {   // 'niavg': masked mean of the history vectors (models.py:422-441)
+    RC(lstur_masked_mean_fwd(B, c.W, D, docv, W<float>(p, ws, "gru_mask"), uvec, c.U, st));
   } else {
     cudaMemcpyAsync(uvec, u0, (size_t)B * c.Ue * 4, cudaMemcpyDeviceToDevice, st);
   }
   // 6. score + softmax + loss (k13-k14)
-  RC(lstur_score_softmax_ce(B, c.C, D, uvec, c.U, docv + (size_t)Nh * D, D, b->label, W<float>(p, ws, "logits"),
-                            W<float>(p, ws, "probs"), W<float>(p, ws, "loss_rows"), W<float>(p, ws, "loss"), nullptr, 0,
-                            nullptr, 0, 0.f, st));
+  const float* cand = docv + (size_t)Nh * D;
+  if (c.score_model == LSTUR_SCORE_DOT) {
+    RC(lstur_score_softmax_ce(B, c.C, D, uvec, c.U, cand, D, b->label, W<float>(p, ws, "logits"),
+                              W<float>(p, ws, "probs"), W<float>(p, ws, "loss_rows"), W<float>(p, ws, "loss"), nullptr, 0,
+                              nullptr, 0, 0.f, st));
+  } else if (c.score_model == LSTUR_SCORE_DNN) {
+    // relu Dense on [u ‖ d], Dense(1) (task/paper.py:448-451); the softmax / loss kernel then runs on the raw scores
+    // (inner dimension 1 against a vector of ones)
+    const int K2 = c.U + D;
+    float* sc_cat = W<float>(p, ws, "sc_cat");
+    float* hid = W<float>(p, ws, "sc_hid");
+    float* raw = W<float>(p, ws, "sc_raw");
+    float* ones = W<float>(p, ws, "sc_ones");
+    RC(lstur_pair_concat(p->Nc, c.C, c.U, D, uvec, c.U, cand, D, sc_cat, st));
+    RC(GEMM(0, 0, p->Nc, c.Hs, K2, sc_cat, K2, DP(p, w->dense, "sh_w"), c.Hs, hid, c.Hs, DP(p, w->dense, "sh_b"),
+            LSTUR_GEMM_RELU | LSTUR_GEMM_PRECISE, gws, gwsb, st));
+    RC(lstur_rowdot_bias(p->Nc, c.Hs, hid, DP(p, w->dense, "so_w"), DP(p, w->dense, "so_b"), raw, st));
+    RC(lstur_fill(B, 1.f, ones, st));
+    RC(lstur_score_softmax_ce(B, c.C, 1, ones, 1, raw, 1, b->label, W<float>(p, ws, "logits"), W<float>(p, ws, "probs"),
+                              W<float>(p, ws, "loss_rows"), W<float>(p, ws, "loss"), nullptr, 0, nullptr, 0, 0.f, st));
+  } else {
+    // Dense(Hs) on both sides (tanh in the paper flavour, linear in cook), then dot (task/paper.py:452-455)
+    float* uh = W<float>(p, ws, "sc_uh");
+    float* dh = W<float>(p, ws, "sc_dh");
+    RC(GEMM(0, 0, B, c.Hs, c.U, uvec, c.U, DP(p, w->dense, "su_w"), c.Hs, uh, c.Hs, DP(p, w->dense, "su_b"),
+            LSTUR_GEMM_PRECISE, gws, gwsb, st));
+    RC(GEMM(0, 0, p->Nc, c.Hs, D, cand, D, DP(p, w->dense, "sd_w"), c.Hs, dh, c.Hs, DP(p, w->dense, "sd_b"),
+            LSTUR_GEMM_PRECISE, gws, gwsb, st));
+    if (c.score_model == LSTUR_SCORE_DDOT) {
+      RC(lstur_tanh_fwd((long long)B * c.Hs, uh, st));
+      RC(lstur_tanh_fwd((long long)p->Nc * c.Hs, dh, st));
+    }
+    RC(lstur_score_softmax_ce(B, c.C, c.Hs, uh, c.Hs, dh, c.Hs, b->label, W<float>(p, ws, "logits"),
+                              W<float>(p, ws, "probs"), W<float>(p, ws, "loss_rows"), W<float>(p, ws, "loss"), nullptr, 0,
+                              nullptr, 0, 0.f, st));
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("lstur_forward: %s", cudaGetErrorString(e));
@@ -484,11 +562,52 @@ extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const
   float* uvec = W<float>(p, ws, "user_vec");
   float* d_uvec = W<float>(p, ws, "d_user_vec");
   float* d_docv = W<float>(p, ws, "d_doc_vec");
-  const bool has_gru = c.arch != LSTUR_ARCH_VO, has_user = c.arch != LSTUR_ARCH_NOID;
+  const bool has_gru = c.arch != LSTUR_ARCH_VO && c.arch != LSTUR_ARCH_AVG;
+  const bool has_user = c.arch != LSTUR_ARCH_NOID && c.arch != LSTUR_ARCH_AVG;
   cudaMemsetAsync(dgrad, 0, (size_t)p->dense_count * 4, st);
   // 1. loss / score backward
-  RC(lstur_score_softmax_ce(B, c.C, D, uvec, c.U, docv + (size_t)Nh * D, D, b->label, nullptr, nullptr, nullptr, nullptr,
-                            d_uvec, c.U, d_docv + (size_t)Nh * D, D, grad_scale, st));
+  const float* cand = docv + (size_t)Nh * D;
+  float* d_cand = d_docv + (size_t)Nh * D;
+  if (c.score_model == LSTUR_SCORE_DOT) {
+    RC(lstur_score_softmax_ce(B, c.C, D, uvec, c.U, cand, D, b->label, nullptr, nullptr, nullptr, nullptr,
+                              d_uvec, c.U, d_cand, D, grad_scale, st));
+  } else if (c.score_model == LSTUR_SCORE_DNN) {
+    const int K2 = c.U + D, Hs = c.Hs;
+    const long long Nc = p->Nc;
+    float* hid = W<float>(p, ws, "sc_hid");
+    float* dhid = W<float>(p, ws, "sc_dhid");
+    float* whid = W<float>(p, ws, "sc_whid");
+    float* dcat = W<float>(p, ws, "sc_dcat");
+    float* dl = W<float>(p, ws, "sc_dlogit");
+    RC(lstur_score_softmax_ce(B, c.C, 1, W<float>(p, ws, "sc_ones"), 1, W<float>(p, ws, "sc_raw"), 1, b->label, nullptr,
+                              nullptr, nullptr, nullptr, W<float>(p, ws, "sc_scratch"), 1, dl, 1, grad_scale, st));
+    RC(lstur_dnn_out_bwd(Nc, Hs, hid, DP(p, w->dense, "so_w"), dl, dhid, whid, st));
+    RC(lstur_colsum(Nc, Hs, whid, Hs, DG(p, dgrad, "so_w"), 0, cws, cwsb, st));
+    RC(lstur_colsum(Nc, 1, dl, 1, DG(p, dgrad, "so_b"), 0, cws, cwsb, st));
+    RC(lstur_colsum(Nc, Hs, dhid, Hs, DG(p, dgrad, "sh_b"), 0, cws, cwsb, st));
+    RC(GEMM(1, 0, K2, Hs, (int)Nc, W<float>(p, ws, "sc_cat"), K2, dhid, Hs, DG(p, dgrad, "sh_w"), Hs, nullptr, 0, gws, gwsb, st));
+    RC(GEMM(0, 1, (int)Nc, K2, Hs, dhid, Hs, DP(p, w->dense, "sh_w"), Hs, dcat, K2, nullptr, 0, gws, gwsb, st));
+    RC(lstur_pair_split(B, c.C, c.U, D, dcat, d_uvec, c.U, d_cand, D, st));
+  } else {
+    const int Hs = c.Hs;
+    const long long Nc = p->Nc;
+    float* uh = W<float>(p, ws, "sc_uh");
+    float* dh = W<float>(p, ws, "sc_dh");
+    float* duh = W<float>(p, ws, "sc_duh");
+    float* ddh = W<float>(p, ws, "sc_ddh");
+    RC(lstur_score_softmax_ce(B, c.C, Hs, uh, Hs, dh, Hs, b->label, nullptr, nullptr, nullptr, nullptr, duh, Hs, ddh, Hs,
+                              grad_scale, st));
+    if (c.score_model == LSTUR_SCORE_DDOT) {
+      RC(lstur_tanh_bwd((long long)B * Hs, uh, duh, st));
+      RC(lstur_tanh_bwd(Nc * Hs, dh, ddh, st));
+    }
+    RC(lstur_colsum(B, Hs, duh, Hs, DG(p, dgrad, "su_b"), 0, cws, cwsb, st));
+    RC(lstur_colsum(Nc, Hs, ddh, Hs, DG(p, dgrad, "sd_b"), 0, cws, cwsb, st));
+    RC(GEMM(1, 0, c.U, Hs, B, uvec, c.U, duh, Hs, DG(p, dgrad, "su_w"), Hs, nullptr, 0, gws, gwsb, st));
+    RC(GEMM(1, 0, D, Hs, (int)Nc, cand, D, ddh, Hs, DG(p, dgrad, "sd_w"), Hs, nullptr, 0, gws, gwsb, st));
+    RC(GEMM(0, 1, B, c.U, Hs, duh, Hs, DP(p, w->dense, "su_w"), Hs, d_uvec, c.U, nullptr, 0, gws, gwsb, st));
+    RC(GEMM(0, 1, (int)Nc, D, Hs, ddh, Hs, DP(p, w->dense, "sd_w"), Hs, d_cand, D, nullptr, 0, gws, gwsb, st));
+  }
   // 2. user-encoder head backward
   const float* dhT = d_uvec;
   long long lddh = c.U;
@@ -532,6 +651,8 @@ extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const
     // dH = dA . Wx^T  (rows of masked steps are zero because dA is zero there)
     RC(GEMM(0, 1, Nh, D, 3 * G, dA, 3 * G, DP(p, w->dense, "gru_wx"), 3 * G, d_docv, D, nullptr, 0, gws, gwsb, st));
     if (c.arch == LSTUR_ARCH_INI) { du0 = dh0; lddu0 = G; }
+  } else if (c.arch == LSTUR_ARCH_AVG) {
+    RC(lstur_masked_mean_bwd(B, c.W, D, d_uvec, c.U, W<float>(p, ws, "gru_mask"), W<float>(p, ws, "hist_mask"), d_docv, st));
   } else {
     cudaMemsetAsync(d_docv, 0, (size_t)Nh * D * 4, st);
   }

@@ -147,6 +147,93 @@ __global__ void ranking_metrics_kernel(int n_impr, const int* __restrict__ offse
   }
 }
 
+// ---- 'dnn' / 'ddot' scorers (task/paper.py:448-455, task/cook.py:206-209) and the masked mean of 'niavg'
+// (models.py:422-441): small row-wise kernels around the dense GEMMs.
+
+// out[(b,c)] = [u[b] (U) ‖ d[(b,c)] (D)]
+__global__ void pair_concat_kernel(long long n_pairs, int C, int U, int D, const float* __restrict__ u, long long ldu,
+                                   const float* __restrict__ d, long long ldd, float* __restrict__ out) {
+  const int K = U + D;
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / K;
+  const int k = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % K);
+  if (i >= n_pairs) return;
+  out[i * K + k] = k < U ? u[(i / C) * ldu + k] : d[i * ldd + (k - U)];
+}
+// du[b] = sum_c dcat[(b,c), :U] (fixed order);  dd[(b,c)] = dcat[(b,c), U:]
+__global__ void pair_split_kernel(int B, int C, int U, int D, const float* __restrict__ dcat, float* __restrict__ du,
+                                  long long lddu, float* __restrict__ dd, long long lddd) {
+  const int K = U + D;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = (int)(idx / K), k = (int)(idx % K);
+  if (b >= B) return;
+  if (k < U) {
+    float acc = 0.f;
+    for (int c = 0; c < C; ++c) acc += dcat[((long long)b * C + c) * K + k];
+    du[(long long)b * lddu + k] = acc;
+  } else {
+    for (int c = 0; c < C; ++c) dd[((long long)b * C + c) * lddd + (k - U)] = dcat[((long long)b * C + c) * K + k];
+  }
+}
+// out[i] = h[i] . w + bias[0]; one warp per row
+__global__ void rowdot_bias_kernel(long long n, int H, const float* __restrict__ h, const float* __restrict__ w,
+                                   const float* __restrict__ bias, float* __restrict__ out) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  float acc = 0.f;
+  for (int k = lane; k < H; k += 32) acc = fmaf(h[i * H + k], w[k], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) out[i] = acc + (bias ? bias[0] : 0.f);
+}
+// backward of  logit = relu_hid . w2 + b2:  dhid = (hid > 0) dl w2;  whid = dl hid (column sums = d w2)
+__global__ void dnn_out_bwd_kernel(long long n, int H, const float* __restrict__ hid, const float* __restrict__ w2,
+                                   const float* __restrict__ dl, float* __restrict__ dhid, float* __restrict__ whid) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * H) return;
+  const long long i = idx / H;
+  const int k = (int)(idx % H);
+  const float hv = hid[idx], g = dl[i];
+  dhid[idx] = hv > 0.f ? g * w2[k] : 0.f;
+  whid[idx] = g * hv;
+}
+__global__ void fill_kernel(long long n, float v, float* __restrict__ x) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = v;
+}
+__global__ void tanh_fwd_kernel(long long n, float* __restrict__ x) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = tanhf(x[i]);
+}
+__global__ void tanh_bwd_kernel(long long n, const float* __restrict__ y, float* __restrict__ g) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) g[i] *= 1.f - y[i] * y[i];
+}
+// GlobalAveragePoolingMaskSupport: out[b] = sum_t H[b,t,:] / (sum_t m[b,t] + 1e-7)
+__global__ void masked_mean_fwd_kernel(int B, int W, int D, const float* __restrict__ H, const float* __restrict__ m,
+                                       float* __restrict__ out, long long ldo) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = (int)(idx / D), k = (int)(idx % D);
+  if (b >= B) return;
+  float acc = 0.f, cnt = 0.f;
+  for (int t = 0; t < W; ++t) {
+    acc += H[((long long)b * W + t) * D + k];
+    cnt += m[(long long)b * W + t];
+  }
+  out[(long long)b * ldo + k] = acc / (cnt + 1e-7f);
+}
+// dH[b,t,:] = keep[b,t] * dout[b] / (sum_t m[b,t] + 1e-7)   (keep = the history mask multiplied in before the layer)
+__global__ void masked_mean_bwd_kernel(int B, int W, int D, const float* __restrict__ dout, long long ldd,
+                                       const float* __restrict__ m, const float* __restrict__ keep,
+                                       float* __restrict__ dH) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = (int)(idx / D), k = (int)(idx % D);
+  if (b >= B) return;
+  float cnt = 0.f;
+  for (int t = 0; t < W; ++t) cnt += m[(long long)b * W + t];
+  const float g = dout[(long long)b * ldd + k] / (cnt + 1e-7f);
+  for (int t = 0; t < W; ++t) dH[((long long)b * W + t) * D + k] = keep[(long long)b * W + t] * g;
+}
+
 }  // namespace lstur
 
 using namespace lstur;
@@ -188,5 +275,75 @@ extern "C" int lstur_ranking_metrics(int n_impr, const int* offsets, const float
   if (n_impr == 0) return LSTUR_OK;
   ranking_metrics_kernel<<<n_impr, 128, 0, stream>>>(n_impr, offsets, scores, labels, out);
   LSTUR_CHECK_LAUNCH("lstur_ranking_metrics");
+  return LSTUR_OK;
+}
+
+extern "C" int lstur_pair_concat(long long n_pairs, int C, int U, int D, const float* u, long long ldu, const float* d,
+                                 long long ldd, float* out, cudaStream_t stream) {
+  LSTUR_REQUIRE(n_pairs >= 0 && C >= 1 && U > 0 && D > 0 && u && d && out, "lstur_pair_concat");
+  if (n_pairs == 0) return LSTUR_OK;
+  pair_concat_kernel<<<cdiv(n_pairs * (U + D), 256), 256, 0, stream>>>(n_pairs, C, U, D, u, ldu, d, ldd, out);
+  LSTUR_CHECK_LAUNCH("lstur_pair_concat");
+  return LSTUR_OK;
+}
+extern "C" int lstur_pair_split(int B, int C, int U, int D, const float* dcat, float* du, long long lddu, float* dd,
+                                long long lddd, cudaStream_t stream) {
+  LSTUR_REQUIRE(B >= 0 && C >= 1 && U > 0 && D > 0 && dcat && du && dd, "lstur_pair_split");
+  if (B == 0) return LSTUR_OK;
+  pair_split_kernel<<<cdiv((long long)B * (U + D), 256), 256, 0, stream>>>(B, C, U, D, dcat, du, lddu, dd, lddd);
+  LSTUR_CHECK_LAUNCH("lstur_pair_split");
+  return LSTUR_OK;
+}
+extern "C" int lstur_rowdot_bias(long long n, int H, const float* h, const float* w, const float* bias, float* out,
+                                 cudaStream_t stream) {
+  LSTUR_REQUIRE(n >= 0 && H > 0 && h && w && out, "lstur_rowdot_bias");
+  if (n == 0) return LSTUR_OK;
+  rowdot_bias_kernel<<<cdiv(n * 32, 256), 256, 0, stream>>>(n, H, h, w, bias, out);
+  LSTUR_CHECK_LAUNCH("lstur_rowdot_bias");
+  return LSTUR_OK;
+}
+extern "C" int lstur_dnn_out_bwd(long long n, int H, const float* hid, const float* w2, const float* dlogit, float* dhid,
+                                 float* whid, cudaStream_t stream) {
+  LSTUR_REQUIRE(n >= 0 && H > 0 && hid && w2 && dlogit && dhid && whid, "lstur_dnn_out_bwd");
+  if (n == 0) return LSTUR_OK;
+  dnn_out_bwd_kernel<<<cdiv(n * H, 256), 256, 0, stream>>>(n, H, hid, w2, dlogit, dhid, whid);
+  LSTUR_CHECK_LAUNCH("lstur_dnn_out_bwd");
+  return LSTUR_OK;
+}
+extern "C" int lstur_tanh_fwd(long long n, float* x, cudaStream_t stream) {
+  LSTUR_REQUIRE(n >= 0 && (n == 0 || x), "lstur_tanh_fwd");
+  if (n == 0) return LSTUR_OK;
+  tanh_fwd_kernel<<<cdiv(n, 256), 256, 0, stream>>>(n, x);
+  LSTUR_CHECK_LAUNCH("lstur_tanh_fwd");
+  return LSTUR_OK;
+}
+extern "C" int lstur_tanh_bwd(long long n, const float* y, float* g, cudaStream_t stream) {
+  LSTUR_REQUIRE(n >= 0 && (n == 0 || (y && g)), "lstur_tanh_bwd");
+  if (n == 0) return LSTUR_OK;
+  tanh_bwd_kernel<<<cdiv(n, 256), 256, 0, stream>>>(n, y, g);
+  LSTUR_CHECK_LAUNCH("lstur_tanh_bwd");
+  return LSTUR_OK;
+}
+extern "C" int lstur_masked_mean_fwd(int B, int W, int D, const float* H, const float* mask, float* out, long long ldo,
+                                     cudaStream_t stream) {
+  LSTUR_REQUIRE(B >= 0 && W > 0 && D > 0 && H && mask && out, "lstur_masked_mean_fwd");
+  if (B == 0) return LSTUR_OK;
+  masked_mean_fwd_kernel<<<cdiv((long long)B * D, 256), 256, 0, stream>>>(B, W, D, H, mask, out, ldo);
+  LSTUR_CHECK_LAUNCH("lstur_masked_mean_fwd");
+  return LSTUR_OK;
+}
+extern "C" int lstur_masked_mean_bwd(int B, int W, int D, const float* dout, long long ldd, const float* mask,
+                                     const float* keep, float* dH, cudaStream_t stream) {
+  LSTUR_REQUIRE(B >= 0 && W > 0 && D > 0 && dout && mask && keep && dH, "lstur_masked_mean_bwd");
+  if (B == 0) return LSTUR_OK;
+  masked_mean_bwd_kernel<<<cdiv((long long)B * D, 256), 256, 0, stream>>>(B, W, D, dout, ldd, mask, keep, dH);
+  LSTUR_CHECK_LAUNCH("lstur_masked_mean_bwd");
+  return LSTUR_OK;
+}
+extern "C" int lstur_fill(long long n, float v, float* x, cudaStream_t stream) {
+  LSTUR_REQUIRE(n >= 0 && (n == 0 || x), "lstur_fill");
+  if (n == 0) return LSTUR_OK;
+  fill_kernel<<<cdiv(n, 256), 256, 0, stream>>>(n, v, x);
+  LSTUR_CHECK_LAUNCH("lstur_fill");
   return LSTUR_OK;
 }

@@ -14,11 +14,12 @@ from . import _lib
 from ._lib import lstur_batch, lstur_config, lstur_weights
 
 ARCH = {  # reference arch names -> engine arch; paper.py names
-    'igru': 0, 'gru': 1, 'ngru': 2, 'hgru': 2, 'dgru': 2, 'nigru': 3, 'pgru': 4, 'vo': 5,
+    'igru': 0, 'gru': 1, 'ngru': 2, 'hgru': 2, 'dgru': 2, 'nigru': 3, 'pgru': 4, 'vo': 5, 'niavg': 6,
 }
+SCORE = {'dot': 0, 'dnn': 1, 'ddot': 2}          # task/paper.py:443-458; cook's 'ddot' is linear (task/cook.py:206-209)
 COOK_ARCH = {'ingru': 0, 'igru': 2, 'gru': 3, 'agru': 4, 'vo': 5}   # task/cook.py:146-168
 DENSE_NAMES = ('conv_w', 'conv_b', 'att_w', 'att_b', 'dense_w', 'dense_b', 'vert_emb', 'subvert_emb',
-               'gru_wx', 'gru_wh', 'gru_b', 'con_w', 'con_b')
+               'gru_wx', 'gru_wh', 'gru_b', 'con_w', 'con_b', 'sh_w', 'sh_b', 'so_w', 'so_b', 'su_w', 'su_b', 'sd_w', 'sd_b')
 PREC = {'fp32': 0, 'bf16_tc': 1, 'fp16_tc': 2}
 
 
@@ -35,7 +36,7 @@ class LsturEngine:
     def __init__(self, params, B, W, C, L, arch='igru', flavour='paper', dropout=0.0, lr=1e-3,
                  recurrent_activation='hard_sigmoid', precision='fp32', doc_tokens=None, device=None,
                  training=True, sparse_user_adam=True, trainable_word_emb=False, share_weights_from=None,
-                 doc_vert=None, doc_subvert=None):
+                 doc_vert=None, doc_subvert=None, score_model='dot'):
         if not torch.cuda.is_available():
             raise _lib.LsturError('LsturEngine needs a CUDA device (no CPU fallback)')
         self.lib = _lib.load()
@@ -46,25 +47,35 @@ class LsturEngine:
         if arch not in amap:
             raise Exception('Unsupport user model')                      # task/paper.py:630
         self.arch_name, self.arch = arch, amap[arch]
+        if score_model not in SCORE:
+            raise NotImplementedError                                    # task/paper.py:456-457
+        self.score_model = score_model
+        sm = SCORE[score_model] + (1 if (score_model == 'ddot' and flavour != 'paper') else 0)
+        Hs = {'dot': 0, 'dnn': params['sh_w'].shape[1] if 'sh_w' in params else 0,
+              'ddot': params['su_w'].shape[1] if 'su_w' in params else 0}[score_model]
         ks, E, F = params['conv_w'].shape
         use_dense = 'dense_w' in params
         Dd = params['dense_w'].shape[1] if use_dense else F
         G = params['gru_wh'].shape[0] if 'gru_wh' in params else 0
-        Ue = params['user_emb'].shape[1] if 'user_emb' in params and self.arch != 3 else 0
-        U = {0: G, 1: params['con_w'].shape[1] if 'con_w' in params else 0, 2: G + Ue, 3: G, 4: G, 5: Ue}[self.arch]
+        Ue = params['user_emb'].shape[1] if 'user_emb' in params and self.arch not in (3, 6) else 0
+        if self.arch == 6:
+            G = 0
         # Cook.get_doc_encoder concat (task/cook.py:99-113): [title | Vemb[vert] | Semb[subvert]]
         dv = params['vert_emb'].shape[1] if 'vert_emb' in params else 0
         ds = params['subvert_emb'].shape[1] if 'subvert_emb' in params else 0
+        U = {0: G, 1: params['con_w'].shape[1] if 'con_w' in params else 0, 2: G + Ue, 3: G, 4: G, 5: Ue,
+             6: Dd + dv + ds}[self.arch]
         _sd = share_weights_from.doc_tokens if share_weights_from is not None else None
         n_docs = doc_tokens.shape[0] if doc_tokens is not None else (0 if _sd is None else _sd.shape[0])
         self.cfg = lstur_config(
             B=B, W=W, C=C, L=L, E=E, F=F, KS=ks, use_dense=int(use_dense), Dd=Dd, dv=dv, ds=ds, G=G, Ue=Ue, U=U,
-            arch=self.arch, score_model=0, rec_act=0 if recurrent_activation == 'hard_sigmoid' else 1,
+            arch=self.arch, score_model=sm, rec_act=0 if recurrent_activation == 'hard_sigmoid' else 1,
             precision=PREC[precision], V=params['word_emb'].shape[0],
             n_users=params['user_emb'].shape[0] if Ue else 0,
             n_docs=n_docs, dropout=float(dropout),
             save_for_backward=int(training),
-            n_vert=params['vert_emb'].shape[0] if dv else 0, n_subvert=params['subvert_emb'].shape[0] if ds else 0)
+            n_vert=params['vert_emb'].shape[0] if dv else 0, n_subvert=params['subvert_emb'].shape[0] if ds else 0,
+            Hs=Hs)
         self.B, self.W, self.C, self.L, self.D, self.U, self.Ue, self.G = B, W, C, L, Dd + dv + ds, U, Ue, G
         plan = ctypes.c_void_p()
         _lib.check(self.lib.lstur_plan_create(ctypes.byref(self.cfg), ctypes.byref(plan)))
@@ -304,6 +315,12 @@ class LsturEngine:
         """sigmoid(user_vec . cand_vec) for every (row, candidate) of the last forward — the reference's test head
         (task/paper.py:661-665).  Returns a (B, C) device tensor."""
         out = torch.empty((self.B, self.C), dtype=torch.float32, device=self.device)
+        if self.score_model != 'dot':     # sigmoid of the raw scores the scorer left in the workspace
+            if getattr(self, '_ones', None) is None:
+                self._ones = torch.ones(self.B, dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.lstur_score_sigmoid(self.B * self.C, self.C, 1, _ptr(self._ones), 1,
+                                                    _ptr(self.view('logits')), 1, _ptr(out), 1, self._stream()))
+            return out
         nh = self.B * self.W
         dv = self.view('doc_vec')
         cand = dv[nh * self.D:]

@@ -46,8 +46,9 @@ class History:
 class _Core:
     """Weights + engines shared by `model` (softmax/CE training graph) and `test_model` (sigmoid scoring graph)."""
 
-    def __init__(self, params, cfg, doc_tokens, has_user, arch, predict_rows=256):
+    def __init__(self, params, cfg, doc_tokens, has_user, arch, predict_rows=256, score_model='dot'):
         self.params, self.cfg, self.doc_tokens, self.has_user, self.arch = params, cfg, doc_tokens, has_user, arch
+        self.score_model = score_model
         self.optimizer = Adam(cfg.learning_rate)
         self.train_engine = None
         self.infer_engines = {}
@@ -73,7 +74,7 @@ class _Core:
                 self.params, B, c.window_size, 1 + c.negative_samples, c.title_shape, arch=self.arch,
                 dropout=c.dropout, lr=c.learning_rate, recurrent_activation=c.recurrent_activation,
                 precision=self.precision(), doc_tokens=self.doc_tokens, training=True,
-                sparse_user_adam=bool(c.sparse_user_adam))
+                sparse_user_adam=bool(c.sparse_user_adam), score_model=self.score_model)
             self.infer_engines = {}
         return self.train_engine
 
@@ -84,7 +85,7 @@ class _Core:
             self.infer_engines[C] = LsturEngine(
                 self.params, self.predict_rows, c.window_size, C, c.title_shape, arch=self.arch, dropout=0.0,
                 recurrent_activation=c.recurrent_activation, precision=self.precision(), training=False,
-                share_weights_from=base)
+                share_weights_from=base, score_model=self.score_model)
         return self.infer_engines[C]
 
     def split_inputs(self, x, n_cand):
@@ -118,7 +119,10 @@ class Model:
         user, clicked, cand = core.split_inputs(x, C)
         eng = core.engine_train(clicked.shape[0])
         eng.lr = core.optimizer.lr.value
-        db = eng.to_device_batch(dict(user=user, hist_tok=clicked, cand_tok=cand, label=np.asarray(y)))
+        batch = dict(user=user, hist_tok=clicked, cand_tok=cand, label=np.asarray(y))
+        if core.arch == 'dgru':     # Dropout(0.5, noise_shape=(None, 1)) on the user vector (task/paper.py:609)
+            batch['user_scale'] = (np.random.random(clicked.shape[0]) >= 0.5).astype(np.float32) * 2.0
+        db = eng.to_device_batch(batch)
         loss = eng.train_step(db)
         probs = eng.view('probs').reshape(eng.B, eng.C)
         acc = (probs.argmax(1) == db['label'].argmax(1)).float().mean()
@@ -196,7 +200,8 @@ class Model:
 
     # ---- weights / structure ------------------------------------------------------------------
     WEIGHT_ORDER = ('word_emb', 'conv_w', 'conv_b', 'att_w', 'att_b', 'dense_w', 'dense_b', 'user_emb',
-                    'gru_wx', 'gru_wh', 'gru_b', 'con_w', 'con_b')
+                    'gru_wx', 'gru_wh', 'gru_b', 'con_w', 'con_b', 'sh_w', 'sh_b', 'so_w', 'so_b', 'su_w', 'su_b', 'sd_w',
+                    'sd_b')
 
     def _current(self):
         e = self.core.train_engine

@@ -143,17 +143,23 @@ def make_weights(shape, arch=None, seed=1237, word_emb=None, score_model='dot', 
         P['dense_b'] = bz(U)
     G = U // 2 if arch == 'hgru' else U
     Ue = U // 2 if arch == 'hgru' else U
-    if arch != 'nigru':
+    if arch not in ('nigru', 'niavg'):
         P['user_emb'] = rng.uniform(-0.05, 0.05, (shape.n_users, Ue)).astype(np.float32)
-    if arch != 'vo':
+    if arch not in ('vo', 'niavg'):
         P['gru_wx'] = _glorot(rng, (D, 3 * G), D, 3 * G)
         P['gru_wh'] = np.concatenate([_orthogonal(rng, G, G) for _ in range(3)], 1)
         P['gru_b'] = bz(3 * G)
     if arch == 'gru':
         P['con_w'] = _glorot(rng, (G + Ue, U), G + Ue, U)
         P['con_b'] = bz(U)
+    if score_model == 'dnn':                                   # task/paper.py:448-451
+        Du = 2 * U if arch in ('ngru', 'dgru') else (D if arch == 'niavg' else U)
+        P['sh_w'] = _glorot(rng, (Du + D, U), Du + D, U)
+        P['sh_b'] = bz(U)
+        P['so_w'] = _glorot(rng, (U, 1), U, 1)
+        P['so_b'] = bz(1)
     if score_model == 'ddot':
-        Du = 2 * U if arch in ('ngru', 'dgru') else U
+        Du = 2 * U if arch in ('ngru', 'dgru') else (D if arch == 'niavg' else U)
         P['su_w'] = _glorot(rng, (Du, U), Du, U)
         P['su_b'] = bz(U)
         P['sd_w'] = _glorot(rng, (D, U), D, U)

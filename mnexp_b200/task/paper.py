@@ -131,6 +131,9 @@ class Seq2VecPaperSoftmax(Seq2VecPaper):
         arch = self.config.arch
         if arch not in self.USER_ARCHS:
             raise Exception('Unsupport user model')          # task/paper.py:216-217, 629-630
+        if arch in ('ngru', 'dgru') and self.config.score_model == 'dot':
+            # the reference graph fails to build here too: keras.layers.dot rejects (2U) . (U) (task/paper.py:447)
+            raise ValueError("arch '%s' yields a 2U user vector: use score_model 'dnn' or 'ddot'" % arch)
         return 'nigru' if not self.HAS_USER else arch
 
     def get_user_encoder(self, window_size=None):
@@ -138,9 +141,9 @@ class Seq2VecPaperSoftmax(Seq2VecPaper):
         return self._core                                     # user encoder is part of the fused plan
 
     def _score_model(self, u=None, d=None):
-        if self.config.score_model != 'dot':
-            raise NotImplementedError                          # task/paper.py:456-457 ('dnn'/'ddot': SURVEY §8f row 4)
-        self.score_model = 'dot'
+        if self.config.score_model not in ('dot', 'dnn', 'ddot'):
+            raise NotImplementedError                          # task/paper.py:456-457
+        self.score_model = self.config.score_model
 
     def score_encoder(self, user_vec=None, candidate_vecs=None):
         self._score_model()
@@ -153,13 +156,15 @@ class Seq2VecPaperSoftmax(Seq2VecPaper):
         sh = synth.Shape('cfg', n_users=len(self.data), n_news=self.doc_count - 1, vocab=word_emb.shape[0],
                          L=c.title_shape, W=c.window_size, K=c.negative_samples, B=c.batch_size, E=word_emb.shape[1],
                          F=F, k=k, U=c.user_embedding_dim, arch=self._engine_arch())
-        return synth.make_weights(sh, arch=self._engine_arch(), seed=np.random.randint(1 << 30), word_emb=word_emb)
+        return synth.make_weights(sh, arch=self._engine_arch(), seed=np.random.randint(1 << 30), word_emb=word_emb,
+                                  score_model=c.score_model)
 
     def _build_model(self):
         """task/paper.py:466-495 / 635-665: `model` = softmax CE + Adam, `test_model` = sigmoid score, shared weights."""
         arch = self._engine_arch()
         params = self._init_params()
-        self._core = keras_like._Core(params, self.config, self.doc_token_table(), self.HAS_USER, arch)
+        self._core = keras_like._Core(params, self.config, self.doc_token_table(), self.HAS_USER, arch,
+                                      score_model=self.config.score_model)
         self.doc_encoder = self.get_doc_encoder()
         self.user_encoder = self.get_user_encoder()
         self.score_encoder()
@@ -198,4 +203,5 @@ class Seq2VecPaperSoftmax(Seq2VecPaper):
 class Seq2VecPaperSoftmaxId(Seq2VecPaperSoftmax):
     """LSTUR (task/paper.py:527-665): igru = LSTUR-ini; gru / hgru / ngru / dgru = LSTUR-con."""
     HAS_USER = True
-    USER_ARCHS = ('igru', 'gru', 'hgru', 'nigru', 'pgru', 'vo')   # ngru/dgru/iigru need a non-dot scorer or extra tables
+    # 'iigru' (a second user table, task/paper.py:614-619) is the one arch left out
+    USER_ARCHS = ('igru', 'gru', 'ngru', 'hgru', 'dgru', 'nigru', 'pgru', 'vo', 'niavg')

@@ -140,7 +140,7 @@ def user_encoder(arch, user, H, P, recurrent_activation='hard_sigmoid', u0_scale
     task/cook.py:141-142)."""
     f8 = lambda k: P[k].astype(np.float64)
     user = np.asarray(user).astype(np.int64).reshape(-1)
-    u0 = f8('user_emb')[user] if 'user_emb' in P and arch not in ('nigru',) else None
+    u0 = f8('user_emb')[user] if 'user_emb' in P and arch not in ('nigru', 'niavg') else None
     if u0 is not None and u0_scale is not None:
         u0 = u0 * u0_scale
     gru = lambda h0: gru_last_state(H.astype(np.float64), h0, f8('gru_wx'), f8('gru_wh'), f8('gru_b'), recurrent_activation)
@@ -156,6 +156,10 @@ def user_encoder(arch, user, H, P, recurrent_activation='hard_sigmoid', u0_scale
         return gru(None)
     if arch == 'vo':                         # :620-621
         return u0
+    if arch == 'niavg':                      # :627-628, models.GlobalAveragePoolingMaskSupport (models.py:433-435)
+        H8 = H.astype(np.float64)
+        gm = (H8 != 0).any(-1).astype(np.float64)
+        return H8.sum(-2) / (gm.sum(-1, keepdims=True) + 1e-7)
     raise Exception('Unsupport user model')  # task/paper.py:630
 
 

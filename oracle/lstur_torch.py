@@ -69,7 +69,7 @@ def gru_last_state(H, h0, Wx, Wh, b, recurrent_activation='hard_sigmoid'):
 
 def user_encoder(arch, user, H, P, recurrent_activation='hard_sigmoid', u0_scale=None):
     """task/paper.py:584-633."""
-    u0 = P['user_emb'][user.reshape(-1)] if 'user_emb' in P and arch != 'nigru' else None
+    u0 = P['user_emb'][user.reshape(-1)] if 'user_emb' in P and arch not in ('nigru', 'niavg') else None
     if u0 is not None and u0_scale is not None:
         u0 = u0 * u0_scale
     gru = lambda h0: gru_last_state(H, h0, P['gru_wx'], P['gru_wh'], P['gru_b'], recurrent_activation)
@@ -85,6 +85,9 @@ def user_encoder(arch, user, H, P, recurrent_activation='hard_sigmoid', u0_scale
         return gru(None)
     if arch == 'vo':
         return u0
+    if arch == 'niavg':          # models.GlobalAveragePoolingMaskSupport (models.py:422-441) under Masking()
+        gm = (H != 0).any(-1).to(H.dtype)
+        return H.sum(-2) / (gm.sum(-1, keepdim=True) + EPS)
     raise Exception('Unsupport user model')
 
 

@@ -310,3 +310,50 @@ def test_cook_vertical_concat_and_id_keep(L, precision):
     grads = dict(zip(names, torch.autograd.grad(loss, [Pt[k] for k in names], allow_unused=True)))
     for k in ('vert_emb', 'subvert_emb', 'conv_w', 'gru_wx', 'gru_wh', 'user_emb', 'att_w'):
         assert rel(got[k], grads[k].numpy()) < 5e-5, k
+
+
+# ---------------------------------------------------------------- remaining user encoders and scorers of §8 a8/a9
+@pytest.mark.parametrize('arch,score_model,precision', [
+    ('igru', 'dnn', 'fp32'), ('igru', 'ddot', 'fp32'), ('ngru', 'dnn', 'fp32'), ('ngru', 'ddot', 'fp32'),
+    ('dgru', 'ddot', 'fp32'), ('niavg', 'dot', 'fp32'), ('niavg', 'dnn', 'fp32'), ('gru', 'ddot', 'fp16_tc'),
+    ('ngru', 'dnn', 'fp16_tc'),
+])
+def test_scorers_and_remaining_archs_match_oracle(L, arch, score_model, precision):
+    """'dnn' / 'ddot' scorers (task/paper.py:448-455), 'ngru' / 'dgru' (2U user vector, :600-611, only scorable by
+    those two) and 'niavg' (:627-628): forward outputs, test head and every gradient against the float64 oracle."""
+    sh = synth.SHAPES['tiny']
+    tok, _, _ = synth.make_docs(sh.n_news, sh.L, sh.vocab)
+    P = synth.make_weights(sh, arch=arch, bias_noise=0.05, seed=1250, score_model=score_model)
+    (b,), _ = synth.make_batches(sh, 1, seed=1249)
+    b = dict(b)
+    scale = None
+    if arch == 'dgru':      # Dropout(0.5, noise_shape=(None, 1)) on the user vector: a per-sample multiplier in {0, 2}
+        scale = (np.random.default_rng(5).random(sh.B) < 0.5).astype(np.float32) * 2.0
+        b['user_scale'] = scale
+    eng = engine_for(sh, tok, P, arch, score_model=score_model, precision=precision)
+    db = eng.to_device_batch(b)
+    probs = eng.forward(db, training=True, seed=1).cpu().numpy().copy()
+    sig = eng.score_sigmoid().cpu().numpy()
+    eng.backward(db)
+    torch.cuda.synchronize()
+    got = eng.get_grads_dict()
+    ora = ot.LsturOracle(P, arch=arch, score_model=score_model)
+    u, c, d = ora._ints(b['user'], tok[b['hist_doc']], tok[b['cand_doc']])
+    kw = dict(arch=arch, score_model=score_model, u0_scale=None if scale is None else torch.tensor(scale, dtype=torch.float64)[:, None])
+    out = ot.forward(ora.P, u, c, d, aux=True, **kw)
+    tol = 5e-5 if precision == 'fp32' else TOL_SPEC
+    assert rel(eng.view('user_vec').reshape(sh.B, -1).cpu().numpy(), out['user_vec'].detach().numpy()) < tol
+    assert rel(eng.view('logits').reshape(sh.B, -1).cpu().numpy(), out['logits'].detach().numpy()) < tol
+    assert rel(probs, out['probs'].detach().numpy()) < tol
+    assert rel(sig, torch.sigmoid(out['logits']).detach().numpy()) < tol
+    loss = ot.loss_fn(ora.P, u, c, d, **kw)
+    ref = dict(zip(ora.trainable, torch.autograd.grad(loss, [ora.P[k] for k in ora.trainable], allow_unused=True)))
+    gtol = 5e-5 if precision == 'fp32' else 2e-2
+    for k, g in ref.items():
+        if g is None or k == 'att_b':
+            continue
+        assert k in got, k
+        if k == 'so_b':     # the softmax is shift-invariant: d so_b = sum of d logits = 0 up to rounding
+            assert abs(float(np.asarray(got[k]).reshape(-1)[0])) < 1e-6
+            continue
+        assert rel(got[k], g.numpy()) < gtol, k

@@ -258,3 +258,30 @@ def test_device_batch_assembly_matches_window(lib):
         eng = h._core.engine_train(B)
     loss = float(eng.train_step(bt.next_batch())[0])
     assert np.isfinite(loss)
+
+
+@pytest.mark.parametrize('arch,score_model', [('ngru', 'dnn'), ('dgru', 'ddot'), ('niavg', 'ddot'), ('igru', 'dnn')])
+def test_model_builder_scorers_and_concat_archs(lib, arch, score_model):
+    """--score-model dnn / ddot (task/paper.py:448-455) with the 2U-wide 'ngru' / 'dgru' user vectors and 'niavg',
+    through the reference's task-handler surface."""
+    sh, h = _handler(arch, 'Seq2VecPaperSoftmaxId', score_model=score_model)
+    model = h.build_model(0)
+    x, y = next(h.train)
+    P = _oracle_params(model)
+    for k in ('so_w',):
+        if k in P:
+            P[k] = P[k].reshape(-1, 1)
+    cands = np.stack(x[2:], 1)
+    ref = on.lstur_forward(P, x[0], x[1].astype(int), cands.astype(int), arch=arch, score_model=score_model, aux=True)
+    assert rel(model.predict(x), ref['probs']) < 2e-5
+    s = h.test_model.predict(x[:2] + [x[2]])
+    assert s.shape == (len(y), 1) and rel(s[:, 0], ref['sigmoid'][:, 0]) < 2e-5
+    l0 = model.evaluate(x, y)[0]
+    for _ in range(25):
+        model.train_on_batch(x, y)
+    assert model.evaluate(x, y)[0] < l0
+
+
+def test_concat_archs_need_a_dense_scorer(lib):
+    with pytest.raises(ValueError):
+        _handler('ngru', 'Seq2VecPaperSoftmaxId', score_model='dot')[1].build_model(0)
