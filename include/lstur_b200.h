@@ -48,6 +48,8 @@ typedef struct CUstream_st* cudaStream_t;
 #define LSTUR_ARCH_ADD 4       /* paper 'pgru' / cook 'agru': GRU + user_emb                           */
 #define LSTUR_ARCH_VO 5        /* 'vo': user_emb only                                                  */
 #define LSTUR_ARCH_AVG 6       /* paper 'niavg': GlobalAveragePoolingMaskSupport of the history (models.py:422-441) */
+#define LSTUR_ARCH_INI_CON 7   /* paper 'iigru': Dense([GRU(initial_state=user_emb) ‖ user_emb2]), task/paper.py:614-619;
+                                  the two tables are the column halves of one (n_users, Ue = G + U2) table */
 
 #define LSTUR_SCORE_DOT 0      /* task/paper.py:446-447 */
 #define LSTUR_SCORE_DNN 1      /* Dense(Hs, relu)([u ‖ d]) -> Dense(1), task/paper.py:448-451 */

@@ -94,7 +94,7 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
     set_error("lstur_plan_create: score_model %d not implemented (NotImplementedError, task/paper.py:457)", c.score_model);
     return LSTUR_ERR_UNSUPPORTED;
   }
-  if (c.arch < LSTUR_ARCH_INI || c.arch > LSTUR_ARCH_AVG) {
+  if (c.arch < LSTUR_ARCH_INI || c.arch > LSTUR_ARCH_INI_CON) {
     set_error("lstur_plan_create: Unsupport user model (task/paper.py:630)");
     return LSTUR_ERR_UNSUPPORTED;
   }
@@ -108,11 +108,13 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
   LSTUR_REQUIRE(!has_gru || (c.G > 0 && c.G % 4 == 0 && c.G <= 1024), "lstur_plan_create");
   LSTUR_REQUIRE(!has_user || (c.Ue > 0 && c.n_users > 0), "lstur_plan_create");
   // user-vector dim implied by the architecture
-  int U = c.arch == LSTUR_ARCH_INI ? c.G : c.arch == LSTUR_ARCH_CON_DENSE ? c.U : c.arch == LSTUR_ARCH_CON_CAT ? c.G + c.Ue
+  int U = c.arch == LSTUR_ARCH_INI ? c.G : (c.arch == LSTUR_ARCH_CON_DENSE || c.arch == LSTUR_ARCH_INI_CON) ? c.U
+          : c.arch == LSTUR_ARCH_CON_CAT ? c.G + c.Ue
           : c.arch == LSTUR_ARCH_NOID ? c.G : c.arch == LSTUR_ARCH_ADD ? c.G : c.arch == LSTUR_ARCH_AVG ? D : c.Ue;
   LSTUR_REQUIRE(U == c.U, "lstur_plan_create(U inconsistent with arch)");
   LSTUR_REQUIRE(c.arch != LSTUR_ARCH_INI || c.Ue == c.G, "lstur_plan_create(ini needs Ue == G)");
   LSTUR_REQUIRE(c.arch != LSTUR_ARCH_ADD || c.Ue == c.G, "lstur_plan_create(add needs Ue == G)");
+  LSTUR_REQUIRE(c.arch != LSTUR_ARCH_INI_CON || c.Ue > c.G, "lstur_plan_create(ini+con needs Ue > G)");
   LSTUR_REQUIRE(!dot || U == D, "lstur_plan_create('dot' scorer needs user dim == doc dim)");
   if ((c.precision == LSTUR_PREC_BF16_TC || c.precision == LSTUR_PREC_FP16_TC) && !lstur_tc_supported(c.L, c.E, c.F, c.KS)) {
     set_error("lstur_plan_create: shape (L=%d,E=%d,F=%d,KS=%d) not supported by the tensor-core conv kernel", c.L, c.E, c.F, c.KS);
@@ -147,8 +149,11 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
     add_dense(p, "gru_wh", (long long)G * 3 * G);
     add_dense(p, "gru_b", 3 * G);
   }
-  if (c.arch == LSTUR_ARCH_CON_DENSE) {
-    add_dense(p, "con_w", (long long)(G + c.Ue) * c.U);
+  // width of the user-embedding part that joins the concat ('iigru': the second table = columns G.. of the row)
+  const int Uc = c.arch == LSTUR_ARCH_INI_CON ? c.Ue - G : c.Ue;
+  const bool con_dense = c.arch == LSTUR_ARCH_CON_DENSE || c.arch == LSTUR_ARCH_INI_CON;
+  if (con_dense) {
+    add_dense(p, "con_w", (long long)(G + Uc) * c.U);
     add_dense(p, "con_b", c.U);
   }
   if (dnn) {
@@ -197,7 +202,7 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
       for (const char* n : {"Z", "R", "HH", "HP", "RH"}) add_ws(p, n, Nh * G);
     }
   }
-  if (c.arch == LSTUR_ARCH_CON_DENSE || c.arch == LSTUR_ARCH_CON_CAT) add_ws(p, "cat", B * (G + c.Ue));
+  if (con_dense || c.arch == LSTUR_ARCH_CON_CAT) add_ws(p, "cat", B * (G + Uc));
   add_ws(p, "user_vec", B * c.U);
   if (dnn) {
     add_ws(p, "sc_cat", (long long)p->Nc * (c.U + D));
@@ -233,7 +238,7 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
       add_ws(p, "dA", Nh * 3 * G);
       add_ws(p, "dh0", B * G);
     }
-    if (c.arch == LSTUR_ARCH_CON_DENSE) add_ws(p, "d_cat", B * (G + c.Ue));
+    if (con_dense) add_ws(p, "d_cat", B * (G + Uc));
     if (dnn) {
       add_ws(p, "sc_dhid", (long long)p->Nc * c.Hs);
       add_ws(p, "sc_whid", (long long)p->Nc * c.Hs);
@@ -267,7 +272,7 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
       track_gemm(p, G, 2 * G, (int)Nh);
       track_gemm(p, (int)Nh, D, 3 * G);
     }
-    if (c.arch == LSTUR_ARCH_CON_DENSE) track_gemm(p, G + c.Ue, c.U, (int)B);
+    if (con_dense) track_gemm(p, G + Uc, c.U, (int)B);
   }
   if (has_gru) track_gemm(p, (int)Nh, 3 * G, D);
   add_ws(p, "gemm_ws", (long long)(p->gemm_ws_bytes / 4) + 4);
@@ -385,27 +390,30 @@ int user_and_score(const lstur_plan* p, const lstur_weights* w, const lstur_batc
     float* hT = W<float>(p, ws, "hT");
     float* hdst = hT;
     long long ldo = G;
+    const bool ini = c.arch == LSTUR_ARCH_INI || c.arch == LSTUR_ARCH_INI_CON;
+    const bool con_dense = c.arch == LSTUR_ARCH_CON_DENSE || c.arch == LSTUR_ARCH_INI_CON;
+    const int Uc = c.arch == LSTUR_ARCH_INI_CON ? c.Ue - G : c.Ue;
     if (c.arch == LSTUR_ARCH_INI || c.arch == LSTUR_ARCH_NOID) hdst = uvec;
-    if (cat) { hdst = cat; ldo = G + c.Ue; }
+    if (cat) { hdst = cat; ldo = G + Uc; }
     // tensor-core precision modes run the recurrence on tcgen05 (gru_tc.cu) when its weights fit tensor memory
     const bool tc_gru = (c.precision == LSTUR_PREC_BF16_TC || c.precision == LSTUR_PREC_FP16_TC) &&
                         lstur_gru_tc_supported(B, c.W, G) && !getenv("LSTUR_GRU_TC_OFF");
     if (tc_gru) {
-      RC(lstur_gru_fwd_tc(B, c.W, G, XW, W<float>(p, ws, "gru_mask"), c.arch == LSTUR_ARCH_INI ? u0 : nullptr, c.Ue,
+      RC(lstur_gru_fwd_tc(B, c.W, G, XW, W<float>(p, ws, "gru_mask"), ini ? u0 : nullptr, c.Ue,
                           DP(p, w->dense, "gru_wh"), c.rec_act, hdst, ldo, bw ? W<float>(p, ws, "Z") : nullptr,
                           bw ? W<float>(p, ws, "R") : nullptr, bw ? W<float>(p, ws, "HH") : nullptr,
                           bw ? W<float>(p, ws, "HP") : nullptr, bw ? W<float>(p, ws, "RH") : nullptr, nullptr, st));
     } else {
-      RC(lstur_gru_fwd(B, c.W, G, XW, W<float>(p, ws, "gru_mask"), c.arch == LSTUR_ARCH_INI ? u0 : nullptr, c.Ue,
+      RC(lstur_gru_fwd(B, c.W, G, XW, W<float>(p, ws, "gru_mask"), ini ? u0 : nullptr, c.Ue,
                        DP(p, w->dense, "gru_wh"), c.rec_act, hdst, ldo, bw ? W<float>(p, ws, "Z") : nullptr,
                        bw ? W<float>(p, ws, "R") : nullptr, bw ? W<float>(p, ws, "HH") : nullptr,
                        bw ? W<float>(p, ws, "HP") : nullptr, bw ? W<float>(p, ws, "RH") : nullptr, st));
     }
     if (cat) {
-      cudaMemcpy2DAsync(cat + G, (size_t)(G + c.Ue) * 4, u0, (size_t)c.Ue * 4, (size_t)c.Ue * 4, B,
+      cudaMemcpy2DAsync(cat + G, (size_t)(G + Uc) * 4, u0 + (c.Ue - Uc), (size_t)c.Ue * 4, (size_t)Uc * 4, B,
                         cudaMemcpyDeviceToDevice, st);
-      if (c.arch == LSTUR_ARCH_CON_DENSE) {
-        RC(GEMM(0, 0, B, c.U, G + c.Ue, cat, G + c.Ue, DP(p, w->dense, "con_w"), c.U, uvec, c.U,
+      if (con_dense) {
+        RC(GEMM(0, 0, B, c.U, G + Uc, cat, G + Uc, DP(p, w->dense, "con_w"), c.U, uvec, c.U,
                           DP(p, w->dense, "con_b"), LSTUR_GEMM_PRECISE, gws, gwsb, st));
       } else {
         cudaMemcpyAsync(uvec, cat, (size_t)B * c.U * 4, cudaMemcpyDeviceToDevice, st);
@@ -613,10 +621,11 @@ extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const
   long long lddh = c.U;
   const float* du0 = nullptr;
   long long lddu0 = 0;
-  if (c.arch == LSTUR_ARCH_CON_DENSE) {
+  const int Uc = c.arch == LSTUR_ARCH_INI_CON ? c.Ue - G : c.Ue;
+  if (c.arch == LSTUR_ARCH_CON_DENSE || c.arch == LSTUR_ARCH_INI_CON) {
     float* cat = W<float>(p, ws, "cat");
     float* d_cat = W<float>(p, ws, "d_cat");
-    const int K2 = G + c.Ue;
+    const int K2 = G + Uc;
     RC(GEMM(0, 1, B, K2, c.U, d_uvec, c.U, DP(p, w->dense, "con_w"), c.U, d_cat, K2, nullptr, 0, gws, gwsb, st));
     RC(GEMM(1, 0, K2, c.U, B, cat, K2, d_uvec, c.U, DG(p, dgrad, "con_w"), c.U, nullptr, 0, gws, gwsb, st));
     RC(lstur_colsum(B, c.U, d_uvec, c.U, DG(p, dgrad, "con_b"), 0, cws, cwsb, st));
@@ -651,6 +660,12 @@ extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const
     // dH = dA . Wx^T  (rows of masked steps are zero because dA is zero there)
     RC(GEMM(0, 1, Nh, D, 3 * G, dA, 3 * G, DP(p, w->dense, "gru_wx"), 3 * G, d_docv, D, nullptr, 0, gws, gwsb, st));
     if (c.arch == LSTUR_ARCH_INI) { du0 = dh0; lddu0 = G; }
+    if (c.arch == LSTUR_ARCH_INI_CON) {   // d row = [d h0 ‖ d of the concat part]
+      float* d_u0 = W<float>(p, ws, "d_u0");
+      cudaMemcpy2DAsync(d_u0, (size_t)c.Ue * 4, dh0, (size_t)G * 4, (size_t)G * 4, B, cudaMemcpyDeviceToDevice, st);
+      cudaMemcpy2DAsync(d_u0 + G, (size_t)c.Ue * 4, du0, (size_t)lddu0 * 4, (size_t)Uc * 4, B, cudaMemcpyDeviceToDevice, st);
+      du0 = nullptr;
+    }
   } else if (c.arch == LSTUR_ARCH_AVG) {
     RC(lstur_masked_mean_bwd(B, c.W, D, d_uvec, c.U, W<float>(p, ws, "gru_mask"), W<float>(p, ws, "hist_mask"), d_docv, st));
   } else {
@@ -663,7 +678,7 @@ extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const
     // contiguous per-sample copy (also what the data-parallel sparse exchange sends); the user-vector multiplier
     // (dgru / id_keep) scales the gradient of its embedding row
     float* d_u0 = W<float>(p, ws, "d_u0");
-    cudaMemcpy2DAsync(d_u0, (size_t)c.Ue * 4, du0, (size_t)lddu0 * 4, (size_t)c.Ue * 4, B, cudaMemcpyDeviceToDevice, st);
+    if (du0) cudaMemcpy2DAsync(d_u0, (size_t)c.Ue * 4, du0, (size_t)lddu0 * 4, (size_t)c.Ue * 4, B, cudaMemcpyDeviceToDevice, st);
     if (b->user_scale) RC(lstur_scale_rows(B, c.Ue, b->user_scale, d_u0, c.Ue, st));
     RC(lstur_segment_sum_rows(B, c.Ue, W<int>(p, ws, "n_user_rows"), W<int>(p, ws, "seg_start"),
                               W<int>(p, ws, "sorted_pos"), d_u0, c.Ue, W<float>(p, ws, "d_user_rows"), st));

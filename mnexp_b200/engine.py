@@ -14,7 +14,7 @@ from . import _lib
 from ._lib import lstur_batch, lstur_config, lstur_weights
 
 ARCH = {  # reference arch names -> engine arch; paper.py names
-    'igru': 0, 'gru': 1, 'ngru': 2, 'hgru': 2, 'dgru': 2, 'nigru': 3, 'pgru': 4, 'vo': 5, 'niavg': 6,
+    'igru': 0, 'gru': 1, 'ngru': 2, 'hgru': 2, 'dgru': 2, 'nigru': 3, 'pgru': 4, 'vo': 5, 'niavg': 6, 'iigru': 7,
 }
 SCORE = {'dot': 0, 'dnn': 1, 'ddot': 2}          # task/paper.py:443-458; cook's 'ddot' is linear (task/cook.py:206-209)
 COOK_ARCH = {'ingru': 0, 'igru': 2, 'gru': 3, 'agru': 4, 'vo': 5}   # task/cook.py:146-168
@@ -47,6 +47,11 @@ class LsturEngine:
         if arch not in amap:
             raise Exception('Unsupport user model')                      # task/paper.py:630
         self.arch_name, self.arch = arch, amap[arch]
+        if self.arch == 7:
+            # 'iigru' has two user tables (task/paper.py:614-619): one (n_users, 2U) device table [user_emb | user_emb2]
+            # — the first U columns seed the GRU, the rest join the concat; row-wise Adam is the same arithmetic
+            params = dict(params)
+            params['user_emb'] = np.concatenate([params['user_emb'], params['user_emb2']], 1)
         if score_model not in SCORE:
             raise NotImplementedError                                    # task/paper.py:456-457
         self.score_model = score_model
@@ -64,7 +69,7 @@ class LsturEngine:
         dv = params['vert_emb'].shape[1] if 'vert_emb' in params else 0
         ds = params['subvert_emb'].shape[1] if 'subvert_emb' in params else 0
         U = {0: G, 1: params['con_w'].shape[1] if 'con_w' in params else 0, 2: G + Ue, 3: G, 4: G, 5: Ue,
-             6: Dd + dv + ds}[self.arch]
+             6: Dd + dv + ds, 7: params['con_w'].shape[1] if 'con_w' in params else 0}[self.arch]
         _sd = share_weights_from.doc_tokens if share_weights_from is not None else None
         n_docs = doc_tokens.shape[0] if doc_tokens is not None else (0 if _sd is None else _sd.shape[0])
         self.cfg = lstur_config(
@@ -149,7 +154,10 @@ class LsturEngine:
             self.word_emb.copy_(torch.as_tensor(np.ascontiguousarray(params['word_emb'], dtype=np.float32)))
             self._emb_version[0] += 1
         if self.user_emb is not None and 'user_emb' in params:
-            self.user_emb.copy_(torch.as_tensor(np.ascontiguousarray(params['user_emb'], dtype=np.float32)))
+            ue = params['user_emb']
+            if self.arch == 7 and ue.shape[1] != self.Ue:
+                ue = np.concatenate([ue, params['user_emb2']], 1)
+            self.user_emb.copy_(torch.as_tensor(np.ascontiguousarray(ue, dtype=np.float32)))
 
     def _unflatten(self, flat):
         host = flat.detach().cpu().numpy()
@@ -160,6 +168,8 @@ class LsturEngine:
         out['word_emb'] = self.word_emb.cpu().numpy()
         if self.user_emb is not None:
             out['user_emb'] = self.user_emb.cpu().numpy()
+            if self.arch == 7:
+                out['user_emb'], out['user_emb2'] = out['user_emb'][:, :self.G].copy(), out['user_emb'][:, self.G:].copy()
         return out
 
     def get_grads_dict(self):
@@ -171,6 +181,8 @@ class LsturEngine:
             rows = self.view('user_rows', torch.int32)[:n].cpu().numpy()
             g[rows] = self.view('d_user_rows').reshape(-1, self.Ue)[:n].cpu().numpy()
             out['user_emb'] = g
+            if self.arch == 7:
+                out['user_emb'], out['user_emb2'] = g[:, :self.G].copy(), g[:, self.G:].copy()
         return out
 
     # ---- workspace views ------------------------------------------------------------------

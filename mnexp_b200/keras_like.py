@@ -199,7 +199,7 @@ class Model:
         return list(tot / max(1, steps))
 
     # ---- weights / structure ------------------------------------------------------------------
-    WEIGHT_ORDER = ('word_emb', 'conv_w', 'conv_b', 'att_w', 'att_b', 'dense_w', 'dense_b', 'user_emb',
+    WEIGHT_ORDER = ('word_emb', 'conv_w', 'conv_b', 'att_w', 'att_b', 'dense_w', 'dense_b', 'user_emb', 'user_emb2',
                     'gru_wx', 'gru_wh', 'gru_b', 'con_w', 'con_b', 'sh_w', 'sh_b', 'so_w', 'so_b', 'su_w', 'su_b', 'sd_w',
                     'sd_b')
 

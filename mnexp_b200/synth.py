@@ -149,9 +149,11 @@ def make_weights(shape, arch=None, seed=1237, word_emb=None, score_model='dot', 
         P['gru_wx'] = _glorot(rng, (D, 3 * G), D, 3 * G)
         P['gru_wh'] = np.concatenate([_orthogonal(rng, G, G) for _ in range(3)], 1)
         P['gru_b'] = bz(3 * G)
-    if arch == 'gru':
+    if arch in ('gru', 'iigru'):
         P['con_w'] = _glorot(rng, (G + Ue, U), G + Ue, U)
         P['con_b'] = bz(U)
+    if arch == 'iigru':                                        # second user table, task/paper.py:616
+        P['user_emb2'] = rng.uniform(-0.05, 0.05, (shape.n_users, Ue)).astype(np.float32)
     if score_model == 'dnn':                                   # task/paper.py:448-451
         Du = 2 * U if arch in ('ngru', 'dgru') else (D if arch == 'niavg' else U)
         P['sh_w'] = _glorot(rng, (Du + D, U), Du + D, U)

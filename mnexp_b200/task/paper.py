@@ -203,5 +203,4 @@ class Seq2VecPaperSoftmax(Seq2VecPaper):
 class Seq2VecPaperSoftmaxId(Seq2VecPaperSoftmax):
     """LSTUR (task/paper.py:527-665): igru = LSTUR-ini; gru / hgru / ngru / dgru = LSTUR-con."""
     HAS_USER = True
-    # 'iigru' (a second user table, task/paper.py:614-619) is the one arch left out
-    USER_ARCHS = ('igru', 'gru', 'ngru', 'hgru', 'dgru', 'nigru', 'pgru', 'vo', 'niavg')
+    USER_ARCHS = ('igru', 'gru', 'ngru', 'hgru', 'dgru', 'iigru', 'nigru', 'pgru', 'vo', 'niavg')   # task/paper.py:596-628

@@ -148,6 +148,8 @@ def user_encoder(arch, user, H, P, recurrent_activation='hard_sigmoid', u0_scale
         return gru(u0)
     if arch == 'gru':                        # LSTUR-con + Dense, :596-599
         return np.concatenate([gru(None), u0], -1) @ f8('con_w') + f8('con_b')
+    if arch == 'iigru':                      # :614-619
+        return np.concatenate([gru(u0), f8('user_emb2')[user]], -1) @ f8('con_w') + f8('con_b')
     if arch in ('ngru', 'hgru', 'dgru'):     # LSTUR-con plain concat, :600-611
         return np.concatenate([gru(None), u0], -1)
     if arch == 'pgru':                       # :622-624

@@ -77,6 +77,9 @@ def user_encoder(arch, user, H, P, recurrent_activation='hard_sigmoid', u0_scale
         return gru(u0)
     if arch == 'gru':
         return torch.cat([gru(None), u0], -1) @ P['con_w'] + P['con_b']
+    if arch == 'iigru':          # task/paper.py:614-619: initial state from table 1, concat with table 2, Dense
+        u2 = P['user_emb2'][user.reshape(-1)]
+        return torch.cat([gru(u0), u2], -1) @ P['con_w'] + P['con_b']
     if arch in ('ngru', 'hgru', 'dgru'):
         return torch.cat([gru(None), u0], -1)
     if arch == 'pgru':

@@ -316,7 +316,7 @@ def test_cook_vertical_concat_and_id_keep(L, precision):
 @pytest.mark.parametrize('arch,score_model,precision', [
     ('igru', 'dnn', 'fp32'), ('igru', 'ddot', 'fp32'), ('ngru', 'dnn', 'fp32'), ('ngru', 'ddot', 'fp32'),
     ('dgru', 'ddot', 'fp32'), ('niavg', 'dot', 'fp32'), ('niavg', 'dnn', 'fp32'), ('gru', 'ddot', 'fp16_tc'),
-    ('ngru', 'dnn', 'fp16_tc'),
+    ('ngru', 'dnn', 'fp16_tc'), ('iigru', 'dot', 'fp32'), ('iigru', 'dnn', 'fp16_tc'),
 ])
 def test_scorers_and_remaining_archs_match_oracle(L, arch, score_model, precision):
     """'dnn' / 'ddot' scorers (task/paper.py:448-455), 'ngru' / 'dgru' (2U user vector, :600-611, only scorable by

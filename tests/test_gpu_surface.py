@@ -260,7 +260,8 @@ def test_device_batch_assembly_matches_window(lib):
     assert np.isfinite(loss)
 
 
-@pytest.mark.parametrize('arch,score_model', [('ngru', 'dnn'), ('dgru', 'ddot'), ('niavg', 'ddot'), ('igru', 'dnn')])
+@pytest.mark.parametrize('arch,score_model', [('ngru', 'dnn'), ('dgru', 'ddot'), ('niavg', 'ddot'), ('igru', 'dnn'),
+                                               ('iigru', 'dot')])
 def test_model_builder_scorers_and_concat_archs(lib, arch, score_model):
     """--score-model dnn / ddot (task/paper.py:448-455) with the 2U-wide 'ngru' / 'dgru' user vectors and 'niavg',
     through the reference's task-handler surface."""
