@@ -48,6 +48,7 @@ typedef struct CUstream_st* cudaStream_t;
 #define LSTUR_ARCH_ADD 4       /* paper 'pgru' / cook 'agru': GRU + user_emb                           */
 #define LSTUR_ARCH_VO 5        /* 'vo': user_emb only                                                  */
 #define LSTUR_ARCH_AVG 6       /* paper 'niavg': GlobalAveragePoolingMaskSupport of the history (models.py:422-441) */
+#define LSTUR_ARCH_INI_CAT 8   /* Seq2VecPaperId 'iigru': [GRU(initial_state=user_emb) ‖ user_emb2], task/paper.py:338-343 */
 #define LSTUR_ARCH_INI_CON 7   /* paper 'iigru': Dense([GRU(initial_state=user_emb) ‖ user_emb2]), task/paper.py:614-619;
                                   the two tables are the column halves of one (n_users, Ue = G + U2) table */
 
@@ -55,6 +56,9 @@ typedef struct CUstream_st* cudaStream_t;
 #define LSTUR_SCORE_DNN 1      /* Dense(Hs, relu)([u ‖ d]) -> Dense(1), task/paper.py:448-451 */
 #define LSTUR_SCORE_DDOT 2     /* tanh Dense(Hs) on both sides, then dot, task/paper.py:452-455 */
 #define LSTUR_SCORE_DDOT_LINEAR 3 /* cook flavour: linear Dense(Hs) on both sides, task/cook.py:206-209 */
+
+#define LSTUR_LOSS_SOFTMAX_CE 0   /* (1+K)-way softmax + categorical cross-entropy, task/paper.py:460-464, 657 */
+#define LSTUR_LOSS_WEIGHTED_BCE 1 /* sigmoid + Seq2Vec.loss, task/paper.py:222-256, task/seq2vec.py:213-216     */
 
 #define LSTUR_ACT_HARD_SIGMOID 0 /* Keras <= 2.2.x GRU recurrent_activation default */
 #define LSTUR_ACT_SIGMOID 1      /* Keras >= 2.3 */
@@ -217,6 +221,13 @@ int lstur_rowdot_bias(long long n, int H, const float* h, const float* w, const 
                       cudaStream_t stream);
 int lstur_dnn_out_bwd(long long n, int H, const float* hid, const float* w2, const float* dlogit, float* dhid,
                       float* whid, cudaStream_t stream);
+/* Sigmoid-family head (Seq2VecPaper / Seq2VecPaperDot / Seq2VecPaperId): p = sigmoid(score) and the weighted binary
+ * cross-entropy Seq2Vec.loss (task/seq2vec.py:213-216); dscores (optional) = grad_scale * dL_i/dscore_i with grad_scale
+ * = 1/global batch.  lstur_dot_score_bwd: backward of score[(b,c)] = u[b] . d[(b,c)]. */
+int lstur_bce_loss(long long n, const float* scores, const float* label, float gain, int negative_samples, float* probs,
+                   float* loss_rows, float* loss_mean, float* dscores, float grad_scale, cudaStream_t stream);
+int lstur_dot_score_bwd(int B, int C, int D, const float* u, long long ldu, const float* d, long long ldd,
+                        const float* dscores, float* du, long long lddu, float* dd, long long lddd, cudaStream_t stream);
 int lstur_fill(long long n, float v, float* x, cudaStream_t stream);
 int lstur_tanh_fwd(long long n, float* x, cudaStream_t stream);
 int lstur_tanh_bwd(long long n, const float* y, float* g, cudaStream_t stream);
@@ -276,6 +287,9 @@ typedef struct lstur_config {
   int save_for_backward; /* 0: inference plan (smaller workspace)                            */
   int n_vert, n_subvert; /* rows of the vertical / subvertical tables (16 / 307, utils.py:153-228) */
   int Hs;                /* hidden width of the 'dnn' / 'ddot' scorers (= user_embedding_dim), 0 for 'dot'   */
+  int loss_model;        /* LSTUR_LOSS_SOFTMAX_CE | LSTUR_LOSS_WEIGHTED_BCE (then C == 1 and label is required) */
+  int bce_neg;           /* negative_samples of the weighted BCE (task/seq2vec.py:213-216)                   */
+  float gain;            /* its positive-class gain                                                           */
 } lstur_config;
 
 typedef struct lstur_weights {

@@ -94,7 +94,7 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
     set_error("lstur_plan_create: score_model %d not implemented (NotImplementedError, task/paper.py:457)", c.score_model);
     return LSTUR_ERR_UNSUPPORTED;
   }
-  if (c.arch < LSTUR_ARCH_INI || c.arch > LSTUR_ARCH_INI_CON) {
+  if (c.arch < LSTUR_ARCH_INI || c.arch > LSTUR_ARCH_INI_CAT) {
     set_error("lstur_plan_create: Unsupport user model (task/paper.py:630)");
     return LSTUR_ERR_UNSUPPORTED;
   }
@@ -105,16 +105,19 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
   const bool has_user = c.arch != LSTUR_ARCH_NOID && c.arch != LSTUR_ARCH_AVG;
   const bool dot = c.score_model == LSTUR_SCORE_DOT, dnn = c.score_model == LSTUR_SCORE_DNN, ddot = !dot && !dnn;
   LSTUR_REQUIRE(dot || c.Hs > 0, "lstur_plan_create('dnn' / 'ddot' scorers need Hs)");
+  const bool bce = c.loss_model == LSTUR_LOSS_WEIGHTED_BCE;
+  LSTUR_REQUIRE(c.loss_model == LSTUR_LOSS_SOFTMAX_CE || bce, "lstur_plan_create(loss_model)");
+  LSTUR_REQUIRE(!bce || (c.C == 1 && c.bce_neg >= 1 && c.gain > 0.f), "lstur_plan_create(weighted BCE: C == 1, bce_neg >= 1, gain > 0)");
   LSTUR_REQUIRE(!has_gru || (c.G > 0 && c.G % 4 == 0 && c.G <= 1024), "lstur_plan_create");
   LSTUR_REQUIRE(!has_user || (c.Ue > 0 && c.n_users > 0), "lstur_plan_create");
   // user-vector dim implied by the architecture
   int U = c.arch == LSTUR_ARCH_INI ? c.G : (c.arch == LSTUR_ARCH_CON_DENSE || c.arch == LSTUR_ARCH_INI_CON) ? c.U
-          : c.arch == LSTUR_ARCH_CON_CAT ? c.G + c.Ue
+          : c.arch == LSTUR_ARCH_CON_CAT ? c.G + c.Ue : c.arch == LSTUR_ARCH_INI_CAT ? c.Ue
           : c.arch == LSTUR_ARCH_NOID ? c.G : c.arch == LSTUR_ARCH_ADD ? c.G : c.arch == LSTUR_ARCH_AVG ? D : c.Ue;
   LSTUR_REQUIRE(U == c.U, "lstur_plan_create(U inconsistent with arch)");
   LSTUR_REQUIRE(c.arch != LSTUR_ARCH_INI || c.Ue == c.G, "lstur_plan_create(ini needs Ue == G)");
   LSTUR_REQUIRE(c.arch != LSTUR_ARCH_ADD || c.Ue == c.G, "lstur_plan_create(add needs Ue == G)");
-  LSTUR_REQUIRE(c.arch != LSTUR_ARCH_INI_CON || c.Ue > c.G, "lstur_plan_create(ini+con needs Ue > G)");
+  LSTUR_REQUIRE((c.arch != LSTUR_ARCH_INI_CON && c.arch != LSTUR_ARCH_INI_CAT) || c.Ue > c.G, "lstur_plan_create(ini+con needs Ue > G)");
   LSTUR_REQUIRE(!dot || U == D, "lstur_plan_create('dot' scorer needs user dim == doc dim)");
   if ((c.precision == LSTUR_PREC_BF16_TC || c.precision == LSTUR_PREC_FP16_TC) && !lstur_tc_supported(c.L, c.E, c.F, c.KS)) {
     set_error("lstur_plan_create: shape (L=%d,E=%d,F=%d,KS=%d) not supported by the tensor-core conv kernel", c.L, c.E, c.F, c.KS);
@@ -150,7 +153,7 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
     add_dense(p, "gru_b", 3 * G);
   }
   // width of the user-embedding part that joins the concat ('iigru': the second table = columns G.. of the row)
-  const int Uc = c.arch == LSTUR_ARCH_INI_CON ? c.Ue - G : c.Ue;
+  const int Uc = (c.arch == LSTUR_ARCH_INI_CON || c.arch == LSTUR_ARCH_INI_CAT) ? c.Ue - G : c.Ue;
   const bool con_dense = c.arch == LSTUR_ARCH_CON_DENSE || c.arch == LSTUR_ARCH_INI_CON;
   if (con_dense) {
     add_dense(p, "con_w", (long long)(G + Uc) * c.U);
@@ -202,7 +205,7 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
       for (const char* n : {"Z", "R", "HH", "HP", "RH"}) add_ws(p, n, Nh * G);
     }
   }
-  if (con_dense || c.arch == LSTUR_ARCH_CON_CAT) add_ws(p, "cat", B * (G + Uc));
+  if (con_dense || c.arch == LSTUR_ARCH_CON_CAT || c.arch == LSTUR_ARCH_INI_CAT) add_ws(p, "cat", B * (G + Uc));
   add_ws(p, "user_vec", B * c.U);
   if (dnn) {
     add_ws(p, "sc_cat", (long long)p->Nc * (c.U + D));
@@ -225,6 +228,7 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
   track_gemm(p, (int)N, Dd, F);
   if (bw) {
     add_ws(p, "d_user_vec", B * c.U);
+    if (bce) add_ws(p, "d_logits", B * c.C);
     add_ws(p, "d_doc_vec", N * D);
     add_ws(p, "d_pooled", N * F);
     if (!tcp) add_ws(p, "dPre", N * Lp * F);
@@ -390,9 +394,9 @@ int user_and_score(const lstur_plan* p, const lstur_weights* w, const lstur_batc
     float* hT = W<float>(p, ws, "hT");
     float* hdst = hT;
     long long ldo = G;
-    const bool ini = c.arch == LSTUR_ARCH_INI || c.arch == LSTUR_ARCH_INI_CON;
+    const bool ini = c.arch == LSTUR_ARCH_INI || c.arch == LSTUR_ARCH_INI_CON || c.arch == LSTUR_ARCH_INI_CAT;
     const bool con_dense = c.arch == LSTUR_ARCH_CON_DENSE || c.arch == LSTUR_ARCH_INI_CON;
-    const int Uc = c.arch == LSTUR_ARCH_INI_CON ? c.Ue - G : c.Ue;
+    const int Uc = (c.arch == LSTUR_ARCH_INI_CON || c.arch == LSTUR_ARCH_INI_CAT) ? c.Ue - G : c.Ue;
     if (c.arch == LSTUR_ARCH_INI || c.arch == LSTUR_ARCH_NOID) hdst = uvec;
     if (cat) { hdst = cat; ldo = G + Uc; }
     // tensor-core precision modes run the recurrence on tcgen05 (gru_tc.cu) when its weights fit tensor memory
@@ -429,13 +433,16 @@ int user_and_score(const lstur_plan* p, const lstur_weights* w, const lstur_batc
   }
   // 6. score + softmax + loss (k13-k14)
   const float* cand = docv + (size_t)Nh * D;
-  if (c.score_model == LSTUR_SCORE_DOT) {
-    RC(lstur_score_softmax_ce(B, c.C, D, uvec, c.U, cand, D, b->label, W<float>(p, ws, "logits"),
-                              W<float>(p, ws, "probs"), W<float>(p, ws, "loss_rows"), W<float>(p, ws, "loss"), nullptr, 0,
-                              nullptr, 0, 0.f, st));
-  } else if (c.score_model == LSTUR_SCORE_DNN) {
-    // relu Dense on [u ‖ d], Dense(1) (task/paper.py:448-451); the softmax / loss kernel then runs on the raw scores
-    // (inner dimension 1 against a vector of ones)
+  const bool bce = c.loss_model == LSTUR_LOSS_WEIGHTED_BCE;
+  float* logits = W<float>(p, ws, "logits");
+  float* probs = W<float>(p, ws, "probs");
+  float* loss_rows = W<float>(p, ws, "loss_rows");
+  float* loss = W<float>(p, ws, "loss");
+  // raw scores of the scorer; the softmax / CE kernel fuses the final dot product, the sigmoid head takes raw scores
+  const float* su = uvec; long long ldsu = c.U; const float* sd = cand; long long ldsd = D; int sdim = D;
+  if (c.score_model == LSTUR_SCORE_DNN) {
+    // relu Dense on [u ‖ d], Dense(1) (task/paper.py:448-451, 222-226); the softmax / loss kernel then runs on the raw
+    // scores (inner dimension 1 against a vector of ones)
     const int K2 = c.U + D;
     float* sc_cat = W<float>(p, ws, "sc_cat");
     float* hid = W<float>(p, ws, "sc_hid");
@@ -446,9 +453,8 @@ int user_and_score(const lstur_plan* p, const lstur_weights* w, const lstur_batc
             LSTUR_GEMM_RELU | LSTUR_GEMM_PRECISE, gws, gwsb, st));
     RC(lstur_rowdot_bias(p->Nc, c.Hs, hid, DP(p, w->dense, "so_w"), DP(p, w->dense, "so_b"), raw, st));
     RC(lstur_fill(B, 1.f, ones, st));
-    RC(lstur_score_softmax_ce(B, c.C, 1, ones, 1, raw, 1, b->label, W<float>(p, ws, "logits"), W<float>(p, ws, "probs"),
-                              W<float>(p, ws, "loss_rows"), W<float>(p, ws, "loss"), nullptr, 0, nullptr, 0, 0.f, st));
-  } else {
+    su = ones; ldsu = 1; sd = raw; ldsd = 1; sdim = 1;
+  } else if (c.score_model != LSTUR_SCORE_DOT) {
     // Dense(Hs) on both sides (tanh in the paper flavour, linear in cook), then dot (task/paper.py:452-455)
     float* uh = W<float>(p, ws, "sc_uh");
     float* dh = W<float>(p, ws, "sc_dh");
@@ -460,9 +466,17 @@ int user_and_score(const lstur_plan* p, const lstur_weights* w, const lstur_batc
       RC(lstur_tanh_fwd((long long)B * c.Hs, uh, st));
       RC(lstur_tanh_fwd((long long)p->Nc * c.Hs, dh, st));
     }
-    RC(lstur_score_softmax_ce(B, c.C, c.Hs, uh, c.Hs, dh, c.Hs, b->label, W<float>(p, ws, "logits"),
-                              W<float>(p, ws, "probs"), W<float>(p, ws, "loss_rows"), W<float>(p, ws, "loss"), nullptr, 0,
+    su = uh; ldsu = c.Hs; sd = dh; ldsd = c.Hs; sdim = c.Hs;
+  }
+  if (!bce) {
+    RC(lstur_score_softmax_ce(B, c.C, sdim, su, ldsu, sd, ldsd, b->label, logits, probs, loss_rows, loss, nullptr, 0,
                               nullptr, 0, 0.f, st));
+  } else {
+    // sigmoid head + weighted BCE (task/paper.py:222-256, task/seq2vec.py:213-216); without labels (inference) only
+    // the probabilities are produced
+    RC(lstur_score_sigmoid(p->Nc, c.C, sdim, su, ldsu, sd, ldsd, logits, 0, st));
+    if (b->label) RC(lstur_bce_loss(p->Nc, logits, b->label, c.gain, c.bce_neg, probs, loss_rows, loss, nullptr, 0.f, st));
+    else RC(lstur_score_sigmoid(p->Nc, c.C, sdim, su, ldsu, sd, ldsd, probs, 1, st));
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -576,9 +590,17 @@ extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const
   // 1. loss / score backward
   const float* cand = docv + (size_t)Nh * D;
   float* d_cand = d_docv + (size_t)Nh * D;
+  const bool bce = c.loss_model == LSTUR_LOSS_WEIGHTED_BCE;
+  float* d_logits = bce ? W<float>(p, ws, "d_logits") : nullptr;
+  if (bce) {
+    LSTUR_REQUIRE(b->label != nullptr, "lstur_backward(weighted BCE needs labels)");
+    RC(lstur_bce_loss(p->Nc, W<float>(p, ws, "logits"), b->label, c.gain, c.bce_neg, nullptr, nullptr, nullptr, d_logits,
+                      grad_scale, st));
+  }
   if (c.score_model == LSTUR_SCORE_DOT) {
-    RC(lstur_score_softmax_ce(B, c.C, D, uvec, c.U, cand, D, b->label, nullptr, nullptr, nullptr, nullptr,
-                              d_uvec, c.U, d_cand, D, grad_scale, st));
+    if (bce) RC(lstur_dot_score_bwd(B, c.C, D, uvec, c.U, cand, D, d_logits, d_uvec, c.U, d_cand, D, st));
+    else RC(lstur_score_softmax_ce(B, c.C, D, uvec, c.U, cand, D, b->label, nullptr, nullptr, nullptr, nullptr,
+                                   d_uvec, c.U, d_cand, D, grad_scale, st));
   } else if (c.score_model == LSTUR_SCORE_DNN) {
     const int K2 = c.U + D, Hs = c.Hs;
     const long long Nc = p->Nc;
@@ -586,9 +608,10 @@ extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const
     float* dhid = W<float>(p, ws, "sc_dhid");
     float* whid = W<float>(p, ws, "sc_whid");
     float* dcat = W<float>(p, ws, "sc_dcat");
-    float* dl = W<float>(p, ws, "sc_dlogit");
-    RC(lstur_score_softmax_ce(B, c.C, 1, W<float>(p, ws, "sc_ones"), 1, W<float>(p, ws, "sc_raw"), 1, b->label, nullptr,
-                              nullptr, nullptr, nullptr, W<float>(p, ws, "sc_scratch"), 1, dl, 1, grad_scale, st));
+    float* dl = bce ? d_logits : W<float>(p, ws, "sc_dlogit");
+    if (!bce) RC(lstur_score_softmax_ce(B, c.C, 1, W<float>(p, ws, "sc_ones"), 1, W<float>(p, ws, "sc_raw"), 1, b->label,
+                                        nullptr, nullptr, nullptr, nullptr, W<float>(p, ws, "sc_scratch"), 1, dl, 1,
+                                        grad_scale, st));
     RC(lstur_dnn_out_bwd(Nc, Hs, hid, DP(p, w->dense, "so_w"), dl, dhid, whid, st));
     RC(lstur_colsum(Nc, Hs, whid, Hs, DG(p, dgrad, "so_w"), 0, cws, cwsb, st));
     RC(lstur_colsum(Nc, 1, dl, 1, DG(p, dgrad, "so_b"), 0, cws, cwsb, st));
@@ -603,8 +626,9 @@ extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const
     float* dh = W<float>(p, ws, "sc_dh");
     float* duh = W<float>(p, ws, "sc_duh");
     float* ddh = W<float>(p, ws, "sc_ddh");
-    RC(lstur_score_softmax_ce(B, c.C, Hs, uh, Hs, dh, Hs, b->label, nullptr, nullptr, nullptr, nullptr, duh, Hs, ddh, Hs,
-                              grad_scale, st));
+    if (bce) RC(lstur_dot_score_bwd(B, c.C, Hs, uh, Hs, dh, Hs, d_logits, duh, Hs, ddh, Hs, st));
+    else RC(lstur_score_softmax_ce(B, c.C, Hs, uh, Hs, dh, Hs, b->label, nullptr, nullptr, nullptr, nullptr, duh, Hs, ddh,
+                                   Hs, grad_scale, st));
     if (c.score_model == LSTUR_SCORE_DDOT) {
       RC(lstur_tanh_bwd((long long)B * Hs, uh, duh, st));
       RC(lstur_tanh_bwd(Nc * Hs, dh, ddh, st));
@@ -621,7 +645,7 @@ extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const
   long long lddh = c.U;
   const float* du0 = nullptr;
   long long lddu0 = 0;
-  const int Uc = c.arch == LSTUR_ARCH_INI_CON ? c.Ue - G : c.Ue;
+  const int Uc = (c.arch == LSTUR_ARCH_INI_CON || c.arch == LSTUR_ARCH_INI_CAT) ? c.Ue - G : c.Ue;
   if (c.arch == LSTUR_ARCH_CON_DENSE || c.arch == LSTUR_ARCH_INI_CON) {
     float* cat = W<float>(p, ws, "cat");
     float* d_cat = W<float>(p, ws, "d_cat");
@@ -630,7 +654,7 @@ extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const
     RC(GEMM(1, 0, K2, c.U, B, cat, K2, d_uvec, c.U, DG(p, dgrad, "con_w"), c.U, nullptr, 0, gws, gwsb, st));
     RC(lstur_colsum(B, c.U, d_uvec, c.U, DG(p, dgrad, "con_b"), 0, cws, cwsb, st));
     dhT = d_cat; lddh = K2; du0 = d_cat + G; lddu0 = K2;
-  } else if (c.arch == LSTUR_ARCH_CON_CAT) {
+  } else if (c.arch == LSTUR_ARCH_CON_CAT || c.arch == LSTUR_ARCH_INI_CAT) {
     du0 = d_uvec + G; lddu0 = c.U;
   } else if (c.arch == LSTUR_ARCH_ADD || c.arch == LSTUR_ARCH_VO) {
     du0 = d_uvec; lddu0 = c.U;
@@ -660,7 +684,7 @@ extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const
     // dH = dA . Wx^T  (rows of masked steps are zero because dA is zero there)
     RC(GEMM(0, 1, Nh, D, 3 * G, dA, 3 * G, DP(p, w->dense, "gru_wx"), 3 * G, d_docv, D, nullptr, 0, gws, gwsb, st));
     if (c.arch == LSTUR_ARCH_INI) { du0 = dh0; lddu0 = G; }
-    if (c.arch == LSTUR_ARCH_INI_CON) {   // d row = [d h0 ‖ d of the concat part]
+    if (c.arch == LSTUR_ARCH_INI_CON || c.arch == LSTUR_ARCH_INI_CAT) {   // d row = [d h0 ‖ d of the concat part]
       float* d_u0 = W<float>(p, ws, "d_u0");
       cudaMemcpy2DAsync(d_u0, (size_t)c.Ue * 4, dh0, (size_t)G * 4, (size_t)G * 4, B, cudaMemcpyDeviceToDevice, st);
       cudaMemcpy2DAsync(d_u0 + G, (size_t)c.Ue * 4, du0, (size_t)lddu0 * 4, (size_t)Uc * 4, B, cudaMemcpyDeviceToDevice, st);

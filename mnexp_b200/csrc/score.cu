@@ -234,6 +234,43 @@ __global__ void masked_mean_bwd_kernel(int B, int W, int D, const float* __restr
   for (int t = 0; t < W; ++t) dH[((long long)b * W + t) * D + k] = keep[(long long)b * W + t] * g;
 }
 
+// ---- sigmoid-family head (Seq2VecPaper / Seq2VecPaperDot / Seq2VecPaperId, task/paper.py:222-262): p = sigmoid(s) and
+// the weighted binary cross-entropy Seq2Vec.loss (task/seq2vec.py:213-216):
+//   L = -0.5 (1+K) mean_i [ y_i log(p_i + 1e-8) gain + (1 - y_i) log(1 - p_i + 1e-8) / K ]
+__global__ void bce_fwd_kernel(long long n, const float* __restrict__ s, const float* __restrict__ y, float gain, float K,
+                               float* __restrict__ p_out, float* __restrict__ loss_rows) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float p = 1.f / (1.f + expf(-s[i]));
+  if (p_out) p_out[i] = p;
+  if (loss_rows) loss_rows[i] = -0.5f * (1.f + K) * (y[i] * logf(p + 1e-8f) * gain + (1.f - y[i]) * logf(1.f - p + 1e-8f) / K);
+}
+// ds_i = grad_scale * dL_i/dp_i * p (1 - p)
+__global__ void bce_bwd_kernel(long long n, const float* __restrict__ s, const float* __restrict__ y, float gain, float K,
+                               float grad_scale, float* __restrict__ ds) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float p = 1.f / (1.f + expf(-s[i]));
+  const float dp = -0.5f * (1.f + K) * (y[i] * gain / (p + 1e-8f) - (1.f - y[i]) / (K * (1.f - p + 1e-8f)));
+  ds[i] = grad_scale * dp * p * (1.f - p);
+}
+// backward of s[(b,c)] = u[b] . d[(b,c)]:  du[b] = sum_c ds d (fixed order), dd[(b,c)] = ds u[b]
+__global__ void dot_score_bwd_kernel(int B, int C, int D, const float* __restrict__ u, long long ldu,
+                                     const float* __restrict__ d, long long ldd, const float* __restrict__ ds,
+                                     float* __restrict__ du, long long lddu, float* __restrict__ dd, long long lddd) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = (int)(idx / D), k = (int)(idx % D);
+  if (b >= B) return;
+  const float uk = u[(long long)b * ldu + k];
+  float acc = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float g = ds[(long long)b * C + c];
+    acc = fmaf(g, d[((long long)b * C + c) * ldd + k], acc);
+    dd[((long long)b * C + c) * lddd + k] = g * uk;
+  }
+  du[(long long)b * lddu + k] = acc;
+}
+
 }  // namespace lstur
 
 using namespace lstur;
@@ -345,5 +382,35 @@ extern "C" int lstur_fill(long long n, float v, float* x, cudaStream_t stream) {
   if (n == 0) return LSTUR_OK;
   fill_kernel<<<cdiv(n, 256), 256, 0, stream>>>(n, v, x);
   LSTUR_CHECK_LAUNCH("lstur_fill");
+  return LSTUR_OK;
+}
+
+extern "C" int lstur_bce_loss(long long n, const float* scores, const float* label, float gain, int negative_samples,
+                              float* probs, float* loss_rows, float* loss_mean, float* dscores, float grad_scale,
+                              cudaStream_t stream) {
+  LSTUR_REQUIRE(n >= 0 && negative_samples >= 1 && (n == 0 || (scores && label)), "lstur_bce_loss");
+  LSTUR_REQUIRE(loss_mean == nullptr || loss_rows != nullptr, "lstur_bce_loss");
+  if (n == 0) return LSTUR_OK;
+  if (probs || loss_rows) {
+    bce_fwd_kernel<<<cdiv(n, 256), 256, 0, stream>>>(n, scores, label, gain, (float)negative_samples, probs, loss_rows);
+    LSTUR_CHECK_LAUNCH("lstur_bce_loss(fwd)");
+  }
+  if (loss_mean) {
+    mean_kernel<<<1, 256, 0, stream>>>((int)n, loss_rows, loss_mean);
+    LSTUR_CHECK_LAUNCH("lstur_bce_loss(mean)");
+  }
+  if (dscores) {
+    bce_bwd_kernel<<<cdiv(n, 256), 256, 0, stream>>>(n, scores, label, gain, (float)negative_samples, grad_scale, dscores);
+    LSTUR_CHECK_LAUNCH("lstur_bce_loss(bwd)");
+  }
+  return LSTUR_OK;
+}
+extern "C" int lstur_dot_score_bwd(int B, int C, int D, const float* u, long long ldu, const float* d, long long ldd,
+                                   const float* dscores, float* du, long long lddu, float* dd, long long lddd,
+                                   cudaStream_t stream) {
+  LSTUR_REQUIRE(B >= 0 && C >= 1 && D > 0 && u && d && dscores && du && dd, "lstur_dot_score_bwd");
+  if (B == 0) return LSTUR_OK;
+  dot_score_bwd_kernel<<<cdiv((long long)B * D, 256), 256, 0, stream>>>(B, C, D, u, ldu, d, ldd, dscores, du, lddu, dd, lddd);
+  LSTUR_CHECK_LAUNCH("lstur_dot_score_bwd");
   return LSTUR_OK;
 }

@@ -17,6 +17,8 @@ ARCH = {  # reference arch names -> engine arch; paper.py name
     'igru': 0, 'gru': 1, 'ngru': 2, 'hgru': 2, 'dgru': 2, 'nigru': 3, 'pgru': 4, 'vo': 5, 'niavg': 6, 'iigru': 7,
 }
 SCORE = {'dot': 0, 'dnn': 1, 'ddot': 2}          # task/paper.py:443-458; cook's 'ddot' is linear (task/cook.py:206-209)
+# sigmoid family (Seq2VecPaperId.get_user_encoder, task/paper.py:328-358): 'gru' is the plain concat, 'iigru' has no Dense
+SIGMOID_ARCH = {'gru': 2, 'igru': 0, 'iigru': 8, 'vo': 5, 'nigru': 3, 'niavg': 6}
 COOK_ARCH = {'ingru': 0, 'igru': 2, 'gru': 3, 'agru': 4, 'vo': 5}   # task/cook.py:146-168
 DENSE_NAMES = ('conv_w', 'conv_b', 'att_w', 'att_b', 'dense_w', 'dense_b', 'vert_emb', 'subvert_emb',
                'gru_wx', 'gru_wh', 'gru_b', 'con_w', 'con_b', 'sh_w', 'sh_b', 'so_w', 'so_b', 'su_w', 'su_b', 'sd_w', 'sd_b')
@@ -36,18 +38,21 @@ class LsturEngine:
     def __init__(self, params, B, W, C, L, arch='igru', flavour='paper', dropout=0.0, lr=1e-3,
                  recurrent_activation='hard_sigmoid', precision='fp32', doc_tokens=None, device=None,
                  training=True, sparse_user_adam=True, trainable_word_emb=False, share_weights_from=None,
-                 doc_vert=None, doc_subvert=None, score_model='dot'):
+                 doc_vert=None, doc_subvert=None, score_model='dot', loss='softmax', gain=1.0, bce_neg=4):
         if not torch.cuda.is_available():
             raise _lib.LsturError('LsturEngine needs a CUDA device (no CPU fallback)')
         self.lib = _lib.load()
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         if trainable_word_emb:
             raise NotImplementedError('textual_embedding_trainable=True is not implemented yet')
-        amap = ARCH if flavour == 'paper' else COOK_ARCH
+        amap = {'paper': ARCH, 'sigmoid': SIGMOID_ARCH}.get(flavour, COOK_ARCH)
+        if loss not in ('softmax', 'bce'):
+            raise ValueError(loss)
+        self.loss_model = loss
         if arch not in amap:
             raise Exception('Unsupport user model')                      # task/paper.py:630
         self.arch_name, self.arch = arch, amap[arch]
-        if self.arch == 7:
+        if self.arch in (7, 8):
             # 'iigru' has two user tables (task/paper.py:614-619): one (n_users, 2U) device table [user_emb | user_emb2]
             # — the first U columns seed the GRU, the rest join the concat; row-wise Adam is the same arithmetic
             params = dict(params)
@@ -55,7 +60,7 @@ class LsturEngine:
         if score_model not in SCORE:
             raise NotImplementedError                                    # task/paper.py:456-457
         self.score_model = score_model
-        sm = SCORE[score_model] + (1 if (score_model == 'ddot' and flavour != 'paper') else 0)
+        sm = SCORE[score_model] + (1 if (score_model == 'ddot' and flavour == 'cook') else 0)
         Hs = {'dot': 0, 'dnn': params['sh_w'].shape[1] if 'sh_w' in params else 0,
               'ddot': params['su_w'].shape[1] if 'su_w' in params else 0}[score_model]
         ks, E, F = params['conv_w'].shape
@@ -69,7 +74,7 @@ class LsturEngine:
         dv = params['vert_emb'].shape[1] if 'vert_emb' in params else 0
         ds = params['subvert_emb'].shape[1] if 'subvert_emb' in params else 0
         U = {0: G, 1: params['con_w'].shape[1] if 'con_w' in params else 0, 2: G + Ue, 3: G, 4: G, 5: Ue,
-             6: Dd + dv + ds, 7: params['con_w'].shape[1] if 'con_w' in params else 0}[self.arch]
+             6: Dd + dv + ds, 7: params['con_w'].shape[1] if 'con_w' in params else 0, 8: Ue}[self.arch]
         _sd = share_weights_from.doc_tokens if share_weights_from is not None else None
         n_docs = doc_tokens.shape[0] if doc_tokens is not None else (0 if _sd is None else _sd.shape[0])
         self.cfg = lstur_config(
@@ -80,7 +85,7 @@ class LsturEngine:
             n_docs=n_docs, dropout=float(dropout),
             save_for_backward=int(training),
             n_vert=params['vert_emb'].shape[0] if dv else 0, n_subvert=params['subvert_emb'].shape[0] if ds else 0,
-            Hs=Hs)
+            Hs=Hs, loss_model=1 if loss == 'bce' else 0, bce_neg=int(bce_neg), gain=float(gain))
         self.B, self.W, self.C, self.L, self.D, self.U, self.Ue, self.G = B, W, C, L, Dd + dv + ds, U, Ue, G
         plan = ctypes.c_void_p()
         _lib.check(self.lib.lstur_plan_create(ctypes.byref(self.cfg), ctypes.byref(plan)))
@@ -155,7 +160,7 @@ class LsturEngine:
             self._emb_version[0] += 1
         if self.user_emb is not None and 'user_emb' in params:
             ue = params['user_emb']
-            if self.arch == 7 and ue.shape[1] != self.Ue:
+            if self.arch in (7, 8) and ue.shape[1] != self.Ue:
                 ue = np.concatenate([ue, params['user_emb2']], 1)
             self.user_emb.copy_(torch.as_tensor(np.ascontiguousarray(ue, dtype=np.float32)))
 
@@ -168,7 +173,7 @@ class LsturEngine:
         out['word_emb'] = self.word_emb.cpu().numpy()
         if self.user_emb is not None:
             out['user_emb'] = self.user_emb.cpu().numpy()
-            if self.arch == 7:
+            if self.arch in (7, 8):
                 out['user_emb'], out['user_emb2'] = out['user_emb'][:, :self.G].copy(), out['user_emb'][:, self.G:].copy()
         return out
 
@@ -181,7 +186,7 @@ class LsturEngine:
             rows = self.view('user_rows', torch.int32)[:n].cpu().numpy()
             g[rows] = self.view('d_user_rows').reshape(-1, self.Ue)[:n].cpu().numpy()
             out['user_emb'] = g
-            if self.arch == 7:
+            if self.arch in (7, 8):
                 out['user_emb'], out['user_emb2'] = g[:, :self.G].copy(), g[:, self.G:].copy()
         return out
 

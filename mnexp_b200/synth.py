@@ -152,16 +152,16 @@ def make_weights(shape, arch=None, seed=1237, word_emb=None, score_model='dot', 
     if arch in ('gru', 'iigru'):
         P['con_w'] = _glorot(rng, (G + Ue, U), G + Ue, U)
         P['con_b'] = bz(U)
-    if arch == 'iigru':                                        # second user table, task/paper.py:616
+    if arch in ('iigru', 'iicat'):                              # second user table, task/paper.py:616 / :340
         P['user_emb2'] = rng.uniform(-0.05, 0.05, (shape.n_users, Ue)).astype(np.float32)
     if score_model == 'dnn':                                   # task/paper.py:448-451
-        Du = 2 * U if arch in ('ngru', 'dgru') else (D if arch == 'niavg' else U)
+        Du = 2 * U if arch in ('ngru', 'dgru', 'iicat') else (D if arch == 'niavg' else U)
         P['sh_w'] = _glorot(rng, (Du + D, U), Du + D, U)
         P['sh_b'] = bz(U)
         P['so_w'] = _glorot(rng, (U, 1), U, 1)
         P['so_b'] = bz(1)
     if score_model == 'ddot':
-        Du = 2 * U if arch in ('ngru', 'dgru') else (D if arch == 'niavg' else U)
+        Du = 2 * U if arch in ('ngru', 'dgru', 'iicat') else (D if arch == 'niavg' else U)
         P['su_w'] = _glorot(rng, (Du, U), Du, U)
         P['su_b'] = bz(U)
         P['sd_w'] = _glorot(rng, (D, U), D, U)

@@ -82,6 +82,8 @@ def user_encoder(arch, user, H, P, recurrent_activation='hard_sigmoid', u0_scale
         return torch.cat([gru(u0), u2], -1) @ P['con_w'] + P['con_b']
     if arch in ('ngru', 'hgru', 'dgru'):
         return torch.cat([gru(None), u0], -1)
+    if arch == 'iicat':          # Seq2VecPaperId 'iigru' (task/paper.py:338-343): as 'iigru' without the Dense
+        return torch.cat([gru(u0), P['user_emb2'][user.reshape(-1)]], -1)
     if arch == 'pgru':
         return gru(None) + u0
     if arch == 'nigru':
@@ -116,6 +118,12 @@ def categorical_crossentropy(y, p):
     return (-(y * torch.log(p)).sum(-1)).mean()
 
 
+def weighted_bce(y, p, gain=1.0, negative_samples=4):
+    """Seq2Vec.loss, task/seq2vec.py:213-216 (y, p of the same shape)."""
+    K = float(negative_samples)
+    return -0.5 * (1 + K) * (y * torch.log(p + 1e-8) * gain + (1 - y) * torch.log(1 - p + 1e-8) / K).mean()
+
+
 def _doc_vectors(tok, P, vert=None, subvert=None, **kw):
     """paper.py doc encoder, or cook.py's [title ‖ Vemb[vert] ‖ Semb[subvert]] (task/cook.py:99-113)."""
     d = news_encoder(tok, P, use_dense='dense_w' in P, **kw)
@@ -129,7 +137,7 @@ def _doc_vectors(tok, P, vert=None, subvert=None, **kw):
 
 def forward(P, user, clicked_tok, cand_tok, arch='igru', score_model='dot',
             recurrent_activation='hard_sigmoid', dropout=0.0, training=False, aux=False, hist_vert=None,
-            hist_subvert=None, cand_vert=None, cand_subvert=None, u0_scale=None):
+            hist_subvert=None, cand_vert=None, cand_subvert=None, u0_scale=None, head='softmax'):
     """Seq2VecPaperSoftmaxId._build_model — task/paper.py:635-665."""
     B, W, L = clicked_tok.shape
     C = cand_tok.shape[1]
@@ -141,7 +149,8 @@ def forward(P, user, clicked_tok, cand_tok, arch='igru', score_model='dot',
     dc = _doc_vectors(cand_tok.reshape(B * C, L), P, cand_vert, cand_subvert, dropout=dropout,
                       training=training).reshape(B, C, -1)
     s = score(u, dc, P, score_model)
-    probs = torch.softmax(s, -1)
+    # head='sigmoid': the sigmoid family (Seq2VecPaper / Dot / Id, task/paper.py:222-262), one candidate per row
+    probs = torch.softmax(s, -1) if head == 'softmax' else torch.sigmoid(s)
     if aux:
         return dict(probs=probs, logits=s, user_vec=u, cand_vec=dc, hist_vec=H)
     return probs

@@ -357,3 +357,44 @@ def test_scorers_and_remaining_archs_match_oracle(L, arch, score_model, precisio
             assert abs(float(np.asarray(got[k]).reshape(-1)[0])) < 1e-6
             continue
         assert rel(got[k], g.numpy()) < gtol, k
+
+
+# ---------------------------------------------------------------- sigmoid family: weighted BCE head (a11)
+@pytest.mark.parametrize('arch,oarch,score_model,precision', [
+    ('igru', 'igru', 'dot', 'fp32'), ('gru', 'ngru', 'dnn', 'fp32'), ('iigru', 'iicat', 'dnn', 'fp32'),
+    ('nigru', 'nigru', 'dot', 'fp32'), ('niavg', 'niavg', 'dnn', 'fp32'), ('vo', 'vo', 'ddot', 'fp32'),
+    ('igru', 'igru', 'dnn', 'fp16_tc'),
+])
+def test_sigmoid_family_weighted_bce(L, arch, oarch, score_model, precision):
+    """Seq2VecPaper / Seq2VecPaperDot / Seq2VecPaperId (task/paper.py:222-383): one candidate per row, sigmoid head,
+    Seq2Vec.loss (task/seq2vec.py:213-216) with gain and negative_samples; outputs, loss and gradients vs the oracle."""
+    sh = synth.SHAPES['tiny']
+    tok, _, _ = synth.make_docs(sh.n_news, sh.L, sh.vocab)
+    P = synth.make_weights(sh, arch=oarch, bias_noise=0.05, seed=1260, score_model=score_model)
+    (b,), _ = synth.make_batches(sh, 1, seed=1261)
+    g = np.random.default_rng(9)
+    y = (g.random((sh.B, 1)) < 0.4).astype(np.float32)
+    b = dict(user=b['user'], hist_doc=b['hist_doc'], cand_doc=b['cand_doc'][:, :1], label=y)
+    from mnexp_b200.engine import LsturEngine
+    eng = LsturEngine(P, sh.B, sh.W, 1, sh.L, arch=arch, flavour='sigmoid', doc_tokens=tok, score_model=score_model,
+                      precision=precision, loss='bce', gain=1.7, bce_neg=sh.K)
+    db = eng.to_device_batch(b)
+    p_gpu = eng.forward(db, training=True, seed=1).cpu().numpy().copy()
+    loss_gpu = eng.loss()
+    eng.backward(db)
+    torch.cuda.synchronize()
+    got = eng.get_grads_dict()
+    ora = ot.LsturOracle(P, arch=oarch, score_model=score_model)
+    u, c, d = ora._ints(b['user'], tok[b['hist_doc']], tok[b['cand_doc']])
+    out = ot.forward(ora.P, u, c, d, arch=oarch, score_model=score_model, head='sigmoid')
+    loss = ot.weighted_bce(torch.tensor(y, dtype=torch.float64), out, gain=1.7, negative_samples=sh.K)
+    tol = 5e-5 if precision == 'fp32' else TOL_SPEC
+    assert rel(p_gpu, out.detach().numpy()) < tol
+    assert abs(loss_gpu - float(loss)) < tol * max(1.0, abs(float(loss)))
+    ref = dict(zip(ora.trainable, torch.autograd.grad(loss, [ora.P[k] for k in ora.trainable], allow_unused=True)))
+    gtol = 1e-4 if precision == 'fp32' else 2e-2
+    for k, gr in ref.items():
+        if gr is None or k == 'att_b':
+            continue
+        assert k in got, k
+        assert rel(got[k], gr.numpy()) < gtol, k
