@@ -46,9 +46,10 @@ class History:
 class _Core:
     """Weights + engines shared by `model` (softmax/CE training graph) and `test_model` (sigmoid scoring graph)."""
 
-    def __init__(self, params, cfg, doc_tokens, has_user, arch, predict_rows=256, score_model='dot'):
+    def __init__(self, params, cfg, doc_tokens, has_user, arch, predict_rows=256, score_model='dot', loss='softmax',
+                 flavour='paper'):
         self.params, self.cfg, self.doc_tokens, self.has_user, self.arch = params, cfg, doc_tokens, has_user, arch
-        self.score_model = score_model
+        self.score_model, self.loss, self.flavour = score_model, loss, flavour
         self.optimizer = Adam(cfg.learning_rate)
         self.train_engine = None
         self.infer_engines = {}
@@ -71,10 +72,10 @@ class _Core:
                 self.params = e.get_weights_dict()
             c = self.cfg
             self.train_engine = LsturEngine(
-                self.params, B, c.window_size, 1 + c.negative_samples, c.title_shape, arch=self.arch,
+                self.params, B, c.window_size, self.n_train_cand(), c.title_shape, arch=self.arch,
                 dropout=c.dropout, lr=c.learning_rate, recurrent_activation=c.recurrent_activation,
                 precision=self.precision(), doc_tokens=self.doc_tokens, training=True,
-                sparse_user_adam=bool(c.sparse_user_adam), score_model=self.score_model)
+                sparse_user_adam=bool(c.sparse_user_adam), score_model=self.score_model, **self.head_kw())
             self.infer_engines = {}
         return self.train_engine
 
@@ -85,8 +86,14 @@ class _Core:
             self.infer_engines[C] = LsturEngine(
                 self.params, self.predict_rows, c.window_size, C, c.title_shape, arch=self.arch, dropout=0.0,
                 recurrent_activation=c.recurrent_activation, precision=self.precision(), training=False,
-                share_weights_from=base, score_model=self.score_model)
+                share_weights_from=base, score_model=self.score_model, **self.head_kw())
         return self.infer_engines[C]
+
+    def n_train_cand(self):
+        return 1 if self.loss == 'bce' else 1 + self.cfg.negative_samples
+
+    def head_kw(self):
+        return dict(flavour=self.flavour, loss=self.loss, gain=self.cfg.gain, bce_neg=self.cfg.negative_samples)
 
     def split_inputs(self, x, n_cand):
         x = list(x)
@@ -105,6 +112,8 @@ class Model:
     def __init__(self, core, train, name='model'):
         self.core, self.is_train, self.name = core, train, name
         self.metrics_names = ['loss', 'categorical_accuracy'] if train else ['loss']
+        if core.loss == 'bce':                   # metrics=[utils.auc_roc], task/paper.py:250-255
+            self.metrics_names = ['loss', 'auc_roc']
         self.layers = {}
 
     @property
@@ -115,16 +124,19 @@ class Model:
     def train_on_batch(self, x, y):
         assert self.is_train, 'test_model is not compiled for training'
         core = self.core
-        C = 1 + core.cfg.negative_samples
+        C = core.n_train_cand()
         user, clicked, cand = core.split_inputs(x, C)
         eng = core.engine_train(clicked.shape[0])
         eng.lr = core.optimizer.lr.value
-        batch = dict(user=user, hist_tok=clicked, cand_tok=cand, label=np.asarray(y))
+        batch = dict(user=user, hist_tok=clicked, cand_tok=cand, label=np.asarray(y, dtype=np.float32).reshape(len(clicked), C))
         if core.arch == 'dgru':     # Dropout(0.5, noise_shape=(None, 1)) on the user vector (task/paper.py:609)
             batch['user_scale'] = (np.random.random(clicked.shape[0]) >= 0.5).astype(np.float32) * 2.0
         db = eng.to_device_batch(batch)
         loss = eng.train_step(db)
         probs = eng.view('probs').reshape(eng.B, eng.C)
+        if core.loss == 'bce':
+            from . import metrics
+            return [float(loss[0]), metrics.auc_roc(probs.reshape(-1).cpu().numpy(), np.asarray(y).reshape(-1))]
         acc = (probs.argmax(1) == db['label'].argmax(1)).float().mean()
         return [float(loss[0]), float(acc)]
 
@@ -171,12 +183,12 @@ class Model:
             c = np.zeros((R,) + cand.shape[1:], dtype=np.int32); c[:m] = cand[s:s + m]
             db = eng.to_device_batch(dict(user=u, hist_tok=h, cand_tok=c))
             probs = eng.forward(db, training=False)
-            out = probs if self.is_train else eng.score_sigmoid()
+            out = probs if (self.is_train or core.loss == 'bce') else eng.score_sigmoid()
             outs.append(out[:m].cpu().numpy().copy())
         return np.concatenate(outs) if outs else np.zeros((0, n_cand), dtype=np.float32)
 
     def predict(self, x, batch_size=None, **_):
-        C = 1 + self.core.cfg.negative_samples if self.is_train else 1
+        C = self.core.n_train_cand() if self.is_train else 1
         return self._forward_chunks(x, C)
 
     predict_on_batch = predict
@@ -184,6 +196,11 @@ class Model:
     def evaluate(self, x, y, batch_size=None, verbose=0, **_):
         y = np.asarray(y[0] if isinstance(y, (list, tuple)) else y, dtype=np.float64)
         p = self.predict(x).astype(np.float64)
+        if self.core.loss == 'bce':              # Seq2Vec.loss + utils.auc_roc
+            from . import metrics
+            K, yy, q = float(self.core.cfg.negative_samples), y.reshape(-1), p.reshape(-1)
+            l = -0.5 * (1 + K) * np.mean(yy * np.log(q + 1e-8) * self.core.cfg.gain + (1 - yy) * np.log(1 - q + 1e-8) / K)
+            return [float(l), metrics.auc_roc(q, yy)]
         if self.is_train:
             q = np.clip(p / p.sum(-1, keepdims=True), 1e-7, 1 - 1e-7)
             return [float((-(y * np.log(q)).sum(-1)).mean()), float((p.argmax(1) == y.argmax(1)).mean())]

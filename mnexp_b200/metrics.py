@@ -33,3 +33,15 @@ def ranking_metrics(scores, labels, device=None):
     _lib.check(lib.lstur_ranking_metrics(n, p(o), p(s), p(y), p(out),
                                          ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
     return out.cpu().numpy()
+
+
+def auc_roc(scores, labels):
+    """Batch ROC-AUC reported as the training metric of the sigmoid family (utils.auc_roc wraps tf.metrics.auc,
+    utils.py:84-96; here the exact rank statistic of the batch, ties counted half).  0.5 when one class is absent."""
+    s = np.asarray(scores, dtype=np.float64).reshape(-1)
+    y = np.asarray(labels).reshape(-1) > 0.5
+    pos, neg = s[y], s[~y]
+    if len(pos) == 0 or len(neg) == 0:
+        return 0.5
+    d = pos[:, None] - neg[None, :]
+    return float(((d > 0).sum() + 0.5 * (d == 0).sum()) / d.size)

@@ -1,5 +1,6 @@
 """task.get(config) -> eval(config.task)(config), as the reference's task/__init__.py:15-16."""
-from .paper import Seq2VecPaper, Seq2VecPaperSoftmax, Seq2VecPaperSoftmaxId  # noqa: F401
+from .paper import (Seq2VecPaper, Seq2VecPaperDot, Seq2VecPaperId, Seq2VecPaperSoftmax,  # noqa: F401
+                    Seq2VecPaperSoftmaxId)
 from .seq2vec import Seq2Vec  # noqa: F401
 
 

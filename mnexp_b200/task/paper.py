@@ -52,6 +52,116 @@ class Seq2VecPaper(Seq2Vec):
     def save_model(self):
         pass                                                 # task/paper.py:254-255
 
+    # ---- sigmoid family: one (history, candidate, label) sample per row, weighted BCE (task/paper.py:36-256) ----
+    HAS_USER = False
+    SCORE = 'dnn'                                            # score_encoder: Dense(relu)([u ‖ d]) -> Dense(1, sigmoid), :222-226
+    USER_ARCHS = {'gru': ('nigru', 'nigru'), 'avg': ('niavg', 'niavg')}   # config.arch -> (engine arch, oracle/synth arch)
+    # 'att' (SimpleAttentionMaskSupport over the click window, :206-208) is not built
+
+    def _row(self, user, clicked, title, label):
+        return ((user,) if self.HAS_USER else ()) + (clicked, title, label)
+
+    def train_gen(self):
+        while True:
+            for user, (ih, _) in enumerate(self.data):
+                if ih:
+                    ch = self.Window(self.docs, self.config.window_size)
+                    if len(ih) > self.config.max_impression:
+                        chosen = set(random.sample(range(len(ih)), self.config.max_impression))
+                    else:
+                        chosen = None
+                    for i, impression in enumerate(ih):
+                        trainable = chosen is None or i in chosen
+                        for pos in impression.pos:
+                            if ch.count and trainable:
+                                clicked = ch.get_title()
+                                yield self._row(user, clicked, self.docs[pos].title, 1)
+                                for neg in impression.negative_samples(self.config.negative_samples):
+                                    yield self._row(user, clicked, self.docs[neg].title, 0)
+                            ch.push(pos)
+
+    def valid_gen(self):
+        while True:
+            for user, (ih1, ih2) in enumerate(self.data):
+                if ih1 and ih2:
+                    ch = self.Window(self.docs, self.config.window_size)
+                    for impression in ih1:
+                        for pos in impression.pos:
+                            ch.push(pos)
+                    for impression in ih2:
+                        for pos in impression.pos:
+                            clicked = ch.get_title()
+                            yield self._row(user, clicked, self.docs[pos].title, 1)
+                            for neg in impression.negative_samples(self.config.negative_samples):
+                                yield self._row(user, clicked, self.docs[neg].title, 0)
+                        for pos in impression.pos:
+                            ch.push(pos)
+
+    def test_gen(self):
+        for user, (ih1, ih2) in enumerate(self.data):
+            if ih1 and ih2:
+                ch = self.Window(self.docs, self.config.window_size)
+                for impression in ih1:
+                    for pos in impression.pos:
+                        ch.push(pos)
+                for impression in ih2:
+                    clicked = ch.get_title()
+                    yield [self._row(user, clicked, self.docs[p].title, 1) for p in impression.pos] + \
+                          [self._row(user, clicked, self.docs[n].title, 0) for n in impression.neg]
+                    for pos in impression.pos:
+                        ch.push(pos)
+
+    def _title_embedding(self):
+        if self.config.debug:                                # task/paper.py:109-110
+            return np.load(self.config.title_embedding_input + '.npy')
+        return utils.load_textual_embedding(self.config.title_embedding_input, self.config.textual_embedding_dim)
+
+    def get_doc_encoder(self):
+        if self.config.enable_pretrain_encoder:
+            raise NotImplementedError('enable_pretrain_encoder: loading a Keras json+pkl encoder is out of scope')
+        if self.config.news_encoder != 'cnnatt':
+            raise Exception('Unsupport doc model')           # task/paper.py:130,195
+        if self.config.textual_embedding_trainable:
+            raise NotImplementedError('textual_embedding_trainable (conv dgrad + word-table scatter) is not implemented yet')
+        return keras_like.DocEncoderModel(self._core)
+
+    def _archs(self):
+        if self.config.arch not in self.USER_ARCHS:
+            raise Exception('Unsupport user model')          # task/paper.py:216-217, 355-356
+        return self.USER_ARCHS[self.config.arch]
+
+    def get_user_encoder(self, window_size=None):
+        self._archs()
+        return self._core
+
+    def _build_model(self):
+        """task/paper.py:228-256 / 360-383: `model` = sigmoid score, loss = Seq2Vec.loss (weighted BCE), Adam."""
+        c = self.config
+        eng_arch, syn_arch = self._archs()
+        F, k = c.title_filter_shape
+        word_emb = self._title_embedding().astype(np.float32)
+        sh = synth.Shape('cfg', n_users=len(self.data), n_news=self.doc_count - 1, vocab=word_emb.shape[0],
+                         L=c.title_shape, W=c.window_size, K=c.negative_samples, B=c.batch_size, E=word_emb.shape[1],
+                         F=F, k=k, U=c.user_embedding_dim, arch=syn_arch)
+        params = synth.make_weights(sh, arch=syn_arch, seed=np.random.randint(1 << 30), word_emb=word_emb,
+                                    score_model=self.SCORE)
+        self._core = keras_like._Core(params, c, self.doc_token_table(), self.HAS_USER, eng_arch, score_model=self.SCORE,
+                                      loss='bce', flavour='sigmoid')
+        self.doc_encoder = self.get_doc_encoder()
+        self.user_encoder = self.get_user_encoder()
+        self.model = keras_like.Model(self._core, train=True, name='model')
+        self.model.layers['doc_encoder'] = self.doc_encoder
+
+
+class Seq2VecPaperDot(Seq2VecPaper):
+    SCORE = 'dot'                                            # sigmoid(Dot([1, 1])), task/paper.py:258-262
+
+
+class Seq2VecPaperId(Seq2VecPaper):
+    """User-ID variants of the sigmoid family (task/paper.py:265-383)."""
+    HAS_USER = True
+    USER_ARCHS = {'gru': ('gru', 'ngru'), 'igru': ('igru', 'igru'), 'iigru': ('iigru', 'iicat'), 'vo': ('vo', 'vo')}
+
 
 class Seq2VecPaperSoftmax(Seq2VecPaper):
     HAS_USER = False

@@ -286,3 +286,38 @@ def test_model_builder_scorers_and_concat_archs(lib, arch, score_model):
 def test_concat_archs_need_a_dense_scorer(lib):
     with pytest.raises(ValueError):
         _handler('ngru', 'Seq2VecPaperSoftmaxId', score_model='dot')[1].build_model(0)
+
+
+@pytest.mark.parametrize('task_name,arch,oarch,score', [
+    ('Seq2VecPaperId', 'igru', 'igru', 'dnn'), ('Seq2VecPaperId', 'gru', 'ngru', 'dnn'),
+    ('Seq2VecPaperId', 'iigru', 'iicat', 'dnn'), ('Seq2VecPaperDot', 'gru', 'nigru', 'dot'),
+    ('Seq2VecPaper', 'avg', 'niavg', 'dnn'),
+])
+def test_sigmoid_family_surface(lib, task_name, arch, oarch, score):
+    """Seq2VecPaper / Seq2VecPaperDot / Seq2VecPaperId (task/paper.py:6-383): (history, candidate, label) samples,
+    sigmoid score, weighted BCE; predict == oracle, evaluate == Seq2Vec.loss, training reduces the loss, test yields
+    per-impression (scores, labels)."""
+    from oracle import lstur_torch as ot
+    import torch
+    sh, h = _handler(arch, task_name, gain=1.5)
+    model = h.build_model(0)
+    x, y = next(h.train)
+    assert y.shape == (8,) and len(x) == (3 if h.HAS_USER else 2)
+    P = _oracle_params(model)
+    if 'so_w' in P:
+        P['so_w'] = P['so_w'].reshape(-1, 1)
+    user = x[0] if h.HAS_USER else np.zeros(len(y), dtype=int)
+    clicked, cand = (x[1], x[2]) if h.HAS_USER else (x[0], x[1])
+    ora = ot.LsturOracle(P, arch=oarch, score_model=score)
+    u, c, d = ora._ints(user, clicked.astype(int), cand.astype(int)[:, None])
+    ref = ot.forward(ora.P, u, c, d, arch=oarch, score_model=score, head='sigmoid').detach()
+    p = model.predict(x)
+    assert p.shape == (8, 1) and rel(p, ref.numpy()) < 2e-5
+    ev = model.evaluate(x, y)
+    l_ref = float(ot.weighted_bce(torch.tensor(y, dtype=torch.float64)[:, None], ref, gain=1.5, negative_samples=sh.K))
+    assert abs(ev[0] - l_ref) < 1e-5 and model.metrics_names == ['loss', 'auc_roc']
+    for _ in range(25):
+        out = model.train_on_batch(x, y)
+    assert len(out) == 2 and model.evaluate(x, y)[0] < ev[0]
+    scores, labels = next(h.test)
+    assert scores.shape == labels.shape and scores.ndim == 1 and set(np.unique(labels)) <= {0, 1}
