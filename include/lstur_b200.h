@@ -309,6 +309,12 @@ typedef struct lstur_batch {
   const int* cand_tok;   /* (B,C,L)                                                            */
   const float* label;    /* (B,C) one-hot or NULL (= positive at column 0, task/paper.py:529)  */
   const float* user_scale; /* (B) multiplier on the user embedding or NULL (dgru / id_keep)    */
+  /* cook .npz protocol (task/cook.py:14-17): vertical / subvertical ids per title slot next to the tokens, instead of
+   * doc ids + the doc_vert / doc_subvert tables; all four or none */
+  const int* hist_vert;    /* (B,W) */
+  const int* hist_subvert; /* (B,W) */
+  const int* cand_vert;    /* (B,C) */
+  const int* cand_subvert; /* (B,C) */
 } lstur_batch;
 
 typedef struct lstur_plan lstur_plan;

@@ -34,7 +34,8 @@ class lstur_weights(ctypes.Structure):
 
 class lstur_batch(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in
-                ('user', 'hist_doc', 'cand_doc', 'hist_tok', 'cand_tok', 'label', 'user_scale')]
+                ('user', 'hist_doc', 'cand_doc', 'hist_tok', 'cand_tok', 'label', 'user_scale', 'hist_vert',
+                 'hist_subvert', 'cand_vert', 'cand_subvert')]
 
 
 def parse_header(path=HEADER):

@@ -511,17 +511,27 @@ extern "C" int lstur_forward(const lstur_plan* p, const lstur_weights* w, const 
   }
   // 2. news encoder (k1-k7)
   RC(encode_titles(p, w, ws, N, training, seed, st));
-  if (c.dv + c.ds) {   // [title ‖ Vemb[vert] ‖ Semb[subvert]] (task/cook.py:99-113), doc-id protocol only
-    LSTUR_REQUIRE(b->hist_doc && b->cand_doc && (c.dv == 0 || w->doc_vert) && (c.ds == 0 || w->doc_subvert),
-                  "lstur_forward(vertical concat needs doc ids and the doc_vert / doc_subvert tables)");
+  if (c.dv + c.ds) {   // [title ‖ Vemb[vert] ‖ Semb[subvert]] (task/cook.py:99-113)
     float* docv = W<float>(p, ws, "doc_vec");
     int* tv = W<int>(p, ws, "title_vert");
     int* ts = W<int>(p, ws, "title_subvert");
-    RC(lstur_vert_concat(Nh, D, c.Dd, c.dv, c.ds, c.n_docs, c.n_vert, c.n_subvert, b->hist_doc, w->doc_vert, w->doc_subvert,
-                         DP(p, w->dense, "vert_emb"), DP(p, w->dense, "subvert_emb"), docv, tv, ts, st));
-    RC(lstur_vert_concat(Nc, D, c.Dd, c.dv, c.ds, c.n_docs, c.n_vert, c.n_subvert, b->cand_doc, w->doc_vert, w->doc_subvert,
-                         DP(p, w->dense, "vert_emb"), DP(p, w->dense, "subvert_emb"), docv + (size_t)Nh * D, tv + Nh, ts + Nh,
-                         st));
+    if (b->hist_vert || b->hist_subvert || b->cand_vert || b->cand_subvert) {   // ids per title slot (cook .npz protocol)
+      LSTUR_REQUIRE((c.dv == 0 || (b->hist_vert && b->cand_vert)) && (c.ds == 0 || (b->hist_subvert && b->cand_subvert)),
+                    "lstur_forward(vertical concat: per-slot ids for both history and candidates)");
+      RC(lstur_vert_concat(Nh, D, c.Dd, c.dv, c.ds, Nh, c.n_vert, c.n_subvert, nullptr, b->hist_vert, b->hist_subvert,
+                           DP(p, w->dense, "vert_emb"), DP(p, w->dense, "subvert_emb"), docv, tv, ts, st));
+      RC(lstur_vert_concat(Nc, D, c.Dd, c.dv, c.ds, Nc, c.n_vert, c.n_subvert, nullptr, b->cand_vert, b->cand_subvert,
+                           DP(p, w->dense, "vert_emb"), DP(p, w->dense, "subvert_emb"), docv + (size_t)Nh * D, tv + Nh,
+                           ts + Nh, st));
+    } else {
+      LSTUR_REQUIRE(b->hist_doc && b->cand_doc && (c.dv == 0 || w->doc_vert) && (c.ds == 0 || w->doc_subvert),
+                    "lstur_forward(vertical concat needs doc ids and the doc_vert / doc_subvert tables, or per-slot ids)");
+      RC(lstur_vert_concat(Nh, D, c.Dd, c.dv, c.ds, c.n_docs, c.n_vert, c.n_subvert, b->hist_doc, w->doc_vert, w->doc_subvert,
+                           DP(p, w->dense, "vert_emb"), DP(p, w->dense, "subvert_emb"), docv, tv, ts, st));
+      RC(lstur_vert_concat(Nc, D, c.Dd, c.dv, c.ds, c.n_docs, c.n_vert, c.n_subvert, b->cand_doc, w->doc_vert, w->doc_subvert,
+                           DP(p, w->dense, "vert_emb"), DP(p, w->dense, "subvert_emb"), docv + (size_t)Nh * D, tv + Nh, ts + Nh,
+                           st));
+    }
   }
   // 3. history mask (k9)
   RC(lstur_hist_mask_apply(Nh, L, D, tok, W<float>(p, ws, "doc_vec"), D, W<float>(p, ws, "hist_mask"),

@@ -118,8 +118,11 @@ __global__ void vert_concat_kernel(int n, int D, int col0, int dv, int ds, int n
                                    int* __restrict__ tv, int* __restrict__ ts) {
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= n) return;
-  int d = doc_ids[warp];
-  d = (d < 0 || d >= n_docs) ? 0 : d;
+  int d = warp;                       // doc_ids == NULL: doc_vert / doc_subvert are indexed by the title slot itself
+  if (doc_ids) {
+    d = doc_ids[warp];
+    d = (d < 0 || d >= n_docs) ? 0 : d;
+  }
   int v = dv ? doc_vert[d] : 0, sv = ds ? doc_subvert[d] : 0;
   v = (v < 0 || v >= n_vert) ? 0 : v;
   sv = (sv < 0 || sv >= n_sub) ? 0 : sv;
@@ -251,7 +254,7 @@ extern "C" int lstur_row_gather(int B, int D, int n_rows, const float* table, co
 extern "C" int lstur_vert_concat(int n, int D, int col0, int dv, int ds, int n_docs, int n_vert, int n_subvert, const int* doc_ids,
                                  const int* doc_vert, const int* doc_subvert, const float* vert_emb, const float* subvert_emb,
                                  float* doc_vec, int* title_vert, int* title_subvert, cudaStream_t stream) {
-  LSTUR_REQUIRE(n >= 0 && dv >= 0 && ds >= 0 && col0 >= 0 && col0 + dv + ds <= D && doc_ids && doc_vec, "lstur_vert_concat");
+  LSTUR_REQUIRE(n >= 0 && dv >= 0 && ds >= 0 && col0 >= 0 && col0 + dv + ds <= D && doc_vec, "lstur_vert_concat");
   LSTUR_REQUIRE((dv == 0 || (doc_vert && vert_emb && n_vert > 0)) && (ds == 0 || (doc_subvert && subvert_emb && n_subvert > 0)),
                 "lstur_vert_concat");
   if (n == 0 || dv + ds == 0) return LSTUR_OK;

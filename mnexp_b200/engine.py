@@ -19,7 +19,7 @@ ARCH = {  # reference arch names -> engine arch; paper.py name
 SCORE = {'dot': 0, 'dnn': 1, 'ddot': 2}          # task/paper.py:443-458; cook's 'ddot' is linear (task/cook.py:206-209)
 # sigmoid family (Seq2VecPaperId.get_user_encoder, task/paper.py:328-358): 'gru' is the plain concat, 'iigru' has no Dense
 SIGMOID_ARCH = {'gru': 2, 'igru': 0, 'iigru': 8, 'vo': 5, 'nigru': 3, 'niavg': 6}
-COOK_ARCH = {'ingru': 0, 'igru': 2, 'gru': 3, 'agru': 4, 'vo': 5}   # task/cook.py:146-168
+COOK_ARCH = {'ingru': 0, 'igru': 2, 'gru': 3, 'agru': 4, 'vo': 5, 'avg': 6, 'inigru': 8}   # task/cook.py:146-176
 DENSE_NAMES = ('conv_w', 'conv_b', 'att_w', 'att_b', 'dense_w', 'dense_b', 'vert_emb', 'subvert_emb',
                'gru_wx', 'gru_wh', 'gru_b', 'con_w', 'con_b', 'sh_w', 'sh_b', 'so_w', 'so_b', 'su_w', 'su_b', 'sd_w', 'sd_b')
 PREC = {'fp32': 0, 'bf16_tc': 1, 'fp16_tc': 2}
@@ -222,7 +222,9 @@ class LsturEngine:
     def _cbatch(self, db):
         g = lambda k: db[k].data_ptr() if k in db else None
         return lstur_batch(user=g('user'), hist_doc=g('hist_doc'), cand_doc=g('cand_doc'), hist_tok=g('hist_tok'),
-                           cand_tok=g('cand_tok'), label=g('label'), user_scale=g('user_scale'))
+                           cand_tok=g('cand_tok'), label=g('label'), user_scale=g('user_scale'),
+                           hist_vert=g('hist_vert'), hist_subvert=g('hist_subvert'), cand_vert=g('cand_vert'),
+                           cand_subvert=g('cand_subvert'))
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

@@ -32,6 +32,8 @@ TRAIN_DEFAULTS = dict(           # main.py:12-54
     vertical_embedding_dim=10, subvertical_embedding_dim=20,
     input_training_data_path='.', input_validation_data_path='.', input_previous_model_path='.', output_model_path='.',
     log_dir='.', precision='auto', recurrent_activation='hard_sigmoid', sparse_user_adam=False,
+    # cook-only options (main.py:100-147)
+    id_keep=1.0, lrd_on_epochs=[1, 3], use_vertical=False, use_vertical_type='vs', use_generator=False,
 )
 
 

@@ -82,8 +82,9 @@ def user_encoder(arch, user, H, P, recurrent_activation='hard_sigmoid', u0_scale
         return torch.cat([gru(u0), u2], -1) @ P['con_w'] + P['con_b']
     if arch in ('ngru', 'hgru', 'dgru'):
         return torch.cat([gru(None), u0], -1)
-    if arch == 'iicat':          # Seq2VecPaperId 'iigru' (task/paper.py:338-343): as 'iigru' without the Dense
-        return torch.cat([gru(u0), P['user_emb2'][user.reshape(-1)]], -1)
+    if arch == 'iicat':          # Seq2VecPaperId 'iigru' (task/paper.py:338-343) / cook 'inigru' (task/cook.py:169-176, where
+        u2 = P['user_emb2'][user.reshape(-1)]       # the id mask multiplies the second embedding too)
+        return torch.cat([gru(u0), u2 if u0_scale is None else u2 * u0_scale], -1)
     if arch == 'pgru':
         return gru(None) + u0
     if arch == 'nigru':

@@ -321,3 +321,69 @@ def test_sigmoid_family_surface(lib, task_name, arch, oarch, score):
     assert len(out) == 2 and model.evaluate(x, y)[0] < ev[0]
     scores, labels = next(h.test)
     assert scores.shape == labels.shape and scores.ndim == 1 and set(np.unique(labels)) <= {0, 1}
+
+
+def _cook_npz(d, sh, n_train=24, n_test=10, seed=0):
+    """train/test .npz in the reference's cook layout (task/cook.py:14-28) + Vocab.tsv.npy."""
+    g = np.random.default_rng(seed)
+    tok, _, _ = synth.make_docs(sh.n_news, sh.L, sh.vocab)
+
+    def block(n, C):
+        hd = g.integers(0, sh.n_news + 1, (n, sh.W))
+        hd[:, :2] = 0                                            # left padding
+        cd = g.integers(1, sh.n_news + 1, (n, C))
+        return dict(idx=g.integers(0, 50, (n, 1)), idx_mask=(g.random((n, 1)) < 0.8).astype(np.float32),
+                    ch_title=tok[hd], ch_vert=g.integers(0, 16, (n, sh.W)) * (hd > 0), ch_subvert=g.integers(0, 307, (n, sh.W)) * (hd > 0),
+                    cd_title=tok[cd], cd_vert=g.integers(1, 16, (n, C)), cd_subvert=g.integers(1, 307, (n, C)))
+    tr = block(n_train, 5)
+    tr['cd_label'] = np.eye(5, dtype=np.float32)[np.zeros(n_train, dtype=int)]
+    te = block(n_test, 1)
+    te = dict(te, cd_title=te['cd_title'][:, 0], cd_vert=te['cd_vert'][:, 0], cd_subvert=te['cd_subvert'][:, 0],
+              label=(g.random(n_test) < 0.3).astype(np.float32), user=np.arange(n_test), impr=np.arange(n_test) // 3)
+    np.savez(os.path.join(d, 'train_30days_%dwindow.npz' % sh.W), **tr)
+    np.savez(os.path.join(d, 'test_30days_%dwindow.npz' % sh.W), **te)
+    np.save(os.path.join(d, 'Vocab.tsv.npy'), synth.make_vocab(sh.vocab, sh.E))
+
+
+@pytest.mark.parametrize('arch,oarch,score_model,vtype', [('ingru', 'igru', 'ddot', 'vs'), ('igru', 'ngru', 'dnn', 'v'),
+                                                          ('inigru', 'iicat', 'ddot', 's'), ('avg', 'niavg', 'dnn', 'vs')])
+def test_cook_handler(lib, arch, oarch, score_model, vtype):
+    """Cook (task/cook.py): .npz protocol with per-slot vertical / subvertical ids, [title ‖ Vemb ‖ Semb] news vectors,
+    idx_mask on the user id embedding, linear 'ddot'; train_model / test_model through main.py's cook calls."""
+    from oracle import lstur_torch as ot
+    import torch
+    sh = synth.SHAPES['tiny']
+    d = tempfile.mkdtemp()
+    _cook_npz(d, sh)
+    cfg = settings.Config(dict(task='Cook', arch=arch, input_training_data_path=d, days=30, window_size=sh.W,
+                               batch_size=8, title_filter_shape=(sh.F, 3), user_embedding_dim=sh.U, dropout=0.0,
+                               score_model=score_model, use_vertical=True, use_vertical_type=vtype,
+                               vertical_embedding_dim=3, subvertical_embedding_dim=5, precision='fp32', validation_step=6,
+                               lrd_on_epochs=[0]))
+    h = task.get(cfg)
+    model = h.build_model(0)
+    x, y = h.train()
+    P = {k: np.asarray(v) for k, v in model.get_weights_dict().items()}
+    ora = ot.LsturOracle(P, arch=oarch, score_model=score_model)
+    n = len(y[0])
+    kw = dict(arch=oarch, score_model=score_model, u0_scale=torch.tensor(x[1], dtype=torch.float64).reshape(n, 1))
+    if 'vert_emb' in P:
+        kw.update(hist_vert=x[3], cand_vert=x[6])
+    if 'subvert_emb' in P:
+        kw.update(hist_subvert=x[4], cand_subvert=x[7])
+    u, c, dd = ora._ints(x[0].reshape(-1), x[2], x[5])
+    s = ot.score(*[ot.forward(ora.P, u, c, dd, aux=True, **kw)[k] for k in ('user_vec', 'cand_vec')], ora.P, score_model,
+                 flavour='cook')
+    ref = torch.softmax(s, -1).detach().numpy()
+    assert rel(model.predict(x), ref) < 5e-5
+    l0 = model.evaluate(x, y)[0]
+    hist = model.fit(x, y, 8, epochs=3, initial_epoch=0, shuffle=True)
+    assert len(hist.history['loss']) == 3 and model.evaluate(x, y)[0] < l0
+    lr0 = model.optimizer.lr.value
+    h.callback(0)
+    assert abs(model.optimizer.lr.value - lr0 * cfg.learning_rate_decay) < 1e-12
+    ev = h.test_model.evaluate(*h.valid())
+    assert len(ev) == 2 and h.test_model.metrics_names == ['loss', 'auc_roc'] and np.isfinite(ev[0])
+    feats, (users, imprs, mask, y_true) = h.test()
+    pred = h.test_model.predict(feats).reshape(-1)
+    assert pred.shape == y_true.shape and np.all((pred > 0) & (pred < 1))
