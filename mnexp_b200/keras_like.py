@@ -236,6 +236,19 @@ class Model:
                 out.append(a.reshape(-1, 1) if k == 'att_w' else a.reshape(1) if k == 'att_b' else a)
         return out
 
+    def weight_specs(self):
+        """[(name, shape)] in get_weights() order."""
+        return [(k, tuple(int(d) for d in a.shape)) for k, a in
+                zip([k for k in self.WEIGHT_ORDER if k in self._current()], self.get_weights())]
+
+    def to_json(self):
+        import json
+        c = self.core
+        specs = self.weight_specs()
+        return json.dumps(dict(class_name='mnexp_b200.keras_like.Model', name=self.name, arch=c.arch, flavour=c.flavour,
+                               score_model=c.score_model, loss=c.loss, weight_names=[n for n, _ in specs],
+                               weight_shapes=[list(s) for _, s in specs]))
+
     def set_weights(self, weights):
         cur = self._current()
         names = [k for k in self.WEIGHT_ORDER if k in cur]

@@ -120,3 +120,13 @@ class Seq2Vec:
         if epoch == 0:
             self._build_model()
         return self.model
+
+    def save_model(self):
+        """task/seq2vec.py:324-327 (the paper classes override it with a no-op, task/paper.py:254-255)."""
+        logging.info('[+] saving models')
+        utils.save_model(self.config.model_output, self.model)
+        logging.info('[-] saved models')
+
+    def load_model(self):
+        """Restore the weights written by save_model into the built model."""
+        utils.load_model(self.config.model_output).apply_to(self.build_model(0) if getattr(self, 'model', None) is None else self.model)

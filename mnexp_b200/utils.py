@@ -1,5 +1,7 @@
 """Helpers of the reference's utils.py that the LSTUR path uses: Vocab loader and ranking metrics."""
+import json
 import logging
+import pickle
 
 import numpy as np
 
@@ -50,3 +52,42 @@ def logging_evaluation(evaluations):
     """utils.py:26-31"""
     for k, v in sorted(evaluations.items()):
         logging.info('[*] {}: {}'.format(k, v))
+
+
+# ---- model files: the reference's json + pkl pair (utils.py:66-79, settings model_output) -------------------------
+class LoadedModel:
+    """What utils.load_model returns here: the architecture record of the json file and the weight list of the pkl.
+    `get_weights()` is Keras' call; `apply_to(model)` copies the weights into a built model of the same architecture."""
+
+    def __init__(self, config, weights):
+        self.config, self.weights = config, weights
+
+    def get_weights(self):
+        return self.weights
+
+    def apply_to(self, model):
+        names = [n for n, _ in model.weight_specs()]
+        assert names == self.config['weight_names'], 'architecture mismatch: %s vs %s' % (names, self.config['weight_names'])
+        model.set_weights(self.weights)
+        return model
+
+
+def save_model(paths, model):
+    """json.dump(model.to_json()) + pickle.dump(model.get_weights(), HIGHEST_PROTOCOL), as utils.py:75-79.  The pkl is
+    the same list-of-numpy-arrays a Keras model of this graph pickles; the json string describes the engine's graph
+    (class, arch, scorer, weight names and shapes) instead of Keras' layer config."""
+    json_path, weight_path = paths
+    with open(json_path, 'w') as file:
+        json.dump(model.to_json(), file)
+    with open(weight_path, 'wb') as file:
+        pickle.dump(model.get_weights(), file, protocol=pickle.HIGHEST_PROTOCOL)
+
+
+def load_model(paths):
+    json_path, weight_path = paths
+    with open(json_path, 'r') as file:
+        config = json.loads(json.load(file))
+    with open(weight_path, 'rb') as file:
+        weights = pickle.load(file)
+    assert len(weights) == len(config['weight_names'])
+    return LoadedModel(config, weights)

@@ -96,6 +96,19 @@ def test_model_builder_surface(lib, task_name, arch):
     assert abs(model.get_weights()[1] - 0.01).max() < 1e-7
     model.set_weights(w)
     assert rel(model.get_weights()[1], w[1]) == 0
+    # json + pkl model files (utils.py:66-79): the pkl is a plain pickled list of numpy arrays
+    from mnexp_b200 import utils as mutils
+    import pickle
+    paths = (os.path.join(h.config.input_training_data_path, 'm.json'), os.path.join(h.config.input_training_data_path, 'm.pkl'))
+    mutils.save_model(paths, model)
+    with open(paths[1], 'rb') as f:
+        raw = pickle.load(f)
+    assert isinstance(raw, list) and all(isinstance(a, np.ndarray) for a in raw) and len(raw) == len(w)
+    model.set_weights([a * 0 for a in w])
+    loaded = mutils.load_model(paths)
+    assert loaded.config['arch'] == h._engine_arch() and loaded.config['weight_names'][0] == 'word_emb'
+    loaded.apply_to(model)
+    assert all(np.array_equal(a, b) for a, b in zip(model.get_weights(), w))
     # callback: LR decay + ranking metrics over validation impressions (task/paper.py:497-524)
     lr0 = model.optimizer.lr.value
     h.callback(0)
