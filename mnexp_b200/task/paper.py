@@ -13,7 +13,7 @@ csrc/engine.cu.  Unsupported options raise the reference's own exceptions.
 """
 import logging
 import random
-from datetime import datetime
+from datetime import datetime, timedelta
 
 import numpy as np
 from .. import keras_like, metrics, synth, utils
@@ -167,9 +167,22 @@ class Seq2VecPaperSoftmax(Seq2VecPaper):
     HAS_USER = False
     USER_ARCHS = ('gru',)                                    # Seq2VecPaper.get_user_encoder, task/paper.py:199-221
 
-    # ---- sample generators (task/paper.py:387-441) ------------------------------------------
+    # ---- sample generators (task/paper.py:387-441); the window calls go through four hooks so that the time-window
+    # variants (Seq2VecPaperSoftmaxDays*, task/paper.py:668-792) only replace the Window -----------------------------
+    def _new_window(self):
+        return self.Window(self.docs, self.config.window_size)
+
+    def _w_count(self, ch, impression):
+        return ch.count
+
+    def _w_title(self, ch, impression):
+        return ch.get_title()
+
+    def _w_push(self, ch, pos, impression):
+        ch.push(pos)
+
     def _sample(self, user, ch, pos, impression, label):
-        row = [ch.get_title(), self.docs[pos].title] + \
+        row = [self._w_title(ch, impression), self.docs[pos].title] + \
               [self.docs[neg].title for neg in impression.negative_samples(self.config.negative_samples)] + [label]
         return ([user] + row) if self.HAS_USER else row
 
@@ -178,27 +191,27 @@ class Seq2VecPaperSoftmax(Seq2VecPaper):
         while True:
             for user, (ih, _) in enumerate(self.data):
                 if ih:
-                    ch = self.Window(self.docs, self.config.window_size)
+                    ch = self._new_window()
                     for impression in ih:
                         for pos in impression.pos:
-                            if ch.count:
+                            if self._w_count(ch, impression):
                                 yield self._sample(user, ch, pos, impression, label)
-                            ch.push(pos)
+                            self._w_push(ch, pos, impression)
 
     def valid_gen(self):
         label = [1] + [0 for _ in range(self.config.negative_samples)]
         while True:
             for user, (ih1, ih2) in enumerate(self.data):
                 if ih1 and ih2:
-                    ch = self.Window(self.docs, self.config.window_size)
+                    ch = self._new_window()
                     for impression in ih1:
                         for pos in impression.pos:
-                            ch.push(pos)
+                            self._w_push(ch, pos, impression)
                     for impression in ih2:
                         for pos in impression.pos:
                             yield self._sample(user, ch, pos, impression, label)
                         for pos in impression.pos:
-                            ch.push(pos)
+                            self._w_push(ch, pos, impression)
 
     def test_gen(self):
         def __gen__(_user, _clicked, _impression):
@@ -209,15 +222,15 @@ class Seq2VecPaperSoftmax(Seq2VecPaper):
 
         for user, (ih1, ih2) in enumerate(self.data):
             if ih1 and ih2:
-                ch = self.Window(self.docs, self.config.window_size)
+                ch = self._new_window()
                 for impression in ih1:
                     for pos in impression.pos:
-                        ch.push(pos)
+                        self._w_push(ch, pos, impression)
                 for impression in ih2:
-                    clicked = ch.get_title()
+                    clicked = self._w_title(ch, impression)
                     yield list(__gen__(user, clicked, impression))
                     for pos in impression.pos:
-                        ch.push(pos)
+                        self._w_push(ch, pos, impression)
 
     # ---- builder hooks ----------------------------------------------------------------------------
     def _title_embedding(self):
@@ -314,3 +327,57 @@ class Seq2VecPaperSoftmaxId(Seq2VecPaperSoftmax):
     """LSTUR (task/paper.py:527-665): igru = LSTUR-ini; gru / hgru / ngru / dgru = LSTUR-con."""
     HAS_USER = True
     USER_ARCHS = ('igru', 'gru', 'ngru', 'hgru', 'dgru', 'iigru', 'nigru', 'pgru', 'vo', 'niavg')   # task/paper.py:596-628
+
+
+class _DaysWindowMixin:
+    """Time-window click history (task/paper.py:669-694, 763-792): a click expires `config.days` after it was made;
+    expired slots read as the pad document, and a sample needs at least one live click."""
+
+    class Window:
+        __slots__ = ['docs', 'click_history', 'click_history_time', 'delta']
+        zero = datetime.strptime('01/01/2000', '%m/%d/%Y')
+
+        def __init__(self, docs, window_size, delta):
+            self.docs = docs
+            self.delta = timedelta(days=delta)
+            self.click_history = [0 for _ in range(window_size)]
+            self.click_history_time = [self.zero for _ in range(window_size)]
+
+        def get_ids(self, time):
+            return [i if t >= time else 0 for i, t in zip(self.click_history, self.click_history_time)]
+
+        def get_title(self, time):
+            return np.stack([self.docs[i].title for i in self.get_ids(time)])
+
+        def push(self, doc, time):
+            self.click_history.append(doc)
+            self.click_history.pop(0)
+            self.click_history_time.append(time + self.delta)
+            self.click_history_time.pop(0)
+
+        @property
+        def window_size(self):
+            return len(self.click_history)
+
+        def count(self, time):
+            return sum(1 for t in self.click_history_time if t >= time)
+
+    def _new_window(self):
+        return self.Window(self.docs, self.config.window_size, self.config.days)
+
+    def _w_count(self, ch, impression):
+        return ch.count(impression.time)
+
+    def _w_title(self, ch, impression):
+        return ch.get_title(impression.time)
+
+    def _w_push(self, ch, pos, impression):
+        ch.push(pos, impression.time)
+
+
+class Seq2VecPaperSoftmaxDays(_DaysWindowMixin, Seq2VecPaperSoftmax):
+    """task/paper.py:668-750."""
+
+
+class Seq2VecPaperSoftmaxDaysId(_DaysWindowMixin, Seq2VecPaperSoftmaxId):
+    """task/paper.py:753-881 (the vertical / subvertical columns of its DocMeta are read by the *Vert* subclasses only)."""

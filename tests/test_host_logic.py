@@ -116,3 +116,40 @@ def test_synth_shapes_match_baseline_configs():
     assert b[0]['hist_doc'].shape == (64, 50) and 0.2 < pad < 0.8
     h = b[0]['hist_doc']
     assert np.all((h[:, 1:] != 0) | (h[:, :-1] == 0))             # left padding only
+
+
+def test_days_window_and_sigmoid_generators():
+    """Time-window variants (task/paper.py:668-792) and the sigmoid family's (history, candidate, label) samples."""
+    from datetime import datetime
+    sh, d, emb, tok, cfg = _dataset()
+    mk = lambda **kw: task.get(settings.Config(dict({k: getattr(cfg, k) for k in (
+        'input_training_data_path', 'title_shape', 'window_size', 'negative_samples', 'batch_size',
+        'textual_embedding_dim', 'title_filter_shape', 'user_embedding_dim', 'debug')}, **kw)))
+    h = mk(task='Seq2VecPaperSoftmaxDaysId', arch='igru', days=2)
+    w = h.Window(h.docs, 3, 2)
+    t = lambda day: datetime(2019, 1, day)
+    assert w.count(t(1)) == 0 and w.get_ids(t(1)) == [0, 0, 0]
+    w.push(5, t(1)); w.push(6, t(2)); w.push(7, t(4))
+    assert w.get_ids(t(4)) == [0, 6, 7] and w.count(t(4)) == 2            # the day-1 click expired after 2 days
+    assert w.get_ids(t(7)) == [0, 0, 0] and w.count(t(7)) == 0
+    assert np.array_equal(w.get_title(t(4)), tok[[0, 6, 7]].astype(np.float64))
+    # with an unbounded horizon the time-window generator equals the plain one (same negative-sampling stream)
+    far = mk(task='Seq2VecPaperSoftmaxDaysId', arch='igru', days=100000)
+    plain = mk(task='Seq2VecPaperSoftmaxId', arch='igru')
+    np.random.seed(3); a = [next(g) for g in [far.train_gen()] for _ in range(30)]
+    np.random.seed(3); b = [next(g) for g in [plain.train_gen()] for _ in range(30)]
+    assert all(x[0] == y[0] and all(np.array_equal(p, q) for p, q in zip(x[1:-1], y[1:-1])) for x, y in zip(a, b))
+    # a short horizon only removes history: every sample's live clicks are a subset of the plain window's
+    short = mk(task='Seq2VecPaperSoftmaxDays', arch='gru', days=1)
+    s = next(short.train_gen())
+    assert len(s) == 1 + 1 + sh.K + 1 and (s[0] != 0).any()
+    # sigmoid family: K negatives follow each positive, labels 1, 0, 0, ...
+    sg = mk(task='Seq2VecPaperId', arch='igru')
+    g = sg.train_gen()
+    rows = [next(g) for _ in range(2 * (1 + sh.K))]
+    assert [r[-1] for r in rows] == ([1] + [0] * sh.K) * 2 and all(len(r) == 4 for r in rows)
+    assert all(np.array_equal(rows[0][1], r[1]) for r in rows[:1 + sh.K])     # one history per positive and its negatives
+    x, y = next(sg.train)
+    assert [a.shape for a in x] == [(4,), (4, sh.W, sh.L), (4, sh.L)] and y.shape == (4,)
+    nd = mk(task='Seq2VecPaperDot', arch='gru')
+    assert len(next(nd.train_gen())) == 3
