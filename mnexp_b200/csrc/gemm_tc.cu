@@ -35,7 +35,12 @@ struct GemmParams {
   int flags, ntile, k_per_split, vec_ok;
   int tiles_m, tiles_n, splits;
   float* partial;
+  // optional pre-packed B operand (gemm_pack_b_kernel): per (n tile, K block) one hi [+ one lo] 32 KB tile in the exact
+  // shared-memory layout of a stage, fetched with bulk copies instead of being re-converted by every CTA for every tile
+  const uint8_t* bimg;
+  int nkb_total;
 };
+constexpr int G_BIMG_TILE = 256 * 128;    // bytes reserved per image tile (= G_B_BYTES)
 
 // 8 consecutive floats of row s_idx starting at column c0, zero-filled outside [0, s_lim) x [0, c_lim)
 __device__ __forceinline__ void load_raw(const float* __restrict__ base, long long ld, int s_idx, int s_lim, int c0, int c_lim,
@@ -109,7 +114,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const GemmParams 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, G_PRODUCERS / 32);
+      mbar_init(bar_full + 8 * s, G_PRODUCERS / 32 + (p.bimg ? 1 : 0));   // + the bulk-copy issuer's arrive.expect_tx
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -177,7 +182,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const GemmParams 
       const Tile x = tile_of(t);
       const int m0 = x.m0, n0 = x.n0, nt = x.nt, kend = x.kend;
       const int bgroups = (x.nmma + 63) >> 6;
-      const int nb_pieces = TB ? x.nmma * 8 : bgroups * 512;      // B pieces of this tile per K block
+      const bool img = p.bimg != nullptr;
+      const int nb_pieces = img ? 0 : (TB ? x.nmma * 8 : bgroups * 512);      // B pieces of this tile per K block
+      const uint32_t b_tile_bytes = (uint32_t)(TB ? x.nmma * 128 : bgroups * 8192);
       for (int kb = 0; kb < x.nkb; ++kb) {
         const int k0 = x.kbeg + kb * G_KBLK;
         const uint32_t a_addr = smem_base + s * STAGE_BYTES, b_addr = a_addr + G_A_BYTES;
@@ -219,6 +226,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const GemmParams 
         for (int j = 0; j < BATCH; ++j) piece_load(j, v[j]);
         if (lane == 0) mbar_wait(bar_empty + 8 * s, ph ^ 1, 22);
         __syncwarp();
+        if (img && pt == 0) {     // this stage's B tile(s): bulk copies of the pre-packed image
+          const uint8_t* src = p.bimg + ((size_t)(n0 / p.ntile) * p.nkb_total + (size_t)(k0 / G_KBLK)) * (SPLIT ? 2 : 1) * G_BIMG_TILE;
+          mbar_expect_tx(bar_full + 8 * s, b_tile_bytes * (SPLIT ? 2u : 1u));
+          bulk_g2s(b_addr, src, b_tile_bytes, bar_full + 8 * s);
+          if (SPLIT) bulk_g2s(b_addr + LO_OFF, src + G_BIMG_TILE, b_tile_bytes, bar_full + 8 * s);
+        }
 #pragma unroll
         for (int j = 0; j < BATCH; ++j) piece_store(j, v[j]);
         if (nb_pieces > (BATCH - 4) * G_PRODUCERS) {
@@ -287,6 +300,30 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const GemmParams 
   __syncthreads();
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// B operand -> per (n tile, K block) fp16 tiles [hi][lo?] in the shared-memory layout of a stage (zero-filled outside
+// the matrix).  grid = (K blocks, n tiles).
+template <bool TB, bool SPLIT>
+__global__ void gemm_pack_b_kernel(int N, int K, const float* __restrict__ B, long long ldb, int ntile, int vec_ok,
+                                   uint8_t* __restrict__ img) {
+  const int kb = blockIdx.x, tn = blockIdx.y, nkb_total = gridDim.x;
+  const int n0 = tn * ntile, nt = min(ntile, N - n0), nmma = (nt + 15) & ~15, bgroups = (nmma + 63) >> 6;
+  const int k0 = kb * G_KBLK;
+  const int pieces = TB ? nmma * 8 : bgroups * 512;
+  uint8_t* dst = img + ((size_t)tn * nkb_total + kb) * (SPLIT ? 2 : 1) * G_BIMG_TILE;
+  for (int i = threadIdx.x; i < pieces; i += blockDim.x) {
+    const int c = i & 7, r = i >> 3;
+    float v[8];
+    if (TB) load_raw(B, ldb, n0 + r, n0 + nt, k0 + 8 * c, K, vec_ok != 0, v);
+    else load_raw(B, ldb, k0 + (r & 63), K, n0 + (r >> 6) * 64 + 8 * c, n0 + nt, vec_ok != 0, v);
+    uint4 lo;
+    const uint4 hi = cvt_piece<SPLIT>(v, lo);
+    const uint32_t off = TB ? (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4))
+                            : (uint32_t)((r >> 6) * 8192 + (r & 63) * 128 + ((c ^ (r & 7)) << 4));
+    *reinterpret_cast<uint4*>(dst + off) = hi;
+    if (SPLIT) *reinterpret_cast<uint4*>(dst + G_BIMG_TILE + off) = lo;
   }
 }
 
@@ -602,7 +639,12 @@ extern "C" size_t lstur_gemm_tc_workspace_bytes(int M, int N, int K) {
   gemm_tc_tiling(M, N, K, &nt, &sp);
   gemm_tc_tiling(M, N, K, &nt, &sp2, tc::GA_NT);
   if (sp2 > sp) sp = sp2;
-  return sp > 1 ? (size_t)sp * M * N * sizeof(float) : 0;
+  size_t b = sp > 1 ? (size_t)sp * M * N * sizeof(float) : 0;
+  // pre-packed weight-operand image (hi + lo tiles per (n tile, K block)) for the large-M GEMMs
+  gemm_tc_tiling(M, N, K, &nt, &sp);
+  const size_t img = (size_t)((N + nt - 1) / nt) * ((K + tc::G_KBLK - 1) / tc::G_KBLK) * 2 * tc::G_BIMG_TILE;
+  if (M >= 1024 && img > b) b = img;
+  return b;
 }
 
 // Same contract as lstur_gemm_f32 (fp32 in / fp32 out); operands are rounded to fp16 inside the kernel.
@@ -633,6 +675,7 @@ extern "C" int lstur_gemm_tc(int transA, int transB, int M, int N, int K, const 
   splits = K > 0 ? (K + kps - 1) / kps : 1;
   p.M = M; p.N = N; p.K = K; p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.bias = bias;
   p.flags = flags; p.k_per_split = kps; p.partial = (float*)workspace;
+  p.bimg = nullptr; p.nkb_total = (K + tc::G_KBLK - 1) / tc::G_KBLK;
   p.vec_ok = (lda % 4 == 0) && (ldb % 4 == 0) && ((((uintptr_t)A) & 15) == 0) && ((((uintptr_t)B) & 15) == 0);
   const bool split3 = (flags & LSTUR_GEMM_PRECISE) != 0;
   size_t smem = 1024 + (split3 ? (size_t)2 * tc::G_STAGE_BYTES_S3 : (size_t)tc::G_STAGES * tc::G_STAGE_BYTES) + 256;
@@ -654,6 +697,24 @@ extern "C" int lstur_gemm_tc(int transA, int transB, int M, int N, int K, const 
   p.tiles_n = (N + p.ntile - 1) / p.ntile;
   p.tiles_m = (M + tc::TILE_M - 1) / tc::TILE_M;
   p.splits = splits;
+  // Large-M GEMMs against a small weight matrix (GRU input projection and its input gradient, scorer Dense layers):
+  // pack B once per call into stage-layout fp16 tiles; the CTAs then fetch it with bulk copies.
+  static int img_mode = -1;
+  if (img_mode < 0) { const char* e = getenv("LSTUR_GEMM_BIMG"); img_mode = (e && atoi(e) == 0) ? 0 : 1; }
+  const size_t img_bytes = (size_t)p.tiles_n * p.nkb_total * (split3 ? 2 : 1) * tc::G_BIMG_TILE;
+  if (img_mode && !use_async && !transA && splits == 1 && M >= 1024 && K > 0 && workspace && img_bytes <= workspace_bytes) {
+    dim3 pg((unsigned)p.nkb_total, (unsigned)p.tiles_n);
+    uint8_t* img = (uint8_t*)workspace;
+    if (transB) {
+      if (split3) tc::gemm_pack_b_kernel<true, true><<<pg, 256, 0, stream>>>(N, K, B, ldb, p.ntile, p.vec_ok, img);
+      else tc::gemm_pack_b_kernel<true, false><<<pg, 256, 0, stream>>>(N, K, B, ldb, p.ntile, p.vec_ok, img);
+    } else {
+      if (split3) tc::gemm_pack_b_kernel<false, true><<<pg, 256, 0, stream>>>(N, K, B, ldb, p.ntile, p.vec_ok, img);
+      else tc::gemm_pack_b_kernel<false, false><<<pg, 256, 0, stream>>>(N, K, B, ldb, p.ntile, p.vec_ok, img);
+    }
+    LSTUR_CHECK_LAUNCH("lstur_gemm_tc(pack B)");
+    p.bimg = img;
+  }
   const long long n_tiles = (long long)p.tiles_m * p.tiles_n * splits;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);

@@ -390,7 +390,7 @@ def test_sigmoid_family_weighted_bce(L, arch, oarch, score_model, precision):
     loss = ot.weighted_bce(torch.tensor(y, dtype=torch.float64), out, gain=1.7, negative_samples=sh.K)
     tol = 5e-5 if precision == 'fp32' else TOL_SPEC
     assert rel(p_gpu, out.detach().numpy()) < tol
-    assert abs(loss_gpu - float(loss)) < tol * max(1.0, abs(float(loss)))
+    assert abs(loss_gpu - float(loss.detach())) < tol * max(1.0, abs(float(loss.detach())))
     ref = dict(zip(ora.trainable, torch.autograd.grad(loss, [ora.P[k] for k in ora.trainable], allow_unused=True)))
     gtol = 1e-4 if precision == 'fp32' else 2e-2
     for k, gr in ref.items():
