@@ -47,9 +47,10 @@ class _Core:
     """Weights + engines shared by `model` (softmax/CE training graph) and `test_model` (sigmoid scoring graph)."""
 
     def __init__(self, params, cfg, doc_tokens, has_user, arch, predict_rows=256, score_model='dot', loss='softmax',
-                 flavour='paper'):
+                 flavour='paper', has_vert=False):
         self.params, self.cfg, self.doc_tokens, self.has_user, self.arch = params, cfg, doc_tokens, has_user, arch
         self.score_model, self.loss, self.flavour = score_model, loss, flavour
+        self.has_vert = has_vert        # inputs carry vertical ids next to the titles (task/paper.py:1205-1232)
         self.optimizer = Adam(cfg.learning_rate)
         self.train_engine = None
         self.infer_engines = {}
@@ -96,14 +97,19 @@ class _Core:
         return dict(flavour=self.flavour, loss=self.loss, gain=self.cfg.gain, bce_neg=self.cfg.negative_samples)
 
     def split_inputs(self, x, n_cand):
+        """[user?, clicked, clicked_vert?, cand_0..cand_{C-1}, cand_vert_0..?] -> user, clicked, cand (B,C,L), verts."""
         x = list(x)
         user = np.asarray(x.pop(0)).reshape(-1) if self.has_user else None
-        clicked = np.asarray(x[0])
-        cands = x[1:1 + n_cand]
-        cand = np.stack([np.asarray(c) for c in cands], axis=1)         # (B, C, L)
+        clicked = np.asarray(x.pop(0))
+        verts = None
+        if self.has_vert:
+            hist_vert = np.asarray(x.pop(0)).reshape(clicked.shape[0], -1)
+            cand_vert = np.stack([np.asarray(v).reshape(-1) for v in x[n_cand:2 * n_cand]], axis=1)
+            verts = (hist_vert, cand_vert)
+        cand = np.stack([np.asarray(c) for c in x[:n_cand]], axis=1)     # (B, C, L)
         if user is None:
             user = np.zeros(clicked.shape[0], dtype=np.int32)
-        return user, clicked, cand
+        return user, clicked, cand, verts
 
 
 class Model:
@@ -125,10 +131,12 @@ class Model:
         assert self.is_train, 'test_model is not compiled for training'
         core = self.core
         C = core.n_train_cand()
-        user, clicked, cand = core.split_inputs(x, C)
+        user, clicked, cand, verts = core.split_inputs(x, C)
         eng = core.engine_train(clicked.shape[0])
         eng.lr = core.optimizer.lr.value
         batch = dict(user=user, hist_tok=clicked, cand_tok=cand, label=np.asarray(y, dtype=np.float32).reshape(len(clicked), C))
+        if verts is not None:
+            batch['hist_vert'], batch['cand_vert'] = verts
         if core.arch == 'dgru':     # Dropout(0.5, noise_shape=(None, 1)) on the user vector (task/paper.py:609)
             batch['user_scale'] = (np.random.random(clicked.shape[0]) >= 0.5).astype(np.float32) * 2.0
         db = eng.to_device_batch(batch)
@@ -171,7 +179,7 @@ class Model:
     # ---- inference --------------------------------------------------------------------------
     def _forward_chunks(self, x, n_cand):
         core = self.core
-        user, clicked, cand = core.split_inputs(x, n_cand)
+        user, clicked, cand, verts = core.split_inputs(x, n_cand)
         n = clicked.shape[0]
         eng = core.engine_infer(n_cand)
         R = eng.B
@@ -181,7 +189,12 @@ class Model:
             u = np.zeros(R, dtype=np.int32); u[:m] = user[s:s + m]
             h = np.zeros((R,) + clicked.shape[1:], dtype=np.int32); h[:m] = clicked[s:s + m]
             c = np.zeros((R,) + cand.shape[1:], dtype=np.int32); c[:m] = cand[s:s + m]
-            db = eng.to_device_batch(dict(user=u, hist_tok=h, cand_tok=c))
+            b = dict(user=u, hist_tok=h, cand_tok=c)
+            if verts is not None:
+                hv = np.zeros((R, verts[0].shape[1]), dtype=np.int32); hv[:m] = verts[0][s:s + m]
+                cv = np.zeros((R, n_cand), dtype=np.int32); cv[:m] = verts[1][s:s + m]
+                b['hist_vert'], b['cand_vert'] = hv, cv
+            db = eng.to_device_batch(b)
             probs = eng.forward(db, training=False)
             out = probs if (self.is_train or core.loss == 'bce') else eng.score_sigmoid()
             outs.append(out[:m].cpu().numpy().copy())
@@ -216,7 +229,8 @@ class Model:
         return list(tot / max(1, steps))
 
     # ---- weights / structure ------------------------------------------------------------------
-    WEIGHT_ORDER = ('word_emb', 'conv_w', 'conv_b', 'att_w', 'att_b', 'dense_w', 'dense_b', 'user_emb', 'user_emb2',
+    WEIGHT_ORDER = ('word_emb', 'conv_w', 'conv_b', 'att_w', 'att_b', 'dense_w', 'dense_b', 'vert_emb', 'subvert_emb', 'user_emb',
+                    'user_emb2',
                     'gru_wx', 'gru_wh', 'gru_b', 'con_w', 'con_b', 'sh_w', 'sh_b', 'so_w', 'so_b', 'su_w', 'su_b', 'sd_w',
                     'sd_b')
 
@@ -285,7 +299,10 @@ class DocEncoderModel:
             m = min(R, titles.shape[0] - s)
             c = np.zeros((R, 1, titles.shape[1]), dtype=np.int32); c[:m, 0] = titles[s:s + m]
             h = np.zeros((R, eng.W, titles.shape[1]), dtype=np.int32)
-            eng.forward(eng.to_device_batch(dict(user=np.zeros(R, dtype=np.int32), hist_tok=h, cand_tok=c)))
-            dv = eng.view('doc_vec').reshape(-1, eng.D)[R * eng.W:]
+            b = dict(user=np.zeros(R, dtype=np.int32), hist_tok=h, cand_tok=c)
+            if core.has_vert:       # the doc_encoder layer is the title encoder alone: vertical columns are dropped below
+                b['hist_vert'], b['cand_vert'] = np.zeros((R, eng.W), dtype=np.int32), np.zeros((R, 1), dtype=np.int32)
+            eng.forward(eng.to_device_batch(b))
+            dv = eng.view('doc_vec').reshape(-1, eng.D)[R * eng.W:, :eng.cfg.Dd]
             outs.append(dv[:m].cpu().numpy().copy())
         return np.concatenate(outs)

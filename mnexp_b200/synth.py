@@ -118,7 +118,7 @@ def _orthogonal(rng, rows, cols):
 
 
 def make_weights(shape, arch=None, seed=1237, word_emb=None, score_model='dot', cook=False,
-                 dv=15, ds=35, bias_noise=0.0):
+                 dv=15, ds=35, bias_noise=0.0, paper_vert=0):
     """Keras-initialised parameter dict (names: oracle/lstur_numpy.py docstring).
 
     bias_noise > 0 replaces the all-zero bias initialisers by small normals so
@@ -141,6 +141,10 @@ def make_weights(shape, arch=None, seed=1237, word_emb=None, score_model='dot', 
         D = U
         P['dense_w'] = _glorot(rng, (F, U), F, U)
         P['dense_b'] = bz(U)
+        if paper_vert:      # Seq2VecPaperSoftmaxDaysIdVert (task/paper.py:1205-1232): [Dense(U)(title) ‖ Vemb[vertical]], and
+            D = U + paper_vert          # the user encoder is built with user_embedding_dim + vertical_embedding_dim
+            P['vert_emb'] = rng.uniform(-0.05, 0.05, (16, paper_vert)).astype(np.float32)
+            U = U + paper_vert
     G = U // 2 if arch == 'hgru' else U
     Ue = U // 2 if arch == 'hgru' else U
     if arch not in ('nigru', 'niavg'):
@@ -183,7 +187,8 @@ def write_docmeta_tsv(path, tok, vert=None, subvert=None):
     with open(path, 'w') as f:
         for i in range(1, tok.shape[0]):
             t = ' '.join(str(int(x)) for x in tok[i] if x != 0)
-            f.write('d%d\t%d\tv%d\ts%d\t%s\t%s\n' % (i, i, 0 if vert is None else vert[i],
+            from .utils import VERTICAL_NAMES
+            f.write('d%d\t%d\t%s\ts%d\t%s\t%s\n' % (i, i, VERTICAL_NAMES[0 if vert is None else int(vert[i])],
                                                       0 if subvert is None else subvert[i], t, t))
 
 

@@ -380,4 +380,60 @@ class Seq2VecPaperSoftmaxDays(_DaysWindowMixin, Seq2VecPaperSoftmax):
 
 
 class Seq2VecPaperSoftmaxDaysId(_DaysWindowMixin, Seq2VecPaperSoftmaxId):
-    """task/paper.py:753-881 (the vertical / subvertical columns of its DocMeta are read by the *Vert* subclasses only)."""
+    """task/paper.py:753-881: time windows + the vertical column of DocMeta on every document (:793-822)."""
+
+    class News:
+        __slots__ = ['title', 'body', 'vertical']
+
+        def __init__(self, title, body, vertical=0):
+            self.title, self.body, self.vertical = title, body, vertical
+
+    def _load_docs(self):
+        super(Seq2VecPaperSoftmaxDaysId, self)._load_docs()
+        with open(self.config.doc_meta_input) as file:
+            for line in file:
+                line = line.strip('\n').split('\t')
+                self.docs[int(line[1])].vertical = utils.get_vertical(line[2])
+
+
+class Seq2VecPaperSoftmaxDaysIdVert(Seq2VecPaperSoftmaxDaysId):
+    """task/paper.py:1138-1255: news vector = [Dense(U)(title) ‖ Vemb[vertical]] for history and candidates; the user
+    encoder is built with user_embedding_dim + vertical_embedding_dim.  Inputs:
+    [user, clicked, clicked_vert, cand_0..K, cand_vert_0..K]; test model [user, clicked, clicked_vert, cand, cand_vert]."""
+
+    def _w_vert(self, ch, impression):
+        return [self.docs[i].vertical for i in ch.get_ids(impression.time)]
+
+    def _sample(self, user, ch, pos, impression, label):
+        negs = impression.negative_samples(self.config.negative_samples)
+        return [user, self._w_title(ch, impression), self._w_vert(ch, impression), self.docs[pos].title] + \
+               [self.docs[neg].title for neg in negs] + [self.docs[pos].vertical] + \
+               [self.docs[neg].vertical for neg in negs] + [label]
+
+    def test_gen(self):
+        for user, (ih1, ih2) in enumerate(self.data):
+            if ih1 and ih2:
+                ch = self._new_window()
+                for impression in ih1:
+                    for pos in impression.pos:
+                        self._w_push(ch, pos, impression)
+                for impression in ih2:
+                    clicked, cv = self._w_title(ch, impression), self._w_vert(ch, impression)
+                    yield [(user, clicked, cv, self.docs[p].title, self.docs[p].vertical, 1) for p in impression.pos] + \
+                          [(user, clicked, cv, self.docs[n].title, self.docs[n].vertical, 0) for n in impression.neg]
+                    for pos in impression.pos:
+                        self._w_push(ch, pos, impression)
+
+    def _init_params(self):
+        c = self.config
+        F, k = c.title_filter_shape
+        word_emb = self._title_embedding().astype(np.float32)
+        sh = synth.Shape('cfg', n_users=len(self.data), n_news=self.doc_count - 1, vocab=word_emb.shape[0],
+                         L=c.title_shape, W=c.window_size, K=c.negative_samples, B=c.batch_size, E=word_emb.shape[1],
+                         F=F, k=k, U=c.user_embedding_dim, arch=self._engine_arch())
+        return synth.make_weights(sh, arch=self._engine_arch(), seed=np.random.randint(1 << 30), word_emb=word_emb,
+                                  score_model=c.score_model, paper_vert=c.vertical_embedding_dim)
+
+    def _build_model(self):
+        super(Seq2VecPaperSoftmaxDaysIdVert, self)._build_model()
+        self._core.has_vert = True

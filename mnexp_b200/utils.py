@@ -91,3 +91,13 @@ def load_model(paths):
         weights = pickle.load(file)
     assert len(weights) == len(config['weight_names'])
     return LoadedModel(config, weights)
+
+
+# ---- vertical ids of DocMeta column 2 (utils.py:153-155; 'N/A' and unknown names map to 0) ------------------------
+VERTICAL_NAMES = ('N/A', 'autos', 'entertainment', 'finance', 'foodanddrink', 'health', 'kids', 'lifestyle', 'movies',
+                  'music', 'news', 'sports', 'travel', 'tv', 'video', 'weather')
+verticals = {name: i for i, name in enumerate(VERTICAL_NAMES)}
+
+
+def get_vertical(name):
+    return verticals.get(name, 0)

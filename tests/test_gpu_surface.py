@@ -400,3 +400,31 @@ def test_cook_handler(lib, arch, oarch, score_model, vtype):
     feats, (users, imprs, mask, y_true) = h.test()
     pred = h.test_model.predict(feats).reshape(-1)
     assert pred.shape == y_true.shape and np.all((pred > 0) & (pred < 1))
+
+
+def test_days_id_vert_surface(lib):
+    """Seq2VecPaperSoftmaxDaysIdVert (task/paper.py:1138-1255): vertical ids ride next to the titles; news vector =
+    [Dense(U)(title) ‖ Vemb[vertical]]; user encoder widened by vertical_embedding_dim."""
+    sh, h = _handler('igru', 'Seq2VecPaperSoftmaxDaysIdVert', days=100000, vertical_embedding_dim=4)
+    model = h.build_model(0)
+    x, y = next(h.train)
+    C = 1 + sh.K
+    assert len(x) == 3 + 2 * C and x[2].shape == (8, sh.W) and x[3 + C].shape == (8,)
+    assert set(np.unique(x[2])) <= set(range(16)) and (x[2][x[1].any(-1) == 0] == 0).all()     # pad slots: vertical 'N/A'
+    P = _oracle_params(model)
+    P['vert_emb'] = model._current()['vert_emb']
+    assert P['vert_emb'].shape == (16, 4) and P['gru_wh'].shape[0] == sh.U + 4
+    cands, cverts = np.stack(x[3:3 + C], 1), np.stack(x[3 + C:], 1)
+    ref = on.lstur_forward(P, x[0], x[1].astype(int), cands.astype(int), arch='igru', aux=True, hist_vert=x[2],
+                           cand_vert=cverts)
+    assert rel(model.predict(x), ref['probs']) < 2e-5
+    s = h.test_model.predict(x[:3] + [x[3], x[3 + C]])
+    assert s.shape == (8, 1) and rel(s[:, 0], ref['sigmoid'][:, 0]) < 2e-5
+    l0 = model.evaluate(x, y)[0]
+    for _ in range(25):
+        model.train_on_batch(x, y)
+    assert model.evaluate(x, y)[0] < l0
+    h.callback(0)            # swaps in test_model and ranks the validation impressions (task/paper.py:497-524)
+    assert 0.0 <= h.last_evaluation['auc'] <= 1.0 and h.model is model
+    dv = model.get_layer('doc_encoder').predict(x[1][0])
+    assert dv.shape == (sh.W, sh.U)
