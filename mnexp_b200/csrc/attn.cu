@@ -214,15 +214,16 @@ __global__ void __launch_bounds__(IMG_THREADS)
 attn_bwd_img_kernel(int N, int L, int F, const CT* __restrict__ Cd, const float* __restrict__ a_in,
                     const float* __restrict__ w_in, const float* __restrict__ dp, long long lddp,
                     const float* __restrict__ ka, uint8_t* __restrict__ img, float inv_keep,
-                    float* __restrict__ partials) {
+                    float* __restrict__ partials, int nbuf) {
   extern __shared__ __align__(16) uint8_t att_smem[];
   const int nchunk = F >> 3;                       // 16-byte chunks per row
   // Two title buffers: the (contiguous, L*F*2-byte) saved C of the NEXT title is fetched with one bulk copy while the
   // current one is processed; its d_pooled row and attention weights are prefetched into registers.
   const size_t buf_bytes = (size_t)32 * nchunk * 16;
-  float* sdp = reinterpret_cast<float*>(att_smem + 2 * buf_bytes);   // [F]
+  // nbuf = 2: the next title is fetched while the current one is processed; nbuf = 1: one buffer, more CTAs per SM
+  float* sdp = reinterpret_cast<float*>(att_smem + nbuf * buf_bytes);   // [F]
   float* ska = sdp + F;                                              // [F]
-  float* sred = ska + F;                                             // [3][64][16] reduction scratch
+  float* sred = reinterpret_cast<float*>(att_smem);                  // [3][64][16] reduction scratch, after the title loop
   __shared__ float sdw[32], sdz[32], sw[32];
   __shared__ __align__(8) unsigned long long s_bar[2];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -268,11 +269,15 @@ attn_bwd_img_kernel(int N, int L, int F, const CT* __restrict__ Cd, const float*
   uint32_t phase[2] = {0, 0};
   int it = 0;
   for (int n = blockIdx.x; n < N; n += gridDim.x, ++it) {
-    const int b = it & 1;
+    const int b = nbuf == 2 ? (it & 1) : 0;
     const uint4* sC = reinterpret_cast<const uint4*>(att_smem + b * buf_bytes);  // [L][nchunk]
     __syncthreads();   // previous title fully consumed: its buffer, sdp and sw may be overwritten
     const int n_next = n + gridDim.x;
-    if (tid == 0 && n_next < N) fetch_title(n_next, b ^ 1);
+    if (nbuf == 2) {
+      if (tid == 0 && n_next < N) fetch_title(n_next, b ^ 1);
+    } else if (it > 0) {
+      if (tid == 0) fetch_title(n, 0);
+    }
 #pragma unroll
     for (int i = 0; i < DPR; ++i) {
       const int f = tid + i * IMG_THREADS;
@@ -407,13 +412,22 @@ extern "C" int lstur_attn_pool_fwd(int N, int L, int F, float* C, long long titl
   return LSTUR_OK;
 }
 
-// CTAs of the attention-backward kernels: 3 per SM (shared memory: two 25.6 KB title buffers + 7 KB per CTA at F=400)
+// CTAs of the attention-backward kernels: 4 per SM (shared memory: two 25.6 KB title buffers + 3.2 KB per CTA at F=400;
+// the final reduction scratch aliases the title buffers)
+static int attn_bwd_nbuf() {
+  static int nbuf = 0;
+  if (!nbuf) {
+    const char* e = getenv("LSTUR_ATTN_NBUF");
+    nbuf = (e && atoi(e) == 1) ? 1 : 2;
+  }
+  return nbuf;
+}
 extern "C" int lstur_attn_bwd_grid(int N) {
   static int per_sm = 0;
   if (!per_sm) {
     const char* e = getenv("LSTUR_ATTN_CTAS_PER_SM");
-    per_sm = e ? atoi(e) : 3;
-    if (per_sm < 1 || per_sm > 16) per_sm = 3;
+    per_sm = e ? atoi(e) : 4;
+    if (per_sm < 1 || per_sm > 16) per_sm = 4;
   }
   return N < 148 * per_sm ? (N > 0 ? N : 1) : 148 * per_sm;
 }
@@ -520,18 +534,20 @@ extern "C" int lstur_attn_pool_bwd_img(int fp16, int N, int L, int F, const void
     return LSTUR_OK;
   }
   const float inv_keep = 1.f / (1.f - dropout);
-  size_t smem = (size_t)2 * 32 * (F / 8) * 16 + (size_t)2 * F * sizeof(float) + (size_t)3 * 64 * 16 * sizeof(float);
+  const int nbuf = attn_bwd_nbuf();
+  size_t smem = (size_t)nbuf * 32 * (F / 8) * 16 + (size_t)2 * F * sizeof(float);
+  if (smem < (size_t)3 * 64 * 16 * sizeof(float)) smem = (size_t)3 * 64 * 16 * sizeof(float);   // the final reduction scratch aliases the title buffers
   if (smem > 48 * 1024) {
     cudaFuncSetAttribute(attn_bwd_img_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(attn_bwd_img_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
   if (fp16)
     attn_bwd_img_kernel<__half><<<grid, IMG_THREADS, smem, stream>>>(N, L, F, (const __half*)Cd_16, a_in, w_in, d_pooled, lddp,
-                                                                     att_w, (uint8_t*)dpre_img, inv_keep, partials);
+                                                                     att_w, (uint8_t*)dpre_img, inv_keep, partials, nbuf);
   else
     attn_bwd_img_kernel<__nv_bfloat16><<<grid, IMG_THREADS, smem, stream>>>(N, L, F, (const __nv_bfloat16*)Cd_16, a_in, w_in,
                                                                             d_pooled, lddp, att_w, (uint8_t*)dpre_img,
-                                                                            inv_keep, partials);
+                                                                            inv_keep, partials, nbuf);
   LSTUR_CHECK_LAUNCH("lstur_attn_pool_bwd_img");
   attn_bwd_reduce_kernel<<<cdiv(2 * F + 1, 128), 128, 0, stream>>>(grid, F, partials, d_att_w, d_conv_b, d_att_b, accumulate);
   LSTUR_CHECK_LAUNCH("lstur_attn_pool_bwd_img(reduce)");
