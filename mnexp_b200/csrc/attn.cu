@@ -195,8 +195,12 @@ __device__ __forceinline__ uint4 pack8<__half>(const float* v) {
   uint4 u;
   __half2* h = reinterpret_cast<__half2*>(&u);
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    h[i] = __floats2half2_rn(fminf(fmaxf(v[2 * i], -65504.f), 65504.f), fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f));
+  for (int i = 0; i < 4; ++i) {     // saturating conversion in one instruction per pair
+    uint32_t w;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(v[2 * i + 1]), "f"(v[2 * i]));
+    reinterpret_cast<uint32_t*>(&u)[i] = w;
+  }
+  (void)h;
   return u;
 }
 template <>
@@ -310,7 +314,10 @@ attn_bwd_img_kernel(int N, int L, int F, const CT* __restrict__ Cd, const float*
         dpa[k][0] = lo.x; dpa[k][1] = lo.y; dpa[k][2] = lo.z; dpa[k][3] = lo.w;
         dpa[k][4] = hi.x; dpa[k][5] = hi.y; dpa[k][6] = hi.z; dpa[k][7] = hi.w;
       }
-      for (int t = warp; t < L; t += IMG_THREADS / 32) {
+#pragma unroll
+      for (int tt = 0; tt < 4; ++tt) {
+        const int t = warp + tt * (IMG_THREADS / 32);
+        if (t >= L) break;
         float dot = 0.f;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -337,12 +344,17 @@ attn_bwd_img_kernel(int N, int L, int F, const CT* __restrict__ Cd, const float*
     }
     __syncthreads();
     if (c_ok) {
+      // d_pooled and the attention vector of this chunk, times the dropout keep scale.  (Packed fma.rn.f32x2 arithmetic
+      // was measured here: 3 % slower — the pack/unpack moves cost more issue slots than the pairing saves.)
       float dpf[8], kaf[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { dpf[i] = sdp[c * 8 + i]; kaf[i] = ska[c * 8 + i]; }
+      for (int i = 0; i < 8; ++i) { dpf[i] = sdp[c * 8 + i] * inv_keep; kaf[i] = ska[c * 8 + i] * inv_keep; }
       const int hf = (c * 8 >= Fh) ? 1 : 0, fl = c * 8 - hf * Fh;
       const int g = hf * ngh + (fl >> 6), piece = (fl & 63) >> 3;
-      for (int t = tg; t < 32; t += 4) {
+      uint8_t* dst0 = img + (long long)n * blk_bytes + (long long)g * 4096;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int t = tg + 4 * k;
         float o[8];
         if (t < L) {
           float v[8];
@@ -351,7 +363,7 @@ attn_bwd_img_kernel(int N, int L, int F, const CT* __restrict__ Cd, const float*
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float gi = fmaf(wt, dpf[i], dzt * kaf[i]);
-            o[i] = v[i] > 0.f ? gi * inv_keep : 0.f;
+            o[i] = v[i] > 0.f ? gi : 0.f;
             dka[i] = fmaf(dzt, v[i], dka[i]);
             dbc[i] += o[i];
           }
@@ -359,8 +371,7 @@ attn_bwd_img_kernel(int N, int L, int F, const CT* __restrict__ Cd, const float*
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] = 0.f;
         }
-        uint8_t* dst = img + (long long)n * blk_bytes + (long long)g * 4096 + t * 128 + ((piece ^ (t & 7)) << 4);
-        *reinterpret_cast<uint4*>(dst) = pack8<CT>(o);
+        *reinterpret_cast<uint4*>(dst0 + t * 128 + ((piece ^ (t & 7)) << 4)) = pack8<CT>(o);
       }
     }
   }
