@@ -140,6 +140,7 @@ def test_gru_row_order_is_a_pure_permutation(lib):
     (300, 20, 64, True, 'hard_sigmoid', 'left'),
     (1024, 50, 200, True, 'hard_sigmoid', 'left'),
     (130, 9, 224, True, 'sigmoid', 'left'),               # largest width whose weights fit tensor memory
+    (40, 200, 64, True, 'hard_sigmoid', 'left'),          # C5 window
 ])
 def test_gru_tensor_core_recurrence_vs_oracle(lib, B, W, G, ini, act, pad):
     """tcgen05 recurrence (3-term fp16 split of Wh and of the state, fp32 accumulate): fp32-like accuracy."""
@@ -174,6 +175,7 @@ def test_gru_tensor_core_row_order(lib):
     (300, 20, 64, True, 'hard_sigmoid', 'left', 1.0),
     (1024, 50, 200, True, 'hard_sigmoid', 'left', 1.0 / 1024),
     (130, 9, 224, True, 'sigmoid', 'left', 1.0),
+    (40, 200, 64, True, 'hard_sigmoid', 'holes', 1.0),
 ])
 def test_gru_tensor_core_bptt_vs_oracle(lib, impl, B, W, G, ini, act, pad, gscale):
     """tcgen05 BPTT: weights enter as fp16 (2^-12 relative rounding, like the other tensor-core-mode backward GEMMs), the
