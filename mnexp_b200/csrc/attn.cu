@@ -161,13 +161,22 @@ __global__ void colsum_stage1_kernel(long long rows, int cols, const float* __re
   for (long long r = r0; r < r1; ++r) s += in[r * ld + c];
   partial[(long long)blockIdx.y * cols + c] = s;
 }
+// 256 threads = 32 columns x 8 chunk strides, stride sums combined in ascending order (fixed order, deterministic)
 __global__ void colsum_stage2_kernel(int chunks, int cols, const float* __restrict__ partial, float* __restrict__ out,
                                      int accumulate) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+  __shared__ float sm[8][32];
+  const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int k = 0; k < chunks; ++k) s += partial[(long long)k * cols + c];
-  out[c] = accumulate ? out[c] + s : s;
+  if (c < cols)
+    for (int k = part; k < chunks; k += 8) s += partial[(long long)k * cols + c];
+  sm[part][lane] = s;
+  __syncthreads();
+  if (part != 0 || c >= cols) return;
+  float t = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) t += sm[q][lane];
+  out[c] = accumulate ? out[c] + t : t;
 }
 
 // Tensor-core-mode backward (v2): the title's 16-bit C tile is staged once in shared memory with 16-byte loads,
@@ -396,15 +405,24 @@ attn_bwd_img_kernel(int N, int L, int F, const CT* __restrict__ Cd, const float*
   if (tid == 0) out[2 * F] = dba;
 }
 
-// partials[grid][2F+1] -> d_att_w[F], d_conv_b[F], d_att_b[1] in a fixed order.
+// partials[grid][2F+1] -> d_att_w[F], d_conv_b[F], d_att_b[1] in a fixed order: 256 threads = 32 columns x 8 row
+// strides; the eight stride sums of a column are combined in ascending order.
 __global__ void attn_bwd_reduce_kernel(int grid, int F, const float* __restrict__ partials, float* __restrict__ d_att_w,
                                        float* __restrict__ d_conv_b, float* __restrict__ d_att_b, int accumulate) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c > 2 * F) return;
+  __shared__ float sm[8][32];
+  const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int g = 0; g < grid; ++g) s += partials[(long long)g * (2 * F + 1) + c];
+  if (c <= 2 * F)
+    for (int g = part; g < grid; g += 8) s += partials[(long long)g * (2 * F + 1) + c];
+  sm[part][lane] = s;
+  __syncthreads();
+  if (part != 0 || c > 2 * F) return;
+  float t = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) t += sm[q][lane];
   float* dst = c < F ? d_att_w + c : (c < 2 * F ? d_conv_b + (c - F) : d_att_b);
-  *dst = accumulate ? *dst + s : s;
+  *dst = accumulate ? *dst + t : t;
 }
 
 }  // namespace lstur
@@ -455,7 +473,7 @@ extern "C" int lstur_colsum(long long rows, int cols, const float* in, long long
   dim3 g1(cdiv(cols, 128), chunks);
   colsum_stage1_kernel<<<g1, 128, 0, stream>>>(rows, cols, in, ld, rpc, workspace);
   LSTUR_CHECK_LAUNCH("lstur_colsum(stage1)");
-  colsum_stage2_kernel<<<cdiv(cols, 128), 128, 0, stream>>>(chunks, cols, workspace, out, accumulate);
+  colsum_stage2_kernel<<<cdiv(cols, 32), 256, 0, stream>>>(chunks, cols, workspace, out, accumulate);
   LSTUR_CHECK_LAUNCH("lstur_colsum(stage2)");
   return LSTUR_OK;
 }
@@ -500,7 +518,7 @@ static int attn_pool_bwd_impl(int c_is_bf16, int out_mode, int N, int L, int Lro
 #undef LAUNCH
 #undef LAUNCH_T
   LSTUR_CHECK_LAUNCH("lstur_attn_pool_bwd");
-  attn_bwd_reduce_kernel<<<cdiv(2 * F + 1, 128), 128, 0, stream>>>(grid, F, partials, d_att_w, d_conv_b, d_att_b,
+  attn_bwd_reduce_kernel<<<cdiv(2 * F + 1, 32), 256, 0, stream>>>(grid, F, partials, d_att_w, d_conv_b, d_att_b,
                                                                      accumulate);
   LSTUR_CHECK_LAUNCH("lstur_attn_pool_bwd(reduce)");
   return LSTUR_OK;
@@ -560,7 +578,7 @@ extern "C" int lstur_attn_pool_bwd_img(int fp16, int N, int L, int F, const void
                                                                             d_pooled, lddp, att_w, (uint8_t*)dpre_img,
                                                                             inv_keep, partials, nbuf);
   LSTUR_CHECK_LAUNCH("lstur_attn_pool_bwd_img");
-  attn_bwd_reduce_kernel<<<cdiv(2 * F + 1, 128), 128, 0, stream>>>(grid, F, partials, d_att_w, d_conv_b, d_att_b, accumulate);
+  attn_bwd_reduce_kernel<<<cdiv(2 * F + 1, 32), 256, 0, stream>>>(grid, F, partials, d_att_w, d_conv_b, d_att_b, accumulate);
   LSTUR_CHECK_LAUNCH("lstur_attn_pool_bwd_img(reduce)");
   return LSTUR_OK;
 }

@@ -453,8 +453,9 @@ __global__ void __launch_bounds__(THREADS, 1) gru_fwd_tc_kernel(const Params p) 
 //   dah, daz (elementwise) -> own slice of S_dah / S_daz -> peers;   phase A:  drh_k = sum_j dah_j Wh[k][2G+j]  (critical)
 //   and, behind it on the tensor core, dhp_k = sum_j daz_j Wh[k][j];  dar = drh * hp * act'(r) -> S_dar -> peers;
 //   phase B: dhp_k += sum_j dar_j Wh[k][G+j].   The three weight slices (rows k of Wh, fp16) stay in tensor memory; the
-// exchanged operands are fp16 hi + lo of the value times a per-tile power of two (set from max|dhT| of the tile's rows,
-// so the fp16 range is centred on the tile's gradients; conversions saturate), i.e. 2 MMAs per k step:
+// exchanged operands are fp16 hi + lo of the value times a power of two that follows the cluster-wide max |d h| (the
+// CTAs' maxima ride along with the slices, one step of lag; first step: max|dhT| of the tile), so the fp16 range stays
+// centred on the gradients however they decay or grow over the window; conversions saturate.  2 MMAs per k step:
 // W_hi.S_hi + W_hi.S_lo.  The weight rounding (2^-12 relative) is that of every other backward GEMM of the tensor-core
 // modes.  Matrix rows 64..127 repeat rows 0..63, so all eight epilogue warps read accumulators (8 batch rows each).
 // S_daz is double-buffered by step parity: its MMAs run off the critical path and may still be in flight when the
@@ -473,7 +474,7 @@ constexpr int BROWS = 8;            // batch rows per epilogue thread in the bac
 
 __host__ __device__ inline size_t bwd_smem_bytes(int G, int W) {
   const int KS16 = (G + 15) / 16;
-  return (size_t)10 * KS16 * 1024 + (size_t)W * NROWS + (size_t)((W + 15) / 16) * 16 + 256 + 1024;
+  return (size_t)10 * KS16 * 1024 + (size_t)W * NROWS + (size_t)((W + 15) / 16) * 16 + 512 + 1024;
 }
 
 __global__ void __launch_bounds__(THREADS, 1) gru_bwd_tc_kernel(const BwdParams p) {
@@ -493,7 +494,10 @@ __global__ void __launch_bounds__(THREADS, 1) gru_bwd_tc_kernel(const BwdParams 
   const uint32_t bar_a = smem_base + oBar, bar_r = bar_a + 8, bar_dA = bar_a + 16, bar_dB = bar_a + 24;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + oBar + 32);
   float* sMax = reinterpret_cast<float*>(sm + oBar + 40);
+  uint32_t* sLmax = reinterpret_cast<uint32_t*>(sm + oBar + 44);   // max |d h| of this CTA's units (float bits)
   int* sRow = reinterpret_cast<int*>(sm + oBar + 64);
+  float* sPeer = reinterpret_cast<float*>(sm + oBar + 256);        // [step parity][rank][4]: the CTAs' max |d h|
+  const uint32_t sPeer_addr = smem_base + oBar + 256;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rank = (int)cluster_ctarank();
@@ -509,6 +513,8 @@ __global__ void __launch_bounds__(THREADS, 1) gru_bwd_tc_kernel(const BwdParams 
     mbar_init(bar_dA, 1);
     mbar_init(bar_dB, 1);
     *sMax = 0.f;
+    *sLmax = 0u;
+    for (int i = 0; i < 32; ++i) sPeer[i] = 0.f;
     fence_barrier_init();
   }
   if (warp == 8) {
@@ -579,18 +585,20 @@ __global__ void __launch_bounds__(THREADS, 1) gru_bwd_tc_kernel(const BwdParams 
   tc_fence_after();
   fence_proxy_async();
   cluster_sync_all();
-  // scale = 2^e with max * scale in [2^3, 2^4)
+  // scale = 2^e with max * scale in [2^3, 2^4).  The first step takes it from max |dhT| of the tile; every later step
+  // from the cluster-wide max |d h| the CTAs exchanged one step earlier (so vanishing or growing gradients over long
+  // windows stay inside the fp16 range; one update of lag is covered by the 2^12 headroom).
   float scale = 1.f, inv_scale = 1.f;
-  {
-    const float mx = *sMax;
+  auto set_scale = [&](float mx, float& sc, float& isc) {
     if (mx > 0.f && mx < 3.0e38f) {
       int e;
       frexpf(mx, &e);                       // mx = f * 2^e, f in [0.5, 1)
-      e = max(-100, min(100, 4 - e));
-      scale = ldexpf(1.f, e);
-      inv_scale = ldexpf(1.f, -e);
+      e = max(-120, min(120, 4 - e));
+      sc = ldexpf(1.f, e);
+      isc = ldexpf(1.f, -e);
     }
-  }
+  };
+  set_scale(*sMax, scale, inv_scale);
   auto send_op = [&](uint32_t S, uint32_t bar) {      // hi and lo slices of one operand to every peer
     if (own_bytes) {
 #pragma unroll
@@ -674,6 +682,15 @@ __global__ void __launch_bounds__(THREADS, 1) gru_bwd_tc_kernel(const BwdParams 
       rowoff[i] = (b >= 0 && act) ? (long long)b * W * G + k : -1;
       dh[i] = rowoff[i] >= 0 ? p.dhT[(long long)b * p.lddh + k] : 0.f;
     }
+    auto publish_local_max = [&]() {      // this thread's max |d h| -> CTA-wide max (completed by the next CTA barrier)
+      float mx = 0.f;
+#pragma unroll
+      for (int i = 0; i < BROWS; ++i) mx = fmaxf(mx, fabsf(dh[i]));
+#pragma unroll
+      for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (lane == 0 && mx > 0.f && mx < 3.0e38f) atomicMax(sLmax, __float_as_uint(mx));
+    };
+    publish_local_max();
     auto load_saved = [&](int t, float* z, float* r, float* hh, float* hp) {
 #pragma unroll
       for (int i = 0; i < BROWS; ++i) {
@@ -704,7 +721,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_bwd_tc_kernel(const BwdParams 
           }
     };
     zero_steps(W, t);
-    uint32_t ph_dA = 0, ph_dB = 0, par = 0;
+    uint32_t ph_dA = 0, ph_dB = 0, ph_a = 0, par = 0;
     while (t >= 0) {
       float z[BROWS], r[BROWS], hh[BROWS], hp[BROWS], dah[BROWS], daz[BROWS];
       uint32_t onmask = 0;
@@ -722,9 +739,18 @@ __global__ void __launch_bounds__(THREADS, 1) gru_bwd_tc_kernel(const BwdParams 
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (tid == 0) {
-        mbar_arrive_expect(bar_a, 2 * xbytes);
+        const uint32_t slot = (par * 4 + (uint32_t)rank) * 16;
+        sPeer[slot / 4] = __uint_as_float(*sLmax);      // this CTA's max |d h| rides with the slices
+        *sLmax = 0u;
+        fence_proxy_async();
+        mbar_arrive_expect(bar_a, 2 * xbytes + 3 * 16);
         send_op(S_dah, bar_a);
         send_op(S_daz + par * 2 * s_bytes, bar_a);
+#pragma unroll
+        for (int c = 1; c < CS; ++c) {
+          const uint32_t peer = (uint32_t)((rank + c) % CS);
+          bulk_s2peer(map_to_cta(sPeer_addr + slot, peer), sPeer_addr + slot, 16, map_to_cta(bar_a, peer));
+        }
       }
       // off the critical path: this step's dA (z and candidate parts), the next active step's saved activations
       const int tn = next_active(t);
@@ -740,6 +766,14 @@ __global__ void __launch_bounds__(THREADS, 1) gru_bwd_tc_kernel(const BwdParams 
       mbar_wait(bar_dA, ph_dA, 43);
       ph_dA ^= 1;
       tc_fence_after();
+      // the four CTAs' max |d h| arrived with this step's slices (bar_a completed before the MMAs ran): next step's scale
+      mbar_wait(bar_a, ph_a, 45);
+      ph_a ^= 1;
+      float scale_next = scale, inv_next = inv_scale;
+      {
+        const float* q = sPeer + par * 16;
+        set_scale(fmaxf(fmaxf(q[0], q[4]), fmaxf(q[8], q[12])), scale_next, inv_next);
+      }
       float dar[BROWS], dhn[BROWS];
       {
         uint32_t d[BROWS];
@@ -777,6 +811,8 @@ __global__ void __launch_bounds__(THREADS, 1) gru_bwd_tc_kernel(const BwdParams 
         for (int i = 0; i < BROWS; ++i)
           if ((onmask >> i) & 1) dh[i] = fmaf(__uint_as_float(d[i]), inv_scale, dhn[i]);
       }
+      scale = scale_next; inv_scale = inv_next;
+      publish_local_max();
       par ^= 1;
       t = tn;
     }

@@ -179,13 +179,16 @@ def test_gru_tensor_core_row_order(lib):
 ])
 def test_gru_tensor_core_bptt_vs_oracle(lib, impl, B, W, G, ini, act, pad, gscale):
     """tcgen05 BPTT: weights enter as fp16 (2^-12 relative rounding, like the other tensor-core-mode backward GEMMs), the
-    exchanged gradients as fp16 hi+lo under a per-tile power-of-two scale.  Tolerance 2e-3 of the largest gradient."""
+    exchanged gradients as fp16 hi+lo under a power-of-two scale that follows the cluster-wide max |d h| step by step
+    (the W=200 case decays d h0 to 1e-22, far outside a fixed fp16 window).  Tolerance 2e-3 of the largest gradient at
+    W <= 50; the weight rounding accumulates like sqrt(W) beyond."""
     XW, gm, Wh, h0, dhT = make(B, W, G, seed=B + W + G, ini=ini, pad=pad)
     dhT = dhT * gscale
     hT_ref, dA_ref, dh0_ref = oracle(XW, Wh, h0, dhT, act)
     hT, dA, dh0, sv = run(lib, impl, XW, gm, Wh, h0, dhT, act)
+    tol = 2e-3 * max(1.0, (W / 50.0) ** 0.5)
     assert np.isfinite(dA).all()
-    assert rel(dA, dA_ref) < 2e-3
+    assert rel(dA, dA_ref) < tol
     if ini:
-        assert rel(dh0, dh0_ref) < 2e-3
+        assert rel(dh0, dh0_ref) < tol
     assert np.all(dA[gm == 0] == 0)
