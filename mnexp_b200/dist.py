@@ -75,3 +75,46 @@ class DataParallel:
             ur = (n, self.rows, self.nrows, self.grows)
         e.apply_adam(user_rows=ur)
         return e.view('loss')
+
+
+# ---- sharded decomposed inference (C4; SURVEY.md §8e "Inference"): news sharded by id, one all-gather of the document
+# vectors, then users sharded by id with no further exchange ----------------------------------------------------------
+def shard_range(n, rank, world):
+    """Contiguous [lo, hi) slice of n items owned by `rank`; every rank's slice has ceil(n / world) slots (the last
+    ones may be short)."""
+    per = (n + world - 1) // world
+    return min(n, rank * per), min(n, (rank + 1) * per), per
+
+
+def gather_rows(local_rows, n_total, group=None):
+    """all-gather of equally sized per-rank row blocks (padded to ceil(n/world) rows) -> the first n_total rows.
+    Collective part only: runs on gloo/CPU tensors too (tests/test_dist_cpu.py)."""
+    world = dist.get_world_size(group)
+    full = torch.empty((world * local_rows.shape[0],) + tuple(local_rows.shape[1:]), dtype=local_rows.dtype,
+                       device=local_rows.device)
+    dist.all_gather_into_tensor(full, local_rows.contiguous(), group=group)
+    return full[:n_total]
+
+
+def sharded_doc_table(engine, group=None):
+    """TestPipeline.test_doc_vec over all ranks: rank r encodes documents [lo, hi), the table is all-gathered (C4:
+    130 k x U fp32 = 104 MB over NVLink) and row 0 (pad document) is zeroed like engine.build_doc_table()."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world == 1:
+        return engine.build_doc_table()
+    n_docs = int(engine.doc_tokens.shape[0])
+    lo, hi, per = shard_range(n_docs, rank, world)
+    ids = torch.zeros(per, dtype=torch.int32, device=engine.device)
+    ids[:hi - lo] = torch.arange(lo, hi, dtype=torch.int32, device=engine.device)
+    table = gather_rows(engine.encode_docs(ids), n_docs, group)
+    table[0].zero_()
+    return table
+
+
+def shard_users(n_users, group=None):
+    """[lo, hi) of the users this rank scores against the shared document table (no exchange afterwards)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi, _ = shard_range(n_users, rank, world)
+    return lo, hi
