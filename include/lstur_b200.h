@@ -181,10 +181,13 @@ int lstur_gru_fwd_tc(int B, int W, int G, const float* XW, const float* gm, cons
                      const float* Wh, int rec_act, float* hT, long long ldo, float* Z, float* R, float* HH,
                      float* HP, float* RH, const int* row_order, cudaStream_t stream);
 /* BPTT on the tensor cores; takes Wh itself (not its transpose).  Weights enter as fp16 (like the other backward
- * GEMMs of the tensor-core modes), the exchanged gradients as fp16 hi + lo under a per-tile power-of-two scale. */
+ * GEMMs of the tensor-core modes), the exchanged gradients as fp16 hi + lo under a power-of-two scale that follows the
+ * cluster-wide max |d h|.  db_partial (optional, lstur_gru_tc_db_rows(B) x 3G): partial column sums of dA (the bias
+ * gradient) per (32-row tile, 8-row group); their column sum over all rows is sum_{b,t} dA[b,t,:]. */
+int lstur_gru_tc_db_rows(int B);
 int lstur_gru_bwd_tc(int B, int W, int G, const float* gm, const float* Z, const float* R, const float* HH,
                      const float* HP, const float* Wh, int rec_act, const float* dhT, long long lddh, float* dA,
-                     float* dh0, long long lddh0, const int* row_order, cudaStream_t stream);
+                     float* dh0, long long lddh0, const int* row_order, float* db_partial, cudaStream_t stream);
 int lstur_gru_fwd_streaming(int B, int W, int G, const float* XW, const float* gm, const float* h0, long long ldh0,
                             const float* Wh, int rec_act, float* hT, long long ldo, float* Z, float* R, float* HH,
                             float* HP, float* RH, cudaStream_t stream);

@@ -239,6 +239,7 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
     add_ws(p, "attn_partials", (long long)lstur_attn_bwd_grid((int)N) * (2 * F + 1));
     if (has_gru) {
       add_ws(p, "WhT", (long long)3 * G * G);
+      add_ws(p, "gru_db_partial", (long long)lstur_gru_tc_db_rows((int)B) * 3 * G);
       add_ws(p, "dA", Nh * 3 * G);
       add_ws(p, "dh0", B * G);
     }
@@ -677,15 +678,18 @@ extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const
     const bool tc_gru = (c.precision == LSTUR_PREC_BF16_TC || c.precision == LSTUR_PREC_FP16_TC) &&
                         lstur_gru_tc_supported(B, c.W, G) && !getenv("LSTUR_GRU_TC_OFF");
     if (tc_gru) {
+      // the kernel also leaves per-(tile, row group) column sums of dA: the bias gradient needs no second pass over dA
+      float* dbp = W<float>(p, ws, "gru_db_partial");
       RC(lstur_gru_bwd_tc(B, c.W, G, W<float>(p, ws, "gru_mask"), W<float>(p, ws, "Z"), W<float>(p, ws, "R"),
                           W<float>(p, ws, "HH"), W<float>(p, ws, "HP"), DP(p, w->dense, "gru_wh"), c.rec_act, dhT, lddh,
-                          dA, dh0, G, nullptr, st));
+                          dA, dh0, G, nullptr, dbp, st));
+      RC(lstur_colsum(lstur_gru_tc_db_rows(B), 3 * G, dbp, 3 * G, DG(p, dgrad, "gru_b"), 0, cws, cwsb, st));
     } else {
       RC(lstur_transpose(G, 3 * G, DP(p, w->dense, "gru_wh"), WhT, st));
       RC(lstur_gru_bwd(B, c.W, G, W<float>(p, ws, "gru_mask"), W<float>(p, ws, "Z"), W<float>(p, ws, "R"),
                        W<float>(p, ws, "HH"), W<float>(p, ws, "HP"), WhT, c.rec_act, dhT, lddh, dA, dh0, G, st));
+      RC(lstur_colsum(Nh, 3 * G, dA, 3 * G, DG(p, dgrad, "gru_b"), 0, cws, cwsb, st));
     }
-    RC(lstur_colsum(Nh, 3 * G, dA, 3 * G, DG(p, dgrad, "gru_b"), 0, cws, cwsb, st));
     RC(GEMM(1, 0, D, 3 * G, Nh, docv, D, dA, 3 * G, DG(p, dgrad, "gru_wx"), 3 * G, nullptr, 0, gws, gwsb, st));
     RC(GEMM(1, 0, G, 2 * G, Nh, W<float>(p, ws, "HP"), G, dA, 3 * G, DG(p, dgrad, "gru_wh"), 3 * G, nullptr, 0,
                       gws, gwsb, st));

@@ -469,6 +469,7 @@ struct BwdParams {
   const float* dhT; long long lddh;
   float* dA;                      // (B, W, 3G)
   float* dh0; long long lddh0;
+  float* db_partial;              // optional (4 * tiles, 3G): per (tile, row group) sums of dA over rows and steps
 };
 constexpr int BROWS = 8;            // batch rows per epilogue thread in the backward kernel
 
@@ -722,6 +723,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_bwd_tc_kernel(const BwdParams 
     };
     zero_steps(W, t);
     uint32_t ph_dA = 0, ph_dB = 0, ph_a = 0, par = 0;
+    float sum_z = 0.f, sum_r = 0.f, sum_h = 0.f;      // bias gradient: this thread's share of the column sums of dA
     while (t >= 0) {
       float z[BROWS], r[BROWS], hh[BROWS], hp[BROWS], dah[BROWS], daz[BROWS];
       uint32_t onmask = 0;
@@ -760,6 +762,8 @@ __global__ void __launch_bounds__(THREADS, 1) gru_bwd_tc_kernel(const BwdParams 
           float* d = p.dA + (rowoff[i] - k + (long long)t * G) * 3 + k;
           d[0] = daz[i];
           d[2 * G] = dah[i];
+          sum_z += daz[i];
+          sum_h += dah[i];
         }
       load_saved(tn, nz, nr, nhh, nhp);
       // ---- phase A result: drh
@@ -796,7 +800,10 @@ __global__ void __launch_bounds__(THREADS, 1) gru_bwd_tc_kernel(const BwdParams 
       }
 #pragma unroll
       for (int i = 0; i < BROWS; ++i)
-        if (rowoff[i] >= 0) p.dA[(rowoff[i] - k + (long long)t * G) * 3 + G + k] = dar[i];
+        if (rowoff[i] >= 0) {
+          p.dA[(rowoff[i] - k + (long long)t * G) * 3 + G + k] = dar[i];
+          sum_r += dar[i];
+        }
       zero_steps(t, tn);
       // ---- phase B result: dhp
       mbar_wait(bar_dB, ph_dB, 44);
@@ -823,6 +830,10 @@ __global__ void __launch_bounds__(THREADS, 1) gru_bwd_tc_kernel(const BwdParams 
           const int b = sRow[n0 + i];
           p.dh0[(long long)b * p.lddh0 + k] = dh[i];
         }
+    }
+    if (p.db_partial && act) {      // row (tile, row group); summed by a fixed-order column sum afterwards
+      float* row = p.db_partial + ((long long)tile * 4 + (n0 >> 3)) * G3;
+      row[k] = sum_z; row[G + k] = sum_r; row[2 * G + k] = sum_h;
     }
   }
   tc_fence_before();
@@ -886,16 +897,18 @@ extern "C" int lstur_gru_fwd_tc(int B, int W, int G, const float* XW, const floa
   return LSTUR_OK;
 }
 
+extern "C" int lstur_gru_tc_db_rows(int B) { return 4 * ((B + grutc::NROWS - 1) / grutc::NROWS); }
+
 extern "C" int lstur_gru_bwd_tc(int B, int W, int G, const float* gm, const float* Z, const float* R, const float* HH,
                                 const float* HP, const float* Wh, int rec_act, const float* dhT, long long lddh, float* dA,
-                                float* dh0, long long lddh0, const int* row_order, cudaStream_t stream) {
+                                float* dh0, long long lddh0, const int* row_order, float* db_partial, cudaStream_t stream) {
   LSTUR_REQUIRE(B >= 0 && W > 0 && G > 0 && gm && Z && R && HH && HP && Wh && dhT && dA, "lstur_gru_bwd_tc");
   LSTUR_REQUIRE(lstur_gru_tc_supported(B > 0 ? B : 1, W, G), "lstur_gru_bwd_tc(shape)");
   if (B == 0) return LSTUR_OK;
   grutc::BwdParams p = {};
   p.B = B; p.W = W; p.G = G; p.UC = (G + 3) / 4; p.act = rec_act;
   p.gm = gm; p.row_order = row_order; p.Z = Z; p.R = R; p.HH = HH; p.HP = HP; p.Wh = Wh;
-  p.dhT = dhT; p.lddh = lddh; p.dA = dA; p.dh0 = dh0; p.lddh0 = lddh0;
+  p.dhT = dhT; p.lddh = lddh; p.dA = dA; p.dh0 = dh0; p.lddh0 = lddh0; p.db_partial = db_partial;
   const size_t smem = grutc::bwd_smem_bytes(G, W);
   cudaError_t e = cudaFuncSetAttribute(grutc::gru_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {

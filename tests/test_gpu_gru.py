@@ -76,7 +76,11 @@ def run(lib, impl, XW, gm, Wh, h0, dhT, act, order=None):
         fwd = lib.lstur_gru_fwd_cluster if impl == 'tcb' else lib.lstur_gru_fwd_tc
         rc = fwd(B, W, G, P_(XWd), P_(gmd), P_(h0d), G, P_(Whd), a, P_(hT), G, *[P_(s) for s in sv], P_(od), stream())
         assert rc == 0, lib.lstur_last_error()
-        rc = lib.lstur_gru_bwd_tc(B, W, G, P_(gmd), *[P_(s) for s in sv[:4]], P_(Whd), a, P_(dhTd), G, P_(dA), P_(dh0), G, P_(od), stream())
+        dbp = torch.full((lib.lstur_gru_tc_db_rows(B), 3 * G), float('nan'), device='cuda')
+        rc = lib.lstur_gru_bwd_tc(B, W, G, P_(gmd), *[P_(s) for s in sv[:4]], P_(Whd), a, P_(dhTd), G, P_(dA), P_(dh0), G, P_(od), P_(dbp), stream())
+        torch.cuda.synchronize()
+        # the fused bias-gradient partials add up to the column sums of dA
+        assert torch.allclose(dbp.sum(0), dA.reshape(-1, 3 * G).sum(0), rtol=1e-3, atol=1e-5 * float(dA.abs().max()) * B * W)
         assert rc == 0, lib.lstur_last_error()
     elif impl == 'tc':        # tensor-core forward; its saved tensors feed the cluster backward
         assert lib.lstur_gru_tc_supported(B, W, G) == 1

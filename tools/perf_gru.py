@@ -39,6 +39,6 @@ for name, m, od in (('all steps active', full, None), ('padded, natural order', 
     f_st = lambda: chk(lib.lstur_gru_fwd_streaming(B, W, G, P_(XW), P_(m), P_(h0), G, P_(Wh), 0, P_(hT), G, *[P_(s) for s in sv], st()))
     b_st = lambda: chk(lib.lstur_gru_bwd_streaming(B, W, G, P_(m), *[P_(s) for s in sv[:4]], P_(WhT), 0, P_(dhT), G, P_(dA), P_(dh0), G, st()))
     f_tc = lambda: chk(lib.lstur_gru_fwd_tc(B, W, G, P_(XW), P_(m), P_(h0), G, P_(Wh), 0, P_(hT), G, *[P_(s) for s in sv], P_(od), st()))
-    b_tc = lambda: chk(lib.lstur_gru_bwd_tc(B, W, G, P_(m), *[P_(s) for s in sv[:4]], P_(Wh), 0, P_(dhT), G, P_(dA), P_(dh0), G, P_(od), st()))
+    b_tc = lambda: chk(lib.lstur_gru_bwd_tc(B, W, G, P_(m), *[P_(s) for s in sv[:4]], P_(Wh), 0, P_(dhT), G, P_(dA), P_(dh0), G, P_(od), None, st()))
     print('%-24s tensor-core fwd %7.1f us bwd %7.1f us' % (name, timeit(f_tc), timeit(b_tc)))
     print('%-24s cluster fwd %7.1f us bwd %7.1f us | streaming fwd %7.1f us bwd %7.1f us' % (name, timeit(f_cl), timeit(b_cl), timeit(f_st), timeit(b_st)))
