@@ -106,6 +106,17 @@ int lstur_news_conv_tc_fwd(int n_titles, int L, int E, int F, int V, const int* 
                            void* c_out_16, float* pooled, float* att_a, float* att_wt, float dropout, unsigned seed,
                            int fp16, int max_ctas, cudaStream_t stream);
 
+/* Same kernels with the X-dropout keep bits handed from the forward to the weight-gradient kernel (one byte per 16-byte
+ * piece of an embedding row, lstur_tc_xmask_bytes) instead of replaying the dropout hash there; NULL = replay. */
+size_t lstur_tc_xmask_bytes(int n_titles, int L, int E);
+int lstur_news_conv_tc_fwd_m(int n_titles, int L, int E, int F, int V, const int* tokens, const void* emb_16,
+                             const void* wimg, const float* conv_b, const float* att_w, const float* att_b,
+                             void* c_out_16, float* pooled, float* att_a, float* att_wt, float dropout, unsigned seed,
+                             int fp16, int max_ctas, void* xmask_out, cudaStream_t stream);
+int lstur_conv_wgrad_tc_m(int n_titles, int L, int E, int F, int V, const int* tokens, const void* emb_16,
+                          const void* dpre_img, float* d_conv_w, float dropout, unsigned seed, int fp16,
+                          void* partial_ws, size_t partial_bytes, const void* xmask, cudaStream_t stream);
+
 /* Backward of the tensor-core news encoder: attention/ReLU/mask backward emitting dPre as 16-bit K-block images
  * (lstur_attn_pool_bwd_img), then the Conv1D weight gradient on tcgen05 (lstur_conv_wgrad_tc). */
 int lstur_attn_pool_bwd_img(int fp16, int N, int L, int F, const void* Cd_16, const float* a_in, const float* w_in,

@@ -91,6 +91,8 @@ struct FwdParams {
   float inv_keep;
   uint32_t seed_x, seed_c;
   int dbg;                        // experiments (LSTUR_FWD_DBG): 1 = epilogue only hands the accumulator back, 2 = producers only signal
+  uint8_t* xmask;                 // optional (n_titles, L, Ep/8): keep bits of the X-dropout, one byte per 16-byte piece, so
+                                  // the weight-gradient kernel need not replay the hash (bit j / 4+j: low / high half of word j)
 };
 
 // Stage = one 32-column chunk of the embedding: the three shifted tap tiles of this CTA's 128 token rows (A, 24 KB)
@@ -291,7 +293,8 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
     }
   } else if (warp == 1) {
     // ===================== MMA issuer of the pair =====================
-    if (lane == 0 && crank == 0) {
+    if (crank == 0) {      // the whole warp runs the loop, one elected lane issues (see elect_one)
+      const bool leader = elect_one();
       const uint32_t idesc0 = make_idesc(2 * TILE_M, 2 * n0h, FP16), idesc1 = make_idesc(2 * TILE_M, n1h > 0 ? 2 * n1h : 16, FP16);
       int s = 0;
       uint32_t ph = 0, pht = 0;
@@ -302,22 +305,27 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
         for (int c = 0; c < EC; ++c) {
           mbar_wait(bar_full + 8 * s, ph, 3);
           tc_fence_after();
-          const uint32_t a_stage = smem_base + s * stage_bytes, b_stage = a_stage + A_STAGE_BYTES;
+          if (leader) {
+            const uint32_t a_stage = smem_base + s * stage_bytes, b_stage = a_stage + A_STAGE_BYTES;
 #pragma unroll
-          for (int j = 0; j < TAPS; ++j) {
-            const uint32_t a_addr = a_stage + j * A_TAP_BYTES, b_addr = b_stage + j * b_tap_bytes;
+            for (int j = 0; j < TAPS; ++j) {
+              const uint32_t a_addr = a_stage + j * A_TAP_BYTES, b_addr = b_stage + j * b_tap_bytes;
 #pragma unroll
-            for (int kk = 0; kk < KBLK / 16; ++kk) {
-              const uint64_t ad = make_desc_k64(a_addr + kk * 32);
-              umma_f16_2cta(tmem_base, ad, make_desc_k64(b_addr + kk * 32), idesc0, accum);
-              if (n1h > 0) umma_f16_2cta(tmem_base + 2 * n0h, ad, make_desc_k64(b_addr + n0h * ROWB + kk * 32), idesc1, accum);
-              accum = 1;
+              for (int kk = 0; kk < KBLK / 16; ++kk) {
+                const uint64_t ad = make_desc_k64(a_addr + kk * 32);
+                umma_f16_2cta(tmem_base, ad, make_desc_k64(b_addr + kk * 32), idesc0, accum);
+                if (n1h > 0) umma_f16_2cta(tmem_base + 2 * n0h, ad, make_desc_k64(b_addr + n0h * ROWB + kk * 32), idesc1, accum);
+                accum = 1;
+              }
             }
+            umma_commit_2cta(bar_empty + 8 * s, 3);
           }
-          umma_commit_2cta(bar_empty + 8 * s, 3);
+          accum = 1;
+          __syncwarp();
           if (++s == NUM_STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit_2cta(bar_t_full, 3);
+        if (leader) umma_commit_2cta(bar_t_full, 3);
+        __syncwarp();
         pht ^= 1;
       }
     }
@@ -382,14 +390,21 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
             if (ids[i] == kNoToken) continue;
             const uint32_t lo0 = row_lo[i] + (uint32_t)((c * KBLK + piece * 8) >> 2);
             uint32_t* w = reinterpret_cast<uint32_t*>(&v[i]);
+            uint32_t keep = 0;
 #pragma unroll
             for (int q = 0; q < 2; ++q) {     // two quads per 16-byte piece
               const uint32_t lo = lo0 + q;
               uint32_t u0, u1;
               quad_hash(lo ^ (lo < row_lo[i] ? row_in1[i] : row_in0[i]), u0, u1);
-              w[2 * q] &= quad_mask(u0, p.drop_addend);
-              w[2 * q + 1] &= quad_mask(u1, p.drop_addend);
+              const uint32_t m0 = quad_mask(u0, p.drop_addend), m1 = quad_mask(u1, p.drop_addend);
+              w[2 * q] &= m0;
+              w[2 * q + 1] &= m1;
+              keep |= (m0 & (0x00010001u << (2 * q))) | (m1 & (0x00010001u << (2 * q + 1)));
             }
+            // bits 0-3 (low halves of words 0-3) and 16-19 (high halves) -> one byte
+            if (p.xmask)
+              p.xmask[((long long)n * p.L + (8 * i + rsub)) * (p.Ep >> 3) + c * (KBLK / 8) + piece] =
+                  (uint8_t)((keep | (keep >> 12)) & 0xffu);
           }
         }
         if (lane == 0) mbar_wait(bar_empty + 8 * s, ph ^ 1, 5);   // one poller per warp
@@ -565,12 +580,15 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
 // the multicast commit.
 // The token range is split over CTA.y; partial sums go to global and are reduced in a fixed order.
 constexpr int WG_KTOK = 32;                         // tokens (K rows) per title slot
+constexpr int WG_ES = 40;                           // embedding columns per (tap, e) slice: a slice's 128 M rows are the
+                                                    // three taps of the SAME 40 columns (3 x 40 = 120 rows used), so a token's
+                                                    // 16-byte pieces are gathered once and stored at the three tap shifts
 constexpr int WG_GROUP_BYTES = WG_KTOK * 128;       // one 64-element group of one title: 4 KB
 constexpr int WG_A_TILE_BYTES = 2 * WG_GROUP_BYTES; // A of one title: two 64-column chunks
 constexpr int WG_TPS = 2;                           // titles per pipeline stage (amortises the per-stage handshake,
                                                     // ~500 cycles of issue-thread + commit latency, over 800 MMA cycles)
 constexpr int WG_STAGES = 4;
-constexpr int WG_THREADS = 384;
+constexpr int WG_THREADS = 640;   // 4 control warps + 16 producer warps (8 per title of a stage; warps 8-11 also run the epilogue)
 
 struct WgradParams {
   int n_titles, L, F, EC, Ep, V;
@@ -582,7 +600,9 @@ struct WgradParams {
   uint32_t drop_thr16, drop_addend, seed_x;   // quad-stream threshold (0 = no dropout) and its mask addend
   float scale;
   long long* trace;           // optional: accumulated wait cycles of CTA (0,0)'s roles (tools/perf_conv.py)
-  int dbg;                    // experiments (LSTUR_WGRAD_DBG): 2 = skip all MMAs, 4 = skip bulk copies, 8 = producers only signal
+  int dbg;                    // experiments (LSTUR_WGRAD_DBG): 2 = skip all MMAs, 4 = skip bulk copies, 8 = producers only signal,
+                              // 16 = no proxy fence, 32 = no st.shared (timing only)
+  const uint8_t* xmask;       // optional keep bits written by the forward (FwdParams::xmask); null: replay the hash
 };
 
 template <bool FP16>
@@ -600,6 +620,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const Wgra
   uint8_t* misc_gen = smem_gen + (misc_base - smem_base);
   const uint32_t bar_full = misc_base, bar_empty = misc_base + 64, bar_t_full = misc_base + 128;
   uint32_t* tmem_ptr_smem = (uint32_t*)(misc_gen + 144);
+  uint4* mask_lut = reinterpret_cast<uint4*>(misc_gen + 256);    // keep byte -> four 16x2 AND masks (4 KB)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slice = blockIdx.x, split = blockIdx.y;
   const uint32_t crank = cluster_ctarank();     // 0 = leader (issues the pair's MMAs)
@@ -610,13 +631,23 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const Wgra
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < WG_STAGES; ++s) {
-      // leader: its 8 producer warps + its B loader's expect_tx arrival + the 8 producer warps of the peer (remote
+      // leader: its 16 producer warps + its B loader's expect_tx arrival + the 16 producer warps of the peer (remote
       // arrives; the peer's warp 4 first waits for the peer's own bulk copies).  peer: only its B loader's expect_tx.
-      mbar_init(bar_full + 8 * s, crank == 0 ? 17 : 1);
+      mbar_init(bar_full + 8 * s, crank == 0 ? 33 : 1);
       mbar_init(bar_empty + 8 * s, 1);   // multicast tcgen05.commit of the leader
     }
     mbar_init(bar_t_full, 1);
     fence_barrier_init();
+  }
+  for (uint32_t i = threadIdx.x; i < WG_STAGES * a_stage_bytes / 16; i += WG_THREADS)   // M rows never written stay zero
+    reinterpret_cast<uint4*>(smem_gen)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (p.xmask && threadIdx.x < 256) {
+    const uint32_t b = threadIdx.x;
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = ((b >> j) & 1u ? 0x0000ffffu : 0u) | ((b >> (4 + j)) & 1u ? 0xffff0000u : 0u);
+    mask_lut[b] = make_uint4(w[0], w[1], w[2], w[3]);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
@@ -655,7 +686,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const Wgra
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && crank == 0) {   // MMA issuer of the pair
+    if (crank == 0) {   // MMA issuer of the pair: the whole warp runs the loop, one elected lane issues
+      const bool leader = elect_one();
       const uint32_t idesc0 = make_idesc_mn(2 * TILE_M, 2 * n0h, FP16), idesc1 = make_idesc_mn(2 * TILE_M, n1h > 0 ? 2 * n1h : 16, FP16);
       const uint32_t b1_off = (uint32_t)(n0h / 64) * WG_GROUP_BYTES;
       int s = 0;
@@ -666,119 +698,127 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const Wgra
         mbar_wait(bar_full + 8 * s, ph, 12);
         if (tracing) tw += clock64() - t0;
         tc_fence_after();
-        if (!(p.dbg & 2)) {
+        if (leader) {
+          if (!(p.dbg & 2)) {
 #pragma unroll
-          for (int t = 0; t < WG_TPS; ++t) {
-            const uint32_t a_addr = a_base + s * a_stage_bytes + t * WG_A_TILE_BYTES;
-            const uint32_t b_addr = b_base + s * b_stage_bytes + t * b_tile_bytes;
+            for (int t = 0; t < WG_TPS; ++t) {
+              const uint32_t a_addr = a_base + s * a_stage_bytes + t * WG_A_TILE_BYTES;
+              const uint32_t b_addr = b_base + s * b_stage_bytes + t * b_tile_bytes;
 #pragma unroll
-            for (int kk = 0; kk < WG_KTOK / 16; ++kk) {
-              const uint64_t ad = make_desc_mn128(a_addr + kk * 2048, WG_GROUP_BYTES);
-              umma_f16_2cta(tmem_base, ad, make_desc_mn128(b_addr + kk * 2048, WG_GROUP_BYTES), idesc0, accum);
-              if (n1h > 0)
-                umma_f16_2cta(tmem_base + 2 * n0h, ad, make_desc_mn128(b_addr + b1_off + kk * 2048, WG_GROUP_BYTES), idesc1, accum);
-              accum = 1;
+              for (int kk = 0; kk < WG_KTOK / 16; ++kk) {
+                const uint64_t ad = make_desc_mn128(a_addr + kk * 2048, WG_GROUP_BYTES);
+                umma_f16_2cta(tmem_base, ad, make_desc_mn128(b_addr + kk * 2048, WG_GROUP_BYTES), idesc0, accum);
+                if (n1h > 0)
+                  umma_f16_2cta(tmem_base + 2 * n0h, ad, make_desc_mn128(b_addr + b1_off + kk * 2048, WG_GROUP_BYTES), idesc1, accum);
+                accum = 1;
+              }
             }
           }
+          umma_commit_2cta(bar_empty + 8 * s, 3);
         }
-        umma_commit_2cta(bar_empty + 8 * s, 3);
+        __syncwarp();
         if (++s == WG_STAGES) { s = 0; ph ^= 1; }
       }
-      umma_commit_2cta(bar_t_full, 3);
-      if (tracing) { p.trace[0] = tw; p.trace[1] = clock64() - t_start; p.trace[2] = n_stage_blocks; }
+      if (leader) umma_commit_2cta(bar_t_full, 3);
+      __syncwarp();
+      if (tracing && lane == 0) { p.trace[0] = tw; p.trace[1] = clock64() - t_start; p.trace[2] = n_stage_blocks; }
     }
   }
   if (warp >= 4) {
-    // A producers (8 warps; warps 8-11 run the epilogue afterwards).  Per stage a thread handles (row r, 16-byte piece
-    // q) of both 64-column chunks (u0,u1) of this CTA's (tap, e) slice for each of the stage's titles.  Dropout
-    // replays the forward's stream: hash(pair index), the inner hash of the high word hoisted out of the per-pair work.
-    const int pt = threadIdx.x - 128;          // 0..255
-    const int r = pt >> 3, q = pt & 7;
-    int uj[2], uc[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      int u = 2 * slice + i;
-      uj[i] = u < TAPS * p.EC ? u / p.EC : -1;
-      uc[i] = u < TAPS * p.EC ? u % p.EC : 0;
-    }
+    // A producers (16 warps: 8 per title of a stage; warps 8-11 run the epilogue afterwards).  A producer warp's
+    // instruction stream is latency-bound (few independent instructions between the gather, the dropout mask and the
+    // shared-memory store), so the stage's work is spread over twice the warps rather than 4 pieces per thread: per
+    // stage a thread handles (row r, 16-byte piece q) of both 64-column chunks (u0,u1) of this CTA's (tap, e) slice
+    // for ONE of the stage's titles.  Dropout: keep bytes left by the forward, or a replay of its stream.
+    const int pt = threadIdx.x - 128;          // 0..511
+    const int tsel = pt >> 8;                  // title of the stage
+    const int r = (pt & 255) >> 3, q = pt & 7; // token row, 16-byte piece of the slice's 40 columns (q < 5)
+    const int e0 = slice * WG_ES + q * 8;      // first embedding column of the piece
+    const bool piece_ok = q < WG_ES / 8 && e0 < p.Ep;
     // The token id is NOT inspected when it is loaded (that would stall the warp for the load's full latency every
-    // stage); validity is kept in the row index and the id is clamped when its embedding rows are requested.
+    // stage); validity is kept in the row index and the id is clamped when its embedding row is requested.
     constexpr int kNoTitle = INT_MIN;
-    auto load_id = [&](int kb) { return (kb < kb_end && r < p.L) ? __ldg(p.tok + (long long)kb * p.L + r) : kNoTitle; };
-    auto load_rows = [&](int id, uint4* v) {
-      const bool ok = id != kNoTitle;
-      id = (id < 0 || id >= p.V) ? 0 : id;
-#pragma unroll
-      for (int ui = 0; ui < 2; ++ui) {
-        v[ui] = make_uint4(0, 0, 0, 0);
-        if (ok && uj[ui] >= 0) v[ui] = __ldg((const uint4*)(p.emb + (long long)id * p.Ep + uc[ui] * EPAD + q * 8));
+    const bool use_mask = p.xmask != nullptr && p.drop_thr16 != 0;
+    auto load_id = [&](int kb) { return (piece_ok && kb < kb_end && r < p.L) ? __ldg(p.tok + (long long)kb * p.L + r) : kNoTitle; };
+    auto load_row = [&](int id) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (id != kNoTitle) {
+        id = (id < 0 || id >= p.V) ? 0 : id;
+        v = __ldg((const uint4*)(p.emb + (long long)id * p.Ep + e0));
       }
+      return v;
+    };
+    // keep byte of the piece of title kb (row r): requested with the row, applied when the stage is stored
+    auto load_mask = [&](int kb) {
+      uint32_t m = 0xffu;
+      if (use_mask && piece_ok && kb < kb_end && r < p.L) m = __ldg(p.xmask + ((long long)kb * p.L + r) * (p.Ep >> 3) + (e0 >> 3));
+      return m;
     };
     int s = 0;
     uint32_t ph = 0;
     long long twait = 0, t_start = tracing ? clock64() : 0;
-    // Gather pipeline: the rows of stage sb+1 and the token ids of stage sb+2 are requested while stage sb is hashed
-    // and stored.
-    uint4 vq[3][WG_TPS][2];   // vq[sb % 3]: rows of the titles of stage sb (requested two stages earlier: the gather's
-                              // L2/HBM latency under load is about one stage period)
-    int idn[WG_TPS];          // token ids of the titles of stage sb+2 while stage sb is stored
-#pragma unroll
-    for (int t = 0; t < WG_TPS; ++t) load_rows(load_id(kb_beg + t), vq[0][t]);
-#pragma unroll
-    for (int t = 0; t < WG_TPS; ++t) load_rows(load_id(kb_beg + WG_TPS + t), vq[1][t]);
-#pragma unroll
-    for (int t = 0; t < WG_TPS; ++t) idn[t] = load_id(kb_beg + 2 * WG_TPS + t);
-    auto drop_rows = [&](int kb, uint4* v) {
+    // Gather pipeline: the row of stage sb+2 and the token id of stage sb+3 are requested while stage sb is masked
+    // and stored (the gather's L2/HBM latency under load is about one stage period).
+    uint4 vq[3];              // vq[sb % 3]: this thread's piece of its title of stage sb
+    uint32_t mq[3];           // its keep byte
+    int idn;                  // token id of the title of stage sb+2 while stage sb is stored
+    vq[0] = load_row(load_id(kb_beg + tsel)); mq[0] = load_mask(kb_beg + tsel);
+    vq[1] = load_row(load_id(kb_beg + WG_TPS + tsel)); mq[1] = load_mask(kb_beg + WG_TPS + tsel);
+    idn = load_id(kb_beg + 2 * WG_TPS + tsel);
+    auto drop_piece = [&](int kb, uint4& v) {      // replay of the forward's dropout stream (no keep bytes given)
       const uint64_t rowquad = (((uint64_t)kb * p.L + r) * (uint64_t)p.Ep) >> 2;   // Ep % 4 == 0
       const uint32_t base_lo = (uint32_t)rowquad, hi = (uint32_t)(rowquad >> 32);
       const uint32_t inner0 = quad_key(hi, p.seed_x);
       const uint32_t inner1 = base_lo > 0xfffff000u ? quad_key(hi + 1u, p.seed_x) : inner0;   // carry into the high word
+      const uint32_t lo0 = base_lo + (uint32_t)(e0 >> 2);
+      uint32_t* w = reinterpret_cast<uint32_t*>(&v);
 #pragma unroll
-      for (int ui = 0; ui < 2; ++ui) {
-        if (uj[ui] < 0) continue;
-        const uint32_t lo0 = base_lo + (uint32_t)((uc[ui] * EPAD + q * 8) >> 2);
-        uint32_t* w = reinterpret_cast<uint32_t*>(&v[ui]);
-#pragma unroll
-        for (int x = 0; x < 2; ++x) {     // two quads per 16-byte piece
-          const uint32_t lo = lo0 + x;
-          uint32_t u0, u1;
-          quad_hash(lo ^ (lo < base_lo ? inner1 : inner0), u0, u1);
-          w[2 * x] &= quad_mask(u0, p.drop_addend);
-          w[2 * x + 1] &= quad_mask(u1, p.drop_addend);
-        }
+      for (int x = 0; x < 2; ++x) {     // two quads per 16-byte piece
+        const uint32_t lo = lo0 + x;
+        uint32_t u0, u1;
+        quad_hash(lo ^ (lo < base_lo ? inner1 : inner0), u0, u1);
+        w[2 * x] &= quad_mask(u0, p.drop_addend);
+        w[2 * x + 1] &= quad_mask(u1, p.drop_addend);
       }
     };
-    auto stage_step = [&](int sb, uint4 (*cur)[2], uint4 (*nxt)[2]) {
+    long long tseg[4] = {0, 0, 0, 0};
+    auto stage_step = [&](int sb, uint4& cur, uint4& nxt, uint32_t mcur, uint32_t& mnxt) {
       const int kb0 = kb_beg + sb * WG_TPS;
+      long long tA = tracing ? clock64() : 0;
       if (!(p.dbg & 8)) {
-#pragma unroll
-        for (int t = 0; t < WG_TPS; ++t) {
-          load_rows(idn[t], nxt[t]);                       // stage sb+2
-          idn[t] = load_id(kb0 + 3 * WG_TPS + t);          // stage sb+3
-        }
-        if (p.drop_thr16) {
-#pragma unroll
-          for (int t = 0; t < WG_TPS; ++t) drop_rows(kb0 + t, cur[t]);
+        nxt = load_row(idn);                                // stage sb+2
+        mnxt = load_mask(kb0 + 2 * WG_TPS + tsel);
+        idn = load_id(kb0 + 3 * WG_TPS + tsel);             // stage sb+3
+        if (use_mask) {
+          const uint4 lm = mask_lut[mcur];
+          cur.x &= lm.x; cur.y &= lm.y; cur.z &= lm.z; cur.w &= lm.w;
+        } else if (p.drop_thr16 && piece_ok) {
+          drop_piece(kb0 + tsel, cur);
         }
       }
       long long t0 = tracing ? clock64() : 0;
+      if (tracing) tseg[0] += t0 - tA;
       if (lane == 0) mbar_wait(bar_empty + 8 * s, ph ^ 1, 13);   // one poller per warp
       __syncwarp();
       if (tracing) twait += clock64() - t0;
+      long long tB = tracing ? clock64() : 0;
       if (!(p.dbg & 8)) {
-        const uint32_t stage = a_base + s * a_stage_bytes;
+        if (piece_ok) {
+          const uint32_t tile = a_base + s * a_stage_bytes + tsel * WG_A_TILE_BYTES;
 #pragma unroll
-        for (int t = 0; t < WG_TPS; ++t)
-#pragma unroll
-          for (int ui = 0; ui < 2; ++ui) {
-            const int j = uj[ui] < 0 ? 1 : uj[ui];
+          for (int j = 0; j < TAPS; ++j) {     // M row of (tap j, column e0 + i) = j * 40 + (e0 - slice * 40) + i
+            const int m0 = j * WG_ES + q * 8;
             const int rr = (r + 1 - j) & (WG_KTOK - 1);
-            const uint32_t addr = stage + t * WG_A_TILE_BYTES + ui * WG_GROUP_BYTES + rr * 128 + ((q ^ (rr & 7)) << 4);
-            const uint4 x = cur[t][ui];
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w) : "memory");
+            const uint32_t addr = tile + (m0 >> 6) * WG_GROUP_BYTES + rr * 128 + ((((m0 & 63) >> 3) ^ (rr & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(cur.x), "r"(cur.y), "r"(cur.z), "r"(cur.w) : "memory");
           }
+        }
+        long long tC = tracing ? clock64() : 0;
+        if (tracing) tseg[1] += tC - tB;
         fence_proxy_async();
+        if (tracing) tseg[2] += clock64() - tC;
       }
+      long long tD = tracing ? clock64() : 0;
       __syncwarp();
       if (lane == 0) {
         if (crank == 0) {
@@ -788,16 +828,20 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const Wgra
           mbar_arrive_remote(map_to_cta(bar_full + 8 * s, 0));
         }
       }
+      if (tracing) tseg[3] += clock64() - tD;
       if (++s == WG_STAGES) { s = 0; ph ^= 1; }
     };
     for (int sb = 0; sb < n_stage_blocks; sb += 3) {
-      stage_step(sb, vq[0], vq[2]);
-      if (sb + 1 < n_stage_blocks) stage_step(sb + 1, vq[1], vq[0]);
-      if (sb + 2 < n_stage_blocks) stage_step(sb + 2, vq[2], vq[1]);
+      stage_step(sb, vq[0], vq[2], mq[0], mq[2]);
+      if (sb + 1 < n_stage_blocks) stage_step(sb + 1, vq[1], vq[0], mq[1], mq[0]);
+      if (sb + 2 < n_stage_blocks) stage_step(sb + 2, vq[2], vq[1], mq[2], mq[1]);
     }
-    if (tracing && pt == 0) { p.trace[3] = twait; p.trace[4] = clock64() - t_start; }
+    if (tracing && pt == 0) {
+      p.trace[3] = twait; p.trace[4] = clock64() - t_start;
+      p.trace[6] = tseg[0]; p.trace[7] = tseg[1]; p.trace[8] = tseg[2]; p.trace[9] = tseg[3];
+    }
   }
-  if (warp >= 8) {
+  if (warp >= 8 && warp < 12) {
     // epilogue (once): TMEM -> scaled fp32 partial sums in global memory; accumulator columns are mapped back to f
     const int q = warp & 3;
     mbar_wait(bar_t_full, 0, 14);
@@ -833,7 +877,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const Wgra
   }
 }
 
-// d_conv_w[j][e][f] = sum_split partial[split][j*Ep + e][f]   (fixed order, deterministic)
+// d_conv_w[j][e][f] = sum_split partial[split][(e / 40) * 128 + j * 40 + e % 40][f]   (fixed order, deterministic)
 __global__ void wgrad_reduce_kernel(int E, int Ep, int F, int splits, int rows_total, const float* __restrict__ partial,
                                     float* __restrict__ dW) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -841,7 +885,7 @@ __global__ void wgrad_reduce_kernel(int E, int Ep, int F, int splits, int rows_t
   int f = (int)(i % F);
   int je = (int)(i / F);
   int j = je / E, e = je % E;
-  long long row = (long long)j * Ep + e;
+  long long row = (long long)(e / WG_ES) * TILE_M + j * WG_ES + e % WG_ES;
   float acc = 0.f;
   for (int s = 0; s < splits; ++s) acc += partial[((long long)s * rows_total + row) * F + f];
   dW[i] = acc;
@@ -895,10 +939,23 @@ static void* g_tc_trace_ptr = nullptr;
 extern "C" int lstur_tc_set_trace(void* dev_buf) { g_tc_trace_ptr = dev_buf; return LSTUR_OK; }
 
 // Fused news-encoder forward (k1-k6): tokens (n_titles,L) -> C (bf16, saved), pooled (n_titles,F), att a / w.
+// bytes of the X-dropout keep-bit buffer the forward can leave for the weight-gradient kernel (one byte per 16-byte piece)
+extern "C" size_t lstur_tc_xmask_bytes(int n_titles, int L, int E) {
+  return (size_t)n_titles * L * (lstur_tc_padded_e(E) / 8);
+}
+
 extern "C" int lstur_news_conv_tc_fwd(int n_titles, int L, int E, int F, int V, const int* tokens, const void* emb_bf16,
                                       const void* wimg, const float* conv_b, const float* att_w, const float* att_b,
                                       void* c_out_bf16, float* pooled, float* att_a, float* att_wt, float dropout,
                                       unsigned seed, int fp16, int max_ctas, cudaStream_t stream) {
+  return lstur_news_conv_tc_fwd_m(n_titles, L, E, F, V, tokens, emb_bf16, wimg, conv_b, att_w, att_b, c_out_bf16, pooled,
+                                  att_a, att_wt, dropout, seed, fp16, max_ctas, nullptr, stream);
+}
+
+extern "C" int lstur_news_conv_tc_fwd_m(int n_titles, int L, int E, int F, int V, const int* tokens, const void* emb_bf16,
+                                        const void* wimg, const float* conv_b, const float* att_w, const float* att_b,
+                                        void* c_out_bf16, float* pooled, float* att_a, float* att_wt, float dropout,
+                                        unsigned seed, int fp16, int max_ctas, void* xmask_out, cudaStream_t stream) {
   LSTUR_REQUIRE(n_titles >= 0 && lstur_tc_supported(L, E, F, 3), "lstur_news_conv_tc_fwd");
   LSTUR_REQUIRE(dropout >= 0.f && dropout < 1.f && c_out_bf16 && pooled, "lstur_news_conv_tc_fwd");
   if (n_titles == 0) return LSTUR_OK;
@@ -912,6 +969,7 @@ extern "C" int lstur_news_conv_tc_fwd(int n_titles, int L, int E, int F, int V, 
   p.inv_keep = 1.f / (1.f - dropout);
   p.seed_x = seed * 2u; p.seed_c = seed * 2u + 1u;
   p.dbg = getenv("LSTUR_FWD_DBG") ? atoi(getenv("LSTUR_FWD_DBG")) : 0;
+  p.xmask = (uint8_t*)xmask_out;
   size_t smem = 1024 + (size_t)tc::NUM_STAGES * (tc::A_STAGE_BYTES + (size_t)tc::TAPS * (F / 2) * tc::ROWB) + 256 + 4096 +
                 (((size_t)2 * F * sizeof(float) + 15) & ~(size_t)15) + (size_t)8 * tc::STG_WARP_BYTES;
   static bool attr_set = false;
@@ -976,10 +1034,12 @@ extern "C" int lstur_news_encoder_tc_fwd_internal(const lstur_plan* p, const lst
   }
   RC(lstur_pack_conv_w_tc(c.E, c.F, DP(p, w->dense, "conv_w"), wimg, fp16, st));
   PROBE_BEGIN(p, LSTUR_PROBE_CONV_FWD, st);
-  RC(lstur_news_conv_tc_fwd(n_titles, c.L, c.E, c.F, c.V, W<int>(p, ws, "tokens"), emb, wimg, DP(p, w->dense, "conv_b"),
-                            DP(p, w->dense, "att_w"), DP(p, w->dense, "att_b"), W<void>(p, ws, "C16"),
-                            W<float>(p, ws, "pooled"), W<float>(p, ws, "att_a"), W<float>(p, ws, "att_w"),
-                            training ? c.dropout : 0.f, seed, fp16, 0, st));
+  // a training forward leaves the X-dropout keep bits for the weight-gradient kernel (workspace region "xmask")
+  void* xm = (training && c.dropout > 0.f && n_titles == p->N) ? W<void>(p, ws, "xmask") : nullptr;
+  RC(lstur_news_conv_tc_fwd_m(n_titles, c.L, c.E, c.F, c.V, W<int>(p, ws, "tokens"), emb, wimg, DP(p, w->dense, "conv_b"),
+                              DP(p, w->dense, "att_w"), DP(p, w->dense, "att_b"), W<void>(p, ws, "C16"),
+                              W<float>(p, ws, "pooled"), W<float>(p, ws, "att_a"), W<float>(p, ws, "att_w"),
+                              training ? c.dropout : 0.f, seed, fp16, 0, xm, st));
   PROBE_END(p, LSTUR_PROBE_CONV_FWD, st);
   return LSTUR_OK;
 }
@@ -994,7 +1054,7 @@ extern "C" size_t lstur_tc_dpre_img_bytes(int n_titles, int F) {
   return (size_t)lstur_tc_wgrad_kblocks(n_titles) * 2 * lstur_tc_wgrad_groups(F) * tc::WG_GROUP_BYTES;
 }
 static int wgrad_slices(int E) {
-  int n = (tc::TAPS * lstur_tc_padded_e(E) + tc::TILE_M - 1) / tc::TILE_M;
+  int n = (lstur_tc_padded_e(E) + tc::WG_ES - 1) / tc::WG_ES;     // 40 embedding columns x 3 taps per 128-row slice
   return (n + 1) & ~1;   // CTA pairs
 }
 extern "C" int lstur_tc_wgrad_splits(int n_titles, int E) {
@@ -1015,6 +1075,13 @@ extern "C" size_t lstur_tc_wgrad_partial_bytes(int n_titles, int E, int F) {
 extern "C" int lstur_conv_wgrad_tc(int n_titles, int L, int E, int F, int V, const int* tokens, const void* emb_16,
                                    const void* dpre_img, float* d_conv_w, float dropout, unsigned seed, int fp16,
                                    void* partial_ws, size_t partial_bytes, cudaStream_t stream) {
+  return lstur_conv_wgrad_tc_m(n_titles, L, E, F, V, tokens, emb_16, dpre_img, d_conv_w, dropout, seed, fp16, partial_ws,
+                               partial_bytes, nullptr, stream);
+}
+
+extern "C" int lstur_conv_wgrad_tc_m(int n_titles, int L, int E, int F, int V, const int* tokens, const void* emb_16,
+                                     const void* dpre_img, float* d_conv_w, float dropout, unsigned seed, int fp16,
+                                     void* partial_ws, size_t partial_bytes, const void* xmask, cudaStream_t stream) {
   LSTUR_REQUIRE(n_titles >= 0 && lstur_tc_supported(L, E, F, 3), "lstur_conv_wgrad_tc");
   if (n_titles == 0) {
     cudaMemsetAsync(d_conv_w, 0, (size_t)3 * E * F * sizeof(float), stream);
@@ -1037,7 +1104,8 @@ extern "C" int lstur_conv_wgrad_tc(int n_titles, int L, int E, int F, int V, con
   p.scale = 1.f / (1.f - dropout);
   p.trace = (long long*)g_tc_trace_ptr;
   p.dbg = getenv("LSTUR_WGRAD_DBG") ? atoi(getenv("LSTUR_WGRAD_DBG")) : 0;
-  size_t smem = 1024 + (size_t)tc::WG_STAGES * tc::WG_TPS * (tc::WG_A_TILE_BYTES + (size_t)p.ngh * tc::WG_GROUP_BYTES) + 256;
+  p.xmask = (const uint8_t*)xmask;
+  size_t smem = 1024 + (size_t)tc::WG_STAGES * tc::WG_TPS * (tc::WG_A_TILE_BYTES + (size_t)p.ngh * tc::WG_GROUP_BYTES) + 256 + 4096;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(tc::conv_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -181,6 +181,7 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
     add_ws(p, "emb_bf16", ((long long)c.V * lstur_tc_padded_e(E) + 1) / 2);
     add_ws(p, "wimg", (lstur_tc_wimg_elems(E, F) + 1) / 2);
     add_ws(p, "C16", (N * c.L * F + 1) / 2);
+    if (bw && c.dropout > 0.f) add_ws(p, "xmask", (long long)(lstur_tc_xmask_bytes((int)N, c.L, E) + 3) / 4);
   }
   add_ws(p, "att_a", N * c.L);
   add_ws(p, "att_w", N * c.L);
@@ -750,9 +751,10 @@ extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const
                                DG(p, dgrad, "conv_b"), DG(p, dgrad, "att_b"), 0, W<float>(p, ws, "attn_partials"),
                                (size_t)p->ws.at("attn_partials").count * 4, st));
     PROBE_BEGIN(p, LSTUR_PROBE_CONV_WGRAD, st);
-    RC(lstur_conv_wgrad_tc(N, L, E, F, c.V, W<int>(p, ws, "tokens"), W<void>(p, ws, "emb_bf16"), img,
-                           DG(p, dgrad, "conv_w"), c.dropout, p->last_seed, fp16, W<void>(p, ws, "wgrad_partial"),
-                           (size_t)p->ws.at("wgrad_partial").count * 4, st));
+    RC(lstur_conv_wgrad_tc_m(N, L, E, F, c.V, W<int>(p, ws, "tokens"), W<void>(p, ws, "emb_bf16"), img,
+                             DG(p, dgrad, "conv_w"), c.dropout, p->last_seed, fp16, W<void>(p, ws, "wgrad_partial"),
+                             (size_t)p->ws.at("wgrad_partial").count * 4,
+                             (c.dropout > 0.f && p->last_training) ? W<void>(p, ws, "xmask") : nullptr, st));
     PROBE_END(p, LSTUR_PROBE_CONV_WGRAD, st);
   } else {
     float* dPre = W<float>(p, ws, "dPre");

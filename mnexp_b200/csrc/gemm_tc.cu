@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const GemmParams 
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // the whole warp runs the loop, one elected lane issues (see elect_one)
+      const bool leader = elect_one();
       int s = 0, acc = 0;
       uint32_t ph = 0, pht[2] = {0, 0};
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -148,23 +149,28 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const GemmParams 
           mbar_wait(bar_full + 8 * s, ph, 21);
           tc_fence_after();
           const uint32_t a_addr = smem_base + s * STAGE_BYTES, b_addr = a_addr + G_A_BYTES;
+          if (leader) {
 #pragma unroll
-          for (int kk = 0; kk < G_KBLK / 16; ++kk) {
-            const uint64_t ad = TA ? make_desc_mn128(a_addr + kk * 2048, 8192) : make_desc_k128(a_addr + kk * 32);
-            const uint64_t bd = TB ? make_desc_k128(b_addr + kk * 32) : make_desc_mn128(b_addr + kk * 2048, 8192);
-            umma_bf16(tacc, ad, bd, idesc, accum);
-            accum = 1;
-            if (SPLIT) {
-              const uint64_t al = TA ? make_desc_mn128(a_addr + LO_OFF + kk * 2048, 8192) : make_desc_k128(a_addr + LO_OFF + kk * 32);
-              const uint64_t bl = TB ? make_desc_k128(b_addr + LO_OFF + kk * 32) : make_desc_mn128(b_addr + LO_OFF + kk * 2048, 8192);
-              umma_bf16(tacc, al, bd, idesc, 1);
-              umma_bf16(tacc, ad, bl, idesc, 1);
+            for (int kk = 0; kk < G_KBLK / 16; ++kk) {
+              const uint64_t ad = TA ? make_desc_mn128(a_addr + kk * 2048, 8192) : make_desc_k128(a_addr + kk * 32);
+              const uint64_t bd = TB ? make_desc_k128(b_addr + kk * 32) : make_desc_mn128(b_addr + kk * 2048, 8192);
+              umma_bf16(tacc, ad, bd, idesc, accum);
+              accum = 1;
+              if (SPLIT) {
+                const uint64_t al = TA ? make_desc_mn128(a_addr + LO_OFF + kk * 2048, 8192) : make_desc_k128(a_addr + LO_OFF + kk * 32);
+                const uint64_t bl = TB ? make_desc_k128(b_addr + LO_OFF + kk * 32) : make_desc_mn128(b_addr + LO_OFF + kk * 2048, 8192);
+                umma_bf16(tacc, al, bd, idesc, 1);
+                umma_bf16(tacc, ad, bl, idesc, 1);
+              }
             }
+            umma_commit(bar_empty + 8 * s);
           }
-          umma_commit(bar_empty + 8 * s);
+          accum = 1;
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(bar_t_full + 8 * acc);
+        if (leader) umma_commit(bar_t_full + 8 * acc);
+        __syncwarp();
         pht[acc] ^= 1;
         acc ^= 1;
       }
@@ -404,7 +410,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_async_kernel(const GemmP
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // the whole warp runs the loop, one elected lane issues (see elect_one)
+      const bool leader = elect_one();
       int s = 0, acc = 0;
       uint32_t ph = 0, pht[2] = {0, 0};
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -418,23 +425,28 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_async_kernel(const GemmP
           mbar_wait(bar_full + 8 * s, ph, 21);
           tc_fence_after();
           const uint32_t a_addr = f16_base + s * F16_STAGE, b_addr = a_addr + GA_F16_A;
+          if (leader) {
 #pragma unroll
-          for (int kk = 0; kk < G_KBLK / 16; ++kk) {
-            const uint64_t ad = TA ? make_desc_mn128(a_addr + kk * 2048, 8192) : make_desc_k128(a_addr + kk * 32);
-            const uint64_t bd = TB ? make_desc_k128(b_addr + kk * 32) : make_desc_mn128(b_addr + kk * 2048, 8192);
-            umma_bf16(tacc, ad, bd, idesc, accum);
-            accum = 1;
-            if (SPLIT) {
-              const uint64_t al = TA ? make_desc_mn128(a_addr + LO_OFF + kk * 2048, 8192) : make_desc_k128(a_addr + LO_OFF + kk * 32);
-              const uint64_t bl = TB ? make_desc_k128(b_addr + LO_OFF + kk * 32) : make_desc_mn128(b_addr + LO_OFF + kk * 2048, 8192);
-              umma_bf16(tacc, al, bd, idesc, 1);
-              umma_bf16(tacc, ad, bl, idesc, 1);
+            for (int kk = 0; kk < G_KBLK / 16; ++kk) {
+              const uint64_t ad = TA ? make_desc_mn128(a_addr + kk * 2048, 8192) : make_desc_k128(a_addr + kk * 32);
+              const uint64_t bd = TB ? make_desc_k128(b_addr + kk * 32) : make_desc_mn128(b_addr + kk * 2048, 8192);
+              umma_bf16(tacc, ad, bd, idesc, accum);
+              accum = 1;
+              if (SPLIT) {
+                const uint64_t al = TA ? make_desc_mn128(a_addr + LO_OFF + kk * 2048, 8192) : make_desc_k128(a_addr + LO_OFF + kk * 32);
+                const uint64_t bl = TB ? make_desc_k128(b_addr + LO_OFF + kk * 32) : make_desc_mn128(b_addr + LO_OFF + kk * 2048, 8192);
+                umma_bf16(tacc, al, bd, idesc, 1);
+                umma_bf16(tacc, ad, bl, idesc, 1);
+              }
             }
+            umma_commit(bar_empty + 8 * s);
           }
-          umma_commit(bar_empty + 8 * s);
+          accum = 1;
+          __syncwarp();
           if (++s == FST) { s = 0; ph ^= 1; }
         }
-        umma_commit(bar_t_full + 8 * acc);
+        if (leader) umma_commit(bar_t_full + 8 * acc);
+        __syncwarp();
         pht[acc] ^= 1;
         acc ^= 1;
       }

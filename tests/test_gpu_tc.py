@@ -253,3 +253,48 @@ def test_gemm_tc(lib, ta, tb, M, N, K):
     A64, B64 = A.astype(np.float64), Bm.astype(np.float64)
     ref = np.maximum((A64.T if ta else A64) @ (B64.T if tb else B64) + bias, 0)
     assert rel(C.cpu().numpy(), ref) < (5e-6 if K < 10000 else 3e-5)      # fp32 accumulation over K terms
+
+
+@pytest.mark.parametrize('N,L,E,F', [(5, 7, 12, 32), (64, 30, 300, 400), (333, 30, 300, 400)])
+def test_keep_bits_from_forward_equal_hash_replay(lib, N, L, E, F):
+    """The weight-gradient kernel either replays the X-dropout hash or reads the keep bits the forward left behind
+    (one byte per 16-byte piece): both must give bit-identical gradients, and the bytes must equal the replicated stream."""
+    from mnexp_b200 import rng
+    tok, P = make_enc_case(N, L, E, F, seed=N + F)
+    g = np.random.default_rng(N)
+    dpre = (g.standard_normal((N, L, F)) * (g.random((N, L, F)) < 0.5)).astype(np.float32)
+    V = P['word_emb'].shape[0]
+    Ep = lib.lstur_tc_padded_e(E)
+    emb = torch.zeros((V, Ep), dtype=torch.float16, device='cuda')
+    wimg = torch.zeros(lib.lstur_tc_wimg_elems(E, F), dtype=torch.float16, device='cuda')
+    f32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+    we, cw, cb, aw, ab = (f32(P[k]) for k in ('word_emb', 'conv_w', 'conv_b', 'att_w', 'att_b'))
+    assert lib.lstur_pack_word_emb_16(V, E, P_(we), P_(emb), 1, stream()) == 0
+    assert lib.lstur_pack_conv_w_tc(E, F, P_(cw), P_(wimg), 1, stream()) == 0
+    t = torch.as_tensor(tok).cuda()
+    c_out = torch.empty((N, L, F), dtype=torch.float16, device='cuda')
+    pooled = torch.empty((N, F), device='cuda')
+    nbm = lib.lstur_tc_xmask_bytes(N, L, E)
+    xm = torch.full((nbm,), 0xAA, dtype=torch.uint8, device='cuda')
+    seed, drop = 11, 0.2
+    rc = lib.lstur_news_conv_tc_fwd_m(N, L, E, F, V, P_(t), P_(emb), P_(wimg), P_(cb), P_(aw), P_(ab), P_(c_out), P_(pooled),
+                                      None, None, ctypes.c_float(drop), seed, 1, 0, P_(xm), stream())
+    assert rc == 0, lib.lstur_last_error()
+    # bytes == the replicated quad stream of the X dropout (seed * 2, elements indexed (title, token, column of Ep))
+    keep = rng.quad_keep(seed * 2, N * L * Ep, drop).reshape(N, L, Ep // 8, 4, 2)
+    want = np.zeros((N, L, Ep // 8), dtype=np.uint8)
+    for j in range(4):
+        want |= (keep[..., j, 0].astype(np.uint8) << j) | (keep[..., j, 1].astype(np.uint8) << (4 + j))
+    assert np.array_equal(xm.cpu().numpy().reshape(N, L, Ep // 8), want)
+    img = torch.as_tensor(dpre_image(dpre, 1).view(np.int16)).cuda()
+    nb = lib.lstur_tc_wgrad_partial_bytes(N, E, F)
+    ws = torch.empty(nb, dtype=torch.uint8, device='cuda')
+    outs = []
+    for mask in (None, xm):
+        dW = torch.full((3, E, F), float('nan'), device='cuda')
+        rc = lib.lstur_conv_wgrad_tc_m(N, L, E, F, V, P_(t), P_(emb), P_(img), P_(dW), ctypes.c_float(drop), seed, 1, P_(ws), nb,
+                                       P_(mask) if mask is not None else None, stream())
+        assert rc == 0, lib.lstur_last_error()
+        torch.cuda.synchronize()
+        outs.append(dW.cpu().numpy())
+    assert np.isfinite(outs[0]).all() and np.array_equal(outs[0], outs[1])

@@ -19,6 +19,15 @@ ws = torch.empty(pb, dtype=torch.uint8, device='cuda')
 dW = torch.empty((3, E, F), device='cuda')
 trace = torch.zeros(8 * 16, dtype=torch.int64, device='cuda')
 flop = N * L * 2 * 3 * E * F
+xm = torch.randint(0, 256, (lib.lstur_tc_xmask_bytes(N, L, E),), dtype=torch.uint8, device='cuda')
+def runm(drop, reps=5):
+    for i in range(reps + 2):
+        if i == 2:
+            torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e0.record()
+        rc = lib.lstur_conv_wgrad_tc_m(N, L, E, F, V, P_(tok), P_(emb), P_(img), P_(dW), ctypes.c_float(drop), 1, 1, P_(ws), pb, P_(xm), st())
+        assert rc == 0, lib.lstur_last_error()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
 def runw(drop, reps=5):
     for i in range(reps + 2):
         if i == 2:
@@ -27,6 +36,11 @@ def runw(drop, reps=5):
         assert rc == 0, lib.lstur_last_error()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
+print('wgrad with keep bytes from the forward, dropout=0.2: %.3f ms' % runm(0.2))
+trace.zero_(); lib.lstur_tc_set_trace(P_(trace)); runm(0.2, 1); lib.lstur_tc_set_trace(None)
+tr = trace.cpu().numpy()
+print('  producer (warp 4 of CTA 0) cycles: loads+mask %d, wait_empty %d, st.shared %d, proxy fence %d, syncwarp+arrive %d, total %d over %d stages'
+      % (tr[6], tr[3], tr[7], tr[8], tr[9], tr[4], tr[2]))
 for drop in (0.0, 0.2):
     ms = runw(drop)
     print('wgrad dropout=%.1f %.3f ms %.0f TFLOP/s' % (drop, ms, flop / ms / 1e9))
