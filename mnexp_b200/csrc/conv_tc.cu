@@ -45,7 +45,7 @@ __device__ __forceinline__ uint64_t make_desc_k64(uint32_t saddr) {
   d |= (uint64_t)4 << 61;
   return d;
 }
-constexpr int THREADS = 512;
+constexpr int THREADS = 640;                  // w0 loader, w1 MMA issuer, w4-11 A producers, w12-19 epilogue
 
 // ------------------------------------------------------------------ operand packing kernels
 // fp32 (V,E) -> bf16 (V,Ep), zero-padded columns.
@@ -91,6 +91,7 @@ struct FwdParams {
   float inv_keep;
   uint32_t seed_x, seed_c;
   int dbg;                        // experiments (LSTUR_FWD_DBG): 1 = epilogue only hands the accumulator back, 2 = producers only signal
+  long long* trace;               // optional: wait cycles of pair 0's MMA issuer (tools/perf_fwd.py)
   uint8_t* xmask;                 // optional (n_titles, L, Ep/8): keep bits of the X-dropout, one byte per 16-byte piece, so
                                   // the weight-gradient kernel need not replay the hash (bit j / 4+j: low / high half of word j)
 };
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
     for (int s = 0; s < NUM_STAGES; ++s) {
       // leader: its 4 producer warps + its weight loader's expect_tx arrival + the peer's 4 producer warps (remote
       // arrives; the peer's warp 4 first waits for the peer's own bulk copies).  peer: only its loader's expect_tx.
-      mbar_init(bar_full + 8 * s, crank == 0 ? 9 : 1);
+      mbar_init(bar_full + 8 * s, crank == 0 ? 17 : 1);   // 8 own + 8 peer producer warps + the weight loader
       mbar_init(bar_empty + 8 * s, 1);    // multicast tcgen05.commit of the leader
     }
     mbar_init(bar_t_full, 1);              // multicast tcgen05.commit of the leader
@@ -298,12 +299,18 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
       const uint32_t idesc0 = make_idesc(2 * TILE_M, 2 * n0h, FP16), idesc1 = make_idesc(2 * TILE_M, n1h > 0 ? 2 * n1h : 16, FP16);
       int s = 0;
       uint32_t ph = 0, pht = 0;
+      const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+      long long tw_acc = 0, tw_full = 0, t_start = tracing ? clock64() : 0;
       for (int tp = pair; tp < n_tp; tp += n_pairs) {
+        long long t0 = tracing ? clock64() : 0;
         mbar_wait(bar_t_empty, pht ^ 1, 2);
+        if (tracing) tw_acc += clock64() - t0;
         tc_fence_after();
         uint32_t accum = 0;
         for (int c = 0; c < EC; ++c) {
+          t0 = tracing ? clock64() : 0;
           mbar_wait(bar_full + 8 * s, ph, 3);
+          if (tracing) tw_full += clock64() - t0;
           tc_fence_after();
           if (leader) {
             const uint32_t a_stage = smem_base + s * stage_bytes, b_stage = a_stage + A_STAGE_BYTES;
@@ -328,12 +335,16 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
         __syncwarp();
         pht ^= 1;
       }
+      if (tracing && lane == 0) { p.trace[0] = tw_acc; p.trace[1] = tw_full; p.trace[2] = clock64() - t_start; }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < 12) {
     // ===================== A producers: embedding gather -> three shifted swizzled tap tiles =====================
     // lane -> (row within a group of 8, 16-byte piece of the 64-byte row); loads for chunk c+1 (and the token ids of
     // the next tile) are issued before chunk c is hashed and stored, so L2 latency is off the critical path.
-    const int pw = warp - 4;                 // title slot of the tile
+    // Eight warps: two per title slot, each thread two of the slot's rows per stage (a producer warp's instruction
+    // stream is latency-bound, so the work is spread over more warps rather than over more rows per thread).
+    const int pw = (warp - 4) & 3;           // title slot of the tile
+    const int rh = (warp - 4) >> 2;          // which half of the slot's four 8-row groups
     const int rsub = lane >> 2, piece = lane & 3;
     int s = 0;
     uint32_t ph = 0;
@@ -341,15 +352,15 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
     auto load_ids = [&](int tp, int* ids) {
       const int n = (2 * tp + (int)crank) * TPT + pw;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int t = 8 * i + rsub;
+      for (int i = 0; i < 2; ++i) {
+        const int t = 8 * (2 * rh + i) + rsub;
         // raw id: not inspected here (no stall on the load); clamped when the rows are requested
         ids[i] = (tp < n_tp && n < p.n_titles && t < p.L) ? __ldg(p.tok + (long long)n * p.L + t) : kNoToken;
       }
     };
     auto load_rows = [&](const int* ids, int c, uint4* v) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 2; ++i) {
         v[i] = make_uint4(0, 0, 0, 0);
         if (ids[i] != kNoToken) {
           const int id = (ids[i] < 0 || ids[i] >= p.V) ? 0 : ids[i];
@@ -357,16 +368,16 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
         }
       }
     };
-    int ids[4], ids_next[4];
-    uint4 v[4], v_next[4];
-    uint32_t row_lo[4], row_in0[4], row_in1[4];
+    int ids[2], ids_next[2];
+    uint4 v[2], v_next[2];
+    uint32_t row_lo[2], row_in0[2], row_in1[2];
     load_ids(pair, ids);
     load_rows(ids, 0, v_next);
     for (int tp = pair; tp < n_tp; tp += n_pairs) {
       const int n = (2 * tp + (int)crank) * TPT + pw;
       for (int c = 0; c < EC; ++c) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = v_next[i];
+        for (int i = 0; i < 2; ++i) v[i] = v_next[i];
         if (c + 1 < EC) {
           load_rows(ids, c + 1, v_next);
           if (c + 2 == EC) load_ids(tp + n_pairs, ids_next);
@@ -377,8 +388,8 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
         if (DROP) {
           if (c == 0) {   // per tile: pair index of column 0 of each of this thread's rows, inner hash of its high word
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint64_t rowquad = (((uint64_t)n * p.L + (8 * i + rsub)) * (uint64_t)p.Ep) >> 2;
+            for (int i = 0; i < 2; ++i) {
+              const uint64_t rowquad = (((uint64_t)n * p.L + (8 * (2 * rh + i) + rsub)) * (uint64_t)p.Ep) >> 2;
               const uint32_t hi = (uint32_t)(rowquad >> 32);
               row_lo[i] = (uint32_t)rowquad;
               row_in0[i] = quad_key(hi, p.seed_x);
@@ -386,7 +397,7 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
             }
           }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < 2; ++i) {
             if (ids[i] == kNoToken) continue;
             const uint32_t lo0 = row_lo[i] + (uint32_t)((c * KBLK + piece * 8) >> 2);
             uint32_t* w = reinterpret_cast<uint32_t*>(&v[i]);
@@ -403,7 +414,7 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
             }
             // bits 0-3 (low halves of words 0-3) and 16-19 (high halves) -> one byte
             if (p.xmask)
-              p.xmask[((long long)n * p.L + (8 * i + rsub)) * (p.Ep >> 3) + c * (KBLK / 8) + piece] =
+              p.xmask[((long long)n * p.L + (8 * (2 * rh + i) + rsub)) * (p.Ep >> 3) + c * (KBLK / 8) + piece] =
                   (uint8_t)((keep | (keep >> 12)) & 0xffu);
           }
         }
@@ -412,8 +423,8 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
         const uint32_t stage = smem_base + s * stage_bytes;
         if (!(p.dbg & 2))
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = pw * SLOT + 8 * i + rsub;
+        for (int i = 0; i < 2; ++i) {
+          const int r = pw * SLOT + 8 * (2 * rh + i) + rsub;
 #pragma unroll
           for (int j = 0; j < TAPS; ++j) {
             const int rr = (r + 1 - j) & (TILE_M - 1);
@@ -436,15 +447,15 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
         if (++s == NUM_STAGES) { s = 0; ph ^= 1; }
         if (c + 1 == EC) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) ids[i] = ids_next[i];
+          for (int i = 0; i < 2; ++i) ids[i] = ids_next[i];
         }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 12) {
     // ===================== epilogue: bias/ReLU/masks/dropout/attention pooling =====================
     // Thread (q, lane) owns token row 32q+lane of this CTA's tile = token `lane` of title tile*4+q; the two feature
     // halves of a row are handled by warps ew and ew+4 and combined through shared memory.
-    const int ew = warp - 8, q = ew & 3, half = ew >> 2;
+    const int ew = warp - 12, q = ew & 3, half = ew >> 2;
     const int f_beg = half * Fh, f_end = f_beg + Fh;
     const float att_bias = p.att_b[0];
     EpiCtx ec;
@@ -970,6 +981,7 @@ extern "C" int lstur_news_conv_tc_fwd_m(int n_titles, int L, int E, int F, int V
   p.seed_x = seed * 2u; p.seed_c = seed * 2u + 1u;
   p.dbg = getenv("LSTUR_FWD_DBG") ? atoi(getenv("LSTUR_FWD_DBG")) : 0;
   p.xmask = (uint8_t*)xmask_out;
+  p.trace = (long long*)g_tc_trace_ptr;
   size_t smem = 1024 + (size_t)tc::NUM_STAGES * (tc::A_STAGE_BYTES + (size_t)tc::TAPS * (F / 2) * tc::ROWB) + 256 + 4096 +
                 (((size_t)2 * F * sizeof(float) + 15) & ~(size_t)15) + (size_t)8 * tc::STG_WARP_BYTES;
   static bool attr_set = false;

@@ -27,3 +27,9 @@ for drop in drops:
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
     print('fwd dropout=%.1f  %.3f ms  %.0f TFLOP/s' % (drop, ms, flop / ms / 1e9))
+    trace = torch.zeros(8 * 16, dtype=torch.int64, device='cuda')
+    lib.lstur_tc_set_trace(P_(trace))
+    lib.lstur_news_conv_tc_fwd(N, L, E, F, V, P_(tok), P_(emb), P_(wimg), P_(cb), P_(aw), P_(ab), P_(c_out), P_(pooled), P_(a), P_(w), ctypes.c_float(drop), 1, 1, 0, st())
+    torch.cuda.synchronize(); lib.lstur_tc_set_trace(None)
+    tr = trace.cpu().numpy()
+    print('  MMA issuer of pair 0: waits for the accumulator (epilogue) %d, for full stages (producers / weights) %d, of %d cycles' % (tr[0], tr[1], tr[2]))
