@@ -156,3 +156,50 @@ def test_categorical_crossentropy_clip():
     assert abs(on.categorical_crossentropy(y, np.array([[0.5, 0.25, 0.25]])) - math.log(2)) < 1e-12
     assert abs(on.categorical_crossentropy(y, np.array([[0.0, 0.5, 0.5]])) + math.log(1e-7)) < 1e-9      # clipped
     assert abs(on.categorical_crossentropy(y, np.array([[2.0, 1.0, 1.0]])) - math.log(2)) < 1e-12       # renormalised
+
+
+@pytest.mark.parametrize('arch,score_model', [('igru', 'dnn'), ('igru', 'ddot'), ('ngru', 'dnn'), ('ngru', 'ddot'),
+                                              ('iigru', 'dot'), ('niavg', 'dot'), ('niavg', 'dnn')])
+def test_remaining_archs_and_scorers_two_implementations(arch, score_model):
+    """'dnn' / 'ddot' scorers (task/paper.py:448-455), 'ngru' (2U user vector), 'iigru' (two user tables), 'niavg'
+    (masked mean): the float64 numpy loops and the torch restatement are written independently and must agree."""
+    P = synth.make_weights(SH, arch=arch, bias_noise=0.05, seed=21, score_model=score_model)
+    (b,), _ = synth.make_batches(SH, 1, seed=22)
+    ct, cd = TOK[b['hist_doc']], TOK[b['cand_doc']]
+    pn = on.lstur_forward(P, b['user'], ct, cd, arch=arch, score_model=score_model)
+    pt = ot.LsturOracle(P, arch=arch, score_model=score_model).forward(b['user'], ct, cd).detach().numpy()
+    assert pn.shape == (SH.B, 1 + SH.K) and np.abs(pn - pt).max() < 1e-12
+    assert np.abs(pn.sum(-1) - 1).max() < 1e-12
+
+
+def test_niavg_is_the_masked_mean_by_hand():
+    """models.GlobalAveragePoolingMaskSupport (models.py:433-435): sum over the window / (number of unmasked steps +
+    1e-7); masked (all-zero) steps contribute nothing to either."""
+    H = np.zeros((2, 4, 3))
+    H[0, 1] = [1.0, 2.0, 3.0]
+    H[0, 3] = [3.0, 2.0, 1.0]
+    u = on.user_encoder('niavg', np.zeros(2, dtype=int), H, {})
+    assert np.allclose(u[0], np.array([4.0, 4.0, 4.0]) / (2 + 1e-7)) and np.all(u[1] == 0)
+    ut = ot.user_encoder('niavg', torch.zeros(2, dtype=torch.long), torch.tensor(H), {})
+    assert np.abs(ut.numpy() - u).max() < 1e-15
+
+
+def test_weighted_bce_by_hand_and_gradient():
+    """Seq2Vec.loss (task/seq2vec.py:213-216): -0.5 (1+K) mean(y log(p+1e-8) gain + (1-y) log(1-p+1e-8) / K)."""
+    y = torch.tensor([[1.0], [0.0], [0.0]], dtype=torch.float64)
+    p = torch.tensor([[0.8], [0.3], [0.6]], dtype=torch.float64, requires_grad=True)
+    K, gain = 4, 1.5
+    want = -0.5 * (1 + K) * (math.log(0.8 + 1e-8) * gain + math.log(0.7 + 1e-8) / K + math.log(0.4 + 1e-8) / K) / 3
+    l = ot.weighted_bce(y, p, gain=gain, negative_samples=K)
+    assert abs(float(l.detach()) - want) < 1e-14
+    l.backward()
+    g = p.grad.numpy().reshape(-1)
+    want_g = -0.5 * (1 + K) / 3 * np.array([gain / (0.8 + 1e-8), -1 / (K * (0.7 + 1e-8)), -1 / (K * (0.4 + 1e-8))])
+    assert np.abs(g - want_g).max() < 1e-12
+    # sigmoid head of the torch oracle: one candidate per row
+    P = synth.make_weights(SH, arch='igru', bias_noise=0.05, seed=5, score_model='dnn')
+    (b,), _ = synth.make_batches(SH, 1, seed=6)
+    ora = ot.LsturOracle(P, arch='igru', score_model='dnn')
+    u, c, d = ora._ints(b['user'], TOK[b['hist_doc']], TOK[b['cand_doc']][:, :1])
+    out = ot.forward(ora.P, u, c, d, arch='igru', score_model='dnn', head='sigmoid')
+    assert out.shape == (SH.B, 1) and bool(((out > 0) & (out < 1)).all())
