@@ -428,3 +428,40 @@ def test_days_id_vert_surface(lib):
     assert 0.0 <= h.last_evaluation['auc'] <= 1.0 and h.model is model
     dv = model.get_layer('doc_encoder').predict(x[1][0])
     assert dv.shape == (sh.W, sh.U)
+
+
+def test_engine_matches_variant_golden_fixtures(lib):
+    """Committed fixtures of the remaining archs / scorers / sigmoid family (tests/golden/make_golden_variants.py)."""
+    import importlib.util
+    from mnexp_b200.engine import LsturEngine
+    here = os.path.dirname(__file__)
+    spec = importlib.util.spec_from_file_location('mgv', os.path.join(here, 'golden', 'make_golden_variants.py'))
+    mgv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mgv)
+    gold = np.load(os.path.join(here, 'golden', 'lstur_golden_variants.npz'))
+    sh = synth.SHAPES['tiny']
+    tok, _, _ = synth.make_docs(sh.n_news, sh.L, sh.vocab)
+    eng_arch = {'iicat': 'iigru'}
+    for arch, score_model, head in mgv.CASES:
+        key = '%s-%s-%s' % (arch, score_model, head)
+        P = synth.make_weights(sh, arch=arch, bias_noise=0.05, seed=5150, score_model=score_model)
+        (b,), _ = synth.make_batches(sh, 1, seed=51)
+        b = dict(b)
+        kw = {}
+        if head == 'bce':
+            b['cand_doc'] = b['cand_doc'][:, :1]
+            b['label'] = gold[key + '/label']
+            kw = dict(flavour='sigmoid', loss='bce', gain=mgv.GAIN, bce_neg=sh.K)
+        eng = LsturEngine(P, sh.B, sh.W, b['cand_doc'].shape[1], sh.L, arch=eng_arch.get(arch, arch), doc_tokens=tok,
+                          score_model=score_model, **kw)
+        db = eng.to_device_batch(b)
+        probs = eng.forward(db, training=True, seed=1).cpu().numpy().copy()
+        eng.backward(db)
+        torch.cuda.synchronize()
+        assert rel(probs, gold[key + '/probs']) < 5e-5, key
+        assert abs(eng.loss() - float(gold[key + '/loss'])) < 5e-5 * max(1.0, abs(float(gold[key + '/loss']))), key
+        g = eng.get_grads_dict()
+        for k in g:
+            gk = key + '/grad/' + k
+            if gk in gold.files and k not in ('att_b', 'so_b'):
+                assert rel(g[k], gold[gk]) < 1e-4, (key, k)

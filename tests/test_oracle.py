@@ -203,3 +203,19 @@ def test_weighted_bce_by_hand_and_gradient():
     u, c, d = ora._ints(b['user'], TOK[b['hist_doc']], TOK[b['cand_doc']][:, :1])
     out = ot.forward(ora.P, u, c, d, arch='igru', score_model='dnn', head='sigmoid')
     assert out.shape == (SH.B, 1) and bool(((out > 0) & (out < 1)).all())
+
+
+def test_variant_golden_fixtures_reproduce():
+    """tests/golden/lstur_golden_variants.npz (make_golden_variants.py): remaining archs, scorers and the sigmoid family."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('mgv', os.path.join(os.path.dirname(__file__), 'golden', 'make_golden_variants.py'))
+    mgv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mgv)
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'lstur_golden_variants.npz'))
+    for arch, score_model, head in mgv.CASES:
+        key = '%s-%s-%s' % (arch, score_model, head)
+        _, _, _, _, probs, loss, grads = mgv.run_case(arch, score_model, head, SH, TOK)
+        assert np.array_equal(probs, gold[key + '/probs']) and loss == float(gold[key + '/loss'])
+        for k, g in grads.items():
+            if g is not None and k != 'word_emb':
+                assert np.array_equal(g.numpy(), gold[key + '/grad/' + k]), (key, k)
