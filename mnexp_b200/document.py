@@ -1,36 +1,37 @@
-"""Title token parsers — same behaviour as the reference's document.py:12-54 (token layout consumed by the hot path)."""
+"""Title token parsing with the call surface of the reference's document.py:12-54.
+
+`DocumentParser(step, step, ...)` composes steps left to right; `parse_document` turns the DocMeta text field into
+token-id sentences; `pad_document(size, length)` lays the first `size` non-empty sentences into a zero matrix — this is
+the (L,) token layout every title of the hot path has (float64, like the reference's np.zeros buffer)."""
+from functools import reduce
+
 import numpy as np
 
 
 class DocumentParser:
+    """Callable pipeline: DocumentParser(f, g)(x) == g(f(x))."""
+
     def __init__(self, *func):
-        self.func = func
+        self.func = tuple(func)
 
     def __call__(self, doc):
-        for f in self.func:
-            doc = f(doc)
-        return doc
+        return reduce(lambda value, step: step(value), self.func, doc)
 
 
 def parse_document(sep1='#N#', sep2=' '):
     """'3 7 9#N#4 4' -> [[3, 7, 9], [4, 4]]   (document.py:23-27)"""
-    def f(doc):
-        return [[int(x) for x in d.split(sep2)] for d in doc.split(sep1)]
-    return f
+    def split(text):
+        return [list(map(int, sentence.split(sep2))) for sentence in text.split(sep1)]
+    return split
 
 
 def pad_document(size, length):
-    """First `size` non-empty sentences, right-zero-padded / truncated to `length`; float64 like np.zeros
-    (document.py:37-54)."""
-    def f(doc):
-        result = np.zeros((size, length))
-        i = 0
-        for d in doc:
-            if d:
-                n = min(len(d), length)
-                result[i, :n] = d[:n]
-                i += 1
-                if i == size:
-                    break
-        return result
-    return f
+    """(size, length) float64 matrix of the first `size` non-empty sentences, each cut to `length` tokens and
+    right-padded with 0 (document.py:37-54)."""
+    def pad(sentences):
+        rows = [s[:length] for s in sentences if s][:size]
+        out = np.zeros((size, length))
+        for k, row in enumerate(rows):
+            out[k, :len(row)] = row
+        return out
+    return pad

@@ -7,28 +7,34 @@ import numpy as np
 from .. import document, settings, utils
 
 
+def _stack_columns(samples):
+    """list of sample tuples -> one stacked numpy array per tuple position."""
+    return [np.stack(column) for column in zip(*samples)]
+
+
 class Seq2Vec:
+    """Base task handler: loads DocMeta, exposes `train` / `valid` / `test` batch generators over the subclass's
+    `train_gen` / `valid_gen` / `test_gen` sample generators (task/seq2vec.py:16-216)."""
+
     class Window:
-        """Sliding click history of `window_size` doc ids, left-padded with doc 0 (task/seq2vec.py:17-53)."""
+        """The last `window_size` clicked doc ids, oldest first, unfilled slots = doc 0 (left padding);
+        `count` = number of pushes so far (task/seq2vec.py:17-53)."""
         __slots__ = ['count', 'docs', 'click_history']
 
         def __init__(self, docs, window_size):
-            self.count = 0
-            self.docs = docs
-            self.click_history = [0 for _ in range(window_size)]
-
-        def get_title(self, elimination=None):
-            if elimination:
-                return np.stack([self.docs[i].title if i not in elimination else self.docs[0].title
-                                 for i in self.click_history])
-            return np.stack([self.docs[i].title for i in self.click_history])
+            self.docs, self.count = docs, 0
+            self.click_history = [0] * window_size
 
         def get_ids(self):
             return np.asarray(self.click_history, dtype=np.int32)
 
+        def get_title(self, elimination=None):
+            hidden = elimination or ()
+            return np.stack([self.docs[0 if i in hidden else i].title for i in self.click_history])
+
         def push(self, doc):
+            del self.click_history[0]
             self.click_history.append(doc)
-            self.click_history.pop(0)
             self.count += 1
 
         @property
@@ -36,12 +42,13 @@ class Seq2Vec:
             return len(self.click_history)
 
     class Impression:
+        """'p1 p2#TAB#n1 n2 n3' -> clicked / shown-not-clicked doc ids."""
         __slots__ = ['pos', 'neg']
 
         def __init__(self, d):
-            d = d.split('#TAB#')
-            self.pos = [int(k) for k in d[0].split(' ')]
-            self.neg = [int(k) for k in d[1].split(' ')]
+            clicked, shown = d.split('#TAB#')[:2]
+            self.pos = list(map(int, clicked.split(' ')))
+            self.neg = list(map(int, shown.split(' ')))
 
         def negative_samples(self, n):
             return np.random.choice(self.neg, n)          # with replacement (task/seq2vec.py:61-62)
@@ -50,29 +57,29 @@ class Seq2Vec:
         __slots__ = ['title', 'body']
 
         def __init__(self, title, body):
-            self.title = title
-            self.body = body
+            self.title, self.body = title, body
 
     def _extract_impressions(self, x):
-        return [self.Impression(d) for d in x.split('#N#') if not d.startswith('#TAB#') and not d.endswith('#TAB#')]
+        return [self.Impression(d) for d in x.split('#N#') if not (d.startswith('#TAB#') or d.endswith('#TAB#'))]
 
     def __init__(self, config: settings.Config):
         self.is_training = True
         self.config = config
-        self._load_docs()
-        self._load_users()
-        self._load_data()
+        for load in (self._load_docs, self._load_users, self._load_data):
+            load()
 
     def _load_docs(self):
-        """DocMeta.tsv -> {doc id: News(title (L,), body)} plus the all-zero pad doc 0 (task/seq2vec.py:85-110)."""
+        """DocMeta.tsv (tab-separated: name, id, vertical, subvertical, title tokens, body tokens) ->
+        {doc id: News(title (L,), body)} plus the all-zero pad document 0 (task/seq2vec.py:85-110)."""
         logging.info('[+] loading docs metadata')
-        title_parser = document.DocumentParser(document.parse_document(), document.pad_document(1, self.config.title_shape))
+        to_title = document.DocumentParser(document.parse_document(), document.pad_document(1, self.config.title_shape))
+        self.docs = {}
         with open(self.config.doc_meta_input) as file:
-            docs = [line.strip('\n').split('\t') for line in file]
-        self.docs = {int(line[1]): self.News(title_parser(line[4])[0], None) for line in docs}
-        self.doc_count = max(self.docs.keys()) + 1
-        doc_example = self.docs[self.doc_count - 1]
-        self.docs[0] = self.News(np.zeros_like(doc_example.title), None)
+            for line in file:
+                cols = line.rstrip('\n').split('\t')
+                self.docs[int(cols[1])] = self.News(to_title(cols[4])[0], None)
+        self.doc_count = 1 + max(self.docs)
+        self.docs[0] = self.News(np.zeros(self.config.title_shape), None)
         logging.info('[-] loaded docs metadata')
 
     def doc_token_table(self):
@@ -91,30 +98,32 @@ class Seq2Vec:
 
     @property
     def train(self):
-        """Shuffle pool of 100*batch_size samples, one batch per yield (task/seq2vec.py:182-193)."""
-        pool = []
-        size = self.config.batch_size * 100
-        gen = self.train_gen()
+        """Batches drawn from a shuffle pool of 100 * batch_size samples: fill the pool, shuffle it, emit its first
+        batch_size samples, keep the rest (task/seq2vec.py:182-193).  Yields ([inputs...], labels)."""
+        bs = self.config.batch_size
+        pool, samples = [], self.train_gen()
         while True:
-            pool.append(next(gen))
-            if len(pool) >= size:
-                np.random.shuffle(pool)
-                batch = [np.stack(x) for x in zip(*pool[:self.config.batch_size])]
-                yield batch[:-1], batch[-1]
-                pool = pool[self.config.batch_size:]
+            pool.append(next(samples))
+            if len(pool) < 100 * bs:
+                continue
+            np.random.shuffle(pool)
+            *inputs, labels = _stack_columns(pool[:bs])
+            del pool[:bs]
+            yield inputs, labels
 
     @property
     def valid(self):
-        gen = self.valid_gen()
+        samples = self.valid_gen()
         while True:
-            batch = [np.stack(x) for x in zip(*(next(gen) for _ in range(self.config.batch_size)))]
-            yield batch[:-1], batch[-1]
+            *inputs, labels = _stack_columns([next(samples) for _ in range(self.config.batch_size)])
+            yield inputs, labels
 
     @property
     def test(self):
-        for b in self.test_gen():
-            batch = [np.stack(x) for x in zip(*b)]
-            yield [self.model.predict(batch[:-1]).reshape(-1), batch[-1]]
+        """One impression per yield: [predicted scores (n,), labels (n,)] (task/seq2vec.py:202-206)."""
+        for impression in self.test_gen():
+            *inputs, labels = _stack_columns(impression)
+            yield [self.model.predict(inputs).reshape(-1), labels]
 
     def build_model(self, epoch):
         if epoch == 0:
