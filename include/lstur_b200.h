@@ -97,6 +97,7 @@ int lstur_embed_gather_pad_tcrng(int N, int L, int E, int V, int KS, int Ep, con
 int lstur_conv_tc_available(void);
 int lstur_tc_set_trace(void* dev_buf);   /* profiling hook: clock64 stamps of CTA 0's warp roles; NULL disables */
 int lstur_tc_supported(int L, int E, int F, int KS);
+int lstur_tc_slot(int L);                /* rows of a title slot in the tensor-core kernels: 32 (L <= 31) or 64 (L <= 63) */
 int lstur_tc_padded_e(int E);
 long long lstur_tc_wimg_elems(int E, int F);
 int lstur_pack_word_emb_16(long long V, int E, const float* word_emb, void* emb_16, int fp16, cudaStream_t stream);
@@ -115,15 +116,26 @@ int lstur_news_conv_tc_fwd_m(int n_titles, int L, int E, int F, int V, const int
                              int fp16, int max_ctas, void* xmask_out, cudaStream_t stream);
 int lstur_conv_wgrad_tc_m(int n_titles, int L, int E, int F, int V, const int* tokens, const void* emb_16,
                           const void* dpre_img, float* d_conv_w, float dropout, unsigned seed, int fp16,
-                          void* partial_ws, size_t partial_bytes, const void* xmask, cudaStream_t stream);
+                          void* partial_ws, size_t partial_bytes, const void* xmask, float dpre_scale,
+                          cudaStream_t stream);
+/* Conv1D INPUT gradient on tcgen05 (word-table training: Embedding(trainable=True), task/paper.py:132-138, main.py:36):
+ * dx16 (n_titles, L, lstur_tc_padded_e(E)) 16-bit rows = out_scale * sum_j sum_f dPre[m+1-j, f] * conv_w[j, e, f], from
+ * the dPre image of lstur_attn_pool_bwd_img (its img_scale multiplies through) and the transposed, tap-reversed weight
+ * image of lstur_pack_conv_w_dgrad_tc (lstur_tc_wimg_dgrad_elems 16-bit elements). */
+long long lstur_tc_wimg_dgrad_elems(int E, int F);
+int lstur_pack_conv_w_dgrad_tc(int E, int F, const float* conv_w, void* wimg_d, int fp16, cudaStream_t stream);
+int lstur_conv_dgrad_tc(int n_titles, int L, int E, int F, const void* dpre_img, const void* wimg_d, void* dx16,
+                        float out_scale, int fp16, int max_ctas, cudaStream_t stream);
 
 /* Backward of the tensor-core news encoder: attention/ReLU/mask backward emitting dPre as 16-bit K-block images
- * (lstur_attn_pool_bwd_img), then the Conv1D weight gradient on tcgen05 (lstur_conv_wgrad_tc). */
+ * (lstur_attn_pool_bwd_img; the image holds img_scale * dPre — a power-of-two loss scale that keeps the gradients of a
+ * large-batch mean out of fp16's subnormal range), then the Conv1D weight gradient on tcgen05 (lstur_conv_wgrad_tc;
+ * lstur_conv_wgrad_tc_m takes the image's scale as dpre_scale and divides it out). */
 int lstur_attn_pool_bwd_img(int fp16, int N, int L, int F, const void* Cd_16, const float* a_in, const float* w_in,
                             const float* d_pooled, long long lddp, const float* att_w, void* dpre_img, float dropout,
-                            float* d_att_w, float* d_conv_b, float* d_att_b, int accumulate, float* partials,
-                            size_t partial_bytes, cudaStream_t stream);
-size_t lstur_tc_dpre_img_bytes(int n_titles, int F);
+                            float img_scale, float* d_att_w, float* d_conv_b, float* d_att_b, int accumulate,
+                            float* partials, size_t partial_bytes, cudaStream_t stream);
+size_t lstur_tc_dpre_img_bytes(int n_titles, int L, int F);
 size_t lstur_tc_wgrad_partial_bytes(int n_titles, int E, int F);
 int lstur_conv_wgrad_tc(int n_titles, int L, int E, int F, int V, const int* tokens, const void* emb_16,
                         const void* dpre_img, float* d_conv_w, float dropout, unsigned seed, int fp16,
@@ -269,6 +281,19 @@ int lstur_segment_sum_rows(int n, int D, const int* n_uniq, const int* seg_start
                            const float* src, long long lds, float* out, cudaStream_t stream);
 int lstur_rows_add(int max_rows, const int* n_rows_dev, int D, const int* rows, const float* g_rows, float* table,
                    cudaStream_t stream);
+/* Word-table gradient (keras Embedding(trainable=True) backward, task/paper.py:132-138): d_word_emb (V,E) is overwritten
+ * with sum over token positions p of scale * dX[p,:] * xdrop[p,:] grouped by tokens[p] — stable radix sort of the
+ * positions by token + fixed-tree segment sums, no floating-point atomics (bit-reproducible).  E % 4 == 0, E <= 512.
+ * _16: dX as the 16-bit rows of lstur_conv_dgrad_tc, xmask = the forward's keep bytes (or NULL);
+ * _f32: dXp (n_titles, L+KS-1, E) = gradient of the zero-haloed title buffer of lstur_embed_gather_pad, whose dropout
+ * stream (dropout, seed) is replayed. */
+size_t lstur_word_grad_workspace_bytes(long long n_pos, int V, int E);
+int lstur_word_grad_scatter_16(int n_titles, int L, int E, int V, const int* tokens, const void* dx16, int fp16,
+                               float scale, const void* xmask, float* d_word_emb, void* workspace,
+                               size_t workspace_bytes, cudaStream_t stream);
+int lstur_word_grad_scatter_f32(int n_titles, int L, int KS, int E, int V, const int* tokens, const float* dXp,
+                                float dropout, unsigned seed, float scale, float* d_word_emb, void* workspace,
+                                size_t workspace_bytes, cudaStream_t stream);
 int lstur_axpby(long long n, float a, const float* x, float b, float* y, cudaStream_t stream);
 
 /* Cook.get_doc_encoder concat (task/cook.py:99-113): doc_vec[n, col0 .. col0+dv) = vert_emb[doc_vert[doc_ids[n]]],
@@ -304,6 +329,7 @@ typedef struct lstur_config {
   int loss_model;        /* LSTUR_LOSS_SOFTMAX_CE | LSTUR_LOSS_WEIGHTED_BCE (then C == 1 and label is required) */
   int bce_neg;           /* negative_samples of the weighted BCE (task/seq2vec.py:213-216)                   */
   float gain;            /* its positive-class gain                                                           */
+  int trainable_word_emb; /* textual_embedding_trainable (task/paper.py:136, main.py:36): lstur_backward_w also yields d word_emb */
 } lstur_config;
 
 typedef struct lstur_weights {
@@ -353,6 +379,8 @@ int lstur_plan_view(const lstur_plan* plan, void* workspace, const char* name, v
 #define LSTUR_PROBE_CONV_WGRAD 2
 #define LSTUR_PROBE_GATHER 3
 #define LSTUR_PROBE_GRU_FWD 4
+#define LSTUR_PROBE_CONV_DGRAD 5
+#define LSTUR_PROBE_SCATTER 6
 int lstur_plan_set_probe(lstur_plan* plan, int probe_id, void* start_event, void* stop_event);
 int lstur_event_create(void** ev);
 int lstur_event_destroy(void* ev);
@@ -364,6 +392,10 @@ int lstur_forward(const lstur_plan* plan, const lstur_weights* w, const lstur_ba
  * workspace (views user_rows / d_user_rows / n_user_rows).  grad_scale multiplies d(loss): 1/global_batch. */
 int lstur_backward(const lstur_plan* plan, const lstur_weights* w, const lstur_batch* b, void* workspace,
                    float* dense_grad, float grad_scale, cudaStream_t stream);
+/* Same, for a plan with trainable_word_emb: word_grad (V,E) is overwritten with the dense gradient of the word table
+ * (conv input gradient + segment-sorted scatter-add; rows of tokens absent from the batch are zero). */
+int lstur_backward_w(const lstur_plan* plan, const lstur_weights* w, const lstur_batch* b, void* workspace,
+                     float* dense_grad, float* word_grad, float grad_scale, cudaStream_t stream);
 
 /* Decomposed inference (task/test_pipeline.py:37-211; BASELINE config 4): encode documents once, then run the user
  * encoder and scorer against the cached vectors.  lstur_encode_docs handles n <= B*(W+C) documents per call

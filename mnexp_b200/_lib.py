@@ -25,7 +25,7 @@ class lstur_config(ctypes.Structure):
                  'arch', 'score_model', 'rec_act', 'precision', 'V', 'n_users', 'n_docs')] + \
                [('dropout', ctypes.c_float), ('save_for_backward', ctypes.c_int), ('n_vert', ctypes.c_int),
                 ('n_subvert', ctypes.c_int), ('Hs', ctypes.c_int), ('loss_model', ctypes.c_int),
-                ('bce_neg', ctypes.c_int), ('gain', ctypes.c_float)]
+                ('bce_neg', ctypes.c_int), ('gain', ctypes.c_float), ('trainable_word_emb', ctypes.c_int)]
 
 
 class lstur_weights(ctypes.Structure):

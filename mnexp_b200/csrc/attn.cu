@@ -222,28 +222,35 @@ __device__ __forceinline__ uint4 pack8<__nv_bfloat16>(const float* v) {
 }
 
 constexpr int IMG_THREADS = 256;     // 64 chunk columns x 4 row groups
-template <typename CT>
+// SLOT = rows of a title slot of the image (32 for L <= 31, 64 for L <= 63).  img_scale: power-of-two loss scale of the
+// 16-bit dPre values (gradients of a mean over a large global batch would otherwise sit in fp16's subnormal range);
+// the consumers (conv weight / input gradient) divide it out, and the d conv_b partial sums are unscaled on the way out.
+template <typename CT, int SLOT>
 __global__ void __launch_bounds__(IMG_THREADS)
 attn_bwd_img_kernel(int N, int L, int F, const CT* __restrict__ Cd, const float* __restrict__ a_in,
                     const float* __restrict__ w_in, const float* __restrict__ dp, long long lddp,
-                    const float* __restrict__ ka, uint8_t* __restrict__ img, float inv_keep,
+                    const float* __restrict__ ka, uint8_t* __restrict__ img, float inv_keep, float img_scale,
                     float* __restrict__ partials, int nbuf) {
   extern __shared__ __align__(16) uint8_t att_smem[];
   const int nchunk = F >> 3;                       // 16-byte chunks per row
   // Two title buffers: the (contiguous, L*F*2-byte) saved C of the NEXT title is fetched with one bulk copy while the
   // current one is processed; its d_pooled row and attention weights are prefetched into registers.
-  const size_t buf_bytes = (size_t)32 * nchunk * 16;
+  const size_t buf_bytes = (size_t)SLOT * nchunk * 16;
   // nbuf = 2: the next title is fetched while the current one is processed; nbuf = 1: one buffer, more CTAs per SM
   float* sdp = reinterpret_cast<float*>(att_smem + nbuf * buf_bytes);   // [F]
   float* ska = sdp + F;                                              // [F]
   float* sred = reinterpret_cast<float*>(att_smem);                  // [3][64][16] reduction scratch, after the title loop
-  __shared__ float sdw[32], sdz[32], sw[32];
+  __shared__ float sdw[SLOT], sdz[SLOT], sw[SLOT];
   __shared__ __align__(8) unsigned long long s_bar[2];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c = tid & 63, tg = tid >> 6;           // chunk owned by this thread, row group (0..3)
   const bool c_ok = c < nchunk;
-  const int Fh = F >> 1, ngh = (Fh + 63) >> 6;     // image: [half][group][32 rows][128 B] per title (see store_dpre_img)
-  const long long blk_bytes = (long long)2 * ngh * 4096;
+  const int Fh = F >> 1, ngh = (Fh + 63) >> 6;     // image: [half][group][SLOT rows][128 B] per title
+  constexpr int GROUP_BYTES = SLOT * 128;
+  const long long blk_bytes = (long long)2 * ngh * GROUP_BYTES;
+  // 16-byte pieces between the last feature of a half and the end of its last 32-column K chunk: the input-gradient
+  // kernel reads whole chunks, so they are zeroed (by the otherwise idle chunk threads c >= nchunk)
+  const int pad_pieces = ((((Fh + 31) >> 5) << 5) - Fh) >> 3;
   const uint32_t title_bytes = (uint32_t)L * F * sizeof(CT);
   const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
   const uint32_t buf0 = (uint32_t)__cvta_generic_to_shared(att_smem);
@@ -324,7 +331,7 @@ attn_bwd_img_kernel(int N, int L, int F, const CT* __restrict__ Cd, const float*
         dpa[k][4] = hi.x; dpa[k][5] = hi.y; dpa[k][6] = hi.z; dpa[k][7] = hi.w;
       }
 #pragma unroll
-      for (int tt = 0; tt < 4; ++tt) {
+      for (int tt = 0; tt < SLOT / 8; ++tt) {
         const int t = warp + tt * (IMG_THREADS / 32);
         if (t >= L) break;
         float dot = 0.f;
@@ -343,13 +350,33 @@ attn_bwd_img_kernel(int N, int L, int F, const CT* __restrict__ Cd, const float*
       }
     }
     __syncthreads();
-    if (tid < 32) {
-      const float dwt = tid < L ? sdw[tid] : 0.f, wt = tid < L ? sw[tid] : 0.f;
-      const float q = warp_sum(dwt * wt);
-      const float dz = tid < L ? (dwt - q) * wt * (1.f - a_cur * a_cur) : 0.f;
-      if (tid < L) sdz[tid] = dz;
-      const float dzs = warp_sum(dz);
-      if (tid == 0) dba += dzs;
+    if (SLOT == 32) {
+      if (tid < 32) {
+        const float dwt = tid < L ? sdw[tid] : 0.f, wt = tid < L ? sw[tid] : 0.f;
+        const float q = warp_sum(dwt * wt);
+        const float dz = tid < L ? (dwt - q) * wt * (1.f - a_cur * a_cur) : 0.f;
+        if (tid < L) sdz[tid] = dz;
+        const float dzs = warp_sum(dz);
+        if (tid == 0) dba += dzs;
+      }
+    } else {
+      __shared__ float sq[2], sdzs[2];
+      float dwt = 0.f, wt = 0.f;
+      if (tid < SLOT) {
+        dwt = tid < L ? sdw[tid] : 0.f; wt = tid < L ? sw[tid] : 0.f;
+        const float qh = warp_sum(dwt * wt);
+        if (lane == 0) sq[warp] = qh;
+      }
+      __syncthreads();
+      if (tid < SLOT) {
+        const float q = sq[0] + sq[1];
+        const float dz = tid < L ? (dwt - q) * wt * (1.f - a_cur * a_cur) : 0.f;
+        if (tid < L) sdz[tid] = dz;
+        const float dzs = warp_sum(dz);
+        if (lane == 0) sdzs[warp] = dzs;
+      }
+      __syncthreads();
+      if (tid == 0) dba += sdzs[0] + sdzs[1];
     }
     __syncthreads();
     if (c_ok) {
@@ -357,12 +384,12 @@ attn_bwd_img_kernel(int N, int L, int F, const CT* __restrict__ Cd, const float*
       // was measured here: 3 % slower — the pack/unpack moves cost more issue slots than the pairing saves.)
       float dpf[8], kaf[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { dpf[i] = sdp[c * 8 + i] * inv_keep; kaf[i] = ska[c * 8 + i] * inv_keep; }
+      for (int i = 0; i < 8; ++i) { dpf[i] = sdp[c * 8 + i] * (inv_keep * img_scale); kaf[i] = ska[c * 8 + i] * (inv_keep * img_scale); }
       const int hf = (c * 8 >= Fh) ? 1 : 0, fl = c * 8 - hf * Fh;
       const int g = hf * ngh + (fl >> 6), piece = (fl & 63) >> 3;
-      uint8_t* dst0 = img + (long long)n * blk_bytes + (long long)g * 4096;
+      uint8_t* dst0 = img + (long long)n * blk_bytes + (long long)g * GROUP_BYTES;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
+      for (int k = 0; k < SLOT / 4; ++k) {
         const int t = tg + 4 * k;
         float o[8];
         if (t < L) {
@@ -381,6 +408,15 @@ attn_bwd_img_kernel(int N, int L, int F, const CT* __restrict__ Cd, const float*
           for (int i = 0; i < 8; ++i) o[i] = 0.f;
         }
         *reinterpret_cast<uint4*>(dst0 + t * 128 + ((piece ^ (t & 7)) << 4)) = pack8<CT>(o);
+      }
+    } else if (c - nchunk < 2 * pad_pieces) {
+      const int k = c - nchunk, hf = k / pad_pieces, fl = Fh + (k % pad_pieces) * 8;
+      const int g = hf * ngh + (fl >> 6), piece = (fl & 63) >> 3;
+      uint8_t* dst0 = img + (long long)n * blk_bytes + (long long)g * GROUP_BYTES;
+#pragma unroll
+      for (int kk = 0; kk < SLOT / 4; ++kk) {
+        const int t = tg + 4 * kk;
+        *reinterpret_cast<uint4*>(dst0 + t * 128 + ((piece ^ (t & 7)) << 4)) = make_uint4(0, 0, 0, 0);
       }
     }
   }
@@ -408,7 +444,8 @@ attn_bwd_img_kernel(int N, int L, int F, const CT* __restrict__ Cd, const float*
 // partials[grid][2F+1] -> d_att_w[F], d_conv_b[F], d_att_b[1] in a fixed order: 256 threads = 32 columns x 8 row
 // strides; the eight stride sums of a column are combined in ascending order.
 __global__ void attn_bwd_reduce_kernel(int grid, int F, const float* __restrict__ partials, float* __restrict__ d_att_w,
-                                       float* __restrict__ d_conv_b, float* __restrict__ d_att_b, int accumulate) {
+                                       float* __restrict__ d_conv_b, float* __restrict__ d_att_b, int accumulate,
+                                       float cb_scale) {
   __shared__ float sm[8][32];
   const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
@@ -422,6 +459,7 @@ __global__ void attn_bwd_reduce_kernel(int grid, int F, const float* __restrict_
 #pragma unroll
   for (int q = 0; q < 8; ++q) t += sm[q][lane];
   float* dst = c < F ? d_att_w + c : (c < 2 * F ? d_conv_b + (c - F) : d_att_b);
+  if (c >= F && c < 2 * F) t *= cb_scale;     // d conv_b was summed from loss-scaled dPre values
   *dst = accumulate ? *dst + t : t;
 }
 
@@ -519,7 +557,7 @@ static int attn_pool_bwd_impl(int c_is_bf16, int out_mode, int N, int L, int Lro
 #undef LAUNCH_T
   LSTUR_CHECK_LAUNCH("lstur_attn_pool_bwd");
   attn_bwd_reduce_kernel<<<cdiv(2 * F + 1, 32), 256, 0, stream>>>(grid, F, partials, d_att_w, d_conv_b, d_att_b,
-                                                                     accumulate);
+                                                                     accumulate, 1.f);
   LSTUR_CHECK_LAUNCH("lstur_attn_pool_bwd(reduce)");
   return LSTUR_OK;
 }
@@ -545,13 +583,16 @@ extern "C" int lstur_attn_pool_bwd_16(int fp16, int N, int L, int Lrows, int F, 
                             stream);
 }
 
-// Tensor-core backward: same arithmetic, dPre emitted as 16-bit K-block images for lstur_conv_wgrad_tc
-// (lstur_tc_dpre_img_bytes(N,F) bytes; 32-row title slots, pad rows zero).
+// Tensor-core backward: same arithmetic, dPre emitted as 16-bit K-block images for lstur_conv_wgrad_tc /
+// lstur_conv_dgrad_tc (lstur_tc_dpre_img_bytes(N,L,F) bytes; title slots of lstur_tc_slot(L) rows, pad rows zero).
+// The image holds img_scale * dPre (img_scale > 0, a power of two keeps it exact); the consumers divide it out.
 extern "C" int lstur_attn_pool_bwd_img(int fp16, int N, int L, int F, const void* Cd_16, const float* a_in,
                                        const float* w_in, const float* d_pooled, long long lddp, const float* att_w,
-                                       void* dpre_img, float dropout, float* d_att_w, float* d_conv_b, float* d_att_b,
-                                       int accumulate, float* partials, size_t partial_bytes, cudaStream_t stream) {
-  LSTUR_REQUIRE(N >= 0 && L >= 1 && L <= 31 && F % 16 == 0 && F <= 512 && dpre_img != nullptr, "lstur_attn_pool_bwd_img");
+                                       void* dpre_img, float dropout, float img_scale, float* d_att_w, float* d_conv_b,
+                                       float* d_att_b, int accumulate, float* partials, size_t partial_bytes,
+                                       cudaStream_t stream) {
+  LSTUR_REQUIRE(N >= 0 && L >= 1 && L <= 63 && F % 16 == 0 && F <= 512 && dpre_img != nullptr && img_scale > 0.f,
+                "lstur_attn_pool_bwd_img");
   int grid = lstur_attn_bwd_grid(N);
   LSTUR_REQUIRE(partials != nullptr && partial_bytes >= (size_t)grid * (2 * F + 1) * sizeof(float), "lstur_attn_pool_bwd_img");
   if (N == 0) {
@@ -564,21 +605,23 @@ extern "C" int lstur_attn_pool_bwd_img(int fp16, int N, int L, int F, const void
   }
   const float inv_keep = 1.f / (1.f - dropout);
   const int nbuf = attn_bwd_nbuf();
-  size_t smem = (size_t)nbuf * 32 * (F / 8) * 16 + (size_t)2 * F * sizeof(float);
+  const int slot = L <= 31 ? 32 : 64;
+  size_t smem = (size_t)nbuf * slot * (F / 8) * 16 + (size_t)2 * F * sizeof(float);
   if (smem < (size_t)3 * 64 * 16 * sizeof(float)) smem = (size_t)3 * 64 * 16 * sizeof(float);   // the final reduction scratch aliases the title buffers
-  if (smem > 48 * 1024) {
-    cudaFuncSetAttribute(attn_bwd_img_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(attn_bwd_img_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  }
-  if (fp16)
-    attn_bwd_img_kernel<__half><<<grid, IMG_THREADS, smem, stream>>>(N, L, F, (const __half*)Cd_16, a_in, w_in, d_pooled, lddp,
-                                                                     att_w, (uint8_t*)dpre_img, inv_keep, partials, nbuf);
-  else
-    attn_bwd_img_kernel<__nv_bfloat16><<<grid, IMG_THREADS, smem, stream>>>(N, L, F, (const __nv_bfloat16*)Cd_16, a_in, w_in,
-                                                                            d_pooled, lddp, att_w, (uint8_t*)dpre_img,
-                                                                            inv_keep, partials, nbuf);
+#define IMG_LAUNCH(CT_, SLOT_)                                                                                          \
+  do {                                                                                                                  \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(attn_bwd_img_kernel<CT_, SLOT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    attn_bwd_img_kernel<CT_, SLOT_><<<grid, IMG_THREADS, smem, stream>>>(N, L, F, (const CT_*)Cd_16, a_in, w_in, d_pooled, lddp, \
+                                                                         att_w, (uint8_t*)dpre_img, inv_keep, img_scale, partials, nbuf); \
+  } while (0)
+  if (fp16 && slot == 32) IMG_LAUNCH(__half, 32);
+  else if (fp16) IMG_LAUNCH(__half, 64);
+  else if (slot == 32) IMG_LAUNCH(__nv_bfloat16, 32);
+  else IMG_LAUNCH(__nv_bfloat16, 64);
+#undef IMG_LAUNCH
   LSTUR_CHECK_LAUNCH("lstur_attn_pool_bwd_img");
-  attn_bwd_reduce_kernel<<<cdiv(2 * F + 1, 32), 256, 0, stream>>>(grid, F, partials, d_att_w, d_conv_b, d_att_b, accumulate);
+  attn_bwd_reduce_kernel<<<cdiv(2 * F + 1, 32), 256, 0, stream>>>(grid, F, partials, d_att_w, d_conv_b, d_att_b, accumulate,
+                                                                     1.f / img_scale);
   LSTUR_CHECK_LAUNCH("lstur_attn_pool_bwd_img(reduce)");
   return LSTUR_OK;
 }

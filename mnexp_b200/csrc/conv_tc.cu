@@ -1,23 +1,28 @@
-// News encoder forward on the 5th-gen tensor cores: word-embedding gather fused into the
-// Conv1D implicit GEMM (tcgen05.mma, fp32 accumulator in TMEM) with bias + ReLU + pad mask +
-// Masking + Dropout + additive-attention pooling fused in the epilogue.
+// News encoder on the 5th-gen tensor cores: word-embedding gather fused into the Conv1D implicit GEMM
+// (tcgen05.mma, fp32 accumulator in TMEM) with bias + ReLU + pad mask + Masking + Dropout +
+// additive-attention pooling fused in the epilogue; the Conv1D weight gradient; the Conv1D input gradient.
 //
 // Reference ops replaced (task/paper.py:141-158, models.py:474-489):
 //   Embedding(mask_zero=False) -> Dropout -> Conv1D(F,3,'same',relu) -> pad-token mask ->
-//   Masking -> Dropout -> SimpleAttentionMaskSupport.
+//   Masking -> Dropout -> SimpleAttentionMaskSupport, and their backward.
 //
-// GEMM view: D[m, f] = sum_{j<3} sum_e X[m+j-1, e] * Wc[j, e, f], m = token position.
-//   M tile  = 128 rows = 4 title slots of 32 rows (L <= 31 tokens + >=1 zero row, which is both the
-//             right halo of its title and the left halo of the next one; rows wrap inside the tile).
-//   N       = F (<= 512 TMEM columns), issued as two UMMAs per K step (256 + rest).
-//   K       = 3 taps x Ep (E padded to a multiple of 64), K block = 64 bf16 = one 128B swizzle row.
-// A operand: producer warps gather each embedding row ONCE per 64-column chunk (16B loads, 8 lanes
-//   per row), apply the input dropout mask, and store it into the three tap tiles at row offsets
-//   +1/0/-1 in the canonical K-major SWIZZLE_128B layout (16B chunk index XOR row%8).
-// B operand: the conv weights are re-packed per call into bf16 K-major SWIZZLE_128B images in
-//   consumption order, so one cp.async.bulk (TMA, UBLKCP) per K block lands an MMA-ready tile.
-// Warp roles (512 threads): w0 B loader, w1 TMEM alloc + MMA issuer, w4-7 A producers,
-//   w8-15 epilogue (TMEM lane quarter = warp%4, column half = (warp-8)/4).
+// GEMM view of the forward: D[m, f] = sum_{j<3} sum_e X[m+j-1, e] * Wc[j, e, f], m = token position.
+//   M tile  = 128 rows = title slots of SLOT rows: 4 x 32 (L <= 31) or 2 x 64 (L <= 63).  A slot holds the L tokens
+//             of a title + >= 1 zero row, which is both the right halo of its title and the left halo of the next
+//             one; rows wrap inside the tile.
+//   N       = F (<= 512 TMEM columns), issued as two pair-MMAs per K step (256 + rest).
+//   K       = 3 taps x Ep (E padded to a multiple of 64), pipeline block = 32 columns = one 64-byte swizzle row.
+// CTA pairs (cta_group::2, M = 256): each CTA owns one 128-row token tile and stages half of the weight rows.
+// A operand: producer warps gather each embedding row ONCE per 32-column chunk (16 B loads, 4 lanes per row), apply
+//   the input dropout mask, and store it into the three tap tiles at row offsets +1/0/-1 in the canonical K-major
+//   SWIZZLE_64B layout (16 B chunk index XOR (row>>1)&3).
+// B operand: the conv weights are re-packed per call into 16-bit K-major SWIZZLE_64B images in consumption order, so
+//   one cp.async.bulk per (chunk, tap) lands an MMA-ready tile.
+// Warp roles (640 threads): w0 weight loader, w1 TMEM alloc + MMA issuer (leader CTA), w4-11 A producers,
+//   w12-19 epilogue (TMEM lane quarter = warp%4, feature half = (warp-12)/4).
+// The input gradient (word-table training, task/paper.py:136) runs the SAME main loop with the roles of the operands
+// changed: "embedding rows" are the rows of the dPre image, the weights are Wc transposed with the taps reversed,
+// N = Ep and the epilogue only scales and stores 16-bit rows (see news_conv_tc_kernel, MODE_DGRAD).
 #include <limits.h>
 #include <stdlib.h>
 
@@ -26,8 +31,7 @@
 namespace lstur {
 namespace tc {
 
-constexpr int SLOT = 32;                      // rows per title slot
-constexpr int TPT = TILE_M / SLOT;            // titles per tile
+constexpr int MODE_FWD = 0, MODE_DGRAD = 1;
 constexpr int EPAD = 64;                      // embedding rows are padded to a multiple of 64 columns
 constexpr int KBLK = 32;                      // K elements per pipeline block: 64-byte rows, SWIZZLE_64B
 constexpr int ROWB = KBLK * 2;                // bytes per shared-memory row
@@ -74,6 +78,25 @@ __global__ void pack_conv_w_kernel(int E, int F, int EC, const float* __restrict
   img[blk * per_blk + byte / 2] = to16(v, fp16);
 }
 
+// Input-gradient weights: dX[m, e] = sum_j sum_f dPre[m+1-j, f] * Wc[j, e, f].  The kernel's tap tile j' holds the rows
+// shifted by j'-1, so its weights are Wc[2-j'] transposed; K runs over the dPre IMAGE's column order: chunk
+// c = half * cph + ch covers conv features f = half*Fh + ch*32 + kk (zero weights where ch*32 + kk >= Fh).
+// Per K block i = c*3 + j' an [Eo rows][32 k] 16-bit image, K-major, 64B-swizzled (Eo = padded output width).
+__global__ void pack_conv_w_dgrad_kernel(int E, int F, int Eo, int cph, const float* __restrict__ Wc,
+                                         uint16_t* __restrict__ img, bool fp16) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_blk = (long long)Eo * KBLK;
+  if (i >= per_blk * 2 * cph * TAPS) return;
+  const int blk = (int)(i / per_blk), rem = (int)(i % per_blk);
+  const int e = rem / KBLK, kk = rem % KBLK;
+  const int c = blk / TAPS, jp = blk % TAPS;
+  const int Fh = F >> 1, half = c / cph, ch = c % cph, fl = ch * KBLK + kk;
+  float v = 0.f;
+  if (e < E && fl < Fh) v = Wc[((long long)(TAPS - 1 - jp) * E + e) * F + half * Fh + fl];
+  const long long byte = (long long)e * ROWB + ((((kk >> 3) ^ ((e >> 1) & 3)) << 4) | ((kk & 7) << 1));
+  img[blk * per_blk + byte / 2] = to16(v, fp16);
+}
+
 struct FwdParams {
   int n_titles, L, F, EC, Ep, V;
   const int* tok;                 // (n_titles, L)
@@ -94,6 +117,12 @@ struct FwdParams {
   long long* trace;               // optional: wait cycles of pair 0's MMA issuer (tools/perf_fwd.py)
   uint8_t* xmask;                 // optional (n_titles, L, Ep/8): keep bits of the X-dropout, one byte per 16-byte piece, so
                                   // the weight-gradient kernel need not replay the hash (bit j / 4+j: low / high half of word j)
+  // MODE_DGRAD (conv input gradient): the A rows are rows of the dPre image written by attn_bwd_img_kernel
+  // (per title [F half][64-column group][SLOT rows][128 B], SWIZZLE_128B), K chunk c = (half, 32-column chunk ch) of it;
+  // F is the OUTPUT width (Ep of the word table), EC = 2 * cph chunks, c_out receives (n_titles, L, F) 16-bit rows
+  const uint8_t* dimg;
+  int ngh, cph;                   // 64-column groups / 32-column chunks per half of the conv features
+  float out_scale;                // dX16 = out_scale * accumulator
 };
 
 // Stage = one 32-column chunk of the embedding: the three shifted tap tiles of this CTA's 128 token rows (A, 24 KB)
@@ -121,8 +150,9 @@ constexpr int STG_WARP_BYTES = 32 * STG_ROW_U4 * 16;
 
 struct RowIO {
   uint4* stg;            // this warp's staging buffer
-  uint16_t* title;       // c_out of token 0 of this warp's title (rows are F apart), or null if the title is invalid
-  int F, L, lane;
+  uint16_t* title;       // c_out of the FIRST token row of this warp (token t0 of its title; rows are F apart), or null
+                         // if the title is invalid
+  int F, L, lane;        // L = token rows of the title that this warp covers (title length - t0, may be <= 0)
   // write `npieces` 16-byte pieces of every lane's row (features [f0, f0 + 8*npieces)) to global
   __device__ __forceinline__ void store(const uint32_t* packed, int f0, int npieces) const {
 #pragma unroll
@@ -203,6 +233,28 @@ __device__ __forceinline__ void epi_pass1_chunk(const EpiCtx& ec, const RowIO& i
   }
   if (!(ec.dbg & 8)) io.store(packed, f0, NC / 8);
 }
+// Input-gradient epilogue for NC accumulator columns of one token row: scale, round to 16 bits (saturating), store.
+template <bool FP16, int NC>
+__device__ __forceinline__ void epi_dgrad_chunk(float scale, const RowIO& io, uint32_t taddr, int f0) {
+  uint32_t r[NC];
+  if (NC == 32) { TMEM_LD_32(taddr, r); } else if (NC == 16) { TMEM_LD_16(taddr, r); } else { TMEM_LD_8(taddr, r); }
+  tmem_ld_wait();
+  uint32_t packed[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) packed[i] = 0u;
+#pragma unroll
+  for (int g = 0; g < NC / 2; ++g)
+    packed[g] = pack16x2_sat<FP16>(__uint_as_float(r[2 * g]) * scale, __uint_as_float(r[2 * g + 1]) * scale);
+  io.store(packed, f0, NC / 8);
+}
+template <bool FP16>
+__device__ __forceinline__ void epi_dgrad_segment(float scale, const RowIO& io, uint32_t trow, int ca, int f0, int n) {
+  int c = 0;
+  for (; c + 32 <= n; c += 32) epi_dgrad_chunk<FP16, 32>(scale, io, trow + ca + c, f0 + c);
+  if (c + 16 <= n) { epi_dgrad_chunk<FP16, 16>(scale, io, trow + ca + c, f0 + c); c += 16; }
+  if (c + 8 <= n) epi_dgrad_chunk<FP16, 8>(scale, io, trow + ca + c, f0 + c);
+}
+
 // one accumulator segment [ca, ca+n) -> features [f0, f0+n), n a multiple of 8
 template <bool FP16, bool DROP>
 __device__ __forceinline__ void epi_pass1_segment(const EpiCtx& ec, const RowIO& io, uint32_t trow, int ca, int f0, int n,
@@ -220,8 +272,10 @@ __device__ __forceinline__ void epi_pass1_segment(const EpiCtx& ec, const RowIO&
 //   f = half*Fh + (c % n0h)         for c <  2*n0h    (half = c / n0h,  first MMA,  n0h = min(Fh,128))
 //   f = half*Fh + n0h + (c' % n1h)  for c' = c-2*n0h  (half = c'/ n1h,  second MMA, n1h = Fh - n0h)
 // so an epilogue thread of column half `half` sees one contiguous feature range [half*Fh, (half+1)*Fh).
-template <bool FP16, bool DROP>
-__global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdParams p) {
+template <bool FP16, bool DROP, int SLOT, int MODE>
+__global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParams p) {
+  constexpr int TPT = TILE_M / SLOT;               // titles per 128-row tile
+  constexpr bool DG = MODE == MODE_DGRAD;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -234,11 +288,12 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
   // barriers (8 B each): full[4] empty[4] tmem_full tmem_empty
   const uint32_t bar_full = misc_base, bar_empty = misc_base + 32, bar_t_full = misc_base + 64, bar_t_empty = misc_base + 72;
   uint32_t* tmem_ptr_smem = (uint32_t*)(misc_gen + 80);
-  float* s_z = (float*)(misc_gen + 256);          // [2 parity][2 halves][128 rows]
-  int* s_any = (int*)(misc_gen + 256 + 2048);     // [2][2][128]
-  float* s_bias = (float*)(misc_gen + 256 + 4096);  // [F]  (x conv-dropout keep scale)
+  float* s_w = (float*)(misc_gen + 128);          // [128 rows] attention weights of the tile (SLOT == 64: pass 2 reads both warps' rows)
+  float* s_z = (float*)(misc_gen + 768);          // [2 parity][2 halves][128 rows]
+  int* s_any = (int*)(misc_gen + 768 + 2048);     // [2][2][128]
+  float* s_bias = (float*)(misc_gen + 768 + 4096);  // [F]  (x conv-dropout keep scale)
   float* s_ka = s_bias + F;                          // [F]
-  uint4* s_stg = (uint4*)(misc_gen + 256 + 4096 + (((size_t)2 * F * sizeof(float) + 15) & ~(size_t)15));   // [8 warps] staging
+  uint4* s_stg = (uint4*)(misc_gen + 768 + 4096 + (((size_t)2 * F * sizeof(float) + 15) & ~(size_t)15));   // [8 warps] staging
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
@@ -249,18 +304,20 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NUM_STAGES; ++s) {
-      // leader: its 4 producer warps + its weight loader's expect_tx arrival + the peer's 4 producer warps (remote
+      // leader: its 8 producer warps + its weight loader's expect_tx arrival + the peer's 8 producer warps (remote
       // arrives; the peer's warp 4 first waits for the peer's own bulk copies).  peer: only its loader's expect_tx.
-      mbar_init(bar_full + 8 * s, crank == 0 ? 17 : 1);   // 8 own + 8 peer producer warps + the weight loader
+      mbar_init(bar_full + 8 * s, crank == 0 ? 17 : 1);
       mbar_init(bar_empty + 8 * s, 1);    // multicast tcgen05.commit of the leader
     }
     mbar_init(bar_t_full, 1);              // multicast tcgen05.commit of the leader
     mbar_init(bar_t_empty, 16);            // (leader) one arrival per epilogue warp of BOTH CTAs
     fence_barrier_init();
   }
-  for (int f = threadIdx.x; f < F; f += THREADS) {
-    s_bias[f] = p.conv_b[f] * ik;
-    s_ka[f] = p.att_w[f];
+  if (!DG) {
+    for (int f = threadIdx.x; f < F; f += THREADS) {
+      s_bias[f] = p.conv_b[f] * ik;
+      s_ka[f] = p.att_w[f];
+    }
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
@@ -338,24 +395,29 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
       if (tracing && lane == 0) { p.trace[0] = tw_acc; p.trace[1] = tw_full; p.trace[2] = clock64() - t_start; }
     }
   } else if (warp >= 4 && warp < 12) {
-    // ===================== A producers: embedding gather -> three shifted swizzled tap tiles =====================
-    // lane -> (row within a group of 8, 16-byte piece of the 64-byte row); loads for chunk c+1 (and the token ids of
+    // ===================== A producers: row gather -> three shifted swizzled tap tiles =====================
+    // lane -> (row within a group of 8, 16-byte piece of the 64-byte row); loads for chunk c+1 (and the row ids of
     // the next tile) are issued before chunk c is hashed and stored, so L2 latency is off the critical path.
-    // Eight warps: two per title slot, each thread two of the slot's rows per stage (a producer warp's instruction
-    // stream is latency-bound, so the work is spread over more warps rather than over more rows per thread).
-    const int pw = (warp - 4) & 3;           // title slot of the tile
-    const int rh = (warp - 4) >> 2;          // which half of the slot's four 8-row groups
+    // Eight warps share the tile's title slots (two warps per 32-row slot, four per 64-row slot), each thread two
+    // rows per stage (a producer warp's instruction stream is latency-bound, so the work is spread over more warps
+    // rather than over more rows per thread).
+    const int pw = (warp - 4) % TPT;         // title slot of the tile
+    const int rh = (warp - 4) / TPT;         // which pair of the slot's 8-row groups
     const int rsub = lane >> 2, piece = lane & 3;
     int s = 0;
     uint32_t ph = 0;
     constexpr int kNoToken = INT_MIN;
+    // MODE_FWD: id = token id (clamped when its embedding row is requested).  MODE_DGRAD: id = n * SLOT + t, the slot
+    // row of the dPre image.
     auto load_ids = [&](int tp, int* ids) {
       const int n = (2 * tp + (int)crank) * TPT + pw;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int t = 8 * (2 * rh + i) + rsub;
+        const bool ok = tp < n_tp && n < p.n_titles && t < p.L;
         // raw id: not inspected here (no stall on the load); clamped when the rows are requested
-        ids[i] = (tp < n_tp && n < p.n_titles && t < p.L) ? __ldg(p.tok + (long long)n * p.L + t) : kNoToken;
+        if (DG) ids[i] = ok ? n * SLOT + t : kNoToken;
+        else ids[i] = ok ? __ldg(p.tok + (long long)n * p.L + t) : kNoToken;
       }
     };
     auto load_rows = [&](const int* ids, int c, uint4* v) {
@@ -363,8 +425,15 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
       for (int i = 0; i < 2; ++i) {
         v[i] = make_uint4(0, 0, 0, 0);
         if (ids[i] != kNoToken) {
-          const int id = (ids[i] < 0 || ids[i] >= p.V) ? 0 : ids[i];
-          v[i] = __ldg((const uint4*)(p.emb + (long long)id * p.Ep + c * KBLK + piece * 8));
+          if (DG) {
+            const int n = ids[i] / SLOT, t = ids[i] % SLOT, half = c / p.cph, ch = c % p.cph;
+            const uint8_t* src = p.dimg + ((long long)n * 2 * p.ngh + half * p.ngh + (ch >> 1)) * (SLOT * 128) + t * 128 +
+                                 ((((ch & 1) * 4 + piece) ^ (t & 7)) << 4);
+            v[i] = __ldg((const uint4*)src);
+          } else {
+            const int id = (ids[i] < 0 || ids[i] >= p.V) ? 0 : ids[i];
+            v[i] = __ldg((const uint4*)(p.emb + (long long)id * p.Ep + c * KBLK + piece * 8));
+          }
         }
       }
     };
@@ -452,11 +521,36 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
       }
     }
   } else if (warp >= 12) {
-    // ===================== epilogue: bias/ReLU/masks/dropout/attention pooling =====================
-    // Thread (q, lane) owns token row 32q+lane of this CTA's tile = token `lane` of title tile*4+q; the two feature
-    // halves of a row are handled by warps ew and ew+4 and combined through shared memory.
+    // ===================== epilogue =====================
+    // Thread (q, lane) owns row 32q+lane of this CTA's tile = token t = (32q+lane) % SLOT of title slot (32q+lane) / SLOT;
+    // the two feature halves of a row are handled by warps ew and ew+4 and combined through shared memory.
     const int ew = warp - 12, q = ew & 3, half = ew >> 2;
     const int f_beg = half * Fh, f_end = f_beg + Fh;
+    const int slot = (q * 32) / SLOT, t0 = (q * 32) % SLOT;      // this warp's title slot, its first token
+    uint32_t pht = 0;
+    RowIO io;
+    io.stg = s_stg + (size_t)ew * (STG_WARP_BYTES / 16);
+    io.F = F; io.L = p.L - t0; io.lane = lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (DG) {
+      // ---- input gradient: scale, round, store the 16-bit rows
+      for (int tp = pair; tp < n_tp; tp += n_pairs) {
+        const int n = (2 * tp + (int)crank) * TPT + slot;
+        io.title = n < p.n_titles ? p.c_out + ((long long)n * p.L + t0) * F : nullptr;
+        mbar_wait(bar_t_full, pht, 6);
+        pht ^= 1;
+        tc_fence_after();
+        epi_dgrad_segment<FP16>(p.out_scale, io, trow, half * n0h, f_beg, n0h);
+        if (n1h > 0) epi_dgrad_segment<FP16>(p.out_scale, io, trow, 2 * n0h + half * n1h, f_beg + n0h, n1h);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (crank == 0) mbar_arrive(bar_t_empty);
+          else mbar_arrive_remote(map_to_cta(bar_t_empty, 0));
+        }
+      }
+    } else {
+    // ---- forward: bias/ReLU/masks/dropout/attention pooling
     const float att_bias = p.att_b[0];
     EpiCtx ec;
     ec.sx = DROP ? p.inv_keep * p.inv_keep : 1.f;   // input-dropout and conv-dropout keep scales
@@ -464,17 +558,13 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
     ec.s_ka = s_ka;
     ec.thr = p.drop_addend;
     ec.dbg = p.dbg;
-    uint32_t pht = 0;
     int par = 0;
-    RowIO io;
-    io.stg = s_stg + (size_t)ew * (STG_WARP_BYTES / 16);
-    io.F = F; io.L = p.L; io.lane = lane;
     for (int tp = pair; tp < n_tp; tp += n_pairs) {
-      const int n = (2 * tp + (int)crank) * TPT + q, t = lane;
+      const int n = (2 * tp + (int)crank) * TPT + slot, t = t0 + lane;
       const bool valid = n < p.n_titles && t < p.L;
       const long long m = (long long)n * p.L + t;
       const int tk = valid ? p.tok[m] : 0;
-      io.title = n < p.n_titles ? p.c_out + (long long)n * p.L * F : nullptr;
+      io.title = n < p.n_titles ? p.c_out + ((long long)n * p.L + t0) * F : nullptr;
       if (DROP) {
         const uint64_t base = ((uint64_t)(valid ? m : 0) * (uint64_t)F) >> 2;     // F % 4 == 0: quad index of (m, f) = base + f/4
         ec.base_lo = (uint32_t)base;
@@ -487,7 +577,6 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
       tc_fence_after();
       float z = 0.f;
       uint32_t vmax = 0u;      // OR of the packed pre-dropout values of this row half
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
       if (p.dbg & 1) {
         tc_fence_before();
         __syncwarp();
@@ -512,41 +601,81 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const float zt = s_z[(par * 2) * 128 + row] + s_z[(par * 2 + 1) * 128 + row];
       const int anyt = s_any[(par * 2) * 128 + row] | s_any[(par * 2 + 1) * 128 + row];
-      par ^= 1;
       const float a = tanhf(zt + att_bias);
       const float e = (valid && anyt) ? expf(a) : 0.f;
-      const float S = warp_sum(e);
+      float esum = e;
+      if (SLOT == 64) {
+        // the title's other 32 tokens belong to the neighbour warp (row ^ 32): the same exp() of their logits, so both
+        // warps of a title arrive at the identical softmax denominator
+        const int row2 = row ^ 32, t2 = (t0 ^ 32) + lane;
+        const float zt2 = s_z[(par * 2) * 128 + row2] + s_z[(par * 2 + 1) * 128 + row2];
+        const int any2 = s_any[(par * 2) * 128 + row2] | s_any[(par * 2 + 1) * 128 + row2];
+        const float e2 = (n < p.n_titles && t2 < p.L && any2) ? expf(tanhf(zt2 + att_bias)) : 0.f;
+        esum = t0 == 0 ? e + e2 : e2 + e;       // same operand order in both warps
+      }
+      par ^= 1;
+      const float S = warp_sum(esum);
       const float w = e / (S + 1e-7f);
       if (half == 0 && valid) {
         if (p.att_a) p.att_a[m] = a;
         if (p.att_wt) p.att_wt[m] = w;
       }
-      // ---- pass 2: pooled[n, f] = sum_t w_t * C[t, f].  The stored rows are re-read (own warp's writes, L2) in the
+      // ---- pass 2: pooled[n, f] = sum_t w_t * C[t, f].  The stored rows are re-read (this CTA's writes, L2) in the
       // coalesced mapping — lane (r8 = lane/4, piece = lane%4) holds piece `piece` of rows r8, r8+8, r8+16, r8+24 —
       // weighted with those rows' attention weights, and the 8 lanes that share a piece finish with a 3-stage
       // reduce-scatter (7 shuffles per 32 features): no shared-memory staging on this pass.
+      // SLOT == 64: the two warps of a title split the 32-feature chunks between them (even / odd) and each sums all 64
+      // rows (the neighbour's rows and weights become visible through a second barrier), so no cross-warp reduction.
       if (p.dbg & 4) continue;
-      float wr[4];
+      constexpr int NRH = SLOT / 32;                 // 32-row halves of a title
+      float wr[NRH][4];
+      if (SLOT == 64) {
+        if (half == 0) s_w[row] = w;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
-      for (int i = 0; i < 4; ++i) wr[i] = __shfl_sync(0xffffffffu, w, (lane >> 2) + 8 * i);
+        for (int h = 0; h < NRH; ++h)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) wr[h][i] = s_w[slot * SLOT + h * 32 + (lane >> 2) + 8 * i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) wr[0][i] = __shfl_sync(0xffffffffu, w, (lane >> 2) + 8 * i);
+      }
+      RowIO io2 = io;                                // pass-2 view: all rows of the title from token 0
+      if (SLOT == 64) {
+        io2.title = n < p.n_titles ? p.c_out + (long long)n * p.L * F : nullptr;
+        io2.L = p.L;
+      }
+      const int c_first = f_beg + (SLOT == 64 ? (q & 1) * 32 : 0), c_step = SLOT == 64 ? 64 : 32;
       uint4 nxt[4];
-      io.load_issue(f_beg, min(4, (f_end - f_beg) >> 3), nxt);
+      if (c_first < f_end) io2.load_issue(c_first, min(4, (f_end - c_first) >> 3), nxt);
       const int jfeat = ((lane >> 2) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 4) & 1);   // feature of the piece this lane ends with
-      for (int c0 = f_beg; c0 < f_end; c0 += 32) {
+      for (int c0 = c_first; c0 < f_end; c0 += c_step) {
         const int np = min(4, (f_end - c0) >> 3);
-        uint4 cur[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) cur[g] = nxt[g];
-        if (c0 + 32 < f_end) io.load_issue(c0 + 32, min(4, (f_end - c0 - 32) >> 3), nxt);
         float x[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) x[k] = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          x[0] = fmaf(wr[i], lo16<FP16>(cur[i].x), x[0]); x[1] = fmaf(wr[i], hi16<FP16>(cur[i].x), x[1]);
-          x[2] = fmaf(wr[i], lo16<FP16>(cur[i].y), x[2]); x[3] = fmaf(wr[i], hi16<FP16>(cur[i].y), x[3]);
-          x[4] = fmaf(wr[i], lo16<FP16>(cur[i].z), x[4]); x[5] = fmaf(wr[i], hi16<FP16>(cur[i].z), x[5]);
-          x[6] = fmaf(wr[i], lo16<FP16>(cur[i].w), x[6]); x[7] = fmaf(wr[i], hi16<FP16>(cur[i].w), x[7]);
+        for (int h = 0; h < NRH; ++h) {
+          uint4 cur[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) cur[g] = nxt[g];
+          // prefetch: the title's next 32 rows of this chunk, or the first rows of the next chunk
+          if (h + 1 < NRH) {
+            RowIO io3 = io2;
+            io3.title = io2.title ? io2.title + (long long)32 * (h + 1) * F : nullptr;
+            io3.L = io2.L - 32 * (h + 1);
+            io3.load_issue(c0, np, nxt);
+          } else if (c0 + c_step < f_end) {
+            io2.load_issue(c0 + c_step, min(4, (f_end - c0 - c_step) >> 3), nxt);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float wi = wr[h][i];
+            x[0] = fmaf(wi, lo16<FP16>(cur[i].x), x[0]); x[1] = fmaf(wi, hi16<FP16>(cur[i].x), x[1]);
+            x[2] = fmaf(wi, lo16<FP16>(cur[i].y), x[2]); x[3] = fmaf(wi, hi16<FP16>(cur[i].y), x[3]);
+            x[4] = fmaf(wi, lo16<FP16>(cur[i].z), x[4]); x[5] = fmaf(wi, hi16<FP16>(cur[i].z), x[5]);
+            x[6] = fmaf(wi, lo16<FP16>(cur[i].w), x[6]); x[7] = fmaf(wi, hi16<FP16>(cur[i].w), x[7]);
+          }
         }
 #pragma unroll
         for (int st = 0; st < 3; ++st) {
@@ -561,6 +690,7 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
         }
         if (n < p.n_titles && (lane & 3) < np) p.pooled[(long long)n * F + c0 + (lane & 3) * 8 + jfeat] = x[0];
       }
+    }
     }
   }
   __syncthreads();
@@ -590,14 +720,13 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_fwd_kernel(const FwdP
 // first waits for the peer's own bulk copy); stage-empty and accumulator-full events come back to both CTAs through
 // the multicast commit.
 // The token range is split over CTA.y; partial sums go to global and are reduced in a fixed order.
-constexpr int WG_KTOK = 32;                         // tokens (K rows) per title slot
+// tokens (K rows) per title slot: template parameter KT = 32 (L <= 31) or 64 (L <= 63)
 constexpr int WG_ES = 40;                           // embedding columns per (tap, e) slice: a slice's 128 M rows are the
                                                     // three taps of the SAME 40 columns (3 x 40 = 120 rows used), so a token's
                                                     // 16-byte pieces are gathered once and stored at the three tap shifts
-constexpr int WG_GROUP_BYTES = WG_KTOK * 128;       // one 64-element group of one title: 4 KB
-constexpr int WG_A_TILE_BYTES = 2 * WG_GROUP_BYTES; // A of one title: two 64-column chunks
-constexpr int WG_TPS = 2;                           // titles per pipeline stage (amortises the per-stage handshake,
-                                                    // ~500 cycles of issue-thread + commit latency, over 800 MMA cycles)
+constexpr int WG_STAGE_ROWS = 64;                   // K rows per pipeline stage: two 32-row titles or one 64-row title
+                                                    // (amortises the per-stage handshake, ~500 cycles of issue-thread +
+                                                    // commit latency, over 800 MMA cycles)
 constexpr int WG_STAGES = 4;
 constexpr int WG_THREADS = 640;   // 4 control warps + 16 producer warps (8 per title of a stage; warps 8-11 also run the epilogue)
 
@@ -616,8 +745,12 @@ struct WgradParams {
   const uint8_t* xmask;       // optional keep bits written by the forward (FwdParams::xmask); null: replay the hash
 };
 
-template <bool FP16>
+template <bool FP16, int KT>
 __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const WgradParams p) {
+  constexpr int WG_KTOK = KT;
+  constexpr int WG_GROUP_BYTES = WG_KTOK * 128;       // one 64-element group of one title: 4 / 8 KB
+  constexpr int WG_A_TILE_BYTES = 2 * WG_GROUP_BYTES; // A of one title: two 64-column chunks
+  constexpr int WG_TPS = WG_STAGE_ROWS / KT;          // titles per pipeline stage
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -742,8 +875,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const Wgra
     // stage a thread handles (row r, 16-byte piece q) of both 64-column chunks (u0,u1) of this CTA's (tap, e) slice
     // for ONE of the stage's titles.  Dropout: keep bytes left by the forward, or a replay of its stream.
     const int pt = threadIdx.x - 128;          // 0..511
-    const int tsel = pt >> 8;                  // title of the stage
-    const int r = (pt & 255) >> 3, q = pt & 7; // token row, 16-byte piece of the slice's 40 columns (q < 5)
+    const int tsel = pt / (KT * 8);            // title of the stage
+    const int r = (pt % (KT * 8)) >> 3, q = pt & 7; // token row, 16-byte piece of the slice's 40 columns (q < 5)
     const int e0 = slice * WG_ES + q * 8;      // first embedding column of the piece
     const bool piece_ok = q < WG_ES / 8 && e0 < p.Ep;
     // The token id is NOT inspected when it is loaded (that would stall the warp for the load's full latency every
@@ -941,9 +1074,11 @@ extern "C" int lstur_pack_conv_w_tc(int E, int F, const float* conv_w, void* wim
 }
 
 extern "C" int lstur_tc_supported(int L, int E, int F, int KS) {
-  return KS == 3 && L >= 1 && L <= tc::SLOT - 1 && E >= 1 && F >= 16 && F % 16 == 0 && F <= tc::TMEM_COLS &&
+  return KS == 3 && L >= 1 && L <= 63 && E >= 1 && F >= 16 && F % 16 == 0 && F <= tc::TMEM_COLS &&
          (F <= 256 || F - 256 >= 16);
 }
+// rows of a title slot: the L tokens + at least one zero row (the conv halo), 32 or 64
+extern "C" int lstur_tc_slot(int L) { return L <= 31 ? 32 : 64; }
 
 static void* g_tc_trace_ptr = nullptr;
 // Debug/profiling hook: device buffer of 8*16 int64 receiving clock64() stamps of CTA 0's warp roles (NULL = off).
@@ -953,6 +1088,60 @@ extern "C" int lstur_tc_set_trace(void* dev_buf) { g_tc_trace_ptr = dev_buf; ret
 // bytes of the X-dropout keep-bit buffer the forward can leave for the weight-gradient kernel (one byte per 16-byte piece)
 extern "C" size_t lstur_tc_xmask_bytes(int n_titles, int L, int E) {
   return (size_t)n_titles * L * (lstur_tc_padded_e(E) / 8);
+}
+
+// Launch news_conv_tc_kernel<FP16, DROP, SLOT, MODE> on CTA pairs: persistent, one pair per two 128-row token tiles.
+template <bool FP16, bool DROP, int SLOT, int MODE>
+static cudaError_t tc_launch_one(const tc::FwdParams& p, size_t smem, int pairs, cudaStream_t stream) {
+  static size_t attr_smem = 0;
+  auto kern = tc::news_conv_tc_kernel<FP16, DROP, SLOT, MODE>;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_smem = smem;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(tc::THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+static int tc_launch_conv(const tc::FwdParams& p, int L, bool fp16, bool drop, int mode, int max_ctas, cudaStream_t stream,
+                          const char* name) {
+  const int F = p.F, slot = lstur_tc_slot(L);
+  size_t smem = 1024 + (size_t)tc::NUM_STAGES * (tc::A_STAGE_BYTES + (size_t)tc::TAPS * (F / 2) * tc::ROWB) + 768 + 4096 +
+                (((size_t)2 * F * sizeof(float) + 15) & ~(size_t)15) + (size_t)8 * tc::STG_WARP_BYTES;
+  int n_tiles = (p.n_titles + (tc::TILE_M / slot) - 1) / (tc::TILE_M / slot);
+  int n_tp = (n_tiles + 1) / 2;             // CTA pairs take two token tiles at a time
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  int pairs = n_tp < sms / 2 ? n_tp : sms / 2;
+  if (max_ctas > 0 && pairs > max_ctas / 2) pairs = max_ctas / 2 > 0 ? max_ctas / 2 : 1;
+  cudaError_t e;
+#define TC_DISPATCH_SLOT(FP16_, DROP_, MODE_)                                                        \
+  (slot == 32 ? tc_launch_one<FP16_, DROP_, 32, MODE_>(p, smem, pairs, stream)                      \
+              : tc_launch_one<FP16_, DROP_, 64, MODE_>(p, smem, pairs, stream))
+  if (mode == tc::MODE_DGRAD) e = fp16 ? TC_DISPATCH_SLOT(true, false, tc::MODE_DGRAD) : TC_DISPATCH_SLOT(false, false, tc::MODE_DGRAD);
+  else if (fp16 && drop) e = TC_DISPATCH_SLOT(true, true, tc::MODE_FWD);
+  else if (fp16) e = TC_DISPATCH_SLOT(true, false, tc::MODE_FWD);
+  else if (drop) e = TC_DISPATCH_SLOT(false, true, tc::MODE_FWD);
+  else e = TC_DISPATCH_SLOT(false, false, tc::MODE_FWD);
+#undef TC_DISPATCH_SLOT
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed: %s", name, cudaGetErrorString(e));
+    return LSTUR_ERR_CUDA;
+  }
+  LSTUR_CHECK_LAUNCH(name);
+  return LSTUR_OK;
 }
 
 extern "C" int lstur_news_conv_tc_fwd(int n_titles, int L, int E, int F, int V, const int* tokens, const void* emb_bf16,
@@ -970,7 +1159,7 @@ extern "C" int lstur_news_conv_tc_fwd_m(int n_titles, int L, int E, int F, int V
   LSTUR_REQUIRE(n_titles >= 0 && lstur_tc_supported(L, E, F, 3), "lstur_news_conv_tc_fwd");
   LSTUR_REQUIRE(dropout >= 0.f && dropout < 1.f && c_out_bf16 && pooled, "lstur_news_conv_tc_fwd");
   if (n_titles == 0) return LSTUR_OK;
-  tc::FwdParams p;
+  tc::FwdParams p{};
   p.n_titles = n_titles; p.L = L; p.F = F; p.Ep = lstur_tc_padded_e(E); p.EC = p.Ep / tc::KBLK; p.V = V;
   p.tok = tokens; p.emb = (const uint16_t*)emb_bf16; p.wimg = (const uint16_t*)wimg;
   p.conv_b = conv_b; p.att_w = att_w; p.att_b = att_b;
@@ -982,53 +1171,7 @@ extern "C" int lstur_news_conv_tc_fwd_m(int n_titles, int L, int E, int F, int V
   p.dbg = getenv("LSTUR_FWD_DBG") ? atoi(getenv("LSTUR_FWD_DBG")) : 0;
   p.xmask = (uint8_t*)xmask_out;
   p.trace = (long long*)g_tc_trace_ptr;
-  size_t smem = 1024 + (size_t)tc::NUM_STAGES * (tc::A_STAGE_BYTES + (size_t)tc::TAPS * (F / 2) * tc::ROWB) + 256 + 4096 +
-                (((size_t)2 * F * sizeof(float) + 15) & ~(size_t)15) + (size_t)8 * tc::STG_WARP_BYTES;
-  static bool attr_set = false;
-  static size_t attr_smem = 0;
-  if (!attr_set || smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(tc::news_conv_tc_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::news_conv_tc_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::news_conv_tc_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::news_conv_tc_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_error("lstur_news_conv_tc_fwd: cannot opt in to %zu B of shared memory: %s", smem, cudaGetErrorString(e));
-      return LSTUR_ERR_CUDA;
-    }
-    attr_set = true;
-    attr_smem = smem;
-  }
-  int n_tiles = (n_titles + tc::TPT - 1) / tc::TPT;
-  int n_tp = (n_tiles + 1) / 2;             // CTA pairs take two token tiles at a time
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-  int pairs = n_tp < sms / 2 ? n_tp : sms / 2;
-  if (max_ctas > 0 && pairs > max_ctas / 2) pairs = max_ctas / 2 > 0 ? max_ctas / 2 : 1;
-  const bool drop = p.drop_thr16 != 0;
-  {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(tc::THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e;
-    if (fp16 && drop) e = cudaLaunchKernelEx(&cfg, tc::news_conv_tc_fwd_kernel<true, true>, p);
-    else if (fp16) e = cudaLaunchKernelEx(&cfg, tc::news_conv_tc_fwd_kernel<true, false>, p);
-    else if (drop) e = cudaLaunchKernelEx(&cfg, tc::news_conv_tc_fwd_kernel<false, true>, p);
-    else e = cudaLaunchKernelEx(&cfg, tc::news_conv_tc_fwd_kernel<false, false>, p);
-    if (e != cudaSuccess) {
-      set_error("lstur_news_conv_tc_fwd: launch failed: %s", cudaGetErrorString(e));
-      return LSTUR_ERR_CUDA;
-    }
-  }
-  LSTUR_CHECK_LAUNCH("lstur_news_conv_tc_fwd");
+  RC(tc_launch_conv(p, L, fp16 != 0, p.drop_thr16 != 0, tc::MODE_FWD, max_ctas, stream, "lstur_news_conv_tc_fwd"));
   return LSTUR_OK;
 }
 
@@ -1057,13 +1200,48 @@ extern "C" int lstur_news_encoder_tc_fwd_internal(const lstur_plan* p, const lst
 }
 
 
+// ---- conv input gradient (word-table training: keras Embedding(trainable=True), task/paper.py:132-138) ----------
+extern "C" int lstur_tc_wgrad_groups(int F);
+// 32-column K chunks per half of the conv features in the dPre image
+static int dgrad_cph(int F) { return (F / 2 + tc::KBLK - 1) / tc::KBLK; }
+extern "C" long long lstur_tc_wimg_dgrad_elems(int E, int F) {
+  return (long long)2 * dgrad_cph(F) * tc::TAPS * lstur_tc_padded_e(E) * tc::KBLK;
+}
+extern "C" int lstur_pack_conv_w_dgrad_tc(int E, int F, const float* conv_w, void* wimg_d, int fp16, cudaStream_t stream) {
+  LSTUR_REQUIRE(E > 0 && F > 0 && F % 16 == 0 && conv_w && wimg_d, "lstur_pack_conv_w_dgrad_tc");
+  long long n = lstur_tc_wimg_dgrad_elems(E, F);
+  tc::pack_conv_w_dgrad_kernel<<<cdiv(n, 256), 256, 0, stream>>>(E, F, lstur_tc_padded_e(E), dgrad_cph(F), conv_w,
+                                                                 (uint16_t*)wimg_d, fp16 != 0);
+  LSTUR_CHECK_LAUNCH("lstur_pack_conv_w_dgrad_tc");
+  return LSTUR_OK;
+}
+// dx16 (n_titles, L, Ep) 16-bit rows = out_scale * dX, dX[m, e] = sum_j sum_f dPre[m+1-j, f] Wc[j, e, f] (columns
+// e >= E are zero); dpre_img is the image written by lstur_attn_pool_bwd_img (whose own scale multiplies through).
+extern "C" int lstur_conv_dgrad_tc(int n_titles, int L, int E, int F, const void* dpre_img, const void* wimg_d, void* dx16,
+                                   float out_scale, int fp16, int max_ctas, cudaStream_t stream) {
+  LSTUR_REQUIRE(n_titles >= 0 && lstur_tc_supported(L, E, F, 3) && dpre_img && wimg_d && dx16, "lstur_conv_dgrad_tc");
+  const int Eo = lstur_tc_padded_e(E);
+  LSTUR_REQUIRE(Eo <= tc::TMEM_COLS && (Eo <= 256 || Eo - 256 >= 16), "lstur_conv_dgrad_tc(E too wide for one accumulator)");
+  if (n_titles == 0) return LSTUR_OK;
+  tc::FwdParams p{};
+  p.n_titles = n_titles; p.L = L; p.F = Eo; p.Ep = Eo; p.V = 0;
+  p.cph = dgrad_cph(F); p.ngh = lstur_tc_wgrad_groups(F); p.EC = 2 * p.cph;
+  p.dimg = (const uint8_t*)dpre_img; p.wimg = (const uint16_t*)wimg_d; p.c_out = (uint16_t*)dx16;
+  p.out_scale = out_scale;
+  p.inv_keep = 1.f;
+  p.dbg = 0;
+  p.trace = nullptr;
+  RC(tc_launch_conv(p, L, fp16 != 0, false, tc::MODE_DGRAD, max_ctas, stream, "lstur_conv_dgrad_tc"));
+  return LSTUR_OK;
+}
+
 // ---- wgrad host side ------------------------------------------------------------------------------
 extern "C" int lstur_tc_wgrad_kblocks(int n_titles) { return n_titles; }   // one 32-row slot = one K block
 // 64-column groups per half of the F columns (each CTA of a pair stages one half)
 extern "C" int lstur_tc_wgrad_groups(int F) { return (F / 2 + 63) / 64; }
 // bytes of the dPre image consumed by lstur_conv_wgrad_tc: per title [half][group][32 rows][128 B]
-extern "C" size_t lstur_tc_dpre_img_bytes(int n_titles, int F) {
-  return (size_t)lstur_tc_wgrad_kblocks(n_titles) * 2 * lstur_tc_wgrad_groups(F) * tc::WG_GROUP_BYTES;
+extern "C" size_t lstur_tc_dpre_img_bytes(int n_titles, int L, int F) {
+  return (size_t)lstur_tc_wgrad_kblocks(n_titles) * 2 * lstur_tc_wgrad_groups(F) * lstur_tc_slot(L) * 128;
 }
 static int wgrad_slices(int E) {
   int n = (lstur_tc_padded_e(E) + tc::WG_ES - 1) / tc::WG_ES;     // 40 embedding columns x 3 taps per 128-row slice
@@ -1088,13 +1266,14 @@ extern "C" int lstur_conv_wgrad_tc(int n_titles, int L, int E, int F, int V, con
                                    const void* dpre_img, float* d_conv_w, float dropout, unsigned seed, int fp16,
                                    void* partial_ws, size_t partial_bytes, cudaStream_t stream) {
   return lstur_conv_wgrad_tc_m(n_titles, L, E, F, V, tokens, emb_16, dpre_img, d_conv_w, dropout, seed, fp16, partial_ws,
-                               partial_bytes, nullptr, stream);
+                               partial_bytes, nullptr, 1.f, stream);
 }
 
 extern "C" int lstur_conv_wgrad_tc_m(int n_titles, int L, int E, int F, int V, const int* tokens, const void* emb_16,
                                      const void* dpre_img, float* d_conv_w, float dropout, unsigned seed, int fp16,
-                                     void* partial_ws, size_t partial_bytes, const void* xmask, cudaStream_t stream) {
-  LSTUR_REQUIRE(n_titles >= 0 && lstur_tc_supported(L, E, F, 3), "lstur_conv_wgrad_tc");
+                                     void* partial_ws, size_t partial_bytes, const void* xmask, float dpre_scale,
+                                     cudaStream_t stream) {
+  LSTUR_REQUIRE(n_titles >= 0 && lstur_tc_supported(L, E, F, 3) && dpre_scale > 0.f, "lstur_conv_wgrad_tc");
   if (n_titles == 0) {
     cudaMemsetAsync(d_conv_w, 0, (size_t)3 * E * F * sizeof(float), stream);
     return LSTUR_OK;
@@ -1105,7 +1284,8 @@ extern "C" int lstur_conv_wgrad_tc_m(int n_titles, int L, int E, int F, int V, c
   p.n_slices = wgrad_slices(E);
   int splits = lstur_tc_wgrad_splits(n_titles, E);
   p.kb_per_split = (p.n_kblocks + splits - 1) / splits;
-  p.kb_per_split = (p.kb_per_split + tc::WG_TPS - 1) / tc::WG_TPS * tc::WG_TPS;   // whole pipeline stages per split
+  const int kt = lstur_tc_slot(L), tps = tc::WG_STAGE_ROWS / kt;
+  p.kb_per_split = (p.kb_per_split + tps - 1) / tps * tps;   // whole pipeline stages per split
   p.ngh = lstur_tc_wgrad_groups(F);
   p.tok = tokens; p.emb = (const uint16_t*)emb_16; p.dpre_img = (const uint16_t*)dpre_img;
   p.partial = (float*)partial_ws;
@@ -1113,16 +1293,21 @@ extern "C" int lstur_conv_wgrad_tc_m(int n_titles, int L, int E, int F, int V, c
   p.drop_thr16 = dropout > 0.f ? quad_thr15(dropout) : 0u;
   p.drop_addend = quad_addend(p.drop_thr16);
   p.seed_x = seed * 2u;
-  p.scale = 1.f / (1.f - dropout);
+  p.scale = 1.f / ((1.f - dropout) * dpre_scale);
   p.trace = (long long*)g_tc_trace_ptr;
   p.dbg = getenv("LSTUR_WGRAD_DBG") ? atoi(getenv("LSTUR_WGRAD_DBG")) : 0;
   p.xmask = (const uint8_t*)xmask;
-  size_t smem = 1024 + (size_t)tc::WG_STAGES * tc::WG_TPS * (tc::WG_A_TILE_BYTES + (size_t)p.ngh * tc::WG_GROUP_BYTES) + 256 + 4096;
+  // a stage holds WG_STAGE_ROWS K rows whatever the slot height: A = 2 groups, B = ngh groups of 128-byte rows
+  size_t smem = 1024 + (size_t)tc::WG_STAGES * tc::WG_STAGE_ROWS * 128 * (2 + (size_t)p.ngh) + 256 + 4096;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(tc::conv_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tc::conv_wgrad_tc_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tc::conv_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = cudaFuncSetAttribute(tc::conv_wgrad_tc_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tc::conv_wgrad_tc_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tc::conv_wgrad_tc_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("lstur_conv_wgrad_tc: cannot opt in to %zu B of shared memory: %s", smem, cudaGetErrorString(e));
       return LSTUR_ERR_CUDA;
@@ -1142,8 +1327,11 @@ extern "C" int lstur_conv_wgrad_tc_m(int n_titles, int L, int E, int F, int V, c
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = fp16 ? cudaLaunchKernelEx(&cfg, tc::conv_wgrad_tc_kernel<true>, p)
-                         : cudaLaunchKernelEx(&cfg, tc::conv_wgrad_tc_kernel<false>, p);
+    cudaError_t e;
+    if (kt == 32) e = fp16 ? cudaLaunchKernelEx(&cfg, tc::conv_wgrad_tc_kernel<true, 32>, p)
+                           : cudaLaunchKernelEx(&cfg, tc::conv_wgrad_tc_kernel<false, 32>, p);
+    else e = fp16 ? cudaLaunchKernelEx(&cfg, tc::conv_wgrad_tc_kernel<true, 64>, p)
+                  : cudaLaunchKernelEx(&cfg, tc::conv_wgrad_tc_kernel<false, 64>, p);
     if (e != cudaSuccess) {
       set_error("lstur_conv_wgrad_tc: launch failed: %s", cudaGetErrorString(e));
       return LSTUR_ERR_CUDA;

@@ -124,6 +124,8 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
     return LSTUR_ERR_UNSUPPORTED;
   }
 
+  LSTUR_REQUIRE(!c.trainable_word_emb || (c.save_for_backward && c.E % 4 == 0 && c.E <= 512),
+                "lstur_plan_create(trainable word table: training plan, E % 4 == 0, E <= 512)");
   lstur_plan* p = new lstur_plan();
   p->c = c;
   p->c.Dd = Dd;
@@ -234,8 +236,18 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
     add_ws(p, "d_pooled", N * F);
     if (!tcp) add_ws(p, "dPre", N * Lp * F);
     if (tcp) {
-      add_ws(p, "dpre_img", (long long)(lstur_tc_dpre_img_bytes((int)N, F) / 4));
+      add_ws(p, "dpre_img", (long long)(lstur_tc_dpre_img_bytes((int)N, c.L, F) / 4));
       add_ws(p, "wgrad_partial", (long long)(lstur_tc_wgrad_partial_bytes((int)N, E, F) / 4));
+    }
+    if (c.trainable_word_emb) {   // conv input gradient + word-table scatter (task/paper.py:136)
+      if (tcp) {
+        add_ws(p, "wimg_d", (lstur_tc_wimg_dgrad_elems(E, F) + 1) / 2);
+        add_ws(p, "dx16", (N * c.L * lstur_tc_padded_e(E) + 1) / 2);
+      } else {
+        add_ws(p, "dXp", N * Lp * E);
+        track_gemm(p, (int)(N * Lp), E, F);
+      }
+      add_ws(p, "wg_ws", (long long)(lstur_word_grad_workspace_bytes(N * c.L, c.V, E) / 4) + 4);
     }
     add_ws(p, "attn_partials", (long long)lstur_attn_bwd_grid((int)N) * (2 * F + 1));
     if (has_gru) {
@@ -583,9 +595,15 @@ extern "C" int lstur_forward_docvecs(const lstur_plan* p, const lstur_weights* w
 
 extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const lstur_batch* b, void* ws,
                               float* dgrad, float grad_scale, cudaStream_t st) {
+  return lstur_backward_w(p, w, b, ws, dgrad, nullptr, grad_scale, st);
+}
+
+extern "C" int lstur_backward_w(const lstur_plan* p, const lstur_weights* w, const lstur_batch* b, void* ws,
+                                float* dgrad, float* word_grad, float grad_scale, cudaStream_t st) {
   LSTUR_REQUIRE(p && w && b && ws && dgrad, "lstur_backward");
   const lstur_config& c = p->c;
   LSTUR_REQUIRE(c.save_for_backward != 0, "lstur_backward");
+  LSTUR_REQUIRE(!c.trainable_word_emb || word_grad != nullptr, "lstur_backward(trainable word table needs word_grad: lstur_backward_w)");
   const int N = p->N, Nh = p->Nh, Lp = p->Lp, D = p->D, L = c.L, E = c.E, F = c.F, G = c.G, B = c.B;
   void* gws = W<void>(p, ws, "gemm_ws");
   const size_t gwsb = p->gemm_ws_bytes;
@@ -743,22 +761,47 @@ extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const
   } else {
     dpool = d_docv; lddp = D;
   }
+  // the dropout streams are replayed only if the saved forward was a training forward (an inference forward followed by
+  // a backward differentiates the inference graph)
+  const float bwd_drop = p->last_training ? c.dropout : 0.f;
   if ((c.precision == LSTUR_PREC_BF16_TC || c.precision == LSTUR_PREC_FP16_TC)) {
     const int fp16 = c.precision == LSTUR_PREC_FP16_TC;
     void* img = W<void>(p, ws, "dpre_img");
+    // power-of-two loss scale of the 16-bit dPre image: the gradients carry grad_scale = 1 / global batch, which would
+    // put them in fp16's subnormal range; 16 x the per-impression magnitude leaves 2^12 of headroom
+    float img_scale = 1.f;
+    if (grad_scale > 0.f && grad_scale < 1.f) {
+      int ex = 0;
+      frexpf(1.f / grad_scale, &ex);          // 1/grad_scale = m * 2^ex, m in [0.5, 1)
+      img_scale = ldexpf(1.f, ex - 1 + 4);
+    }
     RC(lstur_attn_pool_bwd_img(fp16, N, L, F, W<void>(p, ws, "C16"), W<float>(p, ws, "att_a"), W<float>(p, ws, "att_w"),
-                               dpool, lddp, DP(p, w->dense, "att_w"), img, c.dropout, DG(p, dgrad, "att_w"),
+                               dpool, lddp, DP(p, w->dense, "att_w"), img, bwd_drop, img_scale, DG(p, dgrad, "att_w"),
                                DG(p, dgrad, "conv_b"), DG(p, dgrad, "att_b"), 0, W<float>(p, ws, "attn_partials"),
                                (size_t)p->ws.at("attn_partials").count * 4, st));
     PROBE_BEGIN(p, LSTUR_PROBE_CONV_WGRAD, st);
     RC(lstur_conv_wgrad_tc_m(N, L, E, F, c.V, W<int>(p, ws, "tokens"), W<void>(p, ws, "emb_bf16"), img,
-                             DG(p, dgrad, "conv_w"), c.dropout, p->last_seed, fp16, W<void>(p, ws, "wgrad_partial"),
+                             DG(p, dgrad, "conv_w"), bwd_drop, p->last_seed, fp16, W<void>(p, ws, "wgrad_partial"),
                              (size_t)p->ws.at("wgrad_partial").count * 4,
-                             (c.dropout > 0.f && p->last_training) ? W<void>(p, ws, "xmask") : nullptr, st));
+                             bwd_drop > 0.f ? W<void>(p, ws, "xmask") : nullptr, img_scale, st));
     PROBE_END(p, LSTUR_PROBE_CONV_WGRAD, st);
+    if (c.trainable_word_emb) {
+      // d X = dPre (*) Wc^T on tcgen05, then d word_emb = segment-sorted sum of the token rows (x the X-dropout mask)
+      void* wimg_d = W<void>(p, ws, "wimg_d");
+      void* dx16 = W<void>(p, ws, "dx16");
+      RC(lstur_pack_conv_w_dgrad_tc(E, F, DP(p, w->dense, "conv_w"), wimg_d, fp16, st));
+      PROBE_BEGIN(p, LSTUR_PROBE_CONV_DGRAD, st);
+      RC(lstur_conv_dgrad_tc(N, L, E, F, img, wimg_d, dx16, 1.f, fp16, 0, st));
+      PROBE_END(p, LSTUR_PROBE_CONV_DGRAD, st);
+      PROBE_BEGIN(p, LSTUR_PROBE_SCATTER, st);
+      RC(lstur_word_grad_scatter_16(N, L, E, c.V, W<int>(p, ws, "tokens"), dx16, fp16, 1.f / ((1.f - bwd_drop) * img_scale),
+                                    bwd_drop > 0.f ? W<void>(p, ws, "xmask") : nullptr, word_grad, W<void>(p, ws, "wg_ws"),
+                                    (size_t)p->ws.at("wg_ws").count * 4, st));
+      PROBE_END(p, LSTUR_PROBE_SCATTER, st);
+    }
   } else {
     float* dPre = W<float>(p, ws, "dPre");
-    const float drop = c.dropout;  // backward always follows a training forward
+    const float drop = bwd_drop;
     RC(lstur_attn_pool_bwd(N, L, Lp, F, W<float>(p, ws, "Cp"), (long long)Lp * F, W<float>(p, ws, "att_a"),
                            W<float>(p, ws, "att_w"), dpool, lddp, DP(p, w->dense, "att_w"), dPre, (long long)Lp * F,
                            drop, DG(p, dgrad, "att_w"), DG(p, dgrad, "conv_b"), DG(p, dgrad, "att_b"), 0,
@@ -768,6 +811,21 @@ extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const
     RC(lstur_gemm_f32(1, 0, c.KS * E, F, N * Lp - (c.KS - 1), W<float>(p, ws, "Xp"), E, dPre, F, DG(p, dgrad, "conv_w"), F,
                       nullptr, 0, gws, gwsb, st));
     PROBE_END(p, LSTUR_PROBE_CONV_WGRAD, st);
+    if (c.trainable_word_emb) {
+      // d Xp[m + j, e] += sum_f dPre[m, f] * Wc[j, e, f]: one accumulating GEMM per tap into the overlapping windows of the
+      // zero-haloed title buffer, then the same segment-sorted scatter
+      float* dXp = W<float>(p, ws, "dXp");
+      cudaMemsetAsync(dXp, 0, (size_t)N * Lp * E * sizeof(float), st);
+      PROBE_BEGIN(p, LSTUR_PROBE_CONV_DGRAD, st);
+      for (int j = 0; j < c.KS; ++j)
+        RC(lstur_gemm_f32(0, 1, N * Lp - (c.KS - 1), E, F, dPre, F, DP(p, w->dense, "conv_w") + (size_t)j * E * F, F,
+                          dXp + (size_t)j * E, E, nullptr, LSTUR_GEMM_ACCUM, gws, gwsb, st));
+      PROBE_END(p, LSTUR_PROBE_CONV_DGRAD, st);
+      PROBE_BEGIN(p, LSTUR_PROBE_SCATTER, st);
+      RC(lstur_word_grad_scatter_f32(N, L, c.KS, E, c.V, W<int>(p, ws, "tokens"), dXp, drop, p->last_seed * 2u + 0u, 1.f,
+                                     word_grad, W<void>(p, ws, "wg_ws"), (size_t)p->ws.at("wg_ws").count * 4, st));
+      PROBE_END(p, LSTUR_PROBE_SCATTER, st);
+    }
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

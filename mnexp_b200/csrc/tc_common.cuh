@@ -177,6 +177,14 @@ __device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
   }
 }
+// round to 16 bits (saturating to +-max finite) + pack, one F2FP instruction
+template <bool FP16>
+__device__ __forceinline__ uint32_t pack16x2_sat(float lo, float hi) {
+  uint32_t r;
+  if (FP16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 // max(x, 0) + round to 16 bits (saturating) + pack, one F2FP instruction
 template <bool FP16>
 __device__ __forceinline__ uint32_t pack16x2_relu(float lo, float hi) {

@@ -42,18 +42,41 @@ def shard_batch(batch, rank, world):
     return out
 
 
+MAX_SORT_KEYS = 16384      # lstur_sort_unique_i32 is a single-CTA bitonic sort (csrc/optim.cu: SORT_MAX)
+
+
+class UserRowReducer:
+    """Deterministic reduction of the exchanged (user id, d user_emb row) pairs of all ranks: the same dedup +
+    segment-sorted sum on every rank (rank-major order), so the replicas stay bit-identical."""
+
+    def __init__(self, engine, n):
+        if n > MAX_SORT_KEYS:
+            raise ValueError('data-parallel user-row dedup sorts world * B = %d keys; the limit is %d '
+                             '(use fewer rows per rank or fewer ranks)' % (n, MAX_SORT_KEYS))
+        dev = engine.device
+        i32 = lambda k: torch.empty(k, dtype=torch.int32, device=dev)
+        self.n = n
+        self.sorted_pos, self.rows, self.seg, self.inv, self.nrows = i32(n), i32(n), i32(n + 1), i32(n), i32(1)
+        self.grows = torch.empty((n, engine.Ue), dtype=torch.float32, device=dev)
+
+    def reduce(self, engine, ids, rows):
+        """-> the `user_rows` tuple LsturEngine.apply_adam takes"""
+        n, st, L = ids.numel(), engine._stream(), engine.lib
+        assert n == self.n
+        _lib.check(L.lstur_sort_unique_i32(n, _ptr(ids), _ptr(self.sorted_pos), _ptr(self.rows), _ptr(self.seg),
+                                           _ptr(self.inv), _ptr(self.nrows), st))
+        _lib.check(L.lstur_segment_sum_rows(n, engine.Ue, _ptr(self.nrows), _ptr(self.seg), _ptr(self.sorted_pos),
+                                            _ptr(rows), engine.Ue, _ptr(self.grows), st))
+        return (n, self.rows, self.nrows, self.grows)
+
+
 class DataParallel:
     def __init__(self, engine, group=None):
         self.eng, self.group = engine, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         e = engine
-        if e.user_emb is not None and self.world > 1:
-            n = self.world * e.B
-            dev = e.device
-            i32 = lambda k: torch.empty(k, dtype=torch.int32, device=dev)
-            self.sorted_pos, self.rows, self.seg, self.inv, self.nrows = i32(n), i32(n), i32(n + 1), i32(n), i32(1)
-            self.grows = torch.empty((n, e.Ue), dtype=torch.float32, device=dev)
+        self.reducer = UserRowReducer(e, self.world * e.B) if (e.user_emb is not None and self.world > 1) else None
 
     def train_step(self, db):
         e = self.eng
@@ -65,15 +88,7 @@ class DataParallel:
         has_user = e.user_emb is not None
         ids, rows = exchange(e.dense_grad, db['user'] if has_user else None,
                              e.view('d_u0').reshape(e.B, e.Ue) if has_user else None, self.group)
-        ur = None
-        if has_user:
-            n, st, L = ids.numel(), e._stream(), e.lib
-            _lib.check(L.lstur_sort_unique_i32(n, _ptr(ids), _ptr(self.sorted_pos), _ptr(self.rows), _ptr(self.seg),
-                                               _ptr(self.inv), _ptr(self.nrows), st))
-            _lib.check(L.lstur_segment_sum_rows(n, e.Ue, _ptr(self.nrows), _ptr(self.seg), _ptr(self.sorted_pos),
-                                                _ptr(rows), e.Ue, _ptr(self.grows), st))
-            ur = (n, self.rows, self.nrows, self.grows)
-        e.apply_adam(user_rows=ur)
+        e.apply_adam(user_rows=self.reducer.reduce(e, ids, rows) if has_user else None)
         return e.view('loss')
 
 

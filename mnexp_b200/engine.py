@@ -43,8 +43,7 @@ class LsturEngine:
             raise _lib.LsturError('LsturEngine needs a CUDA device (no CPU fallback)')
         self.lib = _lib.load()
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
-        if trainable_word_emb:
-            raise NotImplementedError('textual_embedding_trainable=True is not implemented yet')
+        self.trainable_word_emb = bool(trainable_word_emb) and bool(training)
         amap = {'paper': ARCH, 'sigmoid': SIGMOID_ARCH}.get(flavour, COOK_ARCH)
         if loss not in ('softmax', 'bce'):
             raise ValueError(loss)
@@ -85,7 +84,8 @@ class LsturEngine:
             n_docs=n_docs, dropout=float(dropout),
             save_for_backward=int(training),
             n_vert=params['vert_emb'].shape[0] if dv else 0, n_subvert=params['subvert_emb'].shape[0] if ds else 0,
-            Hs=Hs, loss_model=1 if loss == 'bce' else 0, bce_neg=int(bce_neg), gain=float(gain))
+            Hs=Hs, loss_model=1 if loss == 'bce' else 0, bce_neg=int(bce_neg), gain=float(gain),
+            trainable_word_emb=int(self.trainable_word_emb))
         self.B, self.W, self.C, self.L, self.D, self.U, self.Ue, self.G = B, W, C, L, Dd + dv + ds, U, Ue, G
         plan = ctypes.c_void_p()
         _lib.check(self.lib.lstur_plan_create(ctypes.byref(self.cfg), ctypes.byref(plan)))
@@ -130,6 +130,12 @@ class LsturEngine:
                 self.user_m = torch.zeros_like(self.user_emb)
                 self.user_v = torch.zeros_like(self.user_emb)
                 self.user_grad_dense = None if sparse_user_adam else torch.zeros_like(self.user_emb)
+            if self.trainable_word_emb:
+                # keras Embedding(trainable=True) (task/paper.py:136): dense gradient (rows of absent tokens are zero, as
+                # tf.IndexedSlices densify to) and dense Keras-Adam moments — reference semantics, SURVEY.md §9.7
+                self.word_grad = torch.zeros_like(self.word_emb)
+                self.word_m = torch.zeros_like(self.word_emb)
+                self.word_v = torch.zeros_like(self.word_emb)
         self.sparse_user_adam = sparse_user_adam
         self.lr = float(lr)
         self.t = 0
@@ -148,6 +154,18 @@ class LsturEngine:
                 self.plan = None
         except Exception:
             pass
+
+    def adopt_state_from(self, old):
+        """A training engine rebuilt for another batch shape takes over the old one's device weights AND its optimizer
+        state (Adam moments, step count, dropout seed counter), so that changing the batch size mid-training does not
+        reset the optimizer or replay dropout masks."""
+        assert self.training_plan and old.training_plan and self.n_dense == old.n_dense
+        for name in ('dense', 'adam_m', 'adam_v', 'word_emb', 'user_emb', 'user_m', 'user_v', 'word_m', 'word_v'):
+            a, b = getattr(self, name, None), getattr(old, name, None)
+            if a is not None and b is not None:
+                a.copy_(b)
+        self.t, self.step_seed, self.lr = old.t, old.step_seed, old.lr
+        self._emb_version[0] += 1
 
     # ---- weights ------------------------------------------------------------------------
     def set_weights_dict(self, params):
@@ -180,6 +198,8 @@ class LsturEngine:
     def get_grads_dict(self):
         """Dense gradients plus the (densified) user-embedding gradient of the last backward."""
         out = self._unflatten(self.dense_grad)
+        if self.trainable_word_emb:
+            out['word_emb'] = self.word_grad.cpu().numpy()
         if self.user_emb is not None:
             g = np.zeros(tuple(self.user_emb.shape), dtype=np.float32)
             n = int(self.view('n_user_rows', torch.int32)[0])
@@ -279,8 +299,9 @@ class LsturEngine:
     def backward(self, db, grad_scale=None):
         cb = self._cbatch(db)
         gs = 1.0 / self.B if grad_scale is None else grad_scale
-        _lib.check(self.lib.lstur_backward(self.plan, ctypes.byref(self._w), ctypes.byref(cb), _ptr(self.ws),
-                                           _ptr(self.dense_grad), ctypes.c_float(gs), self._stream()))
+        _lib.check(self.lib.lstur_backward_w(self.plan, ctypes.byref(self._w), ctypes.byref(cb), _ptr(self.ws),
+                                             _ptr(self.dense_grad), _ptr(self.word_grad) if self.trainable_word_emb else None,
+                                             ctypes.c_float(gs), self._stream()))
 
     def apply_adam(self, b1=0.9, b2=0.999, eps=1e-7, user_rows=None):
         """Keras Adam on the dense arena and the user table.  user_rows = (max_rows, rows, n_rows, g_rows)
@@ -289,6 +310,10 @@ class LsturEngine:
         st = self._stream()
         _lib.check(self.lib.lstur_adam_dense(self.n_dense, _ptr(self.dense), _ptr(self.dense_grad), _ptr(self.adam_m),
                                              _ptr(self.adam_v), self.lr, self.t, b1, b2, eps, 1.0, st))
+        if self.trainable_word_emb:
+            _lib.check(self.lib.lstur_adam_dense(self.word_emb.numel(), _ptr(self.word_emb), _ptr(self.word_grad),
+                                                 _ptr(self.word_m), _ptr(self.word_v), self.lr, self.t, b1, b2, eps, 1.0, st))
+            self._emb_version[0] += 1          # the plans re-pack their 16-bit operand copy of the table
         if self.user_emb is not None:
             if user_rows is None:
                 user_rows = (self.B, self.view('user_rows', torch.int32), self.view('n_user_rows', torch.int32),

@@ -69,21 +69,27 @@ class _Core:
     def engine_train(self, B):
         e = self.train_engine
         if e is None or e.B != B:
-            if e is not None:                      # batch size changed: carry the weights over
+            old = e
+            if e is not None:                      # batch size changed: carry the weights (and optimizer state, below) over
                 self.params = e.get_weights_dict()
             c = self.cfg
             self.train_engine = LsturEngine(
                 self.params, B, c.window_size, self.n_train_cand(), c.title_shape, arch=self.arch,
                 dropout=c.dropout, lr=c.learning_rate, recurrent_activation=c.recurrent_activation,
                 precision=self.precision(), doc_tokens=self.doc_tokens, training=True,
-                sparse_user_adam=bool(c.sparse_user_adam), score_model=self.score_model, **self.head_kw())
+                sparse_user_adam=bool(c.sparse_user_adam), score_model=self.score_model,
+                trainable_word_emb=bool(getattr(c, 'textual_embedding_trainable', False)), **self.head_kw())
+            if old is not None:
+                self.train_engine.adopt_state_from(old)
             self.infer_engines = {}
         return self.train_engine
 
     def engine_infer(self, C):
         if C not in self.infer_engines:
             c = self.cfg
-            base = self.engine_train(c.batch_size)
+            # share the CURRENT training engine's device weights whatever its batch size (never rebuild it from here:
+            # that would discard its optimizer state); create one only if training has not started
+            base = self.train_engine if self.train_engine is not None else self.engine_train(c.batch_size)
             self.infer_engines[C] = LsturEngine(
                 self.params, self.predict_rows, c.window_size, C, c.title_shape, arch=self.arch, dropout=0.0,
                 recurrent_activation=c.recurrent_activation, precision=self.precision(), training=False,

@@ -221,3 +221,59 @@ def write_dataset(dirname, shape, seed=7):
     write_docmeta_tsv(os.path.join(dirname, 'DocMeta.tsv'), tok, vert, subvert)
     write_clickdata_tsv(os.path.join(dirname, 'ClickData.tsv'), shape.n_users, shape.n_news, rng)
     return emb, tok
+
+
+# ---- a LEARNABLE synthetic click task (training-parity / AUC checks; BASELINE.json north_star: "AUC within 0.002 after
+# a fixed step count").  make_batches() above draws positives at random, so nothing can be learnt from it; here every
+# document carries a latent topic visible in its title tokens and every user prefers one topic, so a model that reads
+# titles and user ids ranks the positive above random negatives after a few hundred steps. -----------------------------
+def make_preference_task(shape, n_train, n_eval, seed=4321, n_topics=8, p_topic_token=0.8, p_pref=0.85):
+    """-> tok (n_news+1, L), word_emb (V, E), train batches, eval batches (lists of dicts user / hist_doc / cand_doc,
+    positive first).  The (frozen) word vectors of a topic's vocabulary slice share a centroid — as pre-trained
+    vectors of related words do — so the topic is visible to the title encoder."""
+    rng = np.random.default_rng(seed)
+    n, L, V, W, K, B = shape.n_news + 1, shape.L, shape.vocab, shape.W, shape.K, shape.B
+    topic = rng.integers(0, n_topics, n)
+    length = np.clip(np.rint(rng.normal(0.6 * L, 0.2 * L, n)), min(3, L), L).astype(np.int64)
+    span = (V - 1) // n_topics
+    in_topic = rng.random((n, L)) < p_topic_token
+    tok = np.where(in_topic, 1 + topic[:, None] * span + rng.integers(0, span, (n, L)), rng.integers(1, V, (n, L))).astype(np.int32)
+    tok[np.arange(L)[None, :] >= length[:, None]] = 0
+    tok[0] = 0
+    by_topic = [np.where(topic[1:] == z)[0] + 1 for z in range(n_topics)]
+    centroid = rng.standard_normal((n_topics, shape.E))
+    word_topic = np.minimum((np.arange(V) - 1) // span, n_topics - 1)
+    word_emb = (0.1 * (0.7 * centroid[word_topic] + 0.7 * rng.standard_normal((V, shape.E)))).astype(np.float32)
+    word_emb[0] = 0.0
+    pref = rng.integers(0, n_topics, shape.n_users)
+
+    def draw(users, size):
+        """documents for `users` (len m) -> (m, size): the preferred topic with probability p_pref, else any document"""
+        m = len(users)
+        out = rng.integers(1, n, (m, size))
+        take = rng.random((m, size)) < p_pref
+        for i, u in enumerate(users):
+            pool = by_topic[pref[u]]
+            k = int(take[i].sum())
+            if k and len(pool):
+                out[i, take[i]] = pool[rng.integers(0, len(pool), k)]
+        return out
+
+    def batch():
+        user = rng.integers(0, shape.n_users, B).astype(np.int32)
+        h = np.minimum(np.clip(rng.geometric(1.0 / (0.6 * W), B), 1, 3 * W), W)
+        hist = draw(user, W).astype(np.int32)
+        hist[np.arange(W)[None, :] < (W - h)[:, None]] = 0
+        pos = draw(user, 1)
+        neg = rng.integers(1, n, (B, K))
+        return dict(user=user, hist_doc=hist, cand_doc=np.concatenate([pos, neg], 1).astype(np.int32))
+
+    return tok, word_emb, [batch() for _ in range(n_train)], [batch() for _ in range(n_eval)]
+
+
+def impression_auc(scores):
+    """Mean per-impression AUC (task/paper.py:504-515 with sklearn's roc_auc_score): scores (n, 1+K), positive first;
+    ties count one half."""
+    s = np.asarray(scores, dtype=np.float64)
+    pos, neg = s[:, :1], s[:, 1:]
+    return float(((pos > neg) + 0.5 * (pos == neg)).mean(1).mean())

@@ -146,8 +146,6 @@ class Cook:
             raise NotImplementedError()                    # task/cook.py:193-194 (iavg / iatt / ilstm / inagru / atgru / algru)
         if c.news_encoder != 'cnnatt':
             raise NotImplementedError()                    # task/cook.py:96-97
-        if c.textual_embedding_trainable:
-            raise NotImplementedError('textual_embedding_trainable (conv dgrad + word-table scatter) is not implemented yet')
         self.get_score_model()
         word_emb = np.load(c.title_embedding_input + '.npy').astype(np.float32)
         self.W, self.L = self.training_data['ch_title'].shape[1:]
@@ -174,17 +172,28 @@ class Cook:
     def current_params(self):
         return self._train_engine.get_weights_dict() if self._train_engine is not None else self.params
 
+    def _precision(self):
+        p = getattr(self.config, 'precision', 'auto')
+        if p != 'auto':
+            return p
+        from .. import _lib
+        ks, E, F = self.params['conv_w'].shape
+        return 'fp16_tc' if _lib.load().lstur_tc_supported(self.L, E, F, ks) else 'fp32'
+
     def engine(self, B, C, training):
         c = self.config
         kw = dict(arch=c.arch, flavour='cook', recurrent_activation=c.recurrent_activation, score_model=c.score_model,
-                  precision=getattr(c, 'precision', 'fp32') if getattr(c, 'precision', 'auto') != 'auto' else 'fp32')
+                  precision=self._precision())
         if training or self._train_engine is None:
             e = self._train_engine
-            if e is None or e.B != B or e.C != C:
+            if e is None or ((e.B != B or e.C != C) and training):
                 if e is not None:
                     self.params = e.get_weights_dict()
                 self._train_engine = LsturEngine(self.params, B, self.W, C, self.L, dropout=c.dropout, lr=c.learning_rate,
-                                                 training=True, sparse_user_adam=bool(c.sparse_user_adam), **kw)
+                                                 training=True, sparse_user_adam=bool(c.sparse_user_adam),
+                                                 trainable_word_emb=bool(c.textual_embedding_trainable), **kw)
+                if e is not None:
+                    self._train_engine.adopt_state_from(e)      # keep Adam moments / step count / dropout seed counter
                 self._infer = {}
             if training:
                 return self._train_engine

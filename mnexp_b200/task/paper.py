@@ -121,8 +121,6 @@ class Seq2VecPaper(Seq2Vec):
             raise NotImplementedError('enable_pretrain_encoder: loading a Keras json+pkl encoder is out of scope')
         if self.config.news_encoder != 'cnnatt':
             raise Exception('Unsupport doc model')           # task/paper.py:130,195
-        if self.config.textual_embedding_trainable:
-            raise NotImplementedError('textual_embedding_trainable (conv dgrad + word-table scatter) is not implemented yet')
         return keras_like.DocEncoderModel(self._core)
 
     def _archs(self):
@@ -246,8 +244,6 @@ class Seq2VecPaperSoftmax(Seq2VecPaper):
             raise NotImplementedError('enable_pretrain_encoder: loading a Keras json+pkl encoder is out of scope')
         if self.config.news_encoder != 'cnnatt':
             raise Exception('Unsupport doc model')           # task/paper.py:130,195 (non-LSTUR encoders are out of scope)
-        if self.config.textual_embedding_trainable:
-            raise NotImplementedError('textual_embedding_trainable (conv dgrad + word-table scatter) is not implemented yet')
         return keras_like.DocEncoderModel(self._core)
 
     def _engine_arch(self):

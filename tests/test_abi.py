@@ -26,7 +26,13 @@ def test_host_only_entry_points(lib):
     assert lib.lstur_version().decode().startswith('lstur_b200')
     assert lib.lstur_tc_padded_e(300) == 320 and lib.lstur_tc_padded_e(64) == 64
     assert lib.lstur_tc_supported(30, 300, 400, 3) == 1
-    assert lib.lstur_tc_supported(50, 300, 400, 3) == 0          # L > 31 needs the 64-row slot variant
+    assert lib.lstur_tc_supported(50, 300, 400, 3) == 1          # 64-row title slots (BASELINE config C5)
+    assert lib.lstur_tc_supported(64, 300, 400, 3) == 0
+    assert lib.lstur_tc_slot(30) == 32 and lib.lstur_tc_slot(31) == 32 and lib.lstur_tc_slot(32) == 64 and lib.lstur_tc_slot(50) == 64
+    assert lib.lstur_tc_dpre_img_bytes(10, 30, 400) == 10 * 2 * 4 * 32 * 128
+    assert lib.lstur_tc_dpre_img_bytes(10, 50, 400) == 10 * 2 * 4 * 64 * 128
+    assert lib.lstur_tc_wimg_dgrad_elems(300, 400) == 2 * 7 * 3 * 320 * 32
+    assert lib.lstur_word_grad_workspace_bytes(1000, 50, 12) > 4 * 4 * 1000
     assert lib.lstur_tc_supported(30, 300, 400, 5) == 0
     assert lib.lstur_tc_wimg_elems(300, 400) == 3 * 320 * 400
     assert lib.lstur_attn_bwd_grid(10) == 10 and lib.lstur_attn_bwd_grid(10 ** 6) % 148 == 0

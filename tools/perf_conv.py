@@ -33,7 +33,7 @@ for drop in (0.0, 0.2):
 trace = torch.zeros(8 * 16, dtype=torch.int64, device='cuda')
 
 # ---- wgrad
-nb = lib.lstur_tc_dpre_img_bytes(N, F)
+nb = lib.lstur_tc_dpre_img_bytes(N, L, F)
 img = (torch.randn(nb // 2, device='cuda') * 0.01).half()
 pb = lib.lstur_tc_wgrad_partial_bytes(N, E, F)
 ws = torch.empty(pb, dtype=torch.uint8, device='cuda')

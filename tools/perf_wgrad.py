@@ -12,7 +12,7 @@ tokd, _, _ = synth.make_docs(130000, L, V)
 tok = torch.as_tensor(tokd[g.integers(0, 130001, N)]).cuda()
 Ep = lib.lstur_tc_padded_e(E)
 emb = (torch.randn(V, Ep, device='cuda') * 0.1).half()
-nb = lib.lstur_tc_dpre_img_bytes(N, F)
+nb = lib.lstur_tc_dpre_img_bytes(N, L, F)
 img = (torch.randn(nb // 2, device='cuda') * 0.01).half()
 pb = lib.lstur_tc_wgrad_partial_bytes(N, E, F)
 ws = torch.empty(pb, dtype=torch.uint8, device='cuda')
@@ -24,7 +24,7 @@ def runm(drop, reps=5):
     for i in range(reps + 2):
         if i == 2:
             torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e0.record()
-        rc = lib.lstur_conv_wgrad_tc_m(N, L, E, F, V, P_(tok), P_(emb), P_(img), P_(dW), ctypes.c_float(drop), 1, 1, P_(ws), pb, P_(xm), st())
+        rc = lib.lstur_conv_wgrad_tc_m(N, L, E, F, V, P_(tok), P_(emb), P_(img), P_(dW), ctypes.c_float(drop), 1, 1, P_(ws), pb, P_(xm), ctypes.c_float(1.0), st())
         assert rc == 0, lib.lstur_last_error()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
