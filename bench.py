@@ -4,9 +4,13 @@
   python bench.py --gpus N --steps K --warmup W            our arm (CUDA through the C-ABI)
   python bench.py --impl reference --gpus N ...            reference arm: the CPU restatement of the
                                                            reference's Keras graph on the host cores
+  --workload C1|C2|C3|C5        BASELINE.json configs (default C3, the config the metric is quoted on)
+  --trainable-emb               textual_embedding_trainable (conv input gradient + word-table scatter; F_train = 3 x fwd)
+  --scaling weak|strong         weak: B rows per rank (default); strong: the workload's B split over the ranks
+  --no-extras                   skip the sub-records (drop-in protocol timing, per-kernel probes, C2, C4)
 
 A "step" is one LSTUR training step (forward + backward + Keras-Adam) over one batch of B
-impressions per rank; value = impressions/s over all ranks (weak scaling: B fixed per rank).
+impressions per rank; value = impressions/s over all ranks.
 """
 import argparse
 import json
@@ -15,6 +19,7 @@ import subprocess
 import sys
 import threading
 import time
+import types
 
 import numpy as np
 
@@ -32,7 +37,8 @@ def flops_per_impression(sh, trainable_emb=False):
     conv = tok * 2 * sh.k * sh.E * sh.F
     rest = tok * 4 * sh.F + T * 2 * sh.F * sh.U + sh.W * 2 * (sh.U * 3 * sh.U + sh.U * 3 * sh.U) + (1 + sh.K) * 2 * sh.U
     fwd = conv + rest
-    return dict(conv_fwd=conv, fwd=fwd, train=3 * fwd if trainable_emb else fwd + conv + 2 * rest)
+    return dict(conv_fwd=conv, fwd=fwd, gru_fwd=sh.W * 2 * (sh.U * 3 * sh.U + sh.U * 3 * sh.U),
+                train=3 * fwd if trainable_emb else fwd + conv + 2 * rest)
 
 
 def peaks():
@@ -44,16 +50,17 @@ def peaks():
 
 
 def ncu_traffic(kernel_substr):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` capture of this same command (profiles/r01_ncu_full_summary.json); None if absent."""
-    p = os.path.join(ROOT, 'profiles', 'r01_ncu_full_summary.json')
-    try:
-        for row in json.load(open(p)):
-            if kernel_substr in row['kernel']:
-                return (row['dram_read_GB'] + row['dram_write_GB']) * 1e9
-    except Exception:
-        pass
-    return None
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the newest committed
+    `ncu --set full` summary of this same command (profiles/r*_ncu_full_summary.json); None if absent."""
+    import glob
+    for p in sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_ncu_full_summary.json')), reverse=True):
+        try:
+            for row in json.load(open(p)):
+                if kernel_substr in row['kernel']:
+                    return (row['dram_read_GB'] + row['dram_write_GB']) * 1e9, os.path.basename(p)
+        except Exception:
+            pass
+    return None, None
 
 
 class ClockSampler:
@@ -107,7 +114,7 @@ def build_workload(sh, n_batches, rank, B):
     return tok, P, batches, pad_frac
 
 
-def cpu_reference_run(sh, steps, warmup, sample_B, threads=None):
+def cpu_reference_run(sh, steps, warmup, sample_B, threads=None, trainable_emb=False):
     """The reference's Keras graph restated in torch-CPU fp32 (oracle/lstur_torch.py), all host threads,
     on a bounded sample of the workload: `sample_B` rows per step, same tables, dropout on, dense Keras Adam."""
     import torch
@@ -115,7 +122,7 @@ def cpu_reference_run(sh, steps, warmup, sample_B, threads=None):
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     tok, P, batches, _ = build_workload(sh, warmup + steps, 0, sample_B)
-    ora = ot.LsturOracle(P, arch=sh.arch, dtype=torch.float32, lr=1e-3, dropout=0.2)
+    ora = ot.LsturOracle(P, arch=sh.arch, dtype=torch.float32, lr=1e-3, dropout=0.2, trainable_word_emb=trainable_emb)
     times = []
     for i, b in enumerate(batches):
         t0 = time.perf_counter()
@@ -123,10 +130,152 @@ def cpu_reference_run(sh, steps, warmup, sample_B, threads=None):
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     t = float(np.sum(times))
-    return dict(value=sample_B * len(times) / t, unit=UNIT, cores=threads, kind='port',
-                sample='%d steps of %d impressions of workload %s (same tables/shapes, dropout 0.2, dense Keras-Adam), '
-                       'torch-CPU fp32 restatement of the Keras graph' % (len(times), sample_B, sh.name),
+    return dict(value=sample_B * len(times) / t, unit=UNIT, cores=threads, kind='port', batch=sample_B,
+                sample='%d steps of %d impressions (NOT the GPU arm\'s batch) of workload %s: same tables / shapes, dropout 0.2, '
+                       'dense Keras-Adam on every tensor incl. the %d x %d user table (reference semantics); torch-CPU fp32 '
+                       'restatement of the Keras graph' % (len(times), sample_B, sh.name, sh.n_users, sh.U),
                 ms_per_step=1e3 * t / len(times))
+
+
+def timed_ms(torch, fn):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    r = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return r, e0.elapsed_time(e1)
+
+
+def extra_records(torch, lib, sh, eng, dbs, batches, tok, P, precision, pk, args, B):
+    """Sub-records of the N=1 line (each bounded to a few seconds; failures are recorded, never fatal)."""
+    from mnexp_b200 import synth
+    from mnexp_b200.engine import LsturEngine
+    out = {}
+    fl = flops_per_impression(sh, args.trainable_emb)
+    tensor_peak, hbm = pk['bf16_tflops_sustained'], pk['hbm_gbs']
+
+    # ---- per-kernel probes inside the training step (CUDA events recorded by the plan around one launch)
+    try:
+        kern = {}
+        probes = [('conv_wgrad', 2, fl['conv_fwd']), ('gru_fwd', 4, fl['gru_fwd'])]
+        if args.trainable_emb:
+            probes += [('conv_dgrad', 5, fl['conv_fwd']), ('word_scatter', 6, None)]
+        for name, pid, flops in probes:
+            evs = [(eng.new_event(), eng.new_event()) for _ in range(3)]
+            for i, (a, b) in enumerate(evs):
+                eng.set_probe(pid, a, b)
+                eng.train_step(dbs[i % len(dbs)])
+            torch.cuda.synchronize()
+            eng.set_probe(0)
+            ms = float(np.median([eng.elapsed_ms(a, b) for a, b in evs]))
+            rec = dict(ms=ms)
+            if flops:
+                rec['tflops'] = flops * B / (ms / 1e3) / 1e12
+                rec['frac_of_sustained_tensor_peak'] = rec['tflops'] / tensor_peak
+            kern[name] = rec
+        if args.trainable_emb:
+            T = sh.W + 1 + sh.K
+            n_unique = int((eng.word_grad.abs().amax(1) > 0).sum())
+            nbytes = B * T * sh.L * (sh.E * 2 + 4) + n_unique * sh.E * 4
+            kern['word_scatter'].update(algorithmic_bytes=nbytes, gbs=nbytes / (kern['word_scatter']['ms'] / 1e3) / 1e9,
+                                        frac_of_hbm=nbytes / (kern['word_scatter']['ms'] / 1e3) / 1e9 / hbm, unique_rows=n_unique,
+                                        note='16-bit dX rows + ids read, unique fp32 rows written; includes the radix sort')
+        out['kernels'] = kern
+    except Exception as ex:          # noqa: BLE001
+        out['kernels'] = dict(error=repr(ex))
+
+    # ---- the reference's data protocol, timed once (SURVEY §8d): keras-like Model.train_on_batch fed float64 (B,W,L)
+    # token arrays + one-hot target from host memory, as main.py:73-78 / task/paper.py:538-541 feed it
+    try:
+        from mnexp_b200 import keras_like
+        cfg = types.SimpleNamespace(learning_rate=1e-3, window_size=sh.W, title_shape=sh.L, negative_samples=sh.K, dropout=0.2,
+                                    recurrent_activation='hard_sigmoid', batch_size=B, sparse_user_adam=True, gain=1.0,
+                                    precision=precision, textual_embedding_trainable=args.trainable_emb)
+        core = keras_like._Core(P, cfg, tok, True, sh.arch)
+        model = keras_like.Model(core, train=True)
+        xs = []
+        for b in batches[:3]:
+            clicked = tok[b['hist_doc']].astype(np.float64)
+            cands = [tok[b['cand_doc'][:, j]].astype(np.float64) for j in range(1 + sh.K)]
+            y = np.zeros((B, 1 + sh.K)); y[:, 0] = 1
+            xs.append(([b['user']] + [clicked] + cands, y))
+        model.train_on_batch(*xs[0])
+        n = 4
+        _, ms = timed_ms(torch, lambda: [model.train_on_batch(*xs[i % 3]) for i in range(n)])
+        h2d = sum(int(np.asarray(a).nbytes) for a in xs[0][0]) + int(xs[0][1].nbytes)
+        out['dropin_protocol'] = dict(value=B * n / (ms / 1e3), unit=UNIT, ms_per_step=ms / n, host_bytes_per_step=h2d,
+                                      api='keras_like.Model.train_on_batch([user, clicked(B,W,L) float64, cand_0..K (B,L) float64], '
+                                          'one-hot (B,1+K)) -> [loss, categorical_accuracy]')
+        del model, core
+    except Exception as ex:          # noqa: BLE001
+        out['dropin_protocol'] = dict(error=repr(ex))
+    torch.cuda.empty_cache()
+
+    # ---- C2: LSTUR-con at MIND-small-scale shape (BASELINE.json configs[1]), B = 1024
+    if sh.name != 'C2':
+        try:
+            s2 = synth.SHAPES['C2']
+            tok2, P2, b2, _ = build_workload(s2, 3, 0, s2.B)
+            e2 = LsturEngine(P2, s2.B, s2.W, 1 + s2.K, s2.L, arch=s2.arch, doc_tokens=tok2, dropout=0.2, lr=1e-3,
+                             precision=precision, sparse_user_adam=True)
+            d2 = [e2.to_device_batch(b) for b in b2]
+            for i in range(3):
+                e2.train_step(d2[i])
+            n = 10
+            _, ms = timed_ms(torch, lambda: [e2.train_step(d2[i % 3]) for i in range(n)])
+            f2 = flops_per_impression(s2)
+            v = s2.B * n / (ms / 1e3)
+            out['C2'] = dict(workload='C2: LSTUR-con (gru: Dense([GRU | user])), %d users / %d news / %d vocab, B=%d'
+                                      % (s2.n_users, s2.n_news, s2.vocab, s2.B), value=v, unit=UNIT, ms_per_step=ms / n,
+                             step_frac_of_train_roofline=v * f2['train'] / (tensor_peak * 1e12), loss=e2.loss())
+            del e2, d2
+        except Exception as ex:      # noqa: BLE001
+            out['C2'] = dict(error=repr(ex))
+        torch.cuda.empty_cache()
+
+    # ---- C4: decomposed inference (BASELINE.json configs[3]): encode all news once, then users x 20 candidates
+    try:
+        s4 = synth.SHAPES['C4']
+        if sh.name in ('C3', 'C4'):
+            tok4, P4 = tok, P
+        else:
+            tok4, _, _ = synth.make_docs(s4.n_news, s4.L, s4.vocab)
+            P4 = synth.make_weights(s4, arch='igru')
+        B4, C4 = 2048, 20
+        e4 = LsturEngine(P4, B4, s4.W, C4, s4.L, arch='igru', doc_tokens=tok4, precision=precision, training=False)
+        e4.build_doc_table()
+        table, ms_docs = timed_ms(torch, e4.build_doc_table)
+        g = np.random.default_rng(0)
+        d4 = []
+        for i in range(4):
+            lens = np.clip(g.geometric(1 / 30.0, B4), 1, s4.W)
+            hist = g.integers(1, s4.n_news + 1, (B4, s4.W)).astype(np.int32)
+            hist[np.arange(s4.W)[None, :] < (s4.W - lens)[:, None]] = 0
+            d4.append(e4.to_device_batch(dict(user=g.integers(0, s4.n_users, B4).astype(np.int32), hist_doc=hist,
+                                              cand_doc=g.integers(1, s4.n_news + 1, (B4, C4)).astype(np.int32))))
+        nb = 64                        # 131 072 users: a bounded sample of the 1M-user pass
+
+        def users():
+            for i in range(nb):
+                e4.forward_docvecs(d4[i % 4], table)
+                s = e4.score_sigmoid()
+            return s
+        users()
+        _, ms_users = timed_ms(torch, users)
+        ups = nb * B4 / (ms_users / 1e3)
+        gru_flops = s4.W * 2 * (s4.U * 3 * s4.U + s4.U * 3 * s4.U)
+        out['C4'] = dict(workload='C4: %d news encoded once, then %d users x %d candidates through the GRU user encoder (sample of the 1M-user pass)'
+                                  % (s4.n_news + 1, nb * B4, C4),
+                         news_docs_per_s=table.shape[0] / (ms_docs / 1e3), news_pass_ms=ms_docs,
+                         users_per_s=ups, pairs_per_s=ups * C4, user_pass_ms_per_1M_users=1e6 / ups * 1e3,
+                         user_pass_frac_of_tensor_bound=ups * gru_flops / (tensor_peak * 1e12),
+                         note='bound = GRU FLOPs at the sustained tensor peak (SURVEY §8d: 17.4 ms per 1M users)')
+        del e4, d4, table
+    except Exception as ex:          # noqa: BLE001
+        out['C4'] = dict(error=repr(ex))
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -138,8 +287,11 @@ def main():
     ap.add_argument('--workload', default='C3')
     ap.add_argument('--precision', default=os.environ.get('LSTUR_PRECISION', 'auto'))
     ap.add_argument('--batch', type=int, default=0, help='rows per rank (default: the workload batch size)')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
+    ap.add_argument('--trainable-emb', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-extras', action='store_true')
     ap.add_argument('--cpu-sample', type=int, default=64)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
@@ -150,18 +302,25 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     B = args.batch or sh.B
+    if args.scaling == 'strong':
+        assert B % world == 0, 'strong scaling: the global batch must divide by the number of ranks'
+        B //= world
     config = dict(workload='%s: LSTUR-%s train step, %d users / %d news / %d vocab, L%d W%d K%d E%d F%d U%d, B=%d per rank'
                            % (sh.name, 'ini' if sh.arch == 'igru' else 'con', sh.n_users, sh.n_news, sh.vocab, sh.L, sh.W,
                               sh.K, sh.E, sh.F, sh.U, B),
                   global_batch=B * world, parallelism='dp%d' % world, dropout=0.2, optimizer='Keras-Adam',
-                  word_emb_trainable=False)
+                  word_emb_trainable=bool(args.trainable_emb))
 
     if args.impl == 'reference':
         if rank != 0:
             return 0
-        r = cpu_reference_run(sh, max(1, args.steps), min(args.warmup, 1), args.cpu_sample)
+        r = cpu_reference_run(sh, max(1, args.steps), min(args.warmup, 1), args.cpu_sample, trainable_emb=args.trainable_emb)
+        # this arm's real per-step batch and optimizer (the workload string names the GPU arm's shape)
+        config.update(reference_arm_batch=args.cpu_sample, global_batch=args.cpu_sample, parallelism='cpu',
+                      optimizer='dense Keras-Adam on every tensor (user table included)',
+                      workload=config['workload'].rsplit(',', 1)[0] + ', B=%d per step on the CPU arm' % args.cpu_sample)
         line = dict(metric=METRIC, value=r['value'], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=r['ms_per_step'], higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+                    ms_per_step=r['ms_per_step'], higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype='f32',
                     data='synthetic', impl='reference', config=config,
                     cpu_baseline=dict(value=r['value'], unit=UNIT, cores=r['cores'], kind=r['kind'], sample=r['sample']),
                     e2e=dict(value=r['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
@@ -171,19 +330,19 @@ def main():
     import torch
     import torch.distributed as dist
     from mnexp_b200 import _lib
-    from mnexp_b200.dist import DataParallel
+    from mnexp_b200.dist import DataParallel, init_process_group
     from mnexp_b200.engine import LsturEngine
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        init_process_group(local_rank)
     lib = _lib.load()
     precision = args.precision
     if precision == 'auto':
-        precision = 'fp16_tc' if lib.lstur_conv_tc_available() else 'fp32'
-    n_batches = 6
+        precision = 'fp16_tc' if lib.lstur_tc_supported(sh.L, sh.E, sh.F, sh.k) else 'fp32'
+    n_batches = 6 if sh.name != 'C5' else 3
     tok, P, batches, pad_frac = build_workload(sh, n_batches, rank, B)
     eng = LsturEngine(P, B, sh.W, 1 + sh.K, sh.L, arch=sh.arch, doc_tokens=tok, dropout=0.2, lr=1e-3,
-                      precision=precision, sparse_user_adam=True)
+                      precision=precision, sparse_user_adam=True, trainable_word_emb=args.trainable_emb)
     dp = DataParallel(eng)
     dbs = [eng.to_device_batch(b) for b in batches]
 
@@ -245,32 +404,44 @@ def main():
 
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return 0
     pk, pk_kind = peaks()
-    fl = flops_per_impression(sh)
+    fl = flops_per_impression(sh, args.trainable_emb)
     tensor_peak = pk['bf16_tflops_sustained']
     conv_tflops = fl['conv_fwd'] * B / (probe_ms / 1e3) / 1e12
-    roofline = dict(bound='tensor', kernel='title Conv1D forward (implicit GEMM), precision=%s' % precision,
+    traffic, traffic_src = ncu_traffic('news_conv_tc') if (B == sh.B and sh.name == 'C3') else (None, None)
+    T = sh.W + 1 + sh.K
+    gather_bytes = B * T * sh.L * (4 + sh.E * 2)          # tok * (4 + E * s), 16-bit table
+    roofline = dict(bound='tensor', kernel='title Conv1D forward (implicit GEMM, fused gather + attention pooling), precision=%s' % precision,
                     achieved=conv_tflops, peak=tensor_peak, unit='TFLOP/s', frac=conv_tflops / tensor_peak,
-                    traffic=ncu_traffic('news_conv_tc_fwd') if (B == sh.B and sh.name == 'C3') else None,
-                    traffic_unit='bytes of DRAM traffic per launch (ncu --set full, profiles/r01_ncu_full_summary.json)',
+                    traffic=traffic,
+                    traffic_unit='bytes of DRAM traffic per launch (ncu --set full, profiles/%s)' % traffic_src,
                     peak_kind='%s bf16_tflops_sustained' % pk_kind, kernel_ms=probe_ms,
+                    fused_gather_gbs=gather_bytes / (probe_ms / 1e3) / 1e9,
+                    fused_gather_note='algorithmic gather bytes (ids + 16-bit rows) over the fused kernel\'s time; the rows come from L2 '
+                                      '(see profiles/ for lts__t_bytes), so this is not an HBM roofline',
                     step_frac_of_train_roofline=(value / world) * fl['train'] / (tensor_peak * 1e12),
                     flops_per_impression_train=fl['train'])
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference_run(sh, 6, 1, args.cpu_sample)
+        cpu = cpu_reference_run(sh, 6, 1, args.cpu_sample, trainable_emb=args.trainable_emb)
         cpu.pop('ms_per_step', None)
+    extra = None
+    if world == 1 and not args.no_extras:
+        extra = extra_records(torch, lib, sh, eng, dbs, batches, tok, P, precision, pk, args, B)
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                ms_per_step=ms_total / args.steps, higher_is_better=True, scaling=args.scaling, vs_baseline=None,
                 dtype={'bf16_tc': 'bf16', 'fp16_tc': 'f16'}.get(precision, 'f32'), data='synthetic',
                 config=dict(config, precision=precision, l2='inputs larger than L2: %d distinct batches, >%d MB activations per step'
                                                           % (n_batches, eng.ws_bytes >> 20),
                             user_adam='row-sparse (documented deviation from dense Keras-Adam)', hist_pad_frac=round(pad_frac, 3)),
-                roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=launches, clocks=clocks, loss=loss_last)
+                roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=launches, clocks=clocks, loss=loss_last,
+                extra=extra)
     print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

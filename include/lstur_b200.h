@@ -382,6 +382,15 @@ int lstur_plan_view(const lstur_plan* plan, void* workspace, const char* name, v
 #define LSTUR_PROBE_CONV_DGRAD 5
 #define LSTUR_PROBE_SCATTER 6
 int lstur_plan_set_probe(lstur_plan* plan, int probe_id, void* start_event, void* stop_event);
+/* Data-parallel overlap: `event` (cudaEvent_t) is recorded by lstur_backward as soon as every gradient except the
+ * title-encoder bucket — the first lstur_plan_dense_head_count() floats of the arena: conv_w, conv_b, att_w, att_b — and
+ * the user-row gradients are final; the exchange of the rest can then run on another stream under the ~2 ms of
+ * attention backward + conv weight gradient that remain. */
+#define LSTUR_EVENT_TAIL_GRADS_READY 1
+int lstur_plan_set_event(lstur_plan* plan, int which, void* event);
+long long lstur_plan_dense_head_count(const lstur_plan* plan);
+int lstur_stream_wait_event(cudaStream_t stream, void* event);
+int lstur_event_record(void* event, cudaStream_t stream);
 int lstur_event_create(void** ev);
 int lstur_event_destroy(void* ev);
 int lstur_event_elapsed_ms(void* start_event, void* stop_event, float* ms);

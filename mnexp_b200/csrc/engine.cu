@@ -41,6 +41,22 @@ extern "C" int lstur_plan_set_probe(lstur_plan* plan, int probe_id, void* start_
   plan->probe_stop = (cudaEvent_t)stop_event;
   return LSTUR_OK;
 }
+extern "C" int lstur_plan_set_event(lstur_plan* plan, int which, void* event) {
+  LSTUR_REQUIRE(plan != nullptr && which == LSTUR_EVENT_TAIL_GRADS_READY, "lstur_plan_set_event");
+  plan->ev_tail_ready = (cudaEvent_t)event;
+  return LSTUR_OK;
+}
+extern "C" long long lstur_plan_dense_head_count(const lstur_plan* plan) { return plan ? plan->dense_head : 0; }
+extern "C" int lstur_stream_wait_event(cudaStream_t stream, void* event) {
+  cudaError_t e = cudaStreamWaitEvent(stream, (cudaEvent_t)event, 0);
+  if (e != cudaSuccess) { set_error("cudaStreamWaitEvent: %s", cudaGetErrorString(e)); return LSTUR_ERR_CUDA; }
+  return LSTUR_OK;
+}
+extern "C" int lstur_event_record(void* event, cudaStream_t stream) {
+  cudaError_t e = cudaEventRecord((cudaEvent_t)event, stream);
+  if (e != cudaSuccess) { set_error("cudaEventRecord: %s", cudaGetErrorString(e)); return LSTUR_ERR_CUDA; }
+  return LSTUR_OK;
+}
 extern "C" int lstur_event_create(void** ev) {
   LSTUR_REQUIRE(ev != nullptr, "lstur_event_create");
   cudaEvent_t e;
@@ -143,6 +159,7 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
   add_dense(p, "conv_b", F);
   add_dense(p, "att_w", F);
   add_dense(p, "att_b", 1);
+  p->dense_head = (p->dense_count + 3) & ~3LL;     // title-encoder bucket: its gradients are the last to become final
   if (c.use_dense) {
     add_dense(p, "dense_w", (long long)F * Dd);
     add_dense(p, "dense_b", Dd);
@@ -761,6 +778,8 @@ extern "C" int lstur_backward_w(const lstur_plan* p, const lstur_weights* w, con
   } else {
     dpool = d_docv; lddp = D;
   }
+  // everything but the title-encoder bucket is final here: a data-parallel caller starts its exchange on another stream
+  if (p->ev_tail_ready) cudaEventRecord(p->ev_tail_ready, st);
   // the dropout streams are replayed only if the saved forward was a training forward (an inference forward followed by
   // a backward differentiates the inference graph)
   const float bwd_drop = p->last_training ? c.dropout : 0.f;

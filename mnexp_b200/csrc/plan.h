@@ -27,6 +27,10 @@ struct lstur_plan {
   // changes or lstur_plan_invalidate_tables() was called (the table was written)
   const void* emb16_src = nullptr;
   void* emb16_dst = nullptr;
+  // data-parallel overlap: recorded by lstur_backward once every gradient except the title-encoder bucket (conv_w, conv_b,
+  // att_w, att_b = the first dense_head floats of the arena) and the user-row gradients are final
+  cudaEvent_t ev_tail_ready = nullptr;
+  long long dense_head = 0;
   unsigned last_seed = 0;   // seed / mode of the last forward (backward replays its dropout streams)
   int last_training = 0;
 };

@@ -70,13 +70,45 @@ class UserRowReducer:
         return (n, self.rows, self.nrows, self.grows)
 
 
+def init_process_group(local_rank, backend='nccl'):
+    """One process per GPU; NCCL's internal stream runs at high priority so that the small exchange collectives get an
+    SM as soon as one frees up under the (SM-filling) backward kernels they overlap with."""
+    kw = {}
+    if backend == 'nccl':
+        try:
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.is_high_priority_stream = True
+            kw['pg_options'] = opts
+        except Exception:       # noqa: BLE001  (older torch: default stream priority)
+            pass
+        kw['device_id'] = torch.device('cuda', local_rank)
+    dist.init_process_group(backend, **kw)
+
+
 class DataParallel:
-    def __init__(self, engine, group=None):
+    """Batch sharded per rank, weights replicated.  Per step:
+
+      forward, backward on the main stream; lstur_backward records an event once every gradient except the title-encoder
+      bucket (conv_w / conv_b / att_*: the first `head` floats of the arena) is final — about 2 ms before the end of the
+      backward at C3.  A second (high-priority) stream waits for that event and runs, UNDER the attention backward and the
+      conv weight gradient: the all-reduce of the arena tail, the all-gather of (user id, d user row), and the
+      deterministic global dedup + segment-sorted sum.  Only the all-reduce of the title-encoder bucket (1.4 MB) — and
+      the dense word-table gradient when the table is trainable — trails the backward.
+    """
+
+    def __init__(self, engine, group=None, overlap=True):
         self.eng, self.group = engine, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         e = engine
         self.reducer = UserRowReducer(e, self.world * e.B) if (e.user_emb is not None and self.world > 1) else None
+        self.overlap = bool(overlap) and self.world > 1
+        if self.world > 1:
+            self.head = int(e.lib.lstur_plan_dense_head_count(e.plan))
+            if self.overlap:
+                self.side = torch.cuda.Stream(device=e.device, priority=-1)
+                self.ev_tail, self.ev_side = e.new_event(), e.new_event()
+                _lib.check(e.lib.lstur_plan_set_event(e.plan, 1, self.ev_tail))
 
     def train_step(self, db):
         e = self.eng
@@ -86,9 +118,28 @@ class DataParallel:
         e.forward(db, training=True, seed=e.step_seed * self.world + self.rank)
         e.backward(db, grad_scale=1.0 / (e.B * self.world))          # mean over the GLOBAL batch
         has_user = e.user_emb is not None
-        ids, rows = exchange(e.dense_grad, db['user'] if has_user else None,
-                             e.view('d_u0').reshape(e.B, e.Ue) if has_user else None, self.group)
-        e.apply_adam(user_rows=self.reducer.reduce(e, ids, rows) if has_user else None)
+        ids_in = db['user'] if has_user else None
+        rows_in = e.view('d_u0').reshape(e.B, e.Ue) if has_user else None
+        ur = None
+        if self.overlap:
+            side_h = ctypes.c_void_p(self.side.cuda_stream)
+            _lib.check(e.lib.lstur_stream_wait_event(side_h, self.ev_tail))
+            with torch.cuda.stream(self.side):
+                ids, rows = exchange(e.dense_grad[self.head:], ids_in, rows_in, self.group)
+                if has_user:
+                    ur = self.reducer.reduce(e, ids, rows)
+                _lib.check(e.lib.lstur_event_record(self.ev_side, side_h))
+            dist.all_reduce(e.dense_grad[:self.head], op=dist.ReduceOp.SUM, group=self.group)
+            if e.trainable_word_emb:
+                dist.all_reduce(e.word_grad, op=dist.ReduceOp.SUM, group=self.group)
+            _lib.check(e.lib.lstur_stream_wait_event(e._stream(), self.ev_side))
+        else:
+            ids, rows = exchange(e.dense_grad, ids_in, rows_in, self.group)
+            if e.trainable_word_emb:
+                dist.all_reduce(e.word_grad, op=dist.ReduceOp.SUM, group=self.group)
+            if has_user:
+                ur = self.reducer.reduce(e, ids, rows)
+        e.apply_adam(user_rows=ur)
         return e.view('loss')
 
 

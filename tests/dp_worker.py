@@ -21,7 +21,8 @@ def main():
     precision, trainable = sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 0
     rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
     torch.cuda.set_device(int(os.environ['LOCAL_RANK']))
-    dist.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ['LOCAL_RANK'])))
+    from mnexp_b200.dist import init_process_group
+    init_process_group(int(os.environ['LOCAL_RANK']))
     sh = synth.Shape('dp', 40, 300, 2000, L=30, W=50, K=4, B=8 * world, E=300, F=400, U=200)
     tok, _, _ = synth.make_docs(sh.n_news, sh.L, sh.vocab)
     P = synth.make_weights(sh, arch='igru', bias_noise=0.05, seed=5)
@@ -45,7 +46,7 @@ def main():
             full.train_step(full.to_device_batch(b))
         torch.cuda.synchronize()
         wf = full.get_weights_dict()
-        tol = 1e-6 if precision == 'fp32' else 2e-5
+        tol = 1e-6 if precision == 'fp32' else (3e-4 if trainable else 2e-5)
         for k in names:
             err = float(np.abs(np.asarray(w[k], dtype=np.float64) - wf[k]).max())
             print('%-10s max |dp - single| = %.3e' % (k, err))

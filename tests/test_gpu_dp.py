@@ -49,7 +49,10 @@ def test_two_emulated_ranks_equal_one_engine(lib, precision, trainable):
         full.train_step(full.to_device_batch(b))
     torch.cuda.synchronize()
     w0, w1, wf = ranks[0].get_weights_dict(), ranks[1].get_weights_dict(), full.get_weights_dict()
-    tol = 1e-6 if precision == 'fp32' else 2e-5
+    # fp32: reassociation only.  Tensor-core mode: the 16-bit operand copies round-trip through the exchange bit-exactly
+    # while the table is frozen; with the table trainable a 1e-7 reassociation difference in a word row can flip its
+    # 16-bit rounding in the next step's operand copy, which moves later updates by a fraction of one Adam step (lr 1e-3)
+    tol = 1e-6 if precision == 'fp32' else (3e-4 if trainable else 2e-5)
     for k in wf:
         assert np.array_equal(w0[k], w1[k]), k                 # replicas bit-identical
         assert np.abs(w0[k].astype(np.float64) - wf[k]).max() <= tol, (k, float(np.abs(w0[k] - wf[k]).max()))
@@ -57,11 +60,11 @@ def test_two_emulated_ranks_equal_one_engine(lib, precision, trainable):
         assert np.abs(wf['word_emb'] - P['word_emb']).max() > 1e-4      # the table actually moved
 
 
-@pytest.mark.parametrize('precision', ['fp32', 'fp16_tc'])
-def test_two_nccl_ranks_equal_one_engine(lib, precision):
+@pytest.mark.parametrize('precision,trainable', [('fp32', 0), ('fp16_tc', 0), ('fp16_tc', 1)])
+def test_two_nccl_ranks_equal_one_engine(lib, precision, trainable):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr', '127.0.0.1',
-           '--master-port', '29731', os.path.join(ROOT, 'tests', 'dp_worker.py'), precision]
+           '--master-port', '29731', os.path.join(ROOT, 'tests', 'dp_worker.py'), precision, str(trainable)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]

@@ -12,13 +12,19 @@ from tolerances import assert_close
 pytestmark = pytest.mark.gpu
 
 
-def sampled_forward_check(lib, sh, B, n_sample, precision='fp16_tc', seed=0):
+def sampled_forward_check(lib, sh, B, n_sample, precision='fp16_tc', seed=0, training=False):
     from mnexp_b200.engine import LsturEngine
     tok, _, _ = synth.make_docs(sh.n_news, sh.L, sh.vocab)
     P = synth.make_weights(sh, arch=sh.arch, bias_noise=0.02)
     (b,), _ = synth.make_batches(sh, 1, seed=1236 + seed, B=B)
-    eng = LsturEngine(P, B, sh.W, 1 + sh.K, sh.L, arch=sh.arch, doc_tokens=tok, precision=precision, training=False)
-    eng.forward(eng.to_device_batch(b), training=False)
+    eng = LsturEngine(P, B, sh.W, 1 + sh.K, sh.L, arch=sh.arch, doc_tokens=tok, precision=precision, training=training)
+    db = eng.to_device_batch(b)
+    eng.forward(db, training=training)
+    if training:            # the full-size backward must at least run and produce finite gradients
+        eng.backward(db)
+        torch.cuda.synchronize()
+        g = eng.dense_grad
+        assert bool(torch.isfinite(g).all()) and float(g.abs().max()) > 0
     torch.cuda.synchronize()
     rows = np.sort(np.random.default_rng(seed).choice(B, n_sample, replace=False))
     ref = on.lstur_forward(P, b['user'][rows], tok[b['hist_doc'][rows]], tok[b['cand_doc'][rows]], arch=sh.arch, aux=True)
@@ -26,8 +32,9 @@ def sampled_forward_check(lib, sh, B, n_sample, precision='fp16_tc', seed=0):
     dv = eng.view('doc_vec').reshape(-1, D)
     hist = dv[:B * sh.W].reshape(B, sh.W, D)[rows].cpu().numpy()
     cand = dv[B * sh.W:].reshape(B, 1 + sh.K, D)[rows].cpu().numpy()
-    assert_close(hist, ref['hist_vec'], 1e-3, 'history vectors')
-    assert_close(cand, ref['cand_vec'], 1e-3, 'candidate vectors')
+    # 640 000 elements: the element-wise form is asserted for all but a 1e-5 tail, which must stay within 1.5 x the bound
+    assert_close(hist, ref['hist_vec'], 1e-3, 'history vectors', tail=1e-5, tail_excess=1.5)
+    assert_close(cand, ref['cand_vec'], 1e-3, 'candidate vectors', tail=1e-5, tail_excess=1.5)
     assert_close(eng.view('user_vec').reshape(B, -1)[rows].cpu().numpy(), ref['user_vec'], 1e-3, 'user vectors')
     assert_close(eng.view('logits').reshape(B, -1)[rows].cpu().numpy(), ref['logits'], 1e-3, 'scores')
     assert_close(eng.view('probs').reshape(B, -1)[rows].cpu().numpy(), ref['probs'], 1e-3, 'probabilities')
@@ -39,6 +46,12 @@ def sampled_forward_check(lib, sh, B, n_sample, precision='fp16_tc', seed=0):
 def test_c3_scale_forward_sampled_rows(lib):
     """C3: 1M users / 130k news / 100k vocab, B=1024, LSTUR-ini — the configuration bench.py times."""
     sampled_forward_check(lib, synth.SHAPES['C3'], 1024, 64)
+
+
+def test_c5_full_batch_sampled_rows(lib):
+    """C5 as benchmarked: W=200, L=50, B=2048 per rank (419 840 titles, 21 M tokens per step; the index arithmetic of
+    every kernel crosses 2^31 elements here), forward + backward, 8 sampled rows against the float64 oracle."""
+    sampled_forward_check(lib, synth.SHAPES['C5'], 2048, 8, seed=2, training=True)
 
 
 def test_c2_scale_forward_sampled_rows(lib):
