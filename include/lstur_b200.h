@@ -107,17 +107,27 @@ int lstur_news_conv_tc_fwd(int n_titles, int L, int E, int F, int V, const int* 
                            void* c_out_16, float* pooled, float* att_a, float* att_wt, float dropout, unsigned seed,
                            int fp16, int max_ctas, cudaStream_t stream);
 
+/* Title compaction (lstur_compact_titles): the news encoder of an all-pad title — every token 0, i.e. the left padding of
+ * a short click history (task/seq2vec.py:23,46-49) — is identically zero in value and in gradient (pad mask,
+ * task/paper.py:150-155), so the plan runs the tensor-core kernels over the ascending list of live titles only:
+ * n_live (1), live_idx (N: original index of every live title), tokens_c (N,L: their tokens); flags (N) is scratch.  The
+ * kernels below take the live count as a device scalar (n_titles_dev, NULL = all n_titles) and, where a tensor outside the
+ * encoder is touched (pooled rows, d_pooled rows), the original title index (title_idx, NULL = identity). */
+int lstur_compact_titles(int N, int L, const int* tokens, int* flags, int* live_idx, int* n_live, int* tokens_c,
+                         cudaStream_t stream);
+
 /* Same kernels with the X-dropout keep bits handed from the forward to the weight-gradient kernel (one byte per 16-byte
  * piece of an embedding row, lstur_tc_xmask_bytes) instead of replaying the dropout hash there; NULL = replay. */
 size_t lstur_tc_xmask_bytes(int n_titles, int L, int E);
 int lstur_news_conv_tc_fwd_m(int n_titles, int L, int E, int F, int V, const int* tokens, const void* emb_16,
                              const void* wimg, const float* conv_b, const float* att_w, const float* att_b,
                              void* c_out_16, float* pooled, float* att_a, float* att_wt, float dropout, unsigned seed,
-                             int fp16, int max_ctas, void* xmask_out, cudaStream_t stream);
+                             int fp16, int max_ctas, void* xmask_out, const int* n_titles_dev, const int* title_idx,
+                             cudaStream_t stream);
 int lstur_conv_wgrad_tc_m(int n_titles, int L, int E, int F, int V, const int* tokens, const void* emb_16,
                           const void* dpre_img, float* d_conv_w, float dropout, unsigned seed, int fp16,
                           void* partial_ws, size_t partial_bytes, const void* xmask, float dpre_scale,
-                          cudaStream_t stream);
+                          const int* n_titles_dev, cudaStream_t stream);
 /* Conv1D INPUT gradient on tcgen05 (word-table training: Embedding(trainable=True), task/paper.py:132-138, main.py:36):
  * dx16 (n_titles, L, lstur_tc_padded_e(E)) 16-bit rows = out_scale * sum_j sum_f dPre[m+1-j, f] * conv_w[j, e, f], from
  * the dPre image of lstur_attn_pool_bwd_img (its img_scale multiplies through) and the transposed, tap-reversed weight
@@ -125,7 +135,7 @@ int lstur_conv_wgrad_tc_m(int n_titles, int L, int E, int F, int V, const int* t
 long long lstur_tc_wimg_dgrad_elems(int E, int F);
 int lstur_pack_conv_w_dgrad_tc(int E, int F, const float* conv_w, void* wimg_d, int fp16, cudaStream_t stream);
 int lstur_conv_dgrad_tc(int n_titles, int L, int E, int F, const void* dpre_img, const void* wimg_d, void* dx16,
-                        float out_scale, int fp16, int max_ctas, cudaStream_t stream);
+                        float out_scale, int fp16, int max_ctas, const int* n_titles_dev, cudaStream_t stream);
 
 /* Backward of the tensor-core news encoder: attention/ReLU/mask backward emitting dPre as 16-bit K-block images
  * (lstur_attn_pool_bwd_img; the image holds img_scale * dPre — a power-of-two loss scale that keeps the gradients of a
@@ -134,7 +144,8 @@ int lstur_conv_dgrad_tc(int n_titles, int L, int E, int F, const void* dpre_img,
 int lstur_attn_pool_bwd_img(int fp16, int N, int L, int F, const void* Cd_16, const float* a_in, const float* w_in,
                             const float* d_pooled, long long lddp, const float* att_w, void* dpre_img, float dropout,
                             float img_scale, float* d_att_w, float* d_conv_b, float* d_att_b, int accumulate,
-                            float* partials, size_t partial_bytes, cudaStream_t stream);
+                            float* partials, size_t partial_bytes, const int* n_titles_dev, const int* title_idx,
+                            cudaStream_t stream);
 size_t lstur_tc_dpre_img_bytes(int n_titles, int L, int F);
 size_t lstur_tc_wgrad_partial_bytes(int n_titles, int E, int F);
 int lstur_conv_wgrad_tc(int n_titles, int L, int E, int F, int V, const int* tokens, const void* emb_16,
@@ -290,7 +301,7 @@ int lstur_rows_add(int max_rows, const int* n_rows_dev, int D, const int* rows, 
 size_t lstur_word_grad_workspace_bytes(long long n_pos, int V, int E);
 int lstur_word_grad_scatter_16(int n_titles, int L, int E, int V, const int* tokens, const void* dx16, int fp16,
                                float scale, const void* xmask, float* d_word_emb, void* workspace,
-                               size_t workspace_bytes, cudaStream_t stream);
+                               size_t workspace_bytes, const int* n_titles_dev, cudaStream_t stream);
 int lstur_word_grad_scatter_f32(int n_titles, int L, int KS, int E, int V, const int* tokens, const float* dXp,
                                 float dropout, unsigned seed, float scale, float* d_word_emb, void* workspace,
                                 size_t workspace_bytes, cudaStream_t stream);
@@ -381,6 +392,8 @@ int lstur_plan_view(const lstur_plan* plan, void* workspace, const char* name, v
 #define LSTUR_PROBE_GRU_FWD 4
 #define LSTUR_PROBE_CONV_DGRAD 5
 #define LSTUR_PROBE_SCATTER 6
+#define LSTUR_PROBE_ATTN_BWD 7
+#define LSTUR_PROBE_GRU_BWD 8
 int lstur_plan_set_probe(lstur_plan* plan, int probe_id, void* start_event, void* stop_event);
 /* Data-parallel overlap: `event` (cudaEvent_t) is recorded by lstur_backward as soon as every gradient except the
  * title-encoder bucket — the first lstur_plan_dense_head_count() floats of the arena: conv_w, conv_b, att_w, att_b — and

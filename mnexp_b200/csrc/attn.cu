@@ -230,7 +230,9 @@ __global__ void __launch_bounds__(IMG_THREADS)
 attn_bwd_img_kernel(int N, int L, int F, const CT* __restrict__ Cd, const float* __restrict__ a_in,
                     const float* __restrict__ w_in, const float* __restrict__ dp, long long lddp,
                     const float* __restrict__ ka, uint8_t* __restrict__ img, float inv_keep, float img_scale,
-                    float* __restrict__ partials, int nbuf) {
+                    float* __restrict__ partials, int nbuf, const int* __restrict__ n_dev,
+                    const int* __restrict__ title_idx) {
+  if (n_dev) N = min(N, __ldg(n_dev));          // compacted title list: live titles only (lstur_compact_titles)
   extern __shared__ __align__(16) uint8_t att_smem[];
   const int nchunk = F >> 3;                       // 16-byte chunks per row
   // Two title buffers: the (contiguous, L*F*2-byte) saved C of the NEXT title is fetched with one bulk copy while the
@@ -274,10 +276,11 @@ attn_bwd_img_kernel(int N, int L, int F, const CT* __restrict__ Cd, const float*
   constexpr int DPR = 2;                            // d_pooled values per thread (F <= DPR * IMG_THREADS)
   float ndp[DPR], nw = 0.f, na = 0.f;
   auto prefetch_small = [&](int n) {
+    const int no = (title_idx && n < N) ? __ldg(title_idx + n) : n;   // d_pooled rows live at the original title index
 #pragma unroll
     for (int i = 0; i < DPR; ++i) {
       const int f = tid + i * IMG_THREADS;
-      ndp[i] = (n < N && f < F) ? dp[(long long)n * lddp + f] : 0.f;
+      ndp[i] = (n < N && f < F) ? dp[(long long)no * lddp + f] : 0.f;
     }
     nw = (n < N && tid < L) ? w_in[(long long)n * L + tid] : 0.f;
     na = (n < N && tid < L) ? a_in[(long long)n * L + tid] : 0.f;
@@ -590,7 +593,7 @@ extern "C" int lstur_attn_pool_bwd_img(int fp16, int N, int L, int F, const void
                                        const float* w_in, const float* d_pooled, long long lddp, const float* att_w,
                                        void* dpre_img, float dropout, float img_scale, float* d_att_w, float* d_conv_b,
                                        float* d_att_b, int accumulate, float* partials, size_t partial_bytes,
-                                       cudaStream_t stream) {
+                                       const int* n_titles_dev, const int* title_idx, cudaStream_t stream) {
   LSTUR_REQUIRE(N >= 0 && L >= 1 && L <= 63 && F % 16 == 0 && F <= 512 && dpre_img != nullptr && img_scale > 0.f,
                 "lstur_attn_pool_bwd_img");
   int grid = lstur_attn_bwd_grid(N);
@@ -612,7 +615,8 @@ extern "C" int lstur_attn_pool_bwd_img(int fp16, int N, int L, int F, const void
   do {                                                                                                                  \
     if (smem > 48 * 1024) cudaFuncSetAttribute(attn_bwd_img_kernel<CT_, SLOT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     attn_bwd_img_kernel<CT_, SLOT_><<<grid, IMG_THREADS, smem, stream>>>(N, L, F, (const CT_*)Cd_16, a_in, w_in, d_pooled, lddp, \
-                                                                         att_w, (uint8_t*)dpre_img, inv_keep, img_scale, partials, nbuf); \
+                                                                         att_w, (uint8_t*)dpre_img, inv_keep, img_scale, partials, nbuf, \
+                                                                         n_titles_dev, title_idx);                       \
   } while (0)
   if (fp16 && slot == 32) IMG_LAUNCH(__half, 32);
   else if (fp16) IMG_LAUNCH(__half, 64);

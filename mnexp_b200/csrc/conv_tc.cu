@@ -123,6 +123,10 @@ struct FwdParams {
   const uint8_t* dimg;
   int ngh, cph;                   // 64-column groups / 32-column chunks per half of the conv features
   float out_scale;                // dX16 = out_scale * accumulator
+  // compacted title list (lstur_compact_titles): n_dev = device count of titles to process (<= n_titles), title_idx =
+  // original index of every processed title (pooled rows are written there); both optional
+  const int* n_dev;
+  const int* title_idx;
 };
 
 // Stage = one 32-column chunk of the embedding: the three shifted tap tiles of this CTA's 128 token rows (A, 24 KB)
@@ -297,7 +301,9 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
-  const int n_tiles = (p.n_titles + TPT - 1) / TPT;
+  // number of titles: optionally a device scalar (the compacted count of live titles, lstur_compact_titles)
+  const int n_titles = p.n_dev ? min(__ldg(p.n_dev), p.n_titles) : p.n_titles;
+  const int n_tiles = (n_titles + TPT - 1) / TPT;
   const int n_tp = (n_tiles + 1) / 2;                  // tile pairs
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const float ik = DROP ? p.inv_keep : 1.f;
@@ -414,7 +420,7 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int t = 8 * (2 * rh + i) + rsub;
-        const bool ok = tp < n_tp && n < p.n_titles && t < p.L;
+        const bool ok = tp < n_tp && n < n_titles && t < p.L;
         // raw id: not inspected here (no stall on the load); clamped when the rows are requested
         if (DG) ids[i] = ok ? n * SLOT + t : kNoToken;
         else ids[i] = ok ? __ldg(p.tok + (long long)n * p.L + t) : kNoToken;
@@ -536,7 +542,7 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
       // ---- input gradient: scale, round, store the 16-bit rows
       for (int tp = pair; tp < n_tp; tp += n_pairs) {
         const int n = (2 * tp + (int)crank) * TPT + slot;
-        io.title = n < p.n_titles ? p.c_out + ((long long)n * p.L + t0) * F : nullptr;
+        io.title = n < n_titles ? p.c_out + ((long long)n * p.L + t0) * F : nullptr;
         mbar_wait(bar_t_full, pht, 6);
         pht ^= 1;
         tc_fence_after();
@@ -561,10 +567,10 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
     int par = 0;
     for (int tp = pair; tp < n_tp; tp += n_pairs) {
       const int n = (2 * tp + (int)crank) * TPT + slot, t = t0 + lane;
-      const bool valid = n < p.n_titles && t < p.L;
+      const bool valid = n < n_titles && t < p.L;
       const long long m = (long long)n * p.L + t;
       const int tk = valid ? p.tok[m] : 0;
-      io.title = n < p.n_titles ? p.c_out + ((long long)n * p.L + t0) * F : nullptr;
+      io.title = n < n_titles ? p.c_out + ((long long)n * p.L + t0) * F : nullptr;
       if (DROP) {
         const uint64_t base = ((uint64_t)(valid ? m : 0) * (uint64_t)F) >> 2;     // F % 4 == 0: quad index of (m, f) = base + f/4
         ec.base_lo = (uint32_t)base;
@@ -610,7 +616,7 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
         const int row2 = row ^ 32, t2 = (t0 ^ 32) + lane;
         const float zt2 = s_z[(par * 2) * 128 + row2] + s_z[(par * 2 + 1) * 128 + row2];
         const int any2 = s_any[(par * 2) * 128 + row2] | s_any[(par * 2 + 1) * 128 + row2];
-        const float e2 = (n < p.n_titles && t2 < p.L && any2) ? expf(tanhf(zt2 + att_bias)) : 0.f;
+        const float e2 = (n < n_titles && t2 < p.L && any2) ? expf(tanhf(zt2 + att_bias)) : 0.f;
         esum = t0 == 0 ? e + e2 : e2 + e;       // same operand order in both warps
       }
       par ^= 1;
@@ -627,6 +633,8 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
       // SLOT == 64: the two warps of a title split the 32-feature chunks between them (even / odd) and each sums all 64
       // rows (the neighbour's rows and weights become visible through a second barrier), so no cross-warp reduction.
       if (p.dbg & 4) continue;
+      // pooled rows go to the title's ORIGINAL index when the kernel runs over a compacted title list
+      const int n_out = (p.title_idx && n < n_titles) ? __ldg(p.title_idx + n) : n;
       constexpr int NRH = SLOT / 32;                 // 32-row halves of a title
       float wr[NRH][4];
       if (SLOT == 64) {
@@ -642,7 +650,7 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
       }
       RowIO io2 = io;                                // pass-2 view: all rows of the title from token 0
       if (SLOT == 64) {
-        io2.title = n < p.n_titles ? p.c_out + (long long)n * p.L * F : nullptr;
+        io2.title = n < n_titles ? p.c_out + (long long)n * p.L * F : nullptr;
         io2.L = p.L;
       }
       const int c_first = f_beg + (SLOT == 64 ? (q & 1) * 32 : 0), c_step = SLOT == 64 ? 64 : 32;
@@ -688,7 +696,7 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
             x[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
           }
         }
-        if (n < p.n_titles && (lane & 3) < np) p.pooled[(long long)n * F + c0 + (lane & 3) * 8 + jfeat] = x[0];
+        if (n < n_titles && (lane & 3) < np) p.pooled[(long long)n_out * F + c0 + (lane & 3) * 8 + jfeat] = x[0];
       }
     }
     }
@@ -743,6 +751,7 @@ struct WgradParams {
   int dbg;                    // experiments (LSTUR_WGRAD_DBG): 2 = skip all MMAs, 4 = skip bulk copies, 8 = producers only signal,
                               // 16 = no proxy fence, 32 = no st.shared (timing only)
   const uint8_t* xmask;       // optional keep bits written by the forward (FwdParams::xmask); null: replay the hash
+  const int* n_dev;           // optional device count of titles (K blocks) to process (<= n_kblocks): compacted title list
 };
 
 template <bool FP16, int KT>
@@ -768,8 +777,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const Wgra
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slice = blockIdx.x, split = blockIdx.y;
   const uint32_t crank = cluster_ctarank();     // 0 = leader (issues the pair's MMAs)
-  const int kb_beg = split * p.kb_per_split;
-  const int kb_end = min(p.n_kblocks, kb_beg + p.kb_per_split);
+  int n_kblocks = p.n_kblocks, kb_per_split = p.kb_per_split;
+  if (p.n_dev) {             // live titles only: the same even split of the (device-side) count over the token splits
+    n_kblocks = min(__ldg(p.n_dev), p.n_kblocks);
+    kb_per_split = ((n_kblocks + (int)gridDim.y - 1) / (int)gridDim.y + WG_TPS - 1) / WG_TPS * WG_TPS;
+  }
+  const int kb_beg = split * kb_per_split;
+  const int kb_end = min(n_kblocks, kb_beg + kb_per_split);
   const int n_stage_blocks = kb_end > kb_beg ? (kb_end - kb_beg + WG_TPS - 1) / WG_TPS : 0;
   const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
 
@@ -821,7 +835,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const Wgra
 #pragma unroll
           for (int t = 0; t < WG_TPS; ++t) {
             // a title past the end re-reads the last valid block: finite values, multiplied by the zero A rows
-            const int kb = min(kb_beg + sb * WG_TPS + t, p.n_kblocks - 1);
+            const int kb = max(0, min(kb_beg + sb * WG_TPS + t, n_kblocks - 1));
             const uint8_t* src = (const uint8_t*)p.dpre_img + ((size_t)kb * 2 + crank) * b_tile_bytes;
             bulk_g2s(b_base + s * b_stage_bytes + t * b_tile_bytes, src, b_tile_bytes, bar_full + 8 * s);
           }
@@ -1149,13 +1163,14 @@ extern "C" int lstur_news_conv_tc_fwd(int n_titles, int L, int E, int F, int V, 
                                       void* c_out_bf16, float* pooled, float* att_a, float* att_wt, float dropout,
                                       unsigned seed, int fp16, int max_ctas, cudaStream_t stream) {
   return lstur_news_conv_tc_fwd_m(n_titles, L, E, F, V, tokens, emb_bf16, wimg, conv_b, att_w, att_b, c_out_bf16, pooled,
-                                  att_a, att_wt, dropout, seed, fp16, max_ctas, nullptr, stream);
+                                  att_a, att_wt, dropout, seed, fp16, max_ctas, nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int lstur_news_conv_tc_fwd_m(int n_titles, int L, int E, int F, int V, const int* tokens, const void* emb_bf16,
                                         const void* wimg, const float* conv_b, const float* att_w, const float* att_b,
                                         void* c_out_bf16, float* pooled, float* att_a, float* att_wt, float dropout,
-                                        unsigned seed, int fp16, int max_ctas, void* xmask_out, cudaStream_t stream) {
+                                        unsigned seed, int fp16, int max_ctas, void* xmask_out, const int* n_titles_dev,
+                                        const int* title_idx, cudaStream_t stream) {
   LSTUR_REQUIRE(n_titles >= 0 && lstur_tc_supported(L, E, F, 3), "lstur_news_conv_tc_fwd");
   LSTUR_REQUIRE(dropout >= 0.f && dropout < 1.f && c_out_bf16 && pooled, "lstur_news_conv_tc_fwd");
   if (n_titles == 0) return LSTUR_OK;
@@ -1170,6 +1185,7 @@ extern "C" int lstur_news_conv_tc_fwd_m(int n_titles, int L, int E, int F, int V
   p.seed_x = seed * 2u; p.seed_c = seed * 2u + 1u;
   p.dbg = getenv("LSTUR_FWD_DBG") ? atoi(getenv("LSTUR_FWD_DBG")) : 0;
   p.xmask = (uint8_t*)xmask_out;
+  p.n_dev = n_titles_dev; p.title_idx = title_idx;
   p.trace = (long long*)g_tc_trace_ptr;
   RC(tc_launch_conv(p, L, fp16 != 0, p.drop_thr16 != 0, tc::MODE_FWD, max_ctas, stream, "lstur_news_conv_tc_fwd"));
   return LSTUR_OK;
@@ -1188,13 +1204,20 @@ extern "C" int lstur_news_encoder_tc_fwd_internal(const lstur_plan* p, const lst
     const_cast<lstur_plan*>(p)->emb16_dst = emb;
   }
   RC(lstur_pack_conv_w_tc(c.E, c.F, DP(p, w->dense, "conv_w"), wimg, fp16, st));
+  // Live titles only: an all-pad title (left padding of a short history) pools to exactly 0 and back-propagates exactly 0,
+  // so the kernels run over the compacted title list; pooled rows of the dead titles are zeroed here.
+  int* n_live = W<int>(p, ws, "n_live");
+  int* live_idx = W<int>(p, ws, "live_idx");
+  int* tok_c = W<int>(p, ws, "tokens_c");
+  RC(lstur_compact_titles(n_titles, c.L, W<int>(p, ws, "tokens"), W<int>(p, ws, "title_flags"), live_idx, n_live, tok_c, st));
+  cudaMemsetAsync(W<float>(p, ws, "pooled"), 0, (size_t)n_titles * c.F * sizeof(float), st);
   PROBE_BEGIN(p, LSTUR_PROBE_CONV_FWD, st);
   // a training forward leaves the X-dropout keep bits for the weight-gradient kernel (workspace region "xmask")
   void* xm = (training && c.dropout > 0.f && n_titles == p->N) ? W<void>(p, ws, "xmask") : nullptr;
-  RC(lstur_news_conv_tc_fwd_m(n_titles, c.L, c.E, c.F, c.V, W<int>(p, ws, "tokens"), emb, wimg, DP(p, w->dense, "conv_b"),
+  RC(lstur_news_conv_tc_fwd_m(n_titles, c.L, c.E, c.F, c.V, tok_c, emb, wimg, DP(p, w->dense, "conv_b"),
                               DP(p, w->dense, "att_w"), DP(p, w->dense, "att_b"), W<void>(p, ws, "C16"),
                               W<float>(p, ws, "pooled"), W<float>(p, ws, "att_a"), W<float>(p, ws, "att_w"),
-                              training ? c.dropout : 0.f, seed, fp16, 0, xm, st));
+                              training ? c.dropout : 0.f, seed, fp16, 0, xm, n_live, live_idx, st));
   PROBE_END(p, LSTUR_PROBE_CONV_FWD, st);
   return LSTUR_OK;
 }
@@ -1218,7 +1241,7 @@ extern "C" int lstur_pack_conv_w_dgrad_tc(int E, int F, const float* conv_w, voi
 // dx16 (n_titles, L, Ep) 16-bit rows = out_scale * dX, dX[m, e] = sum_j sum_f dPre[m+1-j, f] Wc[j, e, f] (columns
 // e >= E are zero); dpre_img is the image written by lstur_attn_pool_bwd_img (whose own scale multiplies through).
 extern "C" int lstur_conv_dgrad_tc(int n_titles, int L, int E, int F, const void* dpre_img, const void* wimg_d, void* dx16,
-                                   float out_scale, int fp16, int max_ctas, cudaStream_t stream) {
+                                   float out_scale, int fp16, int max_ctas, const int* n_titles_dev, cudaStream_t stream) {
   LSTUR_REQUIRE(n_titles >= 0 && lstur_tc_supported(L, E, F, 3) && dpre_img && wimg_d && dx16, "lstur_conv_dgrad_tc");
   const int Eo = lstur_tc_padded_e(E);
   LSTUR_REQUIRE(Eo <= tc::TMEM_COLS && (Eo <= 256 || Eo - 256 >= 16), "lstur_conv_dgrad_tc(E too wide for one accumulator)");
@@ -1228,6 +1251,7 @@ extern "C" int lstur_conv_dgrad_tc(int n_titles, int L, int E, int F, const void
   p.cph = dgrad_cph(F); p.ngh = lstur_tc_wgrad_groups(F); p.EC = 2 * p.cph;
   p.dimg = (const uint8_t*)dpre_img; p.wimg = (const uint16_t*)wimg_d; p.c_out = (uint16_t*)dx16;
   p.out_scale = out_scale;
+  p.n_dev = n_titles_dev;
   p.inv_keep = 1.f;
   p.dbg = 0;
   p.trace = nullptr;
@@ -1266,13 +1290,13 @@ extern "C" int lstur_conv_wgrad_tc(int n_titles, int L, int E, int F, int V, con
                                    const void* dpre_img, float* d_conv_w, float dropout, unsigned seed, int fp16,
                                    void* partial_ws, size_t partial_bytes, cudaStream_t stream) {
   return lstur_conv_wgrad_tc_m(n_titles, L, E, F, V, tokens, emb_16, dpre_img, d_conv_w, dropout, seed, fp16, partial_ws,
-                               partial_bytes, nullptr, 1.f, stream);
+                               partial_bytes, nullptr, 1.f, nullptr, stream);
 }
 
 extern "C" int lstur_conv_wgrad_tc_m(int n_titles, int L, int E, int F, int V, const int* tokens, const void* emb_16,
                                      const void* dpre_img, float* d_conv_w, float dropout, unsigned seed, int fp16,
                                      void* partial_ws, size_t partial_bytes, const void* xmask, float dpre_scale,
-                                     cudaStream_t stream) {
+                                     const int* n_titles_dev, cudaStream_t stream) {
   LSTUR_REQUIRE(n_titles >= 0 && lstur_tc_supported(L, E, F, 3) && dpre_scale > 0.f, "lstur_conv_wgrad_tc");
   if (n_titles == 0) {
     cudaMemsetAsync(d_conv_w, 0, (size_t)3 * E * F * sizeof(float), stream);
@@ -1297,6 +1321,7 @@ extern "C" int lstur_conv_wgrad_tc_m(int n_titles, int L, int E, int F, int V, c
   p.trace = (long long*)g_tc_trace_ptr;
   p.dbg = getenv("LSTUR_WGRAD_DBG") ? atoi(getenv("LSTUR_WGRAD_DBG")) : 0;
   p.xmask = (const uint8_t*)xmask;
+  p.n_dev = n_titles_dev;
   // a stage holds WG_STAGE_ROWS K rows whatever the slot height: A = 2 groups, B = ngh groups of 128-byte rows
   size_t smem = 1024 + (size_t)tc::WG_STAGES * tc::WG_STAGE_ROWS * 128 * (2 + (size_t)p.ngh) + 256 + 4096;
   static size_t attr_smem = 0;

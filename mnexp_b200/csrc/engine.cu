@@ -201,6 +201,12 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
     add_ws(p, "wimg", (lstur_tc_wimg_elems(E, F) + 1) / 2);
     add_ws(p, "C16", (N * c.L * F + 1) / 2);
     if (bw && c.dropout > 0.f) add_ws(p, "xmask", (long long)(lstur_tc_xmask_bytes((int)N, c.L, E) + 3) / 4);
+    // compacted list of live titles (lstur_compact_titles): everything inside the encoder (tokens_c, C16, att_a, att_w, keep
+    // bits, dPre image, dX rows) is indexed by the compacted title index
+    add_ws(p, "title_flags", N);
+    add_ws(p, "live_idx", N);
+    add_ws(p, "n_live", 1);
+    add_ws(p, "tokens_c", N * c.L);
   }
   add_ws(p, "att_a", N * c.L);
   add_ws(p, "att_w", N * c.L);
@@ -433,6 +439,7 @@ int user_and_score(const lstur_plan* p, const lstur_weights* w, const lstur_batc
     // tensor-core precision modes run the recurrence on tcgen05 (gru_tc.cu) when its weights fit tensor memory
     const bool tc_gru = (c.precision == LSTUR_PREC_BF16_TC || c.precision == LSTUR_PREC_FP16_TC) &&
                         lstur_gru_tc_supported(B, c.W, G) && !getenv("LSTUR_GRU_TC_OFF");
+    PROBE_BEGIN(p, LSTUR_PROBE_GRU_FWD, st);
     if (tc_gru) {
       RC(lstur_gru_fwd_tc(B, c.W, G, XW, W<float>(p, ws, "gru_mask"), ini ? u0 : nullptr, c.Ue,
                           DP(p, w->dense, "gru_wh"), c.rec_act, hdst, ldo, bw ? W<float>(p, ws, "Z") : nullptr,
@@ -444,6 +451,7 @@ int user_and_score(const lstur_plan* p, const lstur_weights* w, const lstur_batc
                        bw ? W<float>(p, ws, "R") : nullptr, bw ? W<float>(p, ws, "HH") : nullptr,
                        bw ? W<float>(p, ws, "HP") : nullptr, bw ? W<float>(p, ws, "RH") : nullptr, st));
     }
+    PROBE_END(p, LSTUR_PROBE_GRU_FWD, st);
     if (cat) {
       cudaMemcpy2DAsync(cat + G, (size_t)(G + Uc) * 4, u0 + (c.Ue - Uc), (size_t)c.Ue * 4, (size_t)Uc * 4, B,
                         cudaMemcpyDeviceToDevice, st);
@@ -713,6 +721,7 @@ extern "C" int lstur_backward_w(const lstur_plan* p, const lstur_weights* w, con
     float* dh0 = W<float>(p, ws, "dh0");
     const bool tc_gru = (c.precision == LSTUR_PREC_BF16_TC || c.precision == LSTUR_PREC_FP16_TC) &&
                         lstur_gru_tc_supported(B, c.W, G) && !getenv("LSTUR_GRU_TC_OFF");
+    PROBE_BEGIN(p, LSTUR_PROBE_GRU_BWD, st);
     if (tc_gru) {
       // the kernel also leaves per-(tile, row group) column sums of dA: the bias gradient needs no second pass over dA
       float* dbp = W<float>(p, ws, "gru_db_partial");
@@ -726,6 +735,7 @@ extern "C" int lstur_backward_w(const lstur_plan* p, const lstur_weights* w, con
                        W<float>(p, ws, "HH"), W<float>(p, ws, "HP"), WhT, c.rec_act, dhT, lddh, dA, dh0, G, st));
       RC(lstur_colsum(Nh, 3 * G, dA, 3 * G, DG(p, dgrad, "gru_b"), 0, cws, cwsb, st));
     }
+    PROBE_END(p, LSTUR_PROBE_GRU_BWD, st);
     RC(GEMM(1, 0, D, 3 * G, Nh, docv, D, dA, 3 * G, DG(p, dgrad, "gru_wx"), 3 * G, nullptr, 0, gws, gwsb, st));
     RC(GEMM(1, 0, G, 2 * G, Nh, W<float>(p, ws, "HP"), G, dA, 3 * G, DG(p, dgrad, "gru_wh"), 3 * G, nullptr, 0,
                       gws, gwsb, st));
@@ -794,15 +804,20 @@ extern "C" int lstur_backward_w(const lstur_plan* p, const lstur_weights* w, con
       frexpf(1.f / grad_scale, &ex);          // 1/grad_scale = m * 2^ex, m in [0.5, 1)
       img_scale = ldexpf(1.f, ex - 1 + 4);
     }
+    const int* n_live = W<int>(p, ws, "n_live");
+    const int* live_idx = W<int>(p, ws, "live_idx");
+    const int* tok_c = W<int>(p, ws, "tokens_c");
+    PROBE_BEGIN(p, LSTUR_PROBE_ATTN_BWD, st);
     RC(lstur_attn_pool_bwd_img(fp16, N, L, F, W<void>(p, ws, "C16"), W<float>(p, ws, "att_a"), W<float>(p, ws, "att_w"),
                                dpool, lddp, DP(p, w->dense, "att_w"), img, bwd_drop, img_scale, DG(p, dgrad, "att_w"),
                                DG(p, dgrad, "conv_b"), DG(p, dgrad, "att_b"), 0, W<float>(p, ws, "attn_partials"),
-                               (size_t)p->ws.at("attn_partials").count * 4, st));
+                               (size_t)p->ws.at("attn_partials").count * 4, n_live, live_idx, st));
+    PROBE_END(p, LSTUR_PROBE_ATTN_BWD, st);
     PROBE_BEGIN(p, LSTUR_PROBE_CONV_WGRAD, st);
-    RC(lstur_conv_wgrad_tc_m(N, L, E, F, c.V, W<int>(p, ws, "tokens"), W<void>(p, ws, "emb_bf16"), img,
+    RC(lstur_conv_wgrad_tc_m(N, L, E, F, c.V, tok_c, W<void>(p, ws, "emb_bf16"), img,
                              DG(p, dgrad, "conv_w"), bwd_drop, p->last_seed, fp16, W<void>(p, ws, "wgrad_partial"),
                              (size_t)p->ws.at("wgrad_partial").count * 4,
-                             bwd_drop > 0.f ? W<void>(p, ws, "xmask") : nullptr, img_scale, st));
+                             bwd_drop > 0.f ? W<void>(p, ws, "xmask") : nullptr, img_scale, n_live, st));
     PROBE_END(p, LSTUR_PROBE_CONV_WGRAD, st);
     if (c.trainable_word_emb) {
       // d X = dPre (*) Wc^T on tcgen05, then d word_emb = segment-sorted sum of the token rows (x the X-dropout mask)
@@ -810,12 +825,12 @@ extern "C" int lstur_backward_w(const lstur_plan* p, const lstur_weights* w, con
       void* dx16 = W<void>(p, ws, "dx16");
       RC(lstur_pack_conv_w_dgrad_tc(E, F, DP(p, w->dense, "conv_w"), wimg_d, fp16, st));
       PROBE_BEGIN(p, LSTUR_PROBE_CONV_DGRAD, st);
-      RC(lstur_conv_dgrad_tc(N, L, E, F, img, wimg_d, dx16, 1.f, fp16, 0, st));
+      RC(lstur_conv_dgrad_tc(N, L, E, F, img, wimg_d, dx16, 1.f, fp16, 0, n_live, st));
       PROBE_END(p, LSTUR_PROBE_CONV_DGRAD, st);
       PROBE_BEGIN(p, LSTUR_PROBE_SCATTER, st);
-      RC(lstur_word_grad_scatter_16(N, L, E, c.V, W<int>(p, ws, "tokens"), dx16, fp16, 1.f / ((1.f - bwd_drop) * img_scale),
+      RC(lstur_word_grad_scatter_16(N, L, E, c.V, tok_c, dx16, fp16, 1.f / ((1.f - bwd_drop) * img_scale),
                                     bwd_drop > 0.f ? W<void>(p, ws, "xmask") : nullptr, word_grad, W<void>(p, ws, "wg_ws"),
-                                    (size_t)p->ws.at("wg_ws").count * 4, st));
+                                    (size_t)p->ws.at("wg_ws").count * 4, n_live, st));
       PROBE_END(p, LSTUR_PROBE_SCATTER, st);
     }
   } else {

@@ -194,9 +194,66 @@ __global__ void assemble_batch_kernel(int B, int W, int K, const int* __restrict
   }
 }
 
+// ---- title compaction: the news encoder of an all-pad title (every token 0: the left padding of a short click history,
+// task/seq2vec.py:23,46-49) is identically zero in value and gradient (pad mask, task/paper.py:150-155), so the
+// tensor-core kernels run over the compacted list of live titles only.
+__global__ void title_live_kernel(int N, int L, const int* __restrict__ tok, int* __restrict__ flags) {
+  int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  int nz = 0;
+  for (int l = lane; l < L; l += 32) nz |= (tok[(long long)warp * L + l] != 0);
+  nz = warp_or(nz);
+  if (lane == 0) flags[warp] = nz ? 1 : 0;
+}
+// one block: live_idx = ascending list of the titles with flags != 0, n_live = their count
+__global__ void __launch_bounds__(1024) title_scan_kernel(int N, const int* __restrict__ flags, int* __restrict__ live_idx,
+                                                          int* __restrict__ n_live) {
+  __shared__ int part[1024];
+  const int tid = threadIdx.x, per = (N + 1023) / 1024;
+  const int v0 = min(N, tid * per), v1 = min(N, v0 + per);
+  int c = 0;
+  for (int v = v0; v < v1; ++v) c += flags[v];
+  part[tid] = c;
+  __syncthreads();
+  // inclusive scan of the 1024 partial counts (Hillis-Steele, 10 rounds)
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int u = tid >= o ? part[tid - o] : 0;
+    __syncthreads();
+    part[tid] += u;
+    __syncthreads();
+  }
+  int run = part[tid] - c;
+  for (int v = v0; v < v1; ++v)
+    if (flags[v]) live_idx[run++] = v;
+  if (tid == 1023) *n_live = part[1023];
+}
+__global__ void title_compact_kernel(int N, int L, const int* __restrict__ tok, const int* __restrict__ live_idx,
+                                     const int* __restrict__ n_live, int* __restrict__ tok_c) {
+  int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (warp >= *n_live) return;
+  const int n = live_idx[warp];
+  for (int l = lane; l < L; l += 32) tok_c[(long long)warp * L + l] = tok[(long long)n * L + l];
+}
+
 }  // namespace lstur
 
 using namespace lstur;
+
+// tokens (N,L) -> n_live (1), live_idx (N; first n_live entries = ascending indices of the titles that have a non-zero
+// token), tokens_c (N,L; first n_live rows = those titles' tokens); flags (N) is scratch.
+extern "C" int lstur_compact_titles(int N, int L, const int* tokens, int* flags, int* live_idx, int* n_live, int* tokens_c,
+                                    cudaStream_t stream) {
+  LSTUR_REQUIRE(N >= 0 && L > 0 && n_live != nullptr, "lstur_compact_titles");
+  if (N == 0) { cudaMemsetAsync(n_live, 0, sizeof(int), stream); return LSTUR_OK; }
+  LSTUR_REQUIRE(tokens && flags && live_idx && tokens_c, "lstur_compact_titles");
+  title_live_kernel<<<cdiv((long long)N * 32, 256), 256, 0, stream>>>(N, L, tokens, flags);
+  LSTUR_CHECK_LAUNCH("lstur_compact_titles(flags)");
+  title_scan_kernel<<<1, 1024, 0, stream>>>(N, flags, live_idx, n_live);
+  LSTUR_CHECK_LAUNCH("lstur_compact_titles(scan)");
+  title_compact_kernel<<<cdiv((long long)N * 32, 256), 256, 0, stream>>>(N, L, tokens, live_idx, n_live, tokens_c);
+  LSTUR_CHECK_LAUNCH("lstur_compact_titles(gather)");
+  return LSTUR_OK;
+}
 
 extern "C" int lstur_token_gather(int N, int L, int n_docs, const int* doc_tokens, const int* doc_ids, int* tokens,
                                   cudaStream_t stream) {

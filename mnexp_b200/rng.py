@@ -59,3 +59,24 @@ def quad_keep(seed, n, p):
     f = np.stack([u0 & np.uint32(0x7fff), (u0 >> np.uint32(16)) & np.uint32(0x7fff),
                   u1 & np.uint32(0x7fff), (u1 >> np.uint32(16)) & np.uint32(0x7fff)], -1)
     return (f >= thr).reshape(-1)
+
+
+def tc_dropout_multipliers(seed, tokens, E, Ep, F, p, dtype=np.float64):
+    """Inverted-dropout multipliers of the ENGINE's tensor-core path for a forward with step seed `seed`:
+    X stream (seed*2) over rows padded to Ep columns, C stream (seed*2+1) over F columns, both indexed by the COMPACTED
+    title index — the engine runs the title encoder over the live titles only (csrc/gather.cu: lstur_compact_titles), so
+    title n with a non-zero token is row rank(n) of the streams.  tokens (N, L) -> (mx (N, L, E), mc (N, L, F)); all-pad
+    titles get ones (they are never read)."""
+    tokens = np.asarray(tokens)
+    N, L = tokens.shape
+    live = (tokens != 0).any(-1)
+    n_live = int(live.sum())
+    inv = np.float32(1.0) / (np.float32(1.0) - np.float32(p))
+    mx, mc = np.ones((N, L, E), dtype=dtype), np.ones((N, L, F), dtype=dtype)
+    if p <= 0 or n_live == 0:
+        return mx, mc
+    kx = quad_keep(seed * 2, n_live * L * Ep, p).reshape(n_live, L, Ep)[:, :, :E]
+    kc = quad_keep(seed * 2 + 1, n_live * L * F, p).reshape(n_live, L, F)
+    mx[live] = np.where(kx, dtype(inv), dtype(0))
+    mc[live] = np.where(kc, dtype(inv), dtype(0))
+    return mx, mc

@@ -84,10 +84,10 @@ def make_docs(n_news, L, V, seed=1235):
     return tok, vert, subvert
 
 
-def make_batches(shape, n_batches, seed=1236, B=None):
+def make_batches(shape, n_batches, seed=1236, B=None, full_history=False):
     """Pre-tensorised int32 batches: user (B,), hist_doc (B,W) left-padded with 0,
     cand_doc (B,1+K) positive first.  Returns a list of dicts plus the realised
-    fraction of left-padded history slots."""
+    fraction of left-padded history slots.  full_history: every user has W clicks (no padding at all)."""
     rng = np.random.default_rng(seed)
     B = B or shape.B
     W, K = shape.W, shape.K
@@ -97,6 +97,8 @@ def make_batches(shape, n_batches, seed=1236, B=None):
         user = rng.integers(0, shape.n_users, B).astype(np.int32)
         h = np.clip(rng.geometric(1.0 / (0.6 * W), B), 1, 3 * W)
         h = np.minimum(h, W)
+        if full_history:
+            h[:] = W
         hist = (_zipf_sample(rng, cdf, (B, W)) + 1).astype(np.int32)
         hist[np.arange(W)[None, :] < (W - h)[:, None]] = 0          # left padding
         cand = (_zipf_sample(rng, cdf, (B, 1 + K)) + 1).astype(np.int32)

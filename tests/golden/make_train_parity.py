@@ -5,7 +5,7 @@ Arm = oracle.lstur_torch (fp32, dense Keras-Adam on every tensor incl. the user 
 task/paper.py:656) trained for K steps at BASELINE config C1 (LSTUR-ini, B=64) on the seeded learnable task of
 mnexp_b200.synth.make_preference_task, then scored on held-out impressions (per-impression AUC, task/paper.py:504-515).
 Two runs: dropout 0, and dropout 0.2 with the device's counter-based dropout stream replayed mask-for-mask
-(mnexp_b200/rng.py::quad_keep; seed of step s = s, X stream 2s, C stream 2s+1 — LsturEngine.train_step).
+(mnexp_b200/rng.py::tc_dropout_multipliers; seed of step s = s, X stream 2s, C stream 2s+1 — LsturEngine.train_step).
 The GPU test (tests/test_gpu_training_parity.py) trains the engine (fp16_tc, row-sparse and dense Adam) on the same
 data from the same initial weights and compares AUCs.  Run here (CPU container): python tests/golden/make_train_parity.py
 """
@@ -32,12 +32,10 @@ def task():
     return sh, tok, P, train, evalb
 
 
-def quad_masks(seed, N, L, E, F, p):
-    inv = np.float32(1) / (np.float32(1) - np.float32(p))
-    mx = rng.quad_keep(seed * 2, N * L * EP, p).reshape(N * L, EP)[:, :E].reshape(N, L, E)
-    mc = rng.quad_keep(seed * 2 + 1, N * L * F, p).reshape(N, L, F)
-    f = lambda m: torch.from_numpy(np.where(m, inv, np.float32(0)).astype(np.float32))
-    return f(mx), f(mc)
+def quad_masks(seed, toks, E, F, p):
+    """the engine's tensor-core dropout streams of step `seed` (indexed by the compacted title index, mnexp_b200/rng.py)"""
+    mx, mc = rng.tc_dropout_multipliers(seed, toks, E, EP, F, p, dtype=np.float32)
+    return torch.from_numpy(mx), torch.from_numpy(mc)
 
 
 def train_step(ora, sh, tok, b, masks):
@@ -74,11 +72,11 @@ def run(p):
     sh, tok, P, train, evalb = task()
     torch.manual_seed(0)
     ora = ot.LsturOracle(P, arch='igru', dtype=torch.float32, lr=LR)
-    N = sh.B * (sh.W + 1 + sh.K)
     losses = []
     t0 = time.time()
     for s, b in enumerate(train, 1):
-        masks = quad_masks(s, N, sh.L, sh.E, sh.F, p) if p > 0 else None
+        toks = np.concatenate([tok[b['hist_doc']].reshape(-1, sh.L), tok[b['cand_doc']].reshape(-1, sh.L)])
+        masks = quad_masks(s, toks, sh.E, sh.F, p) if p > 0 else None
         losses.append(train_step(ora, sh, tok, b, masks))
         if s % 20 == 0:
             print('p=%.1f step %d loss %.4f (%.0f s)' % (p, s, losses[-1], time.time() - t0), flush=True)
@@ -94,11 +92,17 @@ def evaluate_init(P, tok, evalb):
 if __name__ == '__main__':
     torch.set_num_threads(os.cpu_count())
     out = {}
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'train_parity_c1.npz')
+    only = sys.argv[1:]                       # e.g. `p2`: regenerate one run, keep the others from the existing file
+    if only and os.path.exists(path):
+        out = dict(np.load(path))
     for name, p in (('p0', 0.0), ('p2', 0.2)):
+        if only and name not in only:
+            continue
         losses, logits, logits0 = run(p)
         out['loss_' + name], out['logits_' + name] = losses, logits
         out['auc_' + name] = np.float64(synth.impression_auc(logits))
         out['auc_init'] = np.float64(synth.impression_auc(logits0))
         print(name, 'AUC', out['auc_' + name], 'init', out['auc_init'], flush=True)
     out['k_steps'], out['n_eval'], out['lr'], out['seed'] = K_STEPS, N_EVAL, LR, SEED
-    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'train_parity_c1.npz'), **out)
+    np.savez_compressed(path, **out)

@@ -285,7 +285,7 @@ def test_keep_bits_from_forward_equal_hash_replay(lib, N, L, E, F):
     xm = torch.full((nbm,), 0xAA, dtype=torch.uint8, device='cuda')
     seed, drop = 11, 0.2
     rc = lib.lstur_news_conv_tc_fwd_m(N, L, E, F, V, P_(t), P_(emb), P_(wimg), P_(cb), P_(aw), P_(ab), P_(c_out), P_(pooled),
-                                      None, None, ctypes.c_float(drop), seed, 1, 0, P_(xm), stream())
+                                      None, None, ctypes.c_float(drop), seed, 1, 0, P_(xm), None, None, stream())
     assert rc == 0, lib.lstur_last_error()
     # bytes == the replicated quad stream of the X dropout (seed * 2, elements indexed (title, token, column of Ep))
     keep = rng.quad_keep(seed * 2, N * L * Ep, drop).reshape(N, L, Ep // 8, 4, 2)
@@ -300,7 +300,7 @@ def test_keep_bits_from_forward_equal_hash_replay(lib, N, L, E, F):
     for mask in (None, xm):
         dW = torch.full((3, E, F), float('nan'), device='cuda')
         rc = lib.lstur_conv_wgrad_tc_m(N, L, E, F, V, P_(t), P_(emb), P_(img), P_(dW), ctypes.c_float(drop), seed, 1, P_(ws), nb,
-                                       P_(mask) if mask is not None else None, ctypes.c_float(1.0), stream())
+                                       P_(mask) if mask is not None else None, ctypes.c_float(1.0), None, stream())
         assert rc == 0, lib.lstur_last_error()
         torch.cuda.synchronize()
         outs.append(dW.cpu().numpy())
@@ -334,7 +334,7 @@ def test_tc_conv_dgrad(lib, N, L, E, F, fp16):
     cw = torch.as_tensor(Wc).cuda()
     assert lib.lstur_pack_conv_w_dgrad_tc(E, F, P_(cw), P_(wd), fp16, stream()) == 0
     dx = torch.full((N, L, Ep), float('nan'), dtype=dt16, device='cuda')
-    rc = lib.lstur_conv_dgrad_tc(N, L, E, F, P_(img), P_(wd), P_(dx), ctypes.c_float(0.5), fp16, 0, stream())
+    rc = lib.lstur_conv_dgrad_tc(N, L, E, F, P_(img), P_(wd), P_(dx), ctypes.c_float(0.5), fp16, 0, None, stream())
     assert rc == 0, lib.lstur_last_error()
     torch.cuda.synchronize()
     d16 = round16(dpre, fp16).astype(np.float64)
@@ -380,7 +380,7 @@ def test_word_grad_scatter_16(lib, N, L, E, V, hot, masked):
     for _ in range(2):
         out = torch.full((V, E), float('nan'), device='cuda')
         rc = lib.lstur_word_grad_scatter_16(N, L, E, V, P_(t_d), P_(dx_d), 1, ctypes.c_float(0.25), P_(km) if masked else None,
-                                            P_(out), P_(ws), nb, stream())
+                                            P_(out), P_(ws), nb, None, stream())
         assert rc == 0, lib.lstur_last_error()
         torch.cuda.synchronize()
         outs.append(out.cpu().numpy())
@@ -396,3 +396,54 @@ def test_word_grad_scatter_16(lib, N, L, E, V, hot, masked):
     assert rel(outs[0], ref) < 2e-6
     absent = np.setdiff1d(np.arange(V), np.unique(tok[live.reshape(N, L)]))
     assert np.all(outs[0][absent] == 0)
+
+
+# ---------------------------------------------------------------- live-title compaction
+@pytest.mark.parametrize('N,L', [(1, 7), (1000, 30), (5000, 50), (3, 1)])
+def test_compact_titles_bit_exact(lib, N, L):
+    g = np.random.default_rng(N + L)
+    tok = g.integers(0, 5, (N, L)).astype(np.int32)
+    tok[g.random(N) < 0.45] = 0                      # all-pad titles
+    t = torch.as_tensor(tok).cuda()
+    flags, idx = torch.full((N,), -7, dtype=torch.int32, device='cuda'), torch.full((N,), -7, dtype=torch.int32, device='cuda')
+    n_live, tc_ = torch.full((1,), -7, dtype=torch.int32, device='cuda'), torch.full((N, L), -7, dtype=torch.int32, device='cuda')
+    assert lib.lstur_compact_titles(N, L, P_(t), P_(flags), P_(idx), P_(n_live), P_(tc_), stream()) == 0
+    torch.cuda.synchronize()
+    live = np.where((tok != 0).any(-1))[0]
+    assert int(n_live[0]) == len(live)
+    assert np.array_equal(idx.cpu().numpy()[:len(live)], live)
+    assert np.array_equal(tc_.cpu().numpy()[:len(live)], tok[live])
+
+
+@pytest.mark.parametrize('L', [30, 50])
+def test_tc_forward_over_compacted_titles(lib, L):
+    """the kernel over the compacted live-title list (device-side count, pooled rows written at the original index)
+    == the kernel over all titles, bit for bit; dead titles pool to exactly 0 either way"""
+    N, E, F = 301, 300, 400
+    tok, P = make_enc_case(N, L, E, F, seed=5)
+    tok[np.random.default_rng(1).random(N) < 0.5] = 0
+    c0, pooled0, a0, w0 = run_tc_encoder(lib, tok, P)
+    V, Ep = P['word_emb'].shape[0], lib.lstur_tc_padded_e(E)
+    dev = lambda x, dt: torch.as_tensor(np.ascontiguousarray(x)).to(dt).cuda()
+    emb = torch.zeros((V, Ep), dtype=torch.float16, device='cuda')
+    wimg = torch.zeros(lib.lstur_tc_wimg_elems(E, F), dtype=torch.float16, device='cuda')
+    we, cw = dev(P['word_emb'], torch.float32), dev(P['conv_w'], torch.float32)
+    assert lib.lstur_pack_word_emb_16(V, E, P_(we), P_(emb), 1, stream()) == 0
+    assert lib.lstur_pack_conv_w_tc(E, F, P_(cw), P_(wimg), 1, stream()) == 0
+    t = dev(tok, torch.int32)
+    i32 = lambda *s: torch.zeros(s, dtype=torch.int32, device='cuda')
+    flags, idx, n_live, tok_c = i32(N), i32(N), i32(1), i32(N, L)
+    assert lib.lstur_compact_titles(N, L, P_(t), P_(flags), P_(idx), P_(n_live), P_(tok_c), stream()) == 0
+    cb, aw, ab = dev(P['conv_b'], torch.float32), dev(P['att_w'].reshape(-1), torch.float32), dev(np.asarray(P['att_b']).reshape(1), torch.float32)
+    c_out = torch.zeros((N, L, F), dtype=torch.float16, device='cuda')
+    pooled = torch.zeros((N, F), device='cuda')
+    a, w = torch.zeros((N, L), device='cuda'), torch.zeros((N, L), device='cuda')
+    rc = lib.lstur_news_conv_tc_fwd_m(N, L, E, F, V, P_(tok_c), P_(emb), P_(wimg), P_(cb), P_(aw), P_(ab), P_(c_out), P_(pooled),
+                                      P_(a), P_(w), ctypes.c_float(0.0), 0, 1, 0, None, P_(n_live), P_(idx), stream())
+    assert rc == 0, lib.lstur_last_error()
+    torch.cuda.synchronize()
+    live = np.where((tok != 0).any(-1))[0]
+    assert np.array_equal(pooled.cpu().numpy(), pooled0)
+    assert np.all(pooled0[np.setdiff1d(np.arange(N), live)] == 0)
+    assert np.array_equal(c_out.float().cpu().numpy()[:len(live)], c0[live])
+    assert np.array_equal(w.cpu().numpy()[:len(live)], w0[live])

@@ -75,13 +75,6 @@ def test_word_table_gradient_fp32(lib, dropout):
     assert np.abs(grads[0]['word_emb'][0]).max() > 0            # the pad token's row gets the halo contributions
 
 
-def quad_masks(seed, N, L, E, Ep, F, p):
-    inv = np.float32(1) / (np.float32(1) - np.float32(p))
-    mx = rng.quad_keep(seed * 2, N * L * Ep, p).reshape(N * L, Ep)[:, :E].reshape(N, L, E)
-    mc = rng.quad_keep(seed * 2 + 1, N * L * F, p).reshape(N, L, F)
-    return np.where(mx, np.float64(inv), 0.0), np.where(mc, np.float64(inv), 0.0)
-
-
 @pytest.mark.parametrize('L_,dropout', [(30, 0.0), (30, 0.2), (50, 0.0)])
 def test_word_table_gradient_fp16_tc(lib, L_, dropout):
     """tensor-core mode at full width (E300 F400 U200), both title-slot heights.  The conv bias is shifted so that no
@@ -102,8 +95,8 @@ def test_word_table_gradient_fp16_tc(lib, L_, dropout):
     assert np.array_equal(grads[0]['word_emb'], grads[1]['word_emb'])      # deterministic
     masks = None
     if dropout > 0:
-        N = sh.B * (sh.W + 1 + sh.K)
-        masks = quad_masks(seed, N, sh.L, sh.E, lib.lstur_tc_padded_e(sh.E), sh.F, dropout)
+        toks = np.concatenate([tok[b['hist_doc']].reshape(-1, sh.L), tok[b['cand_doc']].reshape(-1, sh.L)])
+        masks = rng.tc_dropout_multipliers(seed, toks, sh.E, lib.lstur_tc_padded_e(sh.E), sh.F, dropout)
     loss, ref = oracle_grads(P, 'igru', b, tok, masks)
     assert abs(eng.loss() - loss) < 1e-3 * max(1.0, abs(loss))
     g, r = grads[0]['word_emb'].astype(np.float64), ref['word_emb']

@@ -14,7 +14,7 @@ img = torch.empty(lib.lstur_tc_dpre_img_bytes(N, L, F), dtype=torch.uint8, devic
 g = lib.lstur_attn_bwd_grid(N)
 part = torch.empty(g * (2 * F + 1), device='cuda')
 dka = torch.empty(F, device='cuda'); dcb = torch.empty(F, device='cuda'); dab = torch.empty(1, device='cuda')
-f = lambda: lib.lstur_attn_pool_bwd_img(1, N, L, F, P_(C), P_(a), P_(w), P_(dp), F, P_(ka), P_(img), ctypes.c_float(0.2), ctypes.c_float(1.0), P_(dka), P_(dcb), P_(dab), 0, P_(part), part.numel() * 4, st())
+f = lambda: lib.lstur_attn_pool_bwd_img(1, N, L, F, P_(C), P_(a), P_(w), P_(dp), F, P_(ka), P_(img), ctypes.c_float(0.2), ctypes.c_float(1.0), P_(dka), P_(dcb), P_(dab), 0, P_(part), part.numel() * 4, None, None, st())
 for _ in range(3): assert f() == 0, lib.lstur_last_error()
 torch.cuda.synchronize()
 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)

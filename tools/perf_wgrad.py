@@ -24,7 +24,7 @@ def runm(drop, reps=5):
     for i in range(reps + 2):
         if i == 2:
             torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e0.record()
-        rc = lib.lstur_conv_wgrad_tc_m(N, L, E, F, V, P_(tok), P_(emb), P_(img), P_(dW), ctypes.c_float(drop), 1, 1, P_(ws), pb, P_(xm), ctypes.c_float(1.0), st())
+        rc = lib.lstur_conv_wgrad_tc_m(N, L, E, F, V, P_(tok), P_(emb), P_(img), P_(dW), ctypes.c_float(drop), 1, 1, P_(ws), pb, P_(xm), ctypes.c_float(1.0), None, st())
         assert rc == 0, lib.lstur_last_error()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
