@@ -426,6 +426,10 @@ int lstur_backward_w(const lstur_plan* plan, const lstur_weights* w, const lstur
  * slot — and leaves probs / logits / user_vec in the workspace like lstur_forward. */
 int lstur_encode_docs(const lstur_plan* plan, const lstur_weights* weights, void* workspace, int n, const int* doc_ids,
                       float* doc_vec_out, long long ldo, cudaStream_t stream);
+/* The same encoder on explicit token rows (n, L) instead of document ids: `doc_encoder.predict(titles)`, the layer
+ * TestPipeline fetches with get_layer('doc_encoder') (task/test_pipeline.py:27-35, task/paper.py:160). */
+int lstur_encode_titles(const lstur_plan* plan, const lstur_weights* weights, void* workspace, int n, const int* tokens,
+                        float* doc_vec_out, long long ldo, cudaStream_t stream);
 int lstur_forward_docvecs(const lstur_plan* plan, const lstur_weights* weights, const lstur_batch* batch, void* workspace,
                           const float* doc_vec_table, long long ld, int n_rows, cudaStream_t stream);
 

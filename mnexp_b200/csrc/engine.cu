@@ -598,6 +598,26 @@ extern "C" int lstur_encode_docs(const lstur_plan* p, const lstur_weights* w, vo
   return LSTUR_OK;
 }
 
+// doc_encoder.predict on explicit token rows (the `doc_encoder` layer of the model, task/paper.py:160; used by
+// TestPipeline.get_doc_parser / test_doc_vec on parsed titles): tokens (n, L) on the device, n <= B*(W+C).
+extern "C" int lstur_encode_titles(const lstur_plan* p, const lstur_weights* w, void* ws, int n, const int* tokens,
+                                   float* doc_vec_out, long long ldo, cudaStream_t st) {
+  LSTUR_REQUIRE(p && w && ws && w->dense && w->word_emb, "lstur_encode_titles");
+  LSTUR_REQUIRE(n >= 0 && n <= p->N && tokens && doc_vec_out && ldo >= p->D, "lstur_encode_titles");
+  if (n == 0) return LSTUR_OK;
+  const lstur_config& c = p->c;
+  cudaMemcpyAsync(W<int>(p, ws, "tokens"), tokens, (size_t)n * c.L * sizeof(int), cudaMemcpyDeviceToDevice, st);
+  RC(encode_titles(p, w, ws, n, 0, 0u, st));
+  cudaMemcpy2DAsync(doc_vec_out, (size_t)ldo * 4, W<float>(p, ws, "doc_vec"), (size_t)p->D * 4, (size_t)p->D * 4, n,
+                    cudaMemcpyDeviceToDevice, st);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("lstur_encode_titles: %s", cudaGetErrorString(e));
+    return LSTUR_ERR_CUDA;
+  }
+  return LSTUR_OK;
+}
+
 // User encoder + scorer over cached document vectors (test_user_vec / test_user_doc_score, :77-211): history and
 // candidate vectors are rows of doc_vec_table (n_rows, ld); a history slot whose vector is all zero (unknown / pad
 // document, :104-108) is masked, exactly as keras Masking() does inside the user encoder.

@@ -278,6 +278,52 @@ class LsturEngine:
                                                   ctypes.c_void_p(out.data_ptr() + 4 * i * self.D), self.D, self._stream()))
         return out
 
+    def encode_titles(self, titles):
+        """doc_encoder.predict on explicit token rows: (n, L) ids (host or device) -> (n, D) device tensor, in chunks of
+        the plan's title capacity B*(W+C)."""
+        t = titles if torch.is_tensor(titles) else torch.as_tensor(np.ascontiguousarray(titles))
+        t = t.to(self.device)
+        if t.dtype != torch.int32:
+            t = t.to(torch.int32)          # the reference feeds float64 ids (document.py:39)
+        t = t.contiguous()
+        n = int(t.shape[0])
+        assert t.dim() == 2 and t.shape[1] == self.L
+        out = torch.empty((n, self.D), dtype=torch.float32, device=self.device)
+        if self._emb_seen != self._emb_version[0]:
+            _lib.check(self.lib.lstur_plan_invalidate_tables(self.plan))
+            self._emb_seen = self._emb_version[0]
+        cap = self.B * (self.W + self.C)
+        for i in range(0, n, cap):
+            m = min(cap, n - i)
+            _lib.check(self.lib.lstur_encode_titles(self.plan, ctypes.byref(self._w), _ptr(self.ws), m,
+                                                    ctypes.c_void_p(t.data_ptr() + 4 * i * self.L),
+                                                    ctypes.c_void_p(out.data_ptr() + 4 * i * self.D), self.D, self._stream()))
+        return out
+
+    def encode_users(self, users, clicked_vecs):
+        """user_encoder.predict: users (n,) ids (ignored by the archs without a user table), clicked_vecs (n, W, D)
+        history vectors -> (n, U) user vectors.  An all-zero history vector is a masked slot (keras Masking())."""
+        cv = clicked_vecs if torch.is_tensor(clicked_vecs) else torch.as_tensor(np.ascontiguousarray(clicked_vecs, dtype=np.float32))
+        cv = cv.to(self.device, dtype=torch.float32).contiguous()
+        n = int(cv.shape[0])
+        assert cv.shape[1] == self.W and cv.shape[2] == self.D
+        us = torch.as_tensor(np.ascontiguousarray(users)).to(self.device).to(torch.int32).reshape(-1)
+        out = torch.empty((n, self.U), dtype=torch.float32, device=self.device)
+        R = self.B
+        hist = torch.arange(R * self.W, dtype=torch.int32, device=self.device).reshape(R, self.W) + 1    # row 0 = zero vector
+        cand = torch.zeros((R, self.C), dtype=torch.int32, device=self.device)
+        table = torch.zeros((R * self.W + 1, self.D), dtype=torch.float32, device=self.device)
+        for s in range(0, n, R):
+            m = min(R, n - s)
+            table[1:1 + m * self.W] = cv[s:s + m].reshape(m * self.W, self.D)
+            if m < R:
+                table[1 + m * self.W:].zero_()
+            u = torch.zeros(R, dtype=torch.int32, device=self.device)
+            u[:m] = us[s:s + m]
+            self.forward_docvecs(dict(user=u, hist_doc=hist, cand_doc=cand), table)
+            out[s:s + m] = self.view('user_vec').reshape(R, self.U)[:m]
+        return out
+
     def build_doc_table(self):
         """Vectors of every document of the token table, row 0 (the pad / unknown document) zeroed: the reference's
         pipeline leaves history slots without a known document at zero (task/test_pipeline.py:100-108)."""

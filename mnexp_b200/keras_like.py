@@ -84,17 +84,19 @@ class _Core:
             self.infer_engines = {}
         return self.train_engine
 
-    def engine_infer(self, C):
-        if C not in self.infer_engines:
+    def engine_infer(self, C, rows=None):
+        rows = rows or self.predict_rows
+        key = C if rows == self.predict_rows else (C, rows)
+        if key not in self.infer_engines:
             c = self.cfg
             # share the CURRENT training engine's device weights whatever its batch size (never rebuild it from here:
             # that would discard its optimizer state); create one only if training has not started
             base = self.train_engine if self.train_engine is not None else self.engine_train(c.batch_size)
-            self.infer_engines[C] = LsturEngine(
-                self.params, self.predict_rows, c.window_size, C, c.title_shape, arch=self.arch, dropout=0.0,
+            self.infer_engines[key] = LsturEngine(
+                self.params, rows, c.window_size, C, c.title_shape, arch=self.arch, dropout=0.0,
                 recurrent_activation=c.recurrent_activation, precision=self.precision(), training=False,
                 share_weights_from=base, score_model=self.score_model, **self.head_kw())
-        return self.infer_engines[C]
+        return self.infer_engines[key]
 
     def n_train_cand(self):
         return 1 if self.loss == 'bce' else 1 + self.cfg.negative_samples
@@ -183,10 +185,44 @@ class Model:
         return h
 
     # ---- inference --------------------------------------------------------------------------
+    SHARED_C = 32          # candidates per row on the per-impression path (the plan's limit)
+
+    def _score_one_impression(self, user, clicked, cand, verts):
+        """Seq2Vec.test (task/seq2vec.py:202-206) feeds ONE impression per predict call: every row repeats the same user
+        and click history next to a different candidate, so the reference encodes the history n times.  Here the history
+        is encoded once per group of up to 32 candidates: rows = ceil(n / 32), candidates padded with the pad title."""
+        core = self.core
+        n, L = cand.shape[0], cand.shape[2]
+        C = self.SHARED_C
+        rows = (n + C - 1) // C
+        eng = core.engine_infer(C, rows=8)
+        out = np.zeros(n, dtype=np.float32)
+        for r0 in range(0, rows, eng.B):
+            m = min(eng.B, rows - r0)
+            u = np.zeros(eng.B, dtype=np.int32); u[:m] = user[0]
+            h = np.zeros((eng.B,) + clicked.shape[1:], dtype=np.int32); h[:m] = clicked[0]
+            c = np.zeros((eng.B, C, L), dtype=np.int32)
+            k0, k1 = r0 * C, min(n, (r0 + m) * C)
+            c.reshape(-1, L)[:k1 - k0] = cand[k0:k1, 0]
+            b = dict(user=u, hist_tok=h, cand_tok=c)
+            if verts is not None:
+                hv = np.zeros((eng.B, verts[0].shape[1]), dtype=np.int32); hv[:m] = verts[0][0]
+                cv = np.zeros((eng.B, C), dtype=np.int32)
+                cv.reshape(-1)[:k1 - k0] = verts[1][k0:k1, 0]
+                b['hist_vert'], b['cand_vert'] = hv, cv
+            probs = eng.forward(eng.to_device_batch(b), training=False)
+            s = probs if core.loss == 'bce' else eng.score_sigmoid()
+            out[k0:k1] = s.reshape(-1)[:k1 - k0].cpu().numpy()
+        return out.reshape(n, 1)
+
     def _forward_chunks(self, x, n_cand):
         core = self.core
         user, clicked, cand, verts = core.split_inputs(x, n_cand)
         n = clicked.shape[0]
+        if (n_cand == 1 and n > 1 and not self.is_train and core.loss != 'bce' and np.all(user == user[0])
+                and np.array_equal(clicked, np.broadcast_to(clicked[:1], clicked.shape))
+                and (verts is None or np.array_equal(verts[0], np.broadcast_to(verts[0][:1], verts[0].shape)))):
+            return self._score_one_impression(user, clicked, cand, verts)
         eng = core.engine_infer(n_cand)
         R = eng.B
         outs = []
@@ -288,27 +324,54 @@ class Model:
         print('Total params: %d' % sum(np.asarray(v).size for v in w.values()))
 
 
+class _InputLayer:
+    """The slice of keras.layers.InputLayer the reference reads: `.input_shape` (task/test_pipeline.py:29, 88)."""
+
+    def __init__(self, name, shape):
+        self.name, self.input_shape, self.output_shape = name, shape, shape
+
+
 class DocEncoderModel:
     """`doc_encoder` layer: (n, L) token ids -> (n, U) news vectors (task/paper.py:160)."""
     name = 'doc_encoder'
 
     def __init__(self, core):
         self.core = core
+        self.layers = [_InputLayer('doc_encoder_input', (None, core.cfg.title_shape))]
 
     def predict(self, titles, batch_size=None, **_):
+        """title tokens straight through the news-encoder kernels (lstur_encode_titles): no history, no scorer"""
         core = self.core
         titles = np.asarray(titles)
         eng = core.engine_infer(1)
-        R = eng.B
-        outs = []
-        for s in range(0, titles.shape[0], R):
-            m = min(R, titles.shape[0] - s)
-            c = np.zeros((R, 1, titles.shape[1]), dtype=np.int32); c[:m, 0] = titles[s:s + m]
-            h = np.zeros((R, eng.W, titles.shape[1]), dtype=np.int32)
-            b = dict(user=np.zeros(R, dtype=np.int32), hist_tok=h, cand_tok=c)
-            if core.has_vert:       # the doc_encoder layer is the title encoder alone: vertical columns are dropped below
-                b['hist_vert'], b['cand_vert'] = np.zeros((R, eng.W), dtype=np.int32), np.zeros((R, 1), dtype=np.int32)
-            eng.forward(eng.to_device_batch(b))
-            dv = eng.view('doc_vec').reshape(-1, eng.D)[R * eng.W:, :eng.cfg.Dd]
-            outs.append(dv[:m].cpu().numpy().copy())
-        return np.concatenate(outs)
+        dv = eng.encode_titles(titles)
+        return dv[:, :eng.cfg.Dd].cpu().numpy().copy()      # the doc_encoder layer is the title encoder alone (no vertical columns)
+
+
+class UserEncoderModel:
+    """`user_encoder` layer (task/paper.py:584-633): inputs [user (n,1)] + `user_clicked_vec` (n, W, D) -> (n, U); the
+    reference's decomposed pipeline fetches it with get_layer('user_encoder') and reads the shape of its
+    'user_clicked_vec' input (task/test_pipeline.py:87-88)."""
+    name = 'user_encoder'
+
+    def __init__(self, core, doc_dim):
+        self.core = core
+        self._inputs = {'user_clicked_vec': _InputLayer('user_clicked_vec', (None, core.cfg.window_size, doc_dim))}
+        if core.has_user:
+            self._inputs['user'] = _InputLayer('user', (None, 1))
+        self.layers = list(self._inputs.values())
+
+    def get_layer(self, name):
+        return self._inputs[name]
+
+    def predict(self, x, batch_size=None, **_):
+        core = self.core
+        if isinstance(x, (list, tuple)):
+            user, vecs = (x[0], x[1]) if len(x) == 2 else (None, x[0])
+        else:
+            user, vecs = None, x
+        vecs = np.asarray(vecs, dtype=np.float32)
+        if user is None:
+            user = np.zeros(vecs.shape[0], dtype=np.int32)
+        eng = core.engine_infer(1)
+        return eng.encode_users(np.asarray(user).reshape(-1), vecs).cpu().numpy().copy()

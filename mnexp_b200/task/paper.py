@@ -130,7 +130,11 @@ class Seq2VecPaper(Seq2Vec):
 
     def get_user_encoder(self, window_size=None):
         self._archs()
-        return self._core
+        return keras_like.UserEncoderModel(self._core, self._doc_dim())
+
+    def _doc_dim(self):
+        P = self._core.params
+        return int(P['dense_w'].shape[1]) + (int(P['vert_emb'].shape[1]) if 'vert_emb' in P else 0)
 
     def _build_model(self):
         """task/paper.py:228-256 / 360-383: `model` = sigmoid score, loss = Seq2Vec.loss (weighted BCE), Adam."""
@@ -149,6 +153,7 @@ class Seq2VecPaper(Seq2Vec):
         self.user_encoder = self.get_user_encoder()
         self.model = keras_like.Model(self._core, train=True, name='model')
         self.model.layers['doc_encoder'] = self.doc_encoder
+        self.model.layers['user_encoder'] = self.user_encoder
 
 
 class Seq2VecPaperDot(Seq2VecPaper):
@@ -256,8 +261,10 @@ class Seq2VecPaperSoftmax(Seq2VecPaper):
         return 'nigru' if not self.HAS_USER else arch
 
     def get_user_encoder(self, window_size=None):
+        """Model named 'user_encoder' with the input 'user_clicked_vec' (task/paper.py:590, 632): the user-encoder part of
+        the fused plan, callable on cached history vectors (lstur_forward_docvecs)."""
         self._engine_arch()
-        return self._core                                     # user encoder is part of the fused plan
+        return keras_like.UserEncoderModel(self._core, self._doc_dim())
 
     def _score_model(self, u=None, d=None):
         if self.config.score_model not in ('dot', 'dnn', 'ddot'):
@@ -291,6 +298,7 @@ class Seq2VecPaperSoftmax(Seq2VecPaper):
         self.test_model = keras_like.Model(self._core, train=False, name='test_model')
         for m in (self.model, self.test_model):
             m.layers['doc_encoder'] = self.doc_encoder
+            m.layers['user_encoder'] = self.user_encoder
 
     def callback(self, epoch):
         """LR decay + per-impression AUC / nDCG@10 / nDCG@5 / MRR on the validation split (task/paper.py:497-524)."""

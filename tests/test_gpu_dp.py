@@ -11,6 +11,7 @@ import pytest
 import torch
 
 from mnexp_b200 import synth
+from tolerances import rel
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -29,6 +30,7 @@ def test_two_emulated_ranks_equal_one_engine(lib, precision, trainable):
     ranks = [LsturEngine(P, sh.B // world, sh.W, 1 + sh.K, sh.L, **kw) for _ in range(world)]
     full = LsturEngine(P, sh.B, sh.W, 1 + sh.K, sh.L, **kw)
     red = [UserRowReducer(e, sh.B) for e in ranks]
+    first = True
     for b in batches:
         dbs = [e.to_device_batch(shard_batch(b, r, world)) for r, e in enumerate(ranks)]
         for e, db in zip(ranks, dbs):
@@ -41,18 +43,35 @@ def test_two_emulated_ranks_equal_one_engine(lib, precision, trainable):
         ids = torch.cat([db['user'] for db in dbs])
         rows = torch.cat([e.view('d_u0').reshape(e.B, e.Ue) for e in ranks]).contiguous()
         wsum = (ranks[0].word_grad + ranks[1].word_grad) if trainable else None
+        if first:
+            # the exchanged gradients of the first step == the gradients of one engine on the whole batch (before any
+            # optimizer step can amplify rounding differences): fp32 to reassociation, tensor-core mode to the 16-bit
+            # rounding of the saved activations / gradient images (tile-dependent scales in the recurrence)
+            first = False
+            full.step_seed += 1
+            dbf = full.to_device_batch(b)
+            full.forward(dbf, training=True, seed=full.step_seed)
+            full.backward(dbf)
+            gtol = 2e-6 if precision == 'fp32' else 2e-4
+            assert rel(dense.cpu().numpy(), full.dense_grad.cpu().numpy()) < gtol
+            if trainable:
+                assert rel(wsum.cpu().numpy(), full.word_grad.cpu().numpy()) < gtol
+            full.apply_adam()
+        else:
+            full.train_step(full.to_device_batch(b))
         for e, r in zip(ranks, red):
             e.dense_grad.copy_(dense)
             if trainable:
                 e.word_grad.copy_(wsum)
             e.apply_adam(user_rows=r.reduce(e, ids, rows))
-        full.train_step(full.to_device_batch(b))
     torch.cuda.synchronize()
     w0, w1, wf = ranks[0].get_weights_dict(), ranks[1].get_weights_dict(), full.get_weights_dict()
     # fp32: reassociation only.  Tensor-core mode: the 16-bit operand copies round-trip through the exchange bit-exactly
     # while the table is frozen; with the table trainable a 1e-7 reassociation difference in a word row can flip its
     # 16-bit rounding in the next step's operand copy, which moves later updates by a fraction of one Adam step (lr 1e-3)
-    tol = 1e-6 if precision == 'fp32' else (3e-4 if trainable else 2e-5)
+    # ... weights: within a fraction of one Adam step (lr = 1e-3); Adam normalises every gradient to ~lr, so an element
+    # whose gradient is tiny turns a 1e-7 difference into a visible one
+    tol = 1e-6 if precision == 'fp32' else (3e-4 if trainable else 1e-4)
     for k in wf:
         assert np.array_equal(w0[k], w1[k]), k                 # replicas bit-identical
         assert np.abs(w0[k].astype(np.float64) - wf[k]).max() <= tol, (k, float(np.abs(w0[k] - wf[k]).max()))

@@ -465,3 +465,62 @@ def test_engine_matches_variant_golden_fixtures(lib):
             gk = key + '/grad/' + k
             if gk in gold.files and k not in ('att_b', 'so_b'):
                 assert rel(g[k], gold[gk]) < 1e-4, (key, k)
+
+
+def test_named_encoder_layers_and_per_impression_scoring(lib):
+    """get_layer('doc_encoder') / get_layer('user_encoder') with the input 'user_clicked_vec' (task/paper.py:160, 590, 632;
+    task/test_pipeline.py:27-35, 87-88) compose to the full model; Seq2Vec.test's one-impression predict (same history on
+    every row, task/seq2vec.py:202-206) encodes the history once and returns what row-by-row prediction returns."""
+    sh, h = _handler('igru', 'Seq2VecPaperSoftmaxId')
+    model = h.build_model(0)
+    x, y = next(h.train)
+    user, clicked, cands = x[0], x[1], np.stack(x[2:], 1)
+    P = _oracle_params(model)
+    ref = on.lstur_forward(P, user, clicked.astype(int), cands.astype(int), arch='igru', aux=True)
+    ue, de = model.get_layer('user_encoder'), h.test_model.get_layer('doc_encoder')
+    assert ue is h.user_encoder and ue.name == 'user_encoder' and de.name == 'doc_encoder'
+    assert ue.get_layer('user_clicked_vec').input_shape == (None, sh.W, sh.U)
+    assert de.layers[0].input_shape[-1] == sh.L
+    # doc vectors of the history through the doc_encoder layer, masked like ComputeMasking does (task/paper.py:644-645)
+    B, W, L = clicked.shape
+    dv = de.predict(clicked.reshape(B * W, L)).reshape(B, W, -1)
+    dv = dv * (clicked != 0).any(-1)[..., None]
+    assert rel(dv, ref['hist_vec']) < 5e-5
+    uv = ue.predict([user, dv])
+    assert uv.shape == (B, sh.U) and rel(uv, ref['user_vec']) < 5e-5
+    # one impression: 7 candidates against the history of row 0
+    n = 7
+    cand = np.concatenate([cands[0], cands[1][:n - cands.shape[1]]])[:n]
+    imp = [np.repeat(user[:1], n), np.repeat(clicked[:1], n, 0), cand]
+    fast = h.test_model.predict(imp)
+    slow = np.concatenate([h.test_model.predict([a[i:i + 1] for a in imp]) for i in range(n)])
+    assert fast.shape == (n, 1) and rel(fast, slow) < 1e-6
+    # more candidates than one row holds (32): the history is re-encoded once per group of 32
+    n2 = 70
+    cand2 = np.concatenate([cands.reshape(-1, L)] * 3)[:n2]
+    imp2 = [np.repeat(user[:1], n2), np.repeat(clicked[:1], n2, 0), cand2]
+    fast2 = h.test_model.predict(imp2)
+    slow2 = np.concatenate([h.test_model.predict([a[i:i + 1] for a in imp2]) for i in range(0, n2, 9)])
+    assert rel(fast2[::9], slow2) < 1e-6
+
+
+def test_batch_size_change_keeps_optimizer_state(lib):
+    """predict / callbacks between training steps must not reset Adam: the inference engines share the live
+    training engine's weights, and a training engine rebuilt for another batch size adopts moments, step count and the
+    dropout seed counter."""
+    sh, h = _handler('igru', 'Seq2VecPaperSoftmaxId')
+    model = h.build_model(0)
+    x, y = next(h.train)
+    half = [a[:4] for a in x], y[:4]
+    model.train_on_batch(*half)                        # batch 4 != config.batch_size 8
+    e4 = h._core.train_engine
+    assert e4.B == 4 and e4.t == 1
+    model.predict(x)                                   # must not rebuild the training engine
+    h.test_model.predict([x[0], x[1], x[2]])
+    assert h._core.train_engine is e4 and e4.t == 1
+    v_before = e4.adam_v.clone()
+    model.train_on_batch(x, y)                         # batch 8: rebuilt, state adopted
+    e8 = h._core.train_engine
+    assert e8 is not e4 and e8.B == 8 and e8.t == 2 and e8.step_seed == 2
+    # moments carried, not zeroed: v_new = 0.999 v_old + 0.001 g^2 >= 0.999 v_old element-wise
+    assert float(v_before.max()) > 0 and bool((e8.adam_v >= 0.998 * v_before).all())
