@@ -369,9 +369,11 @@ def main():
     l0 = lib.lstur_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    t_host = time.perf_counter()
     for i in range(args.steps):
         eng.set_probe(probe_id, *probes[i])
         dp.train_step(dbs[i % n_batches])
+    host_enqueue_ms = 1e3 * (time.perf_counter() - t_host) / args.steps      # CPU time to enqueue a step (no sync inside)
     ev1.record()
     barrier()
     launches = int(lib.lstur_launch_count() - l0)
@@ -450,7 +452,7 @@ def main():
                                                           % (n_batches, eng.ws_bytes >> 20),
                             user_adam='row-sparse (documented deviation from dense Keras-Adam)', hist_pad_frac=round(pad_frac, 3)),
                 roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=launches, clocks=clocks, loss=loss_last,
-                extra=extra)
+                host_enqueue_ms_per_step=host_enqueue_ms, extra=extra)
     print(json.dumps(line))
     if world > 1:
         dist.barrier()
