@@ -110,10 +110,12 @@ int lstur_news_conv_tc_fwd(int n_titles, int L, int E, int F, int V, const int* 
 /* Title compaction (lstur_compact_titles): the news encoder of an all-pad title — every token 0, i.e. the left padding of
  * a short click history (task/seq2vec.py:23,46-49) — is identically zero in value and in gradient (pad mask,
  * task/paper.py:150-155), so the plan runs the tensor-core kernels over the ascending list of live titles only:
- * n_live (1), live_idx (N: original index of every live title), tokens_c (N,L: their tokens); flags (N) is scratch.  The
+ * n_live (1), live_idx (N: original index of every live title), tokens_c (N,L: their tokens); scratch holds
+ * lstur_compact_titles_scratch_ints(N) ints.  The
  * kernels below take the live count as a device scalar (n_titles_dev, NULL = all n_titles) and, where a tensor outside the
  * encoder is touched (pooled rows, d_pooled rows), the original title index (title_idx, NULL = identity). */
-int lstur_compact_titles(int N, int L, const int* tokens, int* flags, int* live_idx, int* n_live, int* tokens_c,
+long long lstur_compact_titles_scratch_ints(int N);
+int lstur_compact_titles(int N, int L, const int* tokens, int* scratch, int* live_idx, int* n_live, int* tokens_c,
                          cudaStream_t stream);
 
 /* Same kernels with the X-dropout keep bits handed from the forward to the weight-gradient kernel (one byte per 16-byte

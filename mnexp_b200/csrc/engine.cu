@@ -203,7 +203,7 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
     if (bw && c.dropout > 0.f) add_ws(p, "xmask", (long long)(lstur_tc_xmask_bytes((int)N, c.L, E) + 3) / 4);
     // compacted list of live titles (lstur_compact_titles): everything inside the encoder (tokens_c, C16, att_a, att_w, keep
     // bits, dPre image, dX rows) is indexed by the compacted title index
-    add_ws(p, "title_flags", N);
+    add_ws(p, "title_flags", lstur_compact_titles_scratch_ints((int)N));
     add_ws(p, "live_idx", N);
     add_ws(p, "n_live", 1);
     add_ws(p, "tokens_c", N * c.L);

@@ -205,34 +205,49 @@ __global__ void title_live_kernel(int N, int L, const int* __restrict__ tok, int
   nz = warp_or(nz);
   if (lane == 0) flags[warp] = nz ? 1 : 0;
 }
-// one block: live_idx = ascending list of the titles with flags != 0, n_live = their count
-__global__ void __launch_bounds__(1024) title_scan_kernel(int N, const int* __restrict__ flags, int* __restrict__ live_idx,
-                                                          int* __restrict__ n_live) {
-  __shared__ int part[1024];
-  const int tid = threadIdx.x, per = (N + 1023) / 1024;
-  const int v0 = min(N, tid * per), v1 = min(N, v0 + per);
-  int c = 0;
-  for (int v = v0; v < v1; ++v) c += flags[v];
-  part[tid] = c;
+// blocks of 1024 titles: rank of every live title inside its block + the block's live count
+__global__ void __launch_bounds__(1024) title_rank_kernel(int N, const int* __restrict__ flags, int* __restrict__ local_rank,
+                                                          int* __restrict__ block_tot) {
+  __shared__ int wsum[32];
+  const int n = blockIdx.x * 1024 + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int f = (n < N && flags[n]) ? 1 : 0;
+  const unsigned bal = __ballot_sync(0xffffffffu, f);
+  if (lane == 0) wsum[warp] = __popc(bal);
   __syncthreads();
-  // inclusive scan of the 1024 partial counts (Hillis-Steele, 10 rounds)
-  for (int o = 1; o < 1024; o <<= 1) {
-    const int u = tid >= o ? part[tid - o] : 0;
-    __syncthreads();
-    part[tid] += u;
-    __syncthreads();
+  if (warp == 0) {
+    int v = wsum[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    wsum[lane] = v;            // inclusive
   }
-  int run = part[tid] - c;
-  for (int v = v0; v < v1; ++v)
-    if (flags[v]) live_idx[run++] = v;
-  if (tid == 1023) *n_live = part[1023];
+  __syncthreads();
+  if (n < N) local_rank[n] = (warp ? wsum[warp - 1] : 0) + __popc(bal & ((1u << lane) - 1u));
+  if (threadIdx.x == 0) block_tot[blockIdx.x] = wsum[31];
 }
-__global__ void title_compact_kernel(int N, int L, const int* __restrict__ tok, const int* __restrict__ live_idx,
-                                     const int* __restrict__ n_live, int* __restrict__ tok_c) {
+// one warp per title: global rank = live titles of the earlier blocks + rank inside the block; live titles are appended to
+// live_idx (ascending) and their tokens copied
+__global__ void title_compact_kernel(int N, int L, const int* __restrict__ tok, const int* __restrict__ flags,
+                                     const int* __restrict__ local_rank, const int* __restrict__ block_tot, int n_blocks,
+                                     int* __restrict__ live_idx, int* __restrict__ n_live, int* __restrict__ tok_c) {
   int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-  if (warp >= *n_live) return;
-  const int n = live_idx[warp];
-  for (int l = lane; l < L; l += 32) tok_c[(long long)warp * L + l] = tok[(long long)n * L + l];
+  if (warp >= N) return;
+  const int blk = warp >> 10;
+  int before = 0;
+  for (int b = lane; b < n_blocks; b += 32) before += (b < blk || warp == N - 1) ? block_tot[b] : 0;
+  before = __reduce_add_sync(0xffffffffu, before);
+  if (warp == N - 1) {         // the last title's warp summed every block: the live count
+    if (lane == 0) *n_live = before;
+    before = 0;
+    for (int b = lane; b < blk; b += 32) before += block_tot[b];
+    before = __reduce_add_sync(0xffffffffu, before);
+  }
+  if (!flags[warp]) return;
+  const int ci = before + local_rank[warp];
+  if (lane == 0) live_idx[ci] = warp;
+  for (int l = lane; l < L; l += 32) tok_c[(long long)ci * L + l] = tok[(long long)warp * L + l];
 }
 
 }  // namespace lstur
@@ -240,17 +255,21 @@ __global__ void title_compact_kernel(int N, int L, const int* __restrict__ tok, 
 using namespace lstur;
 
 // tokens (N,L) -> n_live (1), live_idx (N; first n_live entries = ascending indices of the titles that have a non-zero
-// token), tokens_c (N,L; first n_live rows = those titles' tokens); flags (N) is scratch.
-extern "C" int lstur_compact_titles(int N, int L, const int* tokens, int* flags, int* live_idx, int* n_live, int* tokens_c,
+// token), tokens_c (N,L; first n_live rows = those titles' tokens); scratch = lstur_compact_titles_scratch_ints(N) ints.
+extern "C" long long lstur_compact_titles_scratch_ints(int N) { return 2LL * N + (N + 1023) / 1024 + 8; }
+extern "C" int lstur_compact_titles(int N, int L, const int* tokens, int* scratch, int* live_idx, int* n_live, int* tokens_c,
                                     cudaStream_t stream) {
   LSTUR_REQUIRE(N >= 0 && L > 0 && n_live != nullptr, "lstur_compact_titles");
   if (N == 0) { cudaMemsetAsync(n_live, 0, sizeof(int), stream); return LSTUR_OK; }
-  LSTUR_REQUIRE(tokens && flags && live_idx && tokens_c, "lstur_compact_titles");
+  LSTUR_REQUIRE(tokens && scratch && live_idx && tokens_c, "lstur_compact_titles");
+  const int nb = (N + 1023) / 1024;
+  int *flags = scratch, *local_rank = scratch + N, *block_tot = scratch + 2 * (long long)N;
   title_live_kernel<<<cdiv((long long)N * 32, 256), 256, 0, stream>>>(N, L, tokens, flags);
   LSTUR_CHECK_LAUNCH("lstur_compact_titles(flags)");
-  title_scan_kernel<<<1, 1024, 0, stream>>>(N, flags, live_idx, n_live);
-  LSTUR_CHECK_LAUNCH("lstur_compact_titles(scan)");
-  title_compact_kernel<<<cdiv((long long)N * 32, 256), 256, 0, stream>>>(N, L, tokens, live_idx, n_live, tokens_c);
+  title_rank_kernel<<<nb, 1024, 0, stream>>>(N, flags, local_rank, block_tot);
+  LSTUR_CHECK_LAUNCH("lstur_compact_titles(rank)");
+  title_compact_kernel<<<cdiv((long long)N * 32, 256), 256, 0, stream>>>(N, L, tokens, flags, local_rank, block_tot, nb, live_idx,
+                                                                        n_live, tokens_c);
   LSTUR_CHECK_LAUNCH("lstur_compact_titles(gather)");
   return LSTUR_OK;
 }

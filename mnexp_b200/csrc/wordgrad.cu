@@ -7,8 +7,8 @@
 //   d word_emb[v, :] = sum over token positions p with tok[p] == v of  dX[p, :] * xdrop[p, :]
 //
 // No floating-point atomics: the positions are sorted by token with a stable LSD radix sort (so a token's positions stay
-// in ascending order), and every token's rows are summed in that order by a fixed tree: chunks of R consecutive rows ->
-// partial rows -> chunks of R partial rows -> ... (three levels; the last one sums whatever is left sequentially).  A
+// in ascending order), and the sorted list is summed by a fixed tree of equal-sized chunks (see reduce_kernel): a chunk
+// finishes every token whose positions it contains entirely and hands at most two partial rows to the next level.  A
 // step is therefore bit-reproducible, and the heavy tokens of a Zipf vocabulary (one token can own > 10 % of all
 // positions) are spread over many warps instead of serialising on one.
 // Positions whose gradient is identically zero are dropped before the sort: a pad position that has no real token
@@ -20,7 +20,8 @@ namespace wg {
 
 constexpr int RB = 9, RADIX = 1 << RB;             // radix-sort digit
 constexpr int SORT_THREADS = 256, SORT_ITEMS = 8, SORT_CH = SORT_THREADS * SORT_ITEMS;
-constexpr int R = 128;                             // rows summed by one work item
+constexpr int R = 64;                              // rows (or piece slots) walked by one warp
+constexpr int BATCH = 4;                           // rows whose loads a warp keeps in flight
 constexpr int RED_THREADS = 256;                   // 8 warps = 8 work items per block
 
 // ---- keys: token id of every live position, V for dead ones (sorted to the end and ignored) --------------------------
@@ -158,67 +159,6 @@ __global__ void bounds_kernel(long long n, int V, const int* __restrict__ keys, 
   if (i + 1 == n || keys[i + 1] != k) seg_end[k] = (int)(i + 1);
 }
 
-// ---- reduction plan: per token v with c = seg_end - seg_beg rows
-//   level 1: np1 = ceil(c / R) work items; the token keeps np1 partial rows iff np1 > 1
-//   level 2: over those partial rows, np2 = ceil(np1 / R) work items (0 if np1 <= 1); keeps np2 partial rows iff np2 > 1
-//   level 3: one work item iff np2 > 1, sums all np2 rows
-// plan[0..5][V+1] = exclusive prefix sums of (np1, np1>1 ? np1 : 0, np2, np2>1 ? np2 : 0, np3) + totals at index V.
-constexpr int PLAN_SEQ = 5;
-__global__ void __launch_bounds__(1024) plan_kernel(int V, const int* __restrict__ seg_beg, const int* __restrict__ seg_end,
-                                                    int* __restrict__ plan) {
-  __shared__ int part[PLAN_SEQ][1024];
-  const int tid = threadIdx.x;
-  const int per = (V + 1023) / 1024;
-  const int v0 = tid * per, v1 = min(V, v0 + per);
-  auto counts = [&](int v, int* o) {
-    const int c = seg_end[v] - seg_beg[v];
-    const int np1 = (c + R - 1) / R, np2 = np1 > 1 ? (np1 + R - 1) / R : 0;
-    o[0] = np1; o[1] = np1 > 1 ? np1 : 0; o[2] = np2; o[3] = np2 > 1 ? np2 : 0; o[4] = np2 > 1 ? 1 : 0;
-  };
-  int sum[PLAN_SEQ] = {0, 0, 0, 0, 0};
-  for (int v = v0; v < v1; ++v) {
-    int o[PLAN_SEQ];
-    counts(v, o);
-#pragma unroll
-    for (int q = 0; q < PLAN_SEQ; ++q) sum[q] += o[q];
-  }
-#pragma unroll
-  for (int q = 0; q < PLAN_SEQ; ++q) part[q][tid] = sum[q];
-  __syncthreads();
-  if (tid < PLAN_SEQ) {       // 1024 partial sums per sequence: one thread each (cheap next to the passes over V)
-    int run = 0;
-    for (int i = 0; i < 1024; ++i) {
-      const int t = part[tid][i];
-      part[tid][i] = run;
-      run += t;
-    }
-    plan[(long long)tid * (V + 1) + V] = run;
-  }
-  __syncthreads();
-  int run[PLAN_SEQ];
-#pragma unroll
-  for (int q = 0; q < PLAN_SEQ; ++q) run[q] = part[q][tid];
-  for (int v = v0; v < v1; ++v) {
-    int o[PLAN_SEQ];
-    counts(v, o);
-#pragma unroll
-    for (int q = 0; q < PLAN_SEQ; ++q) {
-      plan[(long long)q * (V + 1) + v] = run[q];
-      run[q] += o[q];
-    }
-  }
-}
-
-// last index s in [0, V) with a[s] <= w (a is non-decreasing, a[V] > w)
-__device__ __forceinline__ int find_segment(const int* __restrict__ a, int V, int w) {
-  int lo = 0, hi = V;        // invariant: a[lo] <= w < a[hi]
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(a + mid) <= w) lo = mid; else hi = mid;
-  }
-  return lo;
-}
-
 // Row sources.  A lane owns the 4-column pieces lane, lane+32, ... (NP of them) of a row.
 struct Src16 {          // level 1, tensor-core modes: 16-bit dX rows (n_pos, Ep) + keep bytes of the X-dropout
   const uint16_t* dx;
@@ -235,134 +175,191 @@ struct SrcPart {        // levels 2 and 3: fp32 partial rows (rows, E)
   int E;
 };
 
+// A row is fetched (load_row: the loads of several rows are issued back to back, so a warp keeps up to BATCH rows in
+// flight) and then accumulated (add_raw) in position order.
+template <int NP> struct Raw16 { uint2 v[NP]; unsigned m[NP]; };
+template <int NP> struct Raw32 { float4 v[NP]; unsigned m[NP]; };
+template <int NP> struct RawPart { float4 v[NP]; };
+template <typename SRC, int NP> struct RawOf;
+template <int NP> struct RawOf<Src16, NP> { typedef Raw16<NP> type; };
+template <int NP> struct RawOf<Src32, NP> { typedef Raw32<NP> type; };
+template <int NP> struct RawOf<SrcPart, NP> { typedef RawPart<NP> type; };
+
 template <int NP>
-__device__ __forceinline__ void add_row(const Src16& s, long long pos, int lane, float (&acc)[NP][4]) {
+__device__ __forceinline__ void load_row(const Src16& s, long long pos, int lane, Raw16<NP>& r) {
   const uint16_t* row = s.dx + pos * s.Ep;
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     const int piece = lane + 32 * j;
+    r.v[j] = make_uint2(0u, 0u);
+    r.m[j] = 0xffu;
     if (piece * 4 < s.Ep) {
-      const uint2 u = __ldg(reinterpret_cast<const uint2*>(row + piece * 4));
-      unsigned m = 0xffu;
-      if (s.xmask) m = __ldg(s.xmask + pos * (s.Ep >> 3) + (piece >> 1));
-      const int wj = (piece & 1) * 2;      // 32-bit word of the 16-byte piece; bit wj+h / 4+wj+h = low / high half of word wj+h
-      float v[4];
-      if (s.fp16) {
-        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-      } else {
-        v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
-        v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
-      }
-      acc[j][0] += ((m >> wj) & 1u) ? v[0] : 0.f;
-      acc[j][1] += ((m >> (4 + wj)) & 1u) ? v[1] : 0.f;
-      acc[j][2] += ((m >> (wj + 1)) & 1u) ? v[2] : 0.f;
-      acc[j][3] += ((m >> (5 + wj)) & 1u) ? v[3] : 0.f;
+      r.v[j] = __ldg(reinterpret_cast<const uint2*>(row + piece * 4));
+      if (s.xmask) r.m[j] = __ldg(s.xmask + pos * (s.Ep >> 3) + (piece >> 1));
     }
   }
 }
 template <int NP>
-__device__ __forceinline__ void add_row(const Src32& s, long long pos, int lane, float (&acc)[NP][4]) {
+__device__ __forceinline__ void add_raw(const Src16& s, const Raw16<NP>& r, int lane, float (&acc)[NP][4]) {
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const int piece = lane + 32 * j;
+    const uint2 u = r.v[j];
+    const unsigned m = r.m[j];
+    const int wj = (piece & 1) * 2;      // 32-bit word of the 16-byte piece; bit wj+h / 4+wj+h = low / high half of word wj+h
+    float v[4];
+    if (s.fp16) {
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+      v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    } else {
+      v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
+      v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+    }
+    acc[j][0] += ((m >> wj) & 1u) ? v[0] : 0.f;
+    acc[j][1] += ((m >> (4 + wj)) & 1u) ? v[1] : 0.f;
+    acc[j][2] += ((m >> (wj + 1)) & 1u) ? v[2] : 0.f;
+    acc[j][3] += ((m >> (5 + wj)) & 1u) ? v[3] : 0.f;
+  }
+}
+template <int NP>
+__device__ __forceinline__ void load_row(const Src32& s, long long pos, int lane, Raw32<NP>& r) {
   const long long n = pos / s.L;
   const int t = (int)(pos % s.L);
   const float* row = s.dx + (n * s.Lp + t + s.pl) * s.E;
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     const int e = (lane + 32 * j) * 4;
+    r.v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    r.m[j] = 15u;
     if (e < s.E) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(row + e));
-      bool k0 = true, k1 = true, k2 = true, k3 = true;
+      r.v[j] = __ldg(reinterpret_cast<const float4*>(row + e));
       if (s.drop_thr) {
         const uint64_t base = (uint64_t)pos * (uint64_t)s.E + e;
-        k0 = (rng_u32(s.seed, base + 0) >> 8) >= s.drop_thr; k1 = (rng_u32(s.seed, base + 1) >> 8) >= s.drop_thr;
-        k2 = (rng_u32(s.seed, base + 2) >> 8) >= s.drop_thr; k3 = (rng_u32(s.seed, base + 3) >> 8) >= s.drop_thr;
+        r.m[j] = ((rng_u32(s.seed, base + 0) >> 8) >= s.drop_thr ? 1u : 0u) | ((rng_u32(s.seed, base + 1) >> 8) >= s.drop_thr ? 2u : 0u) |
+                 ((rng_u32(s.seed, base + 2) >> 8) >= s.drop_thr ? 4u : 0u) | ((rng_u32(s.seed, base + 3) >> 8) >= s.drop_thr ? 8u : 0u);
       }
-      acc[j][0] += k0 ? v.x : 0.f; acc[j][1] += k1 ? v.y : 0.f; acc[j][2] += k2 ? v.z : 0.f; acc[j][3] += k3 ? v.w : 0.f;
     }
   }
 }
 template <int NP>
-__device__ __forceinline__ void add_row(const SrcPart& s, long long r, int lane, float (&acc)[NP][4]) {
-  const float* row = s.rows + r * s.E;
+__device__ __forceinline__ void add_raw(const Src32&, const Raw32<NP>& r, int, float (&acc)[NP][4]) {
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const float4 v = r.v[j];
+    const unsigned m = r.m[j];
+    acc[j][0] += (m & 1u) ? v.x : 0.f; acc[j][1] += (m & 2u) ? v.y : 0.f; acc[j][2] += (m & 4u) ? v.z : 0.f; acc[j][3] += (m & 8u) ? v.w : 0.f;
+  }
+}
+template <int NP>
+__device__ __forceinline__ void load_row(const SrcPart& s, long long rr, int lane, RawPart<NP>& r) {
+  const float* row = s.rows + rr * s.E;
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     const int e = (lane + 32 * j) * 4;
-    if (e < s.E) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(row + e));
-      acc[j][0] += v.x; acc[j][1] += v.y; acc[j][2] += v.z; acc[j][3] += v.w;
-    }
+    r.v[j] = e < s.E ? __ldg(reinterpret_cast<const float4*>(row + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+template <int NP>
+__device__ __forceinline__ void add_raw(const SrcPart&, const RawPart<NP>& r, int, float (&acc)[NP][4]) {
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    acc[j][0] += r.v[j].x; acc[j][1] += r.v[j].y; acc[j][2] += r.v[j].z; acc[j][3] += r.v[j].w;
   }
 }
 
-// One warp per work item w of level LEVEL (1, 2, 3):
-//   token s = find_segment(wstart, w), k = w - wstart[s]
-//   rows    = item range [ibeg + k*R, min(iend, ibeg + (k+1)*R))  (level 3: the whole range), taken in order
-//   output  = the token's row of d_word_emb (x scale) if this is its only work item at this level, else partial row
-//             pstart[s] + k of this level's partial buffer.
-// Level 1 rows are reached through the sorted position list; levels 2 / 3 read the previous level's partial rows.
-template <typename SRC, int NP, int LEVEL>
-__global__ void __launch_bounds__(RED_THREADS) reduce_kernel(SRC src, int V, int E, const int* __restrict__ plan,
+// ---- chunk tree.  Level 1: chunk c = the R consecutive sorted positions [c*R, (c+1)*R); level l > 1: chunk c = the
+// pieces left by the FAN = R/2 level-(l-1) chunks [c*FAN, (c+1)*FAN) (two slots each), i.e. it spans S_l = R * FAN^(l-1)
+// sorted positions.  One warp walks its chunk's rows in order and sums the runs of equal token id.  A run that covers the
+// token's whole segment [seg_beg, seg_end) of the sorted list is final: it is scaled and written to the token's row of
+// d_word_emb.  Otherwise the segment crosses the chunk's boundary (at most one run per side can): the partial sum goes to
+// one of the chunk's two piece slots (token id + fp32 row; unused slots are tagged -1) and the next level continues.
+// The top level has one chunk, which covers everything.  Summation order = position order at every level: no atomics,
+// bit-reproducible, and every warp has the same amount of work however skewed the token frequencies are.
+constexpr int FAN = R / 2;
+
+template <typename SRC, int NP, bool LEVEL1>
+__global__ void __launch_bounds__(RED_THREADS) reduce_kernel(SRC src, long long n_items, long long span, int V, int E,
+                                                             const int* __restrict__ keys_in, const int* __restrict__ pos_sorted,
                                                              const int* __restrict__ seg_beg, const int* __restrict__ seg_end,
-                                                             const int* __restrict__ pos_sorted, float* __restrict__ part_out,
+                                                             int* __restrict__ piece_keys, float* __restrict__ piece_rows,
                                                              float* __restrict__ d_word_emb, float scale) {
   const int lane = threadIdx.x & 31;
-  const long long w = ((long long)blockIdx.x * RED_THREADS + threadIdx.x) >> 5;
-  const int* wstart = plan + (long long)(LEVEL == 1 ? 0 : LEVEL == 2 ? 2 : 4) * (V + 1);
-  if (w >= wstart[V]) return;
-  const int s = find_segment(wstart, V, (int)w);
-  const int k = (int)w - wstart[s], nparts = wstart[s + 1] - wstart[s];
-  long long ibeg, iend;
-  if (LEVEL == 1) { ibeg = seg_beg[s]; iend = seg_end[s]; }
-  else {            // this token's partial rows of the previous level
-    const int* pprev = plan + (long long)(LEVEL == 2 ? 1 : 3) * (V + 1);
-    ibeg = pprev[s]; iend = pprev[s + 1];
-  }
-  long long i0 = ibeg + (long long)k * R, i1 = LEVEL == 3 ? iend : min(iend, i0 + R);
+  const long long c = ((long long)blockIdx.x * RED_THREADS + threadIdx.x) >> 5;     // chunk
+  const long long i0 = c * R, i1 = min(n_items, i0 + R);
+  if (i0 >= n_items) return;
+  const long long lo = c * span, hi = lo + span;       // sorted positions covered by this chunk
   float acc[NP][4];
+  int cur = -1, n_out = 0;
+  auto flush = [&]() {
+    if (cur < 0) return;
+    const bool whole = __ldg(seg_beg + cur) >= lo && __ldg(seg_end + cur) <= hi;
+    float* dst;
+    float sc = 1.f;
+    if (whole) { dst = d_word_emb + (long long)cur * E; sc = scale; }
+    else {
+      dst = piece_rows + (2 * c + n_out) * E;
+      if (lane == 0) piece_keys[2 * c + n_out] = cur;
+      ++n_out;
+    }
 #pragma unroll
-  for (int j = 0; j < NP; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    for (int j = 0; j < NP; ++j) {
+      const int e = (lane + 32 * j) * 4;
+      if (e < E) *reinterpret_cast<float4*>(dst + e) = make_float4(acc[j][0] * sc, acc[j][1] * sc, acc[j][2] * sc, acc[j][3] * sc);
+    }
+  };
   for (long long b = i0; b < i1; b += 32) {
     const int cntb = (int)min((long long)32, i1 - b);
-    long long mine = b + lane;
-    if (LEVEL == 1) mine = lane < cntb ? pos_sorted[b + lane] : 0;
-#pragma unroll 4
-    for (int j = 0; j < cntb; ++j) {
-      const long long r = __shfl_sync(0xffffffffu, mine, j);
-      add_row<NP>(src, r, lane, acc);
+    int my_key = -1;
+    long long my_row = b + lane;
+    if (lane < cntb) {
+      my_key = keys_in[b + lane];
+      if (LEVEL1) { my_row = pos_sorted[b + lane]; if (my_key >= V) my_key = -1; }     // dead positions sort last
+    }
+    for (int j0 = 0; j0 < cntb; j0 += BATCH) {
+      int ks[BATCH];
+      typename RawOf<SRC, NP>::type raw[BATCH];
+#pragma unroll
+      for (int u = 0; u < BATCH; ++u) {         // issue the loads of BATCH rows
+        ks[u] = __shfl_sync(0xffffffffu, my_key, (j0 + u) & 31);
+        const long long r = __shfl_sync(0xffffffffu, my_row, (j0 + u) & 31);
+        if (j0 + u >= cntb) ks[u] = -1;
+        if (ks[u] >= 0) load_row<NP>(src, r, lane, raw[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < BATCH; ++u) {         // accumulate them in order
+        if (ks[u] < 0) continue;                // empty slot / dead position
+        if (ks[u] != cur) {
+          flush();
+          cur = ks[u];
+#pragma unroll
+          for (int q = 0; q < NP; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
+        }
+        add_raw<NP>(src, raw[u], lane, acc);
+      }
     }
   }
-  float* dst;
-  float sc = 1.f;
-  if (nparts == 1) { dst = d_word_emb + (long long)s * E; sc = scale; }
-  else {
-    const int* pcur = plan + (long long)(LEVEL == 1 ? 1 : 3) * (V + 1);
-    dst = part_out + ((long long)pcur[s] + k) * E;
-  }
-#pragma unroll
-  for (int j = 0; j < NP; ++j) {
-    const int e = (lane + 32 * j) * 4;
-    if (e < E) *reinterpret_cast<float4*>(dst + e) = make_float4(acc[j][0] * sc, acc[j][1] * sc, acc[j][2] * sc, acc[j][3] * sc);
-  }
+  flush();
+  if (piece_keys && lane == 0)
+    for (int j = n_out; j < 2; ++j) piece_keys[2 * c + j] = -1;
 }
 
 struct Ws {          // carve-up of the caller's workspace
-  int *keys_a, *keys_b, *pos_a, *pos_b, *ghist, *bintot, *seg_beg, *seg_end, *plan;
-  float *part1, *part2;
+  int *keys_a, *keys_b, *pos_a, *pos_b, *ghist, *bintot, *seg_beg, *seg_end, *pk1, *pk2;
+  float *pr1, *pr2;
   size_t bytes;
 };
-static long long part1_rows(long long n) { return 2 * (n / R) + 2; }               // tokens with > R rows: sum ceil(c/R) <= n/R + n/R
-static long long part2_rows(long long n) { return 2 * (part1_rows(n) / R) + 2; }
+static long long n_chunks(long long items) { return (items + R - 1) / R; }
 static Ws carve(void* base, long long n, int V, int E) {
   Ws w;
   size_t off = 0;
   auto take = [&](size_t b) { size_t o = off; off = (off + b + 255) & ~(size_t)255; return (char*)base + o; };
   const long long nblk = (n + SORT_CH - 1) / SORT_CH;
+  const long long c1 = n_chunks(n > 0 ? n : 1), c2 = n_chunks(2 * c1);     // chunks of level 1 / level 2 (ping-pong buffers)
   w.keys_a = (int*)take(n * 4); w.keys_b = (int*)take(n * 4); w.pos_a = (int*)take(n * 4); w.pos_b = (int*)take(n * 4);
   w.ghist = (int*)take((size_t)RADIX * nblk * 4); w.bintot = (int*)take(RADIX * 4);
   w.seg_beg = (int*)take((size_t)V * 4 * 2); w.seg_end = w.seg_beg + V;       // contiguous: one memset
-  w.plan = (int*)take((size_t)PLAN_SEQ * (V + 1) * 4);
-  w.part1 = (float*)take((size_t)part1_rows(n) * E * 4);
-  w.part2 = (float*)take((size_t)part2_rows(n) * E * 4);
+  w.pk1 = (int*)take((size_t)2 * c1 * 4); w.pk2 = (int*)take((size_t)2 * c2 * 4);
+  w.pr1 = (float*)take((size_t)2 * c1 * E * 4); w.pr2 = (float*)take((size_t)2 * c2 * E * 4);
   w.bytes = off;
   return w;
 }
@@ -394,26 +391,32 @@ static int run(SRC src, long long n, int L, int V, int E, const int* tokens, con
   cudaMemsetAsync(w.seg_beg, 0, (size_t)V * 4 * 2, st);
   bounds_kernel<<<cdiv(n, 256), 256, 0, st>>>(n, V, ka, w.seg_beg, w.seg_end);
   LSTUR_CHECK_LAUNCH(name);
-  plan_kernel<<<1, 1024, 0, st>>>(V, w.seg_beg, w.seg_end, w.plan);
-  LSTUR_CHECK_LAUNCH(name);
   const int wpb = RED_THREADS / 32;
-  const long long nw1 = n / R + (V < n ? V : n) + 1, nw2 = part1_rows(n) / R + n / R + 2, nw3 = part1_rows(n) / R + 2;
   const int np = (E / 4 + 31) / 32;               // 4-column pieces per lane
-  const SrcPart s1{w.part1, E}, s2{w.part2, E};
-#define WG_LEVELS(NP_)                                                                                                    \
+#define WG_LAUNCH(NP_)                                                                                                    \
   do {                                                                                                                    \
-    reduce_kernel<SRC, NP_, 1><<<cdiv(nw1, wpb), RED_THREADS, 0, st>>>(src, V, E, w.plan, w.seg_beg, w.seg_end, pa, w.part1, d_word_emb, scale); \
+    long long items = n, span = R;                                                                                        \
+    long long nc = n_chunks(items);                                                                                       \
+    reduce_kernel<SRC, NP_, true><<<cdiv(nc, wpb), RED_THREADS, 0, st>>>(src, items, span, V, E, ka, pa, w.seg_beg, w.seg_end, \
+                                                                         nc > 1 ? w.pk1 : nullptr, w.pr1, d_word_emb, scale); \
     LSTUR_CHECK_LAUNCH(name);                                                                                             \
-    reduce_kernel<SrcPart, NP_, 2><<<cdiv(nw2, wpb), RED_THREADS, 0, st>>>(s1, V, E, w.plan, w.seg_beg, w.seg_end, nullptr, w.part2, d_word_emb, scale); \
-    LSTUR_CHECK_LAUNCH(name);                                                                                             \
-    reduce_kernel<SrcPart, NP_, 3><<<cdiv(nw3, wpb), RED_THREADS, 0, st>>>(s2, V, E, w.plan, w.seg_beg, w.seg_end, nullptr, nullptr, d_word_emb, scale); \
-    LSTUR_CHECK_LAUNCH(name);                                                                                             \
+    int* pk_in = w.pk1; float* pr_in = w.pr1; int* pk_out = w.pk2; float* pr_out = w.pr2;                                 \
+    while (nc > 1) {                                                                                                      \
+      items = 2 * nc; span *= FAN; nc = n_chunks(items);                                                                  \
+      const SrcPart sp{pr_in, E};                                                                                         \
+      reduce_kernel<SrcPart, NP_, false><<<cdiv(nc, wpb), RED_THREADS, 0, st>>>(sp, items, span, V, E, pk_in, nullptr, w.seg_beg, \
+                                                                                w.seg_end, nc > 1 ? pk_out : nullptr, pr_out, \
+                                                                                d_word_emb, scale);                       \
+      LSTUR_CHECK_LAUNCH(name);                                                                                           \
+      int* ti = pk_in; pk_in = pk_out; pk_out = ti;                                                                       \
+      float* tf = pr_in; pr_in = pr_out; pr_out = tf;                                                                     \
+    }                                                                                                                     \
   } while (0)
-  if (np <= 1) WG_LEVELS(1);
-  else if (np == 2) WG_LEVELS(2);
-  else if (np == 3) WG_LEVELS(3);
-  else WG_LEVELS(4);
-#undef WG_LEVELS
+  if (np <= 1) WG_LAUNCH(1);
+  else if (np == 2) WG_LAUNCH(2);
+  else if (np == 3) WG_LAUNCH(3);
+  else WG_LAUNCH(4);
+#undef WG_LAUNCH
   return LSTUR_OK;
 }
 

@@ -490,7 +490,8 @@ def test_named_encoder_layers_and_per_impression_scoring(lib):
     assert uv.shape == (B, sh.U) and rel(uv, ref['user_vec']) < 5e-5
     # one impression: 7 candidates against the history of row 0
     n = 7
-    cand = np.concatenate([cands[0], cands[1][:n - cands.shape[1]]])[:n]
+    cand = cands.reshape(-1, L)[:n]
+    assert cand.shape[0] == n
     imp = [np.repeat(user[:1], n), np.repeat(clicked[:1], n, 0), cand]
     fast = h.test_model.predict(imp)
     slow = np.concatenate([h.test_model.predict([a[i:i + 1] for a in imp]) for i in range(n)])

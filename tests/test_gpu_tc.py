@@ -405,7 +405,8 @@ def test_compact_titles_bit_exact(lib, N, L):
     tok = g.integers(0, 5, (N, L)).astype(np.int32)
     tok[g.random(N) < 0.45] = 0                      # all-pad titles
     t = torch.as_tensor(tok).cuda()
-    flags, idx = torch.full((N,), -7, dtype=torch.int32, device='cuda'), torch.full((N,), -7, dtype=torch.int32, device='cuda')
+    flags = torch.full((lib.lstur_compact_titles_scratch_ints(N),), -7, dtype=torch.int32, device='cuda')
+    idx = torch.full((N,), -7, dtype=torch.int32, device='cuda')
     n_live, tc_ = torch.full((1,), -7, dtype=torch.int32, device='cuda'), torch.full((N, L), -7, dtype=torch.int32, device='cuda')
     assert lib.lstur_compact_titles(N, L, P_(t), P_(flags), P_(idx), P_(n_live), P_(tc_), stream()) == 0
     torch.cuda.synchronize()
@@ -432,7 +433,7 @@ def test_tc_forward_over_compacted_titles(lib, L):
     assert lib.lstur_pack_conv_w_tc(E, F, P_(cw), P_(wimg), 1, stream()) == 0
     t = dev(tok, torch.int32)
     i32 = lambda *s: torch.zeros(s, dtype=torch.int32, device='cuda')
-    flags, idx, n_live, tok_c = i32(N), i32(N), i32(1), i32(N, L)
+    flags, idx, n_live, tok_c = i32(lib.lstur_compact_titles_scratch_ints(N)), i32(N), i32(1), i32(N, L)
     assert lib.lstur_compact_titles(N, L, P_(t), P_(flags), P_(idx), P_(n_live), P_(tok_c), stream()) == 0
     cb, aw, ab = dev(P['conv_b'], torch.float32), dev(P['att_w'].reshape(-1), torch.float32), dev(np.asarray(P['att_b']).reshape(1), torch.float32)
     c_out = torch.zeros((N, L, F), dtype=torch.float16, device='cuda')
