@@ -149,14 +149,9 @@ struct EpiCtx {
   float sx;                       // scale applied to the accumulator (input-dropout and conv-dropout keep scales)
   const float* s_bias;            // conv bias x conv-dropout keep scale (ReLU is positively homogeneous)
   const float* s_ka;
-  // conv-dropout keep bits of this thread's token row, written by the mask-generator warps: word w (stride CM_ROWS words)
-  // holds one nibble per quad of features 32w .. 32w+31 = keep flags of [pair 0 low, pair 0 high, pair 1 low, pair 1 high]
-  const uint32_t* cmask;
-  const uint2* lut;               // nibble -> the two 16x2 AND masks of the quad's packed pairs
-  int nw;                         // words per row
+  uint32_t thr, base_lo, inner0, inner1;   // conv-dropout stream of this thread's token row (thr = quad_addend)
   int dbg;
 };
-constexpr int CM_ROWS = TILE_M;   // row stride (words) of the keep-bit buffer [word][row]
 
 // Epilogue pass 1 for NC accumulator columns of one token row -> features [f0, f0+NC): scale + bias + ReLU (+ pad-token
 // mask) -> conv dropout -> 16-bit C stored to global, attention-logit partial sum z (from the ROUNDED values, so forward
@@ -217,6 +212,10 @@ struct RowIO {
 // mask) -> conv dropout -> 16-bit C stored to global, attention-logit partial sum z (from the ROUNDED values, so forward
 // and backward see the same C).  The conv-dropout keep SCALE is folded into the accumulator scale and the bias (ReLU is
 // positively homogeneous), so dropping is a bitwise AND on the packed pair.
+// (Measured alternative, round 2: the keep bits generated ahead of time by the two idle warps into shared memory and
+// expanded here through a 16-entry nibble table — one LDS.64 per quad instead of one hash.  The kernel got 6 % SLOWER
+// (0.85 -> 0.90 ms at C3): this pass is bound by the shared-memory / load-store pipe (staging-buffer stores + loads, operand
+// traffic of the producers for the next tile), not by integer issue slots, so the hash stays.)
 template <bool FP16, bool DROP, int NC>
 __device__ __forceinline__ void epi_pass1_chunk(const EpiCtx& ec, const RowIO& io, uint32_t taddr, int f0, bool live, float& z,
                                                 uint32_t& anybits) {
@@ -227,12 +226,6 @@ __device__ __forceinline__ void epi_pass1_chunk(const EpiCtx& ec, const RowIO& i
 #pragma unroll
   for (int i = 0; i < 16; ++i) packed[i] = 0u;
   if (live) {
-    uint32_t cbits = 0;             // keep nibbles of this chunk's quads
-    if (DROP) {
-      const int q0 = f0 >> 2, w = q0 >> 3;
-      const uint32_t lo = ec.cmask[w * CM_ROWS], hi = (w + 1 < ec.nw) ? ec.cmask[(w + 1) * CM_ROWS] : 0u;
-      cbits = __funnelshift_r(lo, hi, (q0 & 7) * 4);
-    }
 #pragma unroll
     for (int g = 0; g < NC / 4; ++g) {
       const float4 b4 = *reinterpret_cast<const float4*>(ec.s_bias + f0 + 4 * g);
@@ -243,9 +236,11 @@ __device__ __forceinline__ void epi_pass1_chunk(const EpiCtx& ec, const RowIO& i
       uint32_t p0 = pack16x2_relu<FP16>(v0, v1), p1 = pack16x2_relu<FP16>(v2, v3);   // ReLU fused into the conversion
       anybits |= p0 | p1;      // Masking(): any(C != 0) before the dropout, on the values the model actually stores
       if (DROP) {   // the keep scale is already folded into sx / s_bias: dropping is a pure zeroing of the packed halves
-        const uint2 mk = ec.lut[(cbits >> (4 * g)) & 15u];
-        p0 &= mk.x;
-        p1 &= mk.y;
+        const uint32_t lo = ec.base_lo + (uint32_t)((f0 >> 2) + g);          // quad index of features f0+4g .. +3
+        uint32_t u0, u1;
+        quad_hash(lo ^ (lo < ec.base_lo ? ec.inner1 : ec.inner0), u0, u1);
+        p0 &= quad_mask(u0, ec.thr);
+        p1 &= quad_mask(u1, ec.thr);
       }
       packed[2 * g] = p0;
       packed[2 * g + 1] = p1;
@@ -319,13 +314,6 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
   float* s_bias = (float*)(misc_gen + 768 + 4096);  // [F]  (x conv-dropout keep scale)
   float* s_ka = s_bias + F;                          // [F]
   uint4* s_stg = (uint4*)(misc_gen + 768 + 4096 + (((size_t)2 * F * sizeof(float) + 15) & ~(size_t)15));   // [8 warps] staging
-  // conv-dropout keep bits (MODE_FWD with dropout): [2 buffers][nw words][128 rows] + the 16-entry nibble LUT.  They are
-  // produced for the NEXT tile by the two otherwise idle warps 2-3 while the tensor core works on the current one, so the
-  // epilogue — which is serialised with the MMAs of the next tile — does one table lookup per quad instead of one hash.
-  const int nw = (F + 31) >> 5;
-  uint32_t* s_cm = (uint32_t*)((uint8_t*)s_stg + (size_t)8 * STG_WARP_BYTES);
-  uint2* s_lut = (uint2*)(s_cm + (size_t)2 * nw * CM_ROWS);
-  const uint32_t bar_cm_full = misc_base + 88, bar_cm_empty = misc_base + 104;     // [2] each
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
@@ -345,21 +333,12 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
     }
     mbar_init(bar_t_full, 1);              // multicast tcgen05.commit of the leader
     mbar_init(bar_t_empty, 16);            // (leader) one arrival per epilogue warp of BOTH CTAs
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(bar_cm_full + 8 * b, 2);   // the two mask-generator warps
-      mbar_init(bar_cm_empty + 8 * b, 8);  // this CTA's eight epilogue warps
-    }
     fence_barrier_init();
   }
   if (!DG) {
     for (int f = threadIdx.x; f < F; f += THREADS) {
       s_bias[f] = p.conv_b[f] * ik;
       s_ka[f] = p.att_w[f];
-    }
-    if (DROP && threadIdx.x < 16) {
-      const uint32_t nb = threadIdx.x;
-      s_lut[nb] = make_uint2((nb & 1u ? 0x0000ffffu : 0u) | (nb & 2u ? 0xffff0000u : 0u),
-                             (nb & 4u ? 0x0000ffffu : 0u) | (nb & 8u ? 0xffff0000u : 0u));
     }
   }
   if (warp == 1) {
@@ -436,47 +415,6 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
         pht ^= 1;
       }
       if (tracing && lane == 0) { p.trace[0] = tw_acc; p.trace[1] = tw_full; p.trace[2] = clock64() - t_start; }
-    }
-  } else if (warp < 4) {
-    // ===================== conv-dropout mask generators (warps 2-3) =====================
-    // Thread g owns rows g and g + 64 of the tile: for every word (32 features = 8 quads) of the row, eight draws of the
-    // quad stream (element index m*F + f, m = the token's position in the compacted title list) -> eight keep nibbles.
-    if (!DG && DROP && !(p.dbg & 1)) {
-      const int g = threadIdx.x - 64;
-      uint32_t ph = 0;
-      int it = 0;
-      for (int tp = pair; tp < n_tp; tp += n_pairs, ++it) {
-        const int buf = it & 1;
-        if (lane == 0) mbar_wait(bar_cm_empty + 8 * buf, ((ph >> buf) & 1u) ^ 1u, 8);
-        __syncwarp();
-        uint32_t* dst = s_cm + (size_t)buf * nw * CM_ROWS;
-#pragma unroll 1
-        for (int i = 0; i < 2; ++i) {
-          const int r = g + 64 * i;
-          const int n = (2 * tp + (int)crank) * TPT + r / SLOT, t = r % SLOT;
-          if (n >= n_titles || t >= p.L) continue;           // rows that are never drained as live
-          const uint64_t base = ((uint64_t)((long long)n * p.L + t) * (uint64_t)F) >> 2;
-          const uint32_t base_lo = (uint32_t)base, hi = (uint32_t)(base >> 32);
-          const uint32_t in0 = quad_key(hi, p.seed_c), in1 = quad_key(hi + 1u, p.seed_c);
-#pragma unroll 1
-          for (int w = 0; w < nw; ++w) {
-            uint32_t word = 0;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const uint32_t lo = base_lo + (uint32_t)(8 * w + q);
-              uint32_t u0, u1;
-              quad_hash(lo ^ (lo < base_lo ? in1 : in0), u0, u1);
-              const uint32_t t0 = (u0 & 0x7fff7fffu) + p.drop_addend, t1 = (u1 & 0x7fff7fffu) + p.drop_addend;
-              const uint32_t nib = ((t0 >> 15) & 1u) | ((t0 >> 30) & 2u) | ((t1 >> 13) & 4u) | ((t1 >> 28) & 8u);
-              word |= nib << (4 * q);
-            }
-            dst[w * CM_ROWS + r] = word;
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_cm_full + 8 * buf);
-        ph ^= 1u << buf;
-      }
     }
   } else if (warp >= 4 && warp < 12) {
     // ===================== A producers: row gather -> three shifted swizzled tap tiles =====================
@@ -640,19 +578,22 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
     ec.sx = DROP ? p.inv_keep * p.inv_keep : 1.f;   // input-dropout and conv-dropout keep scales
     ec.s_bias = s_bias;
     ec.s_ka = s_ka;
-    ec.lut = s_lut;
-    ec.nw = nw;
+    ec.thr = p.drop_addend;
     ec.dbg = p.dbg;
-    int par = 0, it = 0;
-    uint32_t ph_cm = 0;
-    for (int tp = pair; tp < n_tp; tp += n_pairs, ++it) {
+    int par = 0;
+    for (int tp = pair; tp < n_tp; tp += n_pairs) {
       const int n = (2 * tp + (int)crank) * TPT + slot, t = t0 + lane;
       const bool valid = n < n_titles && t < p.L;
       const long long m = (long long)n * p.L + t;
       const int tk = valid ? p.tok[m] : 0;
       io.title = n < n_titles ? p.c_out + ((long long)n * p.L + t0) * F : nullptr;
-      const int cbuf = it & 1;
-      ec.cmask = s_cm + (size_t)cbuf * nw * CM_ROWS + (q * 32 + lane);
+      if (DROP) {
+        const uint64_t base = ((uint64_t)(valid ? m : 0) * (uint64_t)F) >> 2;     // F % 4 == 0: quad index of (m, f) = base + f/4
+        ec.base_lo = (uint32_t)base;
+        const uint32_t hi = (uint32_t)(base >> 32);
+        ec.inner0 = quad_key(hi, p.seed_c);
+        ec.inner1 = quad_key(hi + 1u, p.seed_c);
+      }
       mbar_wait(bar_t_full, pht, 6);
       pht ^= 1;
       tc_fence_after();
@@ -668,10 +609,6 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
         continue;
       }
       // ---- pass 1: drain this row's accumulator columns (kept short: the next tile's MMAs wait for it)
-      if (DROP) {            // this tile's conv-dropout keep bits are in shared memory
-        mbar_wait(bar_cm_full + 8 * cbuf, (ph_cm >> cbuf) & 1u, 9);
-        ph_cm ^= 1u << cbuf;
-      }
       epi_pass1_segment<FP16, DROP>(ec, io, trow, half * n0h, f_beg, n0h, tk != 0, z, vmax);
       if (n1h > 0) epi_pass1_segment<FP16, DROP>(ec, io, trow, 2 * n0h + half * n1h, f_beg + n0h, n1h, tk != 0, z, vmax);
       tc_fence_before();
@@ -679,7 +616,6 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
       if (lane == 0) {
         if (crank == 0) mbar_arrive(bar_t_empty);
         else mbar_arrive_remote(map_to_cta(bar_t_empty, 0));
-        if (DROP) mbar_arrive(bar_cm_empty + 8 * cbuf);
       }
       const int row = q * 32 + lane;
       s_z[(par * 2 + half) * 128 + row] = z;
@@ -1214,7 +1150,6 @@ static int tc_launch_conv(const tc::FwdParams& p, int L, bool fp16, bool drop, i
   const int F = p.F, slot = lstur_tc_slot(L);
   size_t smem = 1024 + (size_t)tc::NUM_STAGES * (tc::A_STAGE_BYTES + (size_t)tc::TAPS * (F / 2) * tc::ROWB) + 768 + 4096 +
                 (((size_t)2 * F * sizeof(float) + 15) & ~(size_t)15) + (size_t)8 * tc::STG_WARP_BYTES;
-  if (mode == tc::MODE_FWD && drop) smem += (size_t)2 * ((F + 31) / 32) * tc::CM_ROWS * 4 + 128;   // keep bits + nibble LUT
   int n_tiles = (p.n_titles + (tc::TILE_M / slot) - 1) / (tc::TILE_M / slot);
   int n_tp = (n_tiles + 1) / 2;             // CTA pairs take two token tiles at a time
   int sms = 148;
