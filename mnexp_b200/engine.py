@@ -137,6 +137,10 @@ class LsturEngine:
                 self.word_m = torch.zeros_like(self.word_emb)
                 self.word_v = torch.zeros_like(self.word_emb)
         self.sparse_user_adam = sparse_user_adam
+        # `encoder.trainable = False` of a pre-trained title encoder (task/paper.py:103-106): its gradients — the word
+        # table and the conv / attention / Dense tensors, which lead the arena — are zeroed before every update (Adam
+        # moments that never see a gradient never move the weights)
+        self.freeze_encoder = False
         self.lr = float(lr)
         self.t = 0
         self.step_seed = 0
@@ -354,6 +358,12 @@ class LsturEngine:
         device tensors overrides the local unique rows (data-parallel: globally exchanged rows)."""
         self.t += 1
         st = self._stream()
+        if self.freeze_encoder:
+            last = 'dense_b' if 'dense_b' in self.layout else 'att_b'
+            end = self.layout[last][0] + self.layout[last][1]
+            self.dense_grad[:end].zero_()
+            if self.trainable_word_emb:
+                self.word_grad.zero_()
         _lib.check(self.lib.lstur_adam_dense(self.n_dense, _ptr(self.dense), _ptr(self.dense_grad), _ptr(self.adam_m),
                                              _ptr(self.adam_v), self.lr, self.t, b1, b2, eps, 1.0, st))
         if self.trainable_word_emb:

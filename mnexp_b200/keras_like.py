@@ -56,6 +56,7 @@ class _Core:
         self.infer_engines = {}
         self.predict_rows = predict_rows
         self.step_seed = 0
+        self.freeze_encoder = False     # --enable-pretrain-encoder without --pretrain-encoder-trainable (task/paper.py:103-106)
 
     def precision(self):
         p = getattr(self.cfg, 'precision', 'auto')
@@ -81,6 +82,7 @@ class _Core:
                 trainable_word_emb=bool(getattr(c, 'textual_embedding_trainable', False)), **self.head_kw())
             if old is not None:
                 self.train_engine.adopt_state_from(old)
+            self.train_engine.freeze_encoder = self.freeze_encoder
             self.infer_engines = {}
         return self.train_engine
 
@@ -338,6 +340,44 @@ class DocEncoderModel:
     def __init__(self, core):
         self.core = core
         self.layers = [_InputLayer('doc_encoder_input', (None, core.cfg.title_shape))]
+
+    ENC_ORDER = ('word_emb', 'conv_w', 'conv_b', 'att_w', 'att_b', 'dense_w', 'dense_b')   # keras get_weights() order of the
+                                                                                           # encoder graph, task/paper.py:132-160
+    trainable = True       # `encoder.trainable = False` (task/paper.py:105-106) freezes the title encoder's weights
+
+    def __setattr__(self, k, v):
+        object.__setattr__(self, k, v)
+        if k == 'trainable' and 'core' in self.__dict__:
+            self.core.freeze_encoder = not v
+            if self.core.train_engine is not None:
+                self.core.train_engine.freeze_encoder = not v
+
+    def _current(self):
+        e = self.core.train_engine
+        return e.get_weights_dict() if e is not None else self.core.params
+
+    def get_weights(self):
+        w = self._current()
+        return [np.asarray(w[k]).reshape(-1, 1) if k == 'att_w' else np.asarray(w[k]).reshape(1) if k == 'att_b' else np.asarray(w[k])
+                for k in self.ENC_ORDER if k in w]
+
+    def weight_specs(self):
+        return [(k, tuple(int(d) for d in a.shape)) for k, a in zip([k for k in self.ENC_ORDER if k in self._current()], self.get_weights())]
+
+    def to_json(self):
+        import json
+        specs = self.weight_specs()
+        return json.dumps(dict(class_name='mnexp_b200.keras_like.DocEncoderModel', name=self.name, arch='doc_encoder',
+                               weight_names=[n for n, _ in specs], weight_shapes=[list(s) for _, s in specs]))
+
+    def set_weights(self, weights):
+        cur = self._current()
+        names = [k for k in self.ENC_ORDER if k in cur]
+        assert len(names) == len(weights), 'expected %d arrays (%s)' % (len(names), names)
+        new = {k: np.asarray(a, dtype=np.float32).reshape(np.asarray(cur[k]).shape) for k, a in zip(names, weights)}
+        self.core.params = dict(cur, **new)
+        if self.core.train_engine is not None:
+            self.core.train_engine.set_weights_dict(self.core.params)
 
     def predict(self, titles, batch_size=None, **_):
         """title tokens straight through the news-encoder kernels (lstur_encode_titles): no history, no scorer"""

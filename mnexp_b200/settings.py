@@ -70,6 +70,21 @@ class Config:
                 os.path.join(self.output_model_path, 'model{}.pkl'.format(self.name)))
 
     @property
+    def model_input(self):                         # settings.py:127-131
+        return (os.path.join(self.input_previous_model_path, 'model{}.json'.format(self.pretrain_name)),
+                os.path.join(self.input_previous_model_path, 'model{}.pkl'.format(self.pretrain_name)))
+
+    @property
+    def encoder_input(self):                       # settings.py:139-143 (--enable-pretrain-encoder)
+        return (os.path.join(self.input_previous_model_path, 'encoder{}.json'.format(self.pretrain_name)),
+                os.path.join(self.input_previous_model_path, 'encoder{}.pkl'.format(self.pretrain_name)))
+
+    @property
+    def encoder_output(self):                      # settings.py:145-149
+        return (os.path.join(self.output_model_path, 'encoder{}.json'.format(self.name)),
+                os.path.join(self.output_model_path, 'encoder{}.pkl'.format(self.name)))
+
+    @property
     def log_output(self):
         return os.path.join(self.log_dir, 'log{}.txt'.format(self.name))
 

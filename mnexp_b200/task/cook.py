@@ -130,6 +130,17 @@ class Cook:
     def test(self):
         return [self.test_data[x] for x in FEATURES], [self.test_data[x] for x in ['user', 'impr', 'idx_mask', 'label']]
 
+    def aggregate_test(self, batch_size=None):
+        """The evaluation tail of `main.py cook` (main.py:216-297): score the test set with test_model and average the
+        ranking metrics per impression, per user, and per in-vocabulary / out-of-vocabulary user.  Returns the four
+        Result objects of mnexp_b200.evaluation.aggregate and logs them like the reference."""
+        from .. import evaluation, utils
+        feature, (users, imprs, mask, y_true) = self.test()
+        y_pred = self.test_model.predict(feature, batch_size=batch_size or self.config.batch_size).reshape(-1)
+        res = evaluation.aggregate(users, imprs, np.asarray(mask).reshape(-1), y_true, y_pred)
+        evaluation.log_aggregate(res, utils.logging_evaluation)
+        return res
+
     def build_model(self, epoch):
         if epoch == 0:
             self._build_model()

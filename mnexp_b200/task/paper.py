@@ -116,11 +116,31 @@ class Seq2VecPaper(Seq2Vec):
             return np.load(self.config.title_embedding_input + '.npy')
         return utils.load_textual_embedding(self.config.title_embedding_input, self.config.textual_embedding_dim)
 
+    def _pretrained_encoder(self):
+        """--enable-pretrain-encoder (task/paper.py:103-107): the title encoder's weights come from a json + pkl pair
+        (utils.load_model: written by save_model here, or by the reference for a Keras doc encoder) and stay frozen
+        unless --pretrain-encoder-trainable."""
+        loaded = utils.load_model(self.config.encoder_input)
+        enc = keras_like.DocEncoderModel(self._core)
+        P = loaded.params()
+        missing = [k for k in enc.ENC_ORDER if k in self._core.params and k not in P]
+        if missing:
+            raise ValueError('pre-trained encoder file lacks %s' % missing)
+        for k in enc.ENC_ORDER:
+            if k in self._core.params:
+                if tuple(P[k].shape) != tuple(np.asarray(self._core.params[k]).shape):
+                    raise ValueError('pre-trained encoder: %s has shape %s, the configured model needs %s'
+                                     % (k, P[k].shape, np.asarray(self._core.params[k]).shape))
+                self._core.params[k] = P[k]
+        if not self.config.pretrain_encoder_trainable:
+            enc.trainable = False
+        return enc
+
     def get_doc_encoder(self):
-        if self.config.enable_pretrain_encoder:
-            raise NotImplementedError('enable_pretrain_encoder: loading a Keras json+pkl encoder is out of scope')
         if self.config.news_encoder != 'cnnatt':
             raise Exception('Unsupport doc model')           # task/paper.py:130,195
+        if self.config.enable_pretrain_encoder:
+            return self._pretrained_encoder()
         return keras_like.DocEncoderModel(self._core)
 
     def _archs(self):
@@ -245,10 +265,10 @@ class Seq2VecPaperSoftmax(Seq2VecPaper):
         return self._get_doc_encoder(self.config.title_shape)
 
     def _get_doc_encoder(self, input_shape=None):
-        if self.config.enable_pretrain_encoder:
-            raise NotImplementedError('enable_pretrain_encoder: loading a Keras json+pkl encoder is out of scope')
         if self.config.news_encoder != 'cnnatt':
             raise Exception('Unsupport doc model')           # task/paper.py:130,195 (non-LSTUR encoders are out of scope)
+        if self.config.enable_pretrain_encoder:
+            return self._pretrained_encoder()
         return keras_like.DocEncoderModel(self._core)
 
     def _engine_arch(self):

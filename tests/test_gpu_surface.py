@@ -525,3 +525,49 @@ def test_batch_size_change_keeps_optimizer_state(lib):
     assert e8 is not e4 and e8.B == 8 and e8.t == 2 and e8.step_seed == 2
     # moments carried, not zeroed: v_new = 0.999 v_old + 0.001 g^2 >= 0.999 v_old element-wise
     assert float(v_before.max()) > 0 and bool((e8.adam_v >= 0.998 * v_before).all())
+
+
+def test_test_set_aggregation_on_device_metrics(lib):
+    """main.py:224-297 aggregation with the per-impression metrics from the device kernel == with sklearn / numpy"""
+    from mnexp_b200 import evaluation
+    from test_host_logic import _host_metrics, _synthetic_scored_test_set
+    users, imprs, mask, yt, yp = _synthetic_scored_test_set(3)
+    a = evaluation.aggregate(users, imprs, mask, yt, yp)
+    b = evaluation.aggregate(users, imprs, mask, yt, yp, metric_fn=_host_metrics)
+    for key in ('user', 'impr', 'iv_user', 'oov_user'):
+        for f in ('auc', 'mrr', 'ndcgv', 'ndcgx', 'pos', 'size'):
+            assert abs(getattr(a[key], f) - getattr(b[key], f)) < 1e-5, (key, f)
+
+
+def test_enable_pretrain_encoder_round_trip_and_freeze(lib):
+    """--enable-pretrain-encoder (task/paper.py:103-107): encoder{name}.json/.pkl written from one model's doc_encoder is
+    loaded into a new model; without --pretrain-encoder-trainable its weights stay put while the rest trains."""
+    from mnexp_b200 import utils as mutils
+    sh, h = _handler('igru', 'Seq2VecPaperSoftmaxId')
+    m1 = h.build_model(0)
+    x, y = next(h.train)
+    for _ in range(3):
+        m1.train_on_batch(x, y)
+    enc = m1.get_layer('doc_encoder')
+    d = h.config.input_training_data_path
+    h.config.output_model_path = d
+    mutils.save_model(h.config.encoder_output, enc)
+    sh2, h2 = _handler('igru', 'Seq2VecPaperSoftmaxId', enable_pretrain_encoder=True, input_previous_model_path=d)
+    m2 = h2.build_model(0)
+    w1, w2 = enc.get_weights(), m2.get_layer('doc_encoder').get_weights()
+    assert all(np.array_equal(a, b) for a, b in zip(w1, w2))
+    dv1 = enc.predict(x[1][0])
+    assert rel(m2.get_layer('doc_encoder').predict(x[1][0]), dv1) < 1e-6
+    gru_before = h2._core.params['gru_wx'].copy()
+    for _ in range(3):
+        m2.train_on_batch(x, y)
+    w3 = m2.get_layer('doc_encoder').get_weights()
+    assert all(np.array_equal(a, b) for a, b in zip(w2, w3))                       # frozen encoder
+    assert np.abs(h2._core.train_engine.get_weights_dict()['gru_wx'] - gru_before).max() > 1e-4   # the rest trains
+    # --pretrain-encoder-trainable: the encoder moves too
+    sh3, h3 = _handler('igru', 'Seq2VecPaperSoftmaxId', enable_pretrain_encoder=True, pretrain_encoder_trainable=True,
+                       input_previous_model_path=d)
+    m3 = h3.build_model(0)
+    for _ in range(3):
+        m3.train_on_batch(x, y)
+    assert np.abs(m3.get_layer('doc_encoder').get_weights()[1] - w1[1]).max() > 1e-4

@@ -3,6 +3,7 @@ import os
 import tempfile
 
 import numpy as np
+import pytest
 
 from mnexp_b200 import document, rng, settings, synth, task, utils
 
@@ -153,3 +154,90 @@ def test_days_window_and_sigmoid_generators():
     assert [a.shape for a in x] == [(4,), (4, sh.W, sh.L), (4, sh.L)] and y.shape == (4,)
     nd = mk(task='Seq2VecPaperDot', arch='gru')
     assert len(next(nd.train_gen())) == 3
+
+
+def _synthetic_scored_test_set(seed=0):
+    g = np.random.default_rng(seed)
+    users, imprs, mask, yt, yp = [], [], [], [], []
+    for u in range(12):
+        mk = int(g.integers(0, 2))
+        for im in range(int(g.integers(1, 4))):
+            n = int(g.integers(3, 9))
+            lab = np.zeros(n); lab[g.integers(0, n)] = 1
+            users += [u] * n; imprs += [im] * n; mask += [mk] * n; yt += list(lab); yp += list(g.random(n))
+    return tuple(map(np.asarray, (users, imprs, mask, yt, yp)))
+
+
+def _host_metrics(S, Y):
+    from sklearn.metrics import roc_auc_score
+    from mnexp_b200 import utils
+    return np.array([[roc_auc_score(y, s), utils.ndcg_score(y, s, 10), utils.ndcg_score(y, s, 5), utils.mrr_score(y, s)]
+                     for s, y in zip(S, Y)])
+
+
+def test_per_user_in_vocab_oov_aggregation_mirrors_main_loop():
+    """mnexp_b200.evaluation.aggregate == a replay of the state machine of main.py:250-287 (an impression closes on the
+    first row of the next one, the last impression of the file is never closed; users are filed by mask at that row)."""
+    from sklearn.metrics import roc_auc_score
+    from mnexp_b200 import evaluation, utils
+    users, imprs, mask, yt, yp = _synthetic_scored_test_set()
+    res = evaluation.aggregate(users, imprs, mask, yt, yp, metric_fn=_host_metrics)
+    pu, pi, index, ii = users[0], imprs[0], 0, 0
+    IR, UR, IV, OOV = [], [], [], []
+    for i in range(1, len(yp)):
+        u, im = users[i], imprs[i]
+        if u != pu or im != pi:
+            y, s = yt[index:i], yp[index:i]
+            IR.append(dict(auc=roc_auc_score(y, s), mrr=utils.mrr_score(y, s), ndcgv=utils.ndcg_score(y, s, 5),
+                           ndcgx=utils.ndcg_score(y, s, 10), pos=y.sum(), size=i - index, idx=len(IR)))
+            index, pi = i, im
+        if u != pu:
+            avg = {k: np.mean([r[k] for r in IR[ii:]]) for k in IR[0]}
+            UR.append(avg)
+            (IV if mask[index] == 1 else OOV).append(avg)
+            ii, pu = len(IR), u
+    for key, lst in (('impr', IR), ('user', UR), ('iv_user', IV), ('oov_user', OOV)):
+        for f in ('auc', 'mrr', 'ndcgv', 'ndcgx', 'pos', 'size', 'idx'):
+            assert abs(getattr(res[key], f) - np.mean([r[f] for r in lst])) < 1e-9, (key, f)
+    assert res['user'].info['num'] == res['user'].idx * 2 + 1 and set(res['impr'].result) == {'auc', 'ndcgx', 'ndcgv', 'mrr'}
+
+
+def test_pretrained_encoder_files_keras_and_own_format(tmp_path):
+    """utils.load_model reads (a) the json + pkl pair the REFERENCE writes for a doc encoder — json.dump of Keras'
+    to_json() string, pickle of get_weights() (utils.py:66-79) — mapping the arrays by the layer classes of the json, and
+    (b) the pair written by save_model here; unexpected graphs raise instead of guessing."""
+    import json
+    import pickle
+    from mnexp_b200 import utils
+    g = np.random.default_rng(0)
+    V, E, F, U = 20, 12, 16, 8
+    W = [g.standard_normal((V, E)), g.standard_normal((3, E, F)), g.standard_normal(F), g.standard_normal((F, 1)), g.standard_normal(1),
+         g.standard_normal((F, U)), g.standard_normal(U)]
+    W = [a.astype(np.float32) for a in W]
+    layer = lambda cls, name: dict(class_name=cls, name=name, config={})
+    keras_json = dict(class_name='Model', keras_version='2.2.4', backend='tensorflow', config=dict(name='doc_encoder', layers=[
+        layer('InputLayer', 'input_1'), layer('Embedding', 'embedding_1'), layer('Dropout', 'dropout_1'), layer('Conv1D', 'conv1d_1'),
+        layer('Lambda', 'lambda_1'), layer('Masking', 'masking_1'), layer('Dropout', 'dropout_2'),
+        layer('SimpleAttentionMaskSupport', 'simple_attention_mask_support_1'), layer('Dense', 'dense_1')]))
+    jp, pp = str(tmp_path / 'encoder.json'), str(tmp_path / 'encoder.pkl')
+    with open(jp, 'w') as f:
+        json.dump(json.dumps(keras_json), f)             # the reference dumps the json STRING (utils.py:75-77)
+    with open(pp, 'wb') as f:
+        pickle.dump(W, f, protocol=pickle.HIGHEST_PROTOCOL)
+    m = utils.load_model((jp, pp))
+    assert m.config['keras'] and m.config['weight_names'] == ['word_emb', 'conv_w', 'conv_b', 'att_w', 'att_b', 'dense_w', 'dense_b']
+    P = m.params()
+    assert P['att_w'].shape == (F,) and np.array_equal(P['att_w'], W[3][:, 0]) and np.array_equal(P['conv_w'], W[1])
+    # a recurrent layer in the json is not a cnnatt doc encoder: refuse
+    bad = dict(keras_json, config=dict(name='x', layers=keras_json['config']['layers'] + [layer('GRU', 'gru_1')]))
+    with open(jp, 'w') as f:
+        json.dump(json.dumps(bad), f)
+    with pytest.raises(ValueError):
+        utils.load_model((jp, pp))
+    # count mismatch
+    with open(jp, 'w') as f:
+        json.dump(json.dumps(keras_json), f)
+    with open(pp, 'wb') as f:
+        pickle.dump(W[:-1], f)
+    with pytest.raises(ValueError):
+        utils.load_model((jp, pp))
