@@ -51,6 +51,15 @@ typedef struct CUstream_st* cudaStream_t;
 #define LSTUR_ARCH_INI_CAT 8   /* Seq2VecPaperId 'iigru': [GRU(initial_state=user_emb) ‖ user_emb2], task/paper.py:338-343 */
 #define LSTUR_ARCH_INI_CON 7   /* paper 'iigru': Dense([GRU(initial_state=user_emb) ‖ user_emb2]), task/paper.py:614-619;
                                   the two tables are the column halves of one (n_users, Ue = G + U2) table */
+#define LSTUR_ARCH_AVG_CAT 9   /* cook 'iavg': [GlobalAveragePoolingMaskSupport(history) ‖ user_emb], task/cook.py:155-157 */
+#define LSTUR_ARCH_ATT 10      /* Seq2VecPaper 'att': SimpleAttentionMaskSupport(Masking(history)), task/paper.py:206-208 */
+#define LSTUR_ARCH_ATT_CAT 11  /* cook 'iatt': [SimpleAttentionMaskSupport(history) ‖ user_emb], task/cook.py:158-160 */
+#define LSTUR_ARCH_INI_ADD 12  /* cook 'inagru': GRU(initial_state=user_emb) + user_emb2, task/cook.py:177-183 (Ue = 2G) */
+#define LSTUR_ARCH_ATT_PAIR 13 /* cook 'atgru': SimpleAttentionMaskSupport over the two-step sequence [GRU ; user_emb],
+                                  task/cook.py:184-190 */
+#define LSTUR_ARCH_ALPHA 14    /* cook 'algru': models.AlphaAdd([GRU, user_emb]) = alpha h + (1 - alpha) u, task/cook.py:191-193,
+                                  models.py:540-554 (alpha constrained to [0, 1] after every update) */
+#define LSTUR_ARCH_LSTM_CAT 15 /* cook 'ilstm': [keras.layers.LSTM(history) ‖ user_emb], task/cook.py:161-163 */
 
 #define LSTUR_SCORE_DOT 0      /* task/paper.py:446-447 */
 #define LSTUR_SCORE_DNN 1      /* Dense(Hs, relu)([u ‖ d]) -> Dense(1), task/paper.py:448-451 */
@@ -275,6 +284,54 @@ int lstur_masked_mean_fwd(int B, int W, int D, const float* H, const float* mask
 int lstur_masked_mean_bwd(int B, int W, int D, const float* dout, long long ldd, const float* mask, const float* keep,
                           float* dH, cudaStream_t stream);
 
+/* models.SimpleAttentionMaskSupport over a sequence of W vectors per row (models.py:474-489; history pooling of
+ * Seq2VecPaper 'att' task/paper.py:206-208 and cook 'iatt' / 'atgru' task/cook.py:158-160,184-190):
+ * a = tanh(H.att_w + att_b); e = exp(a) * mask; w = e / (sum e + 1e-7); out = sum_t w_t H_t.  H (B,W,D) contiguous; a_out /
+ * w_out (B,W) saved for backward (may be NULL).  Backward: dH = keep * (w dout + d pre att_w) (keep NULL = 1) and per-row
+ * partials (B, D+1) = [d att_w | d att_b] to be column-summed (lstur_colsum) in a fixed order. */
+int lstur_seq_attn_fwd(int B, int W, int D, const float* H, const float* mask, const float* att_w, const float* att_b,
+                       float* out, long long ldo, float* a_out, float* w_out, cudaStream_t stream);
+int lstur_seq_attn_bwd(int B, int W, int D, const float* H, const float* att_w, const float* a_in, const float* w_in,
+                       const float* dout, long long ldd, const float* keep, float* dH, float* partial,
+                       cudaStream_t stream);
+/* key[b] = first unmasked step of row b (W if none).  Sorting the batch rows by this key (lstur_sort_unique_i32 ->
+ * sorted_pos) gives the `row_order` of the recurrence kernels: rows of similar history length share a 32-row tile, and
+ * a tile skips every step at which all of its rows are masked (left-padded histories, task/seq2vec.py:23,46-49). */
+int lstur_first_live_step(int B, int W, const float* mask, int* key, cudaStream_t stream);
+/* keras Masking(): mask[r] = any_k(x[r,k] != 0) */
+int lstur_rows_nonzero(long long rows, int D, const float* x, long long ld, float* mask, cudaStream_t stream);
+/* y[r,:] = ay * y[r,:] + ax * x[r,:] on strided rows (keras.layers.add of cook 'inagru', task/cook.py:183) */
+int lstur_add_rows(int rows, int D, float ax, const float* x, long long ldx, float ay, float* y, long long ldy,
+                   cudaStream_t stream);
+/* models.AlphaAdd (models.py:540-554): out = alpha a + (1 - alpha) b with a learned scalar alpha (device pointer);
+ * backward writes d a, d b and row_partial[r] = sum_k dout (a - b) (column-sum it for d alpha). */
+int lstur_alpha_add_fwd(int rows, int D, const float* alpha, const float* a, long long lda, const float* b, long long ldb,
+                        float* out, long long ldo, cudaStream_t stream);
+int lstur_alpha_add_bwd(int rows, int D, const float* alpha, const float* a, long long lda, const float* b, long long ldb,
+                        const float* dout, long long ldd, float* da, long long ldda, float* db, long long lddb,
+                        float* row_partial, cudaStream_t stream);
+/* softmax + keras.losses.categorical_crossentropy against integer class labels (= one-hot targets): the auxiliary
+ * vertical classifier of Seq2VecPaperSoftmaxDaysIdVertSup (task/paper.py:899-902, 973-990) and the vertical model of
+ * ...VertAlt (:1128-1136).  logits (n, n_classes); probs / loss_rows / loss_mean / dlogits optional;
+ * dlogits = scale * dL_row/dlogits (zero through a saturated clip, like Keras). */
+int lstur_softmax_ce_labels(long long n, int n_classes, const float* logits, const int* label, float* probs,
+                            float* loss_rows, float* loss_mean, float* dlogits, float scale, cudaStream_t stream);
+/* g[i] = 0 where y[i] <= 0: backward of a relu Dense given its output y */
+int lstur_relu_bwd(long long n, const float* y, float* g, cudaStream_t stream);
+/* keras.constraints.MinMaxNorm(lo, hi) on a vector of independent scalars (AlphaAdd.alpha, models.py:545), applied after
+ * the optimizer update: w <- w * clip(|w|, lo, hi) / (1e-7 + |w|). */
+int lstur_minmaxnorm(int n, float lo, float hi, float* w, cudaStream_t stream);
+/* keras.layers.LSTM(G)(Masking()(history)) of cook 'ilstm' (task/cook.py:161-163): recurrent part.  XW (B,W,4G) = H.Wx + b
+ * precomputed, gate order i,f,c,o; masked steps carry (h, c); output = last h.  SI..STC (B,W,G) saved gates / previous
+ * cell / previous state / tanh(c') (all NULL for inference).  Backward yields dA (B,W,4G), zero on masked steps; WhT is
+ * Wh transposed (4G, G). */
+int lstur_lstm_fwd(int B, int W, int G, const float* XW, const float* gm, const float* Wh, int rec_act, float* hT,
+                   long long ldo, float* SI, float* SF, float* SG, float* SO, float* SCP, float* SHP, float* STC,
+                   cudaStream_t stream);
+int lstur_lstm_bwd(int B, int W, int G, const float* gm, const float* SI, const float* SF, const float* SG,
+                   const float* SO, const float* SCP, const float* STC, const float* WhT, int rec_act, const float* dhT,
+                   long long lddh, float* dA, cudaStream_t stream);
+
 /* Per-impression AUC / nDCG@10 / nDCG@5 / MRR (Seq2VecPaperSoftmax.callback, task/paper.py:497-524; utils.py:106-124;
  * sklearn roc_auc_score): offsets (n_impr+1) index scores / labels; out (n_impr, 4); ties ordered by descending index. */
 int lstur_ranking_metrics(int n_impr, const int* offsets, const float* scores, const float* labels, float* out,
@@ -343,6 +400,14 @@ typedef struct lstur_config {
   int bce_neg;           /* negative_samples of the weighted BCE (task/seq2vec.py:213-216)                   */
   float gain;            /* its positive-class gain                                                           */
   int trainable_word_emb; /* textual_embedding_trainable (task/paper.py:136, main.py:36): lstur_backward_w also yields d word_emb */
+  /* Seq2VecPaperSoftmaxDaysIdVertSup (task/paper.py:948-990): TimeDistributed vertical classifier Dense(aux_hidden, relu) ->
+   * Dense(aux_nv, softmax) over the W + C news vectors of every row, loss = CE + aux_gain * mean CE_vertical; 0 = off.
+   * Labels: the batch's hist_vert / cand_vert ids (or doc_vert[hist_doc / cand_doc]). */
+  int aux_nv, aux_hidden;
+  float aux_gain;
+  /* Seq2VecPaperSoftmaxDaysIdVertAlt (task/paper.py:1128-1136): Dense(cls_nv, softmax) on the doc_encoder output, trained by
+   * lstur_title_cls_forward / lstur_title_cls_backward on (title, vertical) batches; 0 = off */
+  int cls_nv;
 } lstur_config;
 
 typedef struct lstur_weights {
@@ -368,6 +433,9 @@ typedef struct lstur_batch {
   const int* hist_subvert; /* (B,W) */
   const int* cand_vert;    /* (B,C) */
   const int* cand_subvert; /* (B,C) */
+  /* two-table archs (cook 'inigru' / 'inagru', task/cook.py:169-183: each id embedding has its OWN Dropout(1 - id_keep)
+   * layer): multiplier of the second table's columns; NULL = user_scale applies to the whole row */
+  const float* user_scale2; /* (B) */
 } lstur_batch;
 
 typedef struct lstur_plan lstur_plan;
@@ -412,6 +480,15 @@ int lstur_event_elapsed_ms(void* start_event, void* stop_event, float* ms);
 
 int lstur_forward(const lstur_plan* plan, const lstur_weights* w, const lstur_batch* b, void* workspace,
                   int training, unsigned seed, cudaStream_t stream);
+/* Vertical model of Seq2VecPaperSoftmaxDaysIdVertAlt (task/paper.py:1128-1136; plan with cls_nv > 0):
+ * Dense(cls_nv, softmax)(doc_encoder(title)) + categorical cross-entropy on n <= B*(W+C) titles.  tokens (n,L), labels (n)
+ * device ints.  Workspace views afterwards: vc_probs (n, cls_nv), vc_loss_rows (n), vc_loss (1).  The backward fills the
+ * whole dense-gradient arena (zero outside vcls_w / vcls_b and the title-encoder tensors) and word_grad when the word table
+ * trains; grad_scale = 1 / (global number of titles). */
+int lstur_title_cls_forward(const lstur_plan* plan, const lstur_weights* w, void* workspace, int n, const int* tokens,
+                            const int* labels, int training, unsigned seed, cudaStream_t stream);
+int lstur_title_cls_backward(const lstur_plan* plan, const lstur_weights* w, void* workspace, float* dgrad,
+                             float* word_grad, float grad_scale, cudaStream_t stream);
 /* dense_grad (dense_count floats) is overwritten.  User-embedding gradient is left as unique rows in the
  * workspace (views user_rows / d_user_rows / n_user_rows).  grad_scale multiplies d(loss): 1/global_batch. */
 int lstur_backward(const lstur_plan* plan, const lstur_weights* w, const lstur_batch* b, void* workspace,

@@ -25,7 +25,9 @@ class lstur_config(ctypes.Structure):
                  'arch', 'score_model', 'rec_act', 'precision', 'V', 'n_users', 'n_docs')] + \
                [('dropout', ctypes.c_float), ('save_for_backward', ctypes.c_int), ('n_vert', ctypes.c_int),
                 ('n_subvert', ctypes.c_int), ('Hs', ctypes.c_int), ('loss_model', ctypes.c_int),
-                ('bce_neg', ctypes.c_int), ('gain', ctypes.c_float), ('trainable_word_emb', ctypes.c_int)]
+                ('bce_neg', ctypes.c_int), ('gain', ctypes.c_float), ('trainable_word_emb', ctypes.c_int),
+                ('aux_nv', ctypes.c_int), ('aux_hidden', ctypes.c_int), ('aux_gain', ctypes.c_float),
+                ('cls_nv', ctypes.c_int)]
 
 
 class lstur_weights(ctypes.Structure):
@@ -35,7 +37,7 @@ class lstur_weights(ctypes.Structure):
 class lstur_batch(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in
                 ('user', 'hist_doc', 'cand_doc', 'hist_tok', 'cand_tok', 'label', 'user_scale', 'hist_vert',
-                 'hist_subvert', 'cand_vert', 'cand_subvert')]
+                 'hist_subvert', 'cand_vert', 'cand_subvert', 'user_scale2')]
 
 
 def parse_header(path=HEADER):

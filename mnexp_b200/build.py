@@ -30,9 +30,14 @@ def build(force=False, verbose=False):
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     objs = []
     procs = []
+    hdrs = glob.glob(os.path.join(CSRC, '*.cuh')) + glob.glob(os.path.join(CSRC, '*.h')) + \
+        glob.glob(os.path.join(HERE, '..', 'include', '*.h'))
+    hdr_t = max(os.path.getmtime(h) for h in hdrs)
     for src in sources():
         obj = os.path.join(HERE, 'lib', os.path.basename(src)[:-3] + '.o')
         objs.append(obj)
+        if not force and not verbose and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
+            continue                     # object newer than its source and every header: keep it
         cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, pr in procs:

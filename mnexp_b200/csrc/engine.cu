@@ -94,6 +94,20 @@ void track_gemm(lstur_plan* p, int M, int N, int K) {
 }
 typedef int (*gemm_fn)(int, int, int, int, int, const float*, long long, const float*, long long, float*, long long,
                        const float*, int, void*, size_t, cudaStream_t);
+// user-encoder architecture classes
+inline bool arch_has_gru(int a) {
+  return a == LSTUR_ARCH_INI || a == LSTUR_ARCH_CON_DENSE || a == LSTUR_ARCH_CON_CAT || a == LSTUR_ARCH_NOID ||
+         a == LSTUR_ARCH_ADD || a == LSTUR_ARCH_INI_CAT || a == LSTUR_ARCH_INI_CON || a == LSTUR_ARCH_INI_ADD ||
+         a == LSTUR_ARCH_ATT_PAIR || a == LSTUR_ARCH_ALPHA;
+}
+inline bool arch_has_lstm(int a) { return a == LSTUR_ARCH_LSTM_CAT; }
+inline bool arch_has_user(int a) { return a != LSTUR_ARCH_NOID && a != LSTUR_ARCH_AVG && a != LSTUR_ARCH_ATT; }
+inline bool arch_hist_avg(int a) { return a == LSTUR_ARCH_AVG || a == LSTUR_ARCH_AVG_CAT; }
+inline bool arch_hist_att(int a) { return a == LSTUR_ARCH_ATT || a == LSTUR_ARCH_ATT_CAT; }
+// width of the user-embedding part that joins a concat / add ('iigru', 'inigru', 'inagru': the second table = columns G..)
+inline int arch_uc(const lstur_config& c) {
+  return (c.arch == LSTUR_ARCH_INI_CON || c.arch == LSTUR_ARCH_INI_CAT || c.arch == LSTUR_ARCH_INI_ADD) ? c.Ue - c.G : c.Ue;
+}
 inline gemm_fn pick_gemm(const lstur_plan* p) {
   return (p->c.precision == LSTUR_PREC_BF16_TC || p->c.precision == LSTUR_PREC_FP16_TC) ? lstur_gemm_tc : lstur_gemm_f32;
 }
@@ -110,30 +124,36 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
     set_error("lstur_plan_create: score_model %d not implemented (NotImplementedError, task/paper.py:457)", c.score_model);
     return LSTUR_ERR_UNSUPPORTED;
   }
-  if (c.arch < LSTUR_ARCH_INI || c.arch > LSTUR_ARCH_INI_CAT) {
+  if (c.arch < LSTUR_ARCH_INI || c.arch > LSTUR_ARCH_LSTM_CAT) {
     set_error("lstur_plan_create: Unsupport user model (task/paper.py:630)");
     return LSTUR_ERR_UNSUPPORTED;
   }
   LSTUR_REQUIRE(c.dv >= 0 && c.ds >= 0 && (c.dv == 0 || c.n_vert > 0) && (c.ds == 0 || c.n_subvert > 0), "lstur_plan_create");
   const int Dd = c.use_dense ? c.Dd : c.F;
   const int D = Dd + c.dv + c.ds;
-  const bool has_gru = c.arch != LSTUR_ARCH_VO && c.arch != LSTUR_ARCH_AVG;
-  const bool has_user = c.arch != LSTUR_ARCH_NOID && c.arch != LSTUR_ARCH_AVG;
+  const bool has_gru = arch_has_gru(c.arch), has_lstm = arch_has_lstm(c.arch), has_rnn = has_gru || has_lstm;
+  const bool has_user = arch_has_user(c.arch);
+  const int NG = has_lstm ? 4 : 3;   // gates of the recurrent layer
   const bool dot = c.score_model == LSTUR_SCORE_DOT, dnn = c.score_model == LSTUR_SCORE_DNN, ddot = !dot && !dnn;
   LSTUR_REQUIRE(dot || c.Hs > 0, "lstur_plan_create('dnn' / 'ddot' scorers need Hs)");
   const bool bce = c.loss_model == LSTUR_LOSS_WEIGHTED_BCE;
   LSTUR_REQUIRE(c.loss_model == LSTUR_LOSS_SOFTMAX_CE || bce, "lstur_plan_create(loss_model)");
   LSTUR_REQUIRE(!bce || (c.C == 1 && c.bce_neg >= 1 && c.gain > 0.f), "lstur_plan_create(weighted BCE: C == 1, bce_neg >= 1, gain > 0)");
-  LSTUR_REQUIRE(!has_gru || (c.G > 0 && c.G % 4 == 0 && c.G <= 1024), "lstur_plan_create");
+  LSTUR_REQUIRE(!has_rnn || (c.G > 0 && c.G % 4 == 0 && c.G <= 1024), "lstur_plan_create");
   LSTUR_REQUIRE(!has_user || (c.Ue > 0 && c.n_users > 0), "lstur_plan_create");
   // user-vector dim implied by the architecture
   int U = c.arch == LSTUR_ARCH_INI ? c.G : (c.arch == LSTUR_ARCH_CON_DENSE || c.arch == LSTUR_ARCH_INI_CON) ? c.U
           : c.arch == LSTUR_ARCH_CON_CAT ? c.G + c.Ue : c.arch == LSTUR_ARCH_INI_CAT ? c.Ue
-          : c.arch == LSTUR_ARCH_NOID ? c.G : c.arch == LSTUR_ARCH_ADD ? c.G : c.arch == LSTUR_ARCH_AVG ? D : c.Ue;
+          : c.arch == LSTUR_ARCH_NOID ? c.G : c.arch == LSTUR_ARCH_ADD ? c.G : c.arch == LSTUR_ARCH_AVG ? D
+          : c.arch == LSTUR_ARCH_AVG_CAT ? D + c.Ue : c.arch == LSTUR_ARCH_ATT ? D : c.arch == LSTUR_ARCH_ATT_CAT ? D + c.Ue
+          : (c.arch == LSTUR_ARCH_INI_ADD || c.arch == LSTUR_ARCH_ATT_PAIR || c.arch == LSTUR_ARCH_ALPHA) ? c.G
+          : c.arch == LSTUR_ARCH_LSTM_CAT ? c.G + c.Ue : c.Ue;
   LSTUR_REQUIRE(U == c.U, "lstur_plan_create(U inconsistent with arch)");
   LSTUR_REQUIRE(c.arch != LSTUR_ARCH_INI || c.Ue == c.G, "lstur_plan_create(ini needs Ue == G)");
   LSTUR_REQUIRE(c.arch != LSTUR_ARCH_ADD || c.Ue == c.G, "lstur_plan_create(add needs Ue == G)");
   LSTUR_REQUIRE((c.arch != LSTUR_ARCH_INI_CON && c.arch != LSTUR_ARCH_INI_CAT) || c.Ue > c.G, "lstur_plan_create(ini+con needs Ue > G)");
+  LSTUR_REQUIRE(c.arch != LSTUR_ARCH_INI_ADD || c.Ue == 2 * c.G, "lstur_plan_create('inagru' needs Ue == 2G)");
+  LSTUR_REQUIRE((c.arch != LSTUR_ARCH_ATT_PAIR && c.arch != LSTUR_ARCH_ALPHA) || c.Ue == c.G, "lstur_plan_create('atgru' / 'algru' need Ue == G)");
   LSTUR_REQUIRE(!dot || U == D, "lstur_plan_create('dot' scorer needs user dim == doc dim)");
   if ((c.precision == LSTUR_PREC_BF16_TC || c.precision == LSTUR_PREC_FP16_TC) && !lstur_tc_supported(c.L, c.E, c.F, c.KS)) {
     set_error("lstur_plan_create: shape (L=%d,E=%d,F=%d,KS=%d) not supported by the tensor-core conv kernel", c.L, c.E, c.F, c.KS);
@@ -171,8 +191,20 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
     add_dense(p, "gru_wh", (long long)G * 3 * G);
     add_dense(p, "gru_b", 3 * G);
   }
-  // width of the user-embedding part that joins the concat ('iigru': the second table = columns G.. of the row)
-  const int Uc = (c.arch == LSTUR_ARCH_INI_CON || c.arch == LSTUR_ARCH_INI_CAT) ? c.Ue - G : c.Ue;
+  if (has_lstm) {
+    add_dense(p, "lstm_wx", (long long)D * 4 * G);
+    add_dense(p, "lstm_wh", (long long)G * 4 * G);
+    add_dense(p, "lstm_b", 4 * G);
+  }
+  // SimpleAttentionMaskSupport over the history (width D) or over [GRU ; id vector] (width G)
+  const int Da = arch_hist_att(c.arch) ? D : c.arch == LSTUR_ARCH_ATT_PAIR ? G : 0;
+  const int Wa = arch_hist_att(c.arch) ? c.W : 2;
+  if (Da) {
+    add_dense(p, "uatt_w", Da);
+    add_dense(p, "uatt_b", 1);
+  }
+  if (c.arch == LSTUR_ARCH_ALPHA) add_dense(p, "alpha", 1);
+  const int Uc = arch_uc(c);
   const bool con_dense = c.arch == LSTUR_ARCH_CON_DENSE || c.arch == LSTUR_ARCH_INI_CON;
   if (con_dense) {
     add_dense(p, "con_w", (long long)(G + Uc) * c.U);
@@ -188,6 +220,17 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
     add_dense(p, "su_b", c.Hs);
     add_dense(p, "sd_w", (long long)D * c.Hs);
     add_dense(p, "sd_b", c.Hs);
+  }
+  LSTUR_REQUIRE(c.aux_nv >= 0 && (c.aux_nv == 0 || c.aux_hidden > 0) && c.cls_nv >= 0, "lstur_plan_create(aux_nv / cls_nv)");
+  if (c.aux_nv) {   // vertical classifier of ...VertSup (task/paper.py:948-952)
+    add_dense(p, "vs_w1", (long long)D * c.aux_hidden);
+    add_dense(p, "vs_b1", c.aux_hidden);
+    add_dense(p, "vs_w2", (long long)c.aux_hidden * c.aux_nv);
+    add_dense(p, "vs_b2", c.aux_nv);
+  }
+  if (c.cls_nv) {   // vertical model of ...VertAlt (task/paper.py:1128-1136)
+    add_dense(p, "vcls_w", (long long)D * c.cls_nv);
+    add_dense(p, "vcls_b", c.cls_nv);
   }
   p->dense_count = (p->dense_count + 3) & ~3LL;
 
@@ -224,12 +267,39 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
   add_ws(p, "hist_mask", Nh);
   add_ws(p, "gru_mask", Nh);
   if (has_user) add_ws(p, "u0", B * c.Ue);
-  if (has_gru) {
-    add_ws(p, "XW", Nh * 3 * G);
+  if (has_rnn) {
+    add_ws(p, "XW", Nh * NG * G);
     add_ws(p, "hT", B * G);
-    if (bw) {
+    // batch rows sorted by history length (lstur_first_live_step) once the recurrence kernels' 4-CTA clusters of 32 rows
+    // outnumber the SMs: the kernel is a W-step dependency chain per tile, so with every tile resident its time is that of
+    // the longest history whatever the order (measured at B = 1024: 3.39 ms with the sort, 3.36 without); in a second wave
+    // short tiles pair up
+    if (has_gru && B > 1184 && B <= 16384) {
+      add_ws(p, "gru_key", B);
+      add_ws(p, "gru_order", B);
+      add_ws(p, "gru_sort_scratch", 3 * B + 2);
+    }
+    if (bw && has_gru) {
       for (const char* n : {"Z", "R", "HH", "HP", "RH"}) add_ws(p, n, Nh * G);
     }
+    if (bw && has_lstm) {
+      for (const char* n : {"LI", "LF", "LG", "LO", "LCP", "LHP", "LTC"}) add_ws(p, n, Nh * G);
+    }
+  }
+  if (Da) {
+    add_ws(p, "ua_a", B * Wa);
+    add_ws(p, "ua_w", B * Wa);
+    if (bw) add_ws(p, "ua_partial", B * (Da + 1));
+  }
+  if (c.arch == LSTUR_ARCH_ATT_PAIR) {
+    add_ws(p, "seq2", B * 2 * G);
+    add_ws(p, "mask2", B * 2);
+    if (bw) add_ws(p, "d_seq2", B * 2 * G);
+  }
+  if (c.arch == LSTUR_ARCH_ALPHA && bw) {
+    add_ws(p, "d_hT", B * G);
+    add_ws(p, "d_uh", B * c.Ue);
+    add_ws(p, "alpha_partial", B);
   }
   if (con_dense || c.arch == LSTUR_ARCH_CON_CAT || c.arch == LSTUR_ARCH_INI_CAT) add_ws(p, "cat", B * (G + Uc));
   add_ws(p, "user_vec", B * c.U);
@@ -244,6 +314,38 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
     add_ws(p, "sc_dh", (long long)p->Nc * c.Hs);
     track_gemm(p, (int)B, c.Hs, c.U);
     track_gemm(p, (int)p->Nc, c.Hs, D);
+  }
+  if (c.aux_nv) {
+    add_ws(p, "vs_label", N);
+    add_ws(p, "vs_hid", N * c.aux_hidden);
+    add_ws(p, "vs_logit", N * c.aux_nv);
+    add_ws(p, "vs_probs", N * c.aux_nv);
+    add_ws(p, "vs_loss_rows", N);
+    add_ws(p, "vs_loss", 1);
+    track_gemm(p, (int)N, c.aux_hidden, D);
+    track_gemm(p, (int)N, c.aux_nv, c.aux_hidden);
+    if (bw) {
+      add_ws(p, "vs_dlogit", N * c.aux_nv);
+      add_ws(p, "vs_dhid", N * c.aux_hidden);
+      add_ws(p, "vs_ddoc", N * D);
+      track_gemm(p, c.aux_hidden, c.aux_nv, (int)N);
+      track_gemm(p, (int)N, c.aux_hidden, c.aux_nv);
+      track_gemm(p, D, c.aux_hidden, (int)N);
+      track_gemm(p, (int)N, D, c.aux_hidden);
+    }
+  }
+  if (c.cls_nv) {
+    add_ws(p, "vc_label", N);
+    add_ws(p, "vc_logit", N * c.cls_nv);
+    add_ws(p, "vc_probs", N * c.cls_nv);
+    add_ws(p, "vc_loss_rows", N);
+    add_ws(p, "vc_loss", 1);
+    track_gemm(p, (int)N, c.cls_nv, D);
+    if (bw) {
+      add_ws(p, "vc_dlogit", N * c.cls_nv);
+      track_gemm(p, D, c.cls_nv, (int)N);
+      track_gemm(p, (int)N, D, c.cls_nv);
+    }
   }
   add_ws(p, "logits", B * c.C);
   add_ws(p, "probs", B * c.C);
@@ -273,10 +375,10 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
       add_ws(p, "wg_ws", (long long)(lstur_word_grad_workspace_bytes(N * c.L, c.V, E) / 4) + 4);
     }
     add_ws(p, "attn_partials", (long long)lstur_attn_bwd_grid((int)N) * (2 * F + 1));
-    if (has_gru) {
-      add_ws(p, "WhT", (long long)3 * G * G);
-      add_ws(p, "gru_db_partial", (long long)lstur_gru_tc_db_rows((int)B) * 3 * G);
-      add_ws(p, "dA", Nh * 3 * G);
+    if (has_rnn) {
+      add_ws(p, "WhT", (long long)NG * G * G);
+      if (has_gru) add_ws(p, "gru_db_partial", (long long)lstur_gru_tc_db_rows((int)B) * 3 * G);
+      add_ws(p, "dA", Nh * NG * G);
       add_ws(p, "dh0", B * G);
     }
     if (con_dense) add_ws(p, "d_cat", B * (G + Uc));
@@ -308,19 +410,22 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
     if (!tcp) track_gemm(p, c.KS * E, F, (int)(N * Lp));
     track_gemm(p, F, Dd, (int)N);
     track_gemm(p, (int)N, F, Dd);
-    if (has_gru) {
-      track_gemm(p, D, 3 * G, (int)Nh);
-      track_gemm(p, G, 2 * G, (int)Nh);
-      track_gemm(p, (int)Nh, D, 3 * G);
+    if (has_rnn) {
+      track_gemm(p, D, NG * G, (int)Nh);
+      track_gemm(p, G, has_lstm ? 4 * G : 2 * G, (int)Nh);
+      track_gemm(p, (int)Nh, D, NG * G);
     }
     if (con_dense) track_gemm(p, G + Uc, c.U, (int)B);
   }
-  if (has_gru) track_gemm(p, (int)Nh, 3 * G, D);
+  if (has_rnn) track_gemm(p, (int)Nh, NG * G, D);
   add_ws(p, "gemm_ws", (long long)(p->gemm_ws_bytes / 4) + 4);
   {
-    int cols = 3 * G > D ? 3 * G : D;
+    int cols = NG * G > D ? NG * G : D;
     if (c.U > cols) cols = c.U;
     if (c.Hs > cols) cols = c.Hs;
+    if (c.aux_hidden > cols) cols = c.aux_hidden;
+    if (c.aux_nv > cols) cols = c.aux_nv;
+    if (c.cls_nv > cols) cols = c.cls_nv;
     add_ws(p, "colsum_ws", (long long)1024 * cols);
   }
   p->ws_bytes = (p->ws_bytes + 255) & ~(size_t)255;
@@ -417,11 +522,16 @@ int user_and_score(const lstur_plan* p, const lstur_weights* w, const lstur_batc
   float* uvec = W<float>(p, ws, "user_vec");
   float* u0 = W<float>(p, ws, "u0");
   float* cat = W<float>(p, ws, "cat");
-  const bool has_gru = c.arch != LSTUR_ARCH_VO && c.arch != LSTUR_ARCH_AVG;
-  const bool has_user = c.arch != LSTUR_ARCH_NOID && c.arch != LSTUR_ARCH_AVG;
+  const bool has_gru = arch_has_gru(c.arch);
+  const bool has_user = arch_has_user(c.arch);
   if (has_user) {
     LSTUR_REQUIRE(w->user_emb != nullptr, "lstur_forward");
-    RC(lstur_row_gather(B, c.Ue, c.n_users, w->user_emb, b->user, b->user_scale, u0, c.Ue, st));
+    const bool two = b->user_scale2 != nullptr && arch_uc(c) != c.Ue;   // independent multipliers for the two tables
+    RC(lstur_row_gather(B, c.Ue, c.n_users, w->user_emb, b->user, two ? nullptr : b->user_scale, u0, c.Ue, st));
+    if (two) {
+      if (b->user_scale) RC(lstur_scale_rows(B, c.G, b->user_scale, u0, c.Ue, st));
+      RC(lstur_scale_rows(B, c.Ue - c.G, b->user_scale2, u0 + c.G, c.Ue, st));
+    }
   }
   // 5. GRU (k11-k12)
   if (has_gru) {
@@ -431,20 +541,35 @@ int user_and_score(const lstur_plan* p, const lstur_weights* w, const lstur_batc
     float* hT = W<float>(p, ws, "hT");
     float* hdst = hT;
     long long ldo = G;
-    const bool ini = c.arch == LSTUR_ARCH_INI || c.arch == LSTUR_ARCH_INI_CON || c.arch == LSTUR_ARCH_INI_CAT;
+    const bool ini = c.arch == LSTUR_ARCH_INI || c.arch == LSTUR_ARCH_INI_CON || c.arch == LSTUR_ARCH_INI_CAT ||
+                     c.arch == LSTUR_ARCH_INI_ADD;
     const bool con_dense = c.arch == LSTUR_ARCH_CON_DENSE || c.arch == LSTUR_ARCH_INI_CON;
-    const int Uc = (c.arch == LSTUR_ARCH_INI_CON || c.arch == LSTUR_ARCH_INI_CAT) ? c.Ue - G : c.Ue;
-    if (c.arch == LSTUR_ARCH_INI || c.arch == LSTUR_ARCH_NOID) hdst = uvec;
+    const int Uc = arch_uc(c);
+    if (c.arch == LSTUR_ARCH_INI || c.arch == LSTUR_ARCH_NOID || c.arch == LSTUR_ARCH_INI_ADD) hdst = uvec;
     if (cat) { hdst = cat; ldo = G + Uc; }
+    if (c.arch == LSTUR_ARCH_ATT_PAIR) { hdst = W<float>(p, ws, "seq2"); ldo = 2 * G; }
     // tensor-core precision modes run the recurrence on tcgen05 (gru_tc.cu) when its weights fit tensor memory
     const bool tc_gru = (c.precision == LSTUR_PREC_BF16_TC || c.precision == LSTUR_PREC_FP16_TC) &&
                         lstur_gru_tc_supported(B, c.W, G) && !getenv("LSTUR_GRU_TC_OFF");
+    // tiles of 32 batch rows skip the steps at which all their rows are masked: order the rows by their first live step
+    int* order = getenv("LSTUR_GRU_SORT_OFF") ? nullptr : W<int>(p, ws, "gru_order");
+    if (order) {
+      int* key = W<int>(p, ws, "gru_key");
+      int* scr = W<int>(p, ws, "gru_sort_scratch");
+      RC(lstur_first_live_step(B, c.W, W<float>(p, ws, "gru_mask"), key, st));
+      RC(lstur_sort_unique_i32(B, key, order, scr, scr + B, scr + 2 * B + 1, scr + 3 * B + 1, st));
+    }
     PROBE_BEGIN(p, LSTUR_PROBE_GRU_FWD, st);
     if (tc_gru) {
       RC(lstur_gru_fwd_tc(B, c.W, G, XW, W<float>(p, ws, "gru_mask"), ini ? u0 : nullptr, c.Ue,
                           DP(p, w->dense, "gru_wh"), c.rec_act, hdst, ldo, bw ? W<float>(p, ws, "Z") : nullptr,
                           bw ? W<float>(p, ws, "R") : nullptr, bw ? W<float>(p, ws, "HH") : nullptr,
-                          bw ? W<float>(p, ws, "HP") : nullptr, bw ? W<float>(p, ws, "RH") : nullptr, nullptr, st));
+                          bw ? W<float>(p, ws, "HP") : nullptr, bw ? W<float>(p, ws, "RH") : nullptr, order, st));
+    } else if (order && lstur_gru_cluster_supported(B, c.W, G)) {
+      RC(lstur_gru_fwd_cluster(B, c.W, G, XW, W<float>(p, ws, "gru_mask"), ini ? u0 : nullptr, c.Ue,
+                               DP(p, w->dense, "gru_wh"), c.rec_act, hdst, ldo, bw ? W<float>(p, ws, "Z") : nullptr,
+                               bw ? W<float>(p, ws, "R") : nullptr, bw ? W<float>(p, ws, "HH") : nullptr,
+                               bw ? W<float>(p, ws, "HP") : nullptr, bw ? W<float>(p, ws, "RH") : nullptr, order, st));
     } else {
       RC(lstur_gru_fwd(B, c.W, G, XW, W<float>(p, ws, "gru_mask"), ini ? u0 : nullptr, c.Ue,
                        DP(p, w->dense, "gru_wh"), c.rec_act, hdst, ldo, bw ? W<float>(p, ws, "Z") : nullptr,
@@ -464,9 +589,37 @@ int user_and_score(const lstur_plan* p, const lstur_weights* w, const lstur_batc
     } else if (c.arch == LSTUR_ARCH_ADD) {
       cudaMemcpyAsync(uvec, hT, (size_t)B * G * 4, cudaMemcpyDeviceToDevice, st);
       RC(lstur_axpby((long long)B * G, 1.f, u0, 1.f, uvec, st));
+    } else if (c.arch == LSTUR_ARCH_INI_ADD) {     // 'inagru': GRU(initial_state = table 1) + table 2 (task/cook.py:177-183)
+      RC(lstur_add_rows(B, G, 1.f, u0 + G, c.Ue, 1.f, uvec, c.U, st));
+    } else if (c.arch == LSTUR_ARCH_ATT_PAIR) {    // 'atgru': attention over the two "steps" [GRU output ; id vector]
+      float* seq2 = W<float>(p, ws, "seq2");
+      float* mask2 = W<float>(p, ws, "mask2");
+      cudaMemcpy2DAsync(seq2 + G, (size_t)2 * G * 4, u0, (size_t)c.Ue * 4, (size_t)G * 4, B, cudaMemcpyDeviceToDevice, st);
+      RC(lstur_rows_nonzero((long long)2 * B, G, seq2, G, mask2, st));
+      RC(lstur_seq_attn_fwd(B, 2, G, seq2, mask2, DP(p, w->dense, "uatt_w"), DP(p, w->dense, "uatt_b"), uvec, c.U,
+                            W<float>(p, ws, "ua_a"), W<float>(p, ws, "ua_w"), st));
+    } else if (c.arch == LSTUR_ARCH_ALPHA) {       // 'algru': models.AlphaAdd (models.py:540-554)
+      RC(lstur_alpha_add_fwd(B, G, DP(p, w->dense, "alpha"), hT, G, u0, c.Ue, uvec, c.U, st));
     }
-  } else if (c.arch == LSTUR_ARCH_AVG) {   // 'niavg': masked mean of the history vectors (models.py:422-441)
+  } else if (arch_has_lstm(c.arch)) {   // 'ilstm': [LSTM(history) ‖ id vector] (task/cook.py:161-163)
+    float* XW = W<float>(p, ws, "XW");
+    RC(GEMM(0, 0, Nh, 4 * G, D, docv, D, DP(p, w->dense, "lstm_wx"), 4 * G, XW, 4 * G, DP(p, w->dense, "lstm_b"),
+            LSTUR_GEMM_PRECISE, gws, gwsb, st));
+    RC(lstur_lstm_fwd(B, c.W, G, XW, W<float>(p, ws, "gru_mask"), DP(p, w->dense, "lstm_wh"), c.rec_act, uvec, c.U,
+                      bw ? W<float>(p, ws, "LI") : nullptr, bw ? W<float>(p, ws, "LF") : nullptr,
+                      bw ? W<float>(p, ws, "LG") : nullptr, bw ? W<float>(p, ws, "LO") : nullptr,
+                      bw ? W<float>(p, ws, "LCP") : nullptr, bw ? W<float>(p, ws, "LHP") : nullptr,
+                      bw ? W<float>(p, ws, "LTC") : nullptr, st));
+    cudaMemcpy2DAsync(uvec + G, (size_t)c.U * 4, u0, (size_t)c.Ue * 4, (size_t)c.Ue * 4, B, cudaMemcpyDeviceToDevice, st);
+  } else if (arch_hist_avg(c.arch)) {   // 'niavg' / cook 'iavg': masked mean of the history vectors (models.py:422-441)
     RC(lstur_masked_mean_fwd(B, c.W, D, docv, W<float>(p, ws, "gru_mask"), uvec, c.U, st));
+    if (c.arch == LSTUR_ARCH_AVG_CAT)
+      cudaMemcpy2DAsync(uvec + D, (size_t)c.U * 4, u0, (size_t)c.Ue * 4, (size_t)c.Ue * 4, B, cudaMemcpyDeviceToDevice, st);
+  } else if (arch_hist_att(c.arch)) {   // 'att' / cook 'iatt': attention pooling of the history (models.py:474-489)
+    RC(lstur_seq_attn_fwd(B, c.W, D, docv, W<float>(p, ws, "gru_mask"), DP(p, w->dense, "uatt_w"),
+                          DP(p, w->dense, "uatt_b"), uvec, c.U, W<float>(p, ws, "ua_a"), W<float>(p, ws, "ua_w"), st));
+    if (c.arch == LSTUR_ARCH_ATT_CAT)
+      cudaMemcpy2DAsync(uvec + D, (size_t)c.U * 4, u0, (size_t)c.Ue * 4, (size_t)c.Ue * 4, B, cudaMemcpyDeviceToDevice, st);
   } else {
     cudaMemcpyAsync(uvec, u0, (size_t)B * c.Ue * 4, cudaMemcpyDeviceToDevice, st);
   }
@@ -575,7 +728,40 @@ extern "C" int lstur_forward(const lstur_plan* p, const lstur_weights* w, const 
   // 3. history mask (k9)
   RC(lstur_hist_mask_apply(Nh, L, D, tok, W<float>(p, ws, "doc_vec"), D, W<float>(p, ws, "hist_mask"),
                            W<float>(p, ws, "gru_mask"), st));
-  return user_and_score(p, w, b, ws, st);
+  RC(user_and_score(p, w, b, ws, st));
+  // auxiliary vertical classifier over [history vectors (masked) ; candidate vectors] (task/paper.py:973-990); without
+  // labels (test_model, :992-997) the head is not part of the graph
+  const bool aux_labels = (b->hist_vert && b->cand_vert) || (b->hist_doc && b->cand_doc && w->doc_vert);
+  const_cast<lstur_plan*>(p)->last_aux = 0;
+  if (c.aux_nv && aux_labels) {
+    const gemm_fn GEMM = pick_gemm(p);
+    void* gws = W<void>(p, ws, "gemm_ws");
+    const size_t gwsb = p->gemm_ws_bytes;
+    int* lab = W<int>(p, ws, "vs_label");
+    if (b->hist_vert && b->cand_vert) {
+      cudaMemcpyAsync(lab, b->hist_vert, (size_t)Nh * 4, cudaMemcpyDeviceToDevice, st);
+      cudaMemcpyAsync(lab + Nh, b->cand_vert, (size_t)Nc * 4, cudaMemcpyDeviceToDevice, st);
+    } else {
+      RC(lstur_token_gather(Nh, 1, c.n_docs, w->doc_vert, b->hist_doc, lab, st));
+      RC(lstur_token_gather(Nc, 1, c.n_docs, w->doc_vert, b->cand_doc, lab + Nh, st));
+    }
+    float* docv = W<float>(p, ws, "doc_vec");
+    float* hid = W<float>(p, ws, "vs_hid");
+    float* lg = W<float>(p, ws, "vs_logit");
+    RC(GEMM(0, 0, N, c.aux_hidden, D, docv, D, DP(p, w->dense, "vs_w1"), c.aux_hidden, hid, c.aux_hidden,
+            DP(p, w->dense, "vs_b1"), LSTUR_GEMM_RELU | LSTUR_GEMM_PRECISE, gws, gwsb, st));
+    RC(GEMM(0, 0, N, c.aux_nv, c.aux_hidden, hid, c.aux_hidden, DP(p, w->dense, "vs_w2"), c.aux_nv, lg, c.aux_nv,
+            DP(p, w->dense, "vs_b2"), LSTUR_GEMM_PRECISE, gws, gwsb, st));
+    RC(lstur_softmax_ce_labels(N, c.aux_nv, lg, lab, W<float>(p, ws, "vs_probs"), W<float>(p, ws, "vs_loss_rows"),
+                               W<float>(p, ws, "vs_loss"), nullptr, 0.f, st));
+    const_cast<lstur_plan*>(p)->last_aux = 1;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("lstur_forward: %s", cudaGetErrorString(e));
+    return LSTUR_ERR_CUDA;
+  }
+  return LSTUR_OK;
 }
 
 // ---- decomposed inference (task/test_pipeline.py:37-211): doc vectors once, then users against the cached vectors
@@ -638,6 +824,170 @@ extern "C" int lstur_forward_docvecs(const lstur_plan* p, const lstur_weights* w
 }
 
 
+namespace {
+
+// News-encoder backward (k1-k7) over the first n title slots: d_doc_vec[0..n) -> dense gradients of the Dense / attention /
+// conv tensors and, with a trainable word table, d word_emb.
+int encoder_backward(const lstur_plan* p, const lstur_weights* w, void* ws, int n, float* dgrad, float* word_grad,
+                     float grad_scale, cudaStream_t st) {
+  const lstur_config& c = p->c;
+  const int Lp = p->Lp, D = p->D, L = c.L, E = c.E, F = c.F;
+  void* gws = W<void>(p, ws, "gemm_ws");
+  const size_t gwsb = p->gemm_ws_bytes;
+  const gemm_fn GEMM = pick_gemm(p);
+  float* cws = W<float>(p, ws, "colsum_ws");
+  const size_t cwsb = p->ws.at("colsum_ws").count * 4;
+  float* d_docv = W<float>(p, ws, "d_doc_vec");
+  float* d_pooled = W<float>(p, ws, "d_pooled");
+  float* pooled = W<float>(p, ws, "pooled");
+  const float* dpool = d_pooled;
+  long long lddp = F;
+  if (c.use_dense) {
+    RC(GEMM(0, 1, n, F, c.Dd, d_docv, D, DP(p, w->dense, "dense_w"), c.Dd, d_pooled, F, nullptr, 0, gws, gwsb, st));
+    RC(GEMM(1, 0, F, c.Dd, n, pooled, F, d_docv, D, DG(p, dgrad, "dense_w"), c.Dd, nullptr, 0, gws, gwsb, st));
+    RC(lstur_colsum(n, c.Dd, d_docv, D, DG(p, dgrad, "dense_b"), 0, cws, cwsb, st));
+  } else {
+    dpool = d_docv; lddp = D;
+  }
+  // everything but the title-encoder bucket is final here: a data-parallel caller starts its exchange on another stream
+  if (p->ev_tail_ready) cudaEventRecord(p->ev_tail_ready, st);
+  // the dropout streams are replayed only if the saved forward was a training forward (an inference forward followed by
+  // a backward differentiates the inference graph)
+  const float bwd_drop = p->last_training ? c.dropout : 0.f;
+  if ((c.precision == LSTUR_PREC_BF16_TC || c.precision == LSTUR_PREC_FP16_TC)) {
+    const int fp16 = c.precision == LSTUR_PREC_FP16_TC;
+    void* img = W<void>(p, ws, "dpre_img");
+    // power-of-two loss scale of the 16-bit dPre image: the gradients carry grad_scale = 1 / global batch, which would
+    // put them in fp16's subnormal range; 16 x the per-impression magnitude leaves 2^12 of headroom
+    float img_scale = 1.f;
+    if (grad_scale > 0.f && grad_scale < 1.f) {
+      int ex = 0;
+      frexpf(1.f / grad_scale, &ex);          // 1/grad_scale = m * 2^ex, m in [0.5, 1)
+      img_scale = ldexpf(1.f, ex - 1 + 4);
+    }
+    const int* n_live = W<int>(p, ws, "n_live");
+    const int* live_idx = W<int>(p, ws, "live_idx");
+    const int* tok_c = W<int>(p, ws, "tokens_c");
+    PROBE_BEGIN(p, LSTUR_PROBE_ATTN_BWD, st);
+    RC(lstur_attn_pool_bwd_img(fp16, n, L, F, W<void>(p, ws, "C16"), W<float>(p, ws, "att_a"), W<float>(p, ws, "att_w"),
+                               dpool, lddp, DP(p, w->dense, "att_w"), img, bwd_drop, img_scale, DG(p, dgrad, "att_w"),
+                               DG(p, dgrad, "conv_b"), DG(p, dgrad, "att_b"), 0, W<float>(p, ws, "attn_partials"),
+                               (size_t)p->ws.at("attn_partials").count * 4, n_live, live_idx, st));
+    PROBE_END(p, LSTUR_PROBE_ATTN_BWD, st);
+    PROBE_BEGIN(p, LSTUR_PROBE_CONV_WGRAD, st);
+    RC(lstur_conv_wgrad_tc_m(n, L, E, F, c.V, tok_c, W<void>(p, ws, "emb_bf16"), img,
+                             DG(p, dgrad, "conv_w"), bwd_drop, p->last_seed, fp16, W<void>(p, ws, "wgrad_partial"),
+                             (size_t)p->ws.at("wgrad_partial").count * 4,
+                             bwd_drop > 0.f ? W<void>(p, ws, "xmask") : nullptr, img_scale, n_live, st));
+    PROBE_END(p, LSTUR_PROBE_CONV_WGRAD, st);
+    if (c.trainable_word_emb) {
+      // d X = dPre (*) Wc^T on tcgen05, then d word_emb = segment-sorted sum of the token rows (x the X-dropout mask)
+      void* wimg_d = W<void>(p, ws, "wimg_d");
+      void* dx16 = W<void>(p, ws, "dx16");
+      RC(lstur_pack_conv_w_dgrad_tc(E, F, DP(p, w->dense, "conv_w"), wimg_d, fp16, st));
+      PROBE_BEGIN(p, LSTUR_PROBE_CONV_DGRAD, st);
+      RC(lstur_conv_dgrad_tc(n, L, E, F, img, wimg_d, dx16, 1.f, fp16, 0, n_live, st));
+      PROBE_END(p, LSTUR_PROBE_CONV_DGRAD, st);
+      PROBE_BEGIN(p, LSTUR_PROBE_SCATTER, st);
+      RC(lstur_word_grad_scatter_16(n, L, E, c.V, tok_c, dx16, fp16, 1.f / ((1.f - bwd_drop) * img_scale),
+                                    bwd_drop > 0.f ? W<void>(p, ws, "xmask") : nullptr, word_grad, W<void>(p, ws, "wg_ws"),
+                                    (size_t)p->ws.at("wg_ws").count * 4, n_live, st));
+      PROBE_END(p, LSTUR_PROBE_SCATTER, st);
+    }
+  } else {
+    float* dPre = W<float>(p, ws, "dPre");
+    const float drop = bwd_drop;
+    RC(lstur_attn_pool_bwd(n, L, Lp, F, W<float>(p, ws, "Cp"), (long long)Lp * F, W<float>(p, ws, "att_a"),
+                           W<float>(p, ws, "att_w"), dpool, lddp, DP(p, w->dense, "att_w"), dPre, (long long)Lp * F,
+                           drop, DG(p, dgrad, "att_w"), DG(p, dgrad, "conv_b"), DG(p, dgrad, "att_b"), 0,
+                           W<float>(p, ws, "attn_partials"), (size_t)p->ws.at("attn_partials").count * 4, st));
+    // d_conv_w[(j,e),f] = sum_m Xp[m+j, e] * dPre[m, f]
+    PROBE_BEGIN(p, LSTUR_PROBE_CONV_WGRAD, st);
+    RC(lstur_gemm_f32(1, 0, c.KS * E, F, n * Lp - (c.KS - 1), W<float>(p, ws, "Xp"), E, dPre, F, DG(p, dgrad, "conv_w"), F,
+                      nullptr, 0, gws, gwsb, st));
+    PROBE_END(p, LSTUR_PROBE_CONV_WGRAD, st);
+    if (c.trainable_word_emb) {
+      // d Xp[m + j, e] += sum_f dPre[m, f] * Wc[j, e, f]: one accumulating GEMM per tap into the overlapping windows of the
+      // zero-haloed title buffer, then the same segment-sorted scatter
+      float* dXp = W<float>(p, ws, "dXp");
+      cudaMemsetAsync(dXp, 0, (size_t)n * Lp * E * sizeof(float), st);
+      PROBE_BEGIN(p, LSTUR_PROBE_CONV_DGRAD, st);
+      for (int j = 0; j < c.KS; ++j)
+        RC(lstur_gemm_f32(0, 1, n * Lp - (c.KS - 1), E, F, dPre, F, DP(p, w->dense, "conv_w") + (size_t)j * E * F, F,
+                          dXp + (size_t)j * E, E, nullptr, LSTUR_GEMM_ACCUM, gws, gwsb, st));
+      PROBE_END(p, LSTUR_PROBE_CONV_DGRAD, st);
+      PROBE_BEGIN(p, LSTUR_PROBE_SCATTER, st);
+      RC(lstur_word_grad_scatter_f32(n, L, c.KS, E, c.V, W<int>(p, ws, "tokens"), dXp, drop, p->last_seed * 2u + 0u, 1.f,
+                                     word_grad, W<void>(p, ws, "wg_ws"), (size_t)p->ws.at("wg_ws").count * 4, st));
+      PROBE_END(p, LSTUR_PROBE_SCATTER, st);
+    }
+  }
+  return LSTUR_OK;
+}
+
+}  // namespace
+
+// ---- vertical model of Seq2VecPaperSoftmaxDaysIdVertAlt (task/paper.py:1128-1136): Dense(cls_nv, softmax)(doc_encoder(title)),
+// categorical cross-entropy; trained on (title, vertical) batches in alternation with the click model, which shares the
+// doc_encoder weights.  tokens (n, L) and labels (n) on the device, n <= B*(W+C).
+extern "C" int lstur_title_cls_forward(const lstur_plan* p, const lstur_weights* w, void* ws, int n, const int* tokens,
+                                       const int* labels, int training, unsigned seed, cudaStream_t st) {
+  LSTUR_REQUIRE(p && w && ws && w->dense && w->word_emb && tokens && labels, "lstur_title_cls_forward");
+  const lstur_config& c = p->c;
+  LSTUR_REQUIRE(c.cls_nv > 0 && n > 0 && n <= p->N, "lstur_title_cls_forward(plan without cls_nv, or n out of range)");
+  LSTUR_REQUIRE(!training || c.save_for_backward, "lstur_title_cls_forward(training needs a save_for_backward plan)");
+  lstur_plan* pm = const_cast<lstur_plan*>(p);
+  pm->last_seed = seed; pm->last_training = training; pm->last_cls_n = n;
+  const int D = p->D;
+  cudaMemcpyAsync(W<int>(p, ws, "tokens"), tokens, (size_t)n * c.L * sizeof(int), cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(W<int>(p, ws, "vc_label"), labels, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, st);
+  RC(encode_titles(p, w, ws, n, training, seed, st));
+  const gemm_fn GEMM = pick_gemm(p);
+  float* lg = W<float>(p, ws, "vc_logit");
+  RC(GEMM(0, 0, n, c.cls_nv, D, W<float>(p, ws, "doc_vec"), D, DP(p, w->dense, "vcls_w"), c.cls_nv, lg, c.cls_nv,
+          DP(p, w->dense, "vcls_b"), LSTUR_GEMM_PRECISE, W<void>(p, ws, "gemm_ws"), p->gemm_ws_bytes, st));
+  RC(lstur_softmax_ce_labels(n, c.cls_nv, lg, W<int>(p, ws, "vc_label"), W<float>(p, ws, "vc_probs"),
+                             W<float>(p, ws, "vc_loss_rows"), W<float>(p, ws, "vc_loss"), nullptr, 0.f, st));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("lstur_title_cls_forward: %s", cudaGetErrorString(e));
+    return LSTUR_ERR_CUDA;
+  }
+  return LSTUR_OK;
+}
+
+// Gradients of the vertical model: dgrad (whole arena; only vcls_* and the title-encoder tensors are non-zero) and, with a
+// trainable word table, word_grad.  grad_scale = 1 / (global number of titles).
+extern "C" int lstur_title_cls_backward(const lstur_plan* p, const lstur_weights* w, void* ws, float* dgrad,
+                                        float* word_grad, float grad_scale, cudaStream_t st) {
+  LSTUR_REQUIRE(p && w && ws && dgrad, "lstur_title_cls_backward");
+  const lstur_config& c = p->c;
+  const int n = p->last_cls_n, D = p->D, nv = c.cls_nv;
+  LSTUR_REQUIRE(nv > 0 && c.save_for_backward && n > 0, "lstur_title_cls_backward(needs a lstur_title_cls_forward on a training plan)");
+  LSTUR_REQUIRE(!c.trainable_word_emb || word_grad != nullptr, "lstur_title_cls_backward(trainable word table needs word_grad)");
+  const gemm_fn GEMM = pick_gemm(p);
+  void* gws = W<void>(p, ws, "gemm_ws");
+  const size_t gwsb = p->gemm_ws_bytes;
+  float* cws = W<float>(p, ws, "colsum_ws");
+  const size_t cwsb = p->ws.at("colsum_ws").count * 4;
+  float* dlg = W<float>(p, ws, "vc_dlogit");
+  float* docv = W<float>(p, ws, "doc_vec");
+  float* d_docv = W<float>(p, ws, "d_doc_vec");
+  cudaMemsetAsync(dgrad, 0, (size_t)p->dense_count * 4, st);
+  RC(lstur_softmax_ce_labels(n, nv, W<float>(p, ws, "vc_logit"), W<int>(p, ws, "vc_label"), nullptr, nullptr, nullptr, dlg,
+                             grad_scale, st));
+  RC(GEMM(1, 0, D, nv, n, docv, D, dlg, nv, DG(p, dgrad, "vcls_w"), nv, nullptr, 0, gws, gwsb, st));
+  RC(lstur_colsum(n, nv, dlg, nv, DG(p, dgrad, "vcls_b"), 0, cws, cwsb, st));
+  RC(GEMM(0, 1, n, D, nv, dlg, nv, DP(p, w->dense, "vcls_w"), nv, d_docv, D, nullptr, 0, gws, gwsb, st));
+  RC(encoder_backward(p, w, ws, n, dgrad, word_grad, grad_scale, st));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("lstur_title_cls_backward: %s", cudaGetErrorString(e));
+    return LSTUR_ERR_CUDA;
+  }
+  return LSTUR_OK;
+}
+
 extern "C" int lstur_backward(const lstur_plan* p, const lstur_weights* w, const lstur_batch* b, void* ws,
                               float* dgrad, float grad_scale, cudaStream_t st) {
   return lstur_backward_w(p, w, b, ws, dgrad, nullptr, grad_scale, st);
@@ -659,8 +1009,8 @@ extern "C" int lstur_backward_w(const lstur_plan* p, const lstur_weights* w, con
   float* uvec = W<float>(p, ws, "user_vec");
   float* d_uvec = W<float>(p, ws, "d_user_vec");
   float* d_docv = W<float>(p, ws, "d_doc_vec");
-  const bool has_gru = c.arch != LSTUR_ARCH_VO && c.arch != LSTUR_ARCH_AVG;
-  const bool has_user = c.arch != LSTUR_ARCH_NOID && c.arch != LSTUR_ARCH_AVG;
+  const bool has_gru = arch_has_gru(c.arch);
+  const bool has_user = arch_has_user(c.arch);
   cudaMemsetAsync(dgrad, 0, (size_t)p->dense_count * 4, st);
   // 1. loss / score backward
   const float* cand = docv + (size_t)Nh * D;
@@ -720,7 +1070,7 @@ extern "C" int lstur_backward_w(const lstur_plan* p, const lstur_weights* w, con
   long long lddh = c.U;
   const float* du0 = nullptr;
   long long lddu0 = 0;
-  const int Uc = (c.arch == LSTUR_ARCH_INI_CON || c.arch == LSTUR_ARCH_INI_CAT) ? c.Ue - G : c.Ue;
+  const int Uc = arch_uc(c);
   if (c.arch == LSTUR_ARCH_CON_DENSE || c.arch == LSTUR_ARCH_INI_CON) {
     float* cat = W<float>(p, ws, "cat");
     float* d_cat = W<float>(p, ws, "d_cat");
@@ -731,8 +1081,28 @@ extern "C" int lstur_backward_w(const lstur_plan* p, const lstur_weights* w, con
     dhT = d_cat; lddh = K2; du0 = d_cat + G; lddu0 = K2;
   } else if (c.arch == LSTUR_ARCH_CON_CAT || c.arch == LSTUR_ARCH_INI_CAT) {
     du0 = d_uvec + G; lddu0 = c.U;
-  } else if (c.arch == LSTUR_ARCH_ADD || c.arch == LSTUR_ARCH_VO) {
+  } else if (c.arch == LSTUR_ARCH_ADD || c.arch == LSTUR_ARCH_VO || c.arch == LSTUR_ARCH_INI_ADD) {
     du0 = d_uvec; lddu0 = c.U;
+  } else if (c.arch == LSTUR_ARCH_LSTM_CAT) {
+    du0 = d_uvec + G; lddu0 = c.U;
+  } else if (c.arch == LSTUR_ARCH_AVG_CAT || c.arch == LSTUR_ARCH_ATT_CAT) {
+    du0 = d_uvec + D; lddu0 = c.U;
+  } else if (c.arch == LSTUR_ARCH_ATT_PAIR) {
+    float* d_seq2 = W<float>(p, ws, "d_seq2");
+    float* part = W<float>(p, ws, "ua_partial");
+    RC(lstur_seq_attn_bwd(B, 2, G, W<float>(p, ws, "seq2"), DP(p, w->dense, "uatt_w"), W<float>(p, ws, "ua_a"),
+                          W<float>(p, ws, "ua_w"), d_uvec, c.U, nullptr, d_seq2, part, st));
+    RC(lstur_colsum(B, G, part, G + 1, DG(p, dgrad, "uatt_w"), 0, cws, cwsb, st));
+    RC(lstur_colsum(B, 1, part + G, G + 1, DG(p, dgrad, "uatt_b"), 0, cws, cwsb, st));
+    dhT = d_seq2; lddh = 2 * G; du0 = d_seq2 + G; lddu0 = 2 * G;
+  } else if (c.arch == LSTUR_ARCH_ALPHA) {
+    float* d_hT = W<float>(p, ws, "d_hT");
+    float* d_uh = W<float>(p, ws, "d_uh");
+    float* part = W<float>(p, ws, "alpha_partial");
+    RC(lstur_alpha_add_bwd(B, G, DP(p, w->dense, "alpha"), W<float>(p, ws, "hT"), G, W<float>(p, ws, "u0"), c.Ue, d_uvec,
+                           c.U, d_hT, G, d_uh, c.Ue, part, st));
+    RC(lstur_colsum(B, 1, part, 1, DG(p, dgrad, "alpha"), 0, cws, cwsb, st));
+    dhT = d_hT; lddh = G; du0 = d_uh; lddu0 = c.Ue;
   }
   // 3. GRU backward
   if (has_gru) {
@@ -741,16 +1111,22 @@ extern "C" int lstur_backward_w(const lstur_plan* p, const lstur_weights* w, con
     float* dh0 = W<float>(p, ws, "dh0");
     const bool tc_gru = (c.precision == LSTUR_PREC_BF16_TC || c.precision == LSTUR_PREC_FP16_TC) &&
                         lstur_gru_tc_supported(B, c.W, G) && !getenv("LSTUR_GRU_TC_OFF");
+    // row order of the last forward (the mask has not changed since)
+    const int* order = getenv("LSTUR_GRU_SORT_OFF") ? nullptr : W<int>(p, ws, "gru_order");
     PROBE_BEGIN(p, LSTUR_PROBE_GRU_BWD, st);
     if (tc_gru) {
       // the kernel also leaves per-(tile, row group) column sums of dA: the bias gradient needs no second pass over dA
       float* dbp = W<float>(p, ws, "gru_db_partial");
       RC(lstur_gru_bwd_tc(B, c.W, G, W<float>(p, ws, "gru_mask"), W<float>(p, ws, "Z"), W<float>(p, ws, "R"),
                           W<float>(p, ws, "HH"), W<float>(p, ws, "HP"), DP(p, w->dense, "gru_wh"), c.rec_act, dhT, lddh,
-                          dA, dh0, G, nullptr, dbp, st));
+                          dA, dh0, G, order, dbp, st));
       RC(lstur_colsum(lstur_gru_tc_db_rows(B), 3 * G, dbp, 3 * G, DG(p, dgrad, "gru_b"), 0, cws, cwsb, st));
     } else {
       RC(lstur_transpose(G, 3 * G, DP(p, w->dense, "gru_wh"), WhT, st));
+      if (order && lstur_gru_cluster_supported(B, c.W, G))
+        RC(lstur_gru_bwd_cluster(B, c.W, G, W<float>(p, ws, "gru_mask"), W<float>(p, ws, "Z"), W<float>(p, ws, "R"),
+                                 W<float>(p, ws, "HH"), W<float>(p, ws, "HP"), WhT, c.rec_act, dhT, lddh, dA, dh0, G, order, st));
+      else
       RC(lstur_gru_bwd(B, c.W, G, W<float>(p, ws, "gru_mask"), W<float>(p, ws, "Z"), W<float>(p, ws, "R"),
                        W<float>(p, ws, "HH"), W<float>(p, ws, "HP"), WhT, c.rec_act, dhT, lddh, dA, dh0, G, st));
       RC(lstur_colsum(Nh, 3 * G, dA, 3 * G, DG(p, dgrad, "gru_b"), 0, cws, cwsb, st));
@@ -764,14 +1140,31 @@ extern "C" int lstur_backward_w(const lstur_plan* p, const lstur_weights* w, con
     // dH = dA . Wx^T  (rows of masked steps are zero because dA is zero there)
     RC(GEMM(0, 1, Nh, D, 3 * G, dA, 3 * G, DP(p, w->dense, "gru_wx"), 3 * G, d_docv, D, nullptr, 0, gws, gwsb, st));
     if (c.arch == LSTUR_ARCH_INI) { du0 = dh0; lddu0 = G; }
-    if (c.arch == LSTUR_ARCH_INI_CON || c.arch == LSTUR_ARCH_INI_CAT) {   // d row = [d h0 ‖ d of the concat part]
+    if (c.arch == LSTUR_ARCH_INI_CON || c.arch == LSTUR_ARCH_INI_CAT || c.arch == LSTUR_ARCH_INI_ADD) {   // d row = [d h0 ‖ d of the concat / add part]
       float* d_u0 = W<float>(p, ws, "d_u0");
       cudaMemcpy2DAsync(d_u0, (size_t)c.Ue * 4, dh0, (size_t)G * 4, (size_t)G * 4, B, cudaMemcpyDeviceToDevice, st);
       cudaMemcpy2DAsync(d_u0 + G, (size_t)c.Ue * 4, du0, (size_t)lddu0 * 4, (size_t)Uc * 4, B, cudaMemcpyDeviceToDevice, st);
       du0 = nullptr;
     }
-  } else if (c.arch == LSTUR_ARCH_AVG) {
+  } else if (arch_has_lstm(c.arch)) {
+    float* WhT = W<float>(p, ws, "WhT");
+    float* dA = W<float>(p, ws, "dA");
+    RC(lstur_transpose(G, 4 * G, DP(p, w->dense, "lstm_wh"), WhT, st));
+    RC(lstur_lstm_bwd(B, c.W, G, W<float>(p, ws, "gru_mask"), W<float>(p, ws, "LI"), W<float>(p, ws, "LF"),
+                      W<float>(p, ws, "LG"), W<float>(p, ws, "LO"), W<float>(p, ws, "LCP"), W<float>(p, ws, "LTC"), WhT,
+                      c.rec_act, dhT, lddh, dA, st));
+    RC(lstur_colsum(Nh, 4 * G, dA, 4 * G, DG(p, dgrad, "lstm_b"), 0, cws, cwsb, st));
+    RC(GEMM(1, 0, D, 4 * G, Nh, docv, D, dA, 4 * G, DG(p, dgrad, "lstm_wx"), 4 * G, nullptr, 0, gws, gwsb, st));
+    RC(GEMM(1, 0, G, 4 * G, Nh, W<float>(p, ws, "LHP"), G, dA, 4 * G, DG(p, dgrad, "lstm_wh"), 4 * G, nullptr, 0, gws, gwsb, st));
+    RC(GEMM(0, 1, Nh, D, 4 * G, dA, 4 * G, DP(p, w->dense, "lstm_wx"), 4 * G, d_docv, D, nullptr, 0, gws, gwsb, st));
+  } else if (arch_hist_avg(c.arch)) {
     RC(lstur_masked_mean_bwd(B, c.W, D, d_uvec, c.U, W<float>(p, ws, "gru_mask"), W<float>(p, ws, "hist_mask"), d_docv, st));
+  } else if (arch_hist_att(c.arch)) {
+    float* part = W<float>(p, ws, "ua_partial");
+    RC(lstur_seq_attn_bwd(B, c.W, D, docv, DP(p, w->dense, "uatt_w"), W<float>(p, ws, "ua_a"), W<float>(p, ws, "ua_w"),
+                          d_uvec, c.U, W<float>(p, ws, "hist_mask"), d_docv, part, st));
+    RC(lstur_colsum(B, D, part, D + 1, DG(p, dgrad, "uatt_w"), 0, cws, cwsb, st));
+    RC(lstur_colsum(B, 1, part + D, D + 1, DG(p, dgrad, "uatt_b"), 0, cws, cwsb, st));
   } else {
     cudaMemsetAsync(d_docv, 0, (size_t)Nh * D * 4, st);
   }
@@ -783,7 +1176,10 @@ extern "C" int lstur_backward_w(const lstur_plan* p, const lstur_weights* w, con
     // (dgru / id_keep) scales the gradient of its embedding row
     float* d_u0 = W<float>(p, ws, "d_u0");
     if (du0) cudaMemcpy2DAsync(d_u0, (size_t)c.Ue * 4, du0, (size_t)lddu0 * 4, (size_t)c.Ue * 4, B, cudaMemcpyDeviceToDevice, st);
-    if (b->user_scale) RC(lstur_scale_rows(B, c.Ue, b->user_scale, d_u0, c.Ue, st));
+    if (b->user_scale2 != nullptr && arch_uc(c) != c.Ue) {
+      if (b->user_scale) RC(lstur_scale_rows(B, G, b->user_scale, d_u0, c.Ue, st));
+      RC(lstur_scale_rows(B, c.Ue - G, b->user_scale2, d_u0 + G, c.Ue, st));
+    } else if (b->user_scale) RC(lstur_scale_rows(B, c.Ue, b->user_scale, d_u0, c.Ue, st));
     RC(lstur_segment_sum_rows(B, c.Ue, W<int>(p, ws, "n_user_rows"), W<int>(p, ws, "seg_start"),
                               W<int>(p, ws, "sorted_pos"), d_u0, c.Ue, W<float>(p, ws, "d_user_rows"), st));
   }
@@ -796,91 +1192,27 @@ extern "C" int lstur_backward_w(const lstur_plan* p, const lstur_weights* w, con
     if (c.ds) RC(lstur_small_table_grad(N, D, c.Dd + c.dv, c.ds, c.n_subvert, W<int>(p, ws, "title_subvert"), d_docv,
                                         DG(p, dgrad, "subvert_emb"), vws, vwsb, st));
   }
+  // 5b. auxiliary vertical classifier backward (task/paper.py:973-990): loss += aux_gain * mean over the B*(W+C) positions
+  if (c.aux_nv && p->last_aux) {
+    const int Hd = c.aux_hidden, nv = c.aux_nv;
+    float* hid = W<float>(p, ws, "vs_hid");
+    float* dlg = W<float>(p, ws, "vs_dlogit");
+    float* dhid = W<float>(p, ws, "vs_dhid");
+    float* ddoc = W<float>(p, ws, "vs_ddoc");
+    RC(lstur_softmax_ce_labels(N, nv, W<float>(p, ws, "vs_logit"), W<int>(p, ws, "vs_label"), nullptr, nullptr, nullptr, dlg,
+                               c.aux_gain * grad_scale / (float)(c.W + c.C), st));
+    RC(GEMM(1, 0, Hd, nv, N, hid, Hd, dlg, nv, DG(p, dgrad, "vs_w2"), nv, nullptr, 0, gws, gwsb, st));
+    RC(lstur_colsum(N, nv, dlg, nv, DG(p, dgrad, "vs_b2"), 0, cws, cwsb, st));
+    RC(GEMM(0, 1, N, Hd, nv, dlg, nv, DP(p, w->dense, "vs_w2"), nv, dhid, Hd, nullptr, 0, gws, gwsb, st));
+    RC(lstur_relu_bwd((long long)N * Hd, hid, dhid, st));
+    RC(GEMM(1, 0, D, Hd, N, docv, D, dhid, Hd, DG(p, dgrad, "vs_w1"), Hd, nullptr, 0, gws, gwsb, st));
+    RC(lstur_colsum(N, Hd, dhid, Hd, DG(p, dgrad, "vs_b1"), 0, cws, cwsb, st));
+    RC(GEMM(0, 1, N, D, Hd, dhid, Hd, DP(p, w->dense, "vs_w1"), Hd, ddoc, D, nullptr, 0, gws, gwsb, st));
+    RC(lstur_scale_rows(Nh, D, W<float>(p, ws, "hist_mask"), ddoc, D, st));     // the classifier saw doc_vec * history mask
+    RC(lstur_axpby((long long)N * D, 1.f, ddoc, 1.f, d_docv, st));
+  }
   // 5. news-encoder backward over all N titles
-  float* d_pooled = W<float>(p, ws, "d_pooled");
-  float* pooled = W<float>(p, ws, "pooled");
-  const float* dpool = d_pooled;
-  long long lddp = F;
-  if (c.use_dense) {
-    RC(GEMM(0, 1, N, F, c.Dd, d_docv, D, DP(p, w->dense, "dense_w"), c.Dd, d_pooled, F, nullptr, 0, gws, gwsb, st));
-    RC(GEMM(1, 0, F, c.Dd, N, pooled, F, d_docv, D, DG(p, dgrad, "dense_w"), c.Dd, nullptr, 0, gws, gwsb, st));
-    RC(lstur_colsum(N, c.Dd, d_docv, D, DG(p, dgrad, "dense_b"), 0, cws, cwsb, st));
-  } else {
-    dpool = d_docv; lddp = D;
-  }
-  // everything but the title-encoder bucket is final here: a data-parallel caller starts its exchange on another stream
-  if (p->ev_tail_ready) cudaEventRecord(p->ev_tail_ready, st);
-  // the dropout streams are replayed only if the saved forward was a training forward (an inference forward followed by
-  // a backward differentiates the inference graph)
-  const float bwd_drop = p->last_training ? c.dropout : 0.f;
-  if ((c.precision == LSTUR_PREC_BF16_TC || c.precision == LSTUR_PREC_FP16_TC)) {
-    const int fp16 = c.precision == LSTUR_PREC_FP16_TC;
-    void* img = W<void>(p, ws, "dpre_img");
-    // power-of-two loss scale of the 16-bit dPre image: the gradients carry grad_scale = 1 / global batch, which would
-    // put them in fp16's subnormal range; 16 x the per-impression magnitude leaves 2^12 of headroom
-    float img_scale = 1.f;
-    if (grad_scale > 0.f && grad_scale < 1.f) {
-      int ex = 0;
-      frexpf(1.f / grad_scale, &ex);          // 1/grad_scale = m * 2^ex, m in [0.5, 1)
-      img_scale = ldexpf(1.f, ex - 1 + 4);
-    }
-    const int* n_live = W<int>(p, ws, "n_live");
-    const int* live_idx = W<int>(p, ws, "live_idx");
-    const int* tok_c = W<int>(p, ws, "tokens_c");
-    PROBE_BEGIN(p, LSTUR_PROBE_ATTN_BWD, st);
-    RC(lstur_attn_pool_bwd_img(fp16, N, L, F, W<void>(p, ws, "C16"), W<float>(p, ws, "att_a"), W<float>(p, ws, "att_w"),
-                               dpool, lddp, DP(p, w->dense, "att_w"), img, bwd_drop, img_scale, DG(p, dgrad, "att_w"),
-                               DG(p, dgrad, "conv_b"), DG(p, dgrad, "att_b"), 0, W<float>(p, ws, "attn_partials"),
-                               (size_t)p->ws.at("attn_partials").count * 4, n_live, live_idx, st));
-    PROBE_END(p, LSTUR_PROBE_ATTN_BWD, st);
-    PROBE_BEGIN(p, LSTUR_PROBE_CONV_WGRAD, st);
-    RC(lstur_conv_wgrad_tc_m(N, L, E, F, c.V, tok_c, W<void>(p, ws, "emb_bf16"), img,
-                             DG(p, dgrad, "conv_w"), bwd_drop, p->last_seed, fp16, W<void>(p, ws, "wgrad_partial"),
-                             (size_t)p->ws.at("wgrad_partial").count * 4,
-                             bwd_drop > 0.f ? W<void>(p, ws, "xmask") : nullptr, img_scale, n_live, st));
-    PROBE_END(p, LSTUR_PROBE_CONV_WGRAD, st);
-    if (c.trainable_word_emb) {
-      // d X = dPre (*) Wc^T on tcgen05, then d word_emb = segment-sorted sum of the token rows (x the X-dropout mask)
-      void* wimg_d = W<void>(p, ws, "wimg_d");
-      void* dx16 = W<void>(p, ws, "dx16");
-      RC(lstur_pack_conv_w_dgrad_tc(E, F, DP(p, w->dense, "conv_w"), wimg_d, fp16, st));
-      PROBE_BEGIN(p, LSTUR_PROBE_CONV_DGRAD, st);
-      RC(lstur_conv_dgrad_tc(N, L, E, F, img, wimg_d, dx16, 1.f, fp16, 0, n_live, st));
-      PROBE_END(p, LSTUR_PROBE_CONV_DGRAD, st);
-      PROBE_BEGIN(p, LSTUR_PROBE_SCATTER, st);
-      RC(lstur_word_grad_scatter_16(N, L, E, c.V, tok_c, dx16, fp16, 1.f / ((1.f - bwd_drop) * img_scale),
-                                    bwd_drop > 0.f ? W<void>(p, ws, "xmask") : nullptr, word_grad, W<void>(p, ws, "wg_ws"),
-                                    (size_t)p->ws.at("wg_ws").count * 4, n_live, st));
-      PROBE_END(p, LSTUR_PROBE_SCATTER, st);
-    }
-  } else {
-    float* dPre = W<float>(p, ws, "dPre");
-    const float drop = bwd_drop;
-    RC(lstur_attn_pool_bwd(N, L, Lp, F, W<float>(p, ws, "Cp"), (long long)Lp * F, W<float>(p, ws, "att_a"),
-                           W<float>(p, ws, "att_w"), dpool, lddp, DP(p, w->dense, "att_w"), dPre, (long long)Lp * F,
-                           drop, DG(p, dgrad, "att_w"), DG(p, dgrad, "conv_b"), DG(p, dgrad, "att_b"), 0,
-                           W<float>(p, ws, "attn_partials"), (size_t)p->ws.at("attn_partials").count * 4, st));
-    // d_conv_w[(j,e),f] = sum_m Xp[m+j, e] * dPre[m, f]
-    PROBE_BEGIN(p, LSTUR_PROBE_CONV_WGRAD, st);
-    RC(lstur_gemm_f32(1, 0, c.KS * E, F, N * Lp - (c.KS - 1), W<float>(p, ws, "Xp"), E, dPre, F, DG(p, dgrad, "conv_w"), F,
-                      nullptr, 0, gws, gwsb, st));
-    PROBE_END(p, LSTUR_PROBE_CONV_WGRAD, st);
-    if (c.trainable_word_emb) {
-      // d Xp[m + j, e] += sum_f dPre[m, f] * Wc[j, e, f]: one accumulating GEMM per tap into the overlapping windows of the
-      // zero-haloed title buffer, then the same segment-sorted scatter
-      float* dXp = W<float>(p, ws, "dXp");
-      cudaMemsetAsync(dXp, 0, (size_t)N * Lp * E * sizeof(float), st);
-      PROBE_BEGIN(p, LSTUR_PROBE_CONV_DGRAD, st);
-      for (int j = 0; j < c.KS; ++j)
-        RC(lstur_gemm_f32(0, 1, N * Lp - (c.KS - 1), E, F, dPre, F, DP(p, w->dense, "conv_w") + (size_t)j * E * F, F,
-                          dXp + (size_t)j * E, E, nullptr, LSTUR_GEMM_ACCUM, gws, gwsb, st));
-      PROBE_END(p, LSTUR_PROBE_CONV_DGRAD, st);
-      PROBE_BEGIN(p, LSTUR_PROBE_SCATTER, st);
-      RC(lstur_word_grad_scatter_f32(N, L, c.KS, E, c.V, W<int>(p, ws, "tokens"), dXp, drop, p->last_seed * 2u + 0u, 1.f,
-                                     word_grad, W<void>(p, ws, "wg_ws"), (size_t)p->ws.at("wg_ws").count * 4, st));
-      PROBE_END(p, LSTUR_PROBE_SCATTER, st);
-    }
-  }
+  RC(encoder_backward(p, w, ws, N, dgrad, word_grad, grad_scale, st));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("lstur_backward: %s", cudaGetErrorString(e));

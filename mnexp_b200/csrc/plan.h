@@ -33,6 +33,8 @@ struct lstur_plan {
   long long dense_head = 0;
   unsigned last_seed = 0;   // seed / mode of the last forward (backward replays its dropout streams)
   int last_training = 0;
+  int last_aux = 0;        // the last forward ran the auxiliary vertical classifier (labels were given)
+  int last_cls_n = 0;      // titles of the last lstur_title_cls_forward
 };
 
 namespace lstur {

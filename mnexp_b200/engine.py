@@ -15,13 +15,19 @@ from ._lib import lstur_batch, lstur_config, lstur_weights
 
 ARCH = {  # reference arch names -> engine arch; paper.py names
     'igru': 0, 'gru': 1, 'ngru': 2, 'hgru': 2, 'dgru': 2, 'nigru': 3, 'pgru': 4, 'vo': 5, 'niavg': 6, 'iigru': 7,
+    'att': 10,                                    # Seq2VecPaper.get_user_encoder (task/paper.py:206-208)
 }
 SCORE = {'dot': 0, 'dnn': 1, 'ddot': 2}          # task/paper.py:443-458; cook's 'ddot' is linear (task/cook.py:206-209)
 # sigmoid family (Seq2VecPaperId.get_user_encoder, task/paper.py:328-358): 'gru' is the plain concat, 'iigru' has no Dense
-SIGMOID_ARCH = {'gru': 2, 'igru': 0, 'iigru': 8, 'vo': 5, 'nigru': 3, 'niavg': 6}
-COOK_ARCH = {'ingru': 0, 'igru': 2, 'gru': 3, 'agru': 4, 'vo': 5, 'avg': 6, 'inigru': 8}   # task/cook.py:146-176
+SIGMOID_ARCH = {'gru': 2, 'igru': 0, 'iigru': 8, 'vo': 5, 'nigru': 3, 'niavg': 6, 'att': 10}
+# task/cook.py:146-193 — every branch of Cook.get_user_encoder
+COOK_ARCH = {'ingru': 0, 'igru': 2, 'gru': 3, 'agru': 4, 'vo': 5, 'avg': 6, 'inigru': 8, 'iavg': 9, 'iatt': 11,
+             'inagru': 12, 'atgru': 13, 'algru': 14, 'ilstm': 15}
+TWO_TABLE_ARCHS = (7, 8, 12)      # [user_emb | user_emb2] as the column halves of one device table
 DENSE_NAMES = ('conv_w', 'conv_b', 'att_w', 'att_b', 'dense_w', 'dense_b', 'vert_emb', 'subvert_emb',
-               'gru_wx', 'gru_wh', 'gru_b', 'con_w', 'con_b', 'sh_w', 'sh_b', 'so_w', 'so_b', 'su_w', 'su_b', 'sd_w', 'sd_b')
+               'gru_wx', 'gru_wh', 'gru_b', 'lstm_wx', 'lstm_wh', 'lstm_b', 'uatt_w', 'uatt_b', 'alpha', 'con_w', 'con_b',
+               'sh_w', 'sh_b', 'so_w', 'so_b', 'su_w', 'su_b', 'sd_w', 'sd_b', 'vs_w1', 'vs_b1', 'vs_w2', 'vs_b2',
+               'vcls_w', 'vcls_b')
 PREC = {'fp32': 0, 'bf16_tc': 1, 'fp16_tc': 2}
 
 
@@ -38,7 +44,7 @@ class LsturEngine:
     def __init__(self, params, B, W, C, L, arch='igru', flavour='paper', dropout=0.0, lr=1e-3,
                  recurrent_activation='hard_sigmoid', precision='fp32', doc_tokens=None, device=None,
                  training=True, sparse_user_adam=True, trainable_word_emb=False, share_weights_from=None,
-                 doc_vert=None, doc_subvert=None, score_model='dot', loss='softmax', gain=1.0, bce_neg=4):
+                 doc_vert=None, doc_subvert=None, score_model='dot', loss='softmax', gain=1.0, bce_neg=4, aux_gain=1.0):
         if not torch.cuda.is_available():
             raise _lib.LsturError('LsturEngine needs a CUDA device (no CPU fallback)')
         self.lib = _lib.load()
@@ -51,7 +57,7 @@ class LsturEngine:
         if arch not in amap:
             raise Exception('Unsupport user model')                      # task/paper.py:630
         self.arch_name, self.arch = arch, amap[arch]
-        if self.arch in (7, 8):
+        if self.arch in TWO_TABLE_ARCHS:
             # 'iigru' has two user tables (task/paper.py:614-619): one (n_users, 2U) device table [user_emb | user_emb2]
             # — the first U columns seed the GRU, the rest join the concat; row-wise Adam is the same arithmetic
             params = dict(params)
@@ -66,14 +72,17 @@ class LsturEngine:
         use_dense = 'dense_w' in params
         Dd = params['dense_w'].shape[1] if use_dense else F
         G = params['gru_wh'].shape[0] if 'gru_wh' in params else 0
-        Ue = params['user_emb'].shape[1] if 'user_emb' in params and self.arch not in (3, 6) else 0
-        if self.arch == 6:
+        if self.arch == 15:
+            G = params['lstm_wh'].shape[0]
+        Ue = params['user_emb'].shape[1] if 'user_emb' in params and self.arch not in (3, 6, 10) else 0
+        if self.arch in (5, 6, 9, 10, 11):
             G = 0
         # Cook.get_doc_encoder concat (task/cook.py:99-113): [title | Vemb[vert] | Semb[subvert]]
         dv = params['vert_emb'].shape[1] if 'vert_emb' in params else 0
         ds = params['subvert_emb'].shape[1] if 'subvert_emb' in params else 0
         U = {0: G, 1: params['con_w'].shape[1] if 'con_w' in params else 0, 2: G + Ue, 3: G, 4: G, 5: Ue,
-             6: Dd + dv + ds, 7: params['con_w'].shape[1] if 'con_w' in params else 0, 8: Ue}[self.arch]
+             6: Dd + dv + ds, 7: params['con_w'].shape[1] if 'con_w' in params else 0, 8: Ue,
+             9: Dd + dv + ds + Ue, 10: Dd + dv + ds, 11: Dd + dv + ds + Ue, 12: G, 13: G, 14: G, 15: G + Ue}[self.arch]
         _sd = share_weights_from.doc_tokens if share_weights_from is not None else None
         n_docs = doc_tokens.shape[0] if doc_tokens is not None else (0 if _sd is None else _sd.shape[0])
         self.cfg = lstur_config(
@@ -85,7 +94,13 @@ class LsturEngine:
             save_for_backward=int(training),
             n_vert=params['vert_emb'].shape[0] if dv else 0, n_subvert=params['subvert_emb'].shape[0] if ds else 0,
             Hs=Hs, loss_model=1 if loss == 'bce' else 0, bce_neg=int(bce_neg), gain=float(gain),
-            trainable_word_emb=int(self.trainable_word_emb))
+            trainable_word_emb=int(self.trainable_word_emb),
+            # auxiliary vertical classifier (...VertSup, task/paper.py:948-990) / vertical model (...VertAlt, :1128-1136):
+            # present iff their weights are
+            aux_nv=params['vs_w2'].shape[1] if 'vs_w2' in params else 0,
+            aux_hidden=params['vs_w1'].shape[1] if 'vs_w1' in params else 0, aux_gain=float(aux_gain),
+            cls_nv=params['vcls_w'].shape[1] if 'vcls_w' in params else 0)
+        self.aux_nv, self.cls_nv, self.aux_gain = self.cfg.aux_nv, self.cfg.cls_nv, float(aux_gain)
         self.B, self.W, self.C, self.L, self.D, self.U, self.Ue, self.G = B, W, C, L, Dd + dv + ds, U, Ue, G
         plan = ctypes.c_void_p()
         _lib.check(self.lib.lstur_plan_create(ctypes.byref(self.cfg), ctypes.byref(plan)))
@@ -182,7 +197,7 @@ class LsturEngine:
             self._emb_version[0] += 1
         if self.user_emb is not None and 'user_emb' in params:
             ue = params['user_emb']
-            if self.arch in (7, 8) and ue.shape[1] != self.Ue:
+            if self.arch in TWO_TABLE_ARCHS and ue.shape[1] != self.Ue:
                 ue = np.concatenate([ue, params['user_emb2']], 1)
             self.user_emb.copy_(torch.as_tensor(np.ascontiguousarray(ue, dtype=np.float32)))
 
@@ -195,7 +210,7 @@ class LsturEngine:
         out['word_emb'] = self.word_emb.cpu().numpy()
         if self.user_emb is not None:
             out['user_emb'] = self.user_emb.cpu().numpy()
-            if self.arch in (7, 8):
+            if self.arch in TWO_TABLE_ARCHS:
                 out['user_emb'], out['user_emb2'] = out['user_emb'][:, :self.G].copy(), out['user_emb'][:, self.G:].copy()
         return out
 
@@ -210,7 +225,7 @@ class LsturEngine:
             rows = self.view('user_rows', torch.int32)[:n].cpu().numpy()
             g[rows] = self.view('d_user_rows').reshape(-1, self.Ue)[:n].cpu().numpy()
             out['user_emb'] = g
-            if self.arch in (7, 8):
+            if self.arch in TWO_TABLE_ARCHS:
                 out['user_emb'], out['user_emb2'] = g[:, :self.G].copy(), g[:, self.G:].copy()
         return out
 
@@ -234,7 +249,7 @@ class LsturEngine:
             if v is None:
                 continue
             t = v if torch.is_tensor(v) else torch.from_numpy(np.ascontiguousarray(v))
-            if k == 'label' or k == 'user_scale':
+            if k in ('label', 'user_scale', 'user_scale2'):
                 t = t.to(self.device, dtype=torch.float32, non_blocking=non_blocking)
             else:
                 t = t.to(self.device, non_blocking=non_blocking)
@@ -248,7 +263,7 @@ class LsturEngine:
         return lstur_batch(user=g('user'), hist_doc=g('hist_doc'), cand_doc=g('cand_doc'), hist_tok=g('hist_tok'),
                            cand_tok=g('cand_tok'), label=g('label'), user_scale=g('user_scale'),
                            hist_vert=g('hist_vert'), hist_subvert=g('hist_subvert'), cand_vert=g('cand_vert'),
-                           cand_subvert=g('cand_subvert'))
+                           cand_subvert=g('cand_subvert'), user_scale2=g('user_scale2'))
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -366,6 +381,9 @@ class LsturEngine:
                 self.word_grad.zero_()
         _lib.check(self.lib.lstur_adam_dense(self.n_dense, _ptr(self.dense), _ptr(self.dense_grad), _ptr(self.adam_m),
                                              _ptr(self.adam_v), self.lr, self.t, b1, b2, eps, 1.0, st))
+        if 'alpha' in self.layout:     # AlphaAdd's constraint MinMaxNorm(0, 1) runs after the update (models.py:545)
+            off = self.layout['alpha'][0]
+            _lib.check(self.lib.lstur_minmaxnorm(1, 0.0, 1.0, ctypes.c_void_p(self.dense.data_ptr() + 4 * off), st))
         if self.trainable_word_emb:
             _lib.check(self.lib.lstur_adam_dense(self.word_emb.numel(), _ptr(self.word_emb), _ptr(self.word_grad),
                                                  _ptr(self.word_m), _ptr(self.word_v), self.lr, self.t, b1, b2, eps, 1.0, st))
@@ -410,6 +428,59 @@ class LsturEngine:
 
     def loss(self):
         return float(self.view('loss')[0])
+
+    def aux_loss(self):
+        """mean categorical cross-entropy of the auxiliary vertical classifier in the last forward (...VertSup); the
+        compiled Keras loss is loss() + aux_gain * aux_loss() (loss_weights=[1, gain], task/paper.py:985)."""
+        return float(self.view('vs_loss')[0])
+
+    # ---- vertical model of ...VertAlt (task/paper.py:1128-1136): its own Adam (a second optimizer over the shared weights)
+    def title_cls_forward(self, tokens, labels, training=False, seed=0):
+        t = tokens if torch.is_tensor(tokens) else torch.as_tensor(np.ascontiguousarray(tokens))
+        t = t.to(self.device).to(torch.int32).contiguous()
+        y = labels if torch.is_tensor(labels) else torch.as_tensor(np.ascontiguousarray(labels))
+        y = y.to(self.device).to(torch.int32).contiguous().reshape(-1)
+        n = int(t.shape[0])
+        assert t.shape[1] == self.L and y.numel() == n
+        if self._emb_seen != self._emb_version[0]:
+            _lib.check(self.lib.lstur_plan_invalidate_tables(self.plan))
+            self._emb_seen = self._emb_version[0]
+        _lib.check(self.lib.lstur_title_cls_forward(self.plan, ctypes.byref(self._w), _ptr(self.ws), n, _ptr(t), _ptr(y),
+                                                    int(training), ctypes.c_uint(seed), self._stream()))
+        self._cls_n = n
+        return self.view('vc_probs')[:n * self.cls_nv].reshape(n, self.cls_nv)
+
+    def title_cls_backward(self, grad_scale=None):
+        gs = 1.0 / self._cls_n if grad_scale is None else grad_scale
+        _lib.check(self.lib.lstur_title_cls_backward(self.plan, ctypes.byref(self._w), _ptr(self.ws), _ptr(self.dense_grad),
+                                                     _ptr(self.word_grad) if self.trainable_word_emb else None,
+                                                     ctypes.c_float(gs), self._stream()))
+
+    def title_cls_train_step(self, tokens, labels, lr=None, b1=0.9, b2=0.999, eps=1e-7):
+        """one step of vert_model.fit: forward, backward, Keras-Adam with the vertical model's OWN moments and step count
+        (keras compiles vert_model with a second Adam, task/paper.py:1132-1136).  Returns (loss, accuracy) device scalars."""
+        if getattr(self, 'cls_m', None) is None:
+            self.cls_m, self.cls_v, self.cls_t = torch.zeros_like(self.dense), torch.zeros_like(self.dense), 0
+            if self.trainable_word_emb:
+                self.cls_word_m, self.cls_word_v = torch.zeros_like(self.word_emb), torch.zeros_like(self.word_emb)
+        self.step_seed += 1
+        probs = self.title_cls_forward(tokens, labels, training=True, seed=self.step_seed)
+        self.title_cls_backward()
+        self.cls_t += 1
+        st = self._stream()
+        lr = self.lr if lr is None else float(lr)
+        if self.freeze_encoder:
+            last = 'dense_b' if 'dense_b' in self.layout else 'att_b'
+            self.dense_grad[:self.layout[last][0] + self.layout[last][1]].zero_()
+        _lib.check(self.lib.lstur_adam_dense(self.n_dense, _ptr(self.dense), _ptr(self.dense_grad), _ptr(self.cls_m),
+                                             _ptr(self.cls_v), lr, self.cls_t, b1, b2, eps, 1.0, st))
+        if self.trainable_word_emb and not self.freeze_encoder:
+            _lib.check(self.lib.lstur_adam_dense(self.word_emb.numel(), _ptr(self.word_emb), _ptr(self.word_grad),
+                                                 _ptr(self.cls_word_m), _ptr(self.cls_word_v), lr, self.cls_t, b1, b2, eps, 1.0, st))
+            self._emb_version[0] += 1
+        lab = self.view('vc_label', torch.int32)[:self._cls_n]
+        acc = (probs.argmax(1) == lab).float().mean()
+        return self.view('vc_loss'), acc
 
     def score_sigmoid(self):
         """sigmoid(user_vec . cand_vec) for every (row, candidate) of the last forward — the reference's test head

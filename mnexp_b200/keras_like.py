@@ -104,7 +104,10 @@ class _Core:
         return 1 if self.loss == 'bce' else 1 + self.cfg.negative_samples
 
     def head_kw(self):
-        return dict(flavour=self.flavour, loss=self.loss, gain=self.cfg.gain, bce_neg=self.cfg.negative_samples)
+        kw = dict(flavour=self.flavour, loss=self.loss, gain=self.cfg.gain, bce_neg=self.cfg.negative_samples)
+        if 'vs_w1' in self.params:      # ...VertSup: loss_weights=[1, config.gain] (task/paper.py:985)
+            kw['aux_gain'] = self.cfg.gain
+        return kw
 
     def split_inputs(self, x, n_cand):
         """[user?, clicked, clicked_vert?, cand_0..cand_{C-1}, cand_vert_0..?] -> user, clicked, cand (B,C,L), verts."""
@@ -275,7 +278,7 @@ class Model:
     # ---- weights / structure ------------------------------------------------------------------
     WEIGHT_ORDER = ('word_emb', 'conv_w', 'conv_b', 'att_w', 'att_b', 'dense_w', 'dense_b', 'vert_emb', 'subvert_emb', 'user_emb',
                     'user_emb2',
-                    'gru_wx', 'gru_wh', 'gru_b', 'con_w', 'con_b', 'sh_w', 'sh_b', 'so_w', 'so_b', 'su_w', 'su_b', 'sd_w',
+                    'gru_wx', 'gru_wh', 'gru_b', 'lstm_wx', 'lstm_wh', 'lstm_b', 'uatt_w', 'uatt_b', 'alpha', 'con_w', 'con_b', 'sh_w', 'sh_b', 'so_w', 'so_b', 'su_w', 'su_b', 'sd_w',
                     'sd_b')
 
     def _current(self):
@@ -324,6 +327,132 @@ class Model:
         lines = ['%-12s %-18s %d' % (k, tuple(np.asarray(v).shape), np.asarray(v).size) for k, v in w.items()]
         print('\n'.join(lines))
         print('Total params: %d' % sum(np.asarray(v).size for v in w.values()))
+
+
+class VertSupModel(Model):
+    """`model` of Seq2VecPaperSoftmaxDaysIdVertSup (task/paper.py:981-987): outputs [ranking (B,1+K), vert (B,W+1+K,n_vert)],
+    losses [categorical CE, categorical CE], loss_weights [1, gain].  Targets arrive as [one-hot clicks, one-hot verticals of
+    the W history slots followed by the 1+K candidates] (:897-902)."""
+
+    def __init__(self, core, name='model'):
+        Model.__init__(self, core, True, name)
+        self.metrics_names = ['loss', 'ranking_loss', 'vert_loss', 'ranking_categorical_accuracy', 'vert_categorical_accuracy']
+
+    def _vert_ids(self, y_vert, W):
+        ids = np.asarray(y_vert).argmax(-1).astype(np.int32)          # to_categorical inverse
+        return ids[:, :W], ids[:, W:]
+
+    def _metrics(self, eng, db):
+        probs = eng.view('probs').reshape(eng.B, eng.C)
+        acc = float((probs.argmax(1) == db['label'].argmax(1)).float().mean())
+        n = eng.B * (eng.W + eng.C)
+        vp = eng.view('vs_probs').reshape(n, eng.aux_nv)
+        lab = torch.cat([db['hist_vert'].reshape(-1), db['cand_vert'].reshape(-1)])
+        vacc = float((vp.argmax(1) == lab).float().mean())
+        main, aux = eng.loss(), eng.aux_loss()
+        return [main + eng.aux_gain * aux, main, aux, acc, vacc]
+
+    def train_on_batch(self, x, y):
+        core = self.core
+        C = core.n_train_cand()
+        user, clicked, cand, _ = core.split_inputs(x, C)
+        eng = core.engine_train(clicked.shape[0])
+        eng.lr = core.optimizer.lr.value
+        hv, cv = self._vert_ids(y[1], clicked.shape[1])
+        batch = dict(user=user, hist_tok=clicked, cand_tok=cand, hist_vert=hv, cand_vert=cv,
+                     label=np.asarray(y[0], dtype=np.float32).reshape(len(clicked), C))
+        db = eng.to_device_batch(batch)
+        eng.train_step(db)
+        return self._metrics(eng, db)
+
+    def evaluate(self, x, y, batch_size=None, verbose=0, **_):
+        core = self.core
+        C = core.n_train_cand()
+        user, clicked, cand, _ = core.split_inputs(x, C)
+        eng = core.engine_train(clicked.shape[0])
+        hv, cv = self._vert_ids(y[1], clicked.shape[1])
+        db = eng.to_device_batch(dict(user=user, hist_tok=clicked, cand_tok=cand, hist_vert=hv, cand_vert=cv,
+                                      label=np.asarray(y[0], dtype=np.float32).reshape(len(clicked), C)))
+        eng.forward(db, training=False)
+        return self._metrics(eng, db)
+
+    def predict(self, x, batch_size=None, **_):
+        """[ranking probabilities (n, 1+K), vertical probabilities (n, W+1+K, n_vert)] like the two-output Keras model."""
+        core = self.core
+        C = core.n_train_cand()
+        user, clicked, cand, _ = core.split_inputs(x, C)
+        eng = core.engine_train(clicked.shape[0])
+        z = np.zeros((clicked.shape[0], clicked.shape[1]), dtype=np.int32)
+        db = eng.to_device_batch(dict(user=user, hist_tok=clicked, cand_tok=cand, hist_vert=z,
+                                      cand_vert=np.zeros((clicked.shape[0], C), dtype=np.int32)))
+        probs = eng.forward(db, training=False).cpu().numpy().copy()
+        B, W = eng.B, eng.W
+        vp = eng.view('vs_probs').reshape(B * (W + C), eng.aux_nv).cpu().numpy()
+        return [probs, np.concatenate([vp[:B * W].reshape(B, W, -1), vp[B * W:].reshape(B, C, -1)], 1)]
+
+    predict_on_batch = predict
+
+
+class VertModel:
+    """`vert_model` of Seq2VecPaperSoftmaxDaysIdVertAlt (task/paper.py:1128-1136): title (n,L) -> softmax over the
+    verticals, categorical cross-entropy, its own Adam; shares the doc_encoder weights with the click model."""
+
+    def __init__(self, core, name='vert_model'):
+        self.core, self.name = core, name
+        self.metrics_names = ['loss', 'categorical_accuracy']
+        self.optimizer = Adam(core.cfg.learning_rate)
+        self.layers = {}
+
+    def _engine(self):
+        c = self.core.cfg
+        return self.core.train_engine if self.core.train_engine is not None else self.core.engine_train(c.batch_size)
+
+    def _chunks(self, eng, n):
+        cap = eng.B * (eng.W + eng.C)
+        return [(s, min(cap, n - s)) for s in range(0, n, cap)]
+
+    def train_on_batch(self, x, y):
+        eng = self._engine()
+        x = np.asarray(x[0] if isinstance(x, (list, tuple)) else x)
+        lab = np.asarray(y[0] if isinstance(y, (list, tuple)) else y).argmax(-1)
+        assert len(x) <= eng.B * (eng.W + eng.C), 'vertical batch exceeds the plan\'s title capacity'
+        loss, acc = eng.title_cls_train_step(x, lab, lr=self.optimizer.lr.value)
+        return [float(loss[0]), float(acc)]
+
+    def fit_generator(self, generator, steps_per_epoch, epochs=1, initial_epoch=0, verbose=0, **_):
+        h = History()
+        for epoch in range(initial_epoch, epochs):
+            tot = np.zeros(2)
+            for _ in range(steps_per_epoch):
+                x, y = next(generator)
+                tot += self.train_on_batch(x, y)
+            h.epoch.append(epoch)
+            for k, v in zip(self.metrics_names, tot / max(1, steps_per_epoch)):
+                h.history.setdefault(k, []).append(float(v))
+        return h
+
+    def predict(self, x, batch_size=None, **_):
+        eng = self._engine()
+        x = np.asarray(x[0] if isinstance(x, (list, tuple)) else x)
+        out = []
+        for s, m in self._chunks(eng, len(x)):
+            out.append(eng.title_cls_forward(x[s:s + m], np.zeros(m, dtype=np.int32)).cpu().numpy().copy())
+        return np.concatenate(out) if out else np.zeros((0, eng.cls_nv), dtype=np.float32)
+
+    predict_on_batch = predict
+
+    def evaluate(self, x, y, batch_size=None, verbose=0, **_):
+        y = np.asarray(y[0] if isinstance(y, (list, tuple)) else y, dtype=np.float64)
+        p = self.predict(x).astype(np.float64)
+        q = np.clip(p / p.sum(-1, keepdims=True), 1e-7, 1 - 1e-7)
+        return [float((-(y * np.log(q)).sum(-1)).mean()), float((p.argmax(1) == y.argmax(1)).mean())]
+
+    def evaluate_generator(self, generator, steps, verbose=0, **_):
+        tot = np.zeros(2)
+        for _ in range(steps):
+            x, y = next(generator)
+            tot += self.evaluate(x, y)
+        return list(tot / max(1, steps))
 
 
 class _InputLayer:

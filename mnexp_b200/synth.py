@@ -120,7 +120,7 @@ def _orthogonal(rng, rows, cols):
 
 
 def make_weights(shape, arch=None, seed=1237, word_emb=None, score_model='dot', cook=False,
-                 dv=15, ds=35, bias_noise=0.0, paper_vert=0):
+                 dv=15, ds=35, bias_noise=0.0, paper_vert=0, vertsup=None, vertalt=0):
     """Keras-initialised parameter dict (names: oracle/lstur_numpy.py docstring).
 
     bias_noise > 0 replaces the all-zero bias initialisers by small normals so
@@ -149,29 +149,49 @@ def make_weights(shape, arch=None, seed=1237, word_emb=None, score_model='dot', 
             U = U + paper_vert
     G = U // 2 if arch == 'hgru' else U
     Ue = U // 2 if arch == 'hgru' else U
-    if arch not in ('nigru', 'niavg'):
+    if arch not in ('nigru', 'niavg', 'att'):
         P['user_emb'] = rng.uniform(-0.05, 0.05, (shape.n_users, Ue)).astype(np.float32)
-    if arch not in ('vo', 'niavg'):
+    if arch not in ('vo', 'niavg', 'iavg', 'att', 'iatt', 'ilstm'):
         P['gru_wx'] = _glorot(rng, (D, 3 * G), D, 3 * G)
         P['gru_wh'] = np.concatenate([_orthogonal(rng, G, G) for _ in range(3)], 1)
         P['gru_b'] = bz(3 * G)
+    if arch == 'ilstm':                                         # keras LSTM (task/cook.py:161-163), unit_forget_bias
+        P['lstm_wx'] = _glorot(rng, (D, 4 * G), D, 4 * G)
+        P['lstm_wh'] = np.concatenate([_orthogonal(rng, G, G) for _ in range(4)], 1)
+        P['lstm_b'] = bz(4 * G)
+        P['lstm_b'][G:2 * G] += 1.0
+    if arch in ('att', 'iatt', 'atgru'):                        # SimpleAttentionMaskSupport kernel (Da, 1) + bias (models.py:456-468)
+        Da = G if arch == 'atgru' else D
+        P['uatt_w'] = _glorot(rng, (Da,), Da, 1)
+        P['uatt_b'] = bz(1)
+    if arch == 'algru':                                         # models.AlphaAdd: Constant(0.5) (models.py:541-545)
+        P['alpha'] = (np.float32(0.5) + bz(1)).astype(np.float32)
     if arch in ('gru', 'iigru'):
         P['con_w'] = _glorot(rng, (G + Ue, U), G + Ue, U)
         P['con_b'] = bz(U)
-    if arch in ('iigru', 'iicat'):                              # second user table, task/paper.py:616 / :340
+    if arch in ('iigru', 'iicat', 'inagru'):                    # second user table, task/paper.py:616 / :340, task/cook.py:178
         P['user_emb2'] = rng.uniform(-0.05, 0.05, (shape.n_users, Ue)).astype(np.float32)
     if score_model == 'dnn':                                   # task/paper.py:448-451
-        Du = 2 * U if arch in ('ngru', 'dgru', 'iicat') else (D if arch == 'niavg' else U)
+        Du = 2 * U if arch in ('ngru', 'dgru', 'iicat', 'ilstm') else (D if arch in ('niavg', 'att') else (D + U if arch in ('iavg', 'iatt') else U))
         P['sh_w'] = _glorot(rng, (Du + D, U), Du + D, U)
         P['sh_b'] = bz(U)
         P['so_w'] = _glorot(rng, (U, 1), U, 1)
         P['so_b'] = bz(1)
     if score_model == 'ddot':
-        Du = 2 * U if arch in ('ngru', 'dgru', 'iicat') else (D if arch == 'niavg' else U)
+        Du = 2 * U if arch in ('ngru', 'dgru', 'iicat', 'ilstm') else (D if arch in ('niavg', 'att') else (D + U if arch in ('iavg', 'iatt') else U))
         P['su_w'] = _glorot(rng, (Du, U), Du, U)
         P['su_b'] = bz(U)
         P['sd_w'] = _glorot(rng, (D, U), D, U)
         P['sd_b'] = bz(U)
+    if vertsup:      # (n_vert, hidden_dim): vertical classifier of ...VertSup, task/paper.py:948-952
+        nv, hd = vertsup
+        P['vs_w1'] = _glorot(rng, (D, hd), D, hd)
+        P['vs_b1'] = bz(hd)
+        P['vs_w2'] = _glorot(rng, (hd, nv), hd, nv)
+        P['vs_b2'] = bz(nv)
+    if vertalt:      # n_vert: Dense(len(self.verticals), softmax) of ...VertAlt's vertical model, task/paper.py:1131
+        P['vcls_w'] = _glorot(rng, (D, vertalt), D, vertalt)
+        P['vcls_b'] = bz(vertalt)
     return P
 
 

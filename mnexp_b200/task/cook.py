@@ -7,8 +7,8 @@ row (`cd_title (n,L), cd_vert, cd_subvert (n,), label, user, impr`).  `train()/v
 (sigmoid score of one candidate), both with the Keras calls main.py's cook loop makes (fit / evaluate / predict /
 predict_on_batch / metrics_names / optimizer.lr / summary).  News vector = [title CNN+attention ‖ Vemb[vert] ‖
 Semb[subvert]] without the Dense (task/cook.py:99-113); the user id embedding is multiplied by
-Dropout(1 - id_keep)(idx_mask) (:139-142).  Archs built: vo, avg, gru, igru, agru, ingru, inigru; the others raise the
-reference's NotImplementedError.
+Dropout(1 - id_keep)(idx_mask) (:139-142).  Every branch of Cook.get_user_encoder is built (vo, avg, gru, igru, iavg,
+iatt, ilstm, agru, ingru, inigru, inagru, atgru, algru, :146-193); unknown names raise the reference's NotImplementedError.
 """
 import logging
 
@@ -37,10 +37,18 @@ class CookModel:
         n = len(rows)
         scale = np.asarray(idx_mask, dtype=np.float32).reshape(n)
         keep = self.owner.config.id_keep
+        scale2 = None
+        two = self.owner.config.arch in ('inigru', 'inagru')    # second id embedding with its own Dropout layer (:169-183)
+        if two:
+            scale2 = scale.copy()
         if training and keep < 1.0:                       # Dropout(1 - id_keep) on the mask (task/cook.py:141-142)
             scale = scale * (np.random.random(n) < keep).astype(np.float32) / keep
+            if two:
+                scale2 = scale2 * (np.random.random(n) < keep).astype(np.float32) / keep
         b = dict(user=np.asarray(idx).reshape(n), user_scale=scale, hist_tok=ch_title,
                  cand_tok=np.asarray(cd_title).reshape(n, C, -1))
+        if two:
+            b['user_scale2'] = scale2
         if self.owner.dv:
             b['hist_vert'] = ch_vert
             b['cand_vert'] = np.asarray(cd_vert).reshape(n, C)
@@ -154,7 +162,7 @@ class Cook:
     def _build_model(self):
         c = self.config
         if c.arch not in COOK_ARCH:
-            raise NotImplementedError()                    # task/cook.py:193-194 (iavg / iatt / ilstm / inagru / atgru / algru)
+            raise NotImplementedError()                    # task/cook.py:193-194
         if c.news_encoder != 'cnnatt':
             raise NotImplementedError()                    # task/cook.py:96-97
         self.get_score_model()
@@ -167,7 +175,7 @@ class Cook:
                          K=self.training_data['cd_title'].shape[1] - 1, B=c.batch_size, E=word_emb.shape[1], F=F, k=k,
                          U=c.user_embedding_dim, arch='igru')
         syn = {'vo': 'vo', 'avg': 'niavg', 'gru': 'nigru', 'igru': 'ngru', 'agru': 'pgru', 'ingru': 'igru',
-               'inigru': 'iicat'}[c.arch]
+               'inigru': 'iicat'}.get(c.arch, c.arch)      # iavg / iatt / ilstm / inagru / atgru / algru keep their names
         P = synth.make_weights(sh, arch=syn, seed=np.random.randint(1 << 30), word_emb=word_emb,
                                score_model=c.score_model, cook=True, dv=self.dv, ds=self.ds)
         if not self.dv:

@@ -55,8 +55,8 @@ class Seq2VecPaper(Seq2Vec):
     # ---- sigmoid family: one (history, candidate, label) sample per row, weighted BCE (task/paper.py:36-256) ----
     HAS_USER = False
     SCORE = 'dnn'                                            # score_encoder: Dense(relu)([u ‖ d]) -> Dense(1, sigmoid), :222-226
-    USER_ARCHS = {'gru': ('nigru', 'nigru'), 'avg': ('niavg', 'niavg')}   # config.arch -> (engine arch, oracle/synth arch)
-    # 'att' (SimpleAttentionMaskSupport over the click window, :206-208) is not built
+    # config.arch -> (engine arch, oracle/synth arch); 'att' = SimpleAttentionMaskSupport over the click window (:206-208)
+    USER_ARCHS = {'gru': ('nigru', 'nigru'), 'avg': ('niavg', 'niavg'), 'att': ('att', 'att')}
 
     def _row(self, user, clicked, title, label):
         return ((user,) if self.HAS_USER else ()) + (clicked, title, label)
@@ -188,7 +188,8 @@ class Seq2VecPaperId(Seq2VecPaper):
 
 class Seq2VecPaperSoftmax(Seq2VecPaper):
     HAS_USER = False
-    USER_ARCHS = ('gru',)                                    # Seq2VecPaper.get_user_encoder, task/paper.py:199-221
+    USER_ARCHS = ('gru', 'avg', 'att')                       # Seq2VecPaper.get_user_encoder (inherited), task/paper.py:199-221
+    NO_USER_ARCH = {'gru': 'nigru', 'avg': 'niavg', 'att': 'att'}
 
     # ---- sample generators (task/paper.py:387-441); the window calls go through four hooks so that the time-window
     # variants (Seq2VecPaperSoftmaxDays*, task/paper.py:668-792) only replace the Window -----------------------------
@@ -278,7 +279,7 @@ class Seq2VecPaperSoftmax(Seq2VecPaper):
         if arch in ('ngru', 'dgru') and self.config.score_model == 'dot':
             # the reference graph fails to build here too: keras.layers.dot rejects (2U) . (U) (task/paper.py:447)
             raise ValueError("arch '%s' yields a 2U user vector: use score_model 'dnn' or 'ddot'" % arch)
-        return 'nigru' if not self.HAS_USER else arch
+        return self.NO_USER_ARCH[arch] if not self.HAS_USER else arch
 
     def get_user_encoder(self, window_size=None):
         """Model named 'user_encoder' with the input 'user_clicked_vec' (task/paper.py:590, 632): the user-encoder part of
@@ -461,3 +462,169 @@ class Seq2VecPaperSoftmaxDaysIdVert(Seq2VecPaperSoftmaxDaysId):
     def _build_model(self):
         super(Seq2VecPaperSoftmaxDaysIdVert, self)._build_model()
         self._core.has_vert = True
+
+
+def _to_categorical(ids, num_classes):
+    out = np.zeros((len(ids), num_classes), dtype=np.float32)
+    out[np.arange(len(ids)), np.asarray(ids, dtype=np.int64)] = 1.0
+    return out
+
+
+class Seq2VecPaperSoftmaxDaysIdVertSup(Seq2VecPaperSoftmaxDaysId):
+    """task/paper.py:884-1000: LSTUR with an auxiliary vertical classifier.  Samples carry a second target, the one-hot
+    verticals of the W history slots and the 1+K candidates (:897-902); the model has two outputs ('ranking', 'vert') and
+    the loss 1 * CE_ranking + config.gain * CE_vert (:981-987); test_model is the plain sigmoid scorer (:989-997)."""
+
+    def _w_vert(self, ch, impression):
+        return [self.docs[i].vertical for i in ch.get_ids(impression.time)]
+
+    def _sample(self, user, ch, pos, impression, label):
+        negs = impression.negative_samples(self.config.negative_samples)
+        verts = self._w_vert(ch, impression) + [self.docs[pos].vertical] + [self.docs[neg].vertical for neg in negs]
+        return [user, self._w_title(ch, impression), self.docs[pos].title] + [self.docs[neg].title for neg in negs] + \
+               [label, _to_categorical(verts, len(utils.verticals))]
+
+    @property
+    def train(self):
+        """Same shuffle pool as Seq2Vec.train, two targets per batch (task/paper.py:928-939)."""
+        from .seq2vec import _stack_columns
+        bs = self.config.batch_size
+        pool, samples = [], self.train_gen()
+        while True:
+            pool.append(next(samples))
+            if len(pool) < 100 * bs:
+                continue
+            np.random.shuffle(pool)
+            batch = _stack_columns(pool[:bs])
+            del pool[:bs]
+            yield batch[:-2], batch[-2:]
+
+    @property
+    def valid(self):
+        from .seq2vec import _stack_columns
+        samples = self.valid_gen()
+        while True:
+            batch = _stack_columns([next(samples) for _ in range(self.config.batch_size)])
+            yield batch[:-2], batch[-2:]
+
+    def get_vertical_classifier(self, input_shape=None):
+        """Dense(hidden_dim, relu) -> Dense(len(utils.verticals), softmax) (task/paper.py:948-952): (n_vert, hidden_dim)."""
+        return len(utils.verticals), self.config.hidden_dim
+
+    def _init_params(self):
+        c = self.config
+        F, k = c.title_filter_shape
+        word_emb = self._title_embedding().astype(np.float32)
+        sh = synth.Shape('cfg', n_users=len(self.data), n_news=self.doc_count - 1, vocab=word_emb.shape[0],
+                         L=c.title_shape, W=c.window_size, K=c.negative_samples, B=c.batch_size, E=word_emb.shape[1],
+                         F=F, k=k, U=c.user_embedding_dim, arch=self._engine_arch())
+        return synth.make_weights(sh, arch=self._engine_arch(), seed=np.random.randint(1 << 30), word_emb=word_emb,
+                                  score_model=c.score_model, vertsup=self.get_vertical_classifier())
+
+    def _build_model(self):
+        super(Seq2VecPaperSoftmaxDaysIdVertSup, self)._build_model()
+        layers = self.model.layers
+        self.model = keras_like.VertSupModel(self._core, name='model')
+        self.model.layers.update(layers)
+
+
+class Seq2VecPaperSoftmaxDaysIdVertAlt(Seq2VecPaperSoftmaxDaysId):
+    """task/paper.py:1003-1136: the click model and a vertical classifier on the shared doc_encoder are trained in
+    alternation — `round - 1` epochs of the vertical model (on 10 % of the documents, validated on the rest), then one
+    epoch of the click model; `callback_valid` switches `self.model` between `seq_model` and `vert_model`."""
+
+    def __init__(self, config):
+        super(Seq2VecPaperSoftmaxDaysIdVertAlt, self).__init__(config)
+        self.round = self.config.round
+        self.config.epochs *= self.round
+
+    def _load_docs(self):
+        super(Seq2VecPaperSoftmaxDaysIdVertAlt, self)._load_docs()
+        names = {}
+        with open(self.config.doc_meta_input) as file:
+            for line in file:
+                cols = line.rstrip('\n').split('\t')
+                names[int(cols[1])] = cols[2]
+        # the reference indexes list(set(names)) (arbitrary order, :1025-1028); sorted here so that runs are reproducible
+        self.verticals = sorted(set(names.values()))
+        ids = [i for i in self.docs if i != 0]
+        self.data_verticals = _to_categorical([self.verticals.index(names[i]) for i in ids], len(self.verticals))
+        self.data_titles = np.stack([self.docs[i].title for i in ids])
+        data = np.arange(len(ids))
+        np.random.shuffle(data)
+        self.train_index = data[:len(ids) // 10]
+        self.valid_index = data[len(ids) // 10:]
+
+    @property
+    def training_step(self):
+        return self.config.training_step if self.train_seq else len(self.train_index) // self.config.batch_size
+
+    @training_step.setter
+    def training_step(self, value):
+        pass
+
+    @property
+    def validation_step(self):
+        return self.config.validation_step if self.train_seq else len(self.valid_index) // self.config.batch_size
+
+    @validation_step.setter
+    def validation_step(self, value):
+        pass
+
+    train_seq = False
+
+    def _vert_batches(self, index, shuffle):
+        bs = self.config.batch_size
+        while True:
+            if shuffle:
+                np.random.shuffle(index)
+            titles, verts = self.data_titles[index], self.data_verticals[index]
+            for end in range(bs, len(index), bs):              # task/paper.py:1073-1075
+                yield titles[end - bs:end], verts[end - bs:end]
+
+    @property
+    def train_vert(self):
+        return self._vert_batches(self.train_index, True)
+
+    @property
+    def valid_vert(self):
+        return self._vert_batches(self.valid_index, False)
+
+    @property
+    def train(self):
+        train_vert = self.train_vert
+        train = super(Seq2VecPaperSoftmaxDaysIdVertAlt, self).train
+        while True:
+            yield next(train) if self.train_seq else next(train_vert)
+
+    @property
+    def valid(self):
+        return super(Seq2VecPaperSoftmaxDaysIdVertAlt, self).valid if self.train_seq else self.valid_vert
+
+    def callback(self, epoch):
+        if self.train_seq:
+            super(Seq2VecPaperSoftmaxDaysIdVertAlt, self).callback(epoch)
+        elif epoch % self.round == self.round - 2:
+            keras_like.backend.set_value(self.model.optimizer.lr,
+                                         keras_like.backend.get_value(self.model.optimizer.lr) * self.config.learning_rate_decay)
+
+    def callback_valid(self, epoch):
+        self.train_seq = epoch % self.round == self.round - 2
+        self.model = self.seq_model if self.train_seq else self.vert_model
+
+    def _init_params(self):
+        c = self.config
+        F, k = c.title_filter_shape
+        word_emb = self._title_embedding().astype(np.float32)
+        sh = synth.Shape('cfg', n_users=len(self.data), n_news=self.doc_count - 1, vocab=word_emb.shape[0],
+                         L=c.title_shape, W=c.window_size, K=c.negative_samples, B=c.batch_size, E=word_emb.shape[1],
+                         F=F, k=k, U=c.user_embedding_dim, arch=self._engine_arch())
+        return synth.make_weights(sh, arch=self._engine_arch(), seed=np.random.randint(1 << 30), word_emb=word_emb,
+                                  score_model=c.score_model, vertalt=len(self.verticals))
+
+    def _build_model(self):
+        self.train_seq = False
+        super(Seq2VecPaperSoftmaxDaysIdVertAlt, self)._build_model()
+        self.seq_model = self.model
+        self.model = self.vert_model = keras_like.VertModel(self._core)
+        self.vert_model.layers['doc_encoder'] = self.doc_encoder

@@ -15,6 +15,9 @@ Parameter dictionary (names used by oracle, engine and tests alike):
   user_emb (n_users,Ue)       Embedding(len(self.data),U)      task/paper.py:589
   gru_wx (D,3G) gru_wh (G,3G) gru_b (3G)   keras GRU, gate order z,r,h [K]
   con_w (G+Ue,U) con_b (U)    Dense after concat, arch 'gru'   task/paper.py:598-599
+  lstm_wx (D,4G) lstm_wh (G,4G) lstm_b (4G)   keras LSTM, gate order i,f,c,o [K]   task/cook.py:161-163
+  uatt_w (Da,) uatt_b ()      SimpleAttentionMaskSupport over the history / over [GRU ; id]   task/cook.py:158-160,184-190
+  alpha ()                    models.AlphaAdd                  models.py:540-554, task/cook.py:191-193
   su_w,su_b,sd_w,sd_b         'ddot' scorer Dense layers       task/paper.py:452-455, task/cook.py:206-209
   sh_w,sh_b,so_w,so_b         'dnn' scorer                     task/paper.py:448-451
 """
@@ -129,6 +132,30 @@ def gru_last_state(H, h0, Wx, Wh, b, recurrent_activation='hard_sigmoid', aux=Fa
     return h
 
 
+def lstm_last_state(H, Wx, Wh, b, recurrent_activation='hard_sigmoid'):
+    """keras.layers.LSTM(G)(Masking()(H)) — task/cook.py:161-163.  Keras 2.2.x defaults [K]: activation tanh,
+    recurrent_activation hard_sigmoid, gate order i,f,c,o, zero initial (h, c), masked steps carry both."""
+    ra = hard_sigmoid if recurrent_activation == 'hard_sigmoid' else sigmoid
+    B, W, D = H.shape
+    G = Wh.shape[0]
+    gm = (H != 0).any(-1)
+    h, c = np.zeros((B, G)), np.zeros((B, G))
+    for t in range(W):
+        a = H[:, t] @ Wx + b + h @ Wh
+        i, f, g, o = ra(a[:, :G]), ra(a[:, G:2 * G]), np.tanh(a[:, 2 * G:3 * G]), ra(a[:, 3 * G:])
+        cn = f * c + i * g
+        hn = o * np.tanh(cn)
+        c = np.where(gm[:, t:t + 1], cn, c)
+        h = np.where(gm[:, t:t + 1], hn, h)
+    return h
+
+
+def masked_attention(X, att_w, att_b):
+    """SimpleAttentionMaskSupport()(Masking()(X)) over the steps of X (B,T,D) — models.py:474-489."""
+    m = (X != 0).any(-1).astype(np.float64)
+    return attention_pool(X * m[..., None], m, att_w, att_b)[0]
+
+
 ARCH_INI = ('igru', 'ingru')          # paper.py igru == cook.py ingru (SURVEY §9.9)
 
 
@@ -140,7 +167,7 @@ def user_encoder(arch, user, H, P, recurrent_activation='hard_sigmoid', u0_scale
     task/cook.py:141-142)."""
     f8 = lambda k: P[k].astype(np.float64)
     user = np.asarray(user).astype(np.int64).reshape(-1)
-    u0 = f8('user_emb')[user] if 'user_emb' in P and arch not in ('nigru', 'niavg') else None
+    u0 = f8('user_emb')[user] if 'user_emb' in P and arch not in ('nigru', 'niavg', 'att') else None
     if u0 is not None and u0_scale is not None:
         u0 = u0 * u0_scale
     gru = lambda h0: gru_last_state(H.astype(np.float64), h0, f8('gru_wx'), f8('gru_wh'), f8('gru_b'), recurrent_activation)
@@ -162,6 +189,26 @@ def user_encoder(arch, user, H, P, recurrent_activation='hard_sigmoid', u0_scale
         H8 = H.astype(np.float64)
         gm = (H8 != 0).any(-1).astype(np.float64)
         return H8.sum(-2) / (gm.sum(-1, keepdims=True) + 1e-7)
+    # ---- cook.py branches (task/cook.py:155-193) and Seq2VecPaper 'att' (task/paper.py:206-208)
+    H8 = H.astype(np.float64)
+    u2 = lambda: f8('user_emb2')[user] * (1.0 if u0_scale is None else u0_scale)   # the id mask multiplies both tables
+    if arch == 'iavg':
+        gm = (H8 != 0).any(-1).astype(np.float64)
+        return np.concatenate([H8.sum(-2) / (gm.sum(-1, keepdims=True) + 1e-7), u0], -1)
+    if arch == 'att':
+        return masked_attention(H8, f8('uatt_w').reshape(-1), float(np.asarray(P['uatt_b']).reshape(-1)[0]))
+    if arch == 'iatt':
+        return np.concatenate([masked_attention(H8, f8('uatt_w').reshape(-1), float(np.asarray(P['uatt_b']).reshape(-1)[0])), u0], -1)
+    if arch == 'ilstm':
+        return np.concatenate([lstm_last_state(H8, f8('lstm_wx'), f8('lstm_wh'), f8('lstm_b'), recurrent_activation), u0], -1)
+    if arch == 'inagru':
+        return gru(u0) + u2()
+    if arch == 'atgru':
+        seq = np.stack([gru(None), u0], 1)
+        return masked_attention(seq, f8('uatt_w').reshape(-1), float(np.asarray(P['uatt_b']).reshape(-1)[0]))
+    if arch == 'algru':
+        al = float(np.asarray(P['alpha']).reshape(-1)[0])
+        return gru(None) * al + u0 * (1.0 - al)
     raise Exception('Unsupport user model')  # task/paper.py:630
 
 
@@ -216,7 +263,7 @@ def _doc_vectors(tok, P, vert=None, subvert=None):
 
 def lstur_forward(P, user, clicked_tok, cand_tok, arch='igru', score_model='dot',
                   recurrent_activation='hard_sigmoid', aux=False, hist_vert=None, hist_subvert=None, cand_vert=None,
-                  cand_subvert=None, u0_scale=None):
+                  cand_subvert=None, u0_scale=None, flavour='paper'):
     """Seq2VecPaperSoftmaxId._build_model forward — task/paper.py:635-665.
 
     clicked_tok (B,W,L), cand_tok (B,C,L) -> softmax probs (B,C) and the
@@ -228,7 +275,7 @@ def lstur_forward(P, user, clicked_tok, cand_tok, arch='igru', score_model='dot'
     H = dh * hm[..., None]                                    # task/paper.py:644-645, task/cook.py:250
     u = user_encoder(arch, user, H, P, recurrent_activation, u0_scale=u0_scale)
     dc = _doc_vectors(cand_tok.reshape(B * C, L), P, cand_vert, cand_subvert).reshape(B, C, -1)
-    s = score(u, dc, P, score_model)
+    s = score(u, dc, P, score_model, flavour)
     out = dict(probs=softmax(s), logits=s, sigmoid=sigmoid(s), user_vec=u, cand_vec=dc, hist_vec=H, hist_mask=hm)
     return out if aux else out['probs']
 

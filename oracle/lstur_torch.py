@@ -67,9 +67,37 @@ def gru_last_state(H, h0, Wx, Wh, b, recurrent_activation='hard_sigmoid'):
     return h
 
 
+def lstm_last_state(H, Wx, Wh, b, recurrent_activation='hard_sigmoid'):
+    """Keras-2.2 LSTM (gate order i,f,c,o), masked steps carry (h, c) — task/cook.py:161-163."""
+    ra = hard_sigmoid if recurrent_activation == 'hard_sigmoid' else torch.sigmoid
+    B, W, D = H.shape
+    G = Wh.shape[0]
+    gm = (H.detach() != 0).any(-1)
+    h, c = H.new_zeros((B, G)), H.new_zeros((B, G))
+    XW = H @ Wx + b
+    for t in range(W):
+        a = XW[:, t] + h @ Wh
+        i, f, g, o = ra(a[:, :G]), ra(a[:, G:2 * G]), torch.tanh(a[:, 2 * G:3 * G]), ra(a[:, 3 * G:])
+        cn = f * c + i * g
+        hn = o * torch.tanh(cn)
+        c = torch.where(gm[:, t:t + 1], cn, c)
+        h = torch.where(gm[:, t:t + 1], hn, h)
+    return h
+
+
+def masked_attention(X, att_w, att_b):
+    """SimpleAttentionMaskSupport()(Masking()(X)) over the steps of X (B,T,D) — models.py:474-489."""
+    m = (X.detach() != 0).any(-1).to(X.dtype)
+    X = X * m.unsqueeze(-1)
+    a = torch.tanh(X @ att_w.reshape(-1) + att_b.reshape(-1)[0])
+    e = torch.exp(a) * m
+    w = e / (e.sum(-1, keepdim=True) + EPS)
+    return (X * w.unsqueeze(-1)).sum(1)
+
+
 def user_encoder(arch, user, H, P, recurrent_activation='hard_sigmoid', u0_scale=None):
-    """task/paper.py:584-633."""
-    u0 = P['user_emb'][user.reshape(-1)] if 'user_emb' in P and arch not in ('nigru', 'niavg') else None
+    """task/paper.py:584-633; cook branches task/cook.py:146-193."""
+    u0 = P['user_emb'][user.reshape(-1)] if 'user_emb' in P and arch not in ('nigru', 'niavg', 'att') else None
     if u0 is not None and u0_scale is not None:
         u0 = u0 * u0_scale
     gru = lambda h0: gru_last_state(H, h0, P['gru_wx'], P['gru_wh'], P['gru_b'], recurrent_activation)
@@ -94,6 +122,23 @@ def user_encoder(arch, user, H, P, recurrent_activation='hard_sigmoid', u0_scale
     if arch == 'niavg':          # models.GlobalAveragePoolingMaskSupport (models.py:422-441) under Masking()
         gm = (H != 0).any(-1).to(H.dtype)
         return H.sum(-2) / (gm.sum(-1, keepdim=True) + EPS)
+    u2 = lambda: P['user_emb2'][user.reshape(-1)] * (1.0 if u0_scale is None else u0_scale)
+    if arch == 'iavg':
+        gm = (H != 0).any(-1).to(H.dtype)
+        return torch.cat([H.sum(-2) / (gm.sum(-1, keepdim=True) + EPS), u0], -1)
+    if arch == 'att':
+        return masked_attention(H, P['uatt_w'], P['uatt_b'])
+    if arch == 'iatt':
+        return torch.cat([masked_attention(H, P['uatt_w'], P['uatt_b']), u0], -1)
+    if arch == 'ilstm':
+        return torch.cat([lstm_last_state(H, P['lstm_wx'], P['lstm_wh'], P['lstm_b'], recurrent_activation), u0], -1)
+    if arch == 'inagru':
+        return gru(u0) + u2()
+    if arch == 'atgru':
+        return masked_attention(torch.stack([gru(None), u0], 1), P['uatt_w'], P['uatt_b'])
+    if arch == 'algru':
+        al = P['alpha'].reshape(-1)[0]
+        return gru(None) * al + u0 * (1.0 - al)
     raise Exception('Unsupport user model')
 
 
@@ -138,7 +183,7 @@ def _doc_vectors(tok, P, vert=None, subvert=None, **kw):
 
 def forward(P, user, clicked_tok, cand_tok, arch='igru', score_model='dot',
             recurrent_activation='hard_sigmoid', dropout=0.0, training=False, aux=False, hist_vert=None,
-            hist_subvert=None, cand_vert=None, cand_subvert=None, u0_scale=None, head='softmax'):
+            hist_subvert=None, cand_vert=None, cand_subvert=None, u0_scale=None, head='softmax', flavour='paper'):
     """Seq2VecPaperSoftmaxId._build_model — task/paper.py:635-665."""
     B, W, L = clicked_tok.shape
     C = cand_tok.shape[1]
@@ -149,7 +194,7 @@ def forward(P, user, clicked_tok, cand_tok, arch='igru', score_model='dot',
     u = user_encoder(arch, user, H, P, recurrent_activation, u0_scale=u0_scale)
     dc = _doc_vectors(cand_tok.reshape(B * C, L), P, cand_vert, cand_subvert, dropout=dropout,
                       training=training).reshape(B, C, -1)
-    s = score(u, dc, P, score_model)
+    s = score(u, dc, P, score_model, flavour)
     # head='sigmoid': the sigmoid family (Seq2VecPaper / Dot / Id, task/paper.py:222-262), one candidate per row
     probs = torch.softmax(s, -1) if head == 'softmax' else torch.sigmoid(s)
     if aux:
@@ -157,12 +202,47 @@ def forward(P, user, clicked_tok, cand_tok, arch='igru', score_model='dot',
     return probs
 
 
-def loss_fn(P, user, clicked_tok, cand_tok, label=None, **kw):
-    probs = forward(P, user, clicked_tok, cand_tok, **kw)
+def vertical_classifier(P, X):
+    """Seq2VecPaperSoftmaxDaysIdVertSup.get_vertical_classifier (task/paper.py:948-952): Dense(hidden_dim, relu) ->
+    Dense(len(utils.verticals), softmax), applied TimeDistributed to X (..., D)."""
+    return torch.softmax(torch.relu(X @ P['vs_w1'] + P['vs_b1']) @ P['vs_w2'] + P['vs_b2'], -1)
+
+
+def loss_fn(P, user, clicked_tok, cand_tok, label=None, vert_labels=None, aux_gain=1.0, parts=False, **kw):
+    """categorical cross-entropy of the click head; with vert_labels = (hist (B,W), cand (B,C)) integer vertical ids also
+    the auxiliary head of ...VertSup (task/paper.py:954-990): the classifier runs over [clicked_vec (history-masked) ;
+    candidate vectors] and the compiled loss is 1 * CE_click + gain * CE_vertical, the latter a mean over all B*(W+C)
+    positions."""
+    if vert_labels is None:
+        probs = forward(P, user, clicked_tok, cand_tok, **kw)
+    else:
+        out = forward(P, user, clicked_tok, cand_tok, aux=True, **kw)
+        probs = out['probs']
     if label is None:
         label = torch.zeros_like(probs)
         label[:, 0] = 1.0
-    return categorical_crossentropy(label, probs)
+    main = categorical_crossentropy(label, probs)
+    if vert_labels is None:
+        return main
+    X = torch.cat([out['hist_vec'], out['cand_vec']], 1)                  # (B, W+C, D)
+    y = torch.cat([torch.as_tensor(vert_labels[0]).long(), torch.as_tensor(vert_labels[1]).long()], 1)
+    vp = vertical_classifier(P, X)
+    onehot = torch.nn.functional.one_hot(y, vp.shape[-1]).to(vp.dtype)
+    aux = categorical_crossentropy(onehot, vp)
+    if parts:
+        return main, aux, vp
+    return main + aux_gain * aux
+
+
+def title_cls_loss(P, tok, labels, dropout=0.0, training=False, drop_x=None, drop_c=None, parts=False):
+    """vert_model of Seq2VecPaperSoftmaxDaysIdVertAlt (task/paper.py:1128-1136): Dense(n_vert, softmax)(doc_encoder(title)),
+    categorical cross-entropy against the one-hot vertical."""
+    d = news_encoder(torch.as_tensor(tok).long(), P, use_dense='dense_w' in P, dropout=dropout, training=training,
+                     drop_x=drop_x, drop_c=drop_c)
+    vp = torch.softmax(d @ P['vcls_w'] + P['vcls_b'], -1)
+    onehot = torch.nn.functional.one_hot(torch.as_tensor(labels).long(), vp.shape[-1]).to(vp.dtype)
+    loss = categorical_crossentropy(onehot, vp)
+    return (loss, vp) if parts else loss
 
 
 class KerasAdam:

@@ -359,7 +359,11 @@ def _cook_npz(d, sh, n_train=24, n_test=10, seed=0):
 
 
 @pytest.mark.parametrize('arch,oarch,score_model,vtype', [('ingru', 'igru', 'ddot', 'vs'), ('igru', 'ngru', 'dnn', 'v'),
-                                                          ('inigru', 'iicat', 'ddot', 's'), ('avg', 'niavg', 'dnn', 'vs')])
+                                                          ('inigru', 'iicat', 'ddot', 's'), ('avg', 'niavg', 'dnn', 'vs'),
+                                                          # the remaining Cook.get_user_encoder branches (task/cook.py:155-193)
+                                                          ('iavg', 'iavg', 'dnn', 'vs'), ('iatt', 'iatt', 'ddot', 'v'),
+                                                          ('ilstm', 'ilstm', 'dnn', 's'), ('inagru', 'inagru', 'ddot', 'vs'),
+                                                          ('atgru', 'atgru', 'dnn', 'vs'), ('algru', 'algru', 'ddot', 'v')])
 def test_cook_handler(lib, arch, oarch, score_model, vtype):
     """Cook (task/cook.py): .npz protocol with per-slot vertical / subvertical ids, [title ‖ Vemb ‖ Semb] news vectors,
     idx_mask on the user id embedding, linear 'ddot'; train_model / test_model through main.py's cook calls."""
@@ -428,6 +432,102 @@ def test_days_id_vert_surface(lib):
     assert 0.0 <= h.last_evaluation['auc'] <= 1.0 and h.model is model
     dv = model.get_layer('doc_encoder').predict(x[1][0])
     assert dv.shape == (sh.W, sh.U)
+
+
+def test_vertsup_surface(lib):
+    """Seq2VecPaperSoftmaxDaysIdVertSup (task/paper.py:884-1000): two targets per batch, two-output model with
+    loss = CE_ranking + gain * CE_vert, Keras' multi-output metric names; test_model is the plain scorer."""
+    from oracle import lstur_torch as ot
+    import torch
+    sh, h = _handler('igru', 'Seq2VecPaperSoftmaxDaysIdVertSup', days=100000, hidden_dim=12, gain=0.5)
+    model = h.build_model(0)
+    x, y = next(h.train)
+    C = 1 + sh.K
+    assert len(x) == 2 + C and len(y) == 2 and y[0].shape == (8, C) and y[1].shape == (8, sh.W + C, 16)
+    assert np.allclose(y[1].sum(-1), 1.0) and (y[1][:, :sh.W].argmax(-1)[x[1].any(-1) == 0] == 0).all()   # pad slots: 'N/A'
+    assert model.metrics_names == ['loss', 'ranking_loss', 'vert_loss', 'ranking_categorical_accuracy', 'vert_categorical_accuracy']
+    P = {k: np.asarray(v) for k, v in h._core.engine_train(8).get_weights_dict().items()}
+    assert P['vs_w1'].shape == (sh.U, 12) and P['vs_w2'].shape == (12, 16)
+    ora = ot.LsturOracle(P, arch='igru')
+    u, c, d = ora._ints(x[0], x[1], np.stack(x[2:], 1))
+    ids = y[1].argmax(-1)
+    main, aux, vp = ot.loss_fn(ora.P, u, c, d, label=torch.tensor(y[0], dtype=torch.float64), arch='igru',
+                               vert_labels=(ids[:, :sh.W], ids[:, sh.W:]), parts=True)
+    ev = model.evaluate(x, y)
+    assert abs(ev[1] - float(main)) < 1e-5 and abs(ev[2] - float(aux)) < 1e-5 and abs(ev[0] - float(main + 0.5 * aux)) < 1e-5
+    pr = model.predict(x)
+    assert pr[0].shape == (8, C) and pr[1].shape == (8, sh.W + C, 16) and rel(pr[1], vp.detach().numpy()) < 2e-5
+    for _ in range(30):
+        out = model.train_on_batch(x, y)
+    ev2 = model.evaluate(x, y)
+    assert len(out) == 5 and ev2[0] < ev[0] and ev2[2] < ev[2]
+    s = h.test_model.predict(x[:2] + [x[2]])
+    assert s.shape == (8, 1) and np.all((s > 0) & (s < 1))
+    h.callback(0)
+    assert 0.0 <= h.last_evaluation['auc'] <= 1.0
+
+
+def test_vertalt_surface(lib):
+    """Seq2VecPaperSoftmaxDaysIdVertAlt (task/paper.py:1003-1136): epochs x round; vertical model on 10 % of the documents;
+    callback_valid alternates self.model between vert_model and seq_model; both share the doc encoder."""
+    sh, h = _handler('igru', 'Seq2VecPaperSoftmaxDaysIdVertAlt', days=100000, round=3)
+    assert h.config.epochs == 2 * 3
+    model = h.build_model(0)
+    assert model is h.vert_model and h.train_seq is False
+    nd = len(h.data_titles)
+    assert len(h.train_index) == nd // 10 and len(h.valid_index) == nd - nd // 10
+    assert h.training_step == len(h.train_index) // 8 and h.validation_step == len(h.valid_index) // 8
+    train = h.train
+    x, y = next(train)
+    assert x.shape == (8, sh.L) and y.shape == (8, len(h.verticals)) and model.metrics_names == ['loss', 'categorical_accuracy']
+    conv0 = h._core.engine_train(8).get_weights_dict()['conv_w'].copy()
+    l0 = model.evaluate(x, y)[0]
+    for _ in range(30):
+        model.train_on_batch(x, y)
+    assert model.evaluate(x, y)[0] < l0
+    conv1 = h._core.train_engine.get_weights_dict()['conv_w']
+    assert np.abs(conv1 - conv0).max() > 0                       # the vertical model trains the shared doc encoder
+    ev = model.evaluate_generator(h.valid, 2)
+    assert len(ev) == 2 and np.isfinite(ev[0])
+    h.callback(0)
+    h.callback_valid(0)                                          # epoch 0 of round 3: stay on the vertical model
+    assert h.train_seq is False and h.build_model(1) is h.vert_model
+    lr0 = model.optimizer.lr.value
+    h.callback(1)                                                # epoch % round == round - 2: decay the vertical lr
+    assert abs(model.optimizer.lr.value - lr0 * h.config.learning_rate_decay) < 1e-12
+    h.callback_valid(1)
+    assert h.train_seq is True and h.build_model(2) is h.seq_model and h.training_step == h.config.training_step
+    xs, ys = next(train)                                         # the same generator now yields click batches
+    assert len(xs) == 2 + 1 + sh.K and ys.shape == (8, 1 + sh.K)
+    before = h.seq_model.evaluate(xs, ys)[0]
+    for _ in range(25):
+        h.seq_model.train_on_batch(xs, ys)
+    assert h.seq_model.evaluate(xs, ys)[0] < before
+    h.callback_valid(2)
+    assert h.train_seq is False and h.model is h.vert_model
+
+
+@pytest.mark.parametrize('task_name,arch,oarch', [('Seq2VecPaperSoftmax', 'att', 'att'), ('Seq2VecPaperSoftmax', 'avg', 'niavg'),
+                                                  ('Seq2VecPaper', 'att', 'att')])
+def test_attention_and_average_user_encoders_of_the_non_id_classes(lib, task_name, arch, oarch):
+    """Seq2VecPaper.get_user_encoder (task/paper.py:199-221, inherited by Seq2VecPaperSoftmax): 'att' / 'avg' / 'gru'."""
+    sh, h = _handler(arch, task_name)
+    model = h.build_model(0)
+    x, y = next(h.train)
+    P = _oracle_params(model)
+    if 'uatt_w' in P:
+        P['uatt_w'] = P['uatt_w'].reshape(-1)
+    if task_name == 'Seq2VecPaperSoftmax':
+        ref = on.lstur_forward(P, np.zeros(len(y), dtype=int), x[0].astype(int), np.stack(x[1:], 1).astype(int), arch=oarch)
+        assert rel(model.predict(x), ref) < 2e-5
+    else:
+        ref = on.lstur_forward(P, np.zeros(len(y), dtype=int), x[0].astype(int), x[1][:, None].astype(int), arch=oarch,
+                               score_model='dnn', aux=True)
+        assert rel(model.predict(x).reshape(-1), ref['sigmoid'].reshape(-1)) < 2e-5
+    l0 = model.evaluate(x, y)[0]
+    for _ in range(25):
+        model.train_on_batch(x, y)
+    assert model.evaluate(x, y)[0] < l0
 
 
 def test_engine_matches_variant_golden_fixtures(lib):

@@ -219,3 +219,53 @@ def test_variant_golden_fixtures_reproduce():
         for k, g in grads.items():
             if g is not None and k != 'word_emb':
                 assert np.array_equal(g.numpy(), gold[key + '/grad/' + k]), (key, k)
+
+
+COOK_NEW = [('iavg', 'dnn'), ('iatt', 'ddot'), ('att', 'dot'), ('ilstm', 'dnn'), ('inagru', 'dot'), ('atgru', 'dot'),
+            ('algru', 'dot')]
+
+
+@pytest.mark.parametrize('arch,score_model', COOK_NEW)
+def test_cook_user_encoders_two_implementations(arch, score_model):
+    """Cook.get_user_encoder branches iavg / iatt / ilstm / inagru / atgru / algru (task/cook.py:155-193) and
+    Seq2VecPaper 'att' (task/paper.py:206-208): numpy float64 loops vs the independent torch restatement."""
+    P = synth.make_weights(SH, arch=arch, bias_noise=0.05, seed=31, score_model=score_model)
+    (b,), _ = synth.make_batches(SH, 1, seed=32)
+    ct, cd = TOK[b['hist_doc']], TOK[b['cand_doc']]
+    pn = on.lstur_forward(P, b['user'], ct, cd, arch=arch, score_model=score_model)
+    pt = ot.LsturOracle(P, arch=arch, score_model=score_model).forward(b['user'], ct, cd).detach().numpy()
+    assert pn.shape == (SH.B, 1 + SH.K) and np.abs(pn - pt).max() < 1e-12
+
+
+def test_cook_heads_by_hand():
+    """SimpleAttentionMaskSupport over two steps, AlphaAdd and the LSTM step, computed by hand."""
+    # atgru: sequence [h ; u], attention kernel k, bias 0 (models.py:474-489); an all-zero id vector is masked out
+    h = np.array([[1.0, 0.0]])
+    u = np.array([[0.0, 2.0]])
+    k = np.array([0.5, -0.25])
+    a = np.tanh(np.array([0.5, -0.5]))
+    e = np.exp(a)
+    want = (e[0] * h + e[1] * u) / (e.sum() + 1e-7)
+    got = on.masked_attention(np.stack([h, u], 1), k, 0.0)
+    assert np.abs(got - want).max() < 1e-15
+    got0 = on.masked_attention(np.stack([h, 0 * u], 1), k, 0.0)
+    assert np.abs(got0 - h * e[0] / (e[0] + 1e-7)).max() < 1e-15
+    # algru (models.py:551-552)
+    P = dict(user_emb=np.array([[2.0, 4.0]]), alpha=np.array([0.25]), gru_wx=np.zeros((2, 6)), gru_wh=np.zeros((2, 6)),
+             gru_b=np.zeros(6))
+    H = np.zeros((1, 3, 2))          # all-masked history: the GRU returns its zero initial state
+    out = on.user_encoder('algru', np.zeros(1, dtype=int), H, P)
+    assert np.allclose(out, 0.75 * P['user_emb'])
+    # one LSTM step from zero state with identity-like weights: c = i * g, h = o * tanh(c)
+    G = 1
+    Wx = np.array([[1.0, 0.0, 2.0, 3.0]])
+    b = np.array([0.0, 1.0, 0.0, 0.0])
+    x = np.array([[[0.5]]])
+    hs = lambda v: np.clip(0.2 * v + 0.5, 0, 1)
+    c = hs(0.5) * np.tanh(1.0)
+    want_h = hs(1.5) * np.tanh(c)
+    got_h = on.lstm_last_state(x, Wx, np.zeros((G, 4 * G)), b)
+    assert abs(got_h[0, 0] - want_h) < 1e-15
+    # a trailing masked (all-zero) step carries the state
+    x2 = np.concatenate([x, np.zeros((1, 1, 1))], 1)
+    assert abs(on.lstm_last_state(x2, Wx, np.zeros((G, 4 * G)), b)[0, 0] - want_h) < 1e-15
