@@ -575,6 +575,8 @@ class Seq2VecPaperSoftmaxDaysIdVertAlt(Seq2VecPaperSoftmaxDaysId):
 
     def _vert_batches(self, index, shuffle):
         bs = self.config.batch_size
+        if len(index) <= bs:       # the reference's loop (task/paper.py:1069-1075) would spin forever without yielding
+            raise ValueError('vertical split of %d documents yields no batch of %d' % (len(index), bs))
         while True:
             if shuffle:
                 np.random.shuffle(index)

@@ -15,12 +15,19 @@ KEYS = {
     'smem_pipe_pct': 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
     'dram_pct_of_peak': 'dram__throughput.avg.pct_of_peak_sustained_elapsed',
     'l2_hit_pct': 'lts__t_sector_hit_rate.pct',
+    'l2_sectors': 'lts__t_sectors.sum',
+    'issue_active_pct': 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
     'warps_active_pct': 'sm__warps_active.avg.pct_of_peak_sustained_active',
     'regs': 'launch__registers_per_thread',
     'grid': 'launch__grid_size',
     'block': 'launch__block_size',
     'smem_dyn_KB': 'launch__shared_mem_per_block_dynamic',
 }
+
+
+# ncu picks a unit per column (ns/us/ms, byte/Kbyte/Mbyte/Gbyte): durations are brought to ms, byte counts to GB
+SCALE = {('ms', 'ns'): 1e-6, ('ms', 'us'): 1e-3, ('ms', 'ms'): 1.0, ('ms', 's'): 1e3,
+         ('GB', 'byte'): 1e-9, ('GB', 'Kbyte'): 1e-6, ('GB', 'Mbyte'): 1e-3, ('GB', 'Gbyte'): 1.0}
 
 
 def main(raw, out):
@@ -32,11 +39,12 @@ def main(raw, out):
         for k, name in KEYS.items():
             if name in hdr:
                 v = r[hdr.index(name)].replace(',', '')
+                u = units[hdr.index(name)]
                 try:
-                    d[k] = float(v)
+                    d[k] = float(v) * SCALE.get((k.split('_')[-1], u), 1.0)
                 except ValueError:
                     d[k] = v
-                d.setdefault('_units', {})[k] = units[hdr.index(name)]
+                d.setdefault('_units', {})[k] = u
         res.append(d)
     json.dump(res, open(out, 'w'), indent=1)
     for d in res:

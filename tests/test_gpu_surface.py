@@ -46,12 +46,12 @@ def test_engine_matches_golden_fixtures(lib, arch):
     assert np.abs(eng2.get_weights_dict()['conv_w'] - GOLD['%s/adam_conv_w' % arch]).max() < 2e-5
 
 
-def _handler(arch='igru', task_name='Seq2VecPaperSoftmaxId', precision='fp32', **kw):
+def _handler(arch='igru', task_name='Seq2VecPaperSoftmaxId', precision='fp32', batch_size=8, **kw):
     sh = synth.SHAPES['tiny']
     d = tempfile.mkdtemp()
     synth.write_dataset(d, sh)
     cfg = settings.Config(dict(task=task_name, arch=arch, input_training_data_path=d, title_shape=sh.L,
-                               window_size=sh.W, negative_samples=sh.K, batch_size=8, textual_embedding_dim=sh.E,
+                               window_size=sh.W, negative_samples=sh.K, batch_size=batch_size, textual_embedding_dim=sh.E,
                                title_filter_shape=(sh.F, 3), user_embedding_dim=sh.U, debug=True, dropout=0.0,
                                precision=precision, validation_impression=5, testing_impression=5, epochs=2, **kw))
     return sh, task.get(cfg)
@@ -470,17 +470,17 @@ def test_vertsup_surface(lib):
 def test_vertalt_surface(lib):
     """Seq2VecPaperSoftmaxDaysIdVertAlt (task/paper.py:1003-1136): epochs x round; vertical model on 10 % of the documents;
     callback_valid alternates self.model between vert_model and seq_model; both share the doc encoder."""
-    sh, h = _handler('igru', 'Seq2VecPaperSoftmaxDaysIdVertAlt', days=100000, round=3)
+    sh, h = _handler('igru', 'Seq2VecPaperSoftmaxDaysIdVertAlt', days=100000, round=3, batch_size=4)
     assert h.config.epochs == 2 * 3
     model = h.build_model(0)
     assert model is h.vert_model and h.train_seq is False
     nd = len(h.data_titles)
     assert len(h.train_index) == nd // 10 and len(h.valid_index) == nd - nd // 10
-    assert h.training_step == len(h.train_index) // 8 and h.validation_step == len(h.valid_index) // 8
+    assert h.training_step == len(h.train_index) // 4 and h.validation_step == len(h.valid_index) // 4
     train = h.train
     x, y = next(train)
-    assert x.shape == (8, sh.L) and y.shape == (8, len(h.verticals)) and model.metrics_names == ['loss', 'categorical_accuracy']
-    conv0 = h._core.engine_train(8).get_weights_dict()['conv_w'].copy()
+    assert x.shape == (4, sh.L) and y.shape == (4, len(h.verticals)) and model.metrics_names == ['loss', 'categorical_accuracy']
+    conv0 = h._core.engine_train(4).get_weights_dict()['conv_w'].copy()
     l0 = model.evaluate(x, y)[0]
     for _ in range(30):
         model.train_on_batch(x, y)
@@ -498,7 +498,7 @@ def test_vertalt_surface(lib):
     h.callback_valid(1)
     assert h.train_seq is True and h.build_model(2) is h.seq_model and h.training_step == h.config.training_step
     xs, ys = next(train)                                         # the same generator now yields click batches
-    assert len(xs) == 2 + 1 + sh.K and ys.shape == (8, 1 + sh.K)
+    assert len(xs) == 2 + 1 + sh.K and ys.shape == (4, 1 + sh.K)
     before = h.seq_model.evaluate(xs, ys)[0]
     for _ in range(25):
         h.seq_model.train_on_batch(xs, ys)

@@ -241,3 +241,45 @@ def test_pretrained_encoder_files_keras_and_own_format(tmp_path):
         pickle.dump(W[:-1], f)
     with pytest.raises(ValueError):
         utils.load_model((jp, pp))
+
+
+def test_vertsup_and_vertalt_generators():
+    """Seq2VecPaperSoftmaxDaysIdVertSup samples carry the one-hot verticals of the W history slots + 1+K candidates
+    (task/paper.py:897-902); ...VertAlt splits the documents 10 % / 90 %, serves (title, one-hot vertical) batches and
+    multiplies config.epochs by config.round (:1003-1090)."""
+    sh, d, emb, tok, cfg = _dataset()
+    base = {k: getattr(cfg, k) for k in ('input_training_data_path', 'title_shape', 'window_size', 'negative_samples',
+                                         'batch_size', 'textual_embedding_dim', 'title_filter_shape',
+                                         'user_embedding_dim', 'debug')}
+    h = task.get(settings.Config(dict(base, task='Seq2VecPaperSoftmaxDaysIdVertSup', arch='igru', days=100000)))
+    s = next(h.train_gen())
+    C = 1 + sh.K
+    assert len(s) == 2 + C + 2 and s[-1].shape == (sh.W + C, len(utils.verticals)) and s[-2] == [1] + [0] * sh.K
+    ids = s[-1].argmax(-1)
+    assert np.all(s[-1].sum(-1) == 1) and np.all(ids[:sh.W][~s[1].any(-1)] == 0)          # pad slots carry 'N/A' = 0
+    # the candidate verticals are those of the candidate titles
+    vert_of_title = {tuple(doc.title.astype(int)): doc.vertical for doc in h.docs.values()}
+    assert [vert_of_title[tuple(t.astype(int))] for t in s[2:2 + C]] == ids[sh.W:].tolist()
+    (x, y) = next(h.valid)
+    assert len(x) == 2 + C and len(y) == 2 and y[1].shape == (4, sh.W + C, len(utils.verticals))
+    assert h.get_vertical_classifier() == (len(utils.verticals), h.config.hidden_dim)
+
+    np.random.seed(5)
+    a = task.get(settings.Config(dict(base, task='Seq2VecPaperSoftmaxDaysIdVertAlt', arch='igru', days=100000, round=4,
+                                      epochs=3)))
+    assert a.round == 4 and a.config.epochs == 12
+    n = len(a.data_titles)
+    assert n == sh.n_news and len(a.train_index) == n // 10 and len(a.valid_index) == n - n // 10
+    assert sorted(np.concatenate([a.train_index, a.valid_index]).tolist()) == list(range(n))
+    assert a.data_verticals.shape == (n, len(a.verticals)) and np.all(a.data_verticals.sum(-1) == 1)
+    a.train_seq = False
+    assert a.training_step == len(a.train_index) // 4 and a.validation_step == len(a.valid_index) // 4
+    t, v = next(a.train_vert)
+    assert t.shape == (4, sh.L) and v.shape == (4, len(a.verticals))
+    gen = a.train
+    assert next(gen)[0].shape == (4, sh.L)
+    a.train_seq = True
+    xb, yb = next(gen)
+    assert len(xb) == 2 + C and yb.shape == (4, C) and a.training_step == a.config.training_step
+    a.training_step = 5                                   # the base class assigns these in _load_data: ignored (:1059-1065)
+    assert a.training_step == a.config.training_step
