@@ -214,6 +214,13 @@ class LsturEngine:
                 out['user_emb'], out['user_emb2'] = out['user_emb'][:, :self.G].copy(), out['user_emb'][:, self.G:].copy()
         return out
 
+    def get_dense_grads_dict(self):
+        """Dense gradients of the last backward (lstur_backward or lstur_title_cls_backward)."""
+        out = self._unflatten(self.dense_grad)
+        if self.trainable_word_emb:
+            out['word_emb'] = self.word_grad.cpu().numpy()
+        return out
+
     def get_grads_dict(self):
         """Dense gradients plus the (densified) user-embedding gradient of the last backward."""
         out = self._unflatten(self.dense_grad)
