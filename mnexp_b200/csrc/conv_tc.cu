@@ -37,7 +37,16 @@ constexpr int KBLK = 32;                      // K elements per pipeline block: 
 constexpr int ROWB = KBLK * 2;                // bytes per shared-memory row
 constexpr int A_TAP_BYTES = TILE_M * ROWB;    // 8 KB
 constexpr int TAPS = 3;
-constexpr int A_STAGE_BYTES = TAPS * A_TAP_BYTES;   // 24 KB: the three shifted tap tiles of one 32-column chunk
+// A operand of one stage.  A_SHIFT: ONE copy of the tile's 128 rows between two 512-byte zero pads; the three taps are
+// read through descriptors whose start address is shifted by -1 / 0 / +1 rows (the 64-byte swizzle is a function of the
+// absolute shared-memory address, so a start anywhere inside the 512-byte-aligned image reads consistently; the pads
+// supply the zero rows -1 and 128).  !A_SHIFT: three tap tiles stored at row offsets +1 / 0 / -1 (rows wrap in the tile).
+#ifndef LSTUR_CONV_A_SHIFT
+#define LSTUR_CONV_A_SHIFT 1
+#endif
+constexpr bool A_SHIFT = LSTUR_CONV_A_SHIFT != 0;
+constexpr int A_PAD = 512;
+constexpr int A_STAGE_BYTES = A_SHIFT ? A_TAP_BYTES + 2 * A_PAD : TAPS * A_TAP_BYTES;   // 9 KB / 24 KB per 32-column chunk
 
 // K-major SWIZZLE_64B descriptor: rows of 64 B, 8-row atoms of 512 B (16B chunk index XOR (row>>1)&3)
 __device__ __forceinline__ uint64_t make_desc_k64(uint32_t saddr) {
@@ -341,6 +350,14 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
       s_ka[f] = p.att_w[f];
     }
   }
+  if (A_SHIFT) {   // zero rows before and after the A tile of every stage (never written afterwards)
+    for (int i = threadIdx.x; i < NUM_STAGES * 2 * (A_PAD / 16); i += THREADS) {
+      const int s = i / (2 * (A_PAD / 16)), r = i % (2 * (A_PAD / 16));
+      const uint32_t off = r < A_PAD / 16 ? (uint32_t)r * 16 : (uint32_t)(A_PAD + A_TAP_BYTES) + (uint32_t)(r - A_PAD / 16) * 16;
+      *reinterpret_cast<uint4*>(smem_gen + (size_t)s * stage_bytes + off) = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async();
+  }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
                  "r"(TMEM_COLS)
@@ -395,7 +412,9 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
             const uint32_t a_stage = smem_base + s * stage_bytes, b_stage = a_stage + A_STAGE_BYTES;
 #pragma unroll
             for (int j = 0; j < TAPS; ++j) {
-              const uint32_t a_addr = a_stage + j * A_TAP_BYTES, b_addr = b_stage + j * b_tap_bytes;
+              // tap j multiplies X[m + j - 1]: its own shifted copy, or the single copy read from row j - 1 on
+              const uint32_t a_addr = A_SHIFT ? a_stage + A_PAD + (uint32_t)((j - 1) * ROWB) : a_stage + j * A_TAP_BYTES;
+              const uint32_t b_addr = b_stage + j * b_tap_bytes;
 #pragma unroll
               for (int kk = 0; kk < KBLK / 16; ++kk) {
                 const uint64_t ad = make_desc_k64(a_addr + kk * 32);
@@ -516,13 +535,20 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int r = pw * SLOT + 8 * (2 * rh + i) + rsub;
-#pragma unroll
-          for (int j = 0; j < TAPS; ++j) {
-            const int rr = (r + 1 - j) & (TILE_M - 1);
-            const uint32_t addr = stage + j * A_TAP_BYTES + rr * ROWB + ((piece ^ ((rr >> 1) & 3)) << 4);
+          if (A_SHIFT) {
+            const uint32_t addr = stage + A_PAD + r * ROWB + ((piece ^ ((r >> 1) & 3)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v[i].x), "r"(v[i].y), "r"(v[i].z),
                          "r"(v[i].w)
                          : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < TAPS; ++j) {
+              const int rr = (r + 1 - j) & (TILE_M - 1);
+              const uint32_t addr = stage + j * A_TAP_BYTES + rr * ROWB + ((piece ^ ((rr >> 1) & 3)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v[i].x), "r"(v[i].y), "r"(v[i].z),
+                           "r"(v[i].w)
+                           : "memory");
+            }
           }
         }
         fence_proxy_async();
