@@ -37,16 +37,12 @@ constexpr int KBLK = 32;                      // K elements per pipeline block: 
 constexpr int ROWB = KBLK * 2;                // bytes per shared-memory row
 constexpr int A_TAP_BYTES = TILE_M * ROWB;    // 8 KB
 constexpr int TAPS = 3;
-// A operand of one stage.  A_SHIFT: ONE copy of the tile's 128 rows between two 512-byte zero pads; the three taps are
+// A operand of one 32-column chunk: ONE copy of the tile's 128 rows between two 512-byte zero pads; the three taps are
 // read through descriptors whose start address is shifted by -1 / 0 / +1 rows (the 64-byte swizzle is a function of the
 // absolute shared-memory address, so a start anywhere inside the 512-byte-aligned image reads consistently; the pads
-// supply the zero rows -1 and 128).  !A_SHIFT: three tap tiles stored at row offsets +1 / 0 / -1 (rows wrap in the tile).
-#ifndef LSTUR_CONV_A_SHIFT
-#define LSTUR_CONV_A_SHIFT 1
-#endif
-constexpr bool A_SHIFT = LSTUR_CONV_A_SHIFT != 0;
+// supply the zero rows -1 and 128).  (Round 1 stored three shifted copies, 24 KB per chunk.)
 constexpr int A_PAD = 512;
-constexpr int A_STAGE_BYTES = A_SHIFT ? A_TAP_BYTES + 2 * A_PAD : TAPS * A_TAP_BYTES;   // 9 KB / 24 KB per 32-column chunk
+constexpr int A_STAGE_BYTES = A_TAP_BYTES + 2 * A_PAD;   // 9 KB per chunk slot
 
 // K-major SWIZZLE_64B descriptor: rows of 64 B, 8-row atoms of 512 B (16B chunk index XOR (row>>1)&3)
 __device__ __forceinline__ uint64_t make_desc_k64(uint32_t saddr) {
@@ -134,7 +130,9 @@ struct FwdParams {
   uint32_t drop_addend;           // quad_addend(threshold)
   float inv_keep;
   uint32_t seed_x, seed_c;
-  int dbg;                        // experiments (LSTUR_FWD_DBG): 1 = epilogue only hands the accumulator back, 2 = producers only signal
+  int dbg;                        // experiments (LSTUR_FWD_DBG): 1 = epilogue only hands the accumulator back, 2 = producers do not
+                                  // store, 16 = producers neither load nor hash, 32 = the weight loader only signals
+  int nstages;                    // depth of the weight-stage ring (<= MAX_STAGES)
   long long* trace;               // optional: wait cycles of pair 0's MMA issuer (tools/perf_fwd.py)
   uint8_t* xmask;                 // optional (n_titles, L, Ep/8): keep bits of the X-dropout, one byte per 16-byte piece, so
                                   // the weight-gradient kernel need not replay the hash (bit j / 4+j: low / high half of word j)
@@ -150,9 +148,13 @@ struct FwdParams {
   const int* title_idx;
 };
 
-// Stage = one 32-column chunk of the embedding: the three shifted tap tiles of this CTA's 128 token rows (A, 24 KB)
-// and this CTA's half of the weight rows of the three taps (B, 3 x F/2 x 64 B).
-constexpr int NUM_STAGES = 3;
+// Shared memory: an A ring with one slot per 32-column chunk of the tile (EC slots of 9 KB, filled once per tile, read by
+// both feature passes) and a B ring of weight stages (this CTA's rows of one (pass, chunk): 3 taps x n0h x 64 B).
+constexpr int MAX_CHUNKS = 16;                // A slots / barrier slots
+constexpr int MAX_STAGES = 8;                 // B stages / barrier slots; the launcher picks the depth (FwdParams::nstages)
+constexpr int DEF_STAGES = 4;
+// rows per CTA of feature pass 0 (pass 1 takes the other Fh - n0h): half of Fh rounded up to a multiple of 8, at most 128
+__host__ __device__ constexpr int conv_n0h(int Fh) { return ((Fh + 15) / 16) * 8 > 128 ? 128 : ((Fh + 15) / 16) * 8; }
 
 struct EpiCtx {
   float sx;                       // scale applied to the accumulator (input-dropout and conv-dropout keep scales)
@@ -298,9 +300,17 @@ __device__ __forceinline__ void epi_pass1_segment(const EpiCtx& ec, const RowIO&
 // accumulator in tensor memory) and stages only the weight rows f in [rank*F/2, (rank+1)*F/2); the pair's MMAs
 // (M = 256, issued by rank 0) read both halves, which halves the weight bytes every SM has to pull through its shared
 // memory — the limiter of the single-CTA version.  Accumulator column c holds feature
-//   f = half*Fh + (c % n0h)         for c <  2*n0h    (half = c / n0h,  first MMA,  n0h = min(Fh,128))
-//   f = half*Fh + n0h + (c' % n1h)  for c' = c-2*n0h  (half = c'/ n1h,  second MMA, n1h = Fh - n0h)
+//   f = half*Fh + (c % n0h)         for c <  2*n0h    (half = c / n0h,  feature pass 0,  n0h ~ Fh/2, see conv_n0h)
+//   f = half*Fh + n0h + (c' % n1h)  for c' = c-2*n0h  (half = c'/ n1h,  feature pass 1,  n1h = Fh - n0h)
 // so an epilogue thread of column half `half` sees one contiguous feature range [half*Fh, (half+1)*Fh).
+// FEATURE PASSES: a tile is computed as two passes over K, pass 0 into accumulator columns [0, 2*n0h) and pass 1 into
+// [2*n0h, F): each pass has its own full / empty barrier, so the epilogue drains pass 0 while the tensor core runs pass 1
+// and drains pass 1 under the next tile's pass 0 — the accumulator (F = 400 of 512 columns) cannot be double-buffered as
+// a whole, and with a single pass the 8.6 k-cycle drain serialised with the 12 k MMA cycles of a tile.  Both passes read
+// the SAME gathered rows: the tile's EC chunks stay in shared memory (one 9 KB slot each — affordable only since the taps
+// are row-shifted views of one copy) until the second pass has consumed them; only the weight rows are streamed per pass.
+// (Measured alternative: re-gathering the rows for the second pass — the producers' gather + dropout hash became the
+// limiter, 1.04 ms instead of 0.78 ms at C3.)
 template <bool FP16, bool DROP, int SLOT, int MODE>
 __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParams p) {
   constexpr int TPT = TILE_M / SLOT;               // titles per 128-row tile
@@ -309,20 +319,26 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int F = p.F, EC = p.EC, Fh = F >> 1;
-  const int n0h = Fh > 128 ? 128 : Fh, n1h = Fh - n0h;
-  const uint32_t b_tap_bytes = (uint32_t)Fh * ROWB;                 // this CTA's weight rows of one tap
-  const uint32_t stage_bytes = A_STAGE_BYTES + TAPS * b_tap_bytes;  // multiple of 512 (Fh % 8 == 0)
-  const uint32_t misc_base = smem_base + NUM_STAGES * stage_bytes;
+  const int n0h = conv_n0h(Fh), n1h = Fh - n0h;
+  const int NP = n1h > 0 ? 2 : 1;                                   // feature passes per tile
+  // shared memory: [A ring: EC slots, one per 32-column chunk of the tile, each read by BOTH feature passes]
+  //                [B ring: NB stages of this CTA's weight rows of one (pass, chunk): 3 taps x n0h rows x 64 B] [misc]
+  const uint32_t b_tap_bytes = (uint32_t)n0h * ROWB;                // room for this CTA's weight rows of one tap of a pass
+  const uint32_t b_stage_bytes = TAPS * b_tap_bytes;                // multiple of 512 (n0h % 8 == 0)
+  const int NB = p.nstages;
+  const uint32_t a_base = smem_base, b_base = a_base + (uint32_t)EC * A_STAGE_BYTES;
+  const uint32_t misc_base = b_base + (uint32_t)NB * b_stage_bytes;
   uint8_t* misc_gen = smem_gen + (misc_base - smem_base);
-  // barriers (8 B each): full[4] empty[4] tmem_full tmem_empty
-  const uint32_t bar_full = misc_base, bar_empty = misc_base + 32, bar_t_full = misc_base + 64, bar_t_empty = misc_base + 72;
-  uint32_t* tmem_ptr_smem = (uint32_t*)(misc_gen + 80);
-  float* s_w = (float*)(misc_gen + 128);          // [128 rows] attention weights of the tile (SLOT == 64: pass 2 reads both warps' rows)
-  float* s_z = (float*)(misc_gen + 768);          // [2 parity][2 halves][128 rows]
-  int* s_any = (int*)(misc_gen + 768 + 2048);     // [2][2][128]
-  float* s_bias = (float*)(misc_gen + 768 + 4096);  // [F]  (x conv-dropout keep scale)
-  float* s_ka = s_bias + F;                          // [F]
-  uint4* s_stg = (uint4*)(misc_gen + 768 + 4096 + (((size_t)2 * F * sizeof(float) + 15) & ~(size_t)15));   // [8 warps] staging
+  // barriers (8 B each): a_full[16] a_empty[16] b_full[8] b_empty[8] tmem_full[2] tmem_empty[2]
+  const uint32_t bar_a_full = misc_base, bar_a_empty = misc_base + 128, bar_b_full = misc_base + 256, bar_b_empty = misc_base + 320;
+  const uint32_t bar_t_full = misc_base + 384, bar_t_empty = misc_base + 400;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(misc_gen + 416);
+  float* s_w = (float*)(misc_gen + 512);          // [128 rows] attention weights of the tile (SLOT == 64: pass 2 reads both warps' rows)
+  float* s_z = (float*)(misc_gen + 1024);         // [2 parity][2 halves][128 rows]
+  int* s_any = (int*)(misc_gen + 1024 + 2048);    // [2][2][128]
+  float* s_bias = (float*)(misc_gen + 1024 + 4096);  // [F]  (x conv-dropout keep scale)
+  float* s_ka = s_bias + F;                           // [F]
+  uint4* s_stg = (uint4*)(misc_gen + 1024 + 4096 + (((size_t)2 * F * sizeof(float) + 15) & ~(size_t)15));   // [8 warps] staging
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
@@ -334,14 +350,21 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
   const float ik = DROP ? p.inv_keep : 1.f;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NUM_STAGES; ++s) {
-      // leader: its 8 producer warps + its weight loader's expect_tx arrival + the peer's 8 producer warps (remote
-      // arrives; the peer's warp 4 first waits for the peer's own bulk copies).  peer: only its loader's expect_tx.
-      mbar_init(bar_full + 8 * s, crank == 0 ? 17 : 1);
-      mbar_init(bar_empty + 8 * s, 1);    // multicast tcgen05.commit of the leader
+    for (int c = 0; c < EC; ++c) {
+      // leader: the 8 producer warps of BOTH CTAs (the peer's arrive remotely).  The slot is free again once the MMAs of
+      // every feature pass that read it have completed (one multicast commit per pass).
+      mbar_init(bar_a_full + 8 * c, 16);
+      mbar_init(bar_a_empty + 8 * c, NP);
     }
-    mbar_init(bar_t_full, 1);              // multicast tcgen05.commit of the leader
-    mbar_init(bar_t_empty, 16);            // (leader) one arrival per epilogue warp of BOTH CTAs
+    for (int s = 0; s < NB; ++s) {
+      // leader: its loader's expect_tx arrival + the peer's "my rows have landed" (remote arrive); peer: its loader only
+      mbar_init(bar_b_full + 8 * s, crank == 0 ? 2 : 1);
+      mbar_init(bar_b_empty + 8 * s, 1);   // multicast tcgen05.commit of the leader
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_t_full + 8 * a, 1);    // multicast tcgen05.commit of the leader
+      mbar_init(bar_t_empty + 8 * a, 16);  // (leader) one arrival per epilogue warp of BOTH CTAs
+    }
     fence_barrier_init();
   }
   if (!DG) {
@@ -350,11 +373,11 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
       s_ka[f] = p.att_w[f];
     }
   }
-  if (A_SHIFT) {   // zero rows before and after the A tile of every stage (never written afterwards)
-    for (int i = threadIdx.x; i < NUM_STAGES * 2 * (A_PAD / 16); i += THREADS) {
-      const int s = i / (2 * (A_PAD / 16)), r = i % (2 * (A_PAD / 16));
+  {   // zero rows before and after the A tile of every slot (never written afterwards)
+    for (int i = threadIdx.x; i < EC * 2 * (A_PAD / 16); i += THREADS) {
+      const int c = i / (2 * (A_PAD / 16)), r = i % (2 * (A_PAD / 16));
       const uint32_t off = r < A_PAD / 16 ? (uint32_t)r * 16 : (uint32_t)(A_PAD + A_TAP_BYTES) + (uint32_t)(r - A_PAD / 16) * 16;
-      *reinterpret_cast<uint4*>(smem_gen + (size_t)s * stage_bytes + off) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(smem_gen + (size_t)c * A_STAGE_BYTES + off) = make_uint4(0, 0, 0, 0);
     }
     fence_proxy_async();
   }
@@ -371,22 +394,41 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    // ===================== weight loader (TMA bulk copies of this CTA's rows of the pre-swizzled K blocks) ===========
+    // ===================== weight loader (bulk copies of this CTA's rows of the pre-swizzled K blocks) ===========
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
       for (int tp = pair; tp < n_tp; tp += n_pairs) {
-        for (int c = 0; c < EC; ++c) {
-          mbar_wait(bar_empty + 8 * s, ph ^ 1, 1);
-          mbar_expect_tx(bar_full + 8 * s, TAPS * b_tap_bytes);
+        for (int fp = 0; fp < NP; ++fp) {
+          const uint32_t rows_bytes = (uint32_t)(fp ? n1h : n0h) * ROWB;
+          const size_t row0 = (size_t)crank * Fh + (fp ? n0h : 0);
+          for (int c = 0; c < EC; ++c) {
+            mbar_wait(bar_b_empty + 8 * s, ph ^ 1, 1);
+            if (p.dbg & 32) {
+              mbar_arrive(bar_b_full + 8 * s);
+            } else {
+              mbar_expect_tx(bar_b_full + 8 * s, TAPS * rows_bytes);
 #pragma unroll
-          for (int j = 0; j < TAPS; ++j)
-            bulk_g2s(smem_base + s * stage_bytes + A_STAGE_BYTES + j * b_tap_bytes,
-                     (const uint8_t*)p.wimg + ((size_t)(c * TAPS + j) * F + (size_t)crank * Fh) * ROWB, b_tap_bytes,
-                     bar_full + 8 * s);
-          if (++s == NUM_STAGES) { s = 0; ph ^= 1; }
+              for (int j = 0; j < TAPS; ++j)
+                bulk_g2s(b_base + s * b_stage_bytes + j * b_tap_bytes,
+                         (const uint8_t*)p.wimg + ((size_t)(c * TAPS + j) * F + row0) * ROWB, rows_bytes, bar_b_full + 8 * s);
+            }
+            if (++s == NB) { s = 0; ph ^= 1; }
+          }
         }
       }
+    }
+  } else if (warp == 2) {
+    // ===================== peer CTA: tell the leader that this CTA's weight rows of a stage have landed ============
+    if (crank != 0 && lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tp = pair; tp < n_tp; tp += n_pairs)
+        for (int k = 0; k < NP * EC; ++k) {
+          mbar_wait(bar_b_full + 8 * s, ph, 7);
+          mbar_arrive_remote(map_to_cta(bar_b_full + 8 * s, 0));
+          if (++s == NB) { s = 0; ph ^= 1; }
+        }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer of the pair =====================
@@ -394,58 +436,62 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
       const bool leader = elect_one();
       const uint32_t idesc0 = make_idesc(2 * TILE_M, 2 * n0h, FP16), idesc1 = make_idesc(2 * TILE_M, n1h > 0 ? 2 * n1h : 16, FP16);
       int s = 0;
-      uint32_t ph = 0, pht = 0;
+      uint32_t ph = 0, pht = 0, pha = 0;
       const bool tracing = p.trace != nullptr && blockIdx.x == 0;
       long long tw_acc = 0, tw_full = 0, t_start = tracing ? clock64() : 0;
       for (int tp = pair; tp < n_tp; tp += n_pairs) {
+       for (int fp = 0; fp < NP; ++fp) {
         long long t0 = tracing ? clock64() : 0;
-        mbar_wait(bar_t_empty, pht ^ 1, 2);
+        mbar_wait(bar_t_empty + 8 * fp, pht ^ 1, 2);     // the epilogue has drained this pass's columns of the previous tile
         if (tracing) tw_acc += clock64() - t0;
         tc_fence_after();
+        const uint32_t tacc = tmem_base + (fp ? 2 * n0h : 0);
+        const uint32_t idesc = fp ? idesc1 : idesc0;
         uint32_t accum = 0;
         for (int c = 0; c < EC; ++c) {
           t0 = tracing ? clock64() : 0;
-          mbar_wait(bar_full + 8 * s, ph, 3);
+          if (fp == 0) mbar_wait(bar_a_full + 8 * c, pha, 3);     // the tile's rows of chunk c (they stay for pass 1)
+          mbar_wait(bar_b_full + 8 * s, ph, 4);
           if (tracing) tw_full += clock64() - t0;
           tc_fence_after();
           if (leader) {
-            const uint32_t a_stage = smem_base + s * stage_bytes, b_stage = a_stage + A_STAGE_BYTES;
+            const uint32_t a_slot = a_base + c * A_STAGE_BYTES, b_stage = b_base + s * b_stage_bytes;
 #pragma unroll
             for (int j = 0; j < TAPS; ++j) {
-              // tap j multiplies X[m + j - 1]: its own shifted copy, or the single copy read from row j - 1 on
-              const uint32_t a_addr = A_SHIFT ? a_stage + A_PAD + (uint32_t)((j - 1) * ROWB) : a_stage + j * A_TAP_BYTES;
+              // tap j multiplies X[m + j - 1]: the single copy of the rows, read from row j - 1 on
+              const uint32_t a_addr = a_slot + A_PAD + (uint32_t)((j - 1) * ROWB);
               const uint32_t b_addr = b_stage + j * b_tap_bytes;
 #pragma unroll
               for (int kk = 0; kk < KBLK / 16; ++kk) {
-                const uint64_t ad = make_desc_k64(a_addr + kk * 32);
-                umma_f16_2cta(tmem_base, ad, make_desc_k64(b_addr + kk * 32), idesc0, accum);
-                if (n1h > 0) umma_f16_2cta(tmem_base + 2 * n0h, ad, make_desc_k64(b_addr + n0h * ROWB + kk * 32), idesc1, accum);
+                umma_f16_2cta(tacc, make_desc_k64(a_addr + kk * 32), make_desc_k64(b_addr + kk * 32), idesc, accum);
                 accum = 1;
               }
             }
-            umma_commit_2cta(bar_empty + 8 * s, 3);
+            umma_commit_2cta(bar_b_empty + 8 * s, 3);
+            umma_commit_2cta(bar_a_empty + 8 * c, 3);
           }
           accum = 1;
           __syncwarp();
-          if (++s == NUM_STAGES) { s = 0; ph ^= 1; }
+          if (++s == NB) { s = 0; ph ^= 1; }
         }
-        if (leader) umma_commit_2cta(bar_t_full, 3);
+        if (leader) umma_commit_2cta(bar_t_full + 8 * fp, 3);
         __syncwarp();
+       }
         pht ^= 1;
+        pha ^= 1;
       }
       if (tracing && lane == 0) { p.trace[0] = tw_acc; p.trace[1] = tw_full; p.trace[2] = clock64() - t_start; }
     }
   } else if (warp >= 4 && warp < 12) {
-    // ===================== A producers: row gather -> three shifted swizzled tap tiles =====================
+    // ===================== A producers: row gather -> the tile's chunk slots =====================
     // lane -> (row within a group of 8, 16-byte piece of the 64-byte row); loads for chunk c+1 (and the row ids of
     // the next tile) are issued before chunk c is hashed and stored, so L2 latency is off the critical path.
     // Eight warps share the tile's title slots (two warps per 32-row slot, four per 64-row slot), each thread two
-    // rows per stage (a producer warp's instruction stream is latency-bound, so the work is spread over more warps
-    // rather than over more rows per thread).
+    // rows per chunk (a producer warp's instruction stream is latency-bound, so the work is spread over more warps
+    // rather than over more rows per thread).  A chunk is produced ONCE per tile and read by both feature passes.
     const int pw = (warp - 4) % TPT;         // title slot of the tile
     const int rh = (warp - 4) / TPT;         // which pair of the slot's 8-row groups
     const int rsub = lane >> 2, piece = lane & 3;
-    int s = 0;
     uint32_t ph = 0;
     constexpr int kNoToken = INT_MIN;
     // MODE_FWD: id = token id (clamped when its embedding row is requested).  MODE_DGRAD: id = n * SLOT + t, the slot
@@ -465,7 +511,7 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         v[i] = make_uint4(0, 0, 0, 0);
-        if (ids[i] != kNoToken) {
+        if (ids[i] != kNoToken && !(p.dbg & 16)) {
           if (DG) {
             const int n = ids[i] / SLOT, t = ids[i] % SLOT, half = c / p.cph, ch = c % p.cph;
             const uint8_t* src = p.dimg + ((long long)n * 2 * p.ngh + half * p.ngh + (ch >> 1)) * (SLOT * 128) + t * 128 +
@@ -495,7 +541,7 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
           if (EC == 1) load_ids(tp + n_pairs, ids_next);
           load_rows(ids_next, 0, v_next);
         }
-        if (DROP) {
+        if (DROP && !(p.dbg & 16)) {
           if (c == 0) {   // per tile: pair index of column 0 of each of this thread's rows, inner hash of its high word
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
@@ -528,45 +574,29 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
                   (uint8_t)((keep | (keep >> 12)) & 0xffu);
           }
         }
-        if (lane == 0) mbar_wait(bar_empty + 8 * s, ph ^ 1, 5);   // one poller per warp
+        if (lane == 0) mbar_wait(bar_a_empty + 8 * c, ph ^ 1, 5);   // one poller per warp: both passes of the previous tile read it
         __syncwarp();
-        const uint32_t stage = smem_base + s * stage_bytes;
+        const uint32_t slot_addr = a_base + c * A_STAGE_BYTES;
         if (!(p.dbg & 2))
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int r = pw * SLOT + 8 * (2 * rh + i) + rsub;
-          if (A_SHIFT) {
-            const uint32_t addr = stage + A_PAD + r * ROWB + ((piece ^ ((r >> 1) & 3)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v[i].x), "r"(v[i].y), "r"(v[i].z),
-                         "r"(v[i].w)
-                         : "memory");
-          } else {
-#pragma unroll
-            for (int j = 0; j < TAPS; ++j) {
-              const int rr = (r + 1 - j) & (TILE_M - 1);
-              const uint32_t addr = stage + j * A_TAP_BYTES + rr * ROWB + ((piece ^ ((rr >> 1) & 3)) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v[i].x), "r"(v[i].y), "r"(v[i].z),
-                           "r"(v[i].w)
-                           : "memory");
-            }
-          }
+          const uint32_t addr = slot_addr + A_PAD + r * ROWB + ((piece ^ ((r >> 1) & 3)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v[i].x), "r"(v[i].y), "r"(v[i].z), "r"(v[i].w)
+                       : "memory");
         }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          if (crank == 0) {
-            mbar_arrive(bar_full + 8 * s);
-          } else {
-            if (warp == 4) mbar_wait(bar_full + 8 * s, ph, 7);   // this CTA's weight rows have landed
-            mbar_arrive_remote(map_to_cta(bar_full + 8 * s, 0));
-          }
+          if (crank == 0) mbar_arrive(bar_a_full + 8 * c);
+          else mbar_arrive_remote(map_to_cta(bar_a_full + 8 * c, 0));
         }
-        if (++s == NUM_STAGES) { s = 0; ph ^= 1; }
         if (c + 1 == EC) {
 #pragma unroll
           for (int i = 0; i < 2; ++i) ids[i] = ids_next[i];
         }
       }
+      ph ^= 1;
     }
   } else if (warp >= 12) {
     // ===================== epilogue =====================
@@ -585,17 +615,19 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
       for (int tp = pair; tp < n_tp; tp += n_pairs) {
         const int n = (2 * tp + (int)crank) * TPT + slot;
         io.title = n < n_titles ? p.c_out + ((long long)n * p.L + t0) * F : nullptr;
-        mbar_wait(bar_t_full, pht, 6);
-        pht ^= 1;
-        tc_fence_after();
-        epi_dgrad_segment<FP16>(p.out_scale, io, trow, half * n0h, f_beg, n0h);
-        if (n1h > 0) epi_dgrad_segment<FP16>(p.out_scale, io, trow, 2 * n0h + half * n1h, f_beg + n0h, n1h);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (crank == 0) mbar_arrive(bar_t_empty);
-          else mbar_arrive_remote(map_to_cta(bar_t_empty, 0));
+        for (int fp = 0; fp < NP; ++fp) {
+          mbar_wait(bar_t_full + 8 * fp, pht, 6);
+          tc_fence_after();
+          if (fp == 0) epi_dgrad_segment<FP16>(p.out_scale, io, trow, half * n0h, f_beg, n0h);
+          else epi_dgrad_segment<FP16>(p.out_scale, io, trow, 2 * n0h + half * n1h, f_beg + n0h, n1h);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (crank == 0) mbar_arrive(bar_t_empty + 8 * fp);
+            else mbar_arrive_remote(map_to_cta(bar_t_empty + 8 * fp, 0));
+          }
         }
+        pht ^= 1;
       }
     } else {
     // ---- forward: bias/ReLU/masks/dropout/attention pooling
@@ -620,29 +652,26 @@ __global__ void __launch_bounds__(THREADS, 1) news_conv_tc_kernel(const FwdParam
         ec.inner0 = quad_key(hi, p.seed_c);
         ec.inner1 = quad_key(hi + 1u, p.seed_c);
       }
-      mbar_wait(bar_t_full, pht, 6);
-      pht ^= 1;
-      tc_fence_after();
       float z = 0.f;
       uint32_t vmax = 0u;      // OR of the packed pre-dropout values of this row half
-      if (p.dbg & 1) {
+      // ---- pass 1: drain this row's accumulator columns, one feature pass at a time (the tensor core meanwhile runs
+      // the other pass / the next tile's first pass)
+      for (int fp = 0; fp < NP; ++fp) {
+        mbar_wait(bar_t_full + 8 * fp, pht, 6);
+        tc_fence_after();
+        if (!(p.dbg & 1)) {
+          if (fp == 0) epi_pass1_segment<FP16, DROP>(ec, io, trow, half * n0h, f_beg, n0h, tk != 0, z, vmax);
+          else epi_pass1_segment<FP16, DROP>(ec, io, trow, 2 * n0h + half * n1h, f_beg + n0h, n1h, tk != 0, z, vmax);
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (crank == 0) mbar_arrive(bar_t_empty);
-          else mbar_arrive_remote(map_to_cta(bar_t_empty, 0));
+          if (crank == 0) mbar_arrive(bar_t_empty + 8 * fp);
+          else mbar_arrive_remote(map_to_cta(bar_t_empty + 8 * fp, 0));
         }
-        continue;
       }
-      // ---- pass 1: drain this row's accumulator columns (kept short: the next tile's MMAs wait for it)
-      epi_pass1_segment<FP16, DROP>(ec, io, trow, half * n0h, f_beg, n0h, tk != 0, z, vmax);
-      if (n1h > 0) epi_pass1_segment<FP16, DROP>(ec, io, trow, 2 * n0h + half * n1h, f_beg + n0h, n1h, tk != 0, z, vmax);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (crank == 0) mbar_arrive(bar_t_empty);
-        else mbar_arrive_remote(map_to_cta(bar_t_empty, 0));
-      }
+      pht ^= 1;
+      if (p.dbg & 1) continue;
       const int row = q * 32 + lane;
       s_z[(par * 2 + half) * 128 + row] = z;
       s_any[(par * 2 + half) * 128 + row] = vmax != 0u ? 1 : 0;
@@ -1129,9 +1158,12 @@ extern "C" int lstur_pack_conv_w_tc(int E, int F, const float* conv_w, void* wim
   return LSTUR_OK;
 }
 
+size_t tc_conv_smem_bytes(int EC, int F, int nstages);
 extern "C" int lstur_tc_supported(int L, int E, int F, int KS) {
-  return KS == 3 && L >= 1 && L <= 63 && E >= 1 && F >= 16 && F % 16 == 0 && F <= tc::TMEM_COLS &&
-         (F <= 256 || F - 256 >= 16);
+  if (!(KS == 3 && L >= 1 && L <= 63 && E >= 1 && F >= 16 && F % 16 == 0 && F <= tc::TMEM_COLS)) return 0;
+  // the tile's K chunks stay resident in shared memory next to >= 2 weight stages
+  const int EC = lstur_tc_padded_e(E) / tc::KBLK;
+  return EC <= tc::MAX_CHUNKS && tc_conv_smem_bytes(EC, F, 2) <= 232448;
 }
 // rows of a title slot: the L tokens + at least one zero row (the conv halo), 32 or 64
 extern "C" int lstur_tc_slot(int L) { return L <= 31 ? 32 : 64; }
@@ -1171,11 +1203,26 @@ static cudaError_t tc_launch_one(const tc::FwdParams& p, size_t smem, int pairs,
   return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
+// dynamic shared memory of news_conv_tc_kernel: alignment slack + A ring + B ring + barriers / epilogue scratch
+constexpr size_t TC_SMEM_LIMIT = 232448;      // 227 KB opt-in maximum per CTA on sm_100
+size_t tc_conv_smem_bytes(int EC, int F, int nstages) {
+  return 1024 + (size_t)EC * tc::A_STAGE_BYTES + (size_t)nstages * tc::TAPS * tc::conv_n0h(F / 2) * tc::ROWB + 1024 + 4096 +
+         (((size_t)2 * F * sizeof(float) + 15) & ~(size_t)15) + (size_t)8 * tc::STG_WARP_BYTES;
+}
+
 static int tc_launch_conv(const tc::FwdParams& p, int L, bool fp16, bool drop, int mode, int max_ctas, cudaStream_t stream,
                           const char* name) {
   const int F = p.F, slot = lstur_tc_slot(L);
-  size_t smem = 1024 + (size_t)tc::NUM_STAGES * (tc::A_STAGE_BYTES + (size_t)tc::TAPS * (F / 2) * tc::ROWB) + 768 + 4096 +
-                (((size_t)2 * F * sizeof(float) + 15) & ~(size_t)15) + (size_t)8 * tc::STG_WARP_BYTES;
+  static int nst_env = -1;
+  if (nst_env < 0) { const char* e = getenv("LSTUR_FWD_STAGES"); nst_env = e ? atoi(e) : 0; }
+  int nst = nst_env >= 2 && nst_env <= tc::MAX_STAGES ? nst_env : tc::DEF_STAGES;
+  while (nst > 2 && tc_conv_smem_bytes(p.EC, F, nst) > TC_SMEM_LIMIT) --nst;
+  if (p.EC > tc::MAX_CHUNKS || tc_conv_smem_bytes(p.EC, F, nst) > TC_SMEM_LIMIT) {
+    set_error("%s: K = %d chunks x N = %d does not fit the shared-memory plan of the tensor-core conv kernel", name, p.EC, F);
+    return LSTUR_ERR_UNSUPPORTED;
+  }
+  const_cast<tc::FwdParams&>(p).nstages = nst;
+  size_t smem = tc_conv_smem_bytes(p.EC, F, nst);
   int n_tiles = (p.n_titles + (tc::TILE_M / slot) - 1) / (tc::TILE_M / slot);
   int n_tp = (n_tiles + 1) / 2;             // CTA pairs take two token tiles at a time
   int sms = 148;
