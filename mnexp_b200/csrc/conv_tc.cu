@@ -152,7 +152,7 @@ struct FwdParams {
 // both feature passes) and a B ring of weight stages (this CTA's rows of one (pass, chunk): 3 taps x n0h x 64 B).
 constexpr int MAX_CHUNKS = 16;                // A slots / barrier slots
 constexpr int MAX_STAGES = 8;                 // B stages / barrier slots; the launcher picks the depth (FwdParams::nstages)
-constexpr int DEF_STAGES = 4;
+constexpr int DEF_STAGES = 3;
 // rows per CTA of feature pass 0 (pass 1 takes the other Fh - n0h): half of Fh rounded up to a multiple of 8, at most 128
 __host__ __device__ constexpr int conv_n0h(int Fh) { return ((Fh + 15) / 16) * 8 > 128 ? 128 : ((Fh + 15) / 16) * 8; }
 
