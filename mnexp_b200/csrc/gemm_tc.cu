@@ -76,6 +76,64 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// Epilogue store of one 32-column accumulator chunk: lane = tile row holds r[0..31] (columns c0.. of the tile).  A
+// row-per-lane float4 store touches 32 different lines per instruction (32 L1 wavefronts, half-filled sectors) — the
+// epilogue, not the tensor core or the staging, bounded the large-M GEMMs.  Through a per-warp staging buffer (rows of
+// 36 floats: conflict-free 16-byte accesses both ways) 8 lanes cover the 128 contiguous bytes of one row, so an
+// instruction writes 4 full lines; bias / accumulate / relu are applied on the way out (one bias load per lane and
+// chunk instead of one dependent scalar load per element, which had halved the speed of the GRU input projection).
+constexpr int G_EPI_ROW = 36;                              // floats per staged row
+constexpr int G_EPI_WARP_BYTES = 32 * G_EPI_ROW * 4;       // 4608
+__device__ __forceinline__ void gemm_epi_store(float* stg, int lane, const uint32_t* r, bool have_acc, float* cbase,
+                                               long long ldc, int row0, int M, int col0, int ncols, const float* bias,
+                                               int flags, bool apply, bool vec_ok) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+    *reinterpret_cast<float4*>(stg + lane * G_EPI_ROW + 4 * g) =
+        have_acc ? make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
+                               __uint_as_float(r[4 * g + 3]))
+                 : make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
+  const int piece = lane & 7, cc = 4 * piece;              // this lane's 4 columns of the chunk
+  if (cc < ncols) {
+    float b4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (apply && bias) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (cc + u < ncols) b4[u] = __ldg(bias + col0 + cc + u);
+    }
+    const bool full = cc + 4 <= ncols && vec_ok;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = (lane >> 3) + 4 * i;
+      if (row0 + row >= M) continue;
+      float4 v = *reinterpret_cast<const float4*>(stg + row * G_EPI_ROW + cc);
+      float* dst = cbase + (long long)(row0 + row) * ldc + col0 + cc;
+      float x[4] = {v.x, v.y, v.z, v.w};
+      if (apply) {
+        if (flags & LSTUR_GEMM_ACCUM) {
+          if (full) { const float4 o = *reinterpret_cast<const float4*>(dst); x[0] += o.x; x[1] += o.y; x[2] += o.z; x[3] += o.w; }
+          else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (cc + u < ncols) x[u] += dst[u];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          x[u] += b4[u];
+          if (flags & LSTUR_GEMM_RELU) x[u] = fmaxf(x[u], 0.f);
+        }
+      }
+      if (full) *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+      else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (cc + u < ncols) dst[u] = x[u];
+      }
+    }
+  }
+  __syncwarp();
+}
+
 // TA: A is stored [K,M] (M contiguous) -> MN-major.  TB: B is stored [N,K] (K contiguous) -> K-major.
 // SPLIT: 3-term fp16 split (Ahi.Bhi + Alo.Bhi + Ahi.Blo) for ~fp32 accuracy on the forward-path GEMMs.
 // Persistent: a CTA walks the (m, n, k-split) tiles t = blockIdx.x, +gridDim.x, ... (n fastest, so CTAs that run
@@ -93,6 +151,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const GemmParams 
   uint8_t* misc_gen = smem_gen + (misc_base - smem_base);
   const uint32_t bar_full = misc_base, bar_empty = misc_base + 64, bar_t_full = misc_base + 128, bar_t_empty = misc_base + 144;
   uint32_t* tmem_ptr_smem = (uint32_t*)(misc_gen + 160);
+  float* s_epi = (float*)(misc_gen + 256);      // [4 epilogue warps] staging rows (G_EPI_WARP_BYTES each)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = p.tiles_m * p.tiles_n * p.splits;
 
@@ -263,39 +322,18 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const GemmParams 
       mbar_wait(bar_t_full + 8 * acc, pht[acc], 23);
       pht[acc] ^= 1;
       tc_fence_after();
-      const int gm = x.m0 + q * 32 + lane;
-      float* crow = split ? p.partial + ((long long)x.z * p.M + gm) * p.N : p.C + (long long)gm * p.ldc;
-      const bool vec_st = split ? (p.N % 4 == 0) : (p.ldc % 4 == 0 && (((uintptr_t)p.C) & 15) == 0);
+      float* cbase = split ? p.partial + (long long)x.z * p.M * p.N : p.C;
+      const long long ldo = split ? (long long)p.N : p.ldc;
+      const bool vec_st = (ldo % 4 == 0) && ((((uintptr_t)cbase) & 15) == 0) && ((x.n0 & 3) == 0);
       for (int c0 = 0; c0 < x.nmma; c0 += 32) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
         if (x.nmma - c0 >= 32) { TMEM_LD_32(taddr, r); } else { TMEM_LD_16(taddr, r); }
         tmem_ld_wait();
-        if (gm >= p.M) continue;
         const int ncols = min(32, x.nt - c0);
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          if (i >= ncols) break;
-          float v[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float xv = x.nkb > 0 ? __uint_as_float(r[i + u]) : 0.f;
-            const int gn = x.n0 + c0 + i + u;
-            if (!split && i + u < ncols) {
-              if (p.bias) xv += p.bias[gn];
-              if (p.flags & LSTUR_GEMM_ACCUM) xv += crow[gn];
-              if (p.flags & LSTUR_GEMM_RELU) xv = fmaxf(xv, 0.f);
-            }
-            v[u] = xv;
-          }
-          if (i + 4 <= ncols && vec_st && ((x.n0 + c0 + i) & 3) == 0) {
-            *reinterpret_cast<float4*>(crow + x.n0 + c0 + i) = make_float4(v[0], v[1], v[2], v[3]);
-          } else {
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (i + u < ncols) crow[x.n0 + c0 + i + u] = v[u];
-          }
-        }
+        if (ncols > 0)
+          gemm_epi_store(s_epi + (warp - 9) * (G_EPI_WARP_BYTES / 4), lane, r, x.nkb > 0, cbase, ldo, x.m0 + q * 32, p.M,
+                         x.n0 + c0, ncols, p.bias, p.flags, !split, vec_st);
       }
       tc_fence_before();
       __syncwarp();
@@ -370,6 +408,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_async_kernel(const GemmP
   uint8_t* misc_gen = smem_gen + (misc_base - smem_base);
   const uint32_t bar_full = misc_base, bar_empty = misc_base + 64, bar_t_full = misc_base + 128, bar_t_empty = misc_base + 144;
   uint32_t* tmem_ptr_smem = (uint32_t*)(misc_gen + 160);
+  float* s_epi = (float*)(misc_gen + 256);      // [4 epilogue warps] staging rows (G_EPI_WARP_BYTES each)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = p.tiles_m * p.tiles_n * p.splits;
 
@@ -564,39 +603,18 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_async_kernel(const GemmP
       mbar_wait(bar_t_full + 8 * acc, pht[acc], 23);
       pht[acc] ^= 1;
       tc_fence_after();
-      const int gm = x.m0 + q * 32 + lane;
-      float* crow = split ? p.partial + ((long long)x.z * p.M + gm) * p.N : p.C + (long long)gm * p.ldc;
-      const bool vec_st = split ? (p.N % 4 == 0) : (p.ldc % 4 == 0 && (((uintptr_t)p.C) & 15) == 0);
+      float* cbase = split ? p.partial + (long long)x.z * p.M * p.N : p.C;
+      const long long ldo = split ? (long long)p.N : p.ldc;
+      const bool vec_st = (ldo % 4 == 0) && ((((uintptr_t)cbase) & 15) == 0) && ((x.n0 & 3) == 0);
       for (int c0 = 0; c0 < x.nmma; c0 += 32) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + acc * 128 + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
         if (x.nmma - c0 >= 32) { TMEM_LD_32(taddr, r); } else { TMEM_LD_16(taddr, r); }
         tmem_ld_wait();
-        if (gm >= p.M) continue;
         const int ncols = min(32, x.nt - c0);
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          if (i >= ncols) break;
-          float v[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float xv = x.nkb > 0 ? __uint_as_float(r[i + u]) : 0.f;
-            const int gn = x.n0 + c0 + i + u;
-            if (!split && i + u < ncols) {
-              if (p.bias) xv += p.bias[gn];
-              if (p.flags & LSTUR_GEMM_ACCUM) xv += crow[gn];
-              if (p.flags & LSTUR_GEMM_RELU) xv = fmaxf(xv, 0.f);
-            }
-            v[u] = xv;
-          }
-          if (i + 4 <= ncols && vec_st && ((x.n0 + c0 + i) & 3) == 0) {
-            *reinterpret_cast<float4*>(crow + x.n0 + c0 + i) = make_float4(v[0], v[1], v[2], v[3]);
-          } else {
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (i + u < ncols) crow[x.n0 + c0 + i + u] = v[u];
-          }
-        }
+        if (ncols > 0)
+          gemm_epi_store(s_epi + (warp - 9) * (G_EPI_WARP_BYTES / 4), lane, r, x.nkb > 0, cbase, ldo, x.m0 + q * 32, p.M,
+                         x.n0 + c0, ncols, p.bias, p.flags, !split, vec_st);
       }
       tc_fence_before();
       __syncwarp();
@@ -690,10 +708,11 @@ extern "C" int lstur_gemm_tc(int transA, int transB, int M, int N, int K, const 
   p.bimg = nullptr; p.nkb_total = (K + tc::G_KBLK - 1) / tc::G_KBLK;
   p.vec_ok = (lda % 4 == 0) && (ldb % 4 == 0) && ((((uintptr_t)A) & 15) == 0) && ((((uintptr_t)B) & 15) == 0);
   const bool split3 = (flags & LSTUR_GEMM_PRECISE) != 0;
-  size_t smem = 1024 + (split3 ? (size_t)2 * tc::G_STAGE_BYTES_S3 : (size_t)tc::G_STAGES * tc::G_STAGE_BYTES) + 256;
+  size_t smem = 1024 + (split3 ? (size_t)2 * tc::G_STAGE_BYTES_S3 : (size_t)tc::G_STAGES * tc::G_STAGE_BYTES) + 256 +
+                4 * tc::G_EPI_WARP_BYTES;
   static bool attr = false;
   if (!attr) {
-    const int big = 1024 + 2 * tc::G_STAGE_BYTES_S3 + 256;
+    const int big = 1024 + 2 * tc::G_STAGE_BYTES_S3 + 256 + 4 * tc::G_EPI_WARP_BYTES;
     cudaError_t e = cudaSuccess;
 #define SETATTR(TA_, TB_, S_) \
   if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<TA_, TB_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)
@@ -731,7 +750,7 @@ extern "C" int lstur_gemm_tc(int transA, int transB, int M, int N, int K, const 
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   dim3 grid((unsigned)(n_tiles < sms ? n_tiles : sms));
-  const size_t smem_async = 1024 + (size_t)2 * tc::GA_F16_STAGE + (size_t)2 * tc::GA_RAW_STAGE + 256;
+  const size_t smem_async = 1024 + (size_t)2 * tc::GA_F16_STAGE + (size_t)2 * tc::GA_RAW_STAGE + 256 + 4 * tc::G_EPI_WARP_BYTES;
   static bool attr_async = false;
   if (use_async && !attr_async) {
     cudaError_t e = cudaSuccess;
