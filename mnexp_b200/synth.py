@@ -120,11 +120,13 @@ def _orthogonal(rng, rows, cols):
 
 
 def make_weights(shape, arch=None, seed=1237, word_emb=None, score_model='dot', cook=False,
-                 dv=15, ds=35, bias_noise=0.0, paper_vert=0, vertsup=None, vertalt=0):
+                 dv=15, ds=35, bias_noise=0.0, paper_vert=0, vertsup=None, vertalt=0, keras_orthogonal=False):
     """Keras-initialised parameter dict (names: oracle/lstur_numpy.py docstring).
 
     bias_noise > 0 replaces the all-zero bias initialisers by small normals so
-    parity tests exercise the bias paths."""
+    parity tests exercise the bias paths.  keras_orthogonal: draw the recurrent kernels as ONE (G, 3G) / (G, 4G)
+    orthogonal matrix (orthonormal rows), as keras.initializers.Orthogonal does for the GRU / LSTM recurrent_kernel; the
+    default (one orthogonal G x G block per gate) is what the committed golden fixtures were generated with."""
     arch = arch or shape.arch
     rng = np.random.default_rng(seed)
     E, F, k, U = shape.E, shape.F, shape.k, shape.U
@@ -147,17 +149,19 @@ def make_weights(shape, arch=None, seed=1237, word_emb=None, score_model='dot', 
             D = U + paper_vert          # the user encoder is built with user_embedding_dim + vertical_embedding_dim
             P['vert_emb'] = rng.uniform(-0.05, 0.05, (16, paper_vert)).astype(np.float32)
             U = U + paper_vert
+    Hs = shape.U        # scorer hidden width = config.user_embedding_dim: score_encoder runs outside the temporary
+                        # user_embedding_dim += vertical_embedding_dim of ...DaysIdVert.get_user_encoder (task/paper.py:1204-1208)
     G = U // 2 if arch == 'hgru' else U
     Ue = U // 2 if arch == 'hgru' else U
     if arch not in ('nigru', 'niavg', 'att'):
         P['user_emb'] = rng.uniform(-0.05, 0.05, (shape.n_users, Ue)).astype(np.float32)
     if arch not in ('vo', 'niavg', 'iavg', 'att', 'iatt', 'ilstm'):
         P['gru_wx'] = _glorot(rng, (D, 3 * G), D, 3 * G)
-        P['gru_wh'] = np.concatenate([_orthogonal(rng, G, G) for _ in range(3)], 1)
+        P['gru_wh'] = _orthogonal(rng, G, 3 * G) if keras_orthogonal else np.concatenate([_orthogonal(rng, G, G) for _ in range(3)], 1)
         P['gru_b'] = bz(3 * G)
     if arch == 'ilstm':                                         # keras LSTM (task/cook.py:161-163), unit_forget_bias
         P['lstm_wx'] = _glorot(rng, (D, 4 * G), D, 4 * G)
-        P['lstm_wh'] = np.concatenate([_orthogonal(rng, G, G) for _ in range(4)], 1)
+        P['lstm_wh'] = _orthogonal(rng, G, 4 * G) if keras_orthogonal else np.concatenate([_orthogonal(rng, G, G) for _ in range(4)], 1)
         P['lstm_b'] = bz(4 * G)
         P['lstm_b'][G:2 * G] += 1.0
     if arch in ('att', 'iatt', 'atgru'):                        # SimpleAttentionMaskSupport kernel (Da, 1) + bias (models.py:456-468)
@@ -173,16 +177,16 @@ def make_weights(shape, arch=None, seed=1237, word_emb=None, score_model='dot', 
         P['user_emb2'] = rng.uniform(-0.05, 0.05, (shape.n_users, Ue)).astype(np.float32)
     if score_model == 'dnn':                                   # task/paper.py:448-451
         Du = 2 * U if arch in ('ngru', 'dgru', 'iicat', 'ilstm') else (D if arch in ('niavg', 'att') else (D + U if arch in ('iavg', 'iatt') else U))
-        P['sh_w'] = _glorot(rng, (Du + D, U), Du + D, U)
-        P['sh_b'] = bz(U)
-        P['so_w'] = _glorot(rng, (U, 1), U, 1)
+        P['sh_w'] = _glorot(rng, (Du + D, Hs), Du + D, Hs)
+        P['sh_b'] = bz(Hs)
+        P['so_w'] = _glorot(rng, (Hs, 1), Hs, 1)
         P['so_b'] = bz(1)
     if score_model == 'ddot':
         Du = 2 * U if arch in ('ngru', 'dgru', 'iicat', 'ilstm') else (D if arch in ('niavg', 'att') else (D + U if arch in ('iavg', 'iatt') else U))
-        P['su_w'] = _glorot(rng, (Du, U), Du, U)
-        P['su_b'] = bz(U)
-        P['sd_w'] = _glorot(rng, (D, U), D, U)
-        P['sd_b'] = bz(U)
+        P['su_w'] = _glorot(rng, (Du, Hs), Du, Hs)
+        P['su_b'] = bz(Hs)
+        P['sd_w'] = _glorot(rng, (D, Hs), D, Hs)
+        P['sd_b'] = bz(Hs)
     if vertsup:      # (n_vert, hidden_dim): vertical classifier of ...VertSup, task/paper.py:948-952
         nv, hd = vertsup
         P['vs_w1'] = _glorot(rng, (D, hd), D, hd)

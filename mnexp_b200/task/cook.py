@@ -176,7 +176,7 @@ class Cook:
                          U=c.user_embedding_dim, arch='igru')
         syn = {'vo': 'vo', 'avg': 'niavg', 'gru': 'nigru', 'igru': 'ngru', 'agru': 'pgru', 'ingru': 'igru',
                'inigru': 'iicat'}.get(c.arch, c.arch)      # iavg / iatt / ilstm / inagru / atgru / algru keep their names
-        P = synth.make_weights(sh, arch=syn, seed=np.random.randint(1 << 30), word_emb=word_emb,
+        P = synth.make_weights(sh, arch=syn, seed=np.random.randint(1 << 30), word_emb=word_emb, keras_orthogonal=True,
                                score_model=c.score_model, cook=True, dv=self.dv, ds=self.ds)
         if not self.dv:
             P.pop('vert_emb', None)

@@ -165,7 +165,7 @@ class Seq2VecPaper(Seq2Vec):
         sh = synth.Shape('cfg', n_users=len(self.data), n_news=self.doc_count - 1, vocab=word_emb.shape[0],
                          L=c.title_shape, W=c.window_size, K=c.negative_samples, B=c.batch_size, E=word_emb.shape[1],
                          F=F, k=k, U=c.user_embedding_dim, arch=syn_arch)
-        params = synth.make_weights(sh, arch=syn_arch, seed=np.random.randint(1 << 30), word_emb=word_emb,
+        params = synth.make_weights(sh, arch=syn_arch, seed=np.random.randint(1 << 30), word_emb=word_emb, keras_orthogonal=True,
                                     score_model=self.SCORE)
         self._core = keras_like._Core(params, c, self.doc_token_table(), self.HAS_USER, eng_arch, score_model=self.SCORE,
                                       loss='bce', flavour='sigmoid')
@@ -303,7 +303,7 @@ class Seq2VecPaperSoftmax(Seq2VecPaper):
         sh = synth.Shape('cfg', n_users=len(self.data), n_news=self.doc_count - 1, vocab=word_emb.shape[0],
                          L=c.title_shape, W=c.window_size, K=c.negative_samples, B=c.batch_size, E=word_emb.shape[1],
                          F=F, k=k, U=c.user_embedding_dim, arch=self._engine_arch())
-        return synth.make_weights(sh, arch=self._engine_arch(), seed=np.random.randint(1 << 30), word_emb=word_emb,
+        return synth.make_weights(sh, arch=self._engine_arch(), seed=np.random.randint(1 << 30), word_emb=word_emb, keras_orthogonal=True,
                                   score_model=c.score_model)
 
     def _build_model(self):
@@ -456,7 +456,7 @@ class Seq2VecPaperSoftmaxDaysIdVert(Seq2VecPaperSoftmaxDaysId):
         sh = synth.Shape('cfg', n_users=len(self.data), n_news=self.doc_count - 1, vocab=word_emb.shape[0],
                          L=c.title_shape, W=c.window_size, K=c.negative_samples, B=c.batch_size, E=word_emb.shape[1],
                          F=F, k=k, U=c.user_embedding_dim, arch=self._engine_arch())
-        return synth.make_weights(sh, arch=self._engine_arch(), seed=np.random.randint(1 << 30), word_emb=word_emb,
+        return synth.make_weights(sh, arch=self._engine_arch(), seed=np.random.randint(1 << 30), word_emb=word_emb, keras_orthogonal=True,
                                   score_model=c.score_model, paper_vert=c.vertical_embedding_dim)
 
     def _build_model(self):
@@ -518,7 +518,7 @@ class Seq2VecPaperSoftmaxDaysIdVertSup(Seq2VecPaperSoftmaxDaysId):
         sh = synth.Shape('cfg', n_users=len(self.data), n_news=self.doc_count - 1, vocab=word_emb.shape[0],
                          L=c.title_shape, W=c.window_size, K=c.negative_samples, B=c.batch_size, E=word_emb.shape[1],
                          F=F, k=k, U=c.user_embedding_dim, arch=self._engine_arch())
-        return synth.make_weights(sh, arch=self._engine_arch(), seed=np.random.randint(1 << 30), word_emb=word_emb,
+        return synth.make_weights(sh, arch=self._engine_arch(), seed=np.random.randint(1 << 30), word_emb=word_emb, keras_orthogonal=True,
                                   score_model=c.score_model, vertsup=self.get_vertical_classifier())
 
     def _build_model(self):
@@ -621,7 +621,7 @@ class Seq2VecPaperSoftmaxDaysIdVertAlt(Seq2VecPaperSoftmaxDaysId):
         sh = synth.Shape('cfg', n_users=len(self.data), n_news=self.doc_count - 1, vocab=word_emb.shape[0],
                          L=c.title_shape, W=c.window_size, K=c.negative_samples, B=c.batch_size, E=word_emb.shape[1],
                          F=F, k=k, U=c.user_embedding_dim, arch=self._engine_arch())
-        return synth.make_weights(sh, arch=self._engine_arch(), seed=np.random.randint(1 << 30), word_emb=word_emb,
+        return synth.make_weights(sh, arch=self._engine_arch(), seed=np.random.randint(1 << 30), word_emb=word_emb, keras_orthogonal=True,
                                   score_model=c.score_model, vertalt=len(self.verticals))
 
     def _build_model(self):
