@@ -174,6 +174,13 @@ size_t lstur_gemm_tc_workspace_bytes(int M, int N, int K);
 int lstur_gemm_tc(int transA, int transB, int M, int N, int K, const float* A, long long lda, const float* B,
                   long long ldb, float* C, long long ldc, const float* bias, int flags, void* workspace,
                   size_t workspace_bytes, cudaStream_t stream);
+/* TN product over a list of reduction rows: C[M,N] = sum_{k in k_rows[0..*k_count)} A[k,:M]^T B[k,:N] (A, B stored [K,.];
+ * k_rows ascending device ints, k_count a device scalar <= K).  Used for the weight gradients of the step, whose
+ * reduction rows — (user, step) rows of the GRU tensors, title rows of the Dense — are identically zero where the
+ * history is padding: the same sum over half the rows. */
+int lstur_gemm_tc_tn_rows(int M, int N, int K, const float* A, long long lda, const float* B, long long ldb, float* C,
+                          long long ldc, const int* k_rows, const int* k_count, void* workspace, size_t workspace_bytes,
+                          cudaStream_t stream);
 
 /* pad mask + Masking + Dropout + models.SimpleAttentionMaskSupport (task/paper.py:150-158, models.py:474-489). */
 int lstur_attn_pool_fwd(int N, int L, int F, float* C, long long title_stride, const int* tokens, const float* att_w,

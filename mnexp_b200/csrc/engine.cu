@@ -375,6 +375,12 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
       add_ws(p, "wg_ws", (long long)(lstur_word_grad_workspace_bytes(N * c.L, c.V, E) / 4) + 4);
     }
     add_ws(p, "attn_partials", (long long)lstur_attn_bwd_grid((int)N) * (2 * F + 1));
+    if (has_rnn && tcp) {   // ascending list of the unmasked (user, step) rows: the reduction rows of the GRU weight gradients
+      add_ws(p, "hist_live_idx", Nh);
+      add_ws(p, "n_hist_live", 1);
+      add_ws(p, "hist_live_scratch", lstur_compact_titles_scratch_ints((int)Nh));
+      add_ws(p, "hist_live_dummy", Nh);
+    }
     if (has_rnn) {
       add_ws(p, "WhT", (long long)NG * G * G);
       if (has_gru) add_ws(p, "gru_db_partial", (long long)lstur_gru_tc_db_rows((int)B) * 3 * G);
@@ -844,7 +850,12 @@ int encoder_backward(const lstur_plan* p, const lstur_weights* w, void* ws, int 
   long long lddp = F;
   if (c.use_dense) {
     RC(GEMM(0, 1, n, F, c.Dd, d_docv, D, DP(p, w->dense, "dense_w"), c.Dd, d_pooled, F, nullptr, 0, gws, gwsb, st));
-    RC(GEMM(1, 0, F, c.Dd, n, pooled, F, d_docv, D, DG(p, dgrad, "dense_w"), c.Dd, nullptr, 0, gws, gwsb, st));
+    // pooled is zero for the all-pad titles: reduce over the live titles of the compacted list (tensor-core modes)
+    if (W<int>(p, ws, "live_idx") && !getenv("LSTUR_GEMM_ROWS_OFF"))
+      RC(lstur_gemm_tc_tn_rows(F, c.Dd, n, pooled, F, d_docv, D, DG(p, dgrad, "dense_w"), c.Dd, W<int>(p, ws, "live_idx"),
+                               W<int>(p, ws, "n_live"), gws, gwsb, st));
+    else
+      RC(GEMM(1, 0, F, c.Dd, n, pooled, F, d_docv, D, DG(p, dgrad, "dense_w"), c.Dd, nullptr, 0, gws, gwsb, st));
     RC(lstur_colsum(n, c.Dd, d_docv, D, DG(p, dgrad, "dense_b"), 0, cws, cwsb, st));
   } else {
     dpool = d_docv; lddp = D;
@@ -1132,11 +1143,25 @@ extern "C" int lstur_backward_w(const lstur_plan* p, const lstur_weights* w, con
       RC(lstur_colsum(Nh, 3 * G, dA, 3 * G, DG(p, dgrad, "gru_b"), 0, cws, cwsb, st));
     }
     PROBE_END(p, LSTUR_PROBE_GRU_BWD, st);
+    int* hl_idx = W<int>(p, ws, "hist_live_idx");
+    if (hl_idx && !getenv("LSTUR_GEMM_ROWS_OFF")) {
+      // dA is zero on masked steps: the weight gradients reduce over the unmasked (user, step) rows only (half of them with
+      // the left-padded histories of short click logs)
+      int* hl_n = W<int>(p, ws, "n_hist_live");
+      RC(lstur_compact_titles(Nh, 1, reinterpret_cast<const int*>(W<float>(p, ws, "gru_mask")), W<int>(p, ws, "hist_live_scratch"),
+                              hl_idx, hl_n, W<int>(p, ws, "hist_live_dummy"), st));
+      RC(lstur_gemm_tc_tn_rows(D, 3 * G, Nh, docv, D, dA, 3 * G, DG(p, dgrad, "gru_wx"), 3 * G, hl_idx, hl_n, gws, gwsb, st));
+      RC(lstur_gemm_tc_tn_rows(G, 2 * G, Nh, W<float>(p, ws, "HP"), G, dA, 3 * G, DG(p, dgrad, "gru_wh"), 3 * G, hl_idx, hl_n, gws,
+                               gwsb, st));
+      RC(lstur_gemm_tc_tn_rows(G, G, Nh, W<float>(p, ws, "RH"), G, dA + 2 * G, 3 * G, DG(p, dgrad, "gru_wh") + 2 * G, 3 * G, hl_idx,
+                               hl_n, gws, gwsb, st));
+    } else {
     RC(GEMM(1, 0, D, 3 * G, Nh, docv, D, dA, 3 * G, DG(p, dgrad, "gru_wx"), 3 * G, nullptr, 0, gws, gwsb, st));
     RC(GEMM(1, 0, G, 2 * G, Nh, W<float>(p, ws, "HP"), G, dA, 3 * G, DG(p, dgrad, "gru_wh"), 3 * G, nullptr, 0,
                       gws, gwsb, st));
     RC(GEMM(1, 0, G, G, Nh, W<float>(p, ws, "RH"), G, dA + 2 * G, 3 * G, DG(p, dgrad, "gru_wh") + 2 * G, 3 * G,
                       nullptr, 0, gws, gwsb, st));
+    }
     // dH = dA . Wx^T  (rows of masked steps are zero because dA is zero there)
     RC(GEMM(0, 1, Nh, D, 3 * G, dA, 3 * G, DP(p, w->dense, "gru_wx"), 3 * G, d_docv, D, nullptr, 0, gws, gwsb, st));
     if (c.arch == LSTUR_ARCH_INI) { du0 = dh0; lddu0 = G; }

@@ -39,6 +39,11 @@ struct GemmParams {
   // shared-memory layout of a stage, fetched with bulk copies instead of being re-converted by every CTA for every tile
   const uint8_t* bimg;
   int nkb_total;
+  // optional row list for the reduction index of a TN product (gemm_tc_async_kernel, A and B both stored [K, .]): only
+  // the rows kidx[0 .. *kcount) of A and B are summed (ascending list of the rows that are not identically zero, e.g. the
+  // unmasked (user, step) rows of the GRU tensors); the split-K ranges are cut from *kcount on the device
+  const int* kidx;
+  const int* kcount;
 };
 constexpr int G_BIMG_TILE = 256 * 128;    // bytes reserved per image tile (= G_B_BYTES)
 
@@ -412,6 +417,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_async_kernel(const GemmP
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = p.tiles_m * p.tiles_n * p.splits;
 
+  // reduction extent: K, or the device-side count of listed rows; the split ranges follow it
+  const int Keff = p.kcount ? min(__ldg(p.kcount), p.K) : p.K;
+  const int kps = p.kcount ? max(G_KBLK, ((Keff + p.splits - 1) / p.splits + G_KBLK - 1) / G_KBLK * G_KBLK) : p.k_per_split;
   struct Tile { int m0, n0, nt, nmma, z, kbeg, kend, nkb; };
   auto tile_of = [&](int t) {
     Tile x;
@@ -421,8 +429,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_async_kernel(const GemmP
     x.n0 = tn * p.ntile;
     x.nt = min(p.ntile, p.N - x.n0);
     x.nmma = (x.nt + 15) & ~15;
-    x.kbeg = x.z * p.k_per_split;
-    x.kend = min(p.K, x.kbeg + p.k_per_split);
+    x.kbeg = x.z * kps;
+    x.kend = min(Keff, x.kbeg + kps);
     x.nkb = x.kend > x.kbeg ? (x.kend - x.kbeg + G_KBLK - 1) / G_KBLK : 0;
     return x;
   };
@@ -507,6 +515,19 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_async_kernel(const GemmP
       it.t += gridDim.x;
       while (it.t < n_tiles && (it.x = tile_of(it.t)).nkb == 0) it.t += gridDim.x;
     };
+    // listed reduction rows (GemmParams::kidx) of this thread's 8 chunk rows of a K block: fetched one K block ahead of
+    // the copies that use them (a dependent index load in front of every cp.async made the kernel slower than the dense
+    // sum over twice the rows)
+    int krows[8];
+    auto fetch_rows = [&](const Iter& it) {
+      if (!p.kidx || it.t >= n_tiles) return;
+      const int k0 = it.x.kbeg + it.kb * G_KBLK;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int kr = (pt >> 5) + 8 * i;
+        krows[i] = (k0 + kr < it.x.kend) ? __ldg(p.kidx + k0 + kr) : 0;
+      }
+    };
     // request the raw fp32 tiles of K block `it` into raw stage rs (a group is committed even when nothing is left)
     auto issue = [&](const Iter& it, int rs) {
       if (it.t < n_tiles) {
@@ -523,7 +544,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_async_kernel(const GemmP
           } else {
             const int kr = ch >> 5, c = ch & 31;
             const bool ok = (k0 + kr < x.kend) && (x.m0 + 4 * c < p.M);
-            cp_async16(ra + kr * 512 + c * 16, p.A + (long long)(ok ? k0 + kr : 0) * p.lda + (ok ? x.m0 + 4 * c : 0), ok);
+            const int krow = !ok ? 0 : (p.kidx ? krows[i] : k0 + kr);
+            cp_async16(ra + kr * 512 + c * 16, p.A + (long long)krow * p.lda + (ok ? x.m0 + 4 * c : 0), ok);
           }
         }
         if (TB) {
@@ -537,15 +559,17 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_async_kernel(const GemmP
           for (int i = 0; i < 8; ++i) {
             const int ch = pt + i * G_PRODUCERS, kr = ch >> 5, c = ch & 31;
             const bool ok = (k0 + kr < x.kend) && (4 * c < x.nt);
-            cp_async16(rb + kr * 512 + c * 16, p.B + (long long)(ok ? k0 + kr : 0) * p.ldb + (ok ? x.n0 + 4 * c : 0), ok);
+            const int krow = !ok ? 0 : (p.kidx ? krows[i] : k0 + kr);
+            cp_async16(rb + kr * 512 + c * 16, p.B + (long long)krow * p.ldb + (ok ? x.n0 + 4 * c : 0), ok);
           }
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
     Iter cur = first(), pre = cur;
-    issue(pre, 0); advance(pre);
-    issue(pre, 1); advance(pre);
+    fetch_rows(pre);
+    issue(pre, 0); advance(pre); fetch_rows(pre);
+    issue(pre, 1); advance(pre); fetch_rows(pre);
     int s = 0, rs = 0;
     uint32_t ph = 0;
     while (cur.t < n_tiles) {
@@ -585,7 +609,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_async_kernel(const GemmP
       }
       fence_proxy_async();
       asm volatile("bar.sync 1, 256;" ::: "memory");            // the raw stage is fully consumed: refill it
-      issue(pre, rs); advance(pre);
+      issue(pre, rs); advance(pre); fetch_rows(pre);
       if (lane == 0) mbar_arrive(bar_full + 8 * s);
       if (++s == FST) { s = 0; ph ^= 1; }
       rs ^= 1;
@@ -677,10 +701,31 @@ extern "C" size_t lstur_gemm_tc_workspace_bytes(int M, int N, int K) {
   return b;
 }
 
+static int gemm_tc_impl(int transA, int transB, int M, int N, int K, const float* A, long long lda, const float* B,
+                        long long ldb, float* C, long long ldc, const float* bias, int flags, void* workspace,
+                        size_t workspace_bytes, const int* kidx, const int* kcount, cudaStream_t stream);
+
 // Same contract as lstur_gemm_f32 (fp32 in / fp32 out); operands are rounded to fp16 inside the kernel.
 extern "C" int lstur_gemm_tc(int transA, int transB, int M, int N, int K, const float* A, long long lda, const float* B,
                              long long ldb, float* C, long long ldc, const float* bias, int flags, void* workspace,
                              size_t workspace_bytes, cudaStream_t stream) {
+  return gemm_tc_impl(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, flags, workspace, workspace_bytes, nullptr, nullptr,
+                      stream);
+}
+
+// C[M,N] = sum over the listed rows k = k_rows[0 .. *k_count) of A[k, :M]^T B[k, :N]   (A, B stored [K, .]; k_rows ascending,
+// k_count a device scalar <= K).  The weight gradients of the step reduce over (user, step) or title rows of which the
+// masked ones are identically zero: summing the live rows only is the same sum (other than fp32 reassociation across the
+// split-K ranges).  Falls back to the full range when the operands do not meet the 16-byte staging conditions.
+extern "C" int lstur_gemm_tc_tn_rows(int M, int N, int K, const float* A, long long lda, const float* B, long long ldb, float* C,
+                                     long long ldc, const int* k_rows, const int* k_count, void* workspace,
+                                     size_t workspace_bytes, cudaStream_t stream) {
+  return gemm_tc_impl(1, 0, M, N, K, A, lda, B, ldb, C, ldc, nullptr, 0, workspace, workspace_bytes, k_rows, k_count, stream);
+}
+
+static int gemm_tc_impl(int transA, int transB, int M, int N, int K, const float* A, long long lda, const float* B,
+                        long long ldb, float* C, long long ldc, const float* bias, int flags, void* workspace,
+                        size_t workspace_bytes, const int* kidx, const int* kcount, cudaStream_t stream) {
   LSTUR_REQUIRE(M >= 0 && N >= 0 && K >= 0, "lstur_gemm_tc");
   if (M == 0 || N == 0) return LSTUR_OK;
   tc::GemmParams p;
@@ -706,6 +751,8 @@ extern "C" int lstur_gemm_tc(int transA, int transB, int M, int N, int K, const 
   p.M = M; p.N = N; p.K = K; p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.bias = bias;
   p.flags = flags; p.k_per_split = kps; p.partial = (float*)workspace;
   p.bimg = nullptr; p.nkb_total = (K + tc::G_KBLK - 1) / tc::G_KBLK;
+  p.kidx = use_async ? kidx : nullptr;            // the row list is honoured by the cp.async kernel only (else: all K rows)
+  p.kcount = use_async ? kcount : nullptr;
   p.vec_ok = (lda % 4 == 0) && (ldb % 4 == 0) && ((((uintptr_t)A) & 15) == 0) && ((((uintptr_t)B) & 15) == 0);
   const bool split3 = (flags & LSTUR_GEMM_PRECISE) != 0;
   size_t smem = 1024 + (split3 ? (size_t)2 * tc::G_STAGE_BYTES_S3 : (size_t)tc::G_STAGES * tc::G_STAGE_BYTES) + 256 +
