@@ -181,6 +181,12 @@ int lstur_gemm_tc(int transA, int transB, int M, int N, int K, const float* A, l
 int lstur_gemm_tc_tn_rows(int M, int N, int K, const float* A, long long lda, const float* B, long long ldb, float* C,
                           long long ldc, const int* k_rows, const int* k_count, void* workspace, size_t workspace_bytes,
                           cudaStream_t stream);
+/* NN / NT product over a list of rows: C[m,:] = A[m,:K] . op(B) (+ bias) (relu) for m in m_rows[0..*m_count) only (A stored
+ * [M,K]); the other rows of C are left untouched.  The dense layers of the step run over (user, step) / title rows half of
+ * which are padding: their result is never read (or is a constant the caller fills in). */
+int lstur_gemm_tc_mrows(int transB, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb, float* C,
+                        long long ldc, const float* bias, int flags, const int* m_rows, const int* m_count, void* workspace,
+                        size_t workspace_bytes, cudaStream_t stream);
 
 /* pad mask + Masking + Dropout + models.SimpleAttentionMaskSupport (task/paper.py:150-158, models.py:474-489). */
 int lstur_attn_pool_fwd(int N, int L, int F, float* C, long long title_stride, const int* tokens, const float* att_w,
@@ -305,6 +311,10 @@ int lstur_seq_attn_bwd(int B, int W, int D, const float* H, const float* att_w, 
  * sorted_pos) gives the `row_order` of the recurrence kernels: rows of similar history length share a 32-row tile, and
  * a tile skips every step at which all of its rows are masked (left-padded histories, task/seq2vec.py:23,46-49). */
 int lstur_first_live_step(int B, int W, const float* mask, int* key, cudaStream_t stream);
+/* out[r,:cols] = bias (or 0 when NULL) for the rows with flags[r] == want: the rows a row-listed GEMM
+ * (lstur_gemm_tc_mrows) leaves out get their constant result — Dense(0) = bias for an all-pad title. */
+int lstur_fill_rows_where(int rows, int cols, const int* flags, int want, const float* bias, float* out, long long ld,
+                          cudaStream_t stream);
 /* keras Masking(): mask[r] = any_k(x[r,k] != 0) */
 int lstur_rows_nonzero(long long rows, int D, const float* x, long long ld, float* mask, cudaStream_t stream);
 /* y[r,:] = ay * y[r,:] + ax * x[r,:] on strided rows (keras.layers.add of cook 'inagru', task/cook.py:183) */

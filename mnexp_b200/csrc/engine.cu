@@ -267,6 +267,12 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
   add_ws(p, "hist_mask", Nh);
   add_ws(p, "gru_mask", Nh);
   if (has_user) add_ws(p, "u0", B * c.Ue);
+  if (has_rnn && tcp) {   // ascending list of the unmasked (user, step) rows: the only rows of the GRU-side GEMMs that matter
+    add_ws(p, "hist_live_idx", Nh);
+    add_ws(p, "n_hist_live", 1);
+    add_ws(p, "hist_live_scratch", lstur_compact_titles_scratch_ints((int)Nh));
+    add_ws(p, "hist_live_dummy", Nh);
+  }
   if (has_rnn) {
     add_ws(p, "XW", Nh * NG * G);
     add_ws(p, "hT", B * G);
@@ -375,12 +381,6 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
       add_ws(p, "wg_ws", (long long)(lstur_word_grad_workspace_bytes(N * c.L, c.V, E) / 4) + 4);
     }
     add_ws(p, "attn_partials", (long long)lstur_attn_bwd_grid((int)N) * (2 * F + 1));
-    if (has_rnn && tcp) {   // ascending list of the unmasked (user, step) rows: the reduction rows of the GRU weight gradients
-      add_ws(p, "hist_live_idx", Nh);
-      add_ws(p, "n_hist_live", 1);
-      add_ws(p, "hist_live_scratch", lstur_compact_titles_scratch_ints((int)Nh));
-      add_ws(p, "hist_live_dummy", Nh);
-    }
     if (has_rnn) {
       add_ws(p, "WhT", (long long)NG * G * G);
       if (has_gru) add_ws(p, "gru_db_partial", (long long)lstur_gru_tc_db_rows((int)B) * 3 * G);
@@ -506,7 +506,12 @@ int encode_titles(const lstur_plan* p, const lstur_weights* w, void* ws, int n, 
     RC(lstur_attn_pool_fwd(n, L, F, Cp, (long long)Lp * F, tok, DP(p, w->dense, "att_w"), DP(p, w->dense, "att_b"),
                            pooled, F, W<float>(p, ws, "att_a"), W<float>(p, ws, "att_w"), drop, seed * 2u + 1u, st));
   }
-  if (c.use_dense) {
+  if (c.use_dense && W<int>(p, ws, "live_idx") && !getenv("LSTUR_GEMM_ROWS_OFF")) {
+    // Dense over the live titles of the compacted list; an all-pad title pools to 0, so its vector is the bias
+    RC(lstur_gemm_tc_mrows(0, n, c.Dd, F, pooled, F, DP(p, w->dense, "dense_w"), c.Dd, docv, D, DP(p, w->dense, "dense_b"),
+                           LSTUR_GEMM_PRECISE, W<int>(p, ws, "live_idx"), W<int>(p, ws, "n_live"), gws, gwsb, st));
+    RC(lstur_fill_rows_where(n, c.Dd, W<int>(p, ws, "title_flags"), 0, DP(p, w->dense, "dense_b"), docv, D, st));
+  } else if (c.use_dense) {
     RC(GEMM(0, 0, n, c.Dd, F, pooled, F, DP(p, w->dense, "dense_w"), c.Dd, docv, D,
                       DP(p, w->dense, "dense_b"), LSTUR_GEMM_PRECISE, gws, gwsb, st));
   } else {
@@ -542,8 +547,22 @@ int user_and_score(const lstur_plan* p, const lstur_weights* w, const lstur_batc
   // 5. GRU (k11-k12)
   if (has_gru) {
     float* XW = W<float>(p, ws, "XW");
-    RC(GEMM(0, 0, Nh, 3 * G, D, docv, D, DP(p, w->dense, "gru_wx"), 3 * G, XW, 3 * G,
-                      DP(p, w->dense, "gru_b"), LSTUR_GEMM_PRECISE, gws, gwsb, st));
+    const bool tc_gru0 = (c.precision == LSTUR_PREC_BF16_TC || c.precision == LSTUR_PREC_FP16_TC) &&
+                         lstur_gru_tc_supported(B, c.W, G) && !getenv("LSTUR_GRU_TC_OFF");
+    int* hl_idx = getenv("LSTUR_GEMM_ROWS_OFF") ? nullptr : W<int>(p, ws, "hist_live_idx");
+    if (hl_idx) {   // unmasked (user, step) rows, ascending (the weight gradients of the backward reduce over them too)
+      RC(lstur_compact_titles(Nh, 1, reinterpret_cast<const int*>(W<float>(p, ws, "gru_mask")), W<int>(p, ws, "hist_live_scratch"),
+                              hl_idx, W<int>(p, ws, "n_hist_live"), W<int>(p, ws, "hist_live_dummy"), st));
+    }
+    if (hl_idx && tc_gru0) {
+      // input projection of the unmasked steps only: the tcgen05 recurrence discards what it computes for a masked step
+      // (select, not multiply), so the rows of XW behind masked steps are never used
+      RC(lstur_gemm_tc_mrows(0, Nh, 3 * G, D, docv, D, DP(p, w->dense, "gru_wx"), 3 * G, XW, 3 * G, DP(p, w->dense, "gru_b"),
+                             LSTUR_GEMM_PRECISE, hl_idx, W<int>(p, ws, "n_hist_live"), gws, gwsb, st));
+    } else {
+      RC(GEMM(0, 0, Nh, 3 * G, D, docv, D, DP(p, w->dense, "gru_wx"), 3 * G, XW, 3 * G,
+                        DP(p, w->dense, "gru_b"), LSTUR_GEMM_PRECISE, gws, gwsb, st));
+    }
     float* hT = W<float>(p, ws, "hT");
     float* hdst = hT;
     long long ldo = G;
@@ -849,7 +868,12 @@ int encoder_backward(const lstur_plan* p, const lstur_weights* w, void* ws, int 
   const float* dpool = d_pooled;
   long long lddp = F;
   if (c.use_dense) {
-    RC(GEMM(0, 1, n, F, c.Dd, d_docv, D, DP(p, w->dense, "dense_w"), c.Dd, d_pooled, F, nullptr, 0, gws, gwsb, st));
+    // d pooled of the live titles only: the attention backward runs over the compacted list and never reads the other rows
+    if (W<int>(p, ws, "live_idx") && !getenv("LSTUR_GEMM_ROWS_OFF"))
+      RC(lstur_gemm_tc_mrows(1, n, F, c.Dd, d_docv, D, DP(p, w->dense, "dense_w"), c.Dd, d_pooled, F, nullptr, 0,
+                             W<int>(p, ws, "live_idx"), W<int>(p, ws, "n_live"), gws, gwsb, st));
+    else
+      RC(GEMM(0, 1, n, F, c.Dd, d_docv, D, DP(p, w->dense, "dense_w"), c.Dd, d_pooled, F, nullptr, 0, gws, gwsb, st));
     // pooled is zero for the all-pad titles: reduce over the live titles of the compacted list (tensor-core modes)
     if (W<int>(p, ws, "live_idx") && !getenv("LSTUR_GEMM_ROWS_OFF"))
       RC(lstur_gemm_tc_tn_rows(F, c.Dd, n, pooled, F, d_docv, D, DG(p, dgrad, "dense_w"), c.Dd, W<int>(p, ws, "live_idx"),
@@ -1147,9 +1171,7 @@ extern "C" int lstur_backward_w(const lstur_plan* p, const lstur_weights* w, con
     if (hl_idx && !getenv("LSTUR_GEMM_ROWS_OFF")) {
       // dA is zero on masked steps: the weight gradients reduce over the unmasked (user, step) rows only (half of them with
       // the left-padded histories of short click logs)
-      int* hl_n = W<int>(p, ws, "n_hist_live");
-      RC(lstur_compact_titles(Nh, 1, reinterpret_cast<const int*>(W<float>(p, ws, "gru_mask")), W<int>(p, ws, "hist_live_scratch"),
-                              hl_idx, hl_n, W<int>(p, ws, "hist_live_dummy"), st));
+      int* hl_n = W<int>(p, ws, "n_hist_live");       // built by the forward (user_and_score)
       RC(lstur_gemm_tc_tn_rows(D, 3 * G, Nh, docv, D, dA, 3 * G, DG(p, dgrad, "gru_wx"), 3 * G, hl_idx, hl_n, gws, gwsb, st));
       RC(lstur_gemm_tc_tn_rows(G, 2 * G, Nh, W<float>(p, ws, "HP"), G, dA, 3 * G, DG(p, dgrad, "gru_wh"), 3 * G, hl_idx, hl_n, gws,
                                gwsb, st));
@@ -1163,6 +1185,11 @@ extern "C" int lstur_backward_w(const lstur_plan* p, const lstur_weights* w, con
                       nullptr, 0, gws, gwsb, st));
     }
     // dH = dA . Wx^T  (rows of masked steps are zero because dA is zero there)
+    if (hl_idx && !getenv("LSTUR_GEMM_ROWS_OFF")) {
+      cudaMemsetAsync(d_docv, 0, (size_t)Nh * D * sizeof(float), st);
+      RC(lstur_gemm_tc_mrows(1, Nh, D, 3 * G, dA, 3 * G, DP(p, w->dense, "gru_wx"), 3 * G, d_docv, D, nullptr, 0, hl_idx,
+                             W<int>(p, ws, "n_hist_live"), gws, gwsb, st));
+    } else
     RC(GEMM(0, 1, Nh, D, 3 * G, dA, 3 * G, DP(p, w->dense, "gru_wx"), 3 * G, d_docv, D, nullptr, 0, gws, gwsb, st));
     if (c.arch == LSTUR_ARCH_INI) { du0 = dh0; lddu0 = G; }
     if (c.arch == LSTUR_ARCH_INI_CON || c.arch == LSTUR_ARCH_INI_CAT || c.arch == LSTUR_ARCH_INI_ADD) {   // d row = [d h0 ‖ d of the concat / add part]

@@ -44,6 +44,10 @@ struct GemmParams {
   // unmasked (user, step) rows of the GRU tensors); the split-K ranges are cut from *kcount on the device
   const int* kidx;
   const int* kcount;
+  // optional row list for the M index of an NN / NT product (gemm_tc_kernel, A stored [M, K]): only the rows
+  // midx[0 .. *mcount) of A are multiplied and only those rows of C are written (ascending list, device count)
+  const int* midx;
+  const int* mcount;
 };
 constexpr int G_BIMG_TILE = 256 * 128;    // bytes reserved per image tile (= G_B_BYTES)
 
@@ -91,7 +95,7 @@ constexpr int G_EPI_ROW = 36;                              // floats per staged 
 constexpr int G_EPI_WARP_BYTES = 32 * G_EPI_ROW * 4;       // 4608
 __device__ __forceinline__ void gemm_epi_store(float* stg, int lane, const uint32_t* r, bool have_acc, float* cbase,
                                                long long ldc, int row0, int M, int col0, int ncols, const float* bias,
-                                               int flags, bool apply, bool vec_ok) {
+                                               int flags, bool apply, bool vec_ok, const int* orow = nullptr) {
 #pragma unroll
   for (int g = 0; g < 8; ++g)
     *reinterpret_cast<float4*>(stg + lane * G_EPI_ROW + 4 * g) =
@@ -111,9 +115,10 @@ __device__ __forceinline__ void gemm_epi_store(float* stg, int lane, const uint3
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int row = (lane >> 3) + 4 * i;
-      if (row0 + row >= M) continue;
+      const int grow = orow ? orow[i] : (row0 + row < M ? row0 + row : -1);      // output row (listed rows: C row of list entry)
+      if (grow < 0) continue;
       float4 v = *reinterpret_cast<const float4*>(stg + row * G_EPI_ROW + cc);
-      float* dst = cbase + (long long)(row0 + row) * ldc + col0 + cc;
+      float* dst = cbase + (long long)grow * ldc + col0 + cc;
       float x[4] = {v.x, v.y, v.z, v.w};
       if (apply) {
         if (flags & LSTUR_GEMM_ACCUM) {
@@ -158,14 +163,17 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const GemmParams 
   uint32_t* tmem_ptr_smem = (uint32_t*)(misc_gen + 160);
   float* s_epi = (float*)(misc_gen + 256);      // [4 epilogue warps] staging rows (G_EPI_WARP_BYTES each)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles = p.tiles_m * p.tiles_n * p.splits;
+  // listed rows: the M extent is the device-side count of the list
+  const int Meff = p.mcount ? min(__ldg(p.mcount), p.M) : p.M;
+  const int tiles_m = p.mcount ? (Meff + TILE_M - 1) / TILE_M : p.tiles_m;
+  const int n_tiles = tiles_m * p.tiles_n * p.splits;
 
   // tile index -> (m0, n0, split) and derived extents
   struct Tile { int m0, n0, nt, nmma, z, kbeg, kend, nkb; };
   auto tile_of = [&](int t) {
     Tile x;
-    const int tn = t % p.tiles_n, tm = (t / p.tiles_n) % p.tiles_m;
-    x.z = t / (p.tiles_n * p.tiles_m);
+    const int tn = t % p.tiles_n, tm = (t / p.tiles_n) % tiles_m;
+    x.z = t / (p.tiles_n * tiles_m);
     x.m0 = tm * TILE_M;
     x.n0 = tn * p.ntile;
     x.nt = min(p.ntile, p.N - x.n0);                       // valid columns of this tile
@@ -255,13 +263,20 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const GemmParams 
       const bool img = p.bimg != nullptr;
       const int nb_pieces = img ? 0 : (TB ? x.nmma * 8 : bgroups * 512);      // B pieces of this tile per K block
       const uint32_t b_tile_bytes = (uint32_t)(TB ? x.nmma * 128 : bgroups * 8192);
+      // rows of A behind this thread's four pieces (the same for every K block of the tile); p.M = "no row"
+      int arow[4];
+#pragma unroll
+      for (int idx = 0; idx < 4; ++idx) {
+        const int r = m0 + ((pt + idx * G_PRODUCERS) >> 3);
+        arow[idx] = r < Meff ? (p.midx ? __ldg(p.midx + r) : r) : p.M;
+      }
       for (int kb = 0; kb < x.nkb; ++kb) {
         const int k0 = x.kbeg + kb * G_KBLK;
         const uint32_t a_addr = smem_base + s * STAGE_BYTES, b_addr = a_addr + G_A_BYTES;
         auto piece_load = [&](int idx, float* v) {
           if (idx < 4) {
             const int i = pt + idx * G_PRODUCERS, c = i & 7, r = i >> 3;
-            if (!TA) load_raw(p.A, p.lda, m0 + r, p.M, k0 + 8 * c, kend, p.vec_ok, v);
+            if (!TA) load_raw(p.A, p.lda, arow[idx], p.M, k0 + 8 * c, kend, p.vec_ok, v);
             else load_raw(p.A, p.lda, k0 + (r & 63), kend, m0 + (r >> 6) * 64 + 8 * c, p.M, p.vec_ok, v);
           } else {
             const int i = pt + (idx - 4) * G_PRODUCERS, c = i & 7, r = i >> 3;
@@ -330,6 +345,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const GemmParams 
       float* cbase = split ? p.partial + (long long)x.z * p.M * p.N : p.C;
       const long long ldo = split ? (long long)p.N : p.ldc;
       const bool vec_st = (ldo % 4 == 0) && ((((uintptr_t)cbase) & 15) == 0) && ((x.n0 & 3) == 0);
+      int orow[8];      // listed rows: the C rows of this lane's eight staged rows
+      if (p.midx) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = x.m0 + q * 32 + (lane >> 3) + 4 * i;
+          orow[i] = rr < Meff ? __ldg(p.midx + rr) : -1;
+        }
+      }
       for (int c0 = 0; c0 < x.nmma; c0 += 32) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
@@ -337,8 +360,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const GemmParams 
         tmem_ld_wait();
         const int ncols = min(32, x.nt - c0);
         if (ncols > 0)
-          gemm_epi_store(s_epi + (warp - 9) * (G_EPI_WARP_BYTES / 4), lane, r, x.nkb > 0, cbase, ldo, x.m0 + q * 32, p.M,
-                         x.n0 + c0, ncols, p.bias, p.flags, !split, vec_st);
+          gemm_epi_store(s_epi + (warp - 9) * (G_EPI_WARP_BYTES / 4), lane, r, x.nkb > 0, cbase, ldo, x.m0 + q * 32, Meff,
+                         x.n0 + c0, ncols, p.bias, p.flags, !split, vec_st, p.midx ? orow : nullptr);
       }
       tc_fence_before();
       __syncwarp();
@@ -703,7 +726,8 @@ extern "C" size_t lstur_gemm_tc_workspace_bytes(int M, int N, int K) {
 
 static int gemm_tc_impl(int transA, int transB, int M, int N, int K, const float* A, long long lda, const float* B,
                         long long ldb, float* C, long long ldc, const float* bias, int flags, void* workspace,
-                        size_t workspace_bytes, const int* kidx, const int* kcount, cudaStream_t stream);
+                        size_t workspace_bytes, const int* kidx, const int* kcount, cudaStream_t stream,
+                        const int* midx = nullptr, const int* mcount = nullptr);
 
 // Same contract as lstur_gemm_f32 (fp32 in / fp32 out); operands are rounded to fp16 inside the kernel.
 extern "C" int lstur_gemm_tc(int transA, int transB, int M, int N, int K, const float* A, long long lda, const float* B,
@@ -723,9 +747,20 @@ extern "C" int lstur_gemm_tc_tn_rows(int M, int N, int K, const float* A, long l
   return gemm_tc_impl(1, 0, M, N, K, A, lda, B, ldb, C, ldc, nullptr, 0, workspace, workspace_bytes, k_rows, k_count, stream);
 }
 
+// C[m, :] = (A[m, :K] . op(B)) (+ bias) (relu) for the listed rows m = m_rows[0 .. *m_count) only (A stored [M, K]; m_rows
+// ascending device ints, m_count a device scalar <= M); the other rows of C are left untouched.  Used where half of the
+// rows are padding whose result nobody reads (or whose result is a constant filled in separately).
+extern "C" int lstur_gemm_tc_mrows(int transB, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb,
+                                   float* C, long long ldc, const float* bias, int flags, const int* m_rows, const int* m_count,
+                                   void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  return gemm_tc_impl(0, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, flags, workspace, workspace_bytes, nullptr, nullptr, stream,
+                      m_rows, m_count);
+}
+
 static int gemm_tc_impl(int transA, int transB, int M, int N, int K, const float* A, long long lda, const float* B,
                         long long ldb, float* C, long long ldc, const float* bias, int flags, void* workspace,
-                        size_t workspace_bytes, const int* kidx, const int* kcount, cudaStream_t stream) {
+                        size_t workspace_bytes, const int* kidx, const int* kcount, cudaStream_t stream,
+                        const int* midx, const int* mcount) {
   LSTUR_REQUIRE(M >= 0 && N >= 0 && K >= 0, "lstur_gemm_tc");
   if (M == 0 || N == 0) return LSTUR_OK;
   tc::GemmParams p;
@@ -753,6 +788,7 @@ static int gemm_tc_impl(int transA, int transB, int M, int N, int K, const float
   p.bimg = nullptr; p.nkb_total = (K + tc::G_KBLK - 1) / tc::G_KBLK;
   p.kidx = use_async ? kidx : nullptr;            // the row list is honoured by the cp.async kernel only (else: all K rows)
   p.kcount = use_async ? kcount : nullptr;
+  p.midx = nullptr; p.mcount = nullptr;
   p.vec_ok = (lda % 4 == 0) && (ldb % 4 == 0) && ((((uintptr_t)A) & 15) == 0) && ((((uintptr_t)B) & 15) == 0);
   const bool split3 = (flags & LSTUR_GEMM_PRECISE) != 0;
   size_t smem = 1024 + (split3 ? (size_t)2 * tc::G_STAGE_BYTES_S3 : (size_t)tc::G_STAGES * tc::G_STAGE_BYTES) + 256 +
@@ -775,6 +811,7 @@ static int gemm_tc_impl(int transA, int transB, int M, int N, int K, const float
   p.tiles_n = (N + p.ntile - 1) / p.ntile;
   p.tiles_m = (M + tc::TILE_M - 1) / tc::TILE_M;
   p.splits = splits;
+  if (midx && mcount && !use_async && !transA && splits == 1) { p.midx = midx; p.mcount = mcount; }   // else: every row (a superset)
   // Large-M GEMMs against a small weight matrix (GRU input projection and its input gradient, scorer Dense layers):
   // pack B once per call into stage-layout fp16 tiles; the CTAs then fetch it with bulk copies.
   static int img_mode = -1;

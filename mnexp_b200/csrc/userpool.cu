@@ -116,6 +116,14 @@ __global__ void first_live_step_kernel(int B, int W, const float* __restrict__ m
   if (lane == 0) key[b] = first;
 }
 
+// out[r, :cols] = bias[:cols] (or 0) for the rows with flags[r] == want   (one warp per row)
+__global__ void fill_rows_where_kernel(int rows, int cols, const int* __restrict__ flags, int want,
+                                       const float* __restrict__ bias, float* __restrict__ out, long long ld) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= rows || flags[r] != want) return;
+  for (int k = lane; k < cols; k += 32) out[(long long)r * ld + k] = bias ? bias[k] : 0.f;
+}
+
 // y[r, :] = ay * y[r, :] + ax * x[r, :]   (strided rows)
 __global__ void add_rows_kernel(int rows, int D, float ax, const float* __restrict__ x, long long ldx, float ay,
                                 float* __restrict__ y, long long ldy) {
@@ -407,6 +415,15 @@ extern "C" int lstur_first_live_step(int B, int W, const float* mask, int* key, 
   if (B == 0) return LSTUR_OK;
   first_live_step_kernel<<<cdiv(B, 8), 256, 0, stream>>>(B, W, mask, key);
   LSTUR_CHECK_LAUNCH("lstur_first_live_step");
+  return LSTUR_OK;
+}
+
+extern "C" int lstur_fill_rows_where(int rows, int cols, const int* flags, int want, const float* bias, float* out,
+                                     long long ld, cudaStream_t stream) {
+  LSTUR_REQUIRE(rows >= 0 && cols > 0 && (rows == 0 || (flags && out)), "lstur_fill_rows_where");
+  if (rows == 0) return LSTUR_OK;
+  fill_rows_where_kernel<<<cdiv(rows, 8), 256, 0, stream>>>(rows, cols, flags, want, bias, out, ld);
+  LSTUR_CHECK_LAUNCH("lstur_fill_rows_where");
   return LSTUR_OK;
 }
 
