@@ -100,6 +100,18 @@ class _Core:
                 share_weights_from=base, score_model=self.score_model, **self.head_kw())
         return self.infer_engines[key]
 
+    def stage_tokens(self, name, arr):
+        """host token array (the reference feeds float64, document.py:39) -> int32 in a reusable PINNED buffer: the cast is
+        one numpy pass (float64 -> int32, ids < 2^24 are exact) and the upload an asynchronous 4-byte-per-id copy instead
+        of a pageable 8-byte-per-id copy followed by a cast on the device."""
+        arr = np.asarray(arr)
+        key = (name, arr.shape)
+        pin = self.__dict__.setdefault('_pinned', {})
+        if key not in pin:
+            pin[key] = torch.empty(arr.shape, dtype=torch.int32).pin_memory()
+        np.copyto(pin[key].numpy(), arr, casting='unsafe')
+        return pin[key]
+
     def n_train_cand(self):
         return 1 if self.loss == 'bce' else 1 + self.cfg.negative_samples
 
@@ -147,12 +159,13 @@ class Model:
         user, clicked, cand, verts = core.split_inputs(x, C)
         eng = core.engine_train(clicked.shape[0])
         eng.lr = core.optimizer.lr.value
-        batch = dict(user=user, hist_tok=clicked, cand_tok=cand, label=np.asarray(y, dtype=np.float32).reshape(len(clicked), C))
+        batch = dict(user=user, hist_tok=core.stage_tokens('hist', clicked), cand_tok=core.stage_tokens('cand', cand),
+                     label=np.asarray(y, dtype=np.float32).reshape(len(clicked), C))
         if verts is not None:
             batch['hist_vert'], batch['cand_vert'] = verts
         if core.arch == 'dgru':     # Dropout(0.5, noise_shape=(None, 1)) on the user vector (task/paper.py:609)
             batch['user_scale'] = (np.random.random(clicked.shape[0]) >= 0.5).astype(np.float32) * 2.0
-        db = eng.to_device_batch(batch)
+        db = eng.to_device_batch(batch, non_blocking=True)
         loss = eng.train_step(db)
         probs = eng.view('probs').reshape(eng.B, eng.C)
         if core.loss == 'bce':
