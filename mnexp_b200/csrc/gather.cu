@@ -250,6 +250,40 @@ __global__ void title_compact_kernel(int N, int L, const int* __restrict__ tok, 
   for (int l = lane; l < L; l += 32) tok_c[(long long)ci * L + l] = tok[(long long)warp * L + l];
 }
 
+// L == 1 (a list of non-zero entries of a mask, e.g. the unmasked (user, step) rows): one THREAD per entry
+__global__ void mask_live_kernel(int N, const int* __restrict__ v, int* __restrict__ flags) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < N) flags[n] = v[n] != 0 ? 1 : 0;
+}
+__global__ void __launch_bounds__(1024) mask_compact_kernel(int N, const int* __restrict__ v, const int* __restrict__ flags,
+                                                            const int* __restrict__ local_rank,
+                                                            const int* __restrict__ block_tot, int n_blocks,
+                                                            int* __restrict__ live_idx, int* __restrict__ n_live,
+                                                            int* __restrict__ v_c) {
+  __shared__ int s_before;
+  const int blk = blockIdx.x, n = blk * 1024 + threadIdx.x;
+  if (threadIdx.x < 32) {          // live entries of the earlier blocks (fixed order); the last block also publishes the total
+    int before = 0, total = 0;
+    for (int b = threadIdx.x; b < n_blocks; b += 32) {
+      const int t = block_tot[b];
+      total += t;
+      if (b < blk) before += t;
+    }
+    before = __reduce_add_sync(0xffffffffu, before);
+    total = __reduce_add_sync(0xffffffffu, total);
+    if (threadIdx.x == 0) {
+      s_before = before;
+      if (blk == n_blocks - 1) *n_live = total;
+    }
+  }
+  __syncthreads();
+  if (n < N && flags[n]) {
+    const int ci = s_before + local_rank[n];
+    live_idx[ci] = n;
+    v_c[ci] = v[n];
+  }
+}
+
 }  // namespace lstur
 
 using namespace lstur;
@@ -264,6 +298,15 @@ extern "C" int lstur_compact_titles(int N, int L, const int* tokens, int* scratc
   LSTUR_REQUIRE(tokens && scratch && live_idx && tokens_c, "lstur_compact_titles");
   const int nb = (N + 1023) / 1024;
   int *flags = scratch, *local_rank = scratch + N, *block_tot = scratch + 2 * (long long)N;
+  if (L == 1) {      // list of the non-zero entries of a vector: thread-per-entry kernels
+    mask_live_kernel<<<cdiv(N, 256), 256, 0, stream>>>(N, tokens, flags);
+    LSTUR_CHECK_LAUNCH("lstur_compact_titles(flags)");
+    title_rank_kernel<<<nb, 1024, 0, stream>>>(N, flags, local_rank, block_tot);
+    LSTUR_CHECK_LAUNCH("lstur_compact_titles(rank)");
+    mask_compact_kernel<<<nb, 1024, 0, stream>>>(N, tokens, flags, local_rank, block_tot, nb, live_idx, n_live, tokens_c);
+    LSTUR_CHECK_LAUNCH("lstur_compact_titles(gather)");
+    return LSTUR_OK;
+  }
   title_live_kernel<<<cdiv((long long)N * 32, 256), 256, 0, stream>>>(N, L, tokens, flags);
   LSTUR_CHECK_LAUNCH("lstur_compact_titles(flags)");
   title_rank_kernel<<<nb, 1024, 0, stream>>>(N, flags, local_rank, block_tot);

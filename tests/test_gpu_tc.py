@@ -399,7 +399,7 @@ def test_word_grad_scatter_16(lib, N, L, E, V, hot, masked):
 
 
 # ---------------------------------------------------------------- live-title compaction
-@pytest.mark.parametrize('N,L', [(1, 7), (1000, 30), (5000, 50), (3, 1)])
+@pytest.mark.parametrize('N,L', [(1, 7), (1000, 30), (5000, 50), (3, 1), (51200, 1), (1025, 1)])
 def test_compact_titles_bit_exact(lib, N, L):
     g = np.random.default_rng(N + L)
     tok = g.integers(0, 5, (N, L)).astype(np.int32)
