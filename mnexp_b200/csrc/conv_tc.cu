@@ -9,17 +9,19 @@
 // GEMM view of the forward: D[m, f] = sum_{j<3} sum_e X[m+j-1, e] * Wc[j, e, f], m = token position.
 //   M tile  = 128 rows = title slots of SLOT rows: 4 x 32 (L <= 31) or 2 x 64 (L <= 63).  A slot holds the L tokens
 //             of a title + >= 1 zero row, which is both the right halo of its title and the left halo of the next
-//             one; rows wrap inside the tile.
-//   N       = F (<= 512 TMEM columns), issued as two pair-MMAs per K step (256 + rest).
+//             one; the rows before / after the tile are zero pads.
+//   N       = F (<= 512 TMEM columns), computed as two FEATURE PASSES over K (columns [0, 2*n0h) then the rest), each
+//             with its own accumulator barriers so that the epilogue drains one pass while the tensor core runs the other.
 //   K       = 3 taps x Ep (E padded to a multiple of 64), pipeline block = 32 columns = one 64-byte swizzle row.
 // CTA pairs (cta_group::2, M = 256): each CTA owns one 128-row token tile and stages half of the weight rows.
-// A operand: producer warps gather each embedding row ONCE per 32-column chunk (16 B loads, 4 lanes per row), apply
-//   the input dropout mask, and store it into the three tap tiles at row offsets +1/0/-1 in the canonical K-major
-//   SWIZZLE_64B layout (16 B chunk index XOR (row>>1)&3).
+// A operand: producer warps gather each embedding row ONCE per tile and 32-column chunk (16 B loads, 4 lanes per row),
+//   apply the input dropout mask, and store ONE copy of it in the canonical K-major SWIZZLE_64B layout (16 B chunk index
+//   XOR (row>>1)&3); the three taps are read through descriptors that start one row earlier / later.  The tile's chunks
+//   stay resident (A ring, one slot per chunk) until both feature passes have read them.
 // B operand: the conv weights are re-packed per call into 16-bit K-major SWIZZLE_64B images in consumption order, so
-//   one cp.async.bulk per (chunk, tap) lands an MMA-ready tile.
-// Warp roles (640 threads): w0 weight loader, w1 TMEM alloc + MMA issuer (leader CTA), w4-11 A producers,
-//   w12-19 epilogue (TMEM lane quarter = warp%4, feature half = (warp-12)/4).
+//   one cp.async.bulk per (pass, chunk, tap) lands an MMA-ready tile in the B ring.
+// Warp roles (640 threads): w0 weight loader, w1 TMEM alloc + MMA issuer (leader CTA), w2 (peer CTA) weight-landed
+//   forwarder, w4-11 A producers, w12-19 epilogue (TMEM lane quarter = warp%4, feature half = (warp-12)/4).
 // The input gradient (word-table training, task/paper.py:136) runs the SAME main loop with the roles of the operands
 // changed: "embedding rows" are the rows of the dPre image, the weights are Wc transposed with the taps reversed,
 // N = Ep and the epilogue only scales and stores 16-bit rows (see news_conv_tc_kernel, MODE_DGRAD).
