@@ -179,6 +179,8 @@ def user_encoder(arch, user, H, P, recurrent_activation='hard_sigmoid', u0_scale
         return np.concatenate([gru(u0), f8('user_emb2')[user]], -1) @ f8('con_w') + f8('con_b')
     if arch in ('ngru', 'hgru', 'dgru'):     # LSTUR-con plain concat, :600-611
         return np.concatenate([gru(None), u0], -1)
+    if arch == 'iicat':                      # Seq2VecPaperId 'iigru', task/paper.py:338-343 (cook 'inigru', task/cook.py:169-176)
+        return np.concatenate([gru(u0), f8('user_emb2')[user] * (1.0 if u0_scale is None else u0_scale)], -1)
     if arch == 'pgru':                       # :622-624
         return gru(None) + u0
     if arch == 'nigru':                      # :625-626

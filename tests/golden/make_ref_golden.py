@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""Generates tests/golden/ref_golden.npz by running the REFERENCE'S OWN, unmodified source files.
+
+    python tests/golden/make_ref_golden.py [--out FILE]          (needs /root/reference: run in the build container)
+
+`/root/reference/{settings,task/*,models,utils,document}.py` are imported where they lie.  Their two third-party
+dependencies, keras 2.2.x and tensorflow 1.x, are neither vendored there nor installable here; `oracle/keras_shim/`
+restates the published behaviour of the layers / backend functions those files call (its README.md says exactly what is
+restated).  Everything the reference itself wrote is therefore EXECUTED, not re-read: `task.get(config)` loads a synthetic
+dataset written in the reference's on-disk formats with its own parsers (document.py, task/seq2vec.py:_load_docs,
+task/paper.py:_load_data), `h.train` / `h.valid` are its own window / negative-sampling / pool-shuffle batchers, and
+`h.build_model(0)` is its own `_build_model` graph assembly (task/paper.py:222-665).
+
+Per case the file holds: the batch `x, y` the reference's batcher produced (np.random.seed fixed), the weights the model was
+given (this repo's parameter names), `model.predict`, `test_model.predict`, the user and candidate vectors, the loss and
+d loss / d weight of `model`'s compiled loss in training mode, and the losses + weights of three `train_on_batch` steps with
+the reference's compiled `keras.optimizers.Adam`.  Cases with dropout > 0 draw their keep masks from this repo's
+counter-based stream (mnexp_b200/rng.py, fp32 verification mode) through the shim's dropout hook, so the CUDA path can be
+run on the same masks.
+
+tests/test_ref_pinned.py checks the oracle (CPU) and the CUDA path (-m gpu) against these vectors, and — when
+/root/reference is present — re-runs this script in a subprocess and requires the committed file to reproduce.
+"""
+import argparse
+import contextlib
+import io
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get('MNEXP_REFERENCE', '/root/reference')
+OUT = os.path.join(HERE, 'ref_golden.npz')
+GAIN = 1.5
+DROP_SEED = 11
+
+# (case name, reference task class, reference arch, score model, this repo's oracle arch, extra config)
+CASES = [
+    ('sid-igru-dot', 'Seq2VecPaperSoftmaxId', 'igru', 'dot', 'igru', {}),
+    ('sid-gru-dot', 'Seq2VecPaperSoftmaxId', 'gru', 'dot', 'gru', {}),
+    ('sid-ngru-dnn', 'Seq2VecPaperSoftmaxId', 'ngru', 'dnn', 'ngru', {}),
+    ('sid-hgru-dot', 'Seq2VecPaperSoftmaxId', 'hgru', 'dot', 'hgru', {}),
+    ('sid-dgru-ddot', 'Seq2VecPaperSoftmaxId', 'dgru', 'ddot', 'dgru', {}),
+    ('sid-iigru-dot', 'Seq2VecPaperSoftmaxId', 'iigru', 'dot', 'iigru', {}),
+    ('sid-vo-dot', 'Seq2VecPaperSoftmaxId', 'vo', 'dot', 'vo', {}),
+    ('sid-pgru-dot', 'Seq2VecPaperSoftmaxId', 'pgru', 'dot', 'pgru', {}),
+    ('sid-nigru-dot', 'Seq2VecPaperSoftmaxId', 'nigru', 'dot', 'nigru', {}),
+    ('sid-niavg-dnn', 'Seq2VecPaperSoftmaxId', 'niavg', 'dnn', 'niavg', {}),
+    ('sid-igru-ddot', 'Seq2VecPaperSoftmaxId', 'igru', 'ddot', 'igru', {}),
+    ('sid-igru-dot-trainable', 'Seq2VecPaperSoftmaxId', 'igru', 'dot', 'igru', {'textual_embedding_trainable': True}),
+    ('sid-igru-dot-dropout', 'Seq2VecPaperSoftmaxId', 'igru', 'dot', 'igru', {'dropout': 0.2}),
+    ('s-gru-dot', 'Seq2VecPaperSoftmax', 'gru', 'dot', 'nigru', {}),
+    ('s-att-dot', 'Seq2VecPaperSoftmax', 'att', 'dot', 'att', {}),
+    ('s-avg-dnn', 'Seq2VecPaperSoftmax', 'avg', 'dnn', 'niavg', {}),
+    ('pid-igru', 'Seq2VecPaperId', 'igru', 'dnn', 'igru', {'gain': GAIN}),
+    ('pid-iigru', 'Seq2VecPaperId', 'iigru', 'dnn', 'iicat', {'gain': GAIN}),
+    ('p-gru', 'Seq2VecPaper', 'gru', 'dnn', 'nigru', {'gain': GAIN}),
+    ('pdot-gru', 'Seq2VecPaperDot', 'gru', 'dot', 'nigru', {'gain': GAIN}),
+]
+
+
+def reference_available():
+    return os.path.isfile(os.path.join(REF, 'task', 'paper.py'))
+
+
+def load_reference():
+    """put the shim and the reference on sys.path and import the reference's own modules"""
+    sys.dont_write_bytecode = True
+    sys.path[:0] = [os.path.join(ROOT, 'oracle', 'keras_shim'), REF]
+    if ROOT not in sys.path:
+        sys.path.append(ROOT)
+    import keras
+    import tensorflow                      # noqa: F401
+    keras.backend.set_floatx('float64')
+    import settings
+    import task
+    return keras, settings, task
+
+
+def reference_config(settings, data_dir, sh, task_name, arch, score_model, **extra):
+    """every option of the reference's CLI (main.py:98-146) at its default, the shape options from `sh`"""
+    cfg = dict(task=task_name, arch=arch, round=6, days=30, epochs=2, batch_size=sh.B, training_step=3, validation_step=2,
+               validation_impression=5, testing_impression=5, learning_rate=0.001, learning_rate_decay=0.2, gain=1.0,
+               window_size=sh.W, dropout=0.0, negative_samples=sh.K, hidden_dim=400, nonlocal_negative_samples=0,
+               enable_baseline=False, title_filter_shape=(sh.F, sh.k), title_shape=sh.L, body_shape=sh.L,
+               user_embedding_dim=sh.U, textual_embedding_dim=sh.E, textual_embedding_trainable=False, debug=True,
+               background=True, name='', pretrain_name='', enable_pretrain_encoder=False, pretrain_encoder_trainable=False,
+               personal_embedding_dim=20, news_encoder='cnnatt', score_model=score_model, id_keep=1.0, body_sent_cnt=50,
+               body_sent_len=30, body_filter_shape=(400, 3), max_impression=200, max_impression_pos=7, max_impression_neg=200,
+               test_window_size=100, vertical_embedding_dim=15, subvertical_embedding_dim=35, use_vertical=False,
+               use_vertical_type='vs', use_generator=False, lrd_on_epochs=[1, 3], input_training_data_path=data_dir,
+               input_validation_data_path=data_dir, input_previous_model_path=data_dir, output_model_path=data_dir,
+               log_dir=data_dir)
+    cfg.update(extra)
+    with contextlib.redirect_stdout(io.StringIO()):          # Config.__init__ pretty-prints itself
+        return settings.Config(cfg)
+
+
+def _uid(layer):
+    return int(layer.name.rsplit('_', 1)[-1]) if layer.name.rsplit('_', 1)[-1].isdigit() else 0
+
+
+def named_variables(h):
+    """this repo's parameter name -> the reference model's weight variable, found by walking the reference's own graph"""
+    model = h.model
+    doc = model.get_layer('doc_encoder')
+    ue = model.get_layer('user_encoder') if any(l.name == 'user_encoder' for l in model.layers) else None
+    out = {}
+    for l in doc.layers:
+        c = l.__class__.__name__
+        if c == 'Embedding':
+            out['word_emb'] = l.embeddings
+        elif c == 'Conv1D':
+            out['conv_w'], out['conv_b'] = l.kernel, l.bias
+        elif c == 'SimpleAttentionMaskSupport':
+            out['att_w'], out['att_b'] = l.kernel, l.bias
+        elif c == 'Dense':
+            out['dense_w'], out['dense_b'] = l.kernel, l.bias
+    if ue is not None:
+        embs = sorted([l for l in ue.layers if l.__class__.__name__ == 'Embedding'], key=_uid)
+        for name, l in zip(('user_emb', 'user_emb2'), embs):
+            out[name] = l.embeddings
+        for l in ue.layers:
+            c = l.__class__.__name__
+            if c == 'GRU':
+                out['gru_wx'], out['gru_wh'], out['gru_b'] = l.kernel, l.recurrent_kernel, l.bias
+            elif c == 'Dense':
+                out['con_w'], out['con_b'] = l.kernel, l.bias
+            elif c == 'SimpleAttentionMaskSupport':
+                out['uatt_w'], out['uatt_b'] = l.kernel, l.bias
+    score_model = getattr(h, 'score_model', None)
+    if score_model is not None and not isinstance(score_model, str):          # softmax family: task/paper.py:441-458
+        dense = sorted([l for l in score_model.layers if l.__class__.__name__ == 'Dense'], key=_uid)
+        names = {'dnn': ('sh', 'so'), 'ddot': ('su', 'sd'), 'dot': ()}[h.config.score_model]
+        for n, l in zip(names, dense):
+            out[n + '_w'], out[n + '_b'] = l.kernel, l.bias
+    else:                                                                      # sigmoid family: task/paper.py:222-226
+        for n, lname in (('sh', 'concat_dense'), ('so', 'socre_dense')):
+            if any(l.name == lname for l in model.layers):
+                l = model.get_layer(lname)
+                out[n + '_w'], out[n + '_b'] = l.kernel, l.bias
+    return out
+
+
+def assign(variables, P):
+    import keras
+    for k, v in variables.items():
+        a = np.asarray(P[k], dtype=np.float64)
+        if k in ('att_w', 'uatt_w'):
+            a = a.reshape(-1, 1)
+        assert tuple(v.shape) == a.shape, 'parameter %s: the reference graph has %s, this repo %s' % (k, tuple(v.shape), a.shape)
+        keras.backend.set_value(v, a)
+    missing = sorted(set(P) - set(variables))
+    assert not missing, 'parameters with no variable in the reference graph: %s' % missing
+
+
+def snapshot(variables):
+    return {k: v.detach().cpu().numpy().reshape(-1).copy() if k in ('att_w', 'uatt_w') else v.detach().cpu().numpy().copy()
+            for k, v in variables.items()}
+
+
+class MaskReplay:
+    """keep masks of mnexp_b200/rng.py (fp32 verification stream) handed to the shim's Dropout layers in the order the
+    reference graph evaluates them: history titles (B*W rows) then candidate k (B rows each); X-dropout has E columns,
+    C-dropout F columns (task/paper.py:147,158)."""
+
+    def __init__(self, sh, p, seed):
+        from mnexp_b200 import rng
+        n = sh.B * (sh.W + 1 + sh.K)
+        self.sh, self.calls = sh, {}
+        self.keep = {sh.E: rng.dropout_multiplier(seed * 2, n * sh.L * sh.E, p).reshape(n, sh.L, sh.E) != 0,
+                     sh.F: rng.dropout_multiplier(seed * 2 + 1, n * sh.L * sh.F, p).reshape(n, sh.L, sh.F) != 0}
+
+    def reset(self):
+        self.calls = {}
+
+    def __call__(self, shape, level):
+        sh, width = self.sh, shape[-1]
+        keep, nh, c = self.keep[width], sh.B * sh.W, 1 + sh.K
+        if shape[0] == nh and (width, 'h') not in self.calls:
+            self.calls[(width, 'h')] = 1
+            return keep[:nh]
+        k = self.calls.get((width, 'c'), 0)
+        self.calls[(width, 'c')] = k + 1
+        assert shape[0] == sh.B and k < c, (shape, k)
+        return keep[nh:].reshape(sh.B, c, sh.L, width)[:, k]
+
+
+def run_case(mods, sh, data_dir, name, task_name, arch, score_model, my_arch, extra):
+    keras, settings, task = mods
+    from keras import _engine
+    from mnexp_b200 import synth
+    keras.backend.clear_session()
+    cfg = reference_config(settings, data_dir, sh, task_name, arch, score_model, **extra)
+    h = task.get(cfg)
+    model = h.build_model(0)
+    variables = named_variables(h)
+    softmax = task_name.startswith('Seq2VecPaperSoftmax')
+    P = synth.make_weights(sh, arch=my_arch, bias_noise=0.05, seed=4242, score_model=score_model if (softmax or task_name != 'Seq2VecPaperDot') else 'dot',
+                           word_emb=np.load(os.path.join(data_dir, 'Vocab.tsv.npy')))
+    if not softmax and task_name == 'Seq2VecPaperDot':
+        P = {k: v for k, v in P.items() if not k.startswith(('sh_', 'so_'))}
+    assign(variables, P)
+    np.random.seed(20190131)
+    gen = h.train
+    x, y = next(gen)
+    out = {'x%d' % i: np.asarray(a) for i, a in enumerate(x)}
+    out['y'] = np.asarray(y)
+    out['n_inputs'] = np.int64(len(x))
+    for k, v in snapshot(variables).items():
+        out['P/' + k] = v
+    out['predict'] = model.predict(x)
+    if hasattr(h, 'test_model'):
+        one = list(x[:2 if len(x) == 3 + sh.K else 1]) + [x[-1]]              # [user,] clicked, ONE candidate (the last)
+        out['test_predict'] = h.test_model.predict(one)
+    # intermediate vectors of the outer graph
+    doc, has_ue = model.get_layer('doc_encoder'), any(l.name == 'user_encoder' for l in model.layers)
+    if has_ue:
+        ue = model.get_layer('user_encoder')
+        n_head = len(ue.inputs)                                               # [user_idx, clicked_vec] or [clicked_vec]
+        uv = keras.Model(model.inputs[:n_head], ue._inbound_nodes[0].outputs[0])
+        out['user_vec'] = uv.predict(list(x[:n_head]))
+    out['cand_vec0'] = doc.predict(x[len(x) - (1 + sh.K) if softmax else len(x) - 1])
+    p = float(extra.get('dropout', 0.0))
+    replay = MaskReplay(sh, p, DROP_SEED) if p > 0 else None
+    _engine._STATE['dropout_hook'] = replay
+    try:
+        if arch == 'dgru':          # Dropout(0.5, noise_shape=(None, 1)) on the id vector: its draw is TensorFlow's, not replayable
+            loss, grads = model.loss_and_gradients(x, y, training=False)
+        else:
+            loss, grads = model.loss_and_gradients(x, y, training=True)
+        out['loss'] = np.float64(loss)
+        by_var = {v.vname: k for k, v in variables.items()}
+        for vname, g in grads.items():
+            k = by_var[vname]
+            out['grad/' + k] = g.reshape(-1) if k in ('att_w', 'uatt_w') else g
+        if arch != 'dgru':
+            losses = []
+            for _ in range(3):
+                if replay:
+                    replay.reset()
+                r = model.train_on_batch(x, y)
+                losses.append(r[0] if isinstance(r, list) else r)
+            out['adam_losses'] = np.asarray(losses, dtype=np.float64)
+            for k, v in snapshot(variables).items():
+                out['adam/' + k] = v
+    finally:
+        _engine._STATE['dropout_hook'] = None
+    # the NEXT batches of the reference's own batchers (host data path parity: a1-a4 of SURVEY 8)
+    x2, y2 = next(gen)
+    for i, a in enumerate(x2):
+        out['next_x%d' % i] = np.asarray(a)
+    out['next_y'] = np.asarray(y2)
+    np.random.seed(7)
+    xv, yv = next(h.valid)
+    for i, a in enumerate(xv):
+        out['valid_x%d' % i] = np.asarray(a)
+    out['valid_y'] = np.asarray(yv)
+    out['layers'] = np.array([l.name for l in model.layers])
+    out['weight_names'] = np.array([w.vname for w in model.weights])
+    return out
+
+
+def generate(path=OUT, verbose=True):
+    mods = load_reference()
+    from mnexp_b200 import synth
+    sh = synth.SHAPES['tiny']
+    data_dir = tempfile.mkdtemp(prefix='refgold_')
+    synth.write_dataset(data_dir, sh)
+    out = {'cases': np.array([c[0] for c in CASES]), 'case_table': np.array([[c[0], c[1], c[2], c[3], c[4]] for c in CASES]),
+           'gain': np.float64(GAIN), 'drop_seed': np.int64(DROP_SEED)}
+    for name, task_name, arch, score_model, my_arch, extra in CASES:
+        res = run_case(mods, sh, data_dir, name, task_name, arch, score_model, my_arch, extra)
+        for k, v in res.items():
+            out[name + '/' + k] = v
+        if verbose:
+            print('%-24s %-24s loss %.6f  layers %d' % (name, task_name, float(res['loss']), len(res['layers'])))
+    np.savez_compressed(path, **out)
+    if verbose:
+        print('wrote %d arrays to %s' % (len(out), path))
+    return out
+
+
+if __name__ == '__main__':
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--out', default=OUT)
+    a = ap.parse_args()
+    if not reference_available():
+        sys.exit('the reference is not present at %s' % REF)
+    generate(a.out)

@@ -1,0 +1,282 @@
+"""Parity pinned on the reference's OWN code: tests/golden/ref_golden.npz holds what /root/reference's unmodified
+task/paper.py produced (batches of its own batchers, `_build_model` graphs evaluated, losses, gradients, Adam steps) when it
+was imported over oracle/keras_shim (tests/golden/make_ref_golden.py explains what is executed and what is restated).
+
+CPU (-m "not gpu"): the oracle (numpy float64 and torch autograd + Keras Adam) and this repo's host data path against
+those vectors; when /root/reference is present the generator is re-run in a subprocess and must reproduce the committed
+file.  GPU (-m gpu): the CUDA path through the drop-in surface (mnexp_b200.task + keras_like Model protocol) against the
+same vectors."""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from mnexp_b200 import rng, settings, synth, task
+from oracle import lstur_numpy as on
+from oracle import lstur_torch as ot
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = np.load(os.path.join(HERE, 'golden', 'ref_golden.npz'))
+TABLE = {row[0]: tuple(row[1:]) for row in GOLD['case_table']}
+CASES = [str(c) for c in GOLD['cases']]
+SH = synth.SHAPES['tiny']
+EXTRA = {'sid-igru-dot-trainable': dict(textual_embedding_trainable=True), 'sid-igru-dot-dropout': dict(dropout=0.2)}
+F64 = 1e-9            # float64 restatement against the float64 run of the reference graph
+P_KEYS = ('word_emb', 'conv_w', 'conv_b', 'att_w', 'att_b', 'dense_w', 'dense_b', 'user_emb', 'user_emb2', 'gru_wx', 'gru_wh',
+          'gru_b', 'con_w', 'con_b', 'uatt_w', 'uatt_b', 'sh_w', 'sh_b', 'so_w', 'so_b', 'su_w', 'su_b', 'sd_w', 'sd_b')
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def case(name):
+    """-> (task class, reference arch, score model, oracle arch, softmax family?, P, user, clicked, cands (B,C,L), y)"""
+    task_name, arch, score_model, my_arch = TABLE[name]
+    g = lambda k: GOLD[name + '/' + k]
+    n = int(g('n_inputs'))
+    x = [g('x%d' % i) for i in range(n)]
+    softmax = task_name.startswith('Seq2VecPaperSoftmax')
+    n_cand = 1 + SH.K if softmax else 1
+    has_user = n == 2 + n_cand
+    user = x[0].astype(np.int64) if has_user else np.zeros(len(x[0]), dtype=np.int64)
+    clicked = x[1 if has_user else 0].astype(np.int64)
+    cands = np.stack(x[-n_cand:], 1).astype(np.int64)
+    P = {k: GOLD[name + '/P/' + k] for k in P_KEYS if name + '/P/' + k in GOLD.files}
+    return task_name, arch, score_model, my_arch, softmax, P, user, clicked, cands, g('y'), x
+
+
+def replayed_masks(p):
+    n = SH.B * (SH.W + 1 + SH.K)
+    seed = int(GOLD['drop_seed'])
+    dx = rng.dropout_multiplier(seed * 2, n * SH.L * SH.E, p).reshape(n, SH.L, SH.E)
+    dc = rng.dropout_multiplier(seed * 2 + 1, n * SH.L * SH.F, p).reshape(n, SH.L, SH.F)
+    return dx, dc
+
+
+def oracle_loss(P, name, training_masks=None):
+    """the compiled loss of the reference model, restated with the torch oracle; -> (loss tensor, probs)"""
+    task_name, arch, score_model, my_arch, softmax, _, user, clicked, cands, y, _ = case(name)
+    u, c, d = (torch.as_tensor(a).long() for a in (user, clicked, cands))
+    B, W, L = c.shape
+    C = d.shape[1]
+    kw = {}
+    if training_masks is not None:
+        dx, dc = (torch.tensor(m) for m in training_masks)
+        nh = B * W
+        kw_h = dict(drop_x=dx[:nh], drop_c=dc[:nh])
+        kw_c = dict(drop_x=dx[nh:], drop_c=dc[nh:])
+    else:
+        kw_h = kw_c = {}
+    dh = ot.news_encoder(c.reshape(B * W, L), P, **kw_h).reshape(B, W, -1)
+    H = dh * (c != 0).any(-1).to(dh.dtype).unsqueeze(-1)
+    uv = ot.user_encoder(my_arch, u, H, P)
+    dv = ot.news_encoder(d.reshape(B * C, L), P, **kw_c).reshape(B, C, -1)
+    s = ot.score(uv, dv, P, score_model if (softmax or task_name != 'Seq2VecPaperDot') else 'dot')
+    yt = torch.tensor(y, dtype=torch.float64)
+    if softmax:
+        probs = torch.softmax(s, -1)
+        return ot.categorical_crossentropy(yt, probs), probs, uv, dv
+    probs = torch.sigmoid(s)
+    return ot.weighted_bce(yt.reshape(probs.shape), probs, gain=float(GOLD['gain']), negative_samples=SH.K), probs, uv, dv
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_numpy_oracle_forward_matches_reference_graph(name):
+    task_name, arch, score_model, my_arch, softmax, P, user, clicked, cands, y, x = case(name)
+    sm = score_model if (softmax or task_name != 'Seq2VecPaperDot') else 'dot'
+    r = on.lstur_forward(P, user, clicked, cands, arch=my_arch, score_model=sm, aux=True)
+    g = lambda k: GOLD[name + '/' + k]
+    if softmax:
+        assert rel(r['probs'], g('predict')) < F64
+        # test_model: sigmoid(score_model([user_vec, doc_encoder(candidate)])) on the LAST candidate (task/paper.py:490-495)
+        assert rel(r['sigmoid'][:, -1:], g('test_predict')) < F64
+    else:
+        assert rel(r['sigmoid'], g('predict')) < F64
+    if name + '/user_vec' in GOLD.files:
+        assert rel(r['user_vec'], g('user_vec')) < F64
+    assert rel(r['cand_vec'][:, 0], g('cand_vec0')) < F64
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_torch_oracle_loss_gradients_and_adam_match_reference_graph(name):
+    task_name, arch, score_model, my_arch, softmax, Pn, user, clicked, cands, y, x = case(name)
+    g = lambda k: GOLD[name + '/' + k]
+    trainable_table = name in EXTRA and EXTRA[name].get('textual_embedding_trainable', False)
+    p_drop = EXTRA.get(name, {}).get('dropout', 0.0)
+    masks = replayed_masks(p_drop) if p_drop > 0 else None
+    P = {k: torch.tensor(v, dtype=torch.float64, requires_grad=(k != 'word_emb' or trainable_table)) for k, v in Pn.items()}
+    trainable = [k for k in P if P[k].requires_grad]
+    loss, _, _, _ = oracle_loss(P, name, masks)
+    assert abs(float(loss) - float(g('loss'))) < F64
+    grads = dict(zip(trainable, torch.autograd.grad(loss, [P[k] for k in trainable], allow_unused=True)))
+    checked = 0
+    for k in trainable:
+        key = name + '/grad/' + k
+        assert key in GOLD.files, 'the reference model does not train %s' % k
+        got = np.zeros(P[k].shape) if grads[k] is None else grads[k].numpy()
+        ref = GOLD[key]
+        assert np.abs(got - ref).max() <= F64 * max(1.0, np.abs(ref).max()), k
+        checked += 1
+    assert checked == len([f for f in GOLD.files if f.startswith(name + '/grad/')])      # same set of trainable tensors
+    if arch == 'dgru':
+        return
+    # three steps of the reference's compiled keras.optimizers.Adam (dense on every tensor, embedding tables included)
+    opt = ot.KerasAdam({k: P[k] for k in trainable}, lr=1e-3)
+    losses = []
+    for _ in range(3):
+        loss, _, _, _ = oracle_loss(P, name, masks)
+        gs = dict(zip(trainable, torch.autograd.grad(loss, [P[k] for k in trainable], allow_unused=True)))
+        opt.step(gs)
+        losses.append(float(loss))
+    assert np.abs(np.array(losses) - g('adam_losses')).max() < F64
+    for k in P:
+        assert np.abs(P[k].detach().numpy() - g('adam/' + k)).max() < 1e-10, k
+
+
+# ---------------------------------------------------------------------------------------------- host data path
+def _mirror(name, precision='fp32', data_dir=None):
+    task_name, arch, score_model, my_arch = TABLE[name]
+    d = data_dir or tempfile.mkdtemp()
+    synth.write_dataset(d, SH)
+    extra = dict(EXTRA.get(name, {}))
+    if not task_name.startswith('Seq2VecPaperSoftmax'):
+        extra['gain'] = float(GOLD['gain'])
+    cfg = settings.Config(dict(task=task_name, arch=arch, score_model=score_model, input_training_data_path=d,
+                               title_shape=SH.L, window_size=SH.W, negative_samples=SH.K, batch_size=SH.B,
+                               textual_embedding_dim=SH.E, title_filter_shape=(SH.F, SH.k), user_embedding_dim=SH.U, debug=True,
+                               dropout=extra.pop('dropout', 0.0), precision=precision, validation_impression=5,
+                               testing_impression=5, epochs=2, learning_rate=0.001, **extra))
+    return task.get(cfg)
+
+
+@pytest.mark.parametrize('name', ['sid-igru-dot', 's-gru-dot', 'pid-igru', 'p-gru'])
+def test_host_batchers_reproduce_the_reference_batches(name):
+    """document.py parsers + Window + Impression.negative_samples + the pool-shuffle batcher (`train`) and `valid`: the
+    mirror fed the same files and the same numpy seed yields the reference's batches bit for bit."""
+    h = _mirror(name)
+    g = lambda k: GOLD[name + '/' + k]
+    n = int(g('n_inputs'))
+    np.random.seed(20190131)
+    gen = h.train
+    for prefix in ('', 'next_'):
+        x, y = next(gen)
+        assert len(x) == n
+        for i, a in enumerate(x):
+            ref = g('%sx%d' % (prefix, i))
+            assert np.asarray(a).shape == ref.shape and np.array_equal(np.asarray(a), ref), (prefix, i)
+        assert np.array_equal(np.asarray(y), g(prefix + 'y'))
+    np.random.seed(7)
+    xv, yv = next(h.valid)
+    for i, a in enumerate(xv):
+        assert np.array_equal(np.asarray(a), g('valid_x%d' % i)), i
+    assert np.array_equal(np.asarray(yv), g('valid_y'))
+
+
+def test_committed_vectors_reproduce_from_the_reference():
+    """re-run the reference under the shim (subprocess: it shadows `keras` / `tensorflow` / `utils` / `task`)"""
+    sys.path.insert(0, os.path.join(HERE, 'golden'))
+    import make_ref_golden as mk
+    if not mk.reference_available():
+        pytest.skip('the reference tree is not present on this machine')
+    out = os.path.join(tempfile.mkdtemp(), 'ref.npz')
+    r = subprocess.run([sys.executable, os.path.join(HERE, 'golden', 'make_ref_golden.py'), '--out', out], capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    new = np.load(out)
+    assert sorted(new.files) == sorted(GOLD.files)
+    for k in GOLD.files:
+        a, b = GOLD[k], new[k]
+        if a.dtype.kind in 'fc':
+            assert np.allclose(a, b, rtol=0, atol=1e-12), k
+        else:
+            assert np.array_equal(a, b), k
+
+
+# ---------------------------------------------------------------------------------------------- CUDA path
+def _names(model):
+    return [k for k in model.WEIGHT_ORDER if k in model._current()]
+
+
+def _set_weights(model, Pn):
+    """the reference model's weights into the mirror's model, by this repo's parameter names"""
+    names = _names(model)
+    assert sorted(names) == sorted(Pn), (names, sorted(Pn))
+    model.set_weights([np.asarray(Pn[k], dtype=np.float32) for k in names])
+
+
+def _get_weights(model):
+    return dict(zip(_names(model), model.get_weights()))
+
+
+GPU_CASES = [c for c in CASES]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('precision', ['fp32', 'fp16_tc'])
+@pytest.mark.parametrize('name', GPU_CASES)
+def test_cuda_path_matches_reference_graph(lib, name, precision):
+    """predict / test_model.predict / three train_on_batch steps through the drop-in surface against the vectors of the
+    reference's own graph.  fp32 verification mode: 2e-5; tensor-core mode: the 1e-3 of north_star."""
+    task_name, arch, score_model, my_arch, softmax, Pn, user, clicked, cands, y, x = case(name)
+    if name in EXTRA and 'dropout' in EXTRA[name]:
+        pytest.skip('dropout case: test_cuda_dropout_step_matches_reference_graph')
+    tol = 2e-5 if precision == 'fp32' else 1e-3
+    h = _mirror(name, precision)
+    h.config.sparse_user_adam = False                      # the reference's dense Keras-Adam
+    model = h.build_model(0)
+    _set_weights(model, Pn)
+    g = lambda k: GOLD[name + '/' + k]
+    same = lambda a, ref: rel(np.asarray(a).reshape(ref.shape), ref)
+    assert same(model.predict(x), g('predict')) < tol
+    if softmax:
+        one = list(x[:len(x) - (1 + SH.K)]) + [x[-1]]
+        assert same(h.test_model.predict(one), g('test_predict')) < tol
+    if arch == 'dgru':
+        return
+    losses = []
+    for _ in range(3):
+        r = model.train_on_batch(x, y)
+        losses.append(float(r[0] if isinstance(r, (list, tuple)) else r))
+    assert np.abs(np.array(losses) - g('adam_losses')).max() < (1e-4 if precision == 'fp32' else 2e-3)
+    if precision == 'fp32':
+        # three dense Keras-Adam steps of lr 1e-3 (|delta| <= 3e-3 per element).  fp32 gradients that agree to 5e-5 keep an
+        # element within a small fraction of one step unless its gradient is at rounding level, where Adam's normalisation
+        # lets the noise pick the sign (tolerances.assert_adam_weights_close): pooled over the model's elements
+        w = _get_weights(model)
+        d = np.concatenate([np.abs(np.asarray(w[k], dtype=np.float64).reshape(-1) - g('adam/' + k).reshape(-1)) for k in Pn])
+        moved = np.concatenate([np.abs(g('adam/' + k).reshape(-1) - np.asarray(Pn[k], dtype=np.float64).reshape(-1)) for k in Pn])
+        assert moved.max() > 1e-3                                  # the reference run did train
+        assert np.mean(d > 2e-5) <= 2e-3 and d.max() <= 6.1e-3, (float(d.max()), float(np.mean(d > 2e-5)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('precision', ['fp32'])
+def test_cuda_dropout_step_matches_reference_graph(lib, precision):
+    """training-mode forward + backward at dropout 0.2 (task/paper.py:147,158): the reference graph was evaluated with the
+    keep masks of the device's own counter-based stream (make_ref_golden.MaskReplay), so loss and gradients must agree."""
+    from mnexp_b200.engine import LsturEngine
+    name = 'sid-igru-dot-dropout'
+    task_name, arch, score_model, my_arch, softmax, Pn, user, clicked, cands, y, x = case(name)
+    P = {k: np.asarray(v, dtype=np.float32) for k, v in Pn.items()}
+    eng = LsturEngine(P, SH.B, SH.W, 1 + SH.K, SH.L, arch=my_arch, dropout=0.2, lr=1e-3, precision=precision,
+                      sparse_user_adam=False, score_model=score_model)
+    db = eng.to_device_batch(dict(user=user.astype(np.int32), hist_tok=clicked.astype(np.int32), cand_tok=cands.astype(np.int32),
+                                  label=np.asarray(y, dtype=np.float32)))
+    eng.forward(db, training=True, seed=int(GOLD['drop_seed']))
+    eng.backward(db)
+    g = lambda k: GOLD[name + '/' + k]
+    assert abs(eng.loss() - float(g('loss'))) < 2e-5
+    grads = eng.get_grads_dict()
+    n = 0
+    for k, got in grads.items():
+        key = name + '/grad/' + k
+        if key in GOLD.files:
+            assert rel(got, GOLD[key].reshape(np.asarray(got).shape)) < 5e-5, k
+            n += 1
+    assert n >= 9
