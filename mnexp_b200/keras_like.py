@@ -292,7 +292,7 @@ class Model:
     WEIGHT_ORDER = ('word_emb', 'conv_w', 'conv_b', 'att_w', 'att_b', 'dense_w', 'dense_b', 'vert_emb', 'subvert_emb', 'user_emb',
                     'user_emb2',
                     'gru_wx', 'gru_wh', 'gru_b', 'lstm_wx', 'lstm_wh', 'lstm_b', 'uatt_w', 'uatt_b', 'alpha', 'con_w', 'con_b', 'sh_w', 'sh_b', 'so_w', 'so_b', 'su_w', 'su_b', 'sd_w',
-                    'sd_b')
+                    'sd_b', 'vs_w1', 'vs_b1', 'vs_w2', 'vs_b2', 'vcls_w', 'vcls_b')
 
     def _current(self):
         e = self.core.train_engine

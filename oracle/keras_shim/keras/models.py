@@ -5,9 +5,43 @@ from . import layers as _layers
 from ._engine import Input, InputLayer, Model, Network          # noqa: F401
 
 
-class Sequential(Model):
+class Sequential(_layers.Layer):
+    """engine/sequential.py, as far as the reference uses it: a stack of layers applied in order, itself usable as a layer
+    (task/paper.py:1214-1216 wraps Sequential([Embedding, Reshape]) in TimeDistributed)."""
+
     def __init__(self, layers=None, name=None):
-        raise NotImplementedError('keras.Sequential is not on the LSTUR path')
+        super().__init__(name=name)
+        self.layers = []
+        for l in layers or []:
+            self.add(l)
+
+    def add(self, layer):
+        self.layers.append(layer)
+
+    def build(self, input_shape=None):
+        self.built = True
+
+    def call(self, inputs, mask=None, training=None):
+        x = inputs
+        for l in self.layers:
+            x = l(x)                        # applied to values: builds on first use
+        return x
+
+    def compute_mask(self, inputs, mask=None):
+        return None
+
+    @property
+    def trainable_weights(self):
+        if not self.trainable:
+            return []
+        return [w for l in self.layers for w in l.trainable_weights]
+
+    @property
+    def non_trainable_weights(self):
+        out = [w for l in self.layers for w in l.non_trainable_weights]
+        if not self.trainable:
+            return [w for l in self.layers for w in l.trainable_weights] + out
+        return out
 
 
 def _from_config(config, custom_objects):

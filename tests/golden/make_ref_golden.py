@@ -36,6 +36,8 @@ REF = os.environ.get('MNEXP_REFERENCE', '/root/reference')
 OUT = os.path.join(HERE, 'ref_golden.npz')
 GAIN = 1.5
 DROP_SEED = 11
+VERT_DIM = 3
+VSUP_HIDDEN = 10
 
 # (case name, reference task class, reference arch, score model, this repo's oracle arch, extra config)
 CASES = [
@@ -59,6 +61,12 @@ CASES = [
     ('pid-iigru', 'Seq2VecPaperId', 'iigru', 'dnn', 'iicat', {'gain': GAIN}),
     ('p-gru', 'Seq2VecPaper', 'gru', 'dnn', 'nigru', {'gain': GAIN}),
     ('pdot-gru', 'Seq2VecPaperDot', 'gru', 'dot', 'nigru', {'gain': GAIN}),
+    # time-window batchers (task/paper.py:667-790) and the vertical variants (:793-1001, :1136-1255)
+    ('sdays-gru-dot', 'Seq2VecPaperSoftmaxDays', 'gru', 'dot', 'nigru', {'days': 3}),
+    ('sdid-igru-dot', 'Seq2VecPaperSoftmaxDaysId', 'igru', 'dot', 'igru', {'days': 3}),
+    ('vert-igru-dot', 'Seq2VecPaperSoftmaxDaysIdVert', 'igru', 'dot', 'igru', {'days': 3, 'vertical_embedding_dim': VERT_DIM}),
+    ('vert-gru-dnn', 'Seq2VecPaperSoftmaxDaysIdVert', 'gru', 'dnn', 'gru', {'days': 3, 'vertical_embedding_dim': VERT_DIM}),
+    ('vsup-igru-dot', 'Seq2VecPaperSoftmaxDaysIdVertSup', 'igru', 'dot', 'igru', {'days': 3, 'hidden_dim': VSUP_HIDDEN, 'gain': 0.5}),
 ]
 
 
@@ -131,6 +139,13 @@ def named_variables(h):
                 out['con_w'], out['con_b'] = l.kernel, l.bias
             elif c == 'SimpleAttentionMaskSupport':
                 out['uatt_w'], out['uatt_b'] = l.kernel, l.bias
+    for l in model.layers:              # the vertical variants: Sequential([Embedding, Reshape]) / the 'vert' classifier
+        inner = getattr(l, 'layer', None)
+        if inner is not None and inner.__class__.__name__ == 'Sequential':
+            out['vert_emb'] = inner.layers[0].embeddings
+        if l.name == 'vert':
+            dense = sorted([d for d in inner.layers if d.__class__.__name__ == 'Dense'], key=_uid)
+            out['vs_w1'], out['vs_b1'], out['vs_w2'], out['vs_b2'] = dense[0].kernel, dense[0].bias, dense[1].kernel, dense[1].bias
     score_model = getattr(h, 'score_model', None)
     if score_model is not None and not isinstance(score_model, str):          # softmax family: task/paper.py:441-458
         dense = sorted([l for l in score_model.layers if l.__class__.__name__ == 'Dense'], key=_uid)
@@ -199,31 +214,51 @@ def run_case(mods, sh, data_dir, name, task_name, arch, score_model, my_arch, ex
     model = h.build_model(0)
     variables = named_variables(h)
     softmax = task_name.startswith('Seq2VecPaperSoftmax')
-    P = synth.make_weights(sh, arch=my_arch, bias_noise=0.05, seed=4242, score_model=score_model if (softmax or task_name != 'Seq2VecPaperDot') else 'dot',
-                           word_emb=np.load(os.path.join(data_dir, 'Vocab.tsv.npy')))
-    if not softmax and task_name == 'Seq2VecPaperDot':
-        P = {k: v for k, v in P.items() if not k.startswith(('sh_', 'so_'))}
+    vert = task_name == 'Seq2VecPaperSoftmaxDaysIdVert'
+    vsup = task_name == 'Seq2VecPaperSoftmaxDaysIdVertSup'
+    import utils as ref_utils
+    kw = {}
+    if vert:
+        kw['paper_vert'] = cfg.vertical_embedding_dim
+    if vsup:
+        kw['vertsup'] = (len(ref_utils.verticals), cfg.hidden_dim)
+    sm = 'dot' if task_name == 'Seq2VecPaperDot' else score_model
+    P = synth.make_weights(sh, arch=my_arch, bias_noise=0.05, seed=4242, score_model=sm,
+                           word_emb=np.load(os.path.join(data_dir, 'Vocab.tsv.npy')), **kw)
+    if 'vert_emb' in P:             # the reference's table has len(utils.verticals) rows
+        P['vert_emb'] = P['vert_emb'][:len(ref_utils.verticals)]
     assign(variables, P)
     np.random.seed(20190131)
     gen = h.train
     x, y = next(gen)
+    n_cand = 1 + sh.K if softmax else 1
+    has_user = any(l.name == 'user_encoder' and len(l.inputs) == 2 for l in model.layers)
+    layout = (['user'] if has_user else []) + ['clicked'] + (['clicked_vert'] if vert else []) + ['cand'] * n_cand + \
+        (['cand_vert'] * n_cand if vert else [])
+    assert len(layout) == len(x), (layout, len(x))
     out = {'x%d' % i: np.asarray(a) for i, a in enumerate(x)}
-    out['y'] = np.asarray(y)
-    out['n_inputs'] = np.int64(len(x))
+    out['layout'] = np.array(layout)
+    ys = list(y) if isinstance(y, (list, tuple)) else [y]
+    for i, a in enumerate(ys):
+        out['y' if i == 0 else 'y%d' % i] = np.asarray(a)
+    out['n_inputs'], out['n_targets'] = np.int64(len(x)), np.int64(len(ys))
     for k, v in snapshot(variables).items():
         out['P/' + k] = v
-    out['predict'] = model.predict(x)
-    if hasattr(h, 'test_model'):
-        one = list(x[:2 if len(x) == 3 + sh.K else 1]) + [x[-1]]              # [user,] clicked, ONE candidate (the last)
+    pred = model.predict(x)
+    preds = pred if isinstance(pred, list) else [pred]
+    for i, a in enumerate(preds):
+        out['predict' if i == 0 else 'predict%d' % i] = a
+    n_head = layout.index('cand')
+    if hasattr(h, 'test_model'):        # [user,] clicked, [clicked_vert,] ONE candidate (the last) [, its vertical]
+        one = list(x[:n_head]) + [x[n_head + n_cand - 1]] + ([x[-1]] if vert else [])
         out['test_predict'] = h.test_model.predict(one)
     # intermediate vectors of the outer graph
     doc, has_ue = model.get_layer('doc_encoder'), any(l.name == 'user_encoder' for l in model.layers)
     if has_ue:
         ue = model.get_layer('user_encoder')
-        n_head = len(ue.inputs)                                               # [user_idx, clicked_vec] or [clicked_vec]
         uv = keras.Model(model.inputs[:n_head], ue._inbound_nodes[0].outputs[0])
         out['user_vec'] = uv.predict(list(x[:n_head]))
-    out['cand_vec0'] = doc.predict(x[len(x) - (1 + sh.K) if softmax else len(x) - 1])
+    out['cand_vec0'] = doc.predict(x[n_head])
     p = float(extra.get('dropout', 0.0))
     replay = MaskReplay(sh, p, DROP_SEED) if p > 0 else None
     _engine._STATE['dropout_hook'] = replay
@@ -238,13 +273,15 @@ def run_case(mods, sh, data_dir, name, task_name, arch, score_model, my_arch, ex
             k = by_var[vname]
             out['grad/' + k] = g.reshape(-1) if k in ('att_w', 'uatt_w') else g
         if arch != 'dgru':
-            losses = []
+            results = []
             for _ in range(3):
                 if replay:
                     replay.reset()
                 r = model.train_on_batch(x, y)
-                losses.append(r[0] if isinstance(r, list) else r)
-            out['adam_losses'] = np.asarray(losses, dtype=np.float64)
+                results.append(r if isinstance(r, list) else [r])
+            out['adam_losses'] = np.asarray([r[0] for r in results], dtype=np.float64)
+            out['adam_results'] = np.asarray(results, dtype=np.float64)           # every entry of metrics_names per step
+            out['metrics_names'] = np.array(model.metrics_names)
             for k, v in snapshot(variables).items():
                 out['adam/' + k] = v
     finally:
@@ -253,12 +290,20 @@ def run_case(mods, sh, data_dir, name, task_name, arch, score_model, my_arch, ex
     x2, y2 = next(gen)
     for i, a in enumerate(x2):
         out['next_x%d' % i] = np.asarray(a)
-    out['next_y'] = np.asarray(y2)
+    for i, a in enumerate(list(y2) if isinstance(y2, (list, tuple)) else [y2]):
+        out['next_y' if i == 0 else 'next_y%d' % i] = np.asarray(a)
     np.random.seed(7)
     xv, yv = next(h.valid)
     for i, a in enumerate(xv):
         out['valid_x%d' % i] = np.asarray(a)
-    out['valid_y'] = np.asarray(yv)
+    for i, a in enumerate(list(yv) if isinstance(yv, (list, tuple)) else [yv]):
+        out['valid_y' if i == 0 else 'valid_y%d' % i] = np.asarray(a)
+    # one impression of the reference's own test generator (task/paper.py:415-436 and overrides)
+    np.random.seed(9)
+    imp = next(iter(h.test_gen()))
+    cols = [np.stack(c) for c in zip(*imp)]
+    for i, a in enumerate(cols):
+        out['test_imp%d' % i] = np.asarray(a)
     out['layers'] = np.array([l.name for l in model.layers])
     out['weight_names'] = np.array([w.vname for w in model.weights])
     return out

@@ -24,10 +24,12 @@ GOLD = np.load(os.path.join(HERE, 'golden', 'ref_golden.npz'))
 TABLE = {row[0]: tuple(row[1:]) for row in GOLD['case_table']}
 CASES = [str(c) for c in GOLD['cases']]
 SH = synth.SHAPES['tiny']
-EXTRA = {'sid-igru-dot-trainable': dict(textual_embedding_trainable=True), 'sid-igru-dot-dropout': dict(dropout=0.2)}
+sys.path.insert(0, os.path.join(HERE, 'golden'))
+import make_ref_golden as mk          # noqa: E402  (numpy-only at import time; the reference is loaded by its functions)
+EXTRA = {c[0]: dict(c[5]) for c in mk.CASES}          # the non-default config options of every case
 F64 = 1e-9            # float64 restatement against the float64 run of the reference graph
 P_KEYS = ('word_emb', 'conv_w', 'conv_b', 'att_w', 'att_b', 'dense_w', 'dense_b', 'user_emb', 'user_emb2', 'gru_wx', 'gru_wh',
-          'gru_b', 'con_w', 'con_b', 'uatt_w', 'uatt_b', 'sh_w', 'sh_b', 'so_w', 'so_b', 'su_w', 'su_b', 'sd_w', 'sd_b')
+          'gru_b', 'con_w', 'con_b', 'uatt_w', 'uatt_b', 'sh_w', 'sh_b', 'so_w', 'so_b', 'su_w', 'su_b', 'sd_w', 'sd_b', 'vert_emb', 'vs_w1', 'vs_b1', 'vs_w2', 'vs_b2')
 
 
 def rel(a, b):
@@ -36,19 +38,39 @@ def rel(a, b):
 
 
 def case(name):
-    """-> (task class, reference arch, score model, oracle arch, softmax family?, P, user, clicked, cands (B,C,L), y)"""
+    """-> (task class, reference arch, score model, oracle arch, softmax family?, P, user, clicked, cands (B,C,L), y, x)"""
     task_name, arch, score_model, my_arch = TABLE[name]
     g = lambda k: GOLD[name + '/' + k]
     n = int(g('n_inputs'))
     x = [g('x%d' % i) for i in range(n)]
+    layout = [str(v) for v in g('layout')]
     softmax = task_name.startswith('Seq2VecPaperSoftmax')
-    n_cand = 1 + SH.K if softmax else 1
-    has_user = n == 2 + n_cand
-    user = x[0].astype(np.int64) if has_user else np.zeros(len(x[0]), dtype=np.int64)
-    clicked = x[1 if has_user else 0].astype(np.int64)
-    cands = np.stack(x[-n_cand:], 1).astype(np.int64)
+    pick = lambda what: [a for a, l in zip(x, layout) if l == what]
+    user = pick('user')[0].astype(np.int64) if 'user' in layout else np.zeros(len(x[0]), dtype=np.int64)
+    clicked = pick('clicked')[0].astype(np.int64)
+    cands = np.stack(pick('cand'), 1).astype(np.int64)
     P = {k: GOLD[name + '/P/' + k] for k in P_KEYS if name + '/P/' + k in GOLD.files}
     return task_name, arch, score_model, my_arch, softmax, P, user, clicked, cands, g('y'), x
+
+
+def verticals(name):
+    """(hist_vert (B,W), cand_vert (B,C)) integer ids of ...DaysIdVert's extra inputs, or None"""
+    g = lambda k: GOLD[name + '/' + k]
+    layout = [str(v) for v in g('layout')]
+    if 'clicked_vert' not in layout:
+        return None, None
+    x = [g('x%d' % i) for i in range(len(layout))]
+    hv = x[layout.index('clicked_vert')].astype(np.int64)
+    cv = np.stack([a.reshape(-1) for a, l in zip(x, layout) if l == 'cand_vert'], 1).astype(np.int64)
+    return hv, cv
+
+
+def vsup_labels(name):
+    """integer vertical labels (hist (B,W), cand (B,C)) from the one-hot second target of ...VertSup, or None"""
+    if name + '/y1' not in GOLD.files:
+        return None
+    y1 = GOLD[name + '/y1'].argmax(-1)
+    return y1[:, :SH.W], y1[:, SH.W:]
 
 
 def replayed_masks(p):
@@ -60,12 +82,11 @@ def replayed_masks(p):
 
 
 def oracle_loss(P, name, training_masks=None):
-    """the compiled loss of the reference model, restated with the torch oracle; -> (loss tensor, probs)"""
+    """the compiled loss of the reference model, restated with the torch oracle; -> (loss, probs, user_vec, cand_vec)"""
     task_name, arch, score_model, my_arch, softmax, _, user, clicked, cands, y, _ = case(name)
     u, c, d = (torch.as_tensor(a).long() for a in (user, clicked, cands))
     B, W, L = c.shape
     C = d.shape[1]
-    kw = {}
     if training_masks is not None:
         dx, dc = (torch.tensor(m) for m in training_masks)
         nh = B * W
@@ -73,15 +94,26 @@ def oracle_loss(P, name, training_masks=None):
         kw_c = dict(drop_x=dx[nh:], drop_c=dc[nh:])
     else:
         kw_h = kw_c = {}
+    hv, cv = verticals(name)
     dh = ot.news_encoder(c.reshape(B * W, L), P, **kw_h).reshape(B, W, -1)
+    dv = ot.news_encoder(d.reshape(B * C, L), P, **kw_c).reshape(B, C, -1)
+    if hv is not None:                      # [Dense(U)(title) | Vemb[vertical]], task/paper.py:1218-1232
+        dh = torch.cat([dh, P['vert_emb'][torch.as_tensor(hv).long()]], -1)
+        dv = torch.cat([dv, P['vert_emb'][torch.as_tensor(cv).long()]], -1)
     H = dh * (c != 0).any(-1).to(dh.dtype).unsqueeze(-1)
     uv = ot.user_encoder(my_arch, u, H, P)
-    dv = ot.news_encoder(d.reshape(B * C, L), P, **kw_c).reshape(B, C, -1)
     s = ot.score(uv, dv, P, score_model if (softmax or task_name != 'Seq2VecPaperDot') else 'dot')
     yt = torch.tensor(y, dtype=torch.float64)
     if softmax:
         probs = torch.softmax(s, -1)
-        return ot.categorical_crossentropy(yt, probs), probs, uv, dv
+        loss = ot.categorical_crossentropy(yt, probs)
+        labels = vsup_labels(name)
+        if labels is not None:              # loss_weights=[1, gain] over [ranking, vert], task/paper.py:984-990
+            vp = ot.vertical_classifier(P, torch.cat([H, dv], 1))
+            onehot = torch.tensor(GOLD[name + '/y1'], dtype=torch.float64)
+            loss = loss + 0.5 * ot.categorical_crossentropy(onehot, vp)
+            return loss, probs, uv, dv, vp
+        return loss, probs, uv, dv
     probs = torch.sigmoid(s)
     return ot.weighted_bce(yt.reshape(probs.shape), probs, gain=float(GOLD['gain']), negative_samples=SH.K), probs, uv, dv
 
@@ -90,8 +122,13 @@ def oracle_loss(P, name, training_masks=None):
 def test_numpy_oracle_forward_matches_reference_graph(name):
     task_name, arch, score_model, my_arch, softmax, P, user, clicked, cands, y, x = case(name)
     sm = score_model if (softmax or task_name != 'Seq2VecPaperDot') else 'dot'
-    r = on.lstur_forward(P, user, clicked, cands, arch=my_arch, score_model=sm, aux=True)
+    hv, cv = verticals(name)
+    r = on.lstur_forward(P, user, clicked, cands, arch=my_arch, score_model=sm, aux=True, hist_vert=hv, cand_vert=cv)
     g = lambda k: GOLD[name + '/' + k]
+    if name + '/predict1' in GOLD.files:         # second output of ...VertSup: the vertical classifier over [history ; candidates]
+        Pt = {k: torch.tensor(v, dtype=torch.float64) for k, v in P.items()}
+        vp = oracle_loss(Pt, name)[4]
+        assert rel(vp.numpy(), g('predict1')) < F64
     if softmax:
         assert rel(r['probs'], g('predict')) < F64
         # test_model: sigmoid(score_model([user_vec, doc_encoder(candidate)])) on the LAST candidate (task/paper.py:490-495)
@@ -100,7 +137,7 @@ def test_numpy_oracle_forward_matches_reference_graph(name):
         assert rel(r['sigmoid'], g('predict')) < F64
     if name + '/user_vec' in GOLD.files:
         assert rel(r['user_vec'], g('user_vec')) < F64
-    assert rel(r['cand_vec'][:, 0], g('cand_vec0')) < F64
+    assert rel(r['cand_vec'][:, 0, :g('cand_vec0').shape[1]], g('cand_vec0')) < F64      # doc_encoder output (before any vertical concat)
 
 
 @pytest.mark.parametrize('name', CASES)
@@ -112,7 +149,7 @@ def test_torch_oracle_loss_gradients_and_adam_match_reference_graph(name):
     masks = replayed_masks(p_drop) if p_drop > 0 else None
     P = {k: torch.tensor(v, dtype=torch.float64, requires_grad=(k != 'word_emb' or trainable_table)) for k, v in Pn.items()}
     trainable = [k for k in P if P[k].requires_grad]
-    loss, _, _, _ = oracle_loss(P, name, masks)
+    loss = oracle_loss(P, name, masks)[0]
     assert abs(float(loss) - float(g('loss'))) < F64
     grads = dict(zip(trainable, torch.autograd.grad(loss, [P[k] for k in trainable], allow_unused=True)))
     checked = 0
@@ -130,7 +167,7 @@ def test_torch_oracle_loss_gradients_and_adam_match_reference_graph(name):
     opt = ot.KerasAdam({k: P[k] for k in trainable}, lr=1e-3)
     losses = []
     for _ in range(3):
-        loss, _, _, _ = oracle_loss(P, name, masks)
+        loss = oracle_loss(P, name, masks)[0]
         gs = dict(zip(trainable, torch.autograd.grad(loss, [P[k] for k in trainable], allow_unused=True)))
         opt.step(gs)
         losses.append(float(loss))
@@ -145,8 +182,6 @@ def _mirror(name, precision='fp32', data_dir=None):
     d = data_dir or tempfile.mkdtemp()
     synth.write_dataset(d, SH)
     extra = dict(EXTRA.get(name, {}))
-    if not task_name.startswith('Seq2VecPaperSoftmax'):
-        extra['gain'] = float(GOLD['gain'])
     cfg = settings.Config(dict(task=task_name, arch=arch, score_model=score_model, input_training_data_path=d,
                                title_shape=SH.L, window_size=SH.W, negative_samples=SH.K, batch_size=SH.B,
                                textual_embedding_dim=SH.E, title_filter_shape=(SH.F, SH.k), user_embedding_dim=SH.U, debug=True,
@@ -155,33 +190,46 @@ def _mirror(name, precision='fp32', data_dir=None):
     return task.get(cfg)
 
 
-@pytest.mark.parametrize('name', ['sid-igru-dot', 's-gru-dot', 'pid-igru', 'p-gru'])
+@pytest.mark.parametrize('name', ['sid-igru-dot', 's-gru-dot', 'pid-igru', 'p-gru', 'sdays-gru-dot', 'sdid-igru-dot', 'vert-igru-dot',
+                                  'vsup-igru-dot'])
 def test_host_batchers_reproduce_the_reference_batches(name):
     """document.py parsers + Window + Impression.negative_samples + the pool-shuffle batcher (`train`) and `valid`: the
     mirror fed the same files and the same numpy seed yields the reference's batches bit for bit."""
     h = _mirror(name)
     g = lambda k: GOLD[name + '/' + k]
-    n = int(g('n_inputs'))
+    n, nt = int(g('n_inputs')), int(g('n_targets'))
+    aslist = lambda y: list(y) if isinstance(y, (list, tuple)) else [y]
+
+    def same(got, prefix, what, count):
+        assert len(got) == count, (prefix, what, len(got), count)
+        for i, a in enumerate(got):
+            ref = g(prefix + what + (str(i) if (what == 'x' or i) else ''))
+            assert np.asarray(a).shape == ref.shape and np.array_equal(np.asarray(a), ref), (prefix, what, i)
+
     np.random.seed(20190131)
     gen = h.train
     for prefix in ('', 'next_'):
         x, y = next(gen)
-        assert len(x) == n
-        for i, a in enumerate(x):
-            ref = g('%sx%d' % (prefix, i))
-            assert np.asarray(a).shape == ref.shape and np.array_equal(np.asarray(a), ref), (prefix, i)
-        assert np.array_equal(np.asarray(y), g(prefix + 'y'))
+        same(x, prefix, 'x', n)
+        same(aslist(y), prefix, 'y', nt)
     np.random.seed(7)
     xv, yv = next(h.valid)
-    for i, a in enumerate(xv):
-        assert np.array_equal(np.asarray(a), g('valid_x%d' % i)), i
-    assert np.array_equal(np.asarray(yv), g('valid_y'))
+    same(xv, 'valid_', 'x', n)
+    same(aslist(yv), 'valid_', 'y', nt)
+    # the first impression of test_gen: rows of ([user,] clicked, [clicked_vert,] title, [vertical,] label)
+    np.random.seed(9)
+    imp = next(iter(h.test_gen()))
+    cols = [np.stack(c) for c in zip(*imp)]
+    k = 0
+    while name + '/test_imp%d' % k in GOLD.files:
+        k += 1
+    assert len(cols) == k
+    for i, a in enumerate(cols):
+        assert np.array_equal(np.asarray(a), g('test_imp%d' % i)), i
 
 
 def test_committed_vectors_reproduce_from_the_reference():
     """re-run the reference under the shim (subprocess: it shadows `keras` / `tensorflow` / `utils` / `task`)"""
-    sys.path.insert(0, os.path.join(HERE, 'golden'))
-    import make_ref_golden as mk
     if not mk.reference_available():
         pytest.skip('the reference tree is not present on this machine')
     out = os.path.join(tempfile.mkdtemp(), 'ref.npz')
@@ -233,17 +281,28 @@ def test_cuda_path_matches_reference_graph(lib, name, precision):
     _set_weights(model, Pn)
     g = lambda k: GOLD[name + '/' + k]
     same = lambda a, ref: rel(np.asarray(a).reshape(ref.shape), ref)
-    assert same(model.predict(x), g('predict')) < tol
+    layout = [str(v) for v in g('layout')]
+    n_head, n_cand = layout.index('cand'), layout.count('cand')
+    pred = model.predict(x)
+    if name + '/predict1' in GOLD.files:             # [ranking, vert] of ...VertSup
+        assert same(pred[0], g('predict')) < tol and same(pred[1], g('predict1')) < tol
+        y = [y, g('y1')]
+    else:
+        assert same(pred, g('predict')) < tol
     if softmax:
-        one = list(x[:len(x) - (1 + SH.K)]) + [x[-1]]
+        one = list(x[:n_head]) + [x[n_head + n_cand - 1]] + ([x[-1]] if 'cand_vert' in layout else [])
         assert same(h.test_model.predict(one), g('test_predict')) < tol
     if arch == 'dgru':
         return
-    losses = []
+    results = []
     for _ in range(3):
         r = model.train_on_batch(x, y)
-        losses.append(float(r[0] if isinstance(r, (list, tuple)) else r))
-    assert np.abs(np.array(losses) - g('adam_losses')).max() < (1e-4 if precision == 'fp32' else 2e-3)
+        results.append([float(v) for v in (r if isinstance(r, (list, tuple)) else [r])])
+    ref = g('adam_results')
+    n_loss = sum(1 for m in g('metrics_names') if str(m).endswith('loss'))
+    assert np.abs(np.array(results)[:, :n_loss] - ref[:, :n_loss]).max() < (1e-4 if precision == 'fp32' else 2e-3)
+    if softmax and precision == 'fp32':              # categorical accuracies of the same probabilities
+        assert np.abs(np.array(results)[:, n_loss:] - ref[:, n_loss:]).max() < 1e-6
     if precision == 'fp32':
         # three dense Keras-Adam steps of lr 1e-3 (|delta| <= 3e-3 per element).  fp32 gradients that agree to 5e-5 keep an
         # element within a small fraction of one step unless its gradient is at rounding level, where Adam's normalisation
