@@ -139,7 +139,7 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
   const bool bce = c.loss_model == LSTUR_LOSS_WEIGHTED_BCE;
   LSTUR_REQUIRE(c.loss_model == LSTUR_LOSS_SOFTMAX_CE || bce, "lstur_plan_create(loss_model)");
   LSTUR_REQUIRE(!bce || (c.C == 1 && c.bce_neg >= 1 && c.gain > 0.f), "lstur_plan_create(weighted BCE: C == 1, bce_neg >= 1, gain > 0)");
-  LSTUR_REQUIRE(!has_rnn || (c.G > 0 && c.G % 4 == 0 && c.G <= 1024), "lstur_plan_create");
+  LSTUR_REQUIRE(!has_rnn || (c.G > 0 && c.G <= 1024), "lstur_plan_create");
   LSTUR_REQUIRE(!has_user || (c.Ue > 0 && c.n_users > 0), "lstur_plan_create");
   // user-vector dim implied by the architecture
   int U = c.arch == LSTUR_ARCH_INI ? c.G : (c.arch == LSTUR_ARCH_CON_DENSE || c.arch == LSTUR_ARCH_INI_CON) ? c.U

@@ -31,8 +31,11 @@ __global__ void gru_fwd_kernel(int B, int W, int G, const float* __restrict__ XW
                                float* __restrict__ hT, long long ldo, float* __restrict__ Z, float* __restrict__ R,
                                float* __restrict__ HH, float* __restrict__ HP, float* __restrict__ RH) {
   extern __shared__ float sm[];
-  float* sh = sm;             // [BT][G]
-  float* srh = sm + BT * G;   // [BT][G]
+  // rows of the mirrored state are padded to a multiple of 4 floats (zero tail) so that any G keeps the 128-bit reads
+  // aligned: G = user_embedding_dim + vertical_embedding_dim = 215 at the reference's defaults (task/paper.py:1204-1208)
+  const int Gs = (G + 3) & ~3;
+  float* sh = sm;              // [BT][Gs]
+  float* srh = sm + BT * Gs;   // [BT][Gs]
   const int j = threadIdx.x, b0 = blockIdx.x * BT;
   const bool act_j = j < G;
   const int G3 = 3 * G;
@@ -41,7 +44,8 @@ __global__ void gru_fwd_kernel(int B, int W, int G, const float* __restrict__ XW
   for (int i = 0; i < BT; ++i) {
     int b = b0 + i;
     h[i] = (act_j && b < B && h0) ? h0[(long long)b * ldh0 + j] : 0.f;
-    if (act_j) sh[i * G + j] = h[i];
+    if (act_j) sh[i * Gs + j] = h[i];
+    else if (j < Gs) { sh[i * Gs + j] = 0.f; srh[i * Gs + j] = 0.f; }
   }
   __syncthreads();
   for (int t = 0; t < W; ++t) {
@@ -77,12 +81,13 @@ __global__ void gru_fwd_kernel(int B, int W, int G, const float* __restrict__ XW
         float wz[4], wr[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          wz[q] = __ldg(Wh + (long long)(k + q) * G3 + j);
-          wr[q] = __ldg(Wh + (long long)(k + q) * G3 + G + j);
+          const bool in = k + q < G;
+          wz[q] = in ? __ldg(Wh + (long long)(k + q) * G3 + j) : 0.f;
+          wr[q] = in ? __ldg(Wh + (long long)(k + q) * G3 + G + j) : 0.f;
         }
 #pragma unroll
         for (int i = 0; i < BT; ++i) {
-          float4 hv = *(const float4*)(sh + i * G + k);
+          float4 hv = *(const float4*)(sh + i * Gs + k);
           az[i] = fmaf(hv.x, wz[0], az[i]); ar[i] = fmaf(hv.x, wr[0], ar[i]);
           az[i] = fmaf(hv.y, wz[1], az[i]); ar[i] = fmaf(hv.y, wr[1], ar[i]);
           az[i] = fmaf(hv.z, wz[2], az[i]); ar[i] = fmaf(hv.z, wr[2], ar[i]);
@@ -95,7 +100,7 @@ __global__ void gru_fwd_kernel(int B, int W, int G, const float* __restrict__ XW
     for (int i = 0; i < BT; ++i) {
       z[i] = rec_act(az[i], act);
       r[i] = rec_act(ar[i], act);
-      if (act_j) srh[i * G + j] = r[i] * h[i];
+      if (act_j) srh[i * Gs + j] = r[i] * h[i];
     }
     __syncthreads();
     float ah[BT];
@@ -108,10 +113,10 @@ __global__ void gru_fwd_kernel(int B, int W, int G, const float* __restrict__ XW
       for (int k = 0; k < G; k += 4) {
         float wh[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) wh[q] = __ldg(Wh + (long long)(k + q) * G3 + 2 * G + j);
+        for (int q = 0; q < 4; ++q) wh[q] = k + q < G ? __ldg(Wh + (long long)(k + q) * G3 + 2 * G + j) : 0.f;
 #pragma unroll
         for (int i = 0; i < BT; ++i) {
-          float4 v = *(const float4*)(srh + i * G + k);
+          float4 v = *(const float4*)(srh + i * Gs + k);
           ah[i] = fmaf(v.x, wh[0], ah[i]);
           ah[i] = fmaf(v.y, wh[1], ah[i]);
           ah[i] = fmaf(v.z, wh[2], ah[i]);
@@ -135,7 +140,7 @@ __global__ void gru_fwd_kernel(int B, int W, int G, const float* __restrict__ XW
         HP[o] = h[i];
       }
       if (on) h[i] = hn;
-      if (act_j) sh[i * G + j] = h[i];
+      if (act_j) sh[i * Gs + j] = h[i];
     }
     __syncthreads();
   }
@@ -158,9 +163,10 @@ __global__ void gru_bwd_kernel(int B, int W, int G, const float* __restrict__ gm
                                const float* __restrict__ dhT, long long lddh, float* __restrict__ dA,
                                float* __restrict__ dh0, long long lddh0) {
   extern __shared__ float sm[];
-  float* s_dah = sm;               // [BT][G]
-  float* s_daz = sm + BT * G;      // [BT][G]
-  float* s_dar = sm + 2 * BT * G;  // [BT][G]
+  const int Gs = (G + 3) & ~3;      // padded row stride, zero tail (see the forward kernel)
+  float* s_dah = sm;                // [BT][Gs]
+  float* s_daz = sm + BT * Gs;      // [BT][Gs]
+  float* s_dar = sm + 2 * BT * Gs;  // [BT][Gs]
   const int k = threadIdx.x, b0 = blockIdx.x * BT;
   const bool act_k = k < G;
   const int G3 = 3 * G;
@@ -169,6 +175,7 @@ __global__ void gru_bwd_kernel(int B, int W, int G, const float* __restrict__ gm
   for (int i = 0; i < BT; ++i) {
     int b = b0 + i;
     dh[i] = (act_k && b < B) ? dhT[(long long)b * lddh + k] : 0.f;
+    if (!act_k && k < Gs) { s_dah[i * Gs + k] = 0.f; s_daz[i * Gs + k] = 0.f; s_dar[i * Gs + k] = 0.f; }
   }
   for (int t = W - 1; t >= 0; --t) {
     unsigned mbits = 0;
@@ -206,8 +213,8 @@ __global__ void gru_bwd_kernel(int B, int W, int G, const float* __restrict__ gm
       daz[i] = on ? dz * rec_act_grad(z[i], act) : 0.f;
       dhp[i] = dh[i] * z[i];
       if (act_k) {
-        s_dah[i * G + k] = dah[i];
-        s_daz[i * G + k] = daz[i];
+        s_dah[i * Gs + k] = dah[i];
+        s_daz[i * Gs + k] = daz[i];
       }
     }
     __syncthreads();
@@ -218,10 +225,10 @@ __global__ void gru_bwd_kernel(int B, int W, int G, const float* __restrict__ gm
       for (int j = 0; j < G; j += 4) {
         float w[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) w[q] = __ldg(WhT + (long long)(2 * G + j + q) * G + k);
+        for (int q = 0; q < 4; ++q) w[q] = j + q < G ? __ldg(WhT + (long long)(2 * G + j + q) * G + k) : 0.f;
 #pragma unroll
         for (int i = 0; i < BT; ++i) {
-          float4 v = *(const float4*)(s_dah + i * G + j);
+          float4 v = *(const float4*)(s_dah + i * Gs + j);
           drh[i] = fmaf(v.x, w[0], drh[i]);
           drh[i] = fmaf(v.y, w[1], drh[i]);
           drh[i] = fmaf(v.z, w[2], drh[i]);
@@ -235,7 +242,7 @@ __global__ void gru_bwd_kernel(int B, int W, int G, const float* __restrict__ gm
       float dr = drh[i] * hp[i];
       dhp[i] = fmaf(drh[i], r[i], dhp[i]);
       dar[i] = dr * rec_act_grad(r[i], act);
-      if (act_k) s_dar[i * G + k] = dar[i];
+      if (act_k) s_dar[i * Gs + k] = dar[i];
     }
     __syncthreads();
     if (act_k) {
@@ -243,13 +250,14 @@ __global__ void gru_bwd_kernel(int B, int W, int G, const float* __restrict__ gm
         float wz[4], wr[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          wz[q] = __ldg(WhT + (long long)(j + q) * G + k);
-          wr[q] = __ldg(WhT + (long long)(G + j + q) * G + k);
+          const bool in = j + q < G;
+          wz[q] = in ? __ldg(WhT + (long long)(j + q) * G + k) : 0.f;
+          wr[q] = in ? __ldg(WhT + (long long)(G + j + q) * G + k) : 0.f;
         }
 #pragma unroll
         for (int i = 0; i < BT; ++i) {
-          float4 vz = *(const float4*)(s_daz + i * G + j);
-          float4 vr = *(const float4*)(s_dar + i * G + j);
+          float4 vz = *(const float4*)(s_daz + i * Gs + j);
+          float4 vr = *(const float4*)(s_dar + i * Gs + j);
           dhp[i] = fmaf(vz.x, wz[0], dhp[i]); dhp[i] = fmaf(vr.x, wr[0], dhp[i]);
           dhp[i] = fmaf(vz.y, wz[1], dhp[i]); dhp[i] = fmaf(vr.y, wr[1], dhp[i]);
           dhp[i] = fmaf(vz.z, wz[2], dhp[i]); dhp[i] = fmaf(vr.z, wr[2], dhp[i]);
@@ -307,11 +315,11 @@ extern "C" int lstur_transpose(int rows, int cols, const float* in, float* out, 
 extern "C" int lstur_gru_fwd_streaming(int B, int W, int G, const float* XW, const float* gm, const float* h0, long long ldh0,
                              const float* Wh, int rec_act, float* hT, long long ldo, float* Z, float* R, float* HH,
                              float* HP, float* RH, cudaStream_t stream) {
-  LSTUR_REQUIRE(B >= 0 && W > 0 && G > 0 && G % 4 == 0 && G <= 1024, "lstur_gru_fwd_streaming");
+  LSTUR_REQUIRE(B >= 0 && W > 0 && G > 0 && G <= 1024, "lstur_gru_fwd_streaming");
   LSTUR_REQUIRE((Z && R && HH && HP && RH) || (!Z && !R && !HH && !HP && !RH), "lstur_gru_fwd_streaming");
   if (B == 0) return LSTUR_OK;
   int threads = cdiv(G, 32) * 32;
-  size_t smem = (size_t)2 * GRU_BT * G * sizeof(float);
+  size_t smem = (size_t)2 * GRU_BT * ((G + 3) & ~3) * sizeof(float);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(gru_fwd_kernel<GRU_BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   gru_fwd_kernel<GRU_BT><<<cdiv(B, GRU_BT), threads, smem, stream>>>(B, W, G, XW, gm, h0, ldh0, Wh, rec_act, hT, ldo, Z,
@@ -323,10 +331,10 @@ extern "C" int lstur_gru_fwd_streaming(int B, int W, int G, const float* XW, con
 extern "C" int lstur_gru_bwd_streaming(int B, int W, int G, const float* gm, const float* Z, const float* R, const float* HH,
                              const float* HP, const float* WhT, int rec_act, const float* dhT, long long lddh,
                              float* dA, float* dh0, long long lddh0, cudaStream_t stream) {
-  LSTUR_REQUIRE(B >= 0 && W > 0 && G > 0 && G % 4 == 0 && G <= 1024, "lstur_gru_bwd_streaming");
+  LSTUR_REQUIRE(B >= 0 && W > 0 && G > 0 && G <= 1024, "lstur_gru_bwd_streaming");
   if (B == 0) return LSTUR_OK;
   int threads = cdiv(G, 32) * 32;
-  size_t smem = (size_t)3 * GRU_BT * G * sizeof(float);
+  size_t smem = (size_t)3 * GRU_BT * ((G + 3) & ~3) * sizeof(float);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(gru_bwd_kernel<GRU_BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   gru_bwd_kernel<GRU_BT><<<cdiv(B, GRU_BT), threads, smem, stream>>>(B, W, G, gm, Z, R, HH, HP, WhT, rec_act, dhT, lddh,

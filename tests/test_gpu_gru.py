@@ -125,6 +125,23 @@ def test_gru_recurrence_vs_oracle(lib, impl, B, W, G, ini, act, pad):
     assert np.all(dA[gm == 0] == 0)
 
 
+@pytest.mark.parametrize('B,W,G,ini,act,pad', [
+    (9, 5, 11, True, 'hard_sigmoid', 'left'),          # U + vertical_embedding_dim of the tiny reference-run case
+    (40, 12, 215, True, 'hard_sigmoid', 'holes'),      # ...DaysIdVert at the reference's defaults: 200 + 15 (task/paper.py:1204-1208)
+    (17, 7, 33, False, 'sigmoid', 'left'),
+])
+def test_gru_streaming_any_width(lib, B, W, G, ini, act, pad):
+    """widths that are no multiple of 4 run on the streaming kernels (padded shared-memory rows)"""
+    assert lib.lstur_gru_cluster_supported(B, W, G) == 0 and lib.lstur_gru_tc_supported(B, W, G) == 0
+    XW, gm, Wh, h0, dhT = make(B, W, G, seed=B + W + G, ini=ini, pad=pad)
+    hT_ref, dA_ref, dh0_ref = oracle(XW, Wh, h0, dhT, act)
+    hT, dA, dh0, sv = run(lib, 'streaming', XW, gm, Wh, h0, dhT, act)
+    assert rel(hT, hT_ref) < TOL and rel(dA, dA_ref) < 5 * TOL
+    if ini:
+        assert rel(dh0, dh0_ref) < 5 * TOL
+    assert all(np.isfinite(s).all() for s in sv) and np.all(dA[gm == 0] == 0)
+
+
 def test_gru_row_order_is_a_pure_permutation(lib):
     """Length-sorted tiles (row_order) must give bit-identical results to the natural order."""
     B, W, G = 200, 30, 200
