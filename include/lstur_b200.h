@@ -55,8 +55,9 @@ typedef struct CUstream_st* cudaStream_t;
 #define LSTUR_ARCH_ATT 10      /* Seq2VecPaper 'att': SimpleAttentionMaskSupport(Masking(history)), task/paper.py:206-208 */
 #define LSTUR_ARCH_ATT_CAT 11  /* cook 'iatt': [SimpleAttentionMaskSupport(history) ‖ user_emb], task/cook.py:158-160 */
 #define LSTUR_ARCH_INI_ADD 12  /* cook 'inagru': GRU(initial_state=user_emb) + user_emb2, task/cook.py:177-183 (Ue = 2G) */
-#define LSTUR_ARCH_ATT_PAIR 13 /* cook 'atgru': SimpleAttentionMaskSupport over the two-step sequence [GRU ; user_emb],
-                                  task/cook.py:184-190 */
+#define LSTUR_ARCH_ATT_PAIR 13 /* cook 'atgru', task/cook.py:184-190 as written: the 2G entries of [GRU ; user_emb] are 2G
+                                  one-feature steps (expand_dims(x, -1), concatenate(axis=-2)); Masking() +
+                                  SimpleAttentionMaskSupport (kernel (1,1)) pool them into ONE scalar per user (U = 1) */
 #define LSTUR_ARCH_ALPHA 14    /* cook 'algru': models.AlphaAdd([GRU, user_emb]) = alpha h + (1 - alpha) u, task/cook.py:191-193,
                                   models.py:540-554 (alpha constrained to [0, 1] after every update) */
 #define LSTUR_ARCH_LSTM_CAT 15 /* cook 'ilstm': [keras.layers.LSTM(history) ‖ user_emb], task/cook.py:161-163 */

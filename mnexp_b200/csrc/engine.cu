@@ -146,7 +146,8 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
           : c.arch == LSTUR_ARCH_CON_CAT ? c.G + c.Ue : c.arch == LSTUR_ARCH_INI_CAT ? c.Ue
           : c.arch == LSTUR_ARCH_NOID ? c.G : c.arch == LSTUR_ARCH_ADD ? c.G : c.arch == LSTUR_ARCH_AVG ? D
           : c.arch == LSTUR_ARCH_AVG_CAT ? D + c.Ue : c.arch == LSTUR_ARCH_ATT ? D : c.arch == LSTUR_ARCH_ATT_CAT ? D + c.Ue
-          : (c.arch == LSTUR_ARCH_INI_ADD || c.arch == LSTUR_ARCH_ATT_PAIR || c.arch == LSTUR_ARCH_ALPHA) ? c.G
+          : c.arch == LSTUR_ARCH_ATT_PAIR ? 1     // 'atgru' pools 2G one-feature steps into one scalar (task/cook.py:184-190)
+          : (c.arch == LSTUR_ARCH_INI_ADD || c.arch == LSTUR_ARCH_ALPHA) ? c.G
           : c.arch == LSTUR_ARCH_LSTM_CAT ? c.G + c.Ue : c.Ue;
   LSTUR_REQUIRE(U == c.U, "lstur_plan_create(U inconsistent with arch)");
   LSTUR_REQUIRE(c.arch != LSTUR_ARCH_INI || c.Ue == c.G, "lstur_plan_create(ini needs Ue == G)");
@@ -196,9 +197,10 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
     add_dense(p, "lstm_wh", (long long)G * 4 * G);
     add_dense(p, "lstm_b", 4 * G);
   }
-  // SimpleAttentionMaskSupport over the history (width D) or over [GRU ; id vector] (width G)
-  const int Da = arch_hist_att(c.arch) ? D : c.arch == LSTUR_ARCH_ATT_PAIR ? G : 0;
-  const int Wa = arch_hist_att(c.arch) ? c.W : 2;
+  // SimpleAttentionMaskSupport over the history (W steps of width D) or, 'atgru', over the 2G entries of [GRU ; id vector]
+  // taken as 2G steps of width 1: keras.backend.expand_dims(x, -1) + concatenate(axis=-2) in task/cook.py:186-188
+  const int Da = arch_hist_att(c.arch) ? D : c.arch == LSTUR_ARCH_ATT_PAIR ? 1 : 0;
+  const int Wa = arch_hist_att(c.arch) ? c.W : 2 * G;
   if (Da) {
     add_dense(p, "uatt_w", Da);
     add_dense(p, "uatt_b", 1);
@@ -299,7 +301,7 @@ extern "C" int lstur_plan_create(const lstur_config* cfg, lstur_plan** out) {
   }
   if (c.arch == LSTUR_ARCH_ATT_PAIR) {
     add_ws(p, "seq2", B * 2 * G);
-    add_ws(p, "mask2", B * 2);
+    add_ws(p, "mask2", B * 2 * G);
     if (bw) add_ws(p, "d_seq2", B * 2 * G);
   }
   if (c.arch == LSTUR_ARCH_ALPHA && bw) {
@@ -616,12 +618,12 @@ int user_and_score(const lstur_plan* p, const lstur_weights* w, const lstur_batc
       RC(lstur_axpby((long long)B * G, 1.f, u0, 1.f, uvec, st));
     } else if (c.arch == LSTUR_ARCH_INI_ADD) {     // 'inagru': GRU(initial_state = table 1) + table 2 (task/cook.py:177-183)
       RC(lstur_add_rows(B, G, 1.f, u0 + G, c.Ue, 1.f, uvec, c.U, st));
-    } else if (c.arch == LSTUR_ARCH_ATT_PAIR) {    // 'atgru': attention over the two "steps" [GRU output ; id vector]
+    } else if (c.arch == LSTUR_ARCH_ATT_PAIR) {    // 'atgru': attention over the 2G scalar "steps" of [GRU output ; id vector]
       float* seq2 = W<float>(p, ws, "seq2");
       float* mask2 = W<float>(p, ws, "mask2");
       cudaMemcpy2DAsync(seq2 + G, (size_t)2 * G * 4, u0, (size_t)c.Ue * 4, (size_t)G * 4, B, cudaMemcpyDeviceToDevice, st);
-      RC(lstur_rows_nonzero((long long)2 * B, G, seq2, G, mask2, st));
-      RC(lstur_seq_attn_fwd(B, 2, G, seq2, mask2, DP(p, w->dense, "uatt_w"), DP(p, w->dense, "uatt_b"), uvec, c.U,
+      RC(lstur_rows_nonzero((long long)2 * G * B, 1, seq2, 1, mask2, st));       // Masking() on one-feature steps
+      RC(lstur_seq_attn_fwd(B, 2 * G, 1, seq2, mask2, DP(p, w->dense, "uatt_w"), DP(p, w->dense, "uatt_b"), uvec, c.U,
                             W<float>(p, ws, "ua_a"), W<float>(p, ws, "ua_w"), st));
     } else if (c.arch == LSTUR_ARCH_ALPHA) {       // 'algru': models.AlphaAdd (models.py:540-554)
       RC(lstur_alpha_add_fwd(B, G, DP(p, w->dense, "alpha"), hT, G, u0, c.Ue, uvec, c.U, st));
@@ -1125,10 +1127,10 @@ extern "C" int lstur_backward_w(const lstur_plan* p, const lstur_weights* w, con
   } else if (c.arch == LSTUR_ARCH_ATT_PAIR) {
     float* d_seq2 = W<float>(p, ws, "d_seq2");
     float* part = W<float>(p, ws, "ua_partial");
-    RC(lstur_seq_attn_bwd(B, 2, G, W<float>(p, ws, "seq2"), DP(p, w->dense, "uatt_w"), W<float>(p, ws, "ua_a"),
+    RC(lstur_seq_attn_bwd(B, 2 * G, 1, W<float>(p, ws, "seq2"), DP(p, w->dense, "uatt_w"), W<float>(p, ws, "ua_a"),
                           W<float>(p, ws, "ua_w"), d_uvec, c.U, nullptr, d_seq2, part, st));
-    RC(lstur_colsum(B, G, part, G + 1, DG(p, dgrad, "uatt_w"), 0, cws, cwsb, st));
-    RC(lstur_colsum(B, 1, part + G, G + 1, DG(p, dgrad, "uatt_b"), 0, cws, cwsb, st));
+    RC(lstur_colsum(B, 1, part, 2, DG(p, dgrad, "uatt_w"), 0, cws, cwsb, st));
+    RC(lstur_colsum(B, 1, part + 1, 2, DG(p, dgrad, "uatt_b"), 0, cws, cwsb, st));
     dhT = d_seq2; lddh = 2 * G; du0 = d_seq2 + G; lddu0 = 2 * G;
   } else if (c.arch == LSTUR_ARCH_ALPHA) {
     float* d_hT = W<float>(p, ws, "d_hT");

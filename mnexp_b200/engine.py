@@ -82,7 +82,8 @@ class LsturEngine:
         ds = params['subvert_emb'].shape[1] if 'subvert_emb' in params else 0
         U = {0: G, 1: params['con_w'].shape[1] if 'con_w' in params else 0, 2: G + Ue, 3: G, 4: G, 5: Ue,
              6: Dd + dv + ds, 7: params['con_w'].shape[1] if 'con_w' in params else 0, 8: Ue,
-             9: Dd + dv + ds + Ue, 10: Dd + dv + ds, 11: Dd + dv + ds + Ue, 12: G, 13: G, 14: G, 15: G + Ue}[self.arch]
+             9: Dd + dv + ds + Ue, 10: Dd + dv + ds, 11: Dd + dv + ds + Ue, 12: G, 13: 1, 14: G, 15: G + Ue}[self.arch]
+        # 13 = cook 'atgru': the 2G entries of [GRU ; id] pooled to ONE scalar per user (task/cook.py:184-190 as written)
         _sd = share_weights_from.doc_tokens if share_weights_from is not None else None
         n_docs = doc_tokens.shape[0] if doc_tokens is not None else (0 if _sd is None else _sd.shape[0])
         self.cfg = lstur_config(

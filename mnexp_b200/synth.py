@@ -165,7 +165,7 @@ def make_weights(shape, arch=None, seed=1237, word_emb=None, score_model='dot', 
         P['lstm_b'] = bz(4 * G)
         P['lstm_b'][G:2 * G] += 1.0
     if arch in ('att', 'iatt', 'atgru'):                        # SimpleAttentionMaskSupport kernel (Da, 1) + bias (models.py:456-468)
-        Da = G if arch == 'atgru' else D
+        Da = 1 if arch == 'atgru' else D           # atgru pools 2U one-feature steps: kernel (1, 1) (task/cook.py:184-190)
         P['uatt_w'] = _glorot(rng, (Da,), Da, 1)
         P['uatt_b'] = bz(1)
     if arch == 'algru':                                         # models.AlphaAdd: Constant(0.5) (models.py:541-545)
@@ -176,13 +176,13 @@ def make_weights(shape, arch=None, seed=1237, word_emb=None, score_model='dot', 
     if arch in ('iigru', 'iicat', 'inagru'):                    # second user table, task/paper.py:616 / :340, task/cook.py:178
         P['user_emb2'] = rng.uniform(-0.05, 0.05, (shape.n_users, Ue)).astype(np.float32)
     if score_model == 'dnn':                                   # task/paper.py:448-451
-        Du = 2 * U if arch in ('ngru', 'dgru', 'iicat', 'ilstm') else (D if arch in ('niavg', 'att') else (D + U if arch in ('iavg', 'iatt') else U))
+        Du = 2 * U if arch in ('ngru', 'dgru', 'iicat', 'ilstm') else (D if arch in ('niavg', 'att') else (D + U if arch in ('iavg', 'iatt') else (1 if arch == 'atgru' else U)))
         P['sh_w'] = _glorot(rng, (Du + D, Hs), Du + D, Hs)
         P['sh_b'] = bz(Hs)
         P['so_w'] = _glorot(rng, (Hs, 1), Hs, 1)
         P['so_b'] = bz(1)
     if score_model == 'ddot':
-        Du = 2 * U if arch in ('ngru', 'dgru', 'iicat', 'ilstm') else (D if arch in ('niavg', 'att') else (D + U if arch in ('iavg', 'iatt') else U))
+        Du = 2 * U if arch in ('ngru', 'dgru', 'iicat', 'ilstm') else (D if arch in ('niavg', 'att') else (D + U if arch in ('iavg', 'iatt') else (1 if arch == 'atgru' else U)))
         P['su_w'] = _glorot(rng, (Du, Hs), Du, Hs)
         P['su_b'] = bz(Hs)
         P['sd_w'] = _glorot(rng, (D, Hs), D, Hs)
@@ -247,6 +247,33 @@ def write_dataset(dirname, shape, seed=7):
     write_docmeta_tsv(os.path.join(dirname, 'DocMeta.tsv'), tok, vert, subvert)
     write_clickdata_tsv(os.path.join(dirname, 'ClickData.tsv'), shape.n_users, shape.n_news, rng)
     return emb, tok
+
+
+def write_cook_npz(dirname, shape, n_train=24, n_test=10, seed=0, days=30):
+    """train / test .npz in the reference's cook layout (task/cook.py:14-28, settings.py train_npz_input / test_npz_input)
+    + Vocab.tsv.npy: idx, idx_mask (n,1); ch_title (n,W,L), ch_vert, ch_subvert (n,W); cd_title (n,5,L), cd_vert, cd_subvert
+    (n,5), cd_label (n,5) — the test file carries one candidate per row plus label / user / impr."""
+    import os
+    g = np.random.default_rng(seed)
+    tok, _, _ = make_docs(shape.n_news, shape.L, shape.vocab)
+
+    def block(n, C):
+        hd = g.integers(0, shape.n_news + 1, (n, shape.W))
+        hd[:, :2] = 0                                            # left padding
+        cd = g.integers(1, shape.n_news + 1, (n, C))
+        return dict(idx=g.integers(0, 50, (n, 1)), idx_mask=(g.random((n, 1)) < 0.8).astype(np.float32),
+                    ch_title=tok[hd], ch_vert=g.integers(0, 16, (n, shape.W)) * (hd > 0),
+                    ch_subvert=g.integers(0, 307, (n, shape.W)) * (hd > 0),
+                    cd_title=tok[cd], cd_vert=g.integers(1, 16, (n, C)), cd_subvert=g.integers(1, 307, (n, C)))
+    tr = block(n_train, 5)
+    tr['cd_label'] = np.eye(5, dtype=np.float32)[np.zeros(n_train, dtype=int)]
+    te = block(n_test, 1)
+    te = dict(te, cd_title=te['cd_title'][:, 0], cd_vert=te['cd_vert'][:, 0], cd_subvert=te['cd_subvert'][:, 0],
+              label=(g.random(n_test) < 0.3).astype(np.float32), user=np.arange(n_test), impr=np.arange(n_test) // 3)
+    os.makedirs(dirname, exist_ok=True)
+    np.savez(os.path.join(dirname, 'train_%ddays_%dwindow.npz' % (days, shape.W)), **tr)
+    np.savez(os.path.join(dirname, 'test_%ddays_%dwindow.npz' % (days, shape.W)), **te)
+    np.save(os.path.join(dirname, 'Vocab.tsv.npy'), make_vocab(shape.vocab, shape.E))
 
 
 # ---- a LEARNABLE synthetic click task (training-parity / AUC checks; BASELINE.json north_star: "AUC within 0.002 after

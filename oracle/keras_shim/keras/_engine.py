@@ -486,6 +486,17 @@ class Network(Layer):
         self.input_names = [s.node.layer.name for s in self.inputs]
         self.output_names = [s.node.layer.name for s in self.outputs]
 
+    def summary(self, *a, **kw):
+        pass
+
+    def count_params(self):
+        seen, n = set(), 0
+        for w in self.weights:
+            if id(w) not in seen:
+                seen.add(id(w))
+                n += int(w.numel())
+        return n
+
     def get_layer(self, name=None, index=None):
         if index is not None:
             return self.layers[index]

@@ -266,6 +266,17 @@ class Dot(_Merge):
         super().__init__(**kwargs)
         self.axes, self.normalize = axes, normalize
 
+    def build(self, input_shape):
+        # layers/merge.py Dot.build: the contracted dimensions must agree
+        s1, s2 = input_shape[0], input_shape[1]
+        if isinstance(self.axes, int):
+            axes = [self.axes % len(s1), self.axes % len(s2)] if self.axes < 0 else [self.axes] * 2
+        else:
+            axes = list(self.axes)
+        if s1[axes[0]] != s2[axes[1]]:
+            raise ValueError('Dimension incompatibility %s != %s. Layer shapes: %s, %s' % (s1[axes[0]], s2[axes[1]], s1, s2))
+        self.built = True
+
     def call(self, inputs):
         x1, x2 = unwrap(inputs[0]), unwrap(inputs[1])
         if isinstance(self.axes, int):

@@ -206,7 +206,11 @@ def user_encoder(arch, user, H, P, recurrent_activation='hard_sigmoid', u0_scale
     if arch == 'inagru':
         return gru(u0) + u2()
     if arch == 'atgru':
-        seq = np.stack([gru(None), u0], 1)
+        # task/cook.py:184-190 as WRITTEN: expand_dims(x, -1) of both vectors, concatenated on axis -2, is a sequence of
+        # 2U "steps" of ONE feature; Masking drops the zero entries and SimpleAttentionMaskSupport (kernel (1, 1)) pools the
+        # 2U scalars into a single number per user — established by running the reference's own code
+        # (tests/golden/make_ref_golden.py), not the two-step (B, 2, U) pooling a reader expects
+        seq = np.concatenate([gru(None), u0], -1)[..., None]
         return masked_attention(seq, f8('uatt_w').reshape(-1), float(np.asarray(P['uatt_b']).reshape(-1)[0]))
     if arch == 'algru':
         al = float(np.asarray(P['alpha']).reshape(-1)[0])

@@ -134,8 +134,8 @@ def user_encoder(arch, user, H, P, recurrent_activation='hard_sigmoid', u0_scale
         return torch.cat([lstm_last_state(H, P['lstm_wx'], P['lstm_wh'], P['lstm_b'], recurrent_activation), u0], -1)
     if arch == 'inagru':
         return gru(u0) + u2()
-    if arch == 'atgru':
-        return masked_attention(torch.stack([gru(None), u0], 1), P['uatt_w'], P['uatt_b'])
+    if arch == 'atgru':          # task/cook.py:184-190 as written: 2U one-feature "steps" pooled to one scalar (lstur_numpy.py)
+        return masked_attention(torch.cat([gru(None), u0], -1).unsqueeze(-1), P['uatt_w'], P['uatt_b'])
     if arch == 'algru':
         al = P['alpha'].reshape(-1)[0]
         return gru(None) * al + u0 * (1.0 - al)

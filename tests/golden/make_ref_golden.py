@@ -309,6 +309,134 @@ def run_case(mods, sh, data_dir, name, task_name, arch, score_model, my_arch, ex
     return out
 
 
+# (case name, reference arch, score model, oracle arch, use_vertical_type)  — task/cook.py:4-285
+COOK_CASES = [
+    ('cook-ingru-ddot-vs', 'ingru', 'ddot', 'igru', 'vs'), ('cook-igru-dnn-v', 'igru', 'dnn', 'ngru', 'v'),
+    ('cook-inigru-dot-s', 'inigru', 'ddot', 'iicat', 's'), ('cook-avg-dnn-vs', 'avg', 'dnn', 'niavg', 'vs'),
+    ('cook-gru-dot-vs', 'gru', 'dot', 'nigru', 'vs'), ('cook-vo-dnn-vs', 'vo', 'dnn', 'vo', 'vs'),
+    ('cook-agru-dot-vs', 'agru', 'dot', 'pgru', 'vs'), ('cook-iavg-dnn-vs', 'iavg', 'dnn', 'iavg', 'vs'),
+    ('cook-iatt-ddot-v', 'iatt', 'ddot', 'iatt', 'v'), ('cook-ilstm-dnn-s', 'ilstm', 'dnn', 'ilstm', 's'),
+    ('cook-inagru-dot-vs', 'inagru', 'dot', 'inagru', 'vs'), ('cook-atgru-dnn-vs', 'atgru', 'dnn', 'atgru', 'vs'),
+    ('cook-algru-dot-vs', 'algru', 'dot', 'algru', 'vs'),
+]
+COOK_DV, COOK_DS, COOK_USERS = 3, 5, 25000
+
+
+def cook_shape(score_model='dnn', vtype='vs'):
+    """'dot' multiplies the user vector with the [title | vert | subvert] news vector directly (task/cook.py:200-201), so
+    the reference graph only builds when user_embedding_dim equals that width"""
+    from mnexp_b200 import synth
+    t = synth.SHAPES['tiny']
+    U = t.U if score_model != 'dot' else t.F + (COOK_DV if vtype != 's' else 0) + (COOK_DS if vtype != 'v' else 0)
+    return synth.Shape('tinycook', COOK_USERS, t.n_news, t.vocab, L=t.L, W=t.W, K=4, B=t.B, E=t.E, F=t.F, U=U)
+
+
+def cook_variables(h):
+    """this repo's parameter name -> variable, walking the graph Cook._build_model assembled (task/cook.py:214-264)"""
+    import utils as ref_utils
+    out, seen = {}, set()
+
+    def walk(model, inside_user):
+        for l in model.layers:
+            inner = getattr(l, 'layer', None)
+            if inner is not None and hasattr(inner, 'layers'):
+                walk(inner, inside_user)
+            if hasattr(l, 'layers') and hasattr(l, 'inputs'):
+                is_user = len(l.inputs) == 3 and len(l.inputs[2]._keras_shape) == 3
+                walk(l, inside_user or is_user)
+            if id(l) in seen:
+                continue
+            seen.add(id(l))
+            c = l.__class__.__name__
+            if c == 'Embedding':
+                if l.input_dim == COOK_USERS:
+                    out.setdefault('_user_embs', []).append(l)
+                elif l.input_dim == len(ref_utils.verticals):
+                    out['vert_emb'] = l.embeddings
+                elif l.input_dim == len(ref_utils.subverticals):
+                    out['subvert_emb'] = l.embeddings
+                else:
+                    out['word_emb'] = l.embeddings
+            elif c == 'Conv1D':
+                out['conv_w'], out['conv_b'] = l.kernel, l.bias
+            elif c == 'SimpleAttentionMaskSupport':
+                n = 'uatt' if inside_user else 'att'
+                out[n + '_w'], out[n + '_b'] = l.kernel, l.bias
+            elif c == 'GRU':
+                out['gru_wx'], out['gru_wh'], out['gru_b'] = l.kernel, l.recurrent_kernel, l.bias
+            elif c == 'LSTM':
+                out['lstm_wx'], out['lstm_wh'], out['lstm_b'] = l.kernel, l.recurrent_kernel, l.bias
+            elif c == 'AlphaAdd':
+                out['alpha'] = l.alpha
+            elif c == 'Dense':
+                out.setdefault('_dense', []).append(l)
+
+    walk(h.train_model, False)
+    for name, l in zip(('user_emb', 'user_emb2'), sorted(out.pop('_user_embs', []), key=_uid)):
+        out[name] = l.embeddings
+    dense = sorted(out.pop('_dense', []), key=_uid)
+    names = {'dnn': ('sh', 'so'), 'ddot': ('su', 'sd'), 'dot': ()}[h.config.score_model]
+    assert len(dense) == len(names), [d.name for d in dense]
+    for n, l in zip(names, dense):
+        out[n + '_w'], out[n + '_b'] = l.kernel, l.bias
+    return out
+
+
+def run_cook_case(mods, data_dir, name, arch, score_model, my_arch, vtype):
+    keras, settings, task = mods
+    from mnexp_b200 import synth
+    keras.backend.clear_session()
+    sh = cook_shape(score_model, vtype)
+    cfg = reference_config(settings, data_dir, sh, 'Cook', arch, score_model, use_vertical=True, use_vertical_type=vtype,
+                           vertical_embedding_dim=COOK_DV, subvertical_embedding_dim=COOK_DS, days=30, id_keep=1.0,
+                           validation_step=6, lrd_on_epochs=[0])
+    h = task.get(cfg)
+    model = h.build_model(0)
+    variables = cook_variables(h)
+    dv = COOK_DV if vtype != 's' else 0
+    ds = COOK_DS if vtype != 'v' else 0
+    P = synth.make_weights(sh, arch=my_arch, bias_noise=0.05, seed=4242, score_model=score_model, cook=True, dv=dv, ds=ds,
+                           word_emb=np.load(os.path.join(data_dir, 'Vocab.tsv.npy')))
+    if not dv:
+        P.pop('vert_emb', None)
+    if not ds:
+        P.pop('subvert_emb', None)
+    P['user_emb'] = P['user_emb'] if 'user_emb' in P else None
+    P = {k: v for k, v in P.items() if v is not None}
+    assign(variables, P)
+    x, y = h.train()
+    out = {'x%d' % i: np.asarray(a) for i, a in enumerate(x)}
+    out['y'] = np.asarray(y[0])
+    for k, v in snapshot(variables).items():
+        # only the rows of the 25000-row id tables that the data can touch (idx < 50) are stored
+        out['P/' + k] = v[:64] if k in ('user_emb', 'user_emb2') else v
+    out['predict'] = model.predict(x)
+    feats, labels = h.test()
+    for i, a in enumerate(feats):
+        out['test_x%d' % i] = np.asarray(a)
+    out['test_predict'] = h.test_model.predict(feats)
+    vx, vy = h.valid()
+    out['valid_eval'] = np.asarray(h.test_model.test_on_batch(vx, vy)[:1], dtype=np.float64)     # binary_crossentropy of test_model
+    loss, grads = model.loss_and_gradients(x, y, training=True)
+    out['loss'] = np.float64(loss)
+    by_var = {v.vname: k for k, v in variables.items()}
+    for vname, g in grads.items():
+        k = by_var[vname]
+        g = g.reshape(-1) if k in ('att_w', 'uatt_w') else g
+        out['grad/' + k] = g[:64] if k in ('user_emb', 'user_emb2') else g
+    results = [model.train_on_batch(x, y) for _ in range(3)]
+    out['adam_results'] = np.asarray(results, dtype=np.float64)
+    out['adam_losses'] = out['adam_results'][:, 0]
+    for k, v in snapshot(variables).items():
+        out['adam/' + k] = v[:64] if k in ('user_emb', 'user_emb2') else v
+    lr0 = float(keras.backend.get_value(model.optimizer.lr))
+    h.callback(0)                                          # lrd_on_epochs = [0]: learning-rate decay (task/cook.py:279-285)
+    out['lr_after_callback'] = np.float64(keras.backend.get_value(model.optimizer.lr))
+    out['lr_before_callback'] = np.float64(lr0)
+    out['layers'] = np.array([l.name for l in model.layers])
+    return out
+
+
 def generate(path=OUT, verbose=True):
     mods = load_reference()
     from mnexp_b200 import synth
@@ -323,6 +451,16 @@ def generate(path=OUT, verbose=True):
             out[name + '/' + k] = v
         if verbose:
             print('%-24s %-24s loss %.6f  layers %d' % (name, task_name, float(res['loss']), len(res['layers'])))
+    cook_dir = tempfile.mkdtemp(prefix='refgold_cook_')
+    synth.write_cook_npz(cook_dir, cook_shape())
+    out['cook_cases'] = np.array([c[0] for c in COOK_CASES])
+    out['cook_table'] = np.array([list(c) for c in COOK_CASES])
+    for name, arch, score_model, my_arch, vtype in COOK_CASES:
+        res = run_cook_case(mods, cook_dir, name, arch, score_model, my_arch, vtype)
+        for k, v in res.items():
+            out[name + '/' + k] = v
+        if verbose:
+            print('%-24s %-24s loss %.6f  layers %d' % (name, 'Cook', float(res['loss']), len(res['layers'])))
     np.savez_compressed(path, **out)
     if verbose:
         print('wrote %d arrays to %s' % (len(out), path))

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 CASES = [
     # engine arch, flavour, oracle arch, scorer
     ('iavg', 'cook', 'iavg', 'dnn'), ('iatt', 'cook', 'iatt', 'ddot'), ('ilstm', 'cook', 'ilstm', 'dnn'),
-    ('inagru', 'cook', 'inagru', 'dot'), ('atgru', 'cook', 'atgru', 'dot'), ('algru', 'cook', 'algru', 'dot'),
+    ('inagru', 'cook', 'inagru', 'dot'), ('atgru', 'cook', 'atgru', 'dnn'), ('algru', 'cook', 'algru', 'dot'),
     ('att', 'sigmoid', 'att', 'dot'),
 ]
 

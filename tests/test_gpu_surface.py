@@ -338,24 +338,7 @@ def test_sigmoid_family_surface(lib, task_name, arch, oarch, score):
 
 def _cook_npz(d, sh, n_train=24, n_test=10, seed=0):
     """train/test .npz in the reference's cook layout (task/cook.py:14-28) + Vocab.tsv.npy."""
-    g = np.random.default_rng(seed)
-    tok, _, _ = synth.make_docs(sh.n_news, sh.L, sh.vocab)
-
-    def block(n, C):
-        hd = g.integers(0, sh.n_news + 1, (n, sh.W))
-        hd[:, :2] = 0                                            # left padding
-        cd = g.integers(1, sh.n_news + 1, (n, C))
-        return dict(idx=g.integers(0, 50, (n, 1)), idx_mask=(g.random((n, 1)) < 0.8).astype(np.float32),
-                    ch_title=tok[hd], ch_vert=g.integers(0, 16, (n, sh.W)) * (hd > 0), ch_subvert=g.integers(0, 307, (n, sh.W)) * (hd > 0),
-                    cd_title=tok[cd], cd_vert=g.integers(1, 16, (n, C)), cd_subvert=g.integers(1, 307, (n, C)))
-    tr = block(n_train, 5)
-    tr['cd_label'] = np.eye(5, dtype=np.float32)[np.zeros(n_train, dtype=int)]
-    te = block(n_test, 1)
-    te = dict(te, cd_title=te['cd_title'][:, 0], cd_vert=te['cd_vert'][:, 0], cd_subvert=te['cd_subvert'][:, 0],
-              label=(g.random(n_test) < 0.3).astype(np.float32), user=np.arange(n_test), impr=np.arange(n_test) // 3)
-    np.savez(os.path.join(d, 'train_30days_%dwindow.npz' % sh.W), **tr)
-    np.savez(os.path.join(d, 'test_30days_%dwindow.npz' % sh.W), **te)
-    np.save(os.path.join(d, 'Vocab.tsv.npy'), synth.make_vocab(sh.vocab, sh.E))
+    synth.write_cook_npz(d, sh, n_train, n_test, seed)
 
 
 @pytest.mark.parametrize('arch,oarch,score_model,vtype', [('ingru', 'igru', 'ddot', 'vs'), ('igru', 'ngru', 'dnn', 'v'),

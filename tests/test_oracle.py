@@ -221,7 +221,7 @@ def test_variant_golden_fixtures_reproduce():
                 assert np.array_equal(g.numpy(), gold[key + '/grad/' + k]), (key, k)
 
 
-COOK_NEW = [('iavg', 'dnn'), ('iatt', 'ddot'), ('att', 'dot'), ('ilstm', 'dnn'), ('inagru', 'dot'), ('atgru', 'dot'),
+COOK_NEW = [('iavg', 'dnn'), ('iatt', 'ddot'), ('att', 'dot'), ('ilstm', 'dnn'), ('inagru', 'dot'), ('atgru', 'dnn'),
             ('algru', 'dot')]
 
 
@@ -239,7 +239,8 @@ def test_cook_user_encoders_two_implementations(arch, score_model):
 
 def test_cook_heads_by_hand():
     """SimpleAttentionMaskSupport over two steps, AlphaAdd and the LSTM step, computed by hand."""
-    # atgru: sequence [h ; u], attention kernel k, bias 0 (models.py:474-489); an all-zero id vector is masked out
+    # SimpleAttentionMaskSupport over a two-step sequence [h ; u], kernel k, bias 0 (models.py:474-489); an all-zero step
+    # is masked out
     h = np.array([[1.0, 0.0]])
     u = np.array([[0.0, 2.0]])
     k = np.array([0.5, -0.25])
@@ -250,6 +251,13 @@ def test_cook_heads_by_hand():
     assert np.abs(got - want).max() < 1e-15
     got0 = on.masked_attention(np.stack([h, 0 * u], 1), k, 0.0)
     assert np.abs(got0 - h * e[0] / (e[0] + 1e-7)).max() < 1e-15
+    # cook 'atgru' as the reference WRITES it (task/cook.py:184-190): the 2U entries of [GRU ; id] are one-feature steps,
+    # zero entries are masked, the output is one scalar: sum_i x_i exp(tanh(k x_i)) / (sum_live exp(tanh(k x_i)) + 1e-7)
+    P = dict(user_emb=np.array([[0.0, 2.0]]), uatt_w=np.array([0.5]), uatt_b=np.array([0.0]), gru_wx=np.zeros((2, 6)),
+             gru_wh=np.zeros((2, 6)), gru_b=np.zeros(6))
+    out = on.user_encoder('atgru', np.zeros(1, dtype=int), np.zeros((1, 3, 2)), P)      # GRU state stays 0: only x = 2 is live
+    e2 = np.exp(np.tanh(0.5 * 2.0))
+    assert out.shape == (1, 1) and abs(out[0, 0] - 2.0 * e2 / (e2 + 1e-7)) < 1e-15
     # algru (models.py:551-552)
     P = dict(user_emb=np.array([[2.0, 4.0]]), alpha=np.array([0.25]), gru_wx=np.zeros((2, 6)), gru_wh=np.zeros((2, 6)),
              gru_b=np.zeros(6))

@@ -339,3 +339,122 @@ def test_cuda_dropout_step_matches_reference_graph(lib, precision):
             assert rel(got, GOLD[key].reshape(np.asarray(got).shape)) < 5e-5, k
             n += 1
     assert n >= 9
+
+
+# ---------------------------------------------------------------------------------------------- Cook (task/cook.py:4-285)
+COOK = [str(c) for c in GOLD['cook_cases']]
+COOK_TABLE = {row[0]: tuple(row[1:]) for row in GOLD['cook_table']}
+COOK_KEYS = P_KEYS + ('subvert_emb', 'lstm_wx', 'lstm_wh', 'lstm_b', 'alpha')
+
+
+def cook_case(name):
+    arch, score_model, my_arch, vtype = COOK_TABLE[name]
+    g = lambda k: GOLD[name + '/' + k]
+    x = [g('x%d' % i) for i in range(8)]
+    P = {k: GOLD[name + '/P/' + k] for k in COOK_KEYS if name + '/P/' + k in GOLD.files}
+    return arch, score_model, my_arch, vtype, P, x, g('y')
+
+
+def cook_oracle(P, name, x=None, one=False):
+    """Cook._build_model restated with the torch oracle -> (logits (n, C), user_vec, cand_vec)"""
+    arch, score_model, my_arch, vtype, _, x0, y = cook_case(name)
+    idx, idx_mask, ch_title, ch_vert, ch_subvert, cd_title, cd_vert, cd_subvert = x if x is not None else x0
+    n = len(idx)
+    t = lambda a: torch.as_tensor(np.asarray(a)).long()
+    cd_title = np.asarray(cd_title).reshape(n, -1, ch_title.shape[-1])
+    kw = dict(arch=my_arch, score_model=score_model, flavour='cook',
+              u0_scale=torch.tensor(np.asarray(idx_mask), dtype=torch.float64).reshape(n, 1))
+    if 'vert_emb' in P:
+        kw.update(hist_vert=np.asarray(ch_vert), cand_vert=np.asarray(cd_vert).reshape(n, -1))
+    if 'subvert_emb' in P:
+        kw.update(hist_subvert=np.asarray(ch_subvert), cand_subvert=np.asarray(cd_subvert).reshape(n, -1))
+    out = ot.forward(P, t(idx).reshape(-1), t(ch_title), t(cd_title), aux=True, **kw)
+    return out['logits'], out['user_vec'], out['cand_vec']
+
+
+@pytest.mark.parametrize('name', COOK)
+def test_oracle_matches_reference_cook_graph(name):
+    """forward of train_model / test_model, the compiled loss, its gradients and three Adam steps of the reference's own
+    Cook._build_model graph (13 user encoders, the three scorers, the three use_vertical_type concatenations)"""
+    arch, score_model, my_arch, vtype, Pn, x, y = cook_case(name)
+    g = lambda k: GOLD[name + '/' + k]
+    P = {k: torch.tensor(v, dtype=torch.float64, requires_grad=(k != 'word_emb')) for k, v in Pn.items()}
+    trainable = [k for k in P if P[k].requires_grad]
+    logits, uv, dv = cook_oracle(P, name)
+    probs = torch.softmax(logits, -1)
+    assert rel(probs.detach().numpy(), g('predict')) < F64
+    tx = [g('test_x%d' % i) for i in range(8)]
+    tl, _, _ = cook_oracle(P, name, tx)
+    assert rel(torch.sigmoid(tl).detach().numpy(), g('test_predict')) < F64
+    loss = ot.categorical_crossentropy(torch.tensor(y, dtype=torch.float64), probs)
+    assert abs(float(loss.detach()) - float(g('loss'))) < F64
+    grads = dict(zip(trainable, torch.autograd.grad(loss, [P[k] for k in trainable], allow_unused=True)))
+    n = 0
+    for k in trainable:
+        key = name + '/grad/' + k
+        assert key in GOLD.files, 'the reference model does not train %s' % k
+        got = np.zeros(P[k].shape) if grads[k] is None else grads[k].numpy()
+        assert np.abs(got - GOLD[key]).max() <= F64 * max(1.0, np.abs(GOLD[key]).max()), k
+        n += 1
+    assert n == len([f for f in GOLD.files if f.startswith(name + '/grad/')])
+    opt = ot.KerasAdam({k: P[k] for k in trainable}, lr=1e-3)
+    losses = []
+    for _ in range(3):
+        logits, _, _ = cook_oracle(P, name)
+        loss = ot.categorical_crossentropy(torch.tensor(y, dtype=torch.float64), torch.softmax(logits, -1))
+        opt.step(dict(zip(trainable, torch.autograd.grad(loss, [P[k] for k in trainable], allow_unused=True))))
+        if 'alpha' in P:                      # models.AlphaAdd: constraint=MinMaxNorm(0, 1), applied after the update
+            with torch.no_grad():
+                a = P['alpha']
+                a.mul_(a.abs().clamp(0.0, 1.0) / (1e-7 + a.abs()))
+        losses.append(float(loss.detach()))
+    assert np.abs(np.array(losses) - g('adam_losses')).max() < F64
+    for k in P:
+        assert np.abs(P[k].detach().numpy() - g('adam/' + k)).max() < 1e-10, k
+    assert abs(float(g('lr_after_callback')) - float(g('lr_before_callback')) * 0.2) < 1e-15     # lrd_on_epochs, cook.py:279-285
+
+
+def _cook_mirror(name, precision):
+    arch, score_model, my_arch, vtype = COOK_TABLE[name]
+    sh = mk.cook_shape(score_model, vtype)
+    d = tempfile.mkdtemp()
+    synth.write_cook_npz(d, sh)
+    cfg = settings.Config(dict(task='Cook', arch=arch, input_training_data_path=d, days=30, window_size=sh.W, batch_size=24,
+                               title_filter_shape=(sh.F, 3), user_embedding_dim=sh.U, dropout=0.0, score_model=score_model,
+                               use_vertical=True, use_vertical_type=vtype, vertical_embedding_dim=mk.COOK_DV,
+                               subvertical_embedding_dim=mk.COOK_DS, precision=precision, validation_step=6,
+                               lrd_on_epochs=[0], learning_rate=0.001, id_keep=1.0))
+    return task.get(cfg)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('precision', ['fp32', 'fp16_tc'])
+@pytest.mark.parametrize('name', COOK)
+def test_cuda_cook_matches_reference_graph(lib, name, precision):
+    """the mirror's Cook handler on the same .npz files and weights: train_model.predict, test_model.predict and three
+    full-batch fit() epochs (= three Adam steps) against the reference's own graph"""
+    arch, score_model, my_arch, vtype, Pn, x, y = cook_case(name)
+    g = lambda k: GOLD[name + '/' + k]
+    tol = 2e-5 if precision == 'fp32' else 1e-3
+    h = _cook_mirror(name, precision)
+    h.config.sparse_user_adam = False
+    model = h.build_model(0)
+    xm, ym = h.train()
+    for a, b in zip(xm, x):                                   # same files -> same features as the reference loaded
+        assert np.array_equal(np.asarray(a), b)
+    P = {}
+    for k, v in h.params.items():
+        assert k in Pn, k
+        ref = np.asarray(Pn[k], dtype=np.float32)
+        if k in ('user_emb', 'user_emb2'):                    # the fixture keeps the 64 rows the data can touch
+            full = np.zeros(np.asarray(v).shape, dtype=np.float32)
+            full[:len(ref)] = ref
+            ref = full
+        P[k] = ref.reshape(np.asarray(v).shape)
+    assert sorted(P) == sorted(Pn)
+    h.params = P
+    assert rel(model.predict(xm), g('predict')) < tol
+    tx, _ = h.test()
+    assert rel(h.test_model.predict(tx).reshape(g('test_predict').shape), g('test_predict')) < tol
+    hist = model.fit(xm, ym, 24, epochs=3, initial_epoch=0, shuffle=False)
+    assert np.abs(np.array(hist.history['loss']) - g('adam_losses')).max() < (1e-4 if precision == 'fp32' else 2e-3)
