@@ -3,7 +3,7 @@
 
 The reference ships no golden vectors for this path and its Keras/TF-1.x runtime cannot be imported here
 (SURVEY.md §8c), so these fixtures pin the ORACLE (and through it every CUDA kernel) against regressions; they
-are not outputs of the reference itself — "parity unpinned" (oracle/__init__.py).
+are not outputs of the reference itself (those are tests/golden/ref_golden.npz, make_ref_golden.py).
 Run from the repo root:  python tests/golden/make_golden.py
 """
 import os

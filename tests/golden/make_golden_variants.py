@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Generates tests/golden/lstur_golden_variants.npz: the remaining user encoders / scorers / the sigmoid family, from the
-float64 torch oracle on seeded synthetic inputs (same status as lstur_golden.npz: pins the oracle, "parity unpinned").
+float64 torch oracle on seeded synthetic inputs (same status as lstur_golden.npz: a regression pin of the oracle; the vectors produced by the reference's own code are
+tests/golden/ref_golden.npz).
 Run from the repo root:  python tests/golden/make_golden_variants.py
 """
 import os
