@@ -249,7 +249,7 @@ def write_dataset(dirname, shape, seed=7):
     return emb, tok
 
 
-def write_cook_npz(dirname, shape, n_train=24, n_test=10, seed=0, days=30):
+def write_cook_npz(dirname, shape, n_train=24, n_test=30, seed=0, days=30):
     """train / test .npz in the reference's cook layout (task/cook.py:14-28, settings.py train_npz_input / test_npz_input)
     + Vocab.tsv.npy: idx, idx_mask (n,1); ch_title (n,W,L), ch_vert, ch_subvert (n,W); cd_title (n,5,L), cd_vert, cd_subvert
     (n,5), cd_label (n,5) — the test file carries one candidate per row plus label / user / impr."""
@@ -268,8 +268,19 @@ def write_cook_npz(dirname, shape, n_train=24, n_test=10, seed=0, days=30):
     tr = block(n_train, 5)
     tr['cd_label'] = np.eye(5, dtype=np.float32)[np.zeros(n_train, dtype=int)]
     te = block(n_test, 1)
+    # rows grouped by (user, impression) as the evaluation tail of `main.py cook` expects (main.py:250-286): users of
+    # `per_user` consecutive impressions of `per_imp` rows, one click per impression, in-vocabulary flag per user
+    per_imp, per_user = 3, 2
+    imp = np.arange(n_test) // per_imp
+    user = imp // per_user
+    label = np.zeros(n_test, dtype=np.float32)
+    for i in range(int(imp.max()) + 1):
+        rows = np.where(imp == i)[0]
+        label[rows[g.integers(0, len(rows))]] = 1.0
+    iv = (g.random(int(user.max()) + 1) < 0.6).astype(np.float32)
+    iv[:2] = [1.0, 0.0]
     te = dict(te, cd_title=te['cd_title'][:, 0], cd_vert=te['cd_vert'][:, 0], cd_subvert=te['cd_subvert'][:, 0],
-              label=(g.random(n_test) < 0.3).astype(np.float32), user=np.arange(n_test), impr=np.arange(n_test) // 3)
+              label=label, user=user, impr=imp, idx_mask=iv[user].reshape(n_test, 1), idx=(user % 50).reshape(n_test, 1))
     os.makedirs(dirname, exist_ok=True)
     np.savez(os.path.join(dirname, 'train_%ddays_%dwindow.npz' % (days, shape.W)), **tr)
     np.savez(os.path.join(dirname, 'test_%ddays_%dwindow.npz' % (days, shape.W)), **te)

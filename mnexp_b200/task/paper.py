@@ -345,6 +345,7 @@ class Seq2VecPaperSoftmax(Seq2VecPaper):
             self.is_training = False
             values = [np.mean(x) for x in zip(*__gen__(self.config.testing_impression))]
             utils.logging_evaluation(dict(auc=values[0], ndcgx=values[1], ndcgv=values[2], mrr=values[3]))
+            utils.logging_evaluation(dict(pos=values[4], size=values[5], num=values[6] * 2 + 1))
         self.model, self.test_model = self.test_model, self.model
 
 

@@ -701,6 +701,18 @@ class Model(Network):
             total, parts, mets = self._losses(self._forward(x, False), y)
         return self._result(total, parts, mets)
 
+    def evaluate(self, x=None, y=None, batch_size=32, verbose=1, sample_weight=None, steps=None):
+        xs = list(x) if isinstance(x, (list, tuple)) else [x]
+        ys = list(y) if isinstance(y, (list, tuple)) else [y]
+        n, acc = len(xs[0]), None
+        for i in range(0, n, batch_size or n):
+            r = self.test_on_batch([np.asarray(a)[i:i + batch_size] for a in xs], [np.asarray(t)[i:i + batch_size] for t in ys])
+            r = r if isinstance(r, list) else [r]
+            b = min(batch_size or n, n - i)
+            acc = [v * b for v in r] if acc is None else [a + v * b for a, v in zip(acc, r)]
+        out = [a / n for a in acc]
+        return out if len(out) > 1 else out[0]
+
     def loss_and_gradients(self, x, y, training=True):
         """(shim extension, used by the fixture generator) loss + d loss / d weight by name, no update"""
         params = self.unique_trainable_weights()

@@ -437,6 +437,118 @@ def run_cook_case(mods, data_dir, name, arch, score_model, my_arch, vtype):
     return out
 
 
+def run_reference_main(mods, command, cfg, variables_fn, P):
+    """Runs the reference's own command function (`main.train` / `main.cook`: its epoch loop, callbacks and evaluation
+    tail) and records what it logs.  Instrumentation only: the two logging helpers of utils.py are replaced by recorders,
+    and `task.get` hands back the handler with a tap on build_model that loads the seeded weights `P` after the first
+    build and fixes numpy's seed — main.py, task/*.py and the rest run unmodified."""
+    keras, settings, task = mods
+    import logging
+    import main as ref_main
+    import utils as ref_utils
+    records, taps = [], {}
+    orig_eval, orig_hist, orig_get = ref_utils.logging_evaluation, ref_utils.logging_history, task.get
+    ref_utils.logging_evaluation = lambda d: records.append(('evaluation', {k: float(v) for k, v in d.items()}))
+    ref_utils.logging_history = lambda h: records.append(('history', {k: [float(x) for x in v] for k, v in h.history.items()}))
+
+    def tapped_get(config):
+        h = orig_get(config)
+        build = h.build_model
+
+        def tapped_build(epoch):
+            m = build(epoch)
+            if epoch == 0:
+                taps['variables'] = variables_fn(h)
+                assign(taps['variables'], P)
+                np.random.seed(4711)
+            return m
+        h.build_model = tapped_build
+        taps['handler'] = h
+        return h
+    task.get = tapped_get
+    keras.backend.clear_session()
+    root = logging.getLogger()
+    level = root.level
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            getattr(ref_main, command).callback(**cfg)
+    finally:
+        ref_utils.logging_evaluation, ref_utils.logging_history, task.get = orig_eval, orig_hist, orig_get
+        for hd in list(root.handlers):
+            root.removeHandler(hd)
+        root.setLevel(level)
+    return taps['handler'], taps['variables'], records
+
+
+def _flatten_records(records):
+    """[(kind, dict)] -> arrays: kinds, keys joined by ',', values concatenated (history lists flattened)"""
+    kinds, keys, values, counts = [], [], [], []
+    for kind, d in records:
+        ks = sorted(d)
+        vals = []
+        for k in ks:
+            v = d[k]
+            vals += list(v) if isinstance(v, (list, tuple)) else [v]
+        kinds.append(kind)
+        keys.append(','.join(ks))
+        counts.append(len(vals))
+        values += vals
+    return dict(kinds=np.array(kinds), keys=np.array(keys), counts=np.array(counts, dtype=np.int64),
+                values=np.array(values, dtype=np.float64))
+
+
+def config_dict(data_dir, sh, task_name, arch, score_model, **extra):
+    """the keyword arguments click would hand to the command function: every option of main.py:98-146 + the group's paths"""
+    cfg = dict(task=task_name, arch=arch, round=6, days=30, epochs=2, batch_size=sh.B, training_step=3, validation_step=2,
+               validation_impression=5, testing_impression=5, learning_rate=0.001, learning_rate_decay=0.2, gain=1.0,
+               window_size=sh.W, dropout=0.0, negative_samples=sh.K, hidden_dim=400, nonlocal_negative_samples=0,
+               enable_baseline=False, title_filter_shape=(sh.F, sh.k), title_shape=sh.L, body_shape=sh.L,
+               user_embedding_dim=sh.U, textual_embedding_dim=sh.E, textual_embedding_trainable=False, debug=True,
+               background=True, name='', pretrain_name='', enable_pretrain_encoder=False, pretrain_encoder_trainable=False,
+               personal_embedding_dim=20, news_encoder='cnnatt', score_model=score_model, id_keep=1.0, body_sent_cnt=50,
+               body_sent_len=30, body_filter_shape=(400, 3), max_impression=200, max_impression_pos=7, max_impression_neg=200,
+               test_window_size=100, vertical_embedding_dim=15, subvertical_embedding_dim=35, use_vertical=False,
+               use_vertical_type='vs', use_generator=False, lrd_on_epochs=[1, 3], input_training_data_path=data_dir,
+               input_validation_data_path=data_dir, input_previous_model_path=data_dir, output_model_path=data_dir,
+               log_dir=data_dir)
+    cfg.update(extra)
+    return cfg
+
+
+def run_main_cases(mods, data_dir, cook_dir):
+    """`main.py train` on Seq2VecPaperSoftmaxId (LSTUR-ini) and `main.py cook` on Cook 'ingru', two epochs each"""
+    from mnexp_b200 import synth
+    out = {}
+    sh = synth.SHAPES['tiny']
+    P = synth.make_weights(sh, arch='igru', bias_noise=0.05, seed=4242, score_model='dot',
+                           word_emb=np.load(os.path.join(data_dir, 'Vocab.tsv.npy')))
+    cfg = config_dict(data_dir, sh, 'Seq2VecPaperSoftmaxId', 'igru', 'dot')
+    h, variables, records = run_reference_main(mods, 'train', cfg, named_variables, P)
+    for k, v in _flatten_records(records).items():
+        out['main-train/log_' + k] = v
+    for k, v in snapshot(variables).items():
+        out['main-train/final/' + k] = v
+    for k, v in P.items():
+        out['main-train/P/' + k] = np.asarray(v, dtype=np.float64)
+    csh = cook_shape('ddot', 'vs')
+    Pc = synth.make_weights(csh, arch='igru', bias_noise=0.05, seed=4242, score_model='ddot', cook=True, dv=COOK_DV, ds=COOK_DS,
+                            word_emb=np.load(os.path.join(cook_dir, 'Vocab.tsv.npy')))
+    cfg = config_dict(cook_dir, csh, 'Cook', 'ingru', 'ddot', use_vertical=True, use_vertical_type='vs', batch_size=8,
+                      vertical_embedding_dim=COOK_DV, subvertical_embedding_dim=COOK_DS, validation_step=6, lrd_on_epochs=[0])
+    h, variables, records = run_reference_main(mods, 'cook', cfg, cook_variables, Pc)
+    for k, v in _flatten_records(records).items():
+        out['main-cook/log_' + k] = v
+    for k, v in snapshot(variables).items():
+        out['main-cook/final/' + k] = v[:64] if k in ('user_emb', 'user_emb2') else v
+    for k, v in Pc.items():
+        out['main-cook/P/' + k] = np.asarray(v[:64] if k in ('user_emb', 'user_emb2') else v, dtype=np.float64)
+    feature, (users, imprs, mask, y_true) = h.test()
+    out['main-cook/test_users'], out['main-cook/test_imprs'] = np.asarray(users), np.asarray(imprs)
+    out['main-cook/test_mask'], out['main-cook/test_y_true'] = np.asarray(mask), np.asarray(y_true)
+    out['main-cook/test_y_pred'] = h.test_model.predict(feature, batch_size=8).reshape(-1)
+    return out
+
+
 def generate(path=OUT, verbose=True):
     mods = load_reference()
     from mnexp_b200 import synth
@@ -461,6 +573,10 @@ def generate(path=OUT, verbose=True):
             out[name + '/' + k] = v
         if verbose:
             print('%-24s %-24s loss %.6f  layers %d' % (name, 'Cook', float(res['loss']), len(res['layers'])))
+    out.update(run_main_cases(mods, data_dir, cook_dir))
+    if verbose:
+        for c in ('main-train', 'main-cook'):
+            print('%-12s %d logged records: %s' % (c, len(out[c + '/log_kinds']), ' | '.join(out[c + '/log_keys'][:6])))
     np.savez_compressed(path, **out)
     if verbose:
         print('wrote %d arrays to %s' % (len(out), path))

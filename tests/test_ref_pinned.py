@@ -458,3 +458,114 @@ def test_cuda_cook_matches_reference_graph(lib, name, precision):
     assert rel(h.test_model.predict(tx).reshape(g('test_predict').shape), g('test_predict')) < tol
     hist = model.fit(xm, ym, 24, epochs=3, initial_epoch=0, shuffle=False)
     assert np.abs(np.array(hist.history['loss']) - g('adam_losses')).max() < (1e-4 if precision == 'fp32' else 2e-3)
+
+
+# ---------------------------------------------------------------------------------------------- main.py loops
+def _records(prefix):
+    """[(kind, {key: value | [values]})] as the reference's main.py logged them (make_ref_golden.run_reference_main)"""
+    kinds, keys = [str(k) for k in GOLD[prefix + '/log_kinds']], [str(k) for k in GOLD[prefix + '/log_keys']]
+    counts, values = GOLD[prefix + '/log_counts'], GOLD[prefix + '/log_values']
+    out, pos = [], 0
+    for kind, ks, n in zip(kinds, keys, counts):
+        ks = ks.split(',')
+        vals = values[pos:pos + n]
+        pos += n
+        per = n // len(ks)
+        out.append((kind, {k: vals[i * per:(i + 1) * per] for i, k in enumerate(ks)}))
+    return out
+
+
+def _compare_records(got, ref, loss_tol, rank_tol):
+    assert [k for k, _ in got] == [k for k, _ in ref], ([k for k, _ in got], [k for k, _ in ref])
+    for (kind, a), (_, b) in zip(got, ref):
+        assert sorted(a) == sorted(b), (kind, sorted(a), sorted(b))
+        for k in b:
+            x, y = np.asarray(a[k], dtype=np.float64).reshape(-1), np.asarray(b[k], dtype=np.float64).reshape(-1)
+            if k == 'auc_roc':            # tf.metrics.auc: a streaming 200-bin approximation in the real thing (utils.py:84-96)
+                continue
+            tol = loss_tol if k.endswith('loss') else rank_tol if k in ('auc', 'mrr', 'ndcgv', 'ndcgx') else 1e-6
+            both_nan = np.isnan(x) & np.isnan(y)
+            assert np.all(both_nan | (np.abs(x - y) <= tol)), (kind, k, x, y)
+
+
+def _host_ranking_metrics(scores, labels):
+    """(n, 4) auc, ndcg@10, ndcg@5, mrr with the host formulas (sklearn + the utils.py mirrors)"""
+    from sklearn.metrics import roc_auc_score
+    from mnexp_b200 import utils as mu
+    return np.array([[roc_auc_score(y, s), mu.ndcg_score(y, s, 10), mu.ndcg_score(y, s, 5), mu.mrr_score(y, s)]
+                     for s, y in zip(scores, labels)])
+
+
+def test_evaluation_tail_matches_reference_main_cook():
+    """main.py:250-297 (per-user / per-impression / in-vocabulary / out-of-vocabulary averages, with the loop's edge
+    effects): evaluation.aggregate on the reference run's own predictions reproduces the eight lines it logged."""
+    from mnexp_b200 import evaluation
+    g = lambda k: GOLD['main-cook/' + k]
+    res = evaluation.aggregate(g('test_users'), g('test_imprs'), g('test_mask').reshape(-1), g('test_y_true'), g('test_y_pred'),
+                               metric_fn=_host_ranking_metrics)
+    got = []
+    evaluation.log_aggregate(res, lambda d: got.append(('evaluation', dict(d))))
+    ref = _records('main-cook')[-8:]
+    _compare_records(got, ref, 1e-9, 1e-6)              # y_pred is stored as float32
+
+
+def _load_paper_weights(prefix):
+    def on_build(h):
+        P = {k[len(prefix) + 3:]: GOLD[k] for k in GOLD.files if k.startswith(prefix + '/P/')}
+        _set_weights(h.model, P)
+        np.random.seed(4711)
+    return on_build
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('precision', ['fp32', 'fp16_tc'])
+def test_cuda_main_train_loop_matches_reference(lib, precision):
+    """`main.py train` on Seq2VecPaperSoftmaxId / igru, two epochs of three steps: fit_generator histories, the callback's
+    per-impression AUC / nDCG / MRR (validation and final test impressions), evaluate_generator — every logged number."""
+    from mnexp_b200 import main as mmain
+    d = tempfile.mkdtemp()
+    synth.write_dataset(d, SH)
+    cfg = settings.Config(dict(task='Seq2VecPaperSoftmaxId', arch='igru', score_model='dot', input_training_data_path=d,
+                               title_shape=SH.L, window_size=SH.W, negative_samples=SH.K, batch_size=SH.B,
+                               textual_embedding_dim=SH.E, title_filter_shape=(SH.F, SH.k), user_embedding_dim=SH.U, debug=True,
+                               dropout=0.0, precision=precision, validation_impression=5, testing_impression=5, epochs=2,
+                               training_step=3, validation_step=2, learning_rate=0.001, learning_rate_decay=0.2,
+                               sparse_user_adam=False))
+    h, got = mmain.train(cfg, on_build=_load_paper_weights('main-train'))
+    _compare_records(got, _records('main-train'), 1e-4 if precision == 'fp32' else 2e-3, 1e-6 if precision == 'fp32' else 0.2)
+    if precision == 'fp32':
+        w = _get_weights(h.model if hasattr(h.model, 'WEIGHT_ORDER') else h.test_model)
+        d = np.concatenate([np.abs(np.asarray(v, dtype=np.float64).reshape(-1) - GOLD['main-train/final/' + k].reshape(-1))
+                            for k, v in w.items()])
+        assert np.mean(d > 5e-5) <= 2e-3 and d.max() <= 2.02e-3 * 6, (float(d.max()), float(np.mean(d > 5e-5)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('precision', ['fp32', 'fp16_tc'])
+def test_cuda_main_cook_loop_matches_reference(lib, precision):
+    """`main.py cook` on Cook / ingru / ddot, two epochs of three shuffled batches: fit histories, test_model.evaluate, the
+    learning-rate decay of callback(0), and the eight aggregated evaluation lines of the scored test set."""
+    from mnexp_b200 import main as mmain
+    sh = mk.cook_shape('ddot', 'vs')
+    d = tempfile.mkdtemp()
+    synth.write_cook_npz(d, sh)
+    cfg = settings.Config(dict(task='Cook', arch='ingru', input_training_data_path=d, days=30, window_size=sh.W, batch_size=8,
+                               title_filter_shape=(sh.F, 3), user_embedding_dim=sh.U, dropout=0.0, score_model='ddot',
+                               use_vertical=True, use_vertical_type='vs', vertical_embedding_dim=mk.COOK_DV,
+                               subvertical_embedding_dim=mk.COOK_DS, precision=precision, validation_step=6, epochs=2,
+                               lrd_on_epochs=[0], learning_rate=0.001, learning_rate_decay=0.2, id_keep=1.0,
+                               sparse_user_adam=False))
+
+    def on_build(h):
+        P = {}
+        for k, v in h.params.items():
+            ref = np.asarray(GOLD['main-cook/P/' + k], dtype=np.float32)
+            if k in ('user_emb', 'user_emb2'):
+                full = np.zeros(np.asarray(v).shape, dtype=np.float32)
+                full[:len(ref)] = ref
+                ref = full
+            P[k] = ref.reshape(np.asarray(v).shape)
+        h.params = P
+        np.random.seed(4711)
+    h, got = mmain.cook(cfg, on_build=on_build)
+    _compare_records(got, _records('main-cook'), 1e-4 if precision == 'fp32' else 2e-3, 1e-6 if precision == 'fp32' else 0.35)
