@@ -222,11 +222,27 @@ def write_clickdata_tsv(path, n_users, n_news, rng, max_imp=4, n_neg=8):
     """ClickData.tsv: column 2 = training impressions, column 3 = validation impressions, each
     ``pos#TAB#neg#TAB#time`` joined by ``#N#`` (task/paper.py:7-35)."""
     cdf = _zipf_cdf(n_news, 1.05)
+
+    def distinct(k):
+        """k different documents (Zipf draws, first occurrences): the candidates of one impression.  A document listed
+        twice gets two identical scores, and the order numpy's argsort leaves ties in — which utils.mrr_score / ndcg_score
+        depend on (utils.py:106-124) — changed between numpy releases (stable insertion sort for short arrays in 1.x, SIMD
+        sorts in 2.x), so impressions with repeated documents have no well-defined reference value."""
+        out = []
+        while len(out) < k:
+            for d in _zipf_sample(rng, cdf, 2 * k) + 1:
+                if d not in out:
+                    out.append(int(d))
+                    if len(out) == k:
+                        break
+        return out
+
     def imps(k):
         out = []
         for i in range(k):
-            pos = _zipf_sample(rng, cdf, rng.integers(1, 3)) + 1
-            neg = _zipf_sample(rng, cdf, n_neg) + 1
+            n_pos = int(rng.integers(1, 3))
+            docs = distinct(n_pos + n_neg)
+            pos, neg = docs[:n_pos], docs[n_pos:]
             out.append('%s#TAB#%s#TAB#01/%02d/2019 %02d:%02d:00 PM' % (' '.join(map(str, pos)), ' '.join(map(str, neg)),
                                                                     1 + i % 28, 1 + i % 12, i % 60))
         return '#N#'.join(out)
@@ -247,6 +263,32 @@ def write_dataset(dirname, shape, seed=7):
     write_docmeta_tsv(os.path.join(dirname, 'DocMeta.tsv'), tok, vert, subvert)
     write_clickdata_tsv(os.path.join(dirname, 'ClickData.tsv'), shape.n_users, shape.n_news, rng)
     return emb, tok
+
+
+def write_pipeline_files(dirname, tok, W, n_docs=40, n_users=11, seed=3):
+    """docs.tsv / UserClick.tsv / userDocPair.tsv of the decomposed scoring pipeline (settings.py pipeline_inputs,
+    task/test_pipeline.py:18-24, 72-79, 152-160): `doc \\t title tokens`, `user id \\t user type \\t clicks joined by #N#`,
+    `user id \\t user type \\t doc`.  One user clicks a document that is not in docs.tsv (stays a zero vector), one pair names
+    an unknown user (skipped)."""
+    import os
+    g = np.random.default_rng(seed)
+    os.makedirs(dirname, exist_ok=True)
+    docs = list(range(1, min(n_docs, tok.shape[0] - 1) + 1))
+    with open(os.path.join(dirname, 'docs.tsv'), 'w') as f:
+        for d in docs:
+            toks = [int(x) for x in tok[d] if x != 0] or [1]
+            f.write('d%d\t%s\n' % (d, ' '.join(map(str, toks))))
+    with open(os.path.join(dirname, 'UserClick.tsv'), 'w') as f:
+        for u in range(n_users):
+            clicks = ['d%d' % docs[i] for i in g.integers(0, len(docs), g.integers(1, W + 3))]
+            if u == 3:
+                clicks.append('d_unknown')
+            f.write('%d\tx\t%s\n' % (u, '#N#'.join(clicks)))
+    with open(os.path.join(dirname, 'userDocPair.tsv'), 'w') as f:
+        for u in range(n_users):
+            for d in g.integers(0, len(docs), 3):
+                f.write('%d\tx\td%d\n' % (u, docs[d]))
+        f.write('999\tx\td%d\n' % docs[0])
 
 
 def write_cook_npz(dirname, shape, n_train=24, n_test=30, seed=0, days=30):

@@ -30,7 +30,8 @@ class TestPipeline:
             handler = task.get(self.config)
             handler.build_model(0)
         self.handler = handler
-        self.model = handler.test_model
+        # the scoring graph: `test_model` of the softmax classes; the sigmoid family's `model` already is one (task/paper.py:228-256)
+        self.model = getattr(handler, 'test_model', None) or handler.model
         self._core = handler._core
         self.score_encoder = None
 
@@ -112,9 +113,18 @@ class TestPipeline:
         print(len(undoc))
 
     def get_score_encoder(self):
-        """'dot' scorer (TestPipelineProduct, :268-283): (user_vec, doc_vec) -> u . d"""
+        """(user_vec, doc_vec) -> raw score.  TestPipeline (task/test_pipeline.py:133-150): the model's own scorer without its
+        final sigmoid — Dense(1)(concat_dense([u ; d])) of the sigmoid family (task/paper.py:222-226), rebuilt from the
+        'concat_dense' / 'socre_dense' weights; TestPipelineProduct (:268-283) and the 'dot' models: u . d.  A few thousand
+        pairs per call on the host in float64, like the reference's own last stage."""
         if self.score_encoder is None:
-            self.score_encoder = lambda u, d: np.sum(np.asarray(u, np.float64) * np.asarray(d, np.float64), -1, keepdims=True)
+            f8 = lambda a: np.asarray(a, np.float64)
+            if self._core.score_model == 'dnn' and not isinstance(self, TestPipelineProduct):
+                w = self.model._current()
+                sh_w, sh_b, so_w, so_b = f8(w['sh_w']), f8(w['sh_b']), f8(w['so_w']), f8(w['so_b'])
+                self.score_encoder = lambda u, d: np.maximum(np.concatenate([f8(u), f8(d)], -1) @ sh_w + sh_b, 0.0) @ so_w + so_b
+            else:
+                self.score_encoder = lambda u, d: np.sum(f8(u) * f8(d), -1, keepdims=True)
         return self.score_encoder
 
     def test_user_doc_score(self):

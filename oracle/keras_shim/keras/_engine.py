@@ -417,6 +417,18 @@ class InputLayer(Layer):
         node.outputs = [Sym(node, 0, ex, None, name=self.name)]
         self._inbound_nodes.append(node)
 
+    @property
+    def input_shape(self):
+        return self.batch_input_shape
+
+    @property
+    def output_shape(self):
+        return self.batch_input_shape
+
+    @property
+    def input(self):
+        return self._inbound_nodes[0].outputs[0]
+
 
 def Input(shape=None, batch_shape=None, name=None, dtype=None, sparse=False, tensor=None):
     if shape is None:

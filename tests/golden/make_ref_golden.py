@@ -113,7 +113,10 @@ def _uid(layer):
 
 def named_variables(h):
     """this repo's parameter name -> the reference model's weight variable, found by walking the reference's own graph"""
-    model = h.model
+    return named_variables_of(h.model, h)
+
+
+def named_variables_of(model, h):
     doc = model.get_layer('doc_encoder')
     ue = model.get_layer('user_encoder') if any(l.name == 'user_encoder' for l in model.layers) else None
     out = {}
@@ -459,7 +462,7 @@ def run_reference_main(mods, command, cfg, variables_fn, P):
             m = build(epoch)
             if epoch == 0:
                 taps['variables'] = variables_fn(h)
-                assign(taps['variables'], P)
+                assign(taps['variables'], P if P is not None else variables_fn.P)
                 np.random.seed(4711)
             return m
         h.build_model = tapped_build
@@ -469,6 +472,7 @@ def run_reference_main(mods, command, cfg, variables_fn, P):
     keras.backend.clear_session()
     root = logging.getLogger()
     level = root.level
+    np.random.seed(4710)            # handlers may draw at construction (VertAlt shuffles its document split there)
     try:
         with contextlib.redirect_stdout(io.StringIO()):
             getattr(ref_main, command).callback(**cfg)
@@ -530,6 +534,30 @@ def run_main_cases(mods, data_dir, cook_dir):
         out['main-train/final/' + k] = v
     for k, v in P.items():
         out['main-train/P/' + k] = np.asarray(v, dtype=np.float64)
+    # the alternating schedule of ...VertAlt (task/paper.py:1003-1135): round = 3 -> two epochs of the vertical model, one of
+    # the click model.  list(set(...)) orders the verticals by string hash, so the classifier columns are stored BY NAME
+    import utils as ref_utils
+    names = sorted(set(l.split('\t')[2] for l in open(os.path.join(data_dir, 'DocMeta.tsv'))))
+    Pv = synth.make_weights(sh, arch='igru', bias_noise=0.05, seed=4242, score_model='dot', vertalt=len(names),
+                            word_emb=np.load(os.path.join(data_dir, 'Vocab.tsv.npy')))
+
+    def vertalt_variables(h):
+        v = named_variables_of(h.seq_model, h)
+        dense = h.vert_model.layers[-1]
+        v['vcls_w'], v['vcls_b'] = dense.kernel, dense.bias
+        order = [names.index(n) for n in h.verticals]           # reference column j <- vertical h.verticals[j]
+        vertalt_variables.P = dict(Pv, vcls_w=Pv['vcls_w'][:, order], vcls_b=Pv['vcls_b'][order])
+        return v
+    cfg = config_dict(data_dir, sh, 'Seq2VecPaperSoftmaxDaysIdVertAlt', 'igru', 'dot', days=3, round=3, epochs=1)
+    h, variables, records = run_reference_main(mods, 'train', cfg, vertalt_variables, None)
+    for k, v in _flatten_records(records).items():
+        out['main-vertalt/log_' + k] = v
+    inv = [h.verticals.index(n) for n in names]                 # back to name order
+    for k, v in snapshot(variables).items():
+        out['main-vertalt/final/' + k] = v[:, inv] if k == 'vcls_w' else v[inv] if k == 'vcls_b' else v
+    for k, v in Pv.items():
+        out['main-vertalt/P/' + k] = np.asarray(v, dtype=np.float64)
+    out['main-vertalt/vertical_names'] = np.array(names)
     csh = cook_shape('ddot', 'vs')
     Pc = synth.make_weights(csh, arch='igru', bias_noise=0.05, seed=4242, score_model='ddot', cook=True, dv=COOK_DV, ds=COOK_DS,
                             word_emb=np.load(os.path.join(cook_dir, 'Vocab.tsv.npy')))
@@ -546,6 +574,51 @@ def run_main_cases(mods, data_dir, cook_dir):
     out['main-cook/test_users'], out['main-cook/test_imprs'] = np.asarray(users), np.asarray(imprs)
     out['main-cook/test_mask'], out['main-cook/test_y_true'] = np.asarray(mask), np.asarray(y_true)
     out['main-cook/test_y_pred'] = h.test_model.predict(feature, batch_size=8).reshape(-1)
+    return out
+
+
+PIPELINE_CASES = [('pipe-dnn', 'TestPipeline', 'Seq2VecPaper', 'gru', 'dnn', 'nigru'),
+                  ('pipe-dot', 'TestPipelineProduct', 'Seq2VecPaperDot', 'gru', 'dot', 'nigru')]
+
+
+def run_pipeline_case(mods, data_dir, name, pipe_class, task_name, arch, score_model, my_arch):
+    """the decomposed scoring pipeline (task/test_pipeline.py): doc vectors once, user vectors from cached doc vectors,
+    pair scores, and its own self-check test_correct().  `load_model` (a Keras json + pkl round trip) is replaced by
+    handing the pipeline the model object the reference's own _build_model assembled; the stages run unmodified."""
+    keras, settings, task = mods
+    from mnexp_b200 import synth
+    sh = synth.SHAPES['tiny']
+    keras.backend.clear_session()
+    pipe_dir = tempfile.mkdtemp(prefix='refgold_pipe_')
+    tok, _, _ = synth.make_docs(sh.n_news, sh.L, sh.vocab, 8)          # the documents write_dataset(seed=7) wrote
+    synth.write_pipeline_files(pipe_dir, tok, sh.W)
+    cfg = reference_config(settings, data_dir, sh, task_name, arch, score_model, gain=GAIN, pipeline_input=pipe_dir, name='t')
+    h = task.get(cfg)
+    h.build_model(0)
+    variables = named_variables(h)
+    P = synth.make_weights(sh, arch=my_arch, bias_noise=0.05, seed=4242, score_model=score_model,
+                           word_emb=np.load(os.path.join(data_dir, 'Vocab.tsv.npy')))
+    if score_model == 'dot':
+        P = {k: v for k, v in P.items() if not k.startswith(('sh_', 'so_'))}
+    assign(variables, P)
+    tp = getattr(task, pipe_class)(cfg)
+    tp.model, tp.score_encoder = h.model, None
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        tp.test_doc_vec()
+        tp.test_user_vec()
+        tp.test_user_doc_score()
+        tp.test_correct()
+    out = {'P/' + k: v for k, v in snapshot(variables).items()}
+    docs, users = sorted(tp.doc_vec), sorted(tp.user_vec)
+    out['doc_keys'], out['doc_vecs'] = np.array(docs), np.stack([tp.doc_vec[d] for d in docs])
+    out['user_keys'], out['user_vecs'] = np.array(users), np.stack([tp.user_vec[u] for u in users])
+    lines = [l.rstrip('\n').split('\t') for l in open(cfg.pipeline_output)]
+    out['score_rows'] = np.array(['\t'.join(l[:3]) for l in lines])
+    out['scores'] = np.array([float(l[3]) for l in lines])
+    out['stdout'] = np.array(buf.getvalue())
+    nums = [float(v) for v in buf.getvalue().replace('[', ' ').replace(']', ' ').split()]
+    out['undoc'], out['pred'], out['sigm'] = np.int64(nums[0]), np.float64(nums[1]), np.float64(nums[2])
     return out
 
 
@@ -573,9 +646,17 @@ def generate(path=OUT, verbose=True):
             out[name + '/' + k] = v
         if verbose:
             print('%-24s %-24s loss %.6f  layers %d' % (name, 'Cook', float(res['loss']), len(res['layers'])))
+    out['pipeline_table'] = np.array([list(c) for c in PIPELINE_CASES])
+    for c in PIPELINE_CASES:
+        res = run_pipeline_case(mods, data_dir, *c)
+        for k, v in res.items():
+            out[c[0] + '/' + k] = v
+        if verbose:
+            print('%-12s %-20s %d docs, %d users, %d scored pairs; test_correct %.8f vs %.8f' % (
+                c[0], c[1], len(res['doc_keys']), len(res['user_keys']), len(res['scores']), res['pred'], res['sigm']))
     out.update(run_main_cases(mods, data_dir, cook_dir))
     if verbose:
-        for c in ('main-train', 'main-cook'):
+        for c in ('main-train', 'main-vertalt', 'main-cook'):
             print('%-12s %d logged records: %s' % (c, len(out[c + '/log_kinds']), ' | '.join(out[c + '/log_keys'][:6])))
     np.savez_compressed(path, **out)
     if verbose:

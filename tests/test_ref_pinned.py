@@ -531,6 +531,7 @@ def test_cuda_main_train_loop_matches_reference(lib, precision):
                                dropout=0.0, precision=precision, validation_impression=5, testing_impression=5, epochs=2,
                                training_step=3, validation_step=2, learning_rate=0.001, learning_rate_decay=0.2,
                                sparse_user_adam=False))
+    np.random.seed(4710)
     h, got = mmain.train(cfg, on_build=_load_paper_weights('main-train'))
     _compare_records(got, _records('main-train'), 1e-4 if precision == 'fp32' else 2e-3, 1e-6 if precision == 'fp32' else 0.2)
     if precision == 'fp32':
@@ -567,5 +568,109 @@ def test_cuda_main_cook_loop_matches_reference(lib, precision):
             P[k] = ref.reshape(np.asarray(v).shape)
         h.params = P
         np.random.seed(4711)
+    np.random.seed(4710)
     h, got = mmain.cook(cfg, on_build=on_build)
     _compare_records(got, _records('main-cook'), 1e-4 if precision == 'fp32' else 2e-3, 1e-6 if precision == 'fp32' else 0.35)
+
+
+# ---------------------------------------------------------------------------------------------- decomposed pipeline (C4)
+PIPE = {row[0]: tuple(row[1:]) for row in GOLD['pipeline_table']}
+
+
+def _pipe_inputs():
+    """what synth.write_pipeline_files wrote for the reference run: doc tokens, per-user click lists, pairs"""
+    d = tempfile.mkdtemp()
+    tok, _, _ = synth.make_docs(SH.n_news, SH.L, SH.vocab, 8)
+    synth.write_pipeline_files(d, tok, SH.W)
+    return d, tok
+
+
+@pytest.mark.parametrize('name', sorted(PIPE))
+def test_oracle_matches_reference_pipeline(name):
+    """task/test_pipeline.py run by the reference: doc vectors, user vectors built from CACHED doc vectors (unknown
+    documents stay zero, newest click last), raw pair scores — against the oracle on the same files and weights."""
+    pipe_class, task_name, arch, score_model, my_arch = PIPE[name]
+    g = lambda k: GOLD[name + '/' + k]
+    P = {k: GOLD[name + '/P/' + k] for k in P_KEYS if name + '/P/' + k in GOLD.files}
+    d, tok = _pipe_inputs()
+    doc_ids = {str(k): int(str(k)[1:]) for k in g('doc_keys')}
+    dv = on.news_encoder(np.stack([tok[doc_ids[str(k)]] for k in g('doc_keys')]), P)
+    assert rel(dv, g('doc_vecs')) < F64
+    vec = {str(k): v for k, v in zip(g('doc_keys'), dv)}
+    users = {}
+    for line in open(os.path.join(d, 'UserClick.tsv')):
+        uid, ut, clicks = line.rstrip('\n').split('\t')
+        H = np.zeros((SH.W, dv.shape[1]))
+        clicks = clicks.split('#N#')
+        for i in range(-1, -1 - min(len(clicks), SH.W), -1):
+            if clicks[i] in vec:
+                H[i] = vec[clicks[i]]
+        users[uid + ut] = on.user_encoder(my_arch, np.zeros(1, dtype=int), H[None], P)[0]
+    uv = np.stack([users[str(k)] for k in g('user_keys')])
+    assert rel(uv, g('user_vecs')) < F64
+    for row, sc in zip(g('score_rows'), g('scores')):
+        uid, ut, doc = str(row).split('\t')
+        s = on.score(users[uid + ut][None], vec[doc][None, None], P, score_model)[0, 0]
+        assert abs(s - sc) < 1e-9
+    assert abs(float(g('pred')) - float(g('sigm'))) < 1e-7 and int(g('undoc')) == 1          # the reference's own self-check
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('precision', ['fp32', 'fp16_tc'])
+@pytest.mark.parametrize('name', sorted(PIPE))
+def test_cuda_pipeline_matches_reference(lib, name, precision):
+    from mnexp_b200.task.test_pipeline import TestPipeline, TestPipelineProduct
+    pipe_class, task_name, arch, score_model, my_arch = PIPE[name]
+    g = lambda k: GOLD[name + '/' + k]
+    tol = 2e-5 if precision == 'fp32' else 1e-3
+    pd, _ = _pipe_inputs()
+    dd = tempfile.mkdtemp()
+    synth.write_dataset(dd, SH)
+    cfg = settings.Config(dict(task=task_name, arch=arch, score_model=score_model, input_training_data_path=dd,
+                               title_shape=SH.L, window_size=SH.W, negative_samples=SH.K, batch_size=SH.B,
+                               textual_embedding_dim=SH.E, title_filter_shape=(SH.F, SH.k), user_embedding_dim=SH.U, debug=True,
+                               dropout=0.0, precision=precision, gain=float(GOLD['gain']), pipeline_input=pd, name='t'))
+    h = task.get(cfg)
+    model = h.build_model(0)
+    _set_weights(model, {k: GOLD[name + '/P/' + k] for k in P_KEYS if name + '/P/' + k in GOLD.files})
+    tp = (TestPipelineProduct if pipe_class == 'TestPipelineProduct' else TestPipeline)(cfg)
+    tp.load_model(h)
+    tp.test_doc_vec()
+    tp.test_user_vec()
+    tp.test_user_doc_score()
+    assert sorted(tp.doc_vec) == sorted(str(k) for k in g('doc_keys')) and sorted(tp.user_vec) == sorted(str(k) for k in g('user_keys'))
+    assert rel(np.stack([tp.doc_vec[str(k)] for k in g('doc_keys')]), g('doc_vecs')) < tol
+    assert rel(np.stack([tp.user_vec[str(k)] for k in g('user_keys')]), g('user_vecs')) < tol
+    lines = [l.rstrip('\n').split('\t') for l in open(cfg.pipeline_output)]
+    assert ['\t'.join(l[:3]) for l in lines] == [str(r) for r in g('score_rows')]
+    got = np.array([float(l[3]) for l in lines])
+    assert np.abs(got - g('scores')).max() <= tol * max(1.0, np.abs(g('scores')).max())
+    pred, sigm = tp.test_correct()
+    assert abs(float(np.asarray(pred).reshape(-1)[0]) - float(g('pred'))) < tol
+    assert abs(float(np.asarray(sigm).reshape(-1)[0]) - float(g('sigm'))) < tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('precision', ['fp32', 'fp16_tc'])
+def test_cuda_main_vertalt_schedule_matches_reference(lib, precision):
+    """`main.py train` on Seq2VecPaperSoftmaxDaysIdVertAlt with round = 3 (task/paper.py:1003-1135): two epochs of the
+    vertical classifier on the shared doc encoder (its own document split, steps and learning-rate decay), then one epoch
+    of the click model with the callback's evaluation — the reference's whole log."""
+    from mnexp_b200 import main as mmain
+    d = tempfile.mkdtemp()
+    synth.write_dataset(d, SH)
+    cfg = settings.Config(dict(task='Seq2VecPaperSoftmaxDaysIdVertAlt', arch='igru', score_model='dot', input_training_data_path=d,
+                               title_shape=SH.L, window_size=SH.W, negative_samples=SH.K, batch_size=SH.B, days=3, round=3,
+                               textual_embedding_dim=SH.E, title_filter_shape=(SH.F, SH.k), user_embedding_dim=SH.U, debug=True,
+                               dropout=0.0, precision=precision, validation_impression=5, testing_impression=5, epochs=1,
+                               training_step=3, validation_step=2, learning_rate=0.001, learning_rate_decay=0.2,
+                               sparse_user_adam=False))
+
+    def on_build(h):
+        assert list(h.verticals) == [str(n) for n in GOLD['main-vertalt/vertical_names']]
+        P = {k[len('main-vertalt/P/'):]: GOLD[k] for k in GOLD.files if k.startswith('main-vertalt/P/')}
+        _set_weights(h.seq_model, P)
+        np.random.seed(4711)
+    np.random.seed(4710)
+    h, got = mmain.train(cfg, on_build=on_build)
+    _compare_records(got, _records('main-vertalt'), 1e-4 if precision == 'fp32' else 2e-3, 1e-6 if precision == 'fp32' else 0.35)
