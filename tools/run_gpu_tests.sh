@@ -3,7 +3,7 @@
 # logs under gpurun_out/.  Usage: tools/run_gpu_tests.sh [file ...]
 mkdir -p gpurun_out
 files="$@"
-if [ -z "$files" ]; then files=$(ls tests/test_gpu_*.py); fi
+if [ -z "$files" ]; then files="$(ls tests/test_gpu_*.py) tests/test_ref_pinned.py"; fi
 rc=0
 for f in $files; do
   name=$(basename $f .py)
