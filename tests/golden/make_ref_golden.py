@@ -577,6 +577,56 @@ def run_main_cases(mods, data_dir, cook_dir):
     return out
 
 
+# ---- one case at the layer widths of the benchmark (BASELINE.json configs: E300 F400 U200 L30 W50 K4), small tables and
+# batch: the tensor-core kernels run their real tile shapes against the reference's own graph.  Weights are re-drawn from
+# the same seed by the test (synth.make_weights), big gradients are stored as strided samples.
+WIDE_STRIDE = 97
+
+
+def wide_shape():
+    from mnexp_b200 import synth
+    return synth.Shape('wide', 300, 400, 2000, L=30, W=50, K=4, B=16, E=300, F=400, U=200)
+
+
+def wide_weights(sh, word_emb):
+    from mnexp_b200 import synth
+    return synth.make_weights(sh, arch='igru', bias_noise=0.05, seed=777, score_model='dot', word_emb=word_emb)
+
+
+def run_wide_case(mods):
+    keras, settings, task = mods
+    from mnexp_b200 import synth
+    keras.backend.clear_session()
+    sh = wide_shape()
+    data_dir = tempfile.mkdtemp(prefix='refgold_wide_')
+    synth.write_dataset(data_dir, sh, seed=17)
+    cfg = reference_config(settings, data_dir, sh, 'Seq2VecPaperSoftmaxId', 'igru', 'dot')
+    h = task.get(cfg)
+    model = h.build_model(0)
+    variables = named_variables(h)
+    P = wide_weights(sh, np.load(os.path.join(data_dir, 'Vocab.tsv.npy')))
+    assign(variables, P)
+    np.random.seed(20190131)
+    x, y = next(h.train)
+    out = {'x%d' % i: np.asarray(a).astype(np.int32) for i, a in enumerate(x)}
+    out['y'] = np.asarray(y).astype(np.float32)
+    out['predict'] = model.predict(x)
+    out['test_predict'] = h.test_model.predict(list(x[:2]) + [x[-1]])
+    ue = model.get_layer('user_encoder')
+    out['user_vec'] = keras.Model(model.inputs[:2], ue._inbound_nodes[0].outputs[0]).predict(list(x[:2]))
+    out['cand_vec0'] = model.get_layer('doc_encoder').predict(x[2])
+    loss, grads = model.loss_and_gradients(x, y, training=True)
+    out['loss'] = np.float64(loss)
+    by_var = {v.vname: k for k, v in variables.items()}
+    for vname, g in grads.items():
+        k = by_var[vname]
+        g = g.reshape(-1)
+        out['grad/' + k] = g if g.size <= 4096 else g[::WIDE_STRIDE]
+        out['gradnorm/' + k] = np.float64(np.abs(g).max())
+    out['adam_losses'] = np.asarray([model.train_on_batch(x, y)[0] for _ in range(3)], dtype=np.float64)
+    return out
+
+
 PIPELINE_CASES = [('pipe-dnn', 'TestPipeline', 'Seq2VecPaper', 'gru', 'dnn', 'nigru'),
                   ('pipe-dot', 'TestPipelineProduct', 'Seq2VecPaperDot', 'gru', 'dot', 'nigru')]
 
@@ -646,6 +696,11 @@ def generate(path=OUT, verbose=True):
             out[name + '/' + k] = v
         if verbose:
             print('%-24s %-24s loss %.6f  layers %d' % (name, 'Cook', float(res['loss']), len(res['layers'])))
+    res = run_wide_case(mods)
+    for k, v in res.items():
+        out['wide/' + k] = v
+    if verbose:
+        print('%-12s E300 F400 U200 L30 W50 B16: loss %.6f, adam losses %s' % ('wide', float(res['loss']), res['adam_losses']))
     out['pipeline_table'] = np.array([list(c) for c in PIPELINE_CASES])
     for c in PIPELINE_CASES:
         res = run_pipeline_case(mods, data_dir, *c)
