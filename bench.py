@@ -133,7 +133,8 @@ def cpu_reference_run(sh, steps, warmup, sample_B, threads=None, trainable_emb=F
     return dict(value=sample_B * len(times) / t, unit=UNIT, cores=threads, kind='port', batch=sample_B,
                 sample='%d steps of %d impressions (NOT the GPU arm\'s batch) of workload %s: same tables / shapes, dropout 0.2, '
                        'dense Keras-Adam on every tensor incl. the %d x %d user table (reference semantics); torch-CPU fp32 '
-                       'restatement of the Keras graph' % (len(times), sample_B, sh.name, sh.n_users, sh.U),
+                       'restatement of the Keras graph (reproduces the reference\'s own code, run over oracle/keras_shim, to 1e-9: '
+                       'tests/test_ref_pinned.py)' % (len(times), sample_B, sh.name, sh.n_users, sh.U),
                 ms_per_step=1e3 * t / len(times))
 
 
