@@ -61,6 +61,10 @@ CASES = [
     ('pid-iigru', 'Seq2VecPaperId', 'iigru', 'dnn', 'iicat', {'gain': GAIN}),
     ('p-gru', 'Seq2VecPaper', 'gru', 'dnn', 'nigru', {'gain': GAIN}),
     ('pdot-gru', 'Seq2VecPaperDot', 'gru', 'dot', 'nigru', {'gain': GAIN}),
+    ('p-att', 'Seq2VecPaper', 'att', 'dnn', 'att', {'gain': GAIN}),
+    ('p-avg', 'Seq2VecPaper', 'avg', 'dnn', 'niavg', {'gain': GAIN}),
+    ('pid-gru', 'Seq2VecPaperId', 'gru', 'dnn', 'ngru', {'gain': GAIN}),
+    ('pid-vo', 'Seq2VecPaperId', 'vo', 'dnn', 'vo', {'gain': GAIN}),
     # time-window batchers (task/paper.py:667-790) and the vertical variants (:793-1001, :1136-1255)
     ('sdays-gru-dot', 'Seq2VecPaperSoftmaxDays', 'gru', 'dot', 'nigru', {'days': 3}),
     ('sdid-igru-dot', 'Seq2VecPaperSoftmaxDaysId', 'igru', 'dot', 'igru', {'days': 3}),
