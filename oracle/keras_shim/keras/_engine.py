@@ -425,6 +425,9 @@ class InputLayer(Layer):
     def output_shape(self):
         return self.batch_input_shape
 
+    def get_config(self):
+        return {'batch_input_shape': list(self.batch_input_shape), 'dtype': self.dtype, 'sparse': False, 'name': self.name}
+
     @property
     def input(self):
         return self._inbound_nodes[0].outputs[0]
@@ -590,22 +593,39 @@ class Network(Layer):
 
     # -- serialisation of utils.save_model / load_model (json + pkl): class names, configs and connectivity
     def get_config(self):
-        cfg = {'name': self.name, 'layers': [], 'input_layers': [[s.node.layer.name, 0, 0] for s in self.inputs],
-               'output_layers': [[s.node.layer.name, s.node.layer._inbound_nodes.index(s.node), s.idx] for s in self.outputs]}
+        # Network.get_config: node indices are re-counted over the nodes that belong to THIS network (node_conversion_map)
         mine = {id(n) for n in self._nodes}
+        conv = {}
+        for layer in self.layers:
+            kept = 0
+            for i, n in enumerate(layer._inbound_nodes):
+                if id(n) in mine:
+                    conv[id(n)] = kept
+                    kept += 1
+        cfg = {'name': self.name, 'layers': []}
         for layer in self.layers:
             nodes = []
             for n in layer._inbound_nodes:
                 if id(n) in mine and n.inputs:
-                    nodes.append([[s.node.layer.name, s.node.layer._inbound_nodes.index(s.node), s.idx, {}] for s in n.inputs])
+                    nodes.append([[s.node.layer.name, conv[id(s.node)], s.idx, {}] for s in n.inputs])
             cfg['layers'].append({'name': layer.name, 'class_name': layer.__class__.__name__, 'config': layer.get_config(),
                                   'inbound_nodes': nodes})
+        cfg['input_layers'] = [[s.node.layer.name, 0, 0] for s in self.inputs]
+        cfg['output_layers'] = [[s.node.layer.name, conv[id(s.node)], s.idx] for s in self.outputs]
         return cfg
 
     def to_json(self, **kw):
         import json
+        def plain(o):
+            if isinstance(o, tuple):
+                return list(o)
+            if isinstance(o, (np.integer,)):
+                return int(o)
+            if isinstance(o, (np.floating,)):
+                return float(o)
+            raise TypeError('Not JSON Serializable: %r' % (o,))
         return json.dumps({'class_name': self.__class__.__name__, 'config': self.get_config(), 'keras_version': '2.2.4',
-                           'backend': 'tensorflow'}, default=lambda o: repr(o), **kw)
+                           'backend': 'tensorflow'}, default=plain, **kw)
 
 
 class Model(Network):

@@ -135,6 +135,60 @@ class Lambda(Layer):
     def compute_mask(self, inputs, mask=None):
         return self.mask(inputs, mask) if callable(self.mask) else self.mask
 
+    def get_config(self):
+        # layers/core.py: a python lambda travels as its marshalled bytecode (utils/generic_utils.func_dump), a named function
+        # by name; only readable by the same python version — true of Keras too
+        if getattr(self.function, '__name__', '') == '<lambda>':
+            function, function_type = func_dump(self.function), 'lambda'
+        else:
+            function, function_type = self.function.__name__, 'function'
+        return dict(super().get_config(), function=function, function_type=function_type, output_shape=None,
+                    output_shape_type='raw', arguments=self.arguments)
+
+    @classmethod
+    def from_config(cls, config, custom_objects=None):
+        config = dict(config)
+        globs = dict(globals())
+        globs.update(custom_objects or {})
+        ftype = config.pop('function_type')
+        if ftype == 'lambda':
+            function = func_load(config['function'], globs=globs)
+        else:
+            function = globs[config['function']]
+        return cls(function, arguments=config.get('arguments') or {}, name=config.get('name'))
+
+
+def func_dump(func):
+    """utils/generic_utils.func_dump: (base64 of the marshalled code object, defaults, closure cell contents)"""
+    import codecs
+    import marshal
+    code = codecs.encode(marshal.dumps(func.__code__), 'base64').decode('ascii')
+    closure = tuple(c.cell_contents for c in func.__closure__) if func.__closure__ else None
+    return code, func.__defaults__, closure
+
+
+def func_load(code, defaults=None, closure=None, globs=None):
+    """utils/generic_utils.func_load"""
+    import codecs
+    import marshal
+    import types
+    if isinstance(code, (tuple, list)):
+        code, defaults, closure = code
+        if isinstance(defaults, list):
+            defaults = tuple(defaults)
+
+    def ensure_value_to_cell(value):
+        def dummy_fn():
+            value          # noqa: B018  (makes `value` a closure cell)
+        cell = dummy_fn.__closure__[0]
+        return value if isinstance(value, type(cell)) else cell
+
+    if closure is not None:
+        closure = tuple(ensure_value_to_cell(v) for v in closure)
+    raw = codecs.decode(code.encode('ascii'), 'base64')
+    return types.FunctionType(marshal.loads(raw), globs if globs is not None else globals(), name='<lambda>',
+                              argdefs=defaults, closure=closure)
+
 
 class Embedding(Layer):
     """layers/embeddings.py: K.gather(embeddings, int32(inputs)); mask = (inputs != 0) only with mask_zero"""

@@ -60,6 +60,8 @@ def _from_config(config, custom_objects):
             return InputLayer(tuple(shape), dtype=cfg.get('dtype'), name=cfg.get('name'))
         if spec['class_name'] == 'TimeDistributed':
             return cls(make(cfg.pop('layer')), name=cfg.get('name'))
+        if spec['class_name'] == 'Lambda':
+            return cls.from_config(cfg, custom_objects)
         cfg.pop('batch_input_shape', None)
         cfg.pop('dtype', None)
         for k in list(cfg):

@@ -54,6 +54,9 @@ CASES = [
     ('sid-igru-ddot', 'Seq2VecPaperSoftmaxId', 'igru', 'ddot', 'igru', {}),
     ('sid-igru-dot-trainable', 'Seq2VecPaperSoftmaxId', 'igru', 'dot', 'igru', {'textual_embedding_trainable': True}),
     ('sid-igru-dot-dropout', 'Seq2VecPaperSoftmaxId', 'igru', 'dot', 'igru', {'dropout': 0.2}),
+    # --enable-pretrain-encoder (task/paper.py:103-107): the doc encoder comes from the json + pkl pair that the reference's
+    # own utils.save_model wrote (utils.py:66-79), frozen
+    ('sid-igru-dot-pretrain', 'Seq2VecPaperSoftmaxId', 'igru', 'dot', 'igru', {'enable_pretrain_encoder': True}),
     ('s-gru-dot', 'Seq2VecPaperSoftmax', 'gru', 'dot', 'nigru', {}),
     ('s-att-dot', 'Seq2VecPaperSoftmax', 'att', 'dot', 'att', {}),
     ('s-avg-dnn', 'Seq2VecPaperSoftmax', 'avg', 'dnn', 'niavg', {}),
@@ -217,9 +220,27 @@ def run_case(mods, sh, data_dir, name, task_name, arch, score_model, my_arch, ex
     from mnexp_b200 import synth
     keras.backend.clear_session()
     cfg = reference_config(settings, data_dir, sh, task_name, arch, score_model, **extra)
+    saved = {}
+    if extra.get('enable_pretrain_encoder'):
+        import json
+        import pickle
+        import utils as ref_utils
+        cfg0 = reference_config(settings, data_dir, sh, task_name, arch, score_model)
+        h0 = task.get(cfg0)
+        h0.build_model(0)
+        P0 = synth.make_weights(sh, arch=my_arch, bias_noise=0.05, seed=4242, score_model=score_model,
+                                word_emb=np.load(os.path.join(data_dir, 'Vocab.tsv.npy')))
+        assign(named_variables(h0), P0)
+        ref_utils.save_model(cfg.encoder_input, h0.doc_encoder)          # writes encoder.json / encoder.pkl
+        saved['encoder_json'] = np.array(json.load(open(cfg.encoder_input[0])))
+        for i, a in enumerate(pickle.load(open(cfg.encoder_input[1], 'rb'))):
+            saved['encoder_pkl_%d' % i] = np.asarray(a)
+        keras.backend.clear_session()
     h = task.get(cfg)
     model = h.build_model(0)
     variables = named_variables(h)
+    for k, v in variables.items():          # layer names may repeat between a loaded encoder and the new layers
+        v.vname = k
     softmax = task_name.startswith('Seq2VecPaperSoftmax')
     vert = task_name == 'Seq2VecPaperSoftmaxDaysIdVert'
     vsup = task_name == 'Seq2VecPaperSoftmaxDaysIdVertSup'
@@ -244,6 +265,7 @@ def run_case(mods, sh, data_dir, name, task_name, arch, score_model, my_arch, ex
         (['cand_vert'] * n_cand if vert else [])
     assert len(layout) == len(x), (layout, len(x))
     out = {'x%d' % i: np.asarray(a) for i, a in enumerate(x)}
+    out.update(saved)
     out['layout'] = np.array(layout)
     ys = list(y) if isinstance(y, (list, tuple)) else [y]
     for i, a in enumerate(ys):

@@ -147,7 +147,10 @@ def test_torch_oracle_loss_gradients_and_adam_match_reference_graph(name):
     trainable_table = name in EXTRA and EXTRA[name].get('textual_embedding_trainable', False)
     p_drop = EXTRA.get(name, {}).get('dropout', 0.0)
     masks = replayed_masks(p_drop) if p_drop > 0 else None
-    P = {k: torch.tensor(v, dtype=torch.float64, requires_grad=(k != 'word_emb' or trainable_table)) for k, v in Pn.items()}
+    frozen = set() if trainable_table else {'word_emb'}
+    if EXTRA.get(name, {}).get('enable_pretrain_encoder'):      # encoder.trainable = False, task/paper.py:105-106
+        frozen |= {'word_emb', 'conv_w', 'conv_b', 'att_w', 'att_b', 'dense_w', 'dense_b'}
+    P = {k: torch.tensor(v, dtype=torch.float64, requires_grad=k not in frozen) for k, v in Pn.items()}
     trainable = [k for k in P if P[k].requires_grad]
     loss = oracle_loss(P, name, masks)[0]
     assert abs(float(loss) - float(g('loss'))) < F64
@@ -182,12 +185,42 @@ def _mirror(name, precision='fp32', data_dir=None):
     d = data_dir or tempfile.mkdtemp()
     synth.write_dataset(d, SH)
     extra = dict(EXTRA.get(name, {}))
+    if extra.get('enable_pretrain_encoder'):                     # the json + pkl pair the reference's utils.save_model wrote
+        _write_encoder_files(name, d)
+        extra.update(input_previous_model_path=d, pretrain_name='')
     cfg = settings.Config(dict(task=task_name, arch=arch, score_model=score_model, input_training_data_path=d,
                                title_shape=SH.L, window_size=SH.W, negative_samples=SH.K, batch_size=SH.B,
                                textual_embedding_dim=SH.E, title_filter_shape=(SH.F, SH.k), user_embedding_dim=SH.U, debug=True,
                                dropout=extra.pop('dropout', 0.0), precision=precision, validation_impression=5,
                                testing_impression=5, epochs=2, learning_rate=0.001, **extra))
     return task.get(cfg)
+
+
+def _write_encoder_files(name, d):
+    import json
+    import pickle
+    n = 0
+    while '%s/encoder_pkl_%d' % (name, n) in GOLD.files:
+        n += 1
+    with open(os.path.join(d, 'encoder.json'), 'w') as f:
+        json.dump(str(GOLD[name + '/encoder_json']), f)            # utils.save_model json.dumps a json STRING (utils.py:75-77)
+    with open(os.path.join(d, 'encoder.pkl'), 'wb') as f:
+        pickle.dump([GOLD['%s/encoder_pkl_%d' % (name, i)] for i in range(n)], f, protocol=pickle.HIGHEST_PROTOCOL)
+    return os.path.join(d, 'encoder.json'), os.path.join(d, 'encoder.pkl')
+
+
+def test_model_files_written_by_the_reference_are_importable():
+    """utils.save_model of the reference (Keras `to_json()` + `get_weights()` pickle, utils.py:66-79) on its own doc
+    encoder -> mnexp_b200.utils.load_model: weight names in Keras' layer order, shapes and values"""
+    from mnexp_b200 import utils as mu
+    name = 'sid-igru-dot-pretrain'
+    loaded = mu.load_model(_write_encoder_files(name, tempfile.mkdtemp()))
+    P = loaded.params()
+    assert list(P) == ['word_emb', 'conv_w', 'conv_b', 'att_w', 'att_b', 'dense_w', 'dense_b']
+    for k, v in P.items():
+        ref = GOLD[name + '/P/' + k]
+        assert np.array_equal(np.asarray(v, dtype=np.float64).reshape(ref.shape), ref.astype(np.float32).astype(np.float64)) or \
+            np.abs(np.asarray(v, dtype=np.float64).reshape(ref.shape) - ref).max() < 1e-7, k
 
 
 @pytest.mark.parametrize('name', ['sid-igru-dot', 's-gru-dot', 'pid-igru', 'p-gru', 'sdays-gru-dot', 'sdid-igru-dot', 'vert-igru-dot',
