@@ -100,12 +100,13 @@ class _Core:
                 share_weights_from=base, score_model=self.score_model, **self.head_kw())
         return self.infer_engines[key]
 
-    def stage_tokens(self, name, arr):
+    def stage_tokens(self, name, arr, slot=0):
         """host token array (the reference feeds float64, document.py:39) -> int32 in a reusable PINNED buffer: the cast is
         one numpy pass (float64 -> int32, ids < 2^24 are exact) and the upload an asynchronous 4-byte-per-id copy instead
-        of a pageable 8-byte-per-id copy followed by a cast on the device."""
+        of a pageable 8-byte-per-id copy followed by a cast on the device.  `slot` selects one of several buffer sets:
+        fit_generator stages batch i+1 while the copy / kernels of batch i may still be in flight."""
         arr = np.asarray(arr)
-        key = (name, arr.shape)
+        key = (name, arr.shape, slot)
         pin = self.__dict__.setdefault('_pinned', {})
         if key not in pin:
             pin[key] = torch.empty(arr.shape, dtype=torch.int32).pin_memory()
@@ -152,14 +153,18 @@ class Model:
         return self.core.optimizer
 
     # ---- training ---------------------------------------------------------------------------
-    def train_on_batch(self, x, y):
+    def _enqueue_train(self, x, y, slot=0):
+        """Stage one batch (pinned buffer set `slot`) and enqueue forward + backward + Adam plus an asynchronous copy of
+        [loss, categorical_accuracy] into a pinned result; the host does not wait for the device.  -> handle for
+        _finish_train.  (The weighted-BCE family reports a host-side AUC of the batch's scores, so its handle keeps the
+        device tensors and has to be finished before the next step is enqueued.)"""
         assert self.is_train, 'test_model is not compiled for training'
         core = self.core
         C = core.n_train_cand()
         user, clicked, cand, verts = core.split_inputs(x, C)
         eng = core.engine_train(clicked.shape[0])
         eng.lr = core.optimizer.lr.value
-        batch = dict(user=user, hist_tok=core.stage_tokens('hist', clicked), cand_tok=core.stage_tokens('cand', cand),
+        batch = dict(user=user, hist_tok=core.stage_tokens('hist', clicked, slot), cand_tok=core.stage_tokens('cand', cand, slot),
                      label=np.asarray(y, dtype=np.float32).reshape(len(clicked), C))
         if verts is not None:
             batch['hist_vert'], batch['cand_vert'] = verts
@@ -169,18 +174,48 @@ class Model:
         loss = eng.train_step(db)
         probs = eng.view('probs').reshape(eng.B, eng.C)
         if core.loss == 'bce':
-            from . import metrics
-            return [float(loss[0]), metrics.auc_roc(probs.reshape(-1).cpu().numpy(), np.asarray(y).reshape(-1))]
+            return ('bce', loss, probs, y)
         acc = (probs.argmax(1) == db['label'].argmax(1)).float().mean()
-        return [float(loss[0]), float(acc)]
+        res = core.__dict__.setdefault('_results', {})
+        if slot not in res:
+            res[slot] = torch.empty(2, dtype=torch.float32).pin_memory()
+        res[slot].copy_(torch.stack([loss[0], acc]), non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        return ('ce', res[slot], done)
+
+    def _finish_train(self, handle):
+        if handle[0] == 'bce':
+            from . import metrics
+            _, loss, probs, y = handle
+            return [float(loss[0]), metrics.auc_roc(probs.reshape(-1).cpu().numpy(), np.asarray(y).reshape(-1))]
+        _, res, done = handle
+        done.synchronize()
+        return [float(res[0]), float(res[1])]
+
+    def train_on_batch(self, x, y):
+        return self._finish_train(self._enqueue_train(x, y))
 
     def fit_generator(self, generator, steps_per_epoch, epochs=1, initial_epoch=0, verbose=0, **_):
+        """main.py:73-78.  Software-pipelined by one step: while the device runs step i, the host pulls batch i+1 from the
+        generator, casts it into the other pinned buffer set and enqueues step i+1; only then does it read step i's
+        [loss, accuracy].  The sequence of updates and the logged averages are those of a plain train_on_batch loop."""
         h = History()
+        pipelined = type(self).train_on_batch is Model.train_on_batch and self.core.loss != 'bce'
         for epoch in range(initial_epoch, epochs):
-            tot = np.zeros(2)
-            for _ in range(steps_per_epoch):
+            tot = np.zeros(len(self.metrics_names))
+            pending = None
+            for step in range(steps_per_epoch):
                 x, y = next(generator)
-                tot += self.train_on_batch(x, y)
+                if not pipelined:
+                    tot += self.train_on_batch(x, y)
+                    continue
+                handle = self._enqueue_train(x, y, slot=step & 1)
+                if pending is not None:
+                    tot += self._finish_train(pending)
+                pending = handle
+            if pending is not None:
+                tot += self._finish_train(pending)
             h.epoch.append(epoch)
             for k, v in zip(self.metrics_names, tot / max(1, steps_per_epoch)):
                 h.history.setdefault(k, []).append(float(v))
