@@ -153,7 +153,7 @@ class Model:
         return self.core.optimizer
 
     # ---- training ---------------------------------------------------------------------------
-    def _enqueue_train(self, x, y, slot=0):
+    def _enqueue_train(self, x, y, slot=0, copy_stream=None):
         """Stage one batch (pinned buffer set `slot`) and enqueue forward + backward + Adam plus an asynchronous copy of
         [loss, categorical_accuracy] into a pinned result; the host does not wait for the device.  -> handle for
         _finish_train.  (The weighted-BCE family reports a host-side AUC of the batch's scores, so its handle keeps the
@@ -170,7 +170,17 @@ class Model:
             batch['hist_vert'], batch['cand_vert'] = verts
         if core.arch == 'dgru':     # Dropout(0.5, noise_shape=(None, 1)) on the user vector (task/paper.py:609)
             batch['user_scale'] = (np.random.random(clicked.shape[0]) >= 0.5).astype(np.float32) * 2.0
-        db = eng.to_device_batch(batch, non_blocking=True)
+        if copy_stream is None:
+            db = eng.to_device_batch(batch, non_blocking=True)
+        else:       # upload on a side stream: it runs under the previous step's kernels; this step waits for it
+            main = torch.cuda.current_stream()
+            with torch.cuda.stream(copy_stream):
+                db = eng.to_device_batch(batch, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy_stream)
+            main.wait_event(ready)
+            for t in db.values():
+                t.record_stream(main)
         loss = eng.train_step(db)
         probs = eng.view('probs').reshape(eng.B, eng.C)
         if core.loss == 'bce':
@@ -198,10 +208,15 @@ class Model:
 
     def fit_generator(self, generator, steps_per_epoch, epochs=1, initial_epoch=0, verbose=0, **_):
         """main.py:73-78.  Software-pipelined by one step: while the device runs step i, the host pulls batch i+1 from the
-        generator, casts it into the other pinned buffer set and enqueues step i+1; only then does it read step i's
-        [loss, accuracy].  The sequence of updates and the logged averages are those of a plain train_on_batch loop."""
+        generator, casts it into the other pinned buffer set, uploads it on a side stream and enqueues step i+1; only then
+        does it read step i's [loss, accuracy].  The sequence of updates and the logged averages are those of a plain train_on_batch loop."""
         h = History()
         pipelined = type(self).train_on_batch is Model.train_on_batch and self.core.loss != 'bce'
+        copy_stream = None
+        if pipelined:
+            if '_copy_stream' not in self.core.__dict__:
+                self.core.__dict__['_copy_stream'] = torch.cuda.Stream()
+            copy_stream = self.core.__dict__['_copy_stream']
         for epoch in range(initial_epoch, epochs):
             tot = np.zeros(len(self.metrics_names))
             pending = None
@@ -210,7 +225,7 @@ class Model:
                 if not pipelined:
                     tot += self.train_on_batch(x, y)
                     continue
-                handle = self._enqueue_train(x, y, slot=step & 1)
+                handle = self._enqueue_train(x, y, slot=step & 1, copy_stream=copy_stream)
                 if pending is not None:
                     tot += self._finish_train(pending)
                 pending = handle
