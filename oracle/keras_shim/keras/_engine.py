@@ -706,7 +706,7 @@ class Model(Network):
         return total, parts, mets
 
     def _result(self, total, parts, mets):
-        r = [float(total)] + ([float(p) for p in parts] if len(parts) > 1 else []) + mets
+        r = [float(total.detach())] + ([float(p.detach()) for p in parts] if len(parts) > 1 else []) + mets
         return r if len(r) > 1 else r[0]
 
     def unique_trainable_weights(self):
@@ -750,7 +750,7 @@ class Model(Network):
         params = self.unique_trainable_weights()
         total, _, _ = self._losses(self._forward(x, training), y)
         grads = torch.autograd.grad(total, params, allow_unused=True)
-        return float(total), {p.vname: (np.zeros(tuple(p.shape)) if g is None else g.detach().cpu().numpy().copy())
+        return float(total.detach()), {p.vname: (np.zeros(tuple(p.shape)) if g is None else g.detach().cpu().numpy().copy())
                               for p, g in zip(params, grads)}
 
     def fit_generator(self, generator, steps_per_epoch=None, epochs=1, verbose=1, callbacks=None, validation_data=None,

@@ -24,7 +24,7 @@ class SGD(Optimizer):
         self.iterations, self.moments = 0, {}
 
     def apply(self, params, grads):
-        lr = float(self.lr) * (1. / (1. + self.decay * self.iterations)) if self.decay > 0 else float(self.lr)
+        lr = float(self.lr.detach()) * (1. / (1. + self.decay * self.iterations)) if self.decay > 0 else float(self.lr.detach())
         self.iterations += 1
         with torch.no_grad():
             for p, g in zip(params, grads):
@@ -44,7 +44,7 @@ class Adam(Optimizer):
         self.iterations, self.ms, self.vs = 0, {}, {}
 
     def apply(self, params, grads):
-        lr = float(self.lr)
+        lr = float(self.lr.detach())
         if self.initial_decay > 0:
             lr = lr * (1. / (1. + self.decay * self.iterations))
         t = self.iterations + 1

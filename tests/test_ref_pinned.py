@@ -153,7 +153,7 @@ def test_torch_oracle_loss_gradients_and_adam_match_reference_graph(name):
     P = {k: torch.tensor(v, dtype=torch.float64, requires_grad=k not in frozen) for k, v in Pn.items()}
     trainable = [k for k in P if P[k].requires_grad]
     loss = oracle_loss(P, name, masks)[0]
-    assert abs(float(loss) - float(g('loss'))) < F64
+    assert abs(float(loss.detach()) - float(g('loss'))) < F64
     grads = dict(zip(trainable, torch.autograd.grad(loss, [P[k] for k in trainable], allow_unused=True)))
     checked = 0
     for k in trainable:
