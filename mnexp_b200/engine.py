@@ -426,11 +426,13 @@ class LsturEngine:
         """Record two CUDA events (new_event()) around one kernel of the step (bench.py roofline)."""
         _lib.check(self.lib.lstur_plan_set_probe(self.plan, probe_id, ev_start, ev_stop))
 
-    def train_step(self, db, seed=None):
-        """forward + backward + Adam on a device batch; returns the loss as a 1-element device tensor."""
+    def train_step(self, db, seed=None, grad_scale=None):
+        """forward + backward + Adam on a device batch; returns the loss (mean over the B rows) as a 1-element device
+        tensor.  grad_scale overrides 1 / B: a ragged last batch of n < B samples is run as B rows whose padding rows carry
+        an all-zero target (no loss, no gradient) with grad_scale = 1 / n."""
         self.step_seed += 1
         self.forward(db, training=True, seed=self.step_seed if seed is None else seed)
-        self.backward(db)
+        self.backward(db, grad_scale=grad_scale)
         self.apply_adam()
         return self.view('loss')
 

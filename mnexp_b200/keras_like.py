@@ -153,7 +153,7 @@ class Model:
         return self.core.optimizer
 
     # ---- training ---------------------------------------------------------------------------
-    def _enqueue_train(self, x, y, slot=0, copy_stream=None):
+    def _enqueue_train(self, x, y, slot=0, copy_stream=None, n_valid=None):
         """Stage one batch (pinned buffer set `slot`) and enqueue forward + backward + Adam plus an asynchronous copy of
         [loss, categorical_accuracy] into a pinned result; the host does not wait for the device.  -> handle for
         _finish_train.  (The weighted-BCE family reports a host-side AUC of the batch's scores, so its handle keeps the
@@ -181,15 +181,16 @@ class Model:
             main.wait_event(ready)
             for t in db.values():
                 t.record_stream(main)
-        loss = eng.train_step(db)
+        nv = eng.B if n_valid is None else int(n_valid)      # rows beyond nv are padding with an all-zero target (fit)
+        loss = eng.train_step(db, grad_scale=None if nv == eng.B else 1.0 / nv)
         probs = eng.view('probs').reshape(eng.B, eng.C)
         if core.loss == 'bce':
             return ('bce', loss, probs, y)
-        acc = (probs.argmax(1) == db['label'].argmax(1)).float().mean()
+        acc = (probs[:nv].argmax(1) == db['label'][:nv].argmax(1)).float().mean()
         res = core.__dict__.setdefault('_results', {})
         if slot not in res:
             res[slot] = torch.empty(2, dtype=torch.float32).pin_memory()
-        res[slot].copy_(torch.stack([loss[0], acc]), non_blocking=True)
+        res[slot].copy_(torch.stack([loss[0] * (eng.B / nv), acc]), non_blocking=True)
         done = torch.cuda.Event()
         done.record()
         return ('ce', res[slot], done)
@@ -243,10 +244,23 @@ class Model:
         for epoch in range(initial_epoch, epochs):
             order = np.random.permutation(n) if shuffle else np.arange(n)
             tot, k = np.zeros(2), 0
-            for s in range(0, n - batch_size + 1, batch_size):       # Keras trains the ragged tail too; the engine's
-                idx = order[s:s + batch_size]                         # plan is per batch size, so the tail is dropped
-                tot += self.train_on_batch([np.asarray(a)[idx] for a in x], np.asarray(y)[idx])
-                k += 1
+            pad_ok = self.core.loss != 'bce' and type(self).train_on_batch is Model.train_on_batch
+            for s in range(0, n, batch_size):
+                idx = order[s:s + batch_size]
+                m = len(idx)
+                if m < batch_size and not pad_ok:
+                    break           # weighted BCE has no neutral target: the ragged tail of the sigmoid family is dropped
+                yb = np.asarray(y)[idx]
+                if m < batch_size:
+                    # Keras trains the ragged last batch too; the plan is per batch size, so the m samples run as
+                    # batch_size rows: padding rows repeat the first sample under an all-zero target (zero loss and
+                    # gradient under categorical cross-entropy), gradient scale 1 / m
+                    idx = np.concatenate([idx, np.full(batch_size - m, idx[0])])
+                    yb = np.concatenate([yb, np.zeros((batch_size - m,) + yb.shape[1:], dtype=yb.dtype)])
+                xb = [np.asarray(a)[idx] for a in x]
+                r = self._finish_train(self._enqueue_train(xb, yb, n_valid=m)) if pad_ok else self.train_on_batch(xb, yb)
+                tot += np.asarray(r) * m
+                k += m                  # Keras logs the sample-weighted mean over the batches
             h.epoch.append(epoch)
             for name, v in zip(self.metrics_names, tot / max(1, k)):
                 h.history.setdefault(name, []).append(float(v))

@@ -67,15 +67,23 @@ class CookModel:
             tot, k = np.zeros(2), 0
             eng = self.owner.engine(batch_size, C, training=True)
             eng.lr = self.optimizer.lr.value
-            for s in range(0, n - batch_size + 1, batch_size):          # the ragged tail is dropped (plan per batch size)
+            for s in range(0, n, batch_size):
                 rows = order[s:s + batch_size]
+                m = len(rows)
+                lab = np.zeros((batch_size, C), dtype=np.float32)
+                lab[:m] = y[rows]
+                if m < batch_size:
+                    # Keras trains the ragged last batch too (training.py fit_loop / make_batches).  The plan is per batch
+                    # size, so the m samples run as batch_size rows: padding rows repeat the first sample under an all-zero
+                    # target (zero loss, zero gradient) and the gradient scale is 1 / m
+                    rows = np.concatenate([rows, np.full(batch_size - m, rows[0])])
                 b = self._batch(x, rows, C, True)
-                b['label'] = y[rows]
+                b['label'] = lab
                 db = eng.to_device_batch(b)
-                loss = eng.train_step(db)
-                probs = eng.view('probs').reshape(eng.B, eng.C)
-                tot += [float(loss[0]), float((probs.argmax(1) == db['label'].argmax(1)).float().mean())]
-                k += 1
+                loss = eng.train_step(db, grad_scale=1.0 / m)
+                probs = eng.view('probs').reshape(eng.B, eng.C)[:m]
+                tot += [float(loss[0]) * batch_size, float((probs.argmax(1) == db['label'][:m].argmax(1)).float().sum())]
+                k += m                              # Keras logs the sample-weighted mean over the batches
             h.epoch.append(epoch)
             for name, v in zip(self.metrics_names, tot / max(1, k)):
                 h.history.setdefault(name, []).append(float(v))

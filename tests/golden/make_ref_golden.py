@@ -349,6 +349,7 @@ COOK_CASES = [
     ('cook-algru-dot-vs', 'algru', 'dot', 'algru', 'vs'),
 ]
 COOK_DV, COOK_DS, COOK_USERS = 3, 5, 25000
+MAIN_COOK_BATCH = 10          # 24 training rows -> batches of 10, 10 and a ragged 4 (Keras trains the tail too)
 
 
 def cook_shape(score_model='dnn', vtype='vs'):
@@ -587,7 +588,7 @@ def run_main_cases(mods, data_dir, cook_dir):
     csh = cook_shape('ddot', 'vs')
     Pc = synth.make_weights(csh, arch='igru', bias_noise=0.05, seed=4242, score_model='ddot', cook=True, dv=COOK_DV, ds=COOK_DS,
                             word_emb=np.load(os.path.join(cook_dir, 'Vocab.tsv.npy')))
-    cfg = config_dict(cook_dir, csh, 'Cook', 'ingru', 'ddot', use_vertical=True, use_vertical_type='vs', batch_size=8,
+    cfg = config_dict(cook_dir, csh, 'Cook', 'ingru', 'ddot', use_vertical=True, use_vertical_type='vs', batch_size=MAIN_COOK_BATCH,
                       vertical_embedding_dim=COOK_DV, subvertical_embedding_dim=COOK_DS, validation_step=6, lrd_on_epochs=[0])
     h, variables, records = run_reference_main(mods, 'cook', cfg, cook_variables, Pc)
     for k, v in _flatten_records(records).items():
@@ -599,7 +600,7 @@ def run_main_cases(mods, data_dir, cook_dir):
     feature, (users, imprs, mask, y_true) = h.test()
     out['main-cook/test_users'], out['main-cook/test_imprs'] = np.asarray(users), np.asarray(imprs)
     out['main-cook/test_mask'], out['main-cook/test_y_true'] = np.asarray(mask), np.asarray(y_true)
-    out['main-cook/test_y_pred'] = h.test_model.predict(feature, batch_size=8).reshape(-1)
+    out['main-cook/test_y_pred'] = h.test_model.predict(feature, batch_size=MAIN_COOK_BATCH).reshape(-1)
     return out
 
 

@@ -577,13 +577,14 @@ def test_cuda_main_train_loop_matches_reference(lib, precision):
 @pytest.mark.gpu
 @pytest.mark.parametrize('precision', ['fp32', 'fp16_tc'])
 def test_cuda_main_cook_loop_matches_reference(lib, precision):
-    """`main.py cook` on Cook / ingru / ddot, two epochs of three shuffled batches: fit histories, test_model.evaluate, the
+    """`main.py cook` on Cook / ingru / ddot, two epochs of three shuffled batches (10 + 10 + a ragged 4 of the 24 rows): fit histories, test_model.evaluate, the
     learning-rate decay of callback(0), and the eight aggregated evaluation lines of the scored test set."""
     from mnexp_b200 import main as mmain
     sh = mk.cook_shape('ddot', 'vs')
     d = tempfile.mkdtemp()
     synth.write_cook_npz(d, sh)
-    cfg = settings.Config(dict(task='Cook', arch='ingru', input_training_data_path=d, days=30, window_size=sh.W, batch_size=8,
+    cfg = settings.Config(dict(task='Cook', arch='ingru', input_training_data_path=d, days=30, window_size=sh.W,
+                               batch_size=mk.MAIN_COOK_BATCH,
                                title_filter_shape=(sh.F, 3), user_embedding_dim=sh.U, dropout=0.0, score_model='ddot',
                                use_vertical=True, use_vertical_type='vs', vertical_embedding_dim=mk.COOK_DV,
                                subvertical_embedding_dim=mk.COOK_DS, precision=precision, validation_step=6, epochs=2,
