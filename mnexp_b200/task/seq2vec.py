@@ -130,6 +130,33 @@ class Seq2Vec:
             self._build_model()
         return self.model
 
+    def callback(self, epoch):
+        """task/seq2vec.py:296-322 — inherited by the sigmoid family (Seq2VecPaper / ...Dot / ...Id): learning-rate decay,
+        then AUC / nDCG@10 / nDCG@5 / MRR averaged over the first `testing_impression` impressions of `test`; after the
+        last epoch once more with is_training = False when a TestData.tsv exists.  The impressions are ranked in one launch
+        of the device kernel (mnexp_b200/metrics.py) instead of one sklearn / numpy call each."""
+        import os
+        from .. import keras_like, metrics
+        lr = self.model.optimizer.lr
+        keras_like.backend.set_value(lr, keras_like.backend.get_value(lr) * self.config.learning_rate_decay)
+
+        def evaluate():
+            preds, trues = [], []
+            for _, (y_pred, y_true) in zip(range(self.config.testing_impression), self.test):
+                preds.append(np.asarray(y_pred).reshape(-1))
+                trues.append(np.asarray(y_true).reshape(-1))
+            m = metrics.ranking_metrics(preds, trues)
+            rows = [(float(r[0]), float(r[1]), float(r[2]), float(r[3]), np.sum(y), len(y), i)
+                    for i, (r, y) in enumerate(zip(m, trues))]
+            values = [np.mean(c) for c in zip(*rows)]
+            self.last_evaluation = dict(auc=values[0], ndcgx=values[1], ndcgv=values[2], mrr=values[3])
+            utils.logging_evaluation(self.last_evaluation)
+            utils.logging_evaluation(dict(pos=values[4], size=values[5], num=values[6] * 2 + 1))
+        evaluate()
+        if epoch == self.config.epochs - 1 and os.path.exists(self.config.testing_data_input):
+            self.is_training = False
+            evaluate()
+
     def save_model(self):
         """task/seq2vec.py:324-327 (the paper classes override it with a no-op, task/paper.py:254-255)."""
         logging.info('[+] saving models')

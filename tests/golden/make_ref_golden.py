@@ -546,6 +546,11 @@ def config_dict(data_dir, sh, task_name, arch, score_model, **extra):
     return cfg
 
 
+def ref_utils_verticals():
+    import utils as ref_utils
+    return ref_utils.verticals
+
+
 def run_main_cases(mods, data_dir, cook_dir):
     """`main.py train` on Seq2VecPaperSoftmaxId (LSTUR-ini) and `main.py cook` on Cook 'ingru', two epochs each"""
     from mnexp_b200 import synth
@@ -561,6 +566,24 @@ def run_main_cases(mods, data_dir, cook_dir):
         out['main-train/final/' + k] = v
     for k, v in P.items():
         out['main-train/P/' + k] = np.asarray(v, dtype=np.float64)
+    # the sigmoid family inherits Seq2Vec.callback (task/seq2vec.py:296-322) and trains on the weighted BCE
+    Pi = synth.make_weights(sh, arch='igru', bias_noise=0.05, seed=4242, score_model='dnn',
+                            word_emb=np.load(os.path.join(data_dir, 'Vocab.tsv.npy')))
+    cfg = config_dict(data_dir, sh, 'Seq2VecPaperId', 'igru', 'dnn', gain=GAIN)
+    h, variables, records = run_reference_main(mods, 'train', cfg, named_variables, Pi)
+    for k, v in _flatten_records(records).items():
+        out['main-paperid/log_' + k] = v
+    for k, v in Pi.items():
+        out['main-paperid/P/' + k] = np.asarray(v, dtype=np.float64)
+    # the two-output model of ...VertSup through the same loop (five logged metrics per step)
+    Ps = synth.make_weights(sh, arch='igru', bias_noise=0.05, seed=4242, score_model='dot',
+                            vertsup=(len(ref_utils_verticals()), VSUP_HIDDEN), word_emb=np.load(os.path.join(data_dir, 'Vocab.tsv.npy')))
+    cfg = config_dict(data_dir, sh, 'Seq2VecPaperSoftmaxDaysIdVertSup', 'igru', 'dot', days=3, hidden_dim=VSUP_HIDDEN, gain=0.5)
+    h, variables, records = run_reference_main(mods, 'train', cfg, named_variables, Ps)
+    for k, v in _flatten_records(records).items():
+        out['main-vertsup/log_' + k] = v
+    for k, v in Ps.items():
+        out['main-vertsup/P/' + k] = np.asarray(v, dtype=np.float64)
     # the alternating schedule of ...VertAlt (task/paper.py:1003-1135): round = 3 -> two epochs of the vertical model, one of
     # the click model.  list(set(...)) orders the verticals by string hash, so the classifier columns are stored BY NAME
     import utils as ref_utils
@@ -738,7 +761,7 @@ def generate(path=OUT, verbose=True):
                 c[0], c[1], len(res['doc_keys']), len(res['user_keys']), len(res['scores']), res['pred'], res['sigm']))
     out.update(run_main_cases(mods, data_dir, cook_dir))
     if verbose:
-        for c in ('main-train', 'main-vertalt', 'main-cook'):
+        for c in ('main-train', 'main-paperid', 'main-vertsup', 'main-vertalt', 'main-cook'):
             print('%-12s %d logged records: %s' % (c, len(out[c + '/log_kinds']), ' | '.join(out[c + '/log_keys'][:6])))
     np.savez_compressed(path, **out)
     if verbose:

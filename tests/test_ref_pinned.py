@@ -780,3 +780,38 @@ def test_cuda_matches_reference_graph_at_benchmark_widths(lib, precision):
     assert n >= 9
     losses = [float(eng.train_step(db)[0]) for _ in range(3)]
     assert np.abs(np.array(losses) - g('adam_losses')).max() < (1e-4 if not tc else 3e-3)
+
+
+def _paper_cfg(task_name, arch, score_model, precision, **extra):
+    d = tempfile.mkdtemp()
+    synth.write_dataset(d, SH)
+    return settings.Config(dict(task=task_name, arch=arch, score_model=score_model, input_training_data_path=d,
+                                title_shape=SH.L, window_size=SH.W, negative_samples=SH.K, batch_size=SH.B,
+                                textual_embedding_dim=SH.E, title_filter_shape=(SH.F, SH.k), user_embedding_dim=SH.U, debug=True,
+                                dropout=0.0, precision=precision, validation_impression=5, testing_impression=5, epochs=2,
+                                training_step=3, validation_step=2, learning_rate=0.001, learning_rate_decay=0.2,
+                                sparse_user_adam=False, **extra))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('precision', ['fp32', 'fp16_tc'])
+def test_cuda_main_train_loop_sigmoid_family_matches_reference(lib, precision):
+    """`main.py train` on Seq2VecPaperId (weighted BCE, Seq2Vec.callback of task/seq2vec.py:296-322: learning-rate decay +
+    ranking metrics over `testing_impression` impressions)"""
+    from mnexp_b200 import main as mmain
+    cfg = _paper_cfg('Seq2VecPaperId', 'igru', 'dnn', precision, gain=float(GOLD['gain']))
+    np.random.seed(4710)
+    h, got = mmain.train(cfg, on_build=_load_paper_weights('main-paperid'))
+    _compare_records(got, _records('main-paperid'), 1e-4 if precision == 'fp32' else 2e-3, 1e-6 if precision == 'fp32' else 0.35)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('precision', ['fp32', 'fp16_tc'])
+def test_cuda_main_train_loop_vertsup_matches_reference(lib, precision):
+    """`main.py train` on ...DaysIdVertSup: the two-output model through fit_generator / evaluate_generator (five logged
+    metrics per step: loss, ranking_loss, vert_loss and the two accuracies) and the callback's evaluation"""
+    from mnexp_b200 import main as mmain
+    cfg = _paper_cfg('Seq2VecPaperSoftmaxDaysIdVertSup', 'igru', 'dot', precision, days=3, hidden_dim=mk.VSUP_HIDDEN, gain=0.5)
+    np.random.seed(4710)
+    h, got = mmain.train(cfg, on_build=_load_paper_weights('main-vertsup'))
+    _compare_records(got, _records('main-vertsup'), 1e-4 if precision == 'fp32' else 3e-3, 1e-6 if precision == 'fp32' else 0.35)
