@@ -17,9 +17,11 @@ importable here.  So:
   ``task/seq2vec.py``, ``models.py``, ``document.py``, ``utils.py``,
   ``settings.py`` are IMPORTED FROM /root/reference AND RUN
   (``tests/golden/make_ref_golden.py``): its loaders, batchers and
-  ``_build_model`` graphs produce ``tests/golden/ref_golden.npz`` — 38 task
+  ``_build_model`` graphs produce ``tests/golden/ref_golden.npz`` — 43 task
   class / user encoder / scorer cases with batches, forward outputs, losses,
-  gradients and Adam steps.
+  gradients and Adam steps, the decomposed pipeline, and five whole runs of the
+  reference's ``main.train`` / ``main.cook`` command functions with everything
+  they log.
 * ``lstur_numpy`` (float64) and ``lstur_torch`` (autograd + Keras Adam), written
   independently a round earlier from a reading of the reference, reproduce
   those vectors to 1e-9 (``tests/test_ref_pinned.py``); where they did not —
