@@ -722,6 +722,49 @@ def run_pipeline_case(mods, data_dir, name, pipe_class, task_name, arch, score_m
     return out
 
 
+HOST_TITLES = ['5 9 2', '7', '1 2 3 4 5 6 7 8 9 10 11 12', '3 4#N#5 6', '12 0 4', '0', '8 8 8 8 8 8 8']
+HOST_CONFIG_PROPERTIES = ['training_data_input', 'testing_data_input', 'title_embedding_input', 'doc_meta_input',
+                          'user_meta_input', 'model_input', 'model_output', 'encoder_input', 'encoder_output',
+                          'user_encoder_output', 'result_output', 'result_input', 'log_output', 'pipeline_inputs',
+                          'pipeline_output', 'doc_punc_index_input', 'vertical2idx_input', 'train_npz_input', 'test_npz_input',
+                          'train_sparse_input', 'test_sparse_input', 'vert_npz_input']
+
+
+def run_host_functions(mods, data_dir):
+    """the small host-side functions of the path, called as the reference defines them: document parsers (document.py),
+    Vocab.tsv loader and ranking metrics (utils.py), vertical tables, the path properties of settings.Config"""
+    keras, settings, task = mods
+    import document as ref_document
+    import utils as ref_utils
+    from mnexp_b200 import synth
+    sh = synth.SHAPES['tiny']
+    out = {}
+    parser = ref_document.DocumentParser(ref_document.parse_document(), ref_document.pad_document(1, sh.L))
+    out['titles'] = np.array(HOST_TITLES)
+    out['parsed_titles'] = np.stack([parser(t)[0] for t in HOST_TITLES])
+    out['parsed_dtype'] = np.array(str(parser(HOST_TITLES[0]).dtype))
+    out['vocab_tsv'] = ref_utils.load_textual_embedding(os.path.join(data_dir, 'Vocab.tsv'), sh.E)
+    g = np.random.default_rng(5)
+    scores = [g.random(n) for n in (2, 5, 11, 30)]
+    labels = [(g.random(len(s_)) < 0.4).astype(np.float64) for s_ in scores]
+    for l_ in labels:
+        l_[0] = 1.0
+    out['metric_scores'] = np.concatenate(scores)
+    out['metric_labels'] = np.concatenate(labels)
+    out['metric_lens'] = np.array([len(s_) for s_ in scores])
+    out['metric_values'] = np.array([[ref_utils.dcg_score(y, s_, 10), ref_utils.ndcg_score(y, s_, 10), ref_utils.ndcg_score(y, s_, 5),
+                                      ref_utils.mrr_score(y, s_)] for s_, y in zip(scores, labels)])
+    out['vertical_names'] = np.array(sorted(ref_utils.verticals, key=ref_utils.verticals.get))
+    out['subvertical_names'] = np.array(sorted(ref_utils.subverticals, key=ref_utils.subverticals.get))
+    out['vertical_lookup'] = np.array([ref_utils.get_vertical(n) for n in ('news', 'sports', 'N/A', 'nope')] +
+                                      [ref_utils.get_subvertical(n) for n in ('animals', 'nope')])
+    cfg = reference_config(settings, '/data', sh, 'Cook', 'igru', 'dot', days=7, window_size=20, name='n1', pretrain_name='p0',
+                           input_previous_model_path='/prev', output_model_path='/out', log_dir='/logs', pipeline_input='/pipe')
+    out['config_properties'] = np.array(HOST_CONFIG_PROPERTIES)
+    out['config_values'] = np.array([repr(getattr(cfg, p)) for p in HOST_CONFIG_PROPERTIES])
+    return out
+
+
 def generate(path=OUT, verbose=True):
     mods = load_reference()
     from mnexp_b200 import synth
@@ -751,6 +794,8 @@ def generate(path=OUT, verbose=True):
         out['wide/' + k] = v
     if verbose:
         print('%-12s E300 F400 U200 L30 W50 B16: loss %.6f, adam losses %s' % ('wide', float(res['loss']), res['adam_losses']))
+    for k, v in run_host_functions(mods, data_dir).items():
+        out['host/' + k] = v
     out['pipeline_table'] = np.array([list(c) for c in PIPELINE_CASES])
     for c in PIPELINE_CASES:
         res = run_pipeline_case(mods, data_dir, *c)

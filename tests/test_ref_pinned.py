@@ -815,3 +815,41 @@ def test_cuda_main_train_loop_vertsup_matches_reference(lib, precision):
     np.random.seed(4710)
     h, got = mmain.train(cfg, on_build=_load_paper_weights('main-vertsup'))
     _compare_records(got, _records('main-vertsup'), 1e-4 if precision == 'fp32' else 3e-3, 1e-6 if precision == 'fp32' else 0.35)
+
+
+# ---------------------------------------------------------------------------------------------- small host functions
+def test_host_functions_match_the_reference():
+    """document.py parsers (float64 rows, right zero padding, truncation, first non-empty clause only), the Vocab.tsv loader,
+    utils.dcg / ndcg / mrr, the vertical tables and every path property of settings.Config — outputs of the reference's own
+    functions (make_ref_golden.run_host_functions) against the mirror's"""
+    from mnexp_b200 import document, utils as mu
+    g = lambda k: GOLD['host/' + k]
+    parser = document.DocumentParser(document.parse_document(), document.pad_document(1, SH.L))
+    got = np.stack([parser(str(t))[0] for t in g('titles')])
+    assert str(got.dtype) == str(g('parsed_dtype')) and np.array_equal(got, g('parsed_titles'))
+    d = tempfile.mkdtemp()
+    synth.write_dataset(d, SH)
+    emb = mu.load_textual_embedding(os.path.join(d, 'Vocab.tsv'), SH.E)
+    assert emb.dtype == g('vocab_tsv').dtype and np.array_equal(emb, g('vocab_tsv'))
+    pos = 0
+    for n, ref in zip(g('metric_lens'), g('metric_values')):
+        s, y = g('metric_scores')[pos:pos + n], g('metric_labels')[pos:pos + n]
+        pos += n
+        mine = [mu.dcg_score(y, s, 10), mu.ndcg_score(y, s, 10), mu.ndcg_score(y, s, 5), mu.mrr_score(y, s)]
+        assert np.abs(np.array(mine) - ref).max() < 1e-15
+    # (the 306-name subvertical table, utils.py:157-228, is not mirrored: the paper classes never read News.subvertical and
+    # Cook receives integer ids in its .npz files; only its SIZE, 307 rows, is part of the model — checked by the Cook cases)
+    look = [mu.get_vertical(n) for n in ('news', 'sports', 'N/A', 'nope')]
+    assert look == [int(v) for v in g('vertical_lookup')[:4]]
+    assert [str(n) for n in g('vertical_names')] == sorted(mu.verticals, key=mu.verticals.get)
+    assert len(g('subvertical_names')) == 307
+    cfg = settings.Config(dict(task='Cook', arch='igru', input_training_data_path='/data', days=7, window_size=20, name='n1',
+                               pretrain_name='p0', input_previous_model_path='/prev', output_model_path='/out', log_dir='/logs',
+                               pipeline_input='/pipe'))
+    out_of_scope = {'user_meta_input', 'user_encoder_output', 'result_output', 'result_input', 'doc_punc_index_input',
+                    'vertical2idx_input', 'train_sparse_input', 'test_sparse_input', 'vert_npz_input'}     # other experiments' files
+    for prop, ref in zip(g('config_properties'), g('config_values')):
+        if hasattr(type(cfg), str(prop)):
+            assert repr(getattr(cfg, str(prop))) == str(ref), prop
+        else:
+            assert str(prop) in out_of_scope, prop
