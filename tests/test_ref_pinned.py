@@ -853,3 +853,18 @@ def test_host_functions_match_the_reference():
             assert repr(getattr(cfg, str(prop))) == str(ref), prop
         else:
             assert str(prop) in out_of_scope, prop
+
+
+def test_training_parity_fixture_matches_reference_graph():
+    """north_star: "AUC within 0.002 after a fixed step count".  tests/golden/train_parity_c1.npz — what the CUDA arms are
+    compared with in tests/test_gpu_training_parity.py — was trained by the oracle; train_parity_c1_ref.npz is the same run
+    (C1, 200 steps, same batches and initial weights, float32) trained by the REFERENCE'S OWN graph and compiled Adam over
+    the shim (tests/golden/make_train_parity_ref.py).  The two agree: per-step losses (fp32 reassociation grows over the
+    200 steps) and the held-out per-impression AUC."""
+    a = np.load(os.path.join(HERE, 'golden', 'train_parity_c1.npz'))
+    b = np.load(os.path.join(HERE, 'golden', 'train_parity_c1_ref.npz'))
+    d = np.abs(a['loss_p0'] - b['ref_loss_p0'])
+    assert len(d) == 200 and d[:10].max() < 1e-4 and d.max() < 5e-3
+    assert abs(float(a['auc_p0']) - float(b['ref_auc_p0'])) <= 0.002
+    assert abs(synth.impression_auc(b['ref_probs_p0']) - float(b['ref_auc_p0'])) < 1e-12
+    assert float(b['ref_auc_p0']) > float(a['auc_init']) + 0.1          # the task was learnt
