@@ -192,12 +192,13 @@ class MaskReplay:
     reference graph evaluates them: history titles (B*W rows) then candidate k (B rows each); X-dropout has E columns,
     C-dropout F columns (task/paper.py:147,158)."""
 
-    def __init__(self, sh, p, seed):
+    def __init__(self, sh, p=None, seed=None, keep=None):
         from mnexp_b200 import rng
         n = sh.B * (sh.W + 1 + sh.K)
         self.sh, self.calls = sh, {}
-        self.keep = {sh.E: rng.dropout_multiplier(seed * 2, n * sh.L * sh.E, p).reshape(n, sh.L, sh.E) != 0,
-                     sh.F: rng.dropout_multiplier(seed * 2 + 1, n * sh.L * sh.F, p).reshape(n, sh.L, sh.F) != 0}
+        self.keep = keep if keep is not None else {
+            sh.E: rng.dropout_multiplier(seed * 2, n * sh.L * sh.E, p).reshape(n, sh.L, sh.E) != 0,
+            sh.F: rng.dropout_multiplier(seed * 2 + 1, n * sh.L * sh.F, p).reshape(n, sh.L, sh.F) != 0}
 
     def reset(self):
         self.calls = {}

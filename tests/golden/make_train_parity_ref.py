@@ -30,26 +30,45 @@ def main():
     synth.write_docmeta_tsv(os.path.join(d, 'DocMeta.tsv'), tok)
     synth.write_clickdata_tsv(os.path.join(d, 'ClickData.tsv'), sh.n_users, sh.n_news, np.random.default_rng(1))
     np.save(os.path.join(d, 'Vocab.tsv.npy'), P['word_emb'])
-    cfg = mk.reference_config(settings, d, sh, 'Seq2VecPaperSoftmaxId', 'igru', 'dot', learning_rate=mtp.LR)
-    h = task.get(cfg)
-    model = h.build_model(0)
-    mk.assign(mk.named_variables(h), P)
 
     def feed(b):
         y = np.zeros((len(b['user']), 1 + sh.K), dtype=np.float32)
         y[:, 0] = 1.0
         return [b['user'], tok[b['hist_doc']]] + [tok[b['cand_doc'][:, j]] for j in range(1 + sh.K)], y
-    losses, t0 = [], time.time()
-    for s, b in enumerate(train, 1):
-        x, y = feed(b)
-        losses.append(model.train_on_batch(x, y)[0])
-        if s % 20 == 0:
-            print('step %d loss %.4f (%.0f s)' % (s, losses[-1], time.time() - t0), flush=True)
-    probs = np.concatenate([model.predict(feed(b)[0], batch_size=sh.B) for b in evalb]).astype(np.float32)
-    out = dict(ref_loss_p0=np.asarray(losses, dtype=np.float32), ref_probs_p0=probs,
-               ref_auc_p0=np.float64(synth.impression_auc(probs)))
-    np.savez_compressed(os.path.join(HERE, 'train_parity_c1_ref.npz'), **out)
-    print('reference-graph AUC after %d steps: %.6f' % (len(losses), out['ref_auc_p0']))
+    from keras import _engine
+    P0 = {k: np.array(v, copy=True) for k, v in P.items()}
+    path = os.path.join(HERE, 'train_parity_c1_ref.npz')
+    out = dict(np.load(path)) if os.path.exists(path) else {}
+    only = sys.argv[1:]
+    for name, p in (('p0', 0.0), ('p2', 0.2)):
+        if only and name not in only:
+            continue
+        # dropout 0.2: the graph is rebuilt with Dropout(0.2) layers; their keep masks are the device's tensor-core stream of
+        # step s (make_train_parity.quad_masks), fed through the shim's dropout hook in the order the graph evaluates them
+        keras.backend.clear_session()
+        cfg = mk.reference_config(settings, d, sh, 'Seq2VecPaperSoftmaxId', 'igru', 'dot', learning_rate=mtp.LR, dropout=p)
+        h = task.get(cfg)
+        model = h.build_model(0)
+        mk.assign(mk.named_variables(h), P0)
+        losses, t0 = [], time.time()
+        for s, b in enumerate(train, 1):
+            x, y = feed(b)
+            if p > 0:
+                toks = np.concatenate([tok[b['hist_doc']].reshape(-1, sh.L), tok[b['cand_doc']].reshape(-1, sh.L)])
+                mx, mc = mtp.quad_masks(s, toks, sh.E, sh.F, p)
+                _engine._STATE['dropout_hook'] = mk.MaskReplay(sh, keep={sh.E: mx.numpy() != 0, sh.F: mc.numpy() != 0})
+            try:
+                losses.append(model.train_on_batch(x, y)[0])
+            finally:
+                _engine._STATE['dropout_hook'] = None
+            if s % 20 == 0:
+                print('%s step %d loss %.4f (%.0f s)' % (name, s, losses[-1], time.time() - t0), flush=True)
+        probs = np.concatenate([model.predict(feed(b)[0], batch_size=sh.B) for b in evalb]).astype(np.float32)
+        out['ref_loss_' + name] = np.asarray(losses, dtype=np.float32)
+        out['ref_probs_' + name] = probs
+        out['ref_auc_' + name] = np.float64(synth.impression_auc(probs))
+        print('%s: reference-graph AUC after %d steps: %.6f' % (name, len(losses), out['ref_auc_' + name]), flush=True)
+    np.savez_compressed(path, **out)
 
 
 if __name__ == '__main__':
