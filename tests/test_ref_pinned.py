@@ -863,8 +863,12 @@ def test_training_parity_fixture_matches_reference_graph():
     200 steps) and the held-out per-impression AUC."""
     a = np.load(os.path.join(HERE, 'golden', 'train_parity_c1.npz'))
     b = np.load(os.path.join(HERE, 'golden', 'train_parity_c1_ref.npz'))
-    d = np.abs(a['loss_p0'] - b['ref_loss_p0'])
-    assert len(d) == 200 and d[:10].max() < 1e-4 and d.max() < 5e-3
-    assert abs(float(a['auc_p0']) - float(b['ref_auc_p0'])) <= 0.002
-    assert abs(synth.impression_auc(b['ref_probs_p0']) - float(b['ref_auc_p0'])) < 1e-12
-    assert float(b['ref_auc_p0']) > float(a['auc_init']) + 0.1          # the task was learnt
+    # p0: dropout 0; p2: dropout 0.2, the device's tensor-core keep masks of every step fed to the reference graph's own
+    # Dropout layers through the shim's hook (measured: losses within 8e-4 / 1.2e-3 over the 200 steps, AUC 0.866455 vs
+    # 0.866455 and 0.86560 vs 0.86511)
+    for run in ('p0', 'p2'):
+        d = np.abs(a['loss_' + run] - b['ref_loss_' + run])
+        assert len(d) == 200 and d[:10].max() < 1e-4 and d.max() < 5e-3, run
+        assert abs(float(a['auc_' + run]) - float(b['ref_auc_' + run])) <= 0.002, run
+        assert abs(synth.impression_auc(b['ref_probs_' + run]) - float(b['ref_auc_' + run])) < 1e-12
+        assert float(b['ref_auc_' + run]) > float(a['auc_init']) + 0.1          # the task was learnt
