@@ -273,10 +273,16 @@ def test_committed_vectors_reproduce_from_the_reference():
     assert sorted(new.files) == sorted(GOLD.files)
     for k in GOLD.files:
         a, b = GOLD[k], new[k]
-        if a.dtype.kind in 'fc':
-            assert np.allclose(a, b, rtol=0, atol=1e-12), k
-        else:
+        if a.dtype.kind not in 'fc':
             assert np.array_equal(a, b), k
+        elif '/adam/' in k or '/final/' in k or k.endswith('log_values'):
+            # weights after Adam steps (and what is logged after them): an element whose gradient is at rounding level takes
+            # +-lr steps of noise-decided sign (tolerances.assert_adam_weights_close), so a different BLAS thread split may
+            # move a few of them; everything else must reproduce to 1e-12
+            d = np.abs(a - b)
+            assert np.mean(d > 1e-9) <= 1e-3 and (d.size == 0 or d.max() <= 2.1e-2), k
+        else:
+            assert np.allclose(a, b, rtol=0, atol=1e-12), k
 
 
 # ---------------------------------------------------------------------------------------------- CUDA path
