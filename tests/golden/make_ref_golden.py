@@ -68,6 +68,8 @@ CASES = [
     ('p-avg', 'Seq2VecPaper', 'avg', 'dnn', 'niavg', {'gain': GAIN}),
     ('pid-gru', 'Seq2VecPaperId', 'gru', 'dnn', 'ngru', {'gain': GAIN}),
     ('pid-vo', 'Seq2VecPaperId', 'vo', 'dnn', 'vo', {'gain': GAIN}),
+    # users with more than max_impression impressions train on a random.sample of them (task/paper.py:272-279)
+    ('pid-igru-maximp', 'Seq2VecPaperId', 'igru', 'dnn', 'igru', {'gain': GAIN, 'max_impression': 1}),
     # time-window batchers (task/paper.py:667-790) and the vertical variants (:793-1001, :1136-1255)
     ('sdays-gru-dot', 'Seq2VecPaperSoftmaxDays', 'gru', 'dot', 'nigru', {'days': 3}),
     ('sdid-igru-dot', 'Seq2VecPaperSoftmaxDaysId', 'igru', 'dot', 'igru', {'days': 3}),
@@ -257,7 +259,9 @@ def run_case(mods, sh, data_dir, name, task_name, arch, score_model, my_arch, ex
     if 'vert_emb' in P:             # the reference's table has len(utils.verticals) rows
         P['vert_emb'] = P['vert_emb'][:len(ref_utils.verticals)]
     assign(variables, P)
+    import random
     np.random.seed(20190131)
+    random.seed(20190131)
     gen = h.train
     x, y = next(gen)
     n_cand = 1 + sh.K if softmax else 1
