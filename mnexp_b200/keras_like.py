@@ -113,6 +113,20 @@ class _Core:
         np.copyto(pin[key].numpy(), arr, casting='unsafe')
         return pin[key]
 
+    def dp(self, eng):
+        """mnexp_b200.dist.DataParallel around the training engine when torch.distributed is initialised with more than one
+        rank (one process per GPU, launched with torchrun): every process runs the same task / model code on its OWN batches
+        of config.batch_size rows, the gradients are exchanged every step (dense arena all-reduce + user-row all-gather,
+        dist.py) and the logged loss / accuracy are the means over the ranks.  None in a single process."""
+        import torch.distributed as tdist
+        if not (tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1):
+            return None
+        cached = self.__dict__.get('_dp')
+        if cached is None or cached.eng is not eng:
+            from .dist import DataParallel
+            cached = self.__dict__['_dp'] = DataParallel(eng)
+        return cached
+
     def n_train_cand(self):
         return 1 if self.loss == 'bce' else 1 + self.cfg.negative_samples
 
@@ -182,15 +196,25 @@ class Model:
             for t in db.values():
                 t.record_stream(main)
         nv = eng.B if n_valid is None else int(n_valid)      # rows beyond nv are padding with an all-zero target (fit)
-        loss = eng.train_step(db, grad_scale=None if nv == eng.B else 1.0 / nv)
+        dp = core.dp(eng)
+        if dp is None:
+            loss = eng.train_step(db, grad_scale=None if nv == eng.B else 1.0 / nv)
+        else:
+            assert nv == eng.B, 'data-parallel training needs full batches on every rank'
+            loss = dp.train_step(db)
         probs = eng.view('probs').reshape(eng.B, eng.C)
         if core.loss == 'bce':
             return ('bce', loss, probs, y)
         acc = (probs[:nv].argmax(1) == db['label'][:nv].argmax(1)).float().mean()
+        out = torch.stack([loss[0] * (eng.B / nv), acc])
+        if dp is not None:                                   # what is logged: the mean over the ranks' equal-sized batches
+            import torch.distributed as tdist
+            tdist.all_reduce(out, group=dp.group)
+            out = out / dp.world
         res = core.__dict__.setdefault('_results', {})
         if slot not in res:
             res[slot] = torch.empty(2, dtype=torch.float32).pin_memory()
-        res[slot].copy_(torch.stack([loss[0] * (eng.B / nv), acc]), non_blocking=True)
+        res[slot].copy_(out, non_blocking=True)
         done = torch.cuda.Event()
         done.record()
         return ('ce', res[slot], done)

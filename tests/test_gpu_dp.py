@@ -87,3 +87,16 @@ def test_two_nccl_ranks_equal_one_engine(lib, precision, trainable):
            '--master-port', '29731', os.path.join(ROOT, 'tests', 'dp_worker.py'), precision, str(trainable)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'fp16_tc'])
+def test_drop_in_surface_data_parallel(lib, precision):
+    """torchrun + the task handler / Keras-protocol model (keras_like routes train steps through dist.DataParallel when a
+    process group exists): two ranks on the halves of the reference-run batch reproduce the update the reference's own graph
+    made on the whole batch (tests/dp_surface_worker.py)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr', '127.0.0.1',
+           '--master-port', '29741', os.path.join(ROOT, 'tests', 'dp_surface_worker.py'), precision]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
