@@ -17,7 +17,7 @@ importable here.  So:
   ``task/seq2vec.py``, ``models.py``, ``document.py``, ``utils.py``,
   ``settings.py`` are IMPORTED FROM /root/reference AND RUN
   (``tests/golden/make_ref_golden.py``): its loaders, batchers and
-  ``_build_model`` graphs produce ``tests/golden/ref_golden.npz`` — 43 task
+  ``_build_model`` graphs produce ``tests/golden/ref_golden.npz`` — 44 task
   class / user encoder / scorer cases with batches, forward outputs, losses,
   gradients and Adam steps, the decomposed pipeline, and five whole runs of the
   reference's ``main.train`` / ``main.cook`` command functions with everything
