@@ -159,7 +159,7 @@ def masked_attention(X, att_w, att_b):
 ARCH_INI = ('igru', 'ingru')          # paper.py igru == cook.py ingru
 
 
-def user_encoder(arch, user, H, P, recurrent_activation='hard_sigmoid', u0_scale=None):
+def user_encoder(arch, user, H, P, recurrent_activation='hard_sigmoid', u0_scale=None, u2_scale=None):
     """Seq2VecPaperSoftmaxId.get_user_encoder — task/paper.py:584-633.
 
     H (B,W,D) already multiplied by the history mask.  u0_scale: optional (B,1)
@@ -168,6 +168,7 @@ def user_encoder(arch, user, H, P, recurrent_activation='hard_sigmoid', u0_scale
     f8 = lambda k: P[k].astype(np.float64)
     user = np.asarray(user).astype(np.int64).reshape(-1)
     u0 = f8('user_emb')[user] if 'user_emb' in P and arch not in ('nigru', 'niavg', 'att') else None
+    u2_scale = u0_scale if u2_scale is None else u2_scale      # second id table: its own Dropout draw (task/cook.py:169-183)
     if u0 is not None and u0_scale is not None:
         u0 = u0 * u0_scale
     gru = lambda h0: gru_last_state(H.astype(np.float64), h0, f8('gru_wx'), f8('gru_wh'), f8('gru_b'), recurrent_activation)
@@ -180,7 +181,7 @@ def user_encoder(arch, user, H, P, recurrent_activation='hard_sigmoid', u0_scale
     if arch in ('ngru', 'hgru', 'dgru'):     # LSTUR-con plain concat, :600-611
         return np.concatenate([gru(None), u0], -1)
     if arch == 'iicat':                      # Seq2VecPaperId 'iigru', task/paper.py:338-343 (cook 'inigru', task/cook.py:169-176)
-        return np.concatenate([gru(u0), f8('user_emb2')[user] * (1.0 if u0_scale is None else u0_scale)], -1)
+        return np.concatenate([gru(u0), f8('user_emb2')[user] * (1.0 if u2_scale is None else u2_scale)], -1)
     if arch == 'pgru':                       # :622-624
         return gru(None) + u0
     if arch == 'nigru':                      # :625-626
@@ -193,7 +194,7 @@ def user_encoder(arch, user, H, P, recurrent_activation='hard_sigmoid', u0_scale
         return H8.sum(-2) / (gm.sum(-1, keepdims=True) + 1e-7)
     # ---- cook.py branches (task/cook.py:155-193) and Seq2VecPaper 'att' (task/paper.py:206-208)
     H8 = H.astype(np.float64)
-    u2 = lambda: f8('user_emb2')[user] * (1.0 if u0_scale is None else u0_scale)   # the id mask multiplies both tables
+    u2 = lambda: f8('user_emb2')[user] * (1.0 if u2_scale is None else u2_scale)   # the id mask multiplies both tables
     if arch == 'iavg':
         gm = (H8 != 0).any(-1).astype(np.float64)
         return np.concatenate([H8.sum(-2) / (gm.sum(-1, keepdims=True) + 1e-7), u0], -1)
@@ -269,7 +270,7 @@ def _doc_vectors(tok, P, vert=None, subvert=None):
 
 def lstur_forward(P, user, clicked_tok, cand_tok, arch='igru', score_model='dot',
                   recurrent_activation='hard_sigmoid', aux=False, hist_vert=None, hist_subvert=None, cand_vert=None,
-                  cand_subvert=None, u0_scale=None, flavour='paper'):
+                  cand_subvert=None, u0_scale=None, flavour='paper', u2_scale=None):
     """Seq2VecPaperSoftmaxId._build_model forward — task/paper.py:635-665.
 
     clicked_tok (B,W,L), cand_tok (B,C,L) -> softmax probs (B,C) and the
@@ -279,7 +280,7 @@ def lstur_forward(P, user, clicked_tok, cand_tok, arch='igru', score_model='dot'
     dh = _doc_vectors(clicked_tok.reshape(B * W, L), P, hist_vert, hist_subvert).reshape(B, W, -1)
     hm = history_mask(clicked_tok)
     H = dh * hm[..., None]                                    # task/paper.py:644-645, task/cook.py:250
-    u = user_encoder(arch, user, H, P, recurrent_activation, u0_scale=u0_scale)
+    u = user_encoder(arch, user, H, P, recurrent_activation, u0_scale=u0_scale, u2_scale=u2_scale)
     dc = _doc_vectors(cand_tok.reshape(B * C, L), P, cand_vert, cand_subvert).reshape(B, C, -1)
     s = score(u, dc, P, score_model, flavour)
     out = dict(probs=softmax(s), logits=s, sigmoid=sigmoid(s), user_vec=u, cand_vec=dc, hist_vec=H, hist_mask=hm)

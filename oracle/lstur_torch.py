@@ -95,9 +95,12 @@ def masked_attention(X, att_w, att_b):
     return (X * w.unsqueeze(-1)).sum(1)
 
 
-def user_encoder(arch, user, H, P, recurrent_activation='hard_sigmoid', u0_scale=None):
+def user_encoder(arch, user, H, P, recurrent_activation='hard_sigmoid', u0_scale=None, u2_scale=None):
     """task/paper.py:584-633; cook branches task/cook.py:146-193."""
     u0 = P['user_emb'][user.reshape(-1)] if 'user_emb' in P and arch not in ('nigru', 'niavg', 'att') else None
+    # u2_scale: multiplier of the SECOND id table of cook 'inigru' / 'inagru', which sits behind its own Dropout(1 - id_keep)
+    # layer (task/cook.py:169-183: two independent draws); defaults to u0_scale (no dropout: both are the id mask)
+    u2_scale = u0_scale if u2_scale is None else u2_scale
     if u0 is not None and u0_scale is not None:
         u0 = u0 * u0_scale
     gru = lambda h0: gru_last_state(H, h0, P['gru_wx'], P['gru_wh'], P['gru_b'], recurrent_activation)
@@ -112,7 +115,7 @@ def user_encoder(arch, user, H, P, recurrent_activation='hard_sigmoid', u0_scale
         return torch.cat([gru(None), u0], -1)
     if arch == 'iicat':          # Seq2VecPaperId 'iigru' (task/paper.py:338-343) / cook 'inigru' (task/cook.py:169-176, where
         u2 = P['user_emb2'][user.reshape(-1)]       # the id mask multiplies the second embedding too)
-        return torch.cat([gru(u0), u2 if u0_scale is None else u2 * u0_scale], -1)
+        return torch.cat([gru(u0), u2 if u2_scale is None else u2 * u2_scale], -1)
     if arch == 'pgru':
         return gru(None) + u0
     if arch == 'nigru':
@@ -122,7 +125,7 @@ def user_encoder(arch, user, H, P, recurrent_activation='hard_sigmoid', u0_scale
     if arch == 'niavg':          # models.GlobalAveragePoolingMaskSupport (models.py:422-441) under Masking()
         gm = (H != 0).any(-1).to(H.dtype)
         return H.sum(-2) / (gm.sum(-1, keepdim=True) + EPS)
-    u2 = lambda: P['user_emb2'][user.reshape(-1)] * (1.0 if u0_scale is None else u0_scale)
+    u2 = lambda: P['user_emb2'][user.reshape(-1)] * (1.0 if u2_scale is None else u2_scale)
     if arch == 'iavg':
         gm = (H != 0).any(-1).to(H.dtype)
         return torch.cat([H.sum(-2) / (gm.sum(-1, keepdim=True) + EPS), u0], -1)
@@ -183,7 +186,7 @@ def _doc_vectors(tok, P, vert=None, subvert=None, **kw):
 
 def forward(P, user, clicked_tok, cand_tok, arch='igru', score_model='dot',
             recurrent_activation='hard_sigmoid', dropout=0.0, training=False, aux=False, hist_vert=None,
-            hist_subvert=None, cand_vert=None, cand_subvert=None, u0_scale=None, head='softmax', flavour='paper'):
+            hist_subvert=None, cand_vert=None, cand_subvert=None, u0_scale=None, head='softmax', flavour='paper', u2_scale=None):
     """Seq2VecPaperSoftmaxId._build_model — task/paper.py:635-665."""
     B, W, L = clicked_tok.shape
     C = cand_tok.shape[1]
@@ -191,7 +194,7 @@ def forward(P, user, clicked_tok, cand_tok, arch='igru', score_model='dot',
                       training=training).reshape(B, W, -1)
     hm = (clicked_tok != 0).any(-1).to(dh.dtype)
     H = dh * hm.unsqueeze(-1)
-    u = user_encoder(arch, user, H, P, recurrent_activation, u0_scale=u0_scale)
+    u = user_encoder(arch, user, H, P, recurrent_activation, u0_scale=u0_scale, u2_scale=u2_scale)
     dc = _doc_vectors(cand_tok.reshape(B * C, L), P, cand_vert, cand_subvert, dropout=dropout,
                       training=training).reshape(B, C, -1)
     s = score(u, dc, P, score_model, flavour)

@@ -297,8 +297,15 @@ def run_case(mods, sh, data_dir, name, task_name, arch, score_model, my_arch, ex
     replay = MaskReplay(sh, p, DROP_SEED) if p > 0 else None
     _engine._STATE['dropout_hook'] = replay
     try:
-        if arch == 'dgru':          # Dropout(0.5, noise_shape=(None, 1)) on the id vector: its draw is TensorFlow's, not replayable
+        if arch == 'dgru':          # Dropout(0.5, noise_shape=(None, 1)) on the id vector (task/paper.py:608-611)
             loss, grads = model.loss_and_gradients(x, y, training=False)
+            keep_rows = (np.random.default_rng(3).random((len(y), 1)) >= 0.5)
+            _engine._STATE['dropout_hook'] = lambda shape, level: keep_rows        # the only Dropout with a rate > 0 here
+            lt, gt = model.loss_and_gradients(x, y, training=True)
+            _engine._STATE['dropout_hook'] = replay
+            out['dgru_keep_rows'], out['dgru_train_loss'] = keep_rows.astype(np.float64), np.float64(lt)
+            for vname, g in gt.items():
+                out['dgru_train_grad/' + vname] = g
         else:
             loss, grads = model.loss_and_gradients(x, y, training=True)
         out['loss'] = np.float64(loss)
@@ -352,7 +359,10 @@ COOK_CASES = [
     ('cook-iatt-ddot-v', 'iatt', 'ddot', 'iatt', 'v'), ('cook-ilstm-dnn-s', 'ilstm', 'dnn', 'ilstm', 's'),
     ('cook-inagru-dot-vs', 'inagru', 'dot', 'inagru', 'vs'), ('cook-atgru-dnn-vs', 'atgru', 'dnn', 'atgru', 'vs'),
     ('cook-algru-dot-vs', 'algru', 'dot', 'algru', 'vs'),
+    # id_keep < 1: Dropout(1 - id_keep) on idx_mask, one layer per id table (task/cook.py:141-142, 171-172); training-mode loss
+    ('cook-inigru-ddot-s-idkeep', 'inigru', 'ddot', 'iicat', 's'),
 ]
+COOK_ID_KEEP = 0.7
 COOK_DV, COOK_DS, COOK_USERS = 3, 5, 25000
 MAIN_COOK_BATCH = 10          # 24 training rows -> batches of 10, 10 and a ragged 4 (Keras trains the tail too)
 
@@ -422,8 +432,9 @@ def run_cook_case(mods, data_dir, name, arch, score_model, my_arch, vtype):
     from mnexp_b200 import synth
     keras.backend.clear_session()
     sh = cook_shape(score_model, vtype)
+    id_keep = COOK_ID_KEEP if name.endswith('-idkeep') else 1.0
     cfg = reference_config(settings, data_dir, sh, 'Cook', arch, score_model, use_vertical=True, use_vertical_type=vtype,
-                           vertical_embedding_dim=COOK_DV, subvertical_embedding_dim=COOK_DS, days=30, id_keep=1.0,
+                           vertical_embedding_dim=COOK_DV, subvertical_embedding_dim=COOK_DS, days=30, id_keep=id_keep,
                            validation_step=6, lrd_on_epochs=[0])
     h = task.get(cfg)
     model = h.build_model(0)
@@ -452,13 +463,32 @@ def run_cook_case(mods, data_dir, name, arch, score_model, my_arch, vtype):
     out['test_predict'] = h.test_model.predict(feats)
     vx, vy = h.valid()
     out['valid_eval'] = np.asarray(h.test_model.test_on_batch(vx, vy)[:1], dtype=np.float64)     # binary_crossentropy of test_model
-    loss, grads = model.loss_and_gradients(x, y, training=True)
+    hook_calls = []
+    if id_keep < 1.0:       # two Dropout layers on idx_mask ('inigru': one per id table), evaluated in graph order
+        from keras import _engine
+        g = np.random.default_rng(4)
+        keeps = [g.random((len(y[0]), 1)) < id_keep, g.random((len(y[0]), 1)) < id_keep]
+        out['idkeep_keep1'], out['idkeep_keep2'] = keeps[0].astype(np.float64), keeps[1].astype(np.float64)
+
+        def hook(shape, level):
+            hook_calls.append((shape, level))
+            return keeps[(len(hook_calls) - 1) % 2]
+        _engine._STATE['dropout_hook'] = hook
+    try:
+        loss, grads = model.loss_and_gradients(x, y, training=True)
+    finally:
+        if id_keep < 1.0:
+            _engine._STATE['dropout_hook'] = None
     out['loss'] = np.float64(loss)
+    out['dropout_calls'] = np.int64(len(hook_calls))
     by_var = {v.vname: k for k, v in variables.items()}
     for vname, g in grads.items():
         k = by_var[vname]
         g = g.reshape(-1) if k in ('att_w', 'uatt_w') else g
         out['grad/' + k] = g[:64] if k in ('user_emb', 'user_emb2') else g
+    if id_keep < 1.0:
+        out['layers'] = np.array([l.name for l in model.layers])
+        return out
     results = [model.train_on_batch(x, y) for _ in range(3)]
     out['adam_results'] = np.asarray(results, dtype=np.float64)
     out['adam_losses'] = out['adam_results'][:, 0]

@@ -383,7 +383,7 @@ def test_cuda_dropout_step_matches_reference_graph(lib, precision):
 
 
 # ---------------------------------------------------------------------------------------------- Cook (task/cook.py:4-285)
-COOK = [str(c) for c in GOLD['cook_cases']]
+COOK = [str(c) for c in GOLD['cook_cases'] if not str(c).endswith('-idkeep')]       # the id_keep case has its own test
 COOK_TABLE = {row[0]: tuple(row[1:]) for row in GOLD['cook_table']}
 COOK_KEYS = P_KEYS + ('subvert_emb', 'lstm_wx', 'lstm_wh', 'lstm_b', 'alpha')
 
@@ -880,3 +880,52 @@ def test_training_parity_fixture_matches_reference_graph():
         assert abs(float(a['auc_' + run]) - float(b['ref_auc_' + run])) <= 0.002, run
         assert abs(synth.impression_auc(b['ref_probs_' + run]) - float(b['ref_auc_' + run])) < 1e-12
         assert float(b['ref_auc_' + run]) > float(a['auc_init']) + 0.1          # the task was learnt
+
+
+
+# ---------------------------------------------------------------------------------------------- dropout on the id vector
+def test_oracle_matches_reference_id_vector_dropout():
+    """Training-mode dropout of the user-id vector, keep draws fed to the reference graph through the shim's hook:
+    `dgru` — Dropout(0.5, noise_shape=(None, 1)) on the id vector, one draw per row (task/paper.py:608-611);
+    Cook `inigru` with id_keep = 0.7 — Dropout(0.3) on idx_mask, one INDEPENDENT layer per id table (task/cook.py:141-142,
+    171-172).  The oracle takes the same draws as explicit multipliers (u0_scale / u2_scale = what the engine's
+    lstur_batch.user_scale / user_scale2 carry)."""
+    # dgru
+    name = 'sid-dgru-ddot'
+    task_name, arch, score_model, my_arch, softmax, Pn, user, clicked, cands, y, x = case(name)
+    g = lambda k: GOLD[name + '/' + k]
+    P = {k: torch.tensor(v, dtype=torch.float64, requires_grad=(k != 'word_emb')) for k, v in Pn.items()}
+    scale = torch.tensor(g('dgru_keep_rows') / 0.5)
+    u, c, d = (torch.as_tensor(a).long() for a in (user, clicked, cands))
+    probs = ot.forward(P, u, c, d, arch=my_arch, score_model=score_model, u0_scale=scale)
+    loss = ot.categorical_crossentropy(torch.tensor(y, dtype=torch.float64), probs)
+    assert abs(float(loss.detach()) - float(g('dgru_train_loss'))) < F64
+    assert abs(float(g('dgru_train_loss')) - float(g('loss'))) > 1e-6             # the draw did change the loss
+    tr = [k for k in P if P[k].requires_grad]
+    for k, gr in zip(tr, torch.autograd.grad(loss, [P[k] for k in tr], allow_unused=True)):
+        ref = GOLD['%s/dgru_train_grad/%s' % (name, k)]
+        got = np.zeros(ref.shape) if gr is None else gr.numpy().reshape(ref.shape)
+        assert np.abs(got - ref).max() <= F64 * max(1.0, np.abs(ref).max()), k
+    # cook inigru, id_keep 0.7
+    name = 'cook-inigru-ddot-s-idkeep'
+    g = lambda k: GOLD[name + '/' + k]
+    assert int(g('dropout_calls')) == 2                                          # two Dropout layers, two draws
+    arch, score_model, my_arch, vtype = [str(v) for v in GOLD['cook_table'][[str(c) for c in GOLD['cook_cases']].index(name)][1:]]
+    xs = [g('x%d' % i) for i in range(8)]
+    Pn = {k: GOLD[name + '/P/' + k] for k in COOK_KEYS if name + '/P/' + k in GOLD.files}
+    P = {k: torch.tensor(v, dtype=torch.float64, requires_grad=(k != 'word_emb')) for k, v in Pn.items()}
+    idx, idx_mask, ch_title, ch_vert, ch_subvert, cd_title, cd_vert, cd_subvert = xs
+    n = len(idx)
+    keep = mk.COOK_ID_KEEP
+    s1 = torch.tensor(idx_mask.reshape(n, 1) * g('idkeep_keep1') / keep)
+    s2 = torch.tensor(idx_mask.reshape(n, 1) * g('idkeep_keep2') / keep)
+    t = lambda a: torch.as_tensor(np.asarray(a)).long()
+    out = ot.forward(P, t(idx).reshape(-1), t(ch_title), t(cd_title), arch=my_arch, score_model=score_model, flavour='cook',
+                     aux=True, u0_scale=s1, u2_scale=s2, hist_subvert=ch_subvert, cand_subvert=cd_subvert)
+    loss = ot.categorical_crossentropy(torch.tensor(g('y'), dtype=torch.float64), torch.softmax(out['logits'], -1))
+    assert abs(float(loss.detach()) - float(g('loss'))) < F64
+    tr = [k for k in P if P[k].requires_grad]
+    for k, gr in zip(tr, torch.autograd.grad(loss, [P[k] for k in tr], allow_unused=True)):
+        ref = g('grad/' + k)
+        got = np.zeros(P[k].shape) if gr is None else gr.numpy()
+        assert np.abs(got.reshape(ref.shape) - ref).max() <= F64 * max(1.0, np.abs(ref).max()), k
