@@ -1,7 +1,5 @@
 """keras.layers (2.2.4) — the layers the LSTUR path of the reference instantiates.  TEST INFRASTRUCTURE
 (oracle/keras_shim/README.md).  Each class names the Keras source file whose published behaviour it restates."""
-import inspect
-
 import numpy as np
 import torch
 

@@ -589,6 +589,7 @@ def ref_utils_verticals():
 def run_main_cases(mods, data_dir, cook_dir):
     """`main.py train` on Seq2VecPaperSoftmaxId (LSTUR-ini) and `main.py cook` on Cook 'ingru', two epochs each"""
     from mnexp_b200 import synth
+    keras, settings, task = mods
     out = {}
     sh = synth.SHAPES['tiny']
     P = synth.make_weights(sh, arch='igru', bias_noise=0.05, seed=4242, score_model='dot',
@@ -643,6 +644,22 @@ def run_main_cases(mods, data_dir, cook_dir):
     for k, v in Pv.items():
         out['main-vertalt/P/' + k] = np.asarray(v, dtype=np.float64)
     out['main-vertalt/vertical_names'] = np.array(names)
+    # the vertical-model batchers of ...VertAlt (task/paper.py:1066-1099): document split drawn at construction, train_vert
+    # reshuffles it every pass; one-hot columns re-ordered to the sorted vertical names (the reference's order is a set's)
+    keras.backend.clear_session()
+    np.random.seed(4710)
+    hv = task.get(reference_config(settings, data_dir, sh, 'Seq2VecPaperSoftmaxDaysIdVertAlt', 'igru', 'dot', days=3, round=3,
+                                   epochs=1))
+    hv.build_model(0)
+    perm = [hv.verticals.index(n) for n in names]
+    np.random.seed(4711)
+    gen = hv.train
+    for i in range(2):
+        tt, vv = next(gen)
+        out['main-vertalt/vert_batch%d_titles' % i], out['main-vertalt/vert_batch%d_labels' % i] = np.asarray(tt), np.asarray(vv)[:, perm]
+    tt, vv = next(hv.valid)
+    out['main-vertalt/vert_valid_titles'], out['main-vertalt/vert_valid_labels'] = np.asarray(tt), np.asarray(vv)[:, perm]
+    out['main-vertalt/steps'] = np.array([hv.training_step, hv.validation_step])
     csh = cook_shape('ddot', 'vs')
     Pc = synth.make_weights(csh, arch='igru', bias_noise=0.05, seed=4242, score_model='ddot', cook=True, dv=COOK_DV, ds=COOK_DS,
                             word_emb=np.load(os.path.join(cook_dir, 'Vocab.tsv.npy')))

@@ -929,3 +929,28 @@ def test_oracle_matches_reference_id_vector_dropout():
         ref = g('grad/' + k)
         got = np.zeros(P[k].shape) if gr is None else gr.numpy()
         assert np.abs(got.reshape(ref.shape) - ref).max() <= F64 * max(1.0, np.abs(ref).max()), k
+
+
+
+def test_vertalt_vertical_batchers_reproduce_the_reference():
+    """...VertAlt's own data path (task/paper.py:1009-1099): the 10 % / 90 % document split shuffled at construction, the
+    reshuffling `train_vert`, `valid_vert`, and the step counts derived from them — same numpy seed, same batches (one-hot
+    columns compared in the order of the sorted vertical names; the reference orders them by a set's iteration)"""
+    d = tempfile.mkdtemp()
+    synth.write_dataset(d, SH)
+    cfg = settings.Config(dict(task='Seq2VecPaperSoftmaxDaysIdVertAlt', arch='igru', score_model='dot', input_training_data_path=d,
+                               title_shape=SH.L, window_size=SH.W, negative_samples=SH.K, batch_size=SH.B, days=3, round=3,
+                               textual_embedding_dim=SH.E, title_filter_shape=(SH.F, SH.k), user_embedding_dim=SH.U, debug=True,
+                               dropout=0.0, epochs=1, training_step=3, validation_step=2))
+    np.random.seed(4710)
+    h = task.get(cfg)
+    g = lambda k: GOLD['main-vertalt/' + k]
+    assert list(h.verticals) == [str(n) for n in g('vertical_names')]
+    assert [h.training_step, h.validation_step] == [int(v) for v in g('steps')]
+    np.random.seed(4711)
+    gen = h.train                      # train_seq is False before the first callback_valid: vertical batches
+    for i in range(2):
+        tt, vv = next(gen)
+        assert np.array_equal(np.asarray(tt), g('vert_batch%d_titles' % i)) and np.array_equal(np.asarray(vv), g('vert_batch%d_labels' % i))
+    tt, vv = next(h.valid)
+    assert np.array_equal(np.asarray(tt), g('vert_valid_titles')) and np.array_equal(np.asarray(vv), g('vert_valid_labels'))
