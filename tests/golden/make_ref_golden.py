@@ -817,6 +817,41 @@ def run_host_functions(mods, data_dir):
     return out
 
 
+# (label, task class, arch, score model, extra config): options the reference rejects (SURVEY 8b "Errors")
+ERROR_CASES = [('softmaxid-arch', 'Seq2VecPaperSoftmaxId', 'nope', 'dot', {}),
+               ('softmax-arch', 'Seq2VecPaperSoftmax', 'igru', 'dot', {}),
+               ('paperid-arch', 'Seq2VecPaperId', 'avg', 'dnn', {}),
+               ('doc-model', 'Seq2VecPaperSoftmaxId', 'igru', 'dot', {'news_encoder': 'nope'}),
+               ('score-model', 'Seq2VecPaperSoftmaxId', 'igru', 'nope', {}),
+               ('dot-width', 'Seq2VecPaperSoftmaxId', 'ngru', 'dot', {}),
+               ('cook-arch', 'Cook', 'nope', 'dot', {}),
+               ('cook-score', 'Cook', 'igru', 'nope', {})]
+
+
+def run_error_cases(mods, data_dir, cook_dir):
+    keras, settings, task = mods
+    from mnexp_b200 import synth
+    sh = synth.SHAPES['tiny']
+    names, kinds, messages = [], [], []
+    for label, task_name, arch, score_model, extra in ERROR_CASES:
+        keras.backend.clear_session()
+        if task_name == 'Cook':
+            cfg = reference_config(settings, cook_dir, cook_shape(), 'Cook', arch, score_model, use_vertical=True, days=30,
+                                   vertical_embedding_dim=COOK_DV, subvertical_embedding_dim=COOK_DS, **extra)
+        else:
+            cfg = reference_config(settings, data_dir, sh, task_name, arch, score_model, **extra)
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                task.get(cfg).build_model(0)
+            kind, msg = 'none', ''
+        except Exception as e:          # noqa: BLE001
+            kind, msg = type(e).__name__, str(e)
+        names.append(label)
+        kinds.append(kind)
+        messages.append(msg)
+    return dict(labels=np.array(names), kinds=np.array(kinds), messages=np.array(messages))
+
+
 def generate(path=OUT, verbose=True):
     mods = load_reference()
     from mnexp_b200 import synth
@@ -856,6 +891,10 @@ def generate(path=OUT, verbose=True):
         if verbose:
             print('%-12s %-20s %d docs, %d users, %d scored pairs; test_correct %.8f vs %.8f' % (
                 c[0], c[1], len(res['doc_keys']), len(res['user_keys']), len(res['scores']), res['pred'], res['sigm']))
+    for k, v in run_error_cases(mods, data_dir, cook_dir).items():
+        out['errors/' + k] = v
+    if verbose:
+        print('errors       ' + ' | '.join('%s: %s' % (a, b) for a, b in zip(out['errors/labels'], out['errors/kinds'])))
     out.update(run_main_cases(mods, data_dir, cook_dir))
     if verbose:
         for c in ('main-train', 'main-paperid', 'main-vertsup', 'main-vertalt', 'main-cook'):

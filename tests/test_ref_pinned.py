@@ -954,3 +954,34 @@ def test_vertalt_vertical_batchers_reproduce_the_reference():
         assert np.array_equal(np.asarray(tt), g('vert_batch%d_titles' % i)) and np.array_equal(np.asarray(vv), g('vert_batch%d_labels' % i))
     tt, vv = next(h.valid)
     assert np.array_equal(np.asarray(tt), g('vert_valid_titles')) and np.array_equal(np.asarray(vv), g('vert_valid_labels'))
+
+
+def test_rejected_options_raise_like_the_reference():
+    """SURVEY 8b "Errors": unsupported user / doc models raise Exception('Unsupport ... model'), unknown scorers
+    NotImplementedError, a 'dot' scorer over vectors of different widths ValueError (keras.layers.Dot.build) — what the
+    reference's own build_model raised for each bad configuration (make_ref_golden.run_error_cases), and what the mirror
+    raises before it ever touches the GPU"""
+    d = tempfile.mkdtemp()
+    synth.write_dataset(d, SH)
+    cd = tempfile.mkdtemp()
+    csh = mk.cook_shape()
+    synth.write_cook_npz(cd, csh)
+    ref = {str(a): (str(b), str(c)) for a, b, c in zip(GOLD['errors/labels'], GOLD['errors/kinds'], GOLD['errors/messages'])}
+    for label, task_name, arch, score_model, extra in mk.ERROR_CASES:
+        if task_name == 'Cook':
+            cfg = settings.Config(dict(task='Cook', arch=arch, input_training_data_path=cd, days=30, window_size=csh.W, batch_size=8,
+                                       title_filter_shape=(csh.F, 3), user_embedding_dim=csh.U, dropout=0.0, score_model=score_model,
+                                       use_vertical=True, vertical_embedding_dim=mk.COOK_DV, subvertical_embedding_dim=mk.COOK_DS,
+                                       precision='fp32', **extra))
+        else:
+            cfg = settings.Config(dict(task=task_name, arch=arch, score_model=score_model, input_training_data_path=d,
+                                       title_shape=SH.L, window_size=SH.W, negative_samples=SH.K, batch_size=SH.B,
+                                       textual_embedding_dim=SH.E, title_filter_shape=(SH.F, SH.k), user_embedding_dim=SH.U,
+                                       debug=True, dropout=0.0, precision='fp32', **extra))
+        kind, msg = ref[label]
+        assert kind != 'none', label
+        with pytest.raises(Exception) as info:
+            task.get(cfg).build_model(0)
+        assert type(info.value).__name__ == kind, (label, type(info.value).__name__, kind, str(info.value))
+        if kind == 'Exception':
+            assert str(info.value) == msg, (label, str(info.value), msg)
